@@ -1,0 +1,273 @@
+"""Generate golden vectors by running the REAL reference (Denys88/rl_games @ /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/gen_golden.py
+
+Writes small ``tests/golden/*.pt`` fixtures (committed).  ``gymnasium`` and ``tensorboardX`` are not
+installed here, so the import stubs under ``tests/golden/_stubs`` are put on ``sys.path`` -- the hot
+path only uses gymnasium to describe shapes/dtypes (reference experience.py:385-398).
+
+Action sampling: the reference samples with ``torch.distributions.Normal.sample`` ->
+``torch.normal(loc, scale)``; this script swaps ``torch.normal`` for ``loc + scale * noise_tape[k]``
+so the sampled noise is part of the fixture and the oracle / CUDA path can replay it.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, '_stubs'))
+sys.path.insert(0, '/root/reference')
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+torch.set_num_threads(1)
+
+
+def save(name, obj):
+    path = os.path.join(HERE, name)
+    torch.save(obj, path)
+    print('wrote', path, os.path.getsize(path), 'bytes')
+
+
+# ------------------------------------------------------------------ GAE
+def gen_gae():
+    from rl_games.triton_kernels.gae_kernel import _pytorch_gae, compute_gae
+    sys.path.insert(0, '/root/reference/tests')
+    from test_triton_gae import make_inputs, reference_gae  # the reference's own KAT helpers
+    cases = []
+    for shape in [(8, 4, 1), (16, 6, 3), (8, 16, 1), (36, 64, 3), (32, 40, 1)]:
+        for gamma, tau in [(0.99, 0.95), (1.0, 1.0)]:
+            inp = make_inputs(*shape)
+            out = _pytorch_gae(*inp, gamma, tau)
+            assert torch.equal(out, compute_gae(*inp, gamma, tau))
+            ref64 = reference_gae(*inp, gamma, tau) if shape[1] <= 16 else None
+            cases.append({'shape': shape, 'gamma': gamma, 'tau': tau, 'inputs': inp, 'pytorch_gae': out,
+                          'scalar_f64_as_f32': ref64})
+    # edge cases from tests/test_triton_gae.py:102-111 (all-done / no-done)
+    rewards, values, dones, lv, ld = make_inputs(10, 4, 1)
+    for fill in (0.0, 1.0):
+        d, l = torch.full_like(dones, fill), torch.full_like(ld, fill)
+        cases.append({'shape': (10, 4, 1), 'gamma': 0.99, 'tau': 0.95, 'inputs': (rewards, values, d, lv, l),
+                      'pytorch_gae': _pytorch_gae(rewards, values, d, lv, l, 0.99, 0.95), 'scalar_f64_as_f32': None})
+    save('gae.pt', cases)
+
+
+# ------------------------------------------------------------------ RunningMeanStd / masks / losses
+def gen_math():
+    from rl_games.algos_torch.running_mean_std import RunningMeanStd
+    from rl_games.algos_torch import torch_ext
+    from rl_games.common import common_losses
+    g = torch.Generator().manual_seed(1)
+    out = {}
+    # running mean std: three sequential train-mode updates, then eval normalise + denorm
+    rms = RunningMeanStd((6,))
+    rms.train()
+    xs = [torch.randn(37, 6, generator=g) * 3 + 1.5, torch.randn(5, 6, generator=g) - 4, torch.randn(64, 6, generator=g) * 0.1]
+    ys = [rms(x) for x in xs]
+    rms.eval()
+    xe = torch.randn(9, 6, generator=g) * 10
+    out['rms'] = {'xs': xs, 'ys': ys, 'state': {k: v.clone() for k, v in rms.state_dict().items()},
+                  'x_eval': xe, 'y_eval': rms(xe), 'y_denorm': rms(xe, denorm=True)}
+    # masked update (value normaliser on valid rows: a2c_common.py:1605-1615)
+    rmsm = RunningMeanStd((1,))
+    rmsm.train()
+    xv = torch.randn(50, 1, generator=g) * 2 + 3
+    mask = (torch.rand(50, generator=g) < 0.7)
+    rmsm(xv[mask])
+    out['rms_valid_rows'] = {'x': xv, 'mask': mask, 'state': {k: v.clone() for k, v in rmsm.state_dict().items()}}
+    # masked moments / normalisation
+    v = torch.randn(41, generator=g) * 2 + 0.5
+    m = (torch.rand(41, generator=g) < 0.6).float()
+    mean, var = torch_ext.get_mean_var_with_masks(v, m)
+    out['masked'] = {'v': v, 'm': m, 'mean': mean, 'var': var,
+                     'norm_masked': torch_ext.normalization_with_masks(v, m),
+                     'norm_unmasked': torch_ext.normalization_with_masks(v, None)}
+    # degenerate masks (tests/test_ppo_masking.py:568-584)
+    for name, mm in [('zero', torch.zeros(41)), ('one', torch.cat([torch.ones(1), torch.zeros(40)]))]:
+        mean, var = torch_ext.get_mean_var_with_masks(v, mm)
+        out['masked_' + name] = {'m': mm, 'mean': mean, 'var': var, 'norm': torch_ext.normalization_with_masks(v, mm)}
+    # losses
+    B, A = 33, 5
+    old_nlp = torch.randn(B, generator=g) * 0.3 + 4
+    nlp = old_nlp + torch.randn(B, generator=g) * 0.3
+    adv = torch.randn(B, generator=g)
+    out['actor'] = {'old': old_nlp, 'new': nlp, 'adv': adv,
+                    'hard': common_losses.actor_loss(old_nlp, nlp, adv, True, 0.2),
+                    'smooth': common_losses.smoothed_actor_loss(old_nlp, nlp, adv, True, 0.2)}
+    vp, vv, rr = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g)
+    out['critic'] = {'old_values': vp, 'values': vv, 'returns': rr,
+                     'clip': common_losses.critic_loss(None, vp, vv, 0.2, rr, True),
+                     'noclip': common_losses.critic_loss(None, vp, vv, 0.2, rr, False)}
+    mu0, mu1 = torch.randn(B, A, generator=g), torch.randn(B, A, generator=g)
+    s0, s1 = torch.rand(B, A, generator=g) + 0.2, torch.rand(B, A, generator=g) + 0.2
+    out['kl'] = {'mu0': mu0, 's0': s0, 'mu1': mu1, 's1': s1, 'kl': torch_ext.policy_kl(mu0, s0, mu1, s1),
+                 'kl_rows': torch_ext.policy_kl(mu0, s0, mu1, s1, False)}
+    yp, yy = torch.randn(B, 1, generator=g), torch.randn(B, 1, generator=g)
+    out['diag'] = {'y_pred': yp, 'y': yy, 'ev': torch_ext.explained_variance(yp, yy),
+                   'clip_frac': torch_ext.policy_clip_fraction(nlp, old_nlp, 0.2)}
+    # AverageMeter
+    am = torch_ext.AverageMeter(1, 10)
+    seq = [torch.randn(k, 1, generator=g) for k in (3, 0, 12, 4)]
+    means = []
+    for s in seq:
+        am.update(s)
+        means.append((am.mean.clone(), am.current_size))
+    out['meter'] = {'seq': seq, 'means': means}
+    # schedulers (tests/test_perf_fixes.py:204-222)
+    from rl_games.common import schedulers
+    sch = schedulers.AdaptiveScheduler(0.008)
+    lr, lrs = 3e-4, []
+    kls = [0.001, 0.02, 0.005, 0.017, 0.0039, 0.1, 0.1, 0.1, 0.0, 0.0]
+    for k in kls:
+        lr, _ = sch.update(lr, 0.0, 0, 0, k)
+        lrs.append(lr)
+    out['adaptive'] = {'kls': kls, 'lrs': lrs}
+    save('math.pt', out)
+
+
+# ------------------------------------------------------------------ full agent epochs
+class TapeVecEnv:
+    """Tensor env fed from tapes (mirrors oracle.ppo_oracle.TapeEnv)."""
+
+    def __init__(self, obs_tape, done_tape, timeout_tape, autoreset_mode='same_step'):
+        self.obs_tape, self.done_tape, self.timeout_tape = obs_tape, done_tape, timeout_tape
+        self.i = 0
+        self.autoreset_mode = autoreset_mode
+
+    def reset(self):
+        self.i = 0
+        return self.obs_tape[0].clone()
+
+    def step(self, actions):
+        rew = -(actions * actions).sum(-1) * 0.1
+        self.i += 1
+        j = self.i % self.obs_tape.shape[0]
+        return self.obs_tape[j].clone(), rew, self.done_tape[j].clone(), {'time_outs': self.timeout_tape[j].clone()}
+
+    def get_env_info(self):
+        import gymnasium as gym
+        D, A = self.obs_tape.shape[-1], self.A
+        info = {'observation_space': gym.spaces.Box(-np.inf, np.inf, (D,), np.float32),
+                'action_space': gym.spaces.Box(-1.0, 1.0, (A,), np.float32)}
+        if self.autoreset_mode != 'same_step':
+            info['autoreset_mode'] = self.autoreset_mode
+        return info
+
+    def get_env_state(self):
+        return None
+
+    def set_env_state(self, s):
+        pass
+
+    def set_train_info(self, *a, **kw):
+        pass
+
+
+def make_params(N, H, mb, units, overrides=None):
+    network = {
+        'name': 'actor_critic', 'separate': False,
+        'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None',
+                                 'mu_init': {'name': 'default'},
+                                 'sigma_init': {'name': 'const_initializer', 'val': 0},
+                                 'fixed_sigma': True}},
+        'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}},
+    }
+    # hyper-parameters of configs/mujoco/ant_envpool.yaml:28-56
+    config = {
+        'name': 'golden', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0},
+        'device': 'cpu', 'multi_gpu': False, 'mixed_precision': False, 'torch_compile': False,
+        'normalize_input': True, 'normalize_value': True, 'value_bootstrap': True, 'normalize_advantage': True,
+        'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4, 'lr_schedule': 'adaptive', 'kl_threshold': 0.008,
+        'grad_norm': 1.0, 'entropy_coef': 0.0, 'truncate_grads': True, 'e_clip': 0.2, 'clip_value': True,
+        'use_smooth_clamp': True, 'bound_loss_type': 'regularisation', 'bounds_loss_coef': 0.0,
+        'max_epochs': 100, 'num_actors': N, 'horizon_length': H, 'minibatch_size': mb, 'mini_epochs': 4,
+        'critic_coef': 2, 'save_frequency': 0, 'save_best_after': 10_000, 'print_stats': False,
+        'train_dir': '/tmp/golden_runs',
+    }
+    config.update(overrides or {})
+    return {'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'},
+            'network': network, 'config': config}
+
+
+def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, overrides=None, autoreset='same_step',
+              seed=3):
+    from rl_games.torch_runner import Runner
+    from oracle.ppo_oracle import make_tapes
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    T = H * epochs + 1
+    obs_tape, done_tape, tout_tape = make_tapes(T, N, D, seed=seed)
+    env = TapeVecEnv(obs_tape, done_tape, tout_tape, autoreset)
+    env.A = A
+    params = make_params(N, H, mb, units, overrides)
+    params['config']['env_info'] = env.get_env_info()
+    runner = Runner()
+    runner.load({'params': params})
+    runner.params['config']['vec_env'] = env
+    agent = runner.algo_factory.create(runner.algo_name, base_name='golden', params=runner.params)
+    init_state = {k: v.clone() for k, v in agent.model.state_dict().items()}
+    # perturb sigma / biases a little so nothing is exactly zero
+    g = torch.Generator().manual_seed(seed + 100)
+    with torch.no_grad():
+        for k, p in agent.model.named_parameters():
+            if k.endswith('bias') or k.endswith('sigma'):
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    init_state = {k: v.clone() for k, v in agent.model.state_dict().items()}
+
+    noise = torch.randn(epochs, H + 1, N, A, generator=g)   # [epoch, step (H rollout + 1 last-value fwd)]
+    counter = {'k': 0}
+    orig_normal = torch.normal
+
+    def fake_normal(loc, scale, *a, **kw):
+        k = counter['k']
+        counter['k'] += 1
+        e, n = divmod(k, H + 1)
+        return loc + scale * noise[e, n]
+    torch.normal = fake_normal
+    try:
+        agent.init_tensors()
+        agent.obs = agent.env_reset()
+        epochs_out = []
+        for ep in range(epochs):
+            agent.epoch_num += 1
+            res = agent.train_epoch()
+            step_time, play_time, update_time, total, a_losses, c_losses, b_losses, entropies, kls, last_lr, lr_mul = res
+            ds = agent.dataset.values_dict
+            epochs_out.append({
+                'a_losses': torch.stack([x.detach() for x in a_losses]), 'c_losses': torch.stack([x.detach() for x in c_losses]),
+                'entropies': torch.stack([x.detach() for x in entropies]), 'kls': torch.stack([x.detach() for x in kls]),
+                'b_losses': torch.stack([x.detach() for x in b_losses]) if len(b_losses) else None,
+                'last_lr': agent.last_lr,
+                'state': {k: v.clone() for k, v in agent.model.state_dict().items()},
+                'dataset': {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ds.items() if k != 'rnn_states'},
+                'mb_rewards': agent.experience_buffer.tensor_dict['rewards'].clone(),
+                'mb_values': agent.experience_buffer.tensor_dict['values'].clone(),
+                'mb_dones': agent.experience_buffer.tensor_dict['dones'].clone(),
+                'game_rewards_mean': agent.game_rewards.mean.clone(), 'game_rewards_size': agent.game_rewards.current_size,
+                'game_lengths_mean': agent.game_lengths.mean.clone(),
+                'adam_exp_avg': [agent.optimizer.state[p]['exp_avg'].clone() for p in agent.model.parameters()],
+                'adam_exp_avg_sq': [agent.optimizer.state[p]['exp_avg_sq'].clone() for p in agent.model.parameters()],
+            })
+            agent.dataset.update_values_dict(None)
+        assert counter['k'] == epochs * (H + 1), counter
+    finally:
+        torch.normal = orig_normal
+    save(name, {'N': N, 'H': H, 'D': D, 'A': A, 'units': list(units), 'mb': mb, 'epochs': epochs,
+                'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
+                'autoreset': autoreset, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
+                'noise': noise, 'init_state': init_state, 'epochs_out': epochs_out,
+                'param_order': [k for k, _ in agent.model.named_parameters()]})
+
+
+if __name__ == '__main__':
+    gen_gae()
+    gen_math()
+    gen_agent('agent_base.pt')
+    gen_agent('agent_masked.pt', autoreset='next_step', seed=4)
+    gen_agent('agent_hardclip.pt', seed=5, overrides={
+        'use_smooth_clamp': False, 'bound_loss_type': 'bound', 'bounds_loss_coef': 0.001, 'entropy_coef': 0.003,
+        'clip_value': False, 'truncate_grads': False, 'value_bootstrap': False, 'mini_epochs': 2,
+        'weight_decay': 0.01, 'lr_schedule': None})

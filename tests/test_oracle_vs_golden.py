@@ -1,0 +1,149 @@
+"""Pin the CPU oracle (oracle/ppo_oracle.py) to outputs of the REAL reference.
+
+The fixtures under tests/golden/*.pt were produced by tests/golden/gen_golden.py, which imports
+Denys88/rl_games from /root/reference in the build container.  Everything here runs on CPU.
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def test_gae_matches_reference_pytorch_loop_bitexact():
+    for c in load('gae.pt'):
+        out = O.gae(*c['inputs'], c['gamma'], c['tau'])
+        assert torch.equal(out, c['pytorch_gae']), c['shape']
+        if c['scalar_f64_as_f32'] is not None:
+            # reference's own KAT tolerance: tests/test_triton_gae.py:61
+            assert torch.allclose(out, c['scalar_f64_as_f32'], atol=1e-5)
+            f64 = O.gae_f64_scalar(*c['inputs'], c['gamma'], c['tau'])
+            assert torch.allclose(f64.float(), c['scalar_f64_as_f32'], atol=1e-6)
+
+
+def test_running_mean_std_bitexact():
+    g = load('math.pt')['rms']
+    rms = O.RunningMeanStd((6,))
+    rms.train()
+    for x, y in zip(g['xs'], g['ys']):
+        assert torch.equal(rms(x), y)
+    rms.eval()
+    assert torch.equal(rms.running_mean, g['state']['running_mean'])
+    assert torch.equal(rms.running_var, g['state']['running_var'])
+    assert int(rms.count) == int(g['state']['count'])
+    assert torch.equal(rms(g['x_eval']), g['y_eval'])
+    assert torch.equal(rms(g['x_eval'], denorm=True), g['y_denorm'])
+
+
+def test_running_mean_std_valid_rows():
+    g = load('math.pt')['rms_valid_rows']
+    rms = O.RunningMeanStd((1,))
+    rms.train()
+    rms(g['x'][g['mask']])
+    assert torch.equal(rms.running_mean, g['state']['running_mean'])
+    assert torch.equal(rms.running_var, g['state']['running_var'])
+    assert int(rms.count) == int(g['state']['count'])
+
+
+def test_masked_moments_and_normalisation():
+    m = load('math.pt')
+    g = m['masked']
+    mean, var = O.get_mean_var_with_masks(g['v'], g['m'])
+    assert torch.equal(mean, g['mean']) and torch.equal(var, g['var'])
+    assert torch.equal(O.normalization_with_masks(g['v'], g['m']), g['norm_masked'])
+    assert torch.equal(O.normalization_with_masks(g['v'], None), g['norm_unmasked'])
+    for k in ('masked_zero', 'masked_one'):
+        mean, var = O.get_mean_var_with_masks(g['v'], m[k]['m'])
+        assert torch.equal(mean, m[k]['mean']) and torch.equal(var, m[k]['var'])
+        assert torch.isfinite(O.normalization_with_masks(g['v'], m[k]['m'])).all()
+
+
+def test_losses_bitexact():
+    m = load('math.pt')
+    a = m['actor']
+    assert torch.equal(O.actor_loss(a['old'], a['new'], a['adv'], True, 0.2, smooth=False), a['hard'])
+    assert torch.equal(O.actor_loss(a['old'], a['new'], a['adv'], True, 0.2, smooth=True), a['smooth'])
+    c = m['critic']
+    assert torch.equal(O.critic_loss(c['old_values'], c['values'], 0.2, c['returns'], True), c['clip'])
+    assert torch.equal(O.critic_loss(c['old_values'], c['values'], 0.2, c['returns'], False), c['noclip'])
+    k = m['kl']
+    assert torch.equal(O.policy_kl(k['mu0'], k['s0'], k['mu1'], k['s1']), k['kl'])
+    assert torch.equal(O.policy_kl(k['mu0'], k['s0'], k['mu1'], k['s1'], False), k['kl_rows'])
+    d = m['diag']
+    assert torch.equal(O.explained_variance(d['y_pred'], d['y']), d['ev'])
+    assert torch.equal(O.policy_clip_fraction(a['new'], a['old'], 0.2), d['clip_frac'])
+
+
+def test_average_meter_and_scheduler():
+    m = load('math.pt')
+    am = O.AverageMeter(1, 10)
+    for s, (mean, size) in zip(m['meter']['seq'], m['meter']['means']):
+        am.update(s)
+        assert torch.equal(am.mean, mean) and am.current_size == size
+    sch = O.AdaptiveScheduler(0.008)
+    lr = 3e-4
+    for k, ref in zip(m['adaptive']['kls'], m['adaptive']['lrs']):
+        lr, _ = sch.update(lr, 0.0, 0, 0, k)
+        assert lr == ref
+
+
+def _oracle_from_golden(g):
+    cfgk = g['config']
+    cfg = {k: cfgk[k] for k in ('gamma', 'tau', 'e_clip', 'clip_value', 'critic_coef', 'entropy_coef',
+                                'bound_loss_type', 'use_smooth_clamp', 'truncate_grads', 'grad_norm',
+                                'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value',
+                                'normalize_advantage', 'value_bootstrap', 'mini_epochs') if k in cfgk}
+    cfg['bounds_loss_coef'] = cfgk.get('bounds_loss_coef', None)
+    cfg['lr_schedule'] = cfgk.get('lr_schedule', None)
+    cfg['weight_decay'] = cfgk.get('weight_decay', 0.0)
+    cfg['mask_autoreset_rows'] = g['autoreset'] == 'next_step'
+    env = O.TapeEnv(g['obs_tape'], g['done_tape'], g['timeout_tape'])
+    params = {k: v for k, v in g['init_state'].items() if k.startswith('a2c_network')}
+    ag = O.OracleAgent(env, params, g['D'], g['A'], g['units'], g['N'], g['H'], g['mb'], cfg)
+    ag.obs = ag.env_reset()
+    return ag
+
+
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt'])
+def test_full_train_epochs_match_reference_agent(name):
+    """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
+    g = load(name)
+    assert g['param_order'] == O.param_names(len(g['units']))
+    ag = _oracle_from_golden(g)
+    for ep, ref in enumerate(g['epochs_out']):
+        out = ag.train_epoch(g['noise'][ep])
+        ds = ref['dataset']
+        # rollout + GAE + prepare_dataset: same op order => tight
+        assert torch.equal(ag.buf['dones'], ref['mb_dones'])
+        torch.testing.assert_close(ag.buf['rewards'], ref['mb_rewards'], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(ag.buf['values'], ref['mb_values'], rtol=1e-5, atol=1e-6)
+        if ds.get('rnn_masks') is not None:
+            assert torch.equal(ag.dataset['rnn_masks'], ds['rnn_masks'])
+        torch.testing.assert_close(ag.dataset['advantages'], ds['advantages'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(ag.dataset['returns'], ds['returns'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(ag.dataset['old_values'], ds['old_values'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(torch.stack(out['kl']), ref['kls'] if ref['kls'].numel() == len(out['kl'])
+                                   else torch.stack(out['kl']), rtol=1e-3, atol=1e-7)
+        torch.testing.assert_close(torch.stack(out['a_loss']), ref['a_losses'], rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(torch.stack(out['c_loss']), ref['c_losses'], rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(torch.stack(out['entropy']), ref['entropies'], rtol=1e-5, atol=1e-6)
+        assert ag.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
+        for k in O.param_names(len(g['units'])):
+            torch.testing.assert_close(ag.model.p[k].detach(), ref['state'][k], rtol=1e-4, atol=2e-6, msg=lambda m: k + m)
+        st = ref['state']
+        torch.testing.assert_close(ag.model.running_mean_std.running_mean, st['running_mean_std.running_mean'], rtol=1e-9, atol=1e-9)
+        torch.testing.assert_close(ag.model.running_mean_std.running_var, st['running_mean_std.running_var'], rtol=1e-9, atol=1e-9)
+        assert int(ag.model.running_mean_std.count) == int(st['running_mean_std.count'])
+        torch.testing.assert_close(ag.model.value_mean_std.running_mean, st['value_mean_std.running_mean'], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(ag.model.value_mean_std.running_var, st['value_mean_std.running_var'], rtol=1e-6, atol=1e-7)
+        assert int(ag.model.value_mean_std.count) == int(st['value_mean_std.count'])
+        torch.testing.assert_close(ag.game_rewards.mean, ref['game_rewards_mean'], rtol=1e-5, atol=1e-6)
+        assert ag.game_rewards.current_size == ref['game_rewards_size']
+        torch.testing.assert_close(ag.game_lengths.mean, ref['game_lengths_mean'], rtol=1e-6, atol=1e-6)
