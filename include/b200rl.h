@@ -1,0 +1,253 @@
+/*
+ * b200rl.h -- C ABI of libb200rl.so: the PPO rollout -> GAE -> minibatch-update hot path of
+ * Denys88/rl_games as hand-written sm_100a CUDA kernels.
+ *
+ * The reference (100% Python) has no FFI; this header is the boundary a maintainer would bind with
+ * ctypes.  Each entry point cites the reference code it replaces
+ * (paths relative to the rl_games repo @ 262cf20).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory,
+ *     kernels never allocate or free;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), CUDA-graph capturable;
+ *   - return value: 0 = OK, <0 = argument error (B200RL_E*), >0 = cudaError_t of the launch;
+ *   - row-major tensors; "rows" of the experience arena are time-major: row(t, env) = t*N + env.
+ *     The reference's flat sample index env*H + t (a2c_common.py:33-40 swap_and_flatten01) is
+ *     preserved as an index MAPPING, never materialised: minibatch i = envs [i*mb/H, (i+1)*mb/H) x all t
+ *     (datasets.py:75-82).
+ */
+#ifndef B200RL_H
+#define B200RL_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_OK 0
+#define B200RL_EINVAL (-1)
+#define B200RL_EUNSUPPORTED (-2)
+#define B200RL_ENOTBUILT (-3)
+
+/* activation ids (network_builder.py:52-60 activations_factory) */
+#define B200RL_ACT_NONE 0
+#define B200RL_ACT_ELU 1
+#define B200RL_ACT_RELU 2
+#define B200RL_ACT_TANH 3
+
+int b200rl_version(void);
+/* compute capability the library was built for (100 => sm_100a) */
+int b200rl_built_arch(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * GAE.  Replaces rl_games/triton_kernels/gae_kernel.py:16-59 (_gae_kernel), :82-118 (_triton_gae)
+ * and the eager loop :62-79; called from a2c_common.py:729-734 (discount_values).
+ *   A_t = d_t + g*l*(1-done_{t+1})*A_{t+1},  d_t = r_t + g*V_{t+1}*(1-done_{t+1}) - V_t
+ * rewards/values/advs: [H,N,V] with element strides (st_t, st_e, st_v); dones: [H,N] strides (st_t, st_e),
+ * u8 (as stored by ExperienceBuffer, experience.py:392) or f32 (as the reference passes after .float()).
+ * returns (optional, may be NULL): advs + values, same strides as advs (a2c_common.py:1060).
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_gae_f32(const float* rewards, const float* values, const void* dones, int dones_is_u8,
+                   const float* last_values, const void* last_dones, int last_dones_is_u8,
+                   float* advs, float* returns,
+                   int H, int N, int V,
+                   int64_t r_st_t, int64_t r_st_e, int64_t r_st_v,
+                   int64_t v_st_t, int64_t v_st_e, int64_t v_st_v,
+                   int64_t d_st_t, int64_t d_st_e,
+                   int64_t a_st_t, int64_t a_st_e, int64_t a_st_v,
+                   double gamma, double tau, void* stream);
+
+/* Fused GAE + returns + per-block moment partials for prepare_dataset (V == 1, contiguous [H,N]).
+ * mask (optional f32 [H,N]) = autoreset validity (a2c_common.py:1002-1006).
+ * partials: [gridDim][8] doubles {n, Sv, Sv2, Sr, Sr2, Sa, Sa2, pad}; *n_blocks_out_host receives grid size. */
+int b200rl_gae_fused_f32(const float* rewards, const float* values, const uint8_t* dones,
+                         const float* last_values, const uint8_t* last_dones, const float* mask,
+                         float* advs, float* returns, double* partials, int max_partials,
+                         int H, int N, double gamma, double tau, int* n_blocks_out_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * prepare_dataset (a2c_common.py:1586-1660): value normaliser update (values THEN returns,
+ * RunningMeanStd Chan merge running_mean_std.py:55-67, fp64 state + int64 count), normalise+clamp
+ * values/returns (:69-114), advantage normalisation (A-mean)/(std_unbiased+1e-8) (:1634) or the masked
+ * variant (torch_ext.py:172-191), advantages = returns - values (:1598).  Consumes the partials of
+ * b200rl_gae_fused_f32 (or b200rl_batch_moments_f64 when the batch was materialised/edited by a caller).
+ * vms_mean/vms_var: double[1], vms_count: int64[1] (updated in place unless freeze_stats).
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_prepare_batch_f32(const float* values, const float* returns, const float* mask,
+                             const double* partials, int n_partials,
+                             double* vms_mean, double* vms_var, int64_t* vms_count,
+                             float* old_values_n, float* returns_n, float* advs_n,
+                             int B, int normalize_value, int normalize_advantage, int freeze_stats,
+                             void* stream);
+
+int b200rl_batch_moments_f64(const float* values, const float* returns, const float* mask, double* partials,
+                             int max_partials, int B, int* n_blocks_out_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RunningMeanStd (running_mean_std.py:19-114) as standalone ops.
+ * x: [R, D] rows given as n_chunks chunks of rows_per_chunk rows, chunk c starting at row c*chunk_stride.
+ * moments_update: batch mean / biased var per feature merged into (mean f64[D], var f64[D], count i64[1])
+ * (the training-mode forward of the obs normaliser never passes a mask: models.py:54-56); also refreshes
+ * mean_f32[D] and std_f32[D] = sqrt(var_f32+eps).
+ * scratch: double[scratch_blocks*2*D] work area, counter: int32[1] zero-initialised once.
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_moments_update_f64(const float* x, int D, int rows_per_chunk, int n_chunks,
+                              int64_t chunk_stride, double* mean, double* var, int64_t* count,
+                              float* mean_f32, float* std_f32, float eps,
+                              double* scratch, int scratch_blocks, int* counter, void* stream);
+/* mean_f32 = (float)mean, std_f32 = sqrt((float)var + eps): the fp32 copies the fused kernels consume */
+int b200rl_refresh_norm_f32(const double* mean, const double* var, float* mean_f32, float* std_f32,
+                            float eps, int D, void* stream);
+/* y = clamp((x-mean)/sqrt(var+eps), -5, 5)  (denorm=0)   |   y = sqrt(var+eps)*clamp(x,-5,5)+mean  (denorm=1) */
+int b200rl_normalize_f32(const float* x, float* y, const double* mean, const double* var, float eps,
+                         int64_t rows, int D, int denorm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32 MLP building blocks (mixed_precision: False path).  network_builder.py:494-512.
+ *   linear_fwd:  Y[M,Nout] = act( norm(X)[M,K] . W[Nout,K]^T + b )      (norm optional: models.py:54-56)
+ *   linear_bwd_data:   dX[M,K] = (dY[M,Nout] . W[Nout,K]) * act'(A_prev)    (A_prev = activation output)
+ *   linear_bwd_weight: dW_part[s*split_stride + ..][Nout,K] = dY_s^T . X_s ; db_part[s*split_stride + ..][Nout] = colsum(dY_s)
+ * X rows may be chunked like in moments_update (arena, time-major); all other operands are dense.
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_linear_fwd_f32(const float* X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
+                          const float* norm_mean, const float* norm_std,
+                          const float* W, const float* b, float* Y, int M, int K, int Nout, int act,
+                          void* stream);
+int b200rl_linear_bwd_data_f32(const float* dY, const float* W, const float* A_prev, float* dX,
+                               int M, int K, int Nout, int act_prev, void* stream);
+int b200rl_linear_bwd_weight_f32(const float* dY, const float* X, int rows_per_chunk, int64_t chunk_stride,
+                                 int64_t x_ld, const float* norm_mean, const float* norm_std,
+                                 float* dW_part, float* db_part, int64_t split_stride, int M, int K, int Nout,
+                                 int n_splits, void* stream);
+/* out[i] = sum_s part[s*split_stride + i]  (deterministic, fixed order) */
+int b200rl_reduce_splits_f32(const float* part, float* out, int n, int n_splits, int64_t split_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PPO loss head.  Replaces a2c_continuous.py:97-134 (calc_losses), :241-257 (bound/reg loss),
+ * common_losses.py:16-82, torch_ext.py:27-36 (policy_kl), :157-170 (apply_masks), models.py:335-364
+ * (sigma=exp(logstd), neglogp, entropy) and the autograd of all of it w.r.t. mu, value, logstd and the
+ * last hidden activation.  Rows are minibatch-local m in [0,M); arena tensors use the chunk mapping.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200rl_loss_cfg {
+    float e_clip;            /* config e_clip */
+    float critic_coef;       /* config critic_coef */
+    float bounds_loss_coef;  /* config bounds_loss_coef (0 if None) */
+    int has_bounds_loss;     /* bounds_loss_coef is not None */
+    int bound_loss_type;     /* 0 = none, 1 = 'bound', 2 = 'regularisation' */
+    int clip_value;          /* config clip_value */
+    int use_smooth_clamp;    /* config use_smooth_clamp */
+    int ppo;                 /* config ppo (True) */
+} b200rl_loss_cfg;
+
+/* per-minibatch scalar outputs (f32 stats[B200RL_NSTATS]) */
+#define B200RL_STAT_ALOSS 0
+#define B200RL_STAT_CLOSS 1
+#define B200RL_STAT_ENTROPY 2
+#define B200RL_STAT_BLOSS 3
+#define B200RL_STAT_KL 4
+#define B200RL_STAT_SUMMASK 5
+#define B200RL_STAT_CLIPFRAC 6
+#define B200RL_STAT_LR 7      /* lr used for this minibatch's Adam step (written by adam) */
+#define B200RL_STAT_GNORM 8   /* global grad norm before clipping (written by adam) */
+#define B200RL_NSTATS 16
+
+/* Head GEMM + loss forward + backward down to d(a_last).
+ *  a_last [M,Hl] last hidden activation (output of act_last); W_head [A+1,Hl] (row 0 = value head,
+ *  rows 1..A = mu head), b_head [A+1], logstd [A] (fixed sigma parameter).
+ *  arena tensors (chunk-mapped rows): actions, old_mu, old_sigma [.,A]; old_values_n, returns_n,
+ *  old_neglogp, advs_n, mask(optional) [.]
+ *  inv_count_dev: device float = 1/max(sum(mask),1) for this minibatch (NULL => 1/M, unmasked).
+ *  outputs: d_head [M, A+1] = (dL/dvalue, dL/dmu_0..A-1); d_alast [M,Hl]; new mu/sigma overwrite
+ *  old_mu/old_sigma (datasets.py:33-43 update_mu_sigma); optional mu_out [M,A], value_out [M], neglogp_out [M];
+ *  block partials [n_blocks][b200rl_loss_partial_stride()] doubles for b200rl_ppo_loss_finalize. */
+int b200rl_ppo_head_loss_f32(const float* a_last, int Hl, const float* W_head, const float* b_head,
+                             const float* logstd, const float* actions, float* old_mu, float* old_sigma,
+                             const float* old_values_n, const float* returns_n, const float* old_neglogp,
+                             const float* advs_n, const float* mask,
+                             int rows_per_chunk, int64_t chunk_stride, int M, int A,
+                             const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
+                             float* d_head, float* d_alast, int act_last,
+                             float* mu_out, float* value_out, float* neglogp_out,
+                             double* partials, int max_partials, int* n_blocks_out_host, void* stream);
+/* partials -> stats[] (means; masked means when inv_count was used) and d_logstd[A]
+ * (includes the -entropy_coef * d(entropy)/d(logstd) term; entropy_coef read from device). */
+int b200rl_ppo_loss_finalize(const double* partials, int n_partials, int A, const float* entropy_coef_dev,
+                             float* stats, float* d_logstd, float* kl_out, void* stream);
+/* inv_count[i] = 1/max(sum_{t, e in minibatch i} mask[t,e], 1)  (torch_ext.py:157-170) */
+int b200rl_mask_inv_counts_f32(const float* mask, int H, int N, int envs_per_mb, float* inv_count, void* stream);
+int b200rl_loss_partial_stride(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimiser step.  Replaces a2c_common.py:493-514 (trancate_gradients_and_step: /world_size,
+ * clip_grad_norm_, optimizer.step) + torch.optim.Adam(eps=1e-8, weight_decay, fused=True)
+ * (a2c_continuous.py:44-48) + the adaptive-KL scheduler (schedulers.py:19-33, a2c_common.py:1557-1563)
+ * with lr living in DEVICE memory so no .item() sync is needed per minibatch.
+ *  state_d: double[2] = {lr, step};  kl_dev: device f32 (already world-averaged), may be NULL.
+ *  counter: int32[1] zero-initialised once.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct b200rl_opt_cfg {
+    double beta1, beta2, eps, weight_decay;
+    double grad_norm;        /* config grad_norm (max norm) */
+    double kl_threshold, min_lr, max_lr, lr_multiplier;
+    double grad_scale;       /* 1/world_size applied to the (summed) gradient */
+    int truncate_grads;      /* config truncate_grads */
+    int adaptive_lr;         /* lr_schedule == 'adaptive' && schedule_type == 'per_minibatch' */
+} b200rl_opt_cfg;
+
+int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
+                         double* state_d, const float* kl_dev, const b200rl_opt_cfg* cfg_host,
+                         float* stats_out, int* counter, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rollout.  a2c_common.py:985-1069 (play_steps) per-step pieces.
+ * policy_head_sample: heads + sigma=exp(logstd) + a = mu + sigma*eps + neglogp + denorm value
+ *   (models.py:329-364, :58-60) written straight into arena time-step t (experience.py:433-456).
+ *   noise: optional [N,A] standard-normal draws; if NULL, Philox4x32-10 keyed by (seed, *rng_epoch_dev,
+ *   step_index, env) is used (counter based => CUDA-graph replayable; bump *rng_epoch_dev once per epoch).
+ *   env_actions (optional): clamp(a,-1,1) rescaled to [low,high] (a2c_common.py:1500-1510, :144-148).
+ *   dones_out[e] = dones_cur[e] (a2c_common.py:1001); valid_out[e] = 1 - prev_dones[e] (:1002-1006).
+ *   values_only != 0: just the (denormalised) value (get_values, a2c_common.py:603-626).
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_policy_head_sample_f32(const float* a_last, int Hl, const float* W_head, const float* b_head,
+                                  const float* logstd, const double* vms_mean, const double* vms_var,
+                                  int normalize_value, const float* noise, uint64_t seed,
+                                  const uint64_t* rng_epoch_dev, uint32_t step_index,
+                                  float* actions, float* mus, float* sigmas, float* neglogp, float* values,
+                                  float* env_actions, int clip_actions, const float* act_low, const float* act_high,
+                                  const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones,
+                                  float* valid_out, int N, int A, int values_only, void* stream);
+
+typedef struct b200rl_shaper_cfg {
+    float scale_value, shift_value, min_val, max_val;  /* tr_helpers.py:16-42 */
+    float gamma;
+    int log_val;
+    int value_bootstrap;     /* config value_bootstrap && 'time_outs' in infos */
+} b200rl_shaper_cfg;
+
+/* post env-step bookkeeping: shaped reward (+ gamma*V*timeout) stored at arena step t, self.dones,
+ * episode accumulators and finished-episode means for the AverageMeters (torch_ext.py:326-352).
+ *  ep_state: float[3][N] = current_rewards, current_shaped_rewards, current_lengths
+ *  meter: double[8] = {mean_reward, mean_shaped_reward, mean_length, current_size, total_done, ...}
+ *  valid_t (optional [N]): next_step-autoreset live rows (a2c_common.py:1027-1033)
+ *  time_outs_kind: 0 none, 1 u8/bool, 2 f32.  scratch: double[scratch_blocks*4]; counter int32[1] zeroed once. */
+int b200rl_post_step_f32(const float* rewards, const void* dones, int dones_is_u8, const void* time_outs,
+                         int time_outs_kind, const float* values_t, const float* valid_t,
+                         float* rewards_out_t, uint8_t* dones_cur, float* prev_dones_f32,
+                         float* ep_state, double* meter, int games_to_track,
+                         double* scratch, int scratch_blocks, int* counter, int N,
+                         const b200rl_shaper_cfg* cfg_host, void* stream);
+
+/* Synthetic on-GPU measurement env (not part of the reference): obs ~ N(0,1) (Philox),
+ * reward = -||a||^2, done = (t >= max_len) | Bernoulli(p_done), time_out = (t>=max_len) & !terminated. */
+int b200rl_synth_env_step(const float* actions, float* obs, float* rewards, uint8_t* dones, uint8_t* time_outs,
+                          int* ep_t, int N, int D, int A, int max_len, float p_done,
+                          uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index, void* stream);
+int b200rl_bump_u64(uint64_t* p, void* stream);
+
+/* L2 flush helper for benchmarking: writes n u32 words. */
+int b200rl_fill_u32(uint32_t* p, int64_t n, uint32_t v, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H */

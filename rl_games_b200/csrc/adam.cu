@@ -1,0 +1,97 @@
+// Optimiser step: (1/world) scaling + global-norm clip + Adam + on-device adaptive-KL LR schedule.
+// Replaces a2c_common.py:493-514 (trancate_gradients_and_step), torch.optim.Adam(eps=1e-8,
+// weight_decay, fused=True) (a2c_continuous.py:44-48) and schedulers.py:19-33 + a2c_common.py:1557-1563
+// (kl.item() host sync per minibatch).  One launch: every CTA recomputes the global grad norm from the
+// (L2-resident) flat gradient buffer in the same order, so no inter-CTA reduction or atomics are needed
+// and the result is deterministic; the last CTA to finish advances (step, lr).
+#include "common.cuh"
+
+namespace {
+
+struct OptCfgDev {
+    double beta1, beta2, eps, weight_decay, grad_norm, kl_threshold, min_lr, max_lr, lr_multiplier, grad_scale;
+    int truncate_grads, adaptive_lr;
+};
+
+__global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ params, const float* __restrict__ grads,
+                                                        float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n,
+                                                        double* state_d, const float* __restrict__ kl_dev, OptCfgDev c,
+                                                        float* __restrict__ stats_out, int* counter) {
+    __shared__ double sm[32];
+    __shared__ int is_last;
+    const double lr = state_d[0];
+    const double step = state_d[1] + 1.0;
+    const float gs = (float)c.grad_scale;
+    // ---- global norm (identical in every CTA) ----
+    double acc[1] = {0.0};
+    if (c.truncate_grads || stats_out) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float g = __ldg(grads + i) * gs;
+            acc[0] += (double)g * (double)g;
+        }
+        block_sum_d<1>(acc, sm);
+    }
+    const float total_norm = (float)sqrt(acc[0]);
+    float coef = 1.0f;
+    if (c.truncate_grads) coef = fminf((float)c.grad_norm / (total_norm + 1e-6f), 1.0f);
+    const float b1 = (float)c.beta1, b2 = (float)c.beta2;
+    const double bc1 = 1.0 - pow(c.beta1, step), bc2 = 1.0 - pow(c.beta2, step);
+    const float step_size = (float)(lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float eps = (float)c.eps, wd = (float)c.weight_decay;
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(i0 + per, n);
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        float g = __ldg(grads + i) * gs;
+        if (c.truncate_grads) g *= coef;
+        float p = params[i];
+        if (wd != 0.f) g = fmaf(wd, p, g);
+        float m = exp_avg[i], v = exp_avg_sq[i];
+        m = m + (g - m) * (1.0f - b1);                 // lerp (torch fused adam)
+        v = b2 * v + (1.0f - b2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        p -= step_size * m / denom;
+        params[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+    }
+    // ---- last CTA advances step / lr (all CTAs have read them by now) ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(counter, 1);
+        is_last = (prev == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        double new_lr = lr;
+        if (c.adaptive_lr && kl_dev) {
+            const double kl = (double)(__ldg(kl_dev) * gs);   // summed over ranks by the all-reduce -> mean (a2c_common.py:1559-1561)
+            // schedulers.py:19-33 (python floats == fp64)
+            if (kl > 2.0 * c.kl_threshold) new_lr = fmax(lr / c.lr_multiplier, c.min_lr);
+            if (kl < 0.5 * c.kl_threshold) new_lr = fmin(lr * c.lr_multiplier, c.max_lr);
+        }
+        state_d[0] = new_lr;
+        state_d[1] = step;
+        if (stats_out) { stats_out[B200RL_STAT_LR] = (float)lr; stats_out[B200RL_STAT_GNORM] = total_norm; }
+        *counter = 0;
+    }
+}
+
+}  // namespace
+
+B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
+                                       double* state_d, const float* kl_dev, const b200rl_opt_cfg* cfg_host,
+                                       float* stats_out, int* counter, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !state_d || !cfg_host || !counter || n <= 0) return B200RL_EINVAL;
+    OptCfgDev c;
+    c.beta1 = cfg_host->beta1; c.beta2 = cfg_host->beta2; c.eps = cfg_host->eps; c.weight_decay = cfg_host->weight_decay;
+    c.grad_norm = cfg_host->grad_norm; c.kl_threshold = cfg_host->kl_threshold; c.min_lr = cfg_host->min_lr;
+    c.max_lr = cfg_host->max_lr; c.lr_multiplier = cfg_host->lr_multiplier; c.grad_scale = cfg_host->grad_scale;
+    c.truncate_grads = cfg_host->truncate_grads; c.adaptive_lr = cfg_host->adaptive_lr;
+    int blocks = (n + 8191) / 8192;
+    if (blocks > 148) blocks = 148;
+    if (blocks < 1) blocks = 1;
+    adam_step_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, state_d, kl_dev, c, stats_out,
+                                                            counter);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}

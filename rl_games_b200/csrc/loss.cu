@@ -1,0 +1,309 @@
+// PPO loss head: head GEMM (mu, value) + distribution math + clipped-surrogate / value / bound losses +
+// analytic KL + the backward pass of all of it down to d(last hidden activation), fused in one kernel.
+// Replaces a2c_continuous.py:97-134 (calc_losses), :241-257, common_losses.py:16-82, torch_ext.py:27-36,
+// :157-170, models.py:335-364 and ~135 eager launches + loss.backward() for this part of the graph.
+// One thread per sample; the [128 x Hl] activation tile and the head weights are staged in shared memory;
+// scalar statistics go through warp-shuffle reductions into per-block fp64 partials (deterministic).
+#include "common.cuh"
+
+namespace {
+
+constexpr int LT = 128;       // threads (= samples) per block
+constexpr int MAXA = 32;      // max action dim + 1 supported by the register tiles
+constexpr int NSC = 8;        // scalar partial slots before the dlogstd block
+
+struct LossCfgDev {
+    float e_clip, critic_coef, bounds_coef;
+    int has_bounds, bound_type, clip_value, smooth, ppo;
+};
+
+__global__ void __launch_bounds__(LT) ppo_head_loss_kernel(
+    const float* __restrict__ a_last, int Hl, const float* __restrict__ Wh, const float* __restrict__ bh,
+    const float* __restrict__ logstd, const float* __restrict__ actions, float* __restrict__ old_mu,
+    float* __restrict__ old_sigma, const float* __restrict__ old_values_n, const float* __restrict__ returns_n,
+    const float* __restrict__ old_neglogp, const float* __restrict__ advs_n, const float* __restrict__ mask,
+    int rows_per_chunk, int64_t chunk_stride, int M, int A, LossCfgDev cfg, const float* __restrict__ inv_count_dev,
+    float* __restrict__ d_head, float* __restrict__ d_alast, int act_last,
+    float* __restrict__ mu_out, float* __restrict__ value_out, float* __restrict__ neglogp_out,
+    double* __restrict__ partials) {
+    extern __shared__ float smf[];
+    const int AH = A + 1;
+    float* tile = smf;                               // [LT][Hl+1]
+    float* sW = tile + LT * (Hl + 1);                // [AH][Hl]
+    float* sB = sW + AH * Hl;                        // [AH]
+    float* sSig = sB + AH;                           // [A] sigma, [A] logstd
+    float* sRed = sSig + 2 * A;                      // [LT/32][NSC + A]
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * LT;
+    const int rows = min(LT, M - m0);
+    // ---- stage tile + head weights ----
+    for (int i = tid; i < rows * Hl; i += LT) {
+        const int r = i / Hl, k = i - r * Hl;
+        tile[r * (Hl + 1) + k] = __ldg(a_last + (int64_t)(m0 + r) * Hl + k);
+    }
+    for (int i = tid; i < AH * Hl; i += LT) sW[i] = __ldg(Wh + i);
+    if (tid < AH) sB[tid] = __ldg(bh + tid);
+    if (tid < A) { const float ls = __ldg(logstd + tid); sSig[tid] = expf(ls); sSig[A + tid] = ls; }
+    __syncthreads();
+
+    float sc[NSC];
+#pragma unroll
+    for (int i = 0; i < NSC; ++i) sc[i] = 0.f;
+    float dls[MAXA];
+#pragma unroll
+    for (int j = 0; j < MAXA; ++j) dls[j] = 0.f;
+    float dh[MAXA];   // dh[0] = dvalue, dh[1+j] = dmu_j
+
+    const int m = m0 + tid;
+    const bool live = tid < rows;
+    if (live) {
+        float head[MAXA];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) head[j] = (j < AH) ? sB[j] : 0.f;
+        const float* row = tile + tid * (Hl + 1);
+        for (int k = 0; k < Hl; ++k) {
+            const float a = row[k];
+#pragma unroll
+            for (int j = 0; j < MAXA; ++j)
+                if (j < AH) head[j] = fmaf(a, sW[j * Hl + k], head[j]);
+        }
+        const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
+        const float val = head[0];
+        const float old_v = __ldg(old_values_n + ar), ret = __ldg(returns_n + ar);
+        const float old_nlp = __ldg(old_neglogp + ar), adv = __ldg(advs_n + ar);
+        const float mk = mask ? __ldg(mask + ar) : 1.f;
+        const float inv_cnt = inv_count_dev ? __ldg(inv_count_dev) : (1.0f / (float)M);
+        const float w = mk * inv_cnt;
+        // ---- neglogp / entropy / KL / bound loss ----
+        float sumz2 = 0.f, sumls = 0.f, ent = 0.f, kl = 0.f, bl = 0.f;
+        float z[MAXA];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) {
+            if (j < A) {
+                const float mu = head[1 + j], sg = sSig[j], ls = sSig[A + j];
+                const float act = __ldg(actions + ar * A + j);
+                const float omu = old_mu[ar * A + j], osg = old_sigma[ar * A + j];
+                z[j] = (act - mu) / sg;
+                sumz2 += z[j] * z[j];
+                sumls += ls;
+                ent += 0.5f + 0.9189385332046727f + logf(sg);           // 0.5 + 0.5*log(2*pi) + log(sigma)
+                const float c1 = logf(osg / sg + 1e-5f);
+                const float dm = omu - mu;
+                const float c2 = (sg * sg + dm * dm) / (2.0f * (osg * osg + 1e-5f));
+                kl += c1 + c2 - 0.5f;
+                if (cfg.has_bounds) {
+                    if (cfg.bound_type == 1) {
+                        const float hi = fmaxf(mu - 1.1f, 0.f), lo = fminf(mu + 1.1f, 0.f);
+                        bl += lo * lo + hi * hi;
+                    } else if (cfg.bound_type == 2) {
+                        bl += mu * mu;
+                    }
+                }
+            } else {
+                z[j] = 0.f;
+            }
+        }
+        const float nlp = 0.5f * sumz2 + 0.9189385332046727f * (float)A + sumls;
+        // ---- actor loss + d/dnlp ----
+        float a_loss, g_a;
+        if (cfg.ppo) {
+            const float ratio = expf(old_nlp - nlp);
+            const float mi = 1.0f - cfg.e_clip, mx = 1.0f + cfg.e_clip;
+            float clamped, dcl;
+            if (cfg.smooth) {
+                const float s = 1.0f / (1.0f + expf((-(ratio - mi) / (mx - mi) + 0.5f) * 4.0f));
+                clamped = s * (mx - mi) + mi;
+                dcl = 4.0f * s * (1.0f - s);
+            } else {
+                clamped = fminf(fmaxf(ratio, mi), mx);
+                dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
+            }
+            const float t1 = -(adv * ratio), t2 = -(adv * clamped);
+            a_loss = fmaxf(t1, t2);
+            const float d1 = adv * ratio, d2 = adv * dcl * ratio;
+            g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
+        } else {
+            a_loss = nlp * adv;
+            g_a = adv;
+        }
+        // ---- critic loss + d/dvalue ----
+        float c_loss, dc;
+        if (cfg.clip_value) {
+            const float delta = val - old_v;
+            const float vpc = old_v + fminf(fmaxf(delta, -cfg.e_clip), cfg.e_clip);
+            const float e1 = val - ret, e2 = vpc - ret;
+            const float l1 = e1 * e1, l2 = e2 * e2;
+            c_loss = fmaxf(l1, l2);
+            const float g1 = 2.0f * e1;
+            const float g2 = (delta >= -cfg.e_clip && delta <= cfg.e_clip) ? 2.0f * e2 : 0.0f;
+            dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
+        } else {
+            const float e1 = ret - val;
+            c_loss = e1 * e1;
+            dc = -2.0f * e1;
+        }
+        // clip fraction (torch_ext.py:217-227)
+        const float lr_ = old_nlp - nlp;
+        const float clipped = (lr_ < log1pf(-cfg.e_clip) || lr_ > log1pf(cfg.e_clip)) ? 1.f : 0.f;
+        // ---- gradients at the heads ----
+        dh[0] = w * 0.5f * cfg.critic_coef * dc;
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j) {
+            if (j < A) {
+                const float mu = head[1 + j], sg = sSig[j];
+                float db = 0.f;
+                if (cfg.has_bounds) {
+                    if (cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
+                    else if (cfg.bound_type == 2) db = 2.0f * mu;
+                }
+                dh[1 + j] = w * (g_a * (-(z[j] / sg)) + cfg.bounds_coef * db);
+                dls[j] = w * g_a * (1.0f - z[j] * z[j]);
+                // new mu/sigma overwrite the old ones (datasets.py:33-43)
+                old_mu[ar * A + j] = mu;
+                old_sigma[ar * A + j] = sg;
+                if (mu_out) mu_out[(int64_t)m * A + j] = mu;
+            }
+        }
+        if (value_out) value_out[m] = val;
+        if (neglogp_out) neglogp_out[m] = nlp;
+        sc[0] = w * a_loss; sc[1] = w * c_loss; sc[2] = w * ent; sc[3] = w * bl; sc[4] = w * kl;
+        sc[5] = mk; sc[6] = mk * clipped; sc[7] = w;
+        // ---- d(head) out, d(a_last) into the tile (row owned by this thread) ----
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j)
+            if (j < AH) d_head[(int64_t)m * AH + j] = dh[j];
+        float* rw = tile + tid * (Hl + 1);
+        for (int k = 0; k < Hl; ++k) {
+            float g = 0.f;
+#pragma unroll
+            for (int j = 0; j < MAXA; ++j)
+                if (j < AH) g = fmaf(dh[j], sW[j * Hl + k], g);
+            rw[k] = g * act_bwd_from_out(rw[k], act_last);
+        }
+    }
+    // ---- block reduction of the scalars: warp shuffles -> smem -> fp64 partial row ----
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < NSC; ++i) sc[i] = warp_sum(sc[i]);
+#pragma unroll
+    for (int j = 0; j < MAXA; ++j)
+        if (j < A) dls[j] = warp_sum(dls[j]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NSC; ++i) sRed[warp * (NSC + A) + i] = sc[i];
+#pragma unroll
+        for (int j = 0; j < MAXA; ++j)
+            if (j < A) sRed[warp * (NSC + A) + NSC + j] = dls[j];
+    }
+    __syncthreads();
+    if (tid < NSC + A) {
+        double s = 0.0;
+        for (int wv = 0; wv < LT / 32; ++wv) s += (double)sRed[wv * (NSC + A) + tid];
+        partials[(int64_t)blockIdx.x * (NSC + MAXA) + tid] = s;
+    }
+    // ---- coalesced store of d(a_last) ----
+    for (int i = tid; i < rows * Hl; i += LT) {
+        const int r = i / Hl, k = i - r * Hl;
+        d_alast[(int64_t)(m0 + r) * Hl + k] = tile[r * (Hl + 1) + k];
+    }
+}
+
+__global__ void __launch_bounds__(256) ppo_loss_finalize_kernel(const double* __restrict__ partials, int n_partials, int A,
+                                                               const float* __restrict__ entropy_coef_dev,
+                                                               float* __restrict__ stats, float* __restrict__ d_logstd, float* __restrict__ kl_out) {
+    __shared__ double sm[256];
+    const int slots = NSC + A;
+    // thread layout: slot = tid % 64 (slots <= 40), lane group = tid / 64 (4 groups) -- fixed order => deterministic
+    const int slot = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    double s = 0.0;
+    if (slot < slots)
+        for (int p = grp; p < n_partials; p += 4) s += partials[(int64_t)p * (NSC + MAXA) + slot];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (grp == 0 && slot < slots) {
+        const double t = (sm[slot] + sm[64 + slot]) + (sm[128 + slot] + sm[192 + slot]);
+        sm[slot] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        stats[B200RL_STAT_ALOSS] = (float)sm[0];
+        stats[B200RL_STAT_CLOSS] = (float)sm[1];
+        stats[B200RL_STAT_ENTROPY] = (float)sm[2];
+        stats[B200RL_STAT_BLOSS] = (float)sm[3];
+        stats[B200RL_STAT_KL] = (float)sm[4];
+        if (kl_out) *kl_out = (float)sm[4];
+        stats[B200RL_STAT_SUMMASK] = (float)sm[5];
+        stats[B200RL_STAT_CLIPFRAC] = (float)(sm[6] / fmax(sm[5], 1.0));
+    }
+    if (threadIdx.x < A) {
+        const double ec = (double)__ldg(entropy_coef_dev);
+        d_logstd[threadIdx.x] = (float)(sm[NSC + threadIdx.x] - ec * sm[7]);
+    }
+}
+
+// inv_count[i] = 1 / max(sum of mask over minibatch i, 1)   (torch_ext.py:157-170 apply_masks)
+__global__ void __launch_bounds__(256) mask_inv_counts_kernel(const float* __restrict__ mask, int H, int N, int envs_per_mb,
+                                                             float* __restrict__ inv_count) {
+    __shared__ double sm[32];
+    const int mb = blockIdx.x;
+    const int e0 = mb * envs_per_mb;
+    double acc[1] = {0.0};
+    for (int i = threadIdx.x; i < H * envs_per_mb; i += blockDim.x) {
+        const int t = i / envs_per_mb, e = e0 + (i - t * envs_per_mb);
+        acc[0] += (double)__ldg(mask + (int64_t)t * N + e);
+    }
+    block_sum_d<1>(acc, sm);
+    if (threadIdx.x == 0) inv_count[mb] = (float)(1.0 / fmax(acc[0], 1.0));
+}
+
+}  // namespace
+
+B200RL_EXPORT int b200rl_ppo_head_loss_f32(const float* a_last, int Hl, const float* W_head, const float* b_head,
+                                           const float* logstd, const float* actions, float* old_mu, float* old_sigma,
+                                           const float* old_values_n, const float* returns_n, const float* old_neglogp,
+                                           const float* advs_n, const float* mask,
+                                           int rows_per_chunk, int64_t chunk_stride, int M, int A,
+                                           const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
+                                           float* d_head, float* d_alast, int act_last,
+                                           float* mu_out, float* value_out, float* neglogp_out,
+                                           double* partials, int max_partials, int* n_blocks_out_host, void* stream) {
+    if (!a_last || !W_head || !b_head || !logstd || !actions || !old_mu || !old_sigma || !old_values_n || !returns_n ||
+        !old_neglogp || !advs_n || !cfg_host || !d_head || !d_alast || !partials)
+        return B200RL_EINVAL;
+    if (M <= 0 || A <= 0 || A + 1 > MAXA || Hl <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
+    const int blocks = (M + LT - 1) / LT;
+    if (n_blocks_out_host) *n_blocks_out_host = blocks;
+    if (blocks > max_partials) return B200RL_EINVAL;
+    const size_t smem = sizeof(float) * ((size_t)LT * (Hl + 1) + (size_t)(A + 1) * Hl + (A + 1) + 2 * A + (LT / 32) * (NSC + A));
+    if (smem > 200 * 1024) return B200RL_EUNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    LossCfgDev c;
+    c.e_clip = cfg_host->e_clip; c.critic_coef = cfg_host->critic_coef; c.bounds_coef = cfg_host->bounds_loss_coef;
+    c.has_bounds = cfg_host->has_bounds_loss; c.bound_type = cfg_host->bound_loss_type; c.clip_value = cfg_host->clip_value;
+    c.smooth = cfg_host->use_smooth_clamp; c.ppo = cfg_host->ppo;
+    ppo_head_loss_kernel<<<blocks, LT, smem, as_stream(stream)>>>(
+        a_last, Hl, W_head, b_head, logstd, actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask,
+        rows_per_chunk, chunk_stride, M, A, c, inv_count_dev, d_head, d_alast, act_last, mu_out, value_out, neglogp_out, partials);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_ppo_loss_finalize(const double* partials, int n_partials, int A, const float* entropy_coef_dev,
+                                           float* stats, float* d_logstd, float* kl_out, void* stream) {
+    if (!partials || !entropy_coef_dev || !stats || !d_logstd || n_partials <= 0 || A <= 0 || A + 1 > MAXA) return B200RL_EINVAL;
+    ppo_loss_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, n_partials, A, entropy_coef_dev, stats, d_logstd, kl_out);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_mask_inv_counts_f32(const float* mask, int H, int N, int envs_per_mb, float* inv_count, void* stream) {
+    if (!mask || !inv_count || H <= 0 || N <= 0 || envs_per_mb <= 0 || N % envs_per_mb != 0) return B200RL_EINVAL;
+    mask_inv_counts_kernel<<<N / envs_per_mb, 256, 0, as_stream(stream)>>>(mask, H, N, envs_per_mb, inv_count);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_loss_partial_stride(void) { return NSC + MAXA; }

@@ -1,0 +1,326 @@
+// Running mean/std + batch preparation kernels (HBM-bound scan/reduce work, no tensor cores).
+//   prepare_batch  -- a2c_common.py:1586-1660 (prepare_dataset): value normaliser update (values THEN
+//                     returns), normalise/clamp, advantage normalisation (unmasked :1634, masked
+//                     torch_ext.py:172-191).  Consumes the block partials written by gae_fused_kernel.
+//   moments_update -- running_mean_std.py:55-114 training-mode update of the obs normaliser on one
+//                     minibatch (rows given as time-major chunks of the arena).
+//   normalize      -- running_mean_std.py:104-113 (eval forward / denorm).
+// Running statistics are fp64 + int64 count like the reference; batch moments are accumulated in fp64.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ void chan_merge(double& mean, double& var, double& count_f, double bm, double bv, double n) {
+    // running_mean_std.py:55-67
+    const double tot = count_f + n;
+    const double delta = bm - mean;
+    const double new_mean = mean + delta * n / tot;
+    const double M2 = var * count_f + bv * n + delta * delta * count_f * n / tot;
+    mean = new_mean; var = M2 / tot; count_f = tot;
+}
+
+__device__ __forceinline__ float norm_clamp(float x, float mean, float std) {
+    const float y = __fdiv_rn(__fsub_rn(x, mean), std);
+    return fminf(fmaxf(y, -5.0f), 5.0f);
+}
+
+template <bool MASKED>
+__global__ void __launch_bounds__(256) prepare_batch_kernel(
+    const float* __restrict__ values, const float* __restrict__ returns,
+    const float* __restrict__ mask, const double* __restrict__ partials, int n_partials,
+    double* vms_mean, double* vms_var, int64_t* vms_count,
+    float* __restrict__ old_values_n, float* __restrict__ returns_n, float* __restrict__ advs_n,
+    int B, int normalize_value, int normalize_advantage, int freeze_stats) {
+    __shared__ double sm[32 * 7];
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int p = threadIdx.x; p < n_partials; p += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) acc[i] += partials[(int64_t)p * 8 + i];
+    }
+    block_sum_d<7>(acc, sm);
+    const double n = acc[0];
+    // ---- value normaliser (values, then returns) ----
+    // Unmasked path (a2c_common.py:1616-1620): `values = vms(values)` updates with the values and normalises
+    // them with THAT intermediate state; `returns = vms(returns)` then updates again and uses the final state.
+    // Masked path (:1605-1615): both updates first, then both tensors are normalised with the final state.
+    double mean = vms_mean[0], var = vms_var[0], cnt = (double)vms_count[0];
+    double mean_v = mean, var_v = var;
+    if (normalize_value && !freeze_stats && n > 0.0) {
+        const double mv = acc[1] / n, vv = fmax(acc[2] / n - mv * mv, 0.0);
+        chan_merge(mean, var, cnt, mv, vv, n);
+        mean_v = mean; var_v = var;
+        const double mr = acc[3] / n, vr = fmax(acc[4] / n - mr * mr, 0.0);
+        chan_merge(mean, var, cnt, mr, vr, n);
+        if (MASKED) { mean_v = mean; var_v = var; }
+    }
+    const float mean_f = (float)mean;
+    const float std_f = __fsqrt_rn(__fadd_rn((float)var, 1e-5f));
+    const float mean_vf = (float)mean_v;
+    const float std_vf = __fsqrt_rn(__fadd_rn((float)var_v, 1e-5f));
+    // ---- advantage normalisation ----
+    float a_mean = 0.f, a_den = 1.f;
+    if (normalize_advantage) {
+        if (!MASKED) {
+            const double m = acc[5] / n;
+            const double v = fmax((acc[6] - n * m * m) / (n - 1.0), 0.0);   // torch .std(): unbiased
+            a_mean = (float)m; a_den = __fadd_rn((float)sqrt(v), 1e-8f);
+        } else {
+            // torch_ext.py:182-191 get_mean_var_with_masks: clamped denominators
+            const double sm_ = fmax(n, 1.0);
+            const double m = acc[5] / sm_;
+            const double min_sqr = acc[6] / sm_ - m * m;
+            const double v = fmax(min_sqr * sm_ / fmax(sm_ - 1.0, 1.0), 0.0);
+            a_mean = (float)m; a_den = __fadd_rn((float)sqrt(v), 1e-8f);
+        }
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+        const float v = values[i], r = returns[i];
+        const float a = __fsub_rn(r, v);   // advantages = returns - values (a2c_common.py:1598), V == 1
+        old_values_n[i] = normalize_value ? norm_clamp(v, mean_vf, std_vf) : v;
+        returns_n[i] = normalize_value ? norm_clamp(r, mean_f, std_f) : r;
+        advs_n[i] = normalize_advantage ? __fdiv_rn(__fsub_rn(a, a_mean), a_den) : a;
+    }
+    // stats write-back happens only AFTER every block has read the old state: all blocks read it at the
+    // top of the kernel, so block 0 may not overwrite it before the others start.  Use a separate
+    // finishing kernel instead (prepare_commit_kernel) -- see host code.
+}
+
+// single-thread commit of the value-normaliser state (same arithmetic as above)
+__global__ void prepare_commit_kernel(const double* __restrict__ partials, int n_partials,
+                                      double* vms_mean, double* vms_var, int64_t* vms_count) {
+    __shared__ double sm[32 * 7];
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int p = threadIdx.x; p < n_partials; p += blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) acc[i] += partials[(int64_t)p * 8 + i];
+    }
+    block_sum_d<7>(acc, sm);
+    if (threadIdx.x == 0) {
+        const double n = acc[0];
+        if (n > 0.0) {
+            double mean = vms_mean[0], var = vms_var[0], cnt = (double)vms_count[0];
+            const double mv = acc[1] / n, vv = fmax(acc[2] / n - mv * mv, 0.0);
+            chan_merge(mean, var, cnt, mv, vv, n);
+            const double mr = acc[3] / n, vr = fmax(acc[4] / n - mr * mr, 0.0);
+            chan_merge(mean, var, cnt, mr, vr, n);
+            vms_mean[0] = mean; vms_var[0] = var;
+            vms_count[0] = vms_count[0] + 2 * (int64_t)llround(n);
+        }
+    }
+}
+
+// ---- obs moments: grid = (blocks_per_chunk, n_chunks), 256 threads ---------------------------------
+// scratch layout: [n_blocks][2*D] doubles (shifted sum, shifted sum of squares)
+__global__ void __launch_bounds__(256) moments_partial_kernel(
+    const float* __restrict__ x, int D, int rows_per_chunk, int64_t chunk_stride,
+    const double* __restrict__ run_mean, double* __restrict__ scratch, int* counter,
+    double* mean, double* var, int64_t* count, float* mean_f32, float* std_f32, float eps, int n_rows_total) {
+    extern __shared__ double smd[];   // [G][2][CW]
+    const int CW = D <= 32 ? 32 : (D <= 64 ? 64 : (D <= 128 ? 128 : 256));
+    const int G = 256 / CW;
+    const int c = threadIdx.x % CW, g = threadIdx.x / CW;
+    const int bpc = gridDim.x;
+    const int rows_per_block = (rows_per_chunk + bpc - 1) / bpc;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, rows_per_chunk);
+    const float* base = x + ((int64_t)blockIdx.y * chunk_stride) * D;
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const int n_blocks = gridDim.x * gridDim.y;
+    for (int c0 = 0; c0 < D; c0 += CW) {
+        const int col = c0 + c;
+        double s = 0.0, q = 0.0;
+        if (col < D) {
+            const float shift = (float)run_mean[col];
+            int r = r0 + g;
+            // 4 independent loads in flight per thread
+            for (; r + 3 * G < r1; r += 4 * G) {
+                const float v0 = __ldg(base + (int64_t)r * D + col), v1 = __ldg(base + (int64_t)(r + G) * D + col);
+                const float v2 = __ldg(base + (int64_t)(r + 2 * G) * D + col), v3 = __ldg(base + (int64_t)(r + 3 * G) * D + col);
+                const double d0 = (double)(v0 - shift), d1 = (double)(v1 - shift), d2 = (double)(v2 - shift), d3 = (double)(v3 - shift);
+                s += (d0 + d1) + (d2 + d3);
+                q += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+            }
+            for (; r < r1; r += G) {
+                const double d0 = (double)(__ldg(base + (int64_t)r * D + col) - shift);
+                s += d0; q += d0 * d0;
+            }
+        }
+        smd[(g * 2 + 0) * CW + c] = s;
+        smd[(g * 2 + 1) * CW + c] = q;
+        __syncthreads();
+        if (g == 0 && col < D) {
+            double ss = 0.0, qq = 0.0;
+            for (int gg = 0; gg < G; ++gg) { ss += smd[(gg * 2 + 0) * CW + c]; qq += smd[(gg * 2 + 1) * CW + c]; }
+            scratch[(int64_t)blk * 2 * D + col] = ss;
+            scratch[(int64_t)blk * 2 * D + D + col] = qq;
+        }
+        __syncthreads();
+    }
+    // ---- last block finalises (fixed order => deterministic) ----
+    __shared__ int is_last;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        const int prev = atomicAdd(counter, 1);
+        is_last = (prev == n_blocks - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double n = (double)n_rows_total;
+    const double cnt0 = (double)count[0];
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+        double ss = 0.0, qq = 0.0;
+        for (int b = 0; b < n_blocks; ++b) {
+            ss += __ldcg(scratch + (int64_t)b * 2 * D + col);
+            qq += __ldcg(scratch + (int64_t)b * 2 * D + D + col);
+        }
+        const double shift = (double)(float)run_mean[col];
+        const double ms = ss / n;
+        const double bm = shift + ms;
+        const double bv = fmax(qq / n - ms * ms, 0.0);
+        double m = mean[col], v = var[col], cf = cnt0;
+        chan_merge(m, v, cf, bm, bv, n);
+        mean[col] = m; var[col] = v;
+        mean_f32[col] = (float)m;
+        std_f32[col] = __fsqrt_rn(__fadd_rn((float)v, eps));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { count[0] = count[0] + (int64_t)n_rows_total; *counter = 0; }
+}
+
+// moments of an already materialised batch (compat path of prepare_dataset when a caller edited batch_dict)
+__global__ void __launch_bounds__(256) batch_moments_kernel(const float* __restrict__ values, const float* __restrict__ returns,
+                                                           const float* __restrict__ mask, double* __restrict__ partials, int B) {
+    __shared__ double sm[32 * 7];
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+        const float v = values[i], r = returns[i];
+        const double w = mask ? (mask[i] != 0.f ? 1.0 : 0.0) : 1.0;
+        const double dv = v, dr = r, da = __fsub_rn(r, v);
+        acc[0] += w; acc[1] += w * dv; acc[2] += w * dv * dv; acc[3] += w * dr; acc[4] += w * dr * dr;
+        acc[5] += w * da; acc[6] += w * da * da;
+    }
+    block_sum_d<7>(acc, sm);
+    if (threadIdx.x == 0) {
+        double* p = partials + (int64_t)blockIdx.x * 8;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) p[i] = acc[i];
+        p[7] = 0.0;
+    }
+}
+
+__global__ void refresh_f32_kernel(const double* mean, const double* var, float* mean_f32, float* std_f32, float eps, int D) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < D) { mean_f32[c] = (float)mean[c]; std_f32[c] = __fsqrt_rn(__fadd_rn((float)var[c], eps)); }
+}
+
+__global__ void __launch_bounds__(256) normalize_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                        const double* __restrict__ mean, const double* __restrict__ var,
+                                                        float eps, int64_t total, int D, int denorm) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int c = (int)(i % D);
+        const float m = (float)mean[c];
+        const float s = __fsqrt_rn(__fadd_rn((float)var[c], eps));
+        const float v = x[i];
+        if (denorm) {
+            const float cl = fminf(fmaxf(v, -5.0f), 5.0f);
+            y[i] = __fadd_rn(__fmul_rn(s, cl), m);
+        } else {
+            y[i] = norm_clamp(v, m, s);
+        }
+    }
+}
+
+}  // namespace
+
+B200RL_EXPORT int b200rl_prepare_batch_f32(const float* values, const float* returns, const float* mask,
+                                           const double* partials, int n_partials,
+                                           double* vms_mean, double* vms_var, int64_t* vms_count,
+                                           float* old_values_n, float* returns_n, float* advs_n,
+                                           int B, int normalize_value, int normalize_advantage, int freeze_stats,
+                                           void* stream) {
+    if (!values || !returns || !partials || !old_values_n || !returns_n || !advs_n || B <= 0 || n_partials <= 0)
+        return B200RL_EINVAL;
+    if (normalize_value && (!vms_mean || !vms_var || !vms_count)) return B200RL_EINVAL;
+    cudaStream_t s = as_stream(stream);
+    const int threads = 256;
+    int blocks = (B + threads * 4 - 1) / (threads * 4);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks < 1) blocks = 1;
+    if (!normalize_value) {
+        // kernel still dereferences vms_* pointers: require them (agent always allocates them)
+        if (!vms_mean || !vms_var || !vms_count) return B200RL_EINVAL;
+    }
+    if (mask)
+        prepare_batch_kernel<true><<<blocks, threads, 0, s>>>(values, returns, mask, partials, n_partials, vms_mean, vms_var,
+                                                              vms_count, old_values_n, returns_n, advs_n, B, normalize_value,
+                                                              normalize_advantage, freeze_stats);
+    else
+        prepare_batch_kernel<false><<<blocks, threads, 0, s>>>(values, returns, mask, partials, n_partials, vms_mean, vms_var,
+                                                               vms_count, old_values_n, returns_n, advs_n, B, normalize_value,
+                                                               normalize_advantage, freeze_stats);
+    B200RL_LAUNCH_CHECK();
+    if (normalize_value && !freeze_stats) {
+        prepare_commit_kernel<<<1, 256, 0, s>>>(partials, n_partials, vms_mean, vms_var, vms_count);
+        B200RL_LAUNCH_CHECK();
+    }
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_batch_moments_f64(const float* values, const float* returns, const float* mask, double* partials,
+                                           int max_partials, int B, int* n_blocks_out_host, void* stream) {
+    if (!values || !returns || !partials || B <= 0 || max_partials <= 0) return B200RL_EINVAL;
+    int blocks = (B + 256 * 8 - 1) / (256 * 8);
+    if (blocks > max_partials) blocks = max_partials;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (n_blocks_out_host) *n_blocks_out_host = blocks;
+    batch_moments_kernel<<<blocks, 256, 0, as_stream(stream)>>>(values, returns, mask, partials, B);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_moments_update_f64(const float* x, int D, int rows_per_chunk, int n_chunks,
+                                            int64_t chunk_stride, double* mean, double* var, int64_t* count,
+                                            float* mean_f32, float* std_f32, float eps,
+                                            double* scratch, int scratch_blocks, int* counter, void* stream) {
+    if (!x || !mean || !var || !count || !mean_f32 || !std_f32 || !scratch || !counter) return B200RL_EINVAL;
+    if (D <= 0 || rows_per_chunk <= 0 || n_chunks <= 0) return B200RL_EINVAL;
+    int bpc = (148 * 4 + n_chunks - 1) / n_chunks;            // ~4 CTAs per SM in total
+    const int max_bpc = (rows_per_chunk + 31) / 32;           // >= 32 rows per block
+    if (bpc > max_bpc) bpc = max_bpc;
+    if (bpc < 1) bpc = 1;
+    while (bpc * n_chunks > scratch_blocks && bpc > 1) --bpc;
+    if (bpc * n_chunks > scratch_blocks) return B200RL_EINVAL;
+    const int CW = D <= 32 ? 32 : (D <= 64 ? 64 : (D <= 128 ? 128 : 256));
+    const int G = 256 / CW;
+    const size_t smem = (size_t)G * 2 * CW * sizeof(double);
+    dim3 grid(bpc, n_chunks);
+    moments_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(x, D, rows_per_chunk, chunk_stride, mean, scratch, counter,
+                                                                   mean, var, count, mean_f32, std_f32, eps,
+                                                                   rows_per_chunk * n_chunks);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_refresh_norm_f32(const double* mean, const double* var, float* mean_f32, float* std_f32,
+                                          float eps, int D, void* stream) {
+    if (!mean || !var || !mean_f32 || !std_f32 || D <= 0) return B200RL_EINVAL;
+    refresh_f32_kernel<<<(D + 127) / 128, 128, 0, as_stream(stream)>>>(mean, var, mean_f32, std_f32, eps, D);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_normalize_f32(const float* x, float* y, const double* mean, const double* var, float eps,
+                                       int64_t rows, int D, int denorm, void* stream) {
+    if (!x || !y || !mean || !var || rows < 0 || D <= 0) return B200RL_EINVAL;
+    if (rows == 0) return B200RL_OK;
+    const int64_t total = rows * D;
+    int64_t blocks = (total + 256 * 4 - 1) / (256 * 4);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    normalize_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, y, mean, var, eps, total, D, denorm);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}

@@ -1,0 +1,287 @@
+"""Policy/value model object for the B200 PPO path.
+
+Mirrors the call surface of the reference's ``ModelA2CContinuousLogStd.Network`` (models.py:304-364)
+wrapped around ``A2CBuilder.Network`` (network_builder.py:211-593) for the subset on the hot path:
+shared MLP trunk (``separate: False``), ``fixed_sigma: True`` continuous head with the 'exp' sigma
+parametrisation, scalar value head, optional obs / value ``RunningMeanStd`` normalisers.
+
+All parameters live in ONE flat fp32 arena (``self.flat``) with matching flat gradient / Adam-moment
+arenas, so the optimiser, the gradient all-reduce and the checkpoint code each touch one buffer:
+
+    [ sigma(A) | W_1 | b_1 | ... | W_L | b_L | W_head(A+1, H_L) | b_head(A+1) ]   (row 0 of the head = value)
+
+``state_dict()`` / ``load_state_dict()`` speak the reference's key names
+(``a2c_network.sigma``, ``a2c_network.actor_mlp.{0,2,..}.{weight,bias}``, ``a2c_network.value.*``,
+``a2c_network.mu.*``, ``running_mean_std.*``, ``value_mean_std.*``) so checkpoints interoperate with the
+reference trainer and players.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+
+
+def _apply_init(t, spec, fan_in):
+    """network_builder.py:61-72 init_factory for the names used by shipped configs."""
+    name = (spec or {}).get('name', 'default')
+    kw = {k: v for k, v in (spec or {}).items() if k != 'name'}
+    if name == 'default':
+        bound = 1.0 / math.sqrt(fan_in)      # torch.nn.Linear default: kaiming_uniform_(a=sqrt(5))
+        t.uniform_(-bound, bound)
+    elif name == 'const_initializer':
+        t.fill_(kw.get('val', kw.get('value', 0)))
+    elif name in ('orthogonal_initializer', 'orthogonal'):
+        torch.nn.init.orthogonal_(t, **kw)
+    elif name == 'glorot_normal_initializer':
+        torch.nn.init.xavier_normal_(t, **kw)
+    elif name == 'glorot_uniform_initializer':
+        torch.nn.init.xavier_uniform_(t, **kw)
+    elif name == 'random_uniform_initializer':
+        torch.nn.init.uniform_(t, **kw)
+    elif name == 'kaiming_normal':
+        torch.nn.init.kaiming_normal_(t, **kw)
+    else:
+        raise ValueError(f'unsupported initializer {name}')
+
+
+class _RunningStats:
+    """Device-resident RunningMeanStd state (running_mean_std.py:19-53): fp64 mean/var, int64 count,
+    plus the fp32 (mean, sqrt(var+eps)) copies the fused kernels read."""
+
+    def __init__(self, size, device):
+        self.size = size
+        self.running_mean = torch.zeros(size, dtype=torch.float64, device=device)
+        self.running_var = torch.ones(size, dtype=torch.float64, device=device)
+        self.count = torch.ones(1, dtype=torch.int64, device=device)
+        self.mean_f32 = torch.zeros(size, dtype=torch.float32, device=device)
+        self.std_f32 = torch.ones(size, dtype=torch.float32, device=device)
+        self.refresh()
+
+    def refresh(self):
+        ops.refresh_norm(self.running_mean, self.running_var, self.mean_f32, self.std_f32)
+
+    def state_dict(self, prefix):
+        return OrderedDict([(prefix + 'running_mean', self.running_mean.clone()),
+                            (prefix + 'running_var', self.running_var.clone()),
+                            (prefix + 'count', self.count.reshape(()).clone())])
+
+    def load_state_dict(self, sd, prefix=''):
+        self.running_mean.copy_(sd[prefix + 'running_mean'].reshape(-1))
+        self.running_var.copy_(sd[prefix + 'running_var'].reshape(-1))
+        self.count.copy_(sd[prefix + 'count'].reshape(-1))
+        self.refresh()
+
+    def __call__(self, x, denorm=False):
+        """Eval-mode forward (running_mean_std.py:104-113)."""
+        return ops.normalize(x, self.running_mean, self.running_var, denorm=denorm)
+
+
+class _NetworkView:
+    """What Runner._override_sigma (torch_runner.py:52-60) touches: ``a2c_network.sigma`` / ``fixed_sigma``."""
+
+    def __init__(self, model):
+        self._m = model
+        self.fixed_sigma = True
+
+    @property
+    def sigma(self):
+        return self._m.sigma
+
+    def is_rnn(self):
+        return False
+
+
+class B200Model:
+    def __init__(self, network_params, obs_dim, act_dim, device, normalize_input, normalize_value, value_size=1,
+                 seed=None):
+        if value_size != 1:
+            raise NotImplementedError('value_size > 1 is not on the B200 hot path yet')
+        mlp = network_params['mlp']
+        self.units = list(mlp['units'])
+        if len(self.units) == 0:
+            raise NotImplementedError('empty MLP')
+        self.activation = mlp.get('activation', 'elu')
+        if self.activation not in ops.ACT:
+            raise NotImplementedError(f'activation {self.activation}')
+        self.act_id = ops.ACT[self.activation]
+        if network_params.get('separate', False):
+            raise NotImplementedError('separate actor/critic trunks are not on the B200 hot path yet')
+        for k in ('cnn', 'rnn'):
+            if k in network_params:
+                raise NotImplementedError(f"'{k}' networks are not on the B200 hot path yet")
+        space = network_params['space']['continuous']
+        if not space.get('fixed_sigma', True):
+            raise NotImplementedError('state-dependent sigma is not on the B200 hot path yet')
+        for k in ('mu_activation', 'sigma_activation'):
+            if space.get(k, 'None') not in ('None', None):
+                raise NotImplementedError(f'{k}={space[k]}')
+        if space.get('sigma_parametrization', 'exp') != 'exp' or space.get('logstd_bounds') or float(space.get('min_sigma', 0)) > 0:
+            raise NotImplementedError("only the plain 'exp' sigma parametrisation is on the B200 hot path")
+        if network_params.get('value_activation', 'None') not in ('None', None):
+            raise NotImplementedError('value_activation')
+        self.D, self.A = int(obs_dim), int(act_dim)
+        self.device = torch.device(device)
+        self.normalize_input, self.normalize_value = bool(normalize_input), bool(normalize_value)
+        # ---- flat arenas ----
+        sizes = [('sigma', (self.A,))]
+        ins = self.D
+        for i, u in enumerate(self.units):
+            sizes += [(f'W{i}', (u, ins)), (f'b{i}', (u,))]
+            ins = u
+        self.Hl = ins
+        sizes += [('W_head', (self.A + 1, ins)), ('b_head', (self.A + 1,))]
+        self.layout = OrderedDict()
+        off = 0
+        for n, shp in sizes:
+            numel = int(torch.Size(shp).numel())
+            self.layout[n] = (off, shp)
+            off += numel
+        self.num_params = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.exp_avg = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(off, dtype=torch.float32, device=self.device)
+        self.W = [self.view(f'W{i}') for i in range(len(self.units))]
+        self.b = [self.view(f'b{i}') for i in range(len(self.units))]
+        self.sigma = self.view('sigma')
+        self.W_head, self.b_head = self.view('W_head'), self.view('b_head')
+        self.gW = [self.view(f'W{i}', self.grad) for i in range(len(self.units))]
+        self.gb = [self.view(f'b{i}', self.grad) for i in range(len(self.units))]
+        self.g_sigma = self.view('sigma', self.grad)
+        self.gW_head, self.gb_head = self.view('W_head', self.grad), self.view('b_head', self.grad)
+        self.running_mean_std = _RunningStats(self.D, self.device) if self.normalize_input else None
+        self.value_mean_std = _RunningStats(1, self.device)   # always allocated; used iff normalize_value
+        self.a2c_network = _NetworkView(self)
+        self._init_weights(network_params, seed)
+        self.training = False
+
+    # -------------------------------------------------------------------------------------------
+    def view(self, name, arena=None):
+        off, shp = self.layout[name]
+        arena = self.flat if arena is None else arena
+        return arena[off:off + int(torch.Size(shp).numel())].view(shp)
+
+    def _init_weights(self, network_params, seed):
+        """network_builder.py:326-348: mlp initializer on every Linear weight, zero biases, mu_init on mu.weight,
+        sigma_init on the sigma parameter."""
+        space = network_params['space']['continuous']
+        mlp_init = network_params['mlp'].get('initializer', {'name': 'default'})
+        cpu = {}
+        ins = self.D
+        for i, u in enumerate(self.units):
+            w = torch.empty(u, ins)
+            _apply_init(w, mlp_init, ins)
+            cpu[f'W{i}'] = w
+            ins = u
+        wh = torch.empty(self.A + 1, ins)
+        _apply_init(wh[:1], mlp_init, ins)                                   # value head: mlp_init
+        _apply_init(wh[1:], mlp_init, ins)
+        mu_init = space.get('mu_init', {'name': 'default'})
+        if mu_init.get('name', 'default') != 'default':
+            _apply_init(wh[1:], mu_init, ins)
+        cpu['W_head'] = wh
+        sg = torch.empty(self.A)
+        _apply_init(sg, space.get('sigma_init', {'name': 'const_initializer', 'val': 0}), 1)
+        cpu['sigma'] = sg
+        for n, t in cpu.items():
+            self.view(n).copy_(t)
+
+    # ------------------------------------------------------------------------------------------- nn.Module-ish
+    def is_rnn(self):
+        return False
+
+    def get_default_rnn_state(self):
+        return None
+
+    def get_aux_loss(self):
+        return None
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode=True):
+        self.training = mode
+        return self
+
+    def to(self, device):
+        return self
+
+    def parameters(self):
+        """Reference parameter order (optimizer state is index-keyed): sigma, actor_mlp.*, value.*, mu.*"""
+        out = [self.sigma]
+        for w, b in zip(self.W, self.b):
+            out += [w, b]
+        out += [self.W_head[:1], self.b_head[:1], self.W_head[1:], self.b_head[1:]]
+        return out
+
+    def _param_views(self, arena):
+        out = [self.view('sigma', arena)]
+        for i in range(len(self.units)):
+            out += [self.view(f'W{i}', arena), self.view(f'b{i}', arena)]
+        wh, bh = self.view('W_head', arena), self.view('b_head', arena)
+        out += [wh[:1], bh[:1], wh[1:], bh[1:]]
+        return out
+
+    def state_dict(self):
+        sd = OrderedDict()
+        if self.normalize_value:
+            sd.update(self.value_mean_std.state_dict('value_mean_std.'))
+        if self.normalize_input:
+            sd.update(self.running_mean_std.state_dict('running_mean_std.'))
+        sd['a2c_network.sigma'] = self.sigma.clone()
+        for i in range(len(self.units)):
+            sd[f'a2c_network.actor_mlp.{2 * i}.weight'] = self.W[i].clone()
+            sd[f'a2c_network.actor_mlp.{2 * i}.bias'] = self.b[i].clone()
+        sd['a2c_network.value.weight'] = self.W_head[:1].clone()
+        sd['a2c_network.value.bias'] = self.b_head[:1].clone()
+        sd['a2c_network.mu.weight'] = self.W_head[1:].clone()
+        sd['a2c_network.mu.bias'] = self.b_head[1:].clone()
+        return sd
+
+    def load_state_dict(self, sd, strict=True):
+        sd = {k.replace('_orig_mod.', ''): v for k, v in sd.items()}
+        need = [k for k in self.state_dict().keys()]
+        missing = [k for k in need if k not in sd]
+        if missing and strict:
+            raise KeyError(f'missing keys in state_dict: {missing}')
+        with torch.no_grad():
+            if 'a2c_network.sigma' in sd:
+                self.sigma.copy_(sd['a2c_network.sigma'])
+            for i in range(len(self.units)):
+                self.W[i].copy_(sd[f'a2c_network.actor_mlp.{2 * i}.weight'])
+                self.b[i].copy_(sd[f'a2c_network.actor_mlp.{2 * i}.bias'])
+            self.W_head[:1].copy_(sd['a2c_network.value.weight'])
+            self.b_head[:1].copy_(sd['a2c_network.value.bias'])
+            self.W_head[1:].copy_(sd['a2c_network.mu.weight'])
+            self.b_head[1:].copy_(sd['a2c_network.mu.bias'])
+            if self.normalize_value and 'value_mean_std.running_mean' in sd:
+                self.value_mean_std.load_state_dict(sd, 'value_mean_std.')
+            if self.normalize_input and 'running_mean_std.running_mean' in sd:
+                self.running_mean_std.load_state_dict(sd, 'running_mean_std.')
+
+    # ------------------------------------------------------------------------------------------- optimizer state
+    def optimizer_state_dict(self, lr, step, weight_decay):
+        """torch.optim.Adam.state_dict() layout (index-keyed, reference parameter order)."""
+        state = {}
+        for i, (m, v) in enumerate(zip(self._param_views(self.exp_avg), self._param_views(self.exp_avg_sq))):
+            state[i] = {'step': torch.tensor(float(step)), 'exp_avg': m.clone(), 'exp_avg_sq': v.clone()}
+        group = {'lr': lr, 'betas': (0.9, 0.999), 'eps': 1e-08, 'weight_decay': weight_decay, 'amsgrad': False,
+                 'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': True,
+                 'decoupled_weight_decay': False, 'params': list(range(len(state)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_optimizer_state_dict(self, osd):
+        """Returns (lr, step)."""
+        st = osd.get('state', {})
+        step = 0
+        ms, vs = self._param_views(self.exp_avg), self._param_views(self.exp_avg_sq)
+        for i in range(len(ms)):
+            if i in st:
+                ms[i].copy_(st[i]['exp_avg'].reshape(ms[i].shape))
+                vs[i].copy_(st[i]['exp_avg_sq'].reshape(vs[i].shape))
+                step = int(float(st[i]['step']))
+        lr = osd['param_groups'][0]['lr'] if osd.get('param_groups') else None
+        return lr, step

@@ -1,0 +1,225 @@
+"""Tensor-level wrappers over the C ABI (include/b200rl.h).  PyTorch is plumbing only: it owns device
+memory and the CUDA stream; every op below is one (or two) hand-written sm_100a kernel launches.
+
+There is no CPU path: tensors must live on a CUDA device, and a missing libb200rl.so raises.
+"""
+import ctypes
+
+import torch
+
+from ._lib import lib, check, ptr
+
+ACT = {'None': 0, None: 0, 'none': 0, 'elu': 1, 'relu': 2, 'tanh': 3}
+
+
+class LossCfg(ctypes.Structure):
+    _fields_ = [('e_clip', ctypes.c_float), ('critic_coef', ctypes.c_float), ('bounds_loss_coef', ctypes.c_float),
+                ('has_bounds_loss', ctypes.c_int), ('bound_loss_type', ctypes.c_int), ('clip_value', ctypes.c_int),
+                ('use_smooth_clamp', ctypes.c_int), ('ppo', ctypes.c_int)]
+
+
+class OptCfg(ctypes.Structure):
+    _fields_ = [('beta1', ctypes.c_double), ('beta2', ctypes.c_double), ('eps', ctypes.c_double),
+                ('weight_decay', ctypes.c_double), ('grad_norm', ctypes.c_double), ('kl_threshold', ctypes.c_double),
+                ('min_lr', ctypes.c_double), ('max_lr', ctypes.c_double), ('lr_multiplier', ctypes.c_double),
+                ('grad_scale', ctypes.c_double), ('truncate_grads', ctypes.c_int), ('adaptive_lr', ctypes.c_int)]
+
+
+class ShaperCfg(ctypes.Structure):
+    _fields_ = [('scale_value', ctypes.c_float), ('shift_value', ctypes.c_float), ('min_val', ctypes.c_float),
+                ('max_val', ctypes.c_float), ('gamma', ctypes.c_float), ('log_val', ctypes.c_int),
+                ('value_bootstrap', ctypes.c_int)]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError('rl_games_b200 ops need CUDA tensors (no CPU fallback)')
+
+
+def compute_gae(mb_rewards, mb_values, mb_dones, last_values, last_dones, gamma, tau, returns_out=None):
+    """Drop-in for rl_games.triton_kernels.compute_gae (gae_kernel.py:124-146): same signature, accepts
+    non-contiguous views and float or uint8 dones; returns a new [H,N,V] fp32 tensor."""
+    _need_cuda(mb_rewards, mb_values, mb_dones, last_values, last_dones)
+    H, N, V = mb_rewards.shape
+    if mb_rewards.dtype != torch.float32:
+        mb_rewards = mb_rewards.float()
+    if mb_values.dtype != torch.float32:
+        mb_values = mb_values.float()
+
+    def _dn(d):
+        if d.dtype in (torch.uint8, torch.bool):
+            return d.view(torch.uint8) if d.dtype == torch.bool else d, 1
+        return (d if d.dtype == torch.float32 else d.float()), 0
+    mb_dones, d_u8 = _dn(mb_dones)
+    last_dones, ld_u8 = _dn(last_dones)
+    last_values = last_values.contiguous().float()
+    last_dones = last_dones.contiguous()
+    advs = torch.empty((H, N, V), dtype=torch.float32, device=mb_rewards.device)
+    if returns_out is not None:
+        assert returns_out.shape == advs.shape and returns_out.is_contiguous()
+    rs, vs, ds, as_ = mb_rewards.stride(), mb_values.stride(), mb_dones.stride(), advs.stride()
+    check(lib.b200rl_gae_f32(ptr(mb_rewards), ptr(mb_values), ptr(mb_dones), d_u8, ptr(last_values), ptr(last_dones),
+                             ld_u8, ptr(advs), ptr(returns_out), H, N, V, rs[0], rs[1], rs[2], vs[0], vs[1], vs[2],
+                             ds[0], ds[1], as_[0], as_[1], as_[2], float(gamma), float(tau), _stream()), 'gae')
+    return advs
+
+
+def gae_fused(rewards, values, dones_u8, last_values, last_dones_u8, mask, advs, returns, partials, gamma, tau):
+    """Fused GAE + returns + moment partials on contiguous [H,N] tensors.  Returns number of partial rows."""
+    H, N = rewards.shape
+    nb = ctypes.c_int(0)
+    check(lib.b200rl_gae_fused_f32(ptr(rewards), ptr(values), ptr(dones_u8), ptr(last_values), ptr(last_dones_u8),
+                                   ptr(mask), ptr(advs), ptr(returns), ptr(partials),
+                                   0 if partials is None else partials.shape[0], H, N, float(gamma), float(tau),
+                                   ctypes.addressof(nb), _stream()), 'gae_fused')
+    return nb.value
+
+
+def prepare_batch(values, returns, mask, partials, n_partials, vms_mean, vms_var, vms_count, old_values_n,
+                  returns_n, advs_n, normalize_value, normalize_advantage, freeze_stats=False):
+    check(lib.b200rl_prepare_batch_f32(ptr(values), ptr(returns), ptr(mask), ptr(partials), n_partials,
+                                       ptr(vms_mean), ptr(vms_var), ptr(vms_count), ptr(old_values_n), ptr(returns_n),
+                                       ptr(advs_n), values.numel(), int(normalize_value), int(normalize_advantage),
+                                       int(freeze_stats), _stream()), 'prepare_batch')
+
+
+def batch_moments(values, returns, mask, partials):
+    nb = ctypes.c_int(0)
+    check(lib.b200rl_batch_moments_f64(ptr(values), ptr(returns), ptr(mask), ptr(partials), partials.shape[0],
+                                       values.numel(), ctypes.addressof(nb), _stream()), 'batch_moments')
+    return nb.value
+
+
+def moments_update(x, D, rows_per_chunk, n_chunks, chunk_stride, mean, var, count, mean_f32, std_f32, scratch, counter,
+                   eps=1e-5):
+    check(lib.b200rl_moments_update_f64(ptr(x), D, rows_per_chunk, n_chunks, chunk_stride, ptr(mean), ptr(var),
+                                        ptr(count), ptr(mean_f32), ptr(std_f32), eps, ptr(scratch),
+                                        scratch.numel() // (2 * D), ptr(counter), _stream()), 'moments_update')
+
+
+def refresh_norm(mean, var, mean_f32, std_f32, eps=1e-5):
+    check(lib.b200rl_refresh_norm_f32(ptr(mean), ptr(var), ptr(mean_f32), ptr(std_f32), eps, mean.numel(), _stream()),
+          'refresh_norm')
+
+
+def normalize(x, mean, var, denorm=False, eps=1e-5, out=None):
+    x = x.contiguous()
+    D = mean.numel()
+    y = torch.empty_like(x) if out is None else out
+    check(lib.b200rl_normalize_f32(ptr(x), ptr(y), ptr(mean), ptr(var), eps, x.numel() // D, D, int(denorm), _stream()),
+          'normalize')
+    return y
+
+
+def linear_fwd(X, W, b, Y, act, rows_per_chunk=None, chunk_stride=0, x_ld=None, norm_mean=None, norm_std=None, M=None):
+    Nout, K = W.shape
+    M = Y.shape[0] if M is None else M
+    check(lib.b200rl_linear_fwd_f32(ptr(X), M if rows_per_chunk is None else rows_per_chunk, chunk_stride,
+                                    K if x_ld is None else x_ld, ptr(norm_mean), ptr(norm_std), ptr(W), ptr(b), ptr(Y),
+                                    M, K, Nout, act, _stream()), 'linear_fwd')
+
+
+def linear_bwd_data(dY, W, A_prev, dX, act_prev, M=None):
+    Nout, K = W.shape
+    M = dY.shape[0] if M is None else M
+    check(lib.b200rl_linear_bwd_data_f32(ptr(dY), ptr(W), ptr(A_prev), ptr(dX), M, K, Nout, act_prev, _stream()),
+          'linear_bwd_data')
+
+
+def linear_bwd_weight(dY, X, dW_part, db_part, K, Nout, n_splits, rows_per_chunk=None, chunk_stride=0, x_ld=None,
+                      norm_mean=None, norm_std=None, M=None, split_stride=None):
+    M = dY.shape[0] if M is None else M
+    if split_stride is None:
+        assert dW_part.stride(0) == db_part.stride(0) or db_part is None or dW_part.dim() == 3
+        split_stride = dW_part.stride(0)
+    check(lib.b200rl_linear_bwd_weight_f32(ptr(dY), ptr(X), M if rows_per_chunk is None else rows_per_chunk,
+                                           chunk_stride, K if x_ld is None else x_ld, ptr(norm_mean), ptr(norm_std),
+                                           ptr(dW_part), ptr(db_part), split_stride, M, K, Nout, n_splits, _stream()),
+          'linear_bwd_weight')
+
+
+def reduce_splits(part, out, n, n_splits, split_stride=None):
+    check(lib.b200rl_reduce_splits_f32(ptr(part), ptr(out), n, n_splits, n if split_stride is None else split_stride,
+                                       _stream()), 'reduce_splits')
+
+
+def loss_partial_stride():
+    return lib.b200rl_loss_partial_stride()
+
+
+def ppo_head_loss(a_last, W_head, b_head, logstd, actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp,
+                  advs_n, mask, rows_per_chunk, chunk_stride, M, A, cfg, inv_count, d_head, d_alast, act_last, partials,
+                  mu_out=None, value_out=None, neglogp_out=None):
+    nb = ctypes.c_int(0)
+    Hl = W_head.shape[1]
+    check(lib.b200rl_ppo_head_loss_f32(ptr(a_last), Hl, ptr(W_head), ptr(b_head), ptr(logstd), ptr(actions), ptr(old_mu),
+                                       ptr(old_sigma), ptr(old_values_n), ptr(returns_n), ptr(old_neglogp), ptr(advs_n),
+                                       ptr(mask), rows_per_chunk, chunk_stride, M, A, ctypes.addressof(cfg),
+                                       ptr(inv_count), ptr(d_head), ptr(d_alast), act_last, ptr(mu_out), ptr(value_out),
+                                       ptr(neglogp_out), ptr(partials), partials.shape[0], ctypes.addressof(nb),
+                                       _stream()), 'ppo_head_loss')
+    return nb.value
+
+
+def ppo_loss_finalize(partials, n_partials, A, entropy_coef_dev, stats, d_logstd, kl_out=None):
+    check(lib.b200rl_ppo_loss_finalize(ptr(partials), n_partials, A, ptr(entropy_coef_dev), ptr(stats), ptr(d_logstd),
+                                       ptr(kl_out), _stream()), 'ppo_loss_finalize')
+
+
+def mask_inv_counts(mask, H, N, envs_per_mb, inv_count):
+    check(lib.b200rl_mask_inv_counts_f32(ptr(mask), H, N, envs_per_mb, ptr(inv_count), _stream()), 'mask_inv_counts')
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None):
+    check(lib.b200rl_adam_step_f32(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq),
+                                   params.numel() if n is None else n, ptr(state_d), ptr(kl_dev), ctypes.addressof(cfg),
+                                   ptr(stats_out), ptr(counter), _stream()), 'adam_step')
+
+
+def policy_head_sample(a_last, W_head, b_head, logstd, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch,
+                       step_index, actions, mus, sigmas, neglogp, values, env_actions, clip_actions, act_low, act_high,
+                       dones_cur, dones_out, prev_dones, valid_out, N, A, values_only=False):
+    Hl = W_head.shape[1]
+    check(lib.b200rl_policy_head_sample_f32(ptr(a_last), Hl, ptr(W_head), ptr(b_head), ptr(logstd), ptr(vms_mean),
+                                            ptr(vms_var), int(normalize_value), ptr(noise), seed, ptr(rng_epoch),
+                                            step_index, ptr(actions), ptr(mus), ptr(sigmas), ptr(neglogp), ptr(values),
+                                            ptr(env_actions), int(clip_actions), ptr(act_low), ptr(act_high),
+                                            ptr(dones_cur), ptr(dones_out), ptr(prev_dones), ptr(valid_out), N, A,
+                                            int(values_only), _stream()), 'policy_head_sample')
+
+
+def post_step(rewards, dones, time_outs, values_t, valid_t, rewards_out_t, dones_cur, prev_dones, ep_state, meter,
+              games_to_track, scratch, counter, N, cfg):
+    d_u8 = 1 if dones.dtype in (torch.uint8, torch.bool) else 0
+    if not d_u8 and dones.dtype != torch.float32:
+        dones = dones.float()
+    kind = 0
+    if time_outs is not None:
+        if time_outs.dtype in (torch.uint8, torch.bool):
+            kind = 1
+        else:
+            kind = 2
+            if time_outs.dtype != torch.float32:
+                time_outs = time_outs.float()
+    check(lib.b200rl_post_step_f32(ptr(rewards), ptr(dones), d_u8, ptr(time_outs), kind, ptr(values_t), ptr(valid_t),
+                                   ptr(rewards_out_t), ptr(dones_cur), ptr(prev_dones), ptr(ep_state), ptr(meter),
+                                   games_to_track, ptr(scratch), scratch.numel() // 4, ptr(counter), N,
+                                   ctypes.addressof(cfg), _stream()), 'post_step')
+
+
+def synth_env_step(actions, obs, rewards, dones, time_outs, ep_t, N, D, A, max_len, p_done, seed, rng_epoch, step_index):
+    check(lib.b200rl_synth_env_step(ptr(actions), ptr(obs), ptr(rewards), ptr(dones), ptr(time_outs), ptr(ep_t), N, D, A,
+                                    max_len, p_done, seed, ptr(rng_epoch), step_index, _stream()), 'synth_env_step')
+
+
+def bump_u64(t):
+    check(lib.b200rl_bump_u64(ptr(t), _stream()), 'bump_u64')
+
+
+def fill_u32(t, v=0):
+    check(lib.b200rl_fill_u32(ptr(t), t.numel() * t.element_size() // 4, v, _stream()), 'fill_u32')
