@@ -1,0 +1,332 @@
+"""bench.py -- PPO env-steps/s on the BASELINE.json workload, one JSON line on stdout (rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference algorithm on host cores
+
+A "step" is one full PPO epoch (`agent.train_epoch()`: H-step rollout on the synthetic on-GPU env -> GAE ->
+mini_epochs x num_minibatches updates) at BASELINE.json configs[1]: 16384 envs x horizon 16, obs 60, act 8,
+MLP [256,128,64], minibatch 32768, 4 mini-epochs, hyper-parameters of configs/mujoco/ant_envpool.yaml.
+N > 1 (torchrun): every rank owns its own 16384-env shard (weak scaling), one NCCL all-reduce of the flat
+gradient (+KL slot) per minibatch; value = all ranks' env-steps / max-over-ranks device time.
+
+Timing: W >= 3 warm-up epochs, then exactly K epochs, each bracketed by CUDA events on the launching stream,
+L2 flushed (256 MiB write) between epochs outside the event pairs, barrier + synchronize on both sides of the
+timed region, max over ranks.  nvidia-smi clocks are sampled during the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    'c2': dict(num_actors=16384, horizon=16, obs_dim=60, act_dim=8, units=[256, 128, 64], minibatch=32768, mini_epochs=4),
+    # BASELINE.json configs[4] per-GPU shard (131072 envs / 8), obs 256, horizon 32
+    'c5': dict(num_actors=16384, horizon=32, obs_dim=256, act_dim=8, units=[256, 128, 64], minibatch=32768, mini_epochs=4),
+}
+
+
+def make_params(w, device, env_name, multi_gpu, graph=True, seed=5):
+    network = {'name': 'actor_critic', 'separate': False,
+               'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                        'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+               'mlp': {'units': list(w['units']), 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    config = {'name': 'bench', 'env_name': env_name, 'reward_shaper': {'scale_value': 1.0}, 'device': device,
+              'multi_gpu': multi_gpu, 'mixed_precision': False, 'normalize_input': True, 'normalize_value': True,
+              'value_bootstrap': True, 'normalize_advantage': True, 'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4,
+              'lr_schedule': 'adaptive', 'kl_threshold': 0.008, 'grad_norm': 1.0, 'entropy_coef': 0.0, 'truncate_grads': True,
+              'e_clip': 0.2, 'clip_value': True, 'use_smooth_clamp': True, 'bound_loss_type': 'regularisation',
+              'bounds_loss_coef': 0.0, 'max_epochs': -1, 'num_actors': w['num_actors'], 'horizon_length': w['horizon'],
+              'minibatch_size': w['minibatch'], 'mini_epochs': w['mini_epochs'], 'critic_coef': 2, 'print_stats': False,
+              'train_dir': '/tmp/b200_bench_runs', 'b200_cuda_graph': graph,
+              'env_config': {'obs_dim': w['obs_dim'], 'act_dim': w['act_dim'], 'device': device, 'seed': seed}}
+    return {'seed': seed, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'},
+            'network': network, 'config': config}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 8]
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = []
+        for i, name in ((4, 'hw_slowdown'), (5, 'hw_thermal_slowdown'), (6, 'sw_thermal_slowdown'), (7, 'sw_power_cap')):
+            if any(r[i].lower().startswith('active') for r in rows):
+                reasons.append(name)
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][2]), 'reasons': reasons, 'samples': len(rows)}
+
+
+def dist_info():
+    return int(os.getenv('RANK', '0')), int(os.getenv('LOCAL_RANK', '0')), int(os.getenv('WORLD_SIZE', '1'))
+
+
+# ===================================================================================== reference arm (CPU)
+def run_cpu_oracle(w, steps, warmup, sample_envs):
+    """The reference algorithm (oracle/ppo_oracle.py: plain-PyTorch restatement pinned to the real reference by
+    tests/golden) on the host cores, all threads.  Returns (env_steps_per_s, ms_per_step, cores)."""
+    from oracle import ppo_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    N = sample_envs
+    mb = max(w['horizon'], w['minibatch'] * N // w['num_actors'])
+    env = O.SyntheticEnvCPU(N, w['obs_dim'], w['act_dim'], seed=5)
+    params = O.init_params(w['obs_dim'], w['units'], w['act_dim'], seed=5)
+    ag = O.OracleAgent(env, params, w['obs_dim'], w['act_dim'], w['units'], N, w['horizon'], mb,
+                       {'mini_epochs': w['mini_epochs']})
+    ag.obs = ag.env_reset()
+    g = torch.Generator().manual_seed(0)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        noise = torch.randn(w['horizon'], N, w['act_dim'], generator=g)
+        ag.train_epoch(noise)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return N * w['horizon'] * steps / total, 1e3 * total / steps, cores
+
+
+def reference_arm(args, w):
+    rank, _, world = dist_info()
+    if rank != 0:
+        return
+    sample = min(w['num_actors'], 4096)
+    val, ms, cores = run_cpu_oracle(w, args.steps, max(1, args.warmup), sample)
+    line = {'impl': 'reference', 'metric': 'ppo_env_steps_per_sec', 'value': val, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.workload, w, 'cpu synthetic env (oracle.SyntheticEnvCPU)'),
+            'cpu_baseline': {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{sample} of {w["num_actors"]} envs per step, same horizon / mini-epochs / '
+                                       f'minibatch count; oracle/ppo_oracle.py (reference is pure Python: port pinned by golden vectors)'},
+            'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, w, env_desc):
+    return {'workload': f'{name}: synthetic PPO, {w["num_actors"]} envs/GPU x horizon {w["horizon"]}, obs {w["obs_dim"]}, '
+                        f'act {w["act_dim"]}, MLP {w["units"]}, minibatch {w["minibatch"]} x {w["mini_epochs"]} mini-epochs '
+                        f'(BASELINE.json configs[{1 if name == "c2" else 4}])',
+            'env': env_desc, 'global_batch': w['num_actors'] * w['horizon'], 'parallelism': 'dp (actors sharded per GPU)',
+            'l2': 'flushed between steps (256 MiB write outside the per-step CUDA-event pairs)',
+            'hyper_params': 'rl_games/configs/mujoco/ant_envpool.yaml:28-56'}
+
+
+# ===================================================================================== B200 arm
+def build_agent(w, device, env_name, multi_gpu, graph=True):
+    from rl_games_b200.runner import Runner
+    r = Runner()
+    r.load({'params': make_params(w, device, env_name, multi_gpu, graph)})
+    agent = r.algo_factory.create(r.algo_name, base_name='bench', params=r.params)
+    agent.init_tensors()
+    agent.obs = agent.env_reset()
+    return agent
+
+
+def timed_epochs(agent, steps, flush, world):
+    import torch.distributed as dist
+    from rl_games_b200 import ops
+    evs = []
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        if flush is not None:
+            ops.fill_u32(flush, 1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        agent.epoch_num += 1
+        agent.train_epoch()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return [s.elapsed_time(e) for s, e in evs]
+
+
+def kernel_breakdown(agent):
+    """One instrumented eager epoch: CUDA events around every C-ABI call -> per-kernel time shares + launch count."""
+    from rl_games_b200._lib import lib
+    graph = agent.use_cuda_graph
+    agent.use_cuda_graph = False
+    lib.start_profile()
+    agent.epoch_num += 1
+    agent.train_epoch()
+    prof = lib.stop_profile()
+    agent.use_cuda_graph = graph
+    return prof
+
+
+def gae_roofline(w, peaks):
+    from rl_games_b200 import ops
+    H, N = w['horizon'], w['num_actors']
+    dev = torch.device('cuda', torch.cuda.current_device())
+    r, v = torch.randn(H, N, device=dev), torch.randn(H, N, device=dev)
+    d = (torch.rand(H, N, device=dev) < 0.05).to(torch.uint8)
+    lv, ld = torch.randn(N, device=dev), (torch.rand(N, device=dev) < 0.05).to(torch.uint8)
+    advs, rets = torch.empty(H, N, device=dev), torch.empty(H, N, device=dev)
+    part = torch.zeros((N + 127) // 128, 8, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for i in range(13):
+        ops.fill_u32(flush, 1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.gae_fused(r, v, d, lv, ld, None, advs, rets, part, 0.99, 0.95)
+        e.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(s.elapsed_time(e))
+    ms = sum(ts) / len(ts)
+    alg = 17 * H * N + 8 * N     # r4 + V4 + done1 read, A4 + returns4 written per element; last_value/last_done per env
+    gbs = alg / (ms * 1e-3) / 1e9
+    return {'kernel': 'gae_fused_kernel (GAE + returns + moment partials)', 'bound': 'hbm', 'achieved': gbs,
+            'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'traffic': None,
+            'alg_bytes_per_launch': alg, 'ms_per_launch': ms, 'peak_source': peaks['source'],
+            'note': 'workload shape (4.5 MB working set: launch/latency bound); large-shape asymptote 0.84-0.87 of measured '
+                    'peak in profiles/r01_gae_sweep*.json (tools/gae_sweep.py)'}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {'hbm_gbs': j['hbm_gbs'], 'bf16_tflops': j['bf16_tflops'], 'bf16_tflops_sustained': j['bf16_tflops_sustained'],
+                'source': 'measured (MEASURED_PEAKS.json)'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback (B200_PROFILING.md)'}
+
+
+def b200_arm(args, w):
+    import torch.distributed as dist
+    rank, local_rank, world = dist_info()
+    multi = world > 1
+    torch.cuda.set_device(local_rank)
+    device = f'cuda:{local_rank}'
+    peaks = load_peaks()
+    agent = build_agent(w, device, 'b200_synthetic', multi, graph=not args.no_graph)
+    if multi:
+        dist.broadcast(agent.model.flat, 0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    W = max(3, args.warmup)
+    timed_epochs(agent, W, flush, world)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ms = timed_epochs(agent, args.steps, flush, world)
+    clocks = sampler.stop()
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=device)
+    if multi:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_s = float(total_ms) * 1e-3
+    B = w['num_actors'] * w['horizon']
+    value = B * world * args.steps / total_s
+    # ---- kernel breakdown + launch count (instrumented eager epoch, not part of the timed region) ----
+    prof = kernel_breakdown(agent)
+    ktot = sum(v['ms'] for v in prof.values()) or 1.0
+    kernels = sorted(({'call': k, 'launches': v['n'], 'ms': round(v['ms'], 4), 'share': round(v['ms'] / ktot, 4)}
+                      for k, v in prof.items()), key=lambda x: -x['ms'])
+    launches_per_step = sum(v['n'] for v in prof.values())
+    line = {'metric': 'ppo_env_steps_per_sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': W, 'ms_per_step': 1e3 * total_s / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': workload_config(args.workload, w, 'b200_synthetic (on-GPU Philox env, one kernel per step)'),
+            'clocks': clocks, 'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
+            'cuda_graph': bool(agent._graph_update is not None), 'kernels': kernels[:12]}
+    if rank == 0:
+        # dominant kernel family of the step -> roofline
+        line['roofline_gae'] = gae_roofline(w, peaks)
+        mlp_ms = sum(v['ms'] for k, v in prof.items() if 'linear' in k)
+        flops = 2 * sum(a * b for a, b in zip([w['obs_dim']] + w['units'], w['units'] + [w['act_dim'] + 1]))
+        step_flops = B * flops * (1 + 3 * w['mini_epochs'])      # rollout fwd + (fwd + dgrad + wgrad) per mini-epoch
+        tf = step_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
+        line['roofline'] = {'kernel': 'MLP fwd/dgrad/wgrad GEMMs (fp32 CUDA-core path, mixed_precision: False)', 'bound': 'tensor',
+                            'achieved': tf, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                            'frac': tf / peaks['bf16_tflops_sustained'], 'traffic': None, 'share_of_step': round(mlp_ms / ktot, 4),
+                            'peak_source': peaks['source'] + ' bf16 sustained; the fp32 SIMT kernels cannot approach it -- '
+                            'the tcgen05 bf16 path is the next milestone'}
+        if world == 1 and not args.skip_e2e:
+            line['e2e'] = e2e_leg(w, device, args)
+        if world == 1 and not args.skip_cpu:
+            val, cms, cores = run_cpu_oracle(w, 2, 1, min(w['num_actors'], 4096))
+            line['cpu_baseline'] = {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+                                    'sample': f'2 epochs of {min(w["num_actors"], 4096)} envs (of {w["num_actors"]}) after 1 warm-up; '
+                                              'oracle/ppo_oracle.py on the host cores'}
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def e2e_leg(w, device, args):
+    """Same metric through the public API with a HOST env: every env step copies obs/rewards/dones/time-outs
+    host->device (pinned) and the actions device->host; the per-epoch stats block is read back."""
+    agent = build_agent(w, device, 'b200_synthetic_host', False, graph=not args.no_graph)
+    K = max(3, min(args.steps, 10))
+    for _ in range(3):
+        agent.epoch_num += 1
+        agent.train_epoch()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        agent.epoch_num += 1
+        agent.train_epoch()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    N, H, D, A = w['num_actors'], w['horizon'], w['obs_dim'], w['act_dim']
+    h2d = H * (N * D * 4 + N * 4 + N + N)
+    d2h = H * N * A * 4 + agent.stats.numel() * 4 + 10 * 8
+    return {'value': N * H * K / dt, 'unit': 'env-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'steps': K, 'env': 'b200_synthetic_host (numpy env in host memory, pinned staging, wall-clock timed)'}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=list(WORKLOADS))
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-cpu', action='store_true')
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == 'reference':
+        reference_arm(args, w)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: the B200 arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    b200_arm(args, w)
+
+
+if __name__ == '__main__':
+    main()

@@ -43,6 +43,7 @@ def parse_header(path=HEADER):
 class _Lib:
     def __init__(self):
         self._cdll = None
+        self._prof = None
         self.protos = parse_header()
 
     def load(self):
@@ -64,8 +65,38 @@ class _Lib:
 
     def __getattr__(self, name):
         if name.startswith('b200rl_'):
-            return getattr(self.load(), name)
+            fn = getattr(self.load(), name)
+            if self.__dict__.get('_prof') is None:
+                return fn
+            return self._profiled(name, fn)
         raise AttributeError(name)
+
+    # ---- optional per-call CUDA-event timing (bench.py kernel breakdown; never on in the product path) ----
+    def start_profile(self):
+        self.__dict__['_prof'] = []
+
+    def _profiled(self, name, fn):
+        import torch
+
+        def wrapped(*args):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = fn(*args)
+            e.record()
+            self.__dict__['_prof'].append((name, s, e))
+            return rc
+        return wrapped
+
+    def stop_profile(self):
+        import torch
+        torch.cuda.synchronize()
+        recs, out = self.__dict__.get('_prof') or [], {}
+        self.__dict__['_prof'] = None
+        for name, s, e in recs:
+            d = out.setdefault(name.replace('b200rl_', ''), {'n': 0, 'ms': 0.0})
+            d['n'] += 2 if name == 'b200rl_prepare_batch_f32' else 1
+            d['ms'] += s.elapsed_time(e)
+        return out
 
 
 lib = _Lib()

@@ -1,0 +1,969 @@
+"""B200-native continuous PPO agent behind the reference's plugin surface.
+
+Same constructor (``A2CAgent(base_name, params)``), config keys / defaults and public methods as
+``rl_games.algos_torch.a2c_continuous.A2CAgent`` + ``rl_games.common.a2c_common.ContinuousA2CBase``
+(a2c_common.py:170-491 config parsing, :985-1069 play_steps, :1517-1584 train_epoch, :1586-1660
+prepare_dataset, :1662-1782 train; a2c_continuous.py:136-234 calc_gradients), but the hot loop is a
+sequence of hand-written sm_100a kernels over one time-major experience arena:
+
+    rollout step t:   [obs copy] -> MLP fwd (norm fused) -> policy_head_sample -> env.step -> post_step
+    epoch end:        values_only fwd -> gae_fused (+returns +moment partials) -> prepare_batch
+    minibatch i:      obs moments+merge -> MLP fwd -> ppo_head_loss -> finalize -> wgrad/dgrad chain ->
+                      split reduce -> [NCCL all-reduce of the flat grad (+KL slot)] -> adam_step (+ on-device
+                      adaptive-KL LR schedule)
+
+No tensor is ever transposed/flattened: the reference's flat sample index env*H+t (swap_and_flatten01,
+a2c_common.py:33-40) and minibatch slices (datasets.py:75-82) are honoured as an index mapping --
+minibatch i = envs [i*mb/H, (i+1)*mb/H) x all t.  The whole update phase (mini_epochs x num_minibatches)
+is captured in one CUDA graph; no .item()/nonzero() host syncs remain inside an epoch.
+"""
+import os
+import time
+from datetime import datetime
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .common import (AdaptiveScheduler, IdentityScheduler, LinearScheduler, DefaultAlgoObserver, DefaultRewardsShaper,
+                     create_vec_env, make_summary_writer)
+from .model import B200Model
+
+STATS_SYNC_MODES = ('pooled', 'broadcast')
+
+
+def swap_and_flatten01(arr):
+    """a2c_common.py:33-40 -- only used to hand reference-layout views to callers (tests, observers)."""
+    if arr is None:
+        return arr
+    s = arr.size()
+    return arr.transpose(0, 1).reshape(s[0] * s[1], *s[2:])
+
+
+def rescale_actions(low, high, action):
+    """a2c_common.py:144-148"""
+    d = (high - low) / 2.0
+    m = (high + low) / 2.0
+    return action * d + m
+
+
+class _MeterView:
+    """torch_ext.AverageMeter look-alike over the device-resident meter block (torch_ext.py:326-352)."""
+
+    def __init__(self, agent, slot):
+        self._a, self._slot = agent, slot
+
+    @property
+    def current_size(self):
+        return int(self._a._meter_host()[3])
+
+    def __len__(self):
+        return self.current_size
+
+    def get_mean(self):
+        return np.asarray([self._a._meter_host()[self._slot]], dtype=np.float32)
+
+    @property
+    def mean(self):
+        return torch.tensor([self._a._meter_host()[self._slot]], dtype=torch.float32)
+
+    def clear(self):
+        self._a.meter.zero_()
+        self._a._meter_cache = None
+
+
+class _Dataset:
+    """datasets.PPODataset look-alike (datasets.py:7-95): len() minibatches, [i] -> dict of reference-layout
+    COPIES of minibatch i (flat order env*H+t) tagged with its index so train_actor_critic() can run the
+    fused kernels on the arena rows the slice denotes."""
+
+    def __init__(self, agent):
+        self.a = agent
+        self.values_dict = None
+
+    def __len__(self):
+        return self.a.num_minibatches
+
+    def update_values_dict(self, d):
+        self.values_dict = d
+
+    def __getitem__(self, i):
+        a = self.a
+        e0, e1 = i * a.envs_per_mb, (i + 1) * a.envs_per_mb
+        fl = lambda t: swap_and_flatten01(t[:, e0:e1])   # noqa: E731
+        d = {'old_values': fl(a.old_values_n).unsqueeze(1), 'old_logp_actions': fl(a.neglogpacs),
+             'advantages': fl(a.advs_n), 'returns': fl(a.returns_n).unsqueeze(1), 'actions': fl(a.actions),
+             'obs': fl(a.obses), 'dones': fl(a.dones_buf), 'mu': fl(a.mus), 'sigma': fl(a.sigmas), '_mb_index': i}
+        if a.mask_autoreset_rows:
+            d['rnn_masks'] = fl(a.valid)
+        return d
+
+
+class A2CAgent:
+    def __init__(self, base_name, params):
+        self.config = config = params['config']
+        self.experiment_name = config.get('full_experiment_name') or (config['name'] + datetime.now().strftime("_%d-%H-%M-%S"))
+        config.setdefault('features', {})
+        self.algo_observer = config['features'].get('observer') or DefaultAlgoObserver()
+        self.algo_observer.before_init(base_name, config, self.experiment_name)
+        self.network_params = params['network']
+        model_name = params.get('model', {}).get('name', 'continuous_a2c_logstd')
+        if model_name != 'continuous_a2c_logstd':
+            raise NotImplementedError(f"model '{model_name}': only continuous_a2c_logstd is on the B200 hot path")
+
+        self.multi_gpu = config.get('multi_gpu', False)
+        self.multi_gpu_sync_stats = config.get('multi_gpu_sync_stats', True)
+        mode = config.get('multi_gpu_sync_stats_mode', 'pooled')
+        if mode not in STATS_SYNC_MODES:
+            raise ValueError(f"multi_gpu_sync_stats_mode must be one of {STATS_SYNC_MODES}, got '{mode}'")
+        self.multi_gpu_sync_stats_mode = mode
+        self.local_rank = self.global_rank = 0
+        self.world_size = 1
+        if self.multi_gpu:
+            self.local_rank = int(os.getenv('LOCAL_RANK', '0'))
+            self.global_rank = int(os.getenv('RANK', '0'))
+            self.world_size = int(os.getenv('WORLD_SIZE', '1'))
+            config['device'] = 'cuda:' + str(self.local_rank)
+            torch.cuda.set_device(self.local_rank)
+            if not dist.is_initialized():
+                dist.init_process_group('nccl', rank=self.global_rank, world_size=self.world_size,
+                                        device_id=torch.device(config['device']))
+            if self.global_rank != 0:
+                config['print_stats'] = False
+        self.ppo_device = config.get('device', 'cuda:0')
+        if not str(self.ppo_device).startswith('cuda'):
+            raise RuntimeError("rl_games_b200.A2CAgent runs on CUDA only (device=%r): there is no CPU fallback" % self.ppo_device)
+        self.device_t = torch.device(self.ppo_device)
+        torch.cuda.set_device(self.device_t)
+
+        self.network_path = config.get('network_path', './nn/')
+        self.env_config = config.get('env_config', {})
+        self.num_actors = config['num_actors']
+        self.env_name = config['env_name']
+        self.env_info = config.get('env_info')
+        if self.env_info is None:
+            self.vec_env = create_vec_env(self.env_name, self.num_actors, **self.env_config)
+            self.env_info = self.vec_env.get_env_info()
+        else:
+            self.vec_env = config.get('vec_env', None)
+        self.value_size = self.env_info.get('value_size', 1)
+        self.observation_space = self.env_info['observation_space']
+        self.weight_decay = config.get('weight_decay', 0.0)
+        if config.get('use_action_masks', False):
+            raise NotImplementedError('action masks are a discrete-PPO feature')
+        self.has_central_value = config.get('central_value_config') is not None
+        if self.has_central_value:
+            raise NotImplementedError('central_value_config is not on the B200 hot path yet (SURVEY 8f)')
+        self.central_value_net = None
+        self.truncate_grads = config.get('truncate_grads', False)
+        self.save_freq = config.get('save_frequency', 0)
+        self.save_best_after = config.get('save_best_after', 100)
+        self.print_stats = config.get('print_stats', True)
+        self.name = base_name
+        self.ppo = config.get('ppo', True)
+        self.max_epochs = config.get('max_epochs', -1)
+        self.max_frames = max(config.get('max_frames', -1), config.get('max_steps', -1))
+        self.stop_fn = config.get('stop_fn', None)
+        if self.stop_fn is not None and not callable(self.stop_fn):
+            raise ValueError(f"'stop_fn' must be callable, got {type(self.stop_fn).__name__}")
+
+        self.is_adaptive_lr = config['lr_schedule'] == 'adaptive'
+        self.linear_lr = config['lr_schedule'] == 'linear'
+        self.schedule_type = config.get('schedule_type', 'per_minibatch')
+        if self.schedule_type == 'legacy':
+            self.schedule_type = 'per_minibatch'
+        if self.is_adaptive_lr and self.schedule_type != 'per_minibatch':
+            raise NotImplementedError("adaptive lr_schedule with schedule_type=%r: only 'per_minibatch' (the default) runs "
+                                      "on the device scheduler" % self.schedule_type)
+        if self.is_adaptive_lr:
+            self.kl_threshold = config['kl_threshold']
+            self.scheduler = AdaptiveScheduler(self.kl_threshold, min_lr=config.get('min_lr', 1e-6),
+                                               max_lr=config.get('max_lr', 1e-2), lr_multiplier=config.get('lr_multiplier', 1.5))
+        elif self.linear_lr:
+            if self.max_epochs == -1 and self.max_frames == -1:
+                self.scheduler = IdentityScheduler()
+            else:
+                use_epochs = self.max_epochs != -1
+                self.scheduler = LinearScheduler(float(config['learning_rate']), min_lr=config.get('min_lr', 1e-6),
+                                                 max_steps=self.max_epochs if use_epochs else self.max_frames,
+                                                 use_epochs=use_epochs, apply_to_entropy=config.get('schedule_entropy', False),
+                                                 start_entropy_coef=config.get('entropy_coef'))
+        else:
+            self.scheduler = IdentityScheduler()
+
+        self.e_clip = config['e_clip']
+        self.clip_value = config['clip_value']
+        rs = config['reward_shaper']
+        self.rewards_shaper = rs if not isinstance(rs, dict) else DefaultRewardsShaper(**rs)
+        self.num_agents = self.env_info.get('agents', 1)
+        if self.num_agents != 1:
+            raise NotImplementedError('multi-agent envs are not on the B200 hot path yet')
+        self.autoreset_mode = (self.env_info or {}).get('autoreset_mode', 'same_step')
+        self.mask_autoreset_rows = self.autoreset_mode == 'next_step'
+        if self.mask_autoreset_rows and self.num_agents > 1:
+            raise ValueError("PPO next_step autoreset masking does not support multi-agent envs; "
+                             "wrap the env with a same_step autoreset adapter instead")
+        self.horizon_length = config['horizon_length']
+        self.seq_length = config.get('seq_length', 4)
+        self.normalize_advantage = config['normalize_advantage']
+        if config.get('normalize_rms_advantage', False):
+            raise NotImplementedError('normalize_rms_advantage (EMA advantage normaliser) is not on the B200 hot path yet')
+        self.normalize_rms_advantage = False
+        self.normalize_input = config['normalize_input']
+        self.normalize_value = config.get('normalize_value', False)
+        if type(self.observation_space).__name__ == 'Dict':
+            raise NotImplementedError('Dict observation spaces are not on the B200 hot path yet')
+        self.obs_shape = self.observation_space.shape
+        if len(self.obs_shape) != 1:
+            raise NotImplementedError('only flat observations are on the B200 hot path')
+        self.critic_coef = config['critic_coef']
+        self.grad_norm = config['grad_norm']
+        self.gamma = config['gamma']
+        self.tau = config['tau']
+        self.games_to_track = config.get('games_to_track', 100)
+        self.batch_size = self.horizon_length * self.num_actors * self.num_agents
+        self.batch_size_envs = self.horizon_length * self.num_actors
+        if 'minibatch_size' not in config and 'minibatch_size_per_env' not in config:
+            raise ValueError("Configuration must include either 'minibatch_size' or 'minibatch_size_per_env'. "
+                             "Neither was found in the provided config.")
+        self.minibatch_size_per_env = config.get('minibatch_size_per_env', 0)
+        self.minibatch_size = config.get('minibatch_size', self.num_actors * self.minibatch_size_per_env)
+        if self.minibatch_size <= 0:
+            raise ValueError(f"'minibatch_size' must be greater than 0. Calculated value: {self.minibatch_size}.")
+        self.num_minibatches = self.batch_size // self.minibatch_size
+        if self.batch_size % self.minibatch_size != 0:
+            raise ValueError(f"'batch_size' ({self.batch_size}) must be divisible by 'minibatch_size' ({self.minibatch_size}). "
+                             "Ensure that 'batch_size' is a multiple of 'minibatch_size'.")
+        if self.minibatch_size % self.horizon_length != 0:
+            raise NotImplementedError("minibatch_size must be a multiple of horizon_length on the B200 path "
+                                      "(minibatches are whole-env slices of the time-major arena)")
+        self.envs_per_mb = self.minibatch_size // self.horizon_length
+        self.mini_epochs_num = config['mini_epochs']
+        self.mixed_precision = config.get('mixed_precision', True)
+        self.last_lr = float(config['learning_rate'])
+        self.frame = 0
+        self.update_time = self.play_time = 0
+        self.mean_rewards = self.last_mean_rewards = -float('inf')
+        self.epoch_num = 0
+        self.curr_frames = 0
+        self.train_dir = config.get('train_dir', 'runs')
+        self.experiment_dir = os.path.join(self.train_dir, self.experiment_name)
+        self.nn_dir = os.path.join(self.experiment_dir, 'nn')
+        self.summaries_dir = os.path.join(self.experiment_dir, 'summaries')
+        for d in (self.train_dir, self.experiment_dir, self.nn_dir, self.summaries_dir):
+            os.makedirs(d, exist_ok=True)
+        self.entropy_coef = config['entropy_coef']
+        self.writer = make_summary_writer(self.summaries_dir) if self.global_rank == 0 else None
+        self.value_bootstrap = config.get('value_bootstrap', True)
+        self.use_smooth_clamp = config.get('use_smooth_clamp', False)
+        self.is_tensor_obses = False
+        self.is_rnn = False
+        self.rnn_states = None
+
+        # ---- ContinuousA2CBase (a2c_common.py:1484-1497) ----
+        self.is_discrete = False
+        action_space = self.env_info['action_space']
+        self.actions_num = action_space.shape[0]
+        self.bounds_loss_coef = config.get('bounds_loss_coef', None)
+        self.bound_loss_type = config.get('bound_loss_type', 'bound')
+        self.clip_actions = config.get('clip_actions', True)
+        self.actions_low = torch.from_numpy(np.asarray(action_space.low).copy()).float().to(self.device_t)
+        self.actions_high = torch.from_numpy(np.asarray(action_space.high).copy()).float().to(self.device_t)
+
+        # ---- A2CAgent (a2c_continuous.py:27-76) ----
+        self.model = B200Model(self.network_params, self.obs_shape[0], self.actions_num, self.device_t,
+                               self.normalize_input, self.normalize_value, self.value_size)
+        self.value_mean_std = self.model.value_mean_std if self.normalize_value else None
+        self.dataset = _Dataset(self)
+        self.has_value_loss = True
+        self.use_cuda_graph = bool(config.get('b200_cuda_graph', True))
+        self.rng_seed = int(config.get('b200_rng_seed', params.get('seed', 0) or 0)) + 7919 * self.global_rank
+        self._stats_snapshots = {}
+        self._graph_update = None
+        self._graph_epoch = None
+        self._meter_cache = None
+        self._tensors_ready = False
+        self.obs = None
+        self.train_result = None
+        self.game_rewards = _MeterView(self, 0)
+        self.game_shaped_rewards = _MeterView(self, 1)
+        self.game_lengths = _MeterView(self, 2)
+        self.algo_observer.after_init(self)
+
+    # =============================================================================== allocation
+    @property
+    def device(self):
+        return self.ppo_device
+
+    def init_tensors(self):
+        """a2c_common.py:634-660 + experience.py:330-398: one time-major arena, zero-initialised."""
+        if self._tensors_ready:
+            return
+        H, N, D, A = self.horizon_length, self.num_actors, self.obs_shape[0], self.actions_num
+        dev = self.device_t
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)   # noqa: E731
+        self.obses = f(H, N, D)
+        self.actions, self.mus, self.sigmas = f(H, N, A), f(H, N, A), f(H, N, A)
+        self.neglogpacs, self.values, self.rewards = f(H, N), f(H, N), f(H, N)
+        self.dones_buf = torch.zeros(H, N, dtype=torch.uint8, device=dev)
+        self.valid = torch.ones(H, N, dtype=torch.float32, device=dev) if self.mask_autoreset_rows else None
+        self.advs, self.returns = f(H, N), f(H, N)
+        self.old_values_n, self.returns_n, self.advs_n = f(H, N), f(H, N), f(H, N)
+        self.last_values = f(N)
+        self.env_actions = f(N, A)
+        # rl_games names (experience.py:372-398) -> arena views, for observers / tests
+        self.tensor_dict = {'obses': self.obses, 'rewards': self.rewards.unsqueeze(2), 'values': self.values.unsqueeze(2),
+                            'neglogpacs': self.neglogpacs, 'dones': self.dones_buf, 'actions': self.actions,
+                            'mus': self.mus, 'sigmas': self.sigmas}
+        # episode bookkeeping (a2c_common.py:662-666)
+        self.ep_state = f(3, N)
+        self.dones = torch.ones(N, dtype=torch.uint8, device=dev)
+        self.prev_dones = f(N) if self.mask_autoreset_rows else None
+        self.meter = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.rng_epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        # workspaces
+        m, mb = self.model, self.minibatch_size
+        self.ra = [f(N, u) for u in m.units]
+        self.ta = [f(mb, u) for u in m.units]
+        self.dA = [f(mb, u) for u in m.units]
+        self.d_head = f(mb, A + 1)
+        self.n_splits = max(1, min(64, mb // 256))
+        self.part = f(self.n_splits, m.num_params)
+        self.gae_partials = torch.zeros((N + 127) // 128, 8, dtype=torch.float64, device=dev)
+        self.loss_partials = torch.zeros((mb + 127) // 128, ops.loss_partial_stride(), dtype=torch.float64, device=dev)
+        self.n_updates = self.mini_epochs_num * self.num_minibatches
+        self.stats = f(self.n_updates, 16)
+        # comm buffer = flat gradient + 1 KL slot (one all-reduce per minibatch, a2c_common.py:493-509 + :1559-1561)
+        self.comm = f(m.num_params + 1)
+        m.grad = self.comm[:m.num_params]
+        m.gW = [m.view(f'W{i}', m.grad) for i in range(len(m.units))]
+        m.gb = [m.view(f'b{i}', m.grad) for i in range(len(m.units))]
+        m.g_sigma = m.view('sigma', m.grad)
+        m.gW_head, m.gb_head = m.view('W_head', m.grad), m.view('b_head', m.grad)
+        self.kl_slot = self.comm[m.num_params:]
+        self.opt_state = torch.tensor([self.last_lr, 0.0], dtype=torch.float64, device=dev)
+        self.entropy_coef_dev = torch.tensor([float(self.entropy_coef)], dtype=torch.float32, device=dev)
+        self.inv_counts = f(self.num_minibatches) if self.mask_autoreset_rows else None
+        self.mom_scratch = torch.zeros(1024 * 2 * D, dtype=torch.float64, device=dev)
+        self.post_scratch = torch.zeros(((N + 255) // 256) * 4, dtype=torch.float64, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.host_stats = torch.zeros(self.n_updates, 16, dtype=torch.float32).pin_memory()
+        self.host_state = torch.zeros(10, dtype=torch.float64).pin_memory()
+        self._events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self._build_cfg_structs()
+        self.update_list = ['actions', 'neglogpacs', 'values', 'mus', 'sigmas']
+        self.tensor_list = self.update_list + ['obses', 'states', 'dones']
+        self._pinned = {}
+        self._tensors_ready = True
+
+    def _build_cfg_structs(self):
+        """POD structs passed (by value at launch) to the kernels; baked into captured graphs, so any change
+        drops the captured graph."""
+        self.loss_cfg = ops.LossCfg(float(self.e_clip), float(self.critic_coef),
+                                    float(self.bounds_loss_coef) if self.bounds_loss_coef is not None else 0.0,
+                                    int(self.bounds_loss_coef is not None),
+                                    {'bound': 1, 'regularisation': 2}.get(self.bound_loss_type, 0), int(bool(self.clip_value)),
+                                    int(bool(self.use_smooth_clamp)), int(bool(self.ppo)))
+        sched = self.scheduler
+        self.opt_cfg = ops.OptCfg(0.9, 0.999, 1e-8, float(self.weight_decay), float(self.grad_norm),
+                                  float(getattr(sched, 'kl_threshold', 0.0)), float(getattr(sched, 'min_lr', 1e-6)),
+                                  float(getattr(sched, 'max_lr', 1e-2)), float(getattr(sched, 'lr_multiplier', 1.5)),
+                                  1.0 / self.world_size, int(bool(self.truncate_grads)),
+                                  int(self.is_adaptive_lr and self.schedule_type == 'per_minibatch'))
+        rs = self.rewards_shaper
+        self.shaper_cfg = ops.ShaperCfg(float(rs.scale_value), float(rs.shift_value), float(rs.min_val), float(rs.max_val),
+                                        float(self.gamma), int(bool(rs.log_val)), int(bool(self.value_bootstrap)))
+        self._graph_update = None
+
+    def _meter_host(self):
+        if self._meter_cache is None:
+            self._meter_cache = self.meter.cpu().numpy()
+        return self._meter_cache
+
+    # =============================================================================== env plumbing
+    def cast_obs(self, obs):
+        if isinstance(obs, torch.Tensor):
+            self.is_tensor_obses = True
+            return obs
+        if isinstance(obs, np.ndarray):
+            # host env: stage through pinned memory, async H2D on the compute stream
+            key = ('obs', obs.shape, obs.dtype.str)
+            buf = self._pinned.get(key)
+            if buf is None:
+                buf = (torch.empty(obs.shape, dtype=torch.float32).pin_memory(),
+                       torch.empty(obs.shape, dtype=torch.float32, device=self.device_t))
+                self._pinned[key] = buf
+            buf[0].copy_(torch.from_numpy(obs))
+            buf[1].copy_(buf[0], non_blocking=True)
+            return buf[1]
+        return obs
+
+    def obs_to_tensors(self, obs):
+        if isinstance(obs, dict):
+            obs = obs['obs'] if 'obs' in obs else obs
+        t = self.cast_obs(obs)
+        return {'obs': t}
+
+    def env_reset(self):
+        obs = self.vec_env.reset()
+        obs = self.obs_to_tensors(obs)
+        if self.prev_dones is not None:
+            self.prev_dones.zero_()
+        return obs
+
+    def _host_to_dev(self, name, arr, dtype):
+        key = (name, arr.shape)
+        buf = self._pinned.get(key)
+        if buf is None:
+            buf = (torch.empty(arr.shape, dtype=dtype).pin_memory(), torch.empty(arr.shape, dtype=dtype, device=self.device_t))
+            self._pinned[key] = buf
+        buf[0].copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(dtype))
+        buf[1].copy_(buf[0], non_blocking=True)
+        return buf[1]
+
+    def env_step(self, actions):
+        """a2c_common.py:708-719 (+ preprocess_actions :1500-1510 already applied by the policy kernel)."""
+        if self.is_tensor_obses:
+            obs, rewards, dones, infos = self.vec_env.step(actions)
+            return self.obs_to_tensors(obs), rewards, dones, infos
+        key = ('act', tuple(actions.shape))
+        hb = self._pinned.get(key)
+        if hb is None:
+            hb = torch.empty(actions.shape, dtype=torch.float32).pin_memory()
+            self._pinned[key] = hb
+        hb.copy_(actions, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        obs, rewards, dones, infos = self.vec_env.step(hb.numpy())
+        obs_t = self.obs_to_tensors(obs)
+        rew = self._host_to_dev('rew', np.asarray(rewards), torch.float32)
+        dn = self._host_to_dev('done', np.asarray(dones), torch.uint8)
+        if isinstance(infos, dict) and 'time_outs' in infos and not isinstance(infos['time_outs'], torch.Tensor):
+            infos = dict(infos)
+            infos['time_outs'] = self._host_to_dev('tout', np.asarray(infos['time_outs']), torch.uint8)
+        return obs_t, rew, dn, infos
+
+    # =============================================================================== policy forward
+    def _trunk(self, x, acts, M, rows_per_chunk=None, chunk_stride=0):
+        m = self.model
+        nm = m.running_mean_std.mean_f32 if self.normalize_input else None
+        ns = m.running_mean_std.std_f32 if self.normalize_input else None
+        ops.linear_fwd(x, m.W[0], m.b[0], acts[0], m.act_id, rows_per_chunk=rows_per_chunk, chunk_stride=chunk_stride,
+                       x_ld=m.D, norm_mean=nm, norm_std=ns, M=M)
+        for i in range(1, len(m.units)):
+            ops.linear_fwd(acts[i - 1], m.W[i], m.b[i], acts[i], m.act_id, M=M)
+
+    def _policy_step(self, obs, t, noise=None):
+        m, N, A = self.model, self.num_actors, self.actions_num
+        self._trunk(obs, self.ra, N)
+        ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
+                               m.value_mean_std.running_var, self.normalize_value, noise, self.rng_seed, self.rng_epoch, t,
+                               self.actions[t], self.mus[t], self.sigmas[t], self.neglogpacs[t], self.values[t],
+                               self.env_actions, self.clip_actions, self.actions_low, self.actions_high,
+                               self.dones, self.dones_buf[t], self.prev_dones, None if self.valid is None else self.valid[t],
+                               N, A)
+
+    def get_values(self, obs):
+        """a2c_common.py:603-626"""
+        o = obs['obs'] if isinstance(obs, dict) else obs
+        m, N, A = self.model, self.num_actors, self.actions_num
+        self._trunk(o, self.ra, N)
+        ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
+                               m.value_mean_std.running_var, self.normalize_value, None, 0, None, 0, None, None, None, None,
+                               self.last_values, None, False, None, None, None, None, None, None, N, A, values_only=True)
+        return self.last_values.unsqueeze(1)
+
+    def get_action_values(self, obs, noise=None):
+        """a2c_common.py:581-601.  Runs the policy on `obs` (writes arena step 0 scratch) and returns the result dict."""
+        o = obs['obs'] if isinstance(obs, dict) else obs
+        self._policy_step(o, 0, noise)
+        return {'actions': self.actions[0], 'neglogpacs': self.neglogpacs[0], 'values': self.values[0].unsqueeze(1),
+                'mus': self.mus[0], 'sigmas': self.sigmas[0], 'rnn_states': None}
+
+    # =============================================================================== rollout
+    def _rollout(self, noise=None):
+        """a2c_common.py:985-1069 without the eager launches: obs copy, trunk, head+sample+store, env, post-step."""
+        H, N = self.horizon_length, self.num_actors
+        step_time = 0.0
+        wants_idx = getattr(self.algo_observer, 'wants_done_indices', True)
+        if hasattr(self.vec_env, 'begin_rollout'):
+            self.vec_env.begin_rollout()
+        for t in range(H):
+            obs = self.obs['obs']
+            self.obses[t].copy_(obs)
+            self._policy_step(obs, t, None if noise is None else noise[t])
+            t0 = time.perf_counter()
+            self.obs, rewards, dones, infos = self.env_step(self.env_actions)
+            step_time += time.perf_counter() - t0
+            tout = infos.get('time_outs') if (self.value_bootstrap and isinstance(infos, dict)) else None
+            ops.post_step(rewards, dones, tout, self.values[t], None if self.valid is None else self.valid[t], self.rewards[t],
+                          self.dones, self.prev_dones, self.ep_state, self.meter, self.games_to_track, self.post_scratch,
+                          self.counters[0:1], N, self.shaper_cfg)
+            if wants_idx:
+                self.algo_observer.process_infos(infos, self.dones.nonzero(as_tuple=False))
+        self.get_values(self.obs)
+        if hasattr(self.vec_env, 'end_rollout'):
+            self.vec_env.end_rollout()
+        ops.bump_u64(self.rng_epoch)
+        self._meter_cache = None
+        return step_time
+
+    def _gae_and_prepare(self):
+        nb = ops.gae_fused(self.rewards, self.values, self.dones_buf, self.last_values, self.dones, self.valid, self.advs,
+                           self.returns, self.gae_partials, self.gamma, self.tau)
+        self._prepare(nb)
+
+    def _prepare(self, n_partials):
+        m = self.model
+        ops.prepare_batch(self.values, self.returns, self.valid, self.gae_partials, n_partials, m.value_mean_std.running_mean,
+                          m.value_mean_std.running_var, m.value_mean_std.count, self.old_values_n, self.returns_n,
+                          self.advs_n, self.normalize_value, self.normalize_advantage,
+                          freeze_stats=bool(self.config.get('freeze_critic', False)))
+        if self.mask_autoreset_rows:
+            ops.mask_inv_counts(self.valid, self.horizon_length, self.num_actors, self.envs_per_mb, self.inv_counts)
+
+    def play_steps(self, noise=None):
+        """Public mirror of A2CBase.play_steps: runs the rollout + GAE and returns the reference's batch_dict
+        (flat [env*H+t] COPIES of the arena; the fused path never needs them)."""
+        self.init_tensors()
+        step_time = self._rollout(noise)
+        nb = ops.gae_fused(self.rewards, self.values, self.dones_buf, self.last_values, self.dones, self.valid, self.advs,
+                           self.returns, self.gae_partials, self.gamma, self.tau)
+        self._n_gae_partials = nb
+        fl = swap_and_flatten01
+        batch_dict = {'actions': fl(self.actions), 'neglogpacs': fl(self.neglogpacs), 'values': fl(self.values.unsqueeze(2)),
+                      'mus': fl(self.mus), 'sigmas': fl(self.sigmas), 'obses': fl(self.obses), 'dones': fl(self.dones_buf),
+                      'returns': fl(self.returns.unsqueeze(2)), 'played_frames': self.batch_size, 'step_time': step_time}
+        if self.mask_autoreset_rows:
+            batch_dict['rnn_masks'] = fl(self.valid)
+        self._batch_dict_ids = {k: (v.data_ptr(), v._version) for k, v in batch_dict.items() if torch.is_tensor(v)}
+        return batch_dict
+
+    def prepare_dataset(self, batch_dict):
+        """a2c_common.py:1586-1660.  Accepts the dict from play_steps (possibly edited by the caller: edited or
+        foreign tensors are scattered back into the arena first)."""
+        H, N = self.horizon_length, self.num_actors
+        unfl = lambda t: t.reshape(N, H, *t.shape[1:]).transpose(0, 1)   # noqa: E731
+        ids = getattr(self, '_batch_dict_ids', {})
+        dirty = False
+        for k, dst in (('actions', self.actions), ('neglogpacs', self.neglogpacs), ('values', self.values.unsqueeze(2)),
+                       ('mus', self.mus), ('sigmas', self.sigmas), ('obses', self.obses), ('returns', self.returns.unsqueeze(2)),
+                       ('rnn_masks', None if self.valid is None else self.valid)):
+            v = batch_dict.get(k)
+            if v is None or dst is None:
+                continue
+            if ids.get(k) != (v.data_ptr(), v._version):
+                dst.copy_(unfl(v.to(self.device_t)))
+                dirty = True
+        if dirty or not hasattr(self, '_n_gae_partials'):
+            self._n_gae_partials = ops.batch_moments(self.values, self.returns, self.valid, self.gae_partials)
+        self._prepare(self._n_gae_partials)
+        self.dataset.update_values_dict({'ready': True})
+
+    # =============================================================================== update
+    def _minibatch_update(self, i, u):
+        """calc_gradients + trancate_gradients_and_step for minibatch i; u = flat update index (stats row)."""
+        m, H, N, A = self.model, self.horizon_length, self.num_actors, self.actions_num
+        epm, mb = self.envs_per_mb, self.minibatch_size
+        e0 = i * epm
+        x = self.obses[0, e0:]
+        L = len(m.units)
+        if self.normalize_input:
+            rms = m.running_mean_std
+            ops.moments_update(x, m.D, epm, H, N, rms.running_mean, rms.running_var, rms.count, rms.mean_f32, rms.std_f32,
+                               self.mom_scratch, self.counters[1:2])
+        self._trunk(x, self.ta, mb, rows_per_chunk=epm, chunk_stride=N)
+        nb = ops.ppo_head_loss(self.ta[-1], m.W_head, m.b_head, m.sigma, self.actions[0, e0:], self.mus[0, e0:],
+                               self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:], self.neglogpacs[0, e0:],
+                               self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:], epm, N, mb, A,
+                               self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.d_head,
+                               self.dA[-1], m.act_id, self.loss_partials)
+        ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], m.g_sigma, self.kl_slot)
+        P, S = m.num_params, self.n_splits
+        off_wh, _ = m.layout['W_head']
+        off_bh, _ = m.layout['b_head']
+        ops.linear_bwd_weight(self.d_head, self.ta[-1], self.part[0, off_wh:], self.part[0, off_bh:], m.Hl, A + 1, S, M=mb,
+                              split_stride=P)
+        nm = m.running_mean_std.mean_f32 if self.normalize_input else None
+        ns = m.running_mean_std.std_f32 if self.normalize_input else None
+        for l in range(L - 1, -1, -1):
+            off_w, shp = m.layout[f'W{l}']
+            off_b, _ = m.layout[f'b{l}']
+            if l > 0:
+                ops.linear_bwd_weight(self.dA[l], self.ta[l - 1], self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
+                                      M=mb, split_stride=P)
+                ops.linear_bwd_data(self.dA[l], m.W[l], self.ta[l - 1], self.dA[l - 1], m.act_id, M=mb)
+            else:
+                ops.linear_bwd_weight(self.dA[0], x, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
+                                      rows_per_chunk=epm, chunk_stride=N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=mb,
+                                      split_stride=P)
+        ops.reduce_splits(self.part[0, A:], m.grad[A:], P - A, S, split_stride=P)
+        if self.multi_gpu:
+            dist.all_reduce(self.comm, op=dist.ReduceOp.SUM)
+        ops.adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_state, self.kl_slot, self.opt_cfg, self.stats[u],
+                      self.counters[2:3], n=P)
+
+    def _update_all(self):
+        u = 0
+        for _ in range(self.mini_epochs_num):
+            for i in range(self.num_minibatches):
+                self._minibatch_update(i, u)
+                u += 1
+
+    def _run_update(self):
+        """Eager the first time (module loading, attribute setup); from the second epoch on the whole
+        mini_epochs x num_minibatches sequence replays as ONE CUDA graph (capture executes nothing)."""
+        if not self.use_cuda_graph or self.multi_gpu:
+            self._update_all()
+            return
+        if not getattr(self, '_update_warm', False):
+            self._update_all()
+            self._update_warm = True
+            return
+        if self._graph_update is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._update_all()
+            self._graph_update = g
+        self._graph_update.replay()
+
+    # =============================================================================== reference-style per-minibatch API
+    def train_actor_critic(self, input_dict, opt_step=True):
+        """a2c_continuous.py:236-239.  `input_dict` must come from ``self.dataset[i]``."""
+        i = input_dict.get('_mb_index')
+        if i is None:
+            raise NotImplementedError('train_actor_critic needs a minibatch produced by agent.dataset[i]')
+        self.init_tensors()
+        u = self._compat_u = getattr(self, '_compat_u', -1) + 1
+        u %= self.n_updates
+        self._minibatch_update(i, u)
+        st = self.stats[u]
+        e0, e1 = i * self.envs_per_mb, (i + 1) * self.envs_per_mb
+        self.train_result = (st[0], st[1], st[2], st[4], self.last_lr, 1.0, swap_and_flatten01(self.mus[:, e0:e1]),
+                             swap_and_flatten01(self.sigmas[:, e0:e1]), st[3])
+        return self.train_result
+
+    def calc_gradients(self, input_dict):
+        return self.train_actor_critic(input_dict)
+
+    # =============================================================================== epoch
+    def set_eval(self):
+        self.model.eval()
+
+    def set_train(self):
+        self.model.train()
+
+    def update_epoch(self):
+        self.epoch_num += 1
+        return self.epoch_num
+
+    def train_epoch(self, noise=None):
+        """a2c_common.py:1517-1584.  Returns the reference tuple; the per-minibatch scalars are 0-dim views of
+        one device stats block, read back with ONE D2H copy + sync per epoch."""
+        self.init_tensors()
+        if self.vec_env is not None and hasattr(self.vec_env, 'set_train_info'):
+            self.vec_env.set_train_info(self.frame, self)
+        ev = self._events
+        self.set_eval()
+        ev[0].record()
+        step_time = self._rollout(noise)
+        self._gae_and_prepare()
+        ev[1].record()
+        self.set_train()
+        self.curr_frames = self.batch_size
+        self.algo_observer.after_steps()
+        if self._lr_dirty():
+            self.opt_state[0:1].fill_(self.last_lr)
+        self._run_update()
+        self.sync_running_stats()
+        ev[2].record()
+        # one D2H read-back per epoch: stats rows + (lr, step) + meter
+        self.host_stats.copy_(self.stats, non_blocking=True)
+        self.host_state[0:2].copy_(self.opt_state, non_blocking=True)
+        self.host_state[2:10].copy_(self.meter, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self._meter_cache = self.host_state[2:10].numpy().copy()
+        st = self.host_stats.clone()
+        hs, n = self.host_state, 0
+        new_lr = float(hs[n])
+        if not self.is_adaptive_lr:
+            # linear / identity schedules depend only on (epoch, frame): evaluate on the host once per epoch
+            # (the reference re-evaluates the same value after every minibatch, a2c_common.py:1557-1563)
+            new_lr, self.entropy_coef = self.scheduler.update(self.last_lr, self.entropy_coef, self.epoch_num, self.frame,
+                                                              float(st[:, 4].mean()))
+            self.entropy_coef_dev.fill_(float(self.entropy_coef))
+        self.last_lr = new_lr
+        self._lr_synced = new_lr
+        play_time = ev[0].elapsed_time(ev[1]) * 1e-3
+        update_time = ev[1].elapsed_time(ev[2]) * 1e-3
+        total_time = play_time + update_time
+        a_losses = [st[u, 0] for u in range(self.n_updates)]
+        c_losses = [st[u, 1] for u in range(self.n_updates)]
+        entropies = [st[u, 2] for u in range(self.n_updates)]
+        b_losses = [st[u, 3] for u in range(self.n_updates)] if self.bounds_loss_coef is not None else []
+        nmb = self.num_minibatches
+        kls = [st[e * nmb:(e + 1) * nmb, 4].mean() for e in range(self.mini_epochs_num)]
+        self.last_stats = st
+        return step_time, play_time, update_time, total_time, a_losses, c_losses, b_losses, entropies, kls, self.last_lr, 1.0
+
+    def _lr_dirty(self):
+        return getattr(self, '_lr_synced', None) != self.last_lr
+
+    # =============================================================================== multi-GPU stats sync
+    def _stats_modules(self):
+        mods = []
+        if self.normalize_input:
+            mods.append(('obs', self.model.running_mean_std))
+        if self.normalize_value:
+            mods.append(('value', self.model.value_mean_std))
+        return mods
+
+    def sync_running_stats(self):
+        """a2c_common.py:782-808: pooled = all-reduce of per-epoch moment DELTAS (merge_rank_stats :61-93), packed into
+        one fp64 all-reduce for all normalisers; broadcast = rank 0's stats."""
+        if not self.multi_gpu or not self.multi_gpu_sync_stats:
+            return
+        mods = self._stats_modules()
+        if not mods:
+            return
+        if self.multi_gpu_sync_stats_mode == 'broadcast':
+            for _, m in mods:
+                for t in (m.count, m.running_mean, m.running_var):
+                    dist.broadcast(t, 0)
+                m.refresh()
+            return
+        packed, bases = [], []
+        for name, m in mods:
+            cnt = m.count.to(torch.float64)
+            cur = (cnt, m.running_mean * cnt, (m.running_var + m.running_mean ** 2) * cnt)
+            prev = self._stats_snapshots.get(name)
+            if prev is None:
+                prev = tuple(torch.zeros_like(c) for c in cur)
+            bases.append(prev)
+            packed += [c - p for c, p in zip(cur, prev)]
+        flat = torch.cat([p.reshape(-1) for p in packed])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        off = 0
+        for (name, m), base in zip(mods, bases):
+            d = []
+            for b in base:
+                d.append(flat[off:off + b.numel()].view_as(b))
+                off += b.numel()
+            n, wm, wsq = base[0] + d[0], base[1] + d[1], base[2] + d[2]
+            m.count.copy_(torch.round(n).to(torch.int64))
+            m.running_mean.copy_(wm / n)
+            m.running_var.copy_((wsq / n - m.running_mean ** 2).clamp_(min=1e-8))
+            m.refresh()
+            self._stats_snapshots[name] = (n.clone(), wm.clone(), wsq.clone())
+
+    def _seed_stats_sync_snapshots(self):
+        """a2c_common.py:767-780"""
+        if not self.multi_gpu or not self.multi_gpu_sync_stats or self.multi_gpu_sync_stats_mode == 'broadcast':
+            return
+        for name, m in self._stats_modules():
+            cnt = m.count.to(torch.float64)
+            self._stats_snapshots[name] = (cnt.clone(), m.running_mean * cnt, (m.running_var + m.running_mean ** 2) * cnt)
+
+    # =============================================================================== train loop
+    def train(self):
+        """a2c_common.py:1662-1782"""
+        self.init_tensors()
+        total_time = 0
+        self.obs = self.env_reset()
+        self.curr_frames = self.batch_size_envs
+        if self.multi_gpu:
+            dist.broadcast(self.model.flat, 0)      # replaces broadcast_object_list of the pickled state_dict (:1670-1680)
+        while True:
+            epoch_num = self.update_epoch()
+            step_time, play_time, update_time, sum_time, a_losses, c_losses, b_losses, entropies, kls, last_lr, lr_mul = self.train_epoch()
+            total_time += sum_time
+            curr_frames = self.curr_frames * self.world_size if self.multi_gpu else self.curr_frames
+            self.frame += curr_frames
+            frame = self.frame // self.num_agents
+            should_exit = False
+            if self.global_rank == 0:
+                if self.print_stats:
+                    st = max(step_time, 1e-9)
+                    print(f'fps step: {curr_frames / st:.0f} fps step and policy inference: {curr_frames / play_time:.0f} '
+                          f'fps total: {curr_frames / sum_time:.0f} epoch: {epoch_num:.0f}/{self.max_epochs:.0f} frames: {frame:.0f}')
+                self.write_stats(total_time, epoch_num, step_time, play_time, update_time, a_losses, c_losses, entropies, kls,
+                                 last_lr, lr_mul, frame, sum_time, play_time, curr_frames)
+                mean_rewards = None
+                if self.game_rewards.current_size > 0:
+                    mh = self._meter_host()
+                    mean_rewards = [float(mh[0])]
+                    self.mean_rewards = mean_rewards[0]
+                    for tag, val in (('rewards', mh[0]), ('shaped_rewards', mh[1])):
+                        self.writer.add_scalar(tag + '/step', val, frame)
+                        self.writer.add_scalar(tag + '/iter', val, epoch_num)
+                        self.writer.add_scalar(tag + '/time', val, total_time)
+                    self.writer.add_scalar('episode_lengths/step', mh[2], frame)
+                    self.writer.add_scalar('episode_lengths/iter', mh[2], epoch_num)
+                    self.writer.add_scalar('episode_lengths/time', mh[2], total_time)
+                    checkpoint_name = self.config['name'] + '_ep_' + str(epoch_num) + '_rew_' + str(mean_rewards[0])
+                    if self.save_freq > 0 and epoch_num % self.save_freq == 0:
+                        self.save(os.path.join(self.nn_dir, 'last_' + checkpoint_name))
+                    if mean_rewards[0] > self.last_mean_rewards and epoch_num >= self.save_best_after:
+                        print('saving next best rewards: ', mean_rewards)
+                        self.last_mean_rewards = mean_rewards[0]
+                        self.save(os.path.join(self.nn_dir, self.config['name']))
+                        if 'score_to_win' in self.config and self.last_mean_rewards > self.config['score_to_win']:
+                            print('Maximum reward achieved. Network won!')
+                            self.save(os.path.join(self.nn_dir, checkpoint_name))
+                            should_exit = True
+                if epoch_num >= self.max_epochs and self.max_epochs != -1:
+                    if self.game_rewards.current_size == 0:
+                        print('WARNING: Max epochs reached before any env terminated at least once')
+                        mean_rewards = -np.inf
+                    self.save(os.path.join(self.nn_dir, 'last_' + self.config['name'] + '_ep_' + str(epoch_num)
+                                           + '_rew_' + str(mean_rewards).replace('[', '_').replace(']', '_')))
+                    print('MAX EPOCHS NUM!')
+                    should_exit = True
+                if self.frame >= self.max_frames and self.max_frames != -1:
+                    if self.game_rewards.current_size == 0:
+                        mean_rewards = -np.inf
+                    self.save(os.path.join(self.nn_dir, 'last_' + self.config['name'] + '_frame_' + str(self.frame)
+                                           + '_rew_' + str(mean_rewards).replace('[', '_').replace(']', '_')))
+                    print('MAX FRAMES NUM!')
+                    should_exit = True
+                if not should_exit and self.stop_fn is not None and self.stop_fn(self):
+                    self.save(os.path.join(self.nn_dir, 'last_' + self.config['name'] + '_custom_stop_ep_' + str(epoch_num)))
+                    print('Custom stop callback returned True. Stopping training.')
+                    should_exit = True
+            if self.multi_gpu:
+                t = torch.tensor(float(should_exit), device=self.device_t)
+                dist.broadcast(t, 0)
+                should_exit = bool(t.item())
+            if should_exit:
+                return self.last_mean_rewards, epoch_num
+
+    def write_stats(self, total_time, epoch_num, step_time, play_time, update_time, a_losses, c_losses, entropies, kls,
+                    last_lr, lr_mul, frame, scaled_time, scaled_play_time, curr_frames):
+        """a2c_common.py:527-547"""
+        w = self.writer
+        w.add_scalar('performance/step_inference_rl_update_fps', curr_frames / scaled_time, frame)
+        w.add_scalar('performance/step_inference_fps', curr_frames / scaled_play_time, frame)
+        w.add_scalar('performance/step_fps', curr_frames / max(step_time, 1e-9), frame)
+        w.add_scalar('performance/rl_update_time', update_time, frame)
+        w.add_scalar('performance/step_inference_time', play_time, frame)
+        w.add_scalar('performance/step_time', step_time, frame)
+        st = self.last_stats
+        w.add_scalar('losses/a_loss', float(st[:, 0].mean()), frame)
+        w.add_scalar('losses/c_loss', float(st[:, 1].mean()), frame)
+        w.add_scalar('losses/entropy', float(st[:, 2].mean()), frame)
+        if self.bounds_loss_coef is not None:
+            w.add_scalar('losses/bounds_loss', float(st[:, 3].mean()), frame)
+        w.add_scalar('info/last_lr', last_lr * lr_mul, frame)
+        w.add_scalar('info/lr_mul', lr_mul, frame)
+        w.add_scalar('info/e_clip', self.e_clip * lr_mul, frame)
+        w.add_scalar('info/kl', float(st[:, 4].mean()), frame)
+        w.add_scalar('info/epochs', epoch_num, frame)
+        self.algo_observer.after_print_stats(frame, epoch_num, total_time)
+
+    def clear_stats(self, clean_rewards=True):
+        self.meter.zero_()
+        self._meter_cache = None
+        if clean_rewards:
+            self.mean_rewards = self.last_mean_rewards = -float('inf')
+        self.algo_observer.after_clear_stats()
+
+    # =============================================================================== checkpoints (a2c_common.py:825-921)
+    def get_weights(self):
+        return {'model': self.model.state_dict()}
+
+    def get_stats_weights(self, model_stats=False):
+        state = {}
+        if model_stats:
+            if self.normalize_input:
+                state['running_mean_std'] = self.model.running_mean_std.state_dict('')
+            if self.normalize_value:
+                state['reward_mean_std'] = self.model.value_mean_std.state_dict('')
+        return state
+
+    def set_stats_weights(self, weights):
+        if self.normalize_input and 'running_mean_std' in weights:
+            self.model.running_mean_std.load_state_dict(weights['running_mean_std'])
+        if self.normalize_value and 'reward_mean_std' in weights:
+            self.model.value_mean_std.load_state_dict(weights['reward_mean_std'])
+
+    def set_weights(self, weights):
+        self.model.load_state_dict(weights['model'])
+        self.set_stats_weights(weights)
+        self._seed_stats_sync_snapshots()
+
+    def get_full_state_weights(self):
+        self.init_tensors()
+        state = self.get_weights()
+        state['epoch'] = self.epoch_num
+        state['frame'] = self.frame
+        lr_step = self.opt_state.cpu()
+        state['optimizer'] = self.model.optimizer_state_dict(self.last_lr, float(lr_step[1]), self.weight_decay)
+        state['last_mean_rewards'] = self.last_mean_rewards
+        if self.vec_env is not None and hasattr(self.vec_env, 'get_env_state'):
+            state['env_state'] = self.vec_env.get_env_state()
+        if self.config.get('capability_manifest') is not None:
+            state['capability_manifest'] = self.config['capability_manifest']
+        return state
+
+    def set_full_state_weights(self, weights, set_epoch=True):
+        self.init_tensors()
+        self.set_weights(weights)
+        if set_epoch:
+            self.epoch_num = weights['epoch']
+            self.frame = weights['frame']
+        lr, step = self.model.load_optimizer_state_dict(weights['optimizer'])
+        if lr is not None:
+            self.last_lr = float(lr)
+        self.opt_state.copy_(torch.tensor([self.last_lr, float(step)], dtype=torch.float64))
+        self._lr_synced = self.last_lr
+        self.last_mean_rewards = weights.get('last_mean_rewards', -float('inf'))
+        if self.vec_env is not None and hasattr(self.vec_env, 'set_env_state'):
+            self.vec_env.set_env_state(weights.get('env_state', None))
+        if 'capability_manifest' in weights and self.config.get('capability_manifest') is None:
+            self.config['capability_manifest'] = weights['capability_manifest']
+        self._seed_stats_sync_snapshots()
+
+    def save(self, fn):
+        """torch_ext.save_checkpoint (torch_ext.py:90-92): `<fn>.pth` via torch.save"""
+        state = self.get_full_state_weights()
+        torch.save(state, fn + '.pth')
+
+    def restore(self, fn, set_epoch=True):
+        """torch_ext.load_checkpoint (torch_ext.py:94-112): strips `_orig_mod.` prefixes"""
+        checkpoint = torch.load(fn, map_location=self.device_t, weights_only=False)
+        if 'model' in checkpoint:
+            checkpoint['model'] = {k.replace('_orig_mod.', ''): v for k, v in checkpoint['model'].items()}
+        self.set_full_state_weights(checkpoint, set_epoch=set_epoch)
+
+    def restore_central_value_function(self, fn):
+        raise NotImplementedError('central value is not on the B200 hot path yet')
+
+    def get_param(self, param_name):
+        if param_name in ['grad_norm', 'critic_coef', 'bounds_loss_coef', 'entropy_coef', 'kl_threshold', 'gamma', 'tau',
+                          'mini_epochs_num', 'e_clip']:
+            return getattr(self, param_name)
+        elif param_name == 'learning_rate':
+            return self.last_lr
+        raise NotImplementedError(f"Can't get param {param_name}")
+
+    def set_param(self, param_name, param_value):
+        if param_name in ['grad_norm', 'critic_coef', 'bounds_loss_coef', 'entropy_coef', 'gamma', 'tau', 'mini_epochs_num',
+                          'e_clip']:
+            setattr(self, param_name, param_value)
+            self._refresh_cfg()
+        elif param_name == 'learning_rate':
+            if self.is_adaptive_lr:
+                raise NotImplementedError("Can't directly mutate LR on this schedule")
+            self.last_lr = float(param_value)
+        elif param_name == 'kl_threshold':
+            if not self.is_adaptive_lr:
+                raise NotImplementedError("Can't directly mutate kl threshold")
+            self.kl_threshold = param_value
+            self.scheduler.kl_threshold = param_value
+            self._refresh_cfg()
+        else:
+            raise NotImplementedError(f'No param found for {param_value}')
+
+    def _refresh_cfg(self):
+        if self._tensors_ready:
+            self._build_cfg_structs()

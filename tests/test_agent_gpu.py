@@ -1,0 +1,226 @@
+"""End-to-end GPU parity: the B200 A2CAgent (CUDA kernels through the C ABI) vs
+ (a) the committed golden fixtures produced by the REAL reference A2CAgent (tests/golden/agent_*.pt) and
+ (b) the CPU oracle at a larger shape,
+on identical env tapes, initial weights and sampling noise.  fp32 path (mixed_precision: False).
+
+Tolerances: rollout tensors / normalised batch: rtol 1e-4; per-minibatch losses / KL: rtol 2e-3;
+weights after 2 epochs (8-16 Adam steps): atol 2e-5 (Adam divides by sqrt(v): tiny-gradient elements
+amplify 1e-7 differences); lr sequence and running-stat counts: exact.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ppo_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+DEV = 'cuda:0'
+
+
+class TapeEnvGPU:
+    """GPU twin of oracle.ppo_oracle.TapeEnv / tests/golden/gen_golden.py::TapeVecEnv."""
+
+    def __init__(self, obs_tape, done_tape, timeout_tape, A, autoreset='same_step'):
+        self.obs_tape, self.done_tape, self.timeout_tape = obs_tape.to(DEV), done_tape.to(DEV), timeout_tape.to(DEV)
+        self.A, self.autoreset, self.i = A, autoreset, 0
+
+    def reset(self):
+        self.i = 0
+        return self.obs_tape[0].clone()
+
+    def step(self, actions):
+        rew = -(actions * actions).sum(-1) * 0.1
+        self.i += 1
+        j = self.i % self.obs_tape.shape[0]
+        return self.obs_tape[j].clone(), rew, self.done_tape[j].clone(), {'time_outs': self.timeout_tape[j].clone()}
+
+    def get_env_info(self):
+        from rl_games_b200.common import Box
+        info = {'observation_space': Box(-np.inf, np.inf, (self.obs_tape.shape[-1],)), 'action_space': Box(-1.0, 1.0, (self.A,))}
+        if self.autoreset != 'same_step':
+            info['autoreset_mode'] = self.autoreset
+        return info
+
+    def get_env_state(self):
+        return None
+
+    def set_env_state(self, s):
+        pass
+
+
+def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state):
+    from rl_games_b200.runner import Runner
+    network = {'name': 'actor_critic', 'separate': False,
+               'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                        'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+               'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    config = {'name': 'gpu_parity', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0}, 'device': DEV,
+              'multi_gpu': False, 'mixed_precision': False, 'normalize_input': True, 'normalize_value': True,
+              'value_bootstrap': True, 'normalize_advantage': True, 'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4,
+              'lr_schedule': 'adaptive', 'kl_threshold': 0.008, 'grad_norm': 1.0, 'entropy_coef': 0.0, 'truncate_grads': True,
+              'e_clip': 0.2, 'clip_value': True, 'use_smooth_clamp': True, 'bound_loss_type': 'regularisation',
+              'bounds_loss_coef': 0.0, 'max_epochs': 100, 'num_actors': N, 'horizon_length': H, 'minibatch_size': mb,
+              'mini_epochs': 4, 'critic_coef': 2, 'print_stats': False, 'train_dir': '/tmp/b200_parity_runs'}
+    config.update(cfg_over)
+    config['env_info'] = env.get_env_info()
+    config['vec_env'] = env
+    params = {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
+              'config': config}
+    r = Runner()
+    r.load({'params': params})
+    r.params['config']['vec_env'] = env
+    agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
+    agent.model.load_state_dict({k: v.to(DEV) for k, v in init_state.items()}, strict=False)
+    agent.init_tensors()
+    agent.obs = agent.env_reset()
+    return agent
+
+
+def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True):
+    fl = O.swap_and_flatten01
+    torch.testing.assert_close(fl(agent.advs_n).cpu(), ref_ds['advantages'], rtol=2e-4, atol=2e-5)
+    torch.testing.assert_close(fl(agent.returns_n.unsqueeze(2)).cpu(), ref_ds['returns'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(fl(agent.old_values_n.unsqueeze(2)).cpu(), ref_ds['old_values'], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(fl(agent.neglogpacs).cpu(), ref_ds['old_logp_actions'], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(fl(agent.actions).cpu(), ref_ds['actions'], rtol=1e-5, atol=1e-5)
+    if ref_ds.get('rnn_masks') is not None:
+        assert torch.equal(fl(agent.valid).cpu(), ref_ds['rnn_masks'])
+    st = agent.last_stats
+    for col, key in ((0, 'a'), (1, 'c'), (2, 'e'), (4, 'kl')):
+        if ref_losses.get(key) is not None:
+            torch.testing.assert_close(st[:, col], ref_losses[key], rtol=2e-3, atol=2e-6, msg=lambda m: key + ': ' + m)
+    assert agent.last_lr == pytest.approx(ref_lr, rel=1e-12)
+    sd = agent.model.state_dict()
+    for k in O.param_names(len(units)):
+        torch.testing.assert_close(sd[k].cpu(), ref_state[k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
+    for pre in ('running_mean_std.', 'value_mean_std.'):
+        assert int(sd[pre + 'count']) == int(ref_state[pre + 'count'])
+        torch.testing.assert_close(sd[pre + 'running_mean'].cpu(), ref_state[pre + 'running_mean'].reshape(-1), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(sd[pre + 'running_var'].cpu(), ref_state[pre + 'running_var'].reshape(-1), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt'])
+@pytest.mark.parametrize('graph', [False, True])
+def test_agent_matches_reference_golden(name, graph):
+    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    cfgk = g['config']
+    over = {k: cfgk[k] for k in ('clip_value', 'use_smooth_clamp', 'bound_loss_type', 'bounds_loss_coef', 'entropy_coef',
+                                 'truncate_grads', 'value_bootstrap', 'mini_epochs', 'lr_schedule', 'weight_decay', 'critic_coef')
+            if k in cfgk}
+    over.setdefault('lr_schedule', None)
+    over['b200_cuda_graph'] = graph
+    env = TapeEnvGPU(g['obs_tape'], g['done_tape'], g['timeout_tape'], g['A'], g['autoreset'])
+    agent = make_agent(over, g['N'], g['H'], g['D'], g['A'], g['units'], g['mb'], env, g['init_state'])
+    for ep, ref in enumerate(g['epochs_out']):
+        agent.epoch_num += 1
+        agent.train_epoch(noise=g['noise'][ep].to(DEV))
+        assert torch.equal(agent.dones_buf.cpu(), ref['mb_dones'])
+        torch.testing.assert_close(agent.rewards.cpu().unsqueeze(2), ref['mb_rewards'], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(agent.values.cpu().unsqueeze(2), ref['mb_values'], rtol=1e-4, atol=1e-5)
+        nmb = agent.num_minibatches
+        # reference returns per-minibatch a/c/entropy lists, per-mini-epoch mean KLs
+        st = agent.last_stats
+        torch.testing.assert_close(torch.stack([st[e * nmb:(e + 1) * nmb, 4].mean() for e in range(agent.mini_epochs_num)]),
+                                   ref['kls'], rtol=2e-3, atol=2e-6)
+        _check_epoch(agent, ref['state'], ref['dataset'], {'a': ref['a_losses'], 'c': ref['c_losses'], 'e': ref['entropies']},
+                     ref['last_lr'], g['units'])
+        torch.testing.assert_close(agent.game_rewards.mean, ref['game_rewards_mean'].reshape(-1), rtol=1e-4, atol=1e-5)
+        assert agent.game_rewards.current_size == ref['game_rewards_size']
+        torch.testing.assert_close(agent.game_lengths.mean, ref['game_lengths_mean'].reshape(-1), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('masked', [False, True])
+def test_agent_matches_oracle_medium(masked):
+    """N=256, H=16, D=60, A=8, MLP[64,32,16], mb=1024: exercises multi-block kernels and chunked minibatch rows."""
+    N, H, D, A, units, mb, epochs = 256, 16, 60, 8, [64, 32, 16], 1024, 2
+    obs_tape, done_tape, tout_tape = O.make_tapes(H * epochs + 1, N, D, seed=11)
+    params = O.init_params(D, units, A, seed=3)
+    g = torch.Generator().manual_seed(5)
+    for k in params:
+        if k.endswith('bias') or k.endswith('sigma'):
+            params[k] = params[k] + torch.randn(params[k].shape, generator=g) * 0.05
+    noise = torch.randn(epochs, H, N, A, generator=g)
+    cfg = {'mask_autoreset_rows': masked, 'mini_epochs': 2}
+    oag = O.OracleAgent(O.TapeEnv(obs_tape, done_tape, tout_tape), params, D, A, units, N, H, mb, cfg)
+    oag.obs = oag.env_reset()
+    env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A, 'next_step' if masked else 'same_step')
+    agent = make_agent({'mini_epochs': 2}, N, H, D, A, units, mb, env, params)
+    for ep in range(epochs):
+        out = oag.train_epoch(noise[ep])
+        agent.epoch_num += 1
+        agent.train_epoch(noise=noise[ep].to(DEV))
+        ref_state = {k: v.detach() for k, v in oag.model.p.items()}
+        for pre, m in (('running_mean_std.', oag.model.running_mean_std), ('value_mean_std.', oag.model.value_mean_std)):
+            ref_state[pre + 'running_mean'], ref_state[pre + 'running_var'], ref_state[pre + 'count'] = \
+                m.running_mean, m.running_var, m.count
+        ds = {k: oag.dataset[k] for k in ('advantages', 'returns', 'old_values', 'old_logp_actions', 'actions', 'rnn_masks')}
+        _check_epoch(agent, ref_state, ds, {'a': torch.stack(out['a_loss']), 'c': torch.stack(out['c_loss']),
+                                            'e': torch.stack(out['entropy']), 'kl': torch.stack(out['kl'])}, oag.last_lr, units)
+
+
+def test_checkpoint_roundtrip_and_reference_keys(tmp_path):
+    N, H, D, A, units, mb = 64, 8, 6, 3, [16, 8], 128
+    obs_tape, done_tape, tout_tape = O.make_tapes(H * 3 + 1, N, D, seed=2)
+    env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
+    agent = make_agent({}, N, H, D, A, units, mb, env, O.init_params(D, units, A, seed=1))
+    agent.epoch_num += 1
+    agent.train_epoch()
+    fn = str(tmp_path / 'ckpt')
+    agent.save(fn)
+    ck = torch.load(fn + '.pth', weights_only=False)
+    # reference checkpoint layout: a2c_common.py:825-850 + state-dict keys
+    assert set(['model', 'epoch', 'frame', 'optimizer', 'last_mean_rewards']).issubset(ck.keys())
+    exp = set(O.param_names(len(units))) | {p + s for p in ('running_mean_std.', 'value_mean_std.')
+                                             for s in ('running_mean', 'running_var', 'count')}
+    assert set(ck['model'].keys()) == exp
+    assert ck['model']['running_mean_std.count'].shape == () and ck['model']['running_mean_std.count'].dtype == torch.int64
+    assert len(ck['optimizer']['state']) == 1 + 2 * len(units) + 4
+    env2 = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
+    agent2 = make_agent({}, N, H, D, A, units, mb, env2, O.init_params(D, units, A, seed=9))
+    agent2.restore(fn + '.pth')
+    assert torch.equal(agent2.model.flat, agent.model.flat)
+    assert torch.equal(agent2.model.exp_avg, agent.model.exp_avg)
+    assert agent2.last_lr == agent.last_lr and agent2.epoch_num == agent.epoch_num
+    assert torch.equal(agent2.opt_state, agent.opt_state)
+
+
+def test_synthetic_env_training_runs_and_graph_replay_is_consistent():
+    """c2-shaped (scaled down) synthetic env through the public Runner API; CUDA-graph replay vs eager updates
+    from identical state must give identical weights (same kernels, same order => deterministic)."""
+    from rl_games_b200.runner import Runner
+
+    def build(graph):
+        params = {'seed': 5, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'},
+                  'network': {'name': 'actor_critic', 'separate': False,
+                              'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None',
+                                                       'mu_init': {'name': 'default'},
+                                                       'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+                              'mlp': {'units': [64, 32], 'activation': 'elu', 'initializer': {'name': 'default'}}},
+                  'config': {'name': 'synt', 'env_name': 'b200_synthetic', 'reward_shaper': {'scale_value': 1.0}, 'device': DEV,
+                             'normalize_input': True, 'normalize_value': True, 'normalize_advantage': True, 'gamma': 0.99,
+                             'tau': 0.95, 'learning_rate': 3e-4, 'lr_schedule': 'adaptive', 'kl_threshold': 0.008,
+                             'grad_norm': 1.0, 'entropy_coef': 0.0, 'truncate_grads': True, 'e_clip': 0.2, 'clip_value': True,
+                             'use_smooth_clamp': True, 'bound_loss_type': 'regularisation', 'bounds_loss_coef': 0.0,
+                             'num_actors': 1024, 'horizon_length': 16, 'minibatch_size': 4096, 'mini_epochs': 2,
+                             'critic_coef': 2, 'print_stats': False, 'train_dir': '/tmp/b200_parity_runs',
+                             'mixed_precision': False, 'b200_cuda_graph': graph,
+                             'env_config': {'obs_dim': 60, 'act_dim': 8, 'device': DEV}}}
+        r = Runner()
+        r.load({'params': params})
+        a = r.algo_factory.create(r.algo_name, base_name='synt', params=r.params)
+        a.init_tensors()
+        a.obs = a.env_reset()
+        return a
+    a, b = build(True), build(False)
+    b.model.load_state_dict(a.model.state_dict())
+    for _ in range(4):
+        a.epoch_num += 1; b.epoch_num += 1
+        a.train_epoch(); b.train_epoch()
+    assert a._graph_update is not None and b._graph_update is None
+    assert torch.equal(a.model.flat, b.model.flat)
+    assert a.last_lr == b.last_lr
+    assert torch.isfinite(a.model.flat).all()
+    assert a.game_rewards.current_size > 0
