@@ -25,6 +25,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+_STDOUT = sys.stdout
 
 WORKLOADS = {
     # BASELINE.json configs[1]
@@ -128,7 +129,7 @@ def reference_arm(args, w):
                              'sample': f'{sample} of {w["num_actors"]} envs per step, same horizon / mini-epochs / '
                                        f'minibatch count; oracle/ppo_oracle.py (reference is pure Python: port pinned by golden vectors)'},
             'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_STDOUT, flush=True)
 
 
 def workload_config(name, w, env_desc):
@@ -280,7 +281,7 @@ def b200_arm(args, w):
             line['cpu_baseline'] = {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
                                     'sample': f'2 epochs of {min(w["num_actors"], 4096)} envs (of {w["num_actors"]}) after 1 warm-up; '
                                               'oracle/ppo_oracle.py on the host cores'}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_STDOUT, flush=True)
     if multi:
         dist.barrier()
         dist.destroy_process_group()
@@ -320,12 +321,17 @@ def main():
     ap.add_argument('--skip-cpu', action='store_true')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
-    if args.impl == 'reference':
-        reference_arm(args, w)
-        return
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py: the B200 arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
-    b200_arm(args, w)
+    # stdout carries exactly ONE JSON line: everything else (Runner's seed banner etc.) goes to stderr
+    import contextlib
+    global _STDOUT
+    _STDOUT = sys.stdout
+    with contextlib.redirect_stdout(sys.stderr):
+        if args.impl == 'reference':
+            reference_arm(args, w)
+            return
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: the B200 arm needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+        b200_arm(args, w)
 
 
 if __name__ == '__main__':
