@@ -244,6 +244,11 @@ int b200rl_synth_env_step(const float* actions, float* obs, float* rewards, uint
                           uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index, void* stream);
 int b200rl_bump_u64(uint64_t* p, void* stream);
 
+/* tcgen05 bring-up / regression: D[128,N] = A[128,K] . B[N,K]^T (bf16 in, fp32 out) on the 5th-gen tensor cores.
+ * a_mn / b_mn != 0: that operand is supplied transposed ([K,128] / [K,N]) and consumed through an MN-major
+ * shared-memory descriptor (the view the weight-gradient MMAs use). */
+int b200rl_tc_gemm_test(const void* A_bf16, const void* B_bf16, float* D, int N, int K, int a_mn, int b_mn, void* stream);
+
 /* L2 flush helper for benchmarking: writes n u32 words. */
 int b200rl_fill_u32(uint32_t* p, int64_t n, uint32_t v, void* stream);
 

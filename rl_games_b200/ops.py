@@ -223,3 +223,9 @@ def bump_u64(t):
 
 def fill_u32(t, v=0):
     check(lib.b200rl_fill_u32(ptr(t), t.numel() * t.element_size() // 4, v, _stream()), 'fill_u32')
+
+
+def tc_gemm_test(A, B, N, K, a_mn=False, b_mn=False):
+    D = torch.empty(128, N, dtype=torch.float32, device=A.device)
+    check(lib.b200rl_tc_gemm_test(ptr(A), ptr(B), ptr(D), N, K, int(a_mn), int(b_mn), _stream()), 'tc_gemm_test')
+    return D
