@@ -244,6 +244,50 @@ int b200rl_synth_env_step(const float* actions, float* obs, float* rewards, uint
                           uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index, void* stream);
 int b200rl_bump_u64(uint64_t* p, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * bf16 tensor-core MLP path (`mixed_precision: True`, the reference's default on bf16-capable GPUs:
+ * a2c_common.py:429, a2c_continuous.py:173).  tcgen05.mma + TMEM accumulators + cp.async.bulk tile moves.
+ * Network geometry supported by this build: obs dim <= 64, MLP [256,128,64], A <= 15 (BASELINE configs[1..2]);
+ * b200rl_tc_supported() tells.  Weights are consumed from ONE packed bf16 copy (b200rl_tc_pack_weights) that
+ * serves the forward (K-major view) and the dgrad (MN-major view).  act1/act2/act3/dhead/delta1/delta2 are
+ * opaque tiled bf16 buffers: n_tiles(M) = ceil(M/128) tiles of b200rl_tc_tile_bytes() bytes each.
+ *   fwd_train : trunk + heads + PPO loss fwd/bwd (same semantics / partial format as b200rl_ppo_head_loss_f32,
+ *               finalise with b200rl_ppo_loss_finalize)
+ *   fwd_rollout: trunk + heads + sample/neglogp/denorm-value epilogue (same semantics as b200rl_policy_head_sample_f32)
+ *   bwd       : delta chain + all weight/bias gradients into part[n_parts][P] at the given flat offsets
+ *               (sum with b200rl_reduce_splits_f32)
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_tc_supported(int D, int u1, int u2, int u3, int A);
+int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A);
+int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int64_t* out4_host);
+int b200rl_tc_pack_weights(const float* W1, const float* W2, const float* W3, const float* W_head,
+                           int D, int u1, int u2, int u3, int A, void* wpack, void* stream);
+int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+                            const float* norm_mean, const float* norm_std, const void* wpack,
+                            const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
+                            int u1, int u2, int u3, int M, int A,
+                            const float* actions, float* old_mu, float* old_sigma, const float* old_values_n,
+                            const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
+                            const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
+                            void* act1, void* act2, void* act3, void* dhead,
+                            double* partials, int max_partials, int* n_blocks_out_host, void* stream);
+int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
+                              const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
+                              int u1, int u2, int u3, int N_rows, int A,
+                              const double* vms_mean, const double* vms_var, int normalize_value,
+                              const float* noise, uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index,
+                              float* actions, float* mus, float* sigmas, float* neglogp, float* values,
+                              float* env_actions, int clip_actions, const float* act_low, const float* act_high,
+                              const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones, float* valid_out,
+                              int values_only, void* stream);
+int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+                      const float* norm_mean, const float* norm_std, const void* wpack,
+                      int u1, int u2, int u3, int M, int A,
+                      const void* act1, const void* act2, const void* act3, const void* dhead,
+                      void* delta2, void* delta1, float* part, int max_parts, int P,
+                      int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
+                      int* n_parts_out_host, void* stream);
+
 /* tcgen05 bring-up / regression: D[128,N] = A[128,K] . B[N,K]^T (bf16 in, fp32 out) on the 5th-gen tensor cores.
  * a_mn / b_mn != 0: that operand is supplied transposed ([K,128] / [K,N]) and consumed through an MN-major
  * shared-memory descriptor (the view the weight-gradient MMAs use). */

@@ -25,7 +25,7 @@ def parse_header(path=HEADER):
     src = re.sub(r'/\*.*?\*/', ' ', src, flags=re.S)
     src = re.sub(r'//[^\n]*', ' ', src)
     protos = {}
-    for m in re.finditer(r'\bint\s+(b200rl_\w+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S):
+    for m in re.finditer(r'\b(?:int|int64_t)\s+(b200rl_\w+)\s*\(([^;{]*?)\)\s*;', src, flags=re.S):
         name, args = m.group(1), m.group(2).strip()
         sig = []
         if args and args != 'void':
@@ -38,6 +38,9 @@ def parse_header(path=HEADER):
                     sig.append((toks[-1], _SCALARS[toks[0]]))
         protos[name] = sig
     return protos
+
+
+RET_I64 = ('b200rl_tc_pack_bytes',)
 
 
 class _Lib:
@@ -56,7 +59,7 @@ class _Lib:
         cdll = ctypes.CDLL(LIB_PATH)
         for name, sig in self.protos.items():
             fn = getattr(cdll, name)   # AttributeError => header/library drift, fail loudly
-            fn.restype = ctypes.c_int
+            fn.restype = ctypes.c_int64 if name in RET_I64 else ctypes.c_int
             fn.argtypes = [t for _, t in sig]
         if cdll.b200rl_built_arch() != 100:
             raise RuntimeError('libb200rl.so was not built for sm_100a')

@@ -5,17 +5,13 @@
 // One thread per sample; the [128 x Hl] activation tile and the head weights are staged in shared memory;
 // scalar statistics go through warp-shuffle reductions into per-block fp64 partials (deterministic).
 #include "common.cuh"
+#include "loss_math.cuh"
 
 namespace {
 
 constexpr int LT = 128;       // threads (= samples) per block
 constexpr int MAXA = 32;      // max action dim + 1 supported by the register tiles
-constexpr int NSC = 8;        // scalar partial slots before the dlogstd block
-
-struct LossCfgDev {
-    float e_clip, critic_coef, bounds_coef;
-    int has_bounds, bound_type, clip_value, smooth, ppo;
-};
+constexpr int NSC = LOSS_NSC; // scalar partial slots before the dlogstd block
 
 __global__ void __launch_bounds__(LT) ppo_head_loss_kernel(
     const float* __restrict__ a_last, int Hl, const float* __restrict__ Wh, const float* __restrict__ bh,
@@ -68,106 +64,16 @@ __global__ void __launch_bounds__(LT) ppo_head_loss_kernel(
                 if (j < AH) head[j] = fmaf(a, sW[j * Hl + k], head[j]);
         }
         const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
-        const float val = head[0];
-        const float old_v = __ldg(old_values_n + ar), ret = __ldg(returns_n + ar);
-        const float old_nlp = __ldg(old_neglogp + ar), adv = __ldg(advs_n + ar);
-        const float mk = mask ? __ldg(mask + ar) : 1.f;
         const float inv_cnt = inv_count_dev ? __ldg(inv_count_dev) : (1.0f / (float)M);
-        const float w = mk * inv_cnt;
-        // ---- neglogp / entropy / KL / bound loss ----
-        float sumz2 = 0.f, sumls = 0.f, ent = 0.f, kl = 0.f, bl = 0.f;
-        float z[MAXA];
+        LossArena la{actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask};
+        const float nlp = ppo_sample_loss<MAXA>(head, A, sSig, la, ar, inv_cnt, cfg, dh, dls, sc);
+        if (mu_out) {
 #pragma unroll
-        for (int j = 0; j < MAXA; ++j) {
-            if (j < A) {
-                const float mu = head[1 + j], sg = sSig[j], ls = sSig[A + j];
-                const float act = __ldg(actions + ar * A + j);
-                const float omu = old_mu[ar * A + j], osg = old_sigma[ar * A + j];
-                z[j] = (act - mu) / sg;
-                sumz2 += z[j] * z[j];
-                sumls += ls;
-                ent += 0.5f + 0.9189385332046727f + logf(sg);           // 0.5 + 0.5*log(2*pi) + log(sigma)
-                const float c1 = logf(osg / sg + 1e-5f);
-                const float dm = omu - mu;
-                const float c2 = (sg * sg + dm * dm) / (2.0f * (osg * osg + 1e-5f));
-                kl += c1 + c2 - 0.5f;
-                if (cfg.has_bounds) {
-                    if (cfg.bound_type == 1) {
-                        const float hi = fmaxf(mu - 1.1f, 0.f), lo = fminf(mu + 1.1f, 0.f);
-                        bl += lo * lo + hi * hi;
-                    } else if (cfg.bound_type == 2) {
-                        bl += mu * mu;
-                    }
-                }
-            } else {
-                z[j] = 0.f;
-            }
+            for (int j = 0; j < MAXA - 1; ++j)
+                if (j < A) mu_out[(int64_t)m * A + j] = head[1 + j];
         }
-        const float nlp = 0.5f * sumz2 + 0.9189385332046727f * (float)A + sumls;
-        // ---- actor loss + d/dnlp ----
-        float a_loss, g_a;
-        if (cfg.ppo) {
-            const float ratio = expf(old_nlp - nlp);
-            const float mi = 1.0f - cfg.e_clip, mx = 1.0f + cfg.e_clip;
-            float clamped, dcl;
-            if (cfg.smooth) {
-                const float s = 1.0f / (1.0f + expf((-(ratio - mi) / (mx - mi) + 0.5f) * 4.0f));
-                clamped = s * (mx - mi) + mi;
-                dcl = 4.0f * s * (1.0f - s);
-            } else {
-                clamped = fminf(fmaxf(ratio, mi), mx);
-                dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
-            }
-            const float t1 = -(adv * ratio), t2 = -(adv * clamped);
-            a_loss = fmaxf(t1, t2);
-            const float d1 = adv * ratio, d2 = adv * dcl * ratio;
-            g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
-        } else {
-            a_loss = nlp * adv;
-            g_a = adv;
-        }
-        // ---- critic loss + d/dvalue ----
-        float c_loss, dc;
-        if (cfg.clip_value) {
-            const float delta = val - old_v;
-            const float vpc = old_v + fminf(fmaxf(delta, -cfg.e_clip), cfg.e_clip);
-            const float e1 = val - ret, e2 = vpc - ret;
-            const float l1 = e1 * e1, l2 = e2 * e2;
-            c_loss = fmaxf(l1, l2);
-            const float g1 = 2.0f * e1;
-            const float g2 = (delta >= -cfg.e_clip && delta <= cfg.e_clip) ? 2.0f * e2 : 0.0f;
-            dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
-        } else {
-            const float e1 = ret - val;
-            c_loss = e1 * e1;
-            dc = -2.0f * e1;
-        }
-        // clip fraction (torch_ext.py:217-227)
-        const float lr_ = old_nlp - nlp;
-        const float clipped = (lr_ < log1pf(-cfg.e_clip) || lr_ > log1pf(cfg.e_clip)) ? 1.f : 0.f;
-        // ---- gradients at the heads ----
-        dh[0] = w * 0.5f * cfg.critic_coef * dc;
-#pragma unroll
-        for (int j = 0; j < MAXA; ++j) {
-            if (j < A) {
-                const float mu = head[1 + j], sg = sSig[j];
-                float db = 0.f;
-                if (cfg.has_bounds) {
-                    if (cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
-                    else if (cfg.bound_type == 2) db = 2.0f * mu;
-                }
-                dh[1 + j] = w * (g_a * (-(z[j] / sg)) + cfg.bounds_coef * db);
-                dls[j] = w * g_a * (1.0f - z[j] * z[j]);
-                // new mu/sigma overwrite the old ones (datasets.py:33-43)
-                old_mu[ar * A + j] = mu;
-                old_sigma[ar * A + j] = sg;
-                if (mu_out) mu_out[(int64_t)m * A + j] = mu;
-            }
-        }
-        if (value_out) value_out[m] = val;
+        if (value_out) value_out[m] = head[0];
         if (neglogp_out) neglogp_out[m] = nlp;
-        sc[0] = w * a_loss; sc[1] = w * c_loss; sc[2] = w * ent; sc[3] = w * bl; sc[4] = w * kl;
-        sc[5] = mk; sc[6] = mk * clipped; sc[7] = w;
         // ---- d(head) out, d(a_last) into the tile (row owned by this thread) ----
 #pragma unroll
         for (int j = 0; j < MAXA; ++j)

@@ -1,0 +1,859 @@
+// bf16 tensor-core (tcgen05 / TMEM / TMA-bulk) MLP kernels: the `mixed_precision: True` path.
+//
+//   fwd  (train)  : per 128-row tile  X -> a1 -> a2 -> a3 -> heads, with the PPO loss forward+backward fused into the
+//                   last epilogue (replaces network_builder.py:494-512 + a2c_continuous.py:97-134 + the loss part of
+//                   loss.backward()); saves a1/a2/a3 and d_head as bf16 operand tiles.
+//   fwd  (rollout): same trunk, epilogue = sample / neglogp / denorm value written into the arena (models.py:329-364).
+//   bwd1          : delta chain d_head -> d3 -> d2 -> d1 (dgrad) + weight grads of the head and layer 3 + bias grads.
+//   bwd2          : weight grads of layers 2 and 1 (+ bias grad of layer 1).
+//
+// All GEMMs are tcgen05.mma (M = 128 rows per tile, fp32 accumulators in TMEM) issued by one thread; operands are
+// INTERLEAVE shared-memory tiles (tc_common.cuh).  One packed bf16 copy of each weight matrix serves the forward
+// (K-major view) and the dgrad (MN-major view); one copy of each activation / delta tile serves the dgrad
+// (K-major) and the wgrad (MN-major) MMAs -- no transposes anywhere.  Tiles move global<->shared with
+// cp.async.bulk (1-D TMA) + mbarrier transaction counts; weight gradients stay resident in TMEM across all tiles a
+// persistent CTA processes and are flushed once per CTA into a [n_cta][P] partial buffer that the deterministic
+// split reducer (mlp_simt.cu) sums.
+#include "common.cuh"
+#include "loss_math.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+// ---- TMA bulk helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(sdst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : (__expf(x) - 1.0f); }
+__device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.f : a + 1.f; }
+__device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(p[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+// ---- network geometry (compile time) ------------------------------------------------------------------------
+// activation-like tiles: 128 rows, C cols: CS = 2048 (col-group stride), RS = 128 (row-group stride), C*256 bytes
+// weight tiles [R rows(out) x C cols(in)]: CS = (R/8)*128, RS = 128
+template <int DPAD_, int U1_, int U2_, int U3_, int AP_>
+struct Net {
+    static constexpr int DPAD = DPAD_, U1 = U1_, U2 = U2_, U3 = U3_, AP = AP_;
+    static constexpr uint32_t ACS = 2048, ARS = 128;
+    static constexpr uint32_t W1_CS = (U1 / 8) * 128, W2_CS = (U2 / 8) * 128, W3_CS = (U3 / 8) * 128, WH_CS = (AP / 8) * 128;
+    static constexpr uint32_t W1_BYTES = U1 * DPAD * 2, W2_BYTES = U2 * U1 * 2, W3_BYTES = U3 * U2 * 2, WH_BYTES = AP * U3 * 2;
+    static constexpr uint32_t W1_OFF = 0, W2_OFF = W1_BYTES, W3_OFF = W2_OFF + W2_BYTES, WH_OFF = W3_OFF + W3_BYTES;
+    static constexpr uint32_t PACK_BYTES = WH_OFF + WH_BYTES;
+    static constexpr uint32_t X_BYTES = DPAD * 256, A1_BYTES = U1 * 256, A2_BYTES = U2 * 256, A3_BYTES = U3 * 256, DH_BYTES = AP * 256;
+    static_assert(U2 == 128, "wgrad tiles assume a 128-wide second hidden layer (M = 128 MMAs)");
+    static_assert(U1 % 128 == 0 && U1 <= 256 && U3 <= 128 && U3 % 16 == 0 && DPAD % 16 == 0 && DPAD <= 256 && AP == 16, "unsupported net");
+};
+using NetC2 = Net<64, 256, 128, 64, 16>;
+
+// ---- weight packing: fp32 [R, C] row-major -> bf16 INTERLEAVE tile [Rpad, Cpad] ------------------------------
+struct PackSeg { const float* src; int R, C, Rpad, Cpad; uint32_t dst_off; };
+struct PackArgs { PackSeg seg[4]; };
+
+__global__ void __launch_bounds__(256) pack_weights_kernel(PackArgs a, uint8_t* __restrict__ dst) {
+    const PackSeg s = a.seg[blockIdx.y];
+    const int ncg = s.Cpad / 8;
+    const uint32_t CS = (uint32_t)(s.Rpad / 8) * 128u;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s.Rpad * ncg; i += gridDim.x * blockDim.x) {
+        const int r = i / ncg, cg = i - r * ncg;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            f[j] = (r < s.R && c < s.C) ? __ldg(s.src + (size_t)r * s.C + c) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dst + s.dst_off + tile_off(r, cg, CS, 128u)) = pack8_bf16(f);
+    }
+}
+
+// ---- X tile: fp32 obs rows -> normalise/clamp -> bf16 operand tile ---------------------------------------------
+template <class N>
+__device__ __forceinline__ void stage_x_tile(uint8_t* sX, const float* __restrict__ obs, int64_t row0, int rows_valid, int D,
+                                             const float* __restrict__ nm, const float* __restrict__ ns) {
+    constexpr int NCG = N::DPAD / 8;
+    for (int i = threadIdx.x; i < 128 * NCG; i += blockDim.x) {
+        const int cg = i / 128, r = i - cg * 128;      // consecutive threads -> consecutive rows (conflict-free 16B stores)
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = cg * 8 + j;
+            float v = 0.f;
+            if (r < rows_valid && c < D) {
+                v = __ldg(obs + (row0 + r) * D + c);
+                if (nm) v = fminf(fmaxf(__fdiv_rn(__fsub_rn(v, __ldg(nm + c)), __ldg(ns + c)), -5.0f), 5.0f);
+            }
+            f[j] = v;
+        }
+        *reinterpret_cast<uint4*>(sX + tile_off(r, cg, N::ACS, N::ARS)) = pack8_bf16(f);
+    }
+}
+
+// epilogue helper: thread (row r) processes 32 accumulator columns [c0, c0+32): v = elu(v + bias) -> bf16 chunks into
+// a shared operand tile and (optionally) the global tiled activation buffer
+__device__ __forceinline__ void store_chunks32(const float (&v)[32], int r, int c0, uint8_t* s_tile, uint8_t* g_tile) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 u = pack8_bf16(&v[q * 8]);
+        const uint32_t off = tile_off(r, c0 / 8 + q, 2048u, 128u);
+        if (s_tile) *reinterpret_cast<uint4*>(s_tile + off) = u;
+        if (g_tile) *reinterpret_cast<uint4*>(g_tile + off) = u;
+    }
+}
+
+struct FwdArgs {
+    const float* obs; int rows_per_chunk; int64_t chunk_stride; int D;
+    const float* nm; const float* ns;
+    const uint8_t* wpack; const float* b1; const float* b2; const float* b3; const float* bh; const float* logstd;
+    int M; int A;
+    // training epilogue
+    LossArena la; const float* inv_count_dev; LossCfgDev cfg;
+    uint8_t* act1; uint8_t* act2; uint8_t* act3; uint8_t* dhead; double* partials;
+    // rollout epilogue
+    const double* vms_mean; const double* vms_var; int normalize_value; const float* noise; uint64_t seed;
+    const uint64_t* rng_epoch; uint32_t step_index;
+    float* actions; float* mus; float* sigmas; float* neglogp; float* values; float* env_actions; int clip_actions;
+    const float* act_low; const float* act_high; const uint8_t* dones_cur; uint8_t* dones_out; const float* prev_dones;
+    float* valid_out; int values_only;
+};
+
+constexpr int FWD_THREADS = 256;
+constexpr int LOSS_SLOTS = LOSS_NSC + 32;   // partial row stride shared with loss.cu (NSC + MAXA)
+
+// ================================================================================================= forward
+template <class N, bool TRAIN>
+__global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sW1 = smem + N::W1_OFF; uint8_t* sW2 = smem + N::W2_OFF; uint8_t* sW3 = smem + N::W3_OFF; uint8_t* sWh = smem + N::WH_OFF;
+    uint8_t* sA1 = smem + N::PACK_BYTES;                 // a1 (then a3 aliases its start)
+    uint8_t* sXA2 = sA1 + N::A1_BYTES;                   // X tile, later a2
+    uint8_t* sA3 = sA1;
+    float* sBias = reinterpret_cast<float*>(sXA2 + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES));
+    float* sB1 = sBias; float* sB2 = sB1 + N::U1; float* sB3 = sB2 + N::U2; float* sBh = sB3 + N::U3;
+    float* sSig = sBh + N::AP;                           // sigma[A], logstd[A] (<= 32 floats)
+    float* sRed = sSig + 32;                             // [8 warps][LOSS_SLOTS]
+    double* sAcc = reinterpret_cast<double*>(sRed + 8 * LOSS_SLOTS);     // [LOSS_SLOTS] per-CTA running partial
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + LOSS_SLOTS);     // [0]=weights, [1..4]=mma stages
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int n_tiles = (p.M + 127) / 128;
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = __ldg(p.b1 + i);
+    for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = __ldg(p.b2 + i);
+    for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = __ldg(p.b3 + i);
+    if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
+    if (tid < p.A) { const float ls = __ldg(p.logstd + tid); sSig[tid] = expf(ls); sSig[p.A + tid] = ls; }
+    if (tid < LOSS_SLOTS) sAcc[tid] = 0.0;
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t T1 = tmem, T2 = tmem + 256, T3 = tmem + 384, T4 = tmem + 448;     // accumulator column bases
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], N::PACK_BYTES);
+        bulk_g2s(sW1, p.wpack + N::W1_OFF, N::W1_BYTES, &bars[0]);
+        bulk_g2s(sW2, p.wpack + N::W2_OFF, N::W2_BYTES, &bars[0]);
+        bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[0]);
+        bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[0]);
+    }
+    uint32_t phase = 0;
+    bool weights_ready = false;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = tile * 128;
+        const int rows_valid = min(128, p.M - m0);
+        const int64_t arow0 = chunk_row(m0, p.rows_per_chunk, p.chunk_stride);   // tile lies inside one chunk (host-checked)
+        stage_x_tile<N>(sXA2, p.obs, arow0, rows_valid, p.D, p.nm, p.ns);
+        fence_async_smem();
+        if (!weights_ready) { mbar_wait(&bars[0], 0); weights_ready = true; }
+        __syncthreads();
+        // ---------------- layer 1: T1[128, U1] = X . W1^T ----------------
+        if (tid == 0) {
+            fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_bf16(128, N::U1, 0, 0);
+#pragma unroll
+            for (int k = 0; k < N::DPAD / 16; ++k)
+                umma_bf16(T1, make_smem_desc(smem_u32(sXA2) + k * 2 * N::ACS, N::ACS, N::ARS),
+                          make_smem_desc(smem_u32(sW1) + k * 2 * N::W1_CS, N::W1_CS, 128), idesc, k > 0);
+            umma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], phase);
+        fence_after_sync();
+        {
+            uint8_t* g1 = TRAIN ? p.act1 + (size_t)tile * N::A1_BYTES : nullptr;
+#pragma unroll 1
+            for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+                float v[32];
+                tmem_ld32(T1 + lane_base + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB1[c0 + j]);
+                store_chunks32(v, row, c0, sA1, g1);
+            }
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        // ---------------- layer 2: T2[128, U2] = a1 . W2^T ----------------
+        if (tid == 0) {
+            fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_bf16(128, N::U2, 0, 0);
+#pragma unroll
+            for (int k = 0; k < N::U1 / 16; ++k)
+                umma_bf16(T2, make_smem_desc(smem_u32(sA1) + k * 2 * N::ACS, N::ACS, N::ARS),
+                          make_smem_desc(smem_u32(sW2) + k * 2 * N::W2_CS, N::W2_CS, 128), idesc, k > 0);
+            umma_commit(&bars[2]);
+        }
+        mbar_wait(&bars[2], phase);
+        fence_after_sync();
+        {
+            uint8_t* g2 = TRAIN ? p.act2 + (size_t)tile * N::A2_BYTES : nullptr;
+#pragma unroll 1
+            for (int c0 = h * (N::U2 / 2); c0 < (h + 1) * (N::U2 / 2); c0 += 32) {
+                float v[32];
+                tmem_ld32(T2 + lane_base + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB2[c0 + j]);
+                store_chunks32(v, row, c0, sXA2, g2);
+            }
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        // ---------------- layer 3: T3[128, U3] = a2 . W3^T ----------------
+        if (tid == 0) {
+            fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_bf16(128, N::U3, 0, 0);
+#pragma unroll
+            for (int k = 0; k < N::U2 / 16; ++k)
+                umma_bf16(T3, make_smem_desc(smem_u32(sXA2) + k * 2 * N::ACS, N::ACS, N::ARS),
+                          make_smem_desc(smem_u32(sW3) + k * 2 * N::W3_CS, N::W3_CS, 128), idesc, k > 0);
+            umma_commit(&bars[3]);
+        }
+        mbar_wait(&bars[3], phase);
+        fence_after_sync();
+        {
+            uint8_t* g3 = TRAIN ? p.act3 + (size_t)tile * N::A3_BYTES : nullptr;
+            // U3/2 = 32 columns per thread
+            const int c0 = h * (N::U3 / 2);
+            float v[32];
+            tmem_ld32(T3 + lane_base + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB3[c0 + j]);
+            store_chunks32(v, row, c0, sA3, g3);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        // ---------------- heads: T4[128, AP] = a3 . Wh^T ----------------
+        if (tid == 0) {
+            fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_bf16(128, N::AP, 0, 0);
+#pragma unroll
+            for (int k = 0; k < N::U3 / 16; ++k)
+                umma_bf16(T4, make_smem_desc(smem_u32(sA3) + k * 2 * N::ACS, N::ACS, N::ARS),
+                          make_smem_desc(smem_u32(sWh) + k * 2 * N::WH_CS, N::WH_CS, 128), idesc, k > 0);
+            umma_commit(&bars[4]);
+        }
+        mbar_wait(&bars[4], phase);
+        fence_after_sync();
+        float sc[LOSS_NSC];
+        float dls[16];
+#pragma unroll
+        for (int i = 0; i < LOSS_NSC; ++i) sc[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dls[j] = 0.f;
+        if (h == 0) {
+            float head[16];
+            tmem_ld16(T4 + lane_base, head);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) head[j] += sBh[j];
+            const int m = m0 + row;
+            if (row < rows_valid) {
+                const int64_t ar = arow0 + row;
+                if (TRAIN) {
+                    float dh[16];
+                    const float inv_cnt = p.inv_count_dev ? __ldg(p.inv_count_dev) : (1.0f / (float)p.M);
+                    ppo_sample_loss<16>(head, p.A, sSig, p.la, ar, inv_cnt, p.cfg, dh, dls, sc);
+                    uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
+                    *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = pack8_bf16(&dh[0]);
+                    *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = pack8_bf16(&dh[8]);
+                } else {
+                    // ---- rollout epilogue: models.py:329-364 eval branch ----
+                    float val = head[0];
+                    if (p.normalize_value) {
+                        const float mm = (float)p.vms_mean[0], ss = __fsqrt_rn(__fadd_rn((float)p.vms_var[0], 1e-5f));
+                        val = __fadd_rn(__fmul_rn(ss, fminf(fmaxf(val, -5.0f), 5.0f)), mm);
+                    }
+                    p.values[m] = val;
+                    if (!p.values_only) {
+                        float eps[16];
+                        if (p.noise) {
+#pragma unroll
+                            for (int j = 0; j < 15; ++j) eps[j] = (j < p.A) ? __ldg(p.noise + (int64_t)m * p.A + j) : 0.f;
+                        } else {
+                            const uint64_t ep = p.rng_epoch ? *p.rng_epoch : 0ull;
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) {
+                                if (qq * 4 < p.A) {
+                                    const Philox4 r4 = philox4x32_10((uint64_t)m, (ep << 20) | ((uint64_t)p.step_index << 4) | (uint64_t)qq, p.seed);
+                                    box_muller(r4.x, r4.y, eps[qq * 4 + 0], eps[qq * 4 + 1]);
+                                    box_muller(r4.z, r4.w, eps[qq * 4 + 2], eps[qq * 4 + 3]);
+                                }
+                            }
+                        }
+                        float sumz2 = 0.f, sumls = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 15; ++j) {
+                            if (j < p.A) {
+                                const float mu = head[1 + j], sg = sSig[j];
+                                const float act = __fadd_rn(mu, __fmul_rn(sg, eps[j]));
+                                const float z = (act - mu) / sg;
+                                sumz2 += z * z;
+                                sumls += sSig[p.A + j];
+                                p.actions[(int64_t)m * p.A + j] = act;
+                                p.mus[(int64_t)m * p.A + j] = mu;
+                                p.sigmas[(int64_t)m * p.A + j] = sg;
+                                if (p.env_actions) {
+                                    float ea = act;
+                                    if (p.clip_actions) {
+                                        const float lo = __ldg(p.act_low + j), hi = __ldg(p.act_high + j);
+                                        ea = fminf(fmaxf(act, -1.0f), 1.0f) * ((hi - lo) * 0.5f) + (hi + lo) * 0.5f;
+                                    }
+                                    p.env_actions[(int64_t)m * p.A + j] = ea;
+                                }
+                            }
+                        }
+                        p.neglogp[m] = 0.5f * sumz2 + 0.9189385332046727f * (float)p.A + sumls;
+                        if (p.dones_out) p.dones_out[m] = p.dones_cur[m];
+                        if (p.valid_out) p.valid_out[m] = p.prev_dones ? (1.0f - p.prev_dones[m]) : 1.0f;
+                    }
+                }
+            } else if (TRAIN) {
+                // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
+                uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
+                const uint4 z4 = make_uint4(0, 0, 0, 0);
+                *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = z4;
+                *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = z4;
+            }
+        }
+        if (TRAIN) {
+            // block reduction of the loss scalars into the per-CTA running partial (fixed order => deterministic)
+#pragma unroll
+            for (int i = 0; i < LOSS_NSC; ++i) sc[i] = warp_sum(sc[i]);
+#pragma unroll
+            for (int j = 0; j < 15; ++j) dls[j] = warp_sum(dls[j]);
+            if (lane == 0) {
+#pragma unroll
+                for (int i = 0; i < LOSS_NSC; ++i) sRed[warp * LOSS_SLOTS + i] = sc[i];
+#pragma unroll
+                for (int j = 0; j < 15; ++j) sRed[warp * LOSS_SLOTS + LOSS_NSC + j] = dls[j];
+            }
+        }
+        fence_before_sync();
+        __syncthreads();
+        if (TRAIN && tid < LOSS_NSC + p.A) {
+            double s = 0.0;
+            for (int wv = 0; wv < 4; ++wv) s += (double)sRed[wv * LOSS_SLOTS + tid];     // only warps with h == 0 contributed
+            sAcc[tid] += s;
+        }
+        phase ^= 1;
+    }
+    if (!weights_ready) mbar_wait(&bars[0], 0);
+    __syncthreads();
+    if (TRAIN && tid < LOSS_NSC + p.A) p.partials[(int64_t)blockIdx.x * LOSS_SLOTS + tid] = sAcc[tid];
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ================================================================================================= backward 1
+struct Bwd1Args {
+    const uint8_t* wpack; const uint8_t* act1; const uint8_t* act2; const uint8_t* act3; const uint8_t* dhead;
+    uint8_t* delta2; uint8_t* delta1; float* part;   // part: [n_cta][P]
+    int M; int A; int P; int off_W3, off_b3, off_b2, off_Wh, off_bh;
+};
+
+template <class N>
+__global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sWh = smem; uint8_t* sW3 = sWh + N::WH_BYTES; uint8_t* sW2 = sW3 + N::W3_BYTES;
+    uint8_t* sDH = sW2 + N::W2_BYTES;
+    uint8_t* sA3 = sDH + N::DH_BYTES;             // padded to 128 columns (upper col-groups stay zero)
+    uint8_t* sA2 = sA3 + 128 * 256;
+    uint8_t* sD3 = sA2 + N::A2_BYTES;
+    uint8_t* sD2 = sD3 + N::A3_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sD2 + N::A2_BYTES);       // [0] weights, [1] tile loads, [2..4] mma
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int n_tiles = (p.M + 127) / 128;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    // zero the padding col-groups of the a3 tile once
+    for (int i = tid; i < (128 * 256 - (int)N::A3_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(sA3 + N::A3_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t TT = tmem, TWH = tmem + 256, TW3 = tmem + 288;     // transient [0,256), dWh^T [256,272), dW3^T [288,352)
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], N::WH_BYTES + N::W3_BYTES + N::W2_BYTES);
+        bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[0]);
+        bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[0]);
+        bulk_g2s(sW2, p.wpack + N::W2_OFF, N::W2_BYTES, &bars[0]);
+    }
+    float bsum3 = 0.f, bsum2 = 0.f, bsumh = 0.f;      // thread <-> column running bias-gradient sums
+    uint32_t phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (tid == 0) {
+            mbar_expect_tx(&bars[1], N::DH_BYTES + N::A3_BYTES + N::A2_BYTES);
+            bulk_g2s(sDH, p.dhead + (size_t)tile * N::DH_BYTES, N::DH_BYTES, &bars[1]);
+            bulk_g2s(sA3, p.act3 + (size_t)tile * N::A3_BYTES, N::A3_BYTES, &bars[1]);
+            bulk_g2s(sA2, p.act2 + (size_t)tile * N::A2_BYTES, N::A2_BYTES, &bars[1]);
+        }
+        if (first) mbar_wait(&bars[0], 0);
+        mbar_wait(&bars[1], phase);
+        // ---- d3pre = d_head . Wh   ;  dWh^T += a3^T . d_head ----
+        if (tid == 0) {
+            fence_after_sync();
+            umma_bf16(TT, make_smem_desc(smem_u32(sDH), N::ACS, N::ARS), make_smem_desc(smem_u32(sWh), 128, N::WH_CS),
+                      make_idesc_bf16(128, N::U3, 0, 1), 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_bf16(TWH, make_smem_desc(smem_u32(sA3) + k * 256, 128, N::ACS), make_smem_desc(smem_u32(sDH) + k * 256, 128, N::ACS),
+                          make_idesc_bf16(128, N::AP, 1, 1), (!first || k > 0) ? 1u : 0u);
+            umma_commit(&bars[2]);
+        }
+        // bias grad of the heads: column sums of the d_head tile (thread c < AP)
+        if (tid < N::AP) {
+            float s = 0.f;
+            for (int r = 0; r < 128; ++r)
+                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sDH + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
+            bsumh += s;
+        }
+        mbar_wait(&bars[2], phase);
+        fence_after_sync();
+        {   // d3 = d3pre * elu'(a3): U3/2 = 32 columns per thread
+            const int c0 = h * (N::U3 / 2);
+            float v[32];
+            tmem_ld32(TT + lane_base + c0, v);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float a[8];
+                unpack8_bf16(*reinterpret_cast<const uint4*>(sA3 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS)), a);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[g * 8 + j] *= elu_grad_from_out(a[j]);
+            }
+            store_chunks32(v, row, c0, sD3, nullptr);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        // ---- d2pre = d3 . W3 ; dW3^T += a2^T . d3 ----
+        if (tid == 0) {
+            fence_after_sync();
+#pragma unroll
+            for (int k = 0; k < N::U3 / 16; ++k)
+                umma_bf16(TT, make_smem_desc(smem_u32(sD3) + k * 2 * N::ACS, N::ACS, N::ARS),
+                          make_smem_desc(smem_u32(sW3) + k * 256, 128, N::W3_CS), make_idesc_bf16(128, N::U2, 0, 1), k > 0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_bf16(TW3, make_smem_desc(smem_u32(sA2) + k * 256, 128, N::ACS), make_smem_desc(smem_u32(sD3) + k * 256, 128, N::ACS),
+                          make_idesc_bf16(128, N::U3, 1, 1), (!first || k > 0) ? 1u : 0u);
+            umma_commit(&bars[3]);
+        }
+        if (tid < N::U3) {
+            float s = 0.f;
+            for (int r = 0; r < 128; ++r)
+                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sD3 + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
+            bsum3 += s;
+        }
+        mbar_wait(&bars[3], phase);
+        fence_after_sync();
+        {   // d2 = d2pre * elu'(a2): U2/2 = 64 columns per thread
+            uint8_t* g2 = p.delta2 + (size_t)tile * N::A2_BYTES;
+#pragma unroll 1
+            for (int c0 = h * (N::U2 / 2); c0 < (h + 1) * (N::U2 / 2); c0 += 32) {
+                float v[32];
+                tmem_ld32(TT + lane_base + c0, v);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float a[8];
+                    unpack8_bf16(*reinterpret_cast<const uint4*>(sA2 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS)), a);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[g * 8 + j] *= elu_grad_from_out(a[j]);
+                }
+                store_chunks32(v, row, c0, sD2, g2);
+            }
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        // ---- d1pre = d2 . W2 ----
+        if (tid == 0) {
+            fence_after_sync();
+#pragma unroll
+            for (int k = 0; k < N::U2 / 16; ++k)
+                umma_bf16(TT, make_smem_desc(smem_u32(sD2) + k * 2 * N::ACS, N::ACS, N::ARS),
+                          make_smem_desc(smem_u32(sW2) + k * 256, 128, N::W2_CS), make_idesc_bf16(128, N::U1, 0, 1), k > 0);
+            umma_commit(&bars[4]);
+        }
+        if (tid < N::U2) {
+            float s = 0.f;
+            for (int r = 0; r < 128; ++r)
+                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sD2 + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
+            bsum2 += s;
+        }
+        mbar_wait(&bars[4], phase);
+        fence_after_sync();
+        {   // d1 = d1pre * elu'(a1) straight to the global tiled buffer (a1 read from its global tile, coalesced 16B)
+            const uint8_t* ga1 = p.act1 + (size_t)tile * N::A1_BYTES;
+            uint8_t* g1 = p.delta1 + (size_t)tile * N::A1_BYTES;
+#pragma unroll 1
+            for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+                float v[32];
+                tmem_ld32(TT + lane_base + c0, v);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float a[8];
+                    unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ga1 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS))), a);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[g * 8 + j] *= elu_grad_from_out(a[j]);
+                }
+                store_chunks32(v, row, c0, nullptr, g1);
+            }
+        }
+        fence_before_sync();
+        __syncthreads();
+        phase ^= 1;
+        first = false;
+    }
+    if (first) mbar_wait(&bars[0], 0);
+    // ---- flush: dW3^T (TMEM rows = in index, cols = out index), dWh^T, bias sums ----
+    float* part = p.part + (size_t)blockIdx.x * p.P;
+    fence_after_sync();
+    if (!first) {
+        {   // dW3^T[i][o] -> grad_W3[o * U2 + i]; thread row = i, cols [32h, 32h+32) of U3 = 64
+            const int c0 = h * (N::U3 / 2);
+            float v[32];
+            tmem_ld32(TW3 + lane_base + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) part[p.off_W3 + (c0 + j) * N::U2 + row] = v[j];
+        }
+        if (h == 0 && row < N::U3) {   // dWh^T[i][o]: rows i < U3 valid; grad_Wh[o * U3 + i], o < A + 1
+            float v[16];
+            tmem_ld16(TWH + lane_base, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                if (j < p.A + 1) part[p.off_Wh + j * N::U3 + row] = v[j];
+        } else if (h == 0) {
+            float v[16];
+            tmem_ld16(TWH + lane_base, v);   // keep the warp-collective load converged
+        }
+    } else {
+        for (int i = tid; i < N::U3 * N::U2; i += 256) part[p.off_W3 + i] = 0.f;
+        for (int i = tid; i < (p.A + 1) * N::U3; i += 256) part[p.off_Wh + i] = 0.f;
+    }
+    if (tid < N::U3) part[p.off_b3 + tid] = bsum3;
+    if (tid < N::U2) part[p.off_b2 + tid] = bsum2;
+    if (tid < p.A + 1) part[p.off_bh + tid] = bsumh;
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ================================================================================================= backward 2
+struct Bwd2Args {
+    const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
+    const uint8_t* act1; const uint8_t* delta2; const uint8_t* delta1; float* part;
+    int M; int P; int off_W2, off_W1, off_b1;
+};
+
+template <class N>
+__global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sD2 = smem; uint8_t* sD1 = sD2 + N::A2_BYTES; uint8_t* sA1 = sD1 + N::A1_BYTES; uint8_t* sX = sA1 + N::A1_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + N::X_BYTES);          // [0] tile loads, [1] mma
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int n_tiles = (p.M + 127) / 128;
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t TW2 = tmem, TW1 = tmem + 256;     // dW2 [128 x U1=256], dW1 halves [128 x DPAD] at +256, +256+DPAD
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float bsum1 = 0.f;
+    uint32_t phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (!first) { mbar_wait(&bars[1], phase ^ 1); fence_after_sync(); }    // previous tile's MMAs done reading the tiles
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bars[0], N::A2_BYTES + 2 * N::A1_BYTES);
+            bulk_g2s(sD2, p.delta2 + (size_t)tile * N::A2_BYTES, N::A2_BYTES, &bars[0]);
+            bulk_g2s(sD1, p.delta1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
+            bulk_g2s(sA1, p.act1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
+        }
+        const int m0 = tile * 128;
+        stage_x_tile<N>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, p.nm, p.ns);
+        fence_async_smem();
+        mbar_wait(&bars[0], phase);
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // dW2[o][i] += sum_r d2[r][o] * a1[r][i]
+                umma_bf16(TW2, make_smem_desc(smem_u32(sD2) + k * 256, 128, N::ACS), make_smem_desc(smem_u32(sA1) + k * 256, 128, N::ACS),
+                          make_idesc_bf16(128, N::U1, 1, 1), (acc || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int hh = 0; hh < N::U1 / 128; ++hh)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)  // dW1[o][i] += sum_r d1[r][o] * x[r][i], o in half hh
+                    umma_bf16(TW1 + hh * N::DPAD, make_smem_desc(smem_u32(sD1) + hh * 16 * N::ACS + k * 256, 128, N::ACS),
+                              make_smem_desc(smem_u32(sX) + k * 256, 128, N::ACS), make_idesc_bf16(128, N::DPAD, 1, 1),
+                              (acc || k > 0) ? 1u : 0u);
+            umma_commit(&bars[1]);
+        }
+        if (tid < N::U1) {
+            float s = 0.f;
+            for (int r = 0; r < 128; ++r)
+                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sD1 + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
+            bsum1 += s;
+        }
+        phase ^= 1;
+        first = false;
+    }
+    float* part = p.part + (size_t)blockIdx.x * p.P;
+    if (!first) {
+        mbar_wait(&bars[1], phase ^ 1);
+        fence_after_sync();
+        // dW2: TMEM row = out o (128), cols = in i (U1): thread writes cols [128h, 128h+128)
+#pragma unroll 1
+        for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+            float v[32];
+            tmem_ld32(TW2 + lane_base + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) part[p.off_W2 + (size_t)row * N::U1 + c0 + j] = v[j];   // (P is odd: no 16B alignment)
+        }
+        // dW1 halves: row = out o (hh*128 + row), cols = in i (DPAD, only D valid): each column-half h takes DPAD/2 cols
+#pragma unroll 1
+        for (int hh = 0; hh < N::U1 / 128; ++hh) {
+#pragma unroll 1
+            for (int c0 = h * (N::DPAD / 2); c0 < (h + 1) * (N::DPAD / 2); c0 += 32) {
+                float v[32];
+                tmem_ld32(TW1 + hh * N::DPAD + lane_base + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < p.D) part[p.off_W1 + (size_t)(hh * 128 + row) * p.D + c0 + j] = v[j];
+            }
+        }
+    } else {
+        for (int i = tid; i < N::U2 * N::U1; i += 256) part[p.off_W2 + i] = 0.f;
+        for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
+    }
+    if (tid < N::U1) part[p.off_b1 + tid] = bsum1;
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <class N> constexpr size_t fwd_smem() {
+    return (size_t)N::PACK_BYTES + N::A1_BYTES + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES) +
+           sizeof(float) * (N::U1 + N::U2 + N::U3 + N::AP + 32 + 8 * LOSS_SLOTS) + sizeof(double) * LOSS_SLOTS + 8 * 8 + 16;
+}
+template <class N> constexpr size_t bwd1_smem() {
+    return (size_t)N::WH_BYTES + N::W3_BYTES + N::W2_BYTES + N::DH_BYTES + 128 * 256 + N::A2_BYTES + N::A3_BYTES + N::A2_BYTES + 8 * 8 + 16;
+}
+template <class N> constexpr size_t bwd2_smem() { return (size_t)N::A2_BYTES + 2 * N::A1_BYTES + N::X_BYTES + 4 * 8 + 16; }
+
+bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D <= 64 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------- C ABI
+B200RL_EXPORT int b200rl_tc_supported(int D, int u1, int u2, int u3, int A) { return net_is_c2(D, u1, u2, u3, A) ? 1 : 0; }
+
+B200RL_EXPORT int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A) {
+    return net_is_c2(D, u1, u2, u3, A) ? (int64_t)NetC2::PACK_BYTES : -1;
+}
+// bytes of one 128-row tile of: act1, act2, act3, d_head  (tiled INTERLEAVE bf16 buffers)
+B200RL_EXPORT int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int64_t* out4_host) {
+    if (!net_is_c2(D, u1, u2, u3, A) || !out4_host) return B200RL_EUNSUPPORTED;
+    out4_host[0] = NetC2::A1_BYTES; out4_host[1] = NetC2::A2_BYTES; out4_host[2] = NetC2::A3_BYTES; out4_host[3] = NetC2::DH_BYTES;
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_tc_pack_weights(const float* W1, const float* W2, const float* W3, const float* W_head,
+                                         int D, int u1, int u2, int u3, int A, void* wpack, void* stream) {
+    if (!W1 || !W2 || !W3 || !W_head || !wpack) return B200RL_EINVAL;
+    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
+    using N = NetC2;
+    PackArgs a;
+    a.seg[0] = PackSeg{W1, u1, D, N::U1, N::DPAD, N::W1_OFF};
+    a.seg[1] = PackSeg{W2, u2, u1, N::U2, N::U1, N::W2_OFF};
+    a.seg[2] = PackSeg{W3, u3, u2, N::U3, N::U2, N::W3_OFF};
+    a.seg[3] = PackSeg{W_head, A + 1, u3, N::AP, N::U3, N::WH_OFF};
+    pack_weights_kernel<<<dim3(16, 4), 256, 0, as_stream(stream)>>>(a, (uint8_t*)wpack);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+static int tc_check_rows(int M, int rows_per_chunk) {
+    if (M <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
+    if (M > rows_per_chunk && rows_per_chunk % 128 != 0) return B200RL_EUNSUPPORTED;   // tiles may not straddle chunks
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+                                          const float* norm_mean, const float* norm_std, const void* wpack,
+                                          const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
+                                          int u1, int u2, int u3, int M, int A,
+                                          const float* actions, float* old_mu, float* old_sigma, const float* old_values_n,
+                                          const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
+                                          const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
+                                          void* act1, void* act2, void* act3, void* dhead,
+                                          double* partials, int max_partials, int* n_blocks_out_host, void* stream) {
+    if (!obs || !wpack || !b1 || !b2 || !b3 || !b_head || !logstd || !actions || !old_mu || !old_sigma || !old_values_n || !returns_n ||
+        !old_neglogp || !advs_n || !cfg_host || !act1 || !act2 || !act3 || !dhead || !partials)
+        return B200RL_EINVAL;
+    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
+    int rc = tc_check_rows(M, rows_per_chunk);
+    if (rc) return rc;
+    using N = NetC2;
+    const int n_tiles = (M + 127) / 128;
+    const int grid = n_tiles < 148 ? n_tiles : 148;
+    if (n_blocks_out_host) *n_blocks_out_host = grid;
+    if (grid > max_partials) return B200RL_EINVAL;
+    FwdArgs p{};
+    p.obs = obs; p.rows_per_chunk = rows_per_chunk; p.chunk_stride = chunk_stride; p.D = D; p.nm = norm_mean; p.ns = norm_std;
+    p.wpack = (const uint8_t*)wpack; p.b1 = b1; p.b2 = b2; p.b3 = b3; p.bh = b_head; p.logstd = logstd; p.M = M; p.A = A;
+    p.la = LossArena{actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask};
+    p.inv_count_dev = inv_count_dev;
+    p.cfg = LossCfgDev{cfg_host->e_clip, cfg_host->critic_coef, cfg_host->bounds_loss_coef, cfg_host->has_bounds_loss,
+                       cfg_host->bound_loss_type, cfg_host->clip_value, cfg_host->use_smooth_clamp, cfg_host->ppo};
+    p.act1 = (uint8_t*)act1; p.act2 = (uint8_t*)act2; p.act3 = (uint8_t*)act3; p.dhead = (uint8_t*)dhead; p.partials = partials;
+    constexpr size_t smem = fwd_smem<N>();
+    static_assert(smem <= 227 * 1024, "forward kernel shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mlp_fwd_tc_kernel<N, true><<<grid, FWD_THREADS, smem, as_stream(stream)>>>(p);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
+                                            const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
+                                            int u1, int u2, int u3, int N_rows, int A,
+                                            const double* vms_mean, const double* vms_var, int normalize_value,
+                                            const float* noise, uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index,
+                                            float* actions, float* mus, float* sigmas, float* neglogp, float* values,
+                                            float* env_actions, int clip_actions, const float* act_low, const float* act_high,
+                                            const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones, float* valid_out,
+                                            int values_only, void* stream) {
+    if (!obs || !wpack || !b1 || !b2 || !b3 || !b_head || !logstd || !values || N_rows <= 0) return B200RL_EINVAL;
+    if (!values_only && (!actions || !mus || !sigmas || !neglogp)) return B200RL_EINVAL;
+    if (normalize_value && (!vms_mean || !vms_var)) return B200RL_EINVAL;
+    if (env_actions && clip_actions && (!act_low || !act_high)) return B200RL_EINVAL;
+    if (dones_out && !dones_cur) return B200RL_EINVAL;
+    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
+    using N = NetC2;
+    const int n_tiles = (N_rows + 127) / 128;
+    const int grid = n_tiles < 148 ? n_tiles : 148;
+    FwdArgs p{};
+    p.obs = obs; p.rows_per_chunk = N_rows; p.chunk_stride = 0; p.D = D; p.nm = norm_mean; p.ns = norm_std;
+    p.wpack = (const uint8_t*)wpack; p.b1 = b1; p.b2 = b2; p.b3 = b3; p.bh = b_head; p.logstd = logstd; p.M = N_rows; p.A = A;
+    p.vms_mean = vms_mean; p.vms_var = vms_var; p.normalize_value = normalize_value; p.noise = noise; p.seed = seed;
+    p.rng_epoch = rng_epoch_dev; p.step_index = step_index; p.actions = actions; p.mus = mus; p.sigmas = sigmas; p.neglogp = neglogp;
+    p.values = values; p.env_actions = env_actions; p.clip_actions = clip_actions; p.act_low = act_low; p.act_high = act_high;
+    p.dones_cur = dones_cur; p.dones_out = dones_out; p.prev_dones = prev_dones; p.valid_out = valid_out; p.values_only = values_only;
+    constexpr size_t smem = fwd_smem<N>();
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    mlp_fwd_tc_kernel<N, false><<<grid, FWD_THREADS, smem, as_stream(stream)>>>(p);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+                                    const float* norm_mean, const float* norm_std, const void* wpack,
+                                    int u1, int u2, int u3, int M, int A,
+                                    const void* act1, const void* act2, const void* act3, const void* dhead,
+                                    void* delta2, void* delta1, float* part, int max_parts, int P,
+                                    int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
+                                    int* n_parts_out_host, void* stream) {
+    if (!obs || !wpack || !act1 || !act2 || !act3 || !dhead || !delta2 || !delta1 || !part) return B200RL_EINVAL;
+    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
+    int rc = tc_check_rows(M, rows_per_chunk);
+    if (rc) return rc;
+    using N = NetC2;
+    const int n_tiles = (M + 127) / 128;
+    const int grid = n_tiles < 148 ? n_tiles : 148;
+    if (n_parts_out_host) *n_parts_out_host = grid;
+    if (grid > max_parts) return B200RL_EINVAL;
+    Bwd1Args a{(const uint8_t*)wpack, (const uint8_t*)act1, (const uint8_t*)act2, (const uint8_t*)act3, (const uint8_t*)dhead,
+               (uint8_t*)delta2, (uint8_t*)delta1, part, M, A, P, off_W3, off_b3, off_b2, off_Wh, off_bh};
+    constexpr size_t smem1 = bwd1_smem<N>();
+    static_assert(smem1 <= 227 * 1024, "bwd1 shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(mlp_bwd1_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    if (e != cudaSuccess) return (int)e;
+    mlp_bwd1_tc_kernel<N><<<grid, 256, smem1, as_stream(stream)>>>(a);
+    B200RL_LAUNCH_CHECK();
+    Bwd2Args b{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
+               (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1};
+    constexpr size_t smem2 = bwd2_smem<N>();
+    static_assert(smem2 <= 227 * 1024, "bwd2 shared memory budget");
+    e = cudaFuncSetAttribute(mlp_bwd2_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    mlp_bwd2_tc_kernel<N><<<grid, 256, smem2, as_stream(stream)>>>(b);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}

@@ -229,3 +229,56 @@ def tc_gemm_test(A, B, N, K, a_mn=False, b_mn=False):
     D = torch.empty(128, N, dtype=torch.float32, device=A.device)
     check(lib.b200rl_tc_gemm_test(ptr(A), ptr(B), ptr(D), N, K, int(a_mn), int(b_mn), _stream()), 'tc_gemm_test')
     return D
+
+
+# ------------------------------------------------------------------------------------------ bf16 tcgen05 path
+def tc_supported(D, units, A):
+    return len(units) == 3 and bool(lib.b200rl_tc_supported(D, units[0], units[1], units[2], A))
+
+
+def tc_pack_bytes(D, units, A):
+    return int(lib.b200rl_tc_pack_bytes(D, units[0], units[1], units[2], A))
+
+
+def tc_tile_bytes(D, units, A):
+    out = (ctypes.c_int64 * 4)()
+    check(lib.b200rl_tc_tile_bytes(D, units[0], units[1], units[2], A, ctypes.addressof(out)), 'tc_tile_bytes')
+    return [int(x) for x in out]
+
+
+def tc_pack_weights(W1, W2, W3, W_head, D, units, A, wpack):
+    check(lib.b200rl_tc_pack_weights(ptr(W1), ptr(W2), ptr(W3), ptr(W_head), D, units[0], units[1], units[2], A, ptr(wpack),
+                                     _stream()), 'tc_pack_weights')
+
+
+def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_head, logstd, units, M, A, actions, old_mu,
+                     old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials):
+    nb = ctypes.c_int(0)
+    check(lib.b200rl_tc_mlp_fwd_train(ptr(obs), rows_per_chunk, chunk_stride, D, ptr(nm), ptr(ns), ptr(wpack), ptr(b[0]), ptr(b[1]),
+                                      ptr(b[2]), ptr(b_head), ptr(logstd), units[0], units[1], units[2], M, A, ptr(actions),
+                                      ptr(old_mu), ptr(old_sigma), ptr(old_values_n), ptr(returns_n), ptr(old_neglogp), ptr(advs_n),
+                                      ptr(mask), ctypes.addressof(cfg), ptr(inv_count), ptr(act[0]), ptr(act[1]), ptr(act[2]),
+                                      ptr(dhead), ptr(partials), partials.shape[0], ctypes.addressof(nb), _stream()),
+          'tc_mlp_fwd_train')
+    return nb.value
+
+
+def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vms_mean, vms_var, normalize_value, noise, seed,
+                       rng_epoch, step_index, actions, mus, sigmas, neglogp, values, env_actions, clip_actions, act_low, act_high,
+                       dones_cur, dones_out, prev_dones, valid_out, values_only=False):
+    check(lib.b200rl_tc_mlp_fwd_rollout(ptr(obs), D, ptr(nm), ptr(ns), ptr(wpack), ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b_head),
+                                        ptr(logstd), units[0], units[1], units[2], N, A, ptr(vms_mean), ptr(vms_var),
+                                        int(normalize_value), ptr(noise), seed, ptr(rng_epoch), step_index, ptr(actions), ptr(mus),
+                                        ptr(sigmas), ptr(neglogp), ptr(values), ptr(env_actions), int(clip_actions), ptr(act_low),
+                                        ptr(act_high), ptr(dones_cur), ptr(dones_out), ptr(prev_dones), ptr(valid_out),
+                                        int(values_only), _stream()), 'tc_mlp_fwd_rollout')
+
+
+def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs):
+    """offs: dict with W0,b0,W1,b1,W2,b2,W_head,b_head flat offsets (model.layout)."""
+    nb = ctypes.c_int(0)
+    check(lib.b200rl_tc_mlp_bwd(ptr(obs), rows_per_chunk, chunk_stride, D, ptr(nm), ptr(ns), ptr(wpack), units[0], units[1], units[2],
+                                M, A, ptr(act[0]), ptr(act[1]), ptr(act[2]), ptr(dhead), ptr(delta2), ptr(delta1), ptr(part),
+                                part.shape[0], P, offs['W0'], offs['b0'], offs['W1'], offs['b1'], offs['W2'], offs['b2'],
+                                offs['W_head'], offs['b_head'], ctypes.addressof(nb), _stream()), 'tc_mlp_bwd')
+    return nb.value
