@@ -35,13 +35,13 @@ WORKLOADS = {
 }
 
 
-def make_params(w, device, env_name, multi_gpu, graph=True, seed=5):
+def make_params(w, device, env_name, multi_gpu, graph=True, seed=5, mixed_precision=True):
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': list(w['units']), 'activation': 'elu', 'initializer': {'name': 'default'}}}
     config = {'name': 'bench', 'env_name': env_name, 'reward_shaper': {'scale_value': 1.0}, 'device': device,
-              'multi_gpu': multi_gpu, 'mixed_precision': False, 'normalize_input': True, 'normalize_value': True,
+              'multi_gpu': multi_gpu, 'mixed_precision': mixed_precision, 'normalize_input': True, 'normalize_value': True,
               'value_bootstrap': True, 'normalize_advantage': True, 'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4,
               'lr_schedule': 'adaptive', 'kl_threshold': 0.008, 'grad_norm': 1.0, 'entropy_coef': 0.0, 'truncate_grads': True,
               'e_clip': 0.2, 'clip_value': True, 'use_smooth_clamp': True, 'bound_loss_type': 'regularisation',
@@ -142,10 +142,10 @@ def workload_config(name, w, env_desc):
 
 
 # ===================================================================================== B200 arm
-def build_agent(w, device, env_name, multi_gpu, graph=True):
+def build_agent(w, device, env_name, multi_gpu, graph=True, mixed_precision=True):
     from rl_games_b200.runner import Runner
     r = Runner()
-    r.load({'params': make_params(w, device, env_name, multi_gpu, graph)})
+    r.load({'params': make_params(w, device, env_name, multi_gpu, graph, mixed_precision=mixed_precision)})
     agent = r.algo_factory.create(r.algo_name, base_name='bench', params=r.params)
     agent.init_tensors()
     agent.obs = agent.env_reset()
@@ -233,7 +233,7 @@ def b200_arm(args, w):
     torch.cuda.set_device(local_rank)
     device = f'cuda:{local_rank}'
     peaks = load_peaks()
-    agent = build_agent(w, device, 'b200_synthetic', multi, graph=not args.no_graph)
+    agent = build_agent(w, device, 'b200_synthetic', multi, graph=not args.no_graph, mixed_precision=not args.fp32)
     if multi:
         dist.broadcast(agent.model.flat, 0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -258,22 +258,25 @@ def b200_arm(args, w):
     launches_per_step = sum(v['n'] for v in prof.values())
     line = {'metric': 'ppo_env_steps_per_sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': W, 'ms_per_step': 1e3 * total_s / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'f32' if args.fp32 else 'bf16', 'data': 'synthetic',
             'config': workload_config(args.workload, w, 'b200_synthetic (on-GPU Philox env, one kernel per step)'),
             'clocks': clocks, 'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
             'cuda_graph': bool(agent._graph_update is not None), 'kernels': kernels[:12]}
     if rank == 0:
         # dominant kernel family of the step -> roofline
         line['roofline_gae'] = gae_roofline(w, peaks)
-        mlp_ms = sum(v['ms'] for k, v in prof.items() if 'linear' in k)
+        mlp_ms = sum(v['ms'] for k, v in prof.items() if 'linear' in k or 'tc_mlp' in k)
         flops = 2 * sum(a * b for a, b in zip([w['obs_dim']] + w['units'], w['units'] + [w['act_dim'] + 1]))
-        step_flops = B * flops * (1 + 3 * w['mini_epochs'])      # rollout fwd + (fwd + dgrad + wgrad) per mini-epoch
+        step_flops = B * flops * (1 + 1.0 / w['horizon'] + 3 * w['mini_epochs'])   # rollout fwd (+ last-value fwd) + (fwd + dgrad + wgrad) per mini-epoch
         tf = step_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-        line['roofline'] = {'kernel': 'MLP fwd/dgrad/wgrad GEMMs (fp32 CUDA-core path, mixed_precision: False)', 'bound': 'tensor',
-                            'achieved': tf, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
-                            'frac': tf / peaks['bf16_tflops_sustained'], 'traffic': None, 'share_of_step': round(mlp_ms / ktot, 4),
-                            'peak_source': peaks['source'] + ' bf16 sustained; the fp32 SIMT kernels cannot approach it -- '
-                            'the tcgen05 bf16 path is the next milestone'}
+        kname = ('MLP GEMM kernels: fp32 CUDA-core path (mixed_precision: False)' if args.fp32 else
+                 'tcgen05 bf16 MLP kernels (mlp_fwd_tc / mlp_bwd1_tc / mlp_bwd2_tc: fused fwd+loss, dgrad+wgrad)')
+        line['roofline'] = {'kernel': kname, 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
+                            'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'], 'traffic': None,
+                            'share_of_step': round(mlp_ms / ktot, 4), 'alg_flops_per_step': step_flops,
+                            'peak_source': peaks['source'] + ' bf16 sustained',
+                            'note': 'K = 60..256, N = 16..256 GEMMs with fused elementwise epilogues: latency/epilogue bound, far below '
+                                    'the dense-GEMM peak by construction'}
         if world == 1 and not args.skip_e2e:
             line['e2e'] = e2e_leg(w, device, args)
         if world == 1 and not args.skip_cpu:
@@ -290,7 +293,7 @@ def b200_arm(args, w):
 def e2e_leg(w, device, args):
     """Same metric through the public API with a HOST env: every env step copies obs/rewards/dones/time-outs
     host->device (pinned) and the actions device->host; the per-epoch stats block is read back."""
-    agent = build_agent(w, device, 'b200_synthetic_host', False, graph=not args.no_graph)
+    agent = build_agent(w, device, 'b200_synthetic_host', False, graph=not args.no_graph, mixed_precision=not args.fp32)
     K = max(3, min(args.steps, 10))
     for _ in range(3):
         agent.epoch_num += 1
@@ -317,6 +320,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=list(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--fp32', action='store_true', help='mixed_precision: False (fp32 CUDA-core MLP kernels)')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     args = ap.parse_args()

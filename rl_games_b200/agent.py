@@ -275,6 +275,13 @@ class A2CAgent:
         self.model = B200Model(self.network_params, self.obs_shape[0], self.actions_num, self.device_t,
                                self.normalize_input, self.normalize_value, self.value_size)
         self.value_mean_std = self.model.value_mean_std if self.normalize_value else None
+        # precision mode: mixed_precision True (reference default on bf16 GPUs, a2c_common.py:429) -> bf16 tcgen05
+        # kernels (mlp_tc.cu); False -> fp32 CUDA-core kernels (mlp_simt.cu).  No silent downgrade.
+        self.use_tc = bool(self.mixed_precision)
+        if self.use_tc and not ops.tc_supported(self.model.D, self.model.units, self.actions_num):
+            raise NotImplementedError(
+                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=64, MLP [256,128,64], actions<=15 in this build; got '
+                f'obs={self.model.D}, units={self.model.units}, actions={self.actions_num}.  Set mixed_precision: False for the fp32 path.')
         self.dataset = _Dataset(self)
         self.has_value_loss = True
         self.use_cuda_graph = bool(config.get('b200_cuda_graph', True))
@@ -324,14 +331,26 @@ class A2CAgent:
         self.rng_epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         # workspaces
         m, mb = self.model, self.minibatch_size
-        self.ra = [f(N, u) for u in m.units]
-        self.ta = [f(mb, u) for u in m.units]
-        self.dA = [f(mb, u) for u in m.units]
-        self.d_head = f(mb, A + 1)
-        self.n_splits = max(1, min(64, mb // 256))
+        if not self.use_tc:
+            self.ra = [f(N, u) for u in m.units]
+            self.ta = [f(mb, u) for u in m.units]
+            self.dA = [f(mb, u) for u in m.units]
+            self.d_head = f(mb, A + 1)
+        if self.use_tc:
+            self.n_splits = 148
+            tb = ops.tc_tile_bytes(m.D, m.units, A)
+            nt = (mb + 127) // 128
+            u8 = lambda n: torch.zeros(n, dtype=torch.uint8, device=dev)   # noqa: E731
+            self.wpack = u8(ops.tc_pack_bytes(m.D, m.units, A))
+            self.tc_act = [u8(nt * tb[0]), u8(nt * tb[1]), u8(nt * tb[2])]
+            self.tc_dhead, self.tc_delta2, self.tc_delta1 = u8(nt * tb[3]), u8(nt * tb[1]), u8(nt * tb[0])
+            self.tc_offs = {k: m.layout[k][0] for k in ('W0', 'b0', 'W1', 'b1', 'W2', 'b2', 'W_head', 'b_head')}
+            self.ra = self.ta = self.dA = []
+        else:
+            self.n_splits = max(1, min(64, mb // 256))
         self.part = f(self.n_splits, m.num_params)
         self.gae_partials = torch.zeros((N + 127) // 128, 8, dtype=torch.float64, device=dev)
-        self.loss_partials = torch.zeros((mb + 127) // 128, ops.loss_partial_stride(), dtype=torch.float64, device=dev)
+        self.loss_partials = torch.zeros(max((mb + 127) // 128, 148), ops.loss_partial_stride(), dtype=torch.float64, device=dev)
         self.n_updates = self.mini_epochs_num * self.num_minibatches
         self.stats = f(self.n_updates, 16)
         # comm buffer = flat gradient + 1 KL slot (one all-reduce per minibatch, a2c_common.py:493-509 + :1559-1561)
@@ -356,6 +375,7 @@ class A2CAgent:
         self.tensor_list = self.update_list + ['obses', 'states', 'dones']
         self._pinned = {}
         self._tensors_ready = True
+        self._repack()
 
     def _build_cfg_structs(self):
         """POD structs passed (by value at launch) to the kernels; baked into captured graphs, so any change
@@ -453,8 +473,27 @@ class A2CAgent:
         for i in range(1, len(m.units)):
             ops.linear_fwd(acts[i - 1], m.W[i], m.b[i], acts[i], m.act_id, M=M)
 
+    def _repack(self):
+        """bf16 operand copy of the weights for the tcgen05 kernels (after every optimiser step / weight load)."""
+        if self.use_tc and self._tensors_ready:
+            m = self.model
+            ops.tc_pack_weights(m.W[0], m.W[1], m.W[2], m.W_head, m.D, m.units, self.actions_num, self.wpack)
+
+    def _norm(self):
+        m = self.model
+        return (m.running_mean_std.mean_f32, m.running_mean_std.std_f32) if self.normalize_input else (None, None)
+
     def _policy_step(self, obs, t, noise=None):
         m, N, A = self.model, self.num_actors, self.actions_num
+        if self.use_tc:
+            nm, ns = self._norm()
+            ops.tc_mlp_fwd_rollout(obs, m.D, nm, ns, self.wpack, m.b, m.b_head, m.sigma, m.units, N, A,
+                                   m.value_mean_std.running_mean, m.value_mean_std.running_var, self.normalize_value, noise,
+                                   self.rng_seed, self.rng_epoch, t, self.actions[t], self.mus[t], self.sigmas[t],
+                                   self.neglogpacs[t], self.values[t], self.env_actions, self.clip_actions, self.actions_low,
+                                   self.actions_high, self.dones, self.dones_buf[t], self.prev_dones,
+                                   None if self.valid is None else self.valid[t])
+            return
         self._trunk(obs, self.ra, N)
         ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
                                m.value_mean_std.running_var, self.normalize_value, noise, self.rng_seed, self.rng_epoch, t,
@@ -467,6 +506,13 @@ class A2CAgent:
         """a2c_common.py:603-626"""
         o = obs['obs'] if isinstance(obs, dict) else obs
         m, N, A = self.model, self.num_actors, self.actions_num
+        if self.use_tc:
+            nm, ns = self._norm()
+            ops.tc_mlp_fwd_rollout(o, m.D, nm, ns, self.wpack, m.b, m.b_head, m.sigma, m.units, N, A,
+                                   m.value_mean_std.running_mean, m.value_mean_std.running_var, self.normalize_value, None, 0, None,
+                                   0, None, None, None, None, self.last_values, None, False, None, None, None, None, None, None,
+                                   values_only=True)
+            return self.last_values.unsqueeze(1)
         self._trunk(o, self.ra, N)
         ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
                                m.value_mean_std.running_var, self.normalize_value, None, 0, None, 0, None, None, None, None,
@@ -572,6 +618,9 @@ class A2CAgent:
             rms = m.running_mean_std
             ops.moments_update(x, m.D, epm, H, N, rms.running_mean, rms.running_var, rms.count, rms.mean_f32, rms.std_f32,
                                self.mom_scratch, self.counters[1:2])
+        if self.use_tc:
+            self._minibatch_update_tc(i, u, x, e0)
+            return
         self._trunk(x, self.ta, mb, rows_per_chunk=epm, chunk_stride=N)
         nb = ops.ppo_head_loss(self.ta[-1], m.W_head, m.b_head, m.sigma, self.actions[0, e0:], self.mus[0, e0:],
                                self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:], self.neglogpacs[0, e0:],
@@ -602,6 +651,26 @@ class A2CAgent:
             dist.all_reduce(self.comm, op=dist.ReduceOp.SUM)
         ops.adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_state, self.kl_slot, self.opt_cfg, self.stats[u],
                       self.counters[2:3], n=P)
+
+    def _minibatch_update_tc(self, i, u, x, e0):
+        """bf16 tcgen05 edition: fused fwd+loss kernel, two backward kernels, split reduce, Adam, repack."""
+        m, H, N, A = self.model, self.horizon_length, self.num_actors, self.actions_num
+        epm, mb, P = self.envs_per_mb, self.minibatch_size, self.model.num_params
+        nm, ns = self._norm()
+        nb = ops.tc_mlp_fwd_train(x, epm, N, m.D, nm, ns, self.wpack, m.b, m.b_head, m.sigma, m.units, mb, A, self.actions[0, e0:],
+                                  self.mus[0, e0:], self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:],
+                                  self.neglogpacs[0, e0:], self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:],
+                                  self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.tc_act,
+                                  self.tc_dhead, self.loss_partials)
+        ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], m.g_sigma, self.kl_slot)
+        npart = ops.tc_mlp_bwd(x, epm, N, m.D, nm, ns, self.wpack, m.units, mb, A, self.tc_act, self.tc_dhead, self.tc_delta2,
+                               self.tc_delta1, self.part, P, self.tc_offs)
+        ops.reduce_splits(self.part[0, A:], m.grad[A:], P - A, npart, split_stride=P)
+        if self.multi_gpu:
+            dist.all_reduce(self.comm, op=dist.ReduceOp.SUM)
+        ops.adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_state, self.kl_slot, self.opt_cfg, self.stats[u],
+                      self.counters[2:3], n=P)
+        self._repack()
 
     def _update_all(self):
         u = 0
@@ -773,6 +842,7 @@ class A2CAgent:
         self.curr_frames = self.batch_size_envs
         if self.multi_gpu:
             dist.broadcast(self.model.flat, 0)      # replaces broadcast_object_list of the pickled state_dict (:1670-1680)
+            self._repack()
         while True:
             epoch_num = self.update_epoch()
             step_time, play_time, update_time, sum_time, a_losses, c_losses, b_losses, entropies, kls, last_lr, lr_mul = self.train_epoch()
@@ -890,6 +960,7 @@ class A2CAgent:
         self.model.load_state_dict(weights['model'])
         self.set_stats_weights(weights)
         self._seed_stats_sync_snapshots()
+        self._repack()
 
     def get_full_state_weights(self):
         self.init_tensors()

@@ -75,6 +75,7 @@ def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state):
     agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
     agent.model.load_state_dict({k: v.to(DEV) for k, v in init_state.items()}, strict=False)
     agent.init_tensors()
+    agent._repack()
     agent.obs = agent.env_reset()
     return agent
 
@@ -224,3 +225,42 @@ def test_synthetic_env_training_runs_and_graph_replay_is_consistent():
     assert a.last_lr == b.last_lr
     assert torch.isfinite(a.model.flat).all()
     assert a.game_rewards.current_size > 0
+
+
+def test_bf16_tcgen05_agent_tracks_fp32_agent():
+    """mixed_precision: True (bf16 tcgen05 kernels) vs mixed_precision: False (fp32 kernels) on the c2 architecture
+    (obs 60, MLP [256,128,64], 8 actions), same tapes / weights / noise.  bf16 tolerance class (8-bit mantissa operands,
+    fp32 accumulate): rollout outputs atol 5e-2, per-minibatch losses rtol 0.1 (+ small atol), parameter update
+    direction cosine > 0.8 after one epoch of Adam steps."""
+    N, H, D, A, units, mb = 512, 8, 60, 8, [256, 128, 64], 2048
+    obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=21)
+    params = O.init_params(D, units, A, seed=4)
+    g = torch.Generator().manual_seed(6)
+    noise = torch.randn(H, N, A, generator=g).to(DEV)
+    agents = []
+    for mp in (False, True):
+        env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
+        a = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False}, N, H, D, A, units, mb, env, params)
+        assert a.use_tc == mp
+        a.epoch_num += 1
+        a.train_epoch(noise=noise)
+        agents.append(a)
+    f, t = agents
+    torch.testing.assert_close(t.values, f.values, rtol=0, atol=6e-2)
+    torch.testing.assert_close(t.mus, f.mus, rtol=0, atol=6e-2)   # after the update: last mini-epoch's mu write-back
+    torch.testing.assert_close(t.advs_n, f.advs_n, rtol=0, atol=0.15)
+    sf, st = f.last_stats, t.last_stats
+    torch.testing.assert_close(st[:, 0], sf[:, 0], rtol=0.1, atol=2e-2)     # a_loss
+    torch.testing.assert_close(st[:, 1], sf[:, 1], rtol=0.1, atol=2e-2)     # c_loss
+    torch.testing.assert_close(st[:, 2], sf[:, 2], rtol=1e-3, atol=1e-3)    # entropy (depends on sigma only)
+    torch.testing.assert_close(st[:, 4], sf[:, 4], rtol=0.35, atol=3e-4)    # kl
+    init = torch.cat([params[k].reshape(-1) for k in O.param_names(3)])
+    # flat order differs from param_names order only by the head packing; compare per tensor through state_dict
+    sdf, sdt = f.model.state_dict(), t.model.state_dict()
+    for k in O.param_names(3):
+        if k.endswith('weight'):
+            du_f = (sdf[k].cpu() - params[k]).flatten(); du_t = (sdt[k].cpu() - params[k]).flatten()
+            cos = float(du_f @ du_t / (du_f.norm() * du_t.norm() + 1e-20))
+            assert cos > 0.8, (k, cos)
+    assert 0.4 < t.last_lr / f.last_lr < 2.5
+    assert int(t.model.running_mean_std.count) == int(f.model.running_mean_std.count)
