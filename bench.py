@@ -94,7 +94,7 @@ def run_cpu_oracle(w, steps, warmup, sample_envs):
     """The reference algorithm (oracle/ppo_oracle.py: plain-PyTorch restatement pinned to the real reference by
     tests/golden) on the host cores, all threads.  Returns (env_steps_per_s, ms_per_step, cores)."""
     from oracle import ppo_oracle as O
-    cores = os.cpu_count() or 1
+    cores = pick_cpu_threads(w)
     torch.set_num_threads(cores)
     N = sample_envs
     mb = max(w['horizon'], w['minibatch'] * N // w['num_actors'])
@@ -113,6 +113,47 @@ def run_cpu_oracle(w, steps, warmup, sample_envs):
             ts.append(time.perf_counter() - t0)
     total = sum(ts)
     return N * w['horizon'] * steps / total, 1e3 * total / steps, cores
+
+
+def available_cpus():
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:   # cgroup v2 CPU quota of the container
+        q, per = open('/sys/fs/cgroup/cpu.max').read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def pick_cpu_threads(w):
+    """All the host threads the reference can USE: intra-op parallelism of small fp32 ops stops scaling (and then
+    collapses) well before 128 threads, so probe a tiny epoch at a few thread counts up to the available CPUs and keep
+    the fastest (the reference's own default is min(4, cores), torch_runner.py:217-225)."""
+    from oracle import ppo_oracle as O
+    avail = available_cpus()
+    cands = sorted({c for c in (avail, 64, 32, 16, 8, 4) if c <= avail})
+    best, best_t = cands[0], float('inf')
+    g = torch.Generator().manual_seed(0)
+    for c in cands:
+        torch.set_num_threads(c)
+        N = 1024
+        ag = O.OracleAgent(O.SyntheticEnvCPU(N, w['obs_dim'], w['act_dim'], seed=5), O.init_params(w['obs_dim'], w['units'], w['act_dim'], seed=5),
+                           w['obs_dim'], w['act_dim'], w['units'], N, w['horizon'], max(w['horizon'], N * w['horizon'] // 8),
+                           {'mini_epochs': 1})
+        ag.obs = ag.env_reset()
+        ts = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            ag.train_epoch(torch.randn(w['horizon'], N, w['act_dim'], generator=g))
+            ts.append(time.perf_counter() - t0)
+        if ts[-1] < best_t:
+            best, best_t = c, ts[-1]
+    return best
 
 
 def reference_arm(args, w):

@@ -173,6 +173,11 @@ int b200rl_ppo_head_loss_f32(const float* a_last, int Hl, const float* W_head, c
  * (includes the -entropy_coef * d(entropy)/d(logstd) term; entropy_coef read from device). */
 int b200rl_ppo_loss_finalize(const double* partials, int n_partials, int A, const float* entropy_coef_dev,
                              float* stats, float* d_logstd, float* kl_out, void* stream);
+/* b200rl_reduce_splits_f32 + b200rl_ppo_loss_finalize in one launch (the two tiny steps between backward and the
+ * gradient all-reduce) */
+int b200rl_reduce_finalize(const float* part, float* out, int n, int n_splits, int64_t split_stride,
+                           const double* partials, int n_partials, int A, const float* entropy_coef_dev,
+                           float* stats, float* d_logstd, float* kl_out, void* stream);
 /* inv_count[i] = 1/max(sum_{t, e in minibatch i} mask[t,e], 1)  (torch_ext.py:157-170) */
 int b200rl_mask_inv_counts_f32(const float* mask, int H, int N, int envs_per_mb, float* inv_count, void* stream);
 int b200rl_loss_partial_stride(void);
@@ -194,9 +199,16 @@ typedef struct b200rl_opt_cfg {
     int adaptive_lr;         /* lr_schedule == 'adaptive' && schedule_type == 'per_minibatch' */
 } b200rl_opt_cfg;
 
+/* optional fused refresh of the packed bf16 weight copy used by the tcgen05 kernels (b200rl_tc_pack_table) */
+typedef struct b200rl_pack_table {
+    int n_seg;
+    int flat_off[4]; int rows[4]; int cols[4];
+    uint32_t cs_bytes[4]; uint32_t dst_off[4];
+} b200rl_pack_table;
+
 int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
                          double* state_d, const float* kl_dev, const b200rl_opt_cfg* cfg_host,
-                         float* stats_out, int* counter, void* stream);
+                         float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Rollout.  a2c_common.py:985-1069 (play_steps) per-step pieces.
@@ -260,6 +272,8 @@ int b200rl_bump_u64(uint64_t* p, void* stream);
 int b200rl_tc_supported(int D, int u1, int u2, int u3, int A);
 int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A);
 int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int64_t* out4_host);
+int b200rl_tc_pack_table(int D, int u1, int u2, int u3, int A, int off_W1, int off_W2, int off_W3, int off_Wh,
+                         b200rl_pack_table* out_host);
 int b200rl_tc_pack_weights(const float* W1, const float* W2, const float* W3, const float* W_head,
                            int D, int u1, int u2, int u3, int A, void* wpack, void* stream);
 int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,

@@ -28,6 +28,7 @@ import torch.distributed as dist
 from . import ops
 from .common import (AdaptiveScheduler, IdentityScheduler, LinearScheduler, DefaultAlgoObserver, DefaultRewardsShaper,
                      create_vec_env, make_summary_writer)
+from .dist_utils import merge_stats_packed, seed_snapshots
 from .model import B200Model
 
 STATS_SYNC_MODES = ('pooled', 'broadcast')
@@ -345,6 +346,7 @@ class A2CAgent:
             self.tc_act = [u8(nt * tb[0]), u8(nt * tb[1]), u8(nt * tb[2])]
             self.tc_dhead, self.tc_delta2, self.tc_delta1 = u8(nt * tb[3]), u8(nt * tb[1]), u8(nt * tb[0])
             self.tc_offs = {k: m.layout[k][0] for k in ('W0', 'b0', 'W1', 'b1', 'W2', 'b2', 'W_head', 'b_head')}
+            self.pack_table = ops.tc_pack_table(m.D, m.units, A, self.tc_offs)
             self.ra = self.ta = self.dA = []
         else:
             self.n_splits = max(1, min(64, mb // 256))
@@ -662,15 +664,14 @@ class A2CAgent:
                                   self.neglogpacs[0, e0:], self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:],
                                   self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.tc_act,
                                   self.tc_dhead, self.loss_partials)
-        ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], m.g_sigma, self.kl_slot)
         npart = ops.tc_mlp_bwd(x, epm, N, m.D, nm, ns, self.wpack, m.units, mb, A, self.tc_act, self.tc_dhead, self.tc_delta2,
                                self.tc_delta1, self.part, P, self.tc_offs)
-        ops.reduce_splits(self.part[0, A:], m.grad[A:], P - A, npart, split_stride=P)
+        ops.reduce_finalize(self.part[0, A:], m.grad[A:], P - A, npart, P, self.loss_partials, nb, A, self.entropy_coef_dev,
+                            self.stats[u], m.g_sigma, self.kl_slot)
         if self.multi_gpu:
             dist.all_reduce(self.comm, op=dist.ReduceOp.SUM)
         ops.adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_state, self.kl_slot, self.opt_cfg, self.stats[u],
-                      self.counters[2:3], n=P)
-        self._repack()
+                      self.counters[2:3], n=P, wpack=self.wpack, pack_table=self.pack_table)
 
     def _update_all(self):
         u = 0
@@ -801,37 +802,17 @@ class A2CAgent:
                     dist.broadcast(t, 0)
                 m.refresh()
             return
-        packed, bases = [], []
-        for name, m in mods:
-            cnt = m.count.to(torch.float64)
-            cur = (cnt, m.running_mean * cnt, (m.running_var + m.running_mean ** 2) * cnt)
-            prev = self._stats_snapshots.get(name)
-            if prev is None:
-                prev = tuple(torch.zeros_like(c) for c in cur)
-            bases.append(prev)
-            packed += [c - p for c, p in zip(cur, prev)]
-        flat = torch.cat([p.reshape(-1) for p in packed])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        off = 0
-        for (name, m), base in zip(mods, bases):
-            d = []
-            for b in base:
-                d.append(flat[off:off + b.numel()].view_as(b))
-                off += b.numel()
-            n, wm, wsq = base[0] + d[0], base[1] + d[1], base[2] + d[2]
-            m.count.copy_(torch.round(n).to(torch.int64))
-            m.running_mean.copy_(wm / n)
-            m.running_var.copy_((wsq / n - m.running_mean ** 2).clamp_(min=1e-8))
+        tensors = [(name, m.count, m.running_mean, m.running_var) for name, m in mods]
+        self._stats_snapshots = merge_stats_packed(tensors, self._stats_snapshots,
+                                                   lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+        for _, m in mods:
             m.refresh()
-            self._stats_snapshots[name] = (n.clone(), wm.clone(), wsq.clone())
 
     def _seed_stats_sync_snapshots(self):
         """a2c_common.py:767-780"""
         if not self.multi_gpu or not self.multi_gpu_sync_stats or self.multi_gpu_sync_stats_mode == 'broadcast':
             return
-        for name, m in self._stats_modules():
-            cnt = m.count.to(torch.float64)
-            self._stats_snapshots[name] = (cnt.clone(), m.running_mean * cnt, (m.running_var + m.running_mean ** 2) * cnt)
+        self._stats_snapshots = seed_snapshots([(n, m.count, m.running_mean, m.running_var) for n, m in self._stats_modules()])
 
     # =============================================================================== train loop
     def train(self):

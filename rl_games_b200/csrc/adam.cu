@@ -5,6 +5,7 @@
 // (L2-resident) flat gradient buffer in the same order, so no inter-CTA reduction or atomics are needed
 // and the result is deterministic; the last CTA to finish advances (step, lr).
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 
@@ -13,10 +14,13 @@ struct OptCfgDev {
     int truncate_grads, adaptive_lr;
 };
 
+struct PackTabDev { int n_seg; int off[4]; int R[4]; int C[4]; unsigned CS[4]; unsigned dst[4]; };
+
 __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ params, const float* __restrict__ grads,
                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n,
                                                         double* state_d, const float* __restrict__ kl_dev, OptCfgDev c,
-                                                        float* __restrict__ stats_out, int* counter) {
+                                                        float* __restrict__ stats_out, int* counter, unsigned char* __restrict__ wpack,
+                                                        PackTabDev tab) {
     __shared__ double sm[32];
     __shared__ int is_last;
     const double lr = state_d[0];
@@ -52,6 +56,21 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
         const float denom = sqrtf(v) / bc2_sqrt + eps;
         p -= step_size * m / denom;
         params[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+        if (wpack) {
+            // refresh the bf16 operand copy the tcgen05 kernels consume (INTERLEAVE weight tile: CS = (Rpad/8)*128, RS = 128)
+#pragma unroll
+            for (int sgi = 0; sgi < 4; ++sgi) {
+                if (sgi < tab.n_seg) {
+                    const int loc = i - tab.off[sgi];
+                    if (loc >= 0 && loc < tab.R[sgi] * tab.C[sgi]) {
+                        const int r = loc / tab.C[sgi], cc = loc - r * tab.C[sgi];
+                        const unsigned o = tab.dst[sgi] + (unsigned)(r & 7) * 16u + (unsigned)(cc >> 3) * tab.CS[sgi] + (unsigned)(r >> 3) * 128u +
+                                           (unsigned)(cc & 7) * 2u;
+                        *reinterpret_cast<__nv_bfloat16*>(wpack + o) = __float2bfloat16_rn(p);
+                    }
+                }
+            }
+        }
     }
     // ---- last CTA advances step / lr (all CTAs have read them by now) ----
     __threadfence();
@@ -80,8 +99,19 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
 
 B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
                                        double* state_d, const float* kl_dev, const b200rl_opt_cfg* cfg_host,
-                                       float* stats_out, int* counter, void* stream) {
+                                       float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host,
+                                       void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !state_d || !cfg_host || !counter || n <= 0) return B200RL_EINVAL;
+    if ((wpack != nullptr) != (tab_host != nullptr)) return B200RL_EINVAL;
+    PackTabDev tab{};
+    if (tab_host) {
+        if (tab_host->n_seg < 0 || tab_host->n_seg > 4) return B200RL_EINVAL;
+        tab.n_seg = tab_host->n_seg;
+        for (int i = 0; i < tab.n_seg; ++i) {
+            tab.off[i] = tab_host->flat_off[i]; tab.R[i] = tab_host->rows[i]; tab.C[i] = tab_host->cols[i];
+            tab.CS[i] = tab_host->cs_bytes[i]; tab.dst[i] = tab_host->dst_off[i];
+        }
+    }
     OptCfgDev c;
     c.beta1 = cfg_host->beta1; c.beta2 = cfg_host->beta2; c.eps = cfg_host->eps; c.weight_decay = cfg_host->weight_decay;
     c.grad_norm = cfg_host->grad_norm; c.kl_threshold = cfg_host->kl_threshold; c.min_lr = cfg_host->min_lr;
@@ -91,7 +121,7 @@ B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float*
     if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
     adam_step_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, state_d, kl_dev, c, stats_out,
-                                                            counter);
+                                                            counter, (unsigned char*)wpack, tab);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }

@@ -147,6 +147,53 @@ __global__ void __launch_bounds__(256) ppo_loss_finalize_kernel(const double* __
     }
 }
 
+// One launch for the two tiny post-backward steps: blocks [0, gridDim-2] sum the split partials of the flat gradient
+// (deterministic, fixed order), the last block finalises the loss partials (stats, d_logstd, KL slot).
+__global__ void __launch_bounds__(256) reduce_finalize_kernel(const float* __restrict__ part, float* __restrict__ out, int n, int n_splits,
+                                                             int64_t split_stride, const double* __restrict__ partials, int n_partials,
+                                                             int A, const float* __restrict__ entropy_coef_dev, float* __restrict__ stats,
+                                                             float* __restrict__ d_logstd, float* __restrict__ kl_out) {
+    if (blockIdx.x + 1 < gridDim.x) {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int k = 0;
+        for (; k + 3 < n_splits; k += 4) {
+            s0 += __ldg(part + (int64_t)k * split_stride + i);
+            s1 += __ldg(part + (int64_t)(k + 1) * split_stride + i);
+            s2 += __ldg(part + (int64_t)(k + 2) * split_stride + i);
+            s3 += __ldg(part + (int64_t)(k + 3) * split_stride + i);
+        }
+        for (; k < n_splits; ++k) s0 += __ldg(part + (int64_t)k * split_stride + i);
+        out[i] = (s0 + s1) + (s2 + s3);
+        return;
+    }
+    __shared__ double sm[256];
+    const int slots = NSC + A;
+    const int slot = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    double s = 0.0;
+    if (slot < slots)
+        for (int p = grp; p < n_partials; p += 4) s += partials[(int64_t)p * (NSC + MAXA) + slot];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    if (grp == 0 && slot < slots) sm[slot] = (sm[slot] + sm[64 + slot]) + (sm[128 + slot] + sm[192 + slot]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        stats[B200RL_STAT_ALOSS] = (float)sm[0];
+        stats[B200RL_STAT_CLOSS] = (float)sm[1];
+        stats[B200RL_STAT_ENTROPY] = (float)sm[2];
+        stats[B200RL_STAT_BLOSS] = (float)sm[3];
+        stats[B200RL_STAT_KL] = (float)sm[4];
+        if (kl_out) *kl_out = (float)sm[4];
+        stats[B200RL_STAT_SUMMASK] = (float)sm[5];
+        stats[B200RL_STAT_CLIPFRAC] = (float)(sm[6] / fmax(sm[5], 1.0));
+    }
+    if (threadIdx.x < A) {
+        const double ec = (double)__ldg(entropy_coef_dev);
+        d_logstd[threadIdx.x] = (float)(sm[NSC + threadIdx.x] - ec * sm[7]);
+    }
+}
+
 // inv_count[i] = 1 / max(sum of mask over minibatch i, 1)   (torch_ext.py:157-170 apply_masks)
 __global__ void __launch_bounds__(256) mask_inv_counts_kernel(const float* __restrict__ mask, int H, int N, int envs_per_mb,
                                                              float* __restrict__ inv_count) {
@@ -201,6 +248,18 @@ B200RL_EXPORT int b200rl_ppo_loss_finalize(const double* partials, int n_partial
                                            float* stats, float* d_logstd, float* kl_out, void* stream) {
     if (!partials || !entropy_coef_dev || !stats || !d_logstd || n_partials <= 0 || A <= 0 || A + 1 > MAXA) return B200RL_EINVAL;
     ppo_loss_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, n_partials, A, entropy_coef_dev, stats, d_logstd, kl_out);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_reduce_finalize(const float* part, float* out, int n, int n_splits, int64_t split_stride,
+                                         const double* partials, int n_partials, int A, const float* entropy_coef_dev,
+                                         float* stats, float* d_logstd, float* kl_out, void* stream) {
+    if (!part || !out || n <= 0 || n_splits <= 0 || !partials || !entropy_coef_dev || !stats || !d_logstd || n_partials <= 0 || A <= 0 ||
+        A + 1 > MAXA)
+        return B200RL_EINVAL;
+    reduce_finalize_kernel<<<(n + 255) / 256 + 1, 256, 0, as_stream(stream)>>>(part, out, n, n_splits, split_stride, partials, n_partials, A,
+                                                                              entropy_coef_dev, stats, d_logstd, kl_out);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }

@@ -732,6 +732,23 @@ B200RL_EXPORT int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int
     return B200RL_OK;
 }
 
+// segments of the packed weight buffer, for the optimiser's fused refresh (b200rl_adam_step_f32)
+B200RL_EXPORT int b200rl_tc_pack_table(int D, int u1, int u2, int u3, int A, int off_W1, int off_W2, int off_W3, int off_Wh,
+                                       b200rl_pack_table* out_host) {
+    if (!out_host) return B200RL_EINVAL;
+    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
+    using N = NetC2;
+    out_host->n_seg = 4;
+    const int offs[4] = {off_W1, off_W2, off_W3, off_Wh};
+    const int rows[4] = {u1, u2, u3, A + 1}, cols[4] = {D, u1, u2, u3};
+    const unsigned cs[4] = {N::W1_CS, N::W2_CS, N::W3_CS, N::WH_CS}, dst[4] = {N::W1_OFF, N::W2_OFF, N::W3_OFF, N::WH_OFF};
+    for (int i = 0; i < 4; ++i) {
+        out_host->flat_off[i] = offs[i]; out_host->rows[i] = rows[i]; out_host->cols[i] = cols[i];
+        out_host->cs_bytes[i] = cs[i]; out_host->dst_off[i] = dst[i];
+    }
+    return B200RL_OK;
+}
+
 B200RL_EXPORT int b200rl_tc_pack_weights(const float* W1, const float* W2, const float* W3, const float* W_head,
                                          int D, int u1, int u2, int u3, int A, void* wpack, void* stream) {
     if (!W1 || !W2 || !W3 || !W_head || !wpack) return B200RL_EINVAL;

@@ -189,6 +189,93 @@ __global__ void __launch_bounds__(256) moments_partial_kernel(
     if (threadIdx.x == 0) { count[0] = count[0] + (int64_t)n_rows_total; *counter = 0; }
 }
 
+// ---- obs moments, vectorised edition (D % 4 == 0): float4 loads, thread <-> fixed 4 columns ----------------------
+// block = RP row-lanes x C4 column-quads (C4 = D/4, RP = 256 / C4 rounded down); grid = (blocks_per_chunk, n_chunks).
+// scratch layout identical to moments_partial_kernel: [n_blocks][2*D] doubles (shifted sum, shifted sum of squares).
+__global__ void __launch_bounds__(256) moments_partial_v4_kernel(
+    const float* __restrict__ x, int D, int rows_per_chunk, int64_t chunk_stride,
+    const double* __restrict__ run_mean, double* __restrict__ scratch, int* counter,
+    double* mean, double* var, int64_t* count, float* mean_f32, float* std_f32, float eps, int n_rows_total) {
+    extern __shared__ double smd[];   // [RP][2*D]
+    const int C4 = D >> 2;
+    const int RP = blockDim.x / C4;
+    const int tid = threadIdx.x;
+    const int rr = tid / C4, c4 = tid - rr * C4;
+    const bool active = rr < RP;
+    const int bpc = gridDim.x;
+    const int rows_per_block = (rows_per_chunk + bpc - 1) / bpc;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, rows_per_chunk);
+    const float4* base = reinterpret_cast<const float4*>(x + ((int64_t)blockIdx.y * chunk_stride) * D);
+    const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const int n_blocks = gridDim.x * gridDim.y;
+    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    if (active) {
+        float sh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sh[j] = (float)run_mean[c4 * 4 + j];
+        int r = r0 + rr;
+        for (; r + 3 * RP < r1; r += 4 * RP) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(base + (int64_t)(r + u * RP) * C4 + c4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double d0 = (double)(v[u].x - sh[0]), d1 = (double)(v[u].y - sh[1]), d2 = (double)(v[u].z - sh[2]), d3 = (double)(v[u].w - sh[3]);
+                s[0] += d0; s[1] += d1; s[2] += d2; s[3] += d3;
+                q[0] += d0 * d0; q[1] += d1 * d1; q[2] += d2 * d2; q[3] += d3 * d3;
+            }
+        }
+        for (; r < r1; r += RP) {
+            const float4 v = __ldg(base + (int64_t)r * C4 + c4);
+            const double d0 = (double)(v.x - sh[0]), d1 = (double)(v.y - sh[1]), d2 = (double)(v.z - sh[2]), d3 = (double)(v.w - sh[3]);
+            s[0] += d0; s[1] += d1; s[2] += d2; s[3] += d3;
+            q[0] += d0 * d0; q[1] += d1 * d1; q[2] += d2 * d2; q[3] += d3 * d3;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { smd[(size_t)rr * 2 * D + c4 * 4 + j] = s[j]; smd[(size_t)rr * 2 * D + D + c4 * 4 + j] = q[j]; }
+    }
+    __syncthreads();
+    for (int j = tid; j < 2 * D; j += blockDim.x) {
+        double a = 0.0;
+        for (int g = 0; g < RP; ++g) a += smd[(size_t)g * 2 * D + j];
+        scratch[(int64_t)blk * 2 * D + j] = a;
+    }
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(counter, 1) == n_blocks - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // final reduction over blocks: 2*D columns x NS slices of blocks, fixed order
+    const int NS = max(1, (int)blockDim.x / (2 * D));
+    __syncthreads();
+    for (int idx = tid; idx < NS * 2 * D; idx += blockDim.x) {
+        const int j = idx % (2 * D), sl = idx / (2 * D);
+        double a = 0.0;
+        for (int b = sl; b < n_blocks; b += NS) a += __ldcg(scratch + (int64_t)b * 2 * D + j);
+        smd[(size_t)sl * 2 * D + j] = a;
+    }
+    __syncthreads();
+    const double n = (double)n_rows_total;
+    const double cnt0 = (double)count[0];
+    for (int col = tid; col < D; col += blockDim.x) {
+        double ss = 0.0, qq = 0.0;
+        for (int g = 0; g < NS; ++g) { ss += smd[(size_t)g * 2 * D + col]; qq += smd[(size_t)g * 2 * D + D + col]; }
+        const double shift = (double)(float)run_mean[col];
+        const double ms = ss / n;
+        const double bm = shift + ms;
+        const double bv = fmax(qq / n - ms * ms, 0.0);
+        double m = mean[col], v = var[col], cf = cnt0;
+        chan_merge(m, v, cf, bm, bv, n);
+        mean[col] = m; var[col] = v;
+        mean_f32[col] = (float)m;
+        std_f32[col] = __fsqrt_rn(__fadd_rn((float)v, eps));
+    }
+    __syncthreads();
+    if (tid == 0) { count[0] = count[0] + (int64_t)n_rows_total; *counter = 0; }
+}
+
 // moments of an already materialised batch (compat path of prepare_dataset when a caller edited batch_dict)
 __global__ void __launch_bounds__(256) batch_moments_kernel(const float* __restrict__ values, const float* __restrict__ returns,
                                                            const float* __restrict__ mask, double* __restrict__ partials, int B) {
@@ -288,6 +375,29 @@ B200RL_EXPORT int b200rl_moments_update_f64(const float* x, int D, int rows_per_
                                             double* scratch, int scratch_blocks, int* counter, void* stream) {
     if (!x || !mean || !var || !count || !mean_f32 || !std_f32 || !scratch || !counter) return B200RL_EINVAL;
     if (D <= 0 || rows_per_chunk <= 0 || n_chunks <= 0) return B200RL_EINVAL;
+    if ((D & 3) == 0 && D <= 512 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((chunk_stride * D) & 3) == 0) {
+        const int C4 = D / 4;
+        const int threads = C4 >= 256 ? 256 : (256 / C4) * C4;
+        const int RP = threads / C4;
+        if (RP >= 1 && threads >= 2 * D / 4) {
+            int bpc2 = (148 + n_chunks - 1) / n_chunks;               // ~1 CTA per SM in total
+            const int max_bpc2 = (rows_per_chunk + 4 * RP - 1) / (4 * RP);
+            if (bpc2 > max_bpc2) bpc2 = max_bpc2;
+            if (bpc2 < 1) bpc2 = 1;
+            while (bpc2 * n_chunks > scratch_blocks && bpc2 > 1) --bpc2;
+            if (bpc2 * n_chunks > scratch_blocks) return B200RL_EINVAL;
+            const int NS = threads / (2 * D) > 1 ? threads / (2 * D) : 1;
+            const size_t smem2 = sizeof(double) * 2 * D * (size_t)(RP > NS ? RP : NS);
+            if (smem2 <= 48 * 1024) {
+                dim3 grid2(bpc2, n_chunks);
+                moments_partial_v4_kernel<<<grid2, threads, smem2, as_stream(stream)>>>(x, D, rows_per_chunk, chunk_stride, mean, scratch,
+                                                                                     counter, mean, var, count, mean_f32, std_f32, eps,
+                                                                                     rows_per_chunk * n_chunks);
+                B200RL_LAUNCH_CHECK();
+                return B200RL_OK;
+            }
+        }
+    }
     int bpc = (148 * 4 + n_chunks - 1) / n_chunks;            // ~4 CTAs per SM in total
     const int max_bpc = (rows_per_chunk + 31) / 32;           // >= 32 rows per block
     if (bpc > max_bpc) bpc = max_bpc;

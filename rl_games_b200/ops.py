@@ -175,10 +175,28 @@ def mask_inv_counts(mask, H, N, envs_per_mb, inv_count):
     check(lib.b200rl_mask_inv_counts_f32(ptr(mask), H, N, envs_per_mb, ptr(inv_count), _stream()), 'mask_inv_counts')
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None):
+class PackTable(ctypes.Structure):
+    _fields_ = [('n_seg', ctypes.c_int), ('flat_off', ctypes.c_int * 4), ('rows', ctypes.c_int * 4), ('cols', ctypes.c_int * 4),
+                ('cs_bytes', ctypes.c_uint32 * 4), ('dst_off', ctypes.c_uint32 * 4)]
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None, wpack=None, pack_table=None):
     check(lib.b200rl_adam_step_f32(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq),
                                    params.numel() if n is None else n, ptr(state_d), ptr(kl_dev), ctypes.addressof(cfg),
-                                   ptr(stats_out), ptr(counter), _stream()), 'adam_step')
+                                   ptr(stats_out), ptr(counter), ptr(wpack),
+                                   None if pack_table is None else ctypes.addressof(pack_table), _stream()), 'adam_step')
+
+
+def reduce_finalize(part, out, n, n_splits, split_stride, partials, n_partials, A, entropy_coef_dev, stats, d_logstd, kl_out=None):
+    check(lib.b200rl_reduce_finalize(ptr(part), ptr(out), n, n_splits, split_stride, ptr(partials), n_partials, A,
+                                     ptr(entropy_coef_dev), ptr(stats), ptr(d_logstd), ptr(kl_out), _stream()), 'reduce_finalize')
+
+
+def tc_pack_table(D, units, A, offs):
+    t = PackTable()
+    check(lib.b200rl_tc_pack_table(D, units[0], units[1], units[2], A, offs['W0'], offs['W1'], offs['W2'], offs['W_head'],
+                                   ctypes.addressof(t)), 'tc_pack_table')
+    return t
 
 
 def policy_head_sample(a_last, W_head, b_head, logstd, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch,
