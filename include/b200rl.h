@@ -187,7 +187,8 @@ int b200rl_loss_partial_stride(void);
  * clip_grad_norm_, optimizer.step) + torch.optim.Adam(eps=1e-8, weight_decay, fused=True)
  * (a2c_continuous.py:44-48) + the adaptive-KL scheduler (schedulers.py:19-33, a2c_common.py:1557-1563)
  * with lr living in DEVICE memory so no .item() sync is needed per minibatch.
- *  state_d: double[2] = {lr, step};  kl_dev: device f32 (already world-averaged), may be NULL.
+ *  state_d: double[4] = {lr, step, beta1^step, beta2^step} (zeros for the last two mean 'fresh');
+ *  kl_dev: device f32 (summed over ranks; scaled by grad_scale inside), may be NULL.
  *  counter: int32[1] zero-initialised once.
  * ------------------------------------------------------------------------------------------- */
 typedef struct b200rl_opt_cfg {

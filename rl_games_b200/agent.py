@@ -363,7 +363,7 @@ class A2CAgent:
         m.g_sigma = m.view('sigma', m.grad)
         m.gW_head, m.gb_head = m.view('W_head', m.grad), m.view('b_head', m.grad)
         self.kl_slot = self.comm[m.num_params:]
-        self.opt_state = torch.tensor([self.last_lr, 0.0], dtype=torch.float64, device=dev)
+        self.opt_state = torch.tensor([self.last_lr, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)   # lr, step, beta1^step, beta2^step
         self.entropy_coef_dev = torch.tensor([float(self.entropy_coef)], dtype=torch.float32, device=dev)
         self.inv_counts = f(self.num_minibatches) if self.mask_autoreset_rows else None
         self.mom_scratch = torch.zeros(1024 * 2 * D, dtype=torch.float64, device=dev)
@@ -749,7 +749,7 @@ class A2CAgent:
         ev[2].record()
         # one D2H read-back per epoch: stats rows + (lr, step) + meter
         self.host_stats.copy_(self.stats, non_blocking=True)
-        self.host_state[0:2].copy_(self.opt_state, non_blocking=True)
+        self.host_state[0:2].copy_(self.opt_state[0:2], non_blocking=True)
         self.host_state[2:10].copy_(self.meter, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self._meter_cache = self.host_state[2:10].numpy().copy()
@@ -966,7 +966,8 @@ class A2CAgent:
         lr, step = self.model.load_optimizer_state_dict(weights['optimizer'])
         if lr is not None:
             self.last_lr = float(lr)
-        self.opt_state.copy_(torch.tensor([self.last_lr, float(step)], dtype=torch.float64))
+        self.opt_state.copy_(torch.tensor([self.last_lr, float(step), 0.9 ** float(step) if step else 0.0, 0.999 ** float(step) if step else 0.0],
+                                          dtype=torch.float64))
         self._lr_synced = self.last_lr
         self.last_mean_rewards = weights.get('last_mean_rewards', -float('inf'))
         if self.vec_env is not None and hasattr(self.vec_env, 'set_env_state'):

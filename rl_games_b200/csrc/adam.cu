@@ -25,21 +25,33 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
     __shared__ int is_last;
     const double lr = state_d[0];
     const double step = state_d[1] + 1.0;
+    // running products beta^step live in the device state (state_d[2], state_d[3]); 0 means "not started" == 1.0
+    const double p1 = (state_d[2] > 0.0 ? state_d[2] : 1.0) * c.beta1;
+    const double p2 = (state_d[3] > 0.0 ? state_d[3] : 1.0) * c.beta2;
     const float gs = (float)c.grad_scale;
-    // ---- global norm (identical in every CTA) ----
+    // ---- global norm (identical in every CTA: same order, fp32 per-thread partials, fp64 block reduction) ----
     double acc[1] = {0.0};
     if (c.truncate_grads || stats_out) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const float g = __ldg(grads + i) * gs;
-            acc[0] += (double)g * (double)g;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const int n4 = ((reinterpret_cast<uintptr_t>(grads) & 15) == 0) ? (n >> 2) : 0;
+        const float4* g4 = reinterpret_cast<const float4*>(grads);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 g = __ldg(g4 + i);
+            a0 = fmaf(g.x * gs, g.x * gs, a0); a1 = fmaf(g.y * gs, g.y * gs, a1);
+            a2 = fmaf(g.z * gs, g.z * gs, a2); a3 = fmaf(g.w * gs, g.w * gs, a3);
         }
+        for (int i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) {
+            const float g = __ldg(grads + i) * gs;
+            a0 = fmaf(g, g, a0);
+        }
+        acc[0] = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
         block_sum_d<1>(acc, sm);
     }
     const float total_norm = (float)sqrt(acc[0]);
     float coef = 1.0f;
     if (c.truncate_grads) coef = fminf((float)c.grad_norm / (total_norm + 1e-6f), 1.0f);
     const float b1 = (float)c.beta1, b2 = (float)c.beta2;
-    const double bc1 = 1.0 - pow(c.beta1, step), bc2 = 1.0 - pow(c.beta2, step);
+    const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
     const float step_size = (float)(lr / bc1);
     const float bc2_sqrt = (float)sqrt(bc2);
     const float eps = (float)c.eps, wd = (float)c.weight_decay;
@@ -90,6 +102,8 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
         }
         state_d[0] = new_lr;
         state_d[1] = step;
+        state_d[2] = p1;
+        state_d[3] = p2;
         if (stats_out) { stats_out[B200RL_STAT_LR] = (float)lr; stats_out[B200RL_STAT_GNORM] = total_norm; }
         *counter = 0;
     }
@@ -117,7 +131,7 @@ B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float*
     c.grad_norm = cfg_host->grad_norm; c.kl_threshold = cfg_host->kl_threshold; c.min_lr = cfg_host->min_lr;
     c.max_lr = cfg_host->max_lr; c.lr_multiplier = cfg_host->lr_multiplier; c.grad_scale = cfg_host->grad_scale;
     c.truncate_grads = cfg_host->truncate_grads; c.adaptive_lr = cfg_host->adaptive_lr;
-    int blocks = (n + 8191) / 8192;
+    int blocks = (n + 2047) / 2048;       // two elements per thread in the update; every CTA re-derives the norm from L2
     if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
     adam_step_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, state_d, kl_dev, c, stats_out,

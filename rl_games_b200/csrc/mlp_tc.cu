@@ -68,6 +68,7 @@ struct Net {
     static constexpr uint32_t PACK_BYTES = WH_OFF + WH_BYTES;
     static constexpr uint32_t X_BYTES = DPAD * 256, A1_BYTES = U1 * 256, A2_BYTES = U2 * 256, A3_BYTES = U3 * 256, DH_BYTES = AP * 256;
     static_assert(U2 == 128, "wgrad tiles assume a 128-wide second hidden layer (M = 128 MMAs)");
+    static_assert(U1 % 128 == 0 && (U1 / 4) % 32 == 0 && (U2 / 4) % 32 == 0, "epilogue column slices are multiples of 32");
     static_assert(U1 % 128 == 0 && U1 <= 256 && U3 <= 128 && U3 % 16 == 0 && DPAD % 16 == 0 && DPAD <= 256 && AP == 16, "unsupported net");
 };
 using NetC2 = Net<64, 256, 128, 64, 16>;
@@ -93,22 +94,46 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(PackArgs a, uint8_t* 
 }
 
 // ---- X tile: fp32 obs rows -> normalise/clamp -> bf16 operand tile ---------------------------------------------
+// sNorm: [2*DPAD] floats in shared memory = (mean, 1/std) per column (identity when normalisation is off).  The bf16
+// rounding of the operand hides the 1-ulp difference between (x-m)/std and (x-m)*(1/std).
+template <class N>
+__device__ __forceinline__ void load_norm_smem(float* sNorm, const float* __restrict__ nm, const float* __restrict__ ns, int D) {
+    for (int c = threadIdx.x; c < N::DPAD; c += blockDim.x) {
+        sNorm[c] = (nm && c < D) ? __ldg(nm + c) : 0.f;
+        sNorm[N::DPAD + c] = (ns && c < D) ? __frcp_rn(__ldg(ns + c)) : 1.f;
+    }
+}
 template <class N>
 __device__ __forceinline__ void stage_x_tile(uint8_t* sX, const float* __restrict__ obs, int64_t row0, int rows_valid, int D,
-                                             const float* __restrict__ nm, const float* __restrict__ ns) {
+                                             const float* __restrict__ sNorm, bool do_norm) {
     constexpr int NCG = N::DPAD / 8;
+    const bool vec = (D & 3) == 0;
     for (int i = threadIdx.x; i < 128 * NCG; i += blockDim.x) {
         const int cg = i / 128, r = i - cg * 128;      // consecutive threads -> consecutive rows (conflict-free 16B stores)
         float f[8];
+        const int c0 = cg * 8;
+        if (r < rows_valid && c0 < D) {
+            const float* src = obs + (row0 + r) * D + c0;
+            if (vec && c0 + 8 <= D) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            } else if (vec && c0 + 4 <= D) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = cg * 8 + j;
-            float v = 0.f;
-            if (r < rows_valid && c < D) {
-                v = __ldg(obs + (row0 + r) * D + c);
-                if (nm) v = fminf(fmaxf(__fdiv_rn(__fsub_rn(v, __ldg(nm + c)), __ldg(ns + c)), -5.0f), 5.0f);
+                for (int j = 4; j < 8; ++j) f[j] = (c0 + j < D) ? __ldg(src + j) : 0.f;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = (c0 + j < D) ? __ldg(src + j) : 0.f;
             }
-            f[j] = v;
+            if (do_norm) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    f[j] = (c0 + j < D) ? fminf(fmaxf((f[j] - sNorm[c0 + j]) * sNorm[N::DPAD + c0 + j], -5.0f), 5.0f) : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.f;
         }
         *reinterpret_cast<uint4*>(sX + tile_off(r, cg, N::ACS, N::ARS)) = pack8_bf16(f);
     }
@@ -142,7 +167,7 @@ struct FwdArgs {
     float* valid_out; int values_only;
 };
 
-constexpr int FWD_THREADS = 256;
+constexpr int FWD_THREADS = 512;   // 16 warps: lane-quarter q = warp & 3 (TMEM lanes 32q..32q+31), column slice h = warp >> 2 (4 slices)
 constexpr int LOSS_SLOTS = LOSS_NSC + 32;   // partial row stride shared with loss.cu (NSC + MAXA)
 
 // ================================================================================================= forward
@@ -156,8 +181,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     float* sBias = reinterpret_cast<float*>(sXA2 + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES));
     float* sB1 = sBias; float* sB2 = sB1 + N::U1; float* sB3 = sB2 + N::U2; float* sBh = sB3 + N::U3;
     float* sSig = sBh + N::AP;                           // sigma[A], logstd[A] (<= 32 floats)
-    float* sRed = sSig + 32;                             // [8 warps][LOSS_SLOTS]
-    double* sAcc = reinterpret_cast<double*>(sRed + 8 * LOSS_SLOTS);     // [LOSS_SLOTS] per-CTA running partial
+    float* sNorm = sSig + 32;                            // [2*DPAD] obs mean, 1/std
+    float* sRed = sNorm + 2 * N::DPAD;                   // [4 warps][LOSS_SLOTS] (only the h == 0 warps run the loss)
+    double* sAcc = reinterpret_cast<double*>(sRed + 4 * LOSS_SLOTS);     // [LOSS_SLOTS] per-CTA running partial
     uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + LOSS_SLOTS);     // [0]=weights, [1..4]=mma stages
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
@@ -177,6 +203,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
     if (tid < p.A) { const float ls = __ldg(p.logstd + tid); sSig[tid] = expf(ls); sSig[p.A + tid] = ls; }
     if (tid < LOSS_SLOTS) sAcc[tid] = 0.0;
+    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
@@ -196,7 +223,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         const int m0 = tile * 128;
         const int rows_valid = min(128, p.M - m0);
         const int64_t arow0 = chunk_row(m0, p.rows_per_chunk, p.chunk_stride);   // tile lies inside one chunk (host-checked)
-        stage_x_tile<N>(sXA2, p.obs, arow0, rows_valid, p.D, p.nm, p.ns);
+        stage_x_tile<N>(sXA2, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr);
         fence_async_smem();
         if (!weights_ready) { mbar_wait(&bars[0], 0); weights_ready = true; }
         __syncthreads();
@@ -215,7 +242,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         {
             uint8_t* g1 = TRAIN ? p.act1 + (size_t)tile * N::A1_BYTES : nullptr;
 #pragma unroll 1
-            for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+            for (int c0 = h * (N::U1 / 4); c0 < (h + 1) * (N::U1 / 4); c0 += 32) {
                 float v[32];
                 tmem_ld32(T1 + lane_base + c0, v);
 #pragma unroll
@@ -241,7 +268,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         {
             uint8_t* g2 = TRAIN ? p.act2 + (size_t)tile * N::A2_BYTES : nullptr;
 #pragma unroll 1
-            for (int c0 = h * (N::U2 / 2); c0 < (h + 1) * (N::U2 / 2); c0 += 32) {
+            for (int c0 = h * (N::U2 / 4); c0 < (h + 1) * (N::U2 / 4); c0 += 32) {
                 float v[32];
                 tmem_ld32(T2 + lane_base + c0, v);
 #pragma unroll
@@ -266,13 +293,20 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         fence_after_sync();
         {
             uint8_t* g3 = TRAIN ? p.act3 + (size_t)tile * N::A3_BYTES : nullptr;
-            // U3/2 = 32 columns per thread
-            const int c0 = h * (N::U3 / 2);
-            float v[32];
-            tmem_ld32(T3 + lane_base + c0, v);
+            // U3/4 = 16 columns per thread
+            static_assert(N::U3 / 4 == 16, "layer-3 epilogue assumes 16 columns per column slice");
+            const int c0 = h * 16;
+            float v[16];
+            tmem_ld16(T3 + lane_base + c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB3[c0 + j]);
-            store_chunks32(v, row, c0, sA3, g3);
+            for (int j = 0; j < 16; ++j) v[j] = elu_fast(v[j] + sB3[c0 + j]);
+#pragma unroll
+            for (int qq = 0; qq < 2; ++qq) {
+                const uint4 u = pack8_bf16(&v[qq * 8]);
+                const uint32_t off = tile_off(row, c0 / 8 + qq, 2048u, 128u);
+                *reinterpret_cast<uint4*>(sA3 + off) = u;
+                if (g3) *reinterpret_cast<uint4*>(g3 + off) = u;
+            }
         }
         fence_async_smem();
         fence_before_sync();
@@ -375,7 +409,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             for (int i = 0; i < LOSS_NSC; ++i) sc[i] = warp_sum(sc[i]);
 #pragma unroll
             for (int j = 0; j < 15; ++j) dls[j] = warp_sum(dls[j]);
-            if (lane == 0) {
+            if (lane == 0 && h == 0) {
 #pragma unroll
                 for (int i = 0; i < LOSS_NSC; ++i) sRed[warp * LOSS_SLOTS + i] = sc[i];
 #pragma unroll
@@ -611,9 +645,13 @@ struct Bwd2Args {
 
 template <class N>
 __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
+    // dW2^T[i][o] = sum_r a1[r][i] d2[r][o]   (two M = 128 halves over i, N = U2)      -> grad_W2[o*U1 + i]
+    // dW1^T[i][o] = sum_r x[r][i]  d1[r][o]   (x tile zero-padded to 128 columns, N = U1) -> grad_W1[o*D + i]
+    // TMEM lanes carry the contiguous `in` index, so the flush stores are coalesced.
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sD2 = smem; uint8_t* sD1 = sD2 + N::A2_BYTES; uint8_t* sA1 = sD1 + N::A1_BYTES; uint8_t* sX = sA1 + N::A1_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + N::X_BYTES);          // [0] tile loads, [1] mma
+    uint8_t* sD2 = smem; uint8_t* sD1 = sD2 + N::A2_BYTES; uint8_t* sA1 = sD1 + N::A1_BYTES; uint8_t* sX = sA1 + N::A1_BYTES;   // sX: 128 cols
+    float* sNorm = reinterpret_cast<float*>(sX + 128 * 256);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + 2 * N::DPAD);          // [0] tile loads, [1] mma
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
@@ -624,11 +662,14 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
+    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
+    for (int i = tid; i < (128 * 256 - (int)N::X_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(sX + N::X_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t TW2 = tmem, TW1 = tmem + 256;     // dW2 [128 x U1=256], dW1 halves [128 x DPAD] at +256, +256+DPAD
+    const uint32_t TW2 = tmem, TW1 = tmem + 256;     // dW2^T halves [128 x U2] at +0, +128 ; dW1^T [128 x U1] at +256
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     float bsum1 = 0.f;
     uint32_t phase = 0;
@@ -643,7 +684,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
             bulk_g2s(sA1, p.act1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
         }
         const int m0 = tile * 128;
-        stage_x_tile<N>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, p.nm, p.ns);
+        stage_x_tile<N>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm, p.nm != nullptr);
         fence_async_smem();
         mbar_wait(&bars[0], phase);
         __syncthreads();
@@ -651,16 +692,16 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
             fence_after_sync();
             const uint32_t acc = first ? 0u : 1u;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)      // dW2[o][i] += sum_r d2[r][o] * a1[r][i]
-                umma_bf16(TW2, make_smem_desc(smem_u32(sD2) + k * 256, 128, N::ACS), make_smem_desc(smem_u32(sA1) + k * 256, 128, N::ACS),
-                          make_idesc_bf16(128, N::U1, 1, 1), (acc || k > 0) ? 1u : 0u);
-#pragma unroll
             for (int hh = 0; hh < N::U1 / 128; ++hh)
 #pragma unroll
-                for (int k = 0; k < 8; ++k)  // dW1[o][i] += sum_r d1[r][o] * x[r][i], o in half hh
-                    umma_bf16(TW1 + hh * N::DPAD, make_smem_desc(smem_u32(sD1) + hh * 16 * N::ACS + k * 256, 128, N::ACS),
-                              make_smem_desc(smem_u32(sX) + k * 256, 128, N::ACS), make_idesc_bf16(128, N::DPAD, 1, 1),
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(TW2 + hh * N::U2, make_smem_desc(smem_u32(sA1) + hh * 16 * N::ACS + k * 256, 128, N::ACS),
+                              make_smem_desc(smem_u32(sD2) + k * 256, 128, N::ACS), make_idesc_bf16(128, N::U2, 1, 1),
                               (acc || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                umma_bf16(TW1, make_smem_desc(smem_u32(sX) + k * 256, 128, N::ACS), make_smem_desc(smem_u32(sD1) + k * 256, 128, N::ACS),
+                          make_idesc_bf16(128, N::U1, 1, 1), (acc || k > 0) ? 1u : 0u);
             umma_commit(&bars[1]);
         }
         if (tid < N::U1) {
@@ -676,24 +717,25 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
     if (!first) {
         mbar_wait(&bars[1], phase ^ 1);
         fence_after_sync();
-        // dW2: TMEM row = out o (128), cols = in i (U1): thread writes cols [128h, 128h+128)
-#pragma unroll 1
-        for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
-            float v[32];
-            tmem_ld32(TW2 + lane_base + c0, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) part[p.off_W2 + (size_t)row * N::U1 + c0 + j] = v[j];   // (P is odd: no 16B alignment)
-        }
-        // dW1 halves: row = out o (hh*128 + row), cols = in i (DPAD, only D valid): each column-half h takes DPAD/2 cols
+        // dW2^T halves: lane = in index i (hh*128 + row), columns = out o: thread takes o in [64h, 64h+64)
 #pragma unroll 1
         for (int hh = 0; hh < N::U1 / 128; ++hh) {
 #pragma unroll 1
-            for (int c0 = h * (N::DPAD / 2); c0 < (h + 1) * (N::DPAD / 2); c0 += 32) {
+            for (int c0 = h * (N::U2 / 2); c0 < (h + 1) * (N::U2 / 2); c0 += 32) {
                 float v[32];
-                tmem_ld32(TW1 + hh * N::DPAD + lane_base + c0, v);
+                tmem_ld32(TW2 + hh * N::U2 + lane_base + c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < p.D) part[p.off_W1 + (size_t)(hh * 128 + row) * p.D + c0 + j] = v[j];
+                for (int j = 0; j < 32; ++j) part[p.off_W2 + (size_t)(c0 + j) * N::U1 + hh * 128 + row] = v[j];
+            }
+        }
+        // dW1^T: lane = in index i = row (< D valid), columns = out o in [128h, 128h+128)
+#pragma unroll 1
+        for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+            float v[32];
+            tmem_ld32(TW1 + lane_base + c0, v);
+            if (row < p.D) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) part[p.off_W1 + (size_t)(c0 + j) * p.D + row] = v[j];
             }
         }
     } else {
@@ -708,12 +750,12 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
 
 template <class N> constexpr size_t fwd_smem() {
     return (size_t)N::PACK_BYTES + N::A1_BYTES + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES) +
-           sizeof(float) * (N::U1 + N::U2 + N::U3 + N::AP + 32 + 8 * LOSS_SLOTS) + sizeof(double) * LOSS_SLOTS + 8 * 8 + 16;
+           sizeof(float) * (N::U1 + N::U2 + N::U3 + N::AP + 32 + 2 * N::DPAD + 4 * LOSS_SLOTS) + sizeof(double) * LOSS_SLOTS + 8 * 8 + 16;
 }
 template <class N> constexpr size_t bwd1_smem() {
     return (size_t)N::WH_BYTES + N::W3_BYTES + N::W2_BYTES + N::DH_BYTES + 128 * 256 + N::A2_BYTES + N::A3_BYTES + N::A2_BYTES + 8 * 8 + 16;
 }
-template <class N> constexpr size_t bwd2_smem() { return (size_t)N::A2_BYTES + 2 * N::A1_BYTES + N::X_BYTES + 4 * 8 + 16; }
+template <class N> constexpr size_t bwd2_smem() { return (size_t)N::A2_BYTES + 2 * N::A1_BYTES + 128 * 256 + sizeof(float) * 2 * N::DPAD + 4 * 8 + 16; }
 
 bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D <= 64 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
 

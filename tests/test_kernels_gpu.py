@@ -317,7 +317,7 @@ def test_adam_step_vs_oracle(ops, truncate, wd):
     opt = O.Adam(params, 3e-4, eps=1e-8, weight_decay=wd)
     sched = O.AdaptiveScheduler(0.008)
     pd = p0.clone().to(DEV); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
-    state = torch.tensor([3e-4, 0.0], dtype=torch.float64, device=DEV)
+    state = torch.tensor([3e-4, 0.0, 0.0, 0.0], dtype=torch.float64, device=DEV)
     counter = torch.zeros(1, dtype=torch.int32, device=DEV)
     cfg = OptCfg(0.9, 0.999, 1e-8, wd, 1.0, 0.008, 1e-6, 1e-2, 1.5, 0.5, int(truncate), 1)
     stats = torch.zeros(16, device=DEV)
