@@ -95,6 +95,14 @@ int b200rl_moments_update_f64(const float* x, int D, int rows_per_chunk, int n_c
                               int64_t chunk_stride, double* mean, double* var, int64_t* count,
                               float* mean_f32, float* std_f32, float eps,
                               double* scratch, int scratch_blocks, int* counter, void* stream);
+/* Observations do not change across mini-epochs, so the (shifted) batch sums of EVERY minibatch are computed once per
+ * epoch in one pass over the arena (x: [H,N,D]); the per-minibatch training-mode update is then only the Chan merge.
+ *  mbmom: double[n_mb][2*D]; mb_shift: float[D] (the running mean at call time); counters: int32[n_mb] zeroed once;
+ *  scratch: double[scratch_blocks*2*D].  Requires D % 4 == 0 (else use b200rl_moments_update_f64 per minibatch). */
+int b200rl_obs_mb_moments_f64(const float* x, int D, int H, int N, int envs_per_mb, const double* run_mean,
+                              double* mbmom, float* mb_shift, double* scratch, int scratch_blocks, int* counters, void* stream);
+int b200rl_obs_stats_merge_f64(const double* mbmom_i, const float* mb_shift, int D, int n_rows, double* mean, double* var,
+                               int64_t* count, float* mean_f32, float* std_f32, float eps, void* stream);
 /* mean_f32 = (float)mean, std_f32 = sqrt((float)var + eps): the fp32 copies the fused kernels consume */
 int b200rl_refresh_norm_f32(const double* mean, const double* var, float* mean_f32, float* std_f32,
                             float eps, int D, void* stream);

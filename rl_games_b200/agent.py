@@ -367,6 +367,10 @@ class A2CAgent:
         self.entropy_coef_dev = torch.tensor([float(self.entropy_coef)], dtype=torch.float32, device=dev)
         self.inv_counts = f(self.num_minibatches) if self.mask_autoreset_rows else None
         self.mom_scratch = torch.zeros(1024 * 2 * D, dtype=torch.float64, device=dev)
+        self.use_mb_moments = self.normalize_input and D % 4 == 0
+        self.mbmom = torch.zeros(self.num_minibatches, 2 * D, dtype=torch.float64, device=dev)
+        self.mb_shift = f(D)
+        self.mb_counters = torch.zeros(self.num_minibatches, dtype=torch.int32, device=dev)
         self.post_scratch = torch.zeros(((N + 255) // 256) * 4, dtype=torch.float64, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
         self.host_stats = torch.zeros(self.n_updates, 16, dtype=torch.float32).pin_memory()
@@ -569,6 +573,10 @@ class A2CAgent:
                           freeze_stats=bool(self.config.get('freeze_critic', False)))
         if self.mask_autoreset_rows:
             ops.mask_inv_counts(self.valid, self.horizon_length, self.num_actors, self.envs_per_mb, self.inv_counts)
+        if self.use_mb_moments:
+            # obs are fixed for the whole update phase: batch sums of every minibatch in ONE pass over the arena
+            ops.obs_mb_moments(self.obses, m.D, self.horizon_length, self.num_actors, self.envs_per_mb,
+                               m.running_mean_std.running_mean, self.mbmom, self.mb_shift, self.mom_scratch, self.mb_counters)
 
     def play_steps(self, noise=None):
         """Public mirror of A2CBase.play_steps: runs the rollout + GAE and returns the reference's batch_dict
@@ -618,8 +626,12 @@ class A2CAgent:
         L = len(m.units)
         if self.normalize_input:
             rms = m.running_mean_std
-            ops.moments_update(x, m.D, epm, H, N, rms.running_mean, rms.running_var, rms.count, rms.mean_f32, rms.std_f32,
-                               self.mom_scratch, self.counters[1:2])
+            if self.use_mb_moments:
+                ops.obs_stats_merge(self.mbmom[i], self.mb_shift, m.D, mb, rms.running_mean, rms.running_var, rms.count,
+                                    rms.mean_f32, rms.std_f32)
+            else:
+                ops.moments_update(x, m.D, epm, H, N, rms.running_mean, rms.running_var, rms.count, rms.mean_f32, rms.std_f32,
+                                   self.mom_scratch, self.counters[1:2])
         if self.use_tc:
             self._minibatch_update_tc(i, u, x, e0)
             return

@@ -195,8 +195,15 @@ __global__ void __launch_bounds__(256) moments_partial_kernel(
 __global__ void __launch_bounds__(256) moments_partial_v4_kernel(
     const float* __restrict__ x, int D, int rows_per_chunk, int64_t chunk_stride,
     const double* __restrict__ run_mean, double* __restrict__ scratch, int* counter,
-    double* mean, double* var, int64_t* count, float* mean_f32, float* std_f32, float eps, int n_rows_total) {
+    double* mean, double* var, int64_t* count, float* mean_f32, float* std_f32, float eps, int n_rows_total,
+    int mb_rows, double* __restrict__ mbmom, float* __restrict__ mb_shift) {
+    // per-minibatch mode (mbmom != nullptr): blockIdx.z = minibatch index; this launch only produces the shifted batch
+    // sums of every minibatch (obs do not change across mini-epochs, so this runs ONCE per epoch); the Chan merge into the
+    // running state happens per minibatch in obs_stats_merge_kernel.
     extern __shared__ double smd[];   // [RP][2*D]
+    x += (int64_t)blockIdx.z * mb_rows * D;
+    scratch += (int64_t)blockIdx.z * gridDim.x * gridDim.y * 2 * D;
+    counter += blockIdx.z;
     const int C4 = D >> 2;
     const int RP = blockDim.x / C4;
     const int tid = threadIdx.x;
@@ -257,6 +264,18 @@ __global__ void __launch_bounds__(256) moments_partial_v4_kernel(
         smd[(size_t)sl * 2 * D + j] = a;
     }
     __syncthreads();
+    if (mbmom) {
+        for (int j = tid; j < 2 * D; j += blockDim.x) {
+            double a = 0.0;
+            for (int g = 0; g < NS; ++g) a += smd[(size_t)g * 2 * D + j];
+            mbmom[(int64_t)blockIdx.z * 2 * D + j] = a;
+        }
+        if (blockIdx.z == 0)
+            for (int col = tid; col < D; col += blockDim.x) mb_shift[col] = (float)run_mean[col];
+        __syncthreads();
+        if (tid == 0) *counter = 0;
+        return;
+    }
     const double n = (double)n_rows_total;
     const double cnt0 = (double)count[0];
     for (int col = tid; col < D; col += blockDim.x) {
@@ -296,6 +315,25 @@ __global__ void __launch_bounds__(256) batch_moments_kernel(const float* __restr
         for (int i = 0; i < 7; ++i) p[i] = acc[i];
         p[7] = 0.0;
     }
+}
+
+// per-minibatch Chan merge of precomputed (shifted) batch sums into the running obs statistics
+__global__ void obs_stats_merge_kernel(const double* __restrict__ mbmom, const float* __restrict__ mb_shift, int D, int n_rows,
+                                       double* mean, double* var, int64_t* count, float* mean_f32, float* std_f32, float eps) {
+    const double n = (double)n_rows;
+    const double cnt0 = (double)count[0];
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+        const double ms = mbmom[col] / n;
+        const double bm = (double)mb_shift[col] + ms;
+        const double bv = fmax(mbmom[D + col] / n - ms * ms, 0.0);
+        double m = mean[col], v = var[col], cf = cnt0;
+        chan_merge(m, v, cf, bm, bv, n);
+        mean[col] = m; var[col] = v;
+        mean_f32[col] = (float)m;
+        std_f32[col] = __fsqrt_rn(__fadd_rn((float)v, eps));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count[0] = count[0] + (int64_t)n_rows;
 }
 
 __global__ void refresh_f32_kernel(const double* mean, const double* var, float* mean_f32, float* std_f32, float eps, int D) {
@@ -380,7 +418,7 @@ B200RL_EXPORT int b200rl_moments_update_f64(const float* x, int D, int rows_per_
         const int threads = C4 >= 256 ? 256 : (256 / C4) * C4;
         const int RP = threads / C4;
         if (RP >= 1 && threads >= 2 * D / 4) {
-            int bpc2 = (148 + n_chunks - 1) / n_chunks;               // ~1 CTA per SM in total
+            int bpc2 = 148 / n_chunks;                                // <= 1 CTA per SM in total (single wave)
             const int max_bpc2 = (rows_per_chunk + 4 * RP - 1) / (4 * RP);
             if (bpc2 > max_bpc2) bpc2 = max_bpc2;
             if (bpc2 < 1) bpc2 = 1;
@@ -392,7 +430,7 @@ B200RL_EXPORT int b200rl_moments_update_f64(const float* x, int D, int rows_per_
                 dim3 grid2(bpc2, n_chunks);
                 moments_partial_v4_kernel<<<grid2, threads, smem2, as_stream(stream)>>>(x, D, rows_per_chunk, chunk_stride, mean, scratch,
                                                                                      counter, mean, var, count, mean_f32, std_f32, eps,
-                                                                                     rows_per_chunk * n_chunks);
+                                                                                     rows_per_chunk * n_chunks, 0, nullptr, nullptr);
                 B200RL_LAUNCH_CHECK();
                 return B200RL_OK;
             }
@@ -411,6 +449,42 @@ B200RL_EXPORT int b200rl_moments_update_f64(const float* x, int D, int rows_per_
     moments_partial_kernel<<<grid, 256, smem, as_stream(stream)>>>(x, D, rows_per_chunk, chunk_stride, mean, scratch, counter,
                                                                    mean, var, count, mean_f32, std_f32, eps,
                                                                    rows_per_chunk * n_chunks);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_obs_mb_moments_f64(const float* x, int D, int H, int N, int envs_per_mb, const double* run_mean,
+                                            double* mbmom, float* mb_shift, double* scratch, int scratch_blocks, int* counters,
+                                            void* stream) {
+    if (!x || !run_mean || !mbmom || !mb_shift || !scratch || !counters || D <= 0 || H <= 0 || N <= 0 || envs_per_mb <= 0 ||
+        N % envs_per_mb != 0)
+        return B200RL_EINVAL;
+    if ((D & 3) != 0 || D > 512 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) return B200RL_EUNSUPPORTED;
+    const int n_mb = N / envs_per_mb;
+    const int C4 = D / 4;
+    const int threads = C4 >= 256 ? 256 : (256 / C4) * C4;
+    const int RP = threads / C4;
+    int bpc = (148 * 2) / (H * n_mb);
+    const int max_bpc = (envs_per_mb + 4 * RP - 1) / (4 * RP);
+    if (bpc > max_bpc) bpc = max_bpc;
+    if (bpc < 1) bpc = 1;
+    while ((int64_t)bpc * H * n_mb > scratch_blocks && bpc > 1) --bpc;
+    if ((int64_t)bpc * H * n_mb > scratch_blocks) return B200RL_EINVAL;
+    const int NS = threads / (2 * D) > 1 ? threads / (2 * D) : 1;
+    const size_t smem = sizeof(double) * 2 * D * (size_t)(RP > NS ? RP : NS);
+    if (smem > 48 * 1024) return B200RL_EUNSUPPORTED;
+    dim3 grid(bpc, H, n_mb);
+    moments_partial_v4_kernel<<<grid, threads, smem, as_stream(stream)>>>(x, D, envs_per_mb, (int64_t)N, run_mean, scratch, counters, nullptr,
+                                                                         nullptr, nullptr, nullptr, nullptr, 0.f, envs_per_mb * H,
+                                                                         envs_per_mb, mbmom, mb_shift);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_obs_stats_merge_f64(const double* mbmom_i, const float* mb_shift, int D, int n_rows, double* mean, double* var,
+                                             int64_t* count, float* mean_f32, float* std_f32, float eps, void* stream) {
+    if (!mbmom_i || !mb_shift || !mean || !var || !count || !mean_f32 || !std_f32 || D <= 0 || n_rows <= 0) return B200RL_EINVAL;
+    obs_stats_merge_kernel<<<1, 128, 0, as_stream(stream)>>>(mbmom_i, mb_shift, D, n_rows, mean, var, count, mean_f32, std_f32, eps);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }

@@ -102,6 +102,16 @@ def moments_update(x, D, rows_per_chunk, n_chunks, chunk_stride, mean, var, coun
                                         scratch.numel() // (2 * D), ptr(counter), _stream()), 'moments_update')
 
 
+def obs_mb_moments(x, D, H, N, envs_per_mb, run_mean, mbmom, mb_shift, scratch, counters):
+    check(lib.b200rl_obs_mb_moments_f64(ptr(x), D, H, N, envs_per_mb, ptr(run_mean), ptr(mbmom), ptr(mb_shift), ptr(scratch),
+                                        scratch.numel() // (2 * D), ptr(counters), _stream()), 'obs_mb_moments')
+
+
+def obs_stats_merge(mbmom_i, mb_shift, D, n_rows, mean, var, count, mean_f32, std_f32, eps=1e-5):
+    check(lib.b200rl_obs_stats_merge_f64(ptr(mbmom_i), ptr(mb_shift), D, n_rows, ptr(mean), ptr(var), ptr(count), ptr(mean_f32),
+                                         ptr(std_f32), eps, _stream()), 'obs_stats_merge')
+
+
 def refresh_norm(mean, var, mean_f32, std_f32, eps=1e-5):
     check(lib.b200rl_refresh_norm_f32(ptr(mean), ptr(var), ptr(mean_f32), ptr(std_f32), eps, mean.numel(), _stream()),
           'refresh_norm')

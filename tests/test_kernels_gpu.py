@@ -168,6 +168,36 @@ def test_moments_update_vs_oracle(ops, D, rpc, nch):
     torch.testing.assert_close(sf.cpu(), torch.sqrt(rms.running_var.float() + 1e-5), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize('D', [60, 256, 8])
+def test_obs_mb_moments_then_merge_vs_oracle(ops, D):
+    """once-per-epoch batch sums of every minibatch + per-minibatch Chan merge == sequential training-mode updates"""
+    g = torch.Generator().manual_seed(D + 1)
+    H, N, epm = 4, 192, 64
+    x = torch.randn(H, N, D, generator=g) * 2.0 + torch.arange(D).float() * 0.05
+    rms = O.RunningMeanStd((D,))
+    rms.load({'running_mean': torch.randn(D, generator=g).double(), 'running_var': torch.rand(D, generator=g).double() + 0.5,
+              'count': torch.tensor(500)})
+    mean = rms.running_mean.clone().to(DEV); var = rms.running_var.clone().to(DEV)
+    cnt = torch.tensor([500], dtype=torch.int64, device=DEV)
+    mf, sf = torch.empty(D, device=DEV), torch.empty(D, device=DEV)
+    n_mb = N // epm
+    mbmom = torch.zeros(n_mb, 2 * D, dtype=torch.float64, device=DEV); shift = torch.empty(D, device=DEV)
+    scratch = torch.zeros(1024 * 2 * D, dtype=torch.float64, device=DEV); counters = torch.zeros(n_mb, dtype=torch.int32, device=DEV)
+    xd = x.to(DEV)
+    for rep in range(2):      # two "mini-epochs" reuse the same precomputed sums
+        if rep == 0:
+            ops.obs_mb_moments(xd, D, H, N, epm, mean, mbmom, shift, scratch, counters)
+            assert int(counters.sum()) == 0
+        for i in range(n_mb):
+            rms.train()
+            rms(x[:, i * epm:(i + 1) * epm].reshape(-1, D))
+            ops.obs_stats_merge(mbmom[i], shift, D, H * epm, mean, var, cnt, mf, sf)
+    assert int(cnt) == int(rms.count)
+    torch.testing.assert_close(mean.cpu(), rms.running_mean, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(var.cpu(), rms.running_var, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(sf.cpu(), torch.sqrt(rms.running_var.float() + 1e-5), rtol=1e-5, atol=1e-6)
+
+
 def test_normalize_bitexact(ops):
     g = load('math.pt')['rms']
     mean, var = g['state']['running_mean'].to(DEV), g['state']['running_var'].to(DEV)
