@@ -277,6 +277,7 @@ def b200_arm(args, w):
     agent = build_agent(w, device, 'b200_synthetic', multi, graph=not args.no_graph, mixed_precision=not args.fp32)
     if multi:
         dist.broadcast(agent.model.flat, 0)
+        agent._repack()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     W = max(3, args.warmup)
     timed_epochs(agent, W, flush, world)
@@ -327,8 +328,14 @@ def b200_arm(args, w):
                                               'oracle/ppo_oracle.py on the host cores'}
         print(json.dumps(line), file=_STDOUT, flush=True)
     if multi:
+        # drop captured graphs (they hold NCCL kernels) before tearing the communicator down; NCCL teardown at interpreter
+        # exit can hang with captured collectives alive, so leave with a hard exit once everything is flushed
+        agent._graph_update = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stderr.flush()
+        _STDOUT.flush()
+        os._exit(0)
 
 
 def e2e_leg(w, device, args):

@@ -286,6 +286,8 @@ class A2CAgent:
         self.dataset = _Dataset(self)
         self.has_value_loss = True
         self.use_cuda_graph = bool(config.get('b200_cuda_graph', True))
+        # NCCL all-reduces are stream-ordered and graph-capturable; opt-out knob for debugging
+        self.graph_multi_gpu = bool(config.get('b200_cuda_graph_multi_gpu', True))
         self.rng_seed = int(config.get('b200_rng_seed', params.get('seed', 0) or 0)) + 7919 * self.global_rank
         self._stats_snapshots = {}
         self._graph_update = None
@@ -695,7 +697,7 @@ class A2CAgent:
     def _run_update(self):
         """Eager the first time (module loading, attribute setup); from the second epoch on the whole
         mini_epochs x num_minibatches sequence replays as ONE CUDA graph (capture executes nothing)."""
-        if not self.use_cuda_graph or self.multi_gpu:
+        if not self.use_cuda_graph or (self.multi_gpu and not self.graph_multi_gpu):
             self._update_all()
             return
         if not getattr(self, '_update_warm', False):
