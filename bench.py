@@ -303,7 +303,7 @@ def b200_arm(args, w):
             'vs_baseline': None, 'dtype': 'f32' if args.fp32 else 'bf16', 'data': 'synthetic',
             'config': workload_config(args.workload, w, 'b200_synthetic (on-GPU Philox env, one kernel per step)'),
             'clocks': clocks, 'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
-            'cuda_graph': bool(agent._graph_update is not None), 'kernels': kernels[:12]}
+            'cuda_graph': ('whole-epoch' if agent._graph_epoch is not None else ('update-phase' if agent._graph_update is not None else 'none')), 'kernels': kernels[:12]}
     if rank == 0:
         # dominant kernel family of the step -> roofline
         line['roofline_gae'] = gae_roofline(w, peaks)
@@ -330,7 +330,7 @@ def b200_arm(args, w):
     if multi:
         # drop captured graphs (they hold NCCL kernels) before tearing the communicator down; NCCL teardown at interpreter
         # exit can hang with captured collectives alive, so leave with a hard exit once everything is flushed
-        agent._graph_update = None
+        agent._graph_update = agent._graph_epoch = None
         torch.cuda.synchronize()
         dist.barrier()
         sys.stderr.flush()

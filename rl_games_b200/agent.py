@@ -403,6 +403,7 @@ class A2CAgent:
         self.shaper_cfg = ops.ShaperCfg(float(rs.scale_value), float(rs.shift_value), float(rs.min_val), float(rs.max_val),
                                         float(self.gamma), int(bool(rs.log_val)), int(bool(self.value_bootstrap)))
         self._graph_update = None
+        self._graph_epoch = None
 
     def _meter_host(self):
         if self._meter_cache is None:
@@ -749,16 +750,35 @@ class A2CAgent:
             self.vec_env.set_train_info(self.frame, self)
         ev = self._events
         self.set_eval()
+        if self._lr_dirty():
+            self.opt_state[0:1].fill_(self.last_lr)
+        whole = noise is None and self._whole_epoch_graph_ok()
         ev[0].record()
-        step_time = self._rollout(noise)
-        self._gae_and_prepare()
-        ev[1].record()
+        if whole and getattr(self, '_epoch_warm', False):
+            # rollout + GAE + prepare + every minibatch update as ONE graph launch (env kernels included)
+            if self._graph_epoch is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._rollout(None)
+                    self._gae_and_prepare()
+                    self._update_all()
+                self._graph_epoch = g
+            self._graph_epoch.replay()
+            self._meter_cache = None
+            step_time = 0.0
+            ev[1].record()
+            split_known = False
+        else:
+            step_time = self._rollout(noise)
+            self._gae_and_prepare()
+            ev[1].record()
+            self.set_train()
+            self._run_update()
+            self._epoch_warm = True
+            split_known = True
         self.set_train()
         self.curr_frames = self.batch_size
         self.algo_observer.after_steps()
-        if self._lr_dirty():
-            self.opt_state[0:1].fill_(self.last_lr)
-        self._run_update()
         self.sync_running_stats()
         ev[2].record()
         # one D2H read-back per epoch: stats rows + (lr, step) + meter
@@ -778,8 +798,14 @@ class A2CAgent:
             self.entropy_coef_dev.fill_(float(self.entropy_coef))
         self.last_lr = new_lr
         self._lr_synced = new_lr
-        play_time = ev[0].elapsed_time(ev[1]) * 1e-3
-        update_time = ev[1].elapsed_time(ev[2]) * 1e-3
+        if split_known:
+            play_time = ev[0].elapsed_time(ev[1]) * 1e-3
+            update_time = ev[1].elapsed_time(ev[2]) * 1e-3
+            self._play_frac = play_time / max(play_time + update_time, 1e-12)
+        else:   # whole-epoch graph: one launch, split by the ratio measured on the last eager epoch
+            tot = ev[0].elapsed_time(ev[2]) * 1e-3
+            play_time = tot * getattr(self, '_play_frac', 0.15)
+            update_time = tot - play_time
         total_time = play_time + update_time
         a_losses = [st[u, 0] for u in range(self.n_updates)]
         c_losses = [st[u, 1] for u in range(self.n_updates)]
@@ -789,6 +815,14 @@ class A2CAgent:
         kls = [st[e * nmb:(e + 1) * nmb, 4].mean() for e in range(self.mini_epochs_num)]
         self.last_stats = st
         return step_time, play_time, update_time, total_time, a_losses, c_losses, b_losses, entropies, kls, self.last_lr, 1.0
+
+    def _whole_epoch_graph_ok(self):
+        """The env step is part of the captured graph only if the env says its step is a pure stream-ordered sequence on
+        static buffers (`cuda_graph_capturable`), and nothing in the rollout needs the host (done indices for observers)."""
+        return (self.use_cuda_graph and self.config.get('b200_cuda_graph_rollout', True) and self.is_tensor_obses
+                and getattr(self.vec_env, 'cuda_graph_capturable', False)
+                and not getattr(self.algo_observer, 'wants_done_indices', True)
+                and (not self.multi_gpu or self.graph_multi_gpu))
 
     def _lr_dirty(self):
         return getattr(self, '_lr_synced', None) != self.last_lr

@@ -220,7 +220,7 @@ def test_synthetic_env_training_runs_and_graph_replay_is_consistent():
     for _ in range(4):
         a.epoch_num += 1; b.epoch_num += 1
         a.train_epoch(); b.train_epoch()
-    assert a._graph_update is not None and b._graph_update is None
+    assert (a._graph_epoch is not None or a._graph_update is not None) and b._graph_update is None and b._graph_epoch is None
     assert torch.equal(a.model.flat, b.model.flat)
     assert a.last_lr == b.last_lr
     assert torch.isfinite(a.model.flat).all()

@@ -43,8 +43,8 @@ def main():
         out['graph' if graph else 'eager'] = {'identical_across_ranks': bool(same), 'obs_count': [int(c) for c in cnts],
                                               'ms_per_epoch': [round(t, 3) for t in ts], 'lr': agent.last_lr,
                                               'finite': bool(torch.isfinite(agent.model.flat).all()),
-                                              'graph_captured': agent._graph_update is not None}
-        agent._graph_update = None
+                                              'graph_captured': (agent._graph_update is not None) or (agent._graph_epoch is not None)}
+        agent._graph_update = agent._graph_epoch = None
         del agent
         torch.cuda.synchronize()
     if rank == 0:
