@@ -27,8 +27,8 @@ __global__ void __launch_bounds__(LT) ppo_head_loss_kernel(
     float* tile = smf;                               // [LT][Hl+1]
     float* sW = tile + LT * (Hl + 1);                // [AH][Hl]
     float* sB = sW + AH * Hl;                        // [AH]
-    float* sSig = sB + AH;                           // [A] sigma, [A] logstd
-    float* sRed = sSig + 2 * A;                      // [LT/32][NSC + A]
+    float* sSig = sB + AH;                           // sigma, logstd, 1/sigma, log(sigma): 4*A
+    float* sRed = sSig + 4 * A;                      // [LT/32][NSC + A]
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * LT;
     const int rows = min(LT, M - m0);
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(LT) ppo_head_loss_kernel(
     }
     for (int i = tid; i < AH * Hl; i += LT) sW[i] = __ldg(Wh + i);
     if (tid < AH) sB[tid] = __ldg(bh + tid);
-    if (tid < A) { const float ls = __ldg(logstd + tid); sSig[tid] = expf(ls); sSig[A + tid] = ls; }
+    if (tid < A) loss_fill_sigma(sSig, logstd, A, tid);
     __syncthreads();
 
     float sc[NSC];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(LT) ppo_head_loss_kernel(
         const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
         const float inv_cnt = inv_count_dev ? __ldg(inv_count_dev) : (1.0f / (float)M);
         LossArena la{actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask};
-        const float nlp = ppo_sample_loss<MAXA>(head, A, sSig, la, ar, inv_cnt, cfg, dh, dls, sc);
+        const float nlp = ppo_sample_loss<MAXA, false>(head, A, sSig, la, ar, inv_cnt, cfg, dh, dls, sc);
         if (mu_out) {
 #pragma unroll
             for (int j = 0; j < MAXA - 1; ++j)
@@ -227,7 +227,7 @@ B200RL_EXPORT int b200rl_ppo_head_loss_f32(const float* a_last, int Hl, const fl
     const int blocks = (M + LT - 1) / LT;
     if (n_blocks_out_host) *n_blocks_out_host = blocks;
     if (blocks > max_partials) return B200RL_EINVAL;
-    const size_t smem = sizeof(float) * ((size_t)LT * (Hl + 1) + (size_t)(A + 1) * Hl + (A + 1) + 2 * A + (LT / 32) * (NSC + A));
+    const size_t smem = sizeof(float) * ((size_t)LT * (Hl + 1) + (size_t)(A + 1) * Hl + (A + 1) + 4 * A + (LT / 32) * (NSC + A));
     if (smem > 200 * 1024) return B200RL_EUNSUPPORTED;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(ppo_head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -237,6 +237,7 @@ B200RL_EXPORT int b200rl_ppo_head_loss_f32(const float* a_last, int Hl, const fl
     c.e_clip = cfg_host->e_clip; c.critic_coef = cfg_host->critic_coef; c.bounds_coef = cfg_host->bounds_loss_coef;
     c.has_bounds = cfg_host->has_bounds_loss; c.bound_type = cfg_host->bound_loss_type; c.clip_value = cfg_host->clip_value;
     c.smooth = cfg_host->use_smooth_clamp; c.ppo = cfg_host->ppo;
+    c.log_lo = log1pf(-cfg_host->e_clip); c.log_hi = log1pf(cfg_host->e_clip);
     ppo_head_loss_kernel<<<blocks, LT, smem, as_stream(stream)>>>(
         a_last, Hl, W_head, b_head, logstd, actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask,
         rows_per_chunk, chunk_stride, M, A, c, inv_count_dev, d_head, d_alast, act_last, mu_out, value_out, neglogp_out, partials);

@@ -8,7 +8,15 @@
 struct LossCfgDev {
     float e_clip, critic_coef, bounds_coef;
     int has_bounds, bound_type, clip_value, smooth, ppo;
+    float log_lo, log_hi;    // log(1 - e_clip), log(1 + e_clip) for the clip-fraction diagnostic (filled on the host)
 };
+
+// fill sSig[0..4A): sigma, logstd, 1/sigma, log(sigma)  (one thread per action); returns nothing
+__device__ __forceinline__ void loss_fill_sigma(float* sSig, const float* __restrict__ logstd, int A, int j) {
+    const float ls = __ldg(logstd + j);
+    const float sg = expf(ls);
+    sSig[j] = sg; sSig[A + j] = ls; sSig[2 * A + j] = 1.0f / sg; sSig[3 * A + j] = logf(sg);
+}
 
 constexpr int LOSS_NSC = 8;   // scalar partial slots: w*a_loss, w*c_loss, w*entropy, w*b_loss, w*kl, mask, mask*clipped, w
 
@@ -17,11 +25,13 @@ struct LossArena {
     const float* old_values_n; const float* returns_n; const float* old_neglogp; const float* advs_n; const float* mask;
 };
 
-// head[0] = value, head[1..A] = mu.  sSig[0..A) = sigma, sSig[A..2A) = logstd (shared memory).
+// head[0] = value, head[1..A] = mu.  sSig (shared memory): sigma[A], logstd[A], 1/sigma[A], log(sigma)[A].
+// FAST (bf16 tensor-core path): divisions -> reciprocal multiplies, exp/log -> ex2/lg2 approximations (the operands were
+// already rounded to bf16 upstream); !FAST (fp32 path): IEEE divisions and full-precision expf/logf for tight parity.
 // ar = arena row.  Outputs: dh[0] = dL/dvalue, dh[1+j] = dL/dmu_j, dls[j] = per-sample dL/dlogstd_j (without the
 // entropy term), sc[] = weighted scalar contributions; writes the new mu / sigma over the old ones
 // (datasets.py:33-43) and returns the sample's neglogp.
-template <int MAXA>
+template <int MAXA, bool FAST>
 __device__ __forceinline__ float ppo_sample_loss(const float (&head)[MAXA], int A, const float* __restrict__ sSig,
                                                  const LossArena& ar_, int64_t ar, float inv_cnt, const LossCfgDev& cfg,
                                                  float (&dh)[MAXA], float (&dls)[MAXA], float (&sc)[LOSS_NSC]) {
@@ -38,13 +48,14 @@ __device__ __forceinline__ float ppo_sample_loss(const float (&head)[MAXA], int 
             const float mu = head[1 + j], sg = sSig[j], ls = sSig[A + j];
             const float act = __ldg(ar_.actions + ar * A + j);
             const float omu = ar_.old_mu[ar * A + j], osg = ar_.old_sigma[ar * A + j];
-            z[j] = (act - mu) / sg;
+            z[j] = FAST ? (act - mu) * sSig[2 * A + j] : (act - mu) / sg;
             sumz2 += z[j] * z[j];
             sumls += ls;
-            ent += 0.5f + 0.9189385332046727f + logf(sg);           // 0.5 + 0.5*log(2*pi) + log(sigma)
-            const float c1 = logf(osg / sg + 1e-5f);
+            ent += 0.5f + 0.9189385332046727f + sSig[3 * A + j];     // 0.5 + 0.5*log(2*pi) + log(sigma)
+            const float c1 = FAST ? __logf(osg * sSig[2 * A + j] + 1e-5f) : logf(osg / sg + 1e-5f);
             const float dm = omu - mu;
-            const float c2 = (sg * sg + dm * dm) / (2.0f * (osg * osg + 1e-5f));
+            const float c2 = FAST ? (sg * sg + dm * dm) * __frcp_rn(2.0f * (osg * osg + 1e-5f))
+                                  : (sg * sg + dm * dm) / (2.0f * (osg * osg + 1e-5f));
             kl += c1 + c2 - 0.5f;
             if (cfg.has_bounds) {
                 if (cfg.bound_type == 1) {
@@ -63,11 +74,12 @@ __device__ __forceinline__ float ppo_sample_loss(const float (&head)[MAXA], int 
     // ---- actor loss + d/dnlp ----
     float a_loss, g_a;
     if (cfg.ppo) {
-        const float ratio = expf(old_nlp - nlp);
+        const float ratio = FAST ? __expf(old_nlp - nlp) : expf(old_nlp - nlp);
         const float mi = 1.0f - cfg.e_clip, mx = 1.0f + cfg.e_clip;
         float clamped, dcl;
         if (cfg.smooth) {
-            const float s = 1.0f / (1.0f + expf((-(ratio - mi) / (mx - mi) + 0.5f) * 4.0f));
+            const float s = FAST ? __frcp_rn(1.0f + __expf((-(ratio - mi) * __frcp_rn(mx - mi) + 0.5f) * 4.0f))
+                                 : 1.0f / (1.0f + expf((-(ratio - mi) / (mx - mi) + 0.5f) * 4.0f));
             clamped = s * (mx - mi) + mi;
             dcl = 4.0f * s * (1.0f - s);
         } else {
@@ -99,7 +111,7 @@ __device__ __forceinline__ float ppo_sample_loss(const float (&head)[MAXA], int 
         dc = -2.0f * e1;
     }
     const float lr_ = old_nlp - nlp;
-    const float clipped = (lr_ < log1pf(-cfg.e_clip) || lr_ > log1pf(cfg.e_clip)) ? 1.f : 0.f;
+    const float clipped = (lr_ < cfg.log_lo || lr_ > cfg.log_hi) ? 1.f : 0.f;
     // ---- gradients at the heads ----
     dh[0] = w * 0.5f * cfg.critic_coef * dc;
 #pragma unroll
@@ -111,7 +123,7 @@ __device__ __forceinline__ float ppo_sample_loss(const float (&head)[MAXA], int 
                 if (cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
                 else if (cfg.bound_type == 2) db = 2.0f * mu;
             }
-            dh[1 + j] = w * (g_a * (-(z[j] / sg)) + cfg.bounds_coef * db);
+            dh[1 + j] = w * (g_a * (FAST ? -(z[j] * sSig[2 * A + j]) : -(z[j] / sg)) + cfg.bounds_coef * db);
             dls[j] = w * g_a * (1.0f - z[j] * z[j]);
             ar_.old_mu[ar * A + j] = mu;          // new mu/sigma overwrite the old ones (datasets.py:33-43)
             ar_.old_sigma[ar * A + j] = sg;

@@ -22,6 +22,8 @@ namespace {
 
 using namespace tc;
 
+constexpr int FWD_THREADS = 512;   // 16 warps: lane-quarter q = warp & 3 (TMEM lanes 32q..32q+31), column slice h = warp >> 2 (4 slices)
+
 // ---- TMA bulk helpers ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -103,37 +105,45 @@ __device__ __forceinline__ void load_norm_smem(float* sNorm, const float* __rest
         sNorm[N::DPAD + c] = (ns && c < D) ? __frcp_rn(__ldg(ns + c)) : 1.f;
     }
 }
-template <class N>
+template <class N, int NTHREADS>
 __device__ __forceinline__ void stage_x_tile(uint8_t* sX, const float* __restrict__ obs, int64_t row0, int rows_valid, int D,
                                              const float* __restrict__ sNorm, bool do_norm) {
     constexpr int NCG = N::DPAD / 8;
+    constexpr int ITEMS = (128 * NCG + NTHREADS - 1) / NTHREADS;
     const bool vec = (D & 3) == 0;
-    for (int i = threadIdx.x; i < 128 * NCG; i += blockDim.x) {
+    float4 va[ITEMS], vb[ITEMS];
+    // phase 1: issue every global load of this thread (ITEMS x 32 B) before touching any of them
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = threadIdx.x + it * NTHREADS;
         const int cg = i / 128, r = i - cg * 128;      // consecutive threads -> consecutive rows (conflict-free 16B stores)
-        float f[8];
         const int c0 = cg * 8;
-        if (r < rows_valid && c0 < D) {
+        va[it] = make_float4(0.f, 0.f, 0.f, 0.f); vb[it] = va[it];
+        if (i < 128 * NCG && r < rows_valid && c0 < D) {
             const float* src = obs + (row0 + r) * D + c0;
-            if (vec && c0 + 8 <= D) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            } else if (vec && c0 + 4 <= D) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-#pragma unroll
-                for (int j = 4; j < 8; ++j) f[j] = (c0 + j < D) ? __ldg(src + j) : 0.f;
+            if (vec) {
+                va[it] = __ldg(reinterpret_cast<const float4*>(src));
+                if (c0 + 4 < D) vb[it] = __ldg(reinterpret_cast<const float4*>(src) + 1);
             } else {
+                float t[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = (c0 + j < D) ? __ldg(src + j) : 0.f;
+                for (int j = 0; j < 8; ++j) t[j] = (c0 + j < D) ? __ldg(src + j) : 0.f;
+                va[it] = make_float4(t[0], t[1], t[2], t[3]); vb[it] = make_float4(t[4], t[5], t[6], t[7]);
             }
-            if (do_norm) {
+        }
+    }
+    // phase 2: normalise / clamp / pack / store
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    f[j] = (c0 + j < D) ? fminf(fmaxf((f[j] - sNorm[c0 + j]) * sNorm[N::DPAD + c0 + j], -5.0f), 5.0f) : 0.f;
-            }
-        } else {
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = threadIdx.x + it * NTHREADS;
+        if (i >= 128 * NCG) break;
+        const int cg = i / 128, r = i - cg * 128;
+        const int c0 = cg * 8;
+        float f[8] = {va[it].x, va[it].y, va[it].z, va[it].w, vb[it].x, vb[it].y, vb[it].z, vb[it].w};
+        if (do_norm) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = 0.f;
+            for (int j = 0; j < 8; ++j)
+                f[j] = (c0 + j < D && r < rows_valid) ? fminf(fmaxf((f[j] - sNorm[c0 + j]) * sNorm[N::DPAD + c0 + j], -5.0f), 5.0f) : 0.f;
         }
         *reinterpret_cast<uint4*>(sX + tile_off(r, cg, N::ACS, N::ARS)) = pack8_bf16(f);
     }
@@ -167,7 +177,6 @@ struct FwdArgs {
     float* valid_out; int values_only;
 };
 
-constexpr int FWD_THREADS = 512;   // 16 warps: lane-quarter q = warp & 3 (TMEM lanes 32q..32q+31), column slice h = warp >> 2 (4 slices)
 constexpr int LOSS_SLOTS = LOSS_NSC + 32;   // partial row stride shared with loss.cu (NSC + MAXA)
 
 // ================================================================================================= forward
@@ -180,8 +189,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     uint8_t* sA3 = sA1;
     float* sBias = reinterpret_cast<float*>(sXA2 + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES));
     float* sB1 = sBias; float* sB2 = sB1 + N::U1; float* sB3 = sB2 + N::U2; float* sBh = sB3 + N::U3;
-    float* sSig = sBh + N::AP;                           // sigma[A], logstd[A] (<= 32 floats)
-    float* sNorm = sSig + 32;                            // [2*DPAD] obs mean, 1/std
+    float* sSig = sBh + N::AP;                           // sigma, logstd, 1/sigma, log(sigma): 4*A <= 64 floats
+    float* sNorm = sSig + 64;                            // [2*DPAD] obs mean, 1/std
     float* sRed = sNorm + 2 * N::DPAD;                   // [4 warps][LOSS_SLOTS] (only the h == 0 warps run the loss)
     double* sAcc = reinterpret_cast<double*>(sRed + 4 * LOSS_SLOTS);     // [LOSS_SLOTS] per-CTA running partial
     uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + LOSS_SLOTS);     // [0]=weights, [1..4]=mma stages
@@ -201,7 +210,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = __ldg(p.b2 + i);
     for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = __ldg(p.b3 + i);
     if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
-    if (tid < p.A) { const float ls = __ldg(p.logstd + tid); sSig[tid] = expf(ls); sSig[p.A + tid] = ls; }
+    if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
     if (tid < LOSS_SLOTS) sAcc[tid] = 0.0;
     load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     fence_before_sync();
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         const int m0 = tile * 128;
         const int rows_valid = min(128, p.M - m0);
         const int64_t arow0 = chunk_row(m0, p.rows_per_chunk, p.chunk_stride);   // tile lies inside one chunk (host-checked)
-        stage_x_tile<N>(sXA2, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr);
+        stage_x_tile<N, FWD_THREADS>(sXA2, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr);
         fence_async_smem();
         if (!weights_ready) { mbar_wait(&bars[0], 0); weights_ready = true; }
         __syncthreads();
@@ -340,7 +349,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                 if (TRAIN) {
                     float dh[16];
                     const float inv_cnt = p.inv_count_dev ? __ldg(p.inv_count_dev) : (1.0f / (float)p.M);
-                    ppo_sample_loss<16>(head, p.A, sSig, p.la, ar, inv_cnt, p.cfg, dh, dls, sc);
+                    ppo_sample_loss<16, true>(head, p.A, sSig, p.la, ar, inv_cnt, p.cfg, dh, dls, sc);
                     uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
                     *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = pack8_bf16(&dh[0]);
                     *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = pack8_bf16(&dh[8]);
@@ -374,7 +383,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                             if (j < p.A) {
                                 const float mu = head[1 + j], sg = sSig[j];
                                 const float act = __fadd_rn(mu, __fmul_rn(sg, eps[j]));
-                                const float z = (act - mu) / sg;
+                                const float z = (act - mu) * sSig[2 * p.A + j];
                                 sumz2 += z * z;
                                 sumls += sSig[p.A + j];
                                 p.actions[(int64_t)m * p.A + j] = act;
@@ -585,12 +594,15 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
             uint8_t* g1 = p.delta1 + (size_t)tile * N::A1_BYTES;
 #pragma unroll 1
             for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+                uint4 ua[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) ua[g] = __ldg(reinterpret_cast<const uint4*>(ga1 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS)));
                 float v[32];
                 tmem_ld32(TT + lane_base + c0, v);
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     float a[8];
-                    unpack8_bf16(__ldg(reinterpret_cast<const uint4*>(ga1 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS))), a);
+                    unpack8_bf16(ua[g], a);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[g * 8 + j] *= elu_grad_from_out(a[j]);
                 }
@@ -684,7 +696,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
             bulk_g2s(sA1, p.act1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
         }
         const int m0 = tile * 128;
-        stage_x_tile<N>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm, p.nm != nullptr);
+        stage_x_tile<N, 256>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm, p.nm != nullptr);
         fence_async_smem();
         mbar_wait(&bars[0], phase);
         __syncthreads();
@@ -750,7 +762,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
 
 template <class N> constexpr size_t fwd_smem() {
     return (size_t)N::PACK_BYTES + N::A1_BYTES + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES) +
-           sizeof(float) * (N::U1 + N::U2 + N::U3 + N::AP + 32 + 2 * N::DPAD + 4 * LOSS_SLOTS) + sizeof(double) * LOSS_SLOTS + 8 * 8 + 16;
+           sizeof(float) * (N::U1 + N::U2 + N::U3 + N::AP + 64 + 2 * N::DPAD + 4 * LOSS_SLOTS) + sizeof(double) * LOSS_SLOTS + 8 * 8 + 16;
 }
 template <class N> constexpr size_t bwd1_smem() {
     return (size_t)N::WH_BYTES + N::W3_BYTES + N::W2_BYTES + N::DH_BYTES + 128 * 256 + N::A2_BYTES + N::A3_BYTES + N::A2_BYTES + 8 * 8 + 16;
@@ -838,7 +850,8 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
     p.la = LossArena{actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask};
     p.inv_count_dev = inv_count_dev;
     p.cfg = LossCfgDev{cfg_host->e_clip, cfg_host->critic_coef, cfg_host->bounds_loss_coef, cfg_host->has_bounds_loss,
-                       cfg_host->bound_loss_type, cfg_host->clip_value, cfg_host->use_smooth_clamp, cfg_host->ppo};
+                       cfg_host->bound_loss_type, cfg_host->clip_value, cfg_host->use_smooth_clamp, cfg_host->ppo,
+                       log1pf(-cfg_host->e_clip), log1pf(cfg_host->e_clip)};
     p.act1 = (uint8_t*)act1; p.act2 = (uint8_t*)act2; p.act3 = (uint8_t*)act3; p.dhead = (uint8_t*)dhead; p.partials = partials;
     constexpr size_t smem = fwd_smem<N>();
     static_assert(smem <= 227 * 1024, "forward kernel shared memory budget");
