@@ -220,6 +220,26 @@ int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, floa
                          float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Multi-GPU: fused gradient all-reduce + clip + Adam over NVLink peer memory (one launch per minibatch).
+ * Replaces a2c_common.py:493-509 (cat -> all_reduce -> /world -> scatter), :1559-1561 (KL all-reduce) and the
+ * optimiser step above.  Every rank's gradient arena (n floats + 1 KL slot) lives in a buffer obtained with
+ * b200rl_ipc_alloc and mapped into every peer with b200rl_ipc_open (handles exchanged by the host, e.g. through
+ * torch.distributed.all_gather_object).  peer_grads_host[r] / peer_flags_host[r]: device addresses (valid in THIS
+ * process) of rank r's gradient buffer for this step's parity and of rank r's flag array (u64[world]);
+ * my_flags == peer_flags_host[rank].  seq_ptr: u64[1] step counter, red: float[n+1] local reduced copy,
+ * nrm_part: double[>= grid], grid_bar: u32[1] (zeroed once).  Gradient buffers must be double-buffered by step parity.
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_ipc_alloc(int64_t bytes, void** dev_ptr_out_host, void* handle64_out_host);
+int b200rl_ipc_open(const void* handle64_host, void** dev_ptr_out_host);
+int b200rl_ipc_close(void* p);
+int b200rl_ipc_free(void* p);
+int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, void* const* peer_flags_host, int world, int rank,
+                              void* my_flags, void* seq_ptr, float* red, double* nrm_part, int nrm_part_len, void* grid_bar,
+                              float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
+                              const b200rl_opt_cfg* cfg_host, float* stats_out, int* counter, void* wpack,
+                              const b200rl_pack_table* tab_host, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Rollout.  a2c_common.py:985-1069 (play_steps) per-step pieces.
  * policy_head_sample: heads + sigma=exp(logstd) + a = mu + sigma*eps + neglogp + denorm value
  *   (models.py:329-364, :58-60) written straight into arena time-step t (experience.py:433-456).

@@ -28,7 +28,7 @@ import torch.distributed as dist
 from . import ops
 from .common import (AdaptiveScheduler, IdentityScheduler, LinearScheduler, DefaultAlgoObserver, DefaultRewardsShaper,
                      create_vec_env, make_summary_writer)
-from .dist_utils import merge_stats_packed, seed_snapshots
+from .dist_utils import PackedStatsSync
 from .model import B200Model
 
 STATS_SYNC_MODES = ('pooled', 'broadcast')
@@ -365,6 +365,10 @@ class A2CAgent:
         m.g_sigma = m.view('sigma', m.grad)
         m.gW_head, m.gb_head = m.view('W_head', m.grad), m.view('b_head', m.grad)
         self.kl_slot = self.comm[m.num_params:]
+        self._gv = [dict(grad=m.grad, g_sigma=m.g_sigma, kl=self.kl_slot, comm=self.comm)] * 2
+        self.fused_allreduce = False
+        if self.multi_gpu and self.world_size > 1 and self.config.get('b200_fused_allreduce', True):
+            self._setup_peer_comm()
         self.opt_state = torch.tensor([self.last_lr, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)   # lr, step, beta1^step, beta2^step
         self.entropy_coef_dev = torch.tensor([float(self.entropy_coef)], dtype=torch.float32, device=dev)
         self.inv_counts = f(self.num_minibatches) if self.mask_autoreset_rows else None
@@ -384,6 +388,49 @@ class A2CAgent:
         self._pinned = {}
         self._tensors_ready = True
         self._repack()
+
+    def _setup_peer_comm(self):
+        """CUDA-IPC mapped, parity-double-buffered gradient arenas + flag arrays for the fused all-reduce/Adam kernel."""
+        if self.world_size > 8:
+            return
+        if self.n_updates % 2 != 0:
+            return      # buffers alternate by update parity across epochs / graph replays: needs an even number of updates per epoch
+        m, dev = self.model, self.device_t
+        P = m.num_params
+        S = ((P + 1 + 3) // 4) * 4
+        nbytes = 2 * S * 4 + 8 * 8
+        base, handle = ops.ipc_alloc(nbytes)
+        handles = [None] * self.world_size
+        dist.all_gather_object(handles, handle)
+        ptrs = [base if r == self.global_rank else ops.ipc_open(handles[r]) for r in range(self.world_size)]
+        self._peer_keepalive = (base, ptrs)
+        self.peer_table = ops.PeerTable([[p + par * S * 4 for p in ptrs] for par in (0, 1)], [p + 2 * S * 4 for p in ptrs])
+        self.my_flags_ptr = base + 2 * S * 4
+        self._gv = []
+        for par in (0, 1):
+            comm = ops.tensor_from_ptr(base + par * S * 4, P + 1, torch.float32, dev)
+            grad = comm[:P]
+            self._gv.append(dict(grad=grad, g_sigma=m.view('sigma', grad), kl=comm[P:], comm=comm))
+        self.ar_seq = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ar_red = torch.zeros(P + 1, dtype=torch.float32, device=dev)
+        self.ar_nrm = torch.zeros(128, dtype=torch.float64, device=dev)
+        self.ar_bar = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._ar_parity = 0
+        self.fused_allreduce = True
+        dist.barrier()
+
+    def _step_optimizer(self, u, gv, P, wpack=None, pack_table=None):
+        """gradient exchange + clip + Adam (+ packed-weight refresh) for update u"""
+        m = self.model
+        if self.fused_allreduce:
+            ops.allreduce_adam(self.peer_table, u & 1, self.global_rank, self.my_flags_ptr, self.ar_seq, self.ar_red, self.ar_nrm,
+                               self.ar_bar, m.flat, m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.stats[u],
+                               self.counters[2:3], wpack=wpack, pack_table=pack_table)
+            return
+        if self.multi_gpu:
+            dist.all_reduce(gv['comm'], op=dist.ReduceOp.SUM)
+        ops.adam_step(m.flat, gv['grad'], m.exp_avg, m.exp_avg_sq, self.opt_state, gv['kl'], self.opt_cfg, self.stats[u],
+                      self.counters[2:3], n=P, wpack=wpack, pack_table=pack_table)
 
     def _build_cfg_structs(self):
         """POD structs passed (by value at launch) to the kernels; baked into captured graphs, so any change
@@ -644,7 +691,8 @@ class A2CAgent:
                                self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:], epm, N, mb, A,
                                self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.d_head,
                                self.dA[-1], m.act_id, self.loss_partials)
-        ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], m.g_sigma, self.kl_slot)
+        gv = self._gv[u & 1]
+        ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], gv['g_sigma'], gv['kl'])
         P, S = m.num_params, self.n_splits
         off_wh, _ = m.layout['W_head']
         off_bh, _ = m.layout['b_head']
@@ -663,11 +711,8 @@ class A2CAgent:
                 ops.linear_bwd_weight(self.dA[0], x, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
                                       rows_per_chunk=epm, chunk_stride=N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=mb,
                                       split_stride=P)
-        ops.reduce_splits(self.part[0, A:], m.grad[A:], P - A, S, split_stride=P)
-        if self.multi_gpu:
-            dist.all_reduce(self.comm, op=dist.ReduceOp.SUM)
-        ops.adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_state, self.kl_slot, self.opt_cfg, self.stats[u],
-                      self.counters[2:3], n=P)
+        ops.reduce_splits(self.part[0, A:], gv['grad'][A:], P - A, S, split_stride=P)
+        self._step_optimizer(u, gv, P)
 
     def _minibatch_update_tc(self, i, u, x, e0):
         """bf16 tcgen05 edition: fused fwd+loss kernel, two backward kernels, split reduce, Adam, repack."""
@@ -681,12 +726,10 @@ class A2CAgent:
                                   self.tc_dhead, self.loss_partials)
         npart = ops.tc_mlp_bwd(x, epm, N, m.D, nm, ns, self.wpack, m.units, mb, A, self.tc_act, self.tc_dhead, self.tc_delta2,
                                self.tc_delta1, self.part, P, self.tc_offs)
-        ops.reduce_finalize(self.part[0, A:], m.grad[A:], P - A, npart, P, self.loss_partials, nb, A, self.entropy_coef_dev,
-                            self.stats[u], m.g_sigma, self.kl_slot)
-        if self.multi_gpu:
-            dist.all_reduce(self.comm, op=dist.ReduceOp.SUM)
-        ops.adam_step(m.flat, m.grad, m.exp_avg, m.exp_avg_sq, self.opt_state, self.kl_slot, self.opt_cfg, self.stats[u],
-                      self.counters[2:3], n=P, wpack=self.wpack, pack_table=self.pack_table)
+        gv = self._gv[u & 1]
+        ops.reduce_finalize(self.part[0, A:], gv['grad'][A:], P - A, npart, P, self.loss_partials, nb, A, self.entropy_coef_dev,
+                            self.stats[u], gv['g_sigma'], gv['kl'])
+        self._step_optimizer(u, gv, P, wpack=self.wpack, pack_table=self.pack_table)
 
     def _update_all(self):
         u = 0
@@ -762,6 +805,7 @@ class A2CAgent:
                     self._rollout(None)
                     self._gae_and_prepare()
                     self._update_all()
+                    self.sync_running_stats()     # in-place tensor math + one NCCL all-reduce: graph-capturable
                 self._graph_epoch = g
             self._graph_epoch.replay()
             self._meter_cache = None
@@ -774,12 +818,12 @@ class A2CAgent:
             ev[1].record()
             self.set_train()
             self._run_update()
+            self.sync_running_stats()
             self._epoch_warm = True
             split_known = True
         self.set_train()
         self.curr_frames = self.batch_size
         self.algo_observer.after_steps()
-        self.sync_running_stats()
         ev[2].record()
         # one D2H read-back per epoch: stats rows + (lr, step) + meter
         self.host_stats.copy_(self.stats, non_blocking=True)
@@ -850,17 +894,20 @@ class A2CAgent:
                     dist.broadcast(t, 0)
                 m.refresh()
             return
-        tensors = [(name, m.count, m.running_mean, m.running_var) for name, m in mods]
-        self._stats_snapshots = merge_stats_packed(tensors, self._stats_snapshots,
-                                                   lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+        self._stats_sync_obj().sync(lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
         for _, m in mods:
             m.refresh()
+
+    def _stats_sync_obj(self):
+        if getattr(self, '_stats_sync', None) is None:
+            self._stats_sync = PackedStatsSync([(n, m.count, m.running_mean, m.running_var) for n, m in self._stats_modules()])
+        return self._stats_sync
 
     def _seed_stats_sync_snapshots(self):
         """a2c_common.py:767-780"""
         if not self.multi_gpu or not self.multi_gpu_sync_stats or self.multi_gpu_sync_stats_mode == 'broadcast':
             return
-        self._stats_snapshots = seed_snapshots([(n, m.count, m.running_mean, m.running_var) for n, m in self._stats_modules()])
+        self._stats_sync_obj().seed()
 
     # =============================================================================== train loop
     def train(self):

@@ -6,6 +6,7 @@
 // and the result is deterministic; the last CTA to finish advances (step, lr).
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <string.h>
 
 namespace {
 
@@ -15,6 +16,37 @@ struct OptCfgDev {
 };
 
 struct PackTabDev { int n_seg; int off[4]; int R[4]; int C[4]; unsigned CS[4]; unsigned dst[4]; };
+
+// one element of the fused Adam update (torch.optim.Adam fused semantics) + refresh of the packed bf16 weight copy
+__device__ __forceinline__ void adam_update_one(int i, float g, int truncate, float coef, float* __restrict__ params,
+                                                float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, float b1, float b2,
+                                                float step_size, float bc2_sqrt, float eps, float wd, unsigned char* __restrict__ wpack,
+                                                const PackTabDev& tab) {
+    if (truncate) g *= coef;
+    float p = params[i];
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    float m = exp_avg[i], v = exp_avg_sq[i];
+    m = m + (g - m) * (1.0f - b1);                 // lerp (torch fused adam)
+    v = b2 * v + (1.0f - b2) * g * g;
+    const float denom = sqrtf(v) / bc2_sqrt + eps;
+    p -= step_size * m / denom;
+    params[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
+    if (wpack) {
+        // refresh the bf16 operand copy the tcgen05 kernels consume (INTERLEAVE weight tile: CS = (Rpad/8)*128, RS = 128)
+#pragma unroll
+        for (int sgi = 0; sgi < 4; ++sgi) {
+            if (sgi < tab.n_seg) {
+                const int loc = i - tab.off[sgi];
+                if (loc >= 0 && loc < tab.R[sgi] * tab.C[sgi]) {
+                    const int r = loc / tab.C[sgi], cc = loc - r * tab.C[sgi];
+                    const unsigned o = tab.dst[sgi] + (unsigned)(r & 7) * 16u + (unsigned)(cc >> 3) * tab.CS[sgi] + (unsigned)(r >> 3) * 128u +
+                                       (unsigned)(cc & 7) * 2u;
+                    *reinterpret_cast<__nv_bfloat16*>(wpack + o) = __float2bfloat16_rn(p);
+                }
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ params, const float* __restrict__ grads,
                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n,
@@ -57,33 +89,9 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
     const float eps = (float)c.eps, wd = (float)c.weight_decay;
     const int per = (n + gridDim.x - 1) / gridDim.x;
     const int i0 = blockIdx.x * per, i1 = min(i0 + per, n);
-    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-        float g = __ldg(grads + i) * gs;
-        if (c.truncate_grads) g *= coef;
-        float p = params[i];
-        if (wd != 0.f) g = fmaf(wd, p, g);
-        float m = exp_avg[i], v = exp_avg_sq[i];
-        m = m + (g - m) * (1.0f - b1);                 // lerp (torch fused adam)
-        v = b2 * v + (1.0f - b2) * g * g;
-        const float denom = sqrtf(v) / bc2_sqrt + eps;
-        p -= step_size * m / denom;
-        params[i] = p; exp_avg[i] = m; exp_avg_sq[i] = v;
-        if (wpack) {
-            // refresh the bf16 operand copy the tcgen05 kernels consume (INTERLEAVE weight tile: CS = (Rpad/8)*128, RS = 128)
-#pragma unroll
-            for (int sgi = 0; sgi < 4; ++sgi) {
-                if (sgi < tab.n_seg) {
-                    const int loc = i - tab.off[sgi];
-                    if (loc >= 0 && loc < tab.R[sgi] * tab.C[sgi]) {
-                        const int r = loc / tab.C[sgi], cc = loc - r * tab.C[sgi];
-                        const unsigned o = tab.dst[sgi] + (unsigned)(r & 7) * 16u + (unsigned)(cc >> 3) * tab.CS[sgi] + (unsigned)(r >> 3) * 128u +
-                                           (unsigned)(cc & 7) * 2u;
-                        *reinterpret_cast<__nv_bfloat16*>(wpack + o) = __float2bfloat16_rn(p);
-                    }
-                }
-            }
-        }
-    }
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x)
+        adam_update_one(i, __ldg(grads + i) * gs, c.truncate_grads, coef, params, exp_avg, exp_avg_sq, b1, b2, step_size, bc2_sqrt, eps, wd,
+                        wpack, tab);
     // ---- last CTA advances step / lr (all CTAs have read them by now) ----
     __threadfence();
     __syncthreads();
@@ -105,6 +113,108 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
         state_d[2] = p1;
         state_d[3] = p2;
         if (stats_out) { stats_out[B200RL_STAT_LR] = (float)lr; stats_out[B200RL_STAT_GNORM] = total_norm; }
+        *counter = 0;
+    }
+}
+
+// =====================================================================================================================
+// Fused gradient all-reduce + clip + Adam over NVLink peer memory (one launch per minibatch, replaces
+// cat -> dist.all_reduce -> /world -> scatter -> clip_grad_norm_ -> optimizer.step of a2c_common.py:493-514 and the
+// KL all-reduce of :1559-1561).  Every rank's gradient arena (+KL slot) lives in a CUDA-IPC mapped buffer; each rank
+//   0. signals "my gradients for step s are ready" into every peer's flag array (st.release.sys) and waits for all peers,
+//   1. sums ALL peers' buffers slice by slice with plain peer loads (fixed rank order => every rank computes bit-identical
+//      reduced gradients), stores the sum locally and records per-CTA sum-of-squares partials,
+//   2. grid barrier (all CTAs are co-resident: grid <= #SMs, one CTA per SM),
+//   3. clip + Adam + packed-bf16 refresh from the local reduced copy; the last CTA advances (lr, step, seq).
+// Gradient buffers are double-buffered by minibatch parity, so the single cross-rank barrier per step also protects the
+// buffer written two steps later (a rank can only reach step s+1 after every rank entered step s+... see DESIGN.md).
+struct PeerPtrs { const float* grads[8]; unsigned long long* flags[8]; };
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, int world, int rank, unsigned long long* my_flags,
+                                                             unsigned long long* seq_ptr, float* __restrict__ red, double* __restrict__ nrm_part,
+                                                             unsigned* grid_bar, float* __restrict__ params, float* __restrict__ exp_avg,
+                                                             float* __restrict__ exp_avg_sq, int n, double* state_d, OptCfgDev c,
+                                                             float* __restrict__ stats_out, int* counter, unsigned char* __restrict__ wpack,
+                                                             PackTabDev tab) {
+    __shared__ double sm[32];
+    __shared__ int is_last;
+    const unsigned long long seq = *seq_ptr + 1ull;
+    // ---- 0. cross-rank barrier: my gradients (written by the previous kernel in this stream) are complete ----
+    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, seq);
+    if (threadIdx.x < world) {
+        while (ld_acquire_sys(my_flags + threadIdx.x) < seq) { }
+    }
+    __syncthreads();
+    const double lr = state_d[0];
+    const double step = state_d[1] + 1.0;
+    const double p1 = (state_d[2] > 0.0 ? state_d[2] : 1.0) * c.beta1;
+    const double p2 = (state_d[3] > 0.0 ? state_d[3] : 1.0) * c.beta2;
+    const float gs = (float)c.grad_scale;
+    // ---- 1. reduce my slice across ranks (n gradient entries + the KL slot at index n) ----
+    const int ntot = n + 1;
+    const int per = (ntot + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(i0 + per, ntot);
+    float a0 = 0.f;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        float sacc = 0.f;
+        for (int pr = 0; pr < world; ++pr) sacc += __ldcv(peers.grads[pr] + i);     // volatile: peer data, never from a stale L1 line
+        red[i] = sacc;
+        if (i < n) { const float g = sacc * gs; a0 = fmaf(g, g, a0); }
+    }
+    double acc[1] = {(double)a0};
+    block_sum_d<1>(acc, sm);
+    if (threadIdx.x == 0) nrm_part[blockIdx.x] = acc[0];
+    // ---- 2. grid barrier (monotonic counter) ----
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned arrived = atomicAdd(grid_bar, 1u);
+        const unsigned target = (arrived / gridDim.x + 1u) * gridDim.x;
+        while (ld_acquire_gpu_u32(grid_bar) < target) { }
+    }
+    __syncthreads();
+    // ---- 3. clip + Adam on my slice ----
+    double nsqv[1] = {threadIdx.x < gridDim.x ? __ldcg(nrm_part + threadIdx.x) : 0.0};     // gridDim.x <= 128 <= blockDim.x
+    block_sum_d<1>(nsqv, sm);
+    const float total_norm = (float)sqrt(nsqv[0]);
+    float coef = 1.0f;
+    if (c.truncate_grads) coef = fminf((float)c.grad_norm / (total_norm + 1e-6f), 1.0f);
+    const float b1 = (float)c.beta1, b2 = (float)c.beta2;
+    const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+    const float step_size = (float)(lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float eps = (float)c.eps, wd = (float)c.weight_decay;
+    for (int i = i0 + threadIdx.x; i < min(i1, n); i += blockDim.x)
+        adam_update_one(i, __ldcg(red + i) * gs, c.truncate_grads, coef, params, exp_avg, exp_avg_sq, b1, b2, step_size, bc2_sqrt, eps, wd,
+                        wpack, tab);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (is_last && threadIdx.x == 0) {
+        double new_lr = lr;
+        if (c.adaptive_lr) {
+            const double kl = (double)(__ldcg(red + n) * gs);
+            if (kl > 2.0 * c.kl_threshold) new_lr = fmax(lr / c.lr_multiplier, c.min_lr);
+            if (kl < 0.5 * c.kl_threshold) new_lr = fmin(lr * c.lr_multiplier, c.max_lr);
+        }
+        state_d[0] = new_lr; state_d[1] = step; state_d[2] = p1; state_d[3] = p2;
+        if (stats_out) { stats_out[B200RL_STAT_LR] = (float)lr; stats_out[B200RL_STAT_GNORM] = total_norm; stats_out[B200RL_STAT_KL] = __ldcg(red + n) * gs; }
+        *seq_ptr = seq;
         *counter = 0;
     }
 }
@@ -136,6 +246,75 @@ B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float*
     if (blocks < 1) blocks = 1;
     adam_step_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, state_d, kl_dev, c, stats_out,
                                                             counter, (unsigned char*)wpack, tab);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+// ---- CUDA-IPC plumbing for the peer-mapped gradient buffers (multi-GPU, one process per GPU) ----------------------
+B200RL_EXPORT int b200rl_ipc_alloc(int64_t bytes, void** dev_ptr_out_host, void* handle64_out_host) {
+    if (bytes <= 0 || !dev_ptr_out_host || !handle64_out_host) return B200RL_EINVAL;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemset(p, 0, (size_t)bytes);
+    if (e != cudaSuccess) return (int)e;
+    cudaIpcMemHandle_t h;
+    e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) return (int)e;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64_out_host, &h, 64);
+    *dev_ptr_out_host = p;
+    return B200RL_OK;
+}
+B200RL_EXPORT int b200rl_ipc_open(const void* handle64_host, void** dev_ptr_out_host) {
+    if (!handle64_host || !dev_ptr_out_host) return B200RL_EINVAL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64_host, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return (int)e;
+    *dev_ptr_out_host = p;
+    return B200RL_OK;
+}
+B200RL_EXPORT int b200rl_ipc_close(void* p) { return p ? (int)cudaIpcCloseMemHandle(p) : B200RL_EINVAL; }
+B200RL_EXPORT int b200rl_ipc_free(void* p) { return p ? (int)cudaFree(p) : B200RL_EINVAL; }
+
+B200RL_EXPORT int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, void* const* peer_flags_host, int world, int rank,
+                                            void* my_flags, void* seq_ptr, float* red, double* nrm_part, int nrm_part_len, void* grid_bar,
+                                            float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
+                                            const b200rl_opt_cfg* cfg_host, float* stats_out, int* counter, void* wpack,
+                                            const b200rl_pack_table* tab_host, void* stream) {
+    if (!peer_grads_host || !peer_flags_host || world < 1 || world > 8 || rank < 0 || rank >= world || !my_flags || !seq_ptr || !red ||
+        !nrm_part || !grid_bar || !params || !exp_avg || !exp_avg_sq || !state_d || !cfg_host || !counter || n <= 0)
+        return B200RL_EINVAL;
+    if ((wpack != nullptr) != (tab_host != nullptr)) return B200RL_EINVAL;
+    PeerPtrs pp{};
+    for (int i = 0; i < world; ++i) {
+        if (!peer_grads_host[i] || !peer_flags_host[i]) return B200RL_EINVAL;
+        pp.grads[i] = (const float*)peer_grads_host[i];
+        pp.flags[i] = (unsigned long long*)peer_flags_host[i];
+    }
+    PackTabDev tab{};
+    if (tab_host) {
+        if (tab_host->n_seg < 0 || tab_host->n_seg > 4) return B200RL_EINVAL;
+        tab.n_seg = tab_host->n_seg;
+        for (int i = 0; i < tab.n_seg; ++i) {
+            tab.off[i] = tab_host->flat_off[i]; tab.R[i] = tab_host->rows[i]; tab.C[i] = tab_host->cols[i];
+            tab.CS[i] = tab_host->cs_bytes[i]; tab.dst[i] = tab_host->dst_off[i];
+        }
+    }
+    OptCfgDev c;
+    c.beta1 = cfg_host->beta1; c.beta2 = cfg_host->beta2; c.eps = cfg_host->eps; c.weight_decay = cfg_host->weight_decay;
+    c.grad_norm = cfg_host->grad_norm; c.kl_threshold = cfg_host->kl_threshold; c.min_lr = cfg_host->min_lr;
+    c.max_lr = cfg_host->max_lr; c.lr_multiplier = cfg_host->lr_multiplier; c.grad_scale = cfg_host->grad_scale;
+    c.truncate_grads = cfg_host->truncate_grads; c.adaptive_lr = cfg_host->adaptive_lr;
+    int blocks = (n + 1 + 2047) / 2048;
+    if (blocks > 128) blocks = 128;       // all CTAs must be co-resident for the in-kernel grid barrier (148 SMs, 1 CTA/SM)
+    if (blocks < 1) blocks = 1;
+    if (blocks > nrm_part_len) return B200RL_EINVAL;
+    allreduce_adam_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(pp, world, rank, (unsigned long long*)my_flags, (unsigned long long*)seq_ptr,
+                                                                 red, nrm_part, (unsigned*)grid_bar, params, exp_avg, exp_avg_sq, n, state_d, c,
+                                                                 stats_out, counter, (unsigned char*)wpack, tab);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }

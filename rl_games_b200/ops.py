@@ -310,3 +310,46 @@ def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A,
                                 part.shape[0], P, offs['W0'], offs['b0'], offs['W1'], offs['b1'], offs['W2'], offs['b2'],
                                 offs['W_head'], offs['b_head'], ctypes.addressof(nb), _stream()), 'tc_mlp_bwd')
     return nb.value
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU peer memory
+def ipc_alloc(nbytes):
+    p = ctypes.c_void_p()
+    h = (ctypes.c_ubyte * 64)()
+    check(lib.b200rl_ipc_alloc(nbytes, ctypes.addressof(p), ctypes.addressof(h)), 'ipc_alloc')
+    return p.value, bytes(h)
+
+
+def ipc_open(handle):
+    p = ctypes.c_void_p()
+    h = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+    check(lib.b200rl_ipc_open(ctypes.addressof(h), ctypes.addressof(p)), 'ipc_open')
+    return p.value
+
+
+class _RawCuda:
+    def __init__(self, ptr_, shape, typestr):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr_), False), 'version': 2}
+
+
+def tensor_from_ptr(ptr_, n, dtype, device):
+    typestr = {torch.float32: '<f4', torch.int64: '<i8', torch.uint8: '|u1'}[dtype]
+    return torch.as_tensor(_RawCuda(ptr_, (n,), typestr), device=device)
+
+
+class PeerTable:
+    """host-side pointer tables handed to b200rl_allreduce_adam_f32"""
+
+    def __init__(self, grads_ptrs, flags_ptrs):
+        self.world = len(flags_ptrs)
+        self.grads = [(ctypes.c_void_p * 8)(*(list(g) + [None] * (8 - len(g)))) for g in grads_ptrs]   # one table per parity
+        self.flags = (ctypes.c_void_p * 8)(*(list(flags_ptrs) + [None] * (8 - len(flags_ptrs))))
+
+
+def allreduce_adam(table, parity, rank, my_flags_ptr, seq, red, nrm_part, grid_bar, params, exp_avg, exp_avg_sq, n, state_d, cfg,
+                   stats_out, counter, wpack=None, pack_table=None):
+    check(lib.b200rl_allreduce_adam_f32(ctypes.addressof(table.grads[parity]), ctypes.addressof(table.flags), table.world, rank,
+                                        my_flags_ptr, ptr(seq), ptr(red), ptr(nrm_part), nrm_part.numel(), ptr(grid_bar), ptr(params),
+                                        ptr(exp_avg), ptr(exp_avg_sq), n, ptr(state_d), ctypes.addressof(cfg), ptr(stats_out),
+                                        ptr(counter), ptr(wpack), None if pack_table is None else ctypes.addressof(pack_table),
+                                        _stream()), 'allreduce_adam')

@@ -473,3 +473,36 @@ def test_synth_env_step(ops):
             assert abs(float(obs.mean())) < 0.02 and abs(float(obs.var()) - 1) < 0.03
     assert int(ep_t.max()) < 100
     assert 0.005 < nd / (120 * N) < 0.03
+
+
+def test_fused_allreduce_adam_world1_matches_adam_step(ops):
+    """The peer-memory all-reduce + clip + Adam kernel with a world of one rank (its own IPC buffer as the only peer)
+    must reproduce b200rl_adam_step_f32 (only the fp64 summation order of the norm partials differs)."""
+    from rl_games_b200.ops import OptCfg
+    g = torch.Generator().manual_seed(8)
+    n = 57361
+    S = ((n + 1 + 3) // 4) * 4
+    base, _ = ops.ipc_alloc(2 * S * 4 + 64)
+    table = ops.PeerTable([[base + par * S * 4] for par in (0, 1)], [base + 2 * S * 4])
+    comm = [ops.tensor_from_ptr(base + par * S * 4, n + 1, torch.float32, DEV) for par in (0, 1)]
+    p0 = torch.randn(n, generator=g) * 0.1
+    pa, pb = p0.clone().to(DEV), p0.clone().to(DEV)
+    ma, va, mb_, vb = (torch.zeros(n, device=DEV) for _ in range(4))
+    sa = torch.tensor([3e-4, 0, 0, 0], dtype=torch.float64, device=DEV); sb = sa.clone()
+    ca, cb = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    cfg = OptCfg(0.9, 0.999, 1e-8, 0.0, 1.0, 0.008, 1e-6, 1e-2, 1.5, 1.0, 1, 1)
+    seq = torch.zeros(1, dtype=torch.int64, device=DEV); red = torch.zeros(n + 1, device=DEV)
+    nrm = torch.zeros(128, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+    sta, stb = torch.zeros(16, device=DEV), torch.zeros(16, device=DEV)
+    for it, klv in enumerate([0.001, 0.05, 0.01, 0.0001]):
+        grad = torch.randn(n, generator=g) * (0.02 if it % 2 else 0.001)
+        buf = comm[it & 1]
+        buf[:n].copy_(grad.to(DEV)); buf[n:].fill_(klv)
+        ops.adam_step(pa, buf[:n], ma, va, sa, buf[n:], cfg, sta, ca)
+        ops.allreduce_adam(table, it & 1, 0, base + 2 * S * 4, seq, red, nrm, bar, pb, mb_, vb, n, sb, cfg, stb, cb)
+        torch.cuda.synchronize()
+        assert int(seq) == it + 1
+        torch.testing.assert_close(sb, sa, rtol=1e-14, atol=0)
+        torch.testing.assert_close(pb, pa, rtol=1e-5, atol=1e-7)
+        assert float(stb[8]) == pytest.approx(float(sta[8]), rel=1e-6)
+    torch.testing.assert_close(vb, va, rtol=1e-5, atol=1e-12)

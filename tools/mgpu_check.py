@@ -18,12 +18,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = f'cuda:{local_rank}'
     out = {}
-    for graph in (False, True):
+    ref_flat = None
+    for mode, graph, fused in (('nccl_eager', False, False), ('nccl_graph', True, False), ('fused_graph', True, True)):
         w = dict(bench.WORKLOADS['c2'])
         from rl_games_b200.runner import Runner
         r = Runner()
         p = bench.make_params(w, dev, 'b200_synthetic', True, graph=True)
         p['config']['b200_cuda_graph_multi_gpu'] = graph
+        p['config']['b200_fused_allreduce'] = fused
         r.load({'params': p})
         agent = r.algo_factory.create(r.algo_name, base_name='mgpu', params=r.params)
         agent.init_tensors()
@@ -40,7 +42,10 @@ def main():
         cnt = torch.tensor([int(agent.model.running_mean_std.count)], device=dev)
         cnts = [torch.empty_like(cnt) for _ in range(world)]
         dist.all_gather(cnts, cnt)
-        out['graph' if graph else 'eager'] = {'identical_across_ranks': bool(same), 'obs_count': [int(c) for c in cnts],
+        if ref_flat is None:
+            ref_flat = agent.model.flat.clone()
+        out[mode] = {'fused_allreduce': agent.fused_allreduce, 'max_abs_diff_vs_nccl_eager': float((agent.model.flat - ref_flat).abs().max()),
+                     'identical_across_ranks': bool(same), 'obs_count': [int(c) for c in cnts],
                                               'ms_per_epoch': [round(t, 3) for t in ts], 'lr': agent.last_lr,
                                               'finite': bool(torch.isfinite(agent.model.flat).all()),
                                               'graph_captured': (agent._graph_update is not None) or (agent._graph_epoch is not None)}
