@@ -298,21 +298,36 @@ class IdentityScheduler:
 ACTIVATIONS = {'elu': F.elu, 'relu': F.relu, 'tanh': torch.tanh, 'None': lambda x: x}
 
 
+RNN_NAMES = ['a2c_network.rnn.rnn.weight_ih_l0', 'a2c_network.rnn.rnn.weight_hh_l0', 'a2c_network.rnn.rnn.bias_ih_l0',
+             'a2c_network.rnn.rnn.bias_hh_l0']
+
+
 def param_names(n_layers, lstm=False):
+    """reference model.parameters() order: sigma, actor_mlp.*, [rnn.rnn.*], value.*, mu.* (module registration order of
+    A2CBuilder.Network.__init__, network_builder.py:219-325: actor_mlp placeholder is registered before self.rnn)"""
     names = ['a2c_network.sigma']
     for i in range(n_layers):
         names += [f'a2c_network.actor_mlp.{2 * i}.weight', f'a2c_network.actor_mlp.{2 * i}.bias']
+    if lstm:
+        names += RNN_NAMES
     names += ['a2c_network.value.weight', 'a2c_network.value.bias', 'a2c_network.mu.weight', 'a2c_network.mu.bias']
     return names
 
 
-def init_params(obs_dim, units, act_dim, value_size=1, seed=0, sigma_init=0.0):
+def init_params(obs_dim, units, act_dim, value_size=1, seed=0, sigma_init=0.0, rnn_units=0):
     """Default torch.nn.Linear init (mlp initializer 'default' == nn.Identity on weights,
     biases zeroed: network_builder.py:332-340), mu_init default, sigma const 0."""
     g = torch.Generator().manual_seed(seed)
     p: Dict[str, torch.Tensor] = {}
     p['a2c_network.sigma'] = torch.full((act_dim,), float(sigma_init))
     ins = obs_dim
+    if rnn_units:   # LSTM before the MLP (torch.nn.LSTM default init U(-1/sqrt(hid), 1/sqrt(hid)); mlp_init does not touch it)
+        k = 1.0 / math.sqrt(rnn_units)
+        p[RNN_NAMES[0]] = (torch.rand(4 * rnn_units, ins, generator=g) * 2 - 1) * k
+        p[RNN_NAMES[1]] = (torch.rand(4 * rnn_units, rnn_units, generator=g) * 2 - 1) * k
+        p[RNN_NAMES[2]] = (torch.rand(4 * rnn_units, generator=g) * 2 - 1) * k
+        p[RNN_NAMES[3]] = (torch.rand(4 * rnn_units, generator=g) * 2 - 1) * k
+        ins = rnn_units
     for i, u in enumerate(units):
         bound = 1.0 / math.sqrt(ins)
         p[f'a2c_network.actor_mlp.{2 * i}.weight'] = (torch.rand(u, ins, generator=g) * 2 - 1) * bound
@@ -344,13 +359,32 @@ def network_forward(p, obs, n_layers, activation='elu', matmul_dtype=None):
     return mu, logstd, value
 
 
+def lstm_with_dones(p, x, h, c, dones):
+    """LSTMWithDones (common/layers/recurrent.py:20-80): single-layer torch.nn.LSTM cell maths, states multiplied by
+    (1 - done[t]) before step t (RnnWithDones.forward :26-58 is equivalent to masking at every step: inside a done-free
+    segment the mask is all ones).  x [T,B,F], h/c [B,hid], dones [T,B] or None.  Gate order i,f,g,o."""
+    w_ih, w_hh, b_ih, b_hh = (p[n] for n in RNN_NAMES)
+    outs = []
+    for t in range(x.shape[0]):
+        if dones is not None:
+            nd = (1.0 - dones[t].float()).unsqueeze(1)
+            h, c = h * nd, c * nd
+        gates = F.linear(x[t], w_ih, b_ih) + F.linear(h, w_hh, b_hh)
+        i, f, g, o = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        outs.append(h)
+    return torch.stack(outs), h, c
+
+
 class OracleModel:
     """ModelA2CContinuousLogStd.Network (models.py:304-364) + BaseModelNetwork (:38-63)."""
 
     def __init__(self, params, obs_dim, units, act_dim, normalize_input=True, normalize_value=True,
-                 activation='elu', value_size=1, matmul_dtype=None):
+                 activation='elu', value_size=1, matmul_dtype=None, rnn_units=0):
         self.p = {k: v.clone().float().requires_grad_(True) for k, v in params.items()}
-        self.names = param_names(len(units))
+        self.rnn_units = rnn_units
+        self.names = param_names(len(units), lstm=rnn_units > 0)
         self.n_layers = len(units)
         self.activation = activation
         self.normalize_input, self.normalize_value = normalize_input, normalize_value
@@ -369,8 +403,19 @@ class OracleModel:
         with torch.no_grad():
             return self.value_mean_std(value, denorm=True) if self.normalize_value else value
 
-    def forward(self, obs, is_train, prev_actions=None, noise=None):
+    def forward(self, obs, is_train, prev_actions=None, noise=None, rnn_states=None, seq_length=1, dones=None):
+        """rnn (before_mlp) branch: network_builder.py:452-492 -- [B,F] -> [num_seqs, seq, F] -> transpose -> LSTM -> back."""
         obs = self.norm_obs(obs)
+        new_states = None
+        if self.rnn_units:
+            B = obs.shape[0]
+            num_seqs = B // seq_length
+            x = obs.reshape(num_seqs, seq_length, -1).transpose(0, 1)
+            d = None if dones is None else dones.reshape(num_seqs, seq_length).transpose(0, 1)
+            out, h, c = lstm_with_dones(self.p, x, rnn_states[0][0], rnn_states[1][0], d)
+            obs = out.transpose(0, 1).contiguous().reshape(B, -1)
+            new_states = (h.unsqueeze(0), c.unsqueeze(0))
+        self.last_rnn_states = new_states
         mu, logstd, value = network_forward(self.p, obs, self.n_layers, self.activation, self.matmul_dtype)
         mu, logstd, value = mu.float(), logstd.float(), value.float()
         sigma = torch.exp(logstd)
@@ -463,7 +508,7 @@ DEFAULT_CFG = dict(
     truncate_grads=True, grad_norm=1.0, learning_rate=3e-4, lr_schedule='adaptive', kl_threshold=0.008,
     min_lr=1e-6, max_lr=1e-2, lr_multiplier=1.5, schedule_type='per_minibatch',
     normalize_input=True, normalize_value=True, normalize_advantage=True, value_bootstrap=True,
-    mini_epochs=4, weight_decay=0.0, ppo=True, reward_scale=1.0, reward_shift=0.0,
+    mini_epochs=4, weight_decay=0.0, ppo=True, reward_scale=1.0, reward_shift=0.0, seq_length=4, rnn_units=0, zero_rnn_on_done=True,
     games_to_track=100, activation='elu', clip_actions=True, mask_autoreset_rows=False,
 )
 
@@ -481,7 +526,9 @@ class OracleAgent:
         assert self.batch_size % minibatch_size == 0
         self.num_minibatches = self.batch_size // minibatch_size
         self.model = OracleModel(params, obs_dim, units, act_dim, c['normalize_input'], c['normalize_value'],
-                                 c['activation'], matmul_dtype=matmul_dtype)
+                                 c['activation'], matmul_dtype=matmul_dtype, rnn_units=c['rnn_units'])
+        self.is_rnn = c['rnn_units'] > 0
+        self.seq_length = c['seq_length']
         self.last_lr = float(c['learning_rate'])
         self.entropy_coef = c['entropy_coef']
         self.optimizer = Adam(self.model.parameters(), self.last_lr, eps=1e-8, weight_decay=c['weight_decay'])
@@ -513,6 +560,10 @@ class OracleAgent:
         self.current_lengths = torch.zeros(N)
         self.dones = torch.ones(N, dtype=torch.uint8)
         self.obs = None
+        if self.is_rnn:   # a2c_common.py:652-660
+            hid = self.cfg['rnn_units']
+            self.rnn_states = [torch.zeros(1, N, hid), torch.zeros(1, N, hid)]
+            self.mb_rnn_states = [torch.zeros(H // self.seq_length, 1, N, hid) for _ in range(2)]
 
     def env_reset(self):
         self._autoreset_prev_dones = None
@@ -535,7 +586,12 @@ class OracleAgent:
         if self.mask_autoreset_rows:
             mb_valid = torch.ones(H, N)
         for n in range(H):
-            res = self.model.forward(self.obs, is_train=False, noise=noise[n])
+            if self.is_rnn and n % self.seq_length == 0:       # play_steps_rnn: a2c_common.py:1081-1083
+                for s_, mb_s in zip(self.rnn_states, self.mb_rnn_states):
+                    mb_s[n // self.seq_length] = s_
+            res = self.model.forward(self.obs, is_train=False, noise=noise[n], rnn_states=self.rnn_states if self.is_rnn else None)
+            if self.is_rnn:
+                self.rnn_states = [t.clone() for t in self.model.last_rnn_states]
             self.buf['obses'][n] = self.obs
             self.buf['dones'][n] = self.dones
             if self.mask_autoreset_rows:
@@ -563,6 +619,9 @@ class OracleAgent:
                 self.current_shaped_rewards.add_(shaped)
                 self.current_lengths.add_(1)
             done_idx = self.dones.nonzero(as_tuple=False)
+            if self.is_rnn and len(done_idx) > 0 and c['zero_rnn_on_done']:     # a2c_common.py:1150-1153
+                for s_ in self.rnn_states:
+                    s_[:, done_idx, :] = 0
             self.game_rewards.update(self.current_rewards[done_idx])
             self.game_shaped_rewards.update(self.current_shaped_rewards[done_idx])
             self.game_lengths.update(self.current_lengths[done_idx])
@@ -570,7 +629,8 @@ class OracleAgent:
             self.current_rewards.mul_(nd)
             self.current_shaped_rewards.mul_(nd)
             self.current_lengths.mul_(nd.squeeze(1))
-        last_values = self.model.forward(self.obs, is_train=False, noise=torch.zeros(N, self.A))['values']
+        last_values = self.model.forward(self.obs, is_train=False, noise=torch.zeros(N, self.A),
+                                         rnn_states=self.rnn_states if self.is_rnn else None)['values']
         fdones = self.dones.float()
         mb_fdones = self.buf['dones'].float()
         mb_advs = gae(self.buf['rewards'], self.buf['values'], mb_fdones, last_values, fdones, c['gamma'], c['tau'])
@@ -581,6 +641,12 @@ class OracleAgent:
         batch['mb_advs'] = mb_advs
         if self.mask_autoreset_rows:
             batch['rnn_masks'] = swap_and_flatten01(mb_valid)
+        if self.is_rnn:    # a2c_common.py:1193-1199
+            states = []
+            for mb_s in self.mb_rnn_states:
+                t_size = mb_s.size()[0] * mb_s.size()[2]
+                states.append(mb_s.permute(1, 2, 0, 3).reshape(-1, t_size, mb_s.size()[3]))
+            batch['rnn_states'] = states
         return batch
 
     def prepare_dataset(self, batch):
@@ -613,12 +679,17 @@ class OracleAgent:
             'old_values': values, 'old_logp_actions': batch['neglogpacs'], 'advantages': advantages,
             'returns': returns, 'actions': batch['actions'], 'obs': batch['obses'], 'dones': batch['dones'],
             'rnn_masks': rnn_masks, 'mu': batch['mus'].clone(), 'sigma': batch['sigmas'].clone(),
+            'rnn_states': batch.get('rnn_states', None),
         }
 
     def get_minibatch(self, i):
         s, e = i * self.minibatch_size, (i + 1) * self.minibatch_size
         self.last_range = (s, e)
-        return {k: (v[s:e] if v is not None else None) for k, v in self.dataset.items()}
+        mb = {k: (v[s:e] if v is not None else None) for k, v in self.dataset.items() if k != 'rnn_states'}
+        if self.is_rnn:    # datasets.py:63-73
+            ng = self.minibatch_size // self.seq_length
+            mb['rnn_states'] = [st[:, i * ng:(i + 1) * ng, :].contiguous() for st in self.dataset['rnn_states']]
+        return mb
 
     def calc_losses(self, mb, res):
         c = self.cfg
@@ -642,7 +713,11 @@ class OracleAgent:
     def train_actor_critic(self, mb):
         c = self.cfg
         rnn_masks = mb.get('rnn_masks', None)
-        res = self.model.forward(mb['obs'], is_train=True, prev_actions=mb['actions'])
+        if self.is_rnn:
+            res = self.model.forward(mb['obs'], is_train=True, prev_actions=mb['actions'], rnn_states=mb['rnn_states'],
+                                     seq_length=self.seq_length, dones=mb['dones'] if c['zero_rnn_on_done'] else None)
+        else:
+            res = self.model.forward(mb['obs'], is_train=True, prev_actions=mb['actions'])
         loss, a_loss, c_loss, entropy, b_loss = self.calc_losses(mb, res)
         params = self.model.parameters()
         for p in params:

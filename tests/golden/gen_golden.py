@@ -166,7 +166,7 @@ class TapeVecEnv:
         pass
 
 
-def make_params(N, H, mb, units, overrides=None):
+def make_params(N, H, mb, units, overrides=None, rnn_units=0):
     network = {
         'name': 'actor_critic', 'separate': False,
         'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None',
@@ -175,6 +175,8 @@ def make_params(N, H, mb, units, overrides=None):
                                  'fixed_sigma': True}},
         'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}},
     }
+    if rnn_units:
+        network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': True}
     # hyper-parameters of configs/mujoco/ant_envpool.yaml:28-56
     config = {
         'name': 'golden', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0},
@@ -193,7 +195,7 @@ def make_params(N, H, mb, units, overrides=None):
 
 
 def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, overrides=None, autoreset='same_step',
-              seed=3):
+              seed=3, rnn_units=0):
     from rl_games.torch_runner import Runner
     from oracle.ppo_oracle import make_tapes
     torch.manual_seed(seed)
@@ -202,7 +204,7 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
     obs_tape, done_tape, tout_tape = make_tapes(T, N, D, seed=seed)
     env = TapeVecEnv(obs_tape, done_tape, tout_tape, autoreset)
     env.A = A
-    params = make_params(N, H, mb, units, overrides)
+    params = make_params(N, H, mb, units, overrides, rnn_units)
     params['config']['env_info'] = env.get_env_info()
     runner = Runner()
     runner.load({'params': params})
@@ -257,7 +259,7 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
         torch.normal = orig_normal
     save(name, {'N': N, 'H': H, 'D': D, 'A': A, 'units': list(units), 'mb': mb, 'epochs': epochs,
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
-                'autoreset': autoreset, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
+                'autoreset': autoreset, 'rnn_units': rnn_units, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
                 'noise': noise, 'init_state': init_state, 'epochs_out': epochs_out,
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
@@ -271,3 +273,4 @@ if __name__ == '__main__':
         'use_smooth_clamp': False, 'bound_loss_type': 'bound', 'bounds_loss_coef': 0.001, 'entropy_coef': 0.003,
         'clip_value': False, 'truncate_grads': False, 'value_bootstrap': False, 'mini_epochs': 2,
         'weight_decay': 0.01, 'lr_schedule': None})
+    gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})

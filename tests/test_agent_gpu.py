@@ -264,3 +264,52 @@ def test_bf16_tcgen05_agent_tracks_fp32_agent():
             assert cos > 0.8, (k, cos)
     assert 0.4 < t.last_lr / f.last_lr < 2.5
     assert int(t.model.running_mean_std.count) == int(f.model.running_mean_std.count)
+
+
+@pytest.mark.parametrize('name,N,H,D,A,mb,masked,mp', [
+    ('c3_ant_envpool_shape', 4096, 64, 27, 8, 32768, True, False),     # BASELINE configs[2]: next_step autoreset => masked path
+    ('c5_per_gpu_shape', 16384, 32, 256, 8, 32768, False, False),      # BASELINE configs[4] per-GPU shard (obs 256): fp32 path
+    ('c2_shape_bf16', 16384, 16, 60, 8, 32768, False, True),           # BASELINE configs[1] on the tcgen05 path
+])
+def test_full_size_configs_one_epoch_vs_oracle(name, N, H, D, A, mb, masked, mp):
+    """BASELINE.json full-size shapes: one complete epoch (rollout -> GAE -> 1 mini-epoch of updates) against the CPU oracle
+    on identical tapes / weights / noise.  fp32 path: rollout + normalised batch rtol 1e-4, losses rtol 5e-3, weights atol 5e-5;
+    bf16 path: bf16 tolerance class."""
+    units = [256, 128, 64]
+    g = torch.Generator().manual_seed(17)
+    T = H + 1
+    obs_tape = torch.randn(T, N, D, generator=g) * 1.5 + 0.3
+    done_tape = (torch.rand(T, N, generator=g) < 0.03).to(torch.uint8)
+    tout_tape = (torch.rand(T, N, generator=g) < 0.3) & done_tape.bool()
+    params = O.init_params(D, units, A, seed=6)
+    noise = torch.randn(H, N, A, generator=g)
+    oag = O.OracleAgent(O.TapeEnv(obs_tape, done_tape, tout_tape), params, D, A, units, N, H, mb,
+                        {'mask_autoreset_rows': masked, 'mini_epochs': 1}, matmul_dtype=torch.bfloat16 if mp else None)
+    oag.obs = oag.env_reset()
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    out = oag.train_epoch(noise)
+    env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A, 'next_step' if masked else 'same_step')
+    agent = make_agent({'mini_epochs': 1, 'mixed_precision': mp}, N, H, D, A, units, mb, env, params)
+    agent.epoch_num += 1
+    agent.train_epoch(noise=noise.to(DEV))
+    fl = O.swap_and_flatten01
+    st = agent.last_stats
+    if not mp:
+        assert torch.equal(agent.dones_buf.cpu(), oag.buf['dones'])
+        torch.testing.assert_close(agent.values.cpu(), oag.buf['values'].squeeze(2), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(fl(agent.advs_n).cpu(), oag.dataset['advantages'], rtol=1e-3, atol=1e-4)
+        torch.testing.assert_close(st[:, 0], torch.stack(out['a_loss']), rtol=5e-3, atol=1e-5)
+        torch.testing.assert_close(st[:, 1], torch.stack(out['c_loss']), rtol=5e-3, atol=1e-5)
+        torch.testing.assert_close(st[:, 4], torch.stack(out['kl']), rtol=1e-2, atol=1e-6)
+        assert agent.last_lr == pytest.approx(oag.last_lr, rel=1e-12)
+        sd = agent.model.state_dict()
+        for k in O.param_names(3):
+            torch.testing.assert_close(sd[k].cpu(), oag.model.p[k].detach(), rtol=1e-3, atol=5e-5, msg=lambda m: k + ': ' + m)
+        assert int(sd['running_mean_std.count']) == int(oag.model.running_mean_std.count)
+        torch.testing.assert_close(sd['running_mean_std.running_mean'].cpu(), oag.model.running_mean_std.running_mean, rtol=1e-5, atol=1e-6)
+    else:
+        torch.testing.assert_close(agent.values.cpu(), oag.buf['values'].squeeze(2), rtol=0, atol=8e-2)
+        torch.testing.assert_close(st[:, 0], torch.stack(out['a_loss']), rtol=0.15, atol=3e-3)
+        torch.testing.assert_close(st[:, 1], torch.stack(out['c_loss']), rtol=0.1, atol=2e-2)
+        torch.testing.assert_close(st[:, 4], torch.stack(out['kl']), rtol=0.3, atol=2e-4)
+        assert int(agent.model.running_mean_std.count) == int(oag.model.running_mean_std.count)

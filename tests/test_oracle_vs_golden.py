@@ -104,6 +104,8 @@ def _oracle_from_golden(g):
     cfg['lr_schedule'] = cfgk.get('lr_schedule', None)
     cfg['weight_decay'] = cfgk.get('weight_decay', 0.0)
     cfg['mask_autoreset_rows'] = g['autoreset'] == 'next_step'
+    cfg['rnn_units'] = g.get('rnn_units', 0)
+    cfg['seq_length'] = cfgk.get('seq_length', 4)
     env = O.TapeEnv(g['obs_tape'], g['done_tape'], g['timeout_tape'])
     params = {k: v for k, v in g['init_state'].items() if k.startswith('a2c_network')}
     ag = O.OracleAgent(env, params, g['D'], g['A'], g['units'], g['N'], g['H'], g['mb'], cfg)
@@ -111,11 +113,12 @@ def _oracle_from_golden(g):
     return ag
 
 
-@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt'])
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
-    assert g['param_order'] == O.param_names(len(g['units']))
+    lstm = g.get('rnn_units', 0) > 0
+    assert g['param_order'] == O.param_names(len(g['units']), lstm=lstm)
     ag = _oracle_from_golden(g)
     for ep, ref in enumerate(g['epochs_out']):
         out = ag.train_epoch(g['noise'][ep])
@@ -135,7 +138,7 @@ def test_full_train_epochs_match_reference_agent(name):
         torch.testing.assert_close(torch.stack(out['c_loss']), ref['c_losses'], rtol=1e-3, atol=1e-6)
         torch.testing.assert_close(torch.stack(out['entropy']), ref['entropies'], rtol=1e-5, atol=1e-6)
         assert ag.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
-        for k in O.param_names(len(g['units'])):
+        for k in O.param_names(len(g['units']), lstm=lstm):
             torch.testing.assert_close(ag.model.p[k].detach(), ref['state'][k], rtol=1e-4, atol=2e-6, msg=lambda m: k + m)
         st = ref['state']
         torch.testing.assert_close(ag.model.running_mean_std.running_mean, st['running_mean_std.running_mean'], rtol=1e-9, atol=1e-9)
