@@ -120,7 +120,7 @@ int b200rl_normalize_f32(const float* x, float* y, const double* mean, const dou
 int b200rl_linear_fwd_f32(const float* X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
                           const float* norm_mean, const float* norm_std,
                           const float* W, const float* b, float* Y, int M, int K, int Nout, int act,
-                          void* stream);
+                          int accumulate /* Y = act(XW^T + b + Y) */, void* stream);
 int b200rl_linear_bwd_data_f32(const float* dY, const float* W, const float* A_prev, float* dX,
                                int M, int K, int Nout, int act_prev, void* stream);
 int b200rl_linear_bwd_weight_f32(const float* dY, const float* X, int rows_per_chunk, int64_t chunk_stride,
@@ -129,6 +129,25 @@ int b200rl_linear_bwd_weight_f32(const float* dY, const float* X, int rows_per_c
                                  int n_splits, void* stream);
 /* out[i] = sum_s part[s*split_stride + i]  (deterministic, fixed order) */
 int b200rl_reduce_splits_f32(const float* part, float* out, int n, int n_splits, int64_t split_stride, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LSTM-with-dones cell (common/layers/recurrent.py:20-80 LSTMWithDones; gate order i,f,g,o; fp32).  The GEMM halves
+ * run on b200rl_linear_*; these are the pointwise halves of the forward step and of its BPTT.
+ *  cell_fwd: gates [S,4Hd] pre-activations -> activations in place; cin = already-masked c_{t-1}; writes c_out, h_out,
+ *            optionally scatters h into an MLP-order buffer (row s -> (s/scatter_rpc)*scatter_stride + s%scatter_rpc) and the
+ *            masked carries (h,c)*(1-done_next) for the next step (done_next rows chunk-mapped).
+ *  cell_bwd: dh = dH[scatter row] + dhin_next*(1-done_next), dc = dcin_next*(1-done_next) -> dgates [S,4Hd], dcin [S,Hd].
+ *  mask_rows: out[s] = in[chunk row s] * (1 - done[chunk row s])  (window-initial states; zeroing after episode ends,
+ *             a2c_common.py:1150-1153)
+ * ------------------------------------------------------------------------------------------- */
+int b200rl_lstm_cell_fwd_f32(float* gates, const float* cin, float* c_out, float* h_out, float* h_scatter, int scatter_rpc,
+                             int64_t scatter_stride, float* hin_next, float* cin_next, const uint8_t* done_next,
+                             int done_rpc, int64_t done_stride, int S, int Hd, void* stream);
+int b200rl_lstm_cell_bwd_f32(const float* gates_act, const float* c_t, const float* cin, const float* dH, int scatter_rpc,
+                             int64_t scatter_stride, const float* dhin_next, const float* dcin_next, const uint8_t* done_next,
+                             int done_rpc, int64_t done_stride, float* dgates, float* dcin, int S, int Hd, void* stream);
+int b200rl_rnn_mask_rows_f32(const float* in, int in_rpc, int64_t in_stride, float* out, const uint8_t* done, int done_rpc,
+                             int64_t done_stride, int S, int Hd, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * PPO loss head.  Replaces a2c_continuous.py:97-134 (calc_losses), :241-257 (bound/reg loss),

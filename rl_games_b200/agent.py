@@ -261,6 +261,7 @@ class A2CAgent:
         self.is_tensor_obses = False
         self.is_rnn = False
         self.rnn_states = None
+        self.zero_rnn_on_done = config.get('zero_rnn_on_done', True)
 
         # ---- ContinuousA2CBase (a2c_common.py:1484-1497) ----
         self.is_discrete = False
@@ -278,6 +279,16 @@ class A2CAgent:
         self.value_mean_std = self.model.value_mean_std if self.normalize_value else None
         # precision mode: mixed_precision True (reference default on bf16 GPUs, a2c_common.py:429) -> bf16 tcgen05
         # kernels (mlp_tc.cu); False -> fp32 CUDA-core kernels (mlp_simt.cu).  No silent downgrade.
+        self.is_rnn = self.model.is_rnn()
+        if self.is_rnn:
+            if self.horizon_length % self.seq_length != 0:
+                raise ValueError(f"Horizon length ({self.horizon_length}) must be divisible by sequence length ({self.seq_length})")
+            if self.mask_autoreset_rows:
+                raise NotImplementedError('rnn policies with next_step-autoreset masking are not on the B200 hot path yet')
+            if not self.zero_rnn_on_done:
+                raise NotImplementedError('zero_rnn_on_done: False is not on the B200 hot path')
+            if self.mixed_precision:
+                raise NotImplementedError('rnn (LSTM) policies run on the fp32 path: set mixed_precision: False')
         self.use_tc = bool(self.mixed_precision)
         if self.use_tc and not ops.tc_supported(self.model.D, self.model.units, self.actions_num):
             raise NotImplementedError(
@@ -352,7 +363,17 @@ class A2CAgent:
             self.ra = self.ta = self.dA = []
         else:
             self.n_splits = max(1, min(64, mb // 256))
-        self.part = f(self.n_splits, m.num_params)
+        self.part_rows = self.n_splits * (self.seq_length if self.is_rnn else 1)
+        self.part = f(self.part_rows, m.num_params)
+        if self.is_rnn:
+            Hd, T = m.rnn_units, self.seq_length
+            S = mb // T
+            self.rnn_h, self.rnn_c = f(N, Hd), f(N, Hd)                       # current states (a2c_common.py:652-655)
+            self.rnn_h0, self.rnn_c0 = f(H // T, N, Hd), f(H // T, N, Hd)     # mb_rnn_states (:656-660), [num_seqs_per_env, N, hid]
+            self.r_gates, self.r_tmp_h, self.r_tmp_c = f(N, 4 * Hd), f(N, Hd), f(N, Hd)
+            self.t_gates, self.t_hin, self.t_cin, self.t_c = f(T, S, 4 * Hd), f(T, S, Hd), f(T, S, Hd), f(T, S, Hd)
+            self.t_hdense, self.t_hmlp, self.t_dHmlp = f(S, Hd), f(mb, Hd), f(mb, Hd)
+            self.t_dgates, self.t_dhin, self.t_dcin = f(S, 4 * Hd), f(S, Hd), f(2, S, Hd)
         self.gae_partials = torch.zeros((N + 127) // 128, 8, dtype=torch.float64, device=dev)
         self.loss_partials = torch.zeros(max((mb + 127) // 128, 148), ops.loss_partial_stride(), dtype=torch.float64, device=dev)
         self.n_updates = self.mini_epochs_num * self.num_minibatches
@@ -522,10 +543,9 @@ class A2CAgent:
     # =============================================================================== policy forward
     def _trunk(self, x, acts, M, rows_per_chunk=None, chunk_stride=0):
         m = self.model
-        nm = m.running_mean_std.mean_f32 if self.normalize_input else None
-        ns = m.running_mean_std.std_f32 if self.normalize_input else None
+        nm, ns = (None, None) if self.is_rnn else self._norm()      # with an LSTM in front the MLP input is h (dense, not normalised)
         ops.linear_fwd(x, m.W[0], m.b[0], acts[0], m.act_id, rows_per_chunk=rows_per_chunk, chunk_stride=chunk_stride,
-                       x_ld=m.D, norm_mean=nm, norm_std=ns, M=M)
+                       x_ld=m.mlp_in, norm_mean=nm, norm_std=ns, M=M)
         for i in range(1, len(m.units)):
             ops.linear_fwd(acts[i - 1], m.W[i], m.b[i], acts[i], m.act_id, M=M)
 
@@ -539,6 +559,15 @@ class A2CAgent:
         m = self.model
         return (m.running_mean_std.mean_f32, m.running_mean_std.std_f32) if self.normalize_input else (None, None)
 
+    def _lstm_step(self, obs, h_in, c_in, h_out, c_out):
+        """one LSTM step for all N envs (seq_length 1, models.py -> network_builder.py:452-492 -> recurrent.py): returns h_out"""
+        m, N = self.model, self.num_actors
+        nm, ns = self._norm()
+        ops.linear_fwd(obs, m.W_ih, m.b_ih, self.r_gates, 0, x_ld=m.D, norm_mean=nm, norm_std=ns, M=N)
+        ops.linear_fwd(h_in, m.W_hh, m.b_hh, self.r_gates, 0, M=N, accumulate=True)
+        ops.lstm_cell_fwd(self.r_gates, c_in, c_out, h_out, N, m.rnn_units)
+        return h_out
+
     def _policy_step(self, obs, t, noise=None):
         m, N, A = self.model, self.num_actors, self.actions_num
         if self.use_tc:
@@ -550,6 +579,8 @@ class A2CAgent:
                                    self.actions_high, self.dones, self.dones_buf[t], self.prev_dones,
                                    None if self.valid is None else self.valid[t])
             return
+        if self.is_rnn:
+            obs = self._lstm_step(obs, self.rnn_h, self.rnn_c, self.rnn_h, self.rnn_c)
         self._trunk(obs, self.ra, N)
         ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
                                m.value_mean_std.running_var, self.normalize_value, noise, self.rng_seed, self.rng_epoch, t,
@@ -569,6 +600,8 @@ class A2CAgent:
                                    0, None, None, None, None, self.last_values, None, False, None, None, None, None, None, None,
                                    values_only=True)
             return self.last_values.unsqueeze(1)
+        if self.is_rnn:     # get_values does not advance the agent's rnn states (a2c_common.py:603-626)
+            o = self._lstm_step(o, self.rnn_h, self.rnn_c, self.r_tmp_h, self.r_tmp_c)
         self._trunk(o, self.ra, N)
         ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
                                m.value_mean_std.running_var, self.normalize_value, None, 0, None, 0, None, None, None, None,
@@ -593,6 +626,9 @@ class A2CAgent:
         for t in range(H):
             obs = self.obs['obs']
             self.obses[t].copy_(obs)
+            if self.is_rnn and t % self.seq_length == 0:      # play_steps_rnn: a2c_common.py:1081-1083
+                self.rnn_h0[t // self.seq_length].copy_(self.rnn_h)
+                self.rnn_c0[t // self.seq_length].copy_(self.rnn_c)
             self._policy_step(obs, t, None if noise is None else noise[t])
             t0 = time.perf_counter()
             self.obs, rewards, dones, infos = self.env_step(self.env_actions)
@@ -601,6 +637,9 @@ class A2CAgent:
             ops.post_step(rewards, dones, tout, self.values[t], None if self.valid is None else self.valid[t], self.rewards[t],
                           self.dones, self.prev_dones, self.ep_state, self.meter, self.games_to_track, self.post_scratch,
                           self.counters[0:1], N, self.shaper_cfg)
+            if self.is_rnn:     # zero the states of finished episodes (a2c_common.py:1150-1153)
+                ops.rnn_mask_rows(self.rnn_h, N, 0, self.rnn_h, N, self.model.rnn_units, done=self.dones, done_rpc=N)
+                ops.rnn_mask_rows(self.rnn_c, N, 0, self.rnn_c, N, self.model.rnn_units, done=self.dones, done_rpc=N)
             if wants_idx:
                 self.algo_observer.process_infos(infos, self.dones.nonzero(as_tuple=False))
         self.get_values(self.obs)
@@ -685,7 +724,11 @@ class A2CAgent:
         if self.use_tc:
             self._minibatch_update_tc(i, u, x, e0)
             return
-        self._trunk(x, self.ta, mb, rows_per_chunk=epm, chunk_stride=N)
+        if self.is_rnn:
+            self._lstm_window_fwd(e0)
+            self._trunk(self.t_hmlp, self.ta, mb)
+        else:
+            self._trunk(x, self.ta, mb, rows_per_chunk=epm, chunk_stride=N)
         nb = ops.ppo_head_loss(self.ta[-1], m.W_head, m.b_head, m.sigma, self.actions[0, e0:], self.mus[0, e0:],
                                self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:], self.neglogpacs[0, e0:],
                                self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:], epm, N, mb, A,
@@ -707,12 +750,59 @@ class A2CAgent:
                 ops.linear_bwd_weight(self.dA[l], self.ta[l - 1], self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
                                       M=mb, split_stride=P)
                 ops.linear_bwd_data(self.dA[l], m.W[l], self.ta[l - 1], self.dA[l - 1], m.act_id, M=mb)
+            elif self.is_rnn:
+                ops.linear_bwd_weight(self.dA[0], self.t_hmlp, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S, M=mb,
+                                      split_stride=P)
+                ops.linear_bwd_data(self.dA[0], m.W[0], None, self.t_dHmlp, 0, M=mb)
+                self._lstm_window_bwd(e0)
             else:
                 ops.linear_bwd_weight(self.dA[0], x, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
                                       rows_per_chunk=epm, chunk_stride=N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=mb,
                                       split_stride=P)
-        ops.reduce_splits(self.part[0, A:], gv['grad'][A:], P - A, S, split_stride=P)
+        ops.reduce_splits(self.part[0, A:], gv['grad'][A:], P - A, self.part_rows, split_stride=P)
         self._step_optimizer(u, gv, P)
+
+    def _lstm_window_fwd(self, e0):
+        """Training forward of the LSTM over the seq_length window of every sequence of the minibatch (network_builder.py:452-492,
+        recurrent.py:26-58): sequences (j, env) in order j*epm + (env - e0); step t uses arena rows (j*T + t, env)."""
+        m, H, N, T = self.model, self.horizon_length, self.num_actors, self.seq_length
+        epm, Hd = self.envs_per_mb, m.rnn_units
+        S = epm * H // T
+        nm, ns = self._norm()
+        # window-initial states = snapshots taken during the rollout, zeroed where the episode ended entering step 0
+        ops.rnn_mask_rows(self.rnn_h0[0, e0:], epm, N, self.t_hin[0], S, Hd, done=self.dones_buf[0, e0:], done_rpc=epm, done_stride=T * N)
+        ops.rnn_mask_rows(self.rnn_c0[0, e0:], epm, N, self.t_cin[0], S, Hd, done=self.dones_buf[0, e0:], done_rpc=epm, done_stride=T * N)
+        for t in range(T):
+            ops.linear_fwd(self.obses[t, e0:], m.W_ih, m.b_ih, self.t_gates[t], 0, rows_per_chunk=epm, chunk_stride=T * N, x_ld=m.D,
+                           norm_mean=nm, norm_std=ns, M=S)
+            ops.linear_fwd(self.t_hin[t], m.W_hh, m.b_hh, self.t_gates[t], 0, M=S, accumulate=True)
+            last = t == T - 1
+            ops.lstm_cell_fwd(self.t_gates[t], self.t_cin[t], self.t_c[t], self.t_hdense, S, Hd,
+                              h_scatter=self.t_hmlp[t * epm:], scatter_rpc=epm, scatter_stride=T * epm,
+                              hin_next=None if last else self.t_hin[t + 1], cin_next=None if last else self.t_cin[t + 1],
+                              done_next=None if last else self.dones_buf[t + 1, e0:], done_rpc=epm, done_stride=T * N)
+
+    def _lstm_window_bwd(self, e0):
+        """BPTT over the window: cell backward, weight gradients of W_ih / W_hh (+ both biases) per step into their own split rows,
+        dgrad through W_hh to the previous step."""
+        m, H, N, T = self.model, self.horizon_length, self.num_actors, self.seq_length
+        epm, Hd, P, Ssp = self.envs_per_mb, m.rnn_units, m.num_params, self.n_splits
+        S = epm * H // T
+        nm, ns = self._norm()
+        o_wih, o_whh, o_bih, o_bhh = (m.layout[k][0] for k in ('W_ih', 'W_hh', 'b_ih', 'b_hh'))
+        for t in range(T - 1, -1, -1):
+            last = t == T - 1
+            ops.lstm_cell_bwd(self.t_gates[t], self.t_c[t], self.t_cin[t], self.t_dgates, self.t_dcin[t & 1], S, Hd,
+                              dH=self.t_dHmlp[t * epm:], scatter_rpc=epm, scatter_stride=T * epm,
+                              dhin_next=None if last else self.t_dhin, dcin_next=None if last else self.t_dcin[(t + 1) & 1],
+                              done_next=None if last else self.dones_buf[t + 1, e0:], done_rpc=epm, done_stride=T * N)
+            row = t * Ssp
+            ops.linear_bwd_weight(self.t_dgates, self.obses[t, e0:], self.part[row, o_wih:], self.part[row, o_bih:], m.D, 4 * Hd, Ssp,
+                                  rows_per_chunk=epm, chunk_stride=T * N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=S, split_stride=P)
+            ops.linear_bwd_weight(self.t_dgates, self.t_hin[t], self.part[row, o_whh:], self.part[row, o_bhh:], Hd, 4 * Hd, Ssp, M=S,
+                                  split_stride=P)
+            if t > 0:
+                ops.linear_bwd_data(self.t_dgates, m.W_hh, None, self.t_dhin, 0, M=S)
 
     def _minibatch_update_tc(self, i, u, x, e0):
         """bf16 tcgen05 edition: fused fwd+loss kernel, two backward kernels, split reduce, Adam, repack."""

@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(NT) linear_fwd_kernel(
     const float* __restrict__ X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
     const float* __restrict__ nm, const float* __restrict__ ns,
     const float* __restrict__ W, const float* __restrict__ bias, float* __restrict__ Y,
-    int M, int K, int N, int act) {
+    int M, int K, int N, int act, int accumulate) {
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -74,7 +74,10 @@ __global__ void __launch_bounds__(NT) linear_fwd_kernel(
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int n = n0 + tx * 4 + j;
-            if (n < N) Y[(int64_t)m * N + n] = act_fwd(acc[i][j] + (bias ? __ldg(bias + n) : 0.f), act);
+            if (n < N) {
+                const float prev = accumulate ? Y[(int64_t)m * N + n] : 0.f;
+                Y[(int64_t)m * N + n] = act_fwd(acc[i][j] + (bias ? __ldg(bias + n) : 0.f) + prev, act);
+            }
         }
     }
 }
@@ -211,12 +214,12 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __re
 B200RL_EXPORT int b200rl_linear_fwd_f32(const float* X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
                                         const float* norm_mean, const float* norm_std,
                                         const float* W, const float* b, float* Y, int M, int K, int Nout, int act,
-                                        void* stream) {
+                                        int accumulate, void* stream) {
     if (!X || !W || !Y || M <= 0 || K <= 0 || Nout <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
     if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200RL_EINVAL;
     dim3 grid((M + BM - 1) / BM, (Nout + BN - 1) / BN);
     linear_fwd_kernel<<<grid, NT, 0, as_stream(stream)>>>(X, rows_per_chunk, chunk_stride, x_ld, norm_mean, norm_std, W, b, Y,
-                                                          M, K, Nout, act);
+                                                          M, K, Nout, act, accumulate);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }

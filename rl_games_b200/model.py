@@ -90,10 +90,13 @@ class _NetworkView:
         return self._m.sigma
 
     def is_rnn(self):
-        return False
+        return self._m.rnn_units > 0
 
 
 class B200Model:
+    RNN_KEYS = (('a2c_network.rnn.rnn.weight_ih_l0', 'W_ih'), ('a2c_network.rnn.rnn.weight_hh_l0', 'W_hh'),
+                ('a2c_network.rnn.rnn.bias_ih_l0', 'b_ih'), ('a2c_network.rnn.rnn.bias_hh_l0', 'b_hh'))
+
     def __init__(self, network_params, obs_dim, act_dim, device, normalize_input, normalize_value, value_size=1,
                  seed=None):
         if value_size != 1:
@@ -108,9 +111,16 @@ class B200Model:
         self.act_id = ops.ACT[self.activation]
         if network_params.get('separate', False):
             raise NotImplementedError('separate actor/critic trunks are not on the B200 hot path yet')
-        for k in ('cnn', 'rnn'):
-            if k in network_params:
-                raise NotImplementedError(f"'{k}' networks are not on the B200 hot path yet")
+        if 'cnn' in network_params:
+            raise NotImplementedError("'cnn' networks are not on the B200 hot path yet")
+        self.rnn_units = 0
+        if 'rnn' in network_params:
+            rnn = network_params['rnn']
+            if rnn.get('name') != 'lstm' or rnn.get('layers', 1) != 1 or not rnn.get('before_mlp', False) or rnn.get('layer_norm', False) \
+                    or rnn.get('concat_input', False) or rnn.get('concat_output', False):
+                raise NotImplementedError("rnn: only a single-layer 'lstm' with before_mlp: True (no layer_norm / concat) is on the B200 "
+                                          "hot path (BASELINE configs[3])")
+            self.rnn_units = int(rnn['units'])
         space = network_params['space']['continuous']
         if not space.get('fixed_sigma', True):
             raise NotImplementedError('state-dependent sigma is not on the B200 hot path yet')
@@ -127,6 +137,10 @@ class B200Model:
         # ---- flat arenas ----
         sizes = [('sigma', (self.A,))]
         ins = self.D
+        if self.rnn_units:
+            Hd = self.rnn_units
+            sizes += [('W_ih', (4 * Hd, ins)), ('W_hh', (4 * Hd, Hd)), ('b_ih', (4 * Hd,)), ('b_hh', (4 * Hd,))]
+            ins = Hd
         for i, u in enumerate(self.units):
             sizes += [(f'W{i}', (u, ins)), (f'b{i}', (u,))]
             ins = u
@@ -146,6 +160,9 @@ class B200Model:
         self.W = [self.view(f'W{i}') for i in range(len(self.units))]
         self.b = [self.view(f'b{i}') for i in range(len(self.units))]
         self.sigma = self.view('sigma')
+        if self.rnn_units:
+            self.W_ih, self.W_hh, self.b_ih, self.b_hh = (self.view(n) for n in ('W_ih', 'W_hh', 'b_ih', 'b_hh'))
+        self.mlp_in = self.rnn_units if self.rnn_units else self.D
         self.W_head, self.b_head = self.view('W_head'), self.view('b_head')
         self.gW = [self.view(f'W{i}', self.grad) for i in range(len(self.units))]
         self.gb = [self.view(f'b{i}', self.grad) for i in range(len(self.units))]
@@ -170,6 +187,12 @@ class B200Model:
         mlp_init = network_params['mlp'].get('initializer', {'name': 'default'})
         cpu = {}
         ins = self.D
+        if self.rnn_units:   # torch.nn.LSTM default init U(-1/sqrt(hid), 1/sqrt(hid)) for all four tensors (mlp_init does not touch it)
+            Hd = self.rnn_units
+            k = 1.0 / math.sqrt(Hd)
+            for n, shp in (('W_ih', (4 * Hd, ins)), ('W_hh', (4 * Hd, Hd)), ('b_ih', (4 * Hd,)), ('b_hh', (4 * Hd,))):
+                cpu[n] = torch.empty(*shp).uniform_(-k, k)
+            ins = Hd
         for i, u in enumerate(self.units):
             w = torch.empty(u, ins)
             _apply_init(w, mlp_init, ins)
@@ -190,10 +213,13 @@ class B200Model:
 
     # ------------------------------------------------------------------------------------------- nn.Module-ish
     def is_rnn(self):
-        return False
+        return self.rnn_units > 0
 
-    def get_default_rnn_state(self):
-        return None
+    def get_default_rnn_state(self, num_seqs=1):
+        """network_builder.py:520-543 (lstm, not separate): (h, c) each [layers, num_seqs, units]"""
+        if not self.rnn_units:
+            return None
+        return (torch.zeros((1, num_seqs, self.rnn_units), device=self.device), torch.zeros((1, num_seqs, self.rnn_units), device=self.device))
 
     def get_aux_loss(self):
         return None
@@ -211,16 +237,14 @@ class B200Model:
 
     def parameters(self):
         """Reference parameter order (optimizer state is index-keyed): sigma, actor_mlp.*, value.*, mu.*"""
-        out = [self.sigma]
-        for w, b in zip(self.W, self.b):
-            out += [w, b]
-        out += [self.W_head[:1], self.b_head[:1], self.W_head[1:], self.b_head[1:]]
-        return out
+        return self._param_views(self.flat)
 
     def _param_views(self, arena):
         out = [self.view('sigma', arena)]
         for i in range(len(self.units)):
             out += [self.view(f'W{i}', arena), self.view(f'b{i}', arena)]
+        if self.rnn_units:   # registration order in A2CBuilder.Network.__init__: actor_mlp placeholder precedes self.rnn
+            out += [self.view(n, arena) for n in ('W_ih', 'W_hh', 'b_ih', 'b_hh')]
         wh, bh = self.view('W_head', arena), self.view('b_head', arena)
         out += [wh[:1], bh[:1], wh[1:], bh[1:]]
         return out
@@ -235,6 +259,9 @@ class B200Model:
         for i in range(len(self.units)):
             sd[f'a2c_network.actor_mlp.{2 * i}.weight'] = self.W[i].clone()
             sd[f'a2c_network.actor_mlp.{2 * i}.bias'] = self.b[i].clone()
+        for key, n in self.RNN_KEYS:
+            if self.rnn_units:
+                sd[key] = self.view(n).clone()
         sd['a2c_network.value.weight'] = self.W_head[:1].clone()
         sd['a2c_network.value.bias'] = self.b_head[:1].clone()
         sd['a2c_network.mu.weight'] = self.W_head[1:].clone()
@@ -253,6 +280,9 @@ class B200Model:
             for i in range(len(self.units)):
                 self.W[i].copy_(sd[f'a2c_network.actor_mlp.{2 * i}.weight'])
                 self.b[i].copy_(sd[f'a2c_network.actor_mlp.{2 * i}.bias'])
+            if self.rnn_units:
+                for key, n in self.RNN_KEYS:
+                    self.view(n).copy_(sd[key])
             self.W_head[:1].copy_(sd['a2c_network.value.weight'])
             self.b_head[:1].copy_(sd['a2c_network.value.bias'])
             self.W_head[1:].copy_(sd['a2c_network.mu.weight'])

@@ -126,12 +126,13 @@ def normalize(x, mean, var, denorm=False, eps=1e-5, out=None):
     return y
 
 
-def linear_fwd(X, W, b, Y, act, rows_per_chunk=None, chunk_stride=0, x_ld=None, norm_mean=None, norm_std=None, M=None):
+def linear_fwd(X, W, b, Y, act, rows_per_chunk=None, chunk_stride=0, x_ld=None, norm_mean=None, norm_std=None, M=None,
+               accumulate=False):
     Nout, K = W.shape
     M = Y.shape[0] if M is None else M
     check(lib.b200rl_linear_fwd_f32(ptr(X), M if rows_per_chunk is None else rows_per_chunk, chunk_stride,
                                     K if x_ld is None else x_ld, ptr(norm_mean), ptr(norm_std), ptr(W), ptr(b), ptr(Y),
-                                    M, K, Nout, act, _stream()), 'linear_fwd')
+                                    M, K, Nout, act, int(accumulate), _stream()), 'linear_fwd')
 
 
 def linear_bwd_data(dY, W, A_prev, dX, act_prev, M=None):
@@ -353,3 +354,23 @@ def allreduce_adam(table, parity, rank, my_flags_ptr, seq, red, nrm_part, grid_b
                                         ptr(exp_avg), ptr(exp_avg_sq), n, ptr(state_d), ctypes.addressof(cfg), ptr(stats_out),
                                         ptr(counter), ptr(wpack), None if pack_table is None else ctypes.addressof(pack_table),
                                         _stream()), 'allreduce_adam')
+
+
+# ------------------------------------------------------------------------------------------ LSTM cell (fp32)
+def lstm_cell_fwd(gates, cin, c_out, h_out, S, Hd, h_scatter=None, scatter_rpc=0, scatter_stride=0, hin_next=None, cin_next=None,
+                  done_next=None, done_rpc=0, done_stride=0):
+    check(lib.b200rl_lstm_cell_fwd_f32(ptr(gates), ptr(cin), ptr(c_out), ptr(h_out), ptr(h_scatter), scatter_rpc, scatter_stride,
+                                       ptr(hin_next), ptr(cin_next), ptr(done_next), done_rpc, done_stride, S, Hd, _stream()),
+          'lstm_cell_fwd')
+
+
+def lstm_cell_bwd(gates_act, c_t, cin, dgates, dcin, S, Hd, dH=None, scatter_rpc=0, scatter_stride=0, dhin_next=None, dcin_next=None,
+                  done_next=None, done_rpc=0, done_stride=0):
+    check(lib.b200rl_lstm_cell_bwd_f32(ptr(gates_act), ptr(c_t), ptr(cin), ptr(dH), scatter_rpc, scatter_stride, ptr(dhin_next),
+                                       ptr(dcin_next), ptr(done_next), done_rpc, done_stride, ptr(dgates), ptr(dcin), S, Hd, _stream()),
+          'lstm_cell_bwd')
+
+
+def rnn_mask_rows(inp, in_rpc, in_stride, out, S, Hd, done=None, done_rpc=0, done_stride=0):
+    check(lib.b200rl_rnn_mask_rows_f32(ptr(inp), in_rpc, in_stride, ptr(out), ptr(done), done_rpc, done_stride, S, Hd, _stream()),
+          'rnn_mask_rows')

@@ -51,12 +51,14 @@ class TapeEnvGPU:
         pass
 
 
-def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state):
+def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0):
     from rl_games_b200.runner import Runner
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    if rnn_units:
+        network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': True}
     config = {'name': 'gpu_parity', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0}, 'device': DEV,
               'multi_gpu': False, 'mixed_precision': False, 'normalize_input': True, 'normalize_value': True,
               'value_bootstrap': True, 'normalize_advantage': True, 'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4,
@@ -80,7 +82,7 @@ def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state):
     return agent
 
 
-def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True):
+def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True, lstm=False):
     fl = O.swap_and_flatten01
     torch.testing.assert_close(fl(agent.advs_n).cpu(), ref_ds['advantages'], rtol=2e-4, atol=2e-5)
     torch.testing.assert_close(fl(agent.returns_n.unsqueeze(2)).cpu(), ref_ds['returns'], rtol=1e-4, atol=1e-5)
@@ -95,7 +97,7 @@ def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True
             torch.testing.assert_close(st[:, col], ref_losses[key], rtol=2e-3, atol=2e-6, msg=lambda m: key + ': ' + m)
     assert agent.last_lr == pytest.approx(ref_lr, rel=1e-12)
     sd = agent.model.state_dict()
-    for k in O.param_names(len(units)):
+    for k in O.param_names(len(units), lstm=lstm):
         torch.testing.assert_close(sd[k].cpu(), ref_state[k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
     for pre in ('running_mean_std.', 'value_mean_std.'):
         assert int(sd[pre + 'count']) == int(ref_state[pre + 'count'])
@@ -103,18 +105,19 @@ def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True
         torch.testing.assert_close(sd[pre + 'running_var'].cpu(), ref_state[pre + 'running_var'].reshape(-1), rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt'])
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt'])
 @pytest.mark.parametrize('graph', [False, True])
 def test_agent_matches_reference_golden(name, graph):
     g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk = g['config']
     over = {k: cfgk[k] for k in ('clip_value', 'use_smooth_clamp', 'bound_loss_type', 'bounds_loss_coef', 'entropy_coef',
-                                 'truncate_grads', 'value_bootstrap', 'mini_epochs', 'lr_schedule', 'weight_decay', 'critic_coef')
+                                 'truncate_grads', 'value_bootstrap', 'mini_epochs', 'lr_schedule', 'weight_decay', 'critic_coef', 'seq_length')
             if k in cfgk}
     over.setdefault('lr_schedule', None)
     over['b200_cuda_graph'] = graph
     env = TapeEnvGPU(g['obs_tape'], g['done_tape'], g['timeout_tape'], g['A'], g['autoreset'])
-    agent = make_agent(over, g['N'], g['H'], g['D'], g['A'], g['units'], g['mb'], env, g['init_state'])
+    lstm = g.get('rnn_units', 0) > 0
+    agent = make_agent(over, g['N'], g['H'], g['D'], g['A'], g['units'], g['mb'], env, g['init_state'], rnn_units=g.get('rnn_units', 0))
     for ep, ref in enumerate(g['epochs_out']):
         agent.epoch_num += 1
         agent.train_epoch(noise=g['noise'][ep].to(DEV))
@@ -127,7 +130,7 @@ def test_agent_matches_reference_golden(name, graph):
         torch.testing.assert_close(torch.stack([st[e * nmb:(e + 1) * nmb, 4].mean() for e in range(agent.mini_epochs_num)]),
                                    ref['kls'], rtol=2e-3, atol=2e-6)
         _check_epoch(agent, ref['state'], ref['dataset'], {'a': ref['a_losses'], 'c': ref['c_losses'], 'e': ref['entropies']},
-                     ref['last_lr'], g['units'])
+                     ref['last_lr'], g['units'], lstm=lstm)
         torch.testing.assert_close(agent.game_rewards.mean, ref['game_rewards_mean'].reshape(-1), rtol=1e-4, atol=1e-5)
         assert agent.game_rewards.current_size == ref['game_rewards_size']
         torch.testing.assert_close(agent.game_lengths.mean, ref['game_lengths_mean'].reshape(-1), rtol=1e-5, atol=1e-5)
@@ -313,3 +316,35 @@ def test_full_size_configs_one_epoch_vs_oracle(name, N, H, D, A, mb, masked, mp)
         torch.testing.assert_close(st[:, 1], torch.stack(out['c_loss']), rtol=0.1, atol=2e-2)
         torch.testing.assert_close(st[:, 4], torch.stack(out['kl']), rtol=0.3, atol=2e-4)
         assert int(agent.model.running_mean_std.count) == int(oag.model.running_mean_std.count)
+
+
+def test_lstm_agent_matches_oracle_medium():
+    """LSTM-before-MLP policy (BASELINE configs[3] structure, scaled down): N=128 envs, H=16, seq_length=4, obs 44, 5 actions, LSTM 32,
+    MLP [64,32]; two epochs with episode ends inside the BPTT windows; fp32 path vs the CPU oracle (pinned to the reference by
+    tests/golden/agent_lstm.pt)."""
+    N, H, D, A, units, mb, hid, epochs = 128, 16, 44, 5, [64, 32], 512, 32, 2
+    obs_tape, done_tape, tout_tape = O.make_tapes(H * epochs + 1, N, D, seed=31, p_done=0.08)
+    params = O.init_params(D, units, A, seed=3, rnn_units=hid)
+    g = torch.Generator().manual_seed(15)
+    noise = torch.randn(epochs, H, N, A, generator=g)
+    cfg = {'mini_epochs': 2, 'rnn_units': hid, 'seq_length': 4}
+    oag = O.OracleAgent(O.TapeEnv(obs_tape, done_tape, tout_tape), params, D, A, units, N, H, mb, cfg)
+    oag.obs = oag.env_reset()
+    env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
+    agent = make_agent({'mini_epochs': 2, 'seq_length': 4}, N, H, D, A, units, mb, env, params, rnn_units=hid)
+    assert agent.is_rnn and not agent.use_tc
+    for ep in range(epochs):
+        out = oag.train_epoch(noise[ep])
+        agent.epoch_num += 1
+        agent.train_epoch(noise=noise[ep].to(DEV))
+        ref_state = {k: v.detach() for k, v in oag.model.p.items()}
+        for pre, m in (('running_mean_std.', oag.model.running_mean_std), ('value_mean_std.', oag.model.value_mean_std)):
+            ref_state[pre + 'running_mean'], ref_state[pre + 'running_var'], ref_state[pre + 'count'] = \
+                m.running_mean, m.running_var, m.count
+        ds = {k: oag.dataset[k] for k in ('advantages', 'returns', 'old_values', 'old_logp_actions', 'actions', 'rnn_masks')}
+        _check_epoch(agent, ref_state, ds, {'a': torch.stack(out['a_loss']), 'c': torch.stack(out['c_loss']),
+                                            'e': torch.stack(out['entropy']), 'kl': torch.stack(out['kl'])}, oag.last_lr, units, lstm=True)
+        # rollout-side state snapshots (mb_rnn_states, a2c_common.py:1081-1083) and the carried states
+        torch.testing.assert_close(agent.rnn_h0.cpu(), oag.mb_rnn_states[0].squeeze(1), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(agent.rnn_c0.cpu(), oag.mb_rnn_states[1].squeeze(1), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(agent.rnn_h.cpu(), oag.rnn_states[0][0], rtol=1e-4, atol=1e-5)
