@@ -484,17 +484,31 @@ class A2CAgent:
             self.is_tensor_obses = True
             return obs
         if isinstance(obs, np.ndarray):
-            # host env: stage through pinned memory, async H2D on the compute stream
+            # host env: async H2D on the compute stream.  If the env hands out page-locked memory (e.g. a pinned ring) the DMA
+            # reads it directly; otherwise stage through a pinned buffer first.
             key = ('obs', obs.shape, obs.dtype.str)
             buf = self._pinned.get(key)
             if buf is None:
                 buf = (torch.empty(obs.shape, dtype=torch.float32).pin_memory(),
                        torch.empty(obs.shape, dtype=torch.float32, device=self.device_t))
                 self._pinned[key] = buf
-            buf[0].copy_(torch.from_numpy(obs))
-            buf[1].copy_(buf[0], non_blocking=True)
+            src = torch.from_numpy(obs)
+            if src.dtype == torch.float32 and src.is_contiguous() and self._is_pinned(src):
+                buf[1].copy_(src, non_blocking=True)
+            else:
+                buf[0].copy_(src)
+                buf[1].copy_(buf[0], non_blocking=True)
             return buf[1]
         return obs
+
+    def _is_pinned(self, t):
+        """page-locked check, cached by base address (the driver query costs a few microseconds)"""
+        cache = self._pinned.setdefault('_pin_cache', {})
+        k = t.data_ptr()
+        r = cache.get(k)
+        if r is None:
+            r = cache[k] = bool(t.is_pinned())
+        return r
 
     def obs_to_tensors(self, obs):
         if isinstance(obs, dict):

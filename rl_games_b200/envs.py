@@ -81,7 +81,18 @@ class SyntheticHostEnv(IVecEnv):
         self.N, self.D, self.A = int(num_actors), int(obs_dim), int(act_dim)
         self.max_len, self.p_done = int(max_len), float(p_done)
         rng = np.random.default_rng(seed)
-        self.ring = [rng.standard_normal((self.N, self.D), dtype=np.float32) for _ in range(ring)]
+        # page-locked ring (like envpool's output buffers): numpy views of pinned torch storage, so H2D copies need no staging
+        self._ring_t = []
+        self.ring = []
+        for _ in range(ring):
+            t = torch.empty(self.N, self.D, dtype=torch.float32)
+            try:
+                t = t.pin_memory()
+            except Exception:
+                pass
+            t.copy_(torch.from_numpy(rng.standard_normal((self.N, self.D), dtype=np.float32)))
+            self._ring_t.append(t)
+            self.ring.append(t.numpy())
         self.term = [(rng.random(self.N) < self.p_done) for _ in range(ring)]
         self.i = 0
         self.t = np.zeros(self.N, dtype=np.int32)
