@@ -234,9 +234,17 @@ typedef struct b200rl_pack_table {
     uint32_t cs_bytes[4]; uint32_t dst_off[4];
 } b200rl_pack_table;
 
+/* optional tail of the optimiser kernels: training-mode obs-normaliser update for the NEXT minibatch from its precomputed
+ * batch sums (== b200rl_obs_stats_merge_f64, folded into the last CTA to save a launch); mbmom == NULL or a NULL struct: off */
+typedef struct b200rl_obs_merge {
+    const double* mbmom; const float* shift; int D; int n_rows;
+    double* mean; double* var; int64_t* count; float* mean_f32; float* std_f32; float eps;
+} b200rl_obs_merge;
+
 int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
                          double* state_d, const float* kl_dev, const b200rl_opt_cfg* cfg_host,
-                         float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host, void* stream);
+                         float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host,
+                         const b200rl_obs_merge* merge_next_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: fused gradient all-reduce + clip + Adam over NVLink peer memory (one launch per minibatch).
@@ -256,7 +264,7 @@ int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, void* const* p
                               void* my_flags, void* seq_ptr, float* red, double* nrm_part, int nrm_part_len, void* grid_bar,
                               float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
                               const b200rl_opt_cfg* cfg_host, float* stats_out, int* counter, void* wpack,
-                              const b200rl_pack_table* tab_host, void* stream);
+                              const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Rollout.  a2c_common.py:985-1069 (play_steps) per-step pieces.

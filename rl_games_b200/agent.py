@@ -398,6 +398,10 @@ class A2CAgent:
         self.mbmom = torch.zeros(self.num_minibatches, 2 * D, dtype=torch.float64, device=dev)
         self.mb_shift = f(D)
         self.mb_counters = torch.zeros(self.num_minibatches, dtype=torch.int32, device=dev)
+        if self.use_mb_moments:
+            r = m.running_mean_std
+            self._merge_structs = [ops.make_obs_merge(self.mbmom[i], self.mb_shift, D, mb, r.running_mean, r.running_var, r.count,
+                                                      r.mean_f32, r.std_f32) for i in range(self.num_minibatches)]
         self.post_scratch = torch.zeros(((N + 255) // 256) * 4, dtype=torch.float64, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
         self.host_stats = torch.zeros(self.n_updates, 16, dtype=torch.float32).pin_memory()
@@ -441,17 +445,21 @@ class A2CAgent:
         dist.barrier()
 
     def _step_optimizer(self, u, gv, P, wpack=None, pack_table=None):
-        """gradient exchange + clip + Adam (+ packed-weight refresh) for update u"""
+        """gradient exchange + clip + Adam (+ packed-weight refresh) for update u; the optimiser kernel's last CTA also performs the
+        obs-normaliser update of the NEXT update's minibatch (the first one of an epoch is merged by _update_all)"""
         m = self.model
+        mn = None
+        if self.use_mb_moments and u + 1 < self.n_updates and not getattr(self, '_compat_mode', False):
+            mn = self._merge_structs[(u + 1) % self.num_minibatches]
         if self.fused_allreduce:
             ops.allreduce_adam(self.peer_table, u & 1, self.global_rank, self.my_flags_ptr, self.ar_seq, self.ar_red, self.ar_nrm,
                                self.ar_bar, m.flat, m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.stats[u],
-                               self.counters[2:3], wpack=wpack, pack_table=pack_table)
+                               self.counters[2:3], wpack=wpack, pack_table=pack_table, merge_next=mn)
             return
         if self.multi_gpu:
             dist.all_reduce(gv['comm'], op=dist.ReduceOp.SUM)
         ops.adam_step(m.flat, gv['grad'], m.exp_avg, m.exp_avg_sq, self.opt_state, gv['kl'], self.opt_cfg, self.stats[u],
-                      self.counters[2:3], n=P, wpack=wpack, pack_table=pack_table)
+                      self.counters[2:3], n=P, wpack=wpack, pack_table=pack_table, merge_next=mn)
 
     def _build_cfg_structs(self):
         """POD structs passed (by value at launch) to the kernels; baked into captured graphs, so any change
@@ -730,8 +738,9 @@ class A2CAgent:
         if self.normalize_input:
             rms = m.running_mean_std
             if self.use_mb_moments:
-                ops.obs_stats_merge(self.mbmom[i], self.mb_shift, m.D, mb, rms.running_mean, rms.running_var, rms.count,
-                                    rms.mean_f32, rms.std_f32)
+                if u == 0 or getattr(self, '_compat_mode', False):    # later minibatches are merged by the previous update's optimiser kernel
+                    ops.obs_stats_merge(self.mbmom[i], self.mb_shift, m.D, mb, rms.running_mean, rms.running_var, rms.count,
+                                        rms.mean_f32, rms.std_f32)
             else:
                 ops.moments_update(x, m.D, epm, H, N, rms.running_mean, rms.running_var, rms.count, rms.mean_f32, rms.std_f32,
                                    self.mom_scratch, self.counters[1:2])
@@ -868,7 +877,11 @@ class A2CAgent:
         self.init_tensors()
         u = self._compat_u = getattr(self, '_compat_u', -1) + 1
         u %= self.n_updates
-        self._minibatch_update(i, u)
+        self._compat_mode = True     # caller-driven order: merge the obs statistics per call, not in the optimiser tail
+        try:
+            self._minibatch_update(i, u)
+        finally:
+            self._compat_mode = False
         st = self.stats[u]
         e0, e1 = i * self.envs_per_mb, (i + 1) * self.envs_per_mb
         self.train_result = (st[0], st[1], st[2], st[4], self.last_lr, 1.0, swap_and_flatten01(self.mus[:, e0:e1]),

@@ -15,6 +15,33 @@ struct OptCfgDev {
     int truncate_grads, adaptive_lr;
 };
 
+// optional tail work of the optimiser kernels' last CTA: training-mode update of the obs normaliser for the NEXT minibatch
+// (Chan merge of its precomputed batch sums, running_mean_std.py:55-67) -- saves one tiny launch per minibatch
+struct ObsMergeDev {
+    const double* mbmom; const float* shift; int D; int n_rows;
+    double* mean; double* var; long long* count; float* mean_f32; float* std_f32; float eps;
+};
+__device__ __forceinline__ void obs_merge_tail(const ObsMergeDev& o) {
+    // called by ALL threads of the last CTA (blockDim >= 1)
+    if (!o.mbmom) return;
+    const double n = (double)o.n_rows;
+    const double cnt0 = (double)o.count[0];
+    for (int col = threadIdx.x; col < o.D; col += blockDim.x) {
+        const double ms = o.mbmom[col] / n;
+        const double bm = (double)o.shift[col] + ms;
+        const double bv = fmax(o.mbmom[o.D + col] / n - ms * ms, 0.0);
+        const double tot = cnt0 + n, delta = bm - o.mean[col];
+        const double new_mean = o.mean[col] + delta * n / tot;
+        const double M2 = o.var[col] * cnt0 + bv * n + delta * delta * cnt0 * n / tot;
+        const double v = M2 / tot;
+        o.mean[col] = new_mean; o.var[col] = v;
+        o.mean_f32[col] = (float)new_mean;
+        o.std_f32[col] = __fsqrt_rn(__fadd_rn((float)v, o.eps));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) o.count[0] = o.count[0] + (long long)o.n_rows;
+}
+
 struct PackTabDev { int n_seg; int off[4]; int R[4]; int C[4]; unsigned CS[4]; unsigned dst[4]; };
 
 // one element of the fused Adam update (torch.optim.Adam fused semantics) + refresh of the packed bf16 weight copy
@@ -52,7 +79,7 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
                                                         float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n,
                                                         double* state_d, const float* __restrict__ kl_dev, OptCfgDev c,
                                                         float* __restrict__ stats_out, int* counter, unsigned char* __restrict__ wpack,
-                                                        PackTabDev tab) {
+                                                        PackTabDev tab, ObsMergeDev om) {
     __shared__ double sm[32];
     __shared__ int is_last;
     const double lr = state_d[0];
@@ -115,6 +142,7 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
         if (stats_out) { stats_out[B200RL_STAT_LR] = (float)lr; stats_out[B200RL_STAT_GNORM] = total_norm; }
         *counter = 0;
     }
+    if (is_last) obs_merge_tail(om);
 }
 
 // =====================================================================================================================
@@ -149,7 +177,7 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
                                                              unsigned* grid_bar, float* __restrict__ params, float* __restrict__ exp_avg,
                                                              float* __restrict__ exp_avg_sq, int n, double* state_d, OptCfgDev c,
                                                              float* __restrict__ stats_out, int* counter, unsigned char* __restrict__ wpack,
-                                                             PackTabDev tab) {
+                                                             PackTabDev tab, ObsMergeDev om) {
     __shared__ double sm[32];
     __shared__ int is_last;
     const unsigned long long seq = *seq_ptr + 1ull;
@@ -217,14 +245,24 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
         *seq_ptr = seq;
         *counter = 0;
     }
+    if (is_last) obs_merge_tail(om);
 }
 
 }  // namespace
 
+static ObsMergeDev make_obs_merge(const b200rl_obs_merge* h) {
+    ObsMergeDev o{};
+    if (h && h->mbmom) {
+        o.mbmom = h->mbmom; o.shift = h->shift; o.D = h->D; o.n_rows = h->n_rows; o.mean = h->mean; o.var = h->var;
+        o.count = (long long*)h->count; o.mean_f32 = h->mean_f32; o.std_f32 = h->std_f32; o.eps = h->eps;
+    }
+    return o;
+}
+
 B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
                                        double* state_d, const float* kl_dev, const b200rl_opt_cfg* cfg_host,
                                        float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host,
-                                       void* stream) {
+                                       const b200rl_obs_merge* merge_next_host, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !state_d || !cfg_host || !counter || n <= 0) return B200RL_EINVAL;
     if ((wpack != nullptr) != (tab_host != nullptr)) return B200RL_EINVAL;
     PackTabDev tab{};
@@ -245,7 +283,7 @@ B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float*
     if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
     adam_step_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, state_d, kl_dev, c, stats_out,
-                                                            counter, (unsigned char*)wpack, tab);
+                                                            counter, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host));
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }
@@ -283,7 +321,7 @@ B200RL_EXPORT int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, 
                                             void* my_flags, void* seq_ptr, float* red, double* nrm_part, int nrm_part_len, void* grid_bar,
                                             float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
                                             const b200rl_opt_cfg* cfg_host, float* stats_out, int* counter, void* wpack,
-                                            const b200rl_pack_table* tab_host, void* stream) {
+                                            const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host, void* stream) {
     if (!peer_grads_host || !peer_flags_host || world < 1 || world > 8 || rank < 0 || rank >= world || !my_flags || !seq_ptr || !red ||
         !nrm_part || !grid_bar || !params || !exp_avg || !exp_avg_sq || !state_d || !cfg_host || !counter || n <= 0)
         return B200RL_EINVAL;
@@ -314,7 +352,7 @@ B200RL_EXPORT int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, 
     if (blocks > nrm_part_len) return B200RL_EINVAL;
     allreduce_adam_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(pp, world, rank, (unsigned long long*)my_flags, (unsigned long long*)seq_ptr,
                                                                  red, nrm_part, (unsigned*)grid_bar, params, exp_avg, exp_avg_sq, n, state_d, c,
-                                                                 stats_out, counter, (unsigned char*)wpack, tab);
+                                                                 stats_out, counter, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host));
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }

@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(LT) ppo_head_loss_kernel(
         const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
         const float inv_cnt = inv_count_dev ? __ldg(inv_count_dev) : (1.0f / (float)M);
         LossArena la{actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask};
-        const float nlp = ppo_sample_loss<MAXA, false>(head, A, sSig, la, ar, inv_cnt, cfg, dh, dls, sc);
+        LossRow<MAXA> lrow;
+        loss_row_load<MAXA>(la, ar, A, lrow);
+        const float nlp = ppo_sample_loss<MAXA, false>(head, A, sSig, la, ar, lrow, inv_cnt, cfg, dh, dls, sc);
         if (mu_out) {
 #pragma unroll
             for (int j = 0; j < MAXA - 1; ++j)

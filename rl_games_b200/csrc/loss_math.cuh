@@ -25,6 +25,41 @@ struct LossArena {
     const float* old_values_n; const float* returns_n; const float* old_neglogp; const float* advs_n; const float* mask;
 };
 
+// All arena inputs of one sample, fetched up front (vector loads when A % 4 == 0) so that their latency overlaps with the
+// GEMM that produces the heads instead of serialising inside the loss arithmetic.
+template <int MAXA>
+struct LossRow {
+    float act[MAXA], omu[MAXA], osg[MAXA];
+    float old_v, ret, old_nlp, adv, mk;
+};
+
+template <int MAXA>
+__device__ __forceinline__ void loss_row_load(const LossArena& a, int64_t ar, int A, LossRow<MAXA>& r) {
+    r.old_v = __ldg(a.old_values_n + ar); r.ret = __ldg(a.returns_n + ar);
+    r.old_nlp = __ldg(a.old_neglogp + ar); r.adv = __ldg(a.advs_n + ar);
+    r.mk = a.mask ? __ldg(a.mask + ar) : 1.f;
+    if ((A & 3) == 0) {
+        const float4* pa = reinterpret_cast<const float4*>(a.actions + ar * A);
+        const float4* pm = reinterpret_cast<const float4*>(a.old_mu + ar * A);
+        const float4* ps = reinterpret_cast<const float4*>(a.old_sigma + ar * A);
+#pragma unroll
+        for (int q = 0; q < (MAXA - 1 + 3) / 4; ++q) {
+            if (q * 4 < A) {
+                const float4 x = __ldg(pa + q), y = pm[q], z = ps[q];
+                if (q * 4 + 0 < MAXA) { r.act[q * 4 + 0] = x.x; r.omu[q * 4 + 0] = y.x; r.osg[q * 4 + 0] = z.x; }
+                if (q * 4 + 1 < MAXA) { r.act[q * 4 + 1] = x.y; r.omu[q * 4 + 1] = y.y; r.osg[q * 4 + 1] = z.y; }
+                if (q * 4 + 2 < MAXA) { r.act[q * 4 + 2] = x.z; r.omu[q * 4 + 2] = y.z; r.osg[q * 4 + 2] = z.z; }
+                if (q * 4 + 3 < MAXA) { r.act[q * 4 + 3] = x.w; r.omu[q * 4 + 3] = y.w; r.osg[q * 4 + 3] = z.w; }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < MAXA - 1; ++j) {
+            if (j < A) { r.act[j] = __ldg(a.actions + ar * A + j); r.omu[j] = a.old_mu[ar * A + j]; r.osg[j] = a.old_sigma[ar * A + j]; }
+        }
+    }
+}
+
 // head[0] = value, head[1..A] = mu.  sSig (shared memory): sigma[A], logstd[A], 1/sigma[A], log(sigma)[A].
 // FAST (bf16 tensor-core path): divisions -> reciprocal multiplies, exp/log -> ex2/lg2 approximations (the operands were
 // already rounded to bf16 upstream); !FAST (fp32 path): IEEE divisions and full-precision expf/logf for tight parity.
@@ -33,12 +68,10 @@ struct LossArena {
 // (datasets.py:33-43) and returns the sample's neglogp.
 template <int MAXA, bool FAST>
 __device__ __forceinline__ float ppo_sample_loss(const float (&head)[MAXA], int A, const float* __restrict__ sSig,
-                                                 const LossArena& ar_, int64_t ar, float inv_cnt, const LossCfgDev& cfg,
-                                                 float (&dh)[MAXA], float (&dls)[MAXA], float (&sc)[LOSS_NSC]) {
+                                                 const LossArena& ar_, int64_t ar, const LossRow<MAXA>& row, float inv_cnt,
+                                                 const LossCfgDev& cfg, float (&dh)[MAXA], float (&dls)[MAXA], float (&sc)[LOSS_NSC]) {
     const float val = head[0];
-    const float old_v = __ldg(ar_.old_values_n + ar), ret = __ldg(ar_.returns_n + ar);
-    const float old_nlp = __ldg(ar_.old_neglogp + ar), adv = __ldg(ar_.advs_n + ar);
-    const float mk = ar_.mask ? __ldg(ar_.mask + ar) : 1.f;
+    const float old_v = row.old_v, ret = row.ret, old_nlp = row.old_nlp, adv = row.adv, mk = row.mk;
     const float w = mk * inv_cnt;
     float sumz2 = 0.f, sumls = 0.f, ent = 0.f, kl = 0.f, bl = 0.f;
     float z[MAXA];
@@ -46,8 +79,8 @@ __device__ __forceinline__ float ppo_sample_loss(const float (&head)[MAXA], int 
     for (int j = 0; j < MAXA - 1; ++j) {
         if (j < A) {
             const float mu = head[1 + j], sg = sSig[j], ls = sSig[A + j];
-            const float act = __ldg(ar_.actions + ar * A + j);
-            const float omu = ar_.old_mu[ar * A + j], osg = ar_.old_sigma[ar * A + j];
+            const float act = row.act[j];
+            const float omu = row.omu[j], osg = row.osg[j];
             z[j] = FAST ? (act - mu) * sSig[2 * A + j] : (act - mu) / sg;
             sumz2 += z[j] * z[j];
             sumls += ls;

@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                           make_smem_desc(smem_u32(sWh) + k * 2 * N::WH_CS, N::WH_CS, 128), idesc, k > 0);
             umma_commit(&bars[4]);
         }
+        // prefetch this row's arena inputs while the heads MMA runs (their latency would otherwise serialise in the loss maths)
+        LossRow<16> lrow;
+        if (TRAIN && h == 0 && row < rows_valid) loss_row_load<16>(p.la, arow0 + row, p.A, lrow);
         mbar_wait(&bars[4], phase);
         fence_after_sync();
         float sc[LOSS_NSC];
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                 if (TRAIN) {
                     float dh[16];
                     const float inv_cnt = p.inv_count_dev ? __ldg(p.inv_count_dev) : (1.0f / (float)p.M);
-                    ppo_sample_loss<16, true>(head, p.A, sSig, p.la, ar, inv_cnt, p.cfg, dh, dls, sc);
+                    ppo_sample_loss<16, true>(head, p.A, sSig, p.la, ar, lrow, inv_cnt, p.cfg, dh, dls, sc);
                     uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
                     *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = pack8_bf16(&dh[0]);
                     *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = pack8_bf16(&dh[8]);

@@ -191,11 +191,23 @@ class PackTable(ctypes.Structure):
                 ('cs_bytes', ctypes.c_uint32 * 4), ('dst_off', ctypes.c_uint32 * 4)]
 
 
-def adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None, wpack=None, pack_table=None):
+class ObsMerge(ctypes.Structure):
+    _fields_ = [('mbmom', ctypes.c_void_p), ('shift', ctypes.c_void_p), ('D', ctypes.c_int), ('n_rows', ctypes.c_int),
+                ('mean', ctypes.c_void_p), ('var', ctypes.c_void_p), ('count', ctypes.c_void_p), ('mean_f32', ctypes.c_void_p),
+                ('std_f32', ctypes.c_void_p), ('eps', ctypes.c_float)]
+
+
+def make_obs_merge(mbmom_i, shift, D, n_rows, mean, var, count, mean_f32, std_f32, eps=1e-5):
+    return ObsMerge(ptr(mbmom_i), ptr(shift), D, n_rows, ptr(mean), ptr(var), ptr(count), ptr(mean_f32), ptr(std_f32), eps)
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None, wpack=None, pack_table=None,
+              merge_next=None):
     check(lib.b200rl_adam_step_f32(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq),
                                    params.numel() if n is None else n, ptr(state_d), ptr(kl_dev), ctypes.addressof(cfg),
                                    ptr(stats_out), ptr(counter), ptr(wpack),
-                                   None if pack_table is None else ctypes.addressof(pack_table), _stream()), 'adam_step')
+                                   None if pack_table is None else ctypes.addressof(pack_table),
+                                   None if merge_next is None else ctypes.addressof(merge_next), _stream()), 'adam_step')
 
 
 def reduce_finalize(part, out, n, n_splits, split_stride, partials, n_partials, A, entropy_coef_dev, stats, d_logstd, kl_out=None):
@@ -348,12 +360,12 @@ class PeerTable:
 
 
 def allreduce_adam(table, parity, rank, my_flags_ptr, seq, red, nrm_part, grid_bar, params, exp_avg, exp_avg_sq, n, state_d, cfg,
-                   stats_out, counter, wpack=None, pack_table=None):
+                   stats_out, counter, wpack=None, pack_table=None, merge_next=None):
     check(lib.b200rl_allreduce_adam_f32(ctypes.addressof(table.grads[parity]), ctypes.addressof(table.flags), table.world, rank,
                                         my_flags_ptr, ptr(seq), ptr(red), ptr(nrm_part), nrm_part.numel(), ptr(grid_bar), ptr(params),
                                         ptr(exp_avg), ptr(exp_avg_sq), n, ptr(state_d), ctypes.addressof(cfg), ptr(stats_out),
                                         ptr(counter), ptr(wpack), None if pack_table is None else ctypes.addressof(pack_table),
-                                        _stream()), 'allreduce_adam')
+                                        None if merge_next is None else ctypes.addressof(merge_next), _stream()), 'allreduce_adam')
 
 
 # ------------------------------------------------------------------------------------------ LSTM cell (fp32)
