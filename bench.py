@@ -49,8 +49,12 @@ def make_params(w, device, env_name, multi_gpu, graph=True, seed=5, mixed_precis
               'minibatch_size': w['minibatch'], 'mini_epochs': w['mini_epochs'], 'critic_coef': 2, 'print_stats': False,
               'train_dir': '/tmp/b200_bench_runs', 'b200_cuda_graph': graph,
               'env_config': {'obs_dim': w['obs_dim'], 'act_dim': w['act_dim'], 'device': device, 'seed': seed}}
+    config.update(CFG_OVERRIDES)     # --cfg key=value: developer A/B switches (b200_* options), recorded in the JSON line
     return {'seed': seed, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'},
             'network': network, 'config': config}
+
+
+CFG_OVERRIDES = {}
 
 
 class ClockSampler(threading.Thread):
@@ -304,6 +308,8 @@ def b200_arm(args, w):
             'config': workload_config(args.workload, w, 'b200_synthetic (on-GPU Philox env, one kernel per step)'),
             'clocks': clocks, 'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
             'cuda_graph': ('whole-epoch' if agent._graph_epoch is not None else ('update-phase' if agent._graph_update is not None else 'none')), 'kernels': kernels[:12]}
+    if CFG_OVERRIDES:
+        line['config']['overrides'] = dict(CFG_OVERRIDES)
     if rank == 0:
         # dominant kernel family of the step -> roofline
         line['roofline_gae'] = gae_roofline(w, peaks)
@@ -369,10 +375,15 @@ def main():
     ap.add_argument('--workload', default='c2', choices=list(WORKLOADS))
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--fp32', action='store_true', help='mixed_precision: False (fp32 CUDA-core MLP kernels)')
+    ap.add_argument('--cfg', action='append', default=[], help='config override key=value (python literal), e.g. b200_pipelined_wgrad=False')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    import ast
+    for kv in args.cfg:
+        k, v = kv.split('=', 1)
+        CFG_OVERRIDES[k] = ast.literal_eval(v)
     # stdout carries exactly ONE JSON line: everything else (Runner's seed banner etc.) goes to stderr
     import contextlib
     global _STDOUT

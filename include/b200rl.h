@@ -38,6 +38,11 @@ extern "C" {
 int b200rl_version(void);
 /* compute capability the library was built for (100 => sm_100a) */
 int b200rl_built_arch(void);
+/* Programmatic dependent launch for the kernels of the per-minibatch chain (forward, backward 1/2, optimiser, post-step):
+ * their CTAs may be scheduled while the predecessor kernel drains; each waits (griddepcontrol.wait) before touching any
+ * memory of the chain.  Default off (measured slower than plain stream order on the c2 workload); returns the previous
+ * setting.  Process-wide. */
+int b200rl_set_pdl(int enable);
 
 /* ---------------------------------------------------------------------------------------------
  * GAE.  Replaces rl_games/triton_kernels/gae_kernel.py:16-59 (_gae_kernel), :82-118 (_triton_gae)
@@ -246,6 +251,18 @@ int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, floa
                          float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host,
                          const b200rl_obs_merge* merge_next_host, void* stream);
 
+/* Single-GPU fused tail of one minibatch: b200rl_reduce_finalize + b200rl_adam_step_f32 in ONE launch (no second trip of
+ * the reduced gradient through memory; one grid barrier, grid <= 148 co-resident CTAs).
+ *  part: split partial gradients, entry i of split k at part[k*split_stride + i], valid for i in [A, n);
+ *  entries [0, A) of the flat gradient (d_logstd) come from the loss partials.  grads[n] receives the reduced gradient.
+ *  nrm_part: double[>= 148] scratch; grid_bar: uint32[1] zero-initialised once (monotonic). */
+int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_t split_stride, const double* loss_partials,
+                           int n_loss_partials, int A, const float* entropy_coef_dev, float* stats, float* kl_out,
+                           float* grads, float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
+                           const b200rl_opt_cfg* cfg_host, int* counter, double* nrm_part, int nrm_part_len, void* grid_bar,
+                           void* wpack, const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host,
+                           void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: fused gradient all-reduce + clip + Adam over NVLink peer memory (one launch per minibatch).
  * Replaces a2c_common.py:493-509 (cat -> all_reduce -> /world -> scatter), :1559-1561 (KL all-reduce) and the
@@ -328,6 +345,9 @@ int b200rl_bump_u64(uint64_t* p, void* stream);
 int b200rl_tc_supported(int D, int u1, int u2, int u3, int A);
 int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A);
 int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int64_t* out4_host);
+/* bytes of one 128-row tile of the normalised bf16 observation buffer the training forward may emit (xtile) for the
+ * pipelined weight-gradient kernel; -1 if the geometry is unsupported */
+int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A);
 int b200rl_tc_pack_table(int D, int u1, int u2, int u3, int A, int off_W1, int off_W2, int off_W3, int off_Wh,
                          b200rl_pack_table* out_host);
 int b200rl_tc_pack_weights(const float* W1, const float* W2, const float* W3, const float* W_head,
@@ -339,7 +359,7 @@ int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_
                             const float* actions, float* old_mu, float* old_sigma, const float* old_values_n,
                             const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
                             const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
-                            void* act1, void* act2, void* act3, void* dhead,
+                            void* act1, void* act2, void* act3, void* dhead, void* xtile,
                             double* partials, int max_partials, int* n_blocks_out_host, void* stream);
 int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
                               const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
@@ -353,7 +373,7 @@ int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, c
 int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                       const float* norm_mean, const float* norm_std, const void* wpack,
                       int u1, int u2, int u3, int M, int A,
-                      const void* act1, const void* act2, const void* act3, const void* dhead,
+                      const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
                       void* delta2, void* delta1, float* part, int max_parts, int P,
                       int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
                       int* n_parts_out_host, void* stream);

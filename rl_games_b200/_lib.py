@@ -11,7 +11,8 @@ import re
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 HEADER = os.path.join(_ROOT, 'include', 'b200rl.h')
-LIB_PATH = os.path.join(_PKG, 'libb200rl.so')
+# B200RL_LIB_PATH: developer override for A/B-timing two builds of the same ABI inside one GPU session
+LIB_PATH = os.environ.get('B200RL_LIB_PATH') or os.path.join(_PKG, 'libb200rl.so')
 
 _SCALARS = {
     'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'uint64_t': ctypes.c_uint64, 'uint32_t': ctypes.c_uint32,
@@ -40,7 +41,7 @@ def parse_header(path=HEADER):
     return protos
 
 
-RET_I64 = ('b200rl_tc_pack_bytes',)
+RET_I64 = ('b200rl_tc_pack_bytes', 'b200rl_tc_xtile_bytes')
 
 
 class _Lib:

@@ -350,6 +350,7 @@ class A2CAgent:
             self.ta = [f(mb, u) for u in m.units]
             self.dA = [f(mb, u) for u in m.units]
             self.d_head = f(mb, A + 1)
+        ops.set_pdl(self.config.get('b200_pdl', False))     # programmatic dependent launch: measured slower on c2 (profiles/r01_summary.md)
         if self.use_tc:
             self.n_splits = 148
             tb = ops.tc_tile_bytes(m.D, m.units, A)
@@ -358,13 +359,17 @@ class A2CAgent:
             self.wpack = u8(ops.tc_pack_bytes(m.D, m.units, A))
             self.tc_act = [u8(nt * tb[0]), u8(nt * tb[1]), u8(nt * tb[2])]
             self.tc_dhead, self.tc_delta2, self.tc_delta1 = u8(nt * tb[3]), u8(nt * tb[1]), u8(nt * tb[0])
+            # normalised bf16 obs tiles: forward -> pipelined weight-gradient kernel (config b200_pipelined_wgrad; default False =
+            # the single-buffered kernel that re-normalises the observations itself, measured faster on c2: profiles/r01_summary.md)
+            self.tc_xt = u8(nt * ops.tc_xtile_bytes(m.D, m.units, A)) if self.config.get('b200_pipelined_wgrad', False) else None
             self.tc_offs = {k: m.layout[k][0] for k in ('W0', 'b0', 'W1', 'b1', 'W2', 'b2', 'W_head', 'b_head')}
             self.pack_table = ops.tc_pack_table(m.D, m.units, A, self.tc_offs)
             self.ra = self.ta = self.dA = []
         else:
             self.n_splits = max(1, min(64, mb // 256))
         self.part_rows = self.n_splits * (self.seq_length if self.is_rnn else 1)
-        self.part = f(self.part_rows, m.num_params)
+        # split-partial gradient rows; the tcgen05 path pads the row stride to 16 bytes so the reduction can use float4 loads
+        self.part = f(self.part_rows, (m.num_params + 3) // 4 * 4 if self.use_tc else m.num_params)
         if self.is_rnn:
             Hd, T = m.rnn_units, self.seq_length
             S = mb // T
@@ -404,6 +409,8 @@ class A2CAgent:
                                                       r.mean_f32, r.std_f32) for i in range(self.num_minibatches)]
         self.post_scratch = torch.zeros(((N + 255) // 256) * 4, dtype=torch.float64, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.ra_nrm = torch.zeros(148, dtype=torch.float64, device=dev)      # reduce_adam: per-CTA sum-of-squares partials
+        self.ra_bar = torch.zeros(1, dtype=torch.int32, device=dev)          # reduce_adam: monotonic grid-barrier counter
         self.host_stats = torch.zeros(self.n_updates, 16, dtype=torch.float32).pin_memory()
         self.host_state = torch.zeros(10, dtype=torch.float64).pin_memory()
         self._events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -444,13 +451,17 @@ class A2CAgent:
         self.fused_allreduce = True
         dist.barrier()
 
+    def _merge_next(self, u):
+        """obs-normaliser merge struct of update u+1's minibatch (performed by the optimiser kernel's last CTA), or None"""
+        if self.use_mb_moments and u + 1 < self.n_updates and not getattr(self, '_compat_mode', False):
+            return self._merge_structs[(u + 1) % self.num_minibatches]
+        return None
+
     def _step_optimizer(self, u, gv, P, wpack=None, pack_table=None):
         """gradient exchange + clip + Adam (+ packed-weight refresh) for update u; the optimiser kernel's last CTA also performs the
         obs-normaliser update of the NEXT update's minibatch (the first one of an epoch is merged by _update_all)"""
         m = self.model
-        mn = None
-        if self.use_mb_moments and u + 1 < self.n_updates and not getattr(self, '_compat_mode', False):
-            mn = self._merge_structs[(u + 1) % self.num_minibatches]
+        mn = self._merge_next(u)
         if self.fused_allreduce:
             ops.allreduce_adam(self.peer_table, u & 1, self.global_rank, self.my_flags_ptr, self.ar_seq, self.ar_red, self.ar_nrm,
                                self.ar_bar, m.flat, m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.stats[u],
@@ -836,11 +847,17 @@ class A2CAgent:
                                   self.mus[0, e0:], self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:],
                                   self.neglogpacs[0, e0:], self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:],
                                   self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.tc_act,
-                                  self.tc_dhead, self.loss_partials)
+                                  self.tc_dhead, self.loss_partials, xtile=self.tc_xt)
         npart = ops.tc_mlp_bwd(x, epm, N, m.D, nm, ns, self.wpack, m.units, mb, A, self.tc_act, self.tc_dhead, self.tc_delta2,
-                               self.tc_delta1, self.part, P, self.tc_offs)
+                               self.tc_delta1, self.part, self.part.shape[1], self.tc_offs, xtile=self.tc_xt)
         gv = self._gv[u & 1]
-        ops.reduce_finalize(self.part[0, A:], gv['grad'][A:], P - A, npart, P, self.loss_partials, nb, A, self.entropy_coef_dev,
+        if not self.multi_gpu:
+            # no exchange between the reduction and the optimiser: one fused launch (reduce + finalise + clip + Adam + repack)
+            ops.reduce_adam(self.part, npart, self.part.shape[1], self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], gv['kl'], gv['grad'],
+                            m.flat, m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.counters[2:3], self.ra_nrm, self.ra_bar,
+                            wpack=self.wpack, pack_table=self.pack_table, merge_next=self._merge_next(u))
+            return
+        ops.reduce_finalize(self.part[0, A:], gv['grad'][A:], P - A, npart, self.part.shape[1], self.loss_partials, nb, A, self.entropy_coef_dev,
                             self.stats[u], gv['g_sigma'], gv['kl'])
         self._step_optimizer(u, gv, P, wpack=self.wpack, pack_table=self.pack_table)
 

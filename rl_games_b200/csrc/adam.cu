@@ -5,6 +5,7 @@
 // (L2-resident) flat gradient buffer in the same order, so no inter-CTA reduction or atomics are needed
 // and the result is deterministic; the last CTA to finish advances (step, lr).
 #include "common.cuh"
+#include "loss_math.cuh"
 #include <cuda_bf16.h>
 #include <string.h>
 
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
                                                         PackTabDev tab, ObsMergeDev om) {
     __shared__ double sm[32];
     __shared__ int is_last;
+    pdl_sync();
     const double lr = state_d[0];
     const double step = state_d[1] + 1.0;
     // running products beta^step live in the device state (state_d[2], state_d[3]); 0 means "not started" == 1.0
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
                                                              PackTabDev tab, ObsMergeDev om) {
     __shared__ double sm[32];
     __shared__ int is_last;
+    pdl_sync();
     const unsigned long long seq = *seq_ptr + 1ull;
     // ---- 0. cross-rank barrier: my gradients (written by the previous kernel in this stream) are complete ----
     if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(peers.flags[threadIdx.x] + rank, seq);
@@ -248,6 +251,181 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
     if (is_last) obs_merge_tail(om);
 }
 
+// =====================================================================================================================
+// Single-GPU fused tail of a minibatch: split-gradient reduction + loss finalisation + clip + Adam (+ packed-weight refresh,
+// LR schedule, next-minibatch obs merge) in ONE launch -- replaces reduce_finalize_kernel + adam_step_kernel when there is
+// no cross-rank exchange in between.  The reduced gradient never makes a second trip: each CTA sums ITS slice of the flat
+// gradient over all splits (fixed order => deterministic), publishes its sum-of-squares partial, crosses one grid barrier
+// (grid <= #SMs, one CTA per SM, all co-resident) and updates the same slice.
+__global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride,
+                                                          const double* __restrict__ lpart, int n_lpart, int lstride, int A,
+                                                          const float* __restrict__ entropy_coef_dev, float* __restrict__ stats,
+                                                          float* __restrict__ kl_out, float* __restrict__ grads, float* __restrict__ params,
+                                                          float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n, double* state_d,
+                                                          OptCfgDev c, int* counter, double* __restrict__ nrm_part, unsigned* grid_bar,
+                                                          unsigned char* __restrict__ wpack, PackTabDev tab, ObsMergeDev om, int kg_log2, int per, int vec4) {
+    __shared__ double sm[32];
+    __shared__ double smf[256];
+    __shared__ float4 sred4[1024];
+    __shared__ int is_last;
+    const int tid = threadIdx.x;
+    pdl_sync();
+    const double lr = state_d[0];
+    const double step = state_d[1] + 1.0;
+    const double p1 = (state_d[2] > 0.0 ? state_d[2] : 1.0) * c.beta1;
+    const double p2 = (state_d[3] > 0.0 ? state_d[3] : 1.0) * c.beta2;
+    const float gs = (float)c.grad_scale;
+    const int i0 = min(blockIdx.x * per, n), i1 = min(i0 + per, n);      // per: slice length (a multiple of 4 when vec4)
+    float a0 = 0.f;
+    // ---- 1a. last CTA: loss partials -> stats, KL slot, d_logstd (= gradient entries [0, A)) ----
+    if (blockIdx.x == gridDim.x - 1) {
+        const int slots = LOSS_NSC + A;
+        if (tid < 256) {
+            const int slot = tid & 63, grp = tid >> 6;
+            double s = 0.0;
+            if (slot < slots)
+                for (int p = grp; p < n_lpart; p += 4) s += lpart[(int64_t)p * lstride + slot];
+            smf[tid] = s;
+        }
+        __syncthreads();
+        if (tid < slots) smf[tid] = (smf[tid] + smf[64 + tid]) + (smf[128 + tid] + smf[192 + tid]);
+        __syncthreads();
+        if (tid == 0) {
+            stats[B200RL_STAT_ALOSS] = (float)smf[0];
+            stats[B200RL_STAT_CLOSS] = (float)smf[1];
+            stats[B200RL_STAT_ENTROPY] = (float)smf[2];
+            stats[B200RL_STAT_BLOSS] = (float)smf[3];
+            stats[B200RL_STAT_KL] = (float)smf[4];
+            if (kl_out) *kl_out = (float)smf[4];
+            stats[B200RL_STAT_SUMMASK] = (float)smf[5];
+            stats[B200RL_STAT_CLIPFRAC] = (float)(smf[6] / fmax(smf[5], 1.0));
+        }
+        if (tid < A) {
+            const double ec = (double)__ldg(entropy_coef_dev);
+            const float g = (float)(smf[LOSS_NSC + tid] - ec * smf[7]);
+            grads[tid] = g;
+            a0 = (g * gs) * (g * gs);
+        }
+    }
+    // ---- 1b. my slice of the flat gradient: sum over the splits, KG k-groups per element ----
+    if (vec4) {
+        // 16-byte edition (split rows and slice bounds are 4-float aligned): 4x the bytes in flight per thread -- the pass is
+        // latency-bound (~232 KB of L2-resident partials per CTA).  Entries < A or >= n inside a group are loaded but ignored.
+        const int KG = 1 << kg_log2, EPB = 1024 >> kg_log2;          // EPB float4 groups per pass
+        const int el = tid & (EPB - 1), kg = tid >> (10 - kg_log2);
+        for (int base = i0; base < i1; base += 4 * EPB) {
+            const int i = base + 4 * el;
+            const bool on = i < i1;
+            float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+            if (on) {
+                const float* src = part + i;
+                int k = kg;
+                for (; k + 3 * KG < n_splits; k += 4 * KG) {
+                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)k * split_stride));
+                    const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(k + KG) * split_stride));
+                    const float4 v2 = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(k + 2 * KG) * split_stride));
+                    const float4 v3 = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)(k + 3 * KG) * split_stride));
+                    s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+                    s1.x += v1.x; s1.y += v1.y; s1.z += v1.z; s1.w += v1.w;
+                    s2.x += v2.x; s2.y += v2.y; s2.z += v2.z; s2.w += v2.w;
+                    s3.x += v3.x; s3.y += v3.y; s3.z += v3.z; s3.w += v3.w;
+                }
+                for (; k < n_splits; k += KG) {
+                    const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src + (int64_t)k * split_stride));
+                    s0.x += v0.x; s0.y += v0.y; s0.z += v0.z; s0.w += v0.w;
+                }
+            }
+            sred4[tid] = make_float4((s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y), (s0.z + s1.z) + (s2.z + s3.z),
+                                     (s0.w + s1.w) + (s2.w + s3.w));
+            __syncthreads();
+            if (on && kg == 0) {
+                float4 g = sred4[el];
+                for (int j = 1; j < KG; ++j) { const float4 t = sred4[j * EPB + el]; g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w; }
+                const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    if (i + cc >= A && i + cc < i1) {
+                        grads[i + cc] = gv[cc];
+                        a0 = fmaf(gv[cc] * gs, gv[cc] * gs, a0);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        float* sred = reinterpret_cast<float*>(sred4);
+        const int KG = 1 << kg_log2, EPB = 1024 >> kg_log2;
+        const int el = tid & (EPB - 1), kg = tid >> (10 - kg_log2);
+        for (int base = i0; base < i1; base += EPB) {
+            const int i = base + el;
+            const bool on = i < i1 && i >= A;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            if (on) {
+                const float* src = part + i;
+                int k = kg;
+                for (; k + 3 * KG < n_splits; k += 4 * KG) {
+                    s0 += __ldcg(src + (int64_t)k * split_stride);
+                    s1 += __ldcg(src + (int64_t)(k + KG) * split_stride);
+                    s2 += __ldcg(src + (int64_t)(k + 2 * KG) * split_stride);
+                    s3 += __ldcg(src + (int64_t)(k + 3 * KG) * split_stride);
+                }
+                for (; k < n_splits; k += KG) s0 += __ldcg(src + (int64_t)k * split_stride);
+            }
+            sred[tid] = (s0 + s1) + (s2 + s3);
+            __syncthreads();
+            if (on && kg == 0) {
+                float g = sred[el];
+                for (int j = 1; j < KG; ++j) g += sred[j * EPB + el];
+                grads[i] = g;
+                a0 = fmaf(g * gs, g * gs, a0);
+            }
+            __syncthreads();
+        }
+    }
+    double acc[1] = {(double)a0};
+    block_sum_d<1>(acc, sm);
+    if (tid == 0) nrm_part[blockIdx.x] = acc[0];
+    // ---- 2. grid barrier (monotonic counter) ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned arrived = atomicAdd(grid_bar, 1u);
+        const unsigned target = (arrived / gridDim.x + 1u) * gridDim.x;
+        while (ld_acquire_gpu_u32(grid_bar) < target) { }
+    }
+    __syncthreads();
+    // ---- 3. clip + Adam on my slice ----
+    double nsqv[1] = {tid < gridDim.x ? __ldcg(nrm_part + tid) : 0.0};     // gridDim.x <= 148 <= blockDim.x
+    block_sum_d<1>(nsqv, sm);
+    const float total_norm = (float)sqrt(nsqv[0]);
+    float coef = 1.0f;
+    if (c.truncate_grads) coef = fminf((float)c.grad_norm / (total_norm + 1e-6f), 1.0f);
+    const float b1 = (float)c.beta1, b2 = (float)c.beta2;
+    const double bc1 = 1.0 - p1, bc2 = 1.0 - p2;
+    const float step_size = (float)(lr / bc1);
+    const float bc2_sqrt = (float)sqrt(bc2);
+    const float eps = (float)c.eps, wd = (float)c.weight_decay;
+    for (int i = i0 + tid; i < i1; i += blockDim.x)
+        adam_update_one(i, __ldcg(grads + i) * gs, c.truncate_grads, coef, params, exp_avg, exp_avg_sq, b1, b2, step_size, bc2_sqrt, eps, wd,
+                        wpack, tab);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (is_last && tid == 0) {
+        double new_lr = lr;
+        if (c.adaptive_lr && kl_out) {
+            const double kl = (double)(__ldcg(kl_out) * gs);
+            if (kl > 2.0 * c.kl_threshold) new_lr = fmax(lr / c.lr_multiplier, c.min_lr);
+            if (kl < 0.5 * c.kl_threshold) new_lr = fmin(lr * c.lr_multiplier, c.max_lr);
+        }
+        state_d[0] = new_lr; state_d[1] = step; state_d[2] = p1; state_d[3] = p2;
+        stats[B200RL_STAT_LR] = (float)lr; stats[B200RL_STAT_GNORM] = total_norm;
+        *counter = 0;
+    }
+    if (is_last) obs_merge_tail(om);
+}
+
 }  // namespace
 
 static ObsMergeDev make_obs_merge(const b200rl_obs_merge* h) {
@@ -257,6 +435,57 @@ static ObsMergeDev make_obs_merge(const b200rl_obs_merge* h) {
         o.count = (long long*)h->count; o.mean_f32 = h->mean_f32; o.std_f32 = h->std_f32; o.eps = h->eps;
     }
     return o;
+}
+
+static int make_pack_tab(const b200rl_pack_table* tab_host, PackTabDev& tab) {
+    if (!tab_host) return B200RL_OK;
+    if (tab_host->n_seg < 0 || tab_host->n_seg > 4) return B200RL_EINVAL;
+    tab.n_seg = tab_host->n_seg;
+    for (int i = 0; i < tab.n_seg; ++i) {
+        tab.off[i] = tab_host->flat_off[i]; tab.R[i] = tab_host->rows[i]; tab.C[i] = tab_host->cols[i];
+        tab.CS[i] = tab_host->cs_bytes[i]; tab.dst[i] = tab_host->dst_off[i];
+    }
+    return B200RL_OK;
+}
+static OptCfgDev make_opt_cfg(const b200rl_opt_cfg* h) {
+    OptCfgDev c;
+    c.beta1 = h->beta1; c.beta2 = h->beta2; c.eps = h->eps; c.weight_decay = h->weight_decay;
+    c.grad_norm = h->grad_norm; c.kl_threshold = h->kl_threshold; c.min_lr = h->min_lr;
+    c.max_lr = h->max_lr; c.lr_multiplier = h->lr_multiplier; c.grad_scale = h->grad_scale;
+    c.truncate_grads = h->truncate_grads; c.adaptive_lr = h->adaptive_lr;
+    return c;
+}
+
+B200RL_EXPORT int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_t split_stride, const double* loss_partials,
+                                         int n_loss_partials, int A, const float* entropy_coef_dev, float* stats, float* kl_out,
+                                         float* grads, float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
+                                         const b200rl_opt_cfg* cfg_host, int* counter, double* nrm_part, int nrm_part_len, void* grid_bar,
+                                         void* wpack, const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host,
+                                         void* stream) {
+    if (!part || !loss_partials || !entropy_coef_dev || !stats || !grads || !params || !exp_avg || !exp_avg_sq || !state_d || !cfg_host ||
+        !counter || !nrm_part || !grid_bar)
+        return B200RL_EINVAL;
+    if (n <= 0 || n_splits <= 0 || n_loss_partials <= 0 || A <= 0 || A + 1 > 16 || A >= n) return B200RL_EINVAL;
+    if ((wpack != nullptr) != (tab_host != nullptr)) return B200RL_EINVAL;
+    PackTabDev tab{};
+    if (make_pack_tab(tab_host, tab) != B200RL_OK) return B200RL_EINVAL;
+    int blocks = (n + 255) / 256;         // a slice of >= 256 entries per CTA; all CTAs must be co-resident (grid barrier)
+    if (blocks > 148) blocks = 148;
+    if (blocks > nrm_part_len) return B200RL_EINVAL;
+    int per = (n + blocks - 1) / blocks;
+    // 16-byte loads when every split row and every slice start is 4-float aligned
+    const int vec4 = (split_stride % 4 == 0) && split_stride >= (int64_t)(n + 3) / 4 * 4 && ((reinterpret_cast<uintptr_t>(part) & 15) == 0);
+    if (vec4) per = (per + 3) / 4 * 4;
+    const int units = vec4 ? per / 4 : per;      // elements (or float4 groups) of one slice
+    int kg_log2 = 0;                      // k-groups per unit: as many as fit in one 1024-thread pass over the slice
+    while (kg_log2 < 3 && (1024 >> (kg_log2 + 1)) >= units) ++kg_log2;
+    cudaError_t le = launch_k(reduce_adam_kernel, dim3(blocks), dim3(1024), 0, as_stream(stream), part, n_splits, split_stride, loss_partials, n_loss_partials,
+                                                              b200rl_loss_partial_stride(), A, entropy_coef_dev, stats, kl_out, grads, params,
+                                                              exp_avg, exp_avg_sq, n, state_d, make_opt_cfg(cfg_host), counter, nrm_part,
+                                                              (unsigned*)grid_bar, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host),
+                                                              kg_log2, per, vec4);
+    if (le != cudaSuccess) return (int)le;
+    return B200RL_OK;
 }
 
 B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,
@@ -282,9 +511,9 @@ B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float*
     int blocks = (n + 2047) / 2048;       // two elements per thread in the update; every CTA re-derives the norm from L2
     if (blocks > 148) blocks = 148;
     if (blocks < 1) blocks = 1;
-    adam_step_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, state_d, kl_dev, c, stats_out,
+    cudaError_t le = launch_k(adam_step_kernel, dim3(blocks), dim3(1024), 0, as_stream(stream), params, grads, exp_avg, exp_avg_sq, n, state_d, kl_dev, c, stats_out,
                                                             counter, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host));
-    B200RL_LAUNCH_CHECK();
+    if (le != cudaSuccess) return (int)le;
     return B200RL_OK;
 }
 
@@ -350,9 +579,9 @@ B200RL_EXPORT int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, 
     if (blocks > 128) blocks = 128;       // all CTAs must be co-resident for the in-kernel grid barrier (148 SMs, 1 CTA/SM)
     if (blocks < 1) blocks = 1;
     if (blocks > nrm_part_len) return B200RL_EINVAL;
-    allreduce_adam_kernel<<<blocks, 1024, 0, as_stream(stream)>>>(pp, world, rank, (unsigned long long*)my_flags, (unsigned long long*)seq_ptr,
+    cudaError_t le = launch_k(allreduce_adam_kernel, dim3(blocks), dim3(1024), 0, as_stream(stream), pp, world, rank, (unsigned long long*)my_flags, (unsigned long long*)seq_ptr,
                                                                  red, nrm_part, (unsigned*)grid_bar, params, exp_avg, exp_avg_sq, n, state_d, c,
                                                                  stats_out, counter, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host));
-    B200RL_LAUNCH_CHECK();
+    if (le != cudaSuccess) return (int)le;
     return B200RL_OK;
 }

@@ -2,8 +2,15 @@
 #include "common.cuh"
 
 
+int g_b200rl_pdl = 0;
+
 B200RL_EXPORT int b200rl_version(void) { return 100; }
 B200RL_EXPORT int b200rl_built_arch(void) { return 100; }
+B200RL_EXPORT int b200rl_set_pdl(int enable) {
+    const int prev = g_b200rl_pdl;
+    g_b200rl_pdl = enable ? 1 : 0;
+    return prev;
+}
 
 namespace {
 __global__ void fill_u32_kernel(uint32_t* p, int64_t n, uint32_t v) {

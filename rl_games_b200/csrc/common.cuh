@@ -13,6 +13,33 @@
 #define B200RL_EXPORT extern "C" __attribute__((visibility("default")))
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// The per-minibatch chain (forward -> backward 1 -> backward 2 -> optimiser) is four dependent launches of persistent kernels
+// whose prologues (TMEM allocation, barrier init, smem zero fill, observation prefetch) need nothing from the predecessor.
+// Kernels launched through launch_k() carry cudaLaunchAttributeProgrammaticStreamSerialization, so their CTAs may be
+// scheduled while the predecessor's last CTAs are still running; every such kernel calls pdl_sync() before it reads or
+// writes ANY global memory the predecessor chain touches (the only pre-wait global reads anywhere are the forward kernel's
+// observation rows, produced by the environment, never by one of these kernels).  pdl_sync() = griddepcontrol.wait (the
+// predecessor grid has completed and its writes are visible) followed by griddepcontrol.launch_dependents; because the
+// trigger comes AFTER the wait, "my successor is running" implies "my predecessor completed", so completion is transitive
+// along the chain.  Without the launch attribute both instructions are no-ops.  Captured by stream capture as programmatic
+// dependency edges of the CUDA graph.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+extern int g_b200rl_pdl;     // api.cu; b200rl_set_pdl()
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_b200rl_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

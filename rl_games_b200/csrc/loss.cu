@@ -155,6 +155,7 @@ __global__ void __launch_bounds__(256) reduce_finalize_kernel(const float* __res
                                                              int64_t split_stride, const double* __restrict__ partials, int n_partials,
                                                              int A, const float* __restrict__ entropy_coef_dev, float* __restrict__ stats,
                                                              float* __restrict__ d_logstd, float* __restrict__ kl_out) {
+    pdl_sync();
     if (blockIdx.x + 1 < gridDim.x) {
         const int i = blockIdx.x * blockDim.x + threadIdx.x;
         if (i >= n) return;
@@ -261,9 +262,9 @@ B200RL_EXPORT int b200rl_reduce_finalize(const float* part, float* out, int n, i
     if (!part || !out || n <= 0 || n_splits <= 0 || !partials || !entropy_coef_dev || !stats || !d_logstd || n_partials <= 0 || A <= 0 ||
         A + 1 > MAXA)
         return B200RL_EINVAL;
-    reduce_finalize_kernel<<<(n + 255) / 256 + 1, 256, 0, as_stream(stream)>>>(part, out, n, n_splits, split_stride, partials, n_partials, A,
-                                                                              entropy_coef_dev, stats, d_logstd, kl_out);
-    B200RL_LAUNCH_CHECK();
+    cudaError_t le = launch_k(reduce_finalize_kernel, dim3((n + 255) / 256 + 1), dim3(256), 0, as_stream(stream), part, out, n, n_splits,
+                              split_stride, partials, n_partials, A, entropy_coef_dev, stats, d_logstd, kl_out);
+    if (le != cudaSuccess) return (int)le;
     return B200RL_OK;
 }
 

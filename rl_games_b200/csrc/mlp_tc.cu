@@ -149,6 +149,70 @@ __device__ __forceinline__ void stage_x_tile(uint8_t* sX, const float* __restric
     }
 }
 
+// Same tile, sourced from a raw fp32 copy of the rows that a 1-D TMA bulk copy (cp.async.bulk) dropped into shared memory
+// while the previous tile was still computing: sRaw[r * D + c].  Requires D % 4 == 0.  Quarter-warps read 8 consecutive
+// rows x 16 B (row stride D*4 bytes: conflict-free for D = 60) and write 8 consecutive 16 B chunks.
+template <class N, int NTHREADS>
+__device__ __forceinline__ void stage_x_tile_smem(uint8_t* sX, const float* sRaw, int rows_valid, int D, const float* __restrict__ sNorm,
+                                                  bool do_norm) {
+    constexpr int NCG = N::DPAD / 8;
+#pragma unroll
+    for (int it = 0; it < (128 * NCG + NTHREADS - 1) / NTHREADS; ++it) {
+        const int i = threadIdx.x + it * NTHREADS;
+        if (i >= 128 * NCG) break;
+        const int cg = i / 128, r = i - cg * 128;
+        const int c0 = cg * 8;
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+        if (r < rows_valid && c0 < D) {
+            const float4* src = reinterpret_cast<const float4*>(sRaw + r * D + c0);
+            va = src[0];
+            if (c0 + 4 < D) vb = src[1];
+        }
+        float f[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+        if (do_norm) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                f[j] = (c0 + j < D && r < rows_valid) ? fminf(fmaxf((f[j] - sNorm[c0 + j]) * sNorm[N::DPAD + c0 + j], -5.0f), 5.0f) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(sX + tile_off(r, cg, N::ACS, N::ARS)) = pack8_bf16(f);
+    }
+}
+
+// Column sums of a bf16 operand tile (bias gradients): R rows, G column groups of 8 columns, column-group stride CS bytes
+// (chunk (g, r) sits at g * CS + r * 16).  Thread (g, rs) = (tid / RS, tid % RS) adds rows rs, rs + RS, ... of its 8 columns
+// (a quarter-warp reads 8 consecutive 16 B chunks: conflict-free), the RS partials are combined with warp shuffles in a fixed
+// order, and the lane with rs == 0 accumulates the result into its 8 running sums.  Whole warps either take part or skip.
+template <int R, int G, uint32_t CS, int T>
+__device__ __forceinline__ void colsum8(const uint8_t* sT, int tid, float (&acc)[8]) {
+    constexpr int RS = (T / G) < 32 ? (T / G) : 32;
+    static_assert((RS & (RS - 1)) == 0 && RS >= 1 && RS * G <= T && (RS * G) % 32 == 0, "colsum8 thread mapping");
+    const int rs = tid % RS, g = tid / RS;
+    if (g >= G) return;
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int r = rs; r < R; r += RS) {
+        float a[8];
+        unpack8_bf16(*reinterpret_cast<const uint4*>(sT + g * CS + r * 16), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += a[j];
+    }
+#pragma unroll
+    for (int o = RS / 2; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    }
+    if (rs == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += s[j];
+    }
+}
+// the thread that owns column group g after colsum8<.., G, .., T> (rs == 0), or -1
+template <int G, int T>
+__device__ __forceinline__ int colsum8_owner_group(int tid) {
+    constexpr int RS = (T / G) < 32 ? (T / G) : 32;
+    return (tid % RS == 0 && tid / RS < G) ? tid / RS : -1;
+}
+
 // epilogue helper: thread (row r) processes 32 accumulator columns [c0, c0+32): v = elu(v + bias) -> bf16 chunks into
 // a shared operand tile and (optionally) the global tiled activation buffer
 __device__ __forceinline__ void store_chunks32(const float (&v)[32], int r, int c0, uint8_t* s_tile, uint8_t* g_tile) {
@@ -161,6 +225,17 @@ __device__ __forceinline__ void store_chunks32(const float (&v)[32], int r, int 
     }
 }
 
+// head[1 + h + 4k] without dynamic register-array indexing (h is a runtime warp-group id, k an unrolled constant)
+__device__ __forceinline__ float pick_mu(const float (&head)[16], int h, int k) {
+    float v = 0.f;
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+        const int idx = 1 + hh + 4 * k;
+        if (idx < 16 && h == hh) v = head[idx];
+    }
+    return v;
+}
+
 struct FwdArgs {
     const float* obs; int rows_per_chunk; int64_t chunk_stride; int D;
     const float* nm; const float* ns;
@@ -169,6 +244,7 @@ struct FwdArgs {
     // training epilogue
     LossArena la; const float* inv_count_dev; LossCfgDev cfg;
     uint8_t* act1; uint8_t* act2; uint8_t* act3; uint8_t* dhead; double* partials;
+    uint8_t* xt;      // optional: normalised bf16 observation tiles for the pipelined backward-2 kernel
     // rollout epilogue
     const double* vms_mean; const double* vms_var; int normalize_value; const float* noise; uint64_t seed;
     const uint64_t* rng_epoch; uint32_t step_index;
@@ -180,6 +256,20 @@ struct FwdArgs {
 constexpr int LOSS_SLOTS = LOSS_NSC + 32;   // partial row stride shared with loss.cu (NSC + MAXA)
 
 // ================================================================================================= forward
+// Opt-in stage timing (tools/tc_stage_timing.py builds a variant with -DB200RL_TC_TIMING): thread 0 of CTA 0 stamps
+// clock64() at every stage boundary of its tiles.  Never compiled into the product library.
+#ifdef B200RL_TC_TIMING
+__device__ long long g_tc_stamp[3 * 128];   // [0,128) fwd, [128,256) bwd1, [256,384) bwd2
+#define TSTAMP() do { if (blockIdx.x == 0 && tid == 0 && n_stamp < 127) g_tc_stamp[TSB + 1 + n_stamp++] = clock64(); } while (0)
+#define TSTAMP_END() do { if (blockIdx.x == 0 && tid == 0) g_tc_stamp[TSB] = n_stamp; } while (0)
+extern "C" B200RL_EXPORT int b200rl_debug_tc_stamps(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_tc_stamp, sizeof(long long) * 3 * 128);
+}
+#else
+#define TSTAMP() do {} while (0)
+#define TSTAMP_END() do {} while (0)
+#endif
+
 template <class N, bool TRAIN>
 __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -187,31 +277,62 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     uint8_t* sA1 = smem + N::PACK_BYTES;                 // a1 (then a3 aliases its start)
     uint8_t* sXA2 = sA1 + N::A1_BYTES;                   // X tile, later a2
     uint8_t* sA3 = sA1;
+    // raw fp32 rows of the NEXT tile (TMA prefetch): the part of the a1 region that a3 does not alias; free once MMA 2 has read a1
+    float* sXraw = reinterpret_cast<float*>(sA1 + N::A3_BYTES);
+    static_assert(N::A3_BYTES + 128 * N::DPAD * 4 <= N::A1_BYTES, "X prefetch buffer must fit behind a3 inside the a1 region");
     float* sBias = reinterpret_cast<float*>(sXA2 + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES));
     float* sB1 = sBias; float* sB2 = sB1 + N::U1; float* sB3 = sB2 + N::U2; float* sBh = sB3 + N::U3;
-    float* sSig = sBh + N::AP;                           // sigma, logstd, 1/sigma, log(sigma): 4*A <= 64 floats
+    float* sSig = sBh + N::AP;                           // sigma, logstd, 1/sigma, log(sigma): 4*A floats, then sum(logstd), entropy
     float* sNorm = sSig + 64;                            // [2*DPAD] obs mean, 1/std
     float* sRed = sNorm + 2 * N::DPAD;                   // [4 warps][LOSS_SLOTS] (only the h == 0 warps run the loss)
     double* sAcc = reinterpret_cast<double*>(sRed + 4 * LOSS_SLOTS);     // [LOSS_SLOTS] per-CTA running partial
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + LOSS_SLOTS);     // [0]=weights, [1..4]=mma stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sAcc + LOSS_SLOTS);     // [0]=W1, [1..4]=mma stages, [5]=X prefetch, [6]=W2, [7]=W3+Wh
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const int n_tiles = (p.M + 127) / 128;
+    int n_stamp = 0; (void)n_stamp;
+    constexpr int TSB = 0; (void)TSB;
+    TSTAMP();   // kernel start
 
+    // ---- prologue, part 1: nothing here depends on the predecessor kernel (PDL: may overlap its tail) ----
+    const bool x_tma = (p.D & 3) == 0;         // 16-byte granularity of the bulk copy
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+        for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
+        if (x_tma && (int)blockIdx.x < n_tiles) {     // observation rows come from the environment, not from the kernel chain
+            const int m0 = blockIdx.x * 128;
+            const uint32_t bytes = (uint32_t)min(128, p.M - m0) * p.D * 4u;
+            mbar_expect_tx(&bars[5], bytes);
+            bulk_g2s(sXraw, p.obs + chunk_row(m0, p.rows_per_chunk, p.chunk_stride) * p.D, bytes, &bars[5]);
+        }
+    }
+    pdl_sync();
+    // ---- prologue, part 2: parameters and normaliser statistics (written by the optimiser kernel) ----
+    if (tid == 0) {
+        // one barrier per consumer so that layer 1 starts as soon as W1 (32 KB of the 114 KB) has landed
+        mbar_expect_tx(&bars[0], N::W1_BYTES);
+        bulk_g2s(sW1, p.wpack + N::W1_OFF, N::W1_BYTES, &bars[0]);
+        mbar_expect_tx(&bars[6], N::W2_BYTES);
+        bulk_g2s(sW2, p.wpack + N::W2_OFF, N::W2_BYTES, &bars[6]);
+        mbar_expect_tx(&bars[7], N::W3_BYTES + N::WH_BYTES);
+        bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[7]);
+        bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[7]);
     }
     for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = __ldg(p.b1 + i);
     for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = __ldg(p.b2 + i);
     for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = __ldg(p.b3 + i);
     if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
     if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
-    if (tid < LOSS_SLOTS) sAcc[tid] = 0.0;
+    __syncthreads();
+    if (tid == 0) {      // row-independent constants: sum(logstd) and the entropy of the diagonal Gaussian
+        float sl = 0.f, en = 0.f;
+        for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
+        sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
+    }
     load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     fence_before_sync();
     __syncthreads();
@@ -219,23 +340,35 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     const uint32_t tmem = *tmem_slot;
     const uint32_t T1 = tmem, T2 = tmem + 256, T3 = tmem + 384, T4 = tmem + 448;     // accumulator column bases
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    if (tid == 0) {
-        mbar_expect_tx(&bars[0], N::PACK_BYTES);
-        bulk_g2s(sW1, p.wpack + N::W1_OFF, N::W1_BYTES, &bars[0]);
-        bulk_g2s(sW2, p.wpack + N::W2_OFF, N::W2_BYTES, &bars[0]);
-        bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[0]);
-        bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[0]);
-    }
     uint32_t phase = 0;
     bool weights_ready = false;
+    // per-thread running loss partials over this CTA's tiles (reduced once, after the tile loop): scalars in the h == 0 threads,
+    // d_logstd slices (actions h, h+4, h+8, h+12) in every thread
+    float sc[LOSS_NSC];
+    float dls[4];
+#pragma unroll
+    for (int i = 0; i < LOSS_NSC; ++i) sc[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dls[k] = 0.f;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int m0 = tile * 128;
         const int rows_valid = min(128, p.M - m0);
         const int64_t arow0 = chunk_row(m0, p.rows_per_chunk, p.chunk_stride);   // tile lies inside one chunk (host-checked)
-        stage_x_tile<N, FWD_THREADS>(sXA2, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr);
+        TSTAMP();   // tile start
+        if (x_tma) {
+            mbar_wait(&bars[5], phase);
+            stage_x_tile_smem<N, FWD_THREADS>(sXA2, sXraw, rows_valid, p.D, sNorm, p.nm != nullptr);
+        } else {
+            stage_x_tile<N, FWD_THREADS>(sXA2, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr);
+        }
         fence_async_smem();
         if (!weights_ready) { mbar_wait(&bars[0], 0); weights_ready = true; }
         __syncthreads();
+        TSTAMP();   // X staged
+        if (TRAIN && p.xt) {      // keep the normalised bf16 tile for the weight-gradient kernel (16 B per thread-iteration, coalesced)
+            uint4* gx = reinterpret_cast<uint4*>(p.xt + (size_t)tile * N::X_BYTES);
+            for (int i = tid; i < (int)N::X_BYTES / 16; i += FWD_THREADS) gx[i] = reinterpret_cast<const uint4*>(sXA2)[i];
+        }
         // ---------------- layer 1: T1[128, U1] = X . W1^T ----------------
         if (tid == 0) {
             fence_after_sync();
@@ -248,6 +381,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         }
         mbar_wait(&bars[1], phase);
         fence_after_sync();
+        TSTAMP();   // MMA 1 done
         {
             uint8_t* g1 = TRAIN ? p.act1 + (size_t)tile * N::A1_BYTES : nullptr;
 #pragma unroll 1
@@ -262,8 +396,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        TSTAMP();   // epilogue 1 done
         // ---------------- layer 2: T2[128, U2] = a1 . W2^T ----------------
         if (tid == 0) {
+            if (tile == (int)blockIdx.x) mbar_wait(&bars[6], 0);       // W2 landed (first tile only)
             fence_after_sync();
             constexpr uint32_t idesc = make_idesc_bf16(128, N::U2, 0, 0);
 #pragma unroll
@@ -274,6 +410,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         }
         mbar_wait(&bars[2], phase);
         fence_after_sync();
+        TSTAMP();   // MMA 2 done
+        if (tid == 0 && x_tma && tile + (int)gridDim.x < n_tiles) {
+            // a1 is dead now (its readers, the layer-2 MMAs, have completed): prefetch the next tile's rows behind a3
+            const int m1 = (tile + gridDim.x) * 128;
+            const uint32_t bytes = (uint32_t)min(128, p.M - m1) * p.D * 4u;
+            mbar_expect_tx(&bars[5], bytes);
+            bulk_g2s(sXraw, p.obs + chunk_row(m1, p.rows_per_chunk, p.chunk_stride) * p.D, bytes, &bars[5]);
+        }
         {
             uint8_t* g2 = TRAIN ? p.act2 + (size_t)tile * N::A2_BYTES : nullptr;
 #pragma unroll 1
@@ -288,8 +432,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        TSTAMP();   // epilogue 2 done
         // ---------------- layer 3: T3[128, U3] = a2 . W3^T ----------------
         if (tid == 0) {
+            if (tile == (int)blockIdx.x) mbar_wait(&bars[7], 0);       // W3 and the head weights landed (first tile only)
             fence_after_sync();
             constexpr uint32_t idesc = make_idesc_bf16(128, N::U3, 0, 0);
 #pragma unroll
@@ -300,6 +446,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         }
         mbar_wait(&bars[3], phase);
         fence_after_sync();
+        TSTAMP();   // MMA 3 done
         {
             uint8_t* g3 = TRAIN ? p.act3 + (size_t)tile * N::A3_BYTES : nullptr;
             // U3/4 = 16 columns per thread
@@ -320,6 +467,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        TSTAMP();   // epilogue 3 done
         // ---------------- heads: T4[128, AP] = a3 . Wh^T ----------------
         if (tid == 0) {
             fence_after_sync();
@@ -330,33 +478,129 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                           make_smem_desc(smem_u32(sWh) + k * 2 * N::WH_CS, N::WH_CS, 128), idesc, k > 0);
             umma_commit(&bars[4]);
         }
-        // prefetch this row's arena inputs while the heads MMA runs (their latency would otherwise serialise in the loss maths)
-        LossRow<16> lrow;
-        if (TRAIN && h == 0 && row < rows_valid) loss_row_load<16>(p.la, arow0 + row, p.A, lrow);
-        mbar_wait(&bars[4], phase);
-        fence_after_sync();
-        float sc[LOSS_NSC];
-        float dls[16];
+        if (TRAIN) {
+            // ---- PPO loss, split 4 ways: the four threads (h = 0..3) that can read TMEM lane `row` each take the actions
+            //      j = h, h+4, h+8, h+12; per-row sums are exchanged through shared memory (the dead a2 tile region).
+            const bool live = row < rows_valid;
+            const int64_t ar = arow0 + row;
+            float act[4], omu[4], osg[4];
+            float old_v = 0.f, ret = 0.f, old_nlp = 0.f, adv = 0.f, mk = 0.f;
+            if (live) {      // arena inputs: issued before the wait on the heads MMA so their latency overlaps with it
+                old_v = __ldg(p.la.old_values_n + ar); ret = __ldg(p.la.returns_n + ar);
+                old_nlp = __ldg(p.la.old_neglogp + ar); adv = __ldg(p.la.advs_n + ar);
+                mk = p.la.mask ? __ldg(p.la.mask + ar) : 1.f;
 #pragma unroll
-        for (int i = 0; i < LOSS_NSC; ++i) sc[i] = 0.f;
+                for (int k = 0; k < 4; ++k) {
+                    const int j = h + 4 * k;
+                    if (j < p.A) { act[k] = __ldg(p.la.actions + ar * p.A + j); omu[k] = p.la.old_mu[ar * p.A + j]; osg[k] = p.la.old_sigma[ar * p.A + j]; }
+                }
+            }
+            mbar_wait(&bars[4], phase);
+            fence_after_sync();
+            TSTAMP();   // MMA 4 done
+            float head[16];
+            tmem_ld16(T4 + lane_base, head);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dls[j] = 0.f;
-        if (h == 0) {
+            for (int j = 0; j < 16; ++j) head[j] += sBh[j];
+            float* sPart = reinterpret_cast<float*>(sXA2);           // [128 rows][4 h][4]: sum z^2, kl, bound loss
+            float z[4];
+            {
+                float sz2 = 0.f, kl = 0.f, bl = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = h + 4 * k;
+                    z[k] = 0.f;
+                    if (live && j < p.A) {
+                        const float mu = pick_mu(head, h, k), sg = sSig[j], isg = sSig[2 * p.A + j];
+                        z[k] = (act[k] - mu) * isg;
+                        sz2 += z[k] * z[k];
+                        const float c1 = __logf(osg[k] * isg + 1e-5f);
+                        const float dm = omu[k] - mu;
+                        kl += c1 + (sg * sg + dm * dm) * __frcp_rn(2.0f * (osg[k] * osg[k] + 1e-5f)) - 0.5f;
+                        if (p.cfg.has_bounds) {
+                            if (p.cfg.bound_type == 1) { const float hi = fmaxf(mu - 1.1f, 0.f), lo = fminf(mu + 1.1f, 0.f); bl += lo * lo + hi * hi; }
+                            else if (p.cfg.bound_type == 2) bl += mu * mu;
+                        }
+                    }
+                }
+                *reinterpret_cast<float4*>(sPart + (row * 4 + h) * 4) = make_float4(sz2, kl, bl, 0.f);
+            }
+            __syncthreads();
+            TSTAMP();   // loss phase A done
+            uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
+            if (live) {
+                float sz2 = 0.f, kl = 0.f, bl = 0.f;
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) { const float4 t4 = *reinterpret_cast<const float4*>(sPart + (row * 4 + hh) * 4); sz2 += t4.x; kl += t4.y; bl += t4.z; }
+                const float nlp = 0.5f * sz2 + 0.9189385332046727f * (float)p.A + sSig[4 * p.A];     // sSig[4A] = sum(logstd), [4A+1] = entropy
+                const float inv_cnt = p.inv_count_dev ? __ldg(p.inv_count_dev) : (1.0f / (float)p.M);
+                const float w = mk * inv_cnt;
+                float a_loss, g_a;
+                if (p.cfg.ppo) {
+                    const float ratio = __expf(old_nlp - nlp);
+                    const float mi = 1.0f - p.cfg.e_clip, mx = 1.0f + p.cfg.e_clip;
+                    float clamped, dcl;
+                    if (p.cfg.smooth) {
+                        const float sg_ = __frcp_rn(1.0f + __expf((-(ratio - mi) * __frcp_rn(mx - mi) + 0.5f) * 4.0f));
+                        clamped = sg_ * (mx - mi) + mi; dcl = 4.0f * sg_ * (1.0f - sg_);
+                    } else {
+                        clamped = fminf(fmaxf(ratio, mi), mx); dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
+                    }
+                    const float t1 = -(adv * ratio), t2 = -(adv * clamped);
+                    a_loss = fmaxf(t1, t2);
+                    const float d1 = adv * ratio, d2 = adv * dcl * ratio;
+                    g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
+                } else { a_loss = nlp * adv; g_a = adv; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = h + 4 * k;
+                    if (j < p.A) {
+                        const float mu = pick_mu(head, h, k), isg = sSig[2 * p.A + j];
+                        float db = 0.f;
+                        if (p.cfg.has_bounds) {
+                            if (p.cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
+                            else if (p.cfg.bound_type == 2) db = 2.0f * mu;
+                        }
+                        const float dmu = w * (g_a * -(z[k] * isg) + p.cfg.bounds_coef * db);
+                        dls[k] += w * g_a * (1.0f - z[k] * z[k]);
+                        p.la.old_mu[ar * p.A + j] = mu;               // new mu/sigma overwrite the old ones (datasets.py:33-43)
+                        p.la.old_sigma[ar * p.A + j] = sSig[j];
+                        const int c = 1 + j;
+                        *reinterpret_cast<__nv_bfloat16*>(gd + tile_off(row, c >> 3, 2048u, 128u) + (c & 7) * 2) = __float2bfloat16_rn(dmu);
+                    }
+                }
+                if (h == 0) {
+                    const float val = head[0];
+                    float c_loss, dc;
+                    if (p.cfg.clip_value) {
+                        const float delta = val - old_v;
+                        const float vpc = old_v + fminf(fmaxf(delta, -p.cfg.e_clip), p.cfg.e_clip);
+                        const float e1 = val - ret, e2 = vpc - ret;
+                        const float l1 = e1 * e1, l2 = e2 * e2;
+                        c_loss = fmaxf(l1, l2);
+                        const float g1 = 2.0f * e1, g2 = (delta >= -p.cfg.e_clip && delta <= p.cfg.e_clip) ? 2.0f * e2 : 0.0f;
+                        dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
+                    } else { const float e1 = ret - val; c_loss = e1 * e1; dc = -2.0f * e1; }
+                    *reinterpret_cast<__nv_bfloat16*>(gd + tile_off(row, 0, 2048u, 128u)) = __float2bfloat16_rn(w * 0.5f * p.cfg.critic_coef * dc);
+                    const float lr_ = old_nlp - nlp;
+                    const float clipped = (lr_ < p.cfg.log_lo || lr_ > p.cfg.log_hi) ? 1.f : 0.f;
+                    sc[0] += w * a_loss; sc[1] += w * c_loss; sc[2] += w * sSig[4 * p.A + 1]; sc[3] += w * bl; sc[4] += w * kl;
+                    sc[5] += mk; sc[6] += mk * clipped; sc[7] += w;
+                }
+            } else if (h < 2) {
+                // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
+                *reinterpret_cast<uint4*>(gd + tile_off(row, h, 2048u, 128u)) = make_uint4(0, 0, 0, 0);
+            }
+        } else if (h == 0) {
+            mbar_wait(&bars[4], phase);
+            fence_after_sync();
             float head[16];
             tmem_ld16(T4 + lane_base, head);
 #pragma unroll
             for (int j = 0; j < 16; ++j) head[j] += sBh[j];
             const int m = m0 + row;
             if (row < rows_valid) {
-                const int64_t ar = arow0 + row;
-                if (TRAIN) {
-                    float dh[16];
-                    const float inv_cnt = p.inv_count_dev ? __ldg(p.inv_count_dev) : (1.0f / (float)p.M);
-                    ppo_sample_loss<16, true>(head, p.A, sSig, p.la, ar, lrow, inv_cnt, p.cfg, dh, dls, sc);
-                    uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
-                    *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = pack8_bf16(&dh[0]);
-                    *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = pack8_bf16(&dh[8]);
-                } else {
+                {
                     // ---- rollout epilogue: models.py:329-364 eval branch ----
                     float val = head[0];
                     if (p.normalize_value) {
@@ -407,41 +651,48 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                         if (p.valid_out) p.valid_out[m] = p.prev_dones ? (1.0f - p.prev_dones[m]) : 1.0f;
                     }
                 }
-            } else if (TRAIN) {
-                // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
-                uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
-                const uint4 z4 = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = z4;
-                *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = z4;
             }
-        }
-        if (TRAIN) {
-            // block reduction of the loss scalars into the per-CTA running partial (fixed order => deterministic)
-#pragma unroll
-            for (int i = 0; i < LOSS_NSC; ++i) sc[i] = warp_sum(sc[i]);
-#pragma unroll
-            for (int j = 0; j < 15; ++j) dls[j] = warp_sum(dls[j]);
-            if (lane == 0 && h == 0) {
-#pragma unroll
-                for (int i = 0; i < LOSS_NSC; ++i) sRed[warp * LOSS_SLOTS + i] = sc[i];
-#pragma unroll
-                for (int j = 0; j < 15; ++j) sRed[warp * LOSS_SLOTS + LOSS_NSC + j] = dls[j];
-            }
+        } else {
+            mbar_wait(&bars[4], phase);      // rollout: the other column slices only wait for the tile to finish
+            fence_after_sync();
         }
         fence_before_sync();
         __syncthreads();
-        if (TRAIN && tid < LOSS_NSC + p.A) {
-            double s = 0.0;
-            for (int wv = 0; wv < 4; ++wv) s += (double)sRed[wv * LOSS_SLOTS + tid];     // only warps with h == 0 contributed
-            sAcc[tid] += s;
-        }
+        TSTAMP();   // loss phase B done (tile end)
         phase ^= 1;
     }
-    if (!weights_ready) mbar_wait(&bars[0], 0);
+    if (!weights_ready) { mbar_wait(&bars[0], 0); mbar_wait(&bars[6], 0); mbar_wait(&bars[7], 0); }
+    if (TRAIN) {
+        // block reduction of the loss partials (fixed order => deterministic): scalars from the four h == 0 warps, d_logstd
+        // slices from all 16 warps (action j lives in the warps with h == j % 4, slot j / 4)
+#pragma unroll
+        for (int i = 0; i < LOSS_NSC; ++i) sc[i] = warp_sum(sc[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dls[k] = warp_sum(dls[k]);
+        if (lane == 0) {
+            if (h == 0) {
+#pragma unroll
+                for (int i = 0; i < LOSS_NSC; ++i) sRed[warp * LOSS_NSC + i] = sc[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sRed[4 * LOSS_NSC + warp * 4 + k] = dls[k];
+        }
+    }
     __syncthreads();
-    if (TRAIN && tid < LOSS_NSC + p.A) p.partials[(int64_t)blockIdx.x * LOSS_SLOTS + tid] = sAcc[tid];
+    if (TRAIN && tid < LOSS_NSC + p.A) {
+        double s = 0.0;
+        if (tid < LOSS_NSC) {
+            for (int wv = 0; wv < 4; ++wv) s += (double)sRed[wv * LOSS_NSC + tid];
+        } else {
+            const int j = tid - LOSS_NSC;
+            for (int qq = 0; qq < 4; ++qq) s += (double)sRed[4 * LOSS_NSC + (qq + 4 * (j & 3)) * 4 + (j >> 2)];
+        }
+        p.partials[(int64_t)blockIdx.x * LOSS_SLOTS + tid] = s;
+    }
     fence_before_sync();
     __syncthreads();
+    TSTAMP();   // kernel end
+    TSTAMP_END();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -452,9 +703,9 @@ struct Bwd1Args {
     int M; int A; int P; int off_W3, off_b3, off_b2, off_Wh, off_bh;
 };
 
+// body: TMEM (512 columns at `tmem`) is allocated by the calling kernel; barriers and shared-memory layout are set up here
 template <class N>
-__global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+__device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, const uint32_t tmem) {
     uint8_t* sWh = smem; uint8_t* sW3 = sWh + N::WH_BYTES; uint8_t* sW2 = sW3 + N::W3_BYTES;
     uint8_t* sDH = sW2 + N::W2_BYTES;
     uint8_t* sA3 = sDH + N::DH_BYTES;             // padded to 128 columns (upper col-groups stay zero)
@@ -462,12 +713,13 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
     uint8_t* sD3 = sA2 + N::A2_BYTES;
     uint8_t* sD2 = sD3 + N::A3_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sD2 + N::A2_BYTES);       // [0] weights, [1] tile loads, [2..4] mma
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const int n_tiles = (p.M + 127) / 128;
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    int n_stamp = 0; (void)n_stamp;
+    constexpr int TSB = 128; (void)TSB;
+    TSTAMP();   // kernel start
     if (tid == 0) {
         for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
         fence_mbar_init();
@@ -478,7 +730,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
+    pdl_sync();      // everything above is CTA-local; all global traffic comes after the predecessor (the forward kernel) completed
     const uint32_t TT = tmem, TWH = tmem + 256, TW3 = tmem + 288;     // transient [0,256), dWh^T [256,272), dW3^T [288,352)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     if (tid == 0) {
@@ -486,19 +738,23 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
         bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[0]);
         bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[0]);
         bulk_g2s(sW2, p.wpack + N::W2_OFF, N::W2_BYTES, &bars[0]);
-    }
-    float bsum3 = 0.f, bsum2 = 0.f, bsumh = 0.f;      // thread <-> column running bias-gradient sums
-    uint32_t phase = 0;
-    bool first = true;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        if (tid == 0) {
+        if ((int)blockIdx.x < n_tiles) {      // first tile's operands
+            const int tile = blockIdx.x;
             mbar_expect_tx(&bars[1], N::DH_BYTES + N::A3_BYTES + N::A2_BYTES);
             bulk_g2s(sDH, p.dhead + (size_t)tile * N::DH_BYTES, N::DH_BYTES, &bars[1]);
             bulk_g2s(sA3, p.act3 + (size_t)tile * N::A3_BYTES, N::A3_BYTES, &bars[1]);
             bulk_g2s(sA2, p.act2 + (size_t)tile * N::A2_BYTES, N::A2_BYTES, &bars[1]);
         }
+    }
+    // running bias-gradient sums: 8 columns per owning thread (colsum8)
+    float bsum3[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bsum2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bsumh[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t phase = 0;
+    bool first = true;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (first) mbar_wait(&bars[0], 0);
+        TSTAMP();   // tile start
         mbar_wait(&bars[1], phase);
+        TSTAMP();   // tile loads landed
         // ---- d3pre = d_head . Wh   ;  dWh^T += a3^T . d_head ----
         if (tid == 0) {
             fence_after_sync();
@@ -510,15 +766,10 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
                           make_idesc_bf16(128, N::AP, 1, 1), (!first || k > 0) ? 1u : 0u);
             umma_commit(&bars[2]);
         }
-        // bias grad of the heads: column sums of the d_head tile (thread c < AP)
-        if (tid < N::AP) {
-            float s = 0.f;
-            for (int r = 0; r < 128; ++r)
-                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sDH + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
-            bsumh += s;
-        }
+        colsum8<128, N::AP / 8, N::ACS, 256>(sDH, tid, bsumh);     // bias grad of the heads
         mbar_wait(&bars[2], phase);
         fence_after_sync();
+        TSTAMP();   // MMA a done
         {   // d3 = d3pre * elu'(a3): U3/2 = 32 columns per thread
             const int c0 = h * (N::U3 / 2);
             float v[32];
@@ -535,6 +786,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        TSTAMP();   // d3 epilogue done
         // ---- d2pre = d3 . W3 ; dW3^T += a2^T . d3 ----
         if (tid == 0) {
             fence_after_sync();
@@ -548,14 +800,10 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
                           make_idesc_bf16(128, N::U3, 1, 1), (!first || k > 0) ? 1u : 0u);
             umma_commit(&bars[3]);
         }
-        if (tid < N::U3) {
-            float s = 0.f;
-            for (int r = 0; r < 128; ++r)
-                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sD3 + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
-            bsum3 += s;
-        }
+        colsum8<128, N::U3 / 8, N::ACS, 256>(sD3, tid, bsum3);
         mbar_wait(&bars[3], phase);
         fence_after_sync();
+        TSTAMP();   // MMA b done
         {   // d2 = d2pre * elu'(a2): U2/2 = 64 columns per thread
             uint8_t* g2 = p.delta2 + (size_t)tile * N::A2_BYTES;
 #pragma unroll 1
@@ -575,23 +823,29 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        TSTAMP();   // d2 epilogue done
         // ---- d1pre = d2 . W2 ----
         if (tid == 0) {
             fence_after_sync();
+            if (tile + (int)gridDim.x < n_tiles) {
+                // d_head / a3 / a2 tiles are dead (MMAs a, b completed, epilogue reads fenced + synced): prefetch the next tile's
+                // operands so that they land while d1pre and its 128-column epilogue run
+                const int nt = tile + gridDim.x;
+                mbar_expect_tx(&bars[1], N::DH_BYTES + N::A3_BYTES + N::A2_BYTES);
+                bulk_g2s(sDH, p.dhead + (size_t)nt * N::DH_BYTES, N::DH_BYTES, &bars[1]);
+                bulk_g2s(sA3, p.act3 + (size_t)nt * N::A3_BYTES, N::A3_BYTES, &bars[1]);
+                bulk_g2s(sA2, p.act2 + (size_t)nt * N::A2_BYTES, N::A2_BYTES, &bars[1]);
+            }
 #pragma unroll
             for (int k = 0; k < N::U2 / 16; ++k)
                 umma_bf16(TT, make_smem_desc(smem_u32(sD2) + k * 2 * N::ACS, N::ACS, N::ARS),
                           make_smem_desc(smem_u32(sW2) + k * 256, 128, N::W2_CS), make_idesc_bf16(128, N::U1, 0, 1), k > 0);
             umma_commit(&bars[4]);
         }
-        if (tid < N::U2) {
-            float s = 0.f;
-            for (int r = 0; r < 128; ++r)
-                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sD2 + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
-            bsum2 += s;
-        }
+        colsum8<128, N::U2 / 8, N::ACS, 256>(sD2, tid, bsum2);
         mbar_wait(&bars[4], phase);
         fence_after_sync();
+        TSTAMP();   // MMA c done
         {   // d1 = d1pre * elu'(a1) straight to the global tiled buffer (a1 read from its global tile, coalesced 16B)
             const uint8_t* ga1 = p.act1 + (size_t)tile * N::A1_BYTES;
             uint8_t* g1 = p.delta1 + (size_t)tile * N::A1_BYTES;
@@ -614,6 +868,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
         }
         fence_before_sync();
         __syncthreads();
+        TSTAMP();   // d1 epilogue done
         phase ^= 1;
         first = false;
     }
@@ -643,12 +898,46 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
         for (int i = tid; i < N::U3 * N::U2; i += 256) part[p.off_W3 + i] = 0.f;
         for (int i = tid; i < (p.A + 1) * N::U3; i += 256) part[p.off_Wh + i] = 0.f;
     }
-    if (tid < N::U3) part[p.off_b3 + tid] = bsum3;
-    if (tid < N::U2) part[p.off_b2 + tid] = bsum2;
-    if (tid < p.A + 1) part[p.off_bh + tid] = bsumh;
+    {
+        int g = colsum8_owner_group<N::U3 / 8, 256>(tid);
+        if (g >= 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[p.off_b3 + g * 8 + j] = bsum3[j];
+        }
+        g = colsum8_owner_group<N::U2 / 8, 256>(tid);
+        if (g >= 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[p.off_b2 + g * 8 + j] = bsum2[j];
+        }
+        g = colsum8_owner_group<N::AP / 8, 256>(tid);
+        if (g >= 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (g * 8 + j < p.A + 1) part[p.off_bh + g * 8 + j] = bsumh[j];
+        }
+    }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    TSTAMP();   // flush done
+    TSTAMP_END();
+}
+
+// TMEM allocation shared by the backward kernels: warp 0 allocates all 512 columns, every thread learns the base
+__device__ __forceinline__ uint32_t bwd_tmem_alloc(uint32_t* slot) {
+    if ((threadIdx.x >> 5) == 0) tmem_alloc(slot, 512);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    return *slot;
+}
+
+template <class N>
+__global__ void __launch_bounds__(256, 1) mlp_bwd1_tc_kernel(const Bwd1Args p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t tmem = bwd_tmem_alloc(&tmem_slot);
+    bwd1_body<N>(p, smem, tmem);
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, 512);
 }
 
 // ================================================================================================= backward 2
@@ -659,39 +948,40 @@ struct Bwd2Args {
 };
 
 template <class N>
-__global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
+__device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, const uint32_t tmem) {
     // dW2^T[i][o] = sum_r a1[r][i] d2[r][o]   (two M = 128 halves over i, N = U2)      -> grad_W2[o*U1 + i]
     // dW1^T[i][o] = sum_r x[r][i]  d1[r][o]   (x tile zero-padded to 128 columns, N = U1) -> grad_W1[o*D + i]
     // TMEM lanes carry the contiguous `in` index, so the flush stores are coalesced.
-    extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sD2 = smem; uint8_t* sD1 = sD2 + N::A2_BYTES; uint8_t* sA1 = sD1 + N::A1_BYTES; uint8_t* sX = sA1 + N::A1_BYTES;   // sX: 128 cols
     float* sNorm = reinterpret_cast<float*>(sX + 128 * 256);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + 2 * N::DPAD);          // [0] tile loads, [1] mma
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const int n_tiles = (p.M + 127) / 128;
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    int n_stamp = 0; (void)n_stamp;
+    constexpr int TSB = 256; (void)TSB;
+    TSTAMP();   // kernel start
     if (tid == 0) {
         mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
         fence_mbar_init();
     }
+    pdl_sync();
     load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     for (int i = tid; i < (128 * 256 - (int)N::X_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(sX + N::X_BYTES)[i] = make_uint4(0, 0, 0, 0);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
     const uint32_t TW2 = tmem, TW1 = tmem + 256;     // dW2^T halves [128 x U2] at +0, +128 ; dW1^T [128 x U1] at +256
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float bsum1 = 0.f;
+    float bsum1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     uint32_t phase = 0;
     bool first = true;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         if (!first) { mbar_wait(&bars[1], phase ^ 1); fence_after_sync(); }    // previous tile's MMAs done reading the tiles
         __syncthreads();
+        TSTAMP();   // tile start (previous MMAs done)
         if (tid == 0) {
             mbar_expect_tx(&bars[0], N::A2_BYTES + 2 * N::A1_BYTES);
             bulk_g2s(sD2, p.delta2 + (size_t)tile * N::A2_BYTES, N::A2_BYTES, &bars[0]);
@@ -701,8 +991,10 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
         const int m0 = tile * 128;
         stage_x_tile<N, 256>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm, p.nm != nullptr);
         fence_async_smem();
+        TSTAMP();   // X staged
         mbar_wait(&bars[0], phase);
         __syncthreads();
+        TSTAMP();   // tile loads landed
         if (tid == 0) {
             fence_after_sync();
             const uint32_t acc = first ? 0u : 1u;
@@ -719,12 +1011,8 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
                           make_idesc_bf16(128, N::U1, 1, 1), (acc || k > 0) ? 1u : 0u);
             umma_commit(&bars[1]);
         }
-        if (tid < N::U1) {
-            float s = 0.f;
-            for (int r = 0; r < 128; ++r)
-                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sD1 + tile_off(r, tid >> 3, N::ACS, N::ARS) + (tid & 7) * 2));
-            bsum1 += s;
-        }
+        colsum8<128, N::U1 / 8, N::ACS, 256>(sD1, tid, bsum1);
+        TSTAMP();   // bias sums done
         phase ^= 1;
         first = false;
     }
@@ -732,6 +1020,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
     if (!first) {
         mbar_wait(&bars[1], phase ^ 1);
         fence_after_sync();
+        TSTAMP();   // last MMAs done
         // dW2^T halves: lane = in index i (hh*128 + row), columns = out o: thread takes o in [64h, 64h+64)
 #pragma unroll 1
         for (int hh = 0; hh < N::U1 / 128; ++hh) {
@@ -757,9 +1046,184 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_tc_kernel(const Bwd2Args p) {
         for (int i = tid; i < N::U2 * N::U1; i += 256) part[p.off_W2 + i] = 0.f;
         for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
     }
-    if (tid < N::U1) part[p.off_b1 + tid] = bsum1;
+    {
+        const int g = colsum8_owner_group<N::U1 / 8, 256>(tid);
+        if (g >= 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) part[p.off_b1 + g * 8 + j] = bsum1[j];
+        }
+    }
     fence_before_sync();
     __syncthreads();
+    TSTAMP();   // flush done
+    TSTAMP_END();
+}
+
+// ---- the whole backward pass in ONE launch: phase 1 = delta chain + dW3/dWh (bwd1_body), phase 2 = dW2/dW1 (bwd2_body).
+//      Phase 2 of a CTA consumes only delta tiles that the SAME CTA produced in phase 1 (both phases walk the tiles
+//      blockIdx.x, blockIdx.x + gridDim.x, ...), so no grid-wide synchronisation is needed -- only the generic-proxy stores
+//      of delta1/delta2 must be ordered before the async-proxy (TMA) loads that read them back.
+struct BwdArgs { Bwd1Args a; Bwd2Args b; };
+
+template <class N>
+__global__ void __launch_bounds__(256, 1) mlp_bwd_tc_kernel(const BwdArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t tmem = bwd_tmem_alloc(&tmem_slot);
+    bwd1_body<N>(p.a, smem, tmem);
+    __threadfence();
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    fence_async_smem();          // phase 2 re-uses the shared memory of phase 1 as TMA destinations
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    bwd2_body<N>(p.b, smem, tmem);
+    if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- backward 2, pipelined edition: the row index is the GEMM K dimension here, so the 128-row tiles are consumed as 64-row
+//      half tiles through a two-stage TMA ring (96 KB per stage): the loads of half j+1 / j+2 are in flight while half j is
+//      multiplied.  The normalised bf16 observation tile comes from the forward kernel (p.xt) instead of being re-derived.
+struct Bwd2DbArgs {
+    const uint8_t* xt; const uint8_t* act1; const uint8_t* delta2; const uint8_t* delta1; float* part;
+    int M; int D; int P; int off_W2, off_W1, off_b1;
+};
+
+template <class N>
+__global__ void __launch_bounds__(256, 1) mlp_bwd2_db_tc_kernel(const Bwd2DbArgs p) {
+    constexpr uint32_t HCS = 1024;                                   // column-group stride of a 64-row half tile (64 rows x 16 B)
+    constexpr uint32_t D2H = N::A2_BYTES / 2, D1H = N::A1_BYTES / 2, A1H = N::A1_BYTES / 2, XH = 16 * HCS;   // X half padded to 128 columns
+    constexpr uint32_t STAGE = D2H + D1H + A1H + XH;
+    constexpr int NCGX = N::DPAD / 8;                                // real column groups of the X tile
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * STAGE);  // [0,1] stage full, [2,3] stage consumed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int n_tiles = (p.M + 127) / 128;
+    int n_stamp = 0; (void)n_stamp;
+    constexpr int TSB = 256; (void)TSB;
+    TSTAMP();   // kernel start
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+        fence_mbar_init();
+    }
+    // zero the padding column groups of both X half tiles once (the TMA copies only ever write the real ones)
+    for (int s = 0; s < 2; ++s) {
+        uint8_t* sX = smem + s * STAGE + D2H + D1H + A1H;
+        for (int i = tid; i < (int)(XH - NCGX * HCS) / 16; i += 256) reinterpret_cast<uint4*>(sX + NCGX * HCS)[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    pdl_sync();      // CTA-local set-up above; the delta tiles below are the predecessor's output
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t TW2 = tmem, TW1 = tmem + 256;     // dW2^T halves [128 x U2] at +0, +128 ; dW1^T [128 x U1] at +256
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int nt = ((int)blockIdx.x < n_tiles) ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int nh = 2 * nt;                            // half tiles of this CTA
+    // warp 0 issues the copies of half tile j into stage j & 1: one 1 KB bulk copy per column group
+    auto issue = [&](int j) {
+        const int s = j & 1, hf = j & 1;
+        const size_t tile = (size_t)blockIdx.x + (size_t)(j >> 1) * gridDim.x;
+        uint8_t* sD2 = smem + s * STAGE; uint8_t* sD1 = sD2 + D2H; uint8_t* sA1 = sD1 + D1H; uint8_t* sX = sA1 + A1H;
+        if (lane == 0) mbar_expect_tx(&bars[s], D2H + D1H + A1H + NCGX * HCS);
+        __syncwarp();
+        const uint8_t* gD2 = p.delta2 + tile * N::A2_BYTES + hf * HCS;
+        const uint8_t* gD1 = p.delta1 + tile * N::A1_BYTES + hf * HCS;
+        const uint8_t* gA1 = p.act1 + tile * N::A1_BYTES + hf * HCS;
+        const uint8_t* gX = p.xt + tile * N::X_BYTES + hf * HCS;
+        for (int g = lane; g < N::U1 / 8; g += 32) {
+            bulk_g2s(sD1 + g * HCS, gD1 + (size_t)g * N::ACS, HCS, &bars[s]);
+            bulk_g2s(sA1 + g * HCS, gA1 + (size_t)g * N::ACS, HCS, &bars[s]);
+        }
+        for (int g = lane; g < N::U2 / 8; g += 32) bulk_g2s(sD2 + g * HCS, gD2 + (size_t)g * N::ACS, HCS, &bars[s]);
+        for (int g = lane; g < NCGX; g += 32) bulk_g2s(sX + g * HCS, gX + (size_t)g * N::ACS, HCS, &bars[s]);
+    };
+    if (warp == 0) {
+        if (nh > 0) issue(0);
+        if (nh > 1) issue(1);
+    }
+    float bsum1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t ph_full = 0, ph_done = 0;     // bit s = phase parity of stage s's barrier
+    for (int j = 0; j < nh; ++j) {
+        const int s = j & 1;
+        uint8_t* sD2 = smem + s * STAGE; uint8_t* sD1 = sD2 + D2H; uint8_t* sA1 = sD1 + D1H; uint8_t* sX = sA1 + A1H;
+        TSTAMP();   // half start
+        mbar_wait(&bars[s], (ph_full >> s) & 1u);
+        ph_full ^= 1u << s;
+        TSTAMP();   // loads landed
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t acc = j > 0 ? 1u : 0u;
+#pragma unroll
+            for (int hh = 0; hh < N::U1 / 128; ++hh)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(TW2 + hh * N::U2, make_smem_desc(smem_u32(sA1) + hh * 16 * HCS + k * 256, 128, HCS),
+                              make_smem_desc(smem_u32(sD2) + k * 256, 128, HCS), make_idesc_bf16(128, N::U2, 1, 1), (acc || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(TW1, make_smem_desc(smem_u32(sX) + k * 256, 128, HCS), make_smem_desc(smem_u32(sD1) + k * 256, 128, HCS),
+                          make_idesc_bf16(128, N::U1, 1, 1), (acc || k > 0) ? 1u : 0u);
+            umma_commit(&bars[2 + s]);
+        }
+        colsum8<64, N::U1 / 8, HCS, 256>(sD1, tid, bsum1);     // bias gradient of layer 1: column sums of the d1 half tile
+        if (j + 2 < nh) {
+            // refill this stage with half j + 2 once its MMAs have consumed it and every thread is done with the column sums
+            mbar_wait(&bars[2 + s], (ph_done >> s) & 1u);
+            ph_done ^= 1u << s;
+            fence_async_smem();
+            __syncthreads();
+            if (warp == 0) issue(j + 2);
+        }
+        TSTAMP();   // half done
+    }
+    float* part = p.part + (size_t)blockIdx.x * p.P;
+    if (nh > 0) {
+        // the last commit covers every earlier MMA
+        const int sl = (nh - 1) & 1;
+        mbar_wait(&bars[2 + sl], (ph_done >> sl) & 1u);
+        if (nh > 1) mbar_wait(&bars[2 + (sl ^ 1)], (ph_done >> (sl ^ 1)) & 1u);
+        fence_after_sync();
+        TSTAMP();   // last MMAs done
+#pragma unroll 1
+        for (int hh = 0; hh < N::U1 / 128; ++hh) {
+#pragma unroll 1
+            for (int c0 = h * (N::U2 / 2); c0 < (h + 1) * (N::U2 / 2); c0 += 32) {
+                float v[32];
+                tmem_ld32(TW2 + hh * N::U2 + lane_base + c0, v);
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) part[p.off_W2 + (size_t)(c0 + jj) * N::U1 + hh * 128 + row] = v[jj];
+            }
+        }
+#pragma unroll 1
+        for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+            float v[32];
+            tmem_ld32(TW1 + lane_base + c0, v);
+            if (row < p.D) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) part[p.off_W1 + (size_t)(c0 + jj) * p.D + row] = v[jj];
+            }
+        }
+    } else {
+        for (int i = tid; i < N::U2 * N::U1; i += 256) part[p.off_W2 + i] = 0.f;
+        for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
+    }
+    {
+        const int g = colsum8_owner_group<N::U1 / 8, 256>(tid);
+        if (g >= 0) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) part[p.off_b1 + g * 8 + jj] = bsum1[jj];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    TSTAMP();   // flush done
+    TSTAMP_END();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -770,7 +1234,9 @@ template <class N> constexpr size_t fwd_smem() {
 template <class N> constexpr size_t bwd1_smem() {
     return (size_t)N::WH_BYTES + N::W3_BYTES + N::W2_BYTES + N::DH_BYTES + 128 * 256 + N::A2_BYTES + N::A3_BYTES + N::A2_BYTES + 8 * 8 + 16;
 }
+template <class N> constexpr size_t bwd2_db_smem() { return (size_t)2 * (N::A2_BYTES / 2 + N::A1_BYTES + 16 * 1024) + 4 * 8 + 16; }
 template <class N> constexpr size_t bwd2_smem() { return (size_t)N::A2_BYTES + 2 * N::A1_BYTES + 128 * 256 + sizeof(float) * 2 * N::DPAD + 4 * 8 + 16; }
+template <class N> constexpr size_t bwd_smem() { return bwd1_smem<N>() > bwd2_smem<N>() ? bwd1_smem<N>() : bwd2_smem<N>(); }
 
 bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D <= 64 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
 
@@ -787,6 +1253,10 @@ B200RL_EXPORT int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int
     if (!net_is_c2(D, u1, u2, u3, A) || !out4_host) return B200RL_EUNSUPPORTED;
     out4_host[0] = NetC2::A1_BYTES; out4_host[1] = NetC2::A2_BYTES; out4_host[2] = NetC2::A3_BYTES; out4_host[3] = NetC2::DH_BYTES;
     return B200RL_OK;
+}
+
+B200RL_EXPORT int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A) {
+    return net_is_c2(D, u1, u2, u3, A) ? (int64_t)NetC2::X_BYTES : -1;
 }
 
 // segments of the packed weight buffer, for the optimiser's fused refresh (b200rl_adam_step_f32)
@@ -834,7 +1304,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
                                           const float* actions, float* old_mu, float* old_sigma, const float* old_values_n,
                                           const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
                                           const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
-                                          void* act1, void* act2, void* act3, void* dhead,
+                                          void* act1, void* act2, void* act3, void* dhead, void* xtile,
                                           double* partials, int max_partials, int* n_blocks_out_host, void* stream) {
     if (!obs || !wpack || !b1 || !b2 || !b3 || !b_head || !logstd || !actions || !old_mu || !old_sigma || !old_values_n || !returns_n ||
         !old_neglogp || !advs_n || !cfg_host || !act1 || !act2 || !act3 || !dhead || !partials)
@@ -856,12 +1326,13 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
                        cfg_host->bound_loss_type, cfg_host->clip_value, cfg_host->use_smooth_clamp, cfg_host->ppo,
                        log1pf(-cfg_host->e_clip), log1pf(cfg_host->e_clip)};
     p.act1 = (uint8_t*)act1; p.act2 = (uint8_t*)act2; p.act3 = (uint8_t*)act3; p.dhead = (uint8_t*)dhead; p.partials = partials;
+    p.xt = (uint8_t*)xtile;
     constexpr size_t smem = fwd_smem<N>();
     static_assert(smem <= 227 * 1024, "forward kernel shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mlp_fwd_tc_kernel<N, true><<<grid, FWD_THREADS, smem, as_stream(stream)>>>(p);
-    B200RL_LAUNCH_CHECK();
+    e = launch_k(mlp_fwd_tc_kernel<N, true>, dim3(grid), dim3(FWD_THREADS), smem, as_stream(stream), p);
+    if (e != cudaSuccess) return (int)e;
     return B200RL_OK;
 }
 
@@ -893,15 +1364,15 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
     constexpr size_t smem = fwd_smem<N>();
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mlp_fwd_tc_kernel<N, false><<<grid, FWD_THREADS, smem, as_stream(stream)>>>(p);
-    B200RL_LAUNCH_CHECK();
+    e = launch_k(mlp_fwd_tc_kernel<N, false>, dim3(grid), dim3(FWD_THREADS), smem, as_stream(stream), p);
+    if (e != cudaSuccess) return (int)e;
     return B200RL_OK;
 }
 
 B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                                     const float* norm_mean, const float* norm_std, const void* wpack,
                                     int u1, int u2, int u3, int M, int A,
-                                    const void* act1, const void* act2, const void* act3, const void* dhead,
+                                    const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
                                     void* delta2, void* delta1, float* part, int max_parts, int P,
                                     int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
                                     int* n_parts_out_host, void* stream) {
@@ -916,19 +1387,34 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     if (grid > max_parts) return B200RL_EINVAL;
     Bwd1Args a{(const uint8_t*)wpack, (const uint8_t*)act1, (const uint8_t*)act2, (const uint8_t*)act3, (const uint8_t*)dhead,
                (uint8_t*)delta2, (uint8_t*)delta1, part, M, A, P, off_W3, off_b3, off_b2, off_Wh, off_bh};
-    constexpr size_t smem1 = bwd1_smem<N>();
-    static_assert(smem1 <= 227 * 1024, "bwd1 shared memory budget");
-    cudaError_t e = cudaFuncSetAttribute(mlp_bwd1_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+    cudaError_t e;
+    if (xtile) {
+        // two launches: delta chain, then the pipelined weight-gradient kernel (observation tiles from the forward kernel,
+        // 64-row half tiles through a two-stage TMA ring)
+        constexpr size_t smem1 = bwd1_smem<N>();
+        static_assert(smem1 <= 227 * 1024, "bwd1 shared memory budget");
+        e = cudaFuncSetAttribute(mlp_bwd1_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        if (e != cudaSuccess) return (int)e;
+        e = launch_k(mlp_bwd1_tc_kernel<N>, dim3(grid), dim3(256), smem1, as_stream(stream), a);
+        if (e != cudaSuccess) return (int)e;
+        Bwd2DbArgs b{(const uint8_t*)xtile, (const uint8_t*)act1, (const uint8_t*)delta2, (const uint8_t*)delta1, part, M, D, P,
+                     off_W2, off_W1, off_b1};
+        constexpr size_t smem2 = bwd2_db_smem<N>();
+        static_assert(smem2 <= 227 * 1024, "bwd2 (pipelined) shared memory budget");
+        e = cudaFuncSetAttribute(mlp_bwd2_db_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return (int)e;
+        e = launch_k(mlp_bwd2_db_tc_kernel<N>, dim3(grid), dim3(256), smem2, as_stream(stream), b);
+        if (e != cudaSuccess) return (int)e;
+        return B200RL_OK;
+    }
+    // default: the whole backward pass in one launch
+    BwdArgs ab{a, Bwd2Args{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
+                           (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1}};
+    constexpr size_t smem = bwd_smem<N>();
+    static_assert(smem <= 227 * 1024, "backward kernel shared memory budget");
+    e = cudaFuncSetAttribute(mlp_bwd_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    mlp_bwd1_tc_kernel<N><<<grid, 256, smem1, as_stream(stream)>>>(a);
-    B200RL_LAUNCH_CHECK();
-    Bwd2Args b{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
-               (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1};
-    constexpr size_t smem2 = bwd2_smem<N>();
-    static_assert(smem2 <= 227 * 1024, "bwd2 shared memory budget");
-    e = cudaFuncSetAttribute(mlp_bwd2_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    e = launch_k(mlp_bwd_tc_kernel<N>, dim3(grid), dim3(256), smem, as_stream(stream), ab);
     if (e != cudaSuccess) return (int)e;
-    mlp_bwd2_tc_kernel<N><<<grid, 256, smem2, as_stream(stream)>>>(b);
-    B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }

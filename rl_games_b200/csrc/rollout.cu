@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(256) post_step_kernel(
     int games_to_track, double* scratch, int* counter, int N, ShaperDev c) {
     __shared__ double sm[32 * 4];
     __shared__ int is_last;
+    pdl_sync();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[4] = {0, 0, 0, 0};
     if (e < N) {
@@ -263,15 +264,14 @@ B200RL_EXPORT int b200rl_post_step_f32(const float* rewards, const void* dones, 
     c.max_val = cfg_host->max_val; c.gamma = cfg_host->gamma; c.log_val = cfg_host->log_val;
     c.value_bootstrap = cfg_host->value_bootstrap;
     cudaStream_t s = as_stream(stream);
+    cudaError_t le;
     if (dones_is_u8)
-        post_step_kernel<uint8_t><<<blocks, 256, 0, s>>>(rewards, (const uint8_t*)dones, time_outs, time_outs_kind, values_t, valid_t,
-                                                         rewards_out_t, dones_cur, prev_dones_f32, ep_state, meter, games_to_track,
-                                                         scratch, counter, N, c);
+        le = launch_k(post_step_kernel<uint8_t>, dim3(blocks), dim3(256), 0, s, rewards, (const uint8_t*)dones, time_outs, time_outs_kind, values_t,
+                      valid_t, rewards_out_t, dones_cur, prev_dones_f32, ep_state, meter, games_to_track, scratch, counter, N, c);
     else
-        post_step_kernel<float><<<blocks, 256, 0, s>>>(rewards, (const float*)dones, time_outs, time_outs_kind, values_t, valid_t,
-                                                       rewards_out_t, dones_cur, prev_dones_f32, ep_state, meter, games_to_track,
-                                                       scratch, counter, N, c);
-    B200RL_LAUNCH_CHECK();
+        le = launch_k(post_step_kernel<float>, dim3(blocks), dim3(256), 0, s, rewards, (const float*)dones, time_outs, time_outs_kind, values_t,
+                      valid_t, rewards_out_t, dones_cur, prev_dones_f32, ep_state, meter, games_to_track, scratch, counter, N, c);
+    if (le != cudaSuccess) return (int)le;
     return B200RL_OK;
 }
 

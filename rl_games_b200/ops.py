@@ -7,7 +7,7 @@ import ctypes
 
 import torch
 
-from ._lib import lib, check, ptr
+from ._lib import lib, check, ptr, B200RLError
 
 ACT = {'None': 0, None: 0, 'none': 0, 'elu': 1, 'relu': 2, 'tanh': 3}
 
@@ -215,6 +215,16 @@ def reduce_finalize(part, out, n, n_splits, split_stride, partials, n_partials, 
                                      ptr(entropy_coef_dev), ptr(stats), ptr(d_logstd), ptr(kl_out), _stream()), 'reduce_finalize')
 
 
+def reduce_adam(part, n_splits, split_stride, loss_partials, n_loss_partials, A, entropy_coef_dev, stats, kl_out, grads, params,
+                exp_avg, exp_avg_sq, n, state_d, cfg, counter, nrm_part, grid_bar, wpack=None, pack_table=None, merge_next=None):
+    """single-GPU fused minibatch tail: split reduce + loss finalise + clip + Adam in one launch"""
+    check(lib.b200rl_reduce_adam_f32(ptr(part), n_splits, split_stride, ptr(loss_partials), n_loss_partials, A, ptr(entropy_coef_dev),
+                                     ptr(stats), ptr(kl_out), ptr(grads), ptr(params), ptr(exp_avg), ptr(exp_avg_sq), n, ptr(state_d),
+                                     ctypes.addressof(cfg), ptr(counter), ptr(nrm_part), nrm_part.numel(), ptr(grid_bar), ptr(wpack),
+                                     None if pack_table is None else ctypes.addressof(pack_table),
+                                     None if merge_next is None else ctypes.addressof(merge_next), _stream()), 'reduce_adam')
+
+
 def tc_pack_table(D, units, A, offs):
     t = PackTable()
     check(lib.b200rl_tc_pack_table(D, units[0], units[1], units[2], A, offs['W0'], offs['W1'], offs['W2'], offs['W_head'],
@@ -287,19 +297,31 @@ def tc_tile_bytes(D, units, A):
     return [int(x) for x in out]
 
 
+def set_pdl(enable):
+    """programmatic dependent launch of the chain kernels (process-wide); returns the previous setting"""
+    return bool(lib.b200rl_set_pdl(int(bool(enable))))
+
+
+def tc_xtile_bytes(D, units, A):
+    n = int(lib.b200rl_tc_xtile_bytes(D, units[0], units[1], units[2], A))
+    if n < 0:
+        raise B200RLError('tc_xtile_bytes: unsupported geometry')
+    return n
+
+
 def tc_pack_weights(W1, W2, W3, W_head, D, units, A, wpack):
     check(lib.b200rl_tc_pack_weights(ptr(W1), ptr(W2), ptr(W3), ptr(W_head), D, units[0], units[1], units[2], A, ptr(wpack),
                                      _stream()), 'tc_pack_weights')
 
 
 def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_head, logstd, units, M, A, actions, old_mu,
-                     old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials):
+                     old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials, xtile=None):
     nb = ctypes.c_int(0)
     check(lib.b200rl_tc_mlp_fwd_train(ptr(obs), rows_per_chunk, chunk_stride, D, ptr(nm), ptr(ns), ptr(wpack), ptr(b[0]), ptr(b[1]),
                                       ptr(b[2]), ptr(b_head), ptr(logstd), units[0], units[1], units[2], M, A, ptr(actions),
                                       ptr(old_mu), ptr(old_sigma), ptr(old_values_n), ptr(returns_n), ptr(old_neglogp), ptr(advs_n),
                                       ptr(mask), ctypes.addressof(cfg), ptr(inv_count), ptr(act[0]), ptr(act[1]), ptr(act[2]),
-                                      ptr(dhead), ptr(partials), partials.shape[0], ctypes.addressof(nb), _stream()),
+                                      ptr(dhead), ptr(xtile), ptr(partials), partials.shape[0], ctypes.addressof(nb), _stream()),
           'tc_mlp_fwd_train')
     return nb.value
 
@@ -315,11 +337,12 @@ def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vm
                                         int(values_only), _stream()), 'tc_mlp_fwd_rollout')
 
 
-def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs):
+def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs,
+               xtile=None):
     """offs: dict with W0,b0,W1,b1,W2,b2,W_head,b_head flat offsets (model.layout)."""
     nb = ctypes.c_int(0)
     check(lib.b200rl_tc_mlp_bwd(ptr(obs), rows_per_chunk, chunk_stride, D, ptr(nm), ptr(ns), ptr(wpack), units[0], units[1], units[2],
-                                M, A, ptr(act[0]), ptr(act[1]), ptr(act[2]), ptr(dhead), ptr(delta2), ptr(delta1), ptr(part),
+                                M, A, ptr(act[0]), ptr(act[1]), ptr(act[2]), ptr(dhead), ptr(xtile), ptr(delta2), ptr(delta1), ptr(part),
                                 part.shape[0], P, offs['W0'], offs['b0'], offs['W1'], offs['b1'], offs['W2'], offs['b2'],
                                 offs['W_head'], offs['b_head'], ctypes.addressof(nb), _stream()), 'tc_mlp_bwd')
     return nb.value

@@ -269,6 +269,41 @@ def test_bf16_tcgen05_agent_tracks_fp32_agent():
     assert int(t.model.running_mean_std.count) == int(f.model.running_mean_std.count)
 
 
+@pytest.mark.parametrize('opt', [{'b200_pdl': True}, {'b200_pipelined_wgrad': True}, {'b200_pdl': True, 'b200_cuda_graph': True}])
+def test_tc_agent_launch_options_do_not_change_results(opt):
+    """programmatic dependent launch (b200_pdl) only changes WHEN the chain kernels may start, never what they compute: weights
+    after two epochs are bit-identical to the plain stream-ordered run (eager and whole-epoch graph).  The pipelined
+    weight-gradient kernel (b200_pipelined_wgrad) sums rows in 64-row halves: fp32 accumulation-order agreement."""
+    from rl_games_b200 import ops
+    N, H, D, A, units, mb = 1024, 8, 60, 8, [256, 128, 64], 4096
+    obs_tape, done_tape, tout_tape = O.make_tapes(2 * H + 1, N, D, seed=23)
+    params = O.init_params(D, units, A, seed=5)
+    g = torch.Generator().manual_seed(7)
+    noise = [torch.randn(H, N, A, generator=g).to(DEV) for _ in range(2)]
+    out = []
+    try:
+        for over in ({}, opt):
+            env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
+            cfg = {'mixed_precision': True, 'mini_epochs': 2, 'b200_cuda_graph': False}
+            cfg.update(over)
+            a = make_agent(cfg, N, H, D, A, units, mb, env, params)
+            assert a.use_tc
+            for e in range(2):
+                a.epoch_num += 1
+                a.train_epoch(noise=noise[e])
+            torch.cuda.synchronize()
+            out.append((a.model.flat.clone(), a.last_stats.clone(), a.last_lr))
+    finally:
+        ops.set_pdl(False)
+    (f0, s0, lr0), (f1, s1, lr1) = out
+    assert torch.isfinite(f1).all()
+    if 'b200_pipelined_wgrad' in opt:
+        torch.testing.assert_close(f1, f0, rtol=0, atol=2e-4)        # Adam steps of 3e-4: a sign flip of a ~0 gradient moves a weight by <= lr
+        torch.testing.assert_close(s1[:, :5], s0[:, :5], rtol=2e-2, atol=1e-3)
+    else:
+        assert torch.equal(f1, f0) and torch.equal(s1, s0) and lr1 == lr0
+
+
 @pytest.mark.parametrize('name,N,H,D,A,mb,masked,mp', [
     ('c3_ant_envpool_shape', 4096, 64, 27, 8, 32768, True, False),     # BASELINE configs[2]: next_step autoreset => masked path
     ('c5_per_gpu_shape', 16384, 32, 256, 8, 32768, False, False),      # BASELINE configs[4] per-GPU shard (obs 256): fp32 path

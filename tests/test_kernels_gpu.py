@@ -371,6 +371,45 @@ def test_adam_step_vs_oracle(ops, truncate, wd):
     torch.testing.assert_close(v.cpu(), opt.v[0], rtol=5e-5, atol=1e-10)
 
 
+@pytest.mark.parametrize('n,n_splits,pad', [(57361, 148, False), (57361, 148, True), (700, 5, False), (703, 7, True), (201737, 148, True)])
+def test_reduce_adam_vs_two_kernel_path(ops, n, n_splits, pad):
+    """fused reduce+finalise+clip+Adam launch == reduce_finalize followed by adam_step (same maths, different summation
+    tree over the splits: fp32 rounding-level agreement)"""
+    from rl_games_b200.ops import OptCfg
+    g = torch.Generator().manual_seed(n)
+    A = 8
+    stride = ops.loss_partial_stride()
+    cfg = OptCfg(0.9, 0.999, 1e-8, 0.0, 1.0, 0.008, 1e-6, 1e-2, 1.5, 1.0, 1, 1)
+    p0 = (torch.randn(n, generator=g) * 0.1).to(DEV)
+    ec = torch.tensor([0.01], device=DEV)
+    st = {}
+    for name in ('two', 'fused'):
+        st[name] = dict(p=p0.clone(), m=torch.zeros(n, device=DEV), v=torch.zeros(n, device=DEV),
+                        state=torch.tensor([3e-4, 0.0, 0.0, 0.0], dtype=torch.float64, device=DEV),
+                        counter=torch.zeros(1, dtype=torch.int32, device=DEV), stats=torch.zeros(16, device=DEV),
+                        grad=torch.zeros(n, device=DEV), kl=torch.zeros(1, device=DEV))
+    nrm = torch.zeros(148, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for it in range(4):
+        pstride = (n + 3) // 4 * 4 if pad else n         # padded rows take the float4 path; the pad / [0, A) entries are never read
+        part = torch.full((n_splits, pstride), float('nan'), device=DEV)
+        part[:, A:n] = (torch.randn(n_splits, n - A, generator=g) * (0.05 if it % 2 else 0.002)).to(DEV)
+        lpart = torch.rand(37, stride, generator=g, dtype=torch.float64).to(DEV) * (0.01 if it < 2 else 0.0005)
+        a = st['two']
+        ops.reduce_finalize(part[0, A:], a['grad'][A:], n - A, n_splits, pstride, lpart, 37, A, ec, a['stats'], a['grad'][:A], a['kl'])
+        ops.adam_step(a['p'], a['grad'], a['m'], a['v'], a['state'], a['kl'], cfg, a['stats'], a['counter'])
+        b = st['fused']
+        ops.reduce_adam(part, n_splits, pstride, lpart, 37, A, ec, b['stats'], b['kl'], b['grad'], b['p'], b['m'], b['v'], n, b['state'], cfg,
+                        b['counter'], nrm, bar)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(b['grad'], a['grad'], rtol=1e-4, atol=1e-6)
+        assert torch.equal(b['grad'][:A], a['grad'][:A]) and torch.equal(b['kl'], a['kl'])
+        assert torch.equal(b['state'], a['state'])
+        torch.testing.assert_close(b['stats'][:9], a['stats'][:9], rtol=1e-5, atol=0)
+        torch.testing.assert_close(b['p'], a['p'], rtol=1e-5, atol=2e-7)
+    torch.testing.assert_close(b['m'], a['m'], rtol=1e-4, atol=1e-8)
+    torch.testing.assert_close(b['v'], a['v'], rtol=2e-4, atol=1e-11)
+
+
 # ------------------------------------------------------------------------------------------ rollout pieces
 def test_policy_head_sample_vs_oracle(ops):
     g = torch.Generator().manual_seed(9)

@@ -102,9 +102,10 @@ def test_tc_fwd_loss_bwd_vs_fp32(H, N, epm, masked):
     delta2 = torch.zeros(n_tiles * tb[1], dtype=torch.uint8, device=DEV); delta1 = torch.zeros(n_tiles * tb[0], dtype=torch.uint8, device=DEV)
     mu_t, sg_t = old_mu.clone(), old_sigma.clone()
     partials_t = torch.zeros(148, stride, dtype=torch.float64, device=DEV)
+    xt = torch.zeros(n_tiles * ops.tc_xtile_bytes(D, UNITS, A), dtype=torch.uint8, device=DEV)
     nbt = ops.tc_mlp_fwd_train(sl(obs), epm, N, D, nm, ns, wpack, b, bh, logstd, UNITS, M, A, sl(actions), sl(mu_t), sl(sg_t),
                                sl(old_v), sl(ret), sl(old_nlp), sl(adv), None if mask is None else sl(mask), cfg, inv, act, dhead,
-                               partials_t)
+                               partials_t, xtile=xt)
     stats_t = torch.zeros(16, device=DEV); dls_t = torch.empty(A, device=DEV)
     ops.ppo_loss_finalize(partials_t, nbt, A, ec, stats_t, dls_t)
     torch.cuda.synchronize()
@@ -131,12 +132,22 @@ def test_tc_fwd_loss_bwd_vs_fp32(H, N, epm, masked):
     offs['W_head'] = o; o += (A + 1) * ins
     offs['b_head'] = o; o += A + 1
     assert o == P
+    # normalised observation tile emitted by the forward (consumed by the pipelined weight-gradient kernel)
+    xn = torch.clamp((torch.cat([obs[t, e0:e0 + epm] for t in range(H)]) - nm) / ns, -5.0, 5.0)
+    xt_dec = decode_tiles(xt, n_tiles, 64)[:M, :D]
+    torch.testing.assert_close(xt_dec, xn.to(torch.bfloat16).float(), rtol=0, atol=4e-2)
     part = torch.full((148, P), float('nan'), device=DEV)
-    npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs)
+    npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=xt)
     grad = torch.zeros(P, device=DEV)
     ops.reduce_splits(part[0, A:], grad[A:], P - A, npart, split_stride=P)
+    # the non-pipelined kernel (no xtile: re-normalises the observations itself) must give the same weight gradients
+    part_b = torch.full((148, P), float('nan'), device=DEV)
+    ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part_b, P, offs)
+    grad_b = torch.zeros(P, device=DEV)
+    ops.reduce_splits(part_b[0, A:], grad_b[A:], P - A, npart, split_stride=P)
     torch.cuda.synchronize()
     assert torch.isfinite(grad).all()
+    torch.testing.assert_close(grad, grad_b, rtol=1e-4, atol=1e-6)
     d2 = decode_tiles(delta2, n_tiles, UNITS[1])[:M]; d1 = decode_tiles(delta1, n_tiles, UNITS[0])[:M]
     assert rel_l2(d2, dA[1]) < 8e-2 and cosine(d2, dA[1]) > 0.997, (rel_l2(d2, dA[1]), cosine(d2, dA[1]))
     assert rel_l2(d1, dA[0]) < 8e-2 and cosine(d1, dA[0]) > 0.997, (rel_l2(d1, dA[0]), cosine(d1, dA[0]))
