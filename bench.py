@@ -255,8 +255,12 @@ def gae_roofline(w, peaks):
     ms = sum(ts) / len(ts)
     alg = 17 * H * N + 8 * N     # r4 + V4 + done1 read, A4 + returns4 written per element; last_value/last_done per env
     gbs = alg / (ms * 1e-3) / 1e9
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('gae_fused_f32')
+    except Exception:
+        tr = None
     return {'kernel': 'gae_fused_kernel (GAE + returns + moment partials)', 'bound': 'hbm', 'achieved': gbs,
-            'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'traffic': None,
+            'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'traffic': tr['traffic'] if tr else None,
             'alg_bytes_per_launch': alg, 'ms_per_launch': ms, 'peak_source': peaks['source'],
             'note': 'workload shape (4.5 MB working set: launch/latency bound); large-shape asymptote 0.84-0.87 of measured '
                     'peak in profiles/r01_gae_sweep*.json (tools/gae_sweep.py)'}
@@ -317,14 +321,37 @@ def b200_arm(args, w):
         flops = 2 * sum(a * b for a, b in zip([w['obs_dim']] + w['units'], w['units'] + [w['act_dim'] + 1]))
         step_flops = B * flops * (1 + 1.0 / w['horizon'] + 3 * w['mini_epochs'])   # rollout fwd (+ last-value fwd) + (fwd + dgrad + wgrad) per mini-epoch
         tf = step_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-        kname = ('MLP GEMM kernels: fp32 CUDA-core path (mixed_precision: False)' if args.fp32 else
-                 'tcgen05 bf16 MLP kernels (mlp_fwd_tc / mlp_bwd1_tc / mlp_bwd2_tc: fused fwd+loss, dgrad+wgrad)')
-        line['roofline'] = {'kernel': kname, 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'],
-                            'unit': 'TFLOP/s', 'frac': tf / peaks['bf16_tflops_sustained'], 'traffic': None,
-                            'share_of_step': round(mlp_ms / ktot, 4), 'alg_flops_per_step': step_flops,
-                            'peak_source': peaks['source'] + ' bf16 sustained',
-                            'note': 'K = 60..256, N = 16..256 GEMMs with fused elementwise epilogues: latency/epilogue bound, far below '
-                                    'the dense-GEMM peak by construction'}
+        fam = ('MLP GEMM kernels: fp32 CUDA-core path (mixed_precision: False)' if args.fp32 else
+               'tcgen05 bf16 MLP kernels (mlp_fwd_tc<train|rollout>, mlp_bwd_tc)')
+        family = {'kernels': fam, 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                  'frac': tf / peaks['bf16_tflops_sustained'], 'share_of_step': round(mlp_ms / ktot, 4), 'alg_flops_per_step': step_flops}
+        # the single dominant kernel of the step (largest share of device time): algorithmic FLOPs per launch / its mean launch
+        # duration (CUDA events around each launch of the instrumented epoch); `traffic` = DRAM bytes per launch from the
+        # committed ncu --set full capture (profiles/traffic.json), null when that kernel has no capture
+        dims = list(zip([w['obs_dim']] + w['units'], w['units'] + [w['act_dim'] + 1]))
+        fwd_fl = 2 * sum(a * b for a, b in dims)
+        dgrad_fl = 2 * sum(a * b for a, b in dims[1:])           # no input gradient for the first layer
+        per_launch = {'tc_mlp_bwd': (fwd_fl + dgrad_fl) * w['minibatch'], 'tc_mlp_fwd_train': fwd_fl * w['minibatch'],
+                      'tc_mlp_fwd_rollout': fwd_fl * w['num_actors']}
+        dom = max((k for k in prof if k in per_launch), key=lambda k: prof[k]['ms'], default=None)
+        if dom is not None:
+            dms = prof[dom]['ms'] / prof[dom]['n']
+            dtf = per_launch[dom] / (dms * 1e-3) / 1e12
+            try:
+                tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dom)
+            except Exception:
+                tr = None
+            line['roofline'] = {'kernel': dom, 'bound': 'tensor', 'achieved': dtf, 'peak': peaks['bf16_tflops_sustained'],
+                                'unit': 'TFLOP/s', 'frac': dtf / peaks['bf16_tflops_sustained'],
+                                'traffic': tr['traffic'] if tr else None, 'traffic_source': tr['source'] if tr else None,
+                                'alg_flops_per_launch': per_launch[dom], 'ms_per_launch': dms,
+                                'share_of_step': round(prof[dom]['ms'] / ktot, 4), 'peak_source': peaks['source'] + ' bf16 sustained',
+                                'family': family,
+                                'note': 'K = 60..256, N = 16..256 GEMMs fused with their elementwise epilogues (ELU, bf16 pack, loss, '
+                                        'delta chain): bound by epilogue latency / MMA issue, far below the dense-GEMM peak by '
+                                        'construction; stage timelines in profiles/r01_stage_timing.md'}
+        else:
+            line['roofline'] = dict(family, kernel=fam, traffic=None, peak_source=peaks['source'] + ' bf16 sustained')
         if world == 1 and not args.skip_e2e:
             line['e2e'] = e2e_leg(w, device, args)
         if world == 1 and not args.skip_cpu:

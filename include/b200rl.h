@@ -263,6 +263,20 @@ int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_t split_stride
                            void* wpack, const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host,
                            void* stream);
 
+/* Multi-GPU edition of b200rl_reduce_adam_f32: split reduction + gradient all-reduce over NVLink peer memory + clip + Adam in
+ * ONE launch.  Each CTA publishes its slice of this rank's exchange buffer to the same CTA index on every peer through
+ * per-CTA flags (peer_cta_flags_host[r]: rank r's uint64[world][160] flag array, my_cta_flags: this rank's, zero-initialised
+ * once) and sums the slice over all ranks in fixed rank order.  peer_grads_host[r]: rank r's exchange buffer of THIS update's
+ * parity (float[n + 1]: gradient + KL slot; the caller alternates two buffers by update parity).  red: float[n + 1] local. */
+#define B200RL_PEER_FLAG_STRIDE 160
+int b200rl_reduce_allreduce_adam_f32(const float* part, int n_splits, int64_t split_stride, const double* loss_partials,
+                                     int n_loss_partials, int A, const float* entropy_coef_dev, float* stats,
+                                     const void* const* peer_grads_host, void* const* peer_cta_flags_host, int world, int rank,
+                                     void* my_cta_flags, void* seq_ptr, float* red, float* params, float* exp_avg,
+                                     float* exp_avg_sq, int n, double* state_d, const b200rl_opt_cfg* cfg_host, int* counter,
+                                     double* nrm_part, int nrm_part_len, void* grid_bar, void* wpack,
+                                     const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Multi-GPU: fused gradient all-reduce + clip + Adam over NVLink peer memory (one launch per minibatch).
  * Replaces a2c_common.py:493-509 (cat -> all_reduce -> /world -> scatter), :1559-1561 (KL all-reduce) and the

@@ -430,14 +430,20 @@ class A2CAgent:
         m, dev = self.model, self.device_t
         P = m.num_params
         S = ((P + 1 + 3) // 4) * 4
-        nbytes = 2 * S * 4 + 8 * 8
+        # two exchange buffers (update parity), 8 per-rank flags (allreduce_adam), 8 x PEER_FLAG_STRIDE per-CTA flags (reduce_allreduce_adam)
+        nbytes = 2 * S * 4 + 8 * 8 + 8 * ops.PEER_FLAG_STRIDE * 8
         base, handle = ops.ipc_alloc(nbytes)
         handles = [None] * self.world_size
         dist.all_gather_object(handles, handle)
         ptrs = [base if r == self.global_rank else ops.ipc_open(handles[r]) for r in range(self.world_size)]
         self._peer_keepalive = (base, ptrs)
-        self.peer_table = ops.PeerTable([[p + par * S * 4 for p in ptrs] for par in (0, 1)], [p + 2 * S * 4 for p in ptrs])
+        self.peer_table = ops.PeerTable([[p + par * S * 4 for p in ptrs] for par in (0, 1)], [p + 2 * S * 4 for p in ptrs],
+                                        [p + 2 * S * 4 + 64 for p in ptrs])
         self.my_flags_ptr = base + 2 * S * 4
+        self.my_cta_flags_ptr = base + 2 * S * 4 + 64
+        # True = split reduction + all-reduce + Adam in ONE launch with per-CTA peer flags (reduce_allreduce_adam); default False =
+        # reduce_finalize + allreduce_adam (two launches), measured faster at 2 GPUs: 3.71 vs 3.91 ms/epoch (profiles/r01_summary.md)
+        self.fused_split_allreduce = bool(self.config.get('b200_fused_split_allreduce', False))
         self._gv = []
         for par in (0, 1):
             comm = ops.tensor_from_ptr(base + par * S * 4, P + 1, torch.float32, dev)
@@ -856,6 +862,12 @@ class A2CAgent:
             ops.reduce_adam(self.part, npart, self.part.shape[1], self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], gv['kl'], gv['grad'],
                             m.flat, m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.counters[2:3], self.ra_nrm, self.ra_bar,
                             wpack=self.wpack, pack_table=self.pack_table, merge_next=self._merge_next(u))
+            return
+        if self.fused_allreduce and self.fused_split_allreduce:
+            ops.reduce_allreduce_adam(self.part, npart, self.part.shape[1], self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u],
+                                      self.peer_table, u & 1, self.global_rank, self.my_cta_flags_ptr, self.ar_seq, self.ar_red, m.flat,
+                                      m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.counters[2:3], self.ra_nrm,
+                                      self.ra_bar, wpack=self.wpack, pack_table=self.pack_table, merge_next=self._merge_next(u))
             return
         ops.reduce_finalize(self.part[0, A:], gv['grad'][A:], P - A, npart, self.part.shape[1], self.loss_partials, nb, A, self.entropy_coef_dev,
                             self.stats[u], gv['g_sigma'], gv['kl'])

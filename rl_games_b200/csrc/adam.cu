@@ -257,13 +257,31 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
 // no cross-rank exchange in between.  The reduced gradient never makes a second trip: each CTA sums ITS slice of the flat
 // gradient over all splits (fixed order => deterministic), publishes its sum-of-squares partial, crosses one grid barrier
 // (grid <= #SMs, one CTA per SM, all co-resident) and updates the same slice.
+//
+// MULTI = true is the multi-GPU edition: `grads` is this rank's CUDA-IPC mapped exchange buffer (n gradient entries + the KL
+// slot at index n).  After a CTA has reduced ITS slice over the splits it publishes "slice b of step seq is ready" to the same
+// CTA index on every peer (st.release.sys into per-CTA flags) and waits for the peers' slice b, then sums the slice over all
+// ranks in fixed rank order straight from peer memory (bit-identical on every rank).  No rank-wide barrier and no second
+// kernel: split reduction, all-reduce, clip and Adam are one launch, and the exchange of slice b overlaps with the split
+// reduction of the other slices.  Buffers alternate by update parity: a CTA only reaches step s+1's wait after every peer's
+// CTA b finished reading step s, so writing the same parity again at step s+2 cannot overtake a reader.
+constexpr int PEER_FLAG_STRIDE = 160;     // u64 flags per source rank (>= max grid of this kernel)
+struct PeerStage {
+    PeerPtrs peers;                       // grads[r]: rank r's exchange buffer (this parity); flags[r]: rank r's per-CTA flag array
+    int world, rank;
+    unsigned long long* my_flags;         // [world][PEER_FLAG_STRIDE]
+    unsigned long long* seq_ptr;
+    float* red;                           // [n + 1] all-reduced gradient + KL (local)
+};
+
+template <bool MULTI>
 __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride,
                                                           const double* __restrict__ lpart, int n_lpart, int lstride, int A,
                                                           const float* __restrict__ entropy_coef_dev, float* __restrict__ stats,
                                                           float* __restrict__ kl_out, float* __restrict__ grads, float* __restrict__ params,
                                                           float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n, double* state_d,
                                                           OptCfgDev c, int* counter, double* __restrict__ nrm_part, unsigned* grid_bar,
-                                                          unsigned char* __restrict__ wpack, PackTabDev tab, ObsMergeDev om, int kg_log2, int per, int vec4) {
+                                                          unsigned char* __restrict__ wpack, PackTabDev tab, ObsMergeDev om, int kg_log2, int per, int vec4, PeerStage ps) {
     __shared__ double sm[32];
     __shared__ double smf[256];
     __shared__ float4 sred4[1024];
@@ -277,8 +295,11 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     const float gs = (float)c.grad_scale;
     const int i0 = min(blockIdx.x * per, n), i1 = min(i0 + per, n);      // per: slice length (a multiple of 4 when vec4)
     float a0 = 0.f;
-    // ---- 1a. last CTA: loss partials -> stats, KL slot, d_logstd (= gradient entries [0, A)) ----
-    if (blockIdx.x == gridDim.x - 1) {
+    unsigned long long seq = 0ull;
+    if (MULTI) seq = *ps.seq_ptr + 1ull;       // advanced by the last CTA at the very end, after every CTA has read it
+    // ---- 1a. one CTA: loss partials -> stats, KL slot, d_logstd (= gradient entries [0, A)).  Single GPU: the last CTA (its
+    //      slice is the shortest); multi GPU: CTA 0, the owner of the slice that contains [0, A) and publisher of the KL slot ----
+    if (blockIdx.x == (MULTI ? 0u : gridDim.x - 1)) {
         const int slots = LOSS_NSC + A;
         if (tid < 256) {
             const int slot = tid & 63, grp = tid >> 6;
@@ -382,6 +403,29 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
             __syncthreads();
         }
     }
+    if (MULTI) {
+        // ---- 1c. exchange: publish my slice, wait for the same slice of every peer, sum over ranks from peer memory ----
+        __threadfence_system();
+        __syncthreads();
+        if (tid < ps.world) st_release_sys(ps.peers.flags[tid] + (size_t)ps.rank * PEER_FLAG_STRIDE + blockIdx.x, seq);
+        if (tid < ps.world) {
+            while (ld_acquire_sys(ps.my_flags + (size_t)tid * PEER_FLAG_STRIDE + blockIdx.x) < seq) { }
+        }
+        __syncthreads();
+        a0 = 0.f;                               // the norm is the norm of the all-reduced gradient
+        for (int i = i0 + tid; i < i1; i += blockDim.x) {
+            float sacc = 0.f;
+            for (int pr = 0; pr < ps.world; ++pr) sacc += __ldcv(ps.peers.grads[pr] + i);     // volatile: peer data, never a stale L1 line
+            ps.red[i] = sacc;
+            a0 = fmaf(sacc * gs, sacc * gs, a0);
+        }
+        if (blockIdx.x == 0 && tid == 0) {
+            float sacc = 0.f;
+            for (int pr = 0; pr < ps.world; ++pr) sacc += __ldcv(ps.peers.grads[pr] + n);     // KL slot
+            ps.red[n] = sacc;
+        }
+    }
+    const float* gsrc = MULTI ? ps.red : grads;
     double acc[1] = {(double)a0};
     block_sum_d<1>(acc, sm);
     if (tid == 0) nrm_part[blockIdx.x] = acc[0];
@@ -406,7 +450,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     const float bc2_sqrt = (float)sqrt(bc2);
     const float eps = (float)c.eps, wd = (float)c.weight_decay;
     for (int i = i0 + tid; i < i1; i += blockDim.x)
-        adam_update_one(i, __ldcg(grads + i) * gs, c.truncate_grads, coef, params, exp_avg, exp_avg_sq, b1, b2, step_size, bc2_sqrt, eps, wd,
+        adam_update_one(i, __ldcg(gsrc + i) * gs, c.truncate_grads, coef, params, exp_avg, exp_avg_sq, b1, b2, step_size, bc2_sqrt, eps, wd,
                         wpack, tab);
     __threadfence();
     __syncthreads();
@@ -414,13 +458,15 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     __syncthreads();
     if (is_last && tid == 0) {
         double new_lr = lr;
-        if (c.adaptive_lr && kl_out) {
-            const double kl = (double)(__ldcg(kl_out) * gs);
+        const float* klp = MULTI ? ps.red + n : kl_out;      // summed over ranks by the exchange -> mean via grad_scale (a2c_common.py:1559-1561)
+        if (c.adaptive_lr && klp) {
+            const double kl = (double)(__ldcg(klp) * gs);
             if (kl > 2.0 * c.kl_threshold) new_lr = fmax(lr / c.lr_multiplier, c.min_lr);
             if (kl < 0.5 * c.kl_threshold) new_lr = fmin(lr * c.lr_multiplier, c.max_lr);
         }
         state_d[0] = new_lr; state_d[1] = step; state_d[2] = p1; state_d[3] = p2;
         stats[B200RL_STAT_LR] = (float)lr; stats[B200RL_STAT_GNORM] = total_norm;
+        if (MULTI) { stats[B200RL_STAT_KL] = __ldcg(ps.red + n) * gs; *ps.seq_ptr = seq; }
         *counter = 0;
     }
     if (is_last) obs_merge_tail(om);
@@ -456,12 +502,11 @@ static OptCfgDev make_opt_cfg(const b200rl_opt_cfg* h) {
     return c;
 }
 
-B200RL_EXPORT int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_t split_stride, const double* loss_partials,
-                                         int n_loss_partials, int A, const float* entropy_coef_dev, float* stats, float* kl_out,
-                                         float* grads, float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
-                                         const b200rl_opt_cfg* cfg_host, int* counter, double* nrm_part, int nrm_part_len, void* grid_bar,
-                                         void* wpack, const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host,
-                                         void* stream) {
+static int reduce_adam_launch(const float* part, int n_splits, int64_t split_stride, const double* loss_partials, int n_loss_partials, int A,
+                              const float* entropy_coef_dev, float* stats, float* kl_out, float* grads, float* params, float* exp_avg,
+                              float* exp_avg_sq, int n, double* state_d, const b200rl_opt_cfg* cfg_host, int* counter, double* nrm_part,
+                              int nrm_part_len, void* grid_bar, void* wpack, const b200rl_pack_table* tab_host,
+                              const b200rl_obs_merge* merge_next_host, const PeerStage* ps, void* stream) {
     if (!part || !loss_partials || !entropy_coef_dev || !stats || !grads || !params || !exp_avg || !exp_avg_sq || !state_d || !cfg_host ||
         !counter || !nrm_part || !grid_bar)
         return B200RL_EINVAL;
@@ -471,7 +516,7 @@ B200RL_EXPORT int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_
     if (make_pack_tab(tab_host, tab) != B200RL_OK) return B200RL_EINVAL;
     int blocks = (n + 255) / 256;         // a slice of >= 256 entries per CTA; all CTAs must be co-resident (grid barrier)
     if (blocks > 148) blocks = 148;
-    if (blocks > nrm_part_len) return B200RL_EINVAL;
+    if (blocks > nrm_part_len || blocks > PEER_FLAG_STRIDE) return B200RL_EINVAL;
     int per = (n + blocks - 1) / blocks;
     // 16-byte loads when every split row and every slice start is 4-float aligned
     const int vec4 = (split_stride % 4 == 0) && split_stride >= (int64_t)(n + 3) / 4 * 4 && ((reinterpret_cast<uintptr_t>(part) & 15) == 0);
@@ -479,13 +524,52 @@ B200RL_EXPORT int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_
     const int units = vec4 ? per / 4 : per;      // elements (or float4 groups) of one slice
     int kg_log2 = 0;                      // k-groups per unit: as many as fit in one 1024-thread pass over the slice
     while (kg_log2 < 3 && (1024 >> (kg_log2 + 1)) >= units) ++kg_log2;
-    cudaError_t le = launch_k(reduce_adam_kernel, dim3(blocks), dim3(1024), 0, as_stream(stream), part, n_splits, split_stride, loss_partials, n_loss_partials,
-                                                              b200rl_loss_partial_stride(), A, entropy_coef_dev, stats, kl_out, grads, params,
-                                                              exp_avg, exp_avg_sq, n, state_d, make_opt_cfg(cfg_host), counter, nrm_part,
-                                                              (unsigned*)grid_bar, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host),
-                                                              kg_log2, per, vec4);
+    cudaError_t le;
+    if (ps)
+        le = launch_k(reduce_adam_kernel<true>, dim3(blocks), dim3(1024), 0, as_stream(stream), part, n_splits, split_stride, loss_partials,
+                      n_loss_partials, b200rl_loss_partial_stride(), A, entropy_coef_dev, stats, kl_out, grads, params, exp_avg, exp_avg_sq, n,
+                      state_d, make_opt_cfg(cfg_host), counter, nrm_part, (unsigned*)grid_bar, (unsigned char*)wpack, tab,
+                      make_obs_merge(merge_next_host), kg_log2, per, vec4, *ps);
+    else
+        le = launch_k(reduce_adam_kernel<false>, dim3(blocks), dim3(1024), 0, as_stream(stream), part, n_splits, split_stride, loss_partials,
+                      n_loss_partials, b200rl_loss_partial_stride(), A, entropy_coef_dev, stats, kl_out, grads, params, exp_avg, exp_avg_sq, n,
+                      state_d, make_opt_cfg(cfg_host), counter, nrm_part, (unsigned*)grid_bar, (unsigned char*)wpack, tab,
+                      make_obs_merge(merge_next_host), kg_log2, per, vec4, PeerStage{});
     if (le != cudaSuccess) return (int)le;
     return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_t split_stride, const double* loss_partials,
+                                         int n_loss_partials, int A, const float* entropy_coef_dev, float* stats, float* kl_out,
+                                         float* grads, float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
+                                         const b200rl_opt_cfg* cfg_host, int* counter, double* nrm_part, int nrm_part_len, void* grid_bar,
+                                         void* wpack, const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host,
+                                         void* stream) {
+    return reduce_adam_launch(part, n_splits, split_stride, loss_partials, n_loss_partials, A, entropy_coef_dev, stats, kl_out, grads, params,
+                              exp_avg, exp_avg_sq, n, state_d, cfg_host, counter, nrm_part, nrm_part_len, grid_bar, wpack, tab_host,
+                              merge_next_host, nullptr, stream);
+}
+
+B200RL_EXPORT int b200rl_reduce_allreduce_adam_f32(const float* part, int n_splits, int64_t split_stride, const double* loss_partials,
+                                                   int n_loss_partials, int A, const float* entropy_coef_dev, float* stats,
+                                                   const void* const* peer_grads_host, void* const* peer_cta_flags_host, int world, int rank,
+                                                   void* my_cta_flags, void* seq_ptr, float* red, float* params, float* exp_avg,
+                                                   float* exp_avg_sq, int n, double* state_d, const b200rl_opt_cfg* cfg_host, int* counter,
+                                                   double* nrm_part, int nrm_part_len, void* grid_bar, void* wpack,
+                                                   const b200rl_pack_table* tab_host, const b200rl_obs_merge* merge_next_host, void* stream) {
+    if (!peer_grads_host || !peer_cta_flags_host || world < 1 || world > 8 || rank < 0 || rank >= world || !my_cta_flags || !seq_ptr || !red)
+        return B200RL_EINVAL;
+    PeerStage ps{};
+    for (int i = 0; i < world; ++i) {
+        if (!peer_grads_host[i] || !peer_cta_flags_host[i]) return B200RL_EINVAL;
+        ps.peers.grads[i] = (const float*)peer_grads_host[i];
+        ps.peers.flags[i] = (unsigned long long*)peer_cta_flags_host[i];
+    }
+    ps.world = world; ps.rank = rank; ps.my_flags = (unsigned long long*)my_cta_flags; ps.seq_ptr = (unsigned long long*)seq_ptr; ps.red = red;
+    float* own = const_cast<float*>(ps.peers.grads[rank]);       // this rank's exchange buffer: [n] gradient entries + the KL slot
+    return reduce_adam_launch(part, n_splits, split_stride, loss_partials, n_loss_partials, A, entropy_coef_dev, stats, own + n, own, params,
+                              exp_avg, exp_avg_sq, n, state_d, cfg_host, counter, nrm_part, nrm_part_len, grid_bar, wpack, tab_host,
+                              merge_next_host, &ps, stream);
 }
 
 B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int n,

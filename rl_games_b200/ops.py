@@ -376,10 +376,12 @@ def tensor_from_ptr(ptr_, n, dtype, device):
 class PeerTable:
     """host-side pointer tables handed to b200rl_allreduce_adam_f32"""
 
-    def __init__(self, grads_ptrs, flags_ptrs):
+    def __init__(self, grads_ptrs, flags_ptrs, cta_flags_ptrs=None):
         self.world = len(flags_ptrs)
         self.grads = [(ctypes.c_void_p * 8)(*(list(g) + [None] * (8 - len(g)))) for g in grads_ptrs]   # one table per parity
         self.flags = (ctypes.c_void_p * 8)(*(list(flags_ptrs) + [None] * (8 - len(flags_ptrs))))
+        cf = list(cta_flags_ptrs) if cta_flags_ptrs is not None else []
+        self.cta_flags = (ctypes.c_void_p * 8)(*(cf + [None] * (8 - len(cf))))      # per-CTA flag arrays (reduce_allreduce_adam)
 
 
 def allreduce_adam(table, parity, rank, my_flags_ptr, seq, red, nrm_part, grid_bar, params, exp_avg, exp_avg_sq, n, state_d, cfg,
@@ -389,6 +391,23 @@ def allreduce_adam(table, parity, rank, my_flags_ptr, seq, red, nrm_part, grid_b
                                         ptr(exp_avg), ptr(exp_avg_sq), n, ptr(state_d), ctypes.addressof(cfg), ptr(stats_out),
                                         ptr(counter), ptr(wpack), None if pack_table is None else ctypes.addressof(pack_table),
                                         None if merge_next is None else ctypes.addressof(merge_next), _stream()), 'allreduce_adam')
+
+
+PEER_FLAG_STRIDE = 160      # B200RL_PEER_FLAG_STRIDE
+
+
+def reduce_allreduce_adam(part, n_splits, split_stride, loss_partials, n_loss_partials, A, entropy_coef_dev, stats, table, parity, rank,
+                          my_cta_flags_ptr, seq, red, params, exp_avg, exp_avg_sq, n, state_d, cfg, counter, nrm_part, grid_bar,
+                          wpack=None, pack_table=None, merge_next=None):
+    """multi-GPU fused minibatch tail: split reduce + loss finalise + peer-memory all-reduce + clip + Adam in one launch"""
+    check(lib.b200rl_reduce_allreduce_adam_f32(ptr(part), n_splits, split_stride, ptr(loss_partials), n_loss_partials, A,
+                                               ptr(entropy_coef_dev), ptr(stats), ctypes.addressof(table.grads[parity]),
+                                               ctypes.addressof(table.cta_flags), table.world, rank, my_cta_flags_ptr, ptr(seq), ptr(red),
+                                               ptr(params), ptr(exp_avg), ptr(exp_avg_sq), n, ptr(state_d), ctypes.addressof(cfg),
+                                               ptr(counter), ptr(nrm_part), nrm_part.numel(), ptr(grid_bar), ptr(wpack),
+                                               None if pack_table is None else ctypes.addressof(pack_table),
+                                               None if merge_next is None else ctypes.addressof(merge_next), _stream()),
+          'reduce_allreduce_adam')
 
 
 # ------------------------------------------------------------------------------------------ LSTM cell (fp32)

@@ -19,13 +19,15 @@ def main():
     dev = f'cuda:{local_rank}'
     out = {}
     ref_flat = None
-    for mode, graph, fused in (('nccl_eager', False, False), ('nccl_graph', True, False), ('fused_graph', True, True)):
+    for mode, graph, fused, split in (('nccl_eager', False, False, False), ('nccl_graph', True, False, False),
+                                      ('fused_two_launch_graph', True, True, False), ('fused_one_launch_graph', True, True, True)):
         w = dict(bench.WORKLOADS['c2'])
         from rl_games_b200.runner import Runner
         r = Runner()
         p = bench.make_params(w, dev, 'b200_synthetic', True, graph=True)
         p['config']['b200_cuda_graph_multi_gpu'] = graph
         p['config']['b200_fused_allreduce'] = fused
+        p['config']['b200_fused_split_allreduce'] = split
         r.load({'params': p})
         agent = r.algo_factory.create(r.algo_name, base_name='mgpu', params=r.params)
         agent.init_tensors()
@@ -44,7 +46,7 @@ def main():
         dist.all_gather(cnts, cnt)
         if ref_flat is None:
             ref_flat = agent.model.flat.clone()
-        out[mode] = {'fused_allreduce': agent.fused_allreduce, 'max_abs_diff_vs_nccl_eager': float((agent.model.flat - ref_flat).abs().max()),
+        out[mode] = {'fused_allreduce': agent.fused_allreduce, 'fused_split_allreduce': bool(fused and split), 'max_abs_diff_vs_nccl_eager': float((agent.model.flat - ref_flat).abs().max()),
                      'identical_across_ranks': bool(same), 'obs_count': [int(c) for c in cnts],
                                               'ms_per_epoch': [round(t, 3) for t in ts], 'lr': agent.last_lr,
                                               'finite': bool(torch.isfinite(agent.model.flat).all()),
