@@ -161,6 +161,45 @@ class RunningMeanStd:
 # ----------------------------------------------------------------------------------------------
 # cross-rank running-stat merge -- rl_games/common/a2c_common.py:43-93
 # ----------------------------------------------------------------------------------------------
+class GeneralizedMovingStats:
+    """EMA advantage normaliser, impl 'mean_std' only (algos_torch/moving_mean_std.py:7-150; created at a2c_common.py:473-475 with
+    decay = adv_rms_momentum when normalize_rms_advantage).  State: int32 step (starts at 1), fp32 mean / mean of squares.
+    Every update moves the statistics by the same decay whatever the number of valid rows; an all-invalid mask is a no-op."""
+
+    def __init__(self, insize, decay=0.99, max=1e5, eps=0.0):
+        self.decay, self.max, self.eps = decay, max, eps
+        self.step = torch.ones(1, dtype=torch.int32)
+        self.mean = torch.zeros(insize, dtype=torch.float32)
+        self.sqrs = torch.zeros(insize, dtype=torch.float32)
+        self.training = True
+
+    def train(self):
+        self.training = True
+
+    def eval(self):
+        self.training = False
+
+    def get_mean_std(self):
+        var = self.sqrs - self.mean.pow(2)
+        return self.mean, torch.sqrt(torch.clamp_min(var, 1 / self.max ** 2) + self.eps)
+
+    def __call__(self, x, mask=None, denorm=False):
+        if self.training:
+            xs = x
+            if mask is not None:
+                valid = mask.reshape(-1) > 0
+                xs = x[valid] if bool(valid.any()) else None
+            if xs is not None:
+                m = self.decay
+                self.step += 1
+                self.mean.mul_(m).add_((1 - m) * torch.mean(xs, dim=0))
+                self.sqrs.mul_(m).add_((1 - m) * torch.mean(xs * xs, dim=0))
+        offset, invscale = self.get_mean_std()
+        if denorm:
+            return x.clone().mul_(invscale).add_(offset)
+        return x.clone().sub_(offset).div_(invscale).clamp_(-5.0, 5.0)
+
+
 def running_stats_totals(m):
     return (m.count.clone(), m.running_mean * m.count, (m.running_var + m.running_mean ** 2) * m.count)
 
@@ -510,6 +549,7 @@ DEFAULT_CFG = dict(
     normalize_input=True, normalize_value=True, normalize_advantage=True, value_bootstrap=True,
     mini_epochs=4, weight_decay=0.0, ppo=True, reward_scale=1.0, reward_shift=0.0, seq_length=4, rnn_units=0, zero_rnn_on_done=True,
     games_to_track=100, activation='elu', clip_actions=True, mask_autoreset_rows=False,
+    normalize_rms_advantage=False, adv_rms_momentum=0.5,
 )
 
 
@@ -670,8 +710,12 @@ class OracleAgent:
                 returns = vms(returns)
                 vms.eval()
         advantages = torch.sum(advantages, axis=1)
-        if c['normalize_advantage']:
-            if rnn_masks is not None:
+        if c['normalize_advantage']:      # a2c_common.py:1622-1632
+            if c.get('normalize_rms_advantage', False):
+                if getattr(self, 'advantage_mean_std', None) is None:
+                    self.advantage_mean_std = GeneralizedMovingStats((1,), decay=c.get('adv_rms_momentum', 0.5))
+                advantages = self.advantage_mean_std(advantages, mask=rnn_masks) if rnn_masks is not None else self.advantage_mean_std(advantages)
+            elif rnn_masks is not None:
                 advantages = normalization_with_masks(advantages, rnn_masks)
             else:
                 advantages = (advantages - advantages.mean()) / (advantages.std() + 1e-8)

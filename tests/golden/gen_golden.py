@@ -128,6 +128,28 @@ def gen_math():
     save('math.pt', out)
 
 
+# ------------------------------------------------------------------ EMA advantage normaliser
+def gen_rms_adv():
+    from rl_games.algos_torch.moving_mean_std import GeneralizedMovingStats
+    g = torch.Generator().manual_seed(2)
+    gms = GeneralizedMovingStats((1,), decay=0.5)
+    gms.train()
+    seq = []
+    for k, (n, masked) in enumerate([(64, False), (37, True), (16, 'none_valid'), (128, False), (5, True)]):
+        x = torch.randn(n, generator=g) * (1 + k) + 0.3 * k
+        if masked == 'none_valid':
+            mask = torch.zeros(n)
+        elif masked:
+            mask = (torch.rand(n, generator=g) < 0.5).float()
+        else:
+            mask = None
+        y = gms(x, mask=mask) if mask is not None else gms(x)
+        seq.append({'x': x, 'mask': mask, 'y': y, 'step': gms.step.clone(), 'mean': gms.mean.clone(), 'sqrs': gms.sqrs.clone()})
+    gms.eval()
+    xe = torch.randn(9, generator=g) * 30
+    save('rms_adv.pt', {'decay': 0.5, 'seq': seq, 'x_eval': xe, 'y_eval': gms(xe), 'y_denorm': gms(xe, denorm=True)})
+
+
 # ------------------------------------------------------------------ full agent epochs
 class TapeVecEnv:
     """Tensor env fed from tapes (mirrors oracle.ppo_oracle.TapeEnv)."""
@@ -264,13 +286,146 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
 
+# ------------------------------------------------------------------ discrete PPO (configs/ppo_cartpole.yaml shape)
+class DiscreteTapeVecEnv:
+    """mirrors oracle.ppo_discrete_oracle.DiscreteTapeEnv behind the reference's tensor-env contract"""
+
+    def __init__(self, obs_tape, done_tape, timeout_tape, K, mask_tape=None, autoreset_mode='same_step'):
+        self.obs_tape, self.done_tape, self.timeout_tape, self.K, self.mask_tape = obs_tape, done_tape, timeout_tape, K, mask_tape
+        self.i = 0
+        self.autoreset_mode = autoreset_mode
+
+    def reset(self):
+        self.i = 0
+        return self.obs_tape[0].clone()
+
+    def get_action_masks(self):
+        return self.mask_tape[self.i % self.mask_tape.shape[0]].numpy()
+
+    def step(self, actions):
+        j0 = self.i % self.obs_tape.shape[0]
+        target = self.obs_tape[j0][:, :self.K].argmax(dim=-1)
+        rew = (actions.long() == target).float()
+        self.i += 1
+        j = self.i % self.obs_tape.shape[0]
+        return self.obs_tape[j].clone(), rew, self.done_tape[j].clone(), {'time_outs': self.timeout_tape[j].clone()}
+
+    def get_env_info(self):
+        import gymnasium as gym
+        info = {'observation_space': gym.spaces.Box(-np.inf, np.inf, (self.obs_tape.shape[-1],), np.float32),
+                'action_space': gym.spaces.Discrete(self.K)}
+        if self.autoreset_mode != 'same_step':
+            info['autoreset_mode'] = self.autoreset_mode
+        return info
+
+    def get_env_state(self):
+        return None
+
+    def set_env_state(self, s):
+        pass
+
+    def set_train_info(self, *a, **kw):
+        pass
+
+
+def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=2, overrides=None, separate=True,
+                       use_action_masks=False, autoreset='same_step', seed=11):
+    from rl_games.torch_runner import Runner
+    from oracle.ppo_oracle import make_tapes
+    from oracle.ppo_discrete_oracle import sample_inverse_cdf
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    T = H * epochs + 1
+    obs_tape, done_tape, tout_tape = make_tapes(T, N, D, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    mask_tape = None
+    if use_action_masks:
+        mask_tape = torch.rand(T, N, K, generator=g) < 0.6
+        forced = torch.randint(0, K, (T, N), generator=g)
+        mask_tape.scatter_(2, forced.unsqueeze(-1), True)          # at least one legal action per row
+    env = DiscreteTapeVecEnv(obs_tape, done_tape, tout_tape, K, mask_tape, autoreset)
+    network = {'name': 'actor_critic', 'separate': separate, 'space': {'discrete': None},
+               'mlp': {'units': list(units), 'activation': 'relu', 'initializer': {'name': 'default'}, 'regularizer': {'name': 'None'}}}
+    # hyper-parameters of configs/ppo_cartpole.yaml:28-52
+    config = {'name': 'golden_discrete', 'env_name': 'unused', 'reward_shaper': {'scale_value': 0.1}, 'normalize_advantage': True,
+              'gamma': 0.99, 'tau': 0.9, 'learning_rate': 2e-4, 'grad_norm': 1.0, 'entropy_coef': 0.01, 'truncate_grads': True,
+              'e_clip': 0.2, 'clip_value': True, 'num_actors': N, 'horizon_length': H, 'minibatch_size': mb, 'mini_epochs': 4,
+              'critic_coef': 1, 'lr_schedule': None, 'kl_threshold': 0.008, 'normalize_input': False, 'normalize_value': False,
+              'device': 'cpu', 'multi_gpu': False, 'mixed_precision': False, 'torch_compile': False, 'max_epochs': 100,
+              'save_frequency': 0, 'save_best_after': 10_000, 'print_stats': False, 'train_dir': '/tmp/golden_runs',
+              'use_action_masks': use_action_masks}
+    config.update(overrides or {})
+    params = {'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'discrete_a2c'}, 'network': network, 'config': config}
+    params['config']['env_info'] = env.get_env_info()
+    runner = Runner()
+    runner.load({'params': params})
+    runner.params['config']['vec_env'] = env
+    agent = runner.algo_factory.create(runner.algo_name, base_name='golden', params=runner.params)
+    with torch.no_grad():
+        for k, p in agent.model.named_parameters():
+            if k.endswith('bias'):
+                p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    init_state = {k: v.clone() for k, v in agent.model.state_dict().items()}
+    u = torch.rand(epochs, H + 1, N, generator=g)     # [epoch, step (H rollout + the get_values forward, which samples too)]
+    counter = {'k': 0}
+    orig_multinomial = torch.multinomial
+
+    def fake_multinomial(probs_2d, num_samples, replacement=False, **kw):
+        assert num_samples == 1
+        k = counter['k']
+        counter['k'] += 1
+        e, n = divmod(k, H + 1)
+        return sample_inverse_cdf(probs_2d, u[e, n]).unsqueeze(-1)
+    torch.multinomial = fake_multinomial
+    try:
+        agent.init_tensors()
+        agent.obs = agent.env_reset()
+        epochs_out = []
+        for ep in range(epochs):
+            agent.epoch_num += 1
+            step_time, play_time, update_time, total, a_losses, c_losses, entropies, kls, last_lr, lr_mul = agent.train_epoch()
+            ds = agent.dataset.values_dict
+            epochs_out.append({
+                'a_losses': torch.stack([x.detach() for x in a_losses]), 'c_losses': torch.stack([x.detach() for x in c_losses]),
+                'entropies': torch.stack([x.detach() for x in entropies]), 'kls': torch.stack([x.detach() for x in kls]),
+                'last_lr': agent.last_lr, 'state': {k: v.clone() for k, v in agent.model.state_dict().items()},
+                'dataset': {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ds.items() if k != 'rnn_states'},
+                'mb_rewards': agent.experience_buffer.tensor_dict['rewards'].clone(),
+                'mb_values': agent.experience_buffer.tensor_dict['values'].clone(),
+                'mb_actions': agent.experience_buffer.tensor_dict['actions'].clone(),
+                'game_rewards_mean': agent.game_rewards.mean.clone(), 'game_rewards_size': agent.game_rewards.current_size,
+                'adam_exp_avg': [agent.optimizer.state[p]['exp_avg'].clone() for p in agent.model.parameters()],
+            })
+            agent.dataset.update_values_dict(None)
+        assert counter['k'] == epochs * (H + 1), counter
+    finally:
+        torch.multinomial = orig_multinomial
+    save(name, {'N': N, 'H': H, 'D': D, 'K': K, 'units': list(units), 'mb': mb, 'epochs': epochs, 'separate': separate,
+                'use_action_masks': use_action_masks, 'autoreset': autoreset,
+                'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
+                'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape, 'mask_tape': mask_tape, 'u': u,
+                'init_state': init_state, 'epochs_out': epochs_out, 'param_order': [k for k, _ in agent.model.named_parameters()]})
+
+
 if __name__ == '__main__':
-    gen_gae()
-    gen_math()
-    gen_agent('agent_base.pt')
-    gen_agent('agent_masked.pt', autoreset='next_step', seed=4)
-    gen_agent('agent_hardclip.pt', seed=5, overrides={
-        'use_smooth_clamp': False, 'bound_loss_type': 'bound', 'bounds_loss_coef': 0.001, 'entropy_coef': 0.003,
-        'clip_value': False, 'truncate_grads': False, 'value_bootstrap': False, 'mini_epochs': 2,
-        'weight_decay': 0.01, 'lr_schedule': None})
-    gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    if 'gae' in which:
+        gen_gae()
+    if 'math' in which:
+        gen_math()
+    if 'continuous' in which:
+        gen_agent('agent_base.pt')
+        gen_agent('agent_masked.pt', autoreset='next_step', seed=4)
+        gen_agent('agent_hardclip.pt', seed=5, overrides={
+            'use_smooth_clamp': False, 'bound_loss_type': 'bound', 'bounds_loss_coef': 0.001, 'entropy_coef': 0.003,
+            'clip_value': False, 'truncate_grads': False, 'value_bootstrap': False, 'mini_epochs': 2,
+            'weight_decay': 0.01, 'lr_schedule': None})
+        gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})
+    if 'rmsadv' in which:
+        gen_rms_adv()
+        gen_agent('agent_rmsadv.pt', autoreset='next_step', seed=7, overrides={'normalize_rms_advantage': True, 'adv_rms_momentum': 0.5})
+    if 'discrete' in which:
+        gen_agent_discrete('agent_discrete.pt')                                   # configs/ppo_cartpole.yaml shape: separate MLP [32,32], 2 actions
+        gen_agent_discrete('agent_discrete_masked.pt', K=5, D=7, units=(16, 8), separate=False, use_action_masks=True, autoreset='next_step',
+                           seed=12, overrides={'normalize_input': True, 'normalize_value': True, 'lr_schedule': 'adaptive',
+                                               'kl_threshold': 0.002, 'value_bootstrap': True})

@@ -99,7 +99,8 @@ def _oracle_from_golden(g):
     cfg = {k: cfgk[k] for k in ('gamma', 'tau', 'e_clip', 'clip_value', 'critic_coef', 'entropy_coef',
                                 'bound_loss_type', 'use_smooth_clamp', 'truncate_grads', 'grad_norm',
                                 'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value',
-                                'normalize_advantage', 'value_bootstrap', 'mini_epochs') if k in cfgk}
+                                'normalize_advantage', 'value_bootstrap', 'mini_epochs', 'normalize_rms_advantage',
+                                'adv_rms_momentum') if k in cfgk}
     cfg['bounds_loss_coef'] = cfgk.get('bounds_loss_coef', None)
     cfg['lr_schedule'] = cfgk.get('lr_schedule', None)
     cfg['weight_decay'] = cfgk.get('weight_decay', 0.0)
@@ -113,7 +114,7 @@ def _oracle_from_golden(g):
     return ag
 
 
-@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt'])
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
@@ -150,3 +151,92 @@ def test_full_train_epochs_match_reference_agent(name):
         torch.testing.assert_close(ag.game_rewards.mean, ref['game_rewards_mean'], rtol=1e-5, atol=1e-6)
         assert ag.game_rewards.current_size == ref['game_rewards_size']
         torch.testing.assert_close(ag.game_lengths.mean, ref['game_lengths_mean'], rtol=1e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ discrete PPO
+@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt'])
+def test_discrete_train_epochs_match_reference_agent(name):
+    """Two train_epoch()s of the reference DiscreteA2CAgent (configs/ppo_cartpole.yaml shape; second fixture: shared trunk,
+    action masks, next_step autoreset, normalisers, adaptive LR per mini-epoch) vs oracle/ppo_discrete_oracle.py on the same
+    tapes and uniform draws.  Sampled actions and masks are integer/bool work: bit-exact."""
+    from oracle import ppo_discrete_oracle as DO
+    g = load(name)
+    assert g['param_order'] == DO.discrete_param_names(len(g['units']), g['separate'])
+    cfgk = g['config']
+    cfg = {k: cfgk[k] for k in ('gamma', 'tau', 'e_clip', 'clip_value', 'critic_coef', 'entropy_coef', 'truncate_grads', 'grad_norm',
+                                'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value', 'normalize_advantage',
+                                'mini_epochs') if k in cfgk}
+    cfg['lr_schedule'] = cfgk.get('lr_schedule', None)
+    cfg['value_bootstrap'] = cfgk.get('value_bootstrap', True)
+    cfg['reward_scale'] = 0.1
+    cfg['mask_autoreset_rows'] = g['autoreset'] == 'next_step'
+    env = DO.DiscreteTapeEnv(g['obs_tape'], g['done_tape'], g['timeout_tape'], g['K'], g['mask_tape'])
+    params = {k: v for k, v in g['init_state'].items() if k.startswith('a2c_network')}
+    ag = DO.DiscreteOracleAgent(env, params, g['D'], g['K'], g['units'], g['N'], g['H'], g['mb'], cfg, separate=g['separate'],
+                                use_action_masks=g['use_action_masks'])
+    ag.obs = ag.env_reset()
+    for ep, ref in enumerate(g['epochs_out']):
+        out = ag.train_epoch(g['u'][ep])
+        ds = ref['dataset']
+        assert torch.equal(ag.buf['actions'], ref['mb_actions'])
+        assert torch.equal(ag.dataset['actions'], ds['actions'])
+        if g['use_action_masks']:
+            assert torch.equal(ag.dataset['action_masks'], ds['action_masks'])
+        if ds.get('rnn_masks') is not None:
+            assert torch.equal(ag.dataset['rnn_masks'], ds['rnn_masks'])
+        torch.testing.assert_close(ag.buf['rewards'], ref['mb_rewards'], rtol=1e-6, atol=1e-6)
+        torch.testing.assert_close(ag.buf['values'], ref['mb_values'], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(ag.dataset['old_logp_actions'], ds['old_logp_actions'], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(ag.dataset['advantages'], ds['advantages'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(ag.dataset['returns'], ds['returns'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(torch.stack(out['a_loss']), ref['a_losses'], rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(torch.stack(out['c_loss']), ref['c_losses'], rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(torch.stack(out['entropy']), ref['entropies'], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(torch.stack(out['kl']), ref['kls'], rtol=2e-3, atol=1e-8)        # one mean KL per mini-epoch
+        assert ag.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
+        for k in g['param_order']:
+            torch.testing.assert_close(ag.model.p[k].detach(), ref['state'][k], rtol=1e-4, atol=2e-6, msg=lambda m: k + m)
+        if cfg['normalize_input']:
+            st = ref['state']
+            torch.testing.assert_close(ag.model.running_mean_std.running_mean, st['running_mean_std.running_mean'], rtol=1e-9, atol=1e-9)
+            assert int(ag.model.running_mean_std.count) == int(st['running_mean_std.count'])
+            torch.testing.assert_close(ag.model.value_mean_std.running_var, st['value_mean_std.running_var'], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(ag.game_rewards.mean, ref['game_rewards_mean'], rtol=1e-5, atol=1e-6)
+        assert ag.game_rewards.current_size == ref['game_rewards_size']
+
+
+def test_inverse_cdf_sampling_and_masked_categorical():
+    """the sampling rule of the discrete path (shared by golden generation, oracle and the future kernel) and CategoricalMasked
+    against torch.distributions on random logits"""
+    from oracle import ppo_discrete_oracle as DO
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(64, 5, generator=g) * 2
+    masks = torch.rand(64, 5, generator=g) < 0.6
+    masks[:, 0] |= ~masks.any(dim=1)
+    nl, probs, ent = DO.categorical_masked(logits, None)
+    ref = torch.distributions.Categorical(logits=logits)
+    torch.testing.assert_close(nl, ref.logits); torch.testing.assert_close(ent, ref.entropy())
+    nl, probs, ent = DO.categorical_masked(logits, masks)
+    assert (probs[~masks] < 1e-30).all() and torch.allclose(probs.sum(-1), torch.ones(64))
+    u = torch.rand(64, generator=g)
+    a = DO.sample_inverse_cdf(probs, u)
+    assert masks.gather(1, a.unsqueeze(1)).all()                     # never samples an illegal action
+    assert (DO.sample_inverse_cdf(probs, torch.zeros(64)) == masks.float().argmax(dim=1)).all()     # u = 0 -> first legal action
+    # empirical frequencies follow the probabilities
+    p1 = torch.tensor([[0.1, 0.2, 0.3, 0.4]]).expand(20000, 4)
+    cnt = torch.bincount(DO.sample_inverse_cdf(p1, torch.rand(20000, generator=g)), minlength=4).float() / 20000
+    torch.testing.assert_close(cnt, p1[0], rtol=0, atol=0.02)
+
+
+def test_ema_advantage_normaliser_bitexact():
+    """GeneralizedMovingStats 'mean_std' (the reference's own test is bit-identity too:
+    tests/test_rms_advantage.py:42-70): unmasked, masked and all-invalid updates, then eval normalise / denormalise"""
+    g = load('rms_adv.pt')
+    gms = O.GeneralizedMovingStats((1,), decay=g['decay'])
+    for s_ in g['seq']:
+        y = gms(s_['x'], mask=s_['mask']) if s_['mask'] is not None else gms(s_['x'])
+        assert torch.equal(y, s_['y'])
+        assert torch.equal(gms.step, s_['step']) and torch.equal(gms.mean, s_['mean']) and torch.equal(gms.sqrs, s_['sqrs'])
+    gms.eval()
+    assert torch.equal(gms(g['x_eval']), g['y_eval'])
+    assert torch.equal(gms(g['x_eval'], denorm=True), g['y_denorm'])
