@@ -85,6 +85,12 @@ int b200rl_prepare_batch_f32(const float* values, const float* returns, const fl
                              int B, int normalize_value, int normalize_advantage, int freeze_stats,
                              void* stream);
 
+/* EMA advantage normaliser (GeneralizedMovingStats 'mean_std', moving_mean_std.py:84-150; a2c_common.py:473-475, :1622-1632):
+ * advs holds the RAW advantages of all B rows (b200rl_prepare_batch_f32 with normalize_advantage = 0) and is normalised in place
+ * with the updated state, clamped to [-5, 5].  partials: the same batch partial sums prepare_batch consumes.  ema_state: float[2]
+ * {mean, mean of squares} (zeros initially), ema_step: int32[1] (1 initially).  training = 0: normalise only. */
+int b200rl_adv_ema_normalize_f32(float* advs, int B, const double* partials, int n_partials, float* ema_state,
+                                 int* ema_step, float decay, int training, void* stream);
 int b200rl_batch_moments_f64(const float* values, const float* returns, const float* mask, double* partials,
                              int max_partials, int B, int* n_blocks_out_host, void* stream);
 

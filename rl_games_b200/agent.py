@@ -208,9 +208,9 @@ class A2CAgent:
         self.horizon_length = config['horizon_length']
         self.seq_length = config.get('seq_length', 4)
         self.normalize_advantage = config['normalize_advantage']
-        if config.get('normalize_rms_advantage', False):
-            raise NotImplementedError('normalize_rms_advantage (EMA advantage normaliser) is not on the B200 hot path yet')
-        self.normalize_rms_advantage = False
+        # EMA advantage normaliser (a2c_common.py:369, :473-475): GeneralizedMovingStats((1,), decay=adv_rms_momentum), 'mean_std'
+        self.normalize_rms_advantage = bool(config.get('normalize_rms_advantage', False)) and self.normalize_advantage
+        self.adv_rms_momentum = float(config.get('adv_rms_momentum', 0.5))
         self.normalize_input = config['normalize_input']
         self.normalize_value = config.get('normalize_value', False)
         if type(self.observation_space).__name__ == 'Dict':
@@ -409,6 +409,9 @@ class A2CAgent:
                                                       r.mean_f32, r.std_f32) for i in range(self.num_minibatches)]
         self.post_scratch = torch.zeros(((N + 255) // 256) * 4, dtype=torch.float64, device=dev)
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        if self.normalize_rms_advantage and not hasattr(self, 'adv_ema_state'):
+            self.adv_ema_state = torch.zeros(2, dtype=torch.float32, device=dev)     # GeneralizedMovingStats: mean, mean of squares
+            self.adv_ema_step = torch.ones(1, dtype=torch.int32, device=dev)
         self.ra_nrm = torch.zeros(148, dtype=torch.float64, device=dev)      # reduce_adam: per-CTA sum-of-squares partials
         self.ra_bar = torch.zeros(1, dtype=torch.int32, device=dev)          # reduce_adam: monotonic grid-barrier counter
         self.host_stats = torch.zeros(self.n_updates, 16, dtype=torch.float32).pin_memory()
@@ -697,8 +700,13 @@ class A2CAgent:
         m = self.model
         ops.prepare_batch(self.values, self.returns, self.valid, self.gae_partials, n_partials, m.value_mean_std.running_mean,
                           m.value_mean_std.running_var, m.value_mean_std.count, self.old_values_n, self.returns_n,
-                          self.advs_n, self.normalize_value, self.normalize_advantage,
+                          self.advs_n, self.normalize_value, self.normalize_advantage and not self.normalize_rms_advantage,
                           freeze_stats=bool(self.config.get('freeze_critic', False)))
+        if self.normalize_rms_advantage:
+            # a2c_common.py:1622-1632: advantages = advantage_mean_std(advantages[, mask]) -- EMA update from the valid rows, then
+            # every row normalised with the updated statistics and clamped to +-5
+            ops.adv_ema_normalize(self.advs_n, self.gae_partials, n_partials, self.adv_ema_state, self.adv_ema_step,
+                                  self.adv_rms_momentum, training=True)
         if self.mask_autoreset_rows:
             ops.mask_inv_counts(self.valid, self.horizon_length, self.num_actors, self.envs_per_mb, self.inv_counts)
         if self.use_mb_moments:
@@ -1192,6 +1200,9 @@ class A2CAgent:
         lr_step = self.opt_state.cpu()
         state['optimizer'] = self.model.optimizer_state_dict(self.last_lr, float(lr_step[1]), self.weight_decay)
         state['last_mean_rewards'] = self.last_mean_rewards
+        if self.normalize_rms_advantage:      # a2c_common.py:896-897: GeneralizedMovingStats.state_dict() keys
+            st = self.adv_ema_state.cpu()
+            state['advantage_mean_std'] = {'step': self.adv_ema_step.cpu().clone(), 'mean': st[0:1].clone(), 'sqrs': st[1:2].clone()}
         if self.vec_env is not None and hasattr(self.vec_env, 'get_env_state'):
             state['env_state'] = self.vec_env.get_env_state()
         if self.config.get('capability_manifest') is not None:
@@ -1211,6 +1222,10 @@ class A2CAgent:
                                           dtype=torch.float64))
         self._lr_synced = self.last_lr
         self.last_mean_rewards = weights.get('last_mean_rewards', -float('inf'))
+        if self.normalize_rms_advantage and 'advantage_mean_std' in weights:      # a2c_common.py:909-911
+            ams = weights['advantage_mean_std']
+            self.adv_ema_state.copy_(torch.cat([ams['mean'].reshape(1).float(), ams['sqrs'].reshape(1).float()]))
+            self.adv_ema_step.copy_(ams['step'].reshape(1).to(torch.int32))
         if self.vec_env is not None and hasattr(self.vec_env, 'set_env_state'):
             self.vec_env.set_env_state(weights.get('env_state', None))
         if 'capability_manifest' in weights and self.config.get('capability_manifest') is None:

@@ -110,6 +110,49 @@ __global__ void prepare_commit_kernel(const double* __restrict__ partials, int n
     }
 }
 
+// ---- EMA advantage normaliser: GeneralizedMovingStats 'mean_std' (moving_mean_std.py:84-150), created with
+//      decay = adv_rms_momentum (a2c_common.py:473-475), applied in prepare_dataset (:1622-1632).  The batch moments come from the
+//      same partial sums as the plain normalisation (slot 0 = valid rows, 5 = sum adv, 6 = sum adv^2); the state (fp32 mean and
+//      mean of squares, int32 step) moves by the same decay whatever the number of valid rows; no valid row = no update.
+//      Every block derives the new state from the OLD state + partials (identical arithmetic), a one-block commit kernel stores it.
+__device__ __forceinline__ bool adv_ema_next(const double* __restrict__ partials, int n_partials, double* sm, const float* __restrict__ state,
+                                             float decay, int training, float& mean, float& sqrs) {
+    double acc[3] = {0, 0, 0};
+    for (int p = threadIdx.x; p < n_partials; p += blockDim.x) {
+        acc[0] += partials[(int64_t)p * 8 + 0]; acc[1] += partials[(int64_t)p * 8 + 5]; acc[2] += partials[(int64_t)p * 8 + 6];
+    }
+    block_sum_d<3>(acc, sm);
+    mean = state[0]; sqrs = state[1];
+    const bool upd = training && acc[0] > 0.0;
+    if (upd) {
+        const float xm = (float)(acc[1] / acc[0]), xs = (float)(acc[2] / acc[0]);
+        const float mf = __fsub_rn(1.0f, decay);
+        mean = __fadd_rn(__fmul_rn(mean, decay), __fmul_rn(mf, xm));      // mean.mul_(m).add_((1 - m) * x_mean)
+        sqrs = __fadd_rn(__fmul_rn(sqrs, decay), __fmul_rn(mf, xs));
+    }
+    return upd;
+}
+
+__global__ void __launch_bounds__(256) adv_ema_normalize_kernel(float* __restrict__ advs, int B, const double* __restrict__ partials,
+                                                               int n_partials, const float* __restrict__ state, float decay, int training) {
+    __shared__ double sm[32 * 3];
+    float mean, sqrs;
+    adv_ema_next(partials, n_partials, sm, state, decay, training, mean, sqrs);
+    const float var = __fsub_rn(sqrs, __fmul_rn(mean, mean));
+    const float stdv = __fsqrt_rn(fmaxf(var, 1e-10f));                    // clamp_min(var, 1 / max^2), max = 1e5, eps = 0
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride)
+        advs[i] = fminf(fmaxf(__fdiv_rn(__fsub_rn(advs[i], mean), stdv), -5.0f), 5.0f);
+}
+
+__global__ void __launch_bounds__(256) adv_ema_commit_kernel(const double* __restrict__ partials, int n_partials, float* state, int* step,
+                                                            float decay, int training) {
+    __shared__ double sm[32 * 3];
+    float mean, sqrs;
+    const bool upd = adv_ema_next(partials, n_partials, sm, state, decay, training, mean, sqrs);
+    if (threadIdx.x == 0 && upd) { state[0] = mean; state[1] = sqrs; step[0] = step[0] + 1; }
+}
+
 // ---- obs moments: grid = (blocks_per_chunk, n_chunks), 256 threads ---------------------------------
 // scratch layout: [n_blocks][2*D] doubles (shifted sum, shifted sum of squares)
 __global__ void __launch_bounds__(256) moments_partial_kernel(
@@ -390,6 +433,21 @@ B200RL_EXPORT int b200rl_prepare_batch_f32(const float* values, const float* ret
     B200RL_LAUNCH_CHECK();
     if (normalize_value && !freeze_stats) {
         prepare_commit_kernel<<<1, 256, 0, s>>>(partials, n_partials, vms_mean, vms_var, vms_count);
+        B200RL_LAUNCH_CHECK();
+    }
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_adv_ema_normalize_f32(float* advs, int B, const double* partials, int n_partials, float* ema_state,
+                                               int* ema_step, float decay, int training, void* stream) {
+    if (!advs || !partials || !ema_state || !ema_step || B <= 0 || n_partials <= 0 || !(decay >= 0.0f && decay <= 1.0f)) return B200RL_EINVAL;
+    cudaStream_t s = as_stream(stream);
+    int blocks = (B + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    adv_ema_normalize_kernel<<<blocks, 256, 0, s>>>(advs, B, partials, n_partials, ema_state, decay, training);
+    B200RL_LAUNCH_CHECK();
+    if (training) {
+        adv_ema_commit_kernel<<<1, 256, 0, s>>>(partials, n_partials, ema_state, ema_step, decay, training);
         B200RL_LAUNCH_CHECK();
     }
     return B200RL_OK;

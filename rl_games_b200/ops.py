@@ -88,6 +88,11 @@ def prepare_batch(values, returns, mask, partials, n_partials, vms_mean, vms_var
                                        int(freeze_stats), _stream()), 'prepare_batch')
 
 
+def adv_ema_normalize(advs, partials, n_partials, ema_state, ema_step, decay, training=True):
+    check(lib.b200rl_adv_ema_normalize_f32(ptr(advs), advs.numel(), ptr(partials), n_partials, ptr(ema_state), ptr(ema_step),
+                                           float(decay), int(training), _stream()), 'adv_ema_normalize')
+
+
 def batch_moments(values, returns, mask, partials):
     nb = ctypes.c_int(0)
     check(lib.b200rl_batch_moments_f64(ptr(values), ptr(returns), ptr(mask), ptr(partials), partials.shape[0],

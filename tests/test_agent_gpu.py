@@ -105,13 +105,14 @@ def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True
         torch.testing.assert_close(sd[pre + 'running_var'].cpu(), ref_state[pre + 'running_var'].reshape(-1), rtol=1e-4, atol=1e-6)
 
 
-@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt'])
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt'])
 @pytest.mark.parametrize('graph', [False, True])
 def test_agent_matches_reference_golden(name, graph):
     g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk = g['config']
     over = {k: cfgk[k] for k in ('clip_value', 'use_smooth_clamp', 'bound_loss_type', 'bounds_loss_coef', 'entropy_coef',
-                                 'truncate_grads', 'value_bootstrap', 'mini_epochs', 'lr_schedule', 'weight_decay', 'critic_coef', 'seq_length')
+                                 'truncate_grads', 'value_bootstrap', 'mini_epochs', 'lr_schedule', 'weight_decay', 'critic_coef', 'seq_length',
+                                 'normalize_rms_advantage', 'adv_rms_momentum')
             if k in cfgk}
     over.setdefault('lr_schedule', None)
     over['b200_cuda_graph'] = graph

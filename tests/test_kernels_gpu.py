@@ -410,6 +410,40 @@ def test_reduce_adam_vs_two_kernel_path(ops, n, n_splits, pad):
     torch.testing.assert_close(b['v'], a['v'], rtol=2e-4, atol=1e-11)
 
 
+@pytest.mark.parametrize('masked', [False, True])
+def test_adv_ema_normalize_vs_oracle(ops, masked):
+    """EMA advantage normaliser against oracle.GeneralizedMovingStats over a sequence of batches incl. an
+    all-invalid one (no state update); the batch moments come from fp64 partial sums instead of torch's fp32 mean: 1e-6 agreement"""
+    g = torch.Generator().manual_seed(17)
+    gms = O.GeneralizedMovingStats((1,), decay=0.5)
+    state = torch.zeros(2, device=DEV); step = torch.ones(1, dtype=torch.int32, device=DEV)
+    for it, B in enumerate([4096, 1000, 777, 20000]):
+        v = torch.randn(B, generator=g); r = v + torch.randn(B, generator=g) * (1 + it) + 0.2 * it
+        if masked:
+            mask = torch.zeros(B) if it == 2 else (torch.rand(B, generator=g) < 0.6).float()
+        else:
+            mask = None
+        adv = r - v
+        ref = gms(adv, mask=mask) if mask is not None else gms(adv)
+        vd, rd = v.to(DEV), r.to(DEV)
+        md = None if mask is None else mask.to(DEV)
+        part = torch.zeros(64, 8, dtype=torch.float64, device=DEV)
+        nb = ops.batch_moments(vd, rd, md, part)
+        out = (rd - vd).clone()
+        ops.adv_ema_normalize(out, part, nb, state, step, 0.5, training=True)
+        torch.cuda.synchronize()
+        torch.testing.assert_close(out.cpu(), ref, rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(state.cpu(), torch.cat([gms.mean, gms.sqrs]), rtol=1e-6, atol=1e-7)
+        assert int(step) == int(gms.step)
+    # eval mode: normalise only
+    x = torch.randn(513, generator=g) * 10
+    gms.eval()
+    out = x.to(DEV).clone()
+    ops.adv_ema_normalize(out, part, nb, state, step, 0.5, training=False)
+    torch.testing.assert_close(out.cpu(), gms(x), rtol=1e-5, atol=2e-6)
+    assert int(step) == int(gms.step)
+
+
 # ------------------------------------------------------------------------------------------ rollout pieces
 def test_policy_head_sample_vs_oracle(ops):
     g = torch.Generator().manual_seed(9)
