@@ -286,6 +286,32 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
 
+# ------------------------------------------------------------------ checkpoint wire format
+def gen_checkpoint(name='ref_checkpoint.pt', N=8, H=8, D=6, A=3, units=(16, 8), mb=32, seed=9):
+    """A checkpoint dict exactly as the reference writes it (A2CBase.get_full_state_weights, a2c_common.py:825-850, after one
+    train_epoch so that the Adam state exists) -- the input of the host-side interop test."""
+    from rl_games.torch_runner import Runner
+    from oracle.ppo_oracle import make_tapes
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    obs_tape, done_tape, tout_tape = make_tapes(H + 1, N, D, seed=seed)
+    env = TapeVecEnv(obs_tape, done_tape, tout_tape)
+    env.A = A
+    params = make_params(N, H, mb, units)
+    params['config']['env_info'] = env.get_env_info()
+    runner = Runner()
+    runner.load({'params': params})
+    runner.params['config']['vec_env'] = env
+    agent = runner.algo_factory.create(runner.algo_name, base_name='golden', params=runner.params)
+    agent.init_tensors()
+    agent.obs = agent.env_reset()
+    agent.epoch_num += 1
+    agent.train_epoch()
+    ck = agent.get_full_state_weights()
+    ck = {k: v for k, v in ck.items() if k in ('model', 'epoch', 'frame', 'optimizer', 'last_mean_rewards')}
+    save(name, {'D': D, 'A': A, 'units': list(units), 'checkpoint': ck, 'param_order': [k for k, _ in agent.model.named_parameters()]})
+
+
 # ------------------------------------------------------------------ discrete PPO (SURVEY 8a row a15; configs/ppo_cartpole.yaml shape)
 class DiscreteTapeVecEnv:
     """mirrors oracle.ppo_discrete_oracle.DiscreteTapeEnv behind the reference's tensor-env contract"""
@@ -408,7 +434,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -421,6 +447,8 @@ if __name__ == '__main__':
             'clip_value': False, 'truncate_grads': False, 'value_bootstrap': False, 'mini_epochs': 2,
             'weight_decay': 0.01, 'lr_schedule': None})
         gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})
+    if 'checkpoint' in which:
+        gen_checkpoint()
     if 'rmsadv' in which:
         gen_rms_adv()
         gen_agent('agent_rmsadv.pt', autoreset='next_step', seed=7, overrides={'normalize_rms_advantage': True, 'adv_rms_momentum': 0.5})

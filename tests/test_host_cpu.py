@@ -176,3 +176,42 @@ def test_merge_matches_reference_merge_rank_stats_with_fake_allreduce():
     torch.testing.assert_close(m.running_var, ref.running_var, rtol=1e-12, atol=1e-15)
     for a, b in zip(snaps['obs'], snap_ref):
         torch.testing.assert_close(a.reshape(-1), b.reshape(-1).double(), rtol=1e-12, atol=0)
+
+
+def test_reference_checkpoint_wire_format_roundtrip(monkeypatch):
+    """a checkpoint dict written by the REAL reference (tests/golden/gen_golden.py checkpoint:
+    A2CBase.get_full_state_weights after one epoch) loads into the flat-arena model and re-exports with the same keys, the same
+    key ORDER (players index `model` by name, torch.optim.Adam.load_state_dict indexes parameters by position) and identical
+    tensors -- weights, normaliser statistics, Adam moments, step and lr.  Pure host logic: runs on CPU tensors."""
+    import torch
+    from rl_games_b200 import ops
+    from rl_games_b200.model import B200Model
+    # the fp32 mirror of the normaliser statistics is refreshed by a CUDA kernel; irrelevant for the key/tensor mapping under test
+    monkeypatch.setattr(ops, 'refresh_norm', lambda *a, **k: None)
+    g = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'ref_checkpoint.pt'), weights_only=False)
+    ck = g['checkpoint']
+    net = {'name': 'actor_critic', 'separate': False,
+           'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                    'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+           'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    m = B200Model(net, g['D'], g['A'], 'cpu', normalize_input=True, normalize_value=True, seed=1)
+    m.load_state_dict(ck['model'])
+    lr, step = m.load_optimizer_state_dict(ck['optimizer'])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ck['model'].keys())
+    for k, v in ck['model'].items():
+        assert sd[k].dtype == v.dtype, k
+        assert torch.equal(sd[k].reshape(v.shape), v), k
+    ref_opt = ck['optimizer']
+    assert lr == ref_opt['param_groups'][0]['lr'] and step == int(ref_opt['state'][0]['step'])
+    osd = m.optimizer_state_dict(lr, step, ref_opt['param_groups'][0]['weight_decay'])
+    assert osd['param_groups'][0]['params'] == ref_opt['param_groups'][0]['params']
+    for key in ('lr', 'betas', 'eps', 'weight_decay', 'amsgrad'):
+        assert osd['param_groups'][0][key] == ref_opt['param_groups'][0][key], key
+    assert sorted(osd['state'].keys()) == sorted(ref_opt['state'].keys())
+    names = g['param_order']          # reference model.parameters() order == the optimizer's positional order
+    for i, name in enumerate(names):
+        for f in ('exp_avg', 'exp_avg_sq'):
+            assert torch.equal(osd['state'][i][f].reshape(ref_opt['state'][i][f].shape), ref_opt['state'][i][f]), (name, f)
+        assert float(osd['state'][i]['step']) == float(ref_opt['state'][i]['step'])
+        assert osd['state'][i]['exp_avg'].numel() == ck['model'][name].numel(), name
