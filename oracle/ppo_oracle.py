@@ -553,9 +553,109 @@ DEFAULT_CFG = dict(
 )
 
 
+# ----------------------------------------------------------------------------------------------
+# Central value (asymmetric critic) -- algos_torch/central_value.py:14-383, models.py:425-464 (ModelCentralValue),
+# A2CBuilder.Network with central_value: True (network_builder.py:498-499: returns value only).  SURVEY 8f rank 1.
+# ----------------------------------------------------------------------------------------------
+def cv_param_names(n_layers):
+    names = []
+    for i in range(n_layers):
+        names += [f'a2c_network.actor_mlp.{2 * i}.weight', f'a2c_network.actor_mlp.{2 * i}.bias']
+    return names + ['a2c_network.value.weight', 'a2c_network.value.bias']
+
+
+class CentralValueOracle:
+    """CentralValueTrain: its own MLP on `states`, own obs normaliser, the (shared) value normaliser, own Adam and lr."""
+
+    def __init__(self, params, state_dim, units, cv_cfg, normalize_value, num_actors, horizon, activation='elu'):
+        self.p = {k: v.clone().float().requires_grad_(True) for k, v in params.items()}
+        self.names = cv_param_names(len(units))
+        self.n_layers, self.activation = len(units), activation
+        c = self.cfg = dict(cv_cfg)
+        self.normalize_input, self.normalize_value = c['normalize_input'], normalize_value
+        self.running_mean_std = RunningMeanStd((state_dim,)) if self.normalize_input else None
+        self.value_mean_std = RunningMeanStd((1,)) if normalize_value else None
+        self.lr = float(c['learning_rate'])
+        self.mini_epoch = c['mini_epochs']
+        self.batch_size = num_actors * horizon
+        self.minibatch_size = c['minibatch_size']
+        self.num_minibatches = self.batch_size // self.minibatch_size
+        self.clip_value, self.e_clip = c['clip_value'], c.get('e_clip', 0.2)
+        self.truncate_grads, self.grad_norm = c.get('truncate_grads', False), c.get('grad_norm', 1)
+        self.optimizer = Adam([self.p[n] for n in self.names], self.lr, eps=1e-8, weight_decay=c.get('weight_decay', 0.0))
+        self.scheduler = IdentityScheduler()          # lr_schedule 'linear' is the only other option (central_value.py:55-62)
+        self.epoch_num, self.frame = 0, 0
+        self.dataset = None
+
+    def parameters(self):
+        return [self.p[n] for n in self.names]
+
+    def forward(self, states, is_train):
+        x = states
+        if self.normalize_input:
+            with torch.no_grad():
+                x = self.running_mean_std(x)
+        act = ACTIVATIONS[self.activation]
+        for i in range(self.n_layers):
+            x = act(F.linear(x, self.p[f'a2c_network.actor_mlp.{2 * i}.weight'], self.p[f'a2c_network.actor_mlp.{2 * i}.bias']))
+        value = F.linear(x, self.p['a2c_network.value.weight'], self.p['a2c_network.value.bias'])
+        if not is_train and self.normalize_value:
+            with torch.no_grad():
+                value = self.value_mean_std(value, denorm=True)
+        return value
+
+    @torch.no_grad()
+    def get_value(self, states):               # central_value.py:207-229: self.eval() first
+        if self.normalize_input:
+            self.running_mean_std.eval()
+        if self.normalize_value:
+            self.value_mean_std.eval()
+        return self.forward(states, is_train=False)
+
+    def update_dataset(self, d):               # central_value.py:153-176
+        self.dataset = d
+
+    def train_net(self):                       # central_value.py:246-274
+        loss = 0.0
+        self.last_losses = []
+        for _ in range(self.mini_epoch):
+            if self.cfg.get('freeze_critic', False):
+                break
+            for i in range(self.num_minibatches):
+                # train_critic -> self.train(): nn.Module.train re-arms BOTH normalisers of the critic model before every
+                # minibatch; the value normaliser in train mode would update from the critic's own outputs in forward... it is
+                # only ever called through denorm in eval mode, so only the obs normaliser moves here
+                if self.normalize_input:
+                    self.running_mean_std.train()
+                s, e = i * self.minibatch_size, (i + 1) * self.minibatch_size
+                values = self.forward(self.dataset['obs'][s:e], is_train=True)
+                masks = self.dataset.get('rnn_masks')
+                l = critic_loss(self.dataset['old_values'][s:e], values, self.e_clip, self.dataset['returns'][s:e], self.clip_value)
+                losses, _ = apply_masks([l], None if masks is None else masks[s:e])
+                l = losses[0]
+                params = self.parameters()
+                for p in params:
+                    p.grad = None
+                l.backward()
+                grads = [p.grad for p in params]
+                if self.truncate_grads:
+                    grads, _ = clip_grad_norm(grads, self.grad_norm)
+                self.optimizer.lr = self.lr
+                self.optimizer.step(grads)
+                self.last_losses.append(l.detach())
+                loss += float(l.detach())
+            if self.normalize_input:
+                self.running_mean_std.eval()
+        self.epoch_num += 1
+        self.lr, _ = self.scheduler.update(self.lr, 0, self.epoch_num, self.frame, 0)
+        self.frame += self.batch_size
+        return loss / (self.mini_epoch * self.num_minibatches)
+
+
 class OracleAgent:
     def __init__(self, env, params, obs_dim, act_dim, units, num_actors, horizon, minibatch_size,
-                 cfg: Optional[dict] = None, matmul_dtype=None, all_reduce=None, world_size=1):
+                 cfg: Optional[dict] = None, matmul_dtype=None, all_reduce=None, world_size=1, central_value=None):
+        self.cv = central_value            # CentralValueOracle or None (a2c_common.py:250-251 has_central_value)
         self.cfg = dict(DEFAULT_CFG)
         self.cfg.update(cfg or {})
         c = self.cfg
@@ -605,9 +705,16 @@ class OracleAgent:
             self.rnn_states = [torch.zeros(1, N, hid), torch.zeros(1, N, hid)]
             self.mb_rnn_states = [torch.zeros(H // self.seq_length, 1, N, hid) for _ in range(2)]
 
+    def _take_obs(self, o):
+        """envs with a central value return {'obs': ..., 'states': ...} (a2c_common.py:1010-1011)"""
+        if isinstance(o, dict):
+            self.states = o['states']
+            return o['obs']
+        return o
+
     def env_reset(self):
         self._autoreset_prev_dones = None
-        return self.env.reset()
+        return self._take_obs(self.env.reset())
 
     # a2c_common.py:1500-1510 + :144-148
     def preprocess_actions(self, actions):
@@ -630,6 +737,9 @@ class OracleAgent:
                 for s_, mb_s in zip(self.rnn_states, self.mb_rnn_states):
                     mb_s[n // self.seq_length] = s_
             res = self.model.forward(self.obs, is_train=False, noise=noise[n], rnn_states=self.rnn_states if self.is_rnn else None)
+            if self.cv is not None:                 # get_action_values: a2c_common.py:593-600
+                res['values'] = self.cv.get_value(self.states)
+                self.buf.setdefault('states', torch.zeros(H, N, self.states.shape[-1]))[n] = self.states
             if self.is_rnn:
                 self.rnn_states = [t.clone() for t in self.model.last_rnn_states]
             self.buf['obses'][n] = self.obs
@@ -641,7 +751,8 @@ class OracleAgent:
                 mb_valid[n] = 1.0 - prev.float()
             for k in ['actions', 'neglogpacs', 'values', 'mus', 'sigmas']:
                 self.buf[k][n] = res[k]
-            self.obs, rewards, self.dones, infos = self.env.step(self.preprocess_actions(res['actions']))
+            o, rewards, self.dones, infos = self.env.step(self.preprocess_actions(res['actions']))
+            self.obs = self._take_obs(o)
             rewards = rewards.unsqueeze(1)
             if self.mask_autoreset_rows:
                 self._autoreset_prev_dones = self.dones.clone()
@@ -669,8 +780,11 @@ class OracleAgent:
             self.current_rewards.mul_(nd)
             self.current_shaped_rewards.mul_(nd)
             self.current_lengths.mul_(nd.squeeze(1))
-        last_values = self.model.forward(self.obs, is_train=False, noise=torch.zeros(N, self.A),
-                                         rnn_states=self.rnn_states if self.is_rnn else None)['values']
+        if self.cv is not None:                     # get_values: a2c_common.py:603-615
+            last_values = self.cv.get_value(self.states)
+        else:
+            last_values = self.model.forward(self.obs, is_train=False, noise=torch.zeros(N, self.A),
+                                             rnn_states=self.rnn_states if self.is_rnn else None)['values']
         fdones = self.dones.float()
         mb_fdones = self.buf['dones'].float()
         mb_advs = gae(self.buf['rewards'], self.buf['values'], mb_fdones, last_values, fdones, c['gamma'], c['tau'])
@@ -679,6 +793,8 @@ class OracleAgent:
                  ['actions', 'neglogpacs', 'values', 'mus', 'sigmas', 'obses', 'dones']}
         batch['returns'] = swap_and_flatten01(mb_returns)
         batch['mb_advs'] = mb_advs
+        if self.cv is not None:
+            batch['states'] = swap_and_flatten01(self.buf['states'])
         if self.mask_autoreset_rows:
             batch['rnn_masks'] = swap_and_flatten01(mb_valid)
         if self.is_rnn:    # a2c_common.py:1193-1199
@@ -695,7 +811,8 @@ class OracleAgent:
         rnn_masks = batch.get('rnn_masks', None)
         advantages = returns - values
         if c['normalize_value']:
-            vms = self.model.value_mean_std
+            # with a central value the agent's value normaliser IS the critic model's (a2c_continuous.py:72-73)
+            vms = self.cv.value_mean_std if self.cv is not None else self.model.value_mean_std
             if rnn_masks is not None:
                 valid = rnn_masks.bool()
                 vms.train()
@@ -725,6 +842,9 @@ class OracleAgent:
             'rnn_masks': rnn_masks, 'mu': batch['mus'].clone(), 'sigma': batch['sigmas'].clone(),
             'rnn_states': batch.get('rnn_states', None),
         }
+        if self.cv is not None:                     # a2c_common.py:1651-1660
+            self.cv.update_dataset({'old_values': values, 'advantages': advantages, 'returns': returns, 'actions': batch['actions'],
+                                    'obs': batch['states'], 'dones': batch['dones'], 'rnn_masks': rnn_masks})
 
     def get_minibatch(self, i):
         s, e = i * self.minibatch_size, (i + 1) * self.minibatch_size
@@ -797,6 +917,8 @@ class OracleAgent:
         batch = self.play_steps(noise)
         self.prepare_dataset(batch)
         out = {'a_loss': [], 'c_loss': [], 'entropy': [], 'kl': [], 'b_loss': [], 'lr': [], 'batch': batch}
+        if self.cv is not None:                     # a2c_common.py:1536-1537 train_central_value() before the actor's mini-epochs
+            out['cv_loss'] = self.cv.train_net()
         for mini_ep in range(self.cfg['mini_epochs']):
             for i in range(self.num_minibatches):
                 # train_actor_critic -> set_train() -> model.train() (a2c_continuous.py:236-239,

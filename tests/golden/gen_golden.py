@@ -286,6 +286,102 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
 
+# ------------------------------------------------------------------ central value / asymmetric critic
+class CVTapeVecEnv(TapeVecEnv):
+    """TapeVecEnv whose observations are {'obs': actor view, 'states': privileged critic view} (state tape = [obs, extra features])"""
+
+    def __init__(self, obs_tape, state_tape, done_tape, timeout_tape, autoreset_mode='same_step'):
+        super().__init__(obs_tape, done_tape, timeout_tape, autoreset_mode)
+        self.state_tape = state_tape
+
+    def reset(self):
+        self.i = 0
+        return {'obs': self.obs_tape[0].clone(), 'states': self.state_tape[0].clone()}
+
+    def step(self, actions):
+        o, rew, done, info = super().step(actions)
+        j = self.i % self.obs_tape.shape[0]
+        return {'obs': o, 'states': self.state_tape[j].clone()}, rew, done, info
+
+    def get_env_info(self):
+        import gymnasium as gym
+        info = super().get_env_info()
+        info['state_space'] = gym.spaces.Box(-np.inf, np.inf, (self.state_tape.shape[-1],), np.float32)
+        return info
+
+
+def gen_agent_cv(name='agent_cv.pt', N=8, H=8, D=6, S=10, A=3, units=(16, 8), cv_units=(24, 12), mb=32, cv_mb=16, epochs=2, seed=8,
+                 autoreset='next_step'):
+    from rl_games.torch_runner import Runner
+    from oracle.ppo_oracle import make_tapes
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    T = H * epochs + 1
+    obs_tape, done_tape, tout_tape = make_tapes(T, N, D, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    state_tape = torch.cat([obs_tape, torch.randn(T, N, S - D, generator=g) * 2.0 - 0.5], dim=-1)
+    env = CVTapeVecEnv(obs_tape, state_tape, done_tape, tout_tape, autoreset)
+    env.A = A
+    cv_cfg = {'minibatch_size': cv_mb, 'mini_epochs': 3, 'learning_rate': 5e-4, 'clip_value': True, 'normalize_input': True,
+              'truncate_grads': True, 'grad_norm': 1.0,
+              'network': {'name': 'actor_critic', 'central_value': True,
+                          'mlp': {'units': list(cv_units), 'activation': 'elu', 'initializer': {'name': 'default'}}}}
+    params = make_params(N, H, mb, units, {'central_value_config': cv_cfg})
+    params['config']['env_info'] = env.get_env_info()
+    runner = Runner()
+    runner.load({'params': params})
+    runner.params['config']['vec_env'] = env
+    agent = runner.algo_factory.create(runner.algo_name, base_name='golden', params=runner.params)
+    with torch.no_grad():
+        for mdl in (agent.model, agent.central_value_net.model):
+            for k, p in mdl.named_parameters():
+                if k.endswith('bias') or k.endswith('sigma'):
+                    p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    init_state = {k: v.clone() for k, v in agent.model.state_dict().items()}
+    cv_init_state = {k: v.clone() for k, v in agent.central_value_net.model.state_dict().items()}
+    noise = torch.randn(epochs, H + 1, N, A, generator=g)
+    counter = {'k': 0}
+    orig_normal = torch.normal
+
+    def fake_normal(loc, scale, *a, **kw):
+        k = counter['k']
+        counter['k'] += 1
+        e, n = divmod(k, H + 1)
+        return loc + scale * noise[e, n]
+    torch.normal = fake_normal
+    try:
+        agent.init_tensors()
+        agent.obs = agent.env_reset()
+        epochs_out = []
+        for ep in range(epochs):
+            agent.epoch_num += 1
+            res = agent.train_epoch()
+            step_time, play_time, update_time, total, a_losses, c_losses, b_losses, entropies, kls, last_lr, lr_mul = res
+            ds = agent.dataset.values_dict
+            cvn = agent.central_value_net
+            epochs_out.append({
+                'a_losses': torch.stack([x.detach() for x in a_losses]), 'c_losses': torch.stack([x.detach() for x in c_losses]),
+                'entropies': torch.stack([x.detach() for x in entropies]), 'kls': torch.stack([x.detach() for x in kls]),
+                'last_lr': agent.last_lr, 'state': {k: v.clone() for k, v in agent.model.state_dict().items()},
+                'cv_state': {k: v.clone() for k, v in cvn.model.state_dict().items()}, 'cv_lr': cvn.lr,
+                'cv_adam_exp_avg': [cvn.optimizer.state[p]['exp_avg'].clone() for p in cvn.model.parameters()],
+                'dataset': {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ds.items() if k != 'rnn_states'},
+                'mb_values': agent.experience_buffer.tensor_dict['values'].clone(),
+                'mb_rewards': agent.experience_buffer.tensor_dict['rewards'].clone(),
+            })
+            agent.dataset.update_values_dict(None)
+        # the normal draws: H rollout steps per epoch only -- get_values goes through the critic when a central value exists
+        assert counter['k'] == epochs * H, counter
+    finally:
+        torch.normal = orig_normal
+    save(name, {'N': N, 'H': H, 'D': D, 'S': S, 'A': A, 'units': list(units), 'cv_units': list(cv_units), 'mb': mb, 'epochs': epochs,
+                'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
+                'cv_config': {k: v for k, v in cv_cfg.items() if isinstance(v, (int, float, str, bool, type(None)))},
+                'autoreset': autoreset, 'obs_tape': obs_tape, 'state_tape': state_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
+                'noise': noise, 'init_state': init_state, 'cv_init_state': cv_init_state, 'epochs_out': epochs_out,
+                'cv_param_order': [k for k, _ in agent.central_value_net.model.named_parameters()]})
+
+
 # ------------------------------------------------------------------ checkpoint wire format (SURVEY 8f rank 3)
 def gen_checkpoint(name='ref_checkpoint.pt', N=8, H=8, D=6, A=3, units=(16, 8), mb=32, seed=9):
     """A checkpoint dict exactly as the reference writes it (A2CBase.get_full_state_weights, a2c_common.py:825-850, after one
@@ -434,7 +530,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -449,6 +545,8 @@ if __name__ == '__main__':
         gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})
     if 'checkpoint' in which:
         gen_checkpoint()
+    if 'cv' in which:
+        gen_agent_cv()
     if 'rmsadv' in which:
         gen_rms_adv()
         gen_agent('agent_rmsadv.pt', autoreset='next_step', seed=7, overrides={'normalize_rms_advantage': True, 'adv_rms_momentum': 0.5})

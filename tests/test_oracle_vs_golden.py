@@ -240,3 +240,60 @@ def test_ema_advantage_normaliser_bitexact():
     gms.eval()
     assert torch.equal(gms(g['x_eval']), g['y_eval'])
     assert torch.equal(gms(g['x_eval'], denorm=True), g['y_denorm'])
+
+
+# ------------------------------------------------------------------------------------------ central value
+def test_central_value_train_epochs_match_reference_agent():
+    """A2CAgent with central_value_config (asymmetric critic on privileged `states`, own normalisers / Adam / minibatching,
+    trained before the actor's mini-epochs; the rollout values and the value normaliser come from the critic) vs the oracle."""
+    g = load('agent_cv.pt')
+    assert g['cv_param_order'] == O.cv_param_names(len(g['cv_units']))
+    cfgk = g['config']
+    cfg = {k: cfgk[k] for k in ('gamma', 'tau', 'e_clip', 'clip_value', 'critic_coef', 'entropy_coef', 'bound_loss_type', 'use_smooth_clamp',
+                                'truncate_grads', 'grad_norm', 'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value',
+                                'normalize_advantage', 'value_bootstrap', 'mini_epochs') if k in cfgk}
+    cfg['bounds_loss_coef'] = cfgk.get('bounds_loss_coef', None)
+    cfg['lr_schedule'] = cfgk.get('lr_schedule', None)
+    cfg['mask_autoreset_rows'] = g['autoreset'] == 'next_step'
+
+    class Env(O.TapeEnv):
+        def __init__(self):
+            super().__init__(g['obs_tape'], g['done_tape'], g['timeout_tape'])
+
+        def reset(self):
+            return {'obs': super().reset(), 'states': g['state_tape'][0].clone()}
+
+        def step(self, actions):
+            o, r, d, info = super().step(actions)
+            return {'obs': o, 'states': g['state_tape'][self.i % g['state_tape'].shape[0]].clone()}, r, d, info
+    cv_params = {k: v for k, v in g['cv_init_state'].items() if k.startswith('a2c_network')}
+    cv = O.CentralValueOracle(cv_params, g['S'], g['cv_units'], g['cv_config'], cfg['normalize_value'], g['N'], g['H'])
+    params = {k: v for k, v in g['init_state'].items() if k.startswith('a2c_network')}
+    ag = O.OracleAgent(Env(), params, g['D'], g['A'], g['units'], g['N'], g['H'], g['mb'], cfg, central_value=cv)
+    ag.obs = ag.env_reset()
+    # with a central value the last-value forward goes through the critic and draws no action noise, so the reference consumed the
+    # tape as one flat stream of H draws per epoch (gen_golden.py asserts counter == epochs * H)
+    flat_noise = g['noise'].reshape(-1, g['N'], g['A'])
+    for ep, ref in enumerate(g['epochs_out']):
+        out = ag.train_epoch(flat_noise[ep * g['H']:(ep + 1) * g['H']])
+        ds = ref['dataset']
+        torch.testing.assert_close(ag.buf['values'], ref['mb_values'], rtol=1e-5, atol=1e-6)        # critic values in the rollout
+        torch.testing.assert_close(ag.buf['rewards'], ref['mb_rewards'], rtol=1e-6, atol=1e-6)      # incl. the time-out bootstrap on them
+        torch.testing.assert_close(ag.dataset['advantages'], ds['advantages'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(ag.dataset['returns'], ds['returns'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(ag.dataset['old_values'], ds['old_values'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(torch.stack(out['a_loss']), ref['a_losses'], rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(torch.stack(out['c_loss']), ref['c_losses'], rtol=1e-3, atol=1e-6)
+        assert ag.last_lr == pytest.approx(ref['last_lr'], rel=1e-12) and cv.lr == pytest.approx(ref['cv_lr'], rel=1e-12)
+        for k in O.param_names(len(g['units'])):
+            torch.testing.assert_close(ag.model.p[k].detach(), ref['state'][k], rtol=1e-4, atol=2e-6, msg=lambda m: k + m)
+        st = ref['cv_state']
+        for k in O.cv_param_names(len(g['cv_units'])):
+            torch.testing.assert_close(cv.p[k].detach(), st[k], rtol=1e-4, atol=2e-6, msg=lambda m: 'cv ' + k + m)
+        torch.testing.assert_close(cv.running_mean_std.running_mean, st['running_mean_std.running_mean'], rtol=1e-9, atol=1e-9)
+        assert int(cv.running_mean_std.count) == int(st['running_mean_std.count'])
+        torch.testing.assert_close(cv.value_mean_std.running_mean, st['value_mean_std.running_mean'], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(cv.value_mean_std.running_var, st['value_mean_std.running_var'], rtol=1e-6, atol=1e-7)
+        assert int(cv.value_mean_std.count) == int(st['value_mean_std.count'])
+        # the actor model's own value normaliser never moves when a central value exists
+        assert int(ref['state']['value_mean_std.count']) == 1
