@@ -215,3 +215,25 @@ def test_reference_checkpoint_wire_format_roundtrip(monkeypatch):
             assert torch.equal(osd['state'][i][f].reshape(ref_opt['state'][i][f].shape), ref_opt['state'][i][f]), (name, f)
         assert float(osd['state'][i]['step']) == float(ref_opt['state'][i]['step'])
         assert osd['state'][i]['exp_avg'].numel() == ck['model'][name].numel(), name
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): exactly ONE JSON line on stdout with the keys of
+    the bench contract, a cpu_baseline block describing the run and an e2e block that repeats the line's own value."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1'],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert k in d, k
+    assert d['impl'] == 'reference' and d['metric'] == 'ppo_env_steps_per_sec' and d['unit'] == 'env-steps/s' and d['higher_is_better'] is True
+    assert d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 1 and 'workload' in d['config']
+    assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
