@@ -73,6 +73,14 @@ class Box:
         self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
 
 
+class Discrete:
+    """Minimal stand-in for gymnasium.spaces.Discrete (only .n is read: a2c_common.py:1213-1216); duck-typed by class name."""
+
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+
+
 # ---- registries: common/vecenv.py:368-391 and common/env_configurations.py:358-366 ----
 vecenv_config = {}
 configurations = {}

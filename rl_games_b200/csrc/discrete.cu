@@ -1,0 +1,218 @@
+// Categorical (discrete-action) policy head for PPO -- SURVEY.md 8a row a15 (a2c_discrete.py:92-209, models.py:95-125,
+// common/extensions/distributions.py:23-44).
+//
+// STATUS: NOT YET RUN ON HARDWARE.  These kernels were written after the round's GPU budget was spent; they compile for
+// sm_100a, are exported through the C ABI and are covered by `pytest -m gpu` tests that are skipped unless
+// B200RL_UNVALIDATED=1 (tests/test_discrete_gpu.py); the agent that uses them (rl_games_b200/agent_discrete.py) refuses to
+// start without `b200_unvalidated: True`.  The CPU oracle they must match (oracle/ppo_discrete_oracle.py) IS pinned to the
+// real reference by golden vectors.
+//
+// Both kernels are one thread per row over small K (<= 64 actions): HBM/latency bound, no tensor-core work.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CAT_MAXK = 64;
+
+struct CatLossDev { float e_clip, critic_coef, entropy_coef; int clip_value, smooth, ppo; };
+
+// masked log-softmax pieces of one row: legal-max m, lse = m + log(sum exp(z - m)); masked logits count as -1e8 (distributions.py:29)
+__device__ __forceinline__ void cat_lse(const float* __restrict__ z, const uint8_t* __restrict__ mask, int K, float& lse) {
+    float m = -3.0e38f;
+    for (int k = 0; k < K; ++k) {
+        const float v = (mask && !mask[k]) ? -1e8f : z[k];
+        m = fmaxf(m, v);
+    }
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) {
+        const float v = (mask && !mask[k]) ? -1e8f : z[k];
+        s += expf(v - m);
+    }
+    lse = m + logf(s);
+}
+
+// ---- rollout: sample (inverse CDF on one uniform per row), neglogp, de-normalised value --------------------------------------
+__global__ void __launch_bounds__(256) categorical_sample_kernel(
+    const float* __restrict__ logits, int ld, int K, const float* __restrict__ value_raw, int value_ld,
+    const uint8_t* __restrict__ action_masks, const float* __restrict__ u_tape, uint64_t seed,
+    const uint64_t* __restrict__ rng_epoch_dev, uint32_t step_index, const double* __restrict__ vms_mean,
+    const double* __restrict__ vms_var, int normalize_value, int64_t* __restrict__ actions, float* __restrict__ neglogp,
+    float* __restrict__ values, const uint8_t* __restrict__ dones_cur, uint8_t* __restrict__ dones_out,
+    const float* __restrict__ prev_dones, float* __restrict__ valid_out, int N, int values_only) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    // value: denorm_value (running_mean_std.py:104-106): sqrt(var + eps) * clamp(v, -5, 5) + mean
+    float val = value_raw[(int64_t)e * value_ld];
+    if (normalize_value) {
+        const float m = (float)vms_mean[0], s = __fsqrt_rn(__fadd_rn((float)vms_var[0], 1e-5f));
+        val = __fadd_rn(__fmul_rn(s, fminf(fmaxf(val, -5.0f), 5.0f)), m);
+    }
+    values[e] = val;
+    if (values_only) return;
+    const float* z = logits + (int64_t)e * ld;
+    const uint8_t* mk = action_masks ? action_masks + (int64_t)e * K : nullptr;
+    float lse;
+    cat_lse(z, mk, K, lse);
+    float u;
+    if (u_tape) {
+        u = u_tape[e];
+    } else {
+        const uint64_t ep = rng_epoch_dev ? *rng_epoch_dev : 0ull;
+        const Philox4 r = philox4x32_10((uint64_t)e, (ep << 20) | ((uint64_t)step_index << 4) | 15ull, seed);
+        u = (float)(r.x >> 8) * (1.0f / 16777216.0f);                     // [0, 1)
+    }
+    // action = #{k : cdf_k <= u}, clamped to the last action of non-zero probability (oracle.sample_inverse_cdf)
+    float cdf = 0.f;
+    int count = 0, last = 0;
+    for (int k = 0; k < K; ++k) {
+        const float v = (mk && !mk[k]) ? -1e8f : z[k];
+        const float p = expf(v - lse);
+        cdf += p;
+        if (cdf <= u) ++count;
+        if (p > 0.f) last = k;
+    }
+    const int a = min(count, last);
+    const float va = (mk && !mk[a]) ? -1e8f : z[a];
+    actions[e] = (int64_t)a;
+    neglogp[e] = -(va - lse);
+    if (dones_out) dones_out[e] = dones_cur[e];
+    if (valid_out) valid_out[e] = prev_dones ? (1.0f - prev_dones[e]) : 1.0f;
+}
+
+// ---- training: loss pieces + gradients at the logits / value for one minibatch -------------------------------------------------
+// partial row (8 doubles per block): sum w*a_loss, sum w*c_loss, sum w*entropy, sum w*kl, sum mask, sum mask*clipped, sum w, 0
+__global__ void __launch_bounds__(256) categorical_loss_kernel(
+    const float* __restrict__ logits, int ld, int K, const float* __restrict__ values, int value_ld,
+    const int64_t* __restrict__ actions, const uint8_t* __restrict__ action_masks, const float* __restrict__ old_values_n,
+    const float* __restrict__ returns_n, const float* __restrict__ old_neglogp, const float* __restrict__ advs_n,
+    const float* __restrict__ mask, int rows_per_chunk, int64_t chunk_stride, int M, CatLossDev c,
+    const float* __restrict__ inv_count_dev, float* __restrict__ d_logits, int d_ld, float* __restrict__ d_value, int dv_ld,
+    double* __restrict__ partials) {
+    __shared__ double sm[32 * 7];
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (m < M) {
+        const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
+        const float* z = logits + (int64_t)m * ld;
+        const uint8_t* mk = action_masks ? action_masks + ar * K : nullptr;
+        float lse;
+        cat_lse(z, mk, K, lse);
+        const int a = (int)actions[ar];
+        const float za = (mk && !mk[a]) ? -1e8f : z[a];
+        const float nlp = -(za - lse);
+        // entropy: -sum p log p over legal actions (distributions.py:38-44; unmasked: torch Categorical.entropy)
+        float ent = 0.f;
+        for (int k = 0; k < K; ++k) {
+            if (mk && !mk[k]) continue;
+            const float lp = z[k] - lse;
+            ent -= expf(lp) * lp;
+        }
+        const float mkr = mask ? mask[ar] : 1.0f;
+        const float inv_cnt = inv_count_dev ? inv_count_dev[0] : (1.0f / (float)M);
+        const float w = mkr * inv_cnt;
+        const float old_nlp = old_neglogp[ar], adv = advs_n[ar], old_v = old_values_n[ar], ret = returns_n[ar];
+        // actor loss + d/dnlp (common_losses.py:41-82)
+        float a_loss, g_a;
+        if (c.ppo) {
+            const float ratio = expf(old_nlp - nlp);
+            const float mi = 1.0f - c.e_clip, mx = 1.0f + c.e_clip;
+            float clamped, dcl;
+            if (c.smooth) {
+                const float s = 1.0f / (1.0f + expf((-(ratio - mi) / (mx - mi) + 0.5f) * 4.0f));
+                clamped = s * (mx - mi) + mi;
+                dcl = 4.0f * s * (1.0f - s);
+            } else {
+                clamped = fminf(fmaxf(ratio, mi), mx);
+                dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
+            }
+            const float t1 = -(adv * ratio), t2 = -(adv * clamped);
+            a_loss = fmaxf(t1, t2);
+            const float d1 = adv * ratio, d2 = adv * dcl * ratio;         // d(-adv * f(ratio))/dnlp = adv * f'(ratio) * ratio
+            g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
+        } else {
+            a_loss = nlp * adv;
+            g_a = adv;
+        }
+        // critic loss + d/dvalue (common_losses.py:7-38)
+        const float val = values[(int64_t)m * value_ld];
+        float c_loss, dc;
+        if (c.clip_value) {
+            const float delta = val - old_v;
+            const float vpc = old_v + fminf(fmaxf(delta, -c.e_clip), c.e_clip);
+            const float e1 = val - ret, e2 = vpc - ret;
+            const float l1 = e1 * e1, l2 = e2 * e2;
+            c_loss = fmaxf(l1, l2);
+            const float g1 = 2.0f * e1, g2 = (delta >= -c.e_clip && delta <= c.e_clip) ? 2.0f * e2 : 0.0f;
+            dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
+        } else {
+            const float e1 = ret - val;
+            c_loss = e1 * e1;
+            dc = -2.0f * e1;
+        }
+        const float dl = old_nlp - nlp;
+        const float kl = 0.5f * dl * dl;                                   // a2c_discrete.py:189
+        const float clipped = (fabsf(expf(dl) - 1.0f) > c.e_clip) ? 1.f : 0.f;
+        // gradients: loss = a + 0.5 * critic_coef * c - entropy_coef * H   (a2c_discrete.py:163-165), each a (masked) mean
+        //   dnlp/dz_k = p_k - [k == a];   dH/dz_k = -p_k (log p_k + H)
+        float* dz = d_logits + (int64_t)m * d_ld;
+        for (int k = 0; k < K; ++k) {
+            float g = 0.f;
+            if (!(mk && !mk[k])) {
+                const float lp = z[k] - lse, p = expf(lp);
+                g = w * (g_a * (p - (k == a ? 1.0f : 0.0f)) + c.entropy_coef * p * (lp + ent));
+            }
+            dz[k] = g;
+        }
+        d_value[(int64_t)m * dv_ld] = w * 0.5f * c.critic_coef * dc;
+        acc[0] = (double)w * a_loss; acc[1] = (double)w * c_loss; acc[2] = (double)w * ent; acc[3] = (double)w * kl;
+        acc[4] = mkr; acc[5] = mkr * clipped; acc[6] = w;
+    }
+    block_sum_d<7>(acc, sm);
+    if (threadIdx.x == 0) {
+        double* p = partials + (int64_t)blockIdx.x * 8;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) p[i] = acc[i];
+        p[7] = 0.0;
+    }
+}
+
+}  // namespace
+
+B200RL_EXPORT int b200rl_categorical_sample_f32(const float* logits, int ld, int K, const float* value_raw, int value_ld,
+                                                const uint8_t* action_masks, const float* u_tape, uint64_t seed,
+                                                const uint64_t* rng_epoch_dev, uint32_t step_index, const double* vms_mean,
+                                                const double* vms_var, int normalize_value, int64_t* actions, float* neglogp,
+                                                float* values, const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones,
+                                                float* valid_out, int N, int values_only, void* stream) {
+    if (!value_raw || !values || N <= 0 || value_ld <= 0) return B200RL_EINVAL;
+    if (!values_only && (!logits || !actions || !neglogp || K <= 0 || K > CAT_MAXK || ld < K)) return B200RL_EINVAL;
+    if (normalize_value && (!vms_mean || !vms_var)) return B200RL_EINVAL;
+    if (dones_out && !dones_cur) return B200RL_EINVAL;
+    categorical_sample_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(
+        logits, ld, K, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch_dev, step_index, vms_mean, vms_var, normalize_value,
+        actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K, const float* values, int value_ld,
+                                              const int64_t* actions, const uint8_t* action_masks, const float* old_values_n,
+                                              const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
+                                              int rows_per_chunk, int64_t chunk_stride, int M, const b200rl_cat_loss_cfg* cfg_host,
+                                              const float* inv_count_dev, float* d_logits, int d_ld, float* d_value, int dv_ld,
+                                              double* partials, int max_partials, int* n_blocks_out_host, void* stream) {
+    if (!logits || !values || !actions || !old_values_n || !returns_n || !old_neglogp || !advs_n || !cfg_host || !d_logits || !d_value ||
+        !partials)
+        return B200RL_EINVAL;
+    if (M <= 0 || K <= 0 || K > CAT_MAXK || ld < K || d_ld < K || value_ld <= 0 || dv_ld <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
+    const int blocks = (M + 255) / 256;
+    if (n_blocks_out_host) *n_blocks_out_host = blocks;
+    if (blocks > max_partials) return B200RL_EINVAL;
+    CatLossDev c{cfg_host->e_clip, cfg_host->critic_coef, cfg_host->entropy_coef, cfg_host->clip_value, cfg_host->use_smooth_clamp,
+                 cfg_host->ppo};
+    categorical_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(logits, ld, K, values, value_ld, actions, action_masks, old_values_n,
+                                                                  returns_n, old_neglogp, advs_n, mask, rows_per_chunk, chunk_stride, M, c,
+                                                                  inv_count_dev, d_logits, d_ld, d_value, dv_ld, partials);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}

@@ -433,3 +433,27 @@ def lstm_cell_bwd(gates_act, c_t, cin, dgates, dcin, S, Hd, dH=None, scatter_rpc
 def rnn_mask_rows(inp, in_rpc, in_stride, out, S, Hd, done=None, done_rpc=0, done_stride=0):
     check(lib.b200rl_rnn_mask_rows_f32(ptr(inp), in_rpc, in_stride, ptr(out), ptr(done), done_rpc, done_stride, S, Hd, _stream()),
           'rnn_mask_rows')
+
+
+# ------------------------------------------------------------------------------------------ categorical head (discrete PPO; csrc/discrete.cu)
+class CatLossCfg(ctypes.Structure):
+    _fields_ = [('e_clip', ctypes.c_float), ('critic_coef', ctypes.c_float), ('entropy_coef', ctypes.c_float),
+                ('clip_value', ctypes.c_int), ('use_smooth_clamp', ctypes.c_int), ('ppo', ctypes.c_int)]
+
+
+def categorical_sample(logits, ld, K, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch, step_index, vms_mean, vms_var,
+                       normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only=False):
+    check(lib.b200rl_categorical_sample_f32(ptr(logits), ld, K, ptr(value_raw), value_ld, ptr(action_masks), ptr(u_tape), seed,
+                                            ptr(rng_epoch), step_index, ptr(vms_mean), ptr(vms_var), int(normalize_value),
+                                            ptr(actions), ptr(neglogp), ptr(values), ptr(dones_cur), ptr(dones_out), ptr(prev_dones),
+                                            ptr(valid_out), N, int(values_only), _stream()), 'categorical_sample')
+
+
+def categorical_loss(logits, ld, K, values, value_ld, actions, action_masks, old_values_n, returns_n, old_neglogp, advs_n, mask,
+                     rows_per_chunk, chunk_stride, M, cfg, inv_count, d_logits, d_ld, d_value, dv_ld, partials):
+    nb = ctypes.c_int(0)
+    check(lib.b200rl_categorical_loss_f32(ptr(logits), ld, K, ptr(values), value_ld, ptr(actions), ptr(action_masks), ptr(old_values_n),
+                                          ptr(returns_n), ptr(old_neglogp), ptr(advs_n), ptr(mask), rows_per_chunk, chunk_stride, M,
+                                          ctypes.addressof(cfg), ptr(inv_count), ptr(d_logits), d_ld, ptr(d_value), dv_ld,
+                                          ptr(partials), partials.shape[0], ctypes.addressof(nb), _stream()), 'categorical_loss')
+    return nb.value

@@ -40,10 +40,17 @@ def _override_sigma(agent, args):
                 print('Cannot set new sigma because fixed_sigma is False')
 
 
+def _discrete_agent(**kwargs):
+    from .agent_discrete import DiscreteA2CAgent
+    return DiscreteA2CAgent(**kwargs)
+
+
 class Runner:
     def __init__(self, algo_observer=None):
         self.algo_factory = ObjectFactory()
         self.algo_factory.register_builder('a2c_continuous', lambda **kwargs: A2CAgent(**kwargs))
+        # discrete PPO: implemented, not yet validated on hardware (agent_discrete.py refuses to start without b200_unvalidated: True)
+        self.algo_factory.register_builder('a2c_discrete', lambda **kwargs: _discrete_agent(**kwargs))
         self.player_factory = ObjectFactory()
         self._observer_was_injected = algo_observer is not None
         self.algo_observer = algo_observer if algo_observer else DefaultAlgoObserver()
