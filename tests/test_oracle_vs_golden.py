@@ -297,3 +297,59 @@ def test_central_value_train_epochs_match_reference_agent():
         assert int(cv.value_mean_std.count) == int(st['value_mean_std.count'])
         # the actor model's own value normaliser never moves when a central value exists
         assert int(ref['state']['value_mean_std.count']) == 1
+
+
+def test_categorical_head_gradient_formulas_match_autograd():
+    """The closed-form gradients that csrc/discrete.cu::categorical_loss_kernel implements, restated with torch ops and checked
+    against autograd through the oracle's loss (the CUDA kernel itself is checked on a GPU by tests/test_discrete_gpu.py):
+        dnlp/dz_k = p_k - [k == a];  dH/dz_k = -p_k (log p_k + H);  d(actor)/dnlp = adv * f'(ratio) * ratio on the active branch;
+        d(critic)/dV from the clipped / unclipped branch;  every term weighted by mask / sum(mask)."""
+    from oracle import ppo_discrete_oracle as DO
+    g = torch.Generator().manual_seed(5)
+    M, K, e_clip, critic_coef, ent_coef = 300, 6, 0.2, 1.0, 0.01
+    for masked in (False, True):
+        logits = (torch.randn(M, K, generator=g) * 1.5).requires_grad_(True)
+        value = torch.randn(M, 1, generator=g).requires_grad_(True)
+        amask = None
+        if masked:
+            amask = torch.rand(M, K, generator=g) < 0.7
+            amask[torch.arange(M), torch.randint(0, K, (M,), generator=g)] = True
+        nl, probs, ent = DO.categorical_masked(logits, amask)
+        actions = DO.sample_inverse_cdf(probs.detach(), torch.rand(M, generator=g))
+        old_nlp = -nl.detach().gather(1, actions.unsqueeze(1)).squeeze(1) + torch.randn(M, generator=g) * 0.2
+        adv, old_v, ret = torch.randn(M, generator=g), torch.randn(M, 1, generator=g), torch.randn(M, 1, generator=g)
+        rmask = (torch.rand(M, generator=g) < 0.8).float() if masked else None
+        nlp = -nl.gather(1, actions.unsqueeze(1)).squeeze(1)
+        a = O.actor_loss(old_nlp, nlp, adv, True, e_clip, smooth=False)
+        c = O.critic_loss(old_v, value, e_clip, ret, True)
+        losses, _ = O.apply_masks([a.unsqueeze(1), c, ent.unsqueeze(1)], rmask)
+        (losses[0] + 0.5 * losses[1] * critic_coef - losses[2] * ent_coef).backward()
+        # ---- the kernel's arithmetic ----
+        with torch.no_grad():
+            z = logits.detach() if amask is None else torch.where(amask, logits.detach(), torch.tensor(-1e8))
+            lse = torch.logsumexp(z, dim=1, keepdim=True)
+            lp = z - lse
+            p = lp.exp()
+            legal = torch.ones_like(p, dtype=torch.bool) if amask is None else amask
+            H = -(torch.where(legal, p * lp, torch.zeros_like(p))).sum(1, keepdim=True)
+            nlp_k = -lp.gather(1, actions.unsqueeze(1)).squeeze(1)
+            w = (torch.ones(M) / M) if rmask is None else rmask / rmask.sum()
+            ratio = torch.exp(old_nlp - nlp_k)
+            clamped = ratio.clamp(1 - e_clip, 1 + e_clip)
+            dcl = ((ratio >= 1 - e_clip) & (ratio <= 1 + e_clip)).float()
+            t1, t2 = -(adv * ratio), -(adv * clamped)
+            d1, d2 = adv * ratio, adv * dcl * ratio
+            g_a = torch.where(t1 > t2, d1, torch.where(t1 < t2, d2, 0.5 * (d1 + d2)))
+            onehot = torch.nn.functional.one_hot(actions, K).float()
+            dz = w.unsqueeze(1) * (g_a.unsqueeze(1) * (p - onehot) + ent_coef * p * (lp + H))
+            dz = torch.where(legal, dz, torch.zeros_like(dz))
+            val = value.detach()
+            delta = val - old_v
+            vpc = old_v + delta.clamp(-e_clip, e_clip)
+            e1, e2 = val - ret, vpc - ret
+            l1, l2 = e1 * e1, e2 * e2
+            g1, g2 = 2 * e1, torch.where((delta >= -e_clip) & (delta <= e_clip), 2 * e2, torch.zeros_like(e2))
+            dc = torch.where(l1 > l2, g1, torch.where(l1 < l2, g2, 0.5 * (g1 + g2)))
+            dv = w.unsqueeze(1) * 0.5 * critic_coef * dc
+        torch.testing.assert_close(dz, logits.grad, rtol=1e-4, atol=1e-8)
+        torch.testing.assert_close(dv, value.grad, rtol=1e-5, atol=1e-9)
