@@ -160,10 +160,8 @@ class DiscreteA2CAgent:
             raise NotImplementedError('multi_gpu is not supported by the discrete B200 agent yet')
         self.multi_gpu, self.world_size, self.global_rank, self.local_rank = False, 1, 0, 0
         self.ppo_device = config.get('device', 'cuda:0')
-        if not str(self.ppo_device).startswith('cuda'):
-            raise RuntimeError('rl_games_b200 agents run on CUDA only (device=%r): there is no CPU fallback' % self.ppo_device)
+        self._require_cuda()
         self.device_t = torch.device(self.ppo_device)
-        torch.cuda.set_device(self.device_t)
         self.num_actors = config['num_actors']
         self.env_name = config['env_name']
         self.env_info = config.get('env_info')
@@ -264,6 +262,16 @@ class DiscreteA2CAgent:
     @property
     def device(self):
         return self.ppo_device
+
+    def _require_cuda(self):
+        """no CPU fallback: the kernels are the product (the host-logic test replaces this hook together with every op)"""
+        if not str(self.ppo_device).startswith('cuda'):
+            raise RuntimeError('rl_games_b200 agents run on CUDA only (device=%r): there is no CPU fallback' % self.ppo_device)
+        torch.cuda.set_device(torch.device(self.ppo_device))
+
+    @staticmethod
+    def _sync():
+        torch.cuda.synchronize()
 
     def _meter_host(self):
         if self._meter_cache is None:
@@ -517,7 +525,7 @@ class DiscreteA2CAgent:
         t0 = time.perf_counter()
         step_time = self.play_steps(u)
         self._gae_and_prepare()
-        torch.cuda.synchronize()
+        self._sync()
         t1 = time.perf_counter()
         self.curr_frames = self.batch_size
         self.algo_observer.after_steps()
@@ -530,7 +538,7 @@ class DiscreteA2CAgent:
                                                                     av_kl.item())                  # one host sync per mini-epoch (:1271)
             self.opt_state[0] = self.last_lr                        # update_lr
             kls.append(av_kl)
-        torch.cuda.synchronize()
+        self._sync()
         t2 = time.perf_counter()
         st = torch.stack(rows)
         self.last_stats = st

@@ -1,0 +1,259 @@
+"""Torch (CPU) stand-ins for the C-ABI ops used by ``rl_games_b200.agent_discrete`` -- TEST INFRASTRUCTURE ONLY.
+
+They restate, tensor for tensor, what each kernel does (argument meaning, arena addressing through (rows_per_chunk, chunk_stride),
+split-partial layout, in-place state updates), so that the HOST logic of the agent (arena views, flat-parameter offsets, call order,
+scheduler, checkpoints) can be exercised against the reference's golden runs without a GPU.  They are installed by monkeypatching
+``rl_games_b200.ops`` inside one test; nothing in the product imports this module, and it proves nothing about the CUDA kernels
+themselves (those are checked on a GPU against the same oracle).
+"""
+import torch
+
+from oracle import ppo_discrete_oracle as DO
+from oracle import ppo_oracle as O
+
+ACT = {0: lambda x: x, 1: torch.nn.functional.elu, 2: torch.relu, 3: torch.tanh}
+
+
+def _act_grad_from_out(a, act):
+    if act == 1:
+        return torch.where(a > 0, torch.ones_like(a), a + 1.0)
+    if act == 2:
+        return (a > 0).float()
+    if act == 3:
+        return 1.0 - a * a
+    return torch.ones_like(a)
+
+
+def _flat(t):
+    """1-D view of the storage from t's first element to the end of the storage (what a raw device pointer addresses)"""
+    n = t.untyped_storage().nbytes() // t.element_size() - t.storage_offset()
+    return torch.as_strided(t, (n,), (1,))
+
+
+def _rows(X, M, K, rows_per_chunk, chunk_stride, x_ld):
+    m = torch.arange(M)
+    if rows_per_chunk is None:
+        r = m
+    else:
+        c = m // rows_per_chunk
+        r = c * chunk_stride + (m - c * rows_per_chunk)
+    idx = r.unsqueeze(1) * x_ld + torch.arange(K).unsqueeze(0)
+    return _flat(X)[idx]
+
+
+def _norm(x, mean, std):
+    return x if mean is None else torch.clamp((x - mean) / std, -5.0, 5.0)
+
+
+def linear_fwd(X, W, b, Y, act, rows_per_chunk=None, chunk_stride=0, x_ld=None, norm_mean=None, norm_std=None, M=None, accumulate=False):
+    Nout, K = W.shape
+    M = Y.shape[0] if M is None else M
+    x = _norm(_rows(X, M, K, rows_per_chunk, chunk_stride, K if x_ld is None else x_ld), norm_mean, norm_std)
+    y = x @ W.t() + b
+    if accumulate:
+        y = y + Y[:M]
+    Y[:M] = ACT[act](y)
+
+
+def linear_bwd_data(dY, W, A_prev, dX, act_prev, M=None):
+    M = dY.shape[0] if M is None else M
+    g = dY[:M] @ W
+    dX[:M] = g if A_prev is None else g * _act_grad_from_out(A_prev[:M], act_prev)
+
+
+def linear_bwd_weight(dY, X, dW_part, db_part, K, Nout, n_splits, rows_per_chunk=None, chunk_stride=0, x_ld=None, norm_mean=None,
+                      norm_std=None, M=None, split_stride=None):
+    M = dY.shape[0] if M is None else M
+    x = _norm(_rows(X, M, K, rows_per_chunk, chunk_stride, K if x_ld is None else x_ld), norm_mean, norm_std)
+    dW, db = dY[:M].t() @ x, dY[:M].sum(0)
+    fw, fb = _flat(dW_part), _flat(db_part)
+    for s in range(n_splits):          # the kernel spreads the rows over the splits; the sum is what matters: all of it in split 0
+        fw[s * split_stride:s * split_stride + Nout * K] = dW.reshape(-1) if s == 0 else 0.0
+        fb[s * split_stride:s * split_stride + Nout] = db if s == 0 else 0.0
+
+
+def reduce_splits(part, out, n, n_splits, split_stride=None):
+    stride = n if split_stride is None else split_stride
+    f = _flat(part)
+    out[:n] = sum(f[s * stride:s * stride + n] for s in range(n_splits))
+
+
+def refresh_norm(mean, var, mean_f32, std_f32, eps=1e-5):
+    mean_f32.copy_(mean.float())
+    std_f32.copy_(torch.sqrt(var.float() + eps))
+
+
+def moments_update(x, D, rows_per_chunk, n_chunks, chunk_stride, mean, var, count, mean_f32, std_f32, scratch, counter, eps=1e-5):
+    rows = _rows(x, rows_per_chunk * n_chunks, D, rows_per_chunk, chunk_stride, D).double()
+    n = rows.shape[0]
+    bm, bv = rows.mean(0), rows.var(0, unbiased=False)
+    tot = count.double() + n
+    delta = bm - mean
+    m2 = var * count.double() + bv * n + delta ** 2 * count.double() * n / tot
+    mean.add_(delta * n / tot)
+    var.copy_(m2 / tot)
+    count.add_(n)
+    refresh_norm(mean, var, mean_f32, std_f32, eps)
+
+
+def mask_inv_counts(mask, H, N, envs_per_mb, inv_count):
+    for i in range(N // envs_per_mb):
+        inv_count[i] = 1.0 / max(float(mask[:, i * envs_per_mb:(i + 1) * envs_per_mb].sum()), 1.0)
+
+
+def gae_fused(rewards, values, dones_u8, last_values, last_dones_u8, mask, advs, returns, partials, gamma, tau):
+    a = O.gae(rewards.unsqueeze(2), values.unsqueeze(2), dones_u8.float(), last_values.unsqueeze(1), last_dones_u8.float(), gamma, tau).squeeze(2)
+    advs.copy_(a)
+    returns.copy_(a + values)
+    w = torch.ones_like(values) if mask is None else (mask != 0).float()
+    da = (returns - values).double()
+    v, r, wd = values.double(), returns.double(), w.double()
+    partials.zero_()
+    partials[0, :7] = torch.stack([wd.sum(), (wd * v).sum(), (wd * v * v).sum(), (wd * r).sum(), (wd * r * r).sum(), (wd * da).sum(),
+                                   (wd * da * da).sum()])
+    return 1
+
+
+def prepare_batch(values, returns, mask, partials, n_partials, vms_mean, vms_var, vms_count, old_values_n, returns_n, advs_n,
+                  normalize_value, normalize_advantage, freeze_stats=False):
+    acc = partials[:n_partials].sum(0)
+    n = float(acc[0])
+    mean, var, cnt = float(vms_mean[0]), float(vms_var[0]), float(vms_count[0])
+
+    def merge(mean, var, cnt, bm, bv, bn):
+        tot = cnt + bn
+        d = bm - mean
+        return mean + d * bn / tot, (var * cnt + bv * bn + d * d * cnt * bn / tot) / tot, tot
+    mean_v, var_v = mean, var
+    if normalize_value and not freeze_stats and n > 0:
+        mv = float(acc[1]) / n
+        mean, var, cnt = merge(mean, var, cnt, mv, max(float(acc[2]) / n - mv * mv, 0.0), n)
+        mean_v, var_v = mean, var
+        mr = float(acc[3]) / n
+        mean, var, cnt = merge(mean, var, cnt, mr, max(float(acc[4]) / n - mr * mr, 0.0), n)
+        if mask is not None:
+            mean_v, var_v = mean, var
+        vms_mean[0], vms_var[0] = mean, var
+        vms_count[0] = int(vms_count[0]) + 2 * int(round(n))
+
+    def nc(x, m, v):
+        return torch.clamp((x - float(torch.tensor(m, dtype=torch.float32))) / torch.sqrt(torch.tensor(v, dtype=torch.float32) + 1e-5), -5.0, 5.0)
+    a = returns - values
+    old_values_n.copy_(nc(values, mean_v, var_v) if normalize_value else values)
+    returns_n.copy_(nc(returns, mean, var) if normalize_value else returns)
+    if normalize_advantage:
+        if mask is None:
+            m = float(acc[5]) / n
+            v = max((float(acc[6]) - n * m * m) / (n - 1.0), 0.0)
+        else:
+            sm = max(n, 1.0)
+            m = float(acc[5]) / sm
+            v = max((float(acc[6]) / sm - m * m) * sm / max(sm - 1.0, 1.0), 0.0)
+        a = (a - m) / (v ** 0.5 + 1e-8)
+    advs_n.copy_(a)
+
+
+def post_step(rewards, dones, time_outs, values_t, valid_t, rewards_out_t, dones_cur, prev_dones, ep_state, meter, games_to_track, scratch,
+              counter, N, cfg):
+    r = rewards.float()
+    sh = torch.clamp((r + cfg.shift_value) * cfg.scale_value, cfg.min_val, cfg.max_val)
+    if cfg.log_val:
+        sh = torch.log(sh)
+    if cfg.value_bootstrap and time_outs is not None:
+        sh = sh + cfg.gamma * values_t * time_outs.float()
+    rewards_out_t.copy_(sh)
+    live = torch.ones(N) if valid_t is None else valid_t
+    cr, cs, cl = ep_state[0] + r * live, ep_state[1] + sh * live, ep_state[2] + live
+    d = dones.float()
+    done = d != 0
+    n = int(done.sum())
+    if n > 0:          # AverageMeter.update (torch_ext.py:333-342)
+        size = min(n, games_to_track)
+        old = min(games_to_track - size, float(meter[3]))
+        tot = old + size
+        for slot, x in ((0, cr), (1, cs), (2, cl)):
+            meter[slot] = (float(meter[slot]) * old + float(x[done].double().mean()) * size) / tot
+        meter[3] = tot
+        meter[4] += n
+    nd = 1.0 - d
+    ep_state[0], ep_state[1], ep_state[2] = cr * nd, cs * nd, cl * nd
+    dones_cur.copy_(done.to(torch.uint8))
+    if prev_dones is not None:
+        prev_dones.copy_(d)
+
+
+def categorical_sample(logits, ld, K, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch, step_index, vms_mean, vms_var,
+                       normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only=False):
+    val = _flat(value_raw)[torch.arange(N) * value_ld]
+    if normalize_value:
+        val = torch.sqrt(vms_var.float() + 1e-5) * torch.clamp(val, -5.0, 5.0) + vms_mean.float()
+    values.copy_(val)
+    if values_only:
+        return
+    z = _flat(logits)[(torch.arange(N) * ld).unsqueeze(1) + torch.arange(K).unsqueeze(0)]
+    nl, probs, _ = DO.categorical_masked(z, None if action_masks is None else action_masks.bool())
+    assert u_tape is not None, 'the host-logic test always supplies the uniform tape'
+    a = DO.sample_inverse_cdf(probs, u_tape)
+    actions.copy_(a)
+    neglogp.copy_(-nl.gather(1, a.unsqueeze(1)).squeeze(1))
+    if dones_out is not None:
+        dones_out.copy_(dones_cur)
+    if valid_out is not None:
+        valid_out.copy_(1.0 - prev_dones if prev_dones is not None else torch.ones(N))
+
+
+def categorical_loss(logits, ld, K, values, value_ld, actions, action_masks, old_values_n, returns_n, old_neglogp, advs_n, mask,
+                     rows_per_chunk, chunk_stride, M, cfg, inv_count, d_logits, d_ld, d_value, dv_ld, partials):
+    mrow = torch.arange(M)
+    z = _flat(logits)[(mrow * ld).unsqueeze(1) + torch.arange(K).unsqueeze(0)].clone().requires_grad_(True)
+    v = _flat(values)[mrow * value_ld].clone().requires_grad_(True)
+
+    def arena(t, width=1):
+        return _rows(t, M, width, rows_per_chunk, chunk_stride, width)
+    act = arena(actions).squeeze(1)
+    am = None if action_masks is None else arena(action_masks, K).bool()
+    rm = None if mask is None else arena(mask).squeeze(1)
+    old_nlp, adv = arena(old_neglogp).squeeze(1), arena(advs_n).squeeze(1)
+    nl, probs, ent = DO.categorical_masked(z, am)
+    nlp = -nl.gather(1, act.unsqueeze(1)).squeeze(1)
+    a = O.actor_loss(old_nlp, nlp, adv, bool(cfg.ppo), cfg.e_clip, smooth=bool(cfg.use_smooth_clamp))
+    c = O.critic_loss(arena(old_values_n), v.unsqueeze(1), cfg.e_clip, arena(returns_n), bool(cfg.clip_value))
+    w = torch.full((M,), 1.0 / M) if inv_count is None else rm * inv_count[0]
+    la, lc, le = (a * w).sum(), (c.squeeze(1) * w).sum(), (ent * w).sum()
+    (la + 0.5 * cfg.critic_coef * lc - cfg.entropy_coef * le).backward()
+    _flat(d_logits)[(mrow * d_ld).unsqueeze(1) + torch.arange(K).unsqueeze(0)] = z.grad
+    _flat(d_value)[mrow * dv_ld] = v.grad
+    kl = (0.5 * (old_nlp - nlp.detach()) ** 2 * w).sum()
+    partials.zero_()
+    partials[0, :4] = torch.stack([la.detach(), lc.detach(), le.detach(), kl]).double()
+    return 1
+
+
+def adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None, wpack=None, pack_table=None,
+              merge_next=None):
+    n = params.numel() if n is None else n
+    g = grads[:n] * float(cfg.grad_scale)
+    if cfg.truncate_grads:
+        g = g * min(float(cfg.grad_norm) / (float(g.norm()) + 1e-6), 1.0)
+    lr, step = float(state_d[0]), float(state_d[1]) + 1.0
+    p1 = (float(state_d[2]) if float(state_d[2]) > 0 else 1.0) * cfg.beta1
+    p2 = (float(state_d[3]) if float(state_d[3]) > 0 else 1.0) * cfg.beta2
+    if cfg.weight_decay:
+        g = g + cfg.weight_decay * params[:n]
+    exp_avg[:n] = exp_avg[:n] + (g - exp_avg[:n]) * (1.0 - cfg.beta1)
+    exp_avg_sq[:n] = cfg.beta2 * exp_avg_sq[:n] + (1.0 - cfg.beta2) * g * g
+    denom = exp_avg_sq[:n].sqrt() / (1.0 - p2) ** 0.5 + cfg.eps
+    params[:n] -= (lr / (1.0 - p1)) * exp_avg[:n] / denom
+    state_d[1], state_d[2], state_d[3] = step, p1, p2
+
+
+def bump_u64(p):
+    p.add_(1)
+
+
+def install(monkeypatch):
+    """replace the ops the discrete agent calls by the stand-ins above"""
+    from rl_games_b200 import ops
+    for name in ('linear_fwd', 'linear_bwd_data', 'linear_bwd_weight', 'reduce_splits', 'refresh_norm', 'moments_update', 'mask_inv_counts',
+                 'gae_fused', 'prepare_batch', 'post_step', 'categorical_sample', 'categorical_loss', 'adam_step', 'bump_u64'):
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -1,0 +1,100 @@
+"""Host logic of rl_games_b200.agent_discrete.DiscreteA2CAgent on CPU: every op it calls is replaced by a torch stand-in
+(tests/_torch_ops.py) that restates the kernel's contract, and the agent is run against the reference's golden discrete runs.
+This checks arena addressing, flat-parameter offsets (incl. the split heads of a separate critic), call order, the per-mini-epoch
+scheduler, meters and checkpoint keys -- NOT the CUDA kernels (tests/test_discrete_gpu.py does that on a GPU)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+class _Env:
+    def __init__(self, g):
+        self.g, self.K, self.i = g, g['K'], 0
+
+    def reset(self):
+        self.i = 0
+        return self.g['obs_tape'][0].clone()
+
+    def get_action_masks(self):
+        return self.g['mask_tape'][self.i % self.g['mask_tape'].shape[0]]
+
+    def step(self, actions):
+        g = self.g
+        j0 = self.i % g['obs_tape'].shape[0]
+        rew = (actions.long() == g['obs_tape'][j0][:, :self.K].argmax(dim=-1)).float()
+        self.i += 1
+        j = self.i % g['obs_tape'].shape[0]
+        return g['obs_tape'][j].clone(), rew, g['done_tape'][j].clone(), {'time_outs': g['timeout_tape'][j].clone()}
+
+    def get_env_info(self):
+        from rl_games_b200.common import Box, Discrete
+        info = {'observation_space': Box(-np.inf, np.inf, (self.g['obs_tape'].shape[-1],)), 'action_space': Discrete(self.K)}
+        if self.g['autoreset'] != 'same_step':
+            info['autoreset_mode'] = self.g['autoreset']
+        return info
+
+
+@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt'])
+def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _torch_ops
+    from rl_games_b200 import agent_discrete
+    from rl_games_b200.runner import Runner
+    _torch_ops.install(monkeypatch)
+    monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_require_cuda', lambda self: None)
+    monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_sync', staticmethod(lambda: None))
+    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    cfgk = g['config']
+    env = _Env(g)
+    config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
+    config.update({'device': 'cpu', 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1},
+                   'b200_unvalidated': True, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+    network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'discrete': None},
+               'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}
+    r = Runner()
+    r.load({'params': {'seed': 1, 'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'discrete_a2c'}, 'network': network, 'config': config}})
+    r.params['config']['vec_env'] = env
+    agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
+    agent.model.load_state_dict(g['init_state'], strict=False)
+    assert agent.model.param_names() == g['param_order']
+    agent.init_tensors()
+    agent.obs = agent.env_reset()
+    fl = lambda t: t.transpose(0, 1).reshape(-1, *t.shape[2:])    # noqa: E731
+    for ep, ref in enumerate(g['epochs_out']):
+        agent.epoch_num += 1
+        res = agent.train_epoch(u=g['u'][ep])
+        ds = ref['dataset']
+        assert torch.equal(agent.actions, ref['mb_actions'])
+        if g['use_action_masks']:
+            assert torch.equal(fl(agent.action_masks).bool(), ds['action_masks'])
+        if ds.get('rnn_masks') is not None:
+            assert torch.equal(fl(agent.valid), ds['rnn_masks'])
+        torch.testing.assert_close(agent.rewards.unsqueeze(2), ref['mb_rewards'], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(agent.values.unsqueeze(2), ref['mb_values'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(fl(agent.advs_n), ds['advantages'], rtol=2e-4, atol=2e-5)
+        torch.testing.assert_close(fl(agent.returns_n).unsqueeze(1), ds['returns'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(fl(agent.neglogpacs), ds['old_logp_actions'], rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(torch.stack(res[4]), ref['a_losses'], rtol=2e-3, atol=2e-6)
+        torch.testing.assert_close(torch.stack(res[5]), ref['c_losses'], rtol=2e-3, atol=2e-6)
+        torch.testing.assert_close(torch.stack(res[6]), ref['entropies'], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(torch.stack(res[7]), ref['kls'], rtol=5e-3, atol=1e-8)
+        assert agent.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
+        sd = agent.model.state_dict()
+        for k in g['param_order']:
+            torch.testing.assert_close(sd[k], ref['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
+        if cfgk.get('normalize_input'):
+            assert int(sd['running_mean_std.count']) == int(ref['state']['running_mean_std.count'])
+            torch.testing.assert_close(sd['value_mean_std.running_var'], ref['state']['value_mean_std.running_var'].reshape(-1), rtol=1e-5, atol=1e-7)
+        assert agent.game_rewards.current_size == ref['game_rewards_size']
+        torch.testing.assert_close(agent.game_rewards.mean, ref['game_rewards_mean'].reshape(-1), rtol=1e-4, atol=1e-5)
+    # checkpoint keys / Adam state in the reference's order
+    ck = agent.get_full_state_weights()
+    assert [k for k in ck['model'] if k.startswith('a2c_network')] == g['param_order']
+    ref_m = g['epochs_out'][-1]['adam_exp_avg']
+    for i, m in enumerate(ref_m):
+        torch.testing.assert_close(ck['optimizer']['state'][i]['exp_avg'].reshape(m.shape), m, rtol=1e-3, atol=1e-7)
