@@ -16,8 +16,11 @@ constexpr int CAT_MAXK = 64;
 
 struct CatLossDev { float e_clip, critic_coef, entropy_coef; int clip_value, smooth, ppo; };
 
+// ---- per-row arithmetic: __host__ __device__ so that the SAME code is exercised on the CPU by the host test entry points at the
+//      end of this file (tests/test_discrete_rows_cpu.py) -- the kernels below only add indexing and the block reduction ----------
+
 // masked log-softmax pieces of one row: legal-max m, lse = m + log(sum exp(z - m)); masked logits count as -1e8 (distributions.py:29)
-__device__ __forceinline__ void cat_lse(const float* __restrict__ z, const uint8_t* __restrict__ mask, int K, float& lse) {
+__host__ __device__ inline void cat_lse(const float* z, const uint8_t* mask, int K, float& lse) {
     float m = -3.0e38f;
     for (int k = 0; k < K; ++k) {
         const float v = (mask && !mask[k]) ? -1e8f : z[k];
@@ -29,6 +32,96 @@ __device__ __forceinline__ void cat_lse(const float* __restrict__ z, const uint8
         s += expf(v - m);
     }
     lse = m + logf(s);
+}
+
+// action = #{k : cdf_k <= u}, clamped to the last action of non-zero probability (oracle.sample_inverse_cdf); returns neglogp too
+__host__ __device__ inline int cat_sample_row(const float* z, const uint8_t* mk, int K, float u, float& neglogp) {
+    float lse;
+    cat_lse(z, mk, K, lse);
+    float cdf = 0.f;
+    int count = 0, last = 0;
+    for (int k = 0; k < K; ++k) {
+        const float v = (mk && !mk[k]) ? -1e8f : z[k];
+        const float p = expf(v - lse);
+        cdf += p;
+        if (cdf <= u) ++count;
+        if (p > 0.f) last = k;
+    }
+    const int a = count < last ? count : last;
+    const float va = (mk && !mk[a]) ? -1e8f : z[a];
+    neglogp = -(va - lse);
+    return a;
+}
+
+struct CatRowOut { float a_loss, c_loss, ent, kl, clipped, d_value; };
+
+// loss pieces of one row and the gradient of  w * (a + 0.5 * critic_coef * c - entropy_coef * H)  w.r.t. its logits (dz[K]) / value
+__host__ __device__ inline CatRowOut cat_loss_row(const float* z, const uint8_t* mk, int K, int a, float val, float old_nlp, float adv,
+                                                  float old_v, float ret, float w, const CatLossDev& c, float* dz) {
+    float lse;
+    cat_lse(z, mk, K, lse);
+    const float za = (mk && !mk[a]) ? -1e8f : z[a];
+    const float nlp = -(za - lse);
+    // entropy: -sum p log p over legal actions (distributions.py:38-44; unmasked: torch Categorical.entropy)
+    float ent = 0.f;
+    for (int k = 0; k < K; ++k) {
+        if (mk && !mk[k]) continue;
+        const float lp = z[k] - lse;
+        ent -= expf(lp) * lp;
+    }
+    // actor loss + d/dnlp (common_losses.py:41-82)
+    float a_loss, g_a;
+    if (c.ppo) {
+        const float ratio = expf(old_nlp - nlp);
+        const float mi = 1.0f - c.e_clip, mx = 1.0f + c.e_clip;
+        float clamped, dcl;
+        if (c.smooth) {
+            const float s = 1.0f / (1.0f + expf((-(ratio - mi) / (mx - mi) + 0.5f) * 4.0f));
+            clamped = s * (mx - mi) + mi;
+            dcl = 4.0f * s * (1.0f - s);
+        } else {
+            clamped = fminf(fmaxf(ratio, mi), mx);
+            dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
+        }
+        const float t1 = -(adv * ratio), t2 = -(adv * clamped);
+        a_loss = fmaxf(t1, t2);
+        const float d1 = adv * ratio, d2 = adv * dcl * ratio;             // d(-adv * f(ratio))/dnlp = adv * f'(ratio) * ratio
+        g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
+    } else {
+        a_loss = nlp * adv;
+        g_a = adv;
+    }
+    // critic loss + d/dvalue (common_losses.py:7-38)
+    float c_loss, dc;
+    if (c.clip_value) {
+        const float delta = val - old_v;
+        const float vpc = old_v + fminf(fmaxf(delta, -c.e_clip), c.e_clip);
+        const float e1 = val - ret, e2 = vpc - ret;
+        const float l1 = e1 * e1, l2 = e2 * e2;
+        c_loss = fmaxf(l1, l2);
+        const float g1 = 2.0f * e1, g2 = (delta >= -c.e_clip && delta <= c.e_clip) ? 2.0f * e2 : 0.0f;
+        dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
+    } else {
+        const float e1 = ret - val;
+        c_loss = e1 * e1;
+        dc = -2.0f * e1;
+    }
+    const float dl = old_nlp - nlp;
+    // gradients: dnlp/dz_k = p_k - [k == a];   dH/dz_k = -p_k (log p_k + H)   (a2c_discrete.py:163-165: each loss is a (masked) mean)
+    for (int k = 0; k < K; ++k) {
+        float g = 0.f;
+        if (!(mk && !mk[k])) {
+            const float lp = z[k] - lse, p = expf(lp);
+            g = w * (g_a * (p - (k == a ? 1.0f : 0.0f)) + c.entropy_coef * p * (lp + ent));
+        }
+        dz[k] = g;
+    }
+    CatRowOut o;
+    o.a_loss = a_loss; o.c_loss = c_loss; o.ent = ent;
+    o.kl = 0.5f * dl * dl;                                                // a2c_discrete.py:189
+    o.clipped = (fabsf(expf(dl) - 1.0f) > c.e_clip) ? 1.f : 0.f;
+    o.d_value = w * 0.5f * c.critic_coef * dc;
+    return o;
 }
 
 // ---- rollout: sample (inverse CDF on one uniform per row), neglogp, de-normalised value --------------------------------------
@@ -49,10 +142,6 @@ __global__ void __launch_bounds__(256) categorical_sample_kernel(
     }
     values[e] = val;
     if (values_only) return;
-    const float* z = logits + (int64_t)e * ld;
-    const uint8_t* mk = action_masks ? action_masks + (int64_t)e * K : nullptr;
-    float lse;
-    cat_lse(z, mk, K, lse);
     float u;
     if (u_tape) {
         u = u_tape[e];
@@ -61,20 +150,10 @@ __global__ void __launch_bounds__(256) categorical_sample_kernel(
         const Philox4 r = philox4x32_10((uint64_t)e, (ep << 20) | ((uint64_t)step_index << 4) | 15ull, seed);
         u = (float)(r.x >> 8) * (1.0f / 16777216.0f);                     // [0, 1)
     }
-    // action = #{k : cdf_k <= u}, clamped to the last action of non-zero probability (oracle.sample_inverse_cdf)
-    float cdf = 0.f;
-    int count = 0, last = 0;
-    for (int k = 0; k < K; ++k) {
-        const float v = (mk && !mk[k]) ? -1e8f : z[k];
-        const float p = expf(v - lse);
-        cdf += p;
-        if (cdf <= u) ++count;
-        if (p > 0.f) last = k;
-    }
-    const int a = min(count, last);
-    const float va = (mk && !mk[a]) ? -1e8f : z[a];
+    float nlp;
+    const int a = cat_sample_row(logits + (int64_t)e * ld, action_masks ? action_masks + (int64_t)e * K : nullptr, K, u, nlp);
     actions[e] = (int64_t)a;
-    neglogp[e] = -(va - lse);
+    neglogp[e] = nlp;
     if (dones_out) dones_out[e] = dones_cur[e];
     if (valid_out) valid_out[e] = prev_dones ? (1.0f - prev_dones[e]) : 1.0f;
 }
@@ -93,79 +172,15 @@ __global__ void __launch_bounds__(256) categorical_loss_kernel(
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     if (m < M) {
         const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
-        const float* z = logits + (int64_t)m * ld;
-        const uint8_t* mk = action_masks ? action_masks + ar * K : nullptr;
-        float lse;
-        cat_lse(z, mk, K, lse);
-        const int a = (int)actions[ar];
-        const float za = (mk && !mk[a]) ? -1e8f : z[a];
-        const float nlp = -(za - lse);
-        // entropy: -sum p log p over legal actions (distributions.py:38-44; unmasked: torch Categorical.entropy)
-        float ent = 0.f;
-        for (int k = 0; k < K; ++k) {
-            if (mk && !mk[k]) continue;
-            const float lp = z[k] - lse;
-            ent -= expf(lp) * lp;
-        }
         const float mkr = mask ? mask[ar] : 1.0f;
         const float inv_cnt = inv_count_dev ? inv_count_dev[0] : (1.0f / (float)M);
         const float w = mkr * inv_cnt;
-        const float old_nlp = old_neglogp[ar], adv = advs_n[ar], old_v = old_values_n[ar], ret = returns_n[ar];
-        // actor loss + d/dnlp (common_losses.py:41-82)
-        float a_loss, g_a;
-        if (c.ppo) {
-            const float ratio = expf(old_nlp - nlp);
-            const float mi = 1.0f - c.e_clip, mx = 1.0f + c.e_clip;
-            float clamped, dcl;
-            if (c.smooth) {
-                const float s = 1.0f / (1.0f + expf((-(ratio - mi) / (mx - mi) + 0.5f) * 4.0f));
-                clamped = s * (mx - mi) + mi;
-                dcl = 4.0f * s * (1.0f - s);
-            } else {
-                clamped = fminf(fmaxf(ratio, mi), mx);
-                dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
-            }
-            const float t1 = -(adv * ratio), t2 = -(adv * clamped);
-            a_loss = fmaxf(t1, t2);
-            const float d1 = adv * ratio, d2 = adv * dcl * ratio;         // d(-adv * f(ratio))/dnlp = adv * f'(ratio) * ratio
-            g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
-        } else {
-            a_loss = nlp * adv;
-            g_a = adv;
-        }
-        // critic loss + d/dvalue (common_losses.py:7-38)
-        const float val = values[(int64_t)m * value_ld];
-        float c_loss, dc;
-        if (c.clip_value) {
-            const float delta = val - old_v;
-            const float vpc = old_v + fminf(fmaxf(delta, -c.e_clip), c.e_clip);
-            const float e1 = val - ret, e2 = vpc - ret;
-            const float l1 = e1 * e1, l2 = e2 * e2;
-            c_loss = fmaxf(l1, l2);
-            const float g1 = 2.0f * e1, g2 = (delta >= -c.e_clip && delta <= c.e_clip) ? 2.0f * e2 : 0.0f;
-            dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
-        } else {
-            const float e1 = ret - val;
-            c_loss = e1 * e1;
-            dc = -2.0f * e1;
-        }
-        const float dl = old_nlp - nlp;
-        const float kl = 0.5f * dl * dl;                                   // a2c_discrete.py:189
-        const float clipped = (fabsf(expf(dl) - 1.0f) > c.e_clip) ? 1.f : 0.f;
-        // gradients: loss = a + 0.5 * critic_coef * c - entropy_coef * H   (a2c_discrete.py:163-165), each a (masked) mean
-        //   dnlp/dz_k = p_k - [k == a];   dH/dz_k = -p_k (log p_k + H)
-        float* dz = d_logits + (int64_t)m * d_ld;
-        for (int k = 0; k < K; ++k) {
-            float g = 0.f;
-            if (!(mk && !mk[k])) {
-                const float lp = z[k] - lse, p = expf(lp);
-                g = w * (g_a * (p - (k == a ? 1.0f : 0.0f)) + c.entropy_coef * p * (lp + ent));
-            }
-            dz[k] = g;
-        }
-        d_value[(int64_t)m * dv_ld] = w * 0.5f * c.critic_coef * dc;
-        acc[0] = (double)w * a_loss; acc[1] = (double)w * c_loss; acc[2] = (double)w * ent; acc[3] = (double)w * kl;
-        acc[4] = mkr; acc[5] = mkr * clipped; acc[6] = w;
+        const CatRowOut o = cat_loss_row(logits + (int64_t)m * ld, action_masks ? action_masks + ar * K : nullptr, K, (int)actions[ar],
+                                         values[(int64_t)m * value_ld], old_neglogp[ar], advs_n[ar], old_values_n[ar], returns_n[ar], w, c,
+                                         d_logits + (int64_t)m * d_ld);
+        d_value[(int64_t)m * dv_ld] = o.d_value;
+        acc[0] = (double)w * o.a_loss; acc[1] = (double)w * o.c_loss; acc[2] = (double)w * o.ent; acc[3] = (double)w * o.kl;
+        acc[4] = mkr; acc[5] = mkr * o.clipped; acc[6] = w;
     }
     block_sum_d<7>(acc, sm);
     if (threadIdx.x == 0) {
@@ -214,5 +229,29 @@ B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K
                                                                   returns_n, old_neglogp, advs_n, mask, rows_per_chunk, chunk_stride, M, c,
                                                                   inv_count_dev, d_logits, d_ld, d_value, dv_ld, partials);
     B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+// ---- host test entry points: the per-row functions above, run on the CPU over HOST arrays (no GPU involved).  Test infrastructure for
+//      tests/test_discrete_rows_cpu.py; not declared in include/b200rl.h and never called by the product. -----------------------------
+B200RL_EXPORT int b200rl_hosttest_categorical_sample_rows(const float* logits, int K, const uint8_t* masks, const float* u, int N,
+                                                         int64_t* actions, float* neglogp) {
+    for (int e = 0; e < N; ++e) actions[e] = cat_sample_row(logits + (int64_t)e * K, masks ? masks + (int64_t)e * K : nullptr, K, u[e], neglogp[e]);
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_hosttest_categorical_loss_rows(const float* logits, int K, const float* values, const int64_t* actions,
+                                                       const uint8_t* masks, const float* old_values_n, const float* returns_n,
+                                                       const float* old_neglogp, const float* advs_n, const float* w, int M,
+                                                       const b200rl_cat_loss_cfg* cfg, float* d_logits, float* d_value, double* sums4) {
+    CatLossDev c{cfg->e_clip, cfg->critic_coef, cfg->entropy_coef, cfg->clip_value, cfg->use_smooth_clamp, cfg->ppo};
+    double acc[4] = {0, 0, 0, 0};
+    for (int m = 0; m < M; ++m) {
+        const CatRowOut o = cat_loss_row(logits + (int64_t)m * K, masks ? masks + (int64_t)m * K : nullptr, K, (int)actions[m], values[m],
+                                         old_neglogp[m], advs_n[m], old_values_n[m], returns_n[m], w[m], c, d_logits + (int64_t)m * K);
+        d_value[m] = o.d_value;
+        acc[0] += (double)w[m] * o.a_loss; acc[1] += (double)w[m] * o.c_loss; acc[2] += (double)w[m] * o.ent; acc[3] += (double)w[m] * o.kl;
+    }
+    for (int i = 0; i < 4; ++i) sums4[i] = acc[i];
     return B200RL_OK;
 }
