@@ -257,3 +257,136 @@ def install(monkeypatch):
     for name in ('linear_fwd', 'linear_bwd_data', 'linear_bwd_weight', 'reduce_splits', 'refresh_norm', 'moments_update', 'mask_inv_counts',
                  'gae_fused', 'prepare_batch', 'post_step', 'categorical_sample', 'categorical_loss', 'adam_step', 'bump_u64'):
         monkeypatch.setattr(ops, name, globals()[name])
+
+
+# ---------------------------------------------------------------------------------------------- continuous (Gaussian) heads, fp32 path
+def policy_head_sample(a_last, W_head, b_head, logstd, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch, step_index, actions, mus,
+                       sigmas, neglogp, values, env_actions, clip_actions, act_low, act_high, dones_cur, dones_out, prev_dones, valid_out, N, A,
+                       values_only=False):
+    head = a_last[:N] @ W_head.t() + b_head
+    val = head[:, 0]
+    if normalize_value:
+        val = torch.sqrt(vms_var.float() + 1e-5) * torch.clamp(val, -5.0, 5.0) + vms_mean.float()
+    values.copy_(val)
+    if values_only:
+        return
+    assert noise is not None, 'the host-logic test always supplies the normal tape'
+    mu, sg = head[:, 1:], torch.exp(logstd).expand(N, A)
+    act = mu + sg * noise
+    actions.copy_(act); mus.copy_(mu); sigmas.copy_(sg)
+    neglogp.copy_(O.neglogp_fn(act, mu, sg, logstd.expand(N, A)))
+    if env_actions is not None:
+        ea = act
+        if clip_actions:
+            ea = torch.clamp(act, -1.0, 1.0) * ((act_high - act_low) * 0.5) + (act_high + act_low) * 0.5
+        env_actions.copy_(ea)
+    if dones_out is not None:
+        dones_out.copy_(dones_cur)
+    if valid_out is not None:
+        valid_out.copy_(1.0 - prev_dones if prev_dones is not None else torch.ones(N))
+
+
+_LOSS_SIDE = {}
+
+
+def ppo_head_loss(a_last, W_head, b_head, logstd, actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask, rows_per_chunk,
+                  chunk_stride, M, A, cfg, inv_count, d_head, d_alast, act_last, partials, mu_out=None, value_out=None, neglogp_out=None):
+    """heads + calc_losses + backward to (head, a_last, logstd); new mu/sigma overwrite the old ones in the arena (datasets.py:33-43).
+    The loss scalars / d_logstd travel to ppo_loss_finalize through a side channel instead of the kernel's partial rows."""
+    def arena(t, width=1):
+        return _rows(t, M, width, rows_per_chunk, chunk_stride, width)
+    al = a_last[:M].clone().requires_grad_(True)
+    ls = logstd.clone().requires_grad_(True)
+    Wh, bh = W_head.clone().requires_grad_(True), b_head.clone().requires_grad_(True)
+    head = al @ Wh.t() + bh
+    head.retain_grad()
+    value, mu = head[:, :1], head[:, 1:]
+    sg = torch.exp(ls).expand(M, A)
+    act, omu, osg = arena(actions, A), arena(old_mu, A), arena(old_sigma, A)
+    rm = None if mask is None else arena(mask).squeeze(1)
+    nlp = O.neglogp_fn(act, mu, sg, ls.expand(M, A))
+    ent = (0.5 + 0.5 * torch.log(torch.tensor(2 * torch.pi)) + torch.log(sg)).sum(-1)
+    a = O.actor_loss(arena(old_neglogp).squeeze(1), nlp, arena(advs_n).squeeze(1), bool(cfg.ppo), cfg.e_clip, smooth=bool(cfg.use_smooth_clamp))
+    c = O.critic_loss(arena(old_values_n), value, cfg.e_clip, arena(returns_n), bool(cfg.clip_value)).squeeze(1)
+    if cfg.has_bounds_loss and cfg.bound_loss_type == 1:
+        b = O.bound_loss(mu, cfg.bounds_loss_coef)
+    elif cfg.has_bounds_loss and cfg.bound_loss_type == 2:
+        b = O.reg_loss(mu, cfg.bounds_loss_coef)
+    else:
+        b = torch.zeros(M)
+    w = torch.full((M,), 1.0 / M) if inv_count is None else rm * inv_count[0]
+    la, lc, le, lb = (a * w).sum(), (c * w).sum(), (ent * w).sum(), (b * w).sum()
+    # entropy's gradient is applied in ppo_loss_finalize (entropy_coef lives in device memory there)
+    (la + 0.5 * cfg.critic_coef * lc + cfg.bounds_loss_coef * lb).backward(retain_graph=True)
+    d_head[:M] = head.grad
+    d_alast[:M] = al.grad * _act_grad_from_out(a_last[:M], act_last)
+    dls = ls.grad.clone()
+    ls.grad = None
+    le.backward()
+    kl = O.policy_kl(mu.detach(), sg.detach(), omu, osg, reduce=False)
+    kl = (kl * w).sum()
+    lr_ = arena(old_neglogp).squeeze(1) - nlp.detach()
+    lo, hi = torch.log1p(torch.tensor(-cfg.e_clip)), torch.log1p(torch.tensor(cfg.e_clip))
+    clipped = ((lr_ < lo) | (lr_ > hi)).float()
+    mk = torch.ones(M) if rm is None else rm
+    _LOSS_SIDE['last'] = dict(stats=[la.detach(), lc.detach(), le.detach(), lb.detach(), kl, mk.sum(), (mk * clipped).sum() / mk.sum().clamp(min=1.0)],
+                              dls=dls, dent=ls.grad.clone())
+    # write-back of the new mu / sigma
+    m_ = torch.arange(M)
+    cidx = m_ // rows_per_chunk
+    r = cidx * chunk_stride + (m_ - cidx * rows_per_chunk)
+    idx = r.unsqueeze(1) * A + torch.arange(A).unsqueeze(0)
+    _flat(old_mu)[idx] = mu.detach()
+    _flat(old_sigma)[idx] = sg.detach()
+    return 1
+
+
+def ppo_loss_finalize(partials, n_partials, A, entropy_coef_dev, stats, d_logstd, kl_out=None):
+    side = _LOSS_SIDE['last']
+    for i, v in enumerate(side['stats']):
+        stats[i] = float(v)
+    d_logstd.copy_(side['dls'] - float(entropy_coef_dev[0]) * side['dent'])
+    if kl_out is not None:
+        kl_out[0] = float(side['stats'][4])
+
+
+def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None, wpack=None, pack_table=None,
+                   merge_next=None):
+    """adam_step + the on-device adaptive-KL schedule (schedulers.py:19-33) and the LR / grad-norm stats slots"""
+    assert merge_next is None and wpack is None
+    lr = float(state_d[0])
+    n = params.numel() if n is None else n
+    gnorm = float((grads[:n] * float(cfg.grad_scale)).norm())
+    adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=n)
+    if cfg.adaptive_lr and kl_dev is not None:
+        kl = float(kl_dev[0]) * float(cfg.grad_scale)
+        new_lr = lr
+        if kl > 2.0 * cfg.kl_threshold:
+            new_lr = max(lr / cfg.lr_multiplier, cfg.min_lr)
+        if kl < 0.5 * cfg.kl_threshold:
+            new_lr = min(lr * cfg.lr_multiplier, cfg.max_lr)
+        state_d[0] = new_lr
+    if stats_out is not None:
+        stats_out[7] = lr
+        stats_out[8] = gnorm
+
+
+def adv_ema_normalize(advs, partials, n_partials, ema_state, ema_step, decay, training=True):
+    acc = partials[:n_partials].sum(0)
+    n = float(acc[0])
+    if training and n > 0:
+        ema_state[0] = ema_state[0] * decay + (1.0 - decay) * float(acc[5] / n)
+        ema_state[1] = ema_state[1] * decay + (1.0 - decay) * float(acc[6] / n)
+        ema_step.add_(1)
+    std = torch.sqrt(torch.clamp_min(ema_state[1] - ema_state[0] ** 2, 1e-10))
+    advs.copy_(torch.clamp((advs - ema_state[0]) / std, -5.0, 5.0))
+
+
+def install_continuous(monkeypatch):
+    """stand-ins for everything rl_games_b200.agent.A2CAgent calls on its fp32 path (mixed_precision: False, no CUDA graph)"""
+    from rl_games_b200 import ops
+    install(monkeypatch)
+    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize'):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(ops, 'adam_step', adam_step_full)
+    monkeypatch.setattr(ops, 'set_pdl', lambda enable: False)

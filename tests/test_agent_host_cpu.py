@@ -1,0 +1,127 @@
+"""Host logic of the validated continuous agent (rl_games_b200.agent.A2CAgent, fp32 path, eager) on CPU: every C-ABI op is replaced
+by a torch stand-in that restates the kernel's contract (tests/_torch_ops.py) and the agent is run against the reference's golden
+runs.  A GPU-less regression net for arena addressing, flat-parameter offsets, call order, the on-device scheduler protocol, meters and
+checkpoints; it proves nothing about the kernels (the `-m gpu` suite does)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+class _CudaLookingStr(str):
+    """'cpu' that answers startswith('cuda'): lets the agent's "CUDA only" guard pass in this one test without touching the product"""
+
+    def __str__(self):
+        return self
+
+    def startswith(self, *a):
+        return True
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        pass
+
+    def record(self):
+        pass
+
+    def elapsed_time(self, other):
+        return 1.0
+
+
+class _Stream:
+    cuda_stream = 0
+
+    def synchronize(self):
+        pass
+
+
+class _Env:
+    def __init__(self, g):
+        self.g, self.i = g, 0
+
+    def reset(self):
+        self.i = 0
+        return self.g['obs_tape'][0].clone()
+
+    def step(self, actions):
+        g = self.g
+        rew = -(actions * actions).sum(-1) * 0.1
+        self.i += 1
+        j = self.i % g['obs_tape'].shape[0]
+        return g['obs_tape'][j].clone(), rew, g['done_tape'][j].clone(), {'time_outs': g['timeout_tape'][j].clone()}
+
+    def get_env_info(self):
+        from rl_games_b200.common import Box
+        info = {'observation_space': Box(-np.inf, np.inf, (self.g['D'],)), 'action_space': Box(-1.0, 1.0, (self.g['A'],))}
+        if self.g['autoreset'] != 'same_step':
+            info['autoreset_mode'] = self.g['autoreset']
+        return info
+
+    def get_env_state(self):
+        return None
+
+    def set_env_state(self, s):
+        pass
+
+
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_rmsadv.pt'])
+def test_continuous_agent_host_logic_matches_reference_golden(name, monkeypatch, tmp_path):
+    import _torch_ops
+    from oracle import ppo_oracle as O
+    from rl_games_b200.runner import Runner
+    _torch_ops.install_continuous(monkeypatch)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(torch.cuda, 'Event', _Event)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _Stream())
+    monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
+    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    cfgk = g['config']
+    env = _Env(g)
+    config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
+    config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
+                   'mixed_precision': False, 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+    network = {'name': 'actor_critic', 'separate': False,
+               'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                        'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+               'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    r = Runner()
+    r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
+                       'config': config}})
+    r.params['config']['vec_env'] = env
+    agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
+    agent.model.load_state_dict(g['init_state'], strict=False)
+    agent.init_tensors()
+    agent.obs = agent.env_reset()
+    fl = O.swap_and_flatten01
+    for ep, ref in enumerate(g['epochs_out']):
+        agent.epoch_num += 1
+        agent.train_epoch(noise=g['noise'][ep])
+        ds = ref['dataset']
+        assert torch.equal(agent.dones_buf, ref['mb_dones'])
+        torch.testing.assert_close(agent.rewards.unsqueeze(2), ref['mb_rewards'], rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(agent.values.unsqueeze(2), ref['mb_values'], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(fl(agent.advs_n), ds['advantages'], rtol=2e-4, atol=2e-5)
+        torch.testing.assert_close(fl(agent.returns_n.unsqueeze(2)), ds['returns'], rtol=1e-4, atol=1e-5)
+        if ds.get('rnn_masks') is not None:
+            assert torch.equal(fl(agent.valid), ds['rnn_masks'])
+        st = agent.last_stats
+        torch.testing.assert_close(st[:, 0], ref['a_losses'], rtol=2e-3, atol=2e-6)
+        torch.testing.assert_close(st[:, 1], ref['c_losses'], rtol=2e-3, atol=2e-6)
+        torch.testing.assert_close(st[:, 2], ref['entropies'], rtol=1e-4, atol=1e-6)
+        assert agent.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
+        sd = agent.model.state_dict()
+        for k in O.param_names(len(g['units'])):
+            torch.testing.assert_close(sd[k], ref['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
+        for pre in ('running_mean_std.', 'value_mean_std.'):
+            assert int(sd[pre + 'count']) == int(ref['state'][pre + 'count'])
+        assert agent.game_rewards.current_size == ref['game_rewards_size']
+        torch.testing.assert_close(agent.game_rewards.mean, ref['game_rewards_mean'].reshape(-1), rtol=1e-4, atol=1e-5)
+    ck = agent.get_full_state_weights()
+    for i, mref in enumerate(g['epochs_out'][-1]['adam_exp_avg']):
+        torch.testing.assert_close(ck['optimizer']['state'][i]['exp_avg'].reshape(mref.shape), mref, rtol=1e-3, atol=1e-7)
