@@ -251,6 +251,14 @@ int b200rl_categorical_loss_f32(const float* logits, int ld, int K, const float*
                                 const float* inv_count_dev, float* d_logits, int d_ld, float* d_value, int dv_ld,
                                 double* partials, int max_partials, int* n_blocks_out_host, void* stream);
 
+/* Value-only loss head of the central value network (central_value.py:276-301).  NOT YET RUN ON HARDWARE (see csrc/critic.cu).
+ * loss = (masked) mean of critic_loss(old_values_n, values, e_clip, returns_n, clip_value); d_value[m*dv_ld] = its gradient;
+ * arena tensors addressed as chunk_row(m, rows_per_chunk, chunk_stride); partial rows of 8 doubles {w*loss, mask, w, 0...}. */
+int b200rl_value_loss_f32(const float* values, int value_ld, const float* old_values_n, const float* returns_n,
+                          const float* mask, int rows_per_chunk, int64_t chunk_stride, int M, float e_clip, int clip_value,
+                          const float* inv_count_dev, float* d_value, int dv_ld, double* partials, int max_partials,
+                          int* n_blocks_out_host, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Optimiser step.  Replaces a2c_common.py:493-514 (trancate_gradients_and_step: /world_size,
  * clip_grad_norm_, optimizer.step) + torch.optim.Adam(eps=1e-8, weight_decay, fused=True)

@@ -457,3 +457,13 @@ def categorical_loss(logits, ld, K, values, value_ld, actions, action_masks, old
                                           ctypes.addressof(cfg), ptr(inv_count), ptr(d_logits), d_ld, ptr(d_value), dv_ld,
                                           ptr(partials), partials.shape[0], ctypes.addressof(nb), _stream()), 'categorical_loss')
     return nb.value
+
+
+def value_loss(values, value_ld, old_values_n, returns_n, mask, rows_per_chunk, chunk_stride, M, e_clip, clip_value, inv_count, d_value, dv_ld,
+               partials):
+    """central-value critic loss + gradient (csrc/critic.cu)"""
+    nb = ctypes.c_int(0)
+    check(lib.b200rl_value_loss_f32(ptr(values), value_ld, ptr(old_values_n), ptr(returns_n), ptr(mask), rows_per_chunk, chunk_stride, M,
+                                    float(e_clip), int(clip_value), ptr(inv_count), ptr(d_value), dv_ld, ptr(partials), partials.shape[0],
+                                    ctypes.addressof(nb), _stream()), 'value_loss')
+    return nb.value

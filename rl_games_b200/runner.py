@@ -40,6 +40,14 @@ def _override_sigma(agent, args):
                 print('Cannot set new sigma because fixed_sigma is False')
 
 
+def _continuous_agent(**kwargs):
+    """central_value_config selects the (not yet hardware-validated, opt-in) asymmetric-critic subclass; everything else is A2CAgent"""
+    if kwargs.get('params', {}).get('config', {}).get('central_value_config') is not None:
+        from .agent_cv import A2CAgentCV
+        return A2CAgentCV(**kwargs)
+    return A2CAgent(**kwargs)
+
+
 def _discrete_agent(**kwargs):
     from .agent_discrete import DiscreteA2CAgent
     return DiscreteA2CAgent(**kwargs)
@@ -48,7 +56,7 @@ def _discrete_agent(**kwargs):
 class Runner:
     def __init__(self, algo_observer=None):
         self.algo_factory = ObjectFactory()
-        self.algo_factory.register_builder('a2c_continuous', lambda **kwargs: A2CAgent(**kwargs))
+        self.algo_factory.register_builder('a2c_continuous', lambda **kwargs: _continuous_agent(**kwargs))
         # discrete PPO: implemented, not yet validated on hardware (agent_discrete.py refuses to start without b200_unvalidated: True)
         self.algo_factory.register_builder('a2c_discrete', lambda **kwargs: _discrete_agent(**kwargs))
         self.player_factory = ObjectFactory()

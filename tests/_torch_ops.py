@@ -382,11 +382,37 @@ def adv_ema_normalize(advs, partials, n_partials, ema_state, ema_step, decay, tr
     advs.copy_(torch.clamp((advs - ema_state[0]) / std, -5.0, 5.0))
 
 
+def normalize(x, mean, var, denorm=False, eps=1e-5, out=None):
+    std = torch.sqrt(var.float() + eps)
+    y = std * torch.clamp(x, -5.0, 5.0) + mean.float() if denorm else torch.clamp((x - mean.float()) / std, -5.0, 5.0)
+    if out is None:
+        return y
+    out.copy_(y.reshape(out.shape))
+    return out
+
+
+def value_loss(values, value_ld, old_values_n, returns_n, mask, rows_per_chunk, chunk_stride, M, e_clip, clip_value, inv_count, d_value, dv_ld,
+               partials):
+    mrow = torch.arange(M)
+    v = _flat(values)[mrow * value_ld].clone().requires_grad_(True)
+
+    def arena(t):
+        return _rows(t, M, 1, rows_per_chunk, chunk_stride, 1)
+    c = O.critic_loss(arena(old_values_n), v.unsqueeze(1), e_clip, arena(returns_n), bool(clip_value)).squeeze(1)
+    w = torch.full((M,), 1.0 / M) if inv_count is None else arena(mask).squeeze(1) * inv_count[0]
+    loss = (c * w).sum()
+    loss.backward()
+    _flat(d_value)[mrow * dv_ld] = v.grad
+    partials.zero_()
+    partials[0, 0] = loss.detach().double()
+    return 1
+
+
 def install_continuous(monkeypatch):
     """stand-ins for everything rl_games_b200.agent.A2CAgent calls on its fp32 path (mixed_precision: False, no CUDA graph)"""
     from rl_games_b200 import ops
     install(monkeypatch)
-    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize'):
+    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'adam_step', adam_step_full)
     monkeypatch.setattr(ops, 'set_pdl', lambda enable: False)
