@@ -353,7 +353,6 @@ def ppo_loss_finalize(partials, n_partials, A, entropy_coef_dev, stats, d_logstd
 def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None, wpack=None, pack_table=None,
                    merge_next=None):
     """adam_step + the on-device adaptive-KL schedule (schedulers.py:19-33) and the LR / grad-norm stats slots"""
-    assert merge_next is None and wpack is None
     lr = float(state_d[0])
     n = params.numel() if n is None else n
     gnorm = float((grads[:n] * float(cfg.grad_scale)).norm())
@@ -369,6 +368,9 @@ def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, sta
     if stats_out is not None:
         stats_out[7] = lr
         stats_out[8] = gnorm
+    if merge_next is not None:          # the optimiser kernel's last CTA merges the NEXT minibatch's observation moments
+        o = merge_next
+        obs_stats_merge(o.mbmom, o.shift, o.D, o.n_rows, o.mean, o.var, o.count, o.mean_f32, o.std_f32, o.eps)
 
 
 def adv_ema_normalize(advs, partials, n_partials, ema_state, ema_step, decay, training=True):
@@ -412,7 +414,124 @@ def install_continuous(monkeypatch):
     """stand-ins for everything rl_games_b200.agent.A2CAgent calls on its fp32 path (mixed_precision: False, no CUDA graph)"""
     from rl_games_b200 import ops
     install(monkeypatch)
-    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss'):
+    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss', 'make_obs_merge',
+                 'obs_mb_moments', 'obs_stats_merge'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'adam_step', adam_step_full)
     monkeypatch.setattr(ops, 'set_pdl', lambda enable: False)
+
+
+# ---------------------------------------------------------------------------------------------- tcgen05 path (host logic only: fp32 maths)
+_TC = {}          # wpack.data_ptr() -> the fp32 weight views tc_pack_weights was given (the kernels read the packed bf16 copy instead)
+
+
+class _ObsMergeRef:
+    """what ops.make_obs_merge packs into a ctypes struct, kept as tensor references"""
+
+    def __init__(self, mbmom_i, shift, D, n_rows, mean, var, count, mean_f32, std_f32, eps=1e-5):
+        self.mbmom, self.shift, self.D, self.n_rows = mbmom_i, shift, D, n_rows
+        self.mean, self.var, self.count, self.mean_f32, self.std_f32, self.eps = mean, var, count, mean_f32, std_f32, eps
+
+
+def make_obs_merge(*a, **k):
+    return _ObsMergeRef(*a, **k)
+
+
+def obs_mb_moments(x, D, H, N, envs_per_mb, run_mean, mbmom, mb_shift, scratch, counters):
+    """per-minibatch batch sums of the observations, shifted by the running mean at the start of the update phase"""
+    mb_shift.copy_(run_mean.float())
+    for i in range(N // envs_per_mb):
+        rows = x[:, i * envs_per_mb:(i + 1) * envs_per_mb].reshape(-1, D).double() - mb_shift.double()
+        mbmom[i, :D] = rows.sum(0)
+        mbmom[i, D:] = (rows * rows).sum(0)
+
+
+def obs_stats_merge(mbmom_i, mb_shift, D, n_rows, mean, var, count, mean_f32, std_f32, eps=1e-5):
+    n, cnt0 = float(n_rows), float(count[0])
+    ms = mbmom_i[:D] / n
+    bm = mb_shift.double() + ms
+    bv = torch.clamp_min(mbmom_i[D:] / n - ms * ms, 0.0)
+    tot = cnt0 + n
+    delta = bm - mean
+    m2 = var * cnt0 + bv * n + delta * delta * cnt0 * n / tot
+    mean.add_(delta * n / tot)
+    var.copy_(m2 / tot)
+    count.add_(int(n_rows))
+    refresh_norm(mean, var, mean_f32, std_f32, eps)
+
+
+def tc_pack_weights(W1, W2, W3, W_head, D, units, A, wpack):
+    _TC[wpack.data_ptr()] = (W1, W2, W3, W_head)
+
+
+def _tc_forward(x, ws, b, b_head, act=1):
+    h = x
+    for W, bb in zip(ws[:3], b):
+        h = ACT[act](h @ W.t() + bb)
+    return h @ ws[3].t() + b_head
+
+
+def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch,
+                       step_index, actions, mus, sigmas, neglogp, values, env_actions, clip_actions, act_low, act_high, dones_cur, dones_out,
+                       prev_dones, valid_out, values_only=False):
+    ws = _TC[wpack.data_ptr()]
+    h = obs[:N].reshape(N, D)
+    for W, bb in zip(ws[:3], b):
+        h = ACT[1]((_norm(h, nm, ns) if W is ws[0] else h) @ W.t() + bb)
+    policy_head_sample(h, ws[3], b_head, logstd, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch, step_index, actions, mus, sigmas,
+                       neglogp, values, env_actions, clip_actions, act_low, act_high, dones_cur, dones_out, prev_dones, valid_out, N, A,
+                       values_only=values_only)
+
+
+def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_head, logstd, units, M, A, actions, old_mu, old_sigma, old_values_n,
+                     returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials, xtile=None):
+    """whole training forward + loss + backward of the MLP in fp32 with autograd; the gradients wait in a side channel for tc_mlp_bwd"""
+    ws = [w.clone().requires_grad_(True) for w in _TC[wpack.data_ptr()]]
+    bs = [t.clone().requires_grad_(True) for t in b]
+    x = _norm(_rows(obs, M, D, rows_per_chunk, chunk_stride, D), nm, ns)
+    h = x
+    for W, bb in zip(ws[:3], bs):
+        h = ACT[1](h @ W.t() + bb)
+    hl = h
+    hl.retain_grad()
+    d_head = torch.zeros(M, A + 1)
+    d_alast = torch.zeros(M, hl.shape[1])
+    ppo_head_loss(hl.detach(), ws[3].detach(), b_head, logstd, actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask,
+                  rows_per_chunk, chunk_stride, M, A, cfg, inv_count, d_head, d_alast, 0, partials)
+    # backward of the trunk from d(loss)/d(a_last) (act_last = 0 above: d_alast is the gradient at the activation OUTPUT)
+    hl.backward(d_alast)
+    _LOSS_SIDE['tc_grads'] = {'W0': ws[0].grad, 'b0': bs[0].grad, 'W1': ws[1].grad, 'b1': bs[1].grad, 'W2': ws[2].grad, 'b2': bs[2].grad,
+                              'W_head': d_head.t() @ hl.detach(), 'b_head': d_head.sum(0)}
+    return 1
+
+
+def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=None):
+    """split partial rows: everything in row 0, zeros elsewhere; P is the row stride"""
+    g = _LOSS_SIDE['tc_grads']
+    f = _flat(part)
+    n_rows = 3
+    for s_ in range(n_rows):
+        for k, v in g.items():
+            f[s_ * P + offs[k]:s_ * P + offs[k] + v.numel()] = v.reshape(-1) if s_ == 0 else 0.0
+    return n_rows
+
+
+def reduce_adam(part, n_splits, split_stride, loss_partials, n_loss_partials, A, entropy_coef_dev, stats, kl_out, grads, params, exp_avg,
+                exp_avg_sq, n, state_d, cfg, counter, nrm_part, grid_bar, wpack=None, pack_table=None, merge_next=None):
+    f = _flat(part)
+    grads[A:n] = sum(f[s_ * split_stride + A:s_ * split_stride + n] for s_ in range(n_splits))
+    ppo_loss_finalize(loss_partials, n_loss_partials, A, entropy_coef_dev, stats, grads[:A], kl_out)
+    adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_out, cfg, stats, counter, n=n, merge_next=merge_next)
+
+
+def install_tc(monkeypatch):
+    """stand-ins for the bf16 tcgen05 path of A2CAgent (mixed_precision: True), computed in fp32"""
+    from rl_games_b200 import ops
+    install_continuous(monkeypatch)
+    for name in ('tc_pack_weights', 'tc_mlp_fwd_rollout', 'tc_mlp_fwd_train', 'tc_mlp_bwd', 'reduce_adam'):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(ops, 'tc_supported', lambda D, units, A: len(units) == 3)
+    monkeypatch.setattr(ops, 'tc_tile_bytes', lambda D, units, A: [units[0] * 256, units[1] * 256, units[2] * 256, 16 * 256])
+    monkeypatch.setattr(ops, 'tc_pack_bytes', lambda D, units, A: 1024)
+    monkeypatch.setattr(ops, 'tc_xtile_bytes', lambda D, units, A: 64 * 256)
+    monkeypatch.setattr(ops, 'tc_pack_table', lambda D, units, A, offs: object())

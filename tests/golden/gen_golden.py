@@ -530,7 +530,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -545,6 +545,10 @@ if __name__ == '__main__':
         gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})
     if 'checkpoint' in which:
         gen_checkpoint()
+    if 'tcshape' in which:
+        # three hidden layers and an observation width that is a multiple of 4: the shape class of the tcgen05 path's host logic
+        # (per-minibatch obs moments precomputed once per epoch, merged in the optimiser tail); masked autoreset on top
+        gen_agent('agent_tcshape.pt', N=8, H=8, D=8, A=3, units=(16, 12, 8), mb=32, seed=10, autoreset='next_step')
     if 'cv' in which:
         gen_agent_cv()
     if 'rmsadv' in which:

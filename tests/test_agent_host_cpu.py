@@ -70,12 +70,15 @@ class _Env:
         pass
 
 
-@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_rmsadv.pt'])
-def test_continuous_agent_host_logic_matches_reference_golden(name, monkeypatch, tmp_path):
+@pytest.mark.parametrize('name,tc', [('agent_base.pt', False), ('agent_masked.pt', False), ('agent_hardclip.pt', False), ('agent_rmsadv.pt', False),
+                                     ('agent_tcshape.pt', False), ('agent_tcshape.pt', True)])
+def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
+    """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
+    stride, fused reduce+Adam tail, per-minibatch obs moments merged by the optimiser tail) with fp32 stand-ins for its kernels"""
     import _torch_ops
     from oracle import ppo_oracle as O
     from rl_games_b200.runner import Runner
-    _torch_ops.install_continuous(monkeypatch)
+    (_torch_ops.install_tc if tc else _torch_ops.install_continuous)(monkeypatch)
     monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
     monkeypatch.setattr(torch.cuda, 'Event', _Event)
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _Stream())
@@ -85,7 +88,7 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, monkeypatch,
     env = _Env(g)
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
-                   'mixed_precision': False, 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+                   'mixed_precision': tc, 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
@@ -95,8 +98,10 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, monkeypatch,
                        'config': config}})
     r.params['config']['vec_env'] = env
     agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
+    assert agent.use_tc == tc
     agent.model.load_state_dict(g['init_state'], strict=False)
     agent.init_tensors()
+    agent._repack()
     agent.obs = agent.env_reset()
     fl = O.swap_and_flatten01
     for ep, ref in enumerate(g['epochs_out']):
