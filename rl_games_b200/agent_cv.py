@@ -125,8 +125,10 @@ class CentralValueNet:
         return sd
 
     def load_state_dict(self, sd, strict=True):
-        sd = {k.replace('_orig_mod.', '').replace('model.', '', 1) if k.startswith('model.') else k.replace('_orig_mod.', ''): v
-              for k, v in sd.items()}
+        def strip(k):          # CentralValueTrain.state_dict() prefixes its model's keys with 'model.'; torch.compile adds '_orig_mod.'
+            k = k.replace('_orig_mod.', '')
+            return k[len('model.'):] if k.startswith('model.') else k
+        sd = {strip(k): v for k, v in sd.items()}
         with torch.no_grad():
             for n, v in zip(self.param_names(), self._param_views()):
                 if n in sd:
