@@ -410,12 +410,68 @@ def value_loss(values, value_ld, old_values_n, returns_n, mask, rows_per_chunk, 
     return 1
 
 
+# ---------------------------------------------------------------------------------------------- LSTM-with-dones cell ops (csrc/rnn.cu)
+def _crow(S, rpc, stride):
+    s_ = torch.arange(S)
+    if rpc <= 0:
+        return s_
+    c = s_ // rpc
+    return c * stride + (s_ - c * rpc)
+
+
+def lstm_cell_fwd(gates, cin, c_out, h_out, S, Hd, h_scatter=None, scatter_rpc=0, scatter_stride=0, hin_next=None, cin_next=None,
+                  done_next=None, done_rpc=0, done_stride=0):
+    g = gates[:S]
+    i, f, gg, o = torch.sigmoid(g[:, :Hd]), torch.sigmoid(g[:, Hd:2 * Hd]), torch.tanh(g[:, 2 * Hd:3 * Hd]), torch.sigmoid(g[:, 3 * Hd:])
+    gates[:S] = torch.cat([i, f, gg, o], dim=1)
+    c = f * cin[:S] + i * gg
+    h = o * torch.tanh(c)
+    c_out[:S] = c
+    h_out[:S] = h
+    if h_scatter is not None:
+        rows = (torch.arange(S) // scatter_rpc) * scatter_stride + torch.arange(S) % scatter_rpc
+        _flat(h_scatter)[rows.unsqueeze(1) * Hd + torch.arange(Hd).unsqueeze(0)] = h
+    if hin_next is not None:
+        m = torch.ones(S, 1)
+        if done_next is not None:
+            m = 1.0 - _flat(done_next)[_crow(S, done_rpc, done_stride)].float().unsqueeze(1)
+        hin_next[:S] = h * m
+        cin_next[:S] = c * m
+
+
+def lstm_cell_bwd(gates_act, c_t, cin, dgates, dcin, S, Hd, dH=None, scatter_rpc=0, scatter_stride=0, dhin_next=None, dcin_next=None,
+                  done_next=None, done_rpc=0, done_stride=0):
+    g = gates_act[:S]
+    i, f, gg, o = g[:, :Hd], g[:, Hd:2 * Hd], g[:, 2 * Hd:3 * Hd], g[:, 3 * Hd:]
+    m = torch.ones(S, 1)
+    if done_next is not None:
+        m = 1.0 - _flat(done_next)[_crow(S, done_rpc, done_stride)].float().unsqueeze(1)
+    dh = torch.zeros(S, Hd)
+    if dH is not None:
+        rows = (torch.arange(S) // scatter_rpc) * scatter_stride + torch.arange(S) % scatter_rpc
+        dh = _flat(dH)[rows.unsqueeze(1) * Hd + torch.arange(Hd).unsqueeze(0)].clone()
+    dc = torch.zeros(S, Hd)
+    if dhin_next is not None:
+        dh = dh + dhin_next[:S] * m
+        dc = dc + dcin_next[:S] * m
+    tc = torch.tanh(c_t[:S])
+    dc = dc + dh * o * (1.0 - tc * tc)
+    dgates[:S] = torch.cat([dc * gg * i * (1.0 - i), dc * cin[:S] * f * (1.0 - f), dc * i * (1.0 - gg * gg), dh * tc * o * (1.0 - o)], dim=1)
+    dcin[:S] = dc * f
+
+
+def rnn_mask_rows(inp, in_rpc, in_stride, out, S, Hd, done=None, done_rpc=0, done_stride=0):
+    m = torch.ones(S, 1) if done is None else 1.0 - _flat(done)[_crow(S, done_rpc, done_stride)].float().unsqueeze(1)
+    rows = _crow(S, in_rpc, in_stride)
+    out[:S] = _flat(inp)[rows.unsqueeze(1) * Hd + torch.arange(Hd).unsqueeze(0)] * m
+
+
 def install_continuous(monkeypatch):
     """stand-ins for everything rl_games_b200.agent.A2CAgent calls on its fp32 path (mixed_precision: False, no CUDA graph)"""
     from rl_games_b200 import ops
     install(monkeypatch)
     for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss', 'make_obs_merge',
-                 'obs_mb_moments', 'obs_stats_merge'):
+                 'obs_mb_moments', 'obs_stats_merge', 'lstm_cell_fwd', 'lstm_cell_bwd', 'rnn_mask_rows'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'adam_step', adam_step_full)
     monkeypatch.setattr(ops, 'set_pdl', lambda enable: False)

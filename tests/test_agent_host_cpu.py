@@ -71,7 +71,7 @@ class _Env:
 
 
 @pytest.mark.parametrize('name,tc', [('agent_base.pt', False), ('agent_masked.pt', False), ('agent_hardclip.pt', False), ('agent_rmsadv.pt', False),
-                                     ('agent_tcshape.pt', False), ('agent_tcshape.pt', True)])
+                                     ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_lstm.pt', False)])
 def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
     """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
     stride, fused reduce+Adam tail, per-minibatch obs moments merged by the optimiser tail) with fp32 stand-ins for its kernels"""
@@ -93,6 +93,9 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    lstm = g.get('rnn_units', 0) > 0
+    if lstm:
+        network['rnn'] = {'name': 'lstm', 'units': g['rnn_units'], 'layers': 1, 'before_mlp': True}
     r = Runner()
     r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
                        'config': config}})
@@ -121,7 +124,7 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
         torch.testing.assert_close(st[:, 2], ref['entropies'], rtol=1e-4, atol=1e-6)
         assert agent.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
         sd = agent.model.state_dict()
-        for k in O.param_names(len(g['units'])):
+        for k in O.param_names(len(g['units']), lstm=lstm):
             torch.testing.assert_close(sd[k], ref['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
         for pre in ('running_mean_std.', 'value_mean_std.'):
             assert int(sd[pre + 'count']) == int(ref['state'][pre + 'count'])
