@@ -133,3 +133,84 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
     ck = agent.get_full_state_weights()
     for i, mref in enumerate(g['epochs_out'][-1]['adam_exp_avg']):
         torch.testing.assert_close(ck['optimizer']['state'][i]['exp_avg'].reshape(mref.shape), mref, rtol=1e-3, atol=1e-7)
+
+
+def _build(monkeypatch, tmp_path, g, env, tc=False, over=None):
+    import _torch_ops
+    from rl_games_b200.runner import Runner
+    (_torch_ops.install_tc if tc else _torch_ops.install_continuous)(monkeypatch)
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+    monkeypatch.setattr(torch.cuda, 'Event', _Event)
+    monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _Stream())
+    monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
+    cfgk = g['config']
+    config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
+    config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
+                   'mixed_precision': tc, 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+    config.update(over or {})
+    network = {'name': 'actor_critic', 'separate': False,
+               'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                        'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+               'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    r = Runner()
+    r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
+                       'config': config}})
+    r.params['config']['vec_env'] = env
+    agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
+    agent.model.load_state_dict(g['init_state'], strict=False)
+    agent.init_tensors()
+    agent._repack()
+    agent.obs = agent.env_reset()
+    return agent
+
+
+class _NumpyEnv(_Env):
+    """the same tapes through the HOST-env contract (numpy in / numpy out): exercises the pinned staging path of env_step"""
+
+    def reset(self):
+        return super().reset().numpy()
+
+    def step(self, actions):
+        assert isinstance(actions, np.ndarray)
+        o, r, d, info = super().step(torch.from_numpy(actions))
+        return o.numpy(), r.numpy(), d.numpy(), {'time_outs': info['time_outs'].numpy()}
+
+
+def test_host_env_path_gives_the_same_epoch_as_the_tensor_env(monkeypatch, tmp_path):
+    g = torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False)
+    out = []
+    for env_cls in (_Env, _NumpyEnv):
+        a = _build(monkeypatch, tmp_path, g, env_cls(g))
+        a.epoch_num += 1
+        a.train_epoch(noise=g['noise'][0])
+        out.append((a.model.flat.clone(), a.rewards.clone(), a.dones_buf.clone(), a.valid.clone()))
+        assert a.is_tensor_obses == (env_cls is _Env)
+    for x, y in zip(*out):
+        assert torch.equal(x, y)
+
+
+def test_reference_style_per_minibatch_api_and_checkpoint_roundtrip(monkeypatch, tmp_path):
+    """play_steps -> prepare_dataset -> train_actor_critic(dataset[i]) (the call sequence of the reference's own tests,
+    tests/test_ppo_masking.py:92-107) gives the same weights as train_epoch; save / restore round-trips weights, Adam state, lr, epoch"""
+    g = torch.load(os.path.join(GOLDEN, 'agent_base.pt'), weights_only=False)
+    a = _build(monkeypatch, tmp_path, g, _Env(g))
+    b = _build(monkeypatch, tmp_path, g, _Env(g))
+    a.epoch_num += 1
+    a.train_epoch(noise=g['noise'][0])
+    b.epoch_num += 1
+    batch = b.play_steps(noise=g['noise'][0])
+    assert batch['obses'].shape == (g['N'] * g['H'], g['D']) and batch['played_frames'] == g['N'] * g['H']
+    b.set_train()
+    b.prepare_dataset(batch)
+    for _ in range(b.mini_epochs_num):
+        for i in range(len(b.dataset)):
+            res = b.train_actor_critic(b.dataset[i])
+            assert len(res) == 9
+    torch.testing.assert_close(b.model.flat, a.model.flat, rtol=1e-6, atol=1e-7)
+    fn = str(tmp_path / 'ck')
+    a.save(fn)
+    c = _build(monkeypatch, tmp_path, g, _Env(g))
+    c.restore(fn + '.pth')
+    assert torch.equal(c.model.flat, a.model.flat) and torch.equal(c.model.exp_avg, a.model.exp_avg)
+    assert c.epoch_num == a.epoch_num and c.last_lr == a.last_lr
+    assert int(c.model.running_mean_std.count) == int(a.model.running_mean_std.count)
