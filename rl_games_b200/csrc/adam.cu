@@ -251,6 +251,18 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
     if (is_last) obs_merge_tail(om);
 }
 
+// Opt-in stage timing of reduce_adam_kernel (tools/tc_stage_timing.py --build compiles a variant with -DB200RL_TC_TIMING): thread 0 of
+// CTA 0 stamps clock64() at the phase boundaries.  Never compiled into the product library.
+#ifdef B200RL_TC_TIMING
+__device__ long long g_ra_stamp[32];
+#define RA_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_ra_stamp[i] = clock64(); } while (0)
+extern "C" B200RL_EXPORT int b200rl_debug_ra_stamps(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_ra_stamp, sizeof(long long) * 32);
+}
+#else
+#define RA_STAMP(i) do {} while (0)
+#endif
+
 // =====================================================================================================================
 // Single-GPU fused tail of a minibatch: split-gradient reduction + loss finalisation + clip + Adam (+ packed-weight refresh,
 // LR schedule, next-minibatch obs merge) in ONE launch -- replaces reduce_finalize_kernel + adam_step_kernel when there is
@@ -287,6 +299,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     __shared__ float4 sred4[1024];
     __shared__ int is_last;
     const int tid = threadIdx.x;
+    RA_STAMP(0);      // kernel start
     pdl_sync();
     const double lr = state_d[0];
     const double step = state_d[1] + 1.0;
@@ -328,6 +341,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
             a0 = (g * gs) * (g * gs);
         }
     }
+    RA_STAMP(1);      // loss finalisation done (CTA 0 does none in the single-GPU edition: it is the last CTA's job)
     // ---- 1b. my slice of the flat gradient: sum over the splits, KG k-groups per element ----
     if (vec4) {
         // 16-byte edition (split rows and slice bounds are 4-float aligned): 4x the bytes in flight per thread -- the pass is
@@ -425,6 +439,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
             ps.red[n] = sacc;
         }
     }
+    RA_STAMP(2);      // split reduction (and peer exchange) done
     const float* gsrc = MULTI ? ps.red : grads;
     double acc[1] = {(double)a0};
     block_sum_d<1>(acc, sm);
@@ -438,6 +453,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
         while (ld_acquire_gpu_u32(grid_bar) < target) { }
     }
     __syncthreads();
+    RA_STAMP(3);      // grid barrier passed
     // ---- 3. clip + Adam on my slice ----
     double nsqv[1] = {tid < gridDim.x ? __ldcg(nrm_part + tid) : 0.0};     // gridDim.x <= 148 <= blockDim.x
     block_sum_d<1>(nsqv, sm);
@@ -452,6 +468,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     for (int i = i0 + tid; i < i1; i += blockDim.x)
         adam_update_one(i, __ldcg(gsrc + i) * gs, c.truncate_grads, coef, params, exp_avg, exp_avg_sq, b1, b2, step_size, bc2_sqrt, eps, wd,
                         wpack, tab);
+    RA_STAMP(4);      // Adam on my slice done
     __threadfence();
     __syncthreads();
     if (tid == 0) is_last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
@@ -470,6 +487,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
         *counter = 0;
     }
     if (is_last) obs_merge_tail(om);
+    RA_STAMP(5);      // kernel end (CTA 0; the last CTA also runs the obs-merge tail)
 }
 
 }  // namespace

@@ -1,0 +1,15 @@
+#!/bin/bash
+# First GPU call of the next round (one B200): promote the code that was written after round 1's GPU budget ran out, then re-confirm
+# the validated suite and the headline.  Usage:  gpurun --timeout 900 -- 'bash tools/round2_first_call.sh'
+set -u
+mkdir -p gpurun_out
+echo "== gated parity tests (discrete PPO, central value) =="
+B200RL_UNVALIDATED=1 timeout 300 python -m pytest tests/test_discrete_gpu.py tests/test_cv_gpu.py -q 2>&1 | tail -40 | tee gpurun_out/r02_gated_tests.log
+echo "== validated suite =="
+timeout 300 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/r02_gpu_tests.log
+echo "== stage timelines incl. the fused reduce+Adam tail (instrumented build; run tools/tc_stage_timing.py --build beforehand) =="
+if [ -f rl_games_b200/libb200rl_timing.so ]; then
+  B200RL_LIB_PATH=$PWD/rl_games_b200/libb200rl_timing.so timeout 120 python tools/tc_stage_timing.py --old-bwd2 2>&1 | tail -80 | tee gpurun_out/r02_stage_timing.log
+fi
+echo "== headline =="
+timeout 200 python bench.py --steps 10 --warmup 3 --skip-cpu --skip-e2e 2>/dev/null | tee gpurun_out/r02_bench_first.json | cut -c1-300

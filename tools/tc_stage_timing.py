@@ -25,9 +25,12 @@ TAIL = {'fwd': ['kernel end'], 'bwd1': ['flush done'], 'bwd2': ['last MMAs done'
 def build():
     from rl_games_b200.csrc import build as b
     b.build(verbose=False)
-    obj = os.path.join(b.OBJ, 'mlp_tc_timing.o')
-    subprocess.check_call([b.NVCC] + b.FLAGS + ['-DB200RL_TC_TIMING', '-c', os.path.join(b.HERE, 'mlp_tc.cu'), '-o', obj])
-    objs = [os.path.join(b.OBJ, s[:-3] + '.o') for s in b._sources() if s != 'mlp_tc.cu'] + [obj]
+    timed = ('mlp_tc.cu', 'adam.cu')          # the sources that carry opt-in stamps
+    objs = [os.path.join(b.OBJ, s[:-3] + '.o') for s in b._sources() if s not in timed]
+    for src in timed:
+        obj = os.path.join(b.OBJ, src[:-3] + '_timing.o')
+        subprocess.check_call([b.NVCC] + b.FLAGS + ['-DB200RL_TC_TIMING', '-c', os.path.join(b.HERE, src), '-o', obj])
+        objs.append(obj)
     out = os.path.join(b.PKG, 'libb200rl_timing.so')
     subprocess.check_call([b.NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', out] + objs + ['-lcuda'])
     print(out)
@@ -101,6 +104,32 @@ def main():
         print('iter %d: fwd+loss %.1f us, bwd1+bwd2 %.1f us (events)' % (it, e0.elapsed_time(e1) * 1e3, e1.elapsed_time(e2) * 1e3))
         if it == 3:
             show('fwd', 0); show('bwd1', 128); show('bwd2_old' if '--old-bwd2' in sys.argv else 'bwd2', 256)
+    # ---- fused reduce + finalise + clip + Adam tail on the partial rows the backward just wrote (L2-hot, like in the real step) ----
+    ra = lib.b200rl_debug_ra_stamps
+    ra.restype = ctypes.c_int
+    ra.argtypes = [ctypes.c_void_p]
+    rbuf = (ctypes.c_longlong * 32)()
+    from rl_games_b200.ops import OptCfg
+    Ppad = (P + 3) // 4 * 4
+    part4 = torch.randn(148, Ppad, device=DEV) * 1e-3
+    flat, m1, m2, grad = torch.randn(P, device=DEV) * 0.1, torch.zeros(P, device=DEV), torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
+    state = torch.tensor([3e-4, 0.0, 0.0, 0.0], dtype=torch.float64, device=DEV)
+    cfg_o = OptCfg(0.9, 0.999, 1e-8, 0.0, 1.0, 0.008, 1e-6, 1e-2, 1.5, 1.0, 1, 1)
+    counter, bar = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    nrm, stats, kl, ec = torch.zeros(148, dtype=torch.float64, device=DEV), torch.zeros(16, device=DEV), torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    for it in range(4):
+        part4.mul_(1.0)          # rewrite the partial rows so that they sit in L2 as after the backward kernel
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.reduce_adam(part4, 148, Ppad, partials, 148, A, ec, stats, kl, grad, flat, m1, m2, P, state, cfg_o, counter, nrm, bar)
+        e1.record()
+        torch.cuda.synchronize()
+        assert ra(ctypes.cast(rbuf, ctypes.c_void_p)) == 0
+        if it == 3:
+            names = ['kernel start', 'finalise branch', 'split reduction', 'grid barrier', 'Adam slice', 'kernel end']
+            print('  [reduce_adam] %.1f us by events; CTA0:' % (e0.elapsed_time(e1) * 1e3))
+            for i in range(1, 6):
+                print('    %-16s +%7.2f us' % (names[i], (rbuf[i] - rbuf[i - 1]) / 1965.0))
 
 
 if __name__ == '__main__':
