@@ -214,3 +214,27 @@ def test_reference_style_per_minibatch_api_and_checkpoint_roundtrip(monkeypatch,
     assert torch.equal(c.model.flat, a.model.flat) and torch.equal(c.model.exp_avg, a.model.exp_avg)
     assert c.epoch_num == a.epoch_num and c.last_lr == a.last_lr
     assert int(c.model.running_mean_std.count) == int(a.model.running_mean_std.count)
+
+
+def test_train_loop_runs_to_max_epochs_and_saves(monkeypatch, tmp_path):
+    """A2CBase.train mirror (a2c_common.py:1662-1782): epoch loop, stats/writer hooks, checkpointing (save_frequency, last checkpoint),
+    return value -- on CPU with the kernel stand-ins (noise comes from the mocked Philox-free path: a fixed tape per step)"""
+    import _torch_ops
+    g = torch.load(os.path.join(GOLDEN, 'agent_base.pt'), weights_only=False)
+    a = _build(monkeypatch, tmp_path, g, _Env(g), over={'max_epochs': 3, 'save_frequency': 2, 'save_best_after': 1, 'print_stats': True,
+                                                        'name': 'loop'})
+    tape = g['noise'][0]
+    orig = _torch_ops.policy_head_sample
+
+    def sample_with_tape(*args, **kw):          # train() passes no noise tape: feed one so that the stand-in needs no RNG of its own
+        args = list(args)
+        if args[7] is None:
+            args[7] = tape[int(args[10]) % tape.shape[0]]
+        return orig(*args, **kw)
+    from rl_games_b200 import ops
+    monkeypatch.setattr(ops, 'policy_head_sample', sample_with_tape)
+    last_mean, epochs = a.train()
+    assert epochs == 3 and a.frame == 3 * g['N'] * g['H']
+    assert torch.isfinite(a.model.flat).all()
+    files = sorted(os.listdir(a.nn_dir))
+    assert any(f.endswith('.pth') for f in files), files
