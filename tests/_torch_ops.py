@@ -192,8 +192,7 @@ def categorical_sample(logits, ld, K, value_raw, value_ld, action_masks, u_tape,
         return
     z = _flat(logits)[(torch.arange(N) * ld).unsqueeze(1) + torch.arange(K).unsqueeze(0)]
     nl, probs, _ = DO.categorical_masked(z, None if action_masks is None else action_masks.bool())
-    assert u_tape is not None, 'the host-logic test always supplies the uniform tape'
-    a = DO.sample_inverse_cdf(probs, u_tape)
+    a = DO.sample_inverse_cdf(probs, torch.rand(N) if u_tape is None else u_tape)      # the kernel draws Philox uniforms when no tape is given
     actions.copy_(a)
     neglogp.copy_(-nl.gather(1, a.unsqueeze(1)).squeeze(1))
     if dones_out is not None:

@@ -98,3 +98,40 @@ def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, t
     ref_m = g['epochs_out'][-1]['adam_exp_avg']
     for i, m in enumerate(ref_m):
         torch.testing.assert_close(ck['optimizer']['state'][i]['exp_avg'].reshape(m.shape), m, rtol=1e-3, atol=1e-7)
+
+
+def test_discrete_train_loop_and_checkpoint_roundtrip(monkeypatch, tmp_path):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _torch_ops
+    from rl_games_b200 import agent_discrete
+    from rl_games_b200.runner import Runner
+    _torch_ops.install(monkeypatch)
+    monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_require_cuda', lambda self: None)
+    monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_sync', staticmethod(lambda: None))
+    g = torch.load(os.path.join(GOLDEN, 'agent_discrete_masked.pt'), weights_only=False)
+
+    def build():
+        env = _Env(g)
+        config = {k: v for k, v in g['config'].items() if k not in ('device', 'torch_compile')}
+        config.update({'device': 'cpu', 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1},
+                       'b200_unvalidated': True, 'train_dir': str(tmp_path), 'lr_schedule': g['config'].get('lr_schedule', None),
+                       'max_epochs': 2, 'print_stats': False, 'name': 'dloop'})
+        network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'discrete': None},
+                   'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}
+        r = Runner()
+        r.load({'params': {'seed': 1, 'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'discrete_a2c'}, 'network': network, 'config': config}})
+        r.params['config']['vec_env'] = env
+        return r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
+    a = build()
+    last, epochs = a.train()
+    assert epochs == 2 and a.frame == 2 * g['N'] * g['H'] and torch.isfinite(a.model.flat).all()
+    fn = str(tmp_path / 'dck')
+    a.save(fn)
+    b = build()
+    b.restore(fn + '.pth')
+    assert torch.equal(b.model.flat, a.model.flat) and torch.equal(b.model.exp_avg_sq, a.model.exp_avg_sq)
+    assert b.epoch_num == a.epoch_num and b.last_lr == a.last_lr
+    # the gate: without the explicit opt-in the constructor refuses
+    with pytest.raises(NotImplementedError, match='not been run on hardware'):
+        agent_discrete.DiscreteA2CAgent('x', {'config': {'name': 'x'}, 'network': a.network_params})
