@@ -226,8 +226,10 @@ int b200rl_loss_partial_stride(void);
  *  b200rl_categorical_sample_f32: rollout head (models.py:95-125 eval branch; CategoricalMasked distributions.py:23-44):
  *    logits [N, ld] (K used), value_raw [N*value_ld], optional action_masks uint8 [N, K], one uniform per row from u_tape [N] or
  *    Philox(seed, *rng_epoch_dev, step_index, row); action = #{k : cdf_k <= u} clamped to the last action with p > 0;
- *    outputs actions int64 [N], neglogp [N], values [N] (de-normalised when normalize_value), dones_out / valid_out bookkeeping
- *    as in b200rl_policy_head_sample_f32.
+ *    outputs actions int64 [N, n_heads], neglogp [N], values [N] (de-normalised when normalize_value), dones_out / valid_out
+ *    bookkeeping as in b200rl_policy_head_sample_f32.  Multi-discrete (Tuple) spaces: the K logits / masks of a row are the
+ *    concatenation of n_heads heads of head_sizes_host[j] actions (sum = K; n_heads = 0 or NULL: one head), one categorical and
+ *    one uniform per head (u_tape [n_heads, N]), neglogp and entropy are sums over the heads (models.py:128-206).
  *  b200rl_categorical_loss_f32: training head (a2c_discrete.py:121-209): per-row neglogp / entropy / actor + critic loss,
  *    kl = 0.5 (old_neglogp - neglogp)^2, gradients d_logits [M, d_ld], d_value [M*dv_ld] of
  *    mean(a) + 0.5 critic_coef mean(c) - entropy_coef mean(H) (masked means when mask / inv_count_dev are given), and
@@ -238,13 +240,15 @@ typedef struct b200rl_cat_loss_cfg {
     float e_clip, critic_coef, entropy_coef;
     int clip_value, use_smooth_clamp, ppo;
 } b200rl_cat_loss_cfg;
-int b200rl_categorical_sample_f32(const float* logits, int ld, int K, const float* value_raw, int value_ld,
+int b200rl_categorical_sample_f32(const float* logits, int ld, int K, int n_heads, const int* head_sizes_host,
+                                  const float* value_raw, int value_ld,
                                   const uint8_t* action_masks, const float* u_tape, uint64_t seed,
                                   const uint64_t* rng_epoch_dev, uint32_t step_index, const double* vms_mean,
                                   const double* vms_var, int normalize_value, int64_t* actions, float* neglogp,
                                   float* values, const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones,
                                   float* valid_out, int N, int values_only, void* stream);
-int b200rl_categorical_loss_f32(const float* logits, int ld, int K, const float* values, int value_ld,
+int b200rl_categorical_loss_f32(const float* logits, int ld, int K, int n_heads, const int* head_sizes_host,
+                                const float* values, int value_ld,
                                 const int64_t* actions, const uint8_t* action_masks, const float* old_values_n,
                                 const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
                                 int rows_per_chunk, int64_t chunk_stride, int M, const b200rl_cat_loss_cfg* cfg_host,

@@ -9,8 +9,8 @@ that promote it.  Everything except the two categorical kernels (csrc/discrete.c
 continuous path: linear_fwd / linear_bwd_* / reduce_splits (mlp_simt.cu), gae_fused, prepare_batch, moments_update,
 mask_inv_counts (stats.cu, gae.cu), post_step (rollout.cu), adam_step (adam.cu).
 
-Scope of this first edition: one GPU, eager launches (no CUDA graph), flat Box observations, a single ``Discrete(K)`` action space
-(K <= 64), no RNN, no central value.  The scheduler steps once per MINI-EPOCH on the mean KL like the reference
+Scope of this first edition: one GPU, eager launches (no CUDA graph), flat Box observations, ``Discrete(K)`` or multi-discrete
+``Tuple(Discrete(K_j))`` action spaces (K_j <= 64, <= 8 heads), no RNN, no central value.  The scheduler steps once per MINI-EPOCH on the mean KL like the reference
 (a2c_common.py:1265-1272), which costs one host sync per mini-epoch.
 """
 import os
@@ -33,7 +33,8 @@ class DiscreteModel:
     W_head [1 + K, Hl] (row 0 = value, rows 1.. = logits) and b_head [1 + K]; ``_param_views`` lists the tensors in the reference's
     ``model.parameters()`` order (actor_mlp.*, critic_mlp.*, value.*, logits.*) for state dicts and the index-keyed Adam state."""
 
-    def __init__(self, network_params, obs_dim, n_actions, device, normalize_input, normalize_value):
+    def __init__(self, network_params, obs_dim, n_actions, device, normalize_input, normalize_value, head_sizes=None):
+        self.head_sizes = list(head_sizes) if head_sizes else None          # multi-discrete: one logits head per Tuple component
         mlp = network_params['mlp']
         self.units = list(mlp['units'])
         if not self.units:
@@ -93,14 +94,26 @@ class DiscreteModel:
             for i in range(len(self.units)):
                 out += [self.view(f'W{p}{i}', arena), self.view(f'b{p}{i}', arena)]
         wh, bh = self.view('W_head', arena), self.view('b_head', arena)
-        return out + [wh[:1], bh[:1], wh[1:], bh[1:]]
+        out += [wh[:1], bh[:1]]
+        if self.head_sizes is None:
+            return out + [wh[1:], bh[1:]]
+        off = 1
+        for k in self.head_sizes:          # ModuleList of heads: logits.{j}.weight / bias (network_builder.py:304-305)
+            out += [wh[off:off + k], bh[off:off + k]]
+            off += k
+        return out
 
     def param_names(self):
         names = []
         for pre in (['actor_mlp', 'critic_mlp'] if self.separate else ['actor_mlp']):
             for i in range(len(self.units)):
                 names += [f'a2c_network.{pre}.{2 * i}.weight', f'a2c_network.{pre}.{2 * i}.bias']
-        return names + ['a2c_network.value.weight', 'a2c_network.value.bias', 'a2c_network.logits.weight', 'a2c_network.logits.bias']
+        names += ['a2c_network.value.weight', 'a2c_network.value.bias']
+        if self.head_sizes is None:
+            return names + ['a2c_network.logits.weight', 'a2c_network.logits.bias']
+        for j in range(len(self.head_sizes)):
+            names += [f'a2c_network.logits.{j}.weight', f'a2c_network.logits.{j}.bias']
+        return names
 
     def state_dict(self):
         sd = OrderedDict()
@@ -181,11 +194,19 @@ class DiscreteA2CAgent:
             raise NotImplementedError('only flat Box observations')
         self.obs_shape = self.observation_space.shape
         action_space = self.env_info['action_space']
-        if type(action_space).__name__ != 'Discrete':        # a2c_common.py:1211-1224 (Tuple = multi-discrete: not yet)
-            raise NotImplementedError(f'action space {type(action_space).__name__}: only Discrete(K) so far')
-        self.actions_num, self.is_discrete, self.is_multi_discrete = int(action_space.n), True, False
-        if self.actions_num > 64:
-            raise NotImplementedError('more than 64 discrete actions')
+        kind = type(action_space).__name__          # a2c_common.py:1211-1224
+        if kind == 'Discrete':
+            self.head_sizes, self.actions_num, self.is_multi_discrete = None, int(action_space.n), False
+        elif kind == 'Tuple':
+            self.head_sizes = [int(a.n) for a in action_space]
+            self.actions_num, self.is_multi_discrete = sum(self.head_sizes), True      # width of the concatenated logits
+            if len(self.head_sizes) > 8:
+                raise NotImplementedError('more than 8 heads in a multi-discrete space')
+        else:
+            raise ValueError(f'Unsupported action space type for DiscreteA2CBase: {type(action_space)}')
+        self.is_discrete = True
+        if max(self.head_sizes or [self.actions_num]) > 64:
+            raise NotImplementedError('more than 64 actions in one discrete head')
         self.use_action_masks = bool(config.get('use_action_masks', False))
         self.autoreset_mode = self.env_info.get('autoreset_mode', 'same_step')
         self.mask_autoreset_rows = self.autoreset_mode == 'next_step'
@@ -249,7 +270,7 @@ class DiscreteA2CAgent:
             os.makedirs(d, exist_ok=True)
         self.writer = make_summary_writer(self.summaries_dir)
         self.model = DiscreteModel(self.network_params, self.obs_shape[0], self.actions_num, self.device_t, self.normalize_input,
-                                   self.normalize_value)
+                                   self.normalize_value, head_sizes=self.head_sizes)
         self.value_mean_std = self.model.value_mean_std
         self.rng_seed = int(config.get('b200_rng_seed', params.get('seed', 0) or 0))
         self.is_rnn, self.rnn_states, self.is_tensor_obses = False, None, True
@@ -286,7 +307,8 @@ class DiscreteA2CAgent:
         dev = self.device_t
         f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)   # noqa: E731
         self.obses = f(H, N, D)
-        self.actions = torch.zeros(H, N, dtype=torch.int64, device=dev)
+        self.actions = (torch.zeros(H, N, len(self.head_sizes), dtype=torch.int64, device=dev) if self.head_sizes
+                        else torch.zeros(H, N, dtype=torch.int64, device=dev))
         self.neglogpacs, self.values, self.rewards = f(H, N), f(H, N), f(H, N)
         self.dones_buf = torch.zeros(H, N, dtype=torch.uint8, device=dev)
         self.action_masks = torch.ones(H, N, K, dtype=torch.uint8, device=dev) if self.use_action_masks else None
@@ -407,7 +429,7 @@ class DiscreteA2CAgent:
             ops.categorical_sample(lg, ld, K, vl, vld, masks, None if u is None else u[t].contiguous(), self.rng_seed, self.rng_epoch, t,
                                    None if vm is None else vm.running_mean, None if vm is None else vm.running_var, self.normalize_value,
                                    self.actions[t], self.neglogpacs[t], self.values[t], self.dones, self.dones_buf[t], self.prev_dones,
-                                   None if self.valid is None else self.valid[t], N)
+                                   None if self.valid is None else self.valid[t], N, head_sizes=self.head_sizes)
             t0 = time.perf_counter()
             self.obs, rewards, dones, infos = self.env_step(self.actions[t])
             step_time += time.perf_counter() - t0
@@ -472,7 +494,7 @@ class DiscreteA2CAgent:
                                   self.old_values_n[0, e0:], self.returns_n[0, e0:], self.neglogpacs[0, e0:], self.advs_n[0, e0:],
                                   None if self.valid is None else self.valid[0, e0:], epm, N, mb, cfg,
                                   None if self.inv_counts is None else self.inv_counts[i:i + 1], d_lg, d_ld, d_vl, d_vld,
-                                  self.loss_partials)
+                                  self.loss_partials, head_sizes=self.head_sizes)
         stats = self.loss_partials[:nb, :4].sum(dim=0).float()
         # ---- backward through the heads and the trunk(s): split partial gradients, then one reduction ----
         off_wh, _ = m.layout['W_head']

@@ -81,6 +81,19 @@ class Discrete:
         self.shape = ()
 
 
+class Tuple:
+    """Minimal stand-in for gymnasium.spaces.Tuple (multi-discrete action spaces: a2c_common.py:1217-1220 reads [a.n for a in space])"""
+
+    def __init__(self, spaces):
+        self.spaces = list(spaces)
+
+    def __iter__(self):
+        return iter(self.spaces)
+
+    def __len__(self):
+        return len(self.spaces)
+
+
 # ---- registries: common/vecenv.py:368-391 and common/env_configurations.py:358-366 ----
 vecenv_config = {}
 configurations = {}

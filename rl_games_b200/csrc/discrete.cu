@@ -34,40 +34,62 @@ __host__ __device__ inline void cat_lse(const float* z, const uint8_t* mask, int
     lse = m + logf(s);
 }
 
-// action = #{k : cdf_k <= u}, clamped to the last action of non-zero probability (oracle.sample_inverse_cdf); returns neglogp too
-__host__ __device__ inline int cat_sample_row(const float* z, const uint8_t* mk, int K, float u, float& neglogp) {
-    float lse;
-    cat_lse(z, mk, K, lse);
-    float cdf = 0.f;
-    int count = 0, last = 0;
-    for (int k = 0; k < K; ++k) {
-        const float v = (mk && !mk[k]) ? -1e8f : z[k];
-        const float p = expf(v - lse);
-        cdf += p;
-        if (cdf <= u) ++count;
-        if (p > 0.f) last = k;
+// one categorical per head (a single Discrete(K) space is one head; a Tuple space = ModelA2CMultiDiscrete, models.py:128-206):
+// logits / action masks of the heads are concatenated along the row, neglogp and entropy are sums over the heads
+constexpr int CAT_MAXH = 8;
+struct CatHeads { int n; int size[CAT_MAXH]; int off[CAT_MAXH]; };
+
+// action_j = #{k : cdf_k <= u_j}, clamped to the last action of non-zero probability (oracle.sample_inverse_cdf); returns sum_j neglogp_j
+__host__ __device__ inline float cat_sample_row(const float* z, const uint8_t* mk, const CatHeads& hd, const float* u, int64_t u_stride,
+                                                int64_t* actions) {
+    float nlp = 0.f;
+    for (int j = 0; j < hd.n; ++j) {
+        const float* zj = z + hd.off[j];
+        const uint8_t* mj = mk ? mk + hd.off[j] : nullptr;
+        const int K = hd.size[j];
+        float lse;
+        cat_lse(zj, mj, K, lse);
+        const float uj = u[(int64_t)j * u_stride];
+        float cdf = 0.f;
+        int count = 0, last = 0;
+        for (int k = 0; k < K; ++k) {
+            const float v = (mj && !mj[k]) ? -1e8f : zj[k];
+            const float p = expf(v - lse);
+            cdf += p;
+            if (cdf <= uj) ++count;
+            if (p > 0.f) last = k;
+        }
+        const int a = count < last ? count : last;
+        const float va = (mj && !mj[a]) ? -1e8f : zj[a];
+        nlp += -(va - lse);
+        actions[j] = (int64_t)a;
     }
-    const int a = count < last ? count : last;
-    const float va = (mk && !mk[a]) ? -1e8f : z[a];
-    neglogp = -(va - lse);
-    return a;
+    return nlp;
 }
 
 struct CatRowOut { float a_loss, c_loss, ent, kl, clipped, d_value; };
 
-// loss pieces of one row and the gradient of  w * (a + 0.5 * critic_coef * c - entropy_coef * H)  w.r.t. its logits (dz[K]) / value
-__host__ __device__ inline CatRowOut cat_loss_row(const float* z, const uint8_t* mk, int K, int a, float val, float old_nlp, float adv,
-                                                  float old_v, float ret, float w, const CatLossDev& c, float* dz) {
-    float lse;
-    cat_lse(z, mk, K, lse);
-    const float za = (mk && !mk[a]) ? -1e8f : z[a];
-    const float nlp = -(za - lse);
-    // entropy: -sum p log p over legal actions (distributions.py:38-44; unmasked: torch Categorical.entropy)
-    float ent = 0.f;
-    for (int k = 0; k < K; ++k) {
-        if (mk && !mk[k]) continue;
-        const float lp = z[k] - lse;
-        ent -= expf(lp) * lp;
+// loss pieces of one row and the gradient of  w * (a + 0.5 * critic_coef * c - entropy_coef * H)  w.r.t. its logits (dz[sum K_j]) / value
+__host__ __device__ inline CatRowOut cat_loss_row(const float* z, const uint8_t* mk, const CatHeads& hd, const int64_t* actions, float val,
+                                                  float old_nlp, float adv, float old_v, float ret, float w, const CatLossDev& c, float* dz) {
+    float lse[CAT_MAXH], entj[CAT_MAXH];
+    float nlp = 0.f, ent = 0.f;
+    for (int j = 0; j < hd.n; ++j) {
+        const float* zj = z + hd.off[j];
+        const uint8_t* mj = mk ? mk + hd.off[j] : nullptr;
+        cat_lse(zj, mj, hd.size[j], lse[j]);
+        const int a = (int)actions[j];
+        const float za = (mj && !mj[a]) ? -1e8f : zj[a];
+        nlp += -(za - lse[j]);
+        // entropy: -sum p log p over legal actions (distributions.py:38-44; unmasked: torch Categorical.entropy)
+        float e = 0.f;
+        for (int k = 0; k < hd.size[j]; ++k) {
+            if (mj && !mj[k]) continue;
+            const float lp = zj[k] - lse[j];
+            e -= expf(lp) * lp;
+        }
+        entj[j] = e;
+        ent += e;
     }
     // actor loss + d/dnlp (common_losses.py:41-82)
     float a_loss, g_a;
@@ -107,14 +129,19 @@ __host__ __device__ inline CatRowOut cat_loss_row(const float* z, const uint8_t*
         dc = -2.0f * e1;
     }
     const float dl = old_nlp - nlp;
-    // gradients: dnlp/dz_k = p_k - [k == a];   dH/dz_k = -p_k (log p_k + H)   (a2c_discrete.py:163-165: each loss is a (masked) mean)
-    for (int k = 0; k < K; ++k) {
-        float g = 0.f;
-        if (!(mk && !mk[k])) {
-            const float lp = z[k] - lse, p = expf(lp);
-            g = w * (g_a * (p - (k == a ? 1.0f : 0.0f)) + c.entropy_coef * p * (lp + ent));
+    // gradients, head by head: dnlp/dz_k = p_k - [k == a_j];   dH/dz_k = -p_k (log p_k + H_j)   (a2c_discrete.py:163-165)
+    for (int j = 0; j < hd.n; ++j) {
+        const float* zj = z + hd.off[j];
+        const uint8_t* mj = mk ? mk + hd.off[j] : nullptr;
+        const int a = (int)actions[j];
+        for (int k = 0; k < hd.size[j]; ++k) {
+            float g = 0.f;
+            if (!(mj && !mj[k])) {
+                const float lp = zj[k] - lse[j], p = expf(lp);
+                g = w * (g_a * (p - (k == a ? 1.0f : 0.0f)) + c.entropy_coef * p * (lp + entj[j]));
+            }
+            dz[hd.off[j] + k] = g;
         }
-        dz[k] = g;
     }
     CatRowOut o;
     o.a_loss = a_loss; o.c_loss = c_loss; o.ent = ent;
@@ -124,9 +151,10 @@ __host__ __device__ inline CatRowOut cat_loss_row(const float* z, const uint8_t*
     return o;
 }
 
-// ---- rollout: sample (inverse CDF on one uniform per row), neglogp, de-normalised value --------------------------------------
+// ---- rollout: sample (inverse CDF, one uniform per row and head), neglogp, de-normalised value --------------------------------
+// actions: int64 [N, n_heads]; u_tape (optional): float [n_heads, N]
 __global__ void __launch_bounds__(256) categorical_sample_kernel(
-    const float* __restrict__ logits, int ld, int K, const float* __restrict__ value_raw, int value_ld,
+    const float* __restrict__ logits, int ld, int K, CatHeads hd, const float* __restrict__ value_raw, int value_ld,
     const uint8_t* __restrict__ action_masks, const float* __restrict__ u_tape, uint64_t seed,
     const uint64_t* __restrict__ rng_epoch_dev, uint32_t step_index, const double* __restrict__ vms_mean,
     const double* __restrict__ vms_var, int normalize_value, int64_t* __restrict__ actions, float* __restrict__ neglogp,
@@ -142,18 +170,21 @@ __global__ void __launch_bounds__(256) categorical_sample_kernel(
     }
     values[e] = val;
     if (values_only) return;
-    float u;
+    float ubuf[CAT_MAXH];
+    const float* u = ubuf;
+    int64_t ustride = 1;
     if (u_tape) {
-        u = u_tape[e];
+        u = u_tape + e;
+        ustride = N;
     } else {
         const uint64_t ep = rng_epoch_dev ? *rng_epoch_dev : 0ull;
-        const Philox4 r = philox4x32_10((uint64_t)e, (ep << 20) | ((uint64_t)step_index << 4) | 15ull, seed);
-        u = (float)(r.x >> 8) * (1.0f / 16777216.0f);                     // [0, 1)
+        for (int j = 0; j < hd.n; ++j) {
+            const Philox4 r = philox4x32_10((uint64_t)e, (ep << 20) | ((uint64_t)step_index << 4) | (uint64_t)(8 + j), seed);
+            ubuf[j] = (float)(r.x >> 8) * (1.0f / 16777216.0f);           // [0, 1)
+        }
     }
-    float nlp;
-    const int a = cat_sample_row(logits + (int64_t)e * ld, action_masks ? action_masks + (int64_t)e * K : nullptr, K, u, nlp);
-    actions[e] = (int64_t)a;
-    neglogp[e] = nlp;
+    neglogp[e] = cat_sample_row(logits + (int64_t)e * ld, action_masks ? action_masks + (int64_t)e * K : nullptr, hd, u, ustride,
+                                actions + (int64_t)e * hd.n);
     if (dones_out) dones_out[e] = dones_cur[e];
     if (valid_out) valid_out[e] = prev_dones ? (1.0f - prev_dones[e]) : 1.0f;
 }
@@ -161,7 +192,7 @@ __global__ void __launch_bounds__(256) categorical_sample_kernel(
 // ---- training: loss pieces + gradients at the logits / value for one minibatch -------------------------------------------------
 // partial row (8 doubles per block): sum w*a_loss, sum w*c_loss, sum w*entropy, sum w*kl, sum mask, sum mask*clipped, sum w, 0
 __global__ void __launch_bounds__(256) categorical_loss_kernel(
-    const float* __restrict__ logits, int ld, int K, const float* __restrict__ values, int value_ld,
+    const float* __restrict__ logits, int ld, int K, CatHeads hd, const float* __restrict__ values, int value_ld,
     const int64_t* __restrict__ actions, const uint8_t* __restrict__ action_masks, const float* __restrict__ old_values_n,
     const float* __restrict__ returns_n, const float* __restrict__ old_neglogp, const float* __restrict__ advs_n,
     const float* __restrict__ mask, int rows_per_chunk, int64_t chunk_stride, int M, CatLossDev c,
@@ -175,7 +206,7 @@ __global__ void __launch_bounds__(256) categorical_loss_kernel(
         const float mkr = mask ? mask[ar] : 1.0f;
         const float inv_cnt = inv_count_dev ? inv_count_dev[0] : (1.0f / (float)M);
         const float w = mkr * inv_cnt;
-        const CatRowOut o = cat_loss_row(logits + (int64_t)m * ld, action_masks ? action_masks + ar * K : nullptr, K, (int)actions[ar],
+        const CatRowOut o = cat_loss_row(logits + (int64_t)m * ld, action_masks ? action_masks + ar * K : nullptr, hd, actions + ar * hd.n,
                                          values[(int64_t)m * value_ld], old_neglogp[ar], advs_n[ar], old_values_n[ar], returns_n[ar], w, c,
                                          d_logits + (int64_t)m * d_ld);
         d_value[(int64_t)m * dv_ld] = o.d_value;
@@ -191,26 +222,42 @@ __global__ void __launch_bounds__(256) categorical_loss_kernel(
     }
 }
 
+// head table from the host: sizes of n_heads heads (NULL / 0 = one head of K actions); returns false on a bad table
+static bool make_heads(int K, int n_heads, const int* head_sizes_host, CatHeads& hd) {
+    if (n_heads <= 0 || !head_sizes_host) { hd.n = 1; hd.size[0] = K; hd.off[0] = 0; return K > 0 && K <= CAT_MAXK; }
+    if (n_heads > CAT_MAXH) return false;
+    hd.n = n_heads;
+    int off = 0;
+    for (int j = 0; j < n_heads; ++j) {
+        if (head_sizes_host[j] <= 0 || head_sizes_host[j] > CAT_MAXK) return false;
+        hd.size[j] = head_sizes_host[j]; hd.off[j] = off; off += head_sizes_host[j];
+    }
+    return off == K;
+}
+
 }  // namespace
 
-B200RL_EXPORT int b200rl_categorical_sample_f32(const float* logits, int ld, int K, const float* value_raw, int value_ld,
+B200RL_EXPORT int b200rl_categorical_sample_f32(const float* logits, int ld, int K, int n_heads, const int* head_sizes_host,
+                                                const float* value_raw, int value_ld,
                                                 const uint8_t* action_masks, const float* u_tape, uint64_t seed,
                                                 const uint64_t* rng_epoch_dev, uint32_t step_index, const double* vms_mean,
                                                 const double* vms_var, int normalize_value, int64_t* actions, float* neglogp,
                                                 float* values, const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones,
                                                 float* valid_out, int N, int values_only, void* stream) {
     if (!value_raw || !values || N <= 0 || value_ld <= 0) return B200RL_EINVAL;
-    if (!values_only && (!logits || !actions || !neglogp || K <= 0 || K > CAT_MAXK || ld < K)) return B200RL_EINVAL;
+    CatHeads hd{};
+    if (!values_only && (!logits || !actions || !neglogp || ld < K || !make_heads(K, n_heads, head_sizes_host, hd))) return B200RL_EINVAL;
     if (normalize_value && (!vms_mean || !vms_var)) return B200RL_EINVAL;
     if (dones_out && !dones_cur) return B200RL_EINVAL;
     categorical_sample_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(
-        logits, ld, K, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch_dev, step_index, vms_mean, vms_var, normalize_value,
+        logits, ld, K, hd, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch_dev, step_index, vms_mean, vms_var, normalize_value,
         actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }
 
-B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K, const float* values, int value_ld,
+B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K, int n_heads, const int* head_sizes_host,
+                                              const float* values, int value_ld,
                                               const int64_t* actions, const uint8_t* action_masks, const float* old_values_n,
                                               const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
                                               int rows_per_chunk, int64_t chunk_stride, int M, const b200rl_cat_loss_cfg* cfg_host,
@@ -219,13 +266,15 @@ B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K
     if (!logits || !values || !actions || !old_values_n || !returns_n || !old_neglogp || !advs_n || !cfg_host || !d_logits || !d_value ||
         !partials)
         return B200RL_EINVAL;
-    if (M <= 0 || K <= 0 || K > CAT_MAXK || ld < K || d_ld < K || value_ld <= 0 || dv_ld <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
+    CatHeads hd{};
+    if (M <= 0 || ld < K || d_ld < K || value_ld <= 0 || dv_ld <= 0 || rows_per_chunk <= 0 || !make_heads(K, n_heads, head_sizes_host, hd))
+        return B200RL_EINVAL;
     const int blocks = (M + 255) / 256;
     if (n_blocks_out_host) *n_blocks_out_host = blocks;
     if (blocks > max_partials) return B200RL_EINVAL;
     CatLossDev c{cfg_host->e_clip, cfg_host->critic_coef, cfg_host->entropy_coef, cfg_host->clip_value, cfg_host->use_smooth_clamp,
                  cfg_host->ppo};
-    categorical_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(logits, ld, K, values, value_ld, actions, action_masks, old_values_n,
+    categorical_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(logits, ld, K, hd, values, value_ld, actions, action_masks, old_values_n,
                                                                   returns_n, old_neglogp, advs_n, mask, rows_per_chunk, chunk_stride, M, c,
                                                                   inv_count_dev, d_logits, d_ld, d_value, dv_ld, partials);
     B200RL_LAUNCH_CHECK();
@@ -234,20 +283,27 @@ B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K
 
 // ---- host test entry points: the per-row functions above, run on the CPU over HOST arrays (no GPU involved).  Test infrastructure for
 //      tests/test_discrete_rows_cpu.py; not declared in include/b200rl.h and never called by the product. -----------------------------
-B200RL_EXPORT int b200rl_hosttest_categorical_sample_rows(const float* logits, int K, const uint8_t* masks, const float* u, int N,
-                                                         int64_t* actions, float* neglogp) {
-    for (int e = 0; e < N; ++e) actions[e] = cat_sample_row(logits + (int64_t)e * K, masks ? masks + (int64_t)e * K : nullptr, K, u[e], neglogp[e]);
+B200RL_EXPORT int b200rl_hosttest_categorical_sample_rows(const float* logits, int K, int n_heads, const int* head_sizes, const uint8_t* masks,
+                                                         const float* u /* [n_heads, N] */, int N, int64_t* actions /* [N, n_heads] */,
+                                                         float* neglogp) {
+    CatHeads hd{};
+    if (!make_heads(K, n_heads, head_sizes, hd)) return B200RL_EINVAL;
+    for (int e = 0; e < N; ++e)
+        neglogp[e] = cat_sample_row(logits + (int64_t)e * K, masks ? masks + (int64_t)e * K : nullptr, hd, u + e, N, actions + (int64_t)e * hd.n);
     return B200RL_OK;
 }
 
-B200RL_EXPORT int b200rl_hosttest_categorical_loss_rows(const float* logits, int K, const float* values, const int64_t* actions,
+B200RL_EXPORT int b200rl_hosttest_categorical_loss_rows(const float* logits, int K, int n_heads, const int* head_sizes, const float* values,
+                                                       const int64_t* actions /* [M, n_heads] */,
                                                        const uint8_t* masks, const float* old_values_n, const float* returns_n,
                                                        const float* old_neglogp, const float* advs_n, const float* w, int M,
                                                        const b200rl_cat_loss_cfg* cfg, float* d_logits, float* d_value, double* sums4) {
     CatLossDev c{cfg->e_clip, cfg->critic_coef, cfg->entropy_coef, cfg->clip_value, cfg->use_smooth_clamp, cfg->ppo};
+    CatHeads hd{};
+    if (!make_heads(K, n_heads, head_sizes, hd)) return B200RL_EINVAL;
     double acc[4] = {0, 0, 0, 0};
     for (int m = 0; m < M; ++m) {
-        const CatRowOut o = cat_loss_row(logits + (int64_t)m * K, masks ? masks + (int64_t)m * K : nullptr, K, (int)actions[m], values[m],
+        const CatRowOut o = cat_loss_row(logits + (int64_t)m * K, masks ? masks + (int64_t)m * K : nullptr, hd, actions + (int64_t)m * hd.n, values[m],
                                          old_neglogp[m], advs_n[m], old_values_n[m], returns_n[m], w[m], c, d_logits + (int64_t)m * K);
         d_value[m] = o.d_value;
         acc[0] += (double)w[m] * o.a_loss; acc[1] += (double)w[m] * o.c_loss; acc[2] += (double)w[m] * o.ent; acc[3] += (double)w[m] * o.kl;

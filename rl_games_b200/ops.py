@@ -441,21 +441,33 @@ class CatLossCfg(ctypes.Structure):
                 ('clip_value', ctypes.c_int), ('use_smooth_clamp', ctypes.c_int), ('ppo', ctypes.c_int)]
 
 
+def _head_table(head_sizes):
+    if not head_sizes:
+        return 0, None
+    arr = (ctypes.c_int * len(head_sizes))(*[int(k) for k in head_sizes])
+    return len(head_sizes), arr
+
+
 def categorical_sample(logits, ld, K, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch, step_index, vms_mean, vms_var,
-                       normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only=False):
-    check(lib.b200rl_categorical_sample_f32(ptr(logits), ld, K, ptr(value_raw), value_ld, ptr(action_masks), ptr(u_tape), seed,
-                                            ptr(rng_epoch), step_index, ptr(vms_mean), ptr(vms_var), int(normalize_value),
-                                            ptr(actions), ptr(neglogp), ptr(values), ptr(dones_cur), ptr(dones_out), ptr(prev_dones),
-                                            ptr(valid_out), N, int(values_only), _stream()), 'categorical_sample')
+                       normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only=False,
+                       head_sizes=None):
+    """head_sizes: sizes of the heads of a multi-discrete (Tuple) space (sum = K; actions [N, n_heads], u_tape [n_heads, N]); None = one head"""
+    nh, tab = _head_table(head_sizes)
+    check(lib.b200rl_categorical_sample_f32(ptr(logits), ld, K, nh, None if tab is None else ctypes.addressof(tab), ptr(value_raw), value_ld,
+                                            ptr(action_masks), ptr(u_tape), seed, ptr(rng_epoch), step_index, ptr(vms_mean), ptr(vms_var),
+                                            int(normalize_value), ptr(actions), ptr(neglogp), ptr(values), ptr(dones_cur), ptr(dones_out),
+                                            ptr(prev_dones), ptr(valid_out), N, int(values_only), _stream()), 'categorical_sample')
 
 
 def categorical_loss(logits, ld, K, values, value_ld, actions, action_masks, old_values_n, returns_n, old_neglogp, advs_n, mask,
-                     rows_per_chunk, chunk_stride, M, cfg, inv_count, d_logits, d_ld, d_value, dv_ld, partials):
+                     rows_per_chunk, chunk_stride, M, cfg, inv_count, d_logits, d_ld, d_value, dv_ld, partials, head_sizes=None):
     nb = ctypes.c_int(0)
-    check(lib.b200rl_categorical_loss_f32(ptr(logits), ld, K, ptr(values), value_ld, ptr(actions), ptr(action_masks), ptr(old_values_n),
-                                          ptr(returns_n), ptr(old_neglogp), ptr(advs_n), ptr(mask), rows_per_chunk, chunk_stride, M,
-                                          ctypes.addressof(cfg), ptr(inv_count), ptr(d_logits), d_ld, ptr(d_value), dv_ld,
-                                          ptr(partials), partials.shape[0], ctypes.addressof(nb), _stream()), 'categorical_loss')
+    nh, tab = _head_table(head_sizes)
+    check(lib.b200rl_categorical_loss_f32(ptr(logits), ld, K, nh, None if tab is None else ctypes.addressof(tab), ptr(values), value_ld,
+                                          ptr(actions), ptr(action_masks), ptr(old_values_n), ptr(returns_n), ptr(old_neglogp), ptr(advs_n),
+                                          ptr(mask), rows_per_chunk, chunk_stride, M, ctypes.addressof(cfg), ptr(inv_count), ptr(d_logits),
+                                          d_ld, ptr(d_value), dv_ld, ptr(partials), partials.shape[0], ctypes.addressof(nb), _stream()),
+          'categorical_loss')
     return nb.value
 
 

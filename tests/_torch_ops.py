@@ -182,8 +182,17 @@ def post_step(rewards, dones, time_outs, values_t, valid_t, rewards_out_t, dones
         prev_dones.copy_(d)
 
 
+def _cat_heads(z, masks, head_sizes):
+    """per-head (normalised logits, probs, entropy) of the concatenated logits; one head when head_sizes is None"""
+    sizes = [z.shape[1]] if not head_sizes else list(head_sizes)
+    zs = torch.split(z, sizes, dim=1)
+    ms = [None] * len(sizes) if masks is None else torch.split(masks.bool(), sizes, dim=1)
+    return [DO.categorical_masked(zz, mm) for zz, mm in zip(zs, ms)]
+
+
 def categorical_sample(logits, ld, K, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch, step_index, vms_mean, vms_var,
-                       normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only=False):
+                       normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only=False,
+                       head_sizes=None):
     val = _flat(value_raw)[torch.arange(N) * value_ld]
     if normalize_value:
         val = torch.sqrt(vms_var.float() + 1e-5) * torch.clamp(val, -5.0, 5.0) + vms_mean.float()
@@ -191,10 +200,12 @@ def categorical_sample(logits, ld, K, value_raw, value_ld, action_masks, u_tape,
     if values_only:
         return
     z = _flat(logits)[(torch.arange(N) * ld).unsqueeze(1) + torch.arange(K).unsqueeze(0)]
-    nl, probs, _ = DO.categorical_masked(z, None if action_masks is None else action_masks.bool())
-    a = DO.sample_inverse_cdf(probs, torch.rand(N) if u_tape is None else u_tape)      # the kernel draws Philox uniforms when no tape is given
-    actions.copy_(a)
-    neglogp.copy_(-nl.gather(1, a.unsqueeze(1)).squeeze(1))
+    heads = _cat_heads(z, action_masks, head_sizes)
+    nh = len(heads)
+    u = torch.rand(nh, N) if u_tape is None else u_tape.reshape(nh, N)      # the kernel draws Philox uniforms when no tape is given
+    acts = [DO.sample_inverse_cdf(h[1], u[j]) for j, h in enumerate(heads)]
+    actions.copy_(torch.stack(acts, dim=-1).reshape(actions.shape))
+    neglogp.copy_(sum(-h[0].gather(1, a.unsqueeze(1)).squeeze(1) for h, a in zip(heads, acts)))
     if dones_out is not None:
         dones_out.copy_(dones_cur)
     if valid_out is not None:
@@ -202,19 +213,21 @@ def categorical_sample(logits, ld, K, value_raw, value_ld, action_masks, u_tape,
 
 
 def categorical_loss(logits, ld, K, values, value_ld, actions, action_masks, old_values_n, returns_n, old_neglogp, advs_n, mask,
-                     rows_per_chunk, chunk_stride, M, cfg, inv_count, d_logits, d_ld, d_value, dv_ld, partials):
+                     rows_per_chunk, chunk_stride, M, cfg, inv_count, d_logits, d_ld, d_value, dv_ld, partials, head_sizes=None):
     mrow = torch.arange(M)
     z = _flat(logits)[(mrow * ld).unsqueeze(1) + torch.arange(K).unsqueeze(0)].clone().requires_grad_(True)
     v = _flat(values)[mrow * value_ld].clone().requires_grad_(True)
+    nh = len(head_sizes) if head_sizes else 1
 
     def arena(t, width=1):
         return _rows(t, M, width, rows_per_chunk, chunk_stride, width)
-    act = arena(actions).squeeze(1)
+    act = arena(actions, nh)
     am = None if action_masks is None else arena(action_masks, K).bool()
     rm = None if mask is None else arena(mask).squeeze(1)
     old_nlp, adv = arena(old_neglogp).squeeze(1), arena(advs_n).squeeze(1)
-    nl, probs, ent = DO.categorical_masked(z, am)
-    nlp = -nl.gather(1, act.unsqueeze(1)).squeeze(1)
+    heads = _cat_heads(z, am, head_sizes)
+    nlp = sum(-h[0].gather(1, act[:, j:j + 1]).squeeze(1) for j, h in enumerate(heads))
+    ent = sum(h[2] for h in heads)
     a = O.actor_loss(old_nlp, nlp, adv, bool(cfg.ppo), cfg.e_clip, smooth=bool(cfg.use_smooth_clamp))
     c = O.critic_loss(arena(old_values_n), v.unsqueeze(1), cfg.e_clip, arena(returns_n), bool(cfg.clip_value))
     w = torch.full((M,), 1.0 / M) if inv_count is None else rm * inv_count[0]

@@ -426,16 +426,23 @@ class DiscreteTapeVecEnv:
 
     def step(self, actions):
         j0 = self.i % self.obs_tape.shape[0]
-        target = self.obs_tape[j0][:, :self.K].argmax(dim=-1)
-        rew = (actions.long() == target).float()
+        if isinstance(self.K, (list, tuple)):
+            off, rew = 0, 0.0
+            for j, k in enumerate(self.K):
+                rew = rew + (actions[:, j].long() == self.obs_tape[j0][:, off:off + k].argmax(dim=-1)).float() / len(self.K)
+                off += k
+        else:
+            target = self.obs_tape[j0][:, :self.K].argmax(dim=-1)
+            rew = (actions.long() == target).float()
         self.i += 1
         j = self.i % self.obs_tape.shape[0]
         return self.obs_tape[j].clone(), rew, self.done_tape[j].clone(), {'time_outs': self.timeout_tape[j].clone()}
 
     def get_env_info(self):
         import gymnasium as gym
+        multi = isinstance(self.K, (list, tuple))
         info = {'observation_space': gym.spaces.Box(-np.inf, np.inf, (self.obs_tape.shape[-1],), np.float32),
-                'action_space': gym.spaces.Discrete(self.K)}
+                'action_space': gym.spaces.Tuple([gym.spaces.Discrete(k) for k in self.K]) if multi else gym.spaces.Discrete(self.K)}
         if self.autoreset_mode != 'same_step':
             info['autoreset_mode'] = self.autoreset_mode
         return info
@@ -461,12 +468,16 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
     obs_tape, done_tape, tout_tape = make_tapes(T, N, D, seed=seed)
     g = torch.Generator().manual_seed(seed + 100)
     mask_tape = None
+    multi = isinstance(K, (list, tuple))
     if use_action_masks:
-        mask_tape = torch.rand(T, N, K, generator=g) < 0.6
-        forced = torch.randint(0, K, (T, N), generator=g)
-        mask_tape.scatter_(2, forced.unsqueeze(-1), True)          # at least one legal action per row
+        mask_tape = torch.rand(T, N, sum(K) if multi else K, generator=g) < 0.6
+        off = 0
+        for k in (K if multi else [K]):                            # at least one legal action per row and head
+            forced = torch.randint(0, k, (T, N), generator=g) + off
+            mask_tape.scatter_(2, forced.unsqueeze(-1), True)
+            off += k
     env = DiscreteTapeVecEnv(obs_tape, done_tape, tout_tape, K, mask_tape, autoreset)
-    network = {'name': 'actor_critic', 'separate': separate, 'space': {'discrete': None},
+    network = {'name': 'actor_critic', 'separate': separate, 'space': {'multi_discrete' if multi else 'discrete': None},
                'mlp': {'units': list(units), 'activation': 'relu', 'initializer': {'name': 'default'}, 'regularizer': {'name': 'None'}}}
     # hyper-parameters of configs/ppo_cartpole.yaml:28-52
     config = {'name': 'golden_discrete', 'env_name': 'unused', 'reward_shaper': {'scale_value': 0.1}, 'normalize_advantage': True,
@@ -477,7 +488,8 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
               'save_frequency': 0, 'save_best_after': 10_000, 'print_stats': False, 'train_dir': '/tmp/golden_runs',
               'use_action_masks': use_action_masks}
     config.update(overrides or {})
-    params = {'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'discrete_a2c'}, 'network': network, 'config': config}
+    params = {'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'multi_discrete_a2c' if multi else 'discrete_a2c'}, 'network': network,
+              'config': config}
     params['config']['env_info'] = env.get_env_info()
     runner = Runner()
     runner.load({'params': params})
@@ -488,7 +500,9 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
             if k.endswith('bias'):
                 p.add_(torch.randn(p.shape, generator=g) * 0.05)
     init_state = {k: v.clone() for k, v in agent.model.state_dict().items()}
-    u = torch.rand(epochs, H + 1, N, generator=g)     # [epoch, step (H rollout + the get_values forward, which samples too)]
+    nh = len(K) if multi else 1
+    # [epoch, step (H rollout + the get_values forward, which samples too), head]: one multinomial call per head, in head order
+    u = torch.rand(epochs, H + 1, nh, N, generator=g)
     counter = {'k': 0}
     orig_multinomial = torch.multinomial
 
@@ -496,8 +510,9 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
         assert num_samples == 1
         k = counter['k']
         counter['k'] += 1
-        e, n = divmod(k, H + 1)
-        return sample_inverse_cdf(probs_2d, u[e, n]).unsqueeze(-1)
+        e, r = divmod(k, (H + 1) * nh)
+        n, j = divmod(r, nh)
+        return sample_inverse_cdf(probs_2d, u[e, n, j]).unsqueeze(-1)
     torch.multinomial = fake_multinomial
     try:
         agent.init_tensors()
@@ -519,9 +534,11 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
                 'adam_exp_avg': [agent.optimizer.state[p]['exp_avg'].clone() for p in agent.model.parameters()],
             })
             agent.dataset.update_values_dict(None)
-        assert counter['k'] == epochs * (H + 1), counter
+        assert counter['k'] == epochs * (H + 1) * nh, counter
     finally:
         torch.multinomial = orig_multinomial
+    if not multi:
+        u = u[:, :, 0]
     save(name, {'N': N, 'H': H, 'D': D, 'K': K, 'units': list(units), 'mb': mb, 'epochs': epochs, 'separate': separate,
                 'use_action_masks': use_action_masks, 'autoreset': autoreset,
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
@@ -556,6 +573,8 @@ if __name__ == '__main__':
         gen_agent('agent_rmsadv.pt', autoreset='next_step', seed=7, overrides={'normalize_rms_advantage': True, 'adv_rms_momentum': 0.5})
     if 'discrete' in which:
         gen_agent_discrete('agent_discrete.pt')                                   # configs/ppo_cartpole.yaml shape: separate MLP [32,32], 2 actions
+        gen_agent_discrete('agent_multidiscrete.pt', K=[3, 4], D=8, units=(16, 8), separate=True, use_action_masks=True, seed=13,
+                           overrides={'normalize_input': True, 'normalize_value': True, 'value_bootstrap': True})
         gen_agent_discrete('agent_discrete_masked.pt', K=5, D=7, units=(16, 8), separate=False, use_action_masks=True, autoreset='next_step',
                            seed=12, overrides={'normalize_input': True, 'normalize_value': True, 'lr_schedule': 'adaptive',
                                                'kl_threshold': 0.002, 'value_bootstrap': True})

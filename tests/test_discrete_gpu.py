@@ -108,20 +108,27 @@ class DiscreteTapeEnvGPU:
 
     def step(self, actions):
         j0 = self.i % self.obs_tape.shape[0]
-        rew = (actions.long() == self.obs_tape[j0][:, :self.K].argmax(dim=-1)).float()
+        if isinstance(self.K, (list, tuple)):
+            off, rew = 0, 0.0
+            for j, k in enumerate(self.K):
+                rew = rew + (actions[:, j].long() == self.obs_tape[j0][:, off:off + k].argmax(dim=-1)).float() / len(self.K)
+                off += k
+        else:
+            rew = (actions.long() == self.obs_tape[j0][:, :self.K].argmax(dim=-1)).float()
         self.i += 1
         j = self.i % self.obs_tape.shape[0]
         return self.obs_tape[j].clone(), rew, self.done_tape[j].clone(), {'time_outs': self.timeout_tape[j].clone()}
 
     def get_env_info(self):
-        from rl_games_b200.common import Box, Discrete
-        info = {'observation_space': Box(-np.inf, np.inf, (self.obs_tape.shape[-1],)), 'action_space': Discrete(self.K)}
+        from rl_games_b200.common import Box, Discrete, Tuple
+        space = Tuple([Discrete(k) for k in self.K]) if isinstance(self.K, (list, tuple)) else Discrete(self.K)
+        info = {'observation_space': Box(-np.inf, np.inf, (self.obs_tape.shape[-1],)), 'action_space': space}
         if self.autoreset != 'same_step':
             info['autoreset_mode'] = self.autoreset
         return info
 
 
-@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt'])
+@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt', 'agent_multidiscrete.pt'])
 def test_discrete_agent_matches_reference_golden(name):
     """two train_epoch()s of the reference DiscreteA2CAgent (tests/golden/gen_golden.py discrete) vs rl_games_b200.DiscreteA2CAgent"""
     from rl_games_b200.runner import Runner
@@ -131,10 +138,12 @@ def test_discrete_agent_matches_reference_golden(name):
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     config.update({'device': DEV, 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1}, 'b200_unvalidated': True,
                    'train_dir': '/tmp/b200_parity_runs', 'lr_schedule': cfgk.get('lr_schedule', None)})
-    network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'discrete': None},
+    multi = isinstance(g['K'], (list, tuple))
+    network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'multi_discrete' if multi else 'discrete': None},
                'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}
     r = Runner()
-    r.load({'params': {'seed': 1, 'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'discrete_a2c'}, 'network': network, 'config': config}})
+    r.load({'params': {'seed': 1, 'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'multi_discrete_a2c' if multi else 'discrete_a2c'},
+                       'network': network, 'config': config}})
     r.params['config']['vec_env'] = env
     agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
     agent.model.load_state_dict({k: v.to(DEV) for k, v in g['init_state'].items()}, strict=False)
@@ -161,3 +170,48 @@ def test_discrete_agent_matches_reference_golden(name):
             torch.testing.assert_close(sd[k].cpu(), ref['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
         assert agent.game_rewards.current_size == ref['game_rewards_size']
         torch.testing.assert_close(agent.game_rewards.mean, ref['game_rewards_mean'].reshape(-1), rtol=1e-4, atol=1e-5)
+
+
+def test_multi_head_kernels_vs_oracle_and_autograd():
+    """multi-discrete: heads [3, 4, 2] concatenated; sample kernel vs the oracle rule, loss kernel vs autograd (the same check runs on the
+    host-compiled row functions in tests/test_discrete_rows_cpu.py)"""
+    from rl_games_b200 import ops
+    from oracle.ppo_oracle import actor_loss, critic_loss
+    g = torch.Generator().manual_seed(21)
+    sizes, M = [3, 4, 2], 900
+    K, nh = sum(sizes), len(sizes)
+    logits = (torch.randn(M, K, generator=g) * 1.5).requires_grad_(True)
+    value = torch.randn(M, 1, generator=g).requires_grad_(True)
+    amask = torch.rand(M, K, generator=g) < 0.6
+    off = 0
+    for k in sizes:
+        amask[torch.arange(M), torch.randint(0, k, (M,), generator=g) + off] = True
+        off += k
+    heads = [DO.categorical_masked(z, m) for z, m in zip(torch.split(logits, sizes, dim=1), torch.split(amask, sizes, dim=1))]
+    u = torch.rand(nh, M, generator=g)
+    a_ref = torch.stack([DO.sample_inverse_cdf(h[1].detach(), u[j]) for j, h in enumerate(heads)], dim=-1)
+    nlp = sum(-h[0].gather(1, a_ref[:, j:j + 1]).squeeze(1) for j, h in enumerate(heads))
+    d = lambda t: t.to(DEV)   # noqa: E731
+    actions = torch.zeros(M, nh, dtype=torch.int64, device=DEV); nlp_k = torch.zeros(M, device=DEV); vals = torch.zeros(M, device=DEV)
+    ops.categorical_sample(d(logits.detach()), K, K, d(value.detach()), 1, d(amask.to(torch.uint8)), d(u.contiguous()), 0, None, 0, None, None,
+                           False, actions, nlp_k, vals, None, None, None, None, M, head_sizes=sizes)
+    torch.cuda.synchronize()
+    same = (actions.cpu() == a_ref).all(dim=1)
+    assert same.float().mean() > 0.998
+    torch.testing.assert_close(nlp_k.cpu()[same], nlp.detach()[same], rtol=1e-5, atol=1e-5)
+    ent = sum(h[2] for h in heads)
+    old_nlp = nlp.detach() + torch.randn(M, generator=g) * 0.2
+    adv, old_v, ret = torch.randn(M, generator=g), torch.randn(M, 1, generator=g), torch.randn(M, 1, generator=g)
+    a = actor_loss(old_nlp, nlp, adv, True, 0.2, smooth=False)
+    c = critic_loss(old_v, value, 0.2, ret, True).squeeze(1)
+    la, lc, le = a.mean(), c.mean(), ent.mean()
+    (la + 0.5 * 1.5 * lc - 0.02 * le).backward()
+    dl, dv = torch.zeros(M, K, device=DEV), torch.zeros(M, 1, device=DEV)
+    part = torch.zeros((M + 255) // 256, 8, dtype=torch.float64, device=DEV)
+    nb = ops.categorical_loss(d(logits.detach()), K, K, d(value.detach()), 1, d(a_ref.contiguous()), d(amask.to(torch.uint8)), d(old_v.squeeze(1)),
+                              d(ret.squeeze(1)), d(old_nlp), d(adv), None, M, 0, M, ops.CatLossCfg(0.2, 1.5, 0.02, 1, 0, 1), None, dl, K, dv, 1, part,
+                              head_sizes=sizes)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(part[:nb, :3].sum(0).cpu().float(), torch.stack([la, lc, le]).detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dl.cpu(), logits.grad, rtol=1e-3, atol=1e-7)
+    torch.testing.assert_close(dv.cpu(), value.grad, rtol=1e-4, atol=1e-8)

@@ -25,20 +25,27 @@ class _Env:
     def step(self, actions):
         g = self.g
         j0 = self.i % g['obs_tape'].shape[0]
-        rew = (actions.long() == g['obs_tape'][j0][:, :self.K].argmax(dim=-1)).float()
+        if isinstance(self.K, (list, tuple)):
+            off, rew = 0, 0.0
+            for j, k in enumerate(self.K):
+                rew = rew + (actions[:, j].long() == g['obs_tape'][j0][:, off:off + k].argmax(dim=-1)).float() / len(self.K)
+                off += k
+        else:
+            rew = (actions.long() == g['obs_tape'][j0][:, :self.K].argmax(dim=-1)).float()
         self.i += 1
         j = self.i % g['obs_tape'].shape[0]
         return g['obs_tape'][j].clone(), rew, g['done_tape'][j].clone(), {'time_outs': g['timeout_tape'][j].clone()}
 
     def get_env_info(self):
-        from rl_games_b200.common import Box, Discrete
-        info = {'observation_space': Box(-np.inf, np.inf, (self.g['obs_tape'].shape[-1],)), 'action_space': Discrete(self.K)}
+        from rl_games_b200.common import Box, Discrete, Tuple
+        space = Tuple([Discrete(k) for k in self.K]) if isinstance(self.K, (list, tuple)) else Discrete(self.K)
+        info = {'observation_space': Box(-np.inf, np.inf, (self.g['obs_tape'].shape[-1],)), 'action_space': space}
         if self.g['autoreset'] != 'same_step':
             info['autoreset_mode'] = self.g['autoreset']
         return info
 
 
-@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt'])
+@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt', 'agent_multidiscrete.pt'])
 def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, tmp_path):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
@@ -54,10 +61,12 @@ def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, t
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     config.update({'device': 'cpu', 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1},
                    'b200_unvalidated': True, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
-    network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'discrete': None},
+    multi = isinstance(g['K'], (list, tuple))
+    network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'multi_discrete' if multi else 'discrete': None},
                'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}
     r = Runner()
-    r.load({'params': {'seed': 1, 'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'discrete_a2c'}, 'network': network, 'config': config}})
+    r.load({'params': {'seed': 1, 'algo': {'name': 'a2c_discrete'}, 'model': {'name': 'multi_discrete_a2c' if multi else 'discrete_a2c'},
+                       'network': network, 'config': config}})
     r.params['config']['vec_env'] = env
     agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
     agent.model.load_state_dict(g['init_state'], strict=False)
