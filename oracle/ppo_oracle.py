@@ -353,14 +353,14 @@ def param_names(n_layers, lstm=False):
     return names
 
 
-def init_params(obs_dim, units, act_dim, value_size=1, seed=0, sigma_init=0.0, rnn_units=0):
+def init_params(obs_dim, units, act_dim, value_size=1, seed=0, sigma_init=0.0, rnn_units=0, rnn_before_mlp=True):
     """Default torch.nn.Linear init (mlp initializer 'default' == nn.Identity on weights,
     biases zeroed: network_builder.py:332-340), mu_init default, sigma const 0."""
     g = torch.Generator().manual_seed(seed)
     p: Dict[str, torch.Tensor] = {}
     p['a2c_network.sigma'] = torch.full((act_dim,), float(sigma_init))
     ins = obs_dim
-    if rnn_units:   # LSTM before the MLP (torch.nn.LSTM default init U(-1/sqrt(hid), 1/sqrt(hid)); mlp_init does not touch it)
+    if rnn_units and rnn_before_mlp:   # LSTM before the MLP (torch.nn.LSTM default init U(-1/sqrt(hid), 1/sqrt(hid)); mlp_init does not touch it)
         k = 1.0 / math.sqrt(rnn_units)
         p[RNN_NAMES[0]] = (torch.rand(4 * rnn_units, ins, generator=g) * 2 - 1) * k
         p[RNN_NAMES[1]] = (torch.rand(4 * rnn_units, rnn_units, generator=g) * 2 - 1) * k
@@ -372,6 +372,13 @@ def init_params(obs_dim, units, act_dim, value_size=1, seed=0, sigma_init=0.0, r
         p[f'a2c_network.actor_mlp.{2 * i}.weight'] = (torch.rand(u, ins, generator=g) * 2 - 1) * bound
         p[f'a2c_network.actor_mlp.{2 * i}.bias'] = torch.zeros(u)
         ins = u
+    if rnn_units and not rnn_before_mlp:      # LSTM between the MLP and the heads
+        k = 1.0 / math.sqrt(rnn_units)
+        p[RNN_NAMES[0]] = (torch.rand(4 * rnn_units, ins, generator=g) * 2 - 1) * k
+        p[RNN_NAMES[1]] = (torch.rand(4 * rnn_units, rnn_units, generator=g) * 2 - 1) * k
+        p[RNN_NAMES[2]] = (torch.rand(4 * rnn_units, generator=g) * 2 - 1) * k
+        p[RNN_NAMES[3]] = (torch.rand(4 * rnn_units, generator=g) * 2 - 1) * k
+        ins = rnn_units
     bound = 1.0 / math.sqrt(ins)
     p['a2c_network.value.weight'] = (torch.rand(value_size, ins, generator=g) * 2 - 1) * bound
     p['a2c_network.value.bias'] = torch.zeros(value_size)
@@ -380,7 +387,7 @@ def init_params(obs_dim, units, act_dim, value_size=1, seed=0, sigma_init=0.0, r
     return p
 
 
-def network_forward(p, obs, n_layers, activation='elu', matmul_dtype=None):
+def network_forward(p, obs, n_layers, activation='elu', matmul_dtype=None, heads_after=None):
     """a2c network forward (non-rnn, non-separate): network_builder.py:448-512.
     matmul_dtype=torch.bfloat16 emulates bf16 autocast of nn.Linear (a2c_continuous.py:173)."""
     act = ACTIVATIONS[activation]
@@ -392,6 +399,8 @@ def network_forward(p, obs, n_layers, activation='elu', matmul_dtype=None):
     out = obs
     for i in range(n_layers):
         out = act(lin(out, p[f'a2c_network.actor_mlp.{2 * i}.weight'], p[f'a2c_network.actor_mlp.{2 * i}.bias']))
+    if heads_after is not None:          # rnn after the MLP (before_mlp: False, network_builder.py:466-492): trunk -> rnn -> heads
+        out = heads_after(out)
     value = lin(out, p['a2c_network.value.weight'], p['a2c_network.value.bias'])
     mu = lin(out, p['a2c_network.mu.weight'], p['a2c_network.mu.bias'])
     logstd = mu * 0 + p['a2c_network.sigma']
@@ -420,9 +429,10 @@ class OracleModel:
     """ModelA2CContinuousLogStd.Network (models.py:304-364) + BaseModelNetwork (:38-63)."""
 
     def __init__(self, params, obs_dim, units, act_dim, normalize_input=True, normalize_value=True,
-                 activation='elu', value_size=1, matmul_dtype=None, rnn_units=0):
+                 activation='elu', value_size=1, matmul_dtype=None, rnn_units=0, rnn_before_mlp=True):
         self.p = {k: v.clone().float().requires_grad_(True) for k, v in params.items()}
         self.rnn_units = rnn_units
+        self.rnn_before_mlp = rnn_before_mlp
         self.names = param_names(len(units), lstm=rnn_units > 0)
         self.n_layers = len(units)
         self.activation = activation
@@ -446,16 +456,24 @@ class OracleModel:
         """rnn (before_mlp) branch: network_builder.py:452-492 -- [B,F] -> [num_seqs, seq, F] -> transpose -> LSTM -> back."""
         obs = self.norm_obs(obs)
         new_states = None
-        if self.rnn_units:
-            B = obs.shape[0]
+
+        def rnn(x_flat):
+            """[B,F] -> [num_seqs, seq, F] -> transpose -> LSTM with dones -> back to [B, hid]"""
+            nonlocal new_states
+            B = x_flat.shape[0]
             num_seqs = B // seq_length
-            x = obs.reshape(num_seqs, seq_length, -1).transpose(0, 1)
+            x = x_flat.reshape(num_seqs, seq_length, -1).transpose(0, 1)
             d = None if dones is None else dones.reshape(num_seqs, seq_length).transpose(0, 1)
             out, h, c = lstm_with_dones(self.p, x, rnn_states[0][0], rnn_states[1][0], d)
-            obs = out.transpose(0, 1).contiguous().reshape(B, -1)
             new_states = (h.unsqueeze(0), c.unsqueeze(0))
+            return out.transpose(0, 1).contiguous().reshape(B, -1)
+        after = None
+        if self.rnn_units and self.rnn_before_mlp:
+            obs = rnn(obs)
+        elif self.rnn_units:
+            after = rnn
+        mu, logstd, value = network_forward(self.p, obs, self.n_layers, self.activation, self.matmul_dtype, heads_after=after)
         self.last_rnn_states = new_states
-        mu, logstd, value = network_forward(self.p, obs, self.n_layers, self.activation, self.matmul_dtype)
         mu, logstd, value = mu.float(), logstd.float(), value.float()
         sigma = torch.exp(logstd)
         if is_train:
@@ -666,7 +684,8 @@ class OracleAgent:
         assert self.batch_size % minibatch_size == 0
         self.num_minibatches = self.batch_size // minibatch_size
         self.model = OracleModel(params, obs_dim, units, act_dim, c['normalize_input'], c['normalize_value'],
-                                 c['activation'], matmul_dtype=matmul_dtype, rnn_units=c['rnn_units'])
+                                 c['activation'], matmul_dtype=matmul_dtype, rnn_units=c['rnn_units'],
+                                 rnn_before_mlp=c.get('rnn_before_mlp', True))
         self.is_rnn = c['rnn_units'] > 0
         self.seq_length = c['seq_length']
         self.last_lr = float(c['learning_rate'])

@@ -188,7 +188,7 @@ class TapeVecEnv:
         pass
 
 
-def make_params(N, H, mb, units, overrides=None, rnn_units=0):
+def make_params(N, H, mb, units, overrides=None, rnn_units=0, rnn_before_mlp=True):
     network = {
         'name': 'actor_critic', 'separate': False,
         'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None',
@@ -198,7 +198,7 @@ def make_params(N, H, mb, units, overrides=None, rnn_units=0):
         'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}},
     }
     if rnn_units:
-        network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': True}
+        network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': rnn_before_mlp}
     # hyper-parameters of configs/mujoco/ant_envpool.yaml:28-56
     config = {
         'name': 'golden', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0},
@@ -217,7 +217,7 @@ def make_params(N, H, mb, units, overrides=None, rnn_units=0):
 
 
 def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, overrides=None, autoreset='same_step',
-              seed=3, rnn_units=0):
+              seed=3, rnn_units=0, rnn_before_mlp=True):
     from rl_games.torch_runner import Runner
     from oracle.ppo_oracle import make_tapes
     torch.manual_seed(seed)
@@ -226,7 +226,7 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
     obs_tape, done_tape, tout_tape = make_tapes(T, N, D, seed=seed)
     env = TapeVecEnv(obs_tape, done_tape, tout_tape, autoreset)
     env.A = A
-    params = make_params(N, H, mb, units, overrides, rnn_units)
+    params = make_params(N, H, mb, units, overrides, rnn_units, rnn_before_mlp)
     params['config']['env_info'] = env.get_env_info()
     runner = Runner()
     runner.load({'params': params})
@@ -281,7 +281,7 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
         torch.normal = orig_normal
     save(name, {'N': N, 'H': H, 'D': D, 'A': A, 'units': list(units), 'mb': mb, 'epochs': epochs,
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
-                'autoreset': autoreset, 'rnn_units': rnn_units, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
+                'autoreset': autoreset, 'rnn_units': rnn_units, 'rnn_before_mlp': rnn_before_mlp, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
                 'noise': noise, 'init_state': init_state, 'epochs_out': epochs_out,
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
@@ -547,7 +547,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -562,6 +562,9 @@ if __name__ == '__main__':
         gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})
     if 'checkpoint' in which:
         gen_checkpoint()
+    if 'lstm_after' in which:
+        # the placement most shipped configs use: MLP -> LSTM -> heads (before_mlp: False is the reference default)
+        gen_agent('agent_lstm_after.pt', seed=14, rnn_units=8, rnn_before_mlp=False, overrides={'seq_length': 4})
     if 'tcshape' in which:
         # three hidden layers and an observation width that is a multiple of 4: the shape class of the tcgen05 path's host logic
         # (per-minibatch obs moments precomputed once per epoch, merged in the optimiser tail); masked autoreset on top

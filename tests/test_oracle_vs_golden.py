@@ -106,6 +106,7 @@ def _oracle_from_golden(g):
     cfg['weight_decay'] = cfgk.get('weight_decay', 0.0)
     cfg['mask_autoreset_rows'] = g['autoreset'] == 'next_step'
     cfg['rnn_units'] = g.get('rnn_units', 0)
+    cfg['rnn_before_mlp'] = g.get('rnn_before_mlp', True)
     cfg['seq_length'] = cfgk.get('seq_length', 4)
     env = O.TapeEnv(g['obs_tape'], g['done_tape'], g['timeout_tape'])
     params = {k: v for k, v in g['init_state'].items() if k.startswith('a2c_network')}
@@ -114,7 +115,8 @@ def _oracle_from_golden(g):
     return ag
 
 
-@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt'])
+@pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt',
+                                  'agent_lstm_after.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
