@@ -289,6 +289,9 @@ class A2CAgent:
                 raise NotImplementedError('zero_rnn_on_done: False is not on the B200 hot path')
             if self.mixed_precision:
                 raise NotImplementedError('rnn (LSTM) policies run on the fp32 path: set mixed_precision: False')
+            if not self.model.rnn_before_mlp and not config.get('b200_unvalidated', False):
+                raise NotImplementedError('rnn before_mlp: False (MLP -> LSTM -> heads) composes validated kernels and its host logic reproduces '
+                                          'the reference on CPU, but it has not been run on hardware yet: set b200_unvalidated: True')
         self.use_tc = bool(self.mixed_precision)
         if self.use_tc and not ops.tc_supported(self.model.D, self.model.units, self.actions_num):
             raise NotImplementedError(
@@ -585,7 +588,8 @@ class A2CAgent:
     # =============================================================================== policy forward
     def _trunk(self, x, acts, M, rows_per_chunk=None, chunk_stride=0):
         m = self.model
-        nm, ns = (None, None) if self.is_rnn else self._norm()      # with an LSTM in front the MLP input is h (dense, not normalised)
+        # with an LSTM in front the MLP input is h (dense, not normalised)
+        nm, ns = (None, None) if (self.is_rnn and m.rnn_before_mlp) else self._norm()
         ops.linear_fwd(x, m.W[0], m.b[0], acts[0], m.act_id, rows_per_chunk=rows_per_chunk, chunk_stride=chunk_stride,
                        x_ld=m.mlp_in, norm_mean=nm, norm_std=ns, M=M)
         for i in range(1, len(m.units)):
@@ -604,8 +608,8 @@ class A2CAgent:
     def _lstm_step(self, obs, h_in, c_in, h_out, c_out):
         """one LSTM step for all N envs (seq_length 1, models.py -> network_builder.py:452-492 -> recurrent.py): returns h_out"""
         m, N = self.model, self.num_actors
-        nm, ns = self._norm()
-        ops.linear_fwd(obs, m.W_ih, m.b_ih, self.r_gates, 0, x_ld=m.D, norm_mean=nm, norm_std=ns, M=N)
+        nm, ns = self._norm() if m.rnn_before_mlp else (None, None)      # after the MLP the LSTM reads the trunk output
+        ops.linear_fwd(obs, m.W_ih, m.b_ih, self.r_gates, 0, x_ld=m.rnn_in, norm_mean=nm, norm_std=ns, M=N)
         ops.linear_fwd(h_in, m.W_hh, m.b_hh, self.r_gates, 0, M=N, accumulate=True)
         ops.lstm_cell_fwd(self.r_gates, c_in, c_out, h_out, N, m.rnn_units)
         return h_out
@@ -621,10 +625,13 @@ class A2CAgent:
                                    self.actions_high, self.dones, self.dones_buf[t], self.prev_dones,
                                    None if self.valid is None else self.valid[t])
             return
-        if self.is_rnn:
+        if self.is_rnn and m.rnn_before_mlp:
             obs = self._lstm_step(obs, self.rnn_h, self.rnn_c, self.rnn_h, self.rnn_c)
         self._trunk(obs, self.ra, N)
-        ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
+        a_last = self.ra[-1]
+        if self.is_rnn and not m.rnn_before_mlp:
+            a_last = self._lstm_step(a_last, self.rnn_h, self.rnn_c, self.rnn_h, self.rnn_c)
+        ops.policy_head_sample(a_last, m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
                                m.value_mean_std.running_var, self.normalize_value, noise, self.rng_seed, self.rng_epoch, t,
                                self.actions[t], self.mus[t], self.sigmas[t], self.neglogpacs[t], self.values[t],
                                self.env_actions, self.clip_actions, self.actions_low, self.actions_high,
@@ -642,10 +649,13 @@ class A2CAgent:
                                    0, None, None, None, None, self.last_values, None, False, None, None, None, None, None, None,
                                    values_only=True)
             return self.last_values.unsqueeze(1)
-        if self.is_rnn:     # get_values does not advance the agent's rnn states (a2c_common.py:603-626)
+        if self.is_rnn and m.rnn_before_mlp:     # get_values does not advance the agent's rnn states (a2c_common.py:603-626)
             o = self._lstm_step(o, self.rnn_h, self.rnn_c, self.r_tmp_h, self.r_tmp_c)
         self._trunk(o, self.ra, N)
-        ops.policy_head_sample(self.ra[-1], m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
+        a_last = self.ra[-1]
+        if self.is_rnn and not m.rnn_before_mlp:
+            a_last = self._lstm_step(a_last, self.rnn_h, self.rnn_c, self.r_tmp_h, self.r_tmp_c)
+        ops.policy_head_sample(a_last, m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
                                m.value_mean_std.running_var, self.normalize_value, None, 0, None, 0, None, None, None, None,
                                self.last_values, None, False, None, None, None, None, None, None, N, A, values_only=True)
         return self.last_values.unsqueeze(1)
@@ -772,23 +782,32 @@ class A2CAgent:
         if self.use_tc:
             self._minibatch_update_tc(i, u, x, e0)
             return
-        if self.is_rnn:
+        rnn_first = self.is_rnn and m.rnn_before_mlp
+        rnn_last = self.is_rnn and not m.rnn_before_mlp
+        if rnn_first:
             self._lstm_window_fwd(e0)
             self._trunk(self.t_hmlp, self.ta, mb)
         else:
             self._trunk(x, self.ta, mb, rows_per_chunk=epm, chunk_stride=N)
-        nb = ops.ppo_head_loss(self.ta[-1], m.W_head, m.b_head, m.sigma, self.actions[0, e0:], self.mus[0, e0:],
+        if rnn_last:        # MLP -> LSTM -> heads: the heads read the LSTM output and hand back dL/dh (no activation in between)
+            self._lstm_window_fwd(e0)
+            a_last, d_alast, act_last = self.t_hmlp, self.t_dHmlp, 0
+        else:
+            a_last, d_alast, act_last = self.ta[-1], self.dA[-1], m.act_id
+        nb = ops.ppo_head_loss(a_last, m.W_head, m.b_head, m.sigma, self.actions[0, e0:], self.mus[0, e0:],
                                self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:], self.neglogpacs[0, e0:],
                                self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:], epm, N, mb, A,
                                self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.d_head,
-                               self.dA[-1], m.act_id, self.loss_partials)
+                               d_alast, act_last, self.loss_partials)
         gv = self._gv[u & 1]
         ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], gv['g_sigma'], gv['kl'])
         P, S = m.num_params, self.n_splits
         off_wh, _ = m.layout['W_head']
         off_bh, _ = m.layout['b_head']
-        ops.linear_bwd_weight(self.d_head, self.ta[-1], self.part[0, off_wh:], self.part[0, off_bh:], m.Hl, A + 1, S, M=mb,
+        ops.linear_bwd_weight(self.d_head, a_last, self.part[0, off_wh:], self.part[0, off_bh:], m.Hl, A + 1, S, M=mb,
                               split_stride=P)
+        if rnn_last:
+            self._lstm_window_bwd(e0)       # also fills dA[-1] = dL/d(pre-activation of the last MLP layer)
         nm = m.running_mean_std.mean_f32 if self.normalize_input else None
         ns = m.running_mean_std.std_f32 if self.normalize_input else None
         for l in range(L - 1, -1, -1):
@@ -798,7 +817,7 @@ class A2CAgent:
                 ops.linear_bwd_weight(self.dA[l], self.ta[l - 1], self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
                                       M=mb, split_stride=P)
                 ops.linear_bwd_data(self.dA[l], m.W[l], self.ta[l - 1], self.dA[l - 1], m.act_id, M=mb)
-            elif self.is_rnn:
+            elif rnn_first:
                 ops.linear_bwd_weight(self.dA[0], self.t_hmlp, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S, M=mb,
                                       split_stride=P)
                 ops.linear_bwd_data(self.dA[0], m.W[0], None, self.t_dHmlp, 0, M=mb)
@@ -816,12 +835,14 @@ class A2CAgent:
         m, H, N, T = self.model, self.horizon_length, self.num_actors, self.seq_length
         epm, Hd = self.envs_per_mb, m.rnn_units
         S = epm * H // T
-        nm, ns = self._norm()
+        nm, ns = self._norm() if m.rnn_before_mlp else (None, None)
         # window-initial states = snapshots taken during the rollout, zeroed where the episode ended entering step 0
         ops.rnn_mask_rows(self.rnn_h0[0, e0:], epm, N, self.t_hin[0], S, Hd, done=self.dones_buf[0, e0:], done_rpc=epm, done_stride=T * N)
         ops.rnn_mask_rows(self.rnn_c0[0, e0:], epm, N, self.t_cin[0], S, Hd, done=self.dones_buf[0, e0:], done_rpc=epm, done_stride=T * N)
         for t in range(T):
-            ops.linear_fwd(self.obses[t, e0:], m.W_ih, m.b_ih, self.t_gates[t], 0, rows_per_chunk=epm, chunk_stride=T * N, x_ld=m.D,
+            # step-t inputs of all S sequences: arena observations (LSTM first) or the trunk output rows (j*T + t)*epm + e (LSTM last)
+            xin, xstride = (self.obses[t, e0:], T * N) if m.rnn_before_mlp else (self.ta[-1][t * epm:], T * epm)
+            ops.linear_fwd(xin, m.W_ih, m.b_ih, self.t_gates[t], 0, rows_per_chunk=epm, chunk_stride=xstride, x_ld=m.rnn_in,
                            norm_mean=nm, norm_std=ns, M=S)
             ops.linear_fwd(self.t_hin[t], m.W_hh, m.b_hh, self.t_gates[t], 0, M=S, accumulate=True)
             last = t == T - 1
@@ -836,7 +857,7 @@ class A2CAgent:
         m, H, N, T = self.model, self.horizon_length, self.num_actors, self.seq_length
         epm, Hd, P, Ssp = self.envs_per_mb, m.rnn_units, m.num_params, self.n_splits
         S = epm * H // T
-        nm, ns = self._norm()
+        nm, ns = self._norm() if m.rnn_before_mlp else (None, None)
         o_wih, o_whh, o_bih, o_bhh = (m.layout[k][0] for k in ('W_ih', 'W_hh', 'b_ih', 'b_hh'))
         for t in range(T - 1, -1, -1):
             last = t == T - 1
@@ -845,12 +866,19 @@ class A2CAgent:
                               dhin_next=None if last else self.t_dhin, dcin_next=None if last else self.t_dcin[(t + 1) & 1],
                               done_next=None if last else self.dones_buf[t + 1, e0:], done_rpc=epm, done_stride=T * N)
             row = t * Ssp
-            ops.linear_bwd_weight(self.t_dgates, self.obses[t, e0:], self.part[row, o_wih:], self.part[row, o_bih:], m.D, 4 * Hd, Ssp,
-                                  rows_per_chunk=epm, chunk_stride=T * N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=S, split_stride=P)
+            xin, xstride = (self.obses[t, e0:], T * N) if m.rnn_before_mlp else (self.ta[-1][t * epm:], T * epm)
+            ops.linear_bwd_weight(self.t_dgates, xin, self.part[row, o_wih:], self.part[row, o_bih:], m.rnn_in, 4 * Hd, Ssp,
+                                  rows_per_chunk=epm, chunk_stride=xstride, x_ld=m.rnn_in, norm_mean=nm, norm_std=ns, M=S, split_stride=P)
             ops.linear_bwd_weight(self.t_dgates, self.t_hin[t], self.part[row, o_whh:], self.part[row, o_bhh:], Hd, 4 * Hd, Ssp, M=S,
                                   split_stride=P)
             if t > 0:
                 ops.linear_bwd_data(self.t_dgates, m.W_hh, None, self.t_dhin, 0, M=S)
+            if not m.rnn_before_mlp:
+                # dgrad through W_ih into the trunk: sequences j*epm..(j+1)*epm-1 at step t are trunk rows (j*T + t)*epm.., one dense
+                # epm-row block each; the last MLP layer's activation derivative is folded in (dA[-1] is d pre-activation)
+                for j in range(H // T):
+                    r0 = (j * T + t) * epm
+                    ops.linear_bwd_data(self.t_dgates[j * epm:], m.W_ih, self.ta[-1][r0:], self.dA[-1][r0:], m.act_id, M=epm)
 
     def _minibatch_update_tc(self, i, u, x, e0):
         """bf16 tcgen05 edition: fused fwd+loss kernel, two backward kernels, split reduce, Adam, repack."""

@@ -116,11 +116,13 @@ class B200Model:
         self.rnn_units = 0
         if 'rnn' in network_params:
             rnn = network_params['rnn']
-            if rnn.get('name') != 'lstm' or rnn.get('layers', 1) != 1 or not rnn.get('before_mlp', False) or rnn.get('layer_norm', False) \
+            if rnn.get('name') != 'lstm' or rnn.get('layers', 1) != 1 or rnn.get('layer_norm', False) \
                     or rnn.get('concat_input', False) or rnn.get('concat_output', False):
-                raise NotImplementedError("rnn: only a single-layer 'lstm' with before_mlp: True (no layer_norm / concat) is on the B200 "
-                                          "hot path (BASELINE configs[3])")
+                raise NotImplementedError("rnn: only a single-layer 'lstm' (no layer_norm / concat) is on the B200 hot path")
             self.rnn_units = int(rnn['units'])
+        # placement (network_builder.py:253-272): before_mlp True = obs -> LSTM -> MLP -> heads (BASELINE configs[3]); False (the reference
+        # default) = obs -> MLP -> LSTM -> heads.  Same parameter names and order either way, different shapes.
+        self.rnn_before_mlp = bool(network_params.get('rnn', {}).get('before_mlp', False)) if self.rnn_units else True
         space = network_params['space']['continuous']
         if not space.get('fixed_sigma', True):
             raise NotImplementedError('state-dependent sigma is not on the B200 hot path yet')
@@ -136,14 +138,16 @@ class B200Model:
         self.normalize_input, self.normalize_value = bool(normalize_input), bool(normalize_value)
         # ---- flat arenas ----
         sizes = [('sigma', (self.A,))]
-        ins = self.D
-        if self.rnn_units:
-            Hd = self.rnn_units
-            sizes += [('W_ih', (4 * Hd, ins)), ('W_hh', (4 * Hd, Hd)), ('b_ih', (4 * Hd,)), ('b_hh', (4 * Hd,))]
-            ins = Hd
+        Hd = self.rnn_units
+        self.rnn_in = (self.D if self.rnn_before_mlp else self.units[-1]) if Hd else 0      # input width of the LSTM
+        if Hd:
+            sizes += [('W_ih', (4 * Hd, self.rnn_in)), ('W_hh', (4 * Hd, Hd)), ('b_ih', (4 * Hd,)), ('b_hh', (4 * Hd,))]
+        ins = Hd if (Hd and self.rnn_before_mlp) else self.D
         for i, u in enumerate(self.units):
             sizes += [(f'W{i}', (u, ins)), (f'b{i}', (u,))]
             ins = u
+        if Hd and not self.rnn_before_mlp:
+            ins = Hd                     # the heads read the LSTM output
         self.Hl = ins
         sizes += [('W_head', (self.A + 1, ins)), ('b_head', (self.A + 1,))]
         self.layout = OrderedDict()
@@ -162,7 +166,7 @@ class B200Model:
         self.sigma = self.view('sigma')
         if self.rnn_units:
             self.W_ih, self.W_hh, self.b_ih, self.b_hh = (self.view(n) for n in ('W_ih', 'W_hh', 'b_ih', 'b_hh'))
-        self.mlp_in = self.rnn_units if self.rnn_units else self.D
+        self.mlp_in = self.rnn_units if (self.rnn_units and self.rnn_before_mlp) else self.D
         self.W_head, self.b_head = self.view('W_head'), self.view('b_head')
         self.gW = [self.view(f'W{i}', self.grad) for i in range(len(self.units))]
         self.gb = [self.view(f'b{i}', self.grad) for i in range(len(self.units))]
@@ -186,18 +190,18 @@ class B200Model:
         space = network_params['space']['continuous']
         mlp_init = network_params['mlp'].get('initializer', {'name': 'default'})
         cpu = {}
-        ins = self.D
         if self.rnn_units:   # torch.nn.LSTM default init U(-1/sqrt(hid), 1/sqrt(hid)) for all four tensors (mlp_init does not touch it)
             Hd = self.rnn_units
             k = 1.0 / math.sqrt(Hd)
-            for n, shp in (('W_ih', (4 * Hd, ins)), ('W_hh', (4 * Hd, Hd)), ('b_ih', (4 * Hd,)), ('b_hh', (4 * Hd,))):
+            for n, shp in (('W_ih', (4 * Hd, self.rnn_in)), ('W_hh', (4 * Hd, Hd)), ('b_ih', (4 * Hd,)), ('b_hh', (4 * Hd,))):
                 cpu[n] = torch.empty(*shp).uniform_(-k, k)
-            ins = Hd
+        ins = self.mlp_in
         for i, u in enumerate(self.units):
             w = torch.empty(u, ins)
             _apply_init(w, mlp_init, ins)
             cpu[f'W{i}'] = w
             ins = u
+        ins = self.Hl
         wh = torch.empty(self.A + 1, ins)
         _apply_init(wh[:1], mlp_init, ins)                                   # value head: mlp_init
         _apply_init(wh[1:], mlp_init, ins)

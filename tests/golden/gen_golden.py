@@ -564,7 +564,7 @@ if __name__ == '__main__':
         gen_checkpoint()
     if 'lstm_after' in which:
         # the placement most shipped configs use: MLP -> LSTM -> heads (before_mlp: False is the reference default)
-        gen_agent('agent_lstm_after.pt', seed=14, rnn_units=8, rnn_before_mlp=False, overrides={'seq_length': 4})
+        gen_agent('agent_lstm_after.pt', seed=14, rnn_units=12, rnn_before_mlp=False, overrides={'seq_length': 4})
     if 'tcshape' in which:
         # three hidden layers and an observation width that is a multiple of 4: the shape class of the tcgen05 path's host logic
         # (per-minibatch obs moments precomputed once per epoch, merged in the optimiser tail); masked autoreset on top

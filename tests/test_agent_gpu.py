@@ -51,14 +51,14 @@ class TapeEnvGPU:
         pass
 
 
-def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0):
+def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0, rnn_before_mlp=True):
     from rl_games_b200.runner import Runner
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}}}
     if rnn_units:
-        network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': True}
+        network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': rnn_before_mlp}
     config = {'name': 'gpu_parity', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0}, 'device': DEV,
               'multi_gpu': False, 'mixed_precision': False, 'normalize_input': True, 'normalize_value': True,
               'value_bootstrap': True, 'normalize_advantage': True, 'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4,
@@ -108,6 +108,19 @@ def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True
 @pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt'])
 @pytest.mark.parametrize('graph', [False, True])
 def test_agent_matches_reference_golden(name, graph):
+    _golden_run(name, graph)
+
+
+@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                    reason='MLP -> LSTM placement not yet run on hardware (host logic checked on CPU): set B200RL_UNVALIDATED=1')
+@pytest.mark.parametrize('graph', [False, True])
+def test_lstm_after_mlp_agent_matches_reference_golden(graph):
+    """rnn before_mlp: False, the reference default (network_builder.py:253-272): same kernels as agent_lstm.pt, composed
+    trunk -> LSTM window -> heads; the fixture comes from the reference itself (tests/golden/gen_golden.py lstm_after)"""
+    _golden_run('agent_lstm_after.pt', graph, {'b200_unvalidated': True})
+
+
+def _golden_run(name, graph, extra=None):
     g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk = g['config']
     over = {k: cfgk[k] for k in ('clip_value', 'use_smooth_clamp', 'bound_loss_type', 'bounds_loss_coef', 'entropy_coef',
@@ -116,9 +129,11 @@ def test_agent_matches_reference_golden(name, graph):
             if k in cfgk}
     over.setdefault('lr_schedule', None)
     over['b200_cuda_graph'] = graph
+    over.update(extra or {})
     env = TapeEnvGPU(g['obs_tape'], g['done_tape'], g['timeout_tape'], g['A'], g['autoreset'])
     lstm = g.get('rnn_units', 0) > 0
-    agent = make_agent(over, g['N'], g['H'], g['D'], g['A'], g['units'], g['mb'], env, g['init_state'], rnn_units=g.get('rnn_units', 0))
+    agent = make_agent(over, g['N'], g['H'], g['D'], g['A'], g['units'], g['mb'], env, g['init_state'], rnn_units=g.get('rnn_units', 0),
+                       rnn_before_mlp=bool(g.get('rnn_before_mlp', True)))
     for ep, ref in enumerate(g['epochs_out']):
         agent.epoch_num += 1
         agent.train_epoch(noise=g['noise'][ep].to(DEV))

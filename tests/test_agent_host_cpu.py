@@ -71,7 +71,8 @@ class _Env:
 
 
 @pytest.mark.parametrize('name,tc', [('agent_base.pt', False), ('agent_masked.pt', False), ('agent_hardclip.pt', False), ('agent_rmsadv.pt', False),
-                                     ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_lstm.pt', False)])
+                                     ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_lstm.pt', False),
+                                     ('agent_lstm_after.pt', False)])
 def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
     """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
     stride, fused reduce+Adam tail, per-minibatch obs moments merged by the optimiser tail) with fp32 stand-ins for its kernels"""
@@ -95,7 +96,8 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
                'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
     lstm = g.get('rnn_units', 0) > 0
     if lstm:
-        network['rnn'] = {'name': 'lstm', 'units': g['rnn_units'], 'layers': 1, 'before_mlp': True}
+        network['rnn'] = {'name': 'lstm', 'units': g['rnn_units'], 'layers': 1, 'before_mlp': bool(g.get('rnn_before_mlp', True))}
+        config['b200_unvalidated'] = not network['rnn']['before_mlp']      # MLP -> LSTM placement: not yet run on hardware
     r = Runner()
     r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
                        'config': config}})
