@@ -673,6 +673,7 @@ class A2CAgent:
         H, N = self.horizon_length, self.num_actors
         step_time = 0.0
         wants_idx = getattr(self.algo_observer, 'wants_done_indices', True)
+        wants_infos = getattr(self.algo_observer, 'wants_infos', False)
         if hasattr(self.vec_env, 'begin_rollout'):
             self.vec_env.begin_rollout()
         for t in range(H):
@@ -694,6 +695,8 @@ class A2CAgent:
                 ops.rnn_mask_rows(self.rnn_c, N, 0, self.rnn_c, N, self.model.rnn_units, done=self.dones, done_rpc=N)
             if wants_idx:
                 self.algo_observer.process_infos(infos, self.dones.nonzero(as_tuple=False))
+            elif wants_infos:       # observers that read the infos but not the done indices: no host sync
+                self.algo_observer.process_infos(infos, None)
         self.get_values(self.obs)
         if hasattr(self.vec_env, 'end_rollout'):
             self.vec_env.end_rollout()
@@ -1048,6 +1051,7 @@ class A2CAgent:
         return (self.use_cuda_graph and self.config.get('b200_cuda_graph_rollout', True) and self.is_tensor_obses
                 and getattr(self.vec_env, 'cuda_graph_capturable', False)
                 and not getattr(self.algo_observer, 'wants_done_indices', True)
+                and not getattr(self.algo_observer, 'wants_infos', False)
                 and (not self.multi_gpu or self.graph_multi_gpu))
 
     def _lr_dirty(self):

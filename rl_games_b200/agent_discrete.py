@@ -439,7 +439,10 @@ class DiscreteA2CAgent:
             ops.post_step(rewards, dones, tout, self.values[t], None if self.valid is None else self.valid[t], self.rewards[t],
                           self.dones, self.prev_dones, self.ep_state, self.meter, self.games_to_track, self.post_scratch,
                           self.counters[0:1], N, self.shaper_cfg)
-            self.algo_observer.process_infos(infos, self.dones.nonzero(as_tuple=False))
+            if getattr(self.algo_observer, 'wants_done_indices', True):
+                self.algo_observer.process_infos(infos, self.dones.nonzero(as_tuple=False))
+            elif getattr(self.algo_observer, 'wants_infos', False):
+                self.algo_observer.process_infos(infos, None)
         # get_values (a2c_common.py:603-626): the reference's forward samples here too; only the value is used
         self._trunk(m.trunk('actor'), self.obs, self.r_a, N)
         if m.separate:

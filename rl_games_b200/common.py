@@ -10,6 +10,8 @@ agent into its own Runner instead.
 """
 import math
 
+import torch
+
 
 class ObjectFactory:
     """common/object_factory.py:1-39"""
@@ -144,6 +146,57 @@ class DefaultAlgoObserver(AlgoObserver):
     def after_init(self, algo):
         self.algo = algo
         self.writer = algo.writer
+
+
+class IsaacAlgoObserver(AlgoObserver):
+    """common/algo_observer.py:95-156 (``algo_observer: isaac``): logs the env's per-episode metrics (``infos['episode']``, a
+    dict of tensors emitted on reset bursts) as ``Episode/<key>`` = mean over everything seen since the last print, plus scalar
+    entries of ``infos`` as ``<key>/frame|iter|time``.
+
+    The reference keeps every burst's dict and concatenates them at print time; here each key owns a device-resident
+    (sum, count) pair updated with two stream-ordered adds per burst -- same mean, O(1) memory, and no host
+    synchronisation until ``after_print_stats`` reads one scalar per key, once per epoch.  ``done_indices`` is never used
+    by this observer, so it does not ask the agent for them (``wants_done_indices = False``: no per-step ``nonzero`` sync);
+    it does need the per-step infos (``wants_infos``), which keeps the env step out of the captured rollout graph."""
+    wants_done_indices = False
+    wants_infos = True
+
+    def after_init(self, algo):
+        self.algo = algo
+        self.writer = algo.writer
+        self.ep_sums = {}
+        self.direct_info = {}
+
+    def process_infos(self, infos, done_indices=None):
+        if not isinstance(infos, dict):
+            raise ValueError(f"{self.__class__.__name__} expected 'infos' as dict. Received: {type(infos)}")
+        ep = infos.get('episode')
+        if ep:
+            dev = getattr(self.algo, 'ppo_device', None)
+            for k, v in ep.items():
+                v = v if isinstance(v, torch.Tensor) else torch.tensor([float(v)])
+                v = v.detach().reshape(-1).to(device=dev, dtype=torch.float32)
+                acc = self.ep_sums.get(k)
+                if acc is None:
+                    acc = self.ep_sums[k] = torch.zeros(2, dtype=torch.float32, device=v.device)
+                acc[0] += v.sum()
+                acc[1] += v.numel()
+        if len(infos) > 0:      # direct logging from the env: scalars only
+            self.direct_info = {k: v for k, v in infos.items()
+                                if isinstance(v, (float, int)) or (isinstance(v, torch.Tensor) and v.dim() == 0)}
+
+    def after_print_stats(self, frame, epoch_num, total_time):
+        if self.ep_sums:
+            keys = sorted(self.ep_sums)
+            host = torch.stack([self.ep_sums[k] for k in keys]).cpu()       # one D2H for all keys
+            for k, (s, n) in zip(keys, host.tolist()):
+                if n > 0:
+                    self.writer.add_scalar('Episode/' + k, s / n, epoch_num)
+            self.ep_sums.clear()
+        for k, v in self.direct_info.items():
+            self.writer.add_scalar(f'{k}/frame', v, frame)
+            self.writer.add_scalar(f'{k}/iter', v, epoch_num)
+            self.writer.add_scalar(f'{k}/time', v, total_time)
 
 
 class DefaultRewardsShaper:

@@ -18,8 +18,9 @@ import numpy as np
 import torch
 
 from .agent import A2CAgent
-from .common import ObjectFactory, DefaultAlgoObserver, DefaultRewardsShaper, configurations, register_env
+from .common import ObjectFactory, DefaultAlgoObserver, IsaacAlgoObserver, DefaultRewardsShaper, configurations, register_env
 from . import envs  # noqa: F401  (registers the synthetic envs)
+from . import env_adapters  # noqa: F401  (registers vecenv type MJLAB)
 
 
 def _restore(agent, args):
@@ -74,6 +75,9 @@ class Runner:
         vecenv_type = config.get('vecenv_type')
         if vecenv_type is not None and config.get('env_name') and config['env_name'] not in configurations:
             register_env(config['env_name'], {'vecenv_type': vecenv_type})
+        observer_name = config.get('algo_observer')     # config-driven observer selection; an injected object still wins
+        if observer_name and not self._observer_was_injected:
+            self.algo_observer = {'default': DefaultAlgoObserver, 'isaac': IsaacAlgoObserver}[observer_name]()
         self.seed = params.get('seed', None)
         if self.seed is None:
             self.seed = int(time.time())

@@ -240,3 +240,49 @@ def test_train_loop_runs_to_max_epochs_and_saves(monkeypatch, tmp_path):
     assert torch.isfinite(a.model.flat).all()
     files = sorted(os.listdir(a.nn_dir))
     assert any(f.endswith('.pth') for f in files), files
+
+
+class _TapeManagerEnv:
+    """the golden tapes behind mjlab's manager-based API (obs groups, terminated / truncated, an extras dict with a per-burst 'log')"""
+
+    def __init__(self, g):
+        self.g, self.i = g, 0
+        self.action_space = type('S', (), {'shape': (g['N'], g['A'])})()
+        self.extras = {}
+
+    def reset(self):
+        self.i = 0
+        return {'actor': self.g['obs_tape'][0].clone()}, self.extras
+
+    def step(self, actions):
+        g = self.g
+        self.i += 1
+        j = self.i % g['obs_tape'].shape[0]
+        done, trunc = g['done_tape'][j].bool(), g['timeout_tape'][j].bool()
+        self.extras['log'] = {'ep_len': done.nonzero().reshape(-1).float()} if bool(done.any()) else {}
+        return {'actor': g['obs_tape'][j].clone()}, -(actions * actions).sum(-1) * 0.1, done & ~trunc, trunc, self.extras
+
+
+def test_manager_based_adapter_and_isaac_observer_in_the_training_loop(monkeypatch, tmp_path):
+    """the adapter's bool dones / time-outs are ingested as they are, the observer sees every step's infos without
+    asking for done indices (no per-step sync), and neither changes the epoch"""
+    from rl_games_b200.env_adapters import ManagerBasedEnvAdapter
+    from rl_games_b200.common import IsaacAlgoObserver
+    g = dict(torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False))
+    g['done_tape'] = ((g['done_tape'] > 0) | (g['timeout_tape'] > 0)).to(g['done_tape'].dtype)      # truncated implies done in this API
+    a = _build(monkeypatch, tmp_path, g, _Env(g))
+    env = ManagerBasedEnvAdapter(_TapeManagerEnv(g))
+    env.get_env_info = lambda base=env.get_env_info: {**base(), 'autoreset_mode': g['autoreset']}
+    b = _build(monkeypatch, tmp_path, g, env, over={'algo_observer': 'isaac'})
+    assert isinstance(b.algo_observer, IsaacAlgoObserver) and not b._whole_epoch_graph_ok()
+    rows = []
+    b.algo_observer.writer = type('W', (), {'add_scalar': lambda self, *r: rows.append(r)})()
+    for ag in (a, b):
+        ag.epoch_num += 1
+        ag.train_epoch(noise=g['noise'][0])
+    for x, y in ((a.model.flat, b.model.flat), (a.rewards, b.rewards), (a.dones_buf, b.dones_buf), (a.valid, b.valid)):
+        assert torch.equal(x, y)
+    H = a.horizon_length
+    want = torch.cat([g['done_tape'][j % g['obs_tape'].shape[0]].nonzero().reshape(-1).float() for j in range(1, H + 1)])
+    b.algo_observer.after_print_stats(123, 1, 0.5)
+    assert rows == [('Episode/ep_len', pytest.approx(want.mean().item(), rel=1e-6), 1)]
