@@ -268,7 +268,8 @@ int b200rl_value_loss_f32(const float* values, int value_ld, const float* old_va
  * clip_grad_norm_, optimizer.step) + torch.optim.Adam(eps=1e-8, weight_decay, fused=True)
  * (a2c_continuous.py:44-48) + the adaptive-KL scheduler (schedulers.py:19-33, a2c_common.py:1557-1563)
  * with lr living in DEVICE memory so no .item() sync is needed per minibatch.
- *  state_d: double[4] = {lr, step, beta1^step, beta2^step} (zeros for the last two mean 'fresh');
+ *  state_d: double[4] = {lr, step, beta1^step, beta2^step} (zeros for the last two mean 'fresh'); double[6] when
+ *    cfg->adaptive_lr is 2 or 3: [4], [5] = running KL sum / count of the current mini-epoch (zero-initialised);
  *  kl_dev: device f32 (summed over ranks; scaled by grad_scale inside), may be NULL.
  *  counter: int32[1] zero-initialised once.
  * ------------------------------------------------------------------------------------------- */
@@ -278,7 +279,10 @@ typedef struct b200rl_opt_cfg {
     double kl_threshold, min_lr, max_lr, lr_multiplier;
     double grad_scale;       /* 1/world_size applied to the (summed) gradient */
     int truncate_grads;      /* config truncate_grads */
-    int adaptive_lr;         /* lr_schedule == 'adaptive' && schedule_type == 'per_minibatch' */
+    int adaptive_lr;         /* adaptive-KL schedule (schedulers.py:19-33) stepped on the device: 0 = off; 1 = after every
+                              * optimiser step on this minibatch's KL (schedule_type 'per_minibatch'); schedule_type 'standard'
+                              * (a2c_common.py:1565-1571, one step per mini-epoch on the mean KL): 2 = accumulate this KL,
+                              * 3 = last minibatch of the mini-epoch: accumulate, step on the mean, reset */
 } b200rl_opt_cfg;
 
 /* optional fused refresh of the packed bf16 weight copy used by the tcgen05 kernels (b200rl_tc_pack_table) */

@@ -939,6 +939,7 @@ class OracleAgent:
         if self.cv is not None:                     # a2c_common.py:1536-1537 train_central_value() before the actor's mini-epochs
             out['cv_loss'] = self.cv.train_net()
         for mini_ep in range(self.cfg['mini_epochs']):
+            ep_kls = []
             for i in range(self.num_minibatches):
                 # train_actor_critic -> set_train() -> model.train() (a2c_continuous.py:236-239,
                 # a2c_common.py:560-563) puts running_mean_std back in TRAIN mode before EVERY
@@ -953,6 +954,7 @@ class OracleAgent:
                 self.dataset['sigma'][s:e] = sigma
                 out['a_loss'].append(a); out['c_loss'].append(cl); out['entropy'].append(ent)
                 out['kl'].append(kl); out['b_loss'].append(b); out['lr'].append(self.last_lr)
+                ep_kls.append(kl)
                 if self.cfg['schedule_type'] == 'per_minibatch':
                     av_kl = kl
                     if self.all_reduce is not None:
@@ -961,6 +963,14 @@ class OracleAgent:
                         av_kl = av_kl / self.world_size
                     self.last_lr, self.entropy_coef = self.scheduler.update(
                         self.last_lr, self.entropy_coef, self.epoch_num, self.frame, av_kl.item())
+            if self.cfg['schedule_type'] == 'standard':
+                # a2c_common.py:1565-1571: ONE scheduler step per mini-epoch on the mean of its minibatch KLs (torch_ext.mean_list)
+                av_kl = torch.stack(ep_kls).mean()
+                if self.all_reduce is not None:
+                    self.all_reduce(av_kl)
+                    av_kl = av_kl / self.world_size
+                self.last_lr, self.entropy_coef = self.scheduler.update(
+                    self.last_lr, self.entropy_coef, self.epoch_num, self.frame, av_kl.item())
             if self.model.normalize_input:
                 self.model.running_mean_std.eval()
         self.frame += self.batch_size * self.world_size

@@ -174,9 +174,12 @@ class A2CAgent:
         self.schedule_type = config.get('schedule_type', 'per_minibatch')
         if self.schedule_type == 'legacy':
             self.schedule_type = 'per_minibatch'
-        if self.is_adaptive_lr and self.schedule_type != 'per_minibatch':
-            raise NotImplementedError("adaptive lr_schedule with schedule_type=%r: only 'per_minibatch' (the default) runs "
-                                      "on the device scheduler" % self.schedule_type)
+        if self.is_adaptive_lr and self.schedule_type not in ('per_minibatch', 'standard'):
+            raise NotImplementedError("adaptive lr_schedule with schedule_type=%r: 'per_minibatch' (the default) and 'standard' "
+                                      "(one step per mini-epoch) run on the device scheduler" % self.schedule_type)
+        if self.is_adaptive_lr and self.schedule_type == 'standard' and not config.get('b200_unvalidated', False):
+            raise NotImplementedError("schedule_type 'standard' (scheduler stepped once per mini-epoch inside the optimiser kernels) reproduces "
+                                      "the reference on CPU but has not been run on hardware yet: set b200_unvalidated: True")
         if self.is_adaptive_lr:
             self.kl_threshold = config['kl_threshold']
             self.scheduler = AdaptiveScheduler(self.kl_threshold, min_lr=config.get('min_lr', 1e-6),
@@ -398,7 +401,8 @@ class A2CAgent:
         self.fused_allreduce = False
         if self.multi_gpu and self.world_size > 1 and self.config.get('b200_fused_allreduce', True):
             self._setup_peer_comm()
-        self.opt_state = torch.tensor([self.last_lr, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)   # lr, step, beta1^step, beta2^step
+        # lr, step, beta1^step, beta2^step, [KL sum, count of the running mini-epoch (schedule_type 'standard')], pad
+        self.opt_state = torch.tensor([self.last_lr, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
         self.entropy_coef_dev = torch.tensor([float(self.entropy_coef)], dtype=torch.float32, device=dev)
         self.inv_counts = f(self.num_minibatches) if self.mask_autoreset_rows else None
         self.mom_scratch = torch.zeros(1024 * 2 * D, dtype=torch.float64, device=dev)
@@ -474,6 +478,7 @@ class A2CAgent:
         obs-normaliser update of the NEXT update's minibatch (the first one of an epoch is merged by _update_all)"""
         m = self.model
         mn = self._merge_next(u)
+        self._set_sched_mode(u)
         if self.fused_allreduce:
             ops.allreduce_adam(self.peer_table, u & 1, self.global_rank, self.my_flags_ptr, self.ar_seq, self.ar_red, self.ar_nrm,
                                self.ar_bar, m.flat, m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.stats[u],
@@ -483,6 +488,13 @@ class A2CAgent:
             dist.all_reduce(gv['comm'], op=dist.ReduceOp.SUM)
         ops.adam_step(m.flat, gv['grad'], m.exp_avg, m.exp_avg_sq, self.opt_state, gv['kl'], self.opt_cfg, self.stats[u],
                       self.counters[2:3], n=P, wpack=wpack, pack_table=pack_table, merge_next=mn)
+
+    def _set_sched_mode(self, u):
+        """schedule_type 'standard' (a2c_common.py:1565-1571): the optimiser kernel of every minibatch adds its KL to the mini-epoch's
+        running sum, the last one of the mini-epoch steps the scheduler on the mean.  The struct is read at launch (by value), so the
+        mode is baked per launch into captured graphs."""
+        if self.is_adaptive_lr and self.schedule_type == 'standard':
+            self.opt_cfg.adaptive_lr = 3 if (u + 1) % self.num_minibatches == 0 else 2
 
     def _build_cfg_structs(self):
         """POD structs passed (by value at launch) to the kernels; baked into captured graphs, so any change
@@ -497,7 +509,7 @@ class A2CAgent:
                                   float(getattr(sched, 'kl_threshold', 0.0)), float(getattr(sched, 'min_lr', 1e-6)),
                                   float(getattr(sched, 'max_lr', 1e-2)), float(getattr(sched, 'lr_multiplier', 1.5)),
                                   1.0 / self.world_size, int(bool(self.truncate_grads)),
-                                  int(self.is_adaptive_lr and self.schedule_type == 'per_minibatch'))
+                                  int(self.is_adaptive_lr))      # 'standard': 2 / 3 per launch (_set_sched_mode)
         rs = self.rewards_shaper
         self.shaper_cfg = ops.ShaperCfg(float(rs.scale_value), float(rs.shift_value), float(rs.min_val), float(rs.max_val),
                                         float(self.gamma), int(bool(rs.log_val)), int(bool(self.value_bootstrap)))
@@ -896,6 +908,7 @@ class A2CAgent:
         npart = ops.tc_mlp_bwd(x, epm, N, m.D, nm, ns, self.wpack, m.units, mb, A, self.tc_act, self.tc_dhead, self.tc_delta2,
                                self.tc_delta1, self.part, self.part.shape[1], self.tc_offs, xtile=self.tc_xt)
         gv = self._gv[u & 1]
+        self._set_sched_mode(u)
         if not self.multi_gpu:
             # no exchange between the reduction and the optimiser: one fused launch (reduce + finalise + clip + Adam + repack)
             ops.reduce_adam(self.part, npart, self.part.shape[1], self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], gv['kl'], gv['grad'],
@@ -914,6 +927,8 @@ class A2CAgent:
 
     def _update_all(self):
         u = 0
+        if self.is_adaptive_lr and self.schedule_type == 'standard':
+            self.opt_state[4:6].zero_()      # a mini-epoch's KL accumulators never survive an interrupted epoch
         for _ in range(self.mini_epochs_num):
             for i in range(self.num_minibatches):
                 self._minibatch_update(i, u)
@@ -1250,8 +1265,8 @@ class A2CAgent:
         lr, step = self.model.load_optimizer_state_dict(weights['optimizer'])
         if lr is not None:
             self.last_lr = float(lr)
-        self.opt_state.copy_(torch.tensor([self.last_lr, float(step), 0.9 ** float(step) if step else 0.0, 0.999 ** float(step) if step else 0.0],
-                                          dtype=torch.float64))
+        self.opt_state.copy_(torch.tensor([self.last_lr, float(step), 0.9 ** float(step) if step else 0.0, 0.999 ** float(step) if step else 0.0,
+                                           0.0, 0.0, 0.0, 0.0], dtype=torch.float64))
         self._lr_synced = self.last_lr
         self.last_mean_rewards = weights.get('last_mean_rewards', -float('inf'))
         if self.normalize_rms_advantage and 'advantage_mean_std' in weights:      # a2c_common.py:909-911

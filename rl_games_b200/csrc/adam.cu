@@ -16,6 +16,25 @@ struct OptCfgDev {
     int truncate_grads, adaptive_lr;
 };
 
+// Adaptive-KL scheduler step (schedulers.py:19-33; python floats == fp64), run by one thread after the optimiser step.
+//   adaptive_lr == 1: schedule_type 'per_minibatch' -- one scheduler step per optimiser step on this minibatch's KL.
+//   adaptive_lr == 2 / 3: schedule_type 'standard' (a2c_common.py:1565-1571) -- one scheduler step per MINI-EPOCH on the mean of its
+//     minibatches' KLs (torch_ext.mean_list): 2 = add this KL to the running sum / count in state_d[4] / state_d[5];
+//     3 = last minibatch of the mini-epoch: add, step the scheduler on the mean, reset the accumulators.
+__device__ __forceinline__ double lr_schedule_step(double lr, double kl, const OptCfgDev& c, double* state_d) {
+    if (c.adaptive_lr >= 2) {
+        const double s = state_d[4] + kl, cnt = state_d[5] + 1.0;
+        const bool apply = c.adaptive_lr == 3;
+        state_d[4] = apply ? 0.0 : s;
+        state_d[5] = apply ? 0.0 : cnt;
+        if (!apply) return lr;
+        kl = s / cnt;
+    }
+    if (kl > 2.0 * c.kl_threshold) return fmax(lr / c.lr_multiplier, c.min_lr);
+    if (kl < 0.5 * c.kl_threshold) return fmin(lr * c.lr_multiplier, c.max_lr);
+    return lr;
+}
+
 // optional tail work of the optimiser kernels' last CTA: training-mode update of the obs normaliser for the NEXT minibatch
 // (Chan merge of its precomputed batch sums, running_mean_std.py:55-67) -- saves one tiny launch per minibatch
 struct ObsMergeDev {
@@ -133,9 +152,7 @@ __global__ void __launch_bounds__(1024) adam_step_kernel(float* __restrict__ par
         double new_lr = lr;
         if (c.adaptive_lr && kl_dev) {
             const double kl = (double)(__ldg(kl_dev) * gs);   // summed over ranks by the all-reduce -> mean (a2c_common.py:1559-1561)
-            // schedulers.py:19-33 (python floats == fp64)
-            if (kl > 2.0 * c.kl_threshold) new_lr = fmax(lr / c.lr_multiplier, c.min_lr);
-            if (kl < 0.5 * c.kl_threshold) new_lr = fmin(lr * c.lr_multiplier, c.max_lr);
+            new_lr = lr_schedule_step(lr, kl, c, state_d);
         }
         state_d[0] = new_lr;
         state_d[1] = step;
@@ -240,8 +257,7 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
         double new_lr = lr;
         if (c.adaptive_lr) {
             const double kl = (double)(__ldcg(red + n) * gs);
-            if (kl > 2.0 * c.kl_threshold) new_lr = fmax(lr / c.lr_multiplier, c.min_lr);
-            if (kl < 0.5 * c.kl_threshold) new_lr = fmin(lr * c.lr_multiplier, c.max_lr);
+            new_lr = lr_schedule_step(lr, kl, c, state_d);
         }
         state_d[0] = new_lr; state_d[1] = step; state_d[2] = p1; state_d[3] = p2;
         if (stats_out) { stats_out[B200RL_STAT_LR] = (float)lr; stats_out[B200RL_STAT_GNORM] = total_norm; stats_out[B200RL_STAT_KL] = __ldcg(red + n) * gs; }
@@ -478,8 +494,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
         const float* klp = MULTI ? ps.red + n : kl_out;      // summed over ranks by the exchange -> mean via grad_scale (a2c_common.py:1559-1561)
         if (c.adaptive_lr && klp) {
             const double kl = (double)(__ldcg(klp) * gs);
-            if (kl > 2.0 * c.kl_threshold) new_lr = fmax(lr / c.lr_multiplier, c.min_lr);
-            if (kl < 0.5 * c.kl_threshold) new_lr = fmin(lr * c.lr_multiplier, c.max_lr);
+            new_lr = lr_schedule_step(lr, kl, c, state_d);
         }
         state_d[0] = new_lr; state_d[1] = step; state_d[2] = p1; state_d[3] = p2;
         stats[B200RL_STAT_LR] = (float)lr; stats[B200RL_STAT_GNORM] = total_norm;

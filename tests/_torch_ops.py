@@ -371,10 +371,16 @@ def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, sta
     adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=n)
     if cfg.adaptive_lr and kl_dev is not None:
         kl = float(kl_dev[0]) * float(cfg.grad_scale)
+        apply = True
+        if cfg.adaptive_lr >= 2:        # schedule_type 'standard': accumulate (2) / accumulate + step on the mean + reset (3)
+            s_, c_ = float(state_d[4]) + kl, float(state_d[5]) + 1.0
+            apply = cfg.adaptive_lr == 3
+            state_d[4], state_d[5] = (0.0, 0.0) if apply else (s_, c_)
+            kl = s_ / c_
         new_lr = lr
-        if kl > 2.0 * cfg.kl_threshold:
+        if apply and kl > 2.0 * cfg.kl_threshold:
             new_lr = max(lr / cfg.lr_multiplier, cfg.min_lr)
-        if kl < 0.5 * cfg.kl_threshold:
+        if apply and kl < 0.5 * cfg.kl_threshold:
             new_lr = min(lr * cfg.lr_multiplier, cfg.max_lr)
         state_d[0] = new_lr
     if stats_out is not None:

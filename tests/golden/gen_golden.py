@@ -547,7 +547,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -565,6 +565,11 @@ if __name__ == '__main__':
     if 'lstm_after' in which:
         # the placement most shipped configs use: MLP -> LSTM -> heads (before_mlp: False is the reference default)
         gen_agent('agent_lstm_after.pt', seed=14, rnn_units=12, rnn_before_mlp=False, overrides={'seq_length': 4})
+    if 'sched' in which:
+        # schedule_type 'standard' (what the shipped mjlab configs use): one adaptive-KL scheduler step per mini-epoch on the mean KL;
+        # 4 minibatches per mini-epoch, a learning rate high enough that the schedule moves both ways
+        gen_agent('agent_sched_standard.pt', N=16, H=8, mb=32, seed=15, epochs=3,
+                  overrides={'schedule_type': 'standard', 'learning_rate': 3e-3, 'kl_threshold': 0.0015})
     if 'tcshape' in which:
         # three hidden layers and an observation width that is a multiple of 4: the shape class of the tcgen05 path's host logic
         # (per-minibatch obs moments precomputed once per epoch, merged in the optimiser tail); masked autoreset on top

@@ -120,12 +120,21 @@ def test_lstm_after_mlp_agent_matches_reference_golden(graph):
     _golden_run('agent_lstm_after.pt', graph, {'b200_unvalidated': True})
 
 
+@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                    reason="schedule_type 'standard' not yet run on hardware (host logic checked on CPU): set B200RL_UNVALIDATED=1")
+@pytest.mark.parametrize('graph', [False, True])
+def test_standard_schedule_agent_matches_reference_golden(graph):
+    """schedule_type 'standard' (what the shipped mjlab configs use): the adaptive-KL scheduler steps once per mini-epoch on the mean
+    KL, inside the optimiser kernel of the mini-epoch's last minibatch -- also when the update phase replays as a CUDA graph"""
+    _golden_run('agent_sched_standard.pt', graph, {'b200_unvalidated': True})
+
+
 def _golden_run(name, graph, extra=None):
     g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk = g['config']
     over = {k: cfgk[k] for k in ('clip_value', 'use_smooth_clamp', 'bound_loss_type', 'bounds_loss_coef', 'entropy_coef',
                                  'truncate_grads', 'value_bootstrap', 'mini_epochs', 'lr_schedule', 'weight_decay', 'critic_coef', 'seq_length',
-                                 'normalize_rms_advantage', 'adv_rms_momentum')
+                                 'normalize_rms_advantage', 'adv_rms_momentum', 'schedule_type', 'learning_rate', 'kl_threshold')
             if k in cfgk}
     over.setdefault('lr_schedule', None)
     over['b200_cuda_graph'] = graph

@@ -371,6 +371,48 @@ def test_adam_step_vs_oracle(ops, truncate, wd):
     torch.testing.assert_close(v.cpu(), opt.v[0], rtol=5e-5, atol=1e-10)
 
 
+@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                    reason="schedule_type 'standard' modes of the optimiser kernels not yet run on hardware: set B200RL_UNVALIDATED=1")
+@pytest.mark.parametrize('kernel', ['adam_step', 'reduce_adam'])
+def test_per_mini_epoch_scheduler_modes(ops, kernel):
+    """cfg.adaptive_lr 2 / 3 (schedule_type 'standard', a2c_common.py:1565-1571): the LR moves only at the last minibatch of a
+    mini-epoch, on the mean of the mini-epoch's KLs; the accumulators return to zero"""
+    from rl_games_b200.ops import OptCfg
+    g = torch.Generator().manual_seed(11)
+    n, A, nmb = 4099, 8, 3
+    stride = ops.loss_partial_stride()
+    sched = O.AdaptiveScheduler(0.008)
+    cfg = OptCfg(0.9, 0.999, 1e-8, 0.0, 1.0, 0.008, 1e-6, 1e-2, 1.5, 1.0, 1, 2)
+    p = (torch.randn(n, generator=g) * 0.1).to(DEV); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    state = torch.tensor([3e-4] + [0.0] * 7, dtype=torch.float64, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV); stats = torch.zeros(16, device=DEV)
+    grad = torch.zeros(n, device=DEV); klt = torch.zeros(1, device=DEV); ec = torch.tensor([0.0], device=DEV)
+    nrm = torch.zeros(148, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+    lr = 3e-4
+    kl_rows = [[0.001, 0.002, 0.0015], [0.05, 0.03, 0.001], [0.006, 0.007, 0.008], [0.0001, 0.03, 0.0001]]
+    for me, row in enumerate(kl_rows):
+        seen = []
+        for i, klv in enumerate(row):
+            cfg.adaptive_lr = 3 if i == nmb - 1 else 2
+            if kernel == 'adam_step':
+                klt.fill_(klv)
+                ops.adam_step(p, (torch.randn(n, generator=g) * 0.01).to(DEV), m, v, state, klt, cfg, stats, counter)
+            else:
+                part = (torch.randn(5, n, generator=g) * 0.01).to(DEV)
+                lpart = torch.zeros(4, stride, dtype=torch.float64, device=DEV)
+                lpart[0, 4] = klv                     # slot 4 of a partial row = weighted KL contribution (loss_math.cuh sc[4])
+                ops.reduce_adam(part, 5, n, lpart, 4, A, ec, stats, klt, grad, p, m, v, n, state, cfg, counter, nrm, bar)
+            torch.cuda.synchronize()
+            seen.append(float(klt[0]))
+            if i < nmb - 1:
+                assert float(state[0]) == lr and float(state[5]) == i + 1          # unchanged inside the mini-epoch
+                assert float(state[4]) == pytest.approx(sum(seen), rel=1e-12)
+        lr, _ = sched.update(lr, 0.0, 0, 0, sum(seen) / nmb)
+        assert float(state[0]) == pytest.approx(lr, rel=1e-14)
+        assert float(state[4]) == 0.0 and float(state[5]) == 0.0
+        assert int(state[1]) == (me + 1) * nmb
+
+
 @pytest.mark.parametrize('n,n_splits,pad', [(57361, 148, False), (57361, 148, True), (700, 5, False), (703, 7, True), (201737, 148, True)])
 def test_reduce_adam_vs_two_kernel_path(ops, n, n_splits, pad):
     """fused reduce+finalise+clip+Adam launch == reduce_finalize followed by adam_step (same maths, different summation

@@ -100,7 +100,7 @@ def _oracle_from_golden(g):
                                 'bound_loss_type', 'use_smooth_clamp', 'truncate_grads', 'grad_norm',
                                 'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value',
                                 'normalize_advantage', 'value_bootstrap', 'mini_epochs', 'normalize_rms_advantage',
-                                'adv_rms_momentum') if k in cfgk}
+                                'adv_rms_momentum', 'schedule_type') if k in cfgk}
     cfg['bounds_loss_coef'] = cfgk.get('bounds_loss_coef', None)
     cfg['lr_schedule'] = cfgk.get('lr_schedule', None)
     cfg['weight_decay'] = cfgk.get('weight_decay', 0.0)
@@ -116,7 +116,7 @@ def _oracle_from_golden(g):
 
 
 @pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt',
-                                  'agent_lstm_after.pt'])
+                                  'agent_lstm_after.pt', 'agent_sched_standard.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
