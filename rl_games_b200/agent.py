@@ -244,7 +244,8 @@ class A2CAgent:
                                       "(minibatches are whole-env slices of the time-major arena)")
         self.envs_per_mb = self.minibatch_size // self.horizon_length
         self.mini_epochs_num = config['mini_epochs']
-        self.mixed_precision = config.get('mixed_precision', True)
+        # None (key absent) = the reference's 'auto' (a2c_common.py:427-429): resolved once the model geometry is known
+        self.mixed_precision = config.get('mixed_precision', None)
         self.last_lr = float(config['learning_rate'])
         self.frame = 0
         self.update_time = self.play_time = 0
@@ -280,9 +281,16 @@ class A2CAgent:
         self.model = B200Model(self.network_params, self.obs_shape[0], self.actions_num, self.device_t,
                                self.normalize_input, self.normalize_value, self.value_size)
         self.value_mean_std = self.model.value_mean_std if self.normalize_value else None
-        # precision mode: mixed_precision True (reference default on bf16 GPUs, a2c_common.py:429) -> bf16 tcgen05
-        # kernels (mlp_tc.cu); False -> fp32 CUDA-core kernels (mlp_simt.cu).  No silent downgrade.
+        # precision mode: mixed_precision True -> bf16 tcgen05 kernels (mlp_tc.cu); False -> fp32 CUDA-core kernels (mlp_simt.cu).
+        # An explicit True is never downgraded (unsupported geometry raises); an ABSENT key is the reference's 'auto' (bf16 where the
+        # hardware supports it, a2c_common.py:427-429) and resolves to the tcgen05 path where this build has kernels for the
+        # geometry, else to fp32 (a HIGHER precision than the reference's default), saying so once.
         self.is_rnn = self.model.is_rnn()
+        if self.mixed_precision is None:
+            self.mixed_precision = (not self.is_rnn) and ops.tc_supported(self.model.D, self.model.units, self.actions_num)
+            if not self.mixed_precision and self.global_rank == 0:
+                print(f'b200: mixed_precision not set -> fp32 kernels for this geometry (obs={self.model.D}, units={self.model.units}, '
+                      f'actions={self.actions_num}{", rnn" if self.is_rnn else ""}); the bf16 tcgen05 kernels cover obs<=64, MLP [256,128,64], actions<=15')
         if self.is_rnn:
             if self.horizon_length % self.seq_length != 0:
                 raise ValueError(f"Horizon length ({self.horizon_length}) must be divisible by sequence length ({self.seq_length})")

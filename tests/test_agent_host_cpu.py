@@ -288,3 +288,19 @@ def test_manager_based_adapter_and_isaac_observer_in_the_training_loop(monkeypat
     want = torch.cat([g['done_tape'][j % g['obs_tape'].shape[0]].nonzero().reshape(-1).float() for j in range(1, H + 1)])
     b.algo_observer.after_print_stats(123, 1, 0.5)
     assert rows == [('Episode/ep_len', pytest.approx(want.mean().item(), rel=1e-6), 1)]
+
+
+def test_mixed_precision_auto_resolves_by_geometry_and_explicit_true_never_downgrades(monkeypatch, tmp_path, capsys):
+    """key absent = the reference's 'auto' (a2c_common.py:427-429): tcgen05 path where this build has kernels for the geometry, fp32
+    otherwise (with a note); an explicit True on an unsupported geometry raises instead of silently changing precision"""
+    g = dict(torch.load(os.path.join(GOLDEN, 'agent_base.pt'), weights_only=False))
+    a = _build(monkeypatch, tmp_path, g, _Env(g), over={'mixed_precision': None})      # MLP (16, 8): no tcgen05 kernel
+    assert a.use_tc is False and a.mixed_precision is False
+    assert 'mixed_precision not set -> fp32 kernels' in capsys.readouterr().out
+    with pytest.raises(NotImplementedError, match='bf16 tcgen05 path'):
+        _build(monkeypatch, tmp_path, g, _Env(g), tc=False, over={'mixed_precision': True})
+    g2 = dict(torch.load(os.path.join(GOLDEN, 'agent_tcshape.pt'), weights_only=False))
+    import _torch_ops
+    _torch_ops.install_tc(monkeypatch)          # its tc_supported stand-in accepts the fixture's small three-layer geometry
+    b = _build(monkeypatch, tmp_path, g2, _Env(g2), tc=True, over={'mixed_precision': None})
+    assert b.use_tc is True and b.mixed_precision is True
