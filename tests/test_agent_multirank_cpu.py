@@ -1,0 +1,102 @@
+"""The N>1 path of the validated agent on CPU: two `gloo` ranks, each running rl_games_b200.agent.A2CAgent (host logic, torch stand-ins
+for the kernels, `b200_fused_allreduce: False` so the exchange is a plain `dist.all_reduce` like on the NCCL fallback path) on its OWN
+experience, checked against the oracle restatement driven by the same collectives (a2c_common.py:493-509 flat gradient SUM / world,
+:1559-1561 KL mean, :782-808 pooled running-stat merge).  Proves: ranks stay byte-identical, gradients and KL are averaged not summed,
+the LR schedule follows the rank-mean KL, the normalisers end up with the pooled moments."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+class _Patch:
+    """monkeypatch.setattr look-alike for the spawned workers (the processes end with the test)"""
+
+    def setattr(self, target, name, value):
+        setattr(target, name, value)
+
+
+def _rank_tapes(g, rank):
+    """rank 0 replays the fixture's tapes, rank 1 a different experience of the same shape (envs reversed, time rolled)"""
+    if rank == 0:
+        return g
+    g = dict(g)
+    for k in ('obs_tape', 'done_tape', 'timeout_tape'):
+        g[k] = torch.roll(torch.flip(g[k], dims=[1]), shifts=3, dims=0).contiguous()
+    g['obs_tape'] = g['obs_tape'] * 1.5 + 0.25
+    g['noise'] = [torch.flip(n, dims=[1]).contiguous() for n in g['noise']]
+    return g
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import _torch_ops
+    import test_agent_host_cpu as H
+    from oracle import ppo_oracle as O
+    from test_oracle_vs_golden import _oracle_from_golden
+    # multi_gpu: True makes the agent name its device 'cuda:<local_rank>' (a2c_common.py:206-220): map that to the CPU in this process
+    real_device = torch.device
+
+    class _Meta(type):
+        def __instancecheck__(cls, obj):
+            return isinstance(obj, real_device)
+
+    class _Dev(metaclass=_Meta):
+        def __new__(cls, *a, **k):
+            if a and isinstance(a[0], str) and a[0].startswith('cuda'):
+                return real_device('cpu')
+            return real_device(*a, **k)
+
+    torch.device = _Dev
+    g = _rank_tapes(torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False), rank)
+    agent = H._build(_Patch(), '/tmp/b200_multirank_%d' % rank, g, H._Env(g),
+                     over={'multi_gpu': True, 'b200_fused_allreduce': False, 'print_stats': False})
+    assert agent.multi_gpu and agent.world_size == 2 and agent.global_rank == rank and not agent.fused_allreduce
+    ar = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)      # noqa: E731
+    orc = _oracle_from_golden(g)
+    orc.all_reduce, orc.world_size = ar, world
+    snaps = {}
+    out = []
+    for ep in range(len(g['epochs_out'])):
+        agent.epoch_num += 1
+        agent.train_epoch(noise=g['noise'][ep])
+        o = orc.train_epoch(g['noise'][ep])
+        for name, m in (('obs', orc.model.running_mean_std), ('val', orc.model.value_mean_std)):      # sync_running_stats, pooled mode
+            snaps[name] = O.merge_rank_stats(m, ar, snaps.get(name))
+        sd = agent.model.state_dict()
+        for k in O.param_names(len(g['units'])):
+            torch.testing.assert_close(sd[k], orc.model.p[k].detach(), rtol=1e-3, atol=2e-5, msg=lambda m: f'rank {rank} epoch {ep} {k}: {m}')
+        assert agent.last_lr == pytest.approx(orc.last_lr, rel=1e-12)
+        torch.testing.assert_close(agent.last_stats[:, 4], torch.stack(o['kl']), rtol=2e-3, atol=1e-7)       # per-rank KL (before the mean)
+        for pre, m in (('running_mean_std.', orc.model.running_mean_std), ('value_mean_std.', orc.model.value_mean_std)):
+            assert int(sd[pre + 'count']) == int(m.count)
+            torch.testing.assert_close(sd[pre + 'running_mean'], m.running_mean.reshape(-1), rtol=1e-6, atol=1e-7)
+            torch.testing.assert_close(sd[pre + 'running_var'], m.running_var.reshape(-1), rtol=1e-5, atol=1e-7)
+        out.append((agent.model.flat.clone(), agent.last_lr, int(sd['running_mean_std.count']), sd['running_mean_std.running_mean'].clone(),
+                    agent.rewards.clone()))
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_agent_matches_oracle_and_ranks_stay_identical():
+    world, port = 2, 29500 + os.getpid() % 400
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    g = torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False)
+    for ep in range(len(g['epochs_out'])):
+        (p0, lr0, c0, m0, r0), (p1, lr1, c1, m1, r1) = ret[0][ep], ret[1][ep]
+        assert torch.equal(p0, p1) and lr0 == lr1                      # same averaged gradient, same schedule -> byte-identical weights
+        assert c0 == c1 and torch.equal(m0, m1)                       # pooled normaliser state
+        assert not torch.equal(r0, r1)                                # ... from different experience
+    # two ranks on different data: not the single-rank golden run any more (flat arena = sigma[A] then actor_mlp.0.weight, ...)
+    w0 = g['epochs_out'][-1]['state']['a2c_network.actor_mlp.0.weight'].reshape(-1)
+    assert not torch.allclose(ret[0][-1][0][g['A']:g['A'] + w0.numel()], w0, rtol=1e-3, atol=1e-5)
