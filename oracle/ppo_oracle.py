@@ -604,6 +604,7 @@ class CentralValueOracle:
         self.scheduler = IdentityScheduler()          # lr_schedule 'linear' is the only other option (central_value.py:55-62)
         self.epoch_num, self.frame = 0, 0
         self.dataset = None
+        self.all_reduce, self.world_size = None, 1     # multi-GPU: set both (central_value.py:322-337)
 
     def parameters(self):
         return [self.p[n] for n in self.names]
@@ -656,6 +657,14 @@ class CentralValueOracle:
                     p.grad = None
                 l.backward()
                 grads = [p.grad for p in params]
+                if self.all_reduce is not None:         # central_value.py:322-337: cat -> all_reduce(SUM) -> / world -> scatter
+                    flat = torch.cat([g.reshape(-1) for g in grads])
+                    self.all_reduce(flat)
+                    off, new = 0, []
+                    for g in grads:
+                        new.append(flat[off:off + g.numel()].view_as(g) / self.world_size)
+                        off += g.numel()
+                    grads = new
                 if self.truncate_grads:
                     grads, _ = clip_grad_norm(grads, self.grad_norm)
                 self.optimizer.lr = self.lr

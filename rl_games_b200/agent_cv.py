@@ -19,6 +19,7 @@ actor still works), identity / linear critic LR schedule.
 from collections import OrderedDict
 
 import torch
+import torch.distributed as dist
 
 from . import ops
 from .agent import A2CAgent
@@ -29,8 +30,9 @@ from .model import _RunningStats
 class CentralValueNet:
     """CentralValueTrain on the fp32 kernels: flat arena [W0 b0 ... W_v b_v] in the reference's parameter order."""
 
-    def __init__(self, cv_config, state_dim, num_actors, horizon, normalize_value, max_epochs, device):
+    def __init__(self, cv_config, state_dim, num_actors, horizon, normalize_value, max_epochs, device, multi_gpu=False, world_size=1):
         net = cv_config['network']
+        self.multi_gpu, self.world_size = bool(multi_gpu) and world_size > 1, int(world_size)
         mlp = net['mlp']
         self.units = list(mlp['units'])
         self.activation = mlp.get('activation', 'elu')
@@ -94,7 +96,9 @@ class CentralValueNet:
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
         self.opt_state = torch.tensor([self.lr, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
         self.adam_stats = f(16)
-        self.opt_cfg = ops.OptCfg(0.9, 0.999, 1e-8, self.weight_decay, self.grad_norm, 0.0, 1e-6, 1e-2, 1.5, 1.0, int(self.truncate_grads), 0)
+        # grad_scale = 1/world: the optimiser kernel scales the SUM the all-reduce leaves in self.grad (central_value.py:322-337)
+        self.opt_cfg = ops.OptCfg(0.9, 0.999, 1e-8, self.weight_decay, self.grad_norm, 0.0, 1e-6, 1e-2, 1.5,
+                                  1.0 / (self.world_size if self.multi_gpu else 1), int(self.truncate_grads), 0)
         self.last_losses = []
 
     def view(self, name, arena=None):
@@ -198,6 +202,8 @@ class CentralValueNet:
                         ops.linear_bwd_weight(self.d_act[0], x, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S_,
                                               rows_per_chunk=epm, chunk_stride=N, x_ld=self.S, norm_mean=nm, norm_std=ns, M=mb, split_stride=P)
                 ops.reduce_splits(self.part, self.grad, P, S_, split_stride=P)
+                if self.multi_gpu:      # the critic's own flat-gradient exchange, one per minibatch (central_value.py:322-337)
+                    dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
                 ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.opt_state, None, self.opt_cfg, self.adam_stats,
                               self.counters[2:3], n=P)
         self.last_losses = rows
@@ -217,8 +223,6 @@ class A2CAgentCV(A2CAgent):
         if not config.get('b200_unvalidated', False):
             raise NotImplementedError('the central-value B200 agent has not been run on hardware yet (oracle + golden vectors are in place): '
                                       'set b200_unvalidated: True to run it anyway')
-        if config.get('multi_gpu', False):
-            raise NotImplementedError('central value with multi_gpu')
         config['central_value_config'] = None          # the base class refuses it; everything it builds is unchanged by the critic
         try:
             super().__init__(base_name, params)
@@ -234,7 +238,7 @@ class A2CAgentCV(A2CAgent):
             raise NotImplementedError('only flat state spaces')
         self.state_shape = space.shape
         self.central_value_net = CentralValueNet(cv_config, space.shape[0], self.num_actors, self.horizon_length, self.normalize_value,
-                                                 self.max_epochs, self.device_t)
+                                                 self.max_epochs, self.device_t, multi_gpu=self.multi_gpu, world_size=self.world_size)
         self.value_mean_std = self.central_value_net.value_mean_std                        # a2c_continuous.py:72-73
         self._states = None
 
@@ -258,6 +262,17 @@ class A2CAgentCV(A2CAgent):
 
     def _whole_epoch_graph_ok(self):
         return False                                   # the critic's training is eager
+
+    def _stats_modules(self):
+        """a2c_common.py:753-765: the cross-rank running-stat sync also covers the critic's normalisers (the value normaliser the
+        agent uses IS the critic's; the actor model's own never moves and merges as a no-op delta)"""
+        mods = super()._stats_modules()
+        cv = self.central_value_net
+        if cv.running_mean_std is not None:
+            mods.append(('cv_obs', cv.running_mean_std))
+        if cv.value_mean_std is not None:
+            mods.append(('cv_value', cv.value_mean_std))
+        return mods
 
     # ---- the agent's value normaliser is the critic's
     def _prepare(self, n_partials):

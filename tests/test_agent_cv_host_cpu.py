@@ -46,9 +46,8 @@ class _Env:
         pass
 
 
-def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tmp_path):
+def _build_cv(monkeypatch, tmp_path, g, over=None):
     import _torch_ops
-    from oracle import ppo_oracle as O
     from rl_games_b200.agent_cv import A2CAgentCV
     from rl_games_b200.runner import Runner
     _torch_ops.install_continuous(monkeypatch)
@@ -56,7 +55,6 @@ def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tm
     monkeypatch.setattr(torch.cuda, 'Event', _Event)
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _Stream())
     monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
-    g = torch.load(os.path.join(GOLDEN, 'agent_cv.pt'), weights_only=False)
     cfgk = g['config']
     env = _Env(g)
     cv_cfg = dict(g['cv_config'])
@@ -66,6 +64,7 @@ def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tm
     config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
                    'mixed_precision': False, 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None),
                    'central_value_config': cv_cfg, 'b200_unvalidated': True})
+    config.update(over or {})
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
@@ -82,6 +81,14 @@ def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tm
     cv.load_state_dict(g['cv_init_state'])
     agent.init_tensors()
     agent.obs = agent.env_reset()
+    return agent
+
+
+def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tmp_path):
+    from oracle import ppo_oracle as O
+    g = torch.load(os.path.join(GOLDEN, 'agent_cv.pt'), weights_only=False)
+    agent = _build_cv(monkeypatch, tmp_path, g)
+    cv = agent.central_value_net
     fl = O.swap_and_flatten01
     flat_noise = g['noise'].reshape(-1, g['N'], g['A'])          # H draws per epoch (the last-value forward goes through the critic)
     for ep, ref in enumerate(g['epochs_out']):

@@ -34,13 +34,9 @@ def _rank_tapes(g, rank):
     return g
 
 
-def _worker(rank, world, port, ret):
+def _init_rank(rank, world, port):
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    import _torch_ops
-    import test_agent_host_cpu as H
-    from oracle import ppo_oracle as O
-    from test_oracle_vs_golden import _oracle_from_golden
     # multi_gpu: True makes the agent name its device 'cuda:<local_rank>' (a2c_common.py:206-220): map that to the CPU in this process
     real_device = torch.device
 
@@ -55,6 +51,13 @@ def _worker(rank, world, port, ret):
             return real_device(*a, **k)
 
     torch.device = _Dev
+
+
+def _worker(rank, world, port, ret):
+    _init_rank(rank, world, port)
+    import test_agent_host_cpu as H
+    from oracle import ppo_oracle as O
+    from test_oracle_vs_golden import _oracle_from_golden
     g = _rank_tapes(torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False), rank)
     agent = H._build(_Patch(), '/tmp/b200_multirank_%d' % rank, g, H._Env(g),
                      over={'multi_gpu': True, 'b200_fused_allreduce': False, 'print_stats': False})
@@ -100,3 +103,58 @@ def test_two_rank_agent_matches_oracle_and_ranks_stay_identical():
     # two ranks on different data: not the single-rank golden run any more (flat arena = sigma[A] then actor_mlp.0.weight, ...)
     w0 = g['epochs_out'][-1]['state']['a2c_network.actor_mlp.0.weight'].reshape(-1)
     assert not torch.allclose(ret[0][-1][0][g['A']:g['A'] + w0.numel()], w0, rtol=1e-3, atol=1e-5)
+
+
+def _worker_cv(rank, world, port, ret):
+    """central value (gated path): the critic has its OWN per-minibatch gradient exchange (central_value.py:322-337) and its normalisers
+    join the pooled stats sync (a2c_common.py:753-765)"""
+    _init_rank(rank, world, port)
+    import test_agent_cv_host_cpu as HC
+    from oracle import ppo_oracle as O
+    from test_oracle_vs_golden import _cv_oracle_from_golden
+    g = _rank_tapes(torch.load(os.path.join(GOLDEN, 'agent_cv.pt'), weights_only=False), rank)
+    if rank:
+        g['state_tape'] = torch.roll(torch.flip(g['state_tape'], dims=[1]), shifts=3, dims=0).contiguous() * 0.75 - 0.1
+        g['noise'] = torch.flip(torch.stack(list(g['noise'])), dims=[2]).contiguous()
+    agent = HC._build_cv(_Patch(), '/tmp/b200_multirank_cv_%d' % rank, g,
+                         over={'multi_gpu': True, 'b200_fused_allreduce': False, 'print_stats': False})
+    cv = agent.central_value_net
+    assert agent.multi_gpu and cv.multi_gpu and cv.world_size == 2
+    ar = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)      # noqa: E731
+    orc, ocv = _cv_oracle_from_golden(g)
+    orc.all_reduce, orc.world_size = ar, world
+    ocv.all_reduce, ocv.world_size = ar, world
+    snaps, out = {}, []
+    flat_noise = g['noise'].reshape(-1, g['N'], g['A'])
+    for ep in range(len(g['epochs_out'])):
+        nz = flat_noise[ep * g['H']:(ep + 1) * g['H']]
+        agent.epoch_num += 1
+        agent.train_epoch(noise=nz)
+        orc.train_epoch(nz)
+        for name, m in (('obs', orc.model.running_mean_std), ('val', orc.model.value_mean_std), ('cv_obs', ocv.running_mean_std),
+                        ('cv_val', ocv.value_mean_std)):
+            snaps[name] = O.merge_rank_stats(m, ar, snaps.get(name))
+        sd, csd = agent.model.state_dict(), cv.state_dict()
+        for k in O.param_names(len(g['units'])):
+            torch.testing.assert_close(sd[k], orc.model.p[k].detach(), rtol=1e-3, atol=2e-5, msg=lambda m: f'rank {rank} epoch {ep} {k}: {m}')
+        for k in g['cv_param_order']:
+            torch.testing.assert_close(csd[k], ocv.p[k].detach(), rtol=1e-3, atol=2e-5, msg=lambda m: f'rank {rank} epoch {ep} cv {k}: {m}')
+        assert agent.last_lr == pytest.approx(orc.last_lr, rel=1e-12) and cv.lr == pytest.approx(ocv.lr, rel=1e-12)
+        for pre, m in (('running_mean_std.', ocv.running_mean_std), ('value_mean_std.', ocv.value_mean_std)):
+            assert int(csd[pre + 'count']) == int(m.count)
+            torch.testing.assert_close(csd[pre + 'running_mean'], m.running_mean.reshape(-1), rtol=1e-6, atol=1e-7)
+            torch.testing.assert_close(csd[pre + 'running_var'], m.running_var.reshape(-1), rtol=1e-5, atol=1e-7)
+        assert int(sd['running_mean_std.count']) == int(orc.model.running_mean_std.count)
+        out.append((agent.model.flat.clone(), cv.flat.clone(), csd['running_mean_std.running_mean'].clone(), int(csd['value_mean_std.count'])))
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_central_value_agent_matches_oracle_and_ranks_stay_identical():
+    world, port = 2, 29900 + os.getpid() % 90
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_cv, args=(world, port, ret), nprocs=world, join=True)
+    for (p0, c0, m0, n0), (p1, c1, m1, n1) in zip(ret[0], ret[1]):
+        assert torch.equal(p0, p1) and torch.equal(c0, c1) and torch.equal(m0, m1) and n0 == n1

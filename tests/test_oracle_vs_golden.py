@@ -246,11 +246,7 @@ def test_ema_advantage_normaliser_bitexact():
 
 
 # ------------------------------------------------------------------------------------------ central value
-def test_central_value_train_epochs_match_reference_agent():
-    """A2CAgent with central_value_config (asymmetric critic on privileged `states`, own normalisers / Adam / minibatching,
-    trained before the actor's mini-epochs; the rollout values and the value normaliser come from the critic) vs the oracle."""
-    g = load('agent_cv.pt')
-    assert g['cv_param_order'] == O.cv_param_names(len(g['cv_units']))
+def _cv_oracle_from_golden(g):
     cfgk = g['config']
     cfg = {k: cfgk[k] for k in ('gamma', 'tau', 'e_clip', 'clip_value', 'critic_coef', 'entropy_coef', 'bound_loss_type', 'use_smooth_clamp',
                                 'truncate_grads', 'grad_norm', 'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value',
@@ -274,6 +270,15 @@ def test_central_value_train_epochs_match_reference_agent():
     params = {k: v for k, v in g['init_state'].items() if k.startswith('a2c_network')}
     ag = O.OracleAgent(Env(), params, g['D'], g['A'], g['units'], g['N'], g['H'], g['mb'], cfg, central_value=cv)
     ag.obs = ag.env_reset()
+    return ag, cv
+
+
+def test_central_value_train_epochs_match_reference_agent():
+    """A2CAgent with central_value_config (asymmetric critic on privileged `states`, own normalisers / Adam / minibatching,
+    trained before the actor's mini-epochs; the rollout values and the value normaliser come from the critic) vs the oracle."""
+    g = load('agent_cv.pt')
+    assert g['cv_param_order'] == O.cv_param_names(len(g['cv_units']))
+    ag, cv = _cv_oracle_from_golden(g)
     # with a central value the last-value forward goes through the critic and draws no action noise, so the reference consumed the
     # tape as one flat stream of H draws per epoch (gen_golden.py asserts counter == epochs * H)
     flat_noise = g['noise'].reshape(-1, g['N'], g['A'])
