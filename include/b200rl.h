@@ -399,8 +399,10 @@ int b200rl_bump_u64(uint64_t* p, void* stream);
 /* ---------------------------------------------------------------------------------------------
  * bf16 tensor-core MLP path (`mixed_precision: True`, the reference's default on bf16-capable GPUs:
  * a2c_common.py:429, a2c_continuous.py:173).  tcgen05.mma + TMEM accumulators + cp.async.bulk tile moves.
- * Network geometry supported by this build: obs dim <= 64, MLP [256,128,64], A <= 15 (BASELINE configs[1..2]);
- * b200rl_tc_supported() tells.  Weights are consumed from ONE packed bf16 copy (b200rl_tc_pack_weights) that
+ * Network geometry supported by this build: MLP [256,128,64], A <= 15, and either obs dim <= 64 (BASELINE configs[1..2]: all
+ * weights resident, b200rl_tc_supported() == 1) or 64 < obs dim <= 256 (BASELINE configs[4]; == 2: layer 1 runs in kernels of its
+ * own -- the training forward / backward calls launch them internally, the rollout forward needs `l1_scratch`, a tiled bf16
+ * buffer of n_tiles(N_rows) * tile_bytes[0]; xtile must be NULL).  0 = unsupported.  Weights are consumed from ONE packed bf16 copy (b200rl_tc_pack_weights) that
  * serves the forward (K-major view) and the dgrad (MN-major view).  act1/act2/act3/dhead/delta1/delta2 are
  * opaque tiled bf16 buffers: n_tiles(M) = ceil(M/128) tiles of b200rl_tc_tile_bytes() bytes each.
  *   fwd_train : trunk + heads + PPO loss fwd/bwd (same semantics / partial format as b200rl_ppo_head_loss_f32,
@@ -436,7 +438,7 @@ int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, c
                               float* actions, float* mus, float* sigmas, float* neglogp, float* values,
                               float* env_actions, int clip_actions, const float* act_low, const float* act_high,
                               const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones, float* valid_out,
-                              int values_only, void* stream);
+                              int values_only, void* l1_scratch, void* stream);
 int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                       const float* norm_mean, const float* norm_std, const void* wpack,
                       int u1, int u2, int u3, int M, int A,

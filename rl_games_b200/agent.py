@@ -286,8 +286,10 @@ class A2CAgent:
         # hardware supports it, a2c_common.py:427-429) and resolves to the tcgen05 path where this build has kernels for the
         # geometry, else to fp32 (a HIGHER precision than the reference's default), saying so once.
         self.is_rnn = self.model.is_rnn()
+        # wide observations (64 < obs <= 256: layer 1 in kernels of its own) compile and are unit-testable but have not run on hardware
+        allow_wide = bool(config.get('b200_unvalidated', False))
         if self.mixed_precision is None:
-            self.mixed_precision = (not self.is_rnn) and ops.tc_supported(self.model.D, self.model.units, self.actions_num)
+            self.mixed_precision = (not self.is_rnn) and ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
             if not self.mixed_precision and self.global_rank == 0:
                 print(f'b200: mixed_precision not set -> fp32 kernels for this geometry (obs={self.model.D}, units={self.model.units}, '
                       f'actions={self.actions_num}{", rnn" if self.is_rnn else ""}); the bf16 tcgen05 kernels cover obs<=64, MLP [256,128,64], actions<=15')
@@ -304,10 +306,15 @@ class A2CAgent:
                 raise NotImplementedError('rnn before_mlp: False (MLP -> LSTM -> heads) composes validated kernels and its host logic reproduces '
                                           'the reference on CPU, but it has not been run on hardware yet: set b200_unvalidated: True')
         self.use_tc = bool(self.mixed_precision)
-        if self.use_tc and not ops.tc_supported(self.model.D, self.model.units, self.actions_num):
+        if self.use_tc and not ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide):
             raise NotImplementedError(
                 f'mixed_precision: True (bf16 tcgen05 path) supports obs<=64, MLP [256,128,64], actions<=15 in this build; got '
-                f'obs={self.model.D}, units={self.model.units}, actions={self.actions_num}.  Set mixed_precision: False for the fp32 path.')
+                f'obs={self.model.D}, units={self.model.units}, actions={self.actions_num}.  Set mixed_precision: False for the fp32 path.'
+                + ('  (64 < obs <= 256 has tcgen05 kernels that have not been run on hardware yet: b200_unvalidated: True enables them.)'
+                   if ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2 else ''))
+        self.tc_wide = self.use_tc and ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2
+        if self.tc_wide and config.get('b200_pipelined_wgrad', False):
+            raise NotImplementedError('b200_pipelined_wgrad is an option of the resident-weights kernels (obs <= 64)')
         self.dataset = _Dataset(self)
         self.has_value_loss = True
         self.use_cuda_graph = bool(config.get('b200_cuda_graph', True))
@@ -371,7 +378,10 @@ class A2CAgent:
             nt = (mb + 127) // 128
             u8 = lambda n: torch.zeros(n, dtype=torch.uint8, device=dev)   # noqa: E731
             self.wpack = u8(ops.tc_pack_bytes(m.D, m.units, A))
-            self.tc_act = [u8(nt * tb[0]), u8(nt * tb[1]), u8(nt * tb[2])]
+            # wide observations: the rollout's layer-1 kernel parks its a1 tiles (N rows) in the act1 buffer between the two launches
+            nt1 = max(nt, (N + 127) // 128) if self.tc_wide else nt
+            self.tc_act = [u8(nt1 * tb[0]), u8(nt * tb[1]), u8(nt * tb[2])]
+            self.tc_l1_scratch = self.tc_act[0] if self.tc_wide else None
             self.tc_dhead, self.tc_delta2, self.tc_delta1 = u8(nt * tb[3]), u8(nt * tb[1]), u8(nt * tb[0])
             # normalised bf16 obs tiles: forward -> pipelined weight-gradient kernel (config b200_pipelined_wgrad; default False =
             # the single-buffered kernel that re-normalises the observations itself, measured faster on c2: profiles/r01_summary.md)
@@ -643,7 +653,7 @@ class A2CAgent:
                                    self.rng_seed, self.rng_epoch, t, self.actions[t], self.mus[t], self.sigmas[t],
                                    self.neglogpacs[t], self.values[t], self.env_actions, self.clip_actions, self.actions_low,
                                    self.actions_high, self.dones, self.dones_buf[t], self.prev_dones,
-                                   None if self.valid is None else self.valid[t])
+                                   None if self.valid is None else self.valid[t], l1_scratch=self.tc_l1_scratch)
             return
         if self.is_rnn and m.rnn_before_mlp:
             obs = self._lstm_step(obs, self.rnn_h, self.rnn_c, self.rnn_h, self.rnn_c)
@@ -667,7 +677,7 @@ class A2CAgent:
             ops.tc_mlp_fwd_rollout(o, m.D, nm, ns, self.wpack, m.b, m.b_head, m.sigma, m.units, N, A,
                                    m.value_mean_std.running_mean, m.value_mean_std.running_var, self.normalize_value, None, 0, None,
                                    0, None, None, None, None, self.last_values, None, False, None, None, None, None, None, None,
-                                   values_only=True)
+                                   values_only=True, l1_scratch=self.tc_l1_scratch)
             return self.last_values.unsqueeze(1)
         if self.is_rnn and m.rnn_before_mlp:     # get_values does not advance the agent's rnn states (a2c_common.py:603-626)
             o = self._lstm_step(o, self.rnn_h, self.rnn_c, self.r_tmp_h, self.r_tmp_c)

@@ -74,6 +74,10 @@ struct Net {
     static_assert(U1 % 128 == 0 && U1 <= 256 && U3 <= 128 && U3 % 16 == 0 && DPAD % 16 == 0 && DPAD <= 256 && AP == 16, "unsupported net");
 };
 using NetC2 = Net<64, 256, 128, 64, 16>;
+// Wide observations (64 < D <= 256, e.g. BASELINE configs[4] obs = 256): same hidden layers; layer 1 does not fit beside the other
+// weights in one CTA's shared memory (W1 alone is 128 KB), so it runs in kernels of its own (l1_fwd_tc_kernel, l1_wgrad_tc_kernel)
+// and the chain kernels are instantiated with XL1 = true ("external layer 1": a1 tiles come from / dW1 goes to those kernels).
+using NetW = Net<256, 256, 128, 64, 16>;
 
 // ---- weight packing: fp32 [R, C] row-major -> bf16 INTERLEAVE tile [Rpad, Cpad] ------------------------------
 struct PackSeg { const float* src; int R, C, Rpad, Cpad; uint32_t dst_off; };
@@ -139,6 +143,49 @@ __device__ __forceinline__ void stage_x_tile(uint8_t* sX, const float* __restric
         if (i >= 128 * NCG) break;
         const int cg = i / 128, r = i - cg * 128;
         const int c0 = cg * 8;
+        float f[8] = {va[it].x, va[it].y, va[it].z, va[it].w, vb[it].x, vb[it].y, vb[it].z, vb[it].w};
+        if (do_norm) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                f[j] = (c0 + j < D && r < rows_valid) ? fminf(fmaxf((f[j] - sNorm[c0 + j]) * sNorm[N::DPAD + c0 + j], -5.0f), 5.0f) : 0.f;
+        }
+        *reinterpret_cast<uint4*>(sX + tile_off(r, cg, N::ACS, N::ARS)) = pack8_bf16(f);
+    }
+}
+
+// Column-group pass of the same staging for wide tiles: col-groups [cg_base, cg_base + NCGP) of a 128-row tile, so that the loads
+// in flight per thread stay bounded (NCGP * 128 / NTHREADS items of 32 B) whatever DPAD is.
+template <class N, int NTHREADS, int NCGP>
+__device__ __forceinline__ void stage_x_cols(uint8_t* sX, const float* __restrict__ obs, int64_t row0, int rows_valid, int D,
+                                             const float* __restrict__ sNorm, bool do_norm, int cg_base) {
+    constexpr int ITEMS = (128 * NCGP + NTHREADS - 1) / NTHREADS;
+    static_assert((128 * NCGP) % NTHREADS == 0, "whole passes only");
+    const bool vec = (D & 3) == 0;
+    float4 va[ITEMS], vb[ITEMS];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = threadIdx.x + it * NTHREADS;
+        const int cgl = i / 128, r = i - cgl * 128;
+        const int c0 = (cg_base + cgl) * 8;
+        va[it] = make_float4(0.f, 0.f, 0.f, 0.f); vb[it] = va[it];
+        if (r < rows_valid && c0 < D) {
+            const float* src = obs + (row0 + r) * D + c0;
+            if (vec) {
+                va[it] = __ldg(reinterpret_cast<const float4*>(src));
+                if (c0 + 4 < D) vb[it] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+            } else {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = (c0 + j < D) ? __ldg(src + j) : 0.f;
+                va[it] = make_float4(t[0], t[1], t[2], t[3]); vb[it] = make_float4(t[4], t[5], t[6], t[7]);
+            }
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = threadIdx.x + it * NTHREADS;
+        const int cgl = i / 128, r = i - cgl * 128;
+        const int cg = cg_base + cgl, c0 = cg * 8;
         float f[8] = {va[it].x, va[it].y, va[it].z, va[it].w, vb[it].x, vb[it].y, vb[it].z, vb[it].w};
         if (do_norm) {
 #pragma unroll
@@ -270,17 +317,23 @@ extern "C" B200RL_EXPORT int b200rl_debug_tc_stamps(long long* host_out) {
 #define TSTAMP_END() do {} while (0)
 #endif
 
-template <class N, bool TRAIN>
+// XL1 ("external layer 1", wide observations): layer 1 ran in l1_fwd_tc_kernel; this kernel TMA-loads the a1 tile from p.act1
+// instead of staging X / multiplying by W1 (which is not resident), a3 gets a region of its own so that the NEXT tile's a1 can
+// be prefetched as soon as the layer-2 MMAs have read the current one.  XL1 = false compiles to exactly the code it always was.
+template <class N, bool TRAIN, bool XL1 = false>
 __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sW1 = smem + N::W1_OFF; uint8_t* sW2 = smem + N::W2_OFF; uint8_t* sW3 = smem + N::W3_OFF; uint8_t* sWh = smem + N::WH_OFF;
-    uint8_t* sA1 = smem + N::PACK_BYTES;                 // a1 (then a3 aliases its start)
+    constexpr uint32_t SW2 = XL1 ? 0u : N::W2_OFF, SW3 = SW2 + N::W2_BYTES, SWH = SW3 + N::W3_BYTES, SPACK = SWH + N::WH_BYTES;
+    static_assert(XL1 || (SW3 == N::W3_OFF && SWH == N::WH_OFF && SPACK == N::PACK_BYTES), "resident-W1 layout unchanged");
+    constexpr uint32_t XA2_BYTES = XL1 ? N::A2_BYTES : (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES);
+    uint8_t* sW1 = smem + N::W1_OFF; uint8_t* sW2 = smem + SW2; uint8_t* sW3 = smem + SW3; uint8_t* sWh = smem + SWH;
+    uint8_t* sA1 = smem + SPACK;                         // a1 (then a3 aliases its start)
     uint8_t* sXA2 = sA1 + N::A1_BYTES;                   // X tile, later a2
-    uint8_t* sA3 = sA1;
+    uint8_t* sA3 = XL1 ? sXA2 + XA2_BYTES : sA1;
     // raw fp32 rows of the NEXT tile (TMA prefetch): the part of the a1 region that a3 does not alias; free once MMA 2 has read a1
     float* sXraw = reinterpret_cast<float*>(sA1 + N::A3_BYTES);
-    static_assert(N::A3_BYTES + 128 * N::DPAD * 4 <= N::A1_BYTES, "X prefetch buffer must fit behind a3 inside the a1 region");
-    float* sBias = reinterpret_cast<float*>(sXA2 + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES));
+    static_assert(XL1 || N::A3_BYTES + 128 * N::DPAD * 4 <= N::A1_BYTES, "X prefetch buffer must fit behind a3 inside the a1 region");
+    float* sBias = reinterpret_cast<float*>(sXA2 + XA2_BYTES + (XL1 ? N::A3_BYTES : 0u));
     float* sB1 = sBias; float* sB2 = sB1 + N::U1; float* sB3 = sB2 + N::U2; float* sBh = sB3 + N::U3;
     float* sSig = sBh + N::AP;                           // sigma, logstd, 1/sigma, log(sigma): 4*A floats, then sum(logstd), entropy
     float* sNorm = sSig + 64;                            // [2*DPAD] obs mean, 1/std
@@ -298,7 +351,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     TSTAMP();   // kernel start
 
     // ---- prologue, part 1: nothing here depends on the predecessor kernel (PDL: may overlap its tail) ----
-    const bool x_tma = (p.D & 3) == 0;         // 16-byte granularity of the bulk copy
+    const bool x_tma = !XL1 && (p.D & 3) == 0;         // 16-byte granularity of the bulk copy
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
@@ -313,9 +366,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     pdl_sync();
     // ---- prologue, part 2: parameters and normaliser statistics (written by the optimiser kernel) ----
     if (tid == 0) {
+        if constexpr (XL1) {
+            if ((int)blockIdx.x < n_tiles) {      // first a1 tile (written by the predecessor kernel: after pdl_sync)
+                mbar_expect_tx(&bars[5], N::A1_BYTES);
+                bulk_g2s(sA1, p.act1 + (size_t)blockIdx.x * N::A1_BYTES, N::A1_BYTES, &bars[5]);
+            }
+        } else {
         // one barrier per consumer so that layer 1 starts as soon as W1 (32 KB of the 114 KB) has landed
         mbar_expect_tx(&bars[0], N::W1_BYTES);
         bulk_g2s(sW1, p.wpack + N::W1_OFF, N::W1_BYTES, &bars[0]);
+        }
         mbar_expect_tx(&bars[6], N::W2_BYTES);
         bulk_g2s(sW2, p.wpack + N::W2_OFF, N::W2_BYTES, &bars[6]);
         mbar_expect_tx(&bars[7], N::W3_BYTES + N::WH_BYTES);
@@ -355,6 +415,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         const int rows_valid = min(128, p.M - m0);
         const int64_t arow0 = chunk_row(m0, p.rows_per_chunk, p.chunk_stride);   // tile lies inside one chunk (host-checked)
         TSTAMP();   // tile start
+        if constexpr (XL1) {
+            mbar_wait(&bars[5], phase);       // a1 tile landed (async-proxy write, async-proxy reader: no generic-proxy fence needed)
+            weights_ready = true;
+        } else {
         if (x_tma) {
             mbar_wait(&bars[5], phase);
             stage_x_tile_smem<N, FWD_THREADS>(sXA2, sXraw, rows_valid, p.D, sNorm, p.nm != nullptr);
@@ -396,6 +460,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        }   // !XL1
         TSTAMP();   // epilogue 1 done
         // ---------------- layer 2: T2[128, U2] = a1 . W2^T ----------------
         if (tid == 0) {
@@ -411,6 +476,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         mbar_wait(&bars[2], phase);
         fence_after_sync();
         TSTAMP();   // MMA 2 done
+        if (XL1 && tid == 0 && tile + (int)gridDim.x < n_tiles) {
+            // a1 is dead now: fetch the next tile's a1 (a3 has its own region in this layout)
+            mbar_expect_tx(&bars[5], N::A1_BYTES);
+            bulk_g2s(sA1, p.act1 + (size_t)(tile + gridDim.x) * N::A1_BYTES, N::A1_BYTES, &bars[5]);
+        }
         if (tid == 0 && x_tma && tile + (int)gridDim.x < n_tiles) {
             // a1 is dead now (its readers, the layer-2 MMAs, have completed): prefetch the next tile's rows behind a3
             const int m1 = (tile + gridDim.x) * 128;
@@ -661,7 +731,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         TSTAMP();   // loss phase B done (tile end)
         phase ^= 1;
     }
-    if (!weights_ready) { mbar_wait(&bars[0], 0); mbar_wait(&bars[6], 0); mbar_wait(&bars[7], 0); }
+    if (!weights_ready) { if (!XL1) mbar_wait(&bars[0], 0); mbar_wait(&bars[6], 0); mbar_wait(&bars[7], 0); }
     if (TRAIN) {
         // block reduction of the loss partials (fixed order => deterministic): scalars from the four h == 0 warps, d_logstd
         // slices from all 16 warps (action j lives in the warps with h == j % 4, slot j / 4)
@@ -947,14 +1017,15 @@ struct Bwd2Args {
     int M; int P; int off_W2, off_W1, off_b1;
 };
 
-template <class N>
+// XL1 (wide observations): dW1 is l1_wgrad_tc_kernel's job -- no X tile, no dW1^T accumulator, no W1 flush here (db1 stays).
+template <class N, bool XL1 = false>
 __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, const uint32_t tmem) {
     // dW2^T[i][o] = sum_r a1[r][i] d2[r][o]   (two M = 128 halves over i, N = U2)      -> grad_W2[o*U1 + i]
     // dW1^T[i][o] = sum_r x[r][i]  d1[r][o]   (x tile zero-padded to 128 columns, N = U1) -> grad_W1[o*D + i]
     // TMEM lanes carry the contiguous `in` index, so the flush stores are coalesced.
     uint8_t* sD2 = smem; uint8_t* sD1 = sD2 + N::A2_BYTES; uint8_t* sA1 = sD1 + N::A1_BYTES; uint8_t* sX = sA1 + N::A1_BYTES;   // sX: 128 cols
-    float* sNorm = reinterpret_cast<float*>(sX + 128 * 256);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + 2 * N::DPAD);          // [0] tile loads, [1] mma
+    float* sNorm = reinterpret_cast<float*>(sX + (XL1 ? 0 : 128 * 256));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + (XL1 ? 0 : 2 * N::DPAD));          // [0] tile loads, [1] mma
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
@@ -967,8 +1038,10 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
         fence_mbar_init();
     }
     pdl_sync();
+    if constexpr (!XL1) {
     load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     for (int i = tid; i < (128 * 256 - (int)N::X_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(sX + N::X_BYTES)[i] = make_uint4(0, 0, 0, 0);
+    }
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -988,9 +1061,11 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
             bulk_g2s(sD1, p.delta1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
             bulk_g2s(sA1, p.act1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
         }
+        if constexpr (!XL1) {
         const int m0 = tile * 128;
         stage_x_tile<N, 256>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm, p.nm != nullptr);
         fence_async_smem();
+        }
         TSTAMP();   // X staged
         mbar_wait(&bars[0], phase);
         __syncthreads();
@@ -1005,10 +1080,12 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
                     umma_bf16(TW2 + hh * N::U2, make_smem_desc(smem_u32(sA1) + hh * 16 * N::ACS + k * 256, 128, N::ACS),
                               make_smem_desc(smem_u32(sD2) + k * 256, 128, N::ACS), make_idesc_bf16(128, N::U2, 1, 1),
                               (acc || k > 0) ? 1u : 0u);
+            if constexpr (!XL1) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 umma_bf16(TW1, make_smem_desc(smem_u32(sX) + k * 256, 128, N::ACS), make_smem_desc(smem_u32(sD1) + k * 256, 128, N::ACS),
                           make_idesc_bf16(128, N::U1, 1, 1), (acc || k > 0) ? 1u : 0u);
+            }
             umma_commit(&bars[1]);
         }
         colsum8<128, N::U1 / 8, N::ACS, 256>(sD1, tid, bsum1);
@@ -1033,6 +1110,7 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
             }
         }
         // dW1^T: lane = in index i = row (< D valid), columns = out o in [128h, 128h+128)
+        if constexpr (!XL1) {
 #pragma unroll 1
         for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
             float v[32];
@@ -1042,9 +1120,10 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
                 for (int j = 0; j < 32; ++j) part[p.off_W1 + (size_t)(c0 + j) * p.D + row] = v[j];
             }
         }
+        }
     } else {
         for (int i = tid; i < N::U2 * N::U1; i += 256) part[p.off_W2 + i] = 0.f;
-        for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
+        if (!XL1) for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
     }
     {
         const int g = colsum8_owner_group<N::U1 / 8, 256>(tid);
@@ -1065,7 +1144,7 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
 //      of delta1/delta2 must be ordered before the async-proxy (TMA) loads that read them back.
 struct BwdArgs { Bwd1Args a; Bwd2Args b; };
 
-template <class N>
+template <class N, bool XL1 = false>
 __global__ void __launch_bounds__(256, 1) mlp_bwd_tc_kernel(const BwdArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint32_t tmem_slot;
@@ -1077,7 +1156,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_tc_kernel(const BwdArgs p) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    bwd2_body<N>(p.b, smem, tmem);
+    bwd2_body<N, XL1>(p.b, smem, tmem);
     if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, 512);
 }
 
@@ -1227,30 +1306,260 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_db_tc_kernel(const Bwd2DbArgs
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-template <class N> constexpr size_t fwd_smem() {
-    return (size_t)N::PACK_BYTES + N::A1_BYTES + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES) +
+
+// ================================================================================================= wide observations: layer 1
+// a1 = elu(norm(obs) . W1^T + b1) for 64 < D <= 256 as a kernel of its own: W1 (U1 x DPAD bf16, 128 KB) stays resident, the whole
+// normalised bf16 X tile (128 x DPAD, 64 KB) is staged per tile, one K = DPAD chain of MMAs fills T1[128, U1], and the epilogue
+// writes the bf16 a1 tile straight to the global tiled buffer the chain kernels read (act1 during training, a scratch during the
+// rollout).  Same operand layouts, descriptors and epilogue as layer 1 of mlp_fwd_tc_kernel.
+struct L1FwdArgs {
+    const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
+    const uint8_t* wpack; const float* b1; int M; uint8_t* act1;
+};
+
+template <class N>
+__global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sW1 = smem; uint8_t* sX = sW1 + N::W1_BYTES;
+    float* sB1 = reinterpret_cast<float*>(sX + N::X_BYTES);
+    float* sNorm = sB1 + N::U1;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + 2 * N::DPAD);       // [0] W1, [1] mma
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int n_tiles = (p.M + 127) / 128;
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    pdl_sync();
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], N::W1_BYTES);
+        bulk_g2s(sW1, p.wpack + N::W1_OFF, N::W1_BYTES, &bars[0]);
+    }
+    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = __ldg(p.b1 + i);
+    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t T1 = *tmem_slot;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t phase = 0;
+    bool weights_ready = false;
+    constexpr int NCGP = 16;       // column groups per staging pass: 128 columns, 4 x 32 B in flight per thread
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = tile * 128;
+        const int rows_valid = min(128, p.M - m0);
+        const int64_t arow0 = chunk_row(m0, p.rows_per_chunk, p.chunk_stride);
+#pragma unroll 1
+        for (int cg = 0; cg < N::DPAD / 8; cg += NCGP)
+            stage_x_cols<N, FWD_THREADS, NCGP>(sX, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr, cg);
+        fence_async_smem();
+        if (!weights_ready) { mbar_wait(&bars[0], 0); weights_ready = true; }
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            constexpr uint32_t idesc = make_idesc_bf16(128, N::U1, 0, 0);
+#pragma unroll
+            for (int k = 0; k < N::DPAD / 16; ++k)
+                umma_bf16(T1, make_smem_desc(smem_u32(sX) + k * 2 * N::ACS, N::ACS, N::ARS),
+                          make_smem_desc(smem_u32(sW1) + k * 2 * N::W1_CS, N::W1_CS, 128), idesc, k > 0);
+            umma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], phase);
+        fence_after_sync();
+        {
+            uint8_t* g1 = p.act1 + (size_t)tile * N::A1_BYTES;
+#pragma unroll 1
+            for (int c0 = h * (N::U1 / 4); c0 < (h + 1) * (N::U1 / 4); c0 += 32) {
+                float v[32];
+                tmem_ld32(T1 + lane_base + c0, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB1[c0 + j]);
+                store_chunks32(v, row, c0, nullptr, g1);
+            }
+        }
+        fence_before_sync();
+        __syncthreads();       // T1 and the X tile are free for the next tile
+        fence_after_sync();
+        phase ^= 1;
+    }
+    if (!weights_ready) mbar_wait(&bars[0], 0);
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(T1, 256);
+}
+
+// dW1^T[i][o] = sum_r x[r][i] d1[r][o] for wide observations: DPAD / 128 halves of the `in` index, each a [128 x U1] fp32
+// accumulator (2 x 256 = all 512 TMEM columns at DPAD = 256).  The delta-1 tiles come from the backward chain kernel (global,
+// TMA), the X tile is re-derived from the observations.  Same MN-major operand trick and coalesced flush as bwd2_body.
+struct L1WgradArgs {
+    const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
+    const uint8_t* delta1; float* part; int M; int P; int off_W1;
+};
+
+template <class N>
+__global__ void __launch_bounds__(256, 1) l1_wgrad_tc_kernel(const L1WgradArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint32_t tmem_slot;
+    constexpr int NH = N::DPAD / 128;
+    static_assert(N::DPAD % 128 == 0 && NH * N::U1 <= 512, "dW1^T halves must fit the 512 TMEM columns");
+    uint8_t* sD1 = smem; uint8_t* sX = sD1 + N::A1_BYTES;
+    float* sNorm = reinterpret_cast<float*>(sX + N::X_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sNorm + 2 * N::DPAD);       // [0] tile load, [1] mma
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int n_tiles = (p.M + 127) / 128;
+    const uint32_t tmem = bwd_tmem_alloc(&tmem_slot);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    pdl_sync();
+    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    uint32_t phase = 0;
+    bool first = true;
+    constexpr int NCGP = 16;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (!first) { mbar_wait(&bars[1], phase ^ 1); fence_after_sync(); }    // previous tile's MMAs done reading the tiles
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bars[0], N::A1_BYTES);
+            bulk_g2s(sD1, p.delta1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
+        }
+        const int m0 = tile * 128;
+#pragma unroll 1
+        for (int cg = 0; cg < N::DPAD / 8; cg += NCGP)
+            stage_x_cols<N, 256, NCGP>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm,
+                                       p.nm != nullptr, cg);
+        fence_async_smem();
+        mbar_wait(&bars[0], phase);
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+            for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + hh * N::U1, make_smem_desc(smem_u32(sX) + hh * 16 * N::ACS + k * 256, 128, N::ACS),
+                              make_smem_desc(smem_u32(sD1) + k * 256, 128, N::ACS), make_idesc_bf16(128, N::U1, 1, 1),
+                              (acc || k > 0) ? 1u : 0u);
+            umma_commit(&bars[1]);
+        }
+        phase ^= 1;
+        first = false;
+    }
+    float* part = p.part + (size_t)blockIdx.x * p.P;
+    if (!first) {
+        mbar_wait(&bars[1], phase ^ 1);
+        fence_after_sync();
+        // lane = in index i = hh * 128 + row (< D valid), columns = out o: thread takes o in [128h, 128h + 128)
+#pragma unroll 1
+        for (int hh = 0; hh < NH; ++hh) {
+            const int i = hh * 128 + row;
+#pragma unroll 1
+            for (int c0 = h * (N::U1 / 2); c0 < (h + 1) * (N::U1 / 2); c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem + hh * N::U1 + lane_base + c0, v);
+                if (i < p.D) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) part[p.off_W1 + (size_t)(c0 + j) * p.D + i] = v[j];
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <class N, bool XL1 = false> constexpr size_t fwd_smem() {
+    return (XL1 ? (size_t)N::W2_BYTES + N::W3_BYTES + N::WH_BYTES + N::A1_BYTES + N::A2_BYTES + N::A3_BYTES
+                : (size_t)N::PACK_BYTES + N::A1_BYTES + (N::A2_BYTES > N::X_BYTES ? N::A2_BYTES : N::X_BYTES)) +
            sizeof(float) * (N::U1 + N::U2 + N::U3 + N::AP + 64 + 2 * N::DPAD + 4 * LOSS_SLOTS) + sizeof(double) * LOSS_SLOTS + 8 * 8 + 16;
 }
+template <class N> constexpr size_t l1_fwd_smem() { return (size_t)N::W1_BYTES + N::X_BYTES + sizeof(float) * (N::U1 + 2 * N::DPAD) + 2 * 8 + 16; }
+template <class N> constexpr size_t l1_wgrad_smem() { return (size_t)N::A1_BYTES + N::X_BYTES + sizeof(float) * 2 * N::DPAD + 2 * 8 + 16; }
 template <class N> constexpr size_t bwd1_smem() {
     return (size_t)N::WH_BYTES + N::W3_BYTES + N::W2_BYTES + N::DH_BYTES + 128 * 256 + N::A2_BYTES + N::A3_BYTES + N::A2_BYTES + 8 * 8 + 16;
 }
 template <class N> constexpr size_t bwd2_db_smem() { return (size_t)2 * (N::A2_BYTES / 2 + N::A1_BYTES + 16 * 1024) + 4 * 8 + 16; }
-template <class N> constexpr size_t bwd2_smem() { return (size_t)N::A2_BYTES + 2 * N::A1_BYTES + 128 * 256 + sizeof(float) * 2 * N::DPAD + 4 * 8 + 16; }
-template <class N> constexpr size_t bwd_smem() { return bwd1_smem<N>() > bwd2_smem<N>() ? bwd1_smem<N>() : bwd2_smem<N>(); }
+template <class N, bool XL1 = false> constexpr size_t bwd2_smem() {
+    return (size_t)N::A2_BYTES + 2 * N::A1_BYTES + (XL1 ? 0 : 128 * 256 + sizeof(float) * 2 * N::DPAD) + 4 * 8 + 16;
+}
+template <class N, bool XL1 = false> constexpr size_t bwd_smem() {
+    return bwd1_smem<N>() > bwd2_smem<N, XL1>() ? bwd1_smem<N>() : bwd2_smem<N, XL1>();
+}
 
 bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D <= 64 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
+// wide observations: the same hidden layers, layer 1 in its own kernels (NetW)
+bool net_is_wide(int D, int u1, int u2, int u3, int A) { return D > 64 && D <= 256 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
+int net_kind(int D, int u1, int u2, int u3, int A) { return net_is_c2(D, u1, u2, u3, A) ? 1 : (net_is_wide(D, u1, u2, u3, A) ? 2 : 0); }
+
+template <class N>
+void fill_pack_table(int D, int u1, int u2, int u3, int A, int off_W1, int off_W2, int off_W3, int off_Wh, b200rl_pack_table* out_host) {
+    out_host->n_seg = 4;
+    const int offs[4] = {off_W1, off_W2, off_W3, off_Wh};
+    const int rows[4] = {u1, u2, u3, A + 1}, cols[4] = {D, u1, u2, u3};
+    const unsigned cs[4] = {N::W1_CS, N::W2_CS, N::W3_CS, N::WH_CS}, dst[4] = {N::W1_OFF, N::W2_OFF, N::W3_OFF, N::WH_OFF};
+    for (int i = 0; i < 4; ++i) {
+        out_host->flat_off[i] = offs[i]; out_host->rows[i] = rows[i]; out_host->cols[i] = cols[i];
+        out_host->cs_bytes[i] = cs[i]; out_host->dst_off[i] = dst[i];
+    }
+}
+
+template <class N>
+int pack_weights_impl(const float* W1, const float* W2, const float* W3, const float* W_head, int D, int u1, int u2, int u3, int A,
+                      void* wpack, void* stream) {
+    PackArgs a;
+    a.seg[0] = PackSeg{W1, u1, D, N::U1, N::DPAD, N::W1_OFF};
+    a.seg[1] = PackSeg{W2, u2, u1, N::U2, N::U1, N::W2_OFF};
+    a.seg[2] = PackSeg{W3, u3, u2, N::U3, N::U2, N::W3_OFF};
+    a.seg[3] = PackSeg{W_head, A + 1, u3, N::AP, N::U3, N::WH_OFF};
+    pack_weights_kernel<<<dim3(16, 4), 256, 0, as_stream(stream)>>>(a, (uint8_t*)wpack);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+// layer 1 of the wide path (see l1_fwd_tc_kernel): a1 tiles of M rows into `act1`
+template <class N>
+int launch_l1_fwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D, const float* nm, const float* ns, const void* wpack,
+                  const float* b1, int M, void* act1, void* stream) {
+    const int n_tiles = (M + 127) / 128;
+    const int grid = n_tiles < 148 ? n_tiles : 148;
+    L1FwdArgs a{obs, rows_per_chunk, chunk_stride, D, nm, ns, (const uint8_t*)wpack, b1, M, (uint8_t*)act1};
+    constexpr size_t smem = l1_fwd_smem<N>();
+    static_assert(smem <= 227 * 1024, "layer-1 forward kernel shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(l1_fwd_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_k(l1_fwd_tc_kernel<N>, dim3(grid), dim3(FWD_THREADS), smem, as_stream(stream), a);
+    return e == cudaSuccess ? B200RL_OK : (int)e;
+}
 
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------- C ABI
-B200RL_EXPORT int b200rl_tc_supported(int D, int u1, int u2, int u3, int A) { return net_is_c2(D, u1, u2, u3, A) ? 1 : 0; }
+// 0 = no tcgen05 kernels for this geometry; 1 = resident-weights kernels (obs <= 64); 2 = wide observations (64 < obs <= 256):
+// layer 1 in its own kernels
+B200RL_EXPORT int b200rl_tc_supported(int D, int u1, int u2, int u3, int A) { return net_kind(D, u1, u2, u3, A); }
 
 B200RL_EXPORT int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A) {
-    return net_is_c2(D, u1, u2, u3, A) ? (int64_t)NetC2::PACK_BYTES : -1;
+    const int kind = net_kind(D, u1, u2, u3, A);
+    return kind == 1 ? (int64_t)NetC2::PACK_BYTES : (kind == 2 ? (int64_t)NetW::PACK_BYTES : -1);
 }
 // bytes of one 128-row tile of: act1, act2, act3, d_head  (tiled INTERLEAVE bf16 buffers)
 B200RL_EXPORT int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int64_t* out4_host) {
-    if (!net_is_c2(D, u1, u2, u3, A) || !out4_host) return B200RL_EUNSUPPORTED;
+    if (!net_kind(D, u1, u2, u3, A) || !out4_host) return B200RL_EUNSUPPORTED;       // the activation tiles do not depend on DPAD
     out4_host[0] = NetC2::A1_BYTES; out4_host[1] = NetC2::A2_BYTES; out4_host[2] = NetC2::A3_BYTES; out4_host[3] = NetC2::DH_BYTES;
     return B200RL_OK;
 }
@@ -1263,32 +1572,20 @@ B200RL_EXPORT int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A
 B200RL_EXPORT int b200rl_tc_pack_table(int D, int u1, int u2, int u3, int A, int off_W1, int off_W2, int off_W3, int off_Wh,
                                        b200rl_pack_table* out_host) {
     if (!out_host) return B200RL_EINVAL;
-    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
-    using N = NetC2;
-    out_host->n_seg = 4;
-    const int offs[4] = {off_W1, off_W2, off_W3, off_Wh};
-    const int rows[4] = {u1, u2, u3, A + 1}, cols[4] = {D, u1, u2, u3};
-    const unsigned cs[4] = {N::W1_CS, N::W2_CS, N::W3_CS, N::WH_CS}, dst[4] = {N::W1_OFF, N::W2_OFF, N::W3_OFF, N::WH_OFF};
-    for (int i = 0; i < 4; ++i) {
-        out_host->flat_off[i] = offs[i]; out_host->rows[i] = rows[i]; out_host->cols[i] = cols[i];
-        out_host->cs_bytes[i] = cs[i]; out_host->dst_off[i] = dst[i];
-    }
+    const int kind = net_kind(D, u1, u2, u3, A);
+    if (!kind) return B200RL_EUNSUPPORTED;
+    if (kind == 1) fill_pack_table<NetC2>(D, u1, u2, u3, A, off_W1, off_W2, off_W3, off_Wh, out_host);
+    else fill_pack_table<NetW>(D, u1, u2, u3, A, off_W1, off_W2, off_W3, off_Wh, out_host);
     return B200RL_OK;
 }
 
 B200RL_EXPORT int b200rl_tc_pack_weights(const float* W1, const float* W2, const float* W3, const float* W_head,
                                          int D, int u1, int u2, int u3, int A, void* wpack, void* stream) {
     if (!W1 || !W2 || !W3 || !W_head || !wpack) return B200RL_EINVAL;
-    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
-    using N = NetC2;
-    PackArgs a;
-    a.seg[0] = PackSeg{W1, u1, D, N::U1, N::DPAD, N::W1_OFF};
-    a.seg[1] = PackSeg{W2, u2, u1, N::U2, N::U1, N::W2_OFF};
-    a.seg[2] = PackSeg{W3, u3, u2, N::U3, N::U2, N::W3_OFF};
-    a.seg[3] = PackSeg{W_head, A + 1, u3, N::AP, N::U3, N::WH_OFF};
-    pack_weights_kernel<<<dim3(16, 4), 256, 0, as_stream(stream)>>>(a, (uint8_t*)wpack);
-    B200RL_LAUNCH_CHECK();
-    return B200RL_OK;
+    const int kind = net_kind(D, u1, u2, u3, A);
+    if (!kind) return B200RL_EUNSUPPORTED;
+    return kind == 1 ? pack_weights_impl<NetC2>(W1, W2, W3, W_head, D, u1, u2, u3, A, wpack, stream)
+                     : pack_weights_impl<NetW>(W1, W2, W3, W_head, D, u1, u2, u3, A, wpack, stream);
 }
 
 static int tc_check_rows(int M, int rows_per_chunk) {
@@ -1309,10 +1606,11 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
     if (!obs || !wpack || !b1 || !b2 || !b3 || !b_head || !logstd || !actions || !old_mu || !old_sigma || !old_values_n || !returns_n ||
         !old_neglogp || !advs_n || !cfg_host || !act1 || !act2 || !act3 || !dhead || !partials)
         return B200RL_EINVAL;
-    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
+    const int kind = net_kind(D, u1, u2, u3, A);
+    if (!kind) return B200RL_EUNSUPPORTED;
+    if (kind == 2 && xtile) return B200RL_EUNSUPPORTED;      // the pipelined weight-gradient kernel is a resident-W1 option
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
-    using N = NetC2;
     const int n_tiles = (M + 127) / 128;
     const int grid = n_tiles < 148 ? n_tiles : 148;
     if (n_blocks_out_host) *n_blocks_out_host = grid;
@@ -1327,6 +1625,18 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
                        log1pf(-cfg_host->e_clip), log1pf(cfg_host->e_clip)};
     p.act1 = (uint8_t*)act1; p.act2 = (uint8_t*)act2; p.act3 = (uint8_t*)act3; p.dhead = (uint8_t*)dhead; p.partials = partials;
     p.xt = (uint8_t*)xtile;
+    if (kind == 2) {
+        // wide observations: layer 1 (a1 tiles -> act1), then the chain kernel in its external-layer-1 form
+        rc = launch_l1_fwd<NetW>(obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, wpack, b1, M, act1, stream);
+        if (rc) return rc;
+        constexpr size_t smemw = fwd_smem<NetW, true>();
+        static_assert(smemw <= 227 * 1024, "forward kernel (external layer 1) shared memory budget");
+        cudaError_t ew = cudaFuncSetAttribute(mlp_fwd_tc_kernel<NetW, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
+        if (ew != cudaSuccess) return (int)ew;
+        ew = launch_k(mlp_fwd_tc_kernel<NetW, true, true>, dim3(grid), dim3(FWD_THREADS), smemw, as_stream(stream), p);
+        return ew == cudaSuccess ? B200RL_OK : (int)ew;
+    }
+    using N = NetC2;
     constexpr size_t smem = fwd_smem<N>();
     static_assert(smem <= 227 * 1024, "forward kernel shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1344,14 +1654,15 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
                                             float* actions, float* mus, float* sigmas, float* neglogp, float* values,
                                             float* env_actions, int clip_actions, const float* act_low, const float* act_high,
                                             const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones, float* valid_out,
-                                            int values_only, void* stream) {
+                                            int values_only, void* l1_scratch, void* stream) {
     if (!obs || !wpack || !b1 || !b2 || !b3 || !b_head || !logstd || !values || N_rows <= 0) return B200RL_EINVAL;
     if (!values_only && (!actions || !mus || !sigmas || !neglogp)) return B200RL_EINVAL;
     if (normalize_value && (!vms_mean || !vms_var)) return B200RL_EINVAL;
     if (env_actions && clip_actions && (!act_low || !act_high)) return B200RL_EINVAL;
     if (dones_out && !dones_cur) return B200RL_EINVAL;
-    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
-    using N = NetC2;
+    const int kind = net_kind(D, u1, u2, u3, A);
+    if (!kind) return B200RL_EUNSUPPORTED;
+    if (kind == 2 && !l1_scratch) return B200RL_EINVAL;
     const int n_tiles = (N_rows + 127) / 128;
     const int grid = n_tiles < 148 ? n_tiles : 148;
     FwdArgs p{};
@@ -1361,6 +1672,17 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
     p.rng_epoch = rng_epoch_dev; p.step_index = step_index; p.actions = actions; p.mus = mus; p.sigmas = sigmas; p.neglogp = neglogp;
     p.values = values; p.env_actions = env_actions; p.clip_actions = clip_actions; p.act_low = act_low; p.act_high = act_high;
     p.dones_cur = dones_cur; p.dones_out = dones_out; p.prev_dones = prev_dones; p.valid_out = valid_out; p.values_only = values_only;
+    if (kind == 2) {
+        int rc = launch_l1_fwd<NetW>(obs, N_rows, 0, D, norm_mean, norm_std, wpack, b1, N_rows, l1_scratch, stream);
+        if (rc) return rc;
+        p.act1 = (uint8_t*)l1_scratch;
+        constexpr size_t smemw = fwd_smem<NetW, true>();
+        cudaError_t ew = cudaFuncSetAttribute(mlp_fwd_tc_kernel<NetW, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
+        if (ew != cudaSuccess) return (int)ew;
+        ew = launch_k(mlp_fwd_tc_kernel<NetW, false, true>, dim3(grid), dim3(FWD_THREADS), smemw, as_stream(stream), p);
+        return ew == cudaSuccess ? B200RL_OK : (int)ew;
+    }
+    using N = NetC2;
     constexpr size_t smem = fwd_smem<N>();
     cudaError_t e = cudaFuncSetAttribute(mlp_fwd_tc_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -1377,7 +1699,9 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
                                     int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
                                     int* n_parts_out_host, void* stream) {
     if (!obs || !wpack || !act1 || !act2 || !act3 || !dhead || !delta2 || !delta1 || !part) return B200RL_EINVAL;
-    if (!net_is_c2(D, u1, u2, u3, A)) return B200RL_EUNSUPPORTED;
+    const int kind = net_kind(D, u1, u2, u3, A);
+    if (!kind) return B200RL_EUNSUPPORTED;
+    if (kind == 2 && xtile) return B200RL_EUNSUPPORTED;
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     using N = NetC2;
@@ -1406,6 +1730,24 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
         e = launch_k(mlp_bwd2_db_tc_kernel<N>, dim3(grid), dim3(256), smem2, as_stream(stream), b);
         if (e != cudaSuccess) return (int)e;
         return B200RL_OK;
+    }
+    if (kind == 2) {
+        // wide observations: the chain kernel without the W1 part, then dW1 in its own kernel (same grid => same split rows)
+        BwdArgs abw{a, Bwd2Args{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
+                                (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1}};
+        constexpr size_t smemw = bwd_smem<NetW, true>();
+        static_assert(smemw <= 227 * 1024, "backward kernel (external layer 1) shared memory budget");
+        e = cudaFuncSetAttribute(mlp_bwd_tc_kernel<NetW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
+        if (e != cudaSuccess) return (int)e;
+        e = launch_k(mlp_bwd_tc_kernel<NetW, true>, dim3(grid), dim3(256), smemw, as_stream(stream), abw);
+        if (e != cudaSuccess) return (int)e;
+        L1WgradArgs w{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)delta1, part, M, P, off_W1};
+        constexpr size_t smem1w = l1_wgrad_smem<NetW>();
+        static_assert(smem1w <= 227 * 1024, "layer-1 weight-gradient kernel shared memory budget");
+        e = cudaFuncSetAttribute(l1_wgrad_tc_kernel<NetW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1w);
+        if (e != cudaSuccess) return (int)e;
+        e = launch_k(l1_wgrad_tc_kernel<NetW>, dim3(grid), dim3(256), smem1w, as_stream(stream), w);
+        return e == cudaSuccess ? B200RL_OK : (int)e;
     }
     // default: the whole backward pass in one launch
     BwdArgs ab{a, Bwd2Args{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,

@@ -288,8 +288,14 @@ def tc_gemm_test(A, B, N, K, a_mn=False, b_mn=False):
 
 
 # ------------------------------------------------------------------------------------------ bf16 tcgen05 path
-def tc_supported(D, units, A):
-    return len(units) == 3 and bool(lib.b200rl_tc_supported(D, units[0], units[1], units[2], A))
+def tc_kind(D, units, A):
+    """0 = no tcgen05 kernels for this geometry, 1 = resident-weights kernels (obs <= 64), 2 = wide observations (64 < obs <= 256)"""
+    return int(lib.b200rl_tc_supported(D, units[0], units[1], units[2], A)) if len(units) == 3 else 0
+
+
+def tc_supported(D, units, A, allow_wide=False):
+    k = tc_kind(D, units, A)
+    return k == 1 or (allow_wide and k == 2)
 
 
 def tc_pack_bytes(D, units, A):
@@ -333,13 +339,13 @@ def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_h
 
 def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vms_mean, vms_var, normalize_value, noise, seed,
                        rng_epoch, step_index, actions, mus, sigmas, neglogp, values, env_actions, clip_actions, act_low, act_high,
-                       dones_cur, dones_out, prev_dones, valid_out, values_only=False):
+                       dones_cur, dones_out, prev_dones, valid_out, values_only=False, l1_scratch=None):
     check(lib.b200rl_tc_mlp_fwd_rollout(ptr(obs), D, ptr(nm), ptr(ns), ptr(wpack), ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b_head),
                                         ptr(logstd), units[0], units[1], units[2], N, A, ptr(vms_mean), ptr(vms_var),
                                         int(normalize_value), ptr(noise), seed, ptr(rng_epoch), step_index, ptr(actions), ptr(mus),
                                         ptr(sigmas), ptr(neglogp), ptr(values), ptr(env_actions), int(clip_actions), ptr(act_low),
                                         ptr(act_high), ptr(dones_cur), ptr(dones_out), ptr(prev_dones), ptr(valid_out),
-                                        int(values_only), _stream()), 'tc_mlp_fwd_rollout')
+                                        int(values_only), ptr(l1_scratch), _stream()), 'tc_mlp_fwd_rollout')
 
 
 def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs,

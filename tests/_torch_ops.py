@@ -547,8 +547,10 @@ def _tc_forward(x, ws, b, b_head, act=1):
 
 def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch,
                        step_index, actions, mus, sigmas, neglogp, values, env_actions, clip_actions, act_low, act_high, dones_cur, dones_out,
-                       prev_dones, valid_out, values_only=False):
+                       prev_dones, valid_out, values_only=False, l1_scratch=None):
     ws = _TC[wpack.data_ptr()]
+    if _TC.get('kind', 1) == 2:      # wide observations: the layer-1 kernel parks N rows of a1 tiles in the scratch between the two launches
+        assert l1_scratch is not None and l1_scratch.numel() >= (N + 127) // 128 * units[0] * 256
     h = obs[:N].reshape(N, D)
     for W, bb in zip(ws[:3], b):
         h = ACT[1]((_norm(h, nm, ns) if W is ws[0] else h) @ W.t() + bb)
@@ -560,6 +562,7 @@ def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vm
 def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_head, logstd, units, M, A, actions, old_mu, old_sigma, old_values_n,
                      returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials, xtile=None):
     """whole training forward + loss + backward of the MLP in fp32 with autograd; the gradients wait in a side channel for tc_mlp_bwd"""
+    assert _TC.get('kind', 1) == 1 or xtile is None
     ws = [w.clone().requires_grad_(True) for w in _TC[wpack.data_ptr()]]
     bs = [t.clone().requires_grad_(True) for t in b]
     x = _norm(_rows(obs, M, D, rows_per_chunk, chunk_stride, D), nm, ns)
@@ -598,13 +601,16 @@ def reduce_adam(part, n_splits, split_stride, loss_partials, n_loss_partials, A,
     adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_out, cfg, stats, counter, n=n, merge_next=merge_next)
 
 
-def install_tc(monkeypatch):
-    """stand-ins for the bf16 tcgen05 path of A2CAgent (mixed_precision: True), computed in fp32"""
+def install_tc(monkeypatch, kind=1):
+    """stand-ins for the bf16 tcgen05 path of A2CAgent (mixed_precision: True), computed in fp32; kind 2 = the wide-observation
+    edition (layer 1 in kernels of its own: only the host-visible contract differs -- scratch buffer, no xtile)"""
     from rl_games_b200 import ops
     install_continuous(monkeypatch)
+    _TC['kind'] = kind
     for name in ('tc_pack_weights', 'tc_mlp_fwd_rollout', 'tc_mlp_fwd_train', 'tc_mlp_bwd', 'reduce_adam'):
         monkeypatch.setattr(ops, name, globals()[name])
-    monkeypatch.setattr(ops, 'tc_supported', lambda D, units, A: len(units) == 3)
+    monkeypatch.setattr(ops, 'tc_kind', lambda D, units, A: kind if len(units) == 3 else 0)
+    monkeypatch.setattr(ops, 'tc_supported', lambda D, units, A, allow_wide=False: len(units) == 3 and (kind == 1 or allow_wide))
     monkeypatch.setattr(ops, 'tc_tile_bytes', lambda D, units, A: [units[0] * 256, units[1] * 256, units[2] * 256, 16 * 256])
     monkeypatch.setattr(ops, 'tc_pack_bytes', lambda D, units, A: 1024)
     monkeypatch.setattr(ops, 'tc_xtile_bytes', lambda D, units, A: 64 * 256)

@@ -260,7 +260,19 @@ def test_bf16_tcgen05_agent_tracks_fp32_agent():
     (obs 60, MLP [256,128,64], 8 actions), same tapes / weights / noise.  bf16 tolerance class (8-bit mantissa operands,
     fp32 accumulate): rollout outputs atol 5e-2, per-minibatch losses rtol 0.1 (+ small atol), parameter update
     direction cosine > 0.8 after one epoch of Adam steps."""
-    N, H, D, A, units, mb = 512, 8, 60, 8, [256, 128, 64], 2048
+    _bf16_vs_fp32_agents(60, {})
+
+
+@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                    reason='wide-observation tcgen05 kernels (64 < obs <= 256) not yet run on hardware: set B200RL_UNVALIDATED=1')
+@pytest.mark.parametrize('D', [256, 105])
+def test_bf16_tcgen05_wide_agent_tracks_fp32_agent(D):
+    """the same comparison on BASELINE configs[4]'s observation width (256) and a ragged one: layer 1 in its own kernels"""
+    _bf16_vs_fp32_agents(D, {'b200_unvalidated': True})
+
+
+def _bf16_vs_fp32_agents(D, extra):
+    N, H, A, units, mb = 512, 8, 8, [256, 128, 64], 2048
     obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=21)
     params = O.init_params(D, units, A, seed=4)
     g = torch.Generator().manual_seed(6)
@@ -268,8 +280,8 @@ def test_bf16_tcgen05_agent_tracks_fp32_agent():
     agents = []
     for mp in (False, True):
         env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
-        a = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False}, N, H, D, A, units, mb, env, params)
-        assert a.use_tc == mp
+        a = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False, **extra}, N, H, D, A, units, mb, env, params)
+        assert a.use_tc == mp and getattr(a, 'tc_wide', False) == (mp and D > 64)
         a.epoch_num += 1
         a.train_epoch(noise=noise)
         agents.append(a)

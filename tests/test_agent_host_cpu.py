@@ -71,7 +71,7 @@ class _Env:
 
 
 @pytest.mark.parametrize('name,tc', [('agent_base.pt', False), ('agent_masked.pt', False), ('agent_hardclip.pt', False), ('agent_rmsadv.pt', False),
-                                     ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_lstm.pt', False),
+                                     ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_tcshape.pt', 2), ('agent_lstm.pt', False),
                                      ('agent_lstm_after.pt', False), ('agent_sched_standard.pt', False)])
 def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
     """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
@@ -79,7 +79,10 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
     import _torch_ops
     from oracle import ppo_oracle as O
     from rl_games_b200.runner import Runner
-    (_torch_ops.install_tc if tc else _torch_ops.install_continuous)(monkeypatch)
+    if tc:          # tc == 2: the wide-observation edition of the tcgen05 path (scratch buffer for the rollout's layer-1 kernel, gated)
+        _torch_ops.install_tc(monkeypatch, kind=int(tc))
+    else:
+        _torch_ops.install_continuous(monkeypatch)
     monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
     monkeypatch.setattr(torch.cuda, 'Event', _Event)
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _Stream())
@@ -88,8 +91,10 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
     cfgk = g['config']
     env = _Env(g)
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
+    if tc == 2:
+        config['b200_unvalidated'] = True
     config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
-                   'mixed_precision': tc, 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+                   'mixed_precision': bool(tc), 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
@@ -105,7 +110,7 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
                        'config': config}})
     r.params['config']['vec_env'] = env
     agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
-    assert agent.use_tc == tc
+    assert agent.use_tc == bool(tc) and getattr(agent, 'tc_wide', False) == (tc == 2)
     agent.model.load_state_dict(g['init_state'], strict=False)
     agent.init_tensors()
     agent._repack()

@@ -4,6 +4,7 @@ Tolerance: bf16 operands (8-bit mantissa) with fp32 accumulation -- activations 
 loss scalars rtol 3e-2, gradients: relative L2 error < 3e-2 and cosine > 0.999 per parameter tensor (the reference's
 own bf16-autocast path has the same error class; a2c_continuous.py:173)."""
 import math
+import os
 
 import pytest
 import torch
@@ -23,7 +24,7 @@ def decode_tiles(buf, n_tiles, C):
     return buf.view(torch.bfloat16)[idx].view(n_tiles * 128, C).float()
 
 
-def make_net(g):
+def make_net(g, D=D):
     ins, W, b = D, [], []
     for u in UNITS:
         W.append((torch.randn(u, ins, generator=g) / math.sqrt(ins)).to(DEV))
@@ -45,11 +46,29 @@ def cosine(a, b):
 
 @pytest.mark.parametrize('H,N,epm,masked', [(4, 512, 256, False), (2, 384, 128, True), (1, 1000, 1000, False)])
 def test_tc_fwd_loss_bwd_vs_fp32(H, N, epm, masked):
+    _fwd_loss_bwd_case(H, N, epm, masked, D)
+
+
+WIDE = pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                          reason='wide-observation tcgen05 kernels (64 < obs <= 256) not yet run on hardware: set B200RL_UNVALIDATED=1')
+
+
+@WIDE
+@pytest.mark.parametrize('H,N,epm,masked,Dw', [(4, 512, 256, False, 256), (2, 384, 128, True, 105), (1, 1000, 1000, False, 65),
+                                               (2, 19072, 19072, False, 256)])
+def test_tc_wide_fwd_loss_bwd_vs_fp32(H, N, epm, masked, Dw):
+    """BASELINE configs[4] geometry (obs 256) and ragged widths: layer 1 in l1_fwd_tc_kernel / l1_wgrad_tc_kernel, the chain kernels
+    in their external-layer-1 form; the last case gives every CTA two or three tiles (298 tiles)"""
+    _fwd_loss_bwd_case(H, N, epm, masked, Dw)
+
+
+def _fwd_loss_bwd_case(H, N, epm, masked, D):
     from rl_games_b200 import ops
     from rl_games_b200.ops import LossCfg
-    assert ops.tc_supported(D, UNITS, A)
+    wide = D > 64
+    assert ops.tc_kind(D, UNITS, A) == (2 if wide else 1)
     g = torch.Generator().manual_seed(H * 100 + N)
-    W, b, Wh, bh, logstd = make_net(g)
+    W, b, Wh, bh, logstd = make_net(g, D)
     M = H * epm
     e0 = 128 if N > epm else 0
     obs = (torch.randn(H, N, D, generator=g) * 2 + 0.5).to(DEV)
@@ -102,7 +121,7 @@ def test_tc_fwd_loss_bwd_vs_fp32(H, N, epm, masked):
     delta2 = torch.zeros(n_tiles * tb[1], dtype=torch.uint8, device=DEV); delta1 = torch.zeros(n_tiles * tb[0], dtype=torch.uint8, device=DEV)
     mu_t, sg_t = old_mu.clone(), old_sigma.clone()
     partials_t = torch.zeros(148, stride, dtype=torch.float64, device=DEV)
-    xt = torch.zeros(n_tiles * ops.tc_xtile_bytes(D, UNITS, A), dtype=torch.uint8, device=DEV)
+    xt = None if wide else torch.zeros(n_tiles * ops.tc_xtile_bytes(D, UNITS, A), dtype=torch.uint8, device=DEV)
     nbt = ops.tc_mlp_fwd_train(sl(obs), epm, N, D, nm, ns, wpack, b, bh, logstd, UNITS, M, A, sl(actions), sl(mu_t), sl(sg_t),
                                sl(old_v), sl(ret), sl(old_nlp), sl(adv), None if mask is None else sl(mask), cfg, inv, act, dhead,
                                partials_t, xtile=xt)
@@ -133,9 +152,10 @@ def test_tc_fwd_loss_bwd_vs_fp32(H, N, epm, masked):
     offs['b_head'] = o; o += A + 1
     assert o == P
     # normalised observation tile emitted by the forward (consumed by the pipelined weight-gradient kernel)
-    xn = torch.clamp((torch.cat([obs[t, e0:e0 + epm] for t in range(H)]) - nm) / ns, -5.0, 5.0)
-    xt_dec = decode_tiles(xt, n_tiles, 64)[:M, :D]
-    torch.testing.assert_close(xt_dec, xn.to(torch.bfloat16).float(), rtol=0, atol=4e-2)
+    if not wide:
+        xn = torch.clamp((torch.cat([obs[t, e0:e0 + epm] for t in range(H)]) - nm) / ns, -5.0, 5.0)
+        xt_dec = decode_tiles(xt, n_tiles, 64)[:M, :D]
+        torch.testing.assert_close(xt_dec, xn.to(torch.bfloat16).float(), rtol=0, atol=4e-2)
     part = torch.full((148, P), float('nan'), device=DEV)
     npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=xt)
     grad = torch.zeros(P, device=DEV)
@@ -158,10 +178,21 @@ def test_tc_fwd_loss_bwd_vs_fp32(H, N, epm, masked):
 
 
 def test_tc_rollout_vs_fp32():
+    _rollout_case(D, 1000)
+
+
+@WIDE
+@pytest.mark.parametrize('Dw,N', [(256, 1000), (105, 128), (72, 20000)])
+def test_tc_wide_rollout_vs_fp32(Dw, N):
+    _rollout_case(Dw, N)
+
+
+def _rollout_case(D, N):
     from rl_games_b200 import ops
+    wide = D > 64
     g = torch.Generator().manual_seed(3)
-    W, b, Wh, bh, logstd = make_net(g)
-    N = 1000
+    W, b, Wh, bh, logstd = make_net(g, D)
+    scratch = torch.zeros((N + 127) // 128 * ops.tc_tile_bytes(D, UNITS, A)[0], dtype=torch.uint8, device=DEV) if wide else None
     obs = (torch.randn(N, D, generator=g) * 2).to(DEV)
     nm = (torch.randn(D, generator=g) * 0.3).to(DEV); ns = (torch.rand(D, generator=g) + 0.7).to(DEV)
     noise = torch.randn(N, A, generator=g).to(DEV)
@@ -182,7 +213,7 @@ def test_tc_rollout_vs_fp32():
     wpack = torch.zeros(ops.tc_pack_bytes(D, UNITS, A), dtype=torch.uint8, device=DEV)
     ops.tc_pack_weights(W[0], W[1], W[2], Wh, D, UNITS, A, wpack)
     ops.tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, bh, logstd, UNITS, N, A, vm, vv, True, noise, 1, None, 0, t['a'], t['m'], t['s'],
-                           t['nl'], t['v'], t['e'], True, lo, hi, dones_cur, t['d'], None, None)
+                           t['nl'], t['v'], t['e'], True, lo, hi, dones_cur, t['d'], None, None, l1_scratch=scratch)
     torch.cuda.synchronize()
     torch.testing.assert_close(t['m'], r['m'], rtol=0, atol=4e-2)
     torch.testing.assert_close(t['a'], r['a'], rtol=0, atol=4e-2)
@@ -194,5 +225,8 @@ def test_tc_rollout_vs_fp32():
     # values_only
     v2 = torch.empty(N, device=DEV)
     ops.tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, bh, logstd, UNITS, N, A, vm, vv, True, None, 0, None, 0, None, None, None, None, v2,
-                           None, False, None, None, None, None, None, None, values_only=True)
+                           None, False, None, None, None, None, None, None, values_only=True, l1_scratch=scratch)
     assert torch.equal(v2, t['v'])
+    if wide:        # the scratch holds the layer-1 activations of all N rows
+        a1 = decode_tiles(scratch, (N + 127) // 128, UNITS[0])[:N]
+        assert rel_l2(a1, ra[0]) < 1.5e-2, rel_l2(a1, ra[0])
