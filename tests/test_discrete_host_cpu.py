@@ -45,17 +45,16 @@ class _Env:
         return info
 
 
-@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt', 'agent_multidiscrete.pt'])
-def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, tmp_path):
+def _build(monkeypatch, tmp_path, g, stand_ins=True):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import _torch_ops
     from rl_games_b200 import agent_discrete
     from rl_games_b200.runner import Runner
-    _torch_ops.install(monkeypatch)
+    if stand_ins:
+        _torch_ops.install(monkeypatch)
     monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_require_cuda', lambda self: None)
     monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_sync', staticmethod(lambda: None))
-    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk = g['config']
     env = _Env(g)
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
@@ -73,6 +72,14 @@ def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, t
     assert agent.model.param_names() == g['param_order']
     agent.init_tensors()
     agent.obs = agent.env_reset()
+    return agent
+
+
+@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt', 'agent_multidiscrete.pt'])
+def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, tmp_path):
+    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    cfgk = g['config']
+    agent = _build(monkeypatch, tmp_path, g)
     fl = lambda t: t.transpose(0, 1).reshape(-1, *t.shape[2:])    # noqa: E731
     for ep, ref in enumerate(g['epochs_out']):
         agent.epoch_num += 1
