@@ -314,12 +314,17 @@ class AdaptiveScheduler:
 
 
 class LinearScheduler:
-    def __init__(self, start_lr, min_lr=1e-6, max_steps=1000000, use_epochs=True):
+    def __init__(self, start_lr, min_lr=1e-6, max_steps=1000000, use_epochs=True, apply_to_entropy=False, start_entropy_coef=0.01,
+                 min_entropy_coef=0.0001):
         self.start_lr, self.min_lr, self.max_steps, self.use_epochs = start_lr, min_lr, max_steps, use_epochs
+        self.apply_to_entropy = apply_to_entropy            # schedulers.py:45-48, :57-58 (config key schedule_entropy)
+        self.start_entropy_coef, self.min_entropy_coef = start_entropy_coef, min_entropy_coef
 
     def update(self, current_lr, entropy_coef, epoch, frames, kl_dist):
         steps = epoch if self.use_epochs else frames
         mul = max(0, self.max_steps - steps) / self.max_steps
+        if self.apply_to_entropy:
+            entropy_coef = self.min_entropy_coef + (self.start_entropy_coef - self.min_entropy_coef) * mul
         return self.min_lr + (self.start_lr - self.min_lr) * mul, entropy_coef
 
 
@@ -565,7 +570,8 @@ DEFAULT_CFG = dict(
     truncate_grads=True, grad_norm=1.0, learning_rate=3e-4, lr_schedule='adaptive', kl_threshold=0.008,
     min_lr=1e-6, max_lr=1e-2, lr_multiplier=1.5, schedule_type='per_minibatch',
     normalize_input=True, normalize_value=True, normalize_advantage=True, value_bootstrap=True,
-    mini_epochs=4, weight_decay=0.0, ppo=True, reward_scale=1.0, reward_shift=0.0, seq_length=4, rnn_units=0, zero_rnn_on_done=True,
+    mini_epochs=4, weight_decay=0.0, ppo=True, reward_scale=1.0, reward_shift=0.0, reward_min=-float('inf'), reward_max=float('inf'),
+    reward_log=False, max_epochs=-1, max_frames=-1, schedule_entropy=False, actions_low=-1.0, actions_high=1.0, seq_length=4, rnn_units=0, zero_rnn_on_done=True,
     games_to_track=100, activation='elu', clip_actions=True, mask_autoreset_rows=False,
     normalize_rms_advantage=False, adv_rms_momentum=0.5,
 )
@@ -702,6 +708,10 @@ class OracleAgent:
         self.optimizer = Adam(self.model.parameters(), self.last_lr, eps=1e-8, weight_decay=c['weight_decay'])
         if c['lr_schedule'] == 'adaptive':
             self.scheduler = AdaptiveScheduler(c['kl_threshold'], c['min_lr'], c['max_lr'], c['lr_multiplier'])
+        elif c['lr_schedule'] == 'linear' and (c['max_epochs'] != -1 or c['max_frames'] != -1):       # a2c_common.py:314-332
+            use_epochs = c['max_epochs'] != -1
+            self.scheduler = LinearScheduler(float(c['learning_rate']), c['min_lr'], c['max_epochs'] if use_epochs else c['max_frames'],
+                                             use_epochs, c['schedule_entropy'], c['entropy_coef'])
         else:
             self.scheduler = IdentityScheduler()
         self.all_reduce, self.world_size = all_reduce, world_size
@@ -711,8 +721,8 @@ class OracleAgent:
         self.game_lengths = AverageMeter(1, c['games_to_track'])
         self.mask_autoreset_rows = c['mask_autoreset_rows']
         self._autoreset_prev_dones = None
-        self.actions_low = torch.full((act_dim,), -1.0)
-        self.actions_high = torch.full((act_dim,), 1.0)
+        self.actions_low = torch.full((act_dim,), float(c['actions_low']))        # the env's action_space bounds (a2c_common.py:1496-1497)
+        self.actions_high = torch.full((act_dim,), float(c['actions_high']))
         self.init_tensors()
 
     # a2c_common.py:634-670
@@ -784,7 +794,7 @@ class OracleAgent:
             rewards = rewards.unsqueeze(1)
             if self.mask_autoreset_rows:
                 self._autoreset_prev_dones = self.dones.clone()
-            shaped = shape_rewards(rewards, c['reward_scale'], c['reward_shift'])
+            shaped = shape_rewards(rewards, c['reward_scale'], c['reward_shift'], c['reward_min'], c['reward_max'], c['reward_log'])
             if c['value_bootstrap'] and 'time_outs' in infos:
                 shaped = shaped + c['gamma'] * res['values'] * infos['time_outs'].unsqueeze(1).float()
             self.buf['rewards'][n] = shaped

@@ -422,6 +422,12 @@ class A2CAgent:
         # lr, step, beta1^step, beta2^step, [KL sum, count of the running mini-epoch (schedule_type 'standard')], pad
         self.opt_state = torch.tensor([self.last_lr, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
         self.entropy_coef_dev = torch.tensor([float(self.entropy_coef)], dtype=torch.float32, device=dev)
+        # linear schedule (a2c_common.py:1557-1563): the reference steps the scheduler AFTER every minibatch with the current epoch
+        # number, so the first minibatch of an epoch still runs on the previous epoch's (lr, entropy_coef) and the others on this
+        # epoch's.  The host knows both before the epoch starts; the switch is two device-to-device copies after the first update.
+        self._sched_switch = self.linear_lr and not isinstance(self.scheduler, IdentityScheduler)
+        self.lr_next_dev = torch.tensor([self.last_lr], dtype=torch.float64, device=dev)
+        self.ent_next_dev = torch.tensor([float(self.entropy_coef)], dtype=torch.float32, device=dev)
         self.inv_counts = f(self.num_minibatches) if self.mask_autoreset_rows else None
         self.mom_scratch = torch.zeros(1024 * 2 * D, dtype=torch.float64, device=dev)
         self.use_mb_moments = self.normalize_input and D % 4 == 0
@@ -950,6 +956,9 @@ class A2CAgent:
         for _ in range(self.mini_epochs_num):
             for i in range(self.num_minibatches):
                 self._minibatch_update(i, u)
+                if u == 0 and self._sched_switch:
+                    self.opt_state[0:1].copy_(self.lr_next_dev)
+                    self.entropy_coef_dev.copy_(self.ent_next_dev)
                 u += 1
 
     def _run_update(self):
@@ -1013,6 +1022,10 @@ class A2CAgent:
         self.set_eval()
         if self._lr_dirty():
             self.opt_state[0:1].fill_(self.last_lr)
+        if self._sched_switch:      # this epoch's schedule value, used from the second minibatch on (outside any captured graph)
+            lr_b, ent_b = self.scheduler.update(self.last_lr, self.entropy_coef, self.epoch_num, self.frame, 0.0)
+            self.lr_next_dev.fill_(float(lr_b))
+            self.ent_next_dev.fill_(float(ent_b))
         whole = noise is None and self._whole_epoch_graph_ok()
         ev[0].record()
         if whole and getattr(self, '_epoch_warm', False):

@@ -172,8 +172,9 @@ class TapeVecEnv:
     def get_env_info(self):
         import gymnasium as gym
         D, A = self.obs_tape.shape[-1], self.A
+        lo, hi = getattr(self, 'act_bounds', (-1.0, 1.0))
         info = {'observation_space': gym.spaces.Box(-np.inf, np.inf, (D,), np.float32),
-                'action_space': gym.spaces.Box(-1.0, 1.0, (A,), np.float32)}
+                'action_space': gym.spaces.Box(lo, hi, (A,), np.float32)}
         if self.autoreset_mode != 'same_step':
             info['autoreset_mode'] = self.autoreset_mode
         return info
@@ -217,7 +218,7 @@ def make_params(N, H, mb, units, overrides=None, rnn_units=0, rnn_before_mlp=Tru
 
 
 def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, overrides=None, autoreset='same_step',
-              seed=3, rnn_units=0, rnn_before_mlp=True):
+              seed=3, rnn_units=0, rnn_before_mlp=True, act_bounds=(-1.0, 1.0)):
     from rl_games.torch_runner import Runner
     from oracle.ppo_oracle import make_tapes
     torch.manual_seed(seed)
@@ -226,8 +227,10 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
     obs_tape, done_tape, tout_tape = make_tapes(T, N, D, seed=seed)
     env = TapeVecEnv(obs_tape, done_tape, tout_tape, autoreset)
     env.A = A
+    env.act_bounds = act_bounds
     params = make_params(N, H, mb, units, overrides, rnn_units, rnn_before_mlp)
     params['config']['env_info'] = env.get_env_info()
+    shaper_cfg = dict(params['config']['reward_shaper'])        # Runner.load_config replaces the dict by a DefaultRewardsShaper object
     runner = Runner()
     runner.load({'params': params})
     runner.params['config']['vec_env'] = env
@@ -281,7 +284,8 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
         torch.normal = orig_normal
     save(name, {'N': N, 'H': H, 'D': D, 'A': A, 'units': list(units), 'mb': mb, 'epochs': epochs,
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
-                'autoreset': autoreset, 'rnn_units': rnn_units, 'rnn_before_mlp': rnn_before_mlp, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
+                'reward_shaper': shaper_cfg,
+                'act_bounds': tuple(act_bounds), 'autoreset': autoreset, 'rnn_units': rnn_units, 'rnn_before_mlp': rnn_before_mlp, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
                 'noise': noise, 'init_state': init_state, 'epochs_out': epochs_out,
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
@@ -547,7 +551,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -565,6 +569,17 @@ if __name__ == '__main__':
     if 'lstm_after' in which:
         # the placement most shipped configs use: MLP -> LSTM -> heads (before_mlp: False is the reference default)
         gen_agent('agent_lstm_after.pt', seed=14, rnn_units=12, rnn_before_mlp=False, overrides={'seq_length': 4})
+    if 'misc' in which:
+        # config keys no other fixture moves: linear LR + entropy schedule, all three normalisers off, the full reward shaper
+        # (shift, scale, clip), unclipped actions into a non-unit action box, different gamma / tau / e_clip / critic_coef, a short meter
+        gen_agent('agent_misc.pt', seed=16, epochs=3, act_bounds=(-2.0, 0.5), overrides={
+            'lr_schedule': 'linear', 'max_epochs': 10, 'schedule_entropy': True, 'entropy_coef': 0.01, 'normalize_input': False,
+            'normalize_value': False, 'normalize_advantage': False, 'clip_actions': False, 'games_to_track': 5, 'e_clip': 0.1,
+            'critic_coef': 1, 'tau': 0.9, 'gamma': 0.95, 'mini_epochs': 2,
+            'reward_shaper': {'scale_value': 0.5, 'shift_value': 0.2, 'min_val': -0.3, 'max_val': 0.25}})
+        # clipped + rescaled actions into the non-unit box, vanilla policy gradient (ppo: False), masked rows, minibatch_size_per_env
+        gen_agent('agent_rescale.pt', seed=17, autoreset='next_step', act_bounds=(-2.0, 0.5), overrides={
+            'ppo': False, 'clip_actions': True, 'minibatch_size_per_env': 4, 'bounds_loss_coef': 0.001, 'bound_loss_type': 'bound'})
     if 'sched' in which:
         # schedule_type 'standard' (what the shipped mjlab configs use): one adaptive-KL scheduler step per mini-epoch on the mean KL;
         # 4 minibatches per mini-epoch, a learning rate high enough that the schedule moves both ways

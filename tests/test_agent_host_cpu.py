@@ -58,7 +58,8 @@ class _Env:
 
     def get_env_info(self):
         from rl_games_b200.common import Box
-        info = {'observation_space': Box(-np.inf, np.inf, (self.g['D'],)), 'action_space': Box(-1.0, 1.0, (self.g['A'],))}
+        lo, hi = self.g.get('act_bounds', (-1.0, 1.0))
+        info = {'observation_space': Box(-np.inf, np.inf, (self.g['D'],)), 'action_space': Box(lo, hi, (self.g['A'],))}
         if self.g['autoreset'] != 'same_step':
             info['autoreset_mode'] = self.g['autoreset']
         return info
@@ -72,7 +73,8 @@ class _Env:
 
 @pytest.mark.parametrize('name,tc', [('agent_base.pt', False), ('agent_masked.pt', False), ('agent_hardclip.pt', False), ('agent_rmsadv.pt', False),
                                      ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_tcshape.pt', 2), ('agent_lstm.pt', False),
-                                     ('agent_lstm_after.pt', False), ('agent_sched_standard.pt', False)])
+                                     ('agent_lstm_after.pt', False), ('agent_sched_standard.pt', False), ('agent_misc.pt', False),
+                                     ('agent_rescale.pt', False)])
 def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
     """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
     stride, fused reduce+Adam tail, per-minibatch obs moments merged by the optimiser tail) with fp32 stand-ins for its kernels"""
@@ -93,8 +95,8 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     if tc == 2:
         config['b200_unvalidated'] = True
-    config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
-                   'mixed_precision': bool(tc), 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+    config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env,
+                   'reward_shaper': dict(g.get('reward_shaper') or {'scale_value': 1.0}), 'mixed_precision': bool(tc), 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
@@ -135,8 +137,11 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
         sd = agent.model.state_dict()
         for k in O.param_names(len(g['units']), lstm=lstm):
             torch.testing.assert_close(sd[k], ref['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
-        for pre in ('running_mean_std.', 'value_mean_std.'):
-            assert int(sd[pre + 'count']) == int(ref['state'][pre + 'count'])
+        for pre, key in (('running_mean_std.', 'normalize_input'), ('value_mean_std.', 'normalize_value')):
+            if cfgk.get(key, True):
+                assert int(sd[pre + 'count']) == int(ref['state'][pre + 'count'])
+            else:
+                assert pre + 'count' not in sd and pre + 'count' not in ref['state']        # same state-dict key set as the reference
         assert agent.game_rewards.current_size == ref['game_rewards_size']
         torch.testing.assert_close(agent.game_rewards.mean, ref['game_rewards_mean'].reshape(-1), rtol=1e-4, atol=1e-5)
     ck = agent.get_full_state_weights()

@@ -100,7 +100,12 @@ def _oracle_from_golden(g):
                                 'bound_loss_type', 'use_smooth_clamp', 'truncate_grads', 'grad_norm',
                                 'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value',
                                 'normalize_advantage', 'value_bootstrap', 'mini_epochs', 'normalize_rms_advantage',
-                                'adv_rms_momentum', 'schedule_type') if k in cfgk}
+                                'adv_rms_momentum', 'schedule_type', 'ppo', 'clip_actions', 'max_epochs', 'schedule_entropy',
+                                'games_to_track') if k in cfgk}
+    rs = g.get('reward_shaper') or {}
+    cfg.update(reward_scale=rs.get('scale_value', 1.0), reward_shift=rs.get('shift_value', 0.0), reward_min=rs.get('min_val', -float('inf')),
+               reward_max=rs.get('max_val', float('inf')), reward_log=rs.get('log_val', False))
+    cfg['actions_low'], cfg['actions_high'] = g.get('act_bounds', (-1.0, 1.0))
     cfg['bounds_loss_coef'] = cfgk.get('bounds_loss_coef', None)
     cfg['lr_schedule'] = cfgk.get('lr_schedule', None)
     cfg['weight_decay'] = cfgk.get('weight_decay', 0.0)
@@ -116,7 +121,7 @@ def _oracle_from_golden(g):
 
 
 @pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt',
-                                  'agent_lstm_after.pt', 'agent_sched_standard.pt'])
+                                  'agent_lstm_after.pt', 'agent_sched_standard.pt', 'agent_misc.pt', 'agent_rescale.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
@@ -144,12 +149,16 @@ def test_full_train_epochs_match_reference_agent(name):
         for k in O.param_names(len(g['units']), lstm=lstm):
             torch.testing.assert_close(ag.model.p[k].detach(), ref['state'][k], rtol=1e-4, atol=2e-6, msg=lambda m: k + m)
         st = ref['state']
-        torch.testing.assert_close(ag.model.running_mean_std.running_mean, st['running_mean_std.running_mean'], rtol=1e-9, atol=1e-9)
-        torch.testing.assert_close(ag.model.running_mean_std.running_var, st['running_mean_std.running_var'], rtol=1e-9, atol=1e-9)
-        assert int(ag.model.running_mean_std.count) == int(st['running_mean_std.count'])
-        torch.testing.assert_close(ag.model.value_mean_std.running_mean, st['value_mean_std.running_mean'], rtol=1e-6, atol=1e-7)
-        torch.testing.assert_close(ag.model.value_mean_std.running_var, st['value_mean_std.running_var'], rtol=1e-6, atol=1e-7)
-        assert int(ag.model.value_mean_std.count) == int(st['value_mean_std.count'])
+        if g['config'].get('normalize_input', True):
+            torch.testing.assert_close(ag.model.running_mean_std.running_mean, st['running_mean_std.running_mean'], rtol=1e-9, atol=1e-9)
+            torch.testing.assert_close(ag.model.running_mean_std.running_var, st['running_mean_std.running_var'], rtol=1e-9, atol=1e-9)
+            assert int(ag.model.running_mean_std.count) == int(st['running_mean_std.count'])
+        else:
+            assert 'running_mean_std.running_mean' not in st
+        if g['config'].get('normalize_value', True):
+            torch.testing.assert_close(ag.model.value_mean_std.running_mean, st['value_mean_std.running_mean'], rtol=1e-6, atol=1e-7)
+            torch.testing.assert_close(ag.model.value_mean_std.running_var, st['value_mean_std.running_var'], rtol=1e-6, atol=1e-7)
+            assert int(ag.model.value_mean_std.count) == int(st['value_mean_std.count'])
         torch.testing.assert_close(ag.game_rewards.mean, ref['game_rewards_mean'], rtol=1e-5, atol=1e-6)
         assert ag.game_rewards.current_size == ref['game_rewards_size']
         torch.testing.assert_close(ag.game_lengths.mean, ref['game_lengths_mean'], rtol=1e-6, atol=1e-6)
