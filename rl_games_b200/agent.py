@@ -1169,7 +1169,8 @@ class A2CAgent:
                 mean_rewards = None
                 if self.game_rewards.current_size > 0:
                     mh = self._meter_host()
-                    mean_rewards = [float(mh[0])]
+                    # float32 array like AverageMeter.get_mean() (torch_ext.py:349-352): checkpoint names embed str() of it
+                    mean_rewards = np.asarray([mh[0]], dtype=np.float32)
                     self.mean_rewards = mean_rewards[0]
                     for tag, val in (('rewards', mh[0]), ('shaped_rewards', mh[1])):
                         self.writer.add_scalar(tag + '/step', val, frame)

@@ -218,7 +218,7 @@ def make_params(N, H, mb, units, overrides=None, rnn_units=0, rnn_before_mlp=Tru
 
 
 def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, overrides=None, autoreset='same_step',
-              seed=3, rnn_units=0, rnn_before_mlp=True, act_bounds=(-1.0, 1.0)):
+              seed=3, rnn_units=0, rnn_before_mlp=True, act_bounds=(-1.0, 1.0), train_loop=False):
     from rl_games.torch_runner import Runner
     from oracle.ppo_oracle import make_tapes
     torch.manual_seed(seed)
@@ -258,9 +258,9 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
         agent.init_tensors()
         agent.obs = agent.env_reset()
         epochs_out = []
-        for ep in range(epochs):
-            agent.epoch_num += 1
-            res = agent.train_epoch()
+        loop_out = {}
+
+        def snapshot(res):
             step_time, play_time, update_time, total, a_losses, c_losses, b_losses, entropies, kls, last_lr, lr_mul = res
             ds = agent.dataset.values_dict
             epochs_out.append({
@@ -277,8 +277,26 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
                 'game_lengths_mean': agent.game_lengths.mean.clone(),
                 'adam_exp_avg': [agent.optimizer.state[p]['exp_avg'].clone() for p in agent.model.parameters()],
                 'adam_exp_avg_sq': [agent.optimizer.state[p]['exp_avg_sq'].clone() for p in agent.model.parameters()],
+                'frame_before': agent.frame, 'epoch_num': agent.epoch_num,
             })
-            agent.dataset.update_values_dict(None)
+        if train_loop:
+            # the reference's own outer loop (a2c_common.py:1662-1782): frame / epoch accounting, stop conditions, checkpoints
+            orig_epoch = agent.train_epoch
+
+            def wrapped():
+                res = orig_epoch()
+                snapshot(res)
+                return res
+            agent.train_epoch = wrapped
+            ret = agent.train()
+            loop_out = {'return': (float(ret[0]), int(ret[1])), 'frame': int(agent.frame), 'epoch_num': int(agent.epoch_num),
+                        'last_mean_rewards': float(agent.last_mean_rewards), 'mean_rewards': float(agent.mean_rewards),
+                        'saved': sorted(os.listdir(agent.nn_dir))}
+        else:
+            for ep in range(epochs):
+                agent.epoch_num += 1
+                snapshot(agent.train_epoch())
+                agent.dataset.update_values_dict(None)
         assert counter['k'] == epochs * (H + 1), counter
     finally:
         torch.normal = orig_normal
@@ -286,7 +304,7 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
                 'reward_shaper': shaper_cfg,
                 'act_bounds': tuple(act_bounds), 'autoreset': autoreset, 'rnn_units': rnn_units, 'rnn_before_mlp': rnn_before_mlp, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
-                'noise': noise, 'init_state': init_state, 'epochs_out': epochs_out,
+                'noise': noise, 'init_state': init_state, 'epochs_out': epochs_out, 'train_loop': loop_out,
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
 
@@ -551,7 +569,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -580,6 +598,12 @@ if __name__ == '__main__':
         # clipped + rescaled actions into the non-unit box, vanilla policy gradient (ppo: False), masked rows, minibatch_size_per_env
         gen_agent('agent_rescale.pt', seed=17, autoreset='next_step', act_bounds=(-2.0, 0.5), overrides={
             'ppo': False, 'clip_actions': True, 'minibatch_size_per_env': 4, 'bounds_loss_coef': 0.001, 'bound_loss_type': 'bound'})
+    if 'train' in which:
+        # the outer loop: stops on max_frames, linear schedule driven by FRAMES, periodic + best + final checkpoints
+        import shutil
+        shutil.rmtree('/tmp/golden_runs', ignore_errors=True)
+        gen_agent('agent_trainloop.pt', seed=18, epochs=3, train_loop=True, overrides={
+            'lr_schedule': 'linear', 'max_epochs': -1, 'max_frames': 3 * 64, 'save_frequency': 2, 'save_best_after': 1, 'games_to_track': 10})
     if 'sched' in which:
         # schedule_type 'standard' (what the shipped mjlab configs use): one adaptive-KL scheduler step per mini-epoch on the mean KL;
         # 4 minibatches per mini-epoch, a learning rate high enough that the schedule moves both ways

@@ -314,3 +314,40 @@ def test_mixed_precision_auto_resolves_by_geometry_and_explicit_true_never_downg
     _torch_ops.install_tc(monkeypatch)          # its tc_supported stand-in accepts the fixture's small three-layer geometry
     b = _build(monkeypatch, tmp_path, g2, _Env(g2), tc=True, over={'mixed_precision': None})
     assert b.use_tc is True and b.mixed_precision is True
+
+
+def test_train_loop_matches_the_reference_outer_loop(monkeypatch, tmp_path):
+    """agent.train() against the reference's own train() (a2c_common.py:1662-1782) on the same tapes: frame / epoch accounting, the
+    linear schedule driven by FRAMES (max_epochs -1), stop on max_frames, periodic / best / final checkpoint names, return value"""
+    from oracle import ppo_oracle as O
+    g = torch.load(os.path.join(GOLDEN, 'agent_trainloop.pt'), weights_only=False)
+    cfgk, ref = g['config'], g['train_loop']
+    agent = _build(monkeypatch, tmp_path, g, _Env(g), over={k: cfgk[k] for k in ('max_frames', 'save_frequency', 'save_best_after', 'games_to_track')})
+    assert agent.max_epochs == -1 and agent.max_frames == 192
+    orig, seen = agent.train_epoch, []
+
+    def with_noise():
+        e = agent.epoch_num - 1
+        seen.append((agent.frame, agent.epoch_num))
+        return orig(noise=g['noise'][e])
+    agent.train_epoch = with_noise
+    ret = agent.train()
+    assert (float(ret[0]), int(ret[1])) == pytest.approx(ref['return'], rel=1e-5)
+    assert agent.frame == ref['frame'] and agent.epoch_num == ref['epoch_num']
+    assert seen == [(e['frame_before'], e['epoch_num']) for e in g['epochs_out']]
+    assert agent.last_lr == pytest.approx(g['epochs_out'][-1]['last_lr'], rel=1e-12)
+    assert float(agent.last_mean_rewards) == pytest.approx(ref['last_mean_rewards'], rel=1e-5)
+    sd = agent.model.state_dict()
+    for k in O.param_names(len(g['units'])):
+        torch.testing.assert_close(sd[k], g['epochs_out'][-1]['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
+    # same files, same name FORMAT (numpy float32 repr of the mean reward); the value itself is a float32 running mean, compared to 1e-5
+    import re
+    num = re.compile(r'_rew__?(-?[0-9.]+)')
+    got, want = sorted(os.listdir(agent.nn_dir)), sorted(n.replace('golden', agent.config['name']) for n in ref['saved'])
+    assert [num.sub('_rew_#', n) for n in got] == [num.sub('_rew_#', n) for n in want] and len(got) == 3
+    for a, b in zip(got, want):
+        ma, mb_ = num.search(a), num.search(b)
+        assert (ma is None) == (mb_ is None)
+        if ma:
+            assert float(ma.group(1).rstrip('.')) == pytest.approx(float(mb_.group(1).rstrip('.')), rel=1e-5)
+            assert len(ma.group(1)) <= len(mb_.group(1)) + 1          # float32 repr, not a 17-digit double
