@@ -304,6 +304,12 @@ int b200rl_adam_step_f32(float* params, const float* grads, float* exp_avg, floa
                          float* stats_out, int* counter, void* wpack, const b200rl_pack_table* tab_host,
                          const b200rl_obs_merge* merge_next_host, void* stream);
 
+/* state_d[0] = adaptive-KL schedule(base_lr, *kl_dev * kl_scale): one scheduler step outside an optimiser launch (used once after a
+ * checkpoint restore, where the reference's first step runs on the checkpoint's optimizer LR while its scheduler continues from the
+ * agent's own last_lr: a2c_common.py:852-866) */
+int b200rl_lr_schedule_apply(double* state_d, const float* kl_dev, double kl_scale, double base_lr,
+                             const b200rl_opt_cfg* cfg_host, void* stream);
+
 /* Single-GPU fused tail of one minibatch: b200rl_reduce_finalize + b200rl_adam_step_f32 in ONE launch (no second trip of
  * the reduced gradient through memory; one grid barrier, grid <= 148 co-resident CTAs).
  *  part: split partial gradients, entry i of split k at part[k*split_stride + i], valid for i in [A, n);

@@ -519,6 +519,8 @@ class A2CAgent:
         mode is baked per launch into captured graphs."""
         if self.is_adaptive_lr and self.schedule_type == 'standard':
             self.opt_cfg.adaptive_lr = 3 if (u + 1) % self.num_minibatches == 0 else 2
+        elif self.is_adaptive_lr:
+            self.opt_cfg.adaptive_lr = 0 if getattr(self, '_hold_sched', False) else 1
 
     def _build_cfg_structs(self):
         """POD structs passed (by value at launch) to the kernels; baked into captured graphs, so any change
@@ -953,13 +955,33 @@ class A2CAgent:
         u = 0
         if self.is_adaptive_lr and self.schedule_type == 'standard':
             self.opt_state[4:6].zero_()      # a mini-epoch's KL accumulators never survive an interrupted epoch
+        resume_lr = getattr(self, '_resume_opt_lr', None)
+        self._resume_opt_lr = None
         for _ in range(self.mini_epochs_num):
             for i in range(self.num_minibatches):
+                if u == 0 and resume_lr is not None and self.is_adaptive_lr:
+                    # the restored optimizer lr drives this one step; the scheduler step that follows it starts from last_lr
+                    if self.schedule_type != 'per_minibatch':
+                        raise NotImplementedError("resume with schedule_type 'standard'")
+                    self._hold_sched = True
                 self._minibatch_update(i, u)
-                if u == 0 and self._sched_switch:
+                if u == 0 and resume_lr is not None and self.is_adaptive_lr:
+                    self._hold_sched = False
+                    self.opt_cfg.adaptive_lr = 1
+                    kl, scale = self._kl_for_sched(0)
+                    ops.lr_schedule_apply(self.opt_state, kl, scale, self.last_lr, self.opt_cfg)
+                elif u == 0 and (self._sched_switch or resume_lr is not None):
                     self.opt_state[0:1].copy_(self.lr_next_dev)
                     self.entropy_coef_dev.copy_(self.ent_next_dev)
                 u += 1
+
+    def _kl_for_sched(self, u):
+        """device location and scale of the KL the scheduler saw for update u (rank mean on several GPUs)"""
+        if self.fused_allreduce:
+            return self.ar_red[self.model.num_params:], 1.0 / self.world_size
+        if self.multi_gpu:
+            return self._gv[u & 1]['kl'], 1.0 / self.world_size
+        return self.stats[u][4:5], 1.0
 
     def _run_update(self):
         """Eager the first time (module loading, attribute setup); from the second epoch on the whole
@@ -1022,6 +1044,11 @@ class A2CAgent:
         self.set_eval()
         if self._lr_dirty():
             self.opt_state[0:1].fill_(self.last_lr)
+        if getattr(self, '_resume_opt_lr', None) is not None:       # first epoch after a restore: one step on the checkpoint's lr
+            self.opt_state[0:1].fill_(self._resume_opt_lr)
+            if not self._sched_switch:
+                self.lr_next_dev.fill_(self.last_lr)
+                self.ent_next_dev.fill_(float(self.entropy_coef))
         if self._sched_switch:      # this epoch's schedule value, used from the second minibatch on (outside any captured graph)
             lr_b, ent_b = self.scheduler.update(self.last_lr, self.entropy_coef, self.epoch_num, self.frame, 0.0)
             self.lr_next_dev.fill_(float(lr_b))
@@ -1277,7 +1304,9 @@ class A2CAgent:
         state['epoch'] = self.epoch_num
         state['frame'] = self.frame
         lr_step = self.opt_state.cpu()
-        state['optimizer'] = self.model.optimizer_state_dict(self.last_lr, float(lr_step[1]), self.weight_decay)
+        # the optimizer's own lr: last_lr, except between a restore and the first step after it (see set_full_state_weights)
+        opt_lr = self._resume_opt_lr if getattr(self, '_resume_opt_lr', None) is not None else self.last_lr
+        state['optimizer'] = self.model.optimizer_state_dict(opt_lr, float(lr_step[1]), self.weight_decay)
         state['last_mean_rewards'] = self.last_mean_rewards
         if self.normalize_rms_advantage:      # a2c_common.py:896-897: GeneralizedMovingStats.state_dict() keys
             st = self.adv_ema_state.cpu()
@@ -1295,8 +1324,12 @@ class A2CAgent:
             self.epoch_num = weights['epoch']
             self.frame = weights['frame']
         lr, step = self.model.load_optimizer_state_dict(weights['optimizer'])
-        if lr is not None:
-            self.last_lr = float(lr)
+        # a2c_common.py:852-866 restores the OPTIMIZER (its param-group lr included) but not self.last_lr: the first optimiser step
+        # after a restore runs on the checkpoint's lr, then update_lr() overwrites it with the scheduler's value computed from this
+        # agent's own last_lr.  Mirrored exactly: the checkpoint lr is held for one step (_update_all), last_lr is left alone.
+        self._resume_opt_lr = float(lr) if lr is not None else None
+        self._graph_update = self._graph_epoch = None
+        self._update_warm = self._epoch_warm = False
         self.opt_state.copy_(torch.tensor([self.last_lr, float(step), 0.9 ** float(step) if step else 0.0, 0.999 ** float(step) if step else 0.0,
                                            0.0, 0.0, 0.0, 0.0], dtype=torch.float64))
         self._lr_synced = self.last_lr

@@ -610,7 +610,7 @@ class DiscreteA2CAgent:
         state = self.get_weights()
         state['epoch'], state['frame'] = self.epoch_num, self.frame
         step = float(self.opt_state.cpu()[1])
-        state['optimizer'] = self.model.optimizer_state_dict(self.last_lr, step, self.weight_decay)
+        state['optimizer'] = self.model.optimizer_state_dict(float(self.opt_state.cpu()[0]), step, self.weight_decay)      # the optimizer's own lr
         state['last_mean_rewards'] = self.last_mean_rewards
         return state
 
@@ -620,9 +620,10 @@ class DiscreteA2CAgent:
         if set_epoch:
             self.epoch_num, self.frame = weights['epoch'], weights['frame']
         lr, step = self.model.load_optimizer_state_dict(weights['optimizer'])
-        if lr is not None:
-            self.last_lr = float(lr)
-        self.opt_state.copy_(torch.tensor([self.last_lr, float(step), 0.9 ** float(step) if step else 0.0,
+        # a2c_common.py:852-866 restores the optimizer (its lr included) but not last_lr: the restored lr drives the optimiser until the
+        # next scheduler step (end of the first mini-epoch), which continues from this agent's own last_lr
+        opt_lr = float(lr) if lr is not None else self.last_lr
+        self.opt_state.copy_(torch.tensor([opt_lr, float(step), 0.9 ** float(step) if step else 0.0,
                                            0.999 ** float(step) if step else 0.0], dtype=torch.float64))
         self.last_mean_rewards = weights.get('last_mean_rewards', -float('inf'))
 

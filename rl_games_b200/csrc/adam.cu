@@ -634,6 +634,24 @@ B200RL_EXPORT int b200rl_adam_step_f32(float* params, const float* grads, float*
     return B200RL_OK;
 }
 
+// One adaptive-KL scheduler step on a given base LR, outside an optimiser launch (state_d[0] = schedule(base_lr, kl * kl_scale)).
+// Used once after a checkpoint restore: the reference's first optimiser step then runs on the checkpoint's optimizer LR while its
+// scheduler continues from the agent's own last_lr (a2c_common.py:852-866 loads the optimizer state but not last_lr).
+__global__ void lr_schedule_apply_kernel(double* state_d, const float* __restrict__ kl_dev, double kl_scale, double base_lr, OptCfgDev c) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        c.adaptive_lr = 1;
+        state_d[0] = lr_schedule_step(base_lr, (double)(*kl_dev) * kl_scale, c, state_d);
+    }
+}
+
+B200RL_EXPORT int b200rl_lr_schedule_apply(double* state_d, const float* kl_dev, double kl_scale, double base_lr,
+                                           const b200rl_opt_cfg* cfg_host, void* stream) {
+    if (!state_d || !kl_dev || !cfg_host) return B200RL_EINVAL;
+    lr_schedule_apply_kernel<<<1, 32, 0, as_stream(stream)>>>(state_d, kl_dev, kl_scale, base_lr, make_opt_cfg(cfg_host));
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
 // ---- CUDA-IPC plumbing for the peer-mapped gradient buffers (multi-GPU, one process per GPU) ----------------------
 B200RL_EXPORT int b200rl_ipc_alloc(int64_t bytes, void** dev_ptr_out_host, void* handle64_out_host) {
     if (bytes <= 0 || !dev_ptr_out_host || !handle64_out_host) return B200RL_EINVAL;

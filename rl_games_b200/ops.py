@@ -206,6 +206,11 @@ def make_obs_merge(mbmom_i, shift, D, n_rows, mean, var, count, mean_f32, std_f3
     return ObsMerge(ptr(mbmom_i), ptr(shift), D, n_rows, ptr(mean), ptr(var), ptr(count), ptr(mean_f32), ptr(std_f32), eps)
 
 
+def lr_schedule_apply(state_d, kl_dev, kl_scale, base_lr, cfg):
+    check(lib.b200rl_lr_schedule_apply(ptr(state_d), ptr(kl_dev), float(kl_scale), float(base_lr), ctypes.addressof(cfg), _stream()),
+          'lr_schedule_apply')
+
+
 def adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=None, wpack=None, pack_table=None,
               merge_next=None):
     check(lib.b200rl_adam_step_f32(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq),

@@ -391,6 +391,16 @@ def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, sta
         obs_stats_merge(o.mbmom, o.shift, o.D, o.n_rows, o.mean, o.var, o.count, o.mean_f32, o.std_f32, o.eps)
 
 
+def lr_schedule_apply(state_d, kl_dev, kl_scale, base_lr, cfg):
+    kl = float(kl_dev[0]) * kl_scale
+    lr = base_lr
+    if kl > 2.0 * cfg.kl_threshold:
+        lr = max(base_lr / cfg.lr_multiplier, cfg.min_lr)
+    if kl < 0.5 * cfg.kl_threshold:
+        lr = min(base_lr * cfg.lr_multiplier, cfg.max_lr)
+    state_d[0] = lr
+
+
 def adv_ema_normalize(advs, partials, n_partials, ema_state, ema_step, decay, training=True):
     acc = partials[:n_partials].sum(0)
     n = float(acc[0])
@@ -488,7 +498,7 @@ def install_continuous(monkeypatch):
     """stand-ins for everything rl_games_b200.agent.A2CAgent calls on its fp32 path (mixed_precision: False, no CUDA graph)"""
     from rl_games_b200 import ops
     install(monkeypatch)
-    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss', 'make_obs_merge',
+    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss', 'make_obs_merge', 'lr_schedule_apply',
                  'obs_mb_moments', 'obs_stats_merge', 'lstm_cell_fwd', 'lstm_cell_bwd', 'rnn_mask_rows'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'adam_step', adam_step_full)

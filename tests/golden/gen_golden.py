@@ -430,6 +430,70 @@ def gen_checkpoint(name='ref_checkpoint.pt', N=8, H=8, D=6, A=3, units=(16, 8), 
     save(name, {'D': D, 'A': A, 'units': list(units), 'checkpoint': ck, 'param_order': [k for k, _ in agent.model.named_parameters()]})
 
 
+def gen_resume(name='agent_resume.pt', N=8, H=8, D=6, A=3, units=(16, 8), mb=32, seed=19):
+    """Resume from a checkpoint: reference agent A trains one epoch and exports get_full_state_weights(); a FRESH reference agent B
+    (different initial weights) imports it with set_full_state_weights(), resets the env and trains one more epoch.  The fixture holds
+    the checkpoint and B's epoch: whoever loads that checkpoint into a fresh trainer must continue exactly like B (weights, Adam
+    moments and step count, normaliser statistics, adaptive LR, epoch / frame counters)."""
+    from rl_games.torch_runner import Runner
+    from oracle.ppo_oracle import make_tapes
+    obs_tape, done_tape, tout_tape = make_tapes(H + 1, N, D, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    noise = torch.randn(2, H + 1, N, A, generator=g)
+    counter = {'k': 0, 'e': 0}
+    orig_normal = torch.normal
+
+    def fake_normal(loc, scale, *a, **kw):
+        k = counter['k']
+        counter['k'] += 1
+        return loc + scale * noise[counter['e'], k]
+
+    def make(seed_):
+        torch.manual_seed(seed_)
+        np.random.seed(seed_)
+        env = TapeVecEnv(obs_tape, done_tape, tout_tape)
+        env.A = A
+        params = make_params(N, H, mb, units, {'weight_decay': 0.01})
+        params['config']['env_info'] = env.get_env_info()
+        runner = Runner()
+        runner.load({'params': params})
+        runner.params['config']['vec_env'] = env
+        ag = runner.algo_factory.create(runner.algo_name, base_name='golden', params=runner.params)
+        ag.init_tensors()
+        return ag, params
+    torch.normal = fake_normal
+    try:
+        a, params = make(seed)
+        a.obs = a.env_reset()
+        a.epoch_num += 1
+        a.train_epoch()
+        a.frame += a.batch_size                       # what train() does after the epoch (a2c_common.py:1686)
+        ck = a.get_full_state_weights()
+        ck = {k: v for k, v in ck.items() if k in ('model', 'epoch', 'frame', 'optimizer', 'last_mean_rewards')}
+        ck = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in ck.items()}
+        import copy
+        ck = copy.deepcopy(ck)
+        b, _ = make(seed + 1)
+        init_b = {k: v.clone() for k, v in b.model.state_dict().items()}
+        b.set_full_state_weights(copy.deepcopy(ck))
+        b.obs = b.env_reset()
+        counter['k'], counter['e'] = 0, 1
+        b.epoch_num += 1
+        res = b.train_epoch()
+        out = {'a_losses': torch.stack([x.detach() for x in res[4]]), 'c_losses': torch.stack([x.detach() for x in res[5]]),
+               'kls': torch.stack([x.detach() for x in res[8]]), 'last_lr': b.last_lr, 'epoch_num': b.epoch_num, 'frame': b.frame,
+               'state': {k: v.clone() for k, v in b.model.state_dict().items()},
+               'adam_exp_avg': [b.optimizer.state[p]['exp_avg'].clone() for p in b.model.parameters()],
+               'adam_step': float(b.optimizer.state[next(iter(b.model.parameters()))]['step']),
+               'mb_values': b.experience_buffer.tensor_dict['values'].clone()}
+    finally:
+        torch.normal = orig_normal
+    save(name, {'N': N, 'H': H, 'D': D, 'A': A, 'units': list(units), 'mb': mb, 'autoreset': 'same_step',
+                'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
+                'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape, 'noise': noise, 'checkpoint': ck,
+                'init_state': init_b, 'resumed_epoch': out, 'lr_at_checkpoint': a.last_lr})
+
+
 # ------------------------------------------------------------------ discrete PPO (SURVEY 8a row a15; configs/ppo_cartpole.yaml shape)
 class DiscreteTapeVecEnv:
     """mirrors oracle.ppo_discrete_oracle.DiscreteTapeEnv behind the reference's tensor-env contract"""
@@ -569,7 +633,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train', 'resume'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -604,6 +668,8 @@ if __name__ == '__main__':
         shutil.rmtree('/tmp/golden_runs', ignore_errors=True)
         gen_agent('agent_trainloop.pt', seed=18, epochs=3, train_loop=True, overrides={
             'lr_schedule': 'linear', 'max_epochs': -1, 'max_frames': 3 * 64, 'save_frequency': 2, 'save_best_after': 1, 'games_to_track': 10})
+    if 'resume' in which:
+        gen_resume()
     if 'sched' in which:
         # schedule_type 'standard' (what the shipped mjlab configs use): one adaptive-KL scheduler step per mini-epoch on the mean KL;
         # 4 minibatches per mini-epoch, a learning rate high enough that the schedule moves both ways

@@ -226,7 +226,9 @@ def test_reference_style_per_minibatch_api_and_checkpoint_roundtrip(monkeypatch,
     c = _build(monkeypatch, tmp_path, g, _Env(g))
     c.restore(fn + '.pth')
     assert torch.equal(c.model.flat, a.model.flat) and torch.equal(c.model.exp_avg, a.model.exp_avg)
-    assert c.epoch_num == a.epoch_num and c.last_lr == a.last_lr
+    # like the reference (a2c_common.py:852-866): the optimizer comes back with its lr, the agent's own last_lr is not part of a restore
+    assert c.epoch_num == a.epoch_num and c._resume_opt_lr == a.last_lr and c.last_lr == g['config']['learning_rate']
+    assert c.get_full_state_weights()['optimizer']['param_groups'][0]['lr'] == a.last_lr
     assert int(c.model.running_mean_std.count) == int(a.model.running_mean_std.count)
 
 
@@ -351,3 +353,37 @@ def test_train_loop_matches_the_reference_outer_loop(monkeypatch, tmp_path):
         if ma:
             assert float(ma.group(1).rstrip('.')) == pytest.approx(float(mb_.group(1).rstrip('.')), rel=1e-5)
             assert len(ma.group(1)) <= len(mb_.group(1)) + 1          # float32 repr, not a 17-digit double
+
+
+def test_resume_from_a_reference_checkpoint_continues_like_the_reference(monkeypatch, tmp_path):
+    """tests/golden/gen_golden.py resume: a checkpoint written by the reference after one epoch, loaded into a FRESH trainer that then
+    runs one more epoch.  The product (set_full_state_weights on a fresh agent, env reset, train_epoch) must land where the reference's
+    own fresh agent landed: weights, Adam moments and step count, adaptive LR carried over, normaliser statistics, epoch / frame."""
+    from oracle import ppo_oracle as O
+    g = torch.load(os.path.join(GOLDEN, 'agent_resume.pt'), weights_only=False)
+    ref, ck = g['resumed_epoch'], g['checkpoint']
+    agent = _build(monkeypatch, tmp_path, g, _Env(g), over={'weight_decay': g['config']['weight_decay']})
+    agent.set_full_state_weights(ck)
+    # the reference restores the optimizer (lr included) but not its own last_lr: one step on the checkpoint's lr, then the scheduler
+    # continues from the configured learning rate (a2c_common.py:852-866)
+    assert agent.epoch_num == ck['epoch'] and agent.frame == ck['frame']
+    assert agent._resume_opt_lr == g['lr_at_checkpoint'] and agent.last_lr == g['config']['learning_rate']
+    agent.obs = agent.env_reset()
+    agent.epoch_num += 1
+    agent.train_epoch(noise=g['noise'][1])
+    assert agent.epoch_num == ref['epoch_num'] and agent.frame == ref['frame']
+    assert agent.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
+    torch.testing.assert_close(agent.values.unsqueeze(2), ref['mb_values'], rtol=1e-4, atol=1e-5)
+    st = agent.last_stats
+    torch.testing.assert_close(st[:, 0], ref['a_losses'], rtol=2e-3, atol=2e-6)
+    torch.testing.assert_close(st[:, 1], ref['c_losses'], rtol=2e-3, atol=2e-6)
+    sd = agent.model.state_dict()
+    for k in O.param_names(len(g['units'])):
+        torch.testing.assert_close(sd[k], ref['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
+    for pre in ('running_mean_std.', 'value_mean_std.'):
+        assert int(sd[pre + 'count']) == int(ref['state'][pre + 'count'])
+        torch.testing.assert_close(sd[pre + 'running_mean'], ref['state'][pre + 'running_mean'].reshape(-1), rtol=1e-6, atol=1e-7)
+    out = agent.get_full_state_weights()
+    assert float(out['optimizer']['state'][0]['step']) == ref['adam_step']
+    for i, mref in enumerate(ref['adam_exp_avg']):
+        torch.testing.assert_close(out['optimizer']['state'][i]['exp_avg'].reshape(mref.shape), mref, rtol=1e-3, atol=1e-7)

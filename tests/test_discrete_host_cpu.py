@@ -147,7 +147,8 @@ def test_discrete_train_loop_and_checkpoint_roundtrip(monkeypatch, tmp_path):
     b = build()
     b.restore(fn + '.pth')
     assert torch.equal(b.model.flat, a.model.flat) and torch.equal(b.model.exp_avg_sq, a.model.exp_avg_sq)
-    assert b.epoch_num == a.epoch_num and b.last_lr == a.last_lr
+    # reference semantics (a2c_common.py:852-866): the optimizer returns with its lr, last_lr is not part of a restore
+    assert b.epoch_num == a.epoch_num and float(b.opt_state[0]) == a.last_lr and b.last_lr == g['config']['learning_rate']
     # the gate: without the explicit opt-in the constructor refuses
     with pytest.raises(NotImplementedError, match='not been run on hardware'):
         agent_discrete.DiscreteA2CAgent('x', {'config': {'name': 'x'}, 'network': a.network_params})
