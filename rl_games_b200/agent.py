@@ -1193,6 +1193,8 @@ class A2CAgent:
                           f'fps total: {curr_frames / sum_time:.0f} epoch: {epoch_num:.0f}/{self.max_epochs:.0f} frames: {frame:.0f}')
                 self.write_stats(total_time, epoch_num, step_time, play_time, update_time, a_losses, c_losses, entropies, kls,
                                  last_lr, lr_mul, frame, sum_time, play_time, curr_frames)
+                if self.bounds_loss_coef is not None:        # a2c_common.py:1705-1706 (after write_stats and the observer's scalars)
+                    self.writer.add_scalar('losses/bounds_loss', float(self.last_stats[:, 3].mean()), frame)
                 mean_rewards = None
                 if self.game_rewards.current_size > 0:
                     mh = self._meter_host()
@@ -1257,8 +1259,6 @@ class A2CAgent:
         w.add_scalar('losses/a_loss', float(st[:, 0].mean()), frame)
         w.add_scalar('losses/c_loss', float(st[:, 1].mean()), frame)
         w.add_scalar('losses/entropy', float(st[:, 2].mean()), frame)
-        if self.bounds_loss_coef is not None:
-            w.add_scalar('losses/bounds_loss', float(st[:, 3].mean()), frame)
         w.add_scalar('info/last_lr', last_lr * lr_mul, frame)
         w.add_scalar('info/lr_mul', lr_mul, frame)
         w.add_scalar('info/e_clip', self.e_clip * lr_mul, frame)

@@ -288,10 +288,14 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
                 snapshot(res)
                 return res
             agent.train_epoch = wrapped
+            scalars = []
+            agent.writer = type('W', (), {'add_scalar': lambda self, tag, v, step=None: scalars.append((tag, float(v), step)),
+                                          'flush': lambda self: None, 'close': lambda self: None})()
+            agent.algo_observer.writer = agent.writer
             ret = agent.train()
             loop_out = {'return': (float(ret[0]), int(ret[1])), 'frame': int(agent.frame), 'epoch_num': int(agent.epoch_num),
                         'last_mean_rewards': float(agent.last_mean_rewards), 'mean_rewards': float(agent.mean_rewards),
-                        'saved': sorted(os.listdir(agent.nn_dir))}
+                        'saved': sorted(os.listdir(agent.nn_dir)), 'scalars': scalars}
         else:
             for ep in range(epochs):
                 agent.epoch_num += 1

@@ -333,7 +333,17 @@ def test_train_loop_matches_the_reference_outer_loop(monkeypatch, tmp_path):
         seen.append((agent.frame, agent.epoch_num))
         return orig(noise=g['noise'][e])
     agent.train_epoch = with_noise
+    scalars = []
+    agent.writer = type('W', (), {'add_scalar': lambda self, tag, v, step=None: scalars.append((tag, float(v), step))})()
+    agent.algo_observer.writer = agent.writer
     ret = agent.train()
+    # the same summary scalars as the reference, tag for tag and step for step (dashboards keep working); values of everything that is not a
+    # wall-clock measurement agree
+    assert [(t, s_) for t, _, s_ in scalars if not t.endswith('/time')] == [(t, s_) for t, _, s_ in ref['scalars'] if not t.endswith('/time')]
+    assert [t for t, _, _ in scalars] == [t for t, _, _ in ref['scalars']]
+    for (t, v, _), (_, rv, _) in zip(scalars, ref['scalars']):
+        if not t.startswith('performance/'):
+            assert v == pytest.approx(rv, rel=2e-3, abs=2e-6), t
     assert (float(ret[0]), int(ret[1])) == pytest.approx(ref['return'], rel=1e-5)
     assert agent.frame == ref['frame'] and agent.epoch_num == ref['epoch_num']
     assert seen == [(e['frame_before'], e['epoch_num']) for e in g['epochs_out']]
