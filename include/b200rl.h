@@ -157,6 +157,9 @@ int b200rl_lstm_cell_fwd_f32(float* gates, const float* cin, float* c_out, float
 int b200rl_lstm_cell_bwd_f32(const float* gates_act, const float* c_t, const float* cin, const float* dH, int scatter_rpc,
                              int64_t scatter_stride, const float* dhin_next, const float* dcin_next, const uint8_t* done_next,
                              int done_rpc, int64_t done_stride, float* dgates, float* dcin, int S, int Hd, void* stream);
+/* train-time reset flags of an RNN policy on a next_step-autoreset env (a2c_common.py:1180-1191):
+ * out[t, n] = dones[t, n] | (t > 0 && valid[t - 1, n] == 0)   ([H, N] contiguous) */
+int b200rl_rnn_train_dones_u8(const uint8_t* dones, const float* valid, uint8_t* out, int H, int N, void* stream);
 int b200rl_rnn_mask_rows_f32(const float* in, int in_rpc, int64_t in_stride, float* out, const uint8_t* done, int done_rpc,
                              int64_t done_stride, int S, int Hd, void* stream);
 

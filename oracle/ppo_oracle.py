@@ -787,6 +787,13 @@ class OracleAgent:
                 if prev is None:
                     prev = torch.zeros_like(self.dones)
                 mb_valid[n] = 1.0 - prev.float()
+                if self.is_rnn and c['zero_rnn_on_done']:
+                    # a2c_common.py:1097-1106: a filler reset row's forward absorbed the dead episode's terminal obs into the freshly
+                    # zeroed state -- re-zero, so that the first real row of the new episode starts clean
+                    reset_idx = prev.nonzero(as_tuple=False)
+                    if len(reset_idx) > 0:
+                        for s_ in self.rnn_states:
+                            s_[:, reset_idx, :] = 0
             for k in ['actions', 'neglogpacs', 'values', 'mus', 'sigmas']:
                 self.buf[k][n] = res[k]
             o, rewards, self.dones, infos = self.env.step(self.preprocess_actions(res['actions']))
@@ -835,6 +842,13 @@ class OracleAgent:
             batch['states'] = swap_and_flatten01(self.buf['states'])
         if self.mask_autoreset_rows:
             batch['rnn_masks'] = swap_and_flatten01(mb_valid)
+            if self.is_rnn and c['zero_rnn_on_done']:
+                # a2c_common.py:1180-1191: the batch's dones feed only the train-time state reset; also reset ENTERING the first real row
+                # after a filler reset row (GAE above used the buffer's own dones)
+                rnn_dones = self.buf['dones'].clone()
+                garbage = (mb_valid == 0.0)
+                rnn_dones[1:] = torch.maximum(rnn_dones[1:], garbage[:-1].to(rnn_dones.dtype))
+                batch['dones'] = swap_and_flatten01(rnn_dones)
         if self.is_rnn:    # a2c_common.py:1193-1199
             states = []
             for mb_s in self.mb_rnn_states:

@@ -296,8 +296,9 @@ class A2CAgent:
         if self.is_rnn:
             if self.horizon_length % self.seq_length != 0:
                 raise ValueError(f"Horizon length ({self.horizon_length}) must be divisible by sequence length ({self.seq_length})")
-            if self.mask_autoreset_rows:
-                raise NotImplementedError('rnn policies with next_step-autoreset masking are not on the B200 hot path yet')
+            if self.mask_autoreset_rows and not config.get('b200_unvalidated', False):
+                raise NotImplementedError('rnn policies on a next_step-autoreset env (masked filler rows + state re-zeroing) reproduce the '
+                                          'reference on CPU but have not been run on hardware yet: set b200_unvalidated: True')
             if not self.zero_rnn_on_done:
                 raise NotImplementedError('zero_rnn_on_done: False is not on the B200 hot path')
             if self.mixed_precision:
@@ -398,6 +399,8 @@ class A2CAgent:
             Hd, T = m.rnn_units, self.seq_length
             S = mb // T
             self.rnn_h, self.rnn_c = f(N, Hd), f(N, Hd)                       # current states (a2c_common.py:652-655)
+            # train-time reset flags: the buffer's dones, plus "entering the first real row after a filler reset row" on next_step envs
+            self.rnn_dones_buf = torch.zeros(H, N, dtype=torch.uint8, device=dev) if self.mask_autoreset_rows else None
             self.rnn_h0, self.rnn_c0 = f(H // T, N, Hd), f(H // T, N, Hd)     # mb_rnn_states (:656-660), [num_seqs_per_env, N, hid]
             self.r_gates, self.r_tmp_h, self.r_tmp_c = f(N, 4 * Hd), f(N, Hd), f(N, Hd)
             self.t_gates, self.t_hin, self.t_cin, self.t_c = f(T, S, 4 * Hd), f(T, S, Hd), f(T, S, Hd), f(T, S, Hd)
@@ -590,6 +593,9 @@ class A2CAgent:
         obs = self.obs_to_tensors(obs)
         if self.prev_dones is not None:
             self.prev_dones.zero_()
+        self._fresh_reset = True            # no pending reset row until the first env step (a2c_common.py:352-353: prev dones = None)
+        if getattr(self, 'is_rnn', False) and self.mask_autoreset_rows:
+            self._graph_epoch = None        # the captured rollout re-zeroes absorbed states on every step; the first one after a reset must not
         return obs
 
     def _host_to_dev(self, name, arr, dtype):
@@ -721,6 +727,12 @@ class A2CAgent:
                 self.rnn_h0[t // self.seq_length].copy_(self.rnn_h)
                 self.rnn_c0[t // self.seq_length].copy_(self.rnn_c)
             self._policy_step(obs, t, None if noise is None else noise[t])
+            if self.is_rnn and self.mask_autoreset_rows and not getattr(self, '_fresh_reset', False):
+                # a2c_common.py:1097-1106: on a filler reset row (previous step ended the episode; self.dones still holds that step's
+                # flags) the forward just absorbed the dead episode's terminal obs into the zeroed state -- zero it again
+                ops.rnn_mask_rows(self.rnn_h, N, 0, self.rnn_h, N, self.model.rnn_units, done=self.dones, done_rpc=N)
+                ops.rnn_mask_rows(self.rnn_c, N, 0, self.rnn_c, N, self.model.rnn_units, done=self.dones, done_rpc=N)
+            self._fresh_reset = False
             t0 = time.perf_counter()
             self.obs, rewards, dones, infos = self.env_step(self.env_actions)
             step_time += time.perf_counter() - t0
@@ -743,6 +755,8 @@ class A2CAgent:
         return step_time
 
     def _gae_and_prepare(self):
+        if self.is_rnn and self.mask_autoreset_rows:      # train-time state-reset flags (a2c_common.py:1180-1191); GAE uses the plain dones
+            ops.rnn_train_dones(self.dones_buf, self.valid, self.rnn_dones_buf)
         nb = ops.gae_fused(self.rewards, self.values, self.dones_buf, self.last_values, self.dones, self.valid, self.advs,
                            self.returns, self.gae_partials, self.gamma, self.tau)
         self._prepare(nb)
@@ -878,8 +892,9 @@ class A2CAgent:
         S = epm * H // T
         nm, ns = self._norm() if m.rnn_before_mlp else (None, None)
         # window-initial states = snapshots taken during the rollout, zeroed where the episode ended entering step 0
-        ops.rnn_mask_rows(self.rnn_h0[0, e0:], epm, N, self.t_hin[0], S, Hd, done=self.dones_buf[0, e0:], done_rpc=epm, done_stride=T * N)
-        ops.rnn_mask_rows(self.rnn_c0[0, e0:], epm, N, self.t_cin[0], S, Hd, done=self.dones_buf[0, e0:], done_rpc=epm, done_stride=T * N)
+        dn = self.rnn_dones_buf if self.rnn_dones_buf is not None else self.dones_buf
+        ops.rnn_mask_rows(self.rnn_h0[0, e0:], epm, N, self.t_hin[0], S, Hd, done=dn[0, e0:], done_rpc=epm, done_stride=T * N)
+        ops.rnn_mask_rows(self.rnn_c0[0, e0:], epm, N, self.t_cin[0], S, Hd, done=dn[0, e0:], done_rpc=epm, done_stride=T * N)
         for t in range(T):
             # step-t inputs of all S sequences: arena observations (LSTM first) or the trunk output rows (j*T + t)*epm + e (LSTM last)
             xin, xstride = (self.obses[t, e0:], T * N) if m.rnn_before_mlp else (self.ta[-1][t * epm:], T * epm)
@@ -890,7 +905,7 @@ class A2CAgent:
             ops.lstm_cell_fwd(self.t_gates[t], self.t_cin[t], self.t_c[t], self.t_hdense, S, Hd,
                               h_scatter=self.t_hmlp[t * epm:], scatter_rpc=epm, scatter_stride=T * epm,
                               hin_next=None if last else self.t_hin[t + 1], cin_next=None if last else self.t_cin[t + 1],
-                              done_next=None if last else self.dones_buf[t + 1, e0:], done_rpc=epm, done_stride=T * N)
+                              done_next=None if last else dn[t + 1, e0:], done_rpc=epm, done_stride=T * N)
 
     def _lstm_window_bwd(self, e0):
         """BPTT over the window: cell backward, weight gradients of W_ih / W_hh (+ both biases) per step into their own split rows,
@@ -900,12 +915,13 @@ class A2CAgent:
         S = epm * H // T
         nm, ns = self._norm() if m.rnn_before_mlp else (None, None)
         o_wih, o_whh, o_bih, o_bhh = (m.layout[k][0] for k in ('W_ih', 'W_hh', 'b_ih', 'b_hh'))
+        dn = self.rnn_dones_buf if self.rnn_dones_buf is not None else self.dones_buf
         for t in range(T - 1, -1, -1):
             last = t == T - 1
             ops.lstm_cell_bwd(self.t_gates[t], self.t_c[t], self.t_cin[t], self.t_dgates, self.t_dcin[t & 1], S, Hd,
                               dH=self.t_dHmlp[t * epm:], scatter_rpc=epm, scatter_stride=T * epm,
                               dhin_next=None if last else self.t_dhin, dcin_next=None if last else self.t_dcin[(t + 1) & 1],
-                              done_next=None if last else self.dones_buf[t + 1, e0:], done_rpc=epm, done_stride=T * N)
+                              done_next=None if last else dn[t + 1, e0:], done_rpc=epm, done_stride=T * N)
             row = t * Ssp
             xin, xstride = (self.obses[t, e0:], T * N) if m.rnn_before_mlp else (self.ta[-1][t * epm:], T * epm)
             ops.linear_bwd_weight(self.t_dgates, xin, self.part[row, o_wih:], self.part[row, o_bih:], m.rnn_in, 4 * Hd, Ssp,

@@ -72,6 +72,18 @@ __global__ void __launch_bounds__(256) rnn_mask_rows_kernel(const float* __restr
     out[idx] = in[chunk_row(s, in_rpc, in_stride) * Hd + k] * m;
 }
 
+// Train-time reset flags of an RNN policy on a next_step-autoreset env (a2c_common.py:1180-1191): besides the buffer's own dones the
+// state reset also fires ENTERING the first real row after a filler reset row (valid == 0), mirroring the rollout-side re-zero.
+//   out[t, n] = dones[t, n] | (t > 0 && valid[t - 1, n] == 0)
+__host__ __device__ inline uint8_t rnn_train_done(const uint8_t* dones, const float* valid, int64_t i, int N) {
+    return (uint8_t)((dones[i] != 0) || (i >= N && valid[i - N] == 0.0f));
+}
+__global__ void __launch_bounds__(256) rnn_train_dones_kernel(const uint8_t* __restrict__ dones, const float* __restrict__ valid,
+                                                              uint8_t* __restrict__ out, int64_t n, int N) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rnn_train_done(dones, valid, i, N);
+}
+
 }  // namespace
 
 B200RL_EXPORT int b200rl_lstm_cell_fwd_f32(float* gates, const float* cin, float* c_out, float* h_out, float* h_scatter, int scatter_rpc,
@@ -109,5 +121,19 @@ B200RL_EXPORT int b200rl_rnn_mask_rows_f32(const float* in, int in_rpc, int64_t 
     rnn_mask_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(in, in_rpc, in_stride, out, done, done_rpc > 0 ? done_rpc : 1,
                                                                                      done_stride, S, Hd);
     B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_rnn_train_dones_u8(const uint8_t* dones, const float* valid, uint8_t* out, int H, int N, void* stream) {
+    if (!dones || !valid || !out || H <= 0 || N <= 0) return B200RL_EINVAL;
+    const int64_t n = (int64_t)H * N;
+    rnn_train_dones_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dones, valid, out, n, N);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+// host test entry point (tests/test_rnn_rows_cpu.py): the element function above over HOST arrays; not in include/b200rl.h
+B200RL_EXPORT int b200rl_hosttest_rnn_train_dones(const uint8_t* dones, const float* valid, uint8_t* out, int H, int N) {
+    for (int64_t i = 0; i < (int64_t)H * N; ++i) out[i] = rnn_train_done(dones, valid, i, N);
     return B200RL_OK;
 }

@@ -391,6 +391,11 @@ def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, sta
         obs_stats_merge(o.mbmom, o.shift, o.D, o.n_rows, o.mean, o.var, o.count, o.mean_f32, o.std_f32, o.eps)
 
 
+def rnn_train_dones(dones_u8, valid, out_u8):
+    out_u8.copy_(dones_u8)
+    out_u8[1:] = torch.maximum(dones_u8[1:], (valid[:-1] == 0).to(torch.uint8))
+
+
 def lr_schedule_apply(state_d, kl_dev, kl_scale, base_lr, cfg):
     kl = float(kl_dev[0]) * kl_scale
     lr = base_lr
@@ -498,7 +503,7 @@ def install_continuous(monkeypatch):
     """stand-ins for everything rl_games_b200.agent.A2CAgent calls on its fp32 path (mixed_precision: False, no CUDA graph)"""
     from rl_games_b200 import ops
     install(monkeypatch)
-    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss', 'make_obs_merge', 'lr_schedule_apply',
+    for name in ('policy_head_sample', 'ppo_head_loss', 'ppo_loss_finalize', 'adv_ema_normalize', 'normalize', 'value_loss', 'make_obs_merge', 'lr_schedule_apply', 'rnn_train_dones',
                  'obs_mb_moments', 'obs_stats_merge', 'lstm_cell_fwd', 'lstm_cell_bwd', 'rnn_mask_rows'):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'adam_step', adam_step_full)

@@ -637,7 +637,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train', 'resume'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train', 'resume', 'lstm_masked'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -666,6 +666,11 @@ if __name__ == '__main__':
         # clipped + rescaled actions into the non-unit box, vanilla policy gradient (ppo: False), masked rows, minibatch_size_per_env
         gen_agent('agent_rescale.pt', seed=17, autoreset='next_step', act_bounds=(-2.0, 0.5), overrides={
             'ppo': False, 'clip_actions': True, 'minibatch_size_per_env': 4, 'bounds_loss_coef': 0.001, 'bound_loss_type': 'bound'})
+    if 'lstm_masked' in which:
+        # LSTM policy on a next_step-autoreset env (envpool-style): filler reset rows are masked, the state absorbed on them is
+        # re-zeroed in the rollout, and the train-time reset also fires entering the first real row (a2c_common.py:1097-1106, :1180-1191)
+        gen_agent('agent_lstm_masked.pt', seed=20, rnn_units=8, autoreset='next_step', overrides={'seq_length': 4})
+        gen_agent('agent_lstm_after_masked.pt', seed=21, rnn_units=12, rnn_before_mlp=False, autoreset='next_step', overrides={'seq_length': 4})
     if 'train' in which:
         # the outer loop: stops on max_frames, linear schedule driven by FRAMES, periodic + best + final checkpoints
         import shutil

@@ -74,7 +74,7 @@ class _Env:
 @pytest.mark.parametrize('name,tc', [('agent_base.pt', False), ('agent_masked.pt', False), ('agent_hardclip.pt', False), ('agent_rmsadv.pt', False),
                                      ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_tcshape.pt', 2), ('agent_lstm.pt', False),
                                      ('agent_lstm_after.pt', False), ('agent_sched_standard.pt', False), ('agent_misc.pt', False),
-                                     ('agent_rescale.pt', False)])
+                                     ('agent_rescale.pt', False), ('agent_lstm_masked.pt', False), ('agent_lstm_after_masked.pt', False)])
 def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
     """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
     stride, fused reduce+Adam tail, per-minibatch obs moments merged by the optimiser tail) with fp32 stand-ins for its kernels"""
@@ -106,7 +106,8 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
     lstm = g.get('rnn_units', 0) > 0
     if lstm:
         network['rnn'] = {'name': 'lstm', 'units': g['rnn_units'], 'layers': 1, 'before_mlp': bool(g.get('rnn_before_mlp', True))}
-        config['b200_unvalidated'] = not network['rnn']['before_mlp']      # MLP -> LSTM placement: not yet run on hardware
+        # MLP -> LSTM placement and LSTM on a next_step-autoreset env: not yet run on hardware
+        config['b200_unvalidated'] = (not network['rnn']['before_mlp']) or g['autoreset'] == 'next_step'
     r = Runner()
     r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
                        'config': config}})

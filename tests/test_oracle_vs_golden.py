@@ -121,7 +121,8 @@ def _oracle_from_golden(g):
 
 
 @pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt',
-                                  'agent_lstm_after.pt', 'agent_sched_standard.pt', 'agent_misc.pt', 'agent_rescale.pt'])
+                                  'agent_lstm_after.pt', 'agent_sched_standard.pt', 'agent_misc.pt', 'agent_rescale.pt', 'agent_lstm_masked.pt',
+                                  'agent_lstm_after_masked.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
