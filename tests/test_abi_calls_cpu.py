@@ -108,6 +108,9 @@ CASES = {
                                 rnn={'name': 'lstm', 'units': 8, 'layers': 1, 'before_mlp': True}),
     'lstm after the mlp': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, over={'seq_length': 4, 'b200_unvalidated': True},
                                rnn={'name': 'lstm', 'units': 12, 'layers': 1, 'before_mlp': False}),
+    'lstm before the mlp, next_step autoreset': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, autoreset='next_step',
+                                                     over={'seq_length': 4, 'b200_unvalidated': True},
+                                                     rnn={'name': 'lstm', 'units': 8, 'layers': 1, 'before_mlp': True}),
     'tcgen05': dict(N=256, H_=4, D=60, A=8, units=(256, 128, 64), mb=512, over={'mixed_precision': True}),
     'tcgen05, pipelined wgrad + masked': dict(N=256, H_=4, D=60, A=8, units=(256, 128, 64), mb=512, autoreset='next_step',
                                               over={'mixed_precision': True, 'b200_pipelined_wgrad': True}),

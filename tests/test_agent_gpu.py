@@ -144,6 +144,16 @@ def test_agent_matches_reference_golden_more_config_keys(name, graph):
     _golden_run(name, graph)
 
 
+@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                    reason='LSTM on a next_step-autoreset env not yet run on hardware (host logic checked on CPU): set B200RL_UNVALIDATED=1')
+@pytest.mark.parametrize('name', ['agent_lstm_masked.pt', 'agent_lstm_after_masked.pt'])
+@pytest.mark.parametrize('graph', [False, True])
+def test_lstm_on_next_step_autoreset_env_matches_reference_golden(name, graph):
+    """envpool-style envs with an LSTM policy (a2c_common.py:1097-1106, :1180-1191): masked filler rows, the absorbed state re-zeroed in
+    the rollout, the train-time reset also entering the first real row"""
+    _golden_run(name, graph, {'b200_unvalidated': True})
+
+
 def _golden_run(name, graph, extra=None):
     g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk = g['config']

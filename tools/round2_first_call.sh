@@ -4,7 +4,7 @@
 set -u
 mkdir -p gpurun_out
 echo "== gated parity tests (discrete PPO, central value) =="
-B200RL_UNVALIDATED=1 timeout 300 python -m pytest tests/test_discrete_gpu.py tests/test_cv_gpu.py tests/test_agent_gpu.py::test_lstm_after_mlp_agent_matches_reference_golden tests/test_agent_gpu.py::test_standard_schedule_agent_matches_reference_golden tests/test_kernels_gpu.py::test_per_mini_epoch_scheduler_modes tests/test_agent_gpu.py::test_agent_matches_reference_golden_more_config_keys tests/test_agent_gpu.py::test_resume_from_a_reference_checkpoint_continues_like_the_reference -q 2>&1 | tail -40 | tee gpurun_out/r02_gated_tests.log
+B200RL_UNVALIDATED=1 timeout 300 python -m pytest tests/test_discrete_gpu.py tests/test_cv_gpu.py tests/test_agent_gpu.py::test_lstm_after_mlp_agent_matches_reference_golden tests/test_agent_gpu.py::test_standard_schedule_agent_matches_reference_golden tests/test_kernels_gpu.py::test_per_mini_epoch_scheduler_modes tests/test_agent_gpu.py::test_agent_matches_reference_golden_more_config_keys tests/test_agent_gpu.py::test_resume_from_a_reference_checkpoint_continues_like_the_reference tests/test_agent_gpu.py::test_lstm_on_next_step_autoreset_env_matches_reference_golden -q 2>&1 | tail -40 | tee gpurun_out/r02_gated_tests.log
 echo "== wide-observation tcgen05 kernels (obs 256: BASELINE configs[4]) =="
 B200RL_UNVALIDATED=1 timeout 300 python -m pytest tests/test_mlp_tc_gpu.py tests/test_agent_gpu.py::test_bf16_tcgen05_wide_agent_tracks_fp32_agent -x -q 2>&1 | tail -40 | tee gpurun_out/r02_wide_tests.log
 echo "== validated suite =="
