@@ -1132,7 +1132,9 @@ class A2CAgent:
         nmb = self.num_minibatches
         kls = [st[e * nmb:(e + 1) * nmb, 4].mean() for e in range(self.mini_epochs_num)]
         self.last_stats = st
-        return step_time, play_time, update_time, total_time, a_losses, c_losses, b_losses, entropies, kls, self.last_lr, 1.0
+        # the tuple's last_lr is what train_actor_critic returned for the LAST minibatch (a2c_common.py:1548, :1582): the lr that
+        # minibatch ran on (stats column 7, written by the optimiser kernel), not self.last_lr after the final scheduler step
+        return step_time, play_time, update_time, total_time, a_losses, c_losses, b_losses, entropies, kls, float(st[-1, 7]), 1.0
 
     def _whole_epoch_graph_ok(self):
         """The env step is part of the captured graph only if the env says its step is a pure stream-ordered sequence on

@@ -556,6 +556,7 @@ class DiscreteA2CAgent:
         self.algo_observer.after_steps()
         rows, kls = [], []
         for _ in range(self.mini_epochs_num):
+            lr_used = self.last_lr          # what train_actor_critic returns for the minibatches of this mini-epoch (:1265, :1289)
             ep = [self._minibatch_update(i) for i in range(self.num_minibatches)]
             rows += ep
             av_kl = torch.stack([r[3] for r in ep]).mean()          # torch_ext.mean_list
@@ -568,35 +569,100 @@ class DiscreteA2CAgent:
         st = torch.stack(rows)
         self.last_stats = st
         a_losses, c_losses, entropies = list(st[:, 0]), list(st[:, 1]), list(st[:, 2])
-        return step_time, t1 - t0, t2 - t1, t2 - t0, a_losses, c_losses, entropies, kls, self.last_lr, 1.0
+        return step_time, t1 - t0, t2 - t1, t2 - t0, a_losses, c_losses, entropies, kls, lr_used, 1.0
+
+    def update_epoch(self):
+        self.epoch_num += 1
+        return self.epoch_num
+
+    def write_stats(self, total_time, epoch_num, step_time, play_time, update_time, a_losses, c_losses, entropies, kls, last_lr, lr_mul, frame,
+                    scaled_time, scaled_play_time, curr_frames):
+        """a2c_common.py:527-547: the same summary scalars, tag for tag"""
+        w = self.writer
+        mean = lambda xs: float(torch.stack(list(xs)).mean())     # noqa: E731  torch_ext.mean_list
+        w.add_scalar('performance/step_inference_rl_update_fps', curr_frames / scaled_time, frame)
+        w.add_scalar('performance/step_inference_fps', curr_frames / scaled_play_time, frame)
+        w.add_scalar('performance/step_fps', curr_frames / max(step_time, 1e-9), frame)
+        w.add_scalar('performance/rl_update_time', update_time, frame)
+        w.add_scalar('performance/step_inference_time', play_time, frame)
+        w.add_scalar('performance/step_time', step_time, frame)
+        w.add_scalar('losses/a_loss', mean(a_losses), frame)
+        w.add_scalar('losses/c_loss', mean(c_losses), frame)
+        w.add_scalar('losses/entropy', mean(entropies), frame)
+        w.add_scalar('info/last_lr', last_lr * lr_mul, frame)
+        w.add_scalar('info/lr_mul', lr_mul, frame)
+        w.add_scalar('info/e_clip', self.e_clip * lr_mul, frame)
+        w.add_scalar('info/kl', mean(kls), frame)
+        w.add_scalar('info/epochs', epoch_num, frame)
+        self.algo_observer.after_print_stats(frame, epoch_num, total_time)
 
     def train(self):
-        """DiscreteA2CBase.train (a2c_common.py:1361-1470), single process; returns (last_mean_rewards, epoch_num)."""
+        """DiscreteA2CBase.train (a2c_common.py:1361-1470), single process: frame / epoch accounting, summary scalars, periodic / best /
+        final checkpoints (same file names), score_to_win / max_epochs / max_frames / stop_fn; returns (last_mean_rewards, epoch_num)."""
         self.init_tensors()
-        self.mean_rewards = -float('inf')
+        self.mean_rewards = -float('inf')      # last_mean_rewards (best-ever watermark) is deliberately NOT reset here
+        total_time = 0
         self.obs = self.env_reset()
-        total_time = 0.0
+        stop_fn = self.config.get('stop_fn', None)
         while True:
-            self.epoch_num += 1
-            res = self.train_epoch()
-            total_time += res[3]
-            self.frame += self.curr_frames
+            epoch_num = self.update_epoch()
+            step_time, play_time, update_time, sum_time, a_losses, c_losses, entropies, kls, last_lr, lr_mul = self.train_epoch()
+            total_time += sum_time
+            curr_frames = self.curr_frames
+            self.frame += curr_frames
+            should_exit = False
+            frame = self.frame // self.num_agents
             if self.print_stats:
-                print(f'epoch: {self.epoch_num}  fps total: {self.curr_frames / res[3]:.0f}  frames: {self.frame}')
+                print(f'fps step: {curr_frames / max(step_time, 1e-9):.0f} fps step and policy inference: {curr_frames / play_time:.0f} '
+                      f'fps total: {curr_frames / sum_time:.0f} epoch: {epoch_num:.0f}/{self.max_epochs:.0f} frames: {frame:.0f}')
             if self.writer is not None:
-                self.writer.add_scalar('losses/a_loss', float(torch.stack(res[4]).mean()), self.frame)
-                self.writer.add_scalar('losses/c_loss', float(torch.stack(res[5]).mean()), self.frame)
-                self.writer.add_scalar('info/last_lr', self.last_lr, self.frame)
-            self.algo_observer.after_print_stats(self.frame, self.epoch_num, total_time)
+                self.write_stats(total_time, epoch_num, step_time, play_time, update_time, a_losses, c_losses, entropies, kls, last_lr, lr_mul,
+                                 frame, sum_time, play_time, curr_frames)
+            mean_rewards = None
             if self.game_rewards.current_size > 0:
-                self.mean_rewards = float(self.game_rewards.get_mean()[0])
-                if self.mean_rewards > self.last_mean_rewards and self.epoch_num >= self.save_best_after:
-                    self.last_mean_rewards = self.mean_rewards
+                mean_rewards = self.game_rewards.get_mean()          # float32 array: checkpoint names embed str() of it
+                mean_shaped, mean_lengths = self.game_shaped_rewards.get_mean(), self.game_lengths.get_mean()
+                self.mean_rewards = mean_rewards[0]
+                if self.writer is not None:
+                    for tag, val in (('rewards', mean_rewards[0]), ('shaped_rewards', mean_shaped[0])):
+                        self.writer.add_scalar(tag + '/step', val, frame)
+                        self.writer.add_scalar(tag + '/iter', val, epoch_num)
+                        self.writer.add_scalar(tag + '/time', val, total_time)
+                    self.writer.add_scalar('episode_lengths/step', mean_lengths[0], frame)
+                    self.writer.add_scalar('episode_lengths/iter', mean_lengths[0], epoch_num)
+                    self.writer.add_scalar('episode_lengths/time', mean_lengths[0], total_time)
+                checkpoint_name = self.config['name'] + '_ep_' + str(epoch_num) + '_rew_' + str(mean_rewards[0])
+                if self.save_freq > 0 and epoch_num % self.save_freq == 0:
+                    self.save(os.path.join(self.nn_dir, 'last_' + checkpoint_name))
+                if mean_rewards[0] > self.last_mean_rewards and epoch_num >= self.save_best_after:
+                    print('saving next best rewards: ', mean_rewards)
+                    self.last_mean_rewards = mean_rewards[0]
                     self.save(os.path.join(self.nn_dir, self.config['name']))
-                if 'score_to_win' in self.config and self.last_mean_rewards > self.config['score_to_win']:
-                    return self.last_mean_rewards, self.epoch_num
-            if (self.max_epochs != -1 and self.epoch_num >= self.max_epochs) or (self.max_frames != -1 and self.frame >= self.max_frames):
-                return self.last_mean_rewards, self.epoch_num
+                    if 'score_to_win' in self.config and self.last_mean_rewards > self.config['score_to_win']:
+                        print('Maximum reward achieved. Network won!')
+                        self.save(os.path.join(self.nn_dir, checkpoint_name))
+                        should_exit = True
+            if epoch_num >= self.max_epochs and self.max_epochs != -1:
+                if self.game_rewards.current_size == 0:
+                    print('WARNING: Max epochs reached before any env terminated at least once')
+                    mean_rewards = -np.inf
+                self.save(os.path.join(self.nn_dir, 'last_' + self.config['name'] + '_ep_' + str(epoch_num)
+                                       + '_rew_' + str(mean_rewards).replace('[', '_').replace(']', '_')))
+                print('MAX EPOCHS NUM!')
+                should_exit = True
+            if self.frame >= self.max_frames and self.max_frames != -1:
+                if self.game_rewards.current_size == 0:
+                    mean_rewards = -np.inf
+                self.save(os.path.join(self.nn_dir, 'last_' + self.config['name'] + '_frame_' + str(self.frame)
+                                       + '_rew_' + str(mean_rewards).replace('[', '_').replace(']', '_')))
+                print('MAX FRAMES NUM!')
+                should_exit = True
+            if not should_exit and stop_fn is not None and stop_fn(self):
+                self.save(os.path.join(self.nn_dir, 'last_' + self.config['name'] + '_custom_stop_ep_' + str(epoch_num)))
+                print('Custom stop callback returned True. Stopping training.')
+                should_exit = True
+            if should_exit:
+                return self.last_mean_rewards, epoch_num
 
     # =============================================================================== weights / checkpoints (a2c_common.py:825-921)
     def get_weights(self):

@@ -548,7 +548,7 @@ class DiscreteTapeVecEnv:
 
 
 def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=2, overrides=None, separate=True,
-                       use_action_masks=False, autoreset='same_step', seed=11):
+                       use_action_masks=False, autoreset='same_step', seed=11, train_loop=False):
     from rl_games.torch_runner import Runner
     from oracle.ppo_oracle import make_tapes
     from oracle.ppo_discrete_oracle import sample_inverse_cdf
@@ -608,9 +608,10 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
         agent.init_tensors()
         agent.obs = agent.env_reset()
         epochs_out = []
-        for ep in range(epochs):
-            agent.epoch_num += 1
-            step_time, play_time, update_time, total, a_losses, c_losses, entropies, kls, last_lr, lr_mul = agent.train_epoch()
+        loop_out = {}
+
+        def snapshot(res):
+            step_time, play_time, update_time, total, a_losses, c_losses, entropies, kls, last_lr, lr_mul = res
             ds = agent.dataset.values_dict
             epochs_out.append({
                 'a_losses': torch.stack([x.detach() for x in a_losses]), 'c_losses': torch.stack([x.detach() for x in c_losses]),
@@ -622,8 +623,29 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
                 'mb_actions': agent.experience_buffer.tensor_dict['actions'].clone(),
                 'game_rewards_mean': agent.game_rewards.mean.clone(), 'game_rewards_size': agent.game_rewards.current_size,
                 'adam_exp_avg': [agent.optimizer.state[p]['exp_avg'].clone() for p in agent.model.parameters()],
+                'frame_before': agent.frame, 'epoch_num': agent.epoch_num,
             })
-            agent.dataset.update_values_dict(None)
+        if train_loop:      # DiscreteA2CBase.train (a2c_common.py:1361-1470): the reference's own outer loop
+            orig_epoch = agent.train_epoch
+
+            def wrapped():
+                res = orig_epoch()
+                snapshot(res)
+                return res
+            agent.train_epoch = wrapped
+            scalars = []
+            agent.writer = type('W', (), {'add_scalar': lambda self, tag, v, step=None: scalars.append((tag, float(v), step)),
+                                          'flush': lambda self: None, 'close': lambda self: None})()
+            agent.algo_observer.writer = agent.writer
+            ret = agent.train()
+            loop_out = {'return': (float(ret[0]), int(ret[1])), 'frame': int(agent.frame), 'epoch_num': int(agent.epoch_num),
+                        'last_mean_rewards': float(agent.last_mean_rewards), 'mean_rewards': float(agent.mean_rewards),
+                        'saved': sorted(os.listdir(agent.nn_dir)), 'scalars': scalars}
+        else:
+            for ep in range(epochs):
+                agent.epoch_num += 1
+                snapshot(agent.train_epoch())
+                agent.dataset.update_values_dict(None)
         assert counter['k'] == epochs * (H + 1) * nh, counter
     finally:
         torch.multinomial = orig_multinomial
@@ -633,11 +655,12 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
                 'use_action_masks': use_action_masks, 'autoreset': autoreset,
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
                 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape, 'mask_tape': mask_tape, 'u': u,
-                'init_state': init_state, 'epochs_out': epochs_out, 'param_order': [k for k, _ in agent.model.named_parameters()]})
+                'init_state': init_state, 'epochs_out': epochs_out, 'train_loop': loop_out,
+                'param_order': [k for k, _ in agent.model.named_parameters()]})
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train', 'resume', 'lstm_masked'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train', 'resume', 'lstm_masked', 'train_discrete'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -671,12 +694,21 @@ if __name__ == '__main__':
         # re-zeroed in the rollout, and the train-time reset also fires entering the first real row (a2c_common.py:1097-1106, :1180-1191)
         gen_agent('agent_lstm_masked.pt', seed=20, rnn_units=8, autoreset='next_step', overrides={'seq_length': 4})
         gen_agent('agent_lstm_after_masked.pt', seed=21, rnn_units=12, rnn_before_mlp=False, autoreset='next_step', overrides={'seq_length': 4})
+    if 'train_discrete' in which:
+        import shutil
+        shutil.rmtree('/tmp/golden_runs', ignore_errors=True)
+        gen_agent_discrete('agent_discrete_trainloop.pt', separate=False, seed=22, epochs=3, autoreset='next_step', train_loop=True, overrides={
+            'normalize_input': True, 'normalize_value': True, 'lr_schedule': 'adaptive', 'kl_threshold': 0.02, 'max_epochs': 3,
+            'save_frequency': 2, 'save_best_after': 1, 'games_to_track': 10})
     if 'train' in which:
         # the outer loop: stops on max_frames, linear schedule driven by FRAMES, periodic + best + final checkpoints
         import shutil
         shutil.rmtree('/tmp/golden_runs', ignore_errors=True)
         gen_agent('agent_trainloop.pt', seed=18, epochs=3, train_loop=True, overrides={
             'lr_schedule': 'linear', 'max_epochs': -1, 'max_frames': 3 * 64, 'save_frequency': 2, 'save_best_after': 1, 'games_to_track': 10})
+        # adaptive schedule: 'info/last_lr' logs the lr the LAST minibatch ran on (train_actor_critic's return value), not the value
+        # after the epoch's final scheduler step; stops on max_epochs
+        gen_agent('agent_trainloop_adaptive.pt', seed=23, epochs=2, train_loop=True, overrides={'max_epochs': 2, 'save_best_after': 1})
     if 'resume' in which:
         gen_resume()
     if 'sched' in which:

@@ -319,14 +319,17 @@ def test_mixed_precision_auto_resolves_by_geometry_and_explicit_true_never_downg
     assert b.use_tc is True and b.mixed_precision is True
 
 
-def test_train_loop_matches_the_reference_outer_loop(monkeypatch, tmp_path):
+@pytest.mark.parametrize('name', ['agent_trainloop.pt', 'agent_trainloop_adaptive.pt'])
+def test_train_loop_matches_the_reference_outer_loop(name, monkeypatch, tmp_path):
     """agent.train() against the reference's own train() (a2c_common.py:1662-1782) on the same tapes: frame / epoch accounting, the
-    linear schedule driven by FRAMES (max_epochs -1), stop on max_frames, periodic / best / final checkpoint names, return value"""
+    linear schedule driven by FRAMES (max_epochs -1) / the adaptive one, stop on max_frames / max_epochs, periodic / best / final
+    checkpoint names, every summary scalar (info/last_lr = the lr of the epoch's LAST minibatch), return value"""
     from oracle import ppo_oracle as O
-    g = torch.load(os.path.join(GOLDEN, 'agent_trainloop.pt'), weights_only=False)
+    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk, ref = g['config'], g['train_loop']
-    agent = _build(monkeypatch, tmp_path, g, _Env(g), over={k: cfgk[k] for k in ('max_frames', 'save_frequency', 'save_best_after', 'games_to_track')})
-    assert agent.max_epochs == -1 and agent.max_frames == 192
+    agent = _build(monkeypatch, tmp_path, g, _Env(g), over={k: cfgk[k] for k in ('max_frames', 'max_epochs', 'save_frequency', 'save_best_after',
+                                                                                 'games_to_track') if k in cfgk})
+    assert (agent.max_epochs, agent.max_frames) == ((-1, 192) if name == 'agent_trainloop.pt' else (2, -1))
     orig, seen = agent.train_epoch, []
 
     def with_noise():
@@ -357,7 +360,7 @@ def test_train_loop_matches_the_reference_outer_loop(monkeypatch, tmp_path):
     import re
     num = re.compile(r'_rew__?(-?[0-9.]+)')
     got, want = sorted(os.listdir(agent.nn_dir)), sorted(n.replace('golden', agent.config['name']) for n in ref['saved'])
-    assert [num.sub('_rew_#', n) for n in got] == [num.sub('_rew_#', n) for n in want] and len(got) == 3
+    assert [num.sub('_rew_#', n) for n in got] == [num.sub('_rew_#', n) for n in want] and len(got) == len(ref['saved'])
     for a, b in zip(got, want):
         ma, mb_ = num.search(a), num.search(b)
         assert (ma is None) == (mb_ is None)

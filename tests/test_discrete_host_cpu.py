@@ -152,3 +152,43 @@ def test_discrete_train_loop_and_checkpoint_roundtrip(monkeypatch, tmp_path):
     # the gate: without the explicit opt-in the constructor refuses
     with pytest.raises(NotImplementedError, match='not been run on hardware'):
         agent_discrete.DiscreteA2CAgent('x', {'config': {'name': 'x'}, 'network': a.network_params})
+
+
+def test_discrete_train_loop_matches_the_reference_outer_loop(monkeypatch, tmp_path):
+    """agent.train() against DiscreteA2CBase.train of the reference (a2c_common.py:1361-1470) on the same tapes and uniform draws:
+    frame / epoch accounting, per-mini-epoch adaptive schedule, every summary scalar (tag, step, value), periodic / best / final
+    checkpoint names, return value"""
+    import re
+    g = torch.load(os.path.join(GOLDEN, 'agent_discrete_trainloop.pt'), weights_only=False)
+    ref = g['train_loop']
+    agent = _build(monkeypatch, tmp_path, g)
+    orig, seen = agent.train_epoch, []
+
+    def with_draws():
+        seen.append((agent.frame, agent.epoch_num))
+        return orig(u=g['u'][agent.epoch_num - 1])
+    agent.train_epoch = with_draws
+    scalars = []
+    agent.writer = type('W', (), {'add_scalar': lambda self, tag, v, step=None: scalars.append((tag, float(v), step))})()
+    agent.algo_observer.writer = agent.writer
+    ret = agent.train()
+    assert (float(ret[0]), int(ret[1])) == pytest.approx(ref['return'], rel=1e-5)
+    assert agent.frame == ref['frame'] and agent.epoch_num == ref['epoch_num']
+    assert seen == [(e['frame_before'], e['epoch_num']) for e in g['epochs_out']]
+    assert agent.last_lr == pytest.approx(g['epochs_out'][-1]['last_lr'], rel=1e-12)
+    assert [(t, s_) for t, _, s_ in scalars if not t.endswith('/time')] == [(t, s_) for t, _, s_ in ref['scalars'] if not t.endswith('/time')]
+    assert [t for t, _, _ in scalars] == [t for t, _, _ in ref['scalars']]
+    for (t, v, _), (_, rv, _) in zip(scalars, ref['scalars']):
+        if not t.startswith('performance/'):
+            assert v == pytest.approx(rv, rel=5e-3, abs=2e-6), t
+    sd = agent.model.state_dict()
+    for k in g['param_order']:
+        torch.testing.assert_close(sd[k], g['epochs_out'][-1]['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
+    num = re.compile(r'_rew__?(-?[0-9.]+)')
+    got, want = sorted(os.listdir(agent.nn_dir)), sorted(ref['saved'])
+    assert [num.sub('_rew_#', n) for n in got] == [num.sub('_rew_#', n) for n in want] and len(got) == 3
+    for a, b in zip(got, want):
+        ma, mb_ = num.search(a), num.search(b)
+        if ma:
+            assert float(ma.group(1).rstrip('.')) == pytest.approx(float(mb_.group(1).rstrip('.')), rel=1e-5)
+            assert len(ma.group(1)) <= len(mb_.group(1)) + 1
