@@ -33,6 +33,7 @@ class CentralValueNet:
     def __init__(self, cv_config, state_dim, num_actors, horizon, normalize_value, max_epochs, device, multi_gpu=False, world_size=1):
         net = cv_config['network']
         self.multi_gpu, self.world_size = bool(multi_gpu) and world_size > 1, int(world_size)
+        self.writter = None             # the agent's summary writer (central_value.py:79; the reference's spelling)
         mlp = net['mlp']
         self.units = list(mlp['units'])
         self.activation = mlp.get('activation', 'elu')
@@ -211,6 +212,9 @@ class CentralValueNet:
         self.lr, _ = self.scheduler.update(self.lr, 0, self.epoch_num, self.frame, 0)
         self.opt_state[0] = self.lr
         self.frame += self.batch_size
+        if self.writter is not None and rows:       # central_value.py:262-272 (one read-back per epoch, like the reference's add_scalar)
+            self.writter.add_scalar('losses/cval_loss', float(torch.stack(rows).sum()) / (self.mini_epoch * self.num_minibatches), self.frame)
+            self.writter.add_scalar('info/cval_lr', self.lr, self.frame)
         return rows
 
 
@@ -239,6 +243,7 @@ class A2CAgentCV(A2CAgent):
         self.state_shape = space.shape
         self.central_value_net = CentralValueNet(cv_config, space.shape[0], self.num_actors, self.horizon_length, self.normalize_value,
                                                  self.max_epochs, self.device_t, multi_gpu=self.multi_gpu, world_size=self.world_size)
+        self.central_value_net.writter = self.writer
         self.value_mean_std = self.central_value_net.value_mean_std                        # a2c_continuous.py:72-73
         self._states = None
 

@@ -379,6 +379,8 @@ def gen_agent_cv(name='agent_cv.pt', N=8, H=8, D=6, S=10, A=3, units=(16, 8), cv
         agent.init_tensors()
         agent.obs = agent.env_reset()
         epochs_out = []
+        cv_scalars = []
+        agent.central_value_net.writter = type('W', (), {'add_scalar': lambda self, tag, v, step=None: cv_scalars.append((tag, float(v), step))})()
         for ep in range(epochs):
             agent.epoch_num += 1
             res = agent.train_epoch()
@@ -404,7 +406,7 @@ def gen_agent_cv(name='agent_cv.pt', N=8, H=8, D=6, S=10, A=3, units=(16, 8), cv
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
                 'cv_config': {k: v for k, v in cv_cfg.items() if isinstance(v, (int, float, str, bool, type(None)))},
                 'autoreset': autoreset, 'obs_tape': obs_tape, 'state_tape': state_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
-                'noise': noise, 'init_state': init_state, 'cv_init_state': cv_init_state, 'epochs_out': epochs_out,
+                'noise': noise, 'init_state': init_state, 'cv_init_state': cv_init_state, 'epochs_out': epochs_out, 'cv_scalars': cv_scalars,
                 'cv_param_order': [k for k, _ in agent.central_value_net.model.named_parameters()]})
 
 

@@ -89,6 +89,8 @@ def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tm
     g = torch.load(os.path.join(GOLDEN, 'agent_cv.pt'), weights_only=False)
     agent = _build_cv(monkeypatch, tmp_path, g)
     cv = agent.central_value_net
+    cv_scalars = []
+    cv.writter = type('W', (), {'add_scalar': lambda self, tag, v, step=None: cv_scalars.append((tag, float(v), step))})()
     fl = O.swap_and_flatten01
     flat_noise = g['noise'].reshape(-1, g['N'], g['A'])          # H draws per epoch (the last-value forward goes through the critic)
     for ep, ref in enumerate(g['epochs_out']):
@@ -114,6 +116,10 @@ def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tm
         assert int(csd['value_mean_std.count']) == int(ref['cv_state']['value_mean_std.count'])
         torch.testing.assert_close(csd['value_mean_std.running_var'], ref['cv_state']['value_mean_std.running_var'].reshape(-1), rtol=1e-5, atol=1e-7)
         assert int(sd['value_mean_std.count']) == 1          # the actor model's own value normaliser never moves
+    # the critic's own summary scalars (central_value.py:270-272), tag / step / value
+    assert [(t, s_) for t, _, s_ in cv_scalars] == [(t, s_) for t, _, s_ in g['cv_scalars']]
+    for (t, v, _), (_, rv, _) in zip(cv_scalars, g['cv_scalars']):
+        assert v == pytest.approx(rv, rel=2e-3), t
     ck = agent.get_full_state_weights()
     assert [k for k in ck['assymetric_vf_nets'] if 'a2c_network' in k] == ['model.' + k for k in g['cv_param_order']]
     for i, mref in enumerate(g['epochs_out'][-1]['cv_adam_exp_avg']):
