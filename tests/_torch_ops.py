@@ -114,6 +114,18 @@ def gae_fused(rewards, values, dones_u8, last_values, last_dones_u8, mask, advs,
     return 1
 
 
+def batch_moments(values, returns, mask, partials):
+    """the moment partials of gae_fused alone (prepare_dataset after a caller edited values / returns)"""
+    w = torch.ones_like(values) if mask is None else (mask != 0).float()
+    da = (returns - values).double()
+    v, r, wd = values.double(), returns.double(), w.double()
+    # masked entries contribute exact zeros whatever they hold (the kernel predicates; a product with a zero weight would turn inf into nan)
+    z = lambda t: torch.where(wd != 0, t, torch.zeros_like(t))       # noqa: E731
+    partials.zero_()
+    partials[0, :7] = torch.stack([wd.sum(), z(v).sum(), z(v * v).sum(), z(r).sum(), z(r * r).sum(), z(da).sum(), z(da * da).sum()])
+    return 1
+
+
 def prepare_batch(values, returns, mask, partials, n_partials, vms_mean, vms_var, vms_count, old_values_n, returns_n, advs_n,
                   normalize_value, normalize_advantage, freeze_stats=False):
     acc = partials[:n_partials].sum(0)
@@ -267,7 +279,7 @@ def install(monkeypatch):
     """replace the ops the discrete agent calls by the stand-ins above"""
     from rl_games_b200 import ops
     for name in ('linear_fwd', 'linear_bwd_data', 'linear_bwd_weight', 'reduce_splits', 'refresh_norm', 'moments_update', 'mask_inv_counts',
-                 'gae_fused', 'prepare_batch', 'post_step', 'categorical_sample', 'categorical_loss', 'adam_step', 'bump_u64'):
+                 'gae_fused', 'batch_moments', 'prepare_batch', 'post_step', 'categorical_sample', 'categorical_loss', 'adam_step', 'bump_u64'):
         monkeypatch.setattr(ops, name, globals()[name])
 
 

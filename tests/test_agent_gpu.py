@@ -271,6 +271,44 @@ def test_resume_from_a_reference_checkpoint_continues_like_the_reference():
     assert float(out['optimizer']['state'][0]['step']) == ref['adam_step']
 
 
+@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                    reason='bit-exactness claim not yet checked on hardware: set B200RL_UNVALIDATED=1 (promote to the default suite once green)')
+@pytest.mark.parametrize('mp', [False, True])
+def test_masked_rows_contribute_zero_gradient(mp):
+    """The reference's poison test (tests/test_ppo_masking.py:153-175), same call sequence: poison returns / values of the filler reset
+    rows before prepare_dataset; one epoch of train_actor_critic from identical weights must give BIT-identical parameters (atol = 0) --
+    masked value-normaliser moments, masked advantage normalisation, zero loss weight.  fp32 kernels and the bf16 tcgen05 kernels."""
+    N, H, D, A, units, mb = (512, 8, 60, 8, [256, 128, 64], 2048) if mp else (64, 8, 6, 3, [16, 8], 128)
+    obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=31)
+    params = O.init_params(D, units, A, seed=5)
+    g = torch.Generator().manual_seed(8)
+    noise = torch.randn(H, N, A, generator=g).to(DEV)
+    results = []
+    for poison in (False, True):
+        env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A, autoreset='next_step')
+        agent = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False}, N, H, D, A, units, mb, env, params)
+        # a first rollout so that the second one starts with pending reset rows at step 0 as well
+        agent.play_steps(noise=noise)
+        batch = agent.play_steps(noise=noise)
+        garbage = batch['rnn_masks'] == 0.0
+        assert 0 < int(garbage.sum()) < garbage.numel()
+        if poison:
+            batch['returns'] = batch['returns'].clone()
+            batch['values'] = batch['values'].clone()
+            batch['returns'][garbage] = 1e6
+            batch['values'][garbage] = -1e6
+        agent.set_train()
+        agent.prepare_dataset(batch)
+        for _ in range(agent.mini_epochs_num):
+            for i in range(len(agent.dataset)):
+                agent.train_actor_critic(agent.dataset[i])
+        torch.cuda.synchronize()
+        results.append({k: v.clone() for k, v in agent.model.state_dict().items()})
+    clean, poisoned = results
+    for k in clean:
+        assert torch.equal(clean[k], poisoned[k]), f'parameter {k} differs: poisoned garbage rows leaked into the update'
+
+
 def test_synthetic_env_training_runs_and_graph_replay_is_consistent():
     """c2-shaped (scaled down) synthetic env through the public Runner API; CUDA-graph replay vs eager updates
     from identical state must give identical weights (same kernels, same order => deterministic)."""

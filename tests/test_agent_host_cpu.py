@@ -401,3 +401,33 @@ def test_resume_from_a_reference_checkpoint_continues_like_the_reference(monkeyp
     assert float(out['optimizer']['state'][0]['step']) == ref['adam_step']
     for i, mref in enumerate(ref['adam_exp_avg']):
         torch.testing.assert_close(out['optimizer']['state'][i]['exp_avg'].reshape(mref.shape), mref, rtol=1e-3, atol=1e-7)
+
+
+def test_poison_flow_of_the_reference_masking_test_runs_through_the_public_api(monkeypatch, tmp_path):
+    """call sequence of tests/test_ppo_masking.py:153-175 (play_steps -> edit returns / values of the filler rows -> prepare_dataset ->
+    train_actor_critic per minibatch) through the host code: the edited tensors are scattered back into the arena, the masked moments are
+    recomputed, and with the stand-ins' exact arithmetic the weights are bit-identical.  The kernels' own claim is the GPU twin
+    (tests/test_agent_gpu.py::test_masked_rows_contribute_zero_gradient)."""
+    g = torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False)
+    results = []
+    for poison in (False, True):
+        agent = _build(monkeypatch, tmp_path, g, _Env(g))
+        agent.play_steps(noise=g['noise'][0])
+        batch = agent.play_steps(noise=g['noise'][1])
+        garbage = batch['rnn_masks'] == 0.0
+        assert 0 < int(garbage.sum()) < garbage.numel()
+        if poison:
+            batch['returns'] = batch['returns'].clone()
+            batch['values'] = batch['values'].clone()
+            batch['returns'][garbage] = 1e6
+            batch['values'][garbage] = -1e6
+        agent.set_train()
+        agent.prepare_dataset(batch)
+        if poison:
+            assert float(agent.returns.max()) == 1e6          # the edit reached the arena
+        for _ in range(agent.mini_epochs_num):
+            for i in range(len(agent.dataset)):
+                agent.train_actor_critic(agent.dataset[i])
+        results.append({k: v.clone() for k, v in agent.model.state_dict().items()})
+    for k in results[0]:
+        assert torch.equal(results[0][k], results[1][k]), k
