@@ -191,17 +191,30 @@ class _NumpyEnv(_Env):
         return o.numpy(), r.numpy(), d.numpy(), {'time_outs': info['time_outs'].numpy()}
 
 
+class _NumpyEnv64(_NumpyEnv):
+    """what gymnasium MuJoCo vector envs hand over: float64 observations and rewards, bool dones / time-outs (a2c_common.py cast_obs:
+    float64 -> float32)"""
+
+    def reset(self):
+        return super().reset().astype(np.float64)
+
+    def step(self, actions):
+        o, r, d, info = super().step(actions)
+        return o.astype(np.float64), r.astype(np.float64), d.astype(bool), {'time_outs': info['time_outs'].astype(bool)}
+
+
 def test_host_env_path_gives_the_same_epoch_as_the_tensor_env(monkeypatch, tmp_path):
     g = torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False)
     out = []
-    for env_cls in (_Env, _NumpyEnv):
+    for env_cls in (_Env, _NumpyEnv, _NumpyEnv64):
         a = _build(monkeypatch, tmp_path, g, env_cls(g))
         a.epoch_num += 1
         a.train_epoch(noise=g['noise'][0])
         out.append((a.model.flat.clone(), a.rewards.clone(), a.dones_buf.clone(), a.valid.clone()))
         assert a.is_tensor_obses == (env_cls is _Env)
-    for x, y in zip(*out):
-        assert torch.equal(x, y)
+    for other in out[1:]:
+        for x, y in zip(out[0], other):
+            assert torch.equal(x, y)
 
 
 def test_reference_style_per_minibatch_api_and_checkpoint_roundtrip(monkeypatch, tmp_path):
