@@ -621,3 +621,34 @@ def test_fused_allreduce_adam_world1_matches_adam_step(ops):
         torch.testing.assert_close(pb, pa, rtol=1e-5, atol=1e-7)
         assert float(stb[8]) == pytest.approx(float(sta[8]), rel=1e-6)
     torch.testing.assert_close(vb, va, rtol=1e-5, atol=1e-12)
+
+
+GATED = pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1', reason='not yet run on hardware: set B200RL_UNVALIDATED=1')
+
+
+@GATED
+@pytest.mark.parametrize('H,N', [(1, 7), (8, 520), (16, 4099)])
+def test_rnn_train_dones_vs_reference_expression(ops, H, N):
+    """a2c_common.py:1180-1191: rnn_dones[1:] = max(rnn_dones[1:], (mb_valid == 0)[:-1])"""
+    g = torch.Generator().manual_seed(H + N)
+    dones = (torch.rand(H, N, generator=g) < 0.3).to(torch.uint8)
+    valid = (torch.rand(H, N, generator=g) < 0.7).float()
+    out = torch.full((H, N), 9, dtype=torch.uint8, device=DEV)
+    ops.rnn_train_dones(dones.to(DEV), valid.to(DEV), out)
+    ref = dones.clone()
+    ref[1:] = torch.maximum(ref[1:], (valid == 0.0)[:-1].to(torch.uint8))
+    assert torch.equal(out.cpu(), ref)
+
+
+@GATED
+def test_lr_schedule_apply_vs_oracle_scheduler(ops):
+    from rl_games_b200.ops import OptCfg
+    sched = O.AdaptiveScheduler(0.008, 1e-6, 1e-2, 1.5)
+    cfg = OptCfg(0.9, 0.999, 1e-8, 0.0, 1.0, 0.008, 1e-6, 1e-2, 1.5, 0.5, 1, 0)       # adaptive_lr of the struct is ignored by this entry point
+    state = torch.tensor([123.0, 7.0, 0.5, 0.25, 0.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=DEV)
+    for base, klv in ((3e-4, 0.001), (3e-4, 0.05), (3e-4, 0.01), (9e-3, 0.0001), (1.2e-6, 0.5)):
+        kl = torch.tensor([klv * 2.0], device=DEV)          # summed over two ranks; kl_scale = 1/world
+        ops.lr_schedule_apply(state, kl, 0.5, base, cfg)
+        want, _ = sched.update(base, 0.0, 0, 0, float(torch.tensor(klv * 2.0, dtype=torch.float32)) * 0.5)
+        assert float(state[0]) == pytest.approx(want, rel=1e-14)
+        assert state[1:].tolist() == [7.0, 0.5, 0.25, 0.0, 0.0, 0.0, 0.0]
