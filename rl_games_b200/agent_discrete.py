@@ -20,9 +20,11 @@ from datetime import datetime
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import ops
 from .agent import _MeterView
+from .dist_utils import PackedStatsSync
 from .common import (AdaptiveScheduler, DefaultAlgoObserver, DefaultRewardsShaper, IdentityScheduler, LinearScheduler, create_vec_env,
                      make_summary_writer)
 from .model import _RunningStats
@@ -169,9 +171,20 @@ class DiscreteA2CAgent:
         self.algo_observer = config['features'].get('observer') or DefaultAlgoObserver()
         self.algo_observer.before_init(base_name, config, self.experiment_name)
         self.network_params = params['network']
-        if config.get('multi_gpu', False):
-            raise NotImplementedError('multi_gpu is not supported by the discrete B200 agent yet')
-        self.multi_gpu, self.world_size, self.global_rank, self.local_rank = False, 1, 0, 0
+        # multi-GPU (a2c_common.py:206-220): one process per GPU, actors sharded by rank; the per-minibatch gradient exchange is an NCCL
+        # all-reduce of the flat gradient in front of the Adam kernel (which applies 1/world), the scheduler sees the rank-mean KL
+        self.multi_gpu, self.world_size, self.global_rank, self.local_rank = bool(config.get('multi_gpu', False)), 1, 0, 0
+        if self.multi_gpu:
+            self.local_rank, self.global_rank = int(os.getenv('LOCAL_RANK', '0')), int(os.getenv('RANK', '0'))
+            self.world_size = int(os.getenv('WORLD_SIZE', '1'))
+            config['device'] = 'cuda:' + str(self.local_rank)
+            if not dist.is_initialized():
+                dist.init_process_group('nccl', rank=self.global_rank, world_size=self.world_size, device_id=torch.device(config['device']))
+            if self.global_rank != 0:
+                config['print_stats'] = False
+        self.multi_gpu_sync_stats = config.get('multi_gpu_sync_stats', True)
+        if config.get('multi_gpu_sync_stats_mode', 'pooled') != 'pooled':
+            raise NotImplementedError("multi_gpu_sync_stats_mode: only 'pooled' for the discrete agent")
         self.ppo_device = config.get('device', 'cuda:0')
         self._require_cuda()
         self.device_t = torch.device(self.ppo_device)
@@ -341,8 +354,8 @@ class DiscreteA2CAgent:
         self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
         self.opt_state = torch.tensor([self.last_lr, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
         self.adam_stats = f(16)
-        self.opt_cfg = ops.OptCfg(0.9, 0.999, 1e-8, float(self.weight_decay), float(self.grad_norm), 0.0, 1e-6, 1e-2, 1.5, 1.0,
-                                  int(bool(self.truncate_grads)), 0)
+        self.opt_cfg = ops.OptCfg(0.9, 0.999, 1e-8, float(self.weight_decay), float(self.grad_norm), 0.0, 1e-6, 1e-2, 1.5,
+                                  1.0 / self.world_size, int(bool(self.truncate_grads)), 0)
         rs = self.rewards_shaper
         self.shaper_cfg = ops.ShaperCfg(float(rs.scale_value), float(rs.shift_value), float(rs.min_val), float(rs.max_val),
                                         float(self.gamma), int(bool(rs.log_val)), int(bool(self.value_bootstrap)))
@@ -528,6 +541,8 @@ class DiscreteA2CAgent:
                     ops.linear_bwd_weight(dacts[0], x, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S, rows_per_chunk=epm,
                                           chunk_stride=N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=mb, split_stride=P)
         ops.reduce_splits(self.part, self.grad, P, S, split_stride=P)
+        if self.multi_gpu:          # a2c_common.py:493-509 (the Adam kernel applies the 1/world scale)
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM)
         ops.adam_step(m.flat, self.grad, m.exp_avg, m.exp_avg_sq, self.opt_state, None, self.opt_cfg, self.adam_stats, self.counters[2:3],
                       n=P)
         return stats
@@ -560,10 +575,14 @@ class DiscreteA2CAgent:
             ep = [self._minibatch_update(i) for i in range(self.num_minibatches)]
             rows += ep
             av_kl = torch.stack([r[3] for r in ep]).mean()          # torch_ext.mean_list
+            if self.multi_gpu:                                      # a2c_common.py:1272-1274
+                dist.all_reduce(av_kl, op=dist.ReduceOp.SUM)
+                av_kl = av_kl / self.world_size
             self.last_lr, self.entropy_coef = self.scheduler.update(self.last_lr, self.entropy_coef, self.epoch_num, self.frame,
                                                                     av_kl.item())                  # one host sync per mini-epoch (:1271)
             self.opt_state[0] = self.last_lr                        # update_lr
             kls.append(av_kl)
+        self.sync_running_stats()
         self._sync()
         t2 = time.perf_counter()
         st = torch.stack(rows)
@@ -574,6 +593,19 @@ class DiscreteA2CAgent:
     def update_epoch(self):
         self.epoch_num += 1
         return self.epoch_num
+
+    def sync_running_stats(self):
+        """a2c_common.py:782-808, pooled mode: every normaliser's per-epoch moment deltas in ONE packed fp64 all-reduce"""
+        if not self.multi_gpu or not self.multi_gpu_sync_stats:
+            return
+        mods = [(n, r) for n, r in (('obs', self.model.running_mean_std), ('value', self.model.value_mean_std)) if r is not None]
+        if not mods:
+            return
+        if getattr(self, '_stats_sync', None) is None:
+            self._stats_sync = PackedStatsSync([(n, r.count, r.running_mean, r.running_var) for n, r in mods])
+        self._stats_sync.sync(lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM))
+        for _, r in mods:
+            r.refresh()
 
     def write_stats(self, total_time, epoch_num, step_time, play_time, update_time, a_losses, c_losses, entropies, kls, last_lr, lr_mul, frame,
                     scaled_time, scaled_play_time, curr_frames):
@@ -604,14 +636,22 @@ class DiscreteA2CAgent:
         total_time = 0
         self.obs = self.env_reset()
         stop_fn = self.config.get('stop_fn', None)
+        if self.multi_gpu:
+            dist.broadcast(self.model.flat, 0)
         while True:
             epoch_num = self.update_epoch()
             step_time, play_time, update_time, sum_time, a_losses, c_losses, entropies, kls, last_lr, lr_mul = self.train_epoch()
             total_time += sum_time
-            curr_frames = self.curr_frames
+            curr_frames = self.curr_frames * self.world_size if self.multi_gpu else self.curr_frames
             self.frame += curr_frames
             should_exit = False
             frame = self.frame // self.num_agents
+            if self.global_rank != 0:       # rank 0 logs, checkpoints and decides when to stop (a2c_common.py:1391, :1463-1466)
+                t = torch.zeros(1, device=self.device_t)
+                dist.broadcast(t, 0)
+                if bool(t.item()):
+                    return self.last_mean_rewards, epoch_num
+                continue
             if self.print_stats:
                 print(f'fps step: {curr_frames / max(step_time, 1e-9):.0f} fps step and policy inference: {curr_frames / play_time:.0f} '
                       f'fps total: {curr_frames / sum_time:.0f} epoch: {epoch_num:.0f}/{self.max_epochs:.0f} frames: {frame:.0f}')
@@ -661,6 +701,8 @@ class DiscreteA2CAgent:
                 self.save(os.path.join(self.nn_dir, 'last_' + self.config['name'] + '_custom_stop_ep_' + str(epoch_num)))
                 print('Custom stop callback returned True. Stopping training.')
                 should_exit = True
+            if self.multi_gpu:
+                dist.broadcast(torch.tensor([float(should_exit)], device=self.device_t), 0)
             if should_exit:
                 return self.last_mean_rewards, epoch_num
 

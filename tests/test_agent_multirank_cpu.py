@@ -158,3 +158,51 @@ def test_two_rank_central_value_agent_matches_oracle_and_ranks_stay_identical():
     mp.spawn(_worker_cv, args=(world, port, ret), nprocs=world, join=True)
     for (p0, c0, m0, n0), (p1, c1, m1, n1) in zip(ret[0], ret[1]):
         assert torch.equal(p0, p1) and torch.equal(c0, c1) and torch.equal(m0, m1) and n0 == n1
+
+
+def _worker_discrete(rank, world, port, ret):
+    """discrete PPO (gated path): NCCL-style flat-gradient all-reduce in front of the Adam kernel, rank-mean KL for the per-mini-epoch
+    scheduler (a2c_common.py:1272-1274), pooled normaliser sync"""
+    _init_rank(rank, world, port)
+    import test_discrete_host_cpu as HD
+    from oracle import ppo_oracle as O
+    from test_oracle_vs_golden import _discrete_oracle_from_golden
+    g = torch.load(os.path.join(GOLDEN, 'agent_discrete_masked.pt'), weights_only=False)
+    if rank:
+        g = dict(g)
+        for k in ('obs_tape', 'done_tape', 'timeout_tape', 'mask_tape'):
+            g[k] = torch.roll(torch.flip(g[k], dims=[1]), shifts=2, dims=0).contiguous()
+        g['u'] = torch.flip(g['u'], dims=[-1]).contiguous()
+    agent = HD._build(_Patch(), '/tmp/b200_multirank_disc_%d' % rank, g, over={'multi_gpu': True, 'print_stats': False})
+    assert agent.multi_gpu and agent.world_size == 2 and agent.global_rank == rank
+    ar = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)      # noqa: E731
+    orc = _discrete_oracle_from_golden(g)
+    orc.all_reduce, orc.world_size = ar, world
+    snaps, out = {}, []
+    for ep in range(len(g['epochs_out'])):
+        agent.epoch_num += 1
+        agent.train_epoch(u=g['u'][ep])
+        orc.train_epoch(g['u'][ep])
+        for name, m in (('obs', orc.model.running_mean_std), ('val', orc.model.value_mean_std)):
+            if m is not None:
+                snaps[name] = O.merge_rank_stats(m, ar, snaps.get(name))
+        sd = agent.model.state_dict()
+        for k in g['param_order']:
+            torch.testing.assert_close(sd[k], orc.model.p[k].detach(), rtol=1e-3, atol=2e-5, msg=lambda m: f'rank {rank} epoch {ep} {k}: {m}')
+        assert agent.last_lr == pytest.approx(orc.last_lr, rel=1e-12)
+        if orc.model.running_mean_std is not None:
+            assert int(sd['running_mean_std.count']) == int(orc.model.running_mean_std.count)
+            torch.testing.assert_close(sd['running_mean_std.running_mean'], orc.model.running_mean_std.running_mean.reshape(-1), rtol=1e-6, atol=1e-7)
+        out.append((agent.model.flat.clone(), agent.last_lr, agent.actions.clone()))
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_discrete_agent_matches_oracle_and_ranks_stay_identical():
+    world, port = 2, 30100 + os.getpid() % 90
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_discrete, args=(world, port, ret), nprocs=world, join=True)
+    for (p0, lr0, a0), (p1, lr1, a1) in zip(ret[0], ret[1]):
+        assert torch.equal(p0, p1) and lr0 == lr1 and not torch.equal(a0, a1)

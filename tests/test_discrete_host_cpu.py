@@ -45,7 +45,7 @@ class _Env:
         return info
 
 
-def _build(monkeypatch, tmp_path, g, stand_ins=True):
+def _build(monkeypatch, tmp_path, g, stand_ins=True, over=None):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     import _torch_ops
@@ -60,6 +60,7 @@ def _build(monkeypatch, tmp_path, g, stand_ins=True):
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     config.update({'device': 'cpu', 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1},
                    'b200_unvalidated': True, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+    config.update(over or {})
     multi = isinstance(g['K'], (list, tuple))
     network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'multi_discrete' if multi else 'discrete': None},
                'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}

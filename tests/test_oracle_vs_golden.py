@@ -165,16 +165,8 @@ def test_full_train_epochs_match_reference_agent(name):
         torch.testing.assert_close(ag.game_lengths.mean, ref['game_lengths_mean'], rtol=1e-6, atol=1e-6)
 
 
-# ------------------------------------------------------------------------------------------ discrete PPO (SURVEY 8a row a15)
-@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt', 'agent_multidiscrete.pt'])
-def test_discrete_train_epochs_match_reference_agent(name):
-    """Two train_epoch()s of the reference DiscreteA2CAgent (configs/ppo_cartpole.yaml shape; second fixture: shared trunk,
-    action masks, next_step autoreset, normalisers, adaptive LR per mini-epoch) vs oracle/ppo_discrete_oracle.py on the same
-    tapes and uniform draws.  Sampled actions and masks are integer/bool work: bit-exact."""
+def _discrete_oracle_from_golden(g):
     from oracle import ppo_discrete_oracle as DO
-    g = load(name)
-    multi = isinstance(g['K'], (list, tuple))     # agent_multidiscrete.pt: Tuple(Discrete(3), Discrete(4)), ModelA2CMultiDiscrete
-    assert g['param_order'] == DO.discrete_param_names(len(g['units']), g['separate'], len(g['K']) if multi else None)
     cfgk = g['config']
     cfg = {k: cfgk[k] for k in ('gamma', 'tau', 'e_clip', 'clip_value', 'critic_coef', 'entropy_coef', 'truncate_grads', 'grad_norm',
                                 'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value', 'normalize_advantage',
@@ -188,6 +180,20 @@ def test_discrete_train_epochs_match_reference_agent(name):
     ag = DO.DiscreteOracleAgent(env, params, g['D'], g['K'], g['units'], g['N'], g['H'], g['mb'], cfg, separate=g['separate'],
                                 use_action_masks=g['use_action_masks'])
     ag.obs = ag.env_reset()
+    return ag
+
+
+# ------------------------------------------------------------------------------------------ discrete PPO (SURVEY 8a row a15)
+@pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt', 'agent_multidiscrete.pt'])
+def test_discrete_train_epochs_match_reference_agent(name):
+    """Two train_epoch()s of the reference DiscreteA2CAgent (configs/ppo_cartpole.yaml shape; second fixture: shared trunk,
+    action masks, next_step autoreset, normalisers, adaptive LR per mini-epoch) vs oracle/ppo_discrete_oracle.py on the same
+    tapes and uniform draws.  Sampled actions and masks are integer/bool work: bit-exact."""
+    from oracle import ppo_discrete_oracle as DO
+    g = load(name)
+    multi = isinstance(g['K'], (list, tuple))     # agent_multidiscrete.pt: Tuple(Discrete(3), Discrete(4)), ModelA2CMultiDiscrete
+    assert g['param_order'] == DO.discrete_param_names(len(g['units']), g['separate'], len(g['K']) if multi else None)
+    ag = _discrete_oracle_from_golden(g)
     for ep, ref in enumerate(g['epochs_out']):
         out = ag.train_epoch(g['u'][ep])          # [H + 1, N], or [H + 1, n_heads, N] for a multi-discrete space
         ds = ref['dataset']
