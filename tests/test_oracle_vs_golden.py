@@ -215,7 +215,7 @@ def test_discrete_train_epochs_match_reference_agent(name):
         assert ag.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
         for k in g['param_order']:
             torch.testing.assert_close(ag.model.p[k].detach(), ref['state'][k], rtol=1e-4, atol=2e-6, msg=lambda m: k + m)
-        if cfg['normalize_input']:
+        if g['config'].get('normalize_input'):
             st = ref['state']
             torch.testing.assert_close(ag.model.running_mean_std.running_mean, st['running_mean_std.running_mean'], rtol=1e-9, atol=1e-9)
             assert int(ag.model.running_mean_std.count) == int(st['running_mean_std.count'])
