@@ -288,11 +288,14 @@ class A2CAgent:
         self.is_rnn = self.model.is_rnn()
         # wide observations (64 < obs <= 256: layer 1 in kernels of its own) compile and are unit-testable but have not run on hardware
         allow_wide = bool(config.get('b200_unvalidated', False))
+        # the tcgen05 kernels hard-wire ELU (the activation of every [256,128,64] config the path was built for); anything else is fp32
+        tc_ok = self.model.activation == 'elu' and ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
         if self.mixed_precision is None:
-            self.mixed_precision = (not self.is_rnn) and ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
+            self.mixed_precision = (not self.is_rnn) and tc_ok
             if not self.mixed_precision and self.global_rank == 0:
                 print(f'b200: mixed_precision not set -> fp32 kernels for this geometry (obs={self.model.D}, units={self.model.units}, '
-                      f'actions={self.actions_num}{", rnn" if self.is_rnn else ""}); the bf16 tcgen05 kernels cover obs<=64, MLP [256,128,64], actions<=15')
+                      f'actions={self.actions_num}, activation={self.model.activation}{", rnn" if self.is_rnn else ""}); the bf16 tcgen05 kernels cover '
+                      f'obs<=64, MLP [256,128,64] with elu, actions<=15')
         if self.is_rnn:
             if self.horizon_length % self.seq_length != 0:
                 raise ValueError(f"Horizon length ({self.horizon_length}) must be divisible by sequence length ({self.seq_length})")
@@ -307,10 +310,11 @@ class A2CAgent:
                 raise NotImplementedError('rnn before_mlp: False (MLP -> LSTM -> heads) composes validated kernels and its host logic reproduces '
                                           'the reference on CPU, but it has not been run on hardware yet: set b200_unvalidated: True')
         self.use_tc = bool(self.mixed_precision)
-        if self.use_tc and not ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide):
+        if self.use_tc and not tc_ok:
             raise NotImplementedError(
-                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=64, MLP [256,128,64], actions<=15 in this build; got '
-                f'obs={self.model.D}, units={self.model.units}, actions={self.actions_num}.  Set mixed_precision: False for the fp32 path.'
+                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=64, MLP [256,128,64] with elu, actions<=15 in this build; got '
+                f'obs={self.model.D}, units={self.model.units}, activation={self.model.activation}, actions={self.actions_num}.  '
+                f'Set mixed_precision: False for the fp32 path.'
                 + ('  (64 < obs <= 256 has tcgen05 kernels that have not been run on hardware yet: b200_unvalidated: True enables them.)'
                    if ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2 else ''))
         self.tc_wide = self.use_tc and ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2

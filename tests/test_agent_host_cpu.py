@@ -444,3 +444,31 @@ def test_poison_flow_of_the_reference_masking_test_runs_through_the_public_api(m
         results.append({k: v.clone() for k, v in agent.model.state_dict().items()})
     for k in results[0]:
         assert torch.equal(results[0][k], results[1][k]), k
+
+
+def test_tcgen05_path_is_refused_for_activations_its_kernels_do_not_implement(monkeypatch, tmp_path):
+    """the tcgen05 kernels hard-wire ELU: a relu network of the supported geometry must never be routed there -- explicit
+    mixed_precision: True raises, an absent key resolves to the fp32 kernels"""
+    import _torch_ops
+    from rl_games_b200.runner import Runner
+    g = dict(torch.load(os.path.join(GOLDEN, 'agent_tcshape.pt'), weights_only=False))
+
+    def build(mp):
+        _torch_ops.install_tc(monkeypatch)
+        monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+        env = _Env(g)
+        config = {k: v for k, v in g['config'].items() if k not in ('device', 'torch_compile')}
+        config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
+                       'mixed_precision': mp, 'b200_cuda_graph': False, 'train_dir': str(tmp_path)})
+        network = {'name': 'actor_critic', 'separate': False,
+                   'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                            'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+                   'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}
+        r = Runner()
+        r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
+                           'config': config}})
+        return r.algo_factory.create(r.algo_name, base_name='x', params=r.params)
+    with pytest.raises(NotImplementedError, match='with elu'):
+        build(True)
+    a = build(None)
+    assert a.use_tc is False and a.model.activation == 'relu'
