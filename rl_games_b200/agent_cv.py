@@ -24,7 +24,7 @@ import torch.distributed as dist
 from . import ops
 from .agent import A2CAgent
 from .common import IdentityScheduler, LinearScheduler
-from .model import _RunningStats
+from .model import _RunningStats, check_network_params
 
 
 class CentralValueNet:
@@ -34,6 +34,7 @@ class CentralValueNet:
         net = cv_config['network']
         self.multi_gpu, self.world_size = bool(multi_gpu) and world_size > 1, int(world_size)
         self.writter = None             # the agent's summary writer (central_value.py:79; the reference's spelling)
+        check_network_params(net)
         mlp = net['mlp']
         self.units = list(mlp['units'])
         self.activation = mlp.get('activation', 'elu')

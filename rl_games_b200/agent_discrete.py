@@ -24,6 +24,7 @@ import torch.distributed as dist
 
 from . import ops
 from .agent import _MeterView
+from .model import check_network_params
 from .dist_utils import PackedStatsSync
 from .common import (AdaptiveScheduler, DefaultAlgoObserver, DefaultRewardsShaper, IdentityScheduler, LinearScheduler, create_vec_env,
                      make_summary_writer)
@@ -37,6 +38,7 @@ class DiscreteModel:
 
     def __init__(self, network_params, obs_dim, n_actions, device, normalize_input, normalize_value, head_sizes=None):
         self.head_sizes = list(head_sizes) if head_sizes else None          # multi-discrete: one logits head per Tuple component
+        check_network_params(network_params)
         mlp = network_params['mlp']
         self.units = list(mlp['units'])
         if not self.units:

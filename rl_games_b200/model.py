@@ -78,6 +78,22 @@ class _RunningStats:
         return ops.normalize(x, self.running_mean, self.running_var, denorm=denorm)
 
 
+def check_network_params(network_params):
+    """Options of A2CBuilder.Network.load (network_builder.py:545-589) that change the maths and have no kernel here must fail loudly,
+    never be ignored: a config that sets them would otherwise train a different network without a word."""
+    name = network_params.get('name', 'actor_critic')
+    if name != 'actor_critic':
+        raise NotImplementedError(f"network '{name}': only 'actor_critic' (A2CBuilder) is on the B200 hot path")
+    mlp = network_params['mlp']
+    if mlp.get('d2rl', False):
+        raise NotImplementedError('mlp.d2rl')
+    if network_params.get('normalization', None) not in (None, 'None'):
+        raise NotImplementedError(f"normalization: {network_params['normalization']} (layer_norm / batch_norm inside the MLP)")
+    if network_params.get('joint_obs_actions', None) is not None:
+        raise NotImplementedError('joint_obs_actions')
+    # mlp.regularizer is read by no code path of the reference's torch builder either: ignored there, ignored here
+
+
 class _NetworkView:
     """What Runner._override_sigma (torch_runner.py:52-60) touches: ``a2c_network.sigma`` / ``fixed_sigma``."""
 
@@ -101,6 +117,7 @@ class B200Model:
                  seed=None):
         if value_size != 1:
             raise NotImplementedError('value_size > 1 is not on the B200 hot path yet')
+        check_network_params(network_params)
         mlp = network_params['mlp']
         self.units = list(mlp['units'])
         if len(self.units) == 0:

@@ -237,3 +237,18 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d['value'] > 0 and d['steps'] == 1 and d['warmup'] == 1 and 'workload' in d['config']
     assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+@pytest.mark.parametrize('patch,what', [({'normalization': 'layer_norm'}, 'normalization'), ({'name': 'resnet_actor_critic'}, 'resnet_actor_critic'),
+                                        ({'mlp': {'units': [16, 8], 'activation': 'elu', 'initializer': {'name': 'default'}, 'd2rl': True}}, 'd2rl'),
+                                        ({'separate': True}, 'separate'), ({'joint_obs_actions': {}}, 'joint_obs_actions')])
+def test_network_options_without_a_kernel_fail_loudly(patch, what):
+    """a config option that changes the network's maths (network_builder.py:545-589) is either implemented or refused -- never ignored"""
+    from rl_games_b200.model import B200Model
+    net = {'name': 'actor_critic', 'separate': False,
+           'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                    'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
+           'mlp': {'units': [16, 8], 'activation': 'elu', 'initializer': {'name': 'default'}, 'regularizer': {'name': 'l2_regularizer'}}}
+    net.update(patch)
+    with pytest.raises(NotImplementedError, match=what):
+        B200Model(net, 6, 3, 'cpu', True, True)
