@@ -104,7 +104,14 @@ class _Dataset:
 class A2CAgent:
     def __init__(self, base_name, params):
         self.config = config = params['config']
-        self.experiment_name = config.get('full_experiment_name') or (config['name'] + datetime.now().strftime("_%d-%H-%M-%S"))
+        # a2c_common.py:172-188: PBT runs carry the policy's index in the experiment name
+        pbt_str = f'_pbt_{config["pbt_idx"]:02d}' if config.get('population_based_training', False) else ''
+        self.experiment_name = config.get('full_experiment_name') or (config['name'] + pbt_str + datetime.now().strftime("_%d-%H-%M-%S"))
+        # options of A2CBase that change what a run does and are not built here: refuse, never ignore
+        if config.get('epochs_between_resets', 0) > 0:
+            raise NotImplementedError('epochs_between_resets (forced env resets, a2c_common.py:553-556)')
+        if config.get('self_play_config') is not None or config.get('self_play', False):
+            raise NotImplementedError('self-play (SelfPlayManager) is outside the B200 hot path')
         config.setdefault('features', {})
         self.algo_observer = config['features'].get('observer') or DefaultAlgoObserver()
         self.algo_observer.before_init(base_name, config, self.experiment_name)
