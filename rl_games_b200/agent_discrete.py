@@ -202,6 +202,12 @@ class DiscreteA2CAgent:
             raise NotImplementedError('multi-agent envs / value_size > 1')
         if config.get('central_value_config') is not None:
             raise NotImplementedError('central_value_config')
+        # options of the reference agent that change what a run does and are not built for the discrete path: refuse, never ignore
+        for key, bad in (('normalize_rms_advantage', bool(config.get('normalize_rms_advantage', False))),
+                         ('epochs_between_resets', config.get('epochs_between_resets', 0) > 0),
+                         ('self_play', config.get('self_play_config') is not None or bool(config.get('self_play', False)))):
+            if bad:
+                raise NotImplementedError(f'{key} is not built for the discrete B200 agent')
         self.has_central_value, self.central_value_net = False, None
         self.num_agents, self.value_size = 1, 1
         self.observation_space = self.env_info['observation_space']
