@@ -364,6 +364,19 @@ def test_bf16_tcgen05_wide_agent_tracks_fp32_agent(D):
     _bf16_vs_fp32_agents(D, {'b200_unvalidated': True})
 
 
+@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
+                    reason='flag combinations of the tcgen05 kernels no default test sets: set B200RL_UNVALIDATED=1 (promote once green)')
+@pytest.mark.parametrize('extra', [{'ppo': False}, {'normalize_input': False, 'normalize_value': False, 'normalize_advantage': False},
+                                   {'clip_actions': False}, {'clip_value': False, 'use_smooth_clamp': False},
+                                   {'bounds_loss_coef': 0.001, 'bound_loss_type': 'bound'}, {'bounds_loss_coef': None},
+                                   {'truncate_grads': False, 'weight_decay': 0.01, 'entropy_coef': 0.01}],
+                         ids=lambda e: ','.join(f'{k}={v}' for k, v in e.items()))
+def test_bf16_tcgen05_agent_tracks_fp32_agent_flag_matrix(extra):
+    """every loss / shaping / optimiser flag the fused tcgen05 kernels branch on, against the fp32 kernels (which the reference golden
+    runs pin): same tolerance class as the default comparison"""
+    _bf16_vs_fp32_agents(60, dict(extra))
+
+
 def _bf16_vs_fp32_agents(D, extra):
     N, H, A, units, mb = 512, 8, 8, [256, 128, 64], 2048
     obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=21)

@@ -12,7 +12,7 @@ timeout 240 python bench.py --steps 10 --warmup 3 --skip-cpu --skip-e2e 2>/dev/n
 echo "== gated: validated kernels in new compositions / flag combinations (LSTM after the MLP, LSTM + autoreset masks, more config keys) =="
 env $G timeout 300 python -m pytest tests/test_agent_gpu.py::test_lstm_after_mlp_agent_matches_reference_golden \
     tests/test_agent_gpu.py::test_lstm_on_next_step_autoreset_env_matches_reference_golden \
-    tests/test_agent_gpu.py::test_agent_matches_reference_golden_more_config_keys tests/test_agent_gpu.py::test_masked_rows_contribute_zero_gradient -q 2>&1 | tail -30 | tee gpurun_out/r02_gated_compositions.log
+    tests/test_agent_gpu.py::test_agent_matches_reference_golden_more_config_keys tests/test_agent_gpu.py::test_masked_rows_contribute_zero_gradient tests/test_agent_gpu.py::test_bf16_tcgen05_agent_tracks_fp32_agent_flag_matrix -q 2>&1 | tail -30 | tee gpurun_out/r02_gated_compositions.log
 echo "== gated: small new kernels (scheduler modes, lr_schedule_apply / resume, discrete PPO, central value) =="
 env $G timeout 300 python -m pytest tests/test_kernels_gpu.py::test_per_mini_epoch_scheduler_modes tests/test_kernels_gpu.py::test_rnn_train_dones_vs_reference_expression tests/test_kernels_gpu.py::test_lr_schedule_apply_vs_oracle_scheduler \
     tests/test_agent_gpu.py::test_standard_schedule_agent_matches_reference_golden \
