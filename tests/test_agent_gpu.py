@@ -409,7 +409,8 @@ def _bf16_vs_fp32_agents(D, extra):
             cos = float(du_f @ du_t / (du_f.norm() * du_t.norm() + 1e-20))
             assert cos > 0.8, (k, cos)
     assert 0.4 < t.last_lr / f.last_lr < 2.5
-    assert int(t.model.running_mean_std.count) == int(f.model.running_mean_std.count)
+    if t.normalize_input:
+        assert int(t.model.running_mean_std.count) == int(f.model.running_mean_std.count)
 
 
 @pytest.mark.parametrize('opt', [{'b200_pdl': True}, {'b200_pipelined_wgrad': True}, {'b200_pdl': True, 'b200_cuda_graph': True}])
