@@ -21,7 +21,7 @@ struct OptCfgDev {
 //   adaptive_lr == 2 / 3: schedule_type 'standard' (a2c_common.py:1565-1571) -- one scheduler step per MINI-EPOCH on the mean of its
 //     minibatches' KLs (torch_ext.mean_list): 2 = add this KL to the running sum / count in state_d[4] / state_d[5];
 //     3 = last minibatch of the mini-epoch: add, step the scheduler on the mean, reset the accumulators.
-__device__ __forceinline__ double lr_schedule_step(double lr, double kl, const OptCfgDev& c, double* state_d) {
+__host__ __device__ __forceinline__ double lr_schedule_step(double lr, double kl, const OptCfgDev& c, double* state_d) {
     if (c.adaptive_lr >= 2) {
         const double s = state_d[4] + kl, cnt = state_d[5] + 1.0;
         const bool apply = c.adaptive_lr == 3;
@@ -719,4 +719,10 @@ B200RL_EXPORT int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, 
                                                                  stats_out, counter, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host));
     if (le != cudaSuccess) return (int)le;
     return B200RL_OK;
+}
+
+// host test entry point: the scheduler step of the optimiser kernels (lr_schedule_step, __host__ __device__) on HOST memory;
+// cfg->adaptive_lr selects the mode (1 per minibatch, 2 accumulate, 3 accumulate + step on the mean + reset).  Not in include/b200rl.h.
+B200RL_EXPORT double b200rl_hosttest_lr_schedule_step(double lr, double kl, const b200rl_opt_cfg* cfg_host, double* state_d) {
+    return lr_schedule_step(lr, kl, make_opt_cfg(cfg_host), state_d);
 }

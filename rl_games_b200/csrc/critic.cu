@@ -24,24 +24,30 @@ __host__ __device__ inline float value_loss_row(float val, float old_v, float re
     return e1 * e1;
 }
 
+struct ValueLossArgs {
+    const float* values; int value_ld; const float* old_values_n; const float* returns_n; const float* mask; int rows_per_chunk;
+    int64_t chunk_stride; int M; float e_clip; int clip_value; const float* inv_count_dev; float* d_value; int dv_ld;
+};
+
+// everything one kernel thread does except the block reduction (__host__ __device__: the arena addressing runs on the CPU too,
+// b200rl_hosttest_value_loss_arena).  acc: sum w*c_loss, sum mask, sum w
+__host__ __device__ inline void value_loss_thread(const ValueLossArgs& a, int m, double (&acc)[3]) {
+    const int c = m / a.rows_per_chunk;
+    const int64_t ar = (int64_t)c * a.chunk_stride + (m - c * a.rows_per_chunk);
+    const float mk = a.mask ? a.mask[ar] : 1.0f;
+    const float w = mk * (a.inv_count_dev ? a.inv_count_dev[0] : (1.0f / (float)a.M));
+    float dc;
+    const float l = value_loss_row(a.values[(int64_t)m * a.value_ld], a.old_values_n[ar], a.returns_n[ar], a.e_clip, a.clip_value, dc);
+    a.d_value[(int64_t)m * a.dv_ld] = w * dc;
+    acc[0] = (double)w * l; acc[1] = mk; acc[2] = w;
+}
+
 // partial row (8 doubles per block): sum w*c_loss, sum mask, sum w, 0...
-__global__ void __launch_bounds__(256) value_loss_kernel(const float* __restrict__ values, int value_ld, const float* __restrict__ old_values_n,
-                                                        const float* __restrict__ returns_n, const float* __restrict__ mask, int rows_per_chunk,
-                                                        int64_t chunk_stride, int M, float e_clip, int clip_value,
-                                                        const float* __restrict__ inv_count_dev, float* __restrict__ d_value, int dv_ld,
-                                                        double* __restrict__ partials) {
+__global__ void __launch_bounds__(256) value_loss_kernel(const ValueLossArgs a, double* __restrict__ partials) {
     __shared__ double sm[32 * 3];
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[3] = {0, 0, 0};
-    if (m < M) {
-        const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
-        const float mk = mask ? mask[ar] : 1.0f;
-        const float w = mk * (inv_count_dev ? inv_count_dev[0] : (1.0f / (float)M));
-        float dc;
-        const float l = value_loss_row(values[(int64_t)m * value_ld], old_values_n[ar], returns_n[ar], e_clip, clip_value, dc);
-        d_value[(int64_t)m * dv_ld] = w * dc;
-        acc[0] = (double)w * l; acc[1] = mk; acc[2] = w;
-    }
+    if (m < a.M) value_loss_thread(a, m, acc);
     block_sum_d<3>(acc, sm);
     if (threadIdx.x == 0) {
         double* p = partials + (int64_t)blockIdx.x * 8;
@@ -62,8 +68,9 @@ B200RL_EXPORT int b200rl_value_loss_f32(const float* values, int value_ld, const
     const int blocks = (M + 255) / 256;
     if (n_blocks_out_host) *n_blocks_out_host = blocks;
     if (blocks > max_partials) return B200RL_EINVAL;
-    value_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(values, value_ld, old_values_n, returns_n, mask, rows_per_chunk, chunk_stride, M,
-                                                            e_clip, clip_value, inv_count_dev, d_value, dv_ld, partials);
+    const ValueLossArgs a{values, value_ld, old_values_n, returns_n, mask, rows_per_chunk, chunk_stride, M, e_clip, clip_value, inv_count_dev,
+                          d_value, dv_ld};
+    value_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, partials);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }
@@ -79,5 +86,21 @@ B200RL_EXPORT int b200rl_hosttest_value_loss_rows(const float* values, const flo
         s += (double)w[m] * l;
     }
     *loss_sum = s;
+    return B200RL_OK;
+}
+
+// the kernel's per-thread body over HOST arrays laid out like the device arena (arguments of the C-ABI entry point, no stream)
+B200RL_EXPORT int b200rl_hosttest_value_loss_arena(const float* values, int value_ld, const float* old_values_n, const float* returns_n,
+                                                  const float* mask, int rows_per_chunk, int64_t chunk_stride, int M, float e_clip, int clip_value,
+                                                  const float* inv_count, float* d_value, int dv_ld, double* partial8) {
+    const ValueLossArgs a{values, value_ld, old_values_n, returns_n, mask, rows_per_chunk, chunk_stride, M, e_clip, clip_value, inv_count, d_value,
+                          dv_ld};
+    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < M; ++m) {
+        double acc[3] = {0, 0, 0};
+        value_loss_thread(a, m, acc);
+        for (int i = 0; i < 3; ++i) tot[i] += acc[i];
+    }
+    for (int i = 0; i < 8; ++i) partial8[i] = tot[i];
     return B200RL_OK;
 }

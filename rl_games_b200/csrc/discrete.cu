@@ -151,68 +151,94 @@ __host__ __device__ inline CatRowOut cat_loss_row(const float* z, const uint8_t*
     return o;
 }
 
-// ---- rollout: sample (inverse CDF, one uniform per row and head), neglogp, de-normalised value --------------------------------
+// ---- per-THREAD bodies: everything a kernel thread does except the block reduction, __host__ __device__ so that the arena
+//      addressing (row strides, chunk mapping, mask / action layouts) is exercised on the CPU too (host test entry points
+//      b200rl_hosttest_categorical_*_arena, tests/test_discrete_rows_cpu.py) ------------------------------------------------------
+__host__ __device__ inline int64_t chunk_row_hd(int m, int rows_per_chunk, int64_t chunk_stride) {
+    const int c = m / rows_per_chunk;
+    return (int64_t)c * chunk_stride + (m - c * rows_per_chunk);
+}
+
+struct CatSampleArgs {
+    const float* logits; int ld; int K; CatHeads hd; const float* value_raw; int value_ld; const uint8_t* action_masks;
+    const float* u_tape; uint64_t seed; const uint64_t* rng_epoch_dev; uint32_t step_index; const double* vms_mean; const double* vms_var;
+    int normalize_value; int64_t* actions; float* neglogp; float* values; const uint8_t* dones_cur; uint8_t* dones_out;
+    const float* prev_dones; float* valid_out; int N; int values_only;
+};
+
+// rollout: sample (inverse CDF, one uniform per row and head), neglogp, de-normalised value.
 // actions: int64 [N, n_heads]; u_tape (optional): float [n_heads, N]
-__global__ void __launch_bounds__(256) categorical_sample_kernel(
-    const float* __restrict__ logits, int ld, int K, CatHeads hd, const float* __restrict__ value_raw, int value_ld,
-    const uint8_t* __restrict__ action_masks, const float* __restrict__ u_tape, uint64_t seed,
-    const uint64_t* __restrict__ rng_epoch_dev, uint32_t step_index, const double* __restrict__ vms_mean,
-    const double* __restrict__ vms_var, int normalize_value, int64_t* __restrict__ actions, float* __restrict__ neglogp,
-    float* __restrict__ values, const uint8_t* __restrict__ dones_cur, uint8_t* __restrict__ dones_out,
-    const float* __restrict__ prev_dones, float* __restrict__ valid_out, int N, int values_only) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= N) return;
+__host__ __device__ inline void cat_sample_thread(const CatSampleArgs& a, int e) {
     // value: denorm_value (running_mean_std.py:104-106): sqrt(var + eps) * clamp(v, -5, 5) + mean
-    float val = value_raw[(int64_t)e * value_ld];
-    if (normalize_value) {
-        const float m = (float)vms_mean[0], s = __fsqrt_rn(__fadd_rn((float)vms_var[0], 1e-5f));
+    float val = a.value_raw[(int64_t)e * a.value_ld];
+    if (a.normalize_value) {
+        const float m = (float)a.vms_mean[0];
+#ifdef __CUDA_ARCH__
+        const float s = __fsqrt_rn(__fadd_rn((float)a.vms_var[0], 1e-5f));
         val = __fadd_rn(__fmul_rn(s, fminf(fmaxf(val, -5.0f), 5.0f)), m);
+#else
+        const float s = sqrtf((float)a.vms_var[0] + 1e-5f);
+        val = s * fminf(fmaxf(val, -5.0f), 5.0f) + m;
+#endif
     }
-    values[e] = val;
-    if (values_only) return;
+    a.values[e] = val;
+    if (a.values_only) return;
     float ubuf[CAT_MAXH];
     const float* u = ubuf;
     int64_t ustride = 1;
-    if (u_tape) {
-        u = u_tape + e;
-        ustride = N;
+    if (a.u_tape) {
+        u = a.u_tape + e;
+        ustride = a.N;
     } else {
-        const uint64_t ep = rng_epoch_dev ? *rng_epoch_dev : 0ull;
-        for (int j = 0; j < hd.n; ++j) {
-            const Philox4 r = philox4x32_10((uint64_t)e, (ep << 20) | ((uint64_t)step_index << 4) | (uint64_t)(8 + j), seed);
+#ifdef __CUDA_ARCH__
+        const uint64_t ep = a.rng_epoch_dev ? *a.rng_epoch_dev : 0ull;
+        for (int j = 0; j < a.hd.n; ++j) {
+            const Philox4 r = philox4x32_10((uint64_t)e, (ep << 20) | ((uint64_t)a.step_index << 4) | (uint64_t)(8 + j), a.seed);
             ubuf[j] = (float)(r.x >> 8) * (1.0f / 16777216.0f);           // [0, 1)
         }
+#else
+        for (int j = 0; j < a.hd.n; ++j) ubuf[j] = 0.5f;                  // the host test always supplies the uniform tape
+#endif
     }
-    neglogp[e] = cat_sample_row(logits + (int64_t)e * ld, action_masks ? action_masks + (int64_t)e * K : nullptr, hd, u, ustride,
-                                actions + (int64_t)e * hd.n);
-    if (dones_out) dones_out[e] = dones_cur[e];
-    if (valid_out) valid_out[e] = prev_dones ? (1.0f - prev_dones[e]) : 1.0f;
+    a.neglogp[e] = cat_sample_row(a.logits + (int64_t)e * a.ld, a.action_masks ? a.action_masks + (int64_t)e * a.K : nullptr, a.hd, u, ustride,
+                                  a.actions + (int64_t)e * a.hd.n);
+    if (a.dones_out) a.dones_out[e] = a.dones_cur[e];
+    if (a.valid_out) a.valid_out[e] = a.prev_dones ? (1.0f - a.prev_dones[e]) : 1.0f;
 }
 
-// ---- training: loss pieces + gradients at the logits / value for one minibatch -------------------------------------------------
-// partial row (8 doubles per block): sum w*a_loss, sum w*c_loss, sum w*entropy, sum w*kl, sum mask, sum mask*clipped, sum w, 0
-__global__ void __launch_bounds__(256) categorical_loss_kernel(
-    const float* __restrict__ logits, int ld, int K, CatHeads hd, const float* __restrict__ values, int value_ld,
-    const int64_t* __restrict__ actions, const uint8_t* __restrict__ action_masks, const float* __restrict__ old_values_n,
-    const float* __restrict__ returns_n, const float* __restrict__ old_neglogp, const float* __restrict__ advs_n,
-    const float* __restrict__ mask, int rows_per_chunk, int64_t chunk_stride, int M, CatLossDev c,
-    const float* __restrict__ inv_count_dev, float* __restrict__ d_logits, int d_ld, float* __restrict__ d_value, int dv_ld,
-    double* __restrict__ partials) {
+__global__ void __launch_bounds__(256) categorical_sample_kernel(const CatSampleArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < a.N) cat_sample_thread(a, e);
+}
+
+// training: loss pieces + gradients at the logits / value for one minibatch
+struct CatLossArgs {
+    const float* logits; int ld; int K; CatHeads hd; const float* values; int value_ld; const int64_t* actions;
+    const uint8_t* action_masks; const float* old_values_n; const float* returns_n; const float* old_neglogp; const float* advs_n;
+    const float* mask; int rows_per_chunk; int64_t chunk_stride; int M; CatLossDev c; const float* inv_count_dev; float* d_logits; int d_ld;
+    float* d_value; int dv_ld;
+};
+
+// acc: sum w*a_loss, sum w*c_loss, sum w*entropy, sum w*kl, sum mask, sum mask*clipped, sum w
+__host__ __device__ inline void cat_loss_thread(const CatLossArgs& a, int m, double (&acc)[7]) {
+    const int64_t ar = chunk_row_hd(m, a.rows_per_chunk, a.chunk_stride);
+    const float mkr = a.mask ? a.mask[ar] : 1.0f;
+    const float inv_cnt = a.inv_count_dev ? a.inv_count_dev[0] : (1.0f / (float)a.M);
+    const float w = mkr * inv_cnt;
+    const CatRowOut o = cat_loss_row(a.logits + (int64_t)m * a.ld, a.action_masks ? a.action_masks + ar * a.K : nullptr, a.hd,
+                                     a.actions + ar * a.hd.n, a.values[(int64_t)m * a.value_ld], a.old_neglogp[ar], a.advs_n[ar],
+                                     a.old_values_n[ar], a.returns_n[ar], w, a.c, a.d_logits + (int64_t)m * a.d_ld);
+    a.d_value[(int64_t)m * a.dv_ld] = o.d_value;
+    acc[0] = (double)w * o.a_loss; acc[1] = (double)w * o.c_loss; acc[2] = (double)w * o.ent; acc[3] = (double)w * o.kl;
+    acc[4] = mkr; acc[5] = mkr * o.clipped; acc[6] = w;
+}
+
+// partial row (8 doubles per block): the seven sums above, 0
+__global__ void __launch_bounds__(256) categorical_loss_kernel(const CatLossArgs a, double* __restrict__ partials) {
     __shared__ double sm[32 * 7];
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (m < M) {
-        const int64_t ar = chunk_row(m, rows_per_chunk, chunk_stride);
-        const float mkr = mask ? mask[ar] : 1.0f;
-        const float inv_cnt = inv_count_dev ? inv_count_dev[0] : (1.0f / (float)M);
-        const float w = mkr * inv_cnt;
-        const CatRowOut o = cat_loss_row(logits + (int64_t)m * ld, action_masks ? action_masks + ar * K : nullptr, hd, actions + ar * hd.n,
-                                         values[(int64_t)m * value_ld], old_neglogp[ar], advs_n[ar], old_values_n[ar], returns_n[ar], w, c,
-                                         d_logits + (int64_t)m * d_ld);
-        d_value[(int64_t)m * dv_ld] = o.d_value;
-        acc[0] = (double)w * o.a_loss; acc[1] = (double)w * o.c_loss; acc[2] = (double)w * o.ent; acc[3] = (double)w * o.kl;
-        acc[4] = mkr; acc[5] = mkr * o.clipped; acc[6] = w;
-    }
+    if (m < a.M) cat_loss_thread(a, m, acc);
     block_sum_d<7>(acc, sm);
     if (threadIdx.x == 0) {
         double* p = partials + (int64_t)blockIdx.x * 8;
@@ -249,9 +275,9 @@ B200RL_EXPORT int b200rl_categorical_sample_f32(const float* logits, int ld, int
     if (!values_only && (!logits || !actions || !neglogp || ld < K || !make_heads(K, n_heads, head_sizes_host, hd))) return B200RL_EINVAL;
     if (normalize_value && (!vms_mean || !vms_var)) return B200RL_EINVAL;
     if (dones_out && !dones_cur) return B200RL_EINVAL;
-    categorical_sample_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(
-        logits, ld, K, hd, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch_dev, step_index, vms_mean, vms_var, normalize_value,
-        actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only);
+    const CatSampleArgs a{logits, ld, K, hd, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch_dev, step_index, vms_mean, vms_var,
+                          normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only};
+    categorical_sample_kernel<<<(N + 255) / 256, 256, 0, as_stream(stream)>>>(a);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }
@@ -274,9 +300,9 @@ B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K
     if (blocks > max_partials) return B200RL_EINVAL;
     CatLossDev c{cfg_host->e_clip, cfg_host->critic_coef, cfg_host->entropy_coef, cfg_host->clip_value, cfg_host->use_smooth_clamp,
                  cfg_host->ppo};
-    categorical_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(logits, ld, K, hd, values, value_ld, actions, action_masks, old_values_n,
-                                                                  returns_n, old_neglogp, advs_n, mask, rows_per_chunk, chunk_stride, M, c,
-                                                                  inv_count_dev, d_logits, d_ld, d_value, dv_ld, partials);
+    const CatLossArgs a{logits, ld, K, hd, values, value_ld, actions, action_masks, old_values_n, returns_n, old_neglogp, advs_n, mask,
+                        rows_per_chunk, chunk_stride, M, c, inv_count_dev, d_logits, d_ld, d_value, dv_ld};
+    categorical_loss_kernel<<<blocks, 256, 0, as_stream(stream)>>>(a, partials);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
 }
@@ -309,5 +335,41 @@ B200RL_EXPORT int b200rl_hosttest_categorical_loss_rows(const float* logits, int
         acc[0] += (double)w[m] * o.a_loss; acc[1] += (double)w[m] * o.c_loss; acc[2] += (double)w[m] * o.ent; acc[3] += (double)w[m] * o.kl;
     }
     for (int i = 0; i < 4; ++i) sums4[i] = acc[i];
+    return B200RL_OK;
+}
+
+// the kernels' per-thread bodies over HOST arrays laid out like the device arena (same arguments as the C-ABI entry points, no stream):
+// arena addressing and strides on the CPU.  One partial row (8 doubles) for the loss.
+B200RL_EXPORT int b200rl_hosttest_categorical_sample_arena(const float* logits, int ld, int K, int n_heads, const int* head_sizes,
+                                                          const float* value_raw, int value_ld, const uint8_t* action_masks, const float* u_tape,
+                                                          const double* vms_mean, const double* vms_var, int normalize_value, int64_t* actions,
+                                                          float* neglogp, float* values, const uint8_t* dones_cur, uint8_t* dones_out,
+                                                          const float* prev_dones, float* valid_out, int N, int values_only) {
+    CatHeads hd{};
+    if (!values_only && !make_heads(K, n_heads, head_sizes, hd)) return B200RL_EINVAL;
+    const CatSampleArgs a{logits, ld, K, hd, value_raw, value_ld, action_masks, u_tape, 0ull, nullptr, 0u, vms_mean, vms_var,
+                          normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only};
+    for (int e = 0; e < N; ++e) cat_sample_thread(a, e);
+    return B200RL_OK;
+}
+
+B200RL_EXPORT int b200rl_hosttest_categorical_loss_arena(const float* logits, int ld, int K, int n_heads, const int* head_sizes,
+                                                        const float* values, int value_ld, const int64_t* actions, const uint8_t* action_masks,
+                                                        const float* old_values_n, const float* returns_n, const float* old_neglogp,
+                                                        const float* advs_n, const float* mask, int rows_per_chunk, int64_t chunk_stride, int M,
+                                                        const b200rl_cat_loss_cfg* cfg, const float* inv_count, float* d_logits, int d_ld,
+                                                        float* d_value, int dv_ld, double* partial8) {
+    CatHeads hd{};
+    if (!make_heads(K, n_heads, head_sizes, hd)) return B200RL_EINVAL;
+    const CatLossDev c{cfg->e_clip, cfg->critic_coef, cfg->entropy_coef, cfg->clip_value, cfg->use_smooth_clamp, cfg->ppo};
+    const CatLossArgs a{logits, ld, K, hd, values, value_ld, actions, action_masks, old_values_n, returns_n, old_neglogp, advs_n, mask,
+                        rows_per_chunk, chunk_stride, M, c, inv_count, d_logits, d_ld, d_value, dv_ld};
+    double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < M; ++m) {
+        double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+        cat_loss_thread(a, m, acc);
+        for (int i = 0; i < 7; ++i) tot[i] += acc[i];
+    }
+    for (int i = 0; i < 8; ++i) partial8[i] = tot[i];
     return B200RL_OK;
 }

@@ -381,7 +381,9 @@ def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, sta
     n = params.numel() if n is None else n
     gnorm = float((grads[:n] * float(cfg.grad_scale)).norm())
     adam_step(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, stats_out, counter, n=n)
-    if cfg.adaptive_lr and kl_dev is not None:
+    if cfg.adaptive_lr and kl_dev is not None and _USE_HOST_SCHED['on']:
+        state_d[0] = lr_schedule_step_host(lr, float(kl_dev[0]) * float(cfg.grad_scale), cfg, state_d)
+    elif cfg.adaptive_lr and kl_dev is not None:
         kl = float(kl_dev[0]) * float(cfg.grad_scale)
         apply = True
         if cfg.adaptive_lr >= 2:        # schedule_type 'standard': accumulate (2) / accumulate + step on the mean + reset (3)
@@ -404,18 +406,22 @@ def adam_step_full(params, grads, exp_avg, exp_avg_sq, state_d, kl_dev, cfg, sta
 
 
 def rnn_train_dones(dones_u8, valid, out_u8):
-    out_u8.copy_(dones_u8)
-    out_u8[1:] = torch.maximum(dones_u8[1:], (valid[:-1] == 0).to(torch.uint8))
+    """the kernel's own element function compiled for the host (csrc/rnn.cu rnn_train_done), checked against the reference's expression"""
+    H, N = dones_u8.shape
+    assert dones_u8.is_contiguous() and valid.is_contiguous() and out_u8.is_contiguous()
+    rc = _host_lib().b200rl_hosttest_rnn_train_dones(_p(dones_u8), _p(valid), _p(out_u8), int(H), int(N))
+    assert rc == 0
+    ref = dones_u8.clone()
+    ref[1:] = torch.maximum(dones_u8[1:], (valid[:-1] == 0).to(torch.uint8))
+    assert torch.equal(out_u8, ref)
 
 
 def lr_schedule_apply(state_d, kl_dev, kl_scale, base_lr, cfg):
-    kl = float(kl_dev[0]) * kl_scale
-    lr = base_lr
-    if kl > 2.0 * cfg.kl_threshold:
-        lr = max(base_lr / cfg.lr_multiplier, cfg.min_lr)
-    if kl < 0.5 * cfg.kl_threshold:
-        lr = min(base_lr * cfg.lr_multiplier, cfg.max_lr)
-    state_d[0] = lr
+    """b200rl_lr_schedule_apply: the kernel forces mode 1 and calls the optimiser kernels' scheduler step -- here that same function, on the host"""
+    import copy
+    c = copy.copy(cfg)
+    c.adaptive_lr = 1
+    state_d[0] = lr_schedule_step_host(base_lr, float(kl_dev[0]) * kl_scale, c, state_d)
 
 
 def adv_ema_normalize(advs, partials, n_partials, ema_state, ema_step, decay, training=True):
@@ -642,3 +648,78 @@ def install_tc(monkeypatch, kind=1):
     monkeypatch.setattr(ops, 'tc_pack_bytes', lambda D, units, A: 1024)
     monkeypatch.setattr(ops, 'tc_xtile_bytes', lambda D, units, A: 64 * 256)
     monkeypatch.setattr(ops, 'tc_pack_table', lambda D, units, A, offs: object())
+
+
+# ---------------------------------------------------------------------------------------------- kernels' own thread bodies on the host
+# The per-thread bodies of the discrete / critic kernels are __host__ __device__; the library exports entry points that run them over
+# HOST arrays laid out like the device arena (csrc/discrete.cu, csrc/critic.cu: b200rl_hosttest_*_arena).  Swapping them in for the torch
+# stand-ins runs the agents' golden tests on the kernels' REAL indexing and arithmetic -- everything except launch geometry and the
+# block reduction.
+def _host_lib():
+    import ctypes
+    from rl_games_b200._lib import LIB_PATH
+    return ctypes.CDLL(LIB_PATH)
+
+
+def _p(t):
+    import ctypes
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def categorical_sample_hostkernel(logits, ld, K, value_raw, value_ld, action_masks, u_tape, seed, rng_epoch, step_index, vms_mean, vms_var,
+                                  normalize_value, actions, neglogp, values, dones_cur, dones_out, prev_dones, valid_out, N, values_only=False,
+                                  head_sizes=None):
+    import ctypes
+    assert values_only or u_tape is not None, 'the host body has no Philox: the tests supply the uniform tape'
+    hs = None if not head_sizes else (ctypes.c_int * len(head_sizes))(*[int(k) for k in head_sizes])
+    rc = _host_lib().b200rl_hosttest_categorical_sample_arena(
+        _p(logits), int(ld), int(K), len(head_sizes) if head_sizes else 0, hs, _p(value_raw), int(value_ld), _p(action_masks), _p(u_tape),
+        _p(vms_mean), _p(vms_var), int(normalize_value), _p(actions), _p(neglogp), _p(values), _p(dones_cur), _p(dones_out), _p(prev_dones),
+        _p(valid_out), int(N), int(values_only))
+    assert rc == 0, rc
+
+
+def categorical_loss_hostkernel(logits, ld, K, values, value_ld, actions, action_masks, old_values_n, returns_n, old_neglogp, advs_n, mask,
+                                rows_per_chunk, chunk_stride, M, cfg, inv_count, d_logits, d_ld, d_value, dv_ld, partials, head_sizes=None):
+    import ctypes
+    hs = None if not head_sizes else (ctypes.c_int * len(head_sizes))(*[int(k) for k in head_sizes])
+    partials.zero_()
+    rc = _host_lib().b200rl_hosttest_categorical_loss_arena(
+        _p(logits), int(ld), int(K), len(head_sizes) if head_sizes else 0, hs, _p(values), int(value_ld), _p(actions), _p(action_masks),
+        _p(old_values_n), _p(returns_n), _p(old_neglogp), _p(advs_n), _p(mask), int(rows_per_chunk), ctypes.c_int64(int(chunk_stride)), int(M),
+        ctypes.c_void_p(ctypes.addressof(cfg)), _p(inv_count), _p(d_logits), int(d_ld), _p(d_value), int(dv_ld), _p(partials))
+    assert rc == 0, rc
+    return 1
+
+
+def value_loss_hostkernel(values, value_ld, old_values_n, returns_n, mask, rows_per_chunk, chunk_stride, M, e_clip, clip_value, inv_count, d_value,
+                          dv_ld, partials):
+    import ctypes
+    partials.zero_()
+    rc = _host_lib().b200rl_hosttest_value_loss_arena(
+        _p(values), int(value_ld), _p(old_values_n), _p(returns_n), _p(mask), int(rows_per_chunk), ctypes.c_int64(int(chunk_stride)), int(M),
+        ctypes.c_float(float(e_clip)), int(clip_value), _p(inv_count), _p(d_value), int(dv_ld), _p(partials))
+    assert rc == 0, rc
+    return 1
+
+
+def lr_schedule_step_host(lr, kl, cfg, state_d):
+    """the optimiser kernels' scheduler step (csrc/adam.cu lr_schedule_step, compiled for the host); state_d: fp64 CPU tensor (>= 6 entries
+    for the per-mini-epoch modes)"""
+    import ctypes
+    fn = _host_lib().b200rl_hosttest_lr_schedule_step
+    fn.restype = ctypes.c_double
+    return float(fn(ctypes.c_double(float(lr)), ctypes.c_double(float(kl)), ctypes.c_void_p(ctypes.addressof(cfg)), _p(state_d)))
+
+
+_USE_HOST_SCHED = {'on': False}
+
+
+def install_host_kernels(monkeypatch):
+    """on top of install*(): ops whose kernels have host-compilable thread bodies run THOSE (compiled for the host) instead of the torch
+    stand-ins -- the categorical sample / loss kernels, the central-value loss kernel, the scheduler step of the optimiser kernels"""
+    from rl_games_b200 import ops
+    monkeypatch.setattr(ops, 'categorical_sample', categorical_sample_hostkernel)
+    monkeypatch.setattr(ops, 'categorical_loss', categorical_loss_hostkernel)
+    monkeypatch.setattr(ops, 'value_loss', value_loss_hostkernel)
+    monkeypatch.setitem(_USE_HOST_SCHED, 'on', True)

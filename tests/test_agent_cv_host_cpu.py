@@ -84,10 +84,16 @@ def _build_cv(monkeypatch, tmp_path, g, over=None):
     return agent
 
 
-def test_central_value_agent_host_logic_matches_reference_golden(monkeypatch, tmp_path):
+@pytest.mark.parametrize('host_kernels', [False, True], ids=['torch-stand-ins', 'kernel-thread-bodies-on-host'])
+def test_central_value_agent_host_logic_matches_reference_golden(host_kernels, monkeypatch, tmp_path):
+    """host_kernels: the critic's loss runs the value-loss kernel's OWN per-thread body (csrc/critic.cu, compiled for the host) over the
+    agent's arena, and the scheduler step is the optimiser kernels' own function"""
     from oracle import ppo_oracle as O
     g = torch.load(os.path.join(GOLDEN, 'agent_cv.pt'), weights_only=False)
     agent = _build_cv(monkeypatch, tmp_path, g)
+    if host_kernels:
+        import _torch_ops
+        _torch_ops.install_host_kernels(monkeypatch)
     cv = agent.central_value_net
     cv_scalars = []
     cv.writter = type('W', (), {'add_scalar': lambda self, tag, v, step=None: cv_scalars.append((tag, float(v), step))})()

@@ -85,6 +85,9 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
         _torch_ops.install_tc(monkeypatch, kind=int(tc))
     else:
         _torch_ops.install_continuous(monkeypatch)
+    # the scheduler step inside the optimiser stand-in is the optimiser kernels' own function compiled for the host (csrc/adam.cu
+    # lr_schedule_step: per-minibatch mode and the per-mini-epoch modes of schedule_type 'standard')
+    monkeypatch.setitem(_torch_ops._USE_HOST_SCHED, 'on', True)
     monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
     monkeypatch.setattr(torch.cuda, 'Event', _Event)
     monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _Stream())

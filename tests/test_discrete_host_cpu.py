@@ -76,11 +76,17 @@ def _build(monkeypatch, tmp_path, g, stand_ins=True, over=None):
     return agent
 
 
+@pytest.mark.parametrize('host_kernels', [False, True], ids=['torch-stand-ins', 'kernel-thread-bodies-on-host'])
 @pytest.mark.parametrize('name', ['agent_discrete.pt', 'agent_discrete_masked.pt', 'agent_multidiscrete.pt'])
-def test_discrete_agent_host_logic_matches_reference_golden(name, monkeypatch, tmp_path):
+def test_discrete_agent_host_logic_matches_reference_golden(name, host_kernels, monkeypatch, tmp_path):
+    """host_kernels: the two categorical ops run the kernels' OWN per-thread bodies (csrc/discrete.cu, __host__ __device__, compiled for the
+    host) over the agent's arena instead of the torch stand-ins -- the kernels' indexing and arithmetic against the reference's golden runs"""
     g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     cfgk = g['config']
     agent = _build(monkeypatch, tmp_path, g)
+    if host_kernels:
+        import _torch_ops
+        _torch_ops.install_host_kernels(monkeypatch)
     fl = lambda t: t.transpose(0, 1).reshape(-1, *t.shape[2:])    # noqa: E731
     for ep, ref in enumerate(g['epochs_out']):
         agent.epoch_num += 1
