@@ -156,34 +156,41 @@ __device__ __forceinline__ void stage_x_tile(uint8_t* sX, const float* __restric
 // Column-group pass of the same staging for wide tiles: col-groups [cg_base, cg_base + NCGP) of a 128-row tile, so that the loads
 // in flight per thread stay bounded (NCGP * 128 / NTHREADS items of 32 B) whatever DPAD is.
 template <class N, int NTHREADS, int NCGP>
-__device__ __forceinline__ void stage_x_cols(uint8_t* sX, const float* __restrict__ obs, int64_t row0, int rows_valid, int D,
-                                             const float* __restrict__ sNorm, bool do_norm, int cg_base) {
+__host__ __device__ __forceinline__ void stage_x_cols(uint8_t* sX, const float* __restrict__ obs, int64_t row0, int rows_valid, int D,
+                                                      const float* __restrict__ sNorm, bool do_norm, int cg_base, int tid) {
+    // __host__ __device__ (tid passed in): the index arithmetic is exercised on the CPU by b200rl_hosttest_stage_x_cols
     constexpr int ITEMS = (128 * NCGP + NTHREADS - 1) / NTHREADS;
     static_assert((128 * NCGP) % NTHREADS == 0, "whole passes only");
     const bool vec = (D & 3) == 0;
     float4 va[ITEMS], vb[ITEMS];
+#ifdef __CUDA_ARCH__
+#define B200RL_LD(p) __ldg(p)
+#else
+#define B200RL_LD(p) (*(p))
+#endif
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        const int i = threadIdx.x + it * NTHREADS;
+        const int i = tid + it * NTHREADS;
         const int cgl = i / 128, r = i - cgl * 128;
         const int c0 = (cg_base + cgl) * 8;
         va[it] = make_float4(0.f, 0.f, 0.f, 0.f); vb[it] = va[it];
         if (r < rows_valid && c0 < D) {
             const float* src = obs + (row0 + r) * D + c0;
             if (vec) {
-                va[it] = __ldg(reinterpret_cast<const float4*>(src));
-                if (c0 + 4 < D) vb[it] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                va[it] = B200RL_LD(reinterpret_cast<const float4*>(src));
+                if (c0 + 4 < D) vb[it] = B200RL_LD(reinterpret_cast<const float4*>(src) + 1);
             } else {
                 float t[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = (c0 + j < D) ? __ldg(src + j) : 0.f;
+                for (int j = 0; j < 8; ++j) t[j] = (c0 + j < D) ? B200RL_LD(src + j) : 0.f;
                 va[it] = make_float4(t[0], t[1], t[2], t[3]); vb[it] = make_float4(t[4], t[5], t[6], t[7]);
             }
         }
     }
+#undef B200RL_LD
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        const int i = threadIdx.x + it * NTHREADS;
+        const int i = tid + it * NTHREADS;
         const int cgl = i / 128, r = i - cgl * 128;
         const int cg = cg_base + cgl, c0 = cg * 8;
         float f[8] = {va[it].x, va[it].y, va[it].z, va[it].w, vb[it].x, vb[it].y, vb[it].z, vb[it].w};
@@ -1355,7 +1362,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
         const int64_t arow0 = chunk_row(m0, p.rows_per_chunk, p.chunk_stride);
 #pragma unroll 1
         for (int cg = 0; cg < N::DPAD / 8; cg += NCGP)
-            stage_x_cols<N, FWD_THREADS, NCGP>(sX, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr, cg);
+            stage_x_cols<N, FWD_THREADS, NCGP>(sX, p.obs, arow0, rows_valid, p.D, sNorm, p.nm != nullptr, cg, tid);
         fence_async_smem();
         if (!weights_ready) { mbar_wait(&bars[0], 0); weights_ready = true; }
         __syncthreads();
@@ -1438,7 +1445,7 @@ __global__ void __launch_bounds__(256, 1) l1_wgrad_tc_kernel(const L1WgradArgs p
 #pragma unroll 1
         for (int cg = 0; cg < N::DPAD / 8; cg += NCGP)
             stage_x_cols<N, 256, NCGP>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm,
-                                       p.nm != nullptr, cg);
+                                       p.nm != nullptr, cg, tid);
         fence_async_smem();
         mbar_wait(&bars[0], phase);
         __syncthreads();
@@ -1758,5 +1765,47 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     if (e != cudaSuccess) return (int)e;
     e = launch_k(mlp_bwd_tc_kernel<N>, dim3(grid), dim3(256), smem, as_stream(stream), ab);
     if (e != cudaSuccess) return (int)e;
+    return B200RL_OK;
+}
+
+// host test entry point (tests/test_tc_rows_cpu.py): the X-tile staging of the wide-observation kernels (stage_x_cols, __host__ __device__)
+// run thread by thread on the CPU -- out_tile receives the 128 x 256 bf16 INTERLEAVE tile (64 KB).  n_threads: 512 (l1_fwd) or 256 (l1_wgrad).
+B200RL_EXPORT int b200rl_hosttest_stage_x_cols(const float* obs, int64_t row0, int rows_valid, int D, const float* norm_mean, const float* norm_std,
+                                               int n_threads, void* out_tile) {
+    using N = NetW;
+    if (!obs || !out_tile || D <= 0 || D > N::DPAD || (n_threads != 512 && n_threads != 256)) return B200RL_EINVAL;
+    static float sNorm[2 * N::DPAD];
+    for (int c = 0; c < N::DPAD; ++c) {          // load_norm_smem
+        sNorm[c] = (norm_mean && c < D) ? norm_mean[c] : 0.f;
+        sNorm[N::DPAD + c] = (norm_std && c < D) ? 1.0f / norm_std[c] : 1.f;
+    }
+    for (int cg = 0; cg < N::DPAD / 8; cg += 16)
+        for (int tid = 0; tid < n_threads; ++tid) {
+            if (n_threads == 512) stage_x_cols<N, 512, 16>((uint8_t*)out_tile, obs, row0, rows_valid, D, sNorm, norm_mean != nullptr, cg, tid);
+            else stage_x_cols<N, 256, 16>((uint8_t*)out_tile, obs, row0, rows_valid, D, sNorm, norm_mean != nullptr, cg, tid);
+        }
+    return B200RL_OK;
+}
+
+// host test entry point (tests/test_tc_rows_cpu.py): the packed-weight layout of the wide net (NetW) produced by the SAME element rule as
+// pack_weights_kernel (chunk (r, cg) of a [Rpad x Cpad] tile at cg * (Rpad / 8) * 128 + tile_off), on the CPU.
+B200RL_EXPORT int b200rl_hosttest_pack_weights_wide(const float* W1, const float* W2, const float* W3, const float* W_head, int D, int A, void* wpack) {
+    using N = NetW;
+    if (!net_is_wide(D, N::U1, N::U2, N::U3, A)) return B200RL_EUNSUPPORTED;
+    const PackSeg seg[4] = {PackSeg{W1, N::U1, D, N::U1, N::DPAD, N::W1_OFF}, PackSeg{W2, N::U2, N::U1, N::U2, N::U1, N::W2_OFF},
+                            PackSeg{W3, N::U3, N::U2, N::U3, N::U2, N::W3_OFF}, PackSeg{W_head, A + 1, N::U3, N::AP, N::U3, N::WH_OFF}};
+    for (const PackSeg& s : seg) {
+        const int ncg = s.Cpad / 8;
+        const uint32_t CS = (uint32_t)(s.Rpad / 8) * 128u;
+        for (int i = 0; i < s.Rpad * ncg; ++i) {
+            const int r = i / ncg, cg = i - r * ncg;
+            float f[8];
+            for (int j = 0; j < 8; ++j) {
+                const int c = cg * 8 + j;
+                f[j] = (r < s.R && c < s.C) ? s.src[(size_t)r * s.C + c] : 0.f;
+            }
+            *reinterpret_cast<uint4*>((uint8_t*)wpack + s.dst_off + tile_off(r, cg, CS, 128u)) = pack8_bf16(f);
+        }
+    }
     return B200RL_OK;
 }

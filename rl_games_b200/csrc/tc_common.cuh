@@ -91,7 +91,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // pack 8 floats -> 8 bf16 (16 bytes)
-__device__ __forceinline__ uint4 pack8_bf16(const float* f) {
+__host__ __device__ __forceinline__ uint4 pack8_bf16(const float* f) {
     __nv_bfloat162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
     __nv_bfloat162 c = __floats2bfloat162_rn(f[4], f[5]), d = __floats2bfloat162_rn(f[6], f[7]);
     uint4 u;
@@ -101,7 +101,7 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* f) {
 }
 
 // byte offset of the 16-byte chunk holding (row r, columns 8*cg .. 8*cg+7) in an INTERLEAVE tile
-__device__ __forceinline__ uint32_t tile_off(int r, int cg, uint32_t CS, uint32_t RS) {
+__host__ __device__ __forceinline__ uint32_t tile_off(int r, int cg, uint32_t CS, uint32_t RS) {
     return (uint32_t)(r & 7) * 16u + (uint32_t)cg * CS + (uint32_t)(r >> 3) * RS;
 }
 
