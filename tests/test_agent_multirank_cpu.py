@@ -53,14 +53,14 @@ def _init_rank(rank, world, port):
     torch.device = _Dev
 
 
-def _worker(rank, world, port, ret):
+def _worker(rank, world, port, ret, name='agent_masked.pt', extra=None):
     _init_rank(rank, world, port)
     import test_agent_host_cpu as H
     from oracle import ppo_oracle as O
     from test_oracle_vs_golden import _oracle_from_golden
-    g = _rank_tapes(torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False), rank)
+    g = _rank_tapes(torch.load(os.path.join(GOLDEN, name), weights_only=False), rank)
     agent = H._build(_Patch(), '/tmp/b200_multirank_%d' % rank, g, H._Env(g),
-                     over={'multi_gpu': True, 'b200_fused_allreduce': False, 'print_stats': False})
+                     over={'multi_gpu': True, 'b200_fused_allreduce': False, 'print_stats': False, **(extra or {})})
     assert agent.multi_gpu and agent.world_size == 2 and agent.global_rank == rank and not agent.fused_allreduce
     ar = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)      # noqa: E731
     orc = _oracle_from_golden(g)
@@ -89,12 +89,15 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_two_rank_agent_matches_oracle_and_ranks_stay_identical():
-    world, port = 2, 29500 + os.getpid() % 400
+@pytest.mark.parametrize('name,extra', [('agent_masked.pt', None),
+                                        ('agent_sched_standard.pt', {'b200_unvalidated': True})],       # one scheduler step per mini-epoch on the
+                         ids=['per-minibatch schedule', 'per-mini-epoch schedule'])                    # rank-mean of the mean KL
+def test_two_rank_agent_matches_oracle_and_ranks_stay_identical(name, extra):
+    world, port = 2, 29500 + (os.getpid() + len(name)) % 400
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
-    g = torch.load(os.path.join(GOLDEN, 'agent_masked.pt'), weights_only=False)
+    mp.spawn(_worker, args=(world, port, ret, name, extra), nprocs=world, join=True)
+    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
     for ep in range(len(g['epochs_out'])):
         (p0, lr0, c0, m0, r0), (p1, lr1, c1, m1, r1) = ret[0][ep], ret[1][ep]
         assert torch.equal(p0, p1) and lr0 == lr1                      # same averaged gradient, same schedule -> byte-identical weights
