@@ -864,7 +864,8 @@ class OracleAgent:
         advantages = returns - values
         if c['normalize_value']:
             # with a central value the agent's value normaliser IS the critic model's (a2c_continuous.py:72-73)
-            vms = self.cv.value_mean_std if self.cv is not None else self.model.value_mean_std
+            cv = getattr(self, 'cv', None)          # (tests build bare agents with __new__ to call this method alone)
+            vms = cv.value_mean_std if cv is not None else self.model.value_mean_std
             if rnn_masks is not None:
                 valid = rnn_masks.bool()
                 vms.train()
@@ -894,7 +895,7 @@ class OracleAgent:
             'rnn_masks': rnn_masks, 'mu': batch['mus'].clone(), 'sigma': batch['sigmas'].clone(),
             'rnn_states': batch.get('rnn_states', None),
         }
-        if self.cv is not None:                     # a2c_common.py:1651-1660
+        if getattr(self, 'cv', None) is not None:   # a2c_common.py:1651-1660
             self.cv.update_dataset({'old_values': values, 'advantages': advantages, 'returns': returns, 'actions': batch['actions'],
                                     'obs': batch['states'], 'dones': batch['dones'], 'rnn_masks': rnn_masks})
 

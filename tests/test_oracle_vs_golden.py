@@ -377,3 +377,18 @@ def test_categorical_head_gradient_formulas_match_autograd():
             dv = w.unsqueeze(1) * 0.5 * critic_coef * dc
         torch.testing.assert_close(dz, logits.grad, rtol=1e-4, atol=1e-8)
         torch.testing.assert_close(dv, value.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_prepare_dataset_works_on_a_bare_agent_like_the_gpu_kernel_test_uses_it():
+    """tests/test_kernels_gpu.py::test_prepare_batch_vs_oracle calls OracleAgent.prepare_dataset on an agent built with __new__ (no env, no
+    central value): keep that entry point usable -- this is the CPU guard for a GPU-only test"""
+    g = torch.Generator().manual_seed(7)
+    B = 64
+    ag = O.OracleAgent.__new__(O.OracleAgent)
+    ag.cfg = dict(O.DEFAULT_CFG)
+    ag.model = O.OracleModel(O.init_params(4, [8], 2), 4, [8], 2)
+    batch = {'returns': torch.randn(B, 1, generator=g), 'values': torch.randn(B, 1, generator=g), 'neglogpacs': torch.zeros(B),
+             'actions': torch.zeros(B, 2), 'obses': torch.zeros(B, 4), 'dones': torch.zeros(B), 'mus': torch.zeros(B, 2), 'sigmas': torch.ones(B, 2),
+             'rnn_masks': (torch.rand(B, generator=g) < 0.8).float()}
+    ag.prepare_dataset(batch)
+    assert torch.isfinite(ag.dataset['advantages']).all() and int(ag.model.value_mean_std.count) > 1
