@@ -78,7 +78,7 @@ for mn in mods:
             values = [v + (list(x) if len(ns) > 1 else [x]) for v in values for x in vals]
             names += ns
         sig = inspect.signature(fn).parameters
-        for vs in values[:3]:
+        for vs in values:
             kw = dict(zip(names, vs))
             if 'ops' in sig: kw['ops'] = ops
             if 'tmp_path' in sig:
