@@ -100,7 +100,7 @@ def _oracle_from_golden(g):
                                 'bound_loss_type', 'use_smooth_clamp', 'truncate_grads', 'grad_norm',
                                 'learning_rate', 'kl_threshold', 'normalize_input', 'normalize_value',
                                 'normalize_advantage', 'value_bootstrap', 'mini_epochs', 'normalize_rms_advantage',
-                                'adv_rms_momentum', 'schedule_type', 'ppo', 'clip_actions', 'max_epochs', 'schedule_entropy',
+                                'adv_rms_momentum', 'schedule_type', 'ppo', 'clip_actions', 'max_epochs', 'max_frames', 'schedule_entropy',
                                 'games_to_track') if k in cfgk}
     rs = g.get('reward_shaper') or {}
     cfg.update(reward_scale=rs.get('scale_value', 1.0), reward_shift=rs.get('shift_value', 0.0), reward_min=rs.get('min_val', -float('inf')),
@@ -122,7 +122,7 @@ def _oracle_from_golden(g):
 
 @pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt',
                                   'agent_lstm_after.pt', 'agent_sched_standard.pt', 'agent_misc.pt', 'agent_rescale.pt', 'agent_lstm_masked.pt',
-                                  'agent_lstm_after_masked.pt'])
+                                  'agent_lstm_after_masked.pt', 'agent_trainloop.pt', 'agent_trainloop_adaptive.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
