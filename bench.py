@@ -160,19 +160,35 @@ def pick_cpu_threads(w):
     return best
 
 
+def cpu_reference_leg(w, steps, warmup):
+    """CPU arm: the UNMODIFIED reference (oracle/_ref, vendored by __graft_entry__.build(); oracle/ref_arm.py) at the FULL workload
+    shape when it is present, else the oracle port on a quarter-size sample.  Returns (value, ms, cpu_baseline dict)."""
+    from oracle import ref_arm
+    if ref_arm.available():
+        cores = ref_arm.pick_threads(w, available_cpus())
+        val, ms, play, upd = ref_arm.run_train_epochs(w, steps, warmup, cores)
+        return val, ms, {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'reference',
+                         'sample': f'{steps} epochs after {warmup} warm-up of the unmodified reference A2CAgent.train_epoch() (rl_games @ oracle/_ref, '
+                                   f'device cpu, fp32, torch_compile off, _pytorch_gae) at the full shape: {w["num_actors"]} envs x horizon '
+                                   f'{w["horizon"]}, minibatch {w["minibatch"]} x {w["mini_epochs"]} mini-epochs',
+                         'same_config': True, 'play_time_s': play, 'update_time_s': upd}
+    sample = min(w['num_actors'], 4096)
+    val, ms, cores = run_cpu_oracle(w, steps, warmup, sample)
+    return val, ms, {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port', 'same_config': False,
+                     'sample': f'{sample} of {w["num_actors"]} envs per step, same horizon / mini-epochs / minibatch count; '
+                               f'oracle/ppo_oracle.py (oracle/_ref absent on this box: port pinned by golden vectors)'}
+
+
 def reference_arm(args, w):
     rank, _, world = dist_info()
     if rank != 0:
         return
-    sample = min(w['num_actors'], 4096)
-    val, ms, cores = run_cpu_oracle(w, args.steps, max(1, args.warmup), sample)
+    val, ms, cb = cpu_reference_leg(w, args.steps, max(1, args.warmup))
     line = {'impl': 'reference', 'metric': 'ppo_env_steps_per_sec', 'value': val, 'unit': 'env-steps/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args.workload, w, 'cpu synthetic env (oracle.SyntheticEnvCPU)'),
-            'cpu_baseline': {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                             'sample': f'{sample} of {w["num_actors"]} envs per step, same horizon / mini-epochs / '
-                                       f'minibatch count; oracle/ppo_oracle.py (reference is pure Python: port pinned by golden vectors)'},
+            'config': workload_config(args.workload, w, 'cpu synthetic env (oracle.ref_arm.SyntheticVecEnvCPU)'),
+            'cpu_baseline': cb,
             'e2e': {'value': val, 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), file=_STDOUT, flush=True)
 
@@ -355,10 +371,7 @@ def b200_arm(args, w):
         if world == 1 and not args.skip_e2e:
             line['e2e'] = e2e_leg(w, device, args)
         if world == 1 and not args.skip_cpu:
-            val, cms, cores = run_cpu_oracle(w, 2, 1, min(w['num_actors'], 4096))
-            line['cpu_baseline'] = {'value': val, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-                                    'sample': f'2 epochs of {min(w["num_actors"], 4096)} envs (of {w["num_actors"]}) after 1 warm-up; '
-                                              'oracle/ppo_oracle.py on the host cores'}
+            _, _, line['cpu_baseline'] = cpu_reference_leg(w, 3, 1)
         print(json.dumps(line), file=_STDOUT, flush=True)
     if multi:
         # drop captured graphs (they hold NCCL kernels) before tearing the communicator down; NCCL teardown at interpreter

@@ -29,7 +29,7 @@ from . import ops
 from .common import (AdaptiveScheduler, IdentityScheduler, LinearScheduler, DefaultAlgoObserver, DefaultRewardsShaper,
                      create_vec_env, make_summary_writer)
 from .dist_utils import PackedStatsSync
-from .model import B200Model
+from .model import B200Model, CompileTolerantModel
 
 STATS_SYNC_MODES = ('pooled', 'broadcast')
 
@@ -101,7 +101,7 @@ class _Dataset:
         return d
 
 
-class A2CAgent:
+class A2CAgent(CompileTolerantModel):
     def __init__(self, base_name, params):
         self.config = config = params['config']
         # a2c_common.py:172-188: PBT runs carry the policy's index in the experiment name
@@ -184,9 +184,6 @@ class A2CAgent:
         if self.is_adaptive_lr and self.schedule_type not in ('per_minibatch', 'standard'):
             raise NotImplementedError("adaptive lr_schedule with schedule_type=%r: 'per_minibatch' (the default) and 'standard' "
                                       "(one step per mini-epoch) run on the device scheduler" % self.schedule_type)
-        if self.is_adaptive_lr and self.schedule_type == 'standard' and not config.get('b200_unvalidated', False):
-            raise NotImplementedError("schedule_type 'standard' (scheduler stepped once per mini-epoch inside the optimiser kernels) reproduces "
-                                      "the reference on CPU but has not been run on hardware yet: set b200_unvalidated: True")
         if self.is_adaptive_lr:
             self.kl_threshold = config['kl_threshold']
             self.scheduler = AdaptiveScheduler(self.kl_threshold, min_lr=config.get('min_lr', 1e-6),
@@ -293,8 +290,8 @@ class A2CAgent:
         # hardware supports it, a2c_common.py:427-429) and resolves to the tcgen05 path where this build has kernels for the
         # geometry, else to fp32 (a HIGHER precision than the reference's default), saying so once.
         self.is_rnn = self.model.is_rnn()
-        # wide observations (64 < obs <= 256: layer 1 in kernels of its own) compile and are unit-testable but have not run on hardware
-        allow_wide = bool(config.get('b200_unvalidated', False))
+        # wide observations (64 < obs <= 256): layer 1 runs in kernels of its own (l1_fwd_tc / l1_wgrad_tc)
+        allow_wide = True
         # the tcgen05 kernels hard-wire ELU (the activation of every [256,128,64] config the path was built for); anything else is fp32
         tc_ok = self.model.activation == 'elu' and ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
         if self.mixed_precision is None:
@@ -302,28 +299,20 @@ class A2CAgent:
             if not self.mixed_precision and self.global_rank == 0:
                 print(f'b200: mixed_precision not set -> fp32 kernels for this geometry (obs={self.model.D}, units={self.model.units}, '
                       f'actions={self.actions_num}, activation={self.model.activation}{", rnn" if self.is_rnn else ""}); the bf16 tcgen05 kernels cover '
-                      f'obs<=64, MLP [256,128,64] with elu, actions<=15')
+                      f'obs<=256, MLP [256,128,64] with elu, actions<=15')
         if self.is_rnn:
             if self.horizon_length % self.seq_length != 0:
                 raise ValueError(f"Horizon length ({self.horizon_length}) must be divisible by sequence length ({self.seq_length})")
-            if self.mask_autoreset_rows and not config.get('b200_unvalidated', False):
-                raise NotImplementedError('rnn policies on a next_step-autoreset env (masked filler rows + state re-zeroing) reproduce the '
-                                          'reference on CPU but have not been run on hardware yet: set b200_unvalidated: True')
             if not self.zero_rnn_on_done:
                 raise NotImplementedError('zero_rnn_on_done: False is not on the B200 hot path')
             if self.mixed_precision:
                 raise NotImplementedError('rnn (LSTM) policies run on the fp32 path: set mixed_precision: False')
-            if not self.model.rnn_before_mlp and not config.get('b200_unvalidated', False):
-                raise NotImplementedError('rnn before_mlp: False (MLP -> LSTM -> heads) composes validated kernels and its host logic reproduces '
-                                          'the reference on CPU, but it has not been run on hardware yet: set b200_unvalidated: True')
         self.use_tc = bool(self.mixed_precision)
         if self.use_tc and not tc_ok:
             raise NotImplementedError(
-                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=64, MLP [256,128,64] with elu, actions<=15 in this build; got '
+                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=256, MLP [256,128,64] with elu, actions<=15 in this build; got '
                 f'obs={self.model.D}, units={self.model.units}, activation={self.model.activation}, actions={self.actions_num}.  '
-                f'Set mixed_precision: False for the fp32 path.'
-                + ('  (64 < obs <= 256 has tcgen05 kernels that have not been run on hardware yet: b200_unvalidated: True enables them.)'
-                   if ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2 else ''))
+                f'Set mixed_precision: False for the fp32 path.')
         self.tc_wide = self.use_tc and ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2
         if self.tc_wide and config.get('b200_pipelined_wgrad', False):
             raise NotImplementedError('b200_pipelined_wgrad is an option of the resident-weights kernels (obs <= 64)')

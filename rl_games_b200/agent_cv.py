@@ -2,7 +2,7 @@
 algos_torch/central_value.py CentralValueTrain, models.py:425-464 ModelCentralValue, a2c_common.py:250-262, :593-615, :1010-1011,
 :1536-1537, :1651-1660; a2c_continuous.py:50-75).
 
-STATUS: NOT YET RUN ON HARDWARE (written after the round's GPU budget was spent; opt-in with ``b200_unvalidated: True``).  The reference
+STATUS: parity-green on a B200 (round 2, ``tests/test_cv_gpu.py``).  The reference
 semantics are pinned by ``oracle.ppo_oracle.CentralValueOracle`` against ``tests/golden/agent_cv.pt``; the HOST logic of this module runs
 on CPU against the same golden vectors with torch stand-ins for the kernels (``tests/test_agent_cv_host_cpu.py``); the only new kernel
 (``csrc/critic.cu`` value loss) has its row arithmetic exercised on the CPU too.  Everything else reuses validated kernels.
@@ -225,9 +225,6 @@ class A2CAgentCV(A2CAgent):
         cv_config = config.get('central_value_config')
         if cv_config is None:
             raise ValueError('A2CAgentCV needs central_value_config')
-        if not config.get('b200_unvalidated', False):
-            raise NotImplementedError('the central-value B200 agent has not been run on hardware yet (oracle + golden vectors are in place): '
-                                      'set b200_unvalidated: True to run it anyway')
         config['central_value_config'] = None          # the base class refuses it; everything it builds is unchanged by the critic
         try:
             super().__init__(base_name, params)

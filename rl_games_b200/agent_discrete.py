@@ -2,11 +2,9 @@
 DiscreteA2CAgent + common/a2c_common.py:1205-1359 DiscreteA2CBase, models.py:62-125 ModelA2C, network_builder.py A2CBuilder with a
 ``discrete`` space, optionally ``separate: True`` actor/critic trunks, optional action masks).
 
-STATUS: NOT YET RUN ON HARDWARE.  Written after the round's GPU budget was spent, against a CPU oracle that IS pinned to the
-reference (oracle/ppo_discrete_oracle.py, tests/golden/agent_discrete*.pt).  The constructor refuses to run unless the config
-says ``b200_unvalidated: True``; ``tests/test_discrete_gpu.py`` (skipped unless ``B200RL_UNVALIDATED=1``) holds the parity tests
-that promote it.  Everything except the two categorical kernels (csrc/discrete.cu) reuses kernels already validated by the
-continuous path: linear_fwd / linear_bwd_* / reduce_splits (mlp_simt.cu), gae_fused, prepare_batch, moments_update,
+STATUS: parity-green on a B200 (round 2, ``tests/test_discrete_gpu.py``) against a CPU oracle that is pinned to the reference
+(oracle/ppo_discrete_oracle.py, tests/golden/agent_discrete*.pt).  Everything except the two categorical kernels
+(csrc/discrete.cu) reuses the kernels of the continuous path: linear_fwd / linear_bwd_* / reduce_splits (mlp_simt.cu), gae_fused, prepare_batch, moments_update,
 mask_inv_counts (stats.cu, gae.cu), post_step (rollout.cu), adam_step (adam.cu).
 
 Scope of this first edition: one GPU, eager launches (no CUDA graph), flat Box observations, ``Discrete(K)`` or multi-discrete
@@ -24,7 +22,7 @@ import torch.distributed as dist
 
 from . import ops
 from .agent import _MeterView
-from .model import check_network_params
+from .model import check_network_params, CompileTolerantModel, _model_call
 from .dist_utils import PackedStatsSync
 from .common import (AdaptiveScheduler, DefaultAlgoObserver, DefaultRewardsShaper, IdentityScheduler, LinearScheduler, create_vec_env,
                      make_summary_writer)
@@ -35,6 +33,8 @@ class DiscreteModel:
     """Flat fp32 parameter arena of A2CBuilder.Network for a discrete space.  Arena order: actor trunk, [critic trunk], fused head
     W_head [1 + K, Hl] (row 0 = value, rows 1.. = logits) and b_head [1 + K]; ``_param_views`` lists the tensors in the reference's
     ``model.parameters()`` order (actor_mlp.*, critic_mlp.*, value.*, logits.*) for state dicts and the index-keyed Adam state."""
+
+    __call__ = _model_call
 
     def __init__(self, network_params, obs_dim, n_actions, device, normalize_input, normalize_value, head_sizes=None):
         self.head_sizes = list(head_sizes) if head_sizes else None          # multi-discrete: one logits head per Tuple component
@@ -161,13 +161,9 @@ class DiscreteModel:
         return (osd['param_groups'][0]['lr'] if osd.get('param_groups') else None), step
 
 
-class DiscreteA2CAgent:
+class DiscreteA2CAgent(CompileTolerantModel):
     def __init__(self, base_name, params):
         self.config = config = params['config']
-        if not config.get('b200_unvalidated', False):
-            raise NotImplementedError(
-                'the discrete-action B200 agent has not been run on hardware yet (written after the GPU budget of its round was '
-                'spent; oracle + golden vectors are in place): set b200_unvalidated: True to run it anyway')
         self.experiment_name = config.get('full_experiment_name') or (config['name'] + datetime.now().strftime("_%d-%H-%M-%S"))
         config.setdefault('features', {})
         self.algo_observer = config['features'].get('observer') or DefaultAlgoObserver()

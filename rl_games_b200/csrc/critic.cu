@@ -1,9 +1,8 @@
 // Value-only loss head of the central value network (asymmetric critic) -- SURVEY.md 8f rank 1 (algos_torch/central_value.py:276-301
 // calc_loss / calc_gradients: loss = masked mean of common_losses.critic_loss).
 //
-// STATUS: NOT YET RUN ON HARDWARE (same situation as csrc/discrete.cu): written after the round's GPU budget was spent; the per-row
-// arithmetic is __host__ __device__ and is exercised on the CPU (tests/test_critic_rows_cpu.py), the agent that uses it
-// (rl_games_b200/agent_cv.py) is opt-in (`b200_unvalidated: True`) and its GPU tests are skipped unless B200RL_UNVALIDATED=1.
+// The per-row arithmetic is __host__ __device__ and is also exercised on the CPU (tests/test_critic_rows_cpu.py); GPU parity:
+// tests/test_cv_gpu.py.
 #include "common.cuh"
 
 namespace {

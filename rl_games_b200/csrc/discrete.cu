@@ -1,11 +1,8 @@
 // Categorical (discrete-action) policy head for PPO -- SURVEY.md 8a row a15 (a2c_discrete.py:92-209, models.py:95-125,
 // common/extensions/distributions.py:23-44).
 //
-// STATUS: NOT YET RUN ON HARDWARE.  These kernels were written after the round's GPU budget was spent; they compile for
-// sm_100a, are exported through the C ABI and are covered by `pytest -m gpu` tests that are skipped unless
-// B200RL_UNVALIDATED=1 (tests/test_discrete_gpu.py); the agent that uses them (rl_games_b200/agent_discrete.py) refuses to
-// start without `b200_unvalidated: True`.  The CPU oracle they must match (oracle/ppo_discrete_oracle.py) IS pinned to the
-// real reference by golden vectors.
+// Parity tests: tests/test_discrete_gpu.py (through the C ABI, against oracle/ppo_discrete_oracle.py, which is pinned to the real
+// reference by golden vectors).
 //
 // Both kernels are one thread per row over small K (<= 64 actions): HBM/latency bound, no tensor-core work.
 #include "common.cuh"

@@ -109,7 +109,34 @@ class _NetworkView:
         return self._m.rnn_units > 0
 
 
+class CompileTolerantModel:
+    """Mixin for agents: `Runner.run_train` of the reference wraps `agent.model` with torch.compile unless the YAML says
+    `torch_compile: False` (torch_runner.py:282-312).  There is no nn.Module to compile here (the hand-written kernels subsume those
+    fusions), so an assignment of anything that is not one of this package's models is ignored, once, with a note -- stock YAMLs
+    run unchanged through the reference's own Runner."""
+
+    @property
+    def model(self):
+        return self.__dict__.get('_b200_model')
+
+    @model.setter
+    def model(self, m):
+        if self.__dict__.get('_b200_model') is not None and not hasattr(m, 'load_optimizer_state_dict'):
+            if not self.__dict__.get('_b200_compile_noted'):
+                print('b200: torch.compile of agent.model ignored (no nn.Module on this path; set torch_compile: False to silence)')
+                self.__dict__['_b200_compile_noted'] = True
+            return
+        self.__dict__['_b200_model'] = m
+
+
+def _model_call(self, *args, **kwargs):
+    raise NotImplementedError('the B200 model is a flat parameter arena driven by fused kernels (agent.get_action_values / train_epoch); '
+                              'it has no module-style forward')
+
+
 class B200Model:
+    __call__ = _model_call
+
     RNN_KEYS = (('a2c_network.rnn.rnn.weight_ih_l0', 'W_ih'), ('a2c_network.rnn.rnn.weight_hh_l0', 'W_hh'),
                 ('a2c_network.rnn.rnn.bias_ih_l0', 'b_ih'), ('a2c_network.rnn.rnn.bias_hh_l0', 'b_hh'))
 

@@ -58,7 +58,6 @@ class Runner:
     def __init__(self, algo_observer=None):
         self.algo_factory = ObjectFactory()
         self.algo_factory.register_builder('a2c_continuous', lambda **kwargs: _continuous_agent(**kwargs))
-        # discrete PPO: implemented, not yet validated on hardware (agent_discrete.py refuses to start without b200_unvalidated: True)
         self.algo_factory.register_builder('a2c_discrete', lambda **kwargs: _discrete_agent(**kwargs))
         self.player_factory = ObjectFactory()
         self._observer_was_injected = algo_observer is not None

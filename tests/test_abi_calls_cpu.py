@@ -102,20 +102,19 @@ def _agent(tmp_path, N, H_, D, A, units, mb, over=None, rnn=None, autoreset='sam
 CASES = {
     'fp32': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32),
     'fp32 masked, rms advantage, standard schedule': dict(N=8, H_=8, D=8, A=3, units=(16, 12, 8), mb=32, autoreset='next_step',
-                                                           over={'normalize_rms_advantage': True, 'schedule_type': 'standard',
-                                                                 'b200_unvalidated': True}),
+                                                           over={'normalize_rms_advantage': True, 'schedule_type': 'standard'}),
     'lstm before the mlp': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, over={'seq_length': 4},
                                 rnn={'name': 'lstm', 'units': 8, 'layers': 1, 'before_mlp': True}),
-    'lstm after the mlp': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, over={'seq_length': 4, 'b200_unvalidated': True},
+    'lstm after the mlp': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, over={'seq_length': 4},
                                rnn={'name': 'lstm', 'units': 12, 'layers': 1, 'before_mlp': False}),
     'lstm before the mlp, next_step autoreset': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, autoreset='next_step',
-                                                     over={'seq_length': 4, 'b200_unvalidated': True},
+                                                     over={'seq_length': 4},
                                                      rnn={'name': 'lstm', 'units': 8, 'layers': 1, 'before_mlp': True}),
     'tcgen05': dict(N=256, H_=4, D=60, A=8, units=(256, 128, 64), mb=512, over={'mixed_precision': True}),
     'tcgen05, pipelined wgrad + masked': dict(N=256, H_=4, D=60, A=8, units=(256, 128, 64), mb=512, autoreset='next_step',
                                               over={'mixed_precision': True, 'b200_pipelined_wgrad': True}),
     'tcgen05 wide observations': dict(N=256, H_=4, D=256, A=8, units=(256, 128, 64), mb=512,
-                                      over={'mixed_precision': True, 'b200_unvalidated': True}),
+                                      over={'mixed_precision': True}),
 }
 
 

@@ -63,7 +63,7 @@ def _build_cv(monkeypatch, tmp_path, g, over=None):
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
                    'mixed_precision': False, 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None),
-                   'central_value_config': cv_cfg, 'b200_unvalidated': True})
+                   'central_value_config': cv_cfg})
     config.update(over or {})
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},

@@ -114,27 +114,20 @@ def test_agent_matches_reference_golden(name, graph):
     _golden_run(name, graph)
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason='MLP -> LSTM placement not yet run on hardware (host logic checked on CPU): set B200RL_UNVALIDATED=1')
 @pytest.mark.parametrize('graph', [False, True])
 def test_lstm_after_mlp_agent_matches_reference_golden(graph):
     """rnn before_mlp: False, the reference default (network_builder.py:253-272): same kernels as agent_lstm.pt, composed
     trunk -> LSTM window -> heads; the fixture comes from the reference itself (tests/golden/gen_golden.py lstm_after)"""
-    _golden_run('agent_lstm_after.pt', graph, {'b200_unvalidated': True})
+    _golden_run('agent_lstm_after.pt', graph, {})
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason="schedule_type 'standard' not yet run on hardware (host logic checked on CPU): set B200RL_UNVALIDATED=1")
 @pytest.mark.parametrize('graph', [False, True])
 def test_standard_schedule_agent_matches_reference_golden(graph):
     """schedule_type 'standard' (what the shipped mjlab configs use): the adaptive-KL scheduler steps once per mini-epoch on the mean
     KL, inside the optimiser kernel of the mini-epoch's last minibatch -- also when the update phase replays as a CUDA graph"""
-    _golden_run('agent_sched_standard.pt', graph, {'b200_unvalidated': True})
+    _golden_run('agent_sched_standard.pt', graph, {})
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason='kernel flags of these fixtures (reward clip, ppo: False, normalisers off, unclipped actions) and the in-epoch '
-                           'switch of the linear schedule have not been run on hardware: set B200RL_UNVALIDATED=1')
 @pytest.mark.parametrize('name', ['agent_misc.pt', 'agent_rescale.pt'])
 @pytest.mark.parametrize('graph', [False, True])
 def test_agent_matches_reference_golden_more_config_keys(name, graph):
@@ -144,14 +137,12 @@ def test_agent_matches_reference_golden_more_config_keys(name, graph):
     _golden_run(name, graph)
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason='LSTM on a next_step-autoreset env not yet run on hardware (host logic checked on CPU): set B200RL_UNVALIDATED=1')
 @pytest.mark.parametrize('name', ['agent_lstm_masked.pt', 'agent_lstm_after_masked.pt'])
 @pytest.mark.parametrize('graph', [False, True])
 def test_lstm_on_next_step_autoreset_env_matches_reference_golden(name, graph):
     """envpool-style envs with an LSTM policy (a2c_common.py:1097-1106, :1180-1191): masked filler rows, the absorbed state re-zeroed in
     the rollout, the train-time reset also entering the first real row"""
-    _golden_run(name, graph, {'b200_unvalidated': True})
+    _golden_run(name, graph, {})
 
 
 def _golden_run(name, graph, extra=None):
@@ -248,8 +239,6 @@ def test_checkpoint_roundtrip_and_reference_keys(tmp_path):
     torch.testing.assert_close(agent2.opt_state[1:4], agent.opt_state[1:4], rtol=1e-12, atol=0)      # step, beta1^step, beta2^step
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason='lr_schedule_apply (one-step hold of the restored optimizer lr) not yet run on hardware: set B200RL_UNVALIDATED=1')
 def test_resume_from_a_reference_checkpoint_continues_like_the_reference():
     """tests/golden/gen_golden.py resume: a checkpoint of the REAL reference loaded into a fresh trainer, one more epoch -> where the
     reference's own fresh agent landed (weights, adaptive LR, Adam step count, normaliser statistics, epoch / frame)"""
@@ -271,8 +260,6 @@ def test_resume_from_a_reference_checkpoint_continues_like_the_reference():
     assert float(out['optimizer']['state'][0]['step']) == ref['adam_step']
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason='bit-exactness claim not yet checked on hardware: set B200RL_UNVALIDATED=1 (promote to the default suite once green)')
 @pytest.mark.parametrize('mp', [False, True])
 def test_masked_rows_contribute_zero_gradient(mp):
     """The reference's poison test (tests/test_ppo_masking.py:153-175), same call sequence: poison returns / values of the filler reset
@@ -356,16 +343,12 @@ def test_bf16_tcgen05_agent_tracks_fp32_agent():
     _bf16_vs_fp32_agents(60, {})
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason='wide-observation tcgen05 kernels (64 < obs <= 256) not yet run on hardware: set B200RL_UNVALIDATED=1')
 @pytest.mark.parametrize('D', [256, 105])
 def test_bf16_tcgen05_wide_agent_tracks_fp32_agent(D):
     """the same comparison on BASELINE configs[4]'s observation width (256) and a ragged one: layer 1 in its own kernels"""
-    _bf16_vs_fp32_agents(D, {'b200_unvalidated': True})
+    _bf16_vs_fp32_agents(D, {})
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason='flag combinations of the tcgen05 kernels no default test sets: set B200RL_UNVALIDATED=1 (promote once green)')
 @pytest.mark.parametrize('extra', [{'ppo': False}, {'normalize_input': False, 'normalize_value': False, 'normalize_advantage': False},
                                    {'clip_actions': False}, {'clip_value': False, 'use_smooth_clamp': False},
                                    {'bounds_loss_coef': 0.001, 'bound_loss_type': 'bound'}, {'bounds_loss_coef': None},

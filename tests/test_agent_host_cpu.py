@@ -96,21 +96,15 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
     cfgk = g['config']
     env = _Env(g)
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
-    if tc == 2:
-        config['b200_unvalidated'] = True
     config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env,
                    'reward_shaper': dict(g.get('reward_shaper') or {'scale_value': 1.0}), 'mixed_precision': bool(tc), 'b200_cuda_graph': False, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
-    if cfgk.get('schedule_type', 'per_minibatch') == 'standard':
-        config['b200_unvalidated'] = True       # per-mini-epoch scheduler inside the optimiser kernels: not yet run on hardware
     lstm = g.get('rnn_units', 0) > 0
     if lstm:
         network['rnn'] = {'name': 'lstm', 'units': g['rnn_units'], 'layers': 1, 'before_mlp': bool(g.get('rnn_before_mlp', True))}
-        # MLP -> LSTM placement and LSTM on a next_step-autoreset env: not yet run on hardware
-        config['b200_unvalidated'] = (not network['rnn']['before_mlp']) or g['autoreset'] == 'next_step'
     r = Runner()
     r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
                        'config': config}})

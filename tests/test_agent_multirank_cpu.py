@@ -90,7 +90,7 @@ def _worker(rank, world, port, ret, name='agent_masked.pt', extra=None):
 
 
 @pytest.mark.parametrize('name,extra', [('agent_masked.pt', None),
-                                        ('agent_sched_standard.pt', {'b200_unvalidated': True})],       # one scheduler step per mini-epoch on the
+                                        ('agent_sched_standard.pt', {})],       # one scheduler step per mini-epoch on the
                          ids=['per-minibatch schedule', 'per-mini-epoch schedule'])                    # rank-mean of the mean KL
 def test_two_rank_agent_matches_oracle_and_ranks_stay_identical(name, extra):
     world, port = 2, 29500 + (os.getpid() + len(name)) % 400

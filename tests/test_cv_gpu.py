@@ -1,6 +1,5 @@
-"""Central value (asymmetric critic) on the GPU -- PENDING FIRST HARDWARE RUN (see rl_games_b200/agent_cv.py, csrc/critic.cu).
-Skipped unless B200RL_UNVALIDATED=1; the host logic and the kernel's row arithmetic are already checked on CPU
-(tests/test_agent_cv_host_cpu.py, tests/test_critic_rows_cpu.py)."""
+"""Central value (asymmetric critic) on the GPU (rl_games_b200/agent_cv.py, csrc/critic.cu); first green on a B200 in round 2.
+The host logic and the kernel's row arithmetic are also checked on CPU (tests/test_agent_cv_host_cpu.py, tests/test_critic_rows_cpu.py)."""
 import os
 
 import numpy as np
@@ -9,9 +8,7 @@ import torch
 
 from oracle import ppo_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                                 reason='central-value path not yet validated on hardware: set B200RL_UNVALIDATED=1 to run')]
+pytestmark = [pytest.mark.gpu]
 DEV = 'cuda:0'
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 
@@ -88,7 +85,7 @@ def test_central_value_agent_matches_reference_golden(graph):
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     config.update({'device': DEV, 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
                    'mixed_precision': False, 'b200_cuda_graph': graph, 'train_dir': '/tmp/b200_parity_runs',
-                   'lr_schedule': cfgk.get('lr_schedule', None), 'central_value_config': cv_cfg, 'b200_unvalidated': True})
+                   'lr_schedule': cfgk.get('lr_schedule', None), 'central_value_config': cv_cfg})
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},

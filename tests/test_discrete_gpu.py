@@ -1,9 +1,6 @@
-"""Discrete-action PPO on the GPU -- PENDING FIRST HARDWARE RUN.
-
-The kernels (rl_games_b200/csrc/discrete.cu) and the agent (rl_games_b200/agent_discrete.py) were written after the GPU budget of
-their round was spent.  These parity tests are the gate that promotes them: they are skipped unless B200RL_UNVALIDATED=1, so that a
-routine `pytest -m gpu` reports only validated code.  The oracle side (oracle/ppo_discrete_oracle.py) is pinned to the real reference
-by tests/test_oracle_vs_golden.py, which runs on CPU."""
+"""Discrete-action PPO on the GPU: kernels rl_games_b200/csrc/discrete.cu, agent rl_games_b200/agent_discrete.py;
+first green on a B200 in round 2.  The oracle side (oracle/ppo_discrete_oracle.py) is pinned to the real reference by
+tests/test_oracle_vs_golden.py, which runs on CPU."""
 import os
 
 import numpy as np
@@ -12,9 +9,7 @@ import torch
 
 from oracle import ppo_discrete_oracle as DO
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                                 reason='discrete path not yet validated on hardware: set B200RL_UNVALIDATED=1 to run')]
+pytestmark = [pytest.mark.gpu]
 DEV = 'cuda:0'
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 
@@ -136,7 +131,7 @@ def test_discrete_agent_matches_reference_golden(name):
     cfgk = g['config']
     env = DiscreteTapeEnvGPU(g)
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
-    config.update({'device': DEV, 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1}, 'b200_unvalidated': True,
+    config.update({'device': DEV, 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1},
                    'train_dir': '/tmp/b200_parity_runs', 'lr_schedule': cfgk.get('lr_schedule', None)})
     multi = isinstance(g['K'], (list, tuple))
     network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'multi_discrete' if multi else 'discrete': None},

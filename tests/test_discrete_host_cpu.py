@@ -59,7 +59,7 @@ def _build(monkeypatch, tmp_path, g, stand_ins=True, over=None):
     env = _Env(g)
     config = {k: v for k, v in cfgk.items() if k not in ('device', 'torch_compile')}
     config.update({'device': 'cpu', 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1},
-                   'b200_unvalidated': True, 'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
+                   'train_dir': str(tmp_path), 'lr_schedule': cfgk.get('lr_schedule', None)})
     config.update(over or {})
     multi = isinstance(g['K'], (list, tuple))
     network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'multi_discrete' if multi else 'discrete': None},
@@ -138,7 +138,7 @@ def test_discrete_train_loop_and_checkpoint_roundtrip(monkeypatch, tmp_path):
         env = _Env(g)
         config = {k: v for k, v in g['config'].items() if k not in ('device', 'torch_compile')}
         config.update({'device': 'cpu', 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 0.1},
-                       'b200_unvalidated': True, 'train_dir': str(tmp_path), 'lr_schedule': g['config'].get('lr_schedule', None),
+                       'train_dir': str(tmp_path), 'lr_schedule': g['config'].get('lr_schedule', None),
                        'max_epochs': 2, 'print_stats': False, 'name': 'dloop'})
         network = {'name': 'actor_critic', 'separate': g['separate'], 'space': {'discrete': None},
                    'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}
@@ -156,9 +156,6 @@ def test_discrete_train_loop_and_checkpoint_roundtrip(monkeypatch, tmp_path):
     assert torch.equal(b.model.flat, a.model.flat) and torch.equal(b.model.exp_avg_sq, a.model.exp_avg_sq)
     # reference semantics (a2c_common.py:852-866): the optimizer returns with its lr, last_lr is not part of a restore
     assert b.epoch_num == a.epoch_num and float(b.opt_state[0]) == a.last_lr and b.last_lr == g['config']['learning_rate']
-    # the gate: without the explicit opt-in the constructor refuses
-    with pytest.raises(NotImplementedError, match='not been run on hardware'):
-        agent_discrete.DiscreteA2CAgent('x', {'config': {'name': 'x'}, 'network': a.network_params})
 
 
 def test_discrete_train_loop_matches_the_reference_outer_loop(monkeypatch, tmp_path):

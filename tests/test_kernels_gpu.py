@@ -371,8 +371,6 @@ def test_adam_step_vs_oracle(ops, truncate, wd):
     torch.testing.assert_close(v.cpu(), opt.v[0], rtol=5e-5, atol=1e-10)
 
 
-@pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                    reason="schedule_type 'standard' modes of the optimiser kernels not yet run on hardware: set B200RL_UNVALIDATED=1")
 @pytest.mark.parametrize('kernel', ['adam_step', 'reduce_adam'])
 def test_per_mini_epoch_scheduler_modes(ops, kernel):
     """cfg.adaptive_lr 2 / 3 (schedule_type 'standard', a2c_common.py:1565-1571): the LR moves only at the last minibatch of a
@@ -623,10 +621,8 @@ def test_fused_allreduce_adam_world1_matches_adam_step(ops):
     torch.testing.assert_close(vb, va, rtol=1e-5, atol=1e-12)
 
 
-GATED = pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1', reason='not yet run on hardware: set B200RL_UNVALIDATED=1')
 
 
-@GATED
 @pytest.mark.parametrize('H,N', [(1, 7), (8, 520), (16, 4099)])
 def test_rnn_train_dones_vs_reference_expression(ops, H, N):
     """a2c_common.py:1180-1191: rnn_dones[1:] = max(rnn_dones[1:], (mb_valid == 0)[:-1])"""
@@ -640,7 +636,6 @@ def test_rnn_train_dones_vs_reference_expression(ops, H, N):
     assert torch.equal(out.cpu(), ref)
 
 
-@GATED
 def test_lr_schedule_apply_vs_oracle_scheduler(ops):
     from rl_games_b200.ops import OptCfg
     sched = O.AdaptiveScheduler(0.008, 1e-6, 1e-2, 1.5)

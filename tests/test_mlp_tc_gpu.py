@@ -49,11 +49,8 @@ def test_tc_fwd_loss_bwd_vs_fp32(H, N, epm, masked):
     _fwd_loss_bwd_case(H, N, epm, masked, D)
 
 
-WIDE = pytest.mark.skipif(os.environ.get('B200RL_UNVALIDATED') != '1',
-                          reason='wide-observation tcgen05 kernels (64 < obs <= 256) not yet run on hardware: set B200RL_UNVALIDATED=1')
 
 
-@WIDE
 @pytest.mark.parametrize('H,N,epm,masked,Dw', [(4, 512, 256, False, 256), (2, 384, 128, True, 105), (1, 1000, 1000, False, 65),
                                                (2, 19072, 19072, False, 256)])
 def test_tc_wide_fwd_loss_bwd_vs_fp32(H, N, epm, masked, Dw):
@@ -181,7 +178,6 @@ def test_tc_rollout_vs_fp32():
     _rollout_case(D, 1000)
 
 
-@WIDE
 @pytest.mark.parametrize('Dw,N', [(256, 1000), (105, 128), (72, 20000)])
 def test_tc_wide_rollout_vs_fp32(Dw, N):
     _rollout_case(Dw, N)

@@ -1,4 +1,4 @@
-"""Developer tool: run the GATED `-m gpu` tests (B200RL_UNVALIDATED) on a machine WITHOUT a GPU, with the C-ABI library replaced by the
+"""Developer tool: run the `-m gpu` tests on a machine WITHOUT a GPU, with the C-ABI library replaced by the
 prototype-checking recorder of tests/test_abi_calls_cpu.py (no compute) and CUDA touch points stubbed.  Python-level errors in the tests
 or in the host code they drive (wrong keyword, missing attribute, bad shape) show up as non-assertion exceptions BEFORE a GPU call is
 spent on them; numeric assertions are expected to stop a test (nothing is computed), tensor comparisons are neutralised to get further.
@@ -58,7 +58,7 @@ class _Any:
     def __eq__(self, o): return True
     def __req__(self, o): return True
 pytest.approx = lambda *a, **k: _Any()
-mods = ['test_agent_gpu', 'test_kernels_gpu', 'test_mlp_tc_gpu', 'test_discrete_gpu', 'test_cv_gpu', 'test_tc_gpu']
+mods = ['test_agent_gpu', 'test_kernels_gpu', 'test_mlp_tc_gpu', 'test_tc_faithful_gpu', 'test_discrete_gpu', 'test_cv_gpu', 'test_tc_gpu']
 # tests that need a real device object even to get going (CUDA generator, IPC allocation): nothing to learn from them here
 NEEDS_DEVICE = {'test_fused_allreduce_adam_world1_matches_adam_step', 'test_gae_full_size_properties'}
 bad = 0
