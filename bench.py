@@ -256,30 +256,51 @@ def gae_roofline(w, peaks):
     d = (torch.rand(H, N, device=dev) < 0.05).to(torch.uint8)
     lv, ld = torch.randn(N, device=dev), (torch.rand(N, device=dev) < 0.05).to(torch.uint8)
     advs, rets = torch.empty(H, N, device=dev), torch.empty(H, N, device=dev)
-    part = torch.zeros((N + 127) // 128, 8, dtype=torch.float64, device=dev)
+    part = torch.zeros((N + 63) // 64, 8, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ts = []
-    for i in range(13):
-        ops.fill_u32(flush, 1)
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        ops.gae_fused(r, v, d, lv, ld, None, advs, rets, part, 0.99, 0.95)
-        e.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(s.elapsed_time(e))
-    ms = sum(ts) / len(ts)
+
+    def timed(fn, cold, n=13):
+        ts = []
+        for i in range(n):
+            if cold:
+                ops.fill_u32(flush, 1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(s.elapsed_time(e))
+        return sum(ts) / len(ts)
+    ours = lambda: ops.gae_fused(r, v, d, lv, ld, None, advs, rets, part, 0.99, 0.95)   # noqa: E731
+    ms, ms_warm = timed(ours, True), timed(ours, False)
     alg = 17 * H * N + 8 * N     # r4 + V4 + done1 read, A4 + returns4 written per element; last_value/last_done per env
     gbs = alg / (ms * 1e-3) / 1e9
     try:
         tr = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get('gae_fused_f32')
     except Exception:
         tr = None
-    return {'kernel': 'gae_fused_kernel (GAE + returns + moment partials)', 'bound': 'hbm', 'achieved': gbs,
-            'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'traffic': tr['traffic'] if tr else None,
-            'alg_bytes_per_launch': alg, 'ms_per_launch': ms, 'peak_source': peaks['source'],
-            'note': 'workload shape (4.5 MB working set: launch/latency bound); large-shape asymptote 0.84-0.87 of measured '
-                    'peak in profiles/r01_gae_sweep*.json (tools/gae_sweep.py)'}
+    out = {'kernel': 'gae_tma_kernel (GAE + returns + moment partials, TMA-staged)', 'bound': 'hbm', 'achieved': gbs,
+           'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm_gbs'], 'traffic': tr['traffic'] if tr else None,
+           'alg_bytes_per_launch': alg, 'ms_per_launch': ms, 'ms_per_launch_l2_resident': ms_warm, 'peak_source': peaks['source'],
+           'note': 'workload shape (4.5 MB working set, one launch ~ one DRAM round trip: latency bound; cold = L2 flushed before each launch, '
+                   'l2_resident = what the kernel sees inside the epoch graph); large-shape asymptote and the comparators at every '
+                   'shape: profiles/r02_gae_sweep.json (tools/gae_sweep.py)'}
+    # the reference's own Triton kernel on the same box, same shape, same timing (gae_kernel.py:16-59 via _triton_gae), fp32 dones like its caller
+    try:
+        from oracle import ref_arm
+        ref_arm.import_reference()
+        from rl_games.triton_kernels.gae_kernel import _triton_gae
+        r3, v3, lv2, df, ldf = r.unsqueeze(2), v.unsqueeze(2), lv.unsqueeze(1), d.float(), ld.float()
+        tfn = lambda: _triton_gae(r3, v3, df, lv2, ldf, 0.99, 0.95)   # noqa: E731
+        tfn()
+        tms, tms_warm = timed(tfn, True), timed(tfn, False)
+        out['reference_triton'] = {'kernel': 'rl_games.triton_kernels.gae_kernel._gae_kernel (advantages only, 16 B/element)', 'ms_per_launch': tms,
+                                   'ms_per_launch_l2_resident': tms_warm, 'GBs': 16 * H * N / (tms * 1e-3) / 1e9,
+                                   'speedup_cold': tms / ms, 'speedup_l2_resident': tms_warm / ms_warm}
+    except Exception as e:
+        out['reference_triton'] = {'unavailable': repr(e)[:200]}
+    return out
 
 
 def load_peaks():
@@ -372,6 +393,30 @@ def b200_arm(args, w):
             line['e2e'] = e2e_leg(w, device, args)
         if world == 1 and not args.skip_cpu:
             _, _, line['cpu_baseline'] = cpu_reference_leg(w, 3, 1)
+    # ---- second workload on the same line: BASELINE configs[4]'s per-GPU shard (obs 256, horizon 32) -- the shape the multi-GPU
+    #      north_star names -- so that the driver's 1/2/4/8-GPU runs carry its curve too (same timing protocol, all ranks)
+    if args.workload == 'c2' and not args.skip_secondary:
+        agent._graph_update = agent._graph_epoch = None
+        del agent
+        torch.cuda.synchronize()
+        w5 = WORKLOADS['c5']
+        agent = build_agent(w5, device, 'b200_synthetic', multi, graph=not args.no_graph, mixed_precision=not args.fp32)
+        if multi:
+            dist.broadcast(agent.model.flat, 0)
+            agent._repack()
+        timed_epochs(agent, 3, flush, world)
+        k5 = max(3, min(args.steps, 10))
+        ms5 = timed_epochs(agent, k5, flush, world)
+        t5 = torch.tensor([sum(ms5)], dtype=torch.float64, device=device)
+        if multi:
+            dist.all_reduce(t5, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            t5s = float(t5) * 1e-3
+            line['c5'] = {'metric': 'ppo_env_steps_per_sec', 'value': w5['num_actors'] * w5['horizon'] * world * k5 / t5s, 'unit': 'env-steps/s',
+                          'n_gpus': world, 'steps': k5, 'warmup': 3, 'ms_per_step': 1e3 * t5s / k5, 'scaling': 'weak', 'dtype': line['dtype'],
+                          'config': workload_config('c5', w5, 'b200_synthetic (on-GPU Philox env, one kernel per step)'),
+                          'kernels': 'l1_fwd_tc + mlp_fwd_tc<XL1> / l1_wgrad_tc + mlp_bwd_tc<XL1> (wide-observation tcgen05 path)'}
+    if rank == 0:
         print(json.dumps(line), file=_STDOUT, flush=True)
     if multi:
         # drop captured graphs (they hold NCCL kernels) before tearing the communicator down; NCCL teardown at interpreter
@@ -418,6 +463,7 @@ def main():
     ap.add_argument('--cfg', action='append', default=[], help='config override key=value (python literal), e.g. b200_pipelined_wgrad=False')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-secondary', action='store_true', help='do not append the c5 block to the c2 line')
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     import ast

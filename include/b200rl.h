@@ -62,9 +62,14 @@ int b200rl_gae_f32(const float* rewards, const float* values, const void* dones,
                    int64_t a_st_t, int64_t a_st_e, int64_t a_st_v,
                    double gamma, double tau, void* stream);
 
+/* Kernel selection for dense [H,N] inputs with N % 16 == 0: 1 (default) = TMA-staged kernel (bulk copies of the tile into shared
+ * memory, scan out of shared memory, bulk stores), 0 = register-chunk kernel.  Same results bit for bit.  Returns the previous value. */
+int b200rl_gae_set_tma(int enable);
+
 /* Fused GAE + returns + per-block moment partials for prepare_dataset (V == 1, contiguous [H,N]).
  * mask (optional f32 [H,N]) = autoreset validity (a2c_common.py:1002-1006).
- * partials: [gridDim][8] doubles {n, Sv, Sv2, Sr, Sr2, Sa, Sa2, pad}; *n_blocks_out_host receives grid size. */
+ * partials: [gridDim][8] doubles {n, Sv, Sv2, Sr, Sr2, Sa, Sa2, pad}; *n_blocks_out_host receives grid size
+ * (at most ceil(N / 64); ceil(N / 128) when max_partials is smaller than that). */
 int b200rl_gae_fused_f32(const float* rewards, const float* values, const uint8_t* dones,
                          const float* last_values, const uint8_t* last_dones, const float* mask,
                          float* advs, float* returns, double* partials, int max_partials,

@@ -406,7 +406,7 @@ class A2CAgent(CompileTolerantModel):
             self.t_gates, self.t_hin, self.t_cin, self.t_c = f(T, S, 4 * Hd), f(T, S, Hd), f(T, S, Hd), f(T, S, Hd)
             self.t_hdense, self.t_hmlp, self.t_dHmlp = f(S, Hd), f(mb, Hd), f(mb, Hd)
             self.t_dgates, self.t_dhin, self.t_dcin = f(S, 4 * Hd), f(S, Hd), f(2, S, Hd)
-        self.gae_partials = torch.zeros((N + 127) // 128, 8, dtype=torch.float64, device=dev)
+        self.gae_partials = torch.zeros((N + 63) // 64, 8, dtype=torch.float64, device=dev)
         self.loss_partials = torch.zeros(max((mb + 127) // 128, 148), ops.loss_partial_stride(), dtype=torch.float64, device=dev)
         self.n_updates = self.mini_epochs_num * self.num_minibatches
         self.stats = f(self.n_updates, 16)
@@ -551,14 +551,19 @@ class A2CAgent(CompileTolerantModel):
         return self._meter_cache
 
     # =============================================================================== env plumbing
-    def cast_obs(self, obs):
+    def cast_obs(self, obs, name='obs'):
         if isinstance(obs, torch.Tensor):
             self.is_tensor_obses = True
+            # the kernels read raw fp32 row-major device memory: anything else (float64 / half observations, a strided view such as
+            # obs_buf[:, :D], a tensor on another device) is normalised once here, like the reference's torch ops would accept it
+            if obs.dtype != torch.float32 or obs.device != self.device_t or not obs.is_contiguous():
+                obs = obs.to(device=self.device_t, dtype=torch.float32).contiguous()
             return obs
         if isinstance(obs, np.ndarray):
             # host env: async H2D on the compute stream.  If the env hands out page-locked memory (e.g. a pinned ring) the DMA
-            # reads it directly; otherwise stage through a pinned buffer first.
-            key = ('obs', obs.shape, obs.dtype.str)
+            # reads it directly; otherwise stage through a pinned buffer first.  `name` keys the staging buffers: two views of equal
+            # shape (actor obs / critic states) must not share one
+            key = (name, obs.shape, obs.dtype.str)
             buf = self._pinned.get(key)
             if buf is None:
                 buf = (torch.empty(obs.shape, dtype=torch.float32).pin_memory(),
@@ -612,6 +617,8 @@ class A2CAgent(CompileTolerantModel):
         """a2c_common.py:708-719 (+ preprocess_actions :1500-1510 already applied by the policy kernel)."""
         if self.is_tensor_obses:
             obs, rewards, dones, infos = self.vec_env.step(actions)
+            if isinstance(rewards, torch.Tensor) and (rewards.dtype != torch.float32 or rewards.device != self.device_t or not rewards.is_contiguous()):
+                rewards = rewards.to(device=self.device_t, dtype=torch.float32).contiguous()
             return self.obs_to_tensors(obs), rewards, dones, infos
         key = ('act', tuple(actions.shape))
         hb = self._pinned.get(key)
@@ -1406,3 +1413,19 @@ class A2CAgent(CompileTolerantModel):
     def _refresh_cfg(self):
         if self._tensors_ready:
             self._build_cfg_structs()
+            # the kernels read the entropy coefficient from device memory (graph replays see the new value): keep it in step with a
+            # set_param('entropy_coef', v), like the reference, which applies a PBT mutation on the next minibatch
+            self.entropy_coef_dev.fill_(float(self.entropy_coef))
+            self.ent_next_dev.fill_(float(self.entropy_coef))
+            if self.mini_epochs_num * self.num_minibatches != self.n_updates:
+                self._resize_updates()
+
+    def _resize_updates(self):
+        """set_param('mini_epochs_num', k) after init: everything sized by the number of updates per epoch follows"""
+        self.n_updates = self.mini_epochs_num * self.num_minibatches
+        self.stats = torch.zeros(self.n_updates, 16, dtype=torch.float32, device=self.device_t)
+        self.host_stats = torch.zeros(self.n_updates, 16, dtype=torch.float32).pin_memory()
+        self._graph_update = self._graph_epoch = None
+        if self.fused_allreduce and self.n_updates % 2 != 0:
+            raise NotImplementedError('the fused peer all-reduce alternates exchange buffers by update parity: mini_epochs x '
+                                      'num_minibatches must stay even (or set b200_fused_allreduce: False)')

@@ -248,9 +248,9 @@ class A2CAgentCV(A2CAgent):
     # ---- env plumbing: keep the privileged view
     def obs_to_tensors(self, obs):
         if isinstance(obs, dict) and 'states' in obs:
-            self._states = self.cast_obs(obs['states'])
+            self._states = self.cast_obs(obs['states'], name='states')
         elif not isinstance(obs, dict) and self.env_info.get('state_space', None) is None:
-            self._states = self.cast_obs(obs)          # state_space fallback = observation_space
+            self._states = self.cast_obs(obs, name='states')          # state_space fallback = observation_space
         return super().obs_to_tensors(obs)
 
     # ---- rollout: the critic supplies the values (a2c_common.py:593-600, :603-615, :1010-1011)

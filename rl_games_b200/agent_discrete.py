@@ -351,7 +351,7 @@ class DiscreteA2CAgent(CompileTolerantModel):
         self.part = f(self.n_splits, m.num_params)
         self.grad = f(m.num_params)
         self.loss_partials = torch.zeros((mb + 255) // 256, 8, dtype=torch.float64, device=dev)
-        self.gae_partials = torch.zeros(max(64, (N + 127) // 128), 8, dtype=torch.float64, device=dev)
+        self.gae_partials = torch.zeros(max(64, (N + 63) // 64), 8, dtype=torch.float64, device=dev)
         self.inv_counts = f(self.num_minibatches) if self.mask_autoreset_rows else None
         self.mom_scratch = torch.zeros(148 * 4 * 2 * D, dtype=torch.float64, device=dev)
         self.post_scratch = torch.zeros(((N + 255) // 256) * 4, dtype=torch.float64, device=dev)

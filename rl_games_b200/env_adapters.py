@@ -37,7 +37,6 @@ class ManagerBasedEnvAdapter(IVecEnv):
         self.observation_space = Box(-np.inf, np.inf, (self.obs_dim,))
         self.action_space = Box(-1.0, 1.0, (int(env.action_space.shape[-1]),))
         self.state_space = Box(-np.inf, np.inf, (int(groups[_PRIVILEGED_GROUP].shape[-1]),)) if self.privileged else None
-        self._pending = groups              # the shapes came from a real reset: hand that observation to the first reset() call
 
     # ---- observation groups -> what the agent reads
     def _view(self, groups):
@@ -62,9 +61,9 @@ class ManagerBasedEnvAdapter(IVecEnv):
         return self._view(groups), reward, torch.logical_or(terminated, truncated), extras
 
     def reset(self):
-        groups, self._pending = self._pending, None
-        if groups is None:
-            groups, _ = self.env.reset()
+        # like the reference adapter (envs/mjlab_vecenv.py:128-132): every reset() resets the env again, the constructor's probing reset
+        # included, so the env's RNG stream is the reference's for the same seed
+        groups, _ = self.env.reset()
         return self._view(groups)
 
     def get_number_of_agents(self):

@@ -69,6 +69,11 @@ def compute_gae(mb_rewards, mb_values, mb_dones, last_values, last_dones, gamma,
     return advs
 
 
+def gae_set_tma(enable):
+    """A/B switch: TMA-staged GAE kernel (default) vs the register-chunk kernel; returns the previous setting"""
+    return bool(lib.b200rl_gae_set_tma(1 if enable else 0))
+
+
 def gae_fused(rewards, values, dones_u8, last_values, last_dones_u8, mask, advs, returns, partials, gamma, tau):
     """Fused GAE + returns + moment partials on contiguous [H,N] tensors.  Returns number of partial rows."""
     H, N = rewards.shape

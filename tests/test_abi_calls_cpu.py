@@ -15,7 +15,7 @@ import test_agent_host_cpu as H  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(__file__), 'golden')
 HOST_ONLY = {'b200rl_tc_supported', 'b200rl_tc_pack_bytes', 'b200rl_tc_tile_bytes', 'b200rl_tc_xtile_bytes', 'b200rl_tc_pack_table',
-             'b200rl_loss_partial_stride', 'b200rl_built_arch', 'b200rl_set_pdl'}
+             'b200rl_loss_partial_stride', 'b200rl_built_arch', 'b200rl_set_pdl', 'b200rl_gae_set_tma'}
 
 
 class _Recorder:

@@ -469,3 +469,56 @@ def test_tcgen05_path_is_refused_for_activations_its_kernels_do_not_implement(mo
         build(True)
     a = build(None)
     assert a.use_tc is False and a.model.activation == 'relu'
+
+
+class _StridedF64Env(_Env):
+    """a tensor env that hands out what torch ops accept but raw-pointer kernels do not: float64 observations that are a strided view
+    of a wider buffer, float64 rewards (cast_obs passed such tensors to the kernels by data_ptr)"""
+
+    def _wrap(self, o):
+        wide = torch.zeros(o.shape[0], o.shape[1] + 3, dtype=torch.float64)
+        wide[:, :o.shape[1]] = o.double()
+        return wide[:, :o.shape[1]]
+
+    def reset(self):
+        return self._wrap(super().reset())
+
+    def step(self, actions):
+        o, r, d, info = super().step(actions)
+        return self._wrap(o), r.double(), d, info
+
+
+def test_tensor_env_with_strided_float64_tensors_is_normalised_once(monkeypatch, tmp_path):
+    g = torch.load(os.path.join(GOLDEN, 'agent_base.pt'), weights_only=False)
+    out = []
+    for env_cls in (_Env, _StridedF64Env):
+        a = _build(monkeypatch, tmp_path, g, env_cls(g))
+        assert a.obs['obs'].dtype == torch.float32 and a.obs['obs'].is_contiguous()
+        a.epoch_num += 1
+        a.train_epoch(noise=g['noise'][0])
+        out.append((a.model.flat.clone(), a.rewards.clone(), a.obses.clone()))
+    for x, y in zip(*out):
+        assert torch.equal(x, y)
+
+
+def test_set_param_reaches_the_device_copies_the_kernels_read(monkeypatch, tmp_path):
+    """PBT-style mutations (a2c_common.py set_param): entropy_coef is read by the kernels from device memory, so it must follow under
+    lr_schedule 'adaptive' too; mini_epochs_num resizes everything that is sized by the number of updates per epoch"""
+    g = torch.load(os.path.join(GOLDEN, 'agent_base.pt'), weights_only=False)
+    a = _build(monkeypatch, tmp_path, g, _Env(g))
+    assert a.is_adaptive_lr
+    a.epoch_num += 1
+    a.train_epoch(noise=g['noise'][0])
+    a.set_param('entropy_coef', 0.0123)
+    assert float(a.entropy_coef_dev) == pytest.approx(0.0123) and float(a.ent_next_dev) == pytest.approx(0.0123)
+    assert a.get_param('entropy_coef') == 0.0123
+    n0 = a.n_updates
+    a.set_param('mini_epochs_num', a.mini_epochs_num + 1)
+    assert a.n_updates == n0 + a.num_minibatches and a.stats.shape[0] == a.n_updates and a.host_stats.shape[0] == a.n_updates
+    a.epoch_num += 1
+    res = a.train_epoch(noise=g['noise'][1])
+    assert len(res[4]) == a.n_updates and len(res[8]) == a.mini_epochs_num          # a_losses per update, kls per mini-epoch
+    a.set_param('mini_epochs_num', 1)
+    a.epoch_num += 1
+    res = a.train_epoch(noise=g['noise'][0])
+    assert len(res[4]) == a.num_minibatches and a.last_stats.shape[0] == a.num_minibatches

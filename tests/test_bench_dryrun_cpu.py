@@ -26,6 +26,8 @@ def test_bench_b200_arm_reaches_its_json_line(extra):
     assert out['dtype'] == ('f32' if '--fp32' in extra else 'bf16')
     assert set(out['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
     assert ('c5' in out['config']['workload']) == ('c5' in extra)
+    if not extra:       # the default (c2) line also carries BASELINE configs[4]'s per-GPU shard
+        assert out['c5']['n_gpus'] == 1 and out['c5']['value'] > 0 and 'obs 256' in out['c5']['config']['workload']
     rec = json.loads([ln for ln in r.stderr.splitlines() if ln.startswith('RECORDED ')][-1][len('RECORDED '):])
     if '--fp32' in extra:
         assert 'b200rl_ppo_head_loss_f32' in rec and 'b200rl_tc_mlp_fwd_train' not in rec

@@ -82,6 +82,37 @@ def test_gae_fused_bitexact_and_partials(ops, H, N, masked):
     torch.testing.assert_close(p[:7], exp, rtol=1e-12, atol=1e-9)
 
 
+@pytest.mark.parametrize('H,N,masked', [(16, 1024, False), (16, 16384, False), (32, 16384, True), (1, 16, False), (17, 48, True), (33, 4096 + 16, False),
+                                        (64, 4096, True), (100, 208, False), (16, 148 * 4 * 64 + 64, False)])
+def test_gae_tma_kernel_bitexact_vs_oracle_and_register_kernel(ops, H, N, masked):
+    """the TMA-staged kernel (dense [H,N], N % 16 == 0: every shape BASELINE.json names) -- single chunk, two chunks in flight, the ring
+    (H > 32), ragged last chunk, tail tile, both tile widths -- bit-exact against the oracle loop and against the register-chunk kernel;
+    partial sums agree to fp64 summation order"""
+    g = torch.Generator().manual_seed(H * 1000 + N)
+    r = torch.randn(H, N, generator=g); v = torch.randn(H, N, generator=g) * 2 + 1
+    d = (torch.rand(H, N, generator=g) < 0.1).to(torch.uint8)
+    lv = torch.randn(N, generator=g); ld = (torch.rand(N, generator=g) < 0.1).to(torch.uint8)
+    m = (torch.rand(H, N, generator=g) < 0.8).float() if masked else None
+    ref = O.gae(r.unsqueeze(2), v.unsqueeze(2), d.float(), lv.unsqueeze(1), ld.float(), 0.99, 0.95).squeeze(2)
+    dev = lambda t: None if t is None else t.to(DEV)   # noqa: E731
+    res = {}
+    try:
+        for tma in (True, False):
+            ops.gae_set_tma(tma)
+            advs = torch.full((H, N), float('nan'), device=DEV); rets = torch.full((H, N), float('nan'), device=DEV)
+            partials = torch.zeros(((N + 63) // 64, 8), dtype=torch.float64, device=DEV)
+            nb = ops.gae_fused(dev(r), dev(v), dev(d), dev(lv), dev(ld), dev(m), advs, rets, partials, 0.99, 0.95)
+            drop = ops.compute_gae(dev(r).unsqueeze(2), dev(v).unsqueeze(2), dev(d), dev(lv).unsqueeze(1), dev(ld), 0.99, 0.95)
+            torch.cuda.synchronize()
+            res[tma] = (advs.cpu(), rets.cpu(), partials[:nb].sum(0).cpu(), nb, drop.squeeze(2).cpu())
+    finally:
+        ops.gae_set_tma(True)
+    for tma in (True, False):
+        assert torch.equal(res[tma][0], ref) and torch.equal(res[tma][1], ref + v) and torch.equal(res[tma][4], ref), tma
+    assert res[True][3] == (N + 63) // 64 if N <= 148 * 4 * 64 else res[True][3] == (N + 127) // 128
+    torch.testing.assert_close(res[True][2], res[False][2], rtol=1e-12, atol=1e-9)
+
+
 def test_gae_full_size_properties(ops):
     """BASELINE c5 per-GPU size (H=32, N=16384) and 1M envs: compare with the eager loop on the GPU
     (same op order => bit-exact) and check the all-done closed form A = r - V."""
