@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     __shared__ double sm[32];
     __shared__ double smf[256];
     __shared__ float4 sred4[1024];
+    double* smf32 = reinterpret_cast<double*>(sred4);       // 1024 doubles = 8 KB of the 16 KB reduction scratch (used before it)
     __shared__ int is_last;
     const int tid = threadIdx.x;
     RA_STAMP(0);      // kernel start
@@ -329,16 +330,24 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     // ---- 1a. one CTA: loss partials -> stats, KL slot, d_logstd (= gradient entries [0, A)).  Single GPU: the last CTA (its
     //      slice is the shortest); multi GPU: CTA 0, the owner of the slice that contains [0, A) and publisher of the KL slot ----
     if (blockIdx.x == (MULTI ? 0u : gridDim.x - 1)) {
-        const int slots = LOSS_NSC + A;
-        if (tid < 256) {
-            const int slot = tid & 63, grp = tid >> 6;
+        // all 1024 threads: slot = tid % 32, 32 row groups -> at most ceil(n_lpart / 32) dependent loads per thread (it was 37 with 4
+        // groups: this CTA is the one every other CTA waits for at the grid barrier); fixed summation order => deterministic
+        const int slots = LOSS_NSC + A;              // <= 24
+        {
+            const int slot = tid & 31, grp = tid >> 5;
             double s = 0.0;
             if (slot < slots)
-                for (int p = grp; p < n_lpart; p += 4) s += lpart[(int64_t)p * lstride + slot];
-            smf[tid] = s;
+                for (int p = grp; p < n_lpart; p += 32) s += lpart[(int64_t)p * lstride + slot];
+            smf32[tid] = s;
         }
         __syncthreads();
-        if (tid < slots) smf[tid] = (smf[tid] + smf[64 + tid]) + (smf[128 + tid] + smf[192 + tid]);
+        if (tid < 256) {      // 8 partial sums per slot
+            const int slot = tid & 31, g8 = tid >> 5;
+            smf[tid] = (smf32[(4 * g8) * 32 + slot] + smf32[(4 * g8 + 1) * 32 + slot]) + (smf32[(4 * g8 + 2) * 32 + slot] + smf32[(4 * g8 + 3) * 32 + slot]);
+        }
+        __syncthreads();
+        if (tid < slots)
+            smf[tid] = ((smf[tid] + smf[32 + tid]) + (smf[64 + tid] + smf[96 + tid])) + ((smf[128 + tid] + smf[160 + tid]) + (smf[192 + tid] + smf[224 + tid]));
         __syncthreads();
         if (tid == 0) {
             stats[B200RL_STAT_ALOSS] = (float)smf[0];

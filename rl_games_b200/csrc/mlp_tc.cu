@@ -49,6 +49,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// issue only (no wait): lets an epilogue put two 32-column loads in flight before the first use (tmem_ld_wait() once)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+        "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : (__expf(x) - 1.0f); }
 __device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.f : a + 1.f; }
 __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
@@ -389,21 +403,24 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[7]);
         bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[7]);
     }
+    // every parameter / statistic load of the prologue is issued before the single barrier below (one global-memory round trip,
+    // not three); the row-independent constants derived from sigma are finished by thread 0 after it -- their first reader is the
+    // loss epilogue, several barriers further on
     for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = __ldg(p.b1 + i);
     for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = __ldg(p.b2 + i);
     for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = __ldg(p.b3 + i);
     if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
+    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
+    fence_before_sync();
     __syncthreads();
+    fence_after_sync();
     if (tid == 0) {      // row-independent constants: sum(logstd) and the entropy of the diagonal Gaussian
         float sl = 0.f, en = 0.f;
         for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
         sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
     }
-    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
+    TSTAMP();   // prologue done
     const uint32_t tmem = *tmem_slot;
     const uint32_t T1 = tmem, T2 = tmem + 256, T3 = tmem + 384, T4 = tmem + 448;     // accumulator column bases
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -455,14 +472,19 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         TSTAMP();   // MMA 1 done
         {
             uint8_t* g1 = TRAIN ? p.act1 + (size_t)tile * N::A1_BYTES : nullptr;
-#pragma unroll 1
-            for (int c0 = h * (N::U1 / 4); c0 < (h + 1) * (N::U1 / 4); c0 += 32) {
-                float v[32];
-                tmem_ld32(T1 + lane_base + c0, v);
+            static_assert(N::U1 / 4 == 64, "layer-1 epilogue: two 32-column loads per thread");
+            const int c0 = h * 64;
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(T1 + lane_base + c0, ra);
+            tmem_ld32_issue(T1 + lane_base + c0 + 32, rb);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB1[c0 + j]);
-                store_chunks32(v, row, c0, sA1, g1);
-            }
+            for (int j = 0; j < 32; ++j) v[j] = elu_fast(__uint_as_float(ra[j]) + sB1[c0 + j]);
+            store_chunks32(v, row, c0, sA1, g1);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = elu_fast(__uint_as_float(rb[j]) + sB1[c0 + 32 + j]);
+            store_chunks32(v, row, c0 + 32, sA1, g1);
         }
         fence_async_smem();
         fence_before_sync();
@@ -557,11 +579,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         }
         if (TRAIN) {
             // ---- PPO loss, split 4 ways: the four threads (h = 0..3) that can read TMEM lane `row` each take the actions
-            //      j = h, h+4, h+8, h+12; per-row sums are exchanged through shared memory (the dead a2 tile region).
+            //      j = h, h+4, h+8, h+12 for the per-action sums (exchanged through shared memory, the dead a2 tile region) and the
+            //      d_logstd slices; the row-wide outputs go out as whole-row vector stores, one kind per thread: h = 0 the value loss
+            //      and the scalar statistics, h = 1 the new mu row, h = 2 the new sigma row, h = 3 the bf16 d_head row (two 16-byte
+            //      chunks, coalesced across the warp) -- no 2- and 4-byte scattered stores.
             const bool live = row < rows_valid;
             const int64_t ar = arow0 + row;
             float act[4], omu[4], osg[4];
+            float actrow[16];
             float old_v = 0.f, ret = 0.f, old_nlp = 0.f, adv = 0.f, mk = 0.f;
+            const bool vecA = (p.A & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.la.actions) | reinterpret_cast<uintptr_t>(p.la.old_mu) |
+                                                reinterpret_cast<uintptr_t>(p.la.old_sigma)) & 15) == 0;
             if (live) {      // arena inputs: issued before the wait on the heads MMA so their latency overlaps with it
                 old_v = __ldg(p.la.old_values_n + ar); ret = __ldg(p.la.returns_n + ar);
                 old_nlp = __ldg(p.la.old_neglogp + ar); adv = __ldg(p.la.advs_n + ar);
@@ -570,6 +598,22 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                 for (int k = 0; k < 4; ++k) {
                     const int j = h + 4 * k;
                     if (j < p.A) { act[k] = __ldg(p.la.actions + ar * p.A + j); omu[k] = p.la.old_mu[ar * p.A + j]; osg[k] = p.la.old_sigma[ar * p.A + j]; }
+                }
+                if (h == 3) {      // the d_head thread needs the whole action row
+                    if (vecA) {
+                        const float4* pa = reinterpret_cast<const float4*>(p.la.actions + ar * p.A);
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            if (qq * 4 < p.A) {
+                                const float4 x = __ldg(pa + qq);
+                                actrow[qq * 4] = x.x; actrow[qq * 4 + 1] = x.y; actrow[qq * 4 + 2] = x.z; actrow[qq * 4 + 3] = x.w;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 15; ++j)
+                            if (j < p.A) actrow[j] = __ldg(p.la.actions + ar * p.A + j);
+                    }
                 }
             }
             mbar_wait(&bars[4], phase);
@@ -631,38 +675,64 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int j = h + 4 * k;
-                    if (j < p.A) {
-                        const float mu = pick_mu(head, h, k), isg = sSig[2 * p.A + j];
-                        float db = 0.f;
-                        if (p.cfg.has_bounds) {
-                            if (p.cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
-                            else if (p.cfg.bound_type == 2) db = 2.0f * mu;
-                        }
-                        const float dmu = w * (g_a * -(z[k] * isg) + p.cfg.bounds_coef * db);
-                        dls[k] += w * g_a * (1.0f - z[k] * z[k]);
-                        p.la.old_mu[ar * p.A + j] = mu;               // new mu/sigma overwrite the old ones (datasets.py:33-43)
-                        p.la.old_sigma[ar * p.A + j] = sSig[j];
-                        const int c = 1 + j;
-                        *reinterpret_cast<__nv_bfloat16*>(gd + tile_off(row, c >> 3, 2048u, 128u) + (c & 7) * 2) = __float2bfloat16_rn(dmu);
-                    }
+                    if (j < p.A) dls[k] += w * g_a * (1.0f - z[k] * z[k]);
                 }
+                // critic loss and its gradient (threads h = 0 and h = 3 use them)
+                const float val = head[0];
+                float c_loss, dc;
+                if (p.cfg.clip_value) {
+                    const float delta = val - old_v;
+                    const float vpc = old_v + fminf(fmaxf(delta, -p.cfg.e_clip), p.cfg.e_clip);
+                    const float e1 = val - ret, e2 = vpc - ret;
+                    const float l1 = e1 * e1, l2 = e2 * e2;
+                    c_loss = fmaxf(l1, l2);
+                    const float g1 = 2.0f * e1, g2 = (delta >= -p.cfg.e_clip && delta <= p.cfg.e_clip) ? 2.0f * e2 : 0.0f;
+                    dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
+                } else { const float e1 = ret - val; c_loss = e1 * e1; dc = -2.0f * e1; }
                 if (h == 0) {
-                    const float val = head[0];
-                    float c_loss, dc;
-                    if (p.cfg.clip_value) {
-                        const float delta = val - old_v;
-                        const float vpc = old_v + fminf(fmaxf(delta, -p.cfg.e_clip), p.cfg.e_clip);
-                        const float e1 = val - ret, e2 = vpc - ret;
-                        const float l1 = e1 * e1, l2 = e2 * e2;
-                        c_loss = fmaxf(l1, l2);
-                        const float g1 = 2.0f * e1, g2 = (delta >= -p.cfg.e_clip && delta <= p.cfg.e_clip) ? 2.0f * e2 : 0.0f;
-                        dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
-                    } else { const float e1 = ret - val; c_loss = e1 * e1; dc = -2.0f * e1; }
-                    *reinterpret_cast<__nv_bfloat16*>(gd + tile_off(row, 0, 2048u, 128u)) = __float2bfloat16_rn(w * 0.5f * p.cfg.critic_coef * dc);
                     const float lr_ = old_nlp - nlp;
                     const float clipped = (lr_ < p.cfg.log_lo || lr_ > p.cfg.log_hi) ? 1.f : 0.f;
                     sc[0] += w * a_loss; sc[1] += w * c_loss; sc[2] += w * sSig[4 * p.A + 1]; sc[3] += w * bl; sc[4] += w * kl;
                     sc[5] += mk; sc[6] += mk * clipped; sc[7] += w;
+                } else if (h == 3) {
+                    // d_head row: column 0 = value gradient, 1 + j = dL/dmu_j, the rest zero -> two 16-byte chunks
+                    float dh[16];
+                    dh[0] = w * 0.5f * p.cfg.critic_coef * dc;
+#pragma unroll
+                    for (int j = 0; j < 15; ++j) {
+                        float dmu = 0.f;
+                        if (j < p.A) {
+                            const float mu = head[1 + j], isg = sSig[2 * p.A + j];
+                            const float zj = (actrow[j] - mu) * isg;
+                            float db = 0.f;
+                            if (p.cfg.has_bounds) {
+                                if (p.cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
+                                else if (p.cfg.bound_type == 2) db = 2.0f * mu;
+                            }
+                            dmu = w * (g_a * -(zj * isg) + p.cfg.bounds_coef * db);
+                        }
+                        dh[1 + j] = dmu;
+                    }
+                    *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = pack8_bf16(&dh[0]);
+                    *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = pack8_bf16(&dh[8]);
+                } else {
+                    // h = 1: new mu row, h = 2: new sigma row, over the old ones (datasets.py:33-43)
+                    float* dst = (h == 1 ? p.la.old_mu : p.la.old_sigma) + ar * p.A;
+                    if (vecA) {
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            if (qq * 4 < p.A) {
+                                float4 o;
+                                if (h == 1) o = make_float4(head[1 + qq * 4], head[2 + qq * 4], head[3 + qq * 4], qq * 4 + 4 < 16 ? head[(4 + qq * 4) & 15] : 0.f);
+                                else o = make_float4(sSig[qq * 4], sSig[qq * 4 + 1], sSig[qq * 4 + 2], sSig[qq * 4 + 3]);
+                                reinterpret_cast<float4*>(dst)[qq] = o;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 15; ++j)
+                            if (j < p.A) dst[j] = (h == 1) ? head[1 + j] : sSig[j];
+                    }
                 }
             } else if (h < 2) {
                 // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
@@ -702,24 +772,48 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                             }
                         }
                         float sumz2 = 0.f, sumls = 0.f;
+                        float av[16], ev[16];
 #pragma unroll
                         for (int j = 0; j < 15; ++j) {
+                            av[j] = 0.f; ev[j] = 0.f;
                             if (j < p.A) {
                                 const float mu = head[1 + j], sg = sSig[j];
                                 const float act = __fadd_rn(mu, __fmul_rn(sg, eps[j]));
                                 const float z = (act - mu) * sSig[2 * p.A + j];
                                 sumz2 += z * z;
                                 sumls += sSig[p.A + j];
-                                p.actions[(int64_t)m * p.A + j] = act;
-                                p.mus[(int64_t)m * p.A + j] = mu;
-                                p.sigmas[(int64_t)m * p.A + j] = sg;
-                                if (p.env_actions) {
-                                    float ea = act;
-                                    if (p.clip_actions) {
-                                        const float lo = __ldg(p.act_low + j), hi = __ldg(p.act_high + j);
-                                        ea = fminf(fmaxf(act, -1.0f), 1.0f) * ((hi - lo) * 0.5f) + (hi + lo) * 0.5f;
-                                    }
-                                    p.env_actions[(int64_t)m * p.A + j] = ea;
+                                av[j] = act;
+                                float ea = act;
+                                if (p.env_actions && p.clip_actions) {
+                                    const float lo = __ldg(p.act_low + j), hi = __ldg(p.act_high + j);
+                                    ea = fminf(fmaxf(act, -1.0f), 1.0f) * ((hi - lo) * 0.5f) + (hi + lo) * 0.5f;
+                                }
+                                ev[j] = ea;
+                            }
+                        }
+                        av[15] = 0.f; ev[15] = 0.f;
+                        // row-wide outputs (A contiguous floats per row in each arena): 16-byte stores when A % 4 == 0
+                        if ((p.A & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.actions) | reinterpret_cast<uintptr_t>(p.mus) | reinterpret_cast<uintptr_t>(p.sigmas) |
+                                                reinterpret_cast<uintptr_t>(p.env_actions)) & 15) == 0) {
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) {
+                                if (qq * 4 < p.A) {
+                                    reinterpret_cast<float4*>(p.actions + (int64_t)m * p.A)[qq] = make_float4(av[qq * 4], av[qq * 4 + 1], av[qq * 4 + 2], av[qq * 4 + 3]);
+                                    reinterpret_cast<float4*>(p.mus + (int64_t)m * p.A)[qq] =
+                                        make_float4(head[1 + qq * 4], head[2 + qq * 4], head[3 + qq * 4], qq < 3 ? head[(4 + qq * 4) & 15] : 0.f);
+                                    reinterpret_cast<float4*>(p.sigmas + (int64_t)m * p.A)[qq] = make_float4(sSig[qq * 4], sSig[qq * 4 + 1], sSig[qq * 4 + 2], sSig[qq * 4 + 3]);
+                                    if (p.env_actions)
+                                        reinterpret_cast<float4*>(p.env_actions + (int64_t)m * p.A)[qq] = make_float4(ev[qq * 4], ev[qq * 4 + 1], ev[qq * 4 + 2], ev[qq * 4 + 3]);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 15; ++j) {
+                                if (j < p.A) {
+                                    p.actions[(int64_t)m * p.A + j] = av[j];
+                                    p.mus[(int64_t)m * p.A + j] = head[1 + j];
+                                    p.sigmas[(int64_t)m * p.A + j] = sSig[j];
+                                    if (p.env_actions) p.env_actions[(int64_t)m * p.A + j] = ev[j];
                                 }
                             }
                         }
@@ -1508,6 +1602,14 @@ template <class N, bool XL1 = false> constexpr size_t bwd_smem() {
     return bwd1_smem<N>() > bwd2_smem<N, XL1>() ? bwd1_smem<N>() : bwd2_smem<N, XL1>();
 }
 
+// Persistent grid for n_tiles row tiles on 148 SMs: the number of waves w = ceil(n_tiles / 148) fixes the critical path; the FEWEST
+// CTAs with that many waves (ceil(n_tiles / w)) give every CTA the same tile count and -- for the backward kernels -- the fewest
+// split-gradient rows for the reducer to read (c2 minibatch: 256 tiles -> 128 CTAs x 2 tiles instead of 148 rows).
+static inline int tc_grid(int n_tiles) {
+    const int waves = (n_tiles + 147) / 148;
+    return (n_tiles + waves - 1) / waves;
+}
+
 bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D <= 64 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
 // wide observations: the same hidden layers, layer 1 in its own kernels (NetW)
 bool net_is_wide(int D, int u1, int u2, int u3, int A) { return D > 64 && D <= 256 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
@@ -1543,7 +1645,7 @@ template <class N>
 int launch_l1_fwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D, const float* nm, const float* ns, const void* wpack,
                   const float* b1, int M, void* act1, void* stream) {
     const int n_tiles = (M + 127) / 128;
-    const int grid = n_tiles < 148 ? n_tiles : 148;
+    const int grid = tc_grid(n_tiles);
     L1FwdArgs a{obs, rows_per_chunk, chunk_stride, D, nm, ns, (const uint8_t*)wpack, b1, M, (uint8_t*)act1};
     constexpr size_t smem = l1_fwd_smem<N>();
     static_assert(smem <= 227 * 1024, "layer-1 forward kernel shared memory budget");
@@ -1619,7 +1721,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     const int n_tiles = (M + 127) / 128;
-    const int grid = n_tiles < 148 ? n_tiles : 148;
+    const int grid = tc_grid(n_tiles);
     if (n_blocks_out_host) *n_blocks_out_host = grid;
     if (grid > max_partials) return B200RL_EINVAL;
     FwdArgs p{};
@@ -1671,7 +1773,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
     if (!kind) return B200RL_EUNSUPPORTED;
     if (kind == 2 && !l1_scratch) return B200RL_EINVAL;
     const int n_tiles = (N_rows + 127) / 128;
-    const int grid = n_tiles < 148 ? n_tiles : 148;
+    const int grid = tc_grid(n_tiles);
     FwdArgs p{};
     p.obs = obs; p.rows_per_chunk = N_rows; p.chunk_stride = 0; p.D = D; p.nm = norm_mean; p.ns = norm_std;
     p.wpack = (const uint8_t*)wpack; p.b1 = b1; p.b2 = b2; p.b3 = b3; p.bh = b_head; p.logstd = logstd; p.M = N_rows; p.A = A;
@@ -1713,7 +1815,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     if (rc) return rc;
     using N = NetC2;
     const int n_tiles = (M + 127) / 128;
-    const int grid = n_tiles < 148 ? n_tiles : 148;
+    const int grid = tc_grid(n_tiles);
     if (n_parts_out_host) *n_parts_out_host = grid;
     if (grid > max_parts) return B200RL_EINVAL;
     Bwd1Args a{(const uint8_t*)wpack, (const uint8_t*)act1, (const uint8_t*)act2, (const uint8_t*)act3, (const uint8_t*)dhead,

@@ -23,4 +23,8 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
     python bench.py --workload c5 --steps 1 --warmup 3 --no-graph --skip-cpu --skip-e2e > gpurun_out/r02_c2_ncu_launches_c5.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:l1_fwd_tc_kernel|l1_wgrad_tc_kernel|reduce_adam_kernel' --launch-skip 400 --launch-count 4 \
     -f -o gpurun_out/r02_prof_c5 python bench.py --workload c5 --steps 1 --warmup 3 --no-graph --skip-cpu --skip-e2e > gpurun_out/r02_c2_ncu_full_c5.log 2>&1
+echo "== stage timelines (instrumented build) =="
+if [ -f rl_games_b200/libb200rl_timing.so ]; then
+  B200RL_LIB_PATH=$PWD/rl_games_b200/libb200rl_timing.so timeout 120 python tools/tc_stage_timing.py --old-bwd2 2>&1 | tail -80 | tee gpurun_out/r02_c2_stage_timing.log
+fi
 ls -la gpurun_out | tail -12

@@ -84,7 +84,8 @@ def main():
         n = buf[base]
         st = [buf[base + 1 + i] for i in range(n)]
         lab = LABELS[kind]
-        names = ['kernel start'] + lab * ((n - 1 - len(TAIL[kind])) // len(lab)) + TAIL[kind]
+        head = ['kernel start'] + (['prologue done'] if kind == 'fwd' else [])
+        names = head + lab * ((n - len(head) - len(TAIL[kind])) // len(lab)) + TAIL[kind]
         print('  [%s] CTA0: %d stamps, total %.1f us @1.965GHz' % (kind, n, (st[-1] - st[0]) / 1965.0))
         for i in range(1, n):
             print('    %-16s +%7.2f us' % (names[i] if i < len(names) else '?', (st[i] - st[i - 1]) / 1965.0))
