@@ -32,7 +32,12 @@ WORKLOADS = {
     'c2': dict(num_actors=16384, horizon=16, obs_dim=60, act_dim=8, units=[256, 128, 64], minibatch=32768, mini_epochs=4),
     # BASELINE.json configs[4] per-GPU shard (131072 envs / 8), obs 256, horizon 32
     'c5': dict(num_actors=16384, horizon=32, obs_dim=256, act_dim=8, units=[256, 128, 64], minibatch=32768, mini_epochs=4),
+    # BASELINE.json configs[3]: Humanoid-shaped LSTM policy (obs 348, 17 actions, LSTM 256 before the MLP [512,256,128] of
+    # configs/mujoco/humanoid_envpool.yaml, seq_length 4), 8192 envs -- BPTT minibatch path; fp32 kernels (rnn.cu + mlp_simt.cu)
+    'c4': dict(num_actors=8192, horizon=32, obs_dim=348, act_dim=17, units=[512, 256, 128], minibatch=32768, mini_epochs=4,
+               rnn_units=256, rnn_before_mlp=True, seq_length=4),
 }
+CONFIG_INDEX = {'c2': 1, 'c4': 3, 'c5': 4}
 
 
 def make_params(w, device, env_name, multi_gpu, graph=True, seed=5, mixed_precision=True):
@@ -40,6 +45,9 @@ def make_params(w, device, env_name, multi_gpu, graph=True, seed=5, mixed_precis
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': list(w['units']), 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    if w.get('rnn_units'):
+        network['rnn'] = {'name': 'lstm', 'units': w['rnn_units'], 'layers': 1, 'before_mlp': w.get('rnn_before_mlp', True)}
+        mixed_precision = False          # the LSTM path runs on the fp32 kernels
     config = {'name': 'bench', 'env_name': env_name, 'reward_shaper': {'scale_value': 1.0}, 'device': device,
               'multi_gpu': multi_gpu, 'mixed_precision': mixed_precision, 'normalize_input': True, 'normalize_value': True,
               'value_bootstrap': True, 'normalize_advantage': True, 'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4,
@@ -49,6 +57,8 @@ def make_params(w, device, env_name, multi_gpu, graph=True, seed=5, mixed_precis
               'minibatch_size': w['minibatch'], 'mini_epochs': w['mini_epochs'], 'critic_coef': 2, 'print_stats': False,
               'train_dir': '/tmp/b200_bench_runs', 'b200_cuda_graph': graph,
               'env_config': {'obs_dim': w['obs_dim'], 'act_dim': w['act_dim'], 'device': device, 'seed': seed}}
+    if w.get('seq_length'):
+        config['seq_length'] = w['seq_length']
     config.update(CFG_OVERRIDES)     # --cfg key=value: developer A/B switches (b200_* options), recorded in the JSON line
     return {'seed': seed, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'},
             'network': network, 'config': config}
@@ -196,7 +206,8 @@ def reference_arm(args, w):
 def workload_config(name, w, env_desc):
     return {'workload': f'{name}: synthetic PPO, {w["num_actors"]} envs/GPU x horizon {w["horizon"]}, obs {w["obs_dim"]}, '
                         f'act {w["act_dim"]}, MLP {w["units"]}, minibatch {w["minibatch"]} x {w["mini_epochs"]} mini-epochs '
-                        f'(BASELINE.json configs[{1 if name == "c2" else 4}])',
+                        f'{"LSTM " + str(w["rnn_units"]) + " before the MLP, seq_length " + str(w["seq_length"]) + " " if w.get("rnn_units") else ""}'
+                        f'(BASELINE.json configs[{CONFIG_INDEX[name]}])',
             'env': env_desc, 'global_batch': w['num_actors'] * w['horizon'], 'parallelism': 'dp (actors sharded per GPU)',
             'l2': 'flushed between steps (256 MiB write outside the per-step CUDA-event pairs)',
             'hyper_params': 'rl_games/configs/mujoco/ant_envpool.yaml:28-56'}
@@ -345,7 +356,7 @@ def b200_arm(args, w):
     launches_per_step = sum(v['n'] for v in prof.values())
     line = {'metric': 'ppo_env_steps_per_sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': W, 'ms_per_step': 1e3 * total_s / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32' if args.fp32 else 'bf16', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'f32' if (args.fp32 or w.get('rnn_units')) else 'bf16', 'data': 'synthetic',
             'config': workload_config(args.workload, w, 'b200_synthetic (on-GPU Philox env, one kernel per step)'),
             'clocks': clocks, 'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
             'cuda_graph': ('whole-epoch' if agent._graph_epoch is not None else ('update-phase' if agent._graph_update is not None else 'none')), 'kernels': kernels[:12]}
@@ -355,17 +366,20 @@ def b200_arm(args, w):
         # dominant kernel family of the step -> roofline
         line['roofline_gae'] = gae_roofline(w, peaks)
         mlp_ms = sum(v['ms'] for k, v in prof.items() if 'linear' in k or 'tc_mlp' in k)
-        flops = 2 * sum(a * b for a, b in zip([w['obs_dim']] + w['units'], w['units'] + [w['act_dim'] + 1]))
+        mlp_in = w.get('rnn_units') or w['obs_dim']
+        flops = 2 * sum(a * b for a, b in zip([mlp_in] + w['units'], w['units'] + [w['act_dim'] + 1]))
+        if w.get('rnn_units'):          # LSTM gate GEMMs: [obs + hidden] x 4 hidden per row
+            flops += 2 * (w['obs_dim'] + w['rnn_units']) * 4 * w['rnn_units']
         step_flops = B * flops * (1 + 1.0 / w['horizon'] + 3 * w['mini_epochs'])   # rollout fwd (+ last-value fwd) + (fwd + dgrad + wgrad) per mini-epoch
         tf = step_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-        fam = ('MLP GEMM kernels: fp32 CUDA-core path (mixed_precision: False)' if args.fp32 else
+        fam = ('MLP / LSTM GEMM kernels: fp32 CUDA-core path (mixed_precision: False)' if (args.fp32 or w.get('rnn_units')) else
                'tcgen05 bf16 MLP kernels (mlp_fwd_tc<train|rollout>, mlp_bwd_tc)')
         family = {'kernels': fam, 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                   'frac': tf / peaks['bf16_tflops_sustained'], 'share_of_step': round(mlp_ms / ktot, 4), 'alg_flops_per_step': step_flops}
         # the single dominant kernel of the step (largest share of device time): algorithmic FLOPs per launch / its mean launch
         # duration (CUDA events around each launch of the instrumented epoch); `traffic` = DRAM bytes per launch from the
         # committed ncu --set full capture (profiles/traffic.json), null when that kernel has no capture
-        dims = list(zip([w['obs_dim']] + w['units'], w['units'] + [w['act_dim'] + 1]))
+        dims = list(zip([mlp_in] + w['units'], w['units'] + [w['act_dim'] + 1]))
         fwd_fl = 2 * sum(a * b for a, b in dims)
         dgrad_fl = 2 * sum(a * b for a, b in dims[1:])           # no input gradient for the first layer
         per_launch = {'tc_mlp_bwd': (fwd_fl + dgrad_fl) * w['minibatch'], 'tc_mlp_fwd_train': fwd_fl * w['minibatch'],

@@ -510,3 +510,38 @@ def test_lstm_agent_matches_oracle_medium():
         torch.testing.assert_close(agent.rnn_h0.cpu(), oag.mb_rnn_states[0].squeeze(1), rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(agent.rnn_c0.cpu(), oag.mb_rnn_states[1].squeeze(1), rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(agent.rnn_h.cpu(), oag.rnn_states[0][0], rtol=1e-4, atol=1e-5)
+
+
+def test_lstm_c4_geometry_full_width_vs_oracle():
+    """BASELINE configs[3] geometry at full width: 8192 envs, obs 348, 17 actions (Humanoid-v5), LSTM 256 before the MLP [512, 256, 128]
+    (configs/mujoco/humanoid_envpool.yaml:23), seq_length 4 -- horizon 8 (two BPTT windows per env; the horizon only repeats windows), one
+    mini-epoch of 4 minibatches, fp32 kernels vs the CPU oracle on identical tapes / weights / noise: rollout values and states rtol 1e-4,
+    losses rtol 5e-3, weights atol 5e-5."""
+    N, H, D, A, units, mb, hid = 8192, 8, 348, 17, [512, 256, 128], 16384, 256
+    g = torch.Generator().manual_seed(41)
+    T = H + 1
+    obs_tape = torch.randn(T, N, D, generator=g) * 1.5 + 0.3
+    done_tape = (torch.rand(T, N, generator=g) < 0.05).to(torch.uint8)
+    tout_tape = (torch.rand(T, N, generator=g) < 0.3) & done_tape.bool()
+    params = O.init_params(D, units, A, seed=9, rnn_units=hid)
+    noise = torch.randn(H, N, A, generator=g)
+    cfg = {'mini_epochs': 1, 'rnn_units': hid, 'seq_length': 4}
+    oag = O.OracleAgent(O.TapeEnv(obs_tape, done_tape, tout_tape), params, D, A, units, N, H, mb, cfg)
+    oag.obs = oag.env_reset()
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    out = oag.train_epoch(noise)
+    env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
+    agent = make_agent({'mini_epochs': 1, 'seq_length': 4}, N, H, D, A, units, mb, env, params, rnn_units=hid)
+    assert agent.is_rnn and not agent.use_tc and agent.model.rnn_units == hid
+    agent.epoch_num += 1
+    agent.train_epoch(noise=noise.to(DEV))
+    st = agent.last_stats
+    torch.testing.assert_close(agent.values.cpu(), oag.buf['values'].squeeze(2), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(agent.rnn_h.cpu(), oag.rnn_states[0][0], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(st[:, 0], torch.stack(out['a_loss']), rtol=5e-3, atol=1e-5)
+    torch.testing.assert_close(st[:, 1], torch.stack(out['c_loss']), rtol=5e-3, atol=1e-5)
+    torch.testing.assert_close(st[:, 4], torch.stack(out['kl']), rtol=1e-2, atol=1e-6)
+    assert agent.last_lr == pytest.approx(oag.last_lr, rel=1e-12)
+    sd = agent.model.state_dict()
+    for k in O.param_names(3, lstm=True):
+        torch.testing.assert_close(sd[k].cpu(), oag.model.p[k].detach(), rtol=1e-3, atol=5e-5, msg=lambda m: k + ': ' + m)
