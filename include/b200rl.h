@@ -424,6 +424,9 @@ int b200rl_bump_u64(uint64_t* p, void* stream);
  *   fwd_rollout: trunk + heads + sample/neglogp/denorm-value epilogue (same semantics as b200rl_policy_head_sample_f32)
  *   bwd       : delta chain + all weight/bias gradients into part[n_parts][P] at the given flat offsets
  *               (sum with b200rl_reduce_splits_f32)
+ * Geometry: three hidden layers u1 <= 256, u2 <= 128, u3 <= 64 (zero-padded to the compiled tile widths [256,128,64]; e.g.
+ * [128,64,32]), observations D <= 64 (kind 1) or 64 < D <= 256 (kind 2: layer 1 in kernels of its own), up to 15 actions;
+ * `activation` = B200RL_ACT_ELU / _RELU / _TANH / _NONE, one for the whole MLP (network_builder.py:132 _build_mlp).
  * ------------------------------------------------------------------------------------------- */
 int b200rl_tc_supported(int D, int u1, int u2, int u3, int A);
 int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A);
@@ -438,7 +441,7 @@ int b200rl_tc_pack_weights(const float* W1, const float* W2, const float* W3, co
 int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                             const float* norm_mean, const float* norm_std, const void* wpack,
                             const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
-                            int u1, int u2, int u3, int M, int A,
+                            int u1, int u2, int u3, int activation, int M, int A,
                             const float* actions, float* old_mu, float* old_sigma, const float* old_values_n,
                             const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
                             const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
@@ -446,7 +449,7 @@ int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_
                             double* partials, int max_partials, int* n_blocks_out_host, void* stream);
 int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
                               const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
-                              int u1, int u2, int u3, int N_rows, int A,
+                              int u1, int u2, int u3, int activation, int N_rows, int A,
                               const double* vms_mean, const double* vms_var, int normalize_value,
                               const float* noise, uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index,
                               float* actions, float* mus, float* sigmas, float* neglogp, float* values,
@@ -455,7 +458,7 @@ int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, c
                               int values_only, void* l1_scratch, void* stream);
 int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                       const float* norm_mean, const float* norm_std, const void* wpack,
-                      int u1, int u2, int u3, int M, int A,
+                      int u1, int u2, int u3, int activation, int M, int A,
                       const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
                       void* delta2, void* delta1, float* part, int max_parts, int P,
                       int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,

@@ -292,14 +292,16 @@ class A2CAgent(CompileTolerantModel):
         self.is_rnn = self.model.is_rnn()
         # wide observations (64 < obs <= 256): layer 1 runs in kernels of its own (l1_fwd_tc / l1_wgrad_tc)
         allow_wide = True
-        # the tcgen05 kernels hard-wire ELU (the activation of every [256,128,64] config the path was built for); anything else is fp32
-        tc_ok = self.model.activation == 'elu' and ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
+        # tcgen05 kernels: three hidden layers that fit the compiled tile widths (u1 <= 256, u2 <= 128, u3 <= 64; narrower layers are
+        # zero-padded), elu / relu / tanh (or no activation), obs <= 256, <= 15 actions; anything else runs on the fp32 kernels
+        tc_ok = self.model.activation in ('elu', 'relu', 'tanh', 'None', None) and \
+            ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
         if self.mixed_precision is None:
             self.mixed_precision = (not self.is_rnn) and tc_ok
             if not self.mixed_precision and self.global_rank == 0:
                 print(f'b200: mixed_precision not set -> fp32 kernels for this geometry (obs={self.model.D}, units={self.model.units}, '
                       f'actions={self.actions_num}, activation={self.model.activation}{", rnn" if self.is_rnn else ""}); the bf16 tcgen05 kernels cover '
-                      f'obs<=256, MLP [256,128,64] with elu, actions<=15')
+                      f'obs<=256, three-layer MLPs up to [256,128,64] with elu / relu / tanh, actions<=15')
         if self.is_rnn:
             if self.horizon_length % self.seq_length != 0:
                 raise ValueError(f"Horizon length ({self.horizon_length}) must be divisible by sequence length ({self.seq_length})")
@@ -310,12 +312,12 @@ class A2CAgent(CompileTolerantModel):
         self.use_tc = bool(self.mixed_precision)
         if self.use_tc and not tc_ok:
             raise NotImplementedError(
-                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=256, MLP [256,128,64] with elu, actions<=15 in this build; got '
+                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=256, three-layer MLPs up to [256,128,64] with elu / relu / tanh, actions<=15 in this build; got '
                 f'obs={self.model.D}, units={self.model.units}, activation={self.model.activation}, actions={self.actions_num}.  '
                 f'Set mixed_precision: False for the fp32 path.')
         self.tc_wide = self.use_tc and ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2
-        if self.tc_wide and config.get('b200_pipelined_wgrad', False):
-            raise NotImplementedError('b200_pipelined_wgrad is an option of the resident-weights kernels (obs <= 64)')
+        if self.use_tc and config.get('b200_pipelined_wgrad', False) and (self.tc_wide or list(self.model.units) != [256, 128, 64]):
+            raise NotImplementedError('b200_pipelined_wgrad is an option of the native resident-weights geometry (obs <= 64, MLP [256,128,64])')
         self.dataset = _Dataset(self)
         self.has_value_loss = True
         self.use_cuda_graph = bool(config.get('b200_cuda_graph', True))
@@ -674,7 +676,7 @@ class A2CAgent(CompileTolerantModel):
                                    self.rng_seed, self.rng_epoch, t, self.actions[t], self.mus[t], self.sigmas[t],
                                    self.neglogpacs[t], self.values[t], self.env_actions, self.clip_actions, self.actions_low,
                                    self.actions_high, self.dones, self.dones_buf[t], self.prev_dones,
-                                   None if self.valid is None else self.valid[t], l1_scratch=self.tc_l1_scratch)
+                                   None if self.valid is None else self.valid[t], l1_scratch=self.tc_l1_scratch, activation=m.act_id)
             return
         if self.is_rnn and m.rnn_before_mlp:
             obs = self._lstm_step(obs, self.rnn_h, self.rnn_c, self.rnn_h, self.rnn_c)
@@ -698,7 +700,7 @@ class A2CAgent(CompileTolerantModel):
             ops.tc_mlp_fwd_rollout(o, m.D, nm, ns, self.wpack, m.b, m.b_head, m.sigma, m.units, N, A,
                                    m.value_mean_std.running_mean, m.value_mean_std.running_var, self.normalize_value, None, 0, None,
                                    0, None, None, None, None, self.last_values, None, False, None, None, None, None, None, None,
-                                   values_only=True, l1_scratch=self.tc_l1_scratch)
+                                   values_only=True, l1_scratch=self.tc_l1_scratch, activation=m.act_id)
             return self.last_values.unsqueeze(1)
         if self.is_rnn and m.rnn_before_mlp:     # get_values does not advance the agent's rnn states (a2c_common.py:603-626)
             o = self._lstm_step(o, self.rnn_h, self.rnn_c, self.r_tmp_h, self.r_tmp_c)
@@ -953,9 +955,9 @@ class A2CAgent(CompileTolerantModel):
                                   self.mus[0, e0:], self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:],
                                   self.neglogpacs[0, e0:], self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:],
                                   self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.tc_act,
-                                  self.tc_dhead, self.loss_partials, xtile=self.tc_xt)
+                                  self.tc_dhead, self.loss_partials, xtile=self.tc_xt, activation=m.act_id)
         npart = ops.tc_mlp_bwd(x, epm, N, m.D, nm, ns, self.wpack, m.units, mb, A, self.tc_act, self.tc_dhead, self.tc_delta2,
-                               self.tc_delta1, self.part, self.part.shape[1], self.tc_offs, xtile=self.tc_xt)
+                               self.tc_delta1, self.part, self.part.shape[1], self.tc_offs, xtile=self.tc_xt, activation=m.act_id)
         gv = self._gv[u & 1]
         self._set_sched_mode(u)
         if not self.multi_gpu:

@@ -65,6 +65,38 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : (__expf(x) - 1.0f); }
 __device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.f : a + 1.f; }
+__device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// v[j] = act(v[j] + bias[j]) over NV accumulator columns; `act` (B200RL_ACT_*) is uniform over the launch, so each branch is a straight
+// unrolled loop (network_builder.py:132 _build_mlp: one activation for the whole MLP; elu / relu / tanh are what the shipped configs use)
+template <int NV>
+__device__ __forceinline__ void bias_act(float (&v)[NV], const float* __restrict__ bias, int act) {
+    if (act == B200RL_ACT_ELU) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = elu_fast(v[j] + bias[j]);
+    } else if (act == B200RL_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j] + bias[j], 0.f);
+    } else if (act == B200RL_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = tanh_fast(v[j] + bias[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = v[j] + bias[j];
+    }
+}
+// v[j] *= act'(.) expressed through the activation OUTPUT a[j] (8 bf16 values of one chunk)
+__device__ __forceinline__ void mul_act_grad8(float* v, const float (&a)[8], int act) {
+    if (act == B200RL_ACT_ELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= elu_grad_from_out(a[j]);
+    } else if (act == B200RL_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = a[j] > 0.f ? v[j] : 0.f;
+    } else if (act == B200RL_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= 1.0f - a[j] * a[j];
+    }
+}
 __device__ __forceinline__ void unpack8_bf16(const uint4& u, float* f) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -309,6 +341,7 @@ struct FwdArgs {
     const float* nm; const float* ns;
     const uint8_t* wpack; const float* b1; const float* b2; const float* b3; const float* bh; const float* logstd;
     int M; int A;
+    int u1, u2, u3, act;      // LOGICAL layer widths (<= the compiled Net widths: the packed weights are zero-padded) and B200RL_ACT_*
     // training epilogue
     LossArena la; const float* inv_count_dev; LossCfgDev cfg;
     uint8_t* act1; uint8_t* act2; uint8_t* act3; uint8_t* dhead; double* partials;
@@ -406,9 +439,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     // every parameter / statistic load of the prologue is issued before the single barrier below (one global-memory round trip,
     // not three); the row-independent constants derived from sigma are finished by thread 0 after it -- their first reader is the
     // loss epilogue, several barriers further on
-    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = __ldg(p.b1 + i);
-    for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = __ldg(p.b2 + i);
-    for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = __ldg(p.b3 + i);
+    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = i < p.u1 ? __ldg(p.b1 + i) : 0.f;
+    for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = i < p.u2 ? __ldg(p.b2 + i) : 0.f;
+    for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = i < p.u3 ? __ldg(p.b3 + i) : 0.f;
     if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
     load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
@@ -480,10 +513,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             tmem_ld_wait();
             float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = elu_fast(__uint_as_float(ra[j]) + sB1[c0 + j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
+            bias_act<32>(v, sB1 + c0, p.act);
             store_chunks32(v, row, c0, sA1, g1);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = elu_fast(__uint_as_float(rb[j]) + sB1[c0 + 32 + j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rb[j]);
+            bias_act<32>(v, sB1 + c0 + 32, p.act);
             store_chunks32(v, row, c0 + 32, sA1, g1);
         }
         fence_async_smem();
@@ -523,8 +558,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             for (int c0 = h * (N::U2 / 4); c0 < (h + 1) * (N::U2 / 4); c0 += 32) {
                 float v[32];
                 tmem_ld32(T2 + lane_base + c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB2[c0 + j]);
+                bias_act<32>(v, sB2 + c0, p.act);
                 store_chunks32(v, row, c0, sXA2, g2);
             }
         }
@@ -553,8 +587,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             const int c0 = h * 16;
             float v[16];
             tmem_ld16(T3 + lane_base + c0, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = elu_fast(v[j] + sB3[c0 + j]);
+            bias_act<16>(v, sB3 + c0, p.act);
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
                 const uint4 u = pack8_bf16(&v[qq * 8]);
@@ -872,6 +905,7 @@ struct Bwd1Args {
     const uint8_t* wpack; const uint8_t* act1; const uint8_t* act2; const uint8_t* act3; const uint8_t* dhead;
     uint8_t* delta2; uint8_t* delta1; float* part;   // part: [n_cta][P]
     int M; int A; int P; int off_W3, off_b3, off_b2, off_Wh, off_bh;
+    int u1, u2, u3, act;
 };
 
 // body: TMEM (512 columns at `tmem`) is allocated by the calling kernel; barriers and shared-memory layout are set up here
@@ -949,8 +983,7 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
             for (int g = 0; g < 4; ++g) {
                 float a[8];
                 unpack8_bf16(*reinterpret_cast<const uint4*>(sA3 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS)), a);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[g * 8 + j] *= elu_grad_from_out(a[j]);
+                mul_act_grad8(&v[g * 8], a, p.act);
             }
             store_chunks32(v, row, c0, sD3, nullptr);
         }
@@ -985,8 +1018,7 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
                 for (int g = 0; g < 4; ++g) {
                     float a[8];
                     unpack8_bf16(*reinterpret_cast<const uint4*>(sA2 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS)), a);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[g * 8 + j] *= elu_grad_from_out(a[j]);
+                    mul_act_grad8(&v[g * 8], a, p.act);
                 }
                 store_chunks32(v, row, c0, sD2, g2);
             }
@@ -1031,8 +1063,7 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
                 for (int g = 0; g < 4; ++g) {
                     float a[8];
                     unpack8_bf16(ua[g], a);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[g * 8 + j] *= elu_grad_from_out(a[j]);
+                    mul_act_grad8(&v[g * 8], a, p.act);
                 }
                 store_chunks32(v, row, c0, nullptr, g1);
             }
@@ -1053,32 +1084,35 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
             float v[32];
             tmem_ld32(TW3 + lane_base + c0, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) part[p.off_W3 + (c0 + j) * N::U2 + row] = v[j];
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.u3 && row < p.u2) part[p.off_W3 + (c0 + j) * p.u2 + row] = v[j];
         }
-        if (h == 0 && row < N::U3) {   // dWh^T[i][o]: rows i < U3 valid; grad_Wh[o * U3 + i], o < A + 1
+        if (h == 0 && row < p.u3) {   // dWh^T[i][o]: rows i < u3 valid; grad_Wh[o * u3 + i], o < A + 1
             float v[16];
             tmem_ld16(TWH + lane_base, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-                if (j < p.A + 1) part[p.off_Wh + j * N::U3 + row] = v[j];
+                if (j < p.A + 1) part[p.off_Wh + j * p.u3 + row] = v[j];
         } else if (h == 0) {
             float v[16];
             tmem_ld16(TWH + lane_base, v);   // keep the warp-collective load converged
         }
     } else {
-        for (int i = tid; i < N::U3 * N::U2; i += 256) part[p.off_W3 + i] = 0.f;
-        for (int i = tid; i < (p.A + 1) * N::U3; i += 256) part[p.off_Wh + i] = 0.f;
+        for (int i = tid; i < p.u3 * p.u2; i += 256) part[p.off_W3 + i] = 0.f;
+        for (int i = tid; i < (p.A + 1) * p.u3; i += 256) part[p.off_Wh + i] = 0.f;
     }
     {
         int g = colsum8_owner_group<N::U3 / 8, 256>(tid);
         if (g >= 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) part[p.off_b3 + g * 8 + j] = bsum3[j];
+            for (int j = 0; j < 8; ++j)
+                if (g * 8 + j < p.u3) part[p.off_b3 + g * 8 + j] = bsum3[j];
         }
         g = colsum8_owner_group<N::U2 / 8, 256>(tid);
         if (g >= 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) part[p.off_b2 + g * 8 + j] = bsum2[j];
+            for (int j = 0; j < 8; ++j)
+                if (g * 8 + j < p.u2) part[p.off_b2 + g * 8 + j] = bsum2[j];
         }
         g = colsum8_owner_group<N::AP / 8, 256>(tid);
         if (g >= 0) {
@@ -1116,6 +1150,7 @@ struct Bwd2Args {
     const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
     const uint8_t* act1; const uint8_t* delta2; const uint8_t* delta1; float* part;
     int M; int P; int off_W2, off_W1, off_b1;
+    int u1, u2;
 };
 
 // XL1 (wide observations): dW1 is l1_wgrad_tc_kernel's job -- no X tile, no dW1^T accumulator, no W1 flush here (db1 stays).
@@ -1207,7 +1242,8 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
                 float v[32];
                 tmem_ld32(TW2 + hh * N::U2 + lane_base + c0, v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) part[p.off_W2 + (size_t)(c0 + j) * N::U1 + hh * 128 + row] = v[j];
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < p.u2 && hh * 128 + row < p.u1) part[p.off_W2 + (size_t)(c0 + j) * p.u1 + hh * 128 + row] = v[j];
             }
         }
         // dW1^T: lane = in index i = row (< D valid), columns = out o in [128h, 128h+128)
@@ -1218,19 +1254,21 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
             tmem_ld32(TW1 + lane_base + c0, v);
             if (row < p.D) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) part[p.off_W1 + (size_t)(c0 + j) * p.D + row] = v[j];
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + j < p.u1) part[p.off_W1 + (size_t)(c0 + j) * p.D + row] = v[j];
             }
         }
         }
     } else {
-        for (int i = tid; i < N::U2 * N::U1; i += 256) part[p.off_W2 + i] = 0.f;
-        if (!XL1) for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
+        for (int i = tid; i < p.u2 * p.u1; i += 256) part[p.off_W2 + i] = 0.f;
+        if (!XL1) for (int i = tid; i < p.u1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
     }
     {
         const int g = colsum8_owner_group<N::U1 / 8, 256>(tid);
         if (g >= 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) part[p.off_b1 + g * 8 + j] = bsum1[j];
+            for (int j = 0; j < 8; ++j)
+                if (g * 8 + j < p.u1) part[p.off_b1 + g * 8 + j] = bsum1[j];
         }
     }
     fence_before_sync();
@@ -1415,7 +1453,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_db_tc_kernel(const Bwd2DbArgs
 // rollout).  Same operand layouts, descriptors and epilogue as layer 1 of mlp_fwd_tc_kernel.
 struct L1FwdArgs {
     const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
-    const uint8_t* wpack; const float* b1; int M; uint8_t* act1;
+    const uint8_t* wpack; const float* b1; int M; uint8_t* act1; int u1, act;
 };
 
 template <class N>
@@ -1440,7 +1478,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
         mbar_expect_tx(&bars[0], N::W1_BYTES);
         bulk_g2s(sW1, p.wpack + N::W1_OFF, N::W1_BYTES, &bars[0]);
     }
-    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = __ldg(p.b1 + i);
+    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = i < p.u1 ? __ldg(p.b1 + i) : 0.f;
     load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     fence_before_sync();
     __syncthreads();
@@ -1477,8 +1515,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
             for (int c0 = h * (N::U1 / 4); c0 < (h + 1) * (N::U1 / 4); c0 += 32) {
                 float v[32];
                 tmem_ld32(T1 + lane_base + c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = elu_fast(v[j] + sB1[c0 + j]);
+                bias_act<32>(v, sB1 + c0, p.act);
                 store_chunks32(v, row, c0, nullptr, g1);
             }
         }
@@ -1498,7 +1535,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
 // TMA), the X tile is re-derived from the observations.  Same MN-major operand trick and coalesced flush as bwd2_body.
 struct L1WgradArgs {
     const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
-    const uint8_t* delta1; float* part; int M; int P; int off_W1;
+    const uint8_t* delta1; float* part; int M; int P; int off_W1; int u1;
 };
 
 template <class N>
@@ -1572,12 +1609,13 @@ __global__ void __launch_bounds__(256, 1) l1_wgrad_tc_kernel(const L1WgradArgs p
                 tmem_ld32(tmem + hh * N::U1 + lane_base + c0, v);
                 if (i < p.D) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) part[p.off_W1 + (size_t)(c0 + j) * p.D + i] = v[j];
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.u1) part[p.off_W1 + (size_t)(c0 + j) * p.D + i] = v[j];
                 }
             }
         }
     } else {
-        for (int i = tid; i < N::U1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
+        for (int i = tid; i < p.u1 * p.D; i += 256) part[p.off_W1 + i] = 0.f;
     }
     fence_before_sync();
     __syncthreads();
@@ -1610,9 +1648,16 @@ static inline int tc_grid(int n_tiles) {
     return (n_tiles + waves - 1) / waves;
 }
 
-bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D <= 64 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
+// Geometries: any three-layer MLP that fits the compiled tile widths (u1 <= 256, u2 <= 128, u3 <= 64, up to 15 actions) runs on the
+// kernels compiled for [256, 128, 64]: the packed bf16 weights are zero-padded to the tile widths (pack_weights_kernel), padded units
+// have zero weights and zero bias, so their activations (elu / relu / tanh of 0) and their deltas are exactly zero, and every flush
+// writes with the LOGICAL strides of the fp32 parameter arena.  [128, 64, 32] (e.g. configs/mujoco/walker2d.yaml) runs this way.
+bool net_fits(int u1, int u2, int u3, int A) { return u1 >= 1 && u2 >= 1 && u3 >= 1 && u1 <= 256 && u2 <= 128 && u3 <= 64 && A >= 1 && A + 1 <= 16; }
+bool net_is_native(int u1, int u2, int u3) { return u1 == 256 && u2 == 128 && u3 == 64; }
+bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D >= 1 && D <= 64 && net_fits(u1, u2, u3, A); }
 // wide observations: the same hidden layers, layer 1 in its own kernels (NetW)
-bool net_is_wide(int D, int u1, int u2, int u3, int A) { return D > 64 && D <= 256 && u1 == 256 && u2 == 128 && u3 == 64 && A + 1 <= 16; }
+bool net_is_wide(int D, int u1, int u2, int u3, int A) { return D > 64 && D <= 256 && net_fits(u1, u2, u3, A); }
+bool act_ok(int act) { return act == B200RL_ACT_NONE || act == B200RL_ACT_ELU || act == B200RL_ACT_RELU || act == B200RL_ACT_TANH; }
 int net_kind(int D, int u1, int u2, int u3, int A) { return net_is_c2(D, u1, u2, u3, A) ? 1 : (net_is_wide(D, u1, u2, u3, A) ? 2 : 0); }
 
 template <class N>
@@ -1643,10 +1688,10 @@ int pack_weights_impl(const float* W1, const float* W2, const float* W3, const f
 // layer 1 of the wide path (see l1_fwd_tc_kernel): a1 tiles of M rows into `act1`
 template <class N>
 int launch_l1_fwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D, const float* nm, const float* ns, const void* wpack,
-                  const float* b1, int M, void* act1, void* stream) {
+                  const float* b1, int M, void* act1, int u1, int act, void* stream) {
     const int n_tiles = (M + 127) / 128;
     const int grid = tc_grid(n_tiles);
-    L1FwdArgs a{obs, rows_per_chunk, chunk_stride, D, nm, ns, (const uint8_t*)wpack, b1, M, (uint8_t*)act1};
+    L1FwdArgs a{obs, rows_per_chunk, chunk_stride, D, nm, ns, (const uint8_t*)wpack, b1, M, (uint8_t*)act1, u1, act};
     constexpr size_t smem = l1_fwd_smem<N>();
     static_assert(smem <= 227 * 1024, "layer-1 forward kernel shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(l1_fwd_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1674,7 +1719,7 @@ B200RL_EXPORT int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int
 }
 
 B200RL_EXPORT int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A) {
-    return net_is_c2(D, u1, u2, u3, A) ? (int64_t)NetC2::X_BYTES : -1;
+    return (net_is_c2(D, u1, u2, u3, A) && net_is_native(u1, u2, u3)) ? (int64_t)NetC2::X_BYTES : -1;
 }
 
 // segments of the packed weight buffer, for the optimiser's fused refresh (b200rl_adam_step_f32)
@@ -1706,7 +1751,7 @@ static int tc_check_rows(int M, int rows_per_chunk) {
 B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                                           const float* norm_mean, const float* norm_std, const void* wpack,
                                           const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
-                                          int u1, int u2, int u3, int M, int A,
+                                          int u1, int u2, int u3, int activation, int M, int A,
                                           const float* actions, float* old_mu, float* old_sigma, const float* old_values_n,
                                           const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
                                           const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
@@ -1716,8 +1761,8 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
         !old_neglogp || !advs_n || !cfg_host || !act1 || !act2 || !act3 || !dhead || !partials)
         return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
-    if (!kind) return B200RL_EUNSUPPORTED;
-    if (kind == 2 && xtile) return B200RL_EUNSUPPORTED;      // the pipelined weight-gradient kernel is a resident-W1 option
+    if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
+    if (xtile && (kind == 2 || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;      // the pipelined weight-gradient kernel is an option of the native resident-W1 geometry
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     const int n_tiles = (M + 127) / 128;
@@ -1727,6 +1772,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
     FwdArgs p{};
     p.obs = obs; p.rows_per_chunk = rows_per_chunk; p.chunk_stride = chunk_stride; p.D = D; p.nm = norm_mean; p.ns = norm_std;
     p.wpack = (const uint8_t*)wpack; p.b1 = b1; p.b2 = b2; p.b3 = b3; p.bh = b_head; p.logstd = logstd; p.M = M; p.A = A;
+    p.u1 = u1; p.u2 = u2; p.u3 = u3; p.act = activation;
     p.la = LossArena{actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask};
     p.inv_count_dev = inv_count_dev;
     p.cfg = LossCfgDev{cfg_host->e_clip, cfg_host->critic_coef, cfg_host->bounds_loss_coef, cfg_host->has_bounds_loss,
@@ -1736,7 +1782,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
     p.xt = (uint8_t*)xtile;
     if (kind == 2) {
         // wide observations: layer 1 (a1 tiles -> act1), then the chain kernel in its external-layer-1 form
-        rc = launch_l1_fwd<NetW>(obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, wpack, b1, M, act1, stream);
+        rc = launch_l1_fwd<NetW>(obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, wpack, b1, M, act1, u1, activation, stream);
         if (rc) return rc;
         constexpr size_t smemw = fwd_smem<NetW, true>();
         static_assert(smemw <= 227 * 1024, "forward kernel (external layer 1) shared memory budget");
@@ -1757,7 +1803,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
 
 B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
                                             const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
-                                            int u1, int u2, int u3, int N_rows, int A,
+                                            int u1, int u2, int u3, int activation, int N_rows, int A,
                                             const double* vms_mean, const double* vms_var, int normalize_value,
                                             const float* noise, uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index,
                                             float* actions, float* mus, float* sigmas, float* neglogp, float* values,
@@ -1770,19 +1816,20 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
     if (env_actions && clip_actions && (!act_low || !act_high)) return B200RL_EINVAL;
     if (dones_out && !dones_cur) return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
-    if (!kind) return B200RL_EUNSUPPORTED;
+    if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
     if (kind == 2 && !l1_scratch) return B200RL_EINVAL;
     const int n_tiles = (N_rows + 127) / 128;
     const int grid = tc_grid(n_tiles);
     FwdArgs p{};
     p.obs = obs; p.rows_per_chunk = N_rows; p.chunk_stride = 0; p.D = D; p.nm = norm_mean; p.ns = norm_std;
     p.wpack = (const uint8_t*)wpack; p.b1 = b1; p.b2 = b2; p.b3 = b3; p.bh = b_head; p.logstd = logstd; p.M = N_rows; p.A = A;
+    p.u1 = u1; p.u2 = u2; p.u3 = u3; p.act = activation;
     p.vms_mean = vms_mean; p.vms_var = vms_var; p.normalize_value = normalize_value; p.noise = noise; p.seed = seed;
     p.rng_epoch = rng_epoch_dev; p.step_index = step_index; p.actions = actions; p.mus = mus; p.sigmas = sigmas; p.neglogp = neglogp;
     p.values = values; p.env_actions = env_actions; p.clip_actions = clip_actions; p.act_low = act_low; p.act_high = act_high;
     p.dones_cur = dones_cur; p.dones_out = dones_out; p.prev_dones = prev_dones; p.valid_out = valid_out; p.values_only = values_only;
     if (kind == 2) {
-        int rc = launch_l1_fwd<NetW>(obs, N_rows, 0, D, norm_mean, norm_std, wpack, b1, N_rows, l1_scratch, stream);
+        int rc = launch_l1_fwd<NetW>(obs, N_rows, 0, D, norm_mean, norm_std, wpack, b1, N_rows, l1_scratch, u1, activation, stream);
         if (rc) return rc;
         p.act1 = (uint8_t*)l1_scratch;
         constexpr size_t smemw = fwd_smem<NetW, true>();
@@ -1802,15 +1849,15 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
 
 B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                                     const float* norm_mean, const float* norm_std, const void* wpack,
-                                    int u1, int u2, int u3, int M, int A,
+                                    int u1, int u2, int u3, int activation, int M, int A,
                                     const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
                                     void* delta2, void* delta1, float* part, int max_parts, int P,
                                     int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
                                     int* n_parts_out_host, void* stream) {
     if (!obs || !wpack || !act1 || !act2 || !act3 || !dhead || !delta2 || !delta1 || !part) return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
-    if (!kind) return B200RL_EUNSUPPORTED;
-    if (kind == 2 && xtile) return B200RL_EUNSUPPORTED;
+    if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
+    if (xtile && (kind == 2 || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     using N = NetC2;
@@ -1819,7 +1866,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     if (n_parts_out_host) *n_parts_out_host = grid;
     if (grid > max_parts) return B200RL_EINVAL;
     Bwd1Args a{(const uint8_t*)wpack, (const uint8_t*)act1, (const uint8_t*)act2, (const uint8_t*)act3, (const uint8_t*)dhead,
-               (uint8_t*)delta2, (uint8_t*)delta1, part, M, A, P, off_W3, off_b3, off_b2, off_Wh, off_bh};
+               (uint8_t*)delta2, (uint8_t*)delta1, part, M, A, P, off_W3, off_b3, off_b2, off_Wh, off_bh, u1, u2, u3, activation};
     cudaError_t e;
     if (xtile) {
         // two launches: delta chain, then the pipelined weight-gradient kernel (observation tiles from the forward kernel,
@@ -1843,14 +1890,14 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     if (kind == 2) {
         // wide observations: the chain kernel without the W1 part, then dW1 in its own kernel (same grid => same split rows)
         BwdArgs abw{a, Bwd2Args{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
-                                (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1}};
+                                (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1, u1, u2}};
         constexpr size_t smemw = bwd_smem<NetW, true>();
         static_assert(smemw <= 227 * 1024, "backward kernel (external layer 1) shared memory budget");
         e = cudaFuncSetAttribute(mlp_bwd_tc_kernel<NetW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
         if (e != cudaSuccess) return (int)e;
         e = launch_k(mlp_bwd_tc_kernel<NetW, true>, dim3(grid), dim3(256), smemw, as_stream(stream), abw);
         if (e != cudaSuccess) return (int)e;
-        L1WgradArgs w{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)delta1, part, M, P, off_W1};
+        L1WgradArgs w{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)delta1, part, M, P, off_W1, u1};
         constexpr size_t smem1w = l1_wgrad_smem<NetW>();
         static_assert(smem1w <= 227 * 1024, "layer-1 weight-gradient kernel shared memory budget");
         e = cudaFuncSetAttribute(l1_wgrad_tc_kernel<NetW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1w);
@@ -1860,7 +1907,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     }
     // default: the whole backward pass in one launch
     BwdArgs ab{a, Bwd2Args{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
-                           (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1}};
+                           (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1, u1, u2}};
     constexpr size_t smem = bwd_smem<N>();
     static_assert(smem <= 227 * 1024, "backward kernel shared memory budget");
     e = cudaFuncSetAttribute(mlp_bwd_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

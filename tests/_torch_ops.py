@@ -580,20 +580,20 @@ def _tc_forward(x, ws, b, b_head, act=1):
 
 def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch,
                        step_index, actions, mus, sigmas, neglogp, values, env_actions, clip_actions, act_low, act_high, dones_cur, dones_out,
-                       prev_dones, valid_out, values_only=False, l1_scratch=None):
+                       prev_dones, valid_out, values_only=False, l1_scratch=None, activation=1):
     ws = _TC[wpack.data_ptr()]
     if _TC.get('kind', 1) == 2:      # wide observations: the layer-1 kernel parks N rows of a1 tiles in the scratch between the two launches
         assert l1_scratch is not None and l1_scratch.numel() >= (N + 127) // 128 * units[0] * 256
     h = obs[:N].reshape(N, D)
     for W, bb in zip(ws[:3], b):
-        h = ACT[1]((_norm(h, nm, ns) if W is ws[0] else h) @ W.t() + bb)
+        h = ACT[activation]((_norm(h, nm, ns) if W is ws[0] else h) @ W.t() + bb)
     policy_head_sample(h, ws[3], b_head, logstd, vms_mean, vms_var, normalize_value, noise, seed, rng_epoch, step_index, actions, mus, sigmas,
                        neglogp, values, env_actions, clip_actions, act_low, act_high, dones_cur, dones_out, prev_dones, valid_out, N, A,
                        values_only=values_only)
 
 
 def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_head, logstd, units, M, A, actions, old_mu, old_sigma, old_values_n,
-                     returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials, xtile=None):
+                     returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials, xtile=None, activation=1):
     """whole training forward + loss + backward of the MLP in fp32 with autograd; the gradients wait in a side channel for tc_mlp_bwd"""
     assert _TC.get('kind', 1) == 1 or xtile is None
     ws = [w.clone().requires_grad_(True) for w in _TC[wpack.data_ptr()]]
@@ -601,7 +601,7 @@ def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_h
     x = _norm(_rows(obs, M, D, rows_per_chunk, chunk_stride, D), nm, ns)
     h = x
     for W, bb in zip(ws[:3], bs):
-        h = ACT[1](h @ W.t() + bb)
+        h = ACT[activation](h @ W.t() + bb)
     hl = h
     hl.retain_grad()
     d_head = torch.zeros(M, A + 1)
@@ -615,7 +615,7 @@ def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_h
     return 1
 
 
-def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=None):
+def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=None, activation=1):
     """split partial rows: everything in row 0, zeros elsewhere; P is the row stride"""
     g = _LOSS_SIDE['tc_grads']
     f = _flat(part)

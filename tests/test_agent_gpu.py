@@ -51,12 +51,12 @@ class TapeEnvGPU:
         pass
 
 
-def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0, rnn_before_mlp=True):
+def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0, rnn_before_mlp=True, activation='elu'):
     from rl_games_b200.runner import Runner
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
-               'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}}}
+               'mlp': {'units': list(units), 'activation': activation, 'initializer': {'name': 'default'}}}
     if rnn_units:
         network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': rnn_before_mlp}
     config = {'name': 'gpu_parity', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0}, 'device': DEV,
@@ -360,8 +360,16 @@ def test_bf16_tcgen05_agent_tracks_fp32_agent_flag_matrix(extra):
     _bf16_vs_fp32_agents(60, dict(extra))
 
 
-def _bf16_vs_fp32_agents(D, extra):
-    N, H, A, units, mb = 512, 8, 8, [256, 128, 64], 2048
+@pytest.mark.parametrize('D,units,activation', [(17, [128, 64, 32], 'relu'), (60, [128, 64, 32], 'tanh'), (111, [200, 100, 50], 'elu'), (60, [256, 128, 64], 'relu')])
+def test_bf16_tcgen05_agent_other_geometries_and_activations_track_fp32_agent(D, units, activation):
+    """three-layer MLPs narrower than the compiled tiles (zero-padded; [128, 64, 32] is configs/mujoco/walker2d.yaml) and relu / tanh
+    networks on the tcgen05 kernels vs the fp32 kernels: the same tolerance class as the native geometry"""
+    _bf16_vs_fp32_agents(D, {}, units=units, activation=activation)
+
+
+def _bf16_vs_fp32_agents(D, extra, units=(256, 128, 64), activation='elu'):
+    N, H, A, mb = 512, 8, 8, 2048
+    units = list(units)
     obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=21)
     params = O.init_params(D, units, A, seed=4)
     g = torch.Generator().manual_seed(6)
@@ -369,7 +377,7 @@ def _bf16_vs_fp32_agents(D, extra):
     agents = []
     for mp in (False, True):
         env = TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
-        a = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False, **extra}, N, H, D, A, units, mb, env, params)
+        a = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False, **extra}, N, H, D, A, units, mb, env, params, activation=activation)
         assert a.use_tc == mp and getattr(a, 'tc_wide', False) == (mp and D > 64)
         a.epoch_num += 1
         a.train_epoch(noise=noise)

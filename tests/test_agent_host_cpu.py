@@ -443,16 +443,31 @@ def test_poison_flow_of_the_reference_masking_test_runs_through_the_public_api(m
         assert torch.equal(results[0][k], results[1][k]), k
 
 
-def test_tcgen05_path_is_refused_for_activations_its_kernels_do_not_implement(monkeypatch, tmp_path):
-    """the tcgen05 kernels hard-wire ELU: a relu network of the supported geometry must never be routed there -- explicit
-    mixed_precision: True raises, an absent key resolves to the fp32 kernels"""
+@pytest.mark.parametrize('activation', ['relu', 'tanh'])
+def test_tcgen05_path_takes_relu_and_tanh_networks(activation, monkeypatch, tmp_path):
+    """the tcgen05 kernels take the MLP activation as a launch argument (elu / relu / tanh): a relu / tanh network of a supported geometry
+    is routed there with mixed_precision: True (or an absent key), the activation id reaches every tcgen05 call, and the host logic
+    around the kernels gives the same epoch as the fp32-kernel route (both computed by fp32 torch stand-ins here)"""
     import _torch_ops
+    from rl_games_b200 import ops
     from rl_games_b200.runner import Runner
     g = dict(torch.load(os.path.join(GOLDEN, 'agent_tcshape.pt'), weights_only=False))
+    seen = []
 
     def build(mp):
-        _torch_ops.install_tc(monkeypatch)
+        (_torch_ops.install_tc if mp is not False else _torch_ops.install_continuous)(monkeypatch)
+        if mp is not False:
+            for name in ('tc_mlp_fwd_train', 'tc_mlp_fwd_rollout', 'tc_mlp_bwd'):
+                inner = getattr(ops, name)
+
+                def spy(*a, _inner=inner, _name=name, **k):
+                    seen.append((_name, k.get('activation')))
+                    return _inner(*a, **k)
+                monkeypatch.setattr(ops, name, spy)
         monkeypatch.setattr(torch.cuda, 'set_device', lambda d: None)
+        monkeypatch.setattr(torch.cuda, 'Event', _Event)
+        monkeypatch.setattr(torch.cuda, 'current_stream', lambda *a: _Stream())
+        monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self: self)
         env = _Env(g)
         config = {k: v for k, v in g['config'].items() if k not in ('device', 'torch_compile')}
         config.update({'device': _CudaLookingStr('cpu'), 'env_info': env.get_env_info(), 'vec_env': env, 'reward_shaper': {'scale_value': 1.0},
@@ -460,15 +475,27 @@ def test_tcgen05_path_is_refused_for_activations_its_kernels_do_not_implement(mo
         network = {'name': 'actor_critic', 'separate': False,
                    'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                             'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
-                   'mlp': {'units': g['units'], 'activation': 'relu', 'initializer': {'name': 'default'}}}
+                   'mlp': {'units': g['units'], 'activation': activation, 'initializer': {'name': 'default'}}}
         r = Runner()
         r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
                            'config': config}})
-        return r.algo_factory.create(r.algo_name, base_name='x', params=r.params)
-    with pytest.raises(NotImplementedError, match='with elu'):
-        build(True)
-    a = build(None)
-    assert a.use_tc is False and a.model.activation == 'relu'
+        r.params['config']['vec_env'] = env
+        a = r.algo_factory.create(r.algo_name, base_name='x', params=r.params)
+        a.model.load_state_dict(g['init_state'], strict=False)
+        a.init_tensors()
+        a._repack()
+        a.obs = a.env_reset()
+        return a
+    assert build(None).use_tc is True
+    t = build(True)
+    assert t.use_tc is True and t.model.activation == activation
+    t.epoch_num += 1
+    t.train_epoch(noise=g['noise'][0])
+    assert seen and all(act == ops.ACT[activation] for _, act in seen) and {n for n, _ in seen} == {'tc_mlp_fwd_train', 'tc_mlp_fwd_rollout', 'tc_mlp_bwd'}
+    f = build(False)
+    f.epoch_num += 1
+    f.train_epoch(noise=g['noise'][0])
+    torch.testing.assert_close(t.model.flat, f.model.flat, rtol=1e-4, atol=2e-6)
 
 
 class _StridedF64Env(_Env):

@@ -18,7 +18,9 @@ import torch.nn.functional as F
 from oracle import ppo_oracle as O
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from test_mlp_tc_gpu import decode_tiles, make_net, rel_l2, cosine, UNITS, A  # noqa: E402
+from test_mlp_tc_gpu import decode_tiles, rel_l2, cosine, A  # noqa: E402
+
+NATIVE = [256, 128, 64]        # the compiled tile widths: narrower layers run zero-padded to these
 
 pytestmark = pytest.mark.gpu
 DEV = 'cuda'
@@ -33,17 +35,41 @@ def mm(a, b):
     return (a.double() @ b.double().t()).float()
 
 
-def elu_grad_from_out(a):
-    return torch.where(a > 0, torch.ones_like(a), a + 1.0)
+def make_net(g, D, units):
+    ins, W, b = D, [], []
+    for u in units:
+        W.append((torch.randn(u, ins, generator=g) / math.sqrt(ins)).to(DEV))
+        b.append((torch.randn(u, generator=g) * 0.1).to(DEV))
+        ins = u
+    Wh = (torch.randn(A + 1, ins, generator=g) / math.sqrt(ins)).to(DEV)
+    bh = (torch.randn(A + 1, generator=g) * 0.1).to(DEV)
+    logstd = (torch.randn(A, generator=g) * 0.2).to(DEV)
+    return W, b, Wh, bh, logstd
 
 
-@pytest.mark.parametrize('H,N,epm,masked,D', [(4, 512, 256, False, 60), (2, 384, 128, True, 60), (1, 1000, 1000, False, 33),
-                                              (4, 512, 256, False, 256), (2, 384, 128, True, 105)])
-def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D):
+ACTS = {'elu': (1, F.elu, lambda a: torch.where(a > 0, torch.ones_like(a), a + 1.0)),
+        'relu': (2, torch.relu, lambda a: (a > 0).float()),
+        'tanh': (3, torch.tanh, lambda a: 1.0 - a * a)}
+
+
+def decode_padded(buf, n_tiles, c_native, c):
+    """tiles are laid out for the compiled width; the logical columns are the first c"""
+    return decode_tiles(buf, n_tiles, c_native)[:, :c]
+
+
+@pytest.mark.parametrize('H,N,epm,masked,D,UNITS,actname', [
+    (4, 512, 256, False, 60, [256, 128, 64], 'elu'), (2, 384, 128, True, 60, [256, 128, 64], 'elu'), (1, 1000, 1000, False, 33, [256, 128, 64], 'elu'),
+    (4, 512, 256, False, 256, [256, 128, 64], 'elu'), (2, 384, 128, True, 105, [256, 128, 64], 'elu'),
+    # other shipped geometries / activations on the same kernels (zero-padded tiles, activation as a launch argument)
+    (4, 512, 256, False, 17, [128, 64, 32], 'relu'), (2, 384, 128, True, 60, [128, 64, 32], 'elu'), (2, 512, 256, False, 111, [128, 64, 32], 'tanh'),
+    (1, 1000, 1000, False, 44, [200, 100, 50], 'tanh'), (2, 256, 256, False, 60, [256, 128, 64], 'relu')])
+def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D, UNITS, actname):
     from rl_games_b200 import ops
     from rl_games_b200.ops import LossCfg
+    act_id, act_fn, act_grad = ACTS[actname]
+    assert ops.tc_kind(D, UNITS, A) == (2 if D > 64 else 1)
     g = torch.Generator().manual_seed(7 * H + N + D)
-    W, b, Wh, bh, logstd = make_net(g, D)
+    W, b, Wh, bh, logstd = make_net(g, D, UNITS)
     M, e0 = H * epm, (128 if N > epm else 0)
     obs = (torch.randn(H, N, D, generator=g) * 2 + 0.5).to(DEV)
     nm = (torch.randn(D, generator=g) * 0.3).to(DEV); ns = (torch.rand(D, generator=g) + 0.7).to(DEV)
@@ -61,9 +87,9 @@ def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D):
     # ---------------- kernel-faithful reference ----------------
     xb = bf(torch.clamp((rows(obs) - nm) * (1.0 / ns), -5.0, 5.0))
     Wb, Whb = [bf(w) for w in W], bf(Wh)
-    a1 = bf(F.elu(mm(xb, Wb[0]) + b[0]))
-    a2 = bf(F.elu(mm(a1, Wb[1]) + b[1]))
-    a3 = bf(F.elu(mm(a2, Wb[2]) + b[2]))
+    a1 = bf(act_fn(mm(xb, Wb[0]) + b[0]))
+    a2 = bf(act_fn(mm(a1, Wb[1]) + b[1]))
+    a3 = bf(act_fn(mm(a2, Wb[2]) + b[2]))
     head = (mm(a3, Whb) + bh).requires_grad_()
     ls = logstd.clone().requires_grad_()
     value, mu = head[:, 0:1], head[:, 1:]
@@ -80,9 +106,9 @@ def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D):
     kl_rows = O.policy_kl(mu.detach(), sigma.detach(), rows(old_mu), rows(old_sigma), reduce=False)
     kl = kl_rows.mean() if mk is None else (kl_rows * mk).sum() / mk.sum().clamp(min=1.0)
     dh = bf(head.grad)
-    d3 = bf(mm(dh, Whb.t().contiguous()) * elu_grad_from_out(a3))
-    d2 = bf(mm(d3, Wb[2].t().contiguous()) * elu_grad_from_out(a2))
-    d1 = bf(mm(d2, Wb[1].t().contiguous()) * elu_grad_from_out(a1))
+    d3 = bf(mm(dh, Whb.t().contiguous()) * act_grad(a3))
+    d2 = bf(mm(d3, Wb[2].t().contiguous()) * act_grad(a2))
+    d1 = bf(mm(d2, Wb[1].t().contiguous()) * act_grad(a1))
     ref = {'W_head': mm(dh.t().contiguous(), a3.t().contiguous()), 'b_head': dh.sum(0),
            'W2': mm(d3.t().contiguous(), a2.t().contiguous()), 'b2': d3.sum(0),
            'W1': mm(d2.t().contiguous(), a1.t().contiguous()), 'b1': d2.sum(0),
@@ -94,13 +120,15 @@ def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D):
     tb = ops.tc_tile_bytes(D, UNITS, A)
     wpack = torch.zeros(ops.tc_pack_bytes(D, UNITS, A), dtype=torch.uint8, device=DEV)
     ops.tc_pack_weights(W[0], W[1], W[2], Wh, D, UNITS, A, wpack)
-    act = [torch.zeros(n_tiles * tb[i], dtype=torch.uint8, device=DEV) for i in range(3)]
+    act_bufs = [torch.zeros(n_tiles * tb[i], dtype=torch.uint8, device=DEV) for i in range(3)]
     dhead = torch.zeros(n_tiles * tb[3], dtype=torch.uint8, device=DEV)
     delta2 = torch.zeros(n_tiles * tb[1], dtype=torch.uint8, device=DEV); delta1 = torch.zeros(n_tiles * tb[0], dtype=torch.uint8, device=DEV)
     mu_t, sg_t = old_mu.clone(), old_sigma.clone()
     partials_t = torch.zeros(148, stride, dtype=torch.float64, device=DEV)
+    act = act_bufs
     nbt = ops.tc_mlp_fwd_train(sl(obs), epm, N, D, nm, ns, wpack, b, bh, logstd, UNITS, M, A, sl(actions), sl(mu_t), sl(sg_t), sl(old_v),
-                               sl(ret), sl(old_nlp), sl(adv), None if mask is None else sl(mask), cfg, inv, act, dhead, partials_t)
+                               sl(ret), sl(old_nlp), sl(adv), None if mask is None else sl(mask), cfg, inv, act, dhead, partials_t,
+                               activation=act_id)
     stats_t = torch.zeros(16, device=DEV); dls_t = torch.empty(A, device=DEV)
     ops.ppo_loss_finalize(partials_t, nbt, A, torch.tensor([0.0], device=DEV), stats_t, dls_t)
     P = A + sum(w.numel() + x.numel() for w, x in zip(W, b)) + Wh.numel() + bh.numel()
@@ -112,14 +140,16 @@ def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D):
     offs['W_head'] = o; o += (A + 1) * ins
     offs['b_head'] = o; o += A + 1
     part = torch.full((148, P), float('nan'), device=DEV)
-    npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs)
+    npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs, activation=act_id)
     grad = torch.zeros(P, device=DEV)
     ops.reduce_splits(part[0, A:], grad[A:], P - A, npart, split_stride=P)
     torch.cuda.synchronize()
 
     report = {}
     for i, (C, r) in enumerate(zip(UNITS, (a1, a2, a3))):
-        got = decode_tiles(act[i], n_tiles, C)[:M]
+        full = decode_tiles(act[i], n_tiles, NATIVE[i])[:M]
+        assert float(full[:, C:].abs().max()) == 0.0 if C < NATIVE[i] else True          # padded units are exactly zero
+        got = full[:, :C]
         report[f'a{i + 1}'] = rel_l2(got, r)
         assert report[f'a{i + 1}'] < 3e-3, (i, report)
     got_mu = rows(mu_t)
@@ -133,15 +163,15 @@ def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D):
     assert report['d_head'] < 1e-2 and cosine(dh_t, dh) > 0.9999, report
     report['d_logstd'] = rel_l2(dls_t, ls.grad)
     assert report['d_logstd'] < 2e-3, report
-    for name, buf, C, r in (('delta2', delta2, UNITS[1], d2), ('delta1', delta1, UNITS[0], d1)):
-        got = decode_tiles(buf, n_tiles, C)[:M]
+    for name, buf, C, CN, r in (('delta2', delta2, UNITS[1], NATIVE[1], d2), ('delta1', delta1, UNITS[0], NATIVE[0], d1)):
+        got = decode_tiles(buf, n_tiles, CN)[:M, :C]
         report[name] = rel_l2(got, r)
         assert report[name] < 1.5e-2 and cosine(got, r) > 0.9999, report
     for k, r in ref.items():
         got = grad[offs[k]:offs[k] + r.numel()].view_as(r)
         report['g' + k] = rel_l2(got, r)
         assert report['g' + k] < 1e-2 and cosine(got, r) > 0.9999, (k, report)
-    print('faithful-reference errors', (H, N, epm, masked, D), {k: (round(v, 6) if isinstance(v, float) else v) for k, v in report.items()})
+    print('faithful-reference errors', (H, N, epm, masked, D, UNITS, actname), {k: (round(v, 6) if isinstance(v, float) else v) for k, v in report.items()})
 
 
 @pytest.mark.parametrize('D,N', [(60, 1000), (256, 1000)])
@@ -150,7 +180,8 @@ def test_tc_rollout_vs_kernel_faithful_reference(D, N):
     fp32/TF32, a2c_common.py:581-600) against the same arithmetic contract in torch: mu / value agree to fp32 accumulation order."""
     from rl_games_b200 import ops
     g = torch.Generator().manual_seed(3)
-    W, b, Wh, bh, logstd = make_net(g, D)
+    UNITS = NATIVE
+    W, b, Wh, bh, logstd = make_net(g, D, UNITS)
     obs = (torch.randn(N, D, generator=g) * 2).to(DEV)
     nm = (torch.randn(D, generator=g) * 0.3).to(DEV); ns = (torch.rand(D, generator=g) + 0.7).to(DEV)
     noise = torch.randn(N, A, generator=g).to(DEV)
