@@ -316,6 +316,12 @@ class A2CAgent(CompileTolerantModel):
                 f'obs={self.model.D}, units={self.model.units}, activation={self.model.activation}, actions={self.actions_num}.  '
                 f'Set mixed_precision: False for the fp32 path.')
         self.tc_wide = self.use_tc and ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2
+        # Rollout precision.  The reference evaluates the policy during the rollout OUTSIDE autocast (a2c_common.py:581-600: fp32 / TF32)
+        # and only calc_gradients under bf16 autocast (a2c_continuous.py:173).  Default here: the rollout uses the same bf16 tcgen05
+        # kernels as the update, so old_neglogp / old mu come from the SAME arithmetic the first mini-epoch re-evaluates (ratio == 1 at
+        # the first minibatch, which the reference's mix does not give).  b200_rollout_fp32: True restores the reference's split: fp32
+        # CUDA-core kernels for get_action_values / get_values, bf16 tensor cores for the update.
+        self.rollout_fp32 = self.use_tc and bool(config.get('b200_rollout_fp32', False))
         if self.use_tc and config.get('b200_pipelined_wgrad', False) and (self.tc_wide or list(self.model.units) != [256, 128, 64]):
             raise NotImplementedError('b200_pipelined_wgrad is an option of the native resident-weights geometry (obs <= 64, MLP [256,128,64])')
         self.dataset = _Dataset(self)
@@ -369,6 +375,8 @@ class A2CAgent(CompileTolerantModel):
         self.rng_epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         # workspaces
         m, mb = self.model, self.minibatch_size
+        if self.rollout_fp32:
+            self.ra = [f(N, u) for u in m.units]
         if not self.use_tc:
             self.ra = [f(N, u) for u in m.units]
             self.ta = [f(mb, u) for u in m.units]
@@ -391,7 +399,9 @@ class A2CAgent(CompileTolerantModel):
             self.tc_xt = u8(nt * ops.tc_xtile_bytes(m.D, m.units, A)) if self.config.get('b200_pipelined_wgrad', False) else None
             self.tc_offs = {k: m.layout[k][0] for k in ('W0', 'b0', 'W1', 'b1', 'W2', 'b2', 'W_head', 'b_head')}
             self.pack_table = ops.tc_pack_table(m.D, m.units, A, self.tc_offs)
-            self.ra = self.ta = self.dA = []
+            self.ta = self.dA = []
+            if not self.rollout_fp32:
+                self.ra = []
         else:
             self.n_splits = max(1, min(64, mb // 256))
         self.part_rows = self.n_splits * (self.seq_length if self.is_rnn else 1)
@@ -669,7 +679,7 @@ class A2CAgent(CompileTolerantModel):
 
     def _policy_step(self, obs, t, noise=None):
         m, N, A = self.model, self.num_actors, self.actions_num
-        if self.use_tc:
+        if self.use_tc and not self.rollout_fp32:
             nm, ns = self._norm()
             ops.tc_mlp_fwd_rollout(obs, m.D, nm, ns, self.wpack, m.b, m.b_head, m.sigma, m.units, N, A,
                                    m.value_mean_std.running_mean, m.value_mean_std.running_var, self.normalize_value, noise,
@@ -695,7 +705,7 @@ class A2CAgent(CompileTolerantModel):
         """a2c_common.py:603-626"""
         o = obs['obs'] if isinstance(obs, dict) else obs
         m, N, A = self.model, self.num_actors, self.actions_num
-        if self.use_tc:
+        if self.use_tc and not self.rollout_fp32:
             nm, ns = self._norm()
             ops.tc_mlp_fwd_rollout(o, m.D, nm, ns, self.wpack, m.b, m.b_head, m.sigma, m.units, N, A,
                                    m.value_mean_std.running_mean, m.value_mean_std.running_var, self.normalize_value, None, 0, None,

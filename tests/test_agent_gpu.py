@@ -553,3 +553,39 @@ def test_lstm_c4_geometry_full_width_vs_oracle():
     sd = agent.model.state_dict()
     for k in O.param_names(3, lstm=True):
         torch.testing.assert_close(sd[k].cpu(), oag.model.p[k].detach(), rtol=1e-3, atol=5e-5, msg=lambda m: k + ': ' + m)
+
+
+def test_rollout_precision_option_reproduces_the_fp32_rollout_exactly():
+    """b200_rollout_fp32 (the reference's precision split: rollout outside autocast, a2c_common.py:581-600; update in bf16,
+    a2c_continuous.py:173): with it the tcgen05 agent's rollout arena is BIT-identical to the fp32 agent's on the same weights / noise;
+    without it (default: bf16 rollout, self-consistent with the bf16 update) the arena differs by the bf16 tolerance class, measured
+    here: |dvalue| <= 6e-2, |dmu| <= 6e-2, and the first-minibatch importance ratio is exactly 1 only in the default mode."""
+    N, H, D, A, units, mb = 512, 8, 60, 8, [256, 128, 64], 2048
+    obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=33)
+    params = O.init_params(D, units, A, seed=8)
+    g = torch.Generator().manual_seed(9)
+    noise = torch.randn(H, N, A, generator=g).to(DEV)
+    ag = {}
+    for name, cfg in (('fp32', {'mixed_precision': False}), ('tc', {'mixed_precision': True}),
+                      ('tc_rollout_fp32', {'mixed_precision': True, 'b200_rollout_fp32': True})):
+        # normalize_input off: the obs normaliser moves between the rollout and the first minibatch (model.train()), which would hide the precision effect
+        a = make_agent({'mini_epochs': 1, 'b200_cuda_graph': False, 'normalize_input': False, **cfg}, N, H, D, A, units, mb,
+                       TapeEnvGPU(obs_tape, done_tape, tout_tape, A), params)
+        a._rollout(noise)
+        a._gae_and_prepare()
+        torch.cuda.synchronize()
+        ag[name] = a
+    f, t, tf = ag['fp32'], ag['tc'], ag['tc_rollout_fp32']
+    assert tf.use_tc and tf.rollout_fp32 and not t.rollout_fp32
+    for k in ('values', 'mus', 'neglogpacs', 'actions', 'rewards', 'advs_n', 'returns_n'):
+        assert torch.equal(getattr(tf, k), getattr(f, k)), k
+    torch.testing.assert_close(t.values, f.values, rtol=0, atol=6e-2)
+    torch.testing.assert_close(t.mus, f.mus, rtol=0, atol=6e-2)
+    # first minibatch: ratio = exp(old_neglogp - neglogp) == 1 <=> a_loss == -mean(adv) ... measured through the KL statistic (0 iff mu, sigma match)
+    for a in (t, tf):
+        a._minibatch_update(0, 0)
+    torch.cuda.synchronize()
+    kl_default, kl_split = float(t.stats[0, 4]), float(tf.stats[0, 4])
+    assert abs(kl_default) < 1e-6, kl_default              # same arithmetic in rollout and update: the policy has not moved yet
+    assert 0.0 <= kl_split < 5e-3, kl_split                # fp32 behaviour policy vs bf16 re-evaluation: bf16 noise shows up as a spurious KL
+    print('rollout precision: first-minibatch KL default (bf16 rollout) %.3e, reference split (fp32 rollout) %.3e' % (kl_default, kl_split))
