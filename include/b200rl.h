@@ -431,8 +431,9 @@ int b200rl_bump_u64(uint64_t* p, void* stream);
 int b200rl_tc_supported(int D, int u1, int u2, int u3, int A);
 int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A);
 int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int64_t* out4_host);
-/* bytes of one 128-row tile of the normalised bf16 observation buffer the training forward may emit (xtile) for the
- * pipelined weight-gradient kernel; -1 if the geometry is unsupported */
+/* bytes of one 128-row tile of the normalised bf16 observation buffer (xtile) the training forward emits for the backward kernel
+ * (obs <= 64: the weight-gradient MMAs of layer 1 TMA-load it instead of re-deriving it from the fp32 observations; with
+ * pipelined_wgrad != 0 the two-stage-ring edition of the weight-gradient kernel runs instead); -1 if the geometry has no X tiles */
 int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A);
 int b200rl_tc_pack_table(int D, int u1, int u2, int u3, int A, int off_W1, int off_W2, int off_W3, int off_Wh,
                          b200rl_pack_table* out_host);
@@ -460,7 +461,7 @@ int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride
                       const float* norm_mean, const float* norm_std, const void* wpack,
                       int u1, int u2, int u3, int activation, int M, int A,
                       const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
-                      void* delta2, void* delta1, float* part, int max_parts, int P,
+                      int pipelined_wgrad, void* delta2, void* delta1, float* part, int max_parts, int P,
                       int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
                       int* n_parts_out_host, void* stream);
 

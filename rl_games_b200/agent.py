@@ -394,9 +394,12 @@ class A2CAgent(CompileTolerantModel):
             self.tc_act = [u8(nt1 * tb[0]), u8(nt * tb[1]), u8(nt * tb[2])]
             self.tc_l1_scratch = self.tc_act[0] if self.tc_wide else None
             self.tc_dhead, self.tc_delta2, self.tc_delta1 = u8(nt * tb[3]), u8(nt * tb[1]), u8(nt * tb[0])
-            # normalised bf16 obs tiles: forward -> pipelined weight-gradient kernel (config b200_pipelined_wgrad; default False =
-            # the single-buffered kernel that re-normalises the observations itself, measured faster on c2: profiles/r01_summary.md)
-            self.tc_xt = u8(nt * ops.tc_xtile_bytes(m.D, m.units, A)) if self.config.get('b200_pipelined_wgrad', False) else None
+            # normalised bf16 obs tiles (obs <= 64): the training forward emits them, the backward's layer-1 weight-gradient MMAs TMA-load
+            # them instead of re-reading and re-normalising the fp32 observations (b200_emit_xtile: False restores that); config
+            # b200_pipelined_wgrad selects the two-stage-ring edition of the weight-gradient kernel (measured slower on c2)
+            self.tc_pipelined_wgrad = bool(self.config.get('b200_pipelined_wgrad', False))
+            want_xt = (not self.tc_wide) and (self.tc_pipelined_wgrad or bool(self.config.get('b200_emit_xtile', True)))
+            self.tc_xt = u8(nt * ops.tc_xtile_bytes(m.D, m.units, A)) if want_xt else None
             self.tc_offs = {k: m.layout[k][0] for k in ('W0', 'b0', 'W1', 'b1', 'W2', 'b2', 'W_head', 'b_head')}
             self.pack_table = ops.tc_pack_table(m.D, m.units, A, self.tc_offs)
             self.ta = self.dA = []
@@ -967,7 +970,8 @@ class A2CAgent(CompileTolerantModel):
                                   self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.tc_act,
                                   self.tc_dhead, self.loss_partials, xtile=self.tc_xt, activation=m.act_id)
         npart = ops.tc_mlp_bwd(x, epm, N, m.D, nm, ns, self.wpack, m.units, mb, A, self.tc_act, self.tc_dhead, self.tc_delta2,
-                               self.tc_delta1, self.part, self.part.shape[1], self.tc_offs, xtile=self.tc_xt, activation=m.act_id)
+                               self.tc_delta1, self.part, self.part.shape[1], self.tc_offs, xtile=self.tc_xt, activation=m.act_id,
+                               pipelined_wgrad=self.tc_pipelined_wgrad)
         gv = self._gv[u & 1]
         self._set_sched_mode(u)
         if not self.multi_gpu:

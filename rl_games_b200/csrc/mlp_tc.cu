@@ -1151,6 +1151,7 @@ struct Bwd2Args {
     const uint8_t* act1; const uint8_t* delta2; const uint8_t* delta1; float* part;
     int M; int P; int off_W2, off_W1, off_b1;
     int u1, u2;
+    const uint8_t* xt;     // optional (resident-W1 geometry): the normalised bf16 observation tiles the training forward emitted
 };
 
 // XL1 (wide observations): dW1 is l1_wgrad_tc_kernel's job -- no X tile, no dW1^T accumulator, no W1 flush here (db1 stays).
@@ -1174,8 +1175,9 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
         fence_mbar_init();
     }
     pdl_sync();
+    const bool x_from_fwd = !XL1 && p.xt != nullptr;     // the forward kernel's bf16 X tile arrives by TMA with the delta tiles
     if constexpr (!XL1) {
-    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
+    if (!x_from_fwd) load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
     for (int i = tid; i < (128 * 256 - (int)N::X_BYTES) / 16; i += 256) reinterpret_cast<uint4*>(sX + N::X_BYTES)[i] = make_uint4(0, 0, 0, 0);
     }
     fence_async_smem();
@@ -1192,15 +1194,18 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
         __syncthreads();
         TSTAMP();   // tile start (previous MMAs done)
         if (tid == 0) {
-            mbar_expect_tx(&bars[0], N::A2_BYTES + 2 * N::A1_BYTES);
+            mbar_expect_tx(&bars[0], N::A2_BYTES + 2 * N::A1_BYTES + (x_from_fwd ? N::X_BYTES : 0u));
             bulk_g2s(sD2, p.delta2 + (size_t)tile * N::A2_BYTES, N::A2_BYTES, &bars[0]);
             bulk_g2s(sD1, p.delta1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
             bulk_g2s(sA1, p.act1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
+            if (x_from_fwd) bulk_g2s(sX, p.xt + (size_t)tile * N::X_BYTES, N::X_BYTES, &bars[0]);
         }
         if constexpr (!XL1) {
+        if (!x_from_fwd) {
         const int m0 = tile * 128;
         stage_x_tile<N, 256>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm, p.nm != nullptr);
         fence_async_smem();
+        }
         }
         TSTAMP();   // X staged
         mbar_wait(&bars[0], phase);
@@ -1719,7 +1724,7 @@ B200RL_EXPORT int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int
 }
 
 B200RL_EXPORT int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A) {
-    return (net_is_c2(D, u1, u2, u3, A) && net_is_native(u1, u2, u3)) ? (int64_t)NetC2::X_BYTES : -1;
+    return net_is_c2(D, u1, u2, u3, A) ? (int64_t)NetC2::X_BYTES : -1;
 }
 
 // segments of the packed weight buffer, for the optimiser's fused refresh (b200rl_adam_step_f32)
@@ -1762,7 +1767,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
         return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
     if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
-    if (xtile && (kind == 2 || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;      // the pipelined weight-gradient kernel is an option of the native resident-W1 geometry
+    if (xtile && kind == 2) return B200RL_EUNSUPPORTED;      // the X tiles are an output of the resident-W1 kernel (obs <= 64)
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     const int n_tiles = (M + 127) / 128;
@@ -1851,13 +1856,14 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
                                     const float* norm_mean, const float* norm_std, const void* wpack,
                                     int u1, int u2, int u3, int activation, int M, int A,
                                     const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
-                                    void* delta2, void* delta1, float* part, int max_parts, int P,
+                                    int pipelined_wgrad, void* delta2, void* delta1, float* part, int max_parts, int P,
                                     int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
                                     int* n_parts_out_host, void* stream) {
     if (!obs || !wpack || !act1 || !act2 || !act3 || !dhead || !delta2 || !delta1 || !part) return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
     if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
-    if (xtile && (kind == 2 || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;
+    if (xtile && kind == 2) return B200RL_EUNSUPPORTED;                                        // X tiles exist for the resident-W1 geometry only
+    if (pipelined_wgrad && (!xtile || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;   // option of the native geometry, needs the X tiles
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     using N = NetC2;
@@ -1868,7 +1874,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     Bwd1Args a{(const uint8_t*)wpack, (const uint8_t*)act1, (const uint8_t*)act2, (const uint8_t*)act3, (const uint8_t*)dhead,
                (uint8_t*)delta2, (uint8_t*)delta1, part, M, A, P, off_W3, off_b3, off_b2, off_Wh, off_bh, u1, u2, u3, activation};
     cudaError_t e;
-    if (xtile) {
+    if (pipelined_wgrad) {
         // two launches: delta chain, then the pipelined weight-gradient kernel (observation tiles from the forward kernel,
         // 64-row half tiles through a two-stage TMA ring)
         constexpr size_t smem1 = bwd1_smem<N>();
@@ -1890,7 +1896,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     if (kind == 2) {
         // wide observations: the chain kernel without the W1 part, then dW1 in its own kernel (same grid => same split rows)
         BwdArgs abw{a, Bwd2Args{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
-                                (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1, u1, u2}};
+                                (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1, u1, u2, nullptr}};
         constexpr size_t smemw = bwd_smem<NetW, true>();
         static_assert(smemw <= 227 * 1024, "backward kernel (external layer 1) shared memory budget");
         e = cudaFuncSetAttribute(mlp_bwd_tc_kernel<NetW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw);
@@ -1907,7 +1913,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     }
     // default: the whole backward pass in one launch
     BwdArgs ab{a, Bwd2Args{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)act1, (const uint8_t*)delta2,
-                           (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1, u1, u2}};
+                           (const uint8_t*)delta1, part, M, P, off_W2, off_W1, off_b1, u1, u2, (const uint8_t*)xtile}};
     constexpr size_t smem = bwd_smem<N>();
     static_assert(smem <= 227 * 1024, "backward kernel shared memory budget");
     e = cudaFuncSetAttribute(mlp_bwd_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -615,7 +615,8 @@ def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_h
     return 1
 
 
-def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=None, activation=1):
+def tc_mlp_bwd(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, units, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=None, activation=1,
+               pipelined_wgrad=False):
     """split partial rows: everything in row 0, zeros elsewhere; P is the row stride"""
     g = _LOSS_SIDE['tc_grads']
     f = _flat(part)

@@ -154,7 +154,9 @@ def _fwd_loss_bwd_case(H, N, epm, masked, D):
         xt_dec = decode_tiles(xt, n_tiles, 64)[:M, :D]
         torch.testing.assert_close(xt_dec, xn.to(torch.bfloat16).float(), rtol=0, atol=4e-2)
     part = torch.full((148, P), float('nan'), device=DEV)
-    npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=xt)
+    # three editions of the layer-1 / layer-2 weight gradients must agree: X tiles from the forward (default), pipelined ring, re-derived X
+    npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=xt,
+                           pipelined_wgrad=not wide)
     grad = torch.zeros(P, device=DEV)
     ops.reduce_splits(part[0, A:], grad[A:], P - A, npart, split_stride=P)
     # the non-pipelined kernel (no xtile: re-normalises the observations itself) must give the same weight gradients
@@ -165,6 +167,13 @@ def _fwd_loss_bwd_case(H, N, epm, masked, D):
     torch.cuda.synchronize()
     assert torch.isfinite(grad).all()
     torch.testing.assert_close(grad, grad_b, rtol=1e-4, atol=1e-6)
+    if not wide:
+        part_c = torch.full((148, P), float('nan'), device=DEV)
+        ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part_c, P, offs, xtile=xt)
+        grad_c = torch.zeros(P, device=DEV)
+        ops.reduce_splits(part_c[0, A:], grad_c[A:], P - A, npart, split_stride=P)
+        torch.cuda.synchronize()
+        assert torch.equal(grad_c, grad_b)        # same single-buffered kernel, same bf16 X tile bytes -> bit-identical
     d2 = decode_tiles(delta2, n_tiles, UNITS[1])[:M]; d1 = decode_tiles(delta1, n_tiles, UNITS[0])[:M]
     assert rel_l2(d2, dA[1]) < 8e-2 and cosine(d2, dA[1]) > 0.997, (rel_l2(d2, dA[1]), cosine(d2, dA[1]))
     assert rel_l2(d1, dA[0]) < 8e-2 and cosine(d1, dA[0]) > 0.997, (rel_l2(d1, dA[0]), cosine(d1, dA[0]))

@@ -97,14 +97,17 @@ def main():
         ops.tc_mlp_fwd_train(sl(obs), epm, N, D, nm, ns, wpack, b, bh, logstd, UNITS, M, A, sl(actions), sl(mu), sl(sg), sl(old_v),
                              sl(ret), sl(old_nlp), sl(adv), None, cfg, None, act, dhead, partials, xtile=xt)
         e1.record()
-        ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=None if '--old-bwd2' in sys.argv else xt)
+        # default: single-buffered weight-gradient phase fed with the forward's bf16 X tiles; --no-xt: X re-derived from the fp32
+        # observations; --pipelined: the two-stage-ring kernel
+        ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs,
+                       xtile=None if '--no-xt' in sys.argv else xt, pipelined_wgrad='--pipelined' in sys.argv)
         e2 = torch.cuda.Event(enable_timing=True)
         e2.record()
         torch.cuda.synchronize()
         assert fn(ctypes.cast(buf, ctypes.c_void_p)) == 0
         print('iter %d: fwd+loss %.1f us, bwd1+bwd2 %.1f us (events)' % (it, e0.elapsed_time(e1) * 1e3, e1.elapsed_time(e2) * 1e3))
         if it == 3:
-            show('fwd', 0); show('bwd1', 128); show('bwd2_old' if '--old-bwd2' in sys.argv else 'bwd2', 256)
+            show('fwd', 0); show('bwd1', 128); show('bwd2' if '--pipelined' in sys.argv else 'bwd2_old', 256)
     # ---- fused reduce + finalise + clip + Adam tail on the partial rows the backward just wrote (L2-hot, like in the real step) ----
     ra = lib.b200rl_debug_ra_stamps
     ra.restype = ctypes.c_int
