@@ -426,7 +426,8 @@ int b200rl_bump_u64(uint64_t* p, void* stream);
  *               (sum with b200rl_reduce_splits_f32)
  * Geometry: three hidden layers u1 <= 256, u2 <= 128, u3 <= 64 (zero-padded to the compiled tile widths [256,128,64]; e.g.
  * [128,64,32]), observations D <= 64 (kind 1) or 64 < D <= 256 (kind 2: layer 1 in kernels of its own), up to 15 actions;
- * `activation` = B200RL_ACT_ELU / _RELU / _TANH / _NONE, one for the whole MLP (network_builder.py:132 _build_mlp).
+ * `activation` = B200RL_ACT_ELU / _RELU / _TANH, one for the whole MLP (network_builder.py:132 _build_mlp); each has its own
+ * set of kernels (the activation is a compile-time constant of the epilogues).
  * ------------------------------------------------------------------------------------------- */
 int b200rl_tc_supported(int D, int u1, int u2, int u3, int A);
 int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A);

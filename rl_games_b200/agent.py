@@ -293,8 +293,8 @@ class A2CAgent(CompileTolerantModel):
         # wide observations (64 < obs <= 256): layer 1 runs in kernels of its own (l1_fwd_tc / l1_wgrad_tc)
         allow_wide = True
         # tcgen05 kernels: three hidden layers that fit the compiled tile widths (u1 <= 256, u2 <= 128, u3 <= 64; narrower layers are
-        # zero-padded), elu / relu / tanh (or no activation), obs <= 256, <= 15 actions; anything else runs on the fp32 kernels
-        tc_ok = self.model.activation in ('elu', 'relu', 'tanh', 'None', None) and \
+        # zero-padded), elu / relu / tanh, obs <= 256, <= 15 actions; anything else runs on the fp32 kernels
+        tc_ok = self.model.activation in ('elu', 'relu', 'tanh') and \
             ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
         if self.mixed_precision is None:
             self.mixed_precision = (not self.is_rnn) and tc_ok

@@ -21,7 +21,8 @@ def _sources():
 
 def _digest(path):
     h = hashlib.sha1()
-    for dep in [path] + [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith(('.cuh', '.h'))] + \
+    extra = [os.path.join(HERE, 'mlp_tc.cu')] if os.path.basename(path) in ('mlp_tc_relu.cu', 'mlp_tc_tanh.cu') else []     # they #include it
+    for dep in [path] + extra + [os.path.join(HERE, f) for f in sorted(os.listdir(HERE)) if f.endswith(('.cuh', '.h'))] + \
             [os.path.join(os.path.dirname(PKG), 'include', 'b200rl.h')]:
         with open(dep, 'rb') as f:
             h.update(f.read())

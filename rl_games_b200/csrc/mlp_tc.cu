@@ -18,7 +18,20 @@
 #include "loss_math.cuh"
 #include "tc_common.cuh"
 
+// One translation unit per MLP activation: the activation is a compile-time constant of every kernel here (a run-time switch inside the
+// epilogues grew the forward kernel by 35 % and cost ~10 % of its time).  mlp_tc.cu itself is the ELU unit and also holds the
+// activation-independent entry points and the dispatcher; mlp_tc_relu.cu / mlp_tc_tanh.cu define B200RL_TC_ACT and include this file,
+// which then only emits their three launchers (b200rl_tcimpl_*_act<N>, hidden visibility).
+#ifndef B200RL_TC_ACT
+#define B200RL_TC_ACT 1          // B200RL_ACT_ELU
+#define B200RL_TC_MAIN 1
+#endif
+#define B200RL_TC_CAT2(a, b) a##b
+#define B200RL_TC_CAT(a, b) B200RL_TC_CAT2(a, b)
+#define TCIMPL(name) B200RL_TC_CAT(name##_act, B200RL_TC_ACT)
+
 namespace {
+constexpr int TC_ACT = B200RL_TC_ACT;
 
 using namespace tc;
 
@@ -66,10 +79,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : (__expf(x) - 1.0f); }
 __device__ __forceinline__ float elu_grad_from_out(float a) { return a > 0.f ? 1.f : a + 1.f; }
 __device__ __forceinline__ float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// v[j] = act(v[j] + bias[j]) over NV accumulator columns; `act` (B200RL_ACT_*) is uniform over the launch, so each branch is a straight
-// unrolled loop (network_builder.py:132 _build_mlp: one activation for the whole MLP; elu / relu / tanh are what the shipped configs use)
+// v[j] = act(v[j] + bias[j]) over NV accumulator columns; the activation (B200RL_ACT_*) is this translation unit's compile-time constant
+// (network_builder.py:132 _build_mlp: one activation for the whole MLP; elu / relu / tanh are what the shipped configs use)
 template <int NV>
-__device__ __forceinline__ void bias_act(float (&v)[NV], const float* __restrict__ bias, int act) {
+__device__ __forceinline__ void bias_act(float (&v)[NV], const float* __restrict__ bias) {
+    constexpr int act = TC_ACT;
     if (act == B200RL_ACT_ELU) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) v[j] = elu_fast(v[j] + bias[j]);
@@ -85,7 +99,8 @@ __device__ __forceinline__ void bias_act(float (&v)[NV], const float* __restrict
     }
 }
 // v[j] *= act'(.) expressed through the activation OUTPUT a[j] (8 bf16 values of one chunk)
-__device__ __forceinline__ void mul_act_grad8(float* v, const float (&a)[8], int act) {
+__device__ __forceinline__ void mul_act_grad8(float* v, const float (&a)[8]) {
+    constexpr int act = TC_ACT;
     if (act == B200RL_ACT_ELU) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] *= elu_grad_from_out(a[j]);
@@ -363,9 +378,11 @@ constexpr int LOSS_SLOTS = LOSS_NSC + 32;   // partial row stride shared with lo
 __device__ long long g_tc_stamp[3 * 128];   // [0,128) fwd, [128,256) bwd1, [256,384) bwd2
 #define TSTAMP() do { if (blockIdx.x == 0 && tid == 0 && n_stamp < 127) g_tc_stamp[TSB + 1 + n_stamp++] = clock64(); } while (0)
 #define TSTAMP_END() do { if (blockIdx.x == 0 && tid == 0) g_tc_stamp[TSB] = n_stamp; } while (0)
+#ifdef B200RL_TC_MAIN
 extern "C" B200RL_EXPORT int b200rl_debug_tc_stamps(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g_tc_stamp, sizeof(long long) * 3 * 128);
 }
+#endif
 #else
 #define TSTAMP() do {} while (0)
 #define TSTAMP_END() do {} while (0)
@@ -436,6 +453,23 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[7]);
         bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[7]);
     }
+#ifdef B200RL_V_PROLOGUE_OLD
+    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = i < p.u1 ? __ldg(p.b1 + i) : 0.f;
+    for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = i < p.u2 ? __ldg(p.b2 + i) : 0.f;
+    for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = i < p.u3 ? __ldg(p.b3 + i) : 0.f;
+    if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
+    if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
+    __syncthreads();
+    if (tid == 0) {      // row-independent constants: sum(logstd) and the entropy of the diagonal Gaussian
+        float sl = 0.f, en = 0.f;
+        for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
+        sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
+    }
+    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+#else
     // every parameter / statistic load of the prologue is issued before the single barrier below (one global-memory round trip,
     // not three); the row-independent constants derived from sigma are finished by thread 0 after it -- their first reader is the
     // loss epilogue, several barriers further on
@@ -453,6 +487,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
         sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
     }
+#endif
     TSTAMP();   // prologue done
     const uint32_t tmem = *tmem_slot;
     const uint32_t T1 = tmem, T2 = tmem + 256, T3 = tmem + 384, T4 = tmem + 448;     // accumulator column bases
@@ -505,6 +540,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         TSTAMP();   // MMA 1 done
         {
             uint8_t* g1 = TRAIN ? p.act1 + (size_t)tile * N::A1_BYTES : nullptr;
+#ifdef B200RL_V_EPI1_OLD
+#pragma unroll 1
+            for (int c0 = h * (N::U1 / 4); c0 < (h + 1) * (N::U1 / 4); c0 += 32) {
+                float v[32];
+                tmem_ld32(T1 + lane_base + c0, v);
+                bias_act<32>(v, sB1 + c0);
+                store_chunks32(v, row, c0, sA1, g1);
+            }
+        }
+#else
             static_assert(N::U1 / 4 == 64, "layer-1 epilogue: two 32-column loads per thread");
             const int c0 = h * 64;
             uint32_t ra[32], rb[32];
@@ -514,13 +559,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-            bias_act<32>(v, sB1 + c0, p.act);
+            bias_act<32>(v, sB1 + c0);
             store_chunks32(v, row, c0, sA1, g1);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rb[j]);
-            bias_act<32>(v, sB1 + c0 + 32, p.act);
+            bias_act<32>(v, sB1 + c0 + 32);
             store_chunks32(v, row, c0 + 32, sA1, g1);
         }
+#endif
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -558,7 +604,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             for (int c0 = h * (N::U2 / 4); c0 < (h + 1) * (N::U2 / 4); c0 += 32) {
                 float v[32];
                 tmem_ld32(T2 + lane_base + c0, v);
-                bias_act<32>(v, sB2 + c0, p.act);
+                bias_act<32>(v, sB2 + c0);
                 store_chunks32(v, row, c0, sXA2, g2);
             }
         }
@@ -587,7 +633,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             const int c0 = h * 16;
             float v[16];
             tmem_ld16(T3 + lane_base + c0, v);
-            bias_act<16>(v, sB3 + c0, p.act);
+            bias_act<16>(v, sB3 + c0);
 #pragma unroll
             for (int qq = 0; qq < 2; ++qq) {
                 const uint4 u = pack8_bf16(&v[qq * 8]);
@@ -610,6 +656,121 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                           make_smem_desc(smem_u32(sWh) + k * 2 * N::WH_CS, N::WH_CS, 128), idesc, k > 0);
             umma_commit(&bars[4]);
         }
+#ifdef B200RL_V_LOSS_OLD      // A/B variant (tools/tc_stage_timing.py --variants): the round-1 loss epilogue
+        if (TRAIN) {
+            // ---- PPO loss, split 4 ways: the four threads (h = 0..3) that can read TMEM lane `row` each take the actions
+            //      j = h, h+4, h+8, h+12; per-row sums are exchanged through shared memory (the dead a2 tile region).
+            const bool live = row < rows_valid;
+            const int64_t ar = arow0 + row;
+            float act[4], omu[4], osg[4];
+            float old_v = 0.f, ret = 0.f, old_nlp = 0.f, adv = 0.f, mk = 0.f;
+            if (live) {      // arena inputs: issued before the wait on the heads MMA so their latency overlaps with it
+                old_v = __ldg(p.la.old_values_n + ar); ret = __ldg(p.la.returns_n + ar);
+                old_nlp = __ldg(p.la.old_neglogp + ar); adv = __ldg(p.la.advs_n + ar);
+                mk = p.la.mask ? __ldg(p.la.mask + ar) : 1.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = h + 4 * k;
+                    if (j < p.A) { act[k] = __ldg(p.la.actions + ar * p.A + j); omu[k] = p.la.old_mu[ar * p.A + j]; osg[k] = p.la.old_sigma[ar * p.A + j]; }
+                }
+            }
+            mbar_wait(&bars[4], phase);
+            fence_after_sync();
+            TSTAMP();   // MMA 4 done
+            float head[16];
+            tmem_ld16(T4 + lane_base, head);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) head[j] += sBh[j];
+            float* sPart = reinterpret_cast<float*>(sXA2);           // [128 rows][4 h][4]: sum z^2, kl, bound loss
+            float z[4];
+            {
+                float sz2 = 0.f, kl = 0.f, bl = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = h + 4 * k;
+                    z[k] = 0.f;
+                    if (live && j < p.A) {
+                        const float mu = pick_mu(head, h, k), sg = sSig[j], isg = sSig[2 * p.A + j];
+                        z[k] = (act[k] - mu) * isg;
+                        sz2 += z[k] * z[k];
+                        const float c1 = __logf(osg[k] * isg + 1e-5f);
+                        const float dm = omu[k] - mu;
+                        kl += c1 + (sg * sg + dm * dm) * __frcp_rn(2.0f * (osg[k] * osg[k] + 1e-5f)) - 0.5f;
+                        if (p.cfg.has_bounds) {
+                            if (p.cfg.bound_type == 1) { const float hi = fmaxf(mu - 1.1f, 0.f), lo = fminf(mu + 1.1f, 0.f); bl += lo * lo + hi * hi; }
+                            else if (p.cfg.bound_type == 2) bl += mu * mu;
+                        }
+                    }
+                }
+                *reinterpret_cast<float4*>(sPart + (row * 4 + h) * 4) = make_float4(sz2, kl, bl, 0.f);
+            }
+            __syncthreads();
+            TSTAMP();   // loss phase A done
+            uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
+            if (live) {
+                float sz2 = 0.f, kl = 0.f, bl = 0.f;
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) { const float4 t4 = *reinterpret_cast<const float4*>(sPart + (row * 4 + hh) * 4); sz2 += t4.x; kl += t4.y; bl += t4.z; }
+                const float nlp = 0.5f * sz2 + 0.9189385332046727f * (float)p.A + sSig[4 * p.A];     // sSig[4A] = sum(logstd), [4A+1] = entropy
+                const float inv_cnt = p.inv_count_dev ? __ldg(p.inv_count_dev) : (1.0f / (float)p.M);
+                const float w = mk * inv_cnt;
+                float a_loss, g_a;
+                if (p.cfg.ppo) {
+                    const float ratio = __expf(old_nlp - nlp);
+                    const float mi = 1.0f - p.cfg.e_clip, mx = 1.0f + p.cfg.e_clip;
+                    float clamped, dcl;
+                    if (p.cfg.smooth) {
+                        const float sg_ = __frcp_rn(1.0f + __expf((-(ratio - mi) * __frcp_rn(mx - mi) + 0.5f) * 4.0f));
+                        clamped = sg_ * (mx - mi) + mi; dcl = 4.0f * sg_ * (1.0f - sg_);
+                    } else {
+                        clamped = fminf(fmaxf(ratio, mi), mx); dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
+                    }
+                    const float t1 = -(adv * ratio), t2 = -(adv * clamped);
+                    a_loss = fmaxf(t1, t2);
+                    const float d1 = adv * ratio, d2 = adv * dcl * ratio;
+                    g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
+                } else { a_loss = nlp * adv; g_a = adv; }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = h + 4 * k;
+                    if (j < p.A) {
+                        const float mu = pick_mu(head, h, k), isg = sSig[2 * p.A + j];
+                        float db = 0.f;
+                        if (p.cfg.has_bounds) {
+                            if (p.cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
+                            else if (p.cfg.bound_type == 2) db = 2.0f * mu;
+                        }
+                        const float dmu = w * (g_a * -(z[k] * isg) + p.cfg.bounds_coef * db);
+                        dls[k] += w * g_a * (1.0f - z[k] * z[k]);
+                        p.la.old_mu[ar * p.A + j] = mu;               // new mu/sigma overwrite the old ones (datasets.py:33-43)
+                        p.la.old_sigma[ar * p.A + j] = sSig[j];
+                        const int c = 1 + j;
+                        *reinterpret_cast<__nv_bfloat16*>(gd + tile_off(row, c >> 3, 2048u, 128u) + (c & 7) * 2) = __float2bfloat16_rn(dmu);
+                    }
+                }
+                if (h == 0) {
+                    const float val = head[0];
+                    float c_loss, dc;
+                    if (p.cfg.clip_value) {
+                        const float delta = val - old_v;
+                        const float vpc = old_v + fminf(fmaxf(delta, -p.cfg.e_clip), p.cfg.e_clip);
+                        const float e1 = val - ret, e2 = vpc - ret;
+                        const float l1 = e1 * e1, l2 = e2 * e2;
+                        c_loss = fmaxf(l1, l2);
+                        const float g1 = 2.0f * e1, g2 = (delta >= -p.cfg.e_clip && delta <= p.cfg.e_clip) ? 2.0f * e2 : 0.0f;
+                        dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
+                    } else { const float e1 = ret - val; c_loss = e1 * e1; dc = -2.0f * e1; }
+                    *reinterpret_cast<__nv_bfloat16*>(gd + tile_off(row, 0, 2048u, 128u)) = __float2bfloat16_rn(w * 0.5f * p.cfg.critic_coef * dc);
+                    const float lr_ = old_nlp - nlp;
+                    const float clipped = (lr_ < p.cfg.log_lo || lr_ > p.cfg.log_hi) ? 1.f : 0.f;
+                    sc[0] += w * a_loss; sc[1] += w * c_loss; sc[2] += w * sSig[4 * p.A + 1]; sc[3] += w * bl; sc[4] += w * kl;
+                    sc[5] += mk; sc[6] += mk * clipped; sc[7] += w;
+                }
+            } else if (h < 2) {
+                // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
+                *reinterpret_cast<uint4*>(gd + tile_off(row, h, 2048u, 128u)) = make_uint4(0, 0, 0, 0);
+            }
+#else
         if (TRAIN) {
             // ---- PPO loss, split 4 ways: the four threads (h = 0..3) that can read TMEM lane `row` each take the actions
             //      j = h, h+4, h+8, h+12 for the per-action sums (exchanged through shared memory, the dead a2 tile region) and the
@@ -771,6 +932,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                 // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
                 *reinterpret_cast<uint4*>(gd + tile_off(row, h, 2048u, 128u)) = make_uint4(0, 0, 0, 0);
             }
+#endif
         } else if (h == 0) {
             mbar_wait(&bars[4], phase);
             fence_after_sync();
@@ -983,7 +1145,7 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
             for (int g = 0; g < 4; ++g) {
                 float a[8];
                 unpack8_bf16(*reinterpret_cast<const uint4*>(sA3 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS)), a);
-                mul_act_grad8(&v[g * 8], a, p.act);
+                mul_act_grad8(&v[g * 8], a);
             }
             store_chunks32(v, row, c0, sD3, nullptr);
         }
@@ -1018,7 +1180,7 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
                 for (int g = 0; g < 4; ++g) {
                     float a[8];
                     unpack8_bf16(*reinterpret_cast<const uint4*>(sA2 + tile_off(row, c0 / 8 + g, N::ACS, N::ARS)), a);
-                    mul_act_grad8(&v[g * 8], a, p.act);
+                    mul_act_grad8(&v[g * 8], a);
                 }
                 store_chunks32(v, row, c0, sD2, g2);
             }
@@ -1063,7 +1225,7 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
                 for (int g = 0; g < 4; ++g) {
                     float a[8];
                     unpack8_bf16(ua[g], a);
-                    mul_act_grad8(&v[g * 8], a, p.act);
+                    mul_act_grad8(&v[g * 8], a);
                 }
                 store_chunks32(v, row, c0, nullptr, g1);
             }
@@ -1077,15 +1239,23 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
     if (first) mbar_wait(&bars[0], 0);
     // ---- flush: dW3^T (TMEM rows = in index, cols = out index), dWh^T, bias sums ----
     float* part = p.part + (size_t)blockIdx.x * p.P;
+    const bool native = p.u1 == N::U1 && p.u2 == N::U2 && p.u3 == N::U3;
     fence_after_sync();
     if (!first) {
         {   // dW3^T[i][o] -> grad_W3[o * U2 + i]; thread row = i, cols [32h, 32h+32) of U3 = 64
             const int c0 = h * (N::U3 / 2);
             float v[32];
             tmem_ld32(TW3 + lane_base + c0, v);
+            if (native) {          // compile-time strides (immediate offsets): the path of the [256,128,64] geometry
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (c0 + j < p.u3 && row < p.u2) part[p.off_W3 + (c0 + j) * p.u2 + row] = v[j];
+                for (int j = 0; j < 32; ++j) part[p.off_W3 + (c0 + j) * N::U2 + row] = v[j];
+            } else if (row < p.u2) {
+                float* dst = part + p.off_W3 + c0 * p.u2 + row;
+                const int nv = p.u3 - c0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) dst[j * p.u2] = v[j];
+            }
         }
         if (h == 0 && row < p.u3) {   // dWh^T[i][o]: rows i < u3 valid; grad_Wh[o * u3 + i], o < A + 1
             float v[16];
@@ -1235,6 +1405,7 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
         first = false;
     }
     float* part = p.part + (size_t)blockIdx.x * p.P;
+    const bool native = p.u1 == N::U1 && p.u2 == N::U2;
     if (!first) {
         mbar_wait(&bars[1], phase ^ 1);
         fence_after_sync();
@@ -1246,9 +1417,16 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
             for (int c0 = h * (N::U2 / 2); c0 < (h + 1) * (N::U2 / 2); c0 += 32) {
                 float v[32];
                 tmem_ld32(TW2 + hh * N::U2 + lane_base + c0, v);
+                if (native) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < p.u2 && hh * 128 + row < p.u1) part[p.off_W2 + (size_t)(c0 + j) * p.u1 + hh * 128 + row] = v[j];
+                    for (int j = 0; j < 32; ++j) part[p.off_W2 + (size_t)(c0 + j) * N::U1 + hh * 128 + row] = v[j];
+                } else if (hh * 128 + row < p.u1) {
+                    float* dst = part + p.off_W2 + c0 * p.u1 + hh * 128 + row;
+                    const int nv = p.u2 - c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nv) dst[j * p.u1] = v[j];
+                }
             }
         }
         // dW1^T: lane = in index i = row (< D valid), columns = out o in [128h, 128h+128)
@@ -1258,9 +1436,16 @@ __device__ __forceinline__ void bwd2_body(const Bwd2Args& p, uint8_t* smem, cons
             float v[32];
             tmem_ld32(TW1 + lane_base + c0, v);
             if (row < p.D) {
+                float* dst = part + p.off_W1 + c0 * p.D + row;
+                if (native) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + j < p.u1) part[p.off_W1 + (size_t)(c0 + j) * p.D + row] = v[j];
+                    for (int j = 0; j < 32; ++j) dst[j * p.D] = v[j];
+                } else {
+                    const int nv = p.u1 - c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nv) dst[j * p.D] = v[j];
+                }
             }
         }
         }
@@ -1520,7 +1705,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
             for (int c0 = h * (N::U1 / 4); c0 < (h + 1) * (N::U1 / 4); c0 += 32) {
                 float v[32];
                 tmem_ld32(T1 + lane_base + c0, v);
-                bias_act<32>(v, sB1 + c0, p.act);
+                bias_act<32>(v, sB1 + c0);
                 store_chunks32(v, row, c0, nullptr, g1);
             }
         }
@@ -1613,9 +1798,11 @@ __global__ void __launch_bounds__(256, 1) l1_wgrad_tc_kernel(const L1WgradArgs p
                 float v[32];
                 tmem_ld32(tmem + hh * N::U1 + lane_base + c0, v);
                 if (i < p.D) {
+                    float* dst = part + p.off_W1 + c0 * p.D + i;
+                    const int nv = p.u1 - c0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < p.u1) part[p.off_W1 + (size_t)(c0 + j) * p.D + i] = v[j];
+                        if (j < nv) dst[j * p.D] = v[j];
                 }
             }
         }
@@ -1662,7 +1849,6 @@ bool net_is_native(int u1, int u2, int u3) { return u1 == 256 && u2 == 128 && u3
 bool net_is_c2(int D, int u1, int u2, int u3, int A) { return D >= 1 && D <= 64 && net_fits(u1, u2, u3, A); }
 // wide observations: the same hidden layers, layer 1 in its own kernels (NetW)
 bool net_is_wide(int D, int u1, int u2, int u3, int A) { return D > 64 && D <= 256 && net_fits(u1, u2, u3, A); }
-bool act_ok(int act) { return act == B200RL_ACT_NONE || act == B200RL_ACT_ELU || act == B200RL_ACT_RELU || act == B200RL_ACT_TANH; }
 int net_kind(int D, int u1, int u2, int u3, int A) { return net_is_c2(D, u1, u2, u3, A) ? 1 : (net_is_wide(D, u1, u2, u3, A) ? 2 : 0); }
 
 template <class N>
@@ -1708,6 +1894,7 @@ int launch_l1_fwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, in
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------- C ABI
+#ifdef B200RL_TC_MAIN
 // 0 = no tcgen05 kernels for this geometry; 1 = resident-weights kernels (obs <= 64); 2 = wide observations (64 < obs <= 256):
 // layer 1 in its own kernels
 B200RL_EXPORT int b200rl_tc_supported(int D, int u1, int u2, int u3, int A) { return net_kind(D, u1, u2, u3, A); }
@@ -1747,13 +1934,15 @@ B200RL_EXPORT int b200rl_tc_pack_weights(const float* W1, const float* W2, const
                      : pack_weights_impl<NetW>(W1, W2, W3, W_head, D, u1, u2, u3, A, wpack, stream);
 }
 
+#endif  // B200RL_TC_MAIN
+
 static int tc_check_rows(int M, int rows_per_chunk) {
     if (M <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
     if (M > rows_per_chunk && rows_per_chunk % 128 != 0) return B200RL_EUNSUPPORTED;   // tiles may not straddle chunks
     return B200RL_OK;
 }
 
-B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+extern "C" int TCIMPL(b200rl_tcimpl_fwd_train)(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                                           const float* norm_mean, const float* norm_std, const void* wpack,
                                           const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
                                           int u1, int u2, int u3, int activation, int M, int A,
@@ -1766,7 +1955,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
         !old_neglogp || !advs_n || !cfg_host || !act1 || !act2 || !act3 || !dhead || !partials)
         return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
-    if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
+    if (!kind || activation != TC_ACT) return B200RL_EUNSUPPORTED;
     if (xtile && kind == 2) return B200RL_EUNSUPPORTED;      // the X tiles are an output of the resident-W1 kernel (obs <= 64)
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
@@ -1806,7 +1995,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, 
     return B200RL_OK;
 }
 
-B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
+extern "C" int TCIMPL(b200rl_tcimpl_fwd_rollout)(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
                                             const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
                                             int u1, int u2, int u3, int activation, int N_rows, int A,
                                             const double* vms_mean, const double* vms_var, int normalize_value,
@@ -1821,7 +2010,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
     if (env_actions && clip_actions && (!act_low || !act_high)) return B200RL_EINVAL;
     if (dones_out && !dones_cur) return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
-    if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
+    if (!kind || activation != TC_ACT) return B200RL_EUNSUPPORTED;
     if (kind == 2 && !l1_scratch) return B200RL_EINVAL;
     const int n_tiles = (N_rows + 127) / 128;
     const int grid = tc_grid(n_tiles);
@@ -1852,7 +2041,7 @@ B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float
     return B200RL_OK;
 }
 
-B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+extern "C" int TCIMPL(b200rl_tcimpl_bwd)(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
                                     const float* norm_mean, const float* norm_std, const void* wpack,
                                     int u1, int u2, int u3, int activation, int M, int A,
                                     const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
@@ -1861,7 +2050,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
                                     int* n_parts_out_host, void* stream) {
     if (!obs || !wpack || !act1 || !act2 || !act3 || !dhead || !delta2 || !delta1 || !part) return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
-    if (!kind || !act_ok(activation)) return B200RL_EUNSUPPORTED;
+    if (!kind || activation != TC_ACT) return B200RL_EUNSUPPORTED;
     if (xtile && kind == 2) return B200RL_EUNSUPPORTED;                                        // X tiles exist for the resident-W1 geometry only
     if (pipelined_wgrad && (!xtile || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;   // option of the native geometry, needs the X tiles
     int rc = tc_check_rows(M, rows_per_chunk);
@@ -1923,6 +2112,73 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
     return B200RL_OK;
 }
 
+#ifdef B200RL_TC_MAIN
+// ---- dispatch on the MLP activation: one set of kernels per activation, compiled in its own translation unit ----
+#define B200RL_TC_DECL(ACTN)                                                                                                                        \
+    extern "C" int b200rl_tcimpl_fwd_train_act##ACTN(const float*, int, int64_t, int, const float*, const float*, const void*, const float*, const float*, \
+                                                      const float*, const float*, const float*, int, int, int, int, int, int, const float*, float*, float*,  \
+                                                      const float*, const float*, const float*, const float*, const float*, const b200rl_loss_cfg*,         \
+                                                      const float*, void*, void*, void*, void*, void*, double*, int, int*, void*);                          \
+    extern "C" int b200rl_tcimpl_fwd_rollout_act##ACTN(const float*, int, const float*, const float*, const void*, const float*, const float*, const float*, \
+                                                        const float*, const float*, int, int, int, int, int, int, const double*, const double*, int,           \
+                                                        const float*, uint64_t, const uint64_t*, uint32_t, float*, float*, float*, float*, float*, float*, int, \
+                                                        const float*, const float*, const uint8_t*, uint8_t*, const float*, float*, int, void*, void*);         \
+    extern "C" int b200rl_tcimpl_bwd_act##ACTN(const float*, int, int64_t, int, const float*, const float*, const void*, int, int, int, int, int, int,        \
+                                                const void*, const void*, const void*, const void*, const void*, int, void*, void*, float*, int, int, int, int, \
+                                                int, int, int, int, int, int, int*, void*);
+B200RL_TC_DECL(1)
+B200RL_TC_DECL(2)
+B200RL_TC_DECL(3)
+#undef B200RL_TC_DECL
+#define B200RL_TC_DISPATCH(fn, ...)                                        \
+    switch (activation) {                                                  \
+        case B200RL_ACT_ELU: return fn##_act1(__VA_ARGS__);                \
+        case B200RL_ACT_RELU: return fn##_act2(__VA_ARGS__);               \
+        case B200RL_ACT_TANH: return fn##_act3(__VA_ARGS__);               \
+        default: return B200RL_EUNSUPPORTED;                               \
+    }
+
+B200RL_EXPORT int b200rl_tc_mlp_fwd_train(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+                                          const float* norm_mean, const float* norm_std, const void* wpack,
+                                          const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
+                                          int u1, int u2, int u3, int activation, int M, int A,
+                                          const float* actions, float* old_mu, float* old_sigma, const float* old_values_n,
+                                          const float* returns_n, const float* old_neglogp, const float* advs_n, const float* mask,
+                                          const b200rl_loss_cfg* cfg_host, const float* inv_count_dev,
+                                          void* act1, void* act2, void* act3, void* dhead, void* xtile,
+                                          double* partials, int max_partials, int* n_blocks_out_host, void* stream) {
+    B200RL_TC_DISPATCH(b200rl_tcimpl_fwd_train, obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, wpack, b1, b2, b3, b_head, logstd, u1, u2, u3,
+                       activation, M, A, actions, old_mu, old_sigma, old_values_n, returns_n, old_neglogp, advs_n, mask, cfg_host, inv_count_dev, act1,
+                       act2, act3, dhead, xtile, partials, max_partials, n_blocks_out_host, stream)
+}
+
+B200RL_EXPORT int b200rl_tc_mlp_fwd_rollout(const float* obs, int D, const float* norm_mean, const float* norm_std, const void* wpack,
+                                            const float* b1, const float* b2, const float* b3, const float* b_head, const float* logstd,
+                                            int u1, int u2, int u3, int activation, int N_rows, int A,
+                                            const double* vms_mean, const double* vms_var, int normalize_value,
+                                            const float* noise, uint64_t seed, const uint64_t* rng_epoch_dev, uint32_t step_index,
+                                            float* actions, float* mus, float* sigmas, float* neglogp, float* values,
+                                            float* env_actions, int clip_actions, const float* act_low, const float* act_high,
+                                            const uint8_t* dones_cur, uint8_t* dones_out, const float* prev_dones, float* valid_out,
+                                            int values_only, void* l1_scratch, void* stream) {
+    B200RL_TC_DISPATCH(b200rl_tcimpl_fwd_rollout, obs, D, norm_mean, norm_std, wpack, b1, b2, b3, b_head, logstd, u1, u2, u3, activation, N_rows, A, vms_mean,
+                       vms_var, normalize_value, noise, seed, rng_epoch_dev, step_index, actions, mus, sigmas, neglogp, values, env_actions, clip_actions,
+                       act_low, act_high, dones_cur, dones_out, prev_dones, valid_out, values_only, l1_scratch, stream)
+}
+
+B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D,
+                                    const float* norm_mean, const float* norm_std, const void* wpack,
+                                    int u1, int u2, int u3, int activation, int M, int A,
+                                    const void* act1, const void* act2, const void* act3, const void* dhead, const void* xtile,
+                                    int pipelined_wgrad, void* delta2, void* delta1, float* part, int max_parts, int P,
+                                    int off_W1, int off_b1, int off_W2, int off_b2, int off_W3, int off_b3, int off_Wh, int off_bh,
+                                    int* n_parts_out_host, void* stream) {
+    B200RL_TC_DISPATCH(b200rl_tcimpl_bwd, obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, wpack, u1, u2, u3, activation, M, A, act1, act2, act3,
+                       dhead, xtile, pipelined_wgrad, delta2, delta1, part, max_parts, P, off_W1, off_b1, off_W2, off_b2, off_W3, off_b3, off_Wh, off_bh,
+                       n_parts_out_host, stream)
+}
+#undef B200RL_TC_DISPATCH
+
 // host test entry point (tests/test_tc_rows_cpu.py): the X-tile staging of the wide-observation kernels (stage_x_cols, __host__ __device__)
 // run thread by thread on the CPU -- out_tile receives the 128 x 256 bf16 INTERLEAVE tile (64 KB).  n_threads: 512 (l1_fwd) or 256 (l1_wgrad).
 B200RL_EXPORT int b200rl_hosttest_stage_x_cols(const float* obs, int64_t row0, int rows_valid, int D, const float* norm_mean, const float* norm_std,
@@ -1964,3 +2220,4 @@ B200RL_EXPORT int b200rl_hosttest_pack_weights_wide(const float* W1, const float
     }
     return B200RL_OK;
 }
+#endif  // B200RL_TC_MAIN

@@ -1,0 +1,3 @@
+// tanh edition of the tcgen05 MLP kernels: see the note at the top of mlp_tc.cu
+#define B200RL_TC_ACT 3   /* B200RL_ACT_TANH */
+#include "mlp_tc.cu"

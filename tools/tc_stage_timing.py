@@ -22,18 +22,34 @@ LABELS = {
 TAIL = {'fwd': ['kernel end'], 'bwd1': ['flush done'], 'bwd2': ['last MMAs done', 'flush done'], 'bwd2_old': ['last MMAs done', 'flush done']}
 
 
-def build():
+VARIANTS = {          # name -> extra -D flags for the A/B builds of the forward kernel's pieces (tools/r02 scripts time each one)
+    'new': [],
+    'epi1_old': ['-DB200RL_V_EPI1_OLD'],
+    'loss_old': ['-DB200RL_V_LOSS_OLD'],
+    'prologue_old': ['-DB200RL_V_PROLOGUE_OLD'],
+    'all_old': ['-DB200RL_V_EPI1_OLD', '-DB200RL_V_LOSS_OLD', '-DB200RL_V_PROLOGUE_OLD'],
+}
+
+
+def build(variants=('new',)):
+    import concurrent.futures as cf
     from rl_games_b200.csrc import build as b
     b.build(verbose=False)
-    timed = ('mlp_tc.cu', 'adam.cu')          # the sources that carry opt-in stamps
-    objs = [os.path.join(b.OBJ, s[:-3] + '.o') for s in b._sources() if s not in timed]
-    for src in timed:
-        obj = os.path.join(b.OBJ, src[:-3] + '_timing.o')
-        subprocess.check_call([b.NVCC] + b.FLAGS + ['-DB200RL_TC_TIMING', '-c', os.path.join(b.HERE, src), '-o', obj])
-        objs.append(obj)
-    out = os.path.join(b.PKG, 'libb200rl_timing.so')
-    subprocess.check_call([b.NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', out] + objs + ['-lcuda'])
-    print(out)
+    timed = ('mlp_tc.cu', 'adam.cu')          # the sources that carry opt-in stamps (the relu / tanh units are linked as they are)
+    base = [os.path.join(b.OBJ, s[:-3] + '.o') for s in b._sources() if s not in timed]
+
+    def one(job):
+        src, name, flags = job
+        obj = os.path.join(b.OBJ, '%s_timing_%s.o' % (src[:-3], name))
+        subprocess.check_call([b.NVCC] + b.FLAGS + ['-DB200RL_TC_TIMING'] + flags + ['-c', os.path.join(b.HERE, src), '-o', obj])
+        return obj
+    jobs = [('adam.cu', 'new', [])] + [('mlp_tc.cu', v, VARIANTS[v]) for v in variants]
+    with cf.ThreadPoolExecutor(max_workers=6) as ex:
+        objs = list(ex.map(one, jobs))
+    for v, obj in zip(variants, objs[1:]):
+        out = os.path.join(b.PKG, 'libb200rl_timing.so' if v == 'new' else 'libb200rl_timing_%s.so' % v)
+        subprocess.check_call([b.NVCC, '-shared', '-gencode', 'arch=compute_100a,code=sm_100a', '-o', out] + base + [objs[0], obj] + ['-lcuda'])
+        print(out)
 
 
 def main():
@@ -137,7 +153,9 @@ def main():
 
 
 if __name__ == '__main__':
-    if '--build' in sys.argv:
+    if '--build-variants' in sys.argv:
+        build(tuple(VARIANTS))
+    elif '--build' in sys.argv:
         build()
     else:
         main()
