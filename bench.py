@@ -271,17 +271,20 @@ def gae_roofline(w, peaks):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def timed(fn, cold, n=13):
+        """cold: one launch per event pair behind an L2 flush (256 MiB write; the launch is enqueued while the flush still runs, so no CPU
+        launch latency is inside the pair); not cold: 20 back-to-back launches inside one pair / 20 (L2-resident inputs, launch latency
+        overlapped: what the kernel costs inside the epoch graph)"""
         ts = []
         for i in range(n):
-            if cold:
-                ops.fill_u32(flush, 1)
+            ops.fill_u32(flush if cold else flush[:1 << 20], 1)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            fn()
+            for _ in range(1 if cold else 20):
+                fn()
             e.record()
             torch.cuda.synchronize()
             if i >= 3:
-                ts.append(s.elapsed_time(e))
+                ts.append(s.elapsed_time(e) / (1 if cold else 20))
         return sum(ts) / len(ts)
     ours = lambda: ops.gae_fused(r, v, d, lv, ld, None, advs, rets, part, 0.99, 0.95)   # noqa: E731
     ms, ms_warm = timed(ours, True), timed(ours, False)

@@ -433,8 +433,8 @@ int b200rl_tc_supported(int D, int u1, int u2, int u3, int A);
 int64_t b200rl_tc_pack_bytes(int D, int u1, int u2, int u3, int A);
 int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int64_t* out4_host);
 /* bytes of one 128-row tile of the normalised bf16 observation buffer (xtile) the training forward emits for the backward kernel
- * (obs <= 64: the weight-gradient MMAs of layer 1 TMA-load it instead of re-deriving it from the fp32 observations; with
- * pipelined_wgrad != 0 the two-stage-ring edition of the weight-gradient kernel runs instead); -1 if the geometry has no X tiles */
+ * (the weight-gradient MMAs of layer 1 TMA-load it instead of re-deriving it from the fp32 observations; obs <= 64 only: with
+ * pipelined_wgrad != 0 the two-stage-ring edition of the weight-gradient kernel runs instead); -1 if the geometry is unsupported */
 int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A);
 int b200rl_tc_pack_table(int D, int u1, int u2, int u3, int A, int off_W1, int off_W2, int off_W3, int off_Wh,
                          b200rl_pack_table* out_host);

@@ -394,11 +394,11 @@ class A2CAgent(CompileTolerantModel):
             self.tc_act = [u8(nt1 * tb[0]), u8(nt * tb[1]), u8(nt * tb[2])]
             self.tc_l1_scratch = self.tc_act[0] if self.tc_wide else None
             self.tc_dhead, self.tc_delta2, self.tc_delta1 = u8(nt * tb[3]), u8(nt * tb[1]), u8(nt * tb[0])
-            # normalised bf16 obs tiles (obs <= 64): the training forward emits them, the backward's layer-1 weight-gradient MMAs TMA-load
+            # normalised bf16 obs tiles: the training forward emits them, the backward's layer-1 weight-gradient MMAs TMA-load
             # them instead of re-reading and re-normalising the fp32 observations (b200_emit_xtile: False restores that); config
             # b200_pipelined_wgrad selects the two-stage-ring edition of the weight-gradient kernel (measured slower on c2)
             self.tc_pipelined_wgrad = bool(self.config.get('b200_pipelined_wgrad', False))
-            want_xt = (not self.tc_wide) and (self.tc_pipelined_wgrad or bool(self.config.get('b200_emit_xtile', True)))
+            want_xt = self.tc_pipelined_wgrad or bool(self.config.get('b200_emit_xtile', True))
             self.tc_xt = u8(nt * ops.tc_xtile_bytes(m.D, m.units, A)) if want_xt else None
             self.tc_offs = {k: m.layout[k][0] for k in ('W0', 'b0', 'W1', 'b1', 'W2', 'b2', 'W_head', 'b_head')}
             self.pack_table = ops.tc_pack_table(m.D, m.units, A, self.tc_offs)

@@ -46,6 +46,11 @@ __device__ __forceinline__ void bulk_g2s(void* sdst, const void* gsrc, uint32_t 
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -1644,6 +1649,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd2_db_tc_kernel(const Bwd2DbArgs
 struct L1FwdArgs {
     const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
     const uint8_t* wpack; const float* b1; int M; uint8_t* act1; int u1, act;
+    uint8_t* xt;      // optional: normalised bf16 observation tiles (128 x DPAD) for l1_wgrad_tc_kernel
 };
 
 template <class N>
@@ -1689,6 +1695,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
         if (!weights_ready) { mbar_wait(&bars[0], 0); weights_ready = true; }
         __syncthreads();
         if (tid == 0) {
+            if (p.xt) {      // keep the normalised bf16 tile for the weight-gradient kernel: one 64 KB bulk store, asynchronous
+                bulk_s2g(p.xt + (size_t)tile * N::X_BYTES, sX, N::X_BYTES);
+                bulk_commit();
+            }
             fence_after_sync();
             constexpr uint32_t idesc = make_idesc_bf16(128, N::U1, 0, 0);
 #pragma unroll
@@ -1709,12 +1719,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
                 store_chunks32(v, row, c0, nullptr, g1);
             }
         }
+        if (p.xt && tid == 0) bulk_wait_read0();      // the tile's copy-out (issued before the MMAs) has finished reading sX
         fence_before_sync();
         __syncthreads();       // T1 and the X tile are free for the next tile
         fence_after_sync();
         phase ^= 1;
     }
     if (!weights_ready) mbar_wait(&bars[0], 0);
+    if (p.xt && tid == 0) bulk_wait_read0();          // shared memory must outlive the last copy-out's reads
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(T1, 256);
@@ -1726,6 +1738,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) l1_fwd_tc_kernel(const L1FwdAr
 struct L1WgradArgs {
     const float* obs; int rows_per_chunk; int64_t chunk_stride; int D; const float* nm; const float* ns;
     const uint8_t* delta1; float* part; int M; int P; int off_W1; int u1;
+    const uint8_t* xt;      // optional: the tiles l1_fwd_tc_kernel emitted (TMA-loaded instead of re-deriving X from the fp32 observations)
 };
 
 template <class N>
@@ -1759,15 +1772,18 @@ __global__ void __launch_bounds__(256, 1) l1_wgrad_tc_kernel(const L1WgradArgs p
         if (!first) { mbar_wait(&bars[1], phase ^ 1); fence_after_sync(); }    // previous tile's MMAs done reading the tiles
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&bars[0], N::A1_BYTES);
+            mbar_expect_tx(&bars[0], N::A1_BYTES + (p.xt ? N::X_BYTES : 0u));
             bulk_g2s(sD1, p.delta1 + (size_t)tile * N::A1_BYTES, N::A1_BYTES, &bars[0]);
+            if (p.xt) bulk_g2s(sX, p.xt + (size_t)tile * N::X_BYTES, N::X_BYTES, &bars[0]);
         }
+        if (!p.xt) {
         const int m0 = tile * 128;
 #pragma unroll 1
         for (int cg = 0; cg < N::DPAD / 8; cg += NCGP)
             stage_x_cols<N, 256, NCGP>(sX, p.obs, chunk_row(m0, p.rows_per_chunk, p.chunk_stride), min(128, p.M - m0), p.D, sNorm,
                                        p.nm != nullptr, cg, tid);
         fence_async_smem();
+        }
         mbar_wait(&bars[0], phase);
         __syncthreads();
         if (tid == 0) {
@@ -1879,10 +1895,10 @@ int pack_weights_impl(const float* W1, const float* W2, const float* W3, const f
 // layer 1 of the wide path (see l1_fwd_tc_kernel): a1 tiles of M rows into `act1`
 template <class N>
 int launch_l1_fwd(const float* obs, int rows_per_chunk, int64_t chunk_stride, int D, const float* nm, const float* ns, const void* wpack,
-                  const float* b1, int M, void* act1, int u1, int act, void* stream) {
+                  const float* b1, int M, void* act1, int u1, int act, void* xt, void* stream) {
     const int n_tiles = (M + 127) / 128;
     const int grid = tc_grid(n_tiles);
-    L1FwdArgs a{obs, rows_per_chunk, chunk_stride, D, nm, ns, (const uint8_t*)wpack, b1, M, (uint8_t*)act1, u1, act};
+    L1FwdArgs a{obs, rows_per_chunk, chunk_stride, D, nm, ns, (const uint8_t*)wpack, b1, M, (uint8_t*)act1, u1, act, (uint8_t*)xt};
     constexpr size_t smem = l1_fwd_smem<N>();
     static_assert(smem <= 227 * 1024, "layer-1 forward kernel shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(l1_fwd_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1911,7 +1927,8 @@ B200RL_EXPORT int b200rl_tc_tile_bytes(int D, int u1, int u2, int u3, int A, int
 }
 
 B200RL_EXPORT int64_t b200rl_tc_xtile_bytes(int D, int u1, int u2, int u3, int A) {
-    return net_is_c2(D, u1, u2, u3, A) ? (int64_t)NetC2::X_BYTES : -1;
+    const int kind = net_kind(D, u1, u2, u3, A);
+    return kind == 1 ? (int64_t)NetC2::X_BYTES : (kind == 2 ? (int64_t)NetW::X_BYTES : -1);
 }
 
 // segments of the packed weight buffer, for the optimiser's fused refresh (b200rl_adam_step_f32)
@@ -1956,7 +1973,6 @@ extern "C" int TCIMPL(b200rl_tcimpl_fwd_train)(const float* obs, int rows_per_ch
         return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
     if (!kind || activation != TC_ACT) return B200RL_EUNSUPPORTED;
-    if (xtile && kind == 2) return B200RL_EUNSUPPORTED;      // the X tiles are an output of the resident-W1 kernel (obs <= 64)
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     const int n_tiles = (M + 127) / 128;
@@ -1976,7 +1992,7 @@ extern "C" int TCIMPL(b200rl_tcimpl_fwd_train)(const float* obs, int rows_per_ch
     p.xt = (uint8_t*)xtile;
     if (kind == 2) {
         // wide observations: layer 1 (a1 tiles -> act1), then the chain kernel in its external-layer-1 form
-        rc = launch_l1_fwd<NetW>(obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, wpack, b1, M, act1, u1, activation, stream);
+        rc = launch_l1_fwd<NetW>(obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, wpack, b1, M, act1, u1, activation, xtile, stream);
         if (rc) return rc;
         constexpr size_t smemw = fwd_smem<NetW, true>();
         static_assert(smemw <= 227 * 1024, "forward kernel (external layer 1) shared memory budget");
@@ -2023,7 +2039,7 @@ extern "C" int TCIMPL(b200rl_tcimpl_fwd_rollout)(const float* obs, int D, const 
     p.values = values; p.env_actions = env_actions; p.clip_actions = clip_actions; p.act_low = act_low; p.act_high = act_high;
     p.dones_cur = dones_cur; p.dones_out = dones_out; p.prev_dones = prev_dones; p.valid_out = valid_out; p.values_only = values_only;
     if (kind == 2) {
-        int rc = launch_l1_fwd<NetW>(obs, N_rows, 0, D, norm_mean, norm_std, wpack, b1, N_rows, l1_scratch, u1, activation, stream);
+        int rc = launch_l1_fwd<NetW>(obs, N_rows, 0, D, norm_mean, norm_std, wpack, b1, N_rows, l1_scratch, u1, activation, nullptr, stream);
         if (rc) return rc;
         p.act1 = (uint8_t*)l1_scratch;
         constexpr size_t smemw = fwd_smem<NetW, true>();
@@ -2051,8 +2067,7 @@ extern "C" int TCIMPL(b200rl_tcimpl_bwd)(const float* obs, int rows_per_chunk, i
     if (!obs || !wpack || !act1 || !act2 || !act3 || !dhead || !delta2 || !delta1 || !part) return B200RL_EINVAL;
     const int kind = net_kind(D, u1, u2, u3, A);
     if (!kind || activation != TC_ACT) return B200RL_EUNSUPPORTED;
-    if (xtile && kind == 2) return B200RL_EUNSUPPORTED;                                        // X tiles exist for the resident-W1 geometry only
-    if (pipelined_wgrad && (!xtile || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;   // option of the native geometry, needs the X tiles
+    if (pipelined_wgrad && (!xtile || kind == 2 || !net_is_native(u1, u2, u3))) return B200RL_EUNSUPPORTED;   // option of the native resident-W1 geometry, needs the X tiles
     int rc = tc_check_rows(M, rows_per_chunk);
     if (rc) return rc;
     using N = NetC2;
@@ -2092,7 +2107,7 @@ extern "C" int TCIMPL(b200rl_tcimpl_bwd)(const float* obs, int rows_per_chunk, i
         if (e != cudaSuccess) return (int)e;
         e = launch_k(mlp_bwd_tc_kernel<NetW, true>, dim3(grid), dim3(256), smemw, as_stream(stream), abw);
         if (e != cudaSuccess) return (int)e;
-        L1WgradArgs w{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)delta1, part, M, P, off_W1, u1};
+        L1WgradArgs w{obs, rows_per_chunk, chunk_stride, D, norm_mean, norm_std, (const uint8_t*)delta1, part, M, P, off_W1, u1, (const uint8_t*)xtile};
         constexpr size_t smem1w = l1_wgrad_smem<NetW>();
         static_assert(smem1w <= 227 * 1024, "layer-1 weight-gradient kernel shared memory budget");
         e = cudaFuncSetAttribute(l1_wgrad_tc_kernel<NetW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1w);

@@ -595,7 +595,6 @@ def tc_mlp_fwd_rollout(obs, D, nm, ns, wpack, b, b_head, logstd, units, N, A, vm
 def tc_mlp_fwd_train(obs, rows_per_chunk, chunk_stride, D, nm, ns, wpack, b, b_head, logstd, units, M, A, actions, old_mu, old_sigma, old_values_n,
                      returns_n, old_neglogp, advs_n, mask, cfg, inv_count, act, dhead, partials, xtile=None, activation=1):
     """whole training forward + loss + backward of the MLP in fp32 with autograd; the gradients wait in a side channel for tc_mlp_bwd"""
-    assert _TC.get('kind', 1) == 1 or xtile is None
     ws = [w.clone().requires_grad_(True) for w in _TC[wpack.data_ptr()]]
     bs = [t.clone().requires_grad_(True) for t in b]
     x = _norm(_rows(obs, M, D, rows_per_chunk, chunk_stride, D), nm, ns)
@@ -637,7 +636,7 @@ def reduce_adam(part, n_splits, split_stride, loss_partials, n_loss_partials, A,
 
 def install_tc(monkeypatch, kind=1):
     """stand-ins for the bf16 tcgen05 path of A2CAgent (mixed_precision: True), computed in fp32; kind 2 = the wide-observation
-    edition (layer 1 in kernels of its own: only the host-visible contract differs -- scratch buffer, no xtile)"""
+    edition (layer 1 in kernels of its own: only the host-visible contract differs -- scratch buffer, 128 x 256 X tiles)"""
     from rl_games_b200 import ops
     install_continuous(monkeypatch)
     _TC['kind'] = kind

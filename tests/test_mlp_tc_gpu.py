@@ -118,7 +118,7 @@ def _fwd_loss_bwd_case(H, N, epm, masked, D):
     delta2 = torch.zeros(n_tiles * tb[1], dtype=torch.uint8, device=DEV); delta1 = torch.zeros(n_tiles * tb[0], dtype=torch.uint8, device=DEV)
     mu_t, sg_t = old_mu.clone(), old_sigma.clone()
     partials_t = torch.zeros(148, stride, dtype=torch.float64, device=DEV)
-    xt = None if wide else torch.zeros(n_tiles * ops.tc_xtile_bytes(D, UNITS, A), dtype=torch.uint8, device=DEV)
+    xt = torch.zeros(n_tiles * ops.tc_xtile_bytes(D, UNITS, A), dtype=torch.uint8, device=DEV)      # 128 x 64 (obs <= 64) or 128 x 256 bf16 per tile
     nbt = ops.tc_mlp_fwd_train(sl(obs), epm, N, D, nm, ns, wpack, b, bh, logstd, UNITS, M, A, sl(actions), sl(mu_t), sl(sg_t),
                                sl(old_v), sl(ret), sl(old_nlp), sl(adv), None if mask is None else sl(mask), cfg, inv, act, dhead,
                                partials_t, xtile=xt)
@@ -149,10 +149,9 @@ def _fwd_loss_bwd_case(H, N, epm, masked, D):
     offs['b_head'] = o; o += A + 1
     assert o == P
     # normalised observation tile emitted by the forward (consumed by the pipelined weight-gradient kernel)
-    if not wide:
-        xn = torch.clamp((torch.cat([obs[t, e0:e0 + epm] for t in range(H)]) - nm) / ns, -5.0, 5.0)
-        xt_dec = decode_tiles(xt, n_tiles, 64)[:M, :D]
-        torch.testing.assert_close(xt_dec, xn.to(torch.bfloat16).float(), rtol=0, atol=4e-2)
+    xn = torch.clamp((torch.cat([obs[t, e0:e0 + epm] for t in range(H)]) - nm) / ns, -5.0, 5.0)
+    xt_dec = decode_tiles(xt, n_tiles, 256 if wide else 64)[:M, :D]
+    torch.testing.assert_close(xt_dec, xn.to(torch.bfloat16).float(), rtol=0, atol=4e-2)
     part = torch.full((148, P), float('nan'), device=DEV)
     # three editions of the layer-1 / layer-2 weight gradients must agree: X tiles from the forward (default), pipelined ring, re-derived X
     npart = ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part, P, offs, xtile=xt,
@@ -167,7 +166,7 @@ def _fwd_loss_bwd_case(H, N, epm, masked, D):
     torch.cuda.synchronize()
     assert torch.isfinite(grad).all()
     torch.testing.assert_close(grad, grad_b, rtol=1e-4, atol=1e-6)
-    if not wide:
+    if True:        # wide observations too: l1_wgrad_tc_kernel TMA-loads the tiles l1_fwd_tc_kernel emitted
         part_c = torch.full((148, P), float('nan'), device=DEV)
         ops.tc_mlp_bwd(sl(obs), epm, N, D, nm, ns, wpack, UNITS, M, A, act, dhead, delta2, delta1, part_c, P, offs, xtile=xt)
         grad_c = torch.zeros(P, device=DEV)

@@ -4,7 +4,8 @@ Algorithmic bytes: 13 B/element for the drop-in kernel with u8 do
 the fused kernel that also writes returns; the reference's Triton kernel is fed fp32 dones like its caller does (16 B/element).
 Times with CUDA events on the launching stream, median of 20, two cache regimes per row:
   cold = L2 flushed (256 MiB write) before every launch -- what the HBM roofline is about;
-  warm = back-to-back launches on L2-resident inputs -- what the kernel sees inside the epoch graph at the BASELINE shapes (4.5 / 9 MB).
+  warm = 20 back-to-back launches inside one event pair / 20, L2-resident inputs -- what the kernel costs inside the epoch graph at the
+         BASELINE shapes (4.5 / 9 MB working sets).
 Comparators on the same box: the reference's own Triton kernel (rl_games/triton_kernels/gae_kernel.py:16-59 through _triton_gae, from the
 vendored oracle/_ref) and its eager loop (_pytorch_gae) on the GPU."""
 import json
@@ -23,12 +24,27 @@ if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')):
 
 
 def time_kernel(fn, flush, iters=20, warm=3):
+    """flush given: one launch per event pair, L2 flushed before it (the flush kernel is still running when the launch is enqueued, so no
+    CPU launch latency is inside the pair).  flush None (L2-resident inputs): `iters` launches back to back inside ONE event pair, divided
+    by iters -- stream-ordered launches overlap their launch latency, which is what the kernel costs inside a CUDA graph."""
     for _ in range(warm):
         fn()
+    if flush is None:
+        ts = []
+        for _ in range(5):
+            ops.fill_u32(flush_small, 1)          # something in front so the first launch is not a cold-start of the queue
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(iters):
+                fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e) / iters)
+        ts.sort()
+        return ts[len(ts) // 2], ts[0]
     ts = []
     for _ in range(iters):
-        if flush is not None:
-            ops.fill_u32(flush, 1)
+        ops.fill_u32(flush, 1)
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); fn(); e.record()
         torch.cuda.synchronize()
@@ -50,7 +66,9 @@ def reference_kernels():
 
 def main():
     dev = 'cuda'
+    global flush_small
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_small = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
     out = []
     quick = '--quick' in sys.argv
     shapes = [(16, 16384), (64, 4096), (32, 16384), (32, 131072), (16, 1 << 20), (32, 1 << 20), (64, 1 << 20), (32, 1 << 22)]
@@ -90,7 +108,7 @@ def main():
         del r, v, d, lv, ld, advs, rets, partials, df, ldf
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump({'peak_gbs': PEAK, 'timing': 'CUDA events, median of 20 after 3 warm-up launches; not under a profiler', 'rows': out},
-              open(os.path.join(ROOT, 'gpurun_out', 'r02_gae_sweep.json'), 'w'), indent=1)
+              open(os.path.join(ROOT, 'gpurun_out', 'r02_gae_sweep_quick.json' if quick else 'r02_gae_sweep.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':
