@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
             bulk_g2s(sXraw, p.obs + chunk_row(m0, p.rows_per_chunk, p.chunk_stride) * p.D, bytes, &bars[5]);
         }
     }
+    TSTAMP();   // TMEM allocated (warp 0), barriers initialised, first X tile requested
     pdl_sync();
     // ---- prologue, part 2: parameters and normaliser statistics (written by the optimiser kernel) ----
     if (tid == 0) {
@@ -458,13 +459,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[7]);
         bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[7]);
     }
-#ifdef B200RL_V_PROLOGUE_OLD
     for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = i < p.u1 ? __ldg(p.b1 + i) : 0.f;
     for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = i < p.u2 ? __ldg(p.b2 + i) : 0.f;
     for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = i < p.u3 ? __ldg(p.b3 + i) : 0.f;
     if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
     if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
+    TSTAMP();   // weight copies issued, parameter loads issued
     __syncthreads();
+    TSTAMP();   // first prologue barrier passed
     if (tid == 0) {      // row-independent constants: sum(logstd) and the entropy of the diagonal Gaussian
         float sl = 0.f, en = 0.f;
         for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
@@ -474,25 +476,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-#else
-    // every parameter / statistic load of the prologue is issued before the single barrier below (one global-memory round trip,
-    // not three); the row-independent constants derived from sigma are finished by thread 0 after it -- their first reader is the
-    // loss epilogue, several barriers further on
-    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = i < p.u1 ? __ldg(p.b1 + i) : 0.f;
-    for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = i < p.u2 ? __ldg(p.b2 + i) : 0.f;
-    for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = i < p.u3 ? __ldg(p.b3 + i) : 0.f;
-    if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
-    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
-    if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    if (tid == 0) {      // row-independent constants: sum(logstd) and the entropy of the diagonal Gaussian
-        float sl = 0.f, en = 0.f;
-        for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
-        sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
-    }
-#endif
     TSTAMP();   // prologue done
     const uint32_t tmem = *tmem_slot;
     const uint32_t T1 = tmem, T2 = tmem + 256, T3 = tmem + 384, T4 = tmem + 448;     // accumulator column bases
@@ -545,7 +528,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         TSTAMP();   // MMA 1 done
         {
             uint8_t* g1 = TRAIN ? p.act1 + (size_t)tile * N::A1_BYTES : nullptr;
-#ifdef B200RL_V_EPI1_OLD
 #pragma unroll 1
             for (int c0 = h * (N::U1 / 4); c0 < (h + 1) * (N::U1 / 4); c0 += 32) {
                 float v[32];
@@ -554,24 +536,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                 store_chunks32(v, row, c0, sA1, g1);
             }
         }
-#else
-            static_assert(N::U1 / 4 == 64, "layer-1 epilogue: two 32-column loads per thread");
-            const int c0 = h * 64;
-            uint32_t ra[32], rb[32];
-            tmem_ld32_issue(T1 + lane_base + c0, ra);
-            tmem_ld32_issue(T1 + lane_base + c0 + 32, rb);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(ra[j]);
-            bias_act<32>(v, sB1 + c0);
-            store_chunks32(v, row, c0, sA1, g1);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rb[j]);
-            bias_act<32>(v, sB1 + c0 + 32);
-            store_chunks32(v, row, c0 + 32, sA1, g1);
-        }
-#endif
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -661,7 +625,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                           make_smem_desc(smem_u32(sWh) + k * 2 * N::WH_CS, N::WH_CS, 128), idesc, k > 0);
             umma_commit(&bars[4]);
         }
-#ifdef B200RL_V_LOSS_OLD      // A/B variant (tools/tc_stage_timing.py --variants): the round-1 loss epilogue
         if (TRAIN) {
             // ---- PPO loss, split 4 ways: the four threads (h = 0..3) that can read TMEM lane `row` each take the actions
             //      j = h, h+4, h+8, h+12; per-row sums are exchanged through shared memory (the dead a2 tile region).
@@ -775,169 +738,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
                 // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
                 *reinterpret_cast<uint4*>(gd + tile_off(row, h, 2048u, 128u)) = make_uint4(0, 0, 0, 0);
             }
-#else
-        if (TRAIN) {
-            // ---- PPO loss, split 4 ways: the four threads (h = 0..3) that can read TMEM lane `row` each take the actions
-            //      j = h, h+4, h+8, h+12 for the per-action sums (exchanged through shared memory, the dead a2 tile region) and the
-            //      d_logstd slices; the row-wide outputs go out as whole-row vector stores, one kind per thread: h = 0 the value loss
-            //      and the scalar statistics, h = 1 the new mu row, h = 2 the new sigma row, h = 3 the bf16 d_head row (two 16-byte
-            //      chunks, coalesced across the warp) -- no 2- and 4-byte scattered stores.
-            const bool live = row < rows_valid;
-            const int64_t ar = arow0 + row;
-            float act[4], omu[4], osg[4];
-            float actrow[16];
-            float old_v = 0.f, ret = 0.f, old_nlp = 0.f, adv = 0.f, mk = 0.f;
-            const bool vecA = (p.A & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.la.actions) | reinterpret_cast<uintptr_t>(p.la.old_mu) |
-                                                reinterpret_cast<uintptr_t>(p.la.old_sigma)) & 15) == 0;
-            if (live) {      // arena inputs: issued before the wait on the heads MMA so their latency overlaps with it
-                old_v = __ldg(p.la.old_values_n + ar); ret = __ldg(p.la.returns_n + ar);
-                old_nlp = __ldg(p.la.old_neglogp + ar); adv = __ldg(p.la.advs_n + ar);
-                mk = p.la.mask ? __ldg(p.la.mask + ar) : 1.f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int j = h + 4 * k;
-                    if (j < p.A) { act[k] = __ldg(p.la.actions + ar * p.A + j); omu[k] = p.la.old_mu[ar * p.A + j]; osg[k] = p.la.old_sigma[ar * p.A + j]; }
-                }
-                if (h == 3) {      // the d_head thread needs the whole action row
-                    if (vecA) {
-                        const float4* pa = reinterpret_cast<const float4*>(p.la.actions + ar * p.A);
-#pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            if (qq * 4 < p.A) {
-                                const float4 x = __ldg(pa + qq);
-                                actrow[qq * 4] = x.x; actrow[qq * 4 + 1] = x.y; actrow[qq * 4 + 2] = x.z; actrow[qq * 4 + 3] = x.w;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 15; ++j)
-                            if (j < p.A) actrow[j] = __ldg(p.la.actions + ar * p.A + j);
-                    }
-                }
-            }
-            mbar_wait(&bars[4], phase);
-            fence_after_sync();
-            TSTAMP();   // MMA 4 done
-            float head[16];
-            tmem_ld16(T4 + lane_base, head);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) head[j] += sBh[j];
-            float* sPart = reinterpret_cast<float*>(sXA2);           // [128 rows][4 h][4]: sum z^2, kl, bound loss
-            float z[4];
-            {
-                float sz2 = 0.f, kl = 0.f, bl = 0.f;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int j = h + 4 * k;
-                    z[k] = 0.f;
-                    if (live && j < p.A) {
-                        const float mu = pick_mu(head, h, k), sg = sSig[j], isg = sSig[2 * p.A + j];
-                        z[k] = (act[k] - mu) * isg;
-                        sz2 += z[k] * z[k];
-                        const float c1 = __logf(osg[k] * isg + 1e-5f);
-                        const float dm = omu[k] - mu;
-                        kl += c1 + (sg * sg + dm * dm) * __frcp_rn(2.0f * (osg[k] * osg[k] + 1e-5f)) - 0.5f;
-                        if (p.cfg.has_bounds) {
-                            if (p.cfg.bound_type == 1) { const float hi = fmaxf(mu - 1.1f, 0.f), lo = fminf(mu + 1.1f, 0.f); bl += lo * lo + hi * hi; }
-                            else if (p.cfg.bound_type == 2) bl += mu * mu;
-                        }
-                    }
-                }
-                *reinterpret_cast<float4*>(sPart + (row * 4 + h) * 4) = make_float4(sz2, kl, bl, 0.f);
-            }
-            __syncthreads();
-            TSTAMP();   // loss phase A done
-            uint8_t* gd = p.dhead + (size_t)tile * N::DH_BYTES;
-            if (live) {
-                float sz2 = 0.f, kl = 0.f, bl = 0.f;
-#pragma unroll
-                for (int hh = 0; hh < 4; ++hh) { const float4 t4 = *reinterpret_cast<const float4*>(sPart + (row * 4 + hh) * 4); sz2 += t4.x; kl += t4.y; bl += t4.z; }
-                const float nlp = 0.5f * sz2 + 0.9189385332046727f * (float)p.A + sSig[4 * p.A];     // sSig[4A] = sum(logstd), [4A+1] = entropy
-                const float inv_cnt = p.inv_count_dev ? __ldg(p.inv_count_dev) : (1.0f / (float)p.M);
-                const float w = mk * inv_cnt;
-                float a_loss, g_a;
-                if (p.cfg.ppo) {
-                    const float ratio = __expf(old_nlp - nlp);
-                    const float mi = 1.0f - p.cfg.e_clip, mx = 1.0f + p.cfg.e_clip;
-                    float clamped, dcl;
-                    if (p.cfg.smooth) {
-                        const float sg_ = __frcp_rn(1.0f + __expf((-(ratio - mi) * __frcp_rn(mx - mi) + 0.5f) * 4.0f));
-                        clamped = sg_ * (mx - mi) + mi; dcl = 4.0f * sg_ * (1.0f - sg_);
-                    } else {
-                        clamped = fminf(fmaxf(ratio, mi), mx); dcl = (ratio >= mi && ratio <= mx) ? 1.0f : 0.0f;
-                    }
-                    const float t1 = -(adv * ratio), t2 = -(adv * clamped);
-                    a_loss = fmaxf(t1, t2);
-                    const float d1 = adv * ratio, d2 = adv * dcl * ratio;
-                    g_a = (t1 > t2) ? d1 : ((t1 < t2) ? d2 : 0.5f * (d1 + d2));
-                } else { a_loss = nlp * adv; g_a = adv; }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int j = h + 4 * k;
-                    if (j < p.A) dls[k] += w * g_a * (1.0f - z[k] * z[k]);
-                }
-                // critic loss and its gradient (threads h = 0 and h = 3 use them)
-                const float val = head[0];
-                float c_loss, dc;
-                if (p.cfg.clip_value) {
-                    const float delta = val - old_v;
-                    const float vpc = old_v + fminf(fmaxf(delta, -p.cfg.e_clip), p.cfg.e_clip);
-                    const float e1 = val - ret, e2 = vpc - ret;
-                    const float l1 = e1 * e1, l2 = e2 * e2;
-                    c_loss = fmaxf(l1, l2);
-                    const float g1 = 2.0f * e1, g2 = (delta >= -p.cfg.e_clip && delta <= p.cfg.e_clip) ? 2.0f * e2 : 0.0f;
-                    dc = (l1 > l2) ? g1 : ((l1 < l2) ? g2 : 0.5f * (g1 + g2));
-                } else { const float e1 = ret - val; c_loss = e1 * e1; dc = -2.0f * e1; }
-                if (h == 0) {
-                    const float lr_ = old_nlp - nlp;
-                    const float clipped = (lr_ < p.cfg.log_lo || lr_ > p.cfg.log_hi) ? 1.f : 0.f;
-                    sc[0] += w * a_loss; sc[1] += w * c_loss; sc[2] += w * sSig[4 * p.A + 1]; sc[3] += w * bl; sc[4] += w * kl;
-                    sc[5] += mk; sc[6] += mk * clipped; sc[7] += w;
-                } else if (h == 3) {
-                    // d_head row: column 0 = value gradient, 1 + j = dL/dmu_j, the rest zero -> two 16-byte chunks
-                    float dh[16];
-                    dh[0] = w * 0.5f * p.cfg.critic_coef * dc;
-#pragma unroll
-                    for (int j = 0; j < 15; ++j) {
-                        float dmu = 0.f;
-                        if (j < p.A) {
-                            const float mu = head[1 + j], isg = sSig[2 * p.A + j];
-                            const float zj = (actrow[j] - mu) * isg;
-                            float db = 0.f;
-                            if (p.cfg.has_bounds) {
-                                if (p.cfg.bound_type == 1) db = 2.0f * fmaxf(mu - 1.1f, 0.f) + 2.0f * fminf(mu + 1.1f, 0.f);
-                                else if (p.cfg.bound_type == 2) db = 2.0f * mu;
-                            }
-                            dmu = w * (g_a * -(zj * isg) + p.cfg.bounds_coef * db);
-                        }
-                        dh[1 + j] = dmu;
-                    }
-                    *reinterpret_cast<uint4*>(gd + tile_off(row, 0, 2048u, 128u)) = pack8_bf16(&dh[0]);
-                    *reinterpret_cast<uint4*>(gd + tile_off(row, 1, 2048u, 128u)) = pack8_bf16(&dh[8]);
-                } else {
-                    // h = 1: new mu row, h = 2: new sigma row, over the old ones (datasets.py:33-43)
-                    float* dst = (h == 1 ? p.la.old_mu : p.la.old_sigma) + ar * p.A;
-                    if (vecA) {
-#pragma unroll
-                        for (int qq = 0; qq < 4; ++qq) {
-                            if (qq * 4 < p.A) {
-                                float4 o;
-                                if (h == 1) o = make_float4(head[1 + qq * 4], head[2 + qq * 4], head[3 + qq * 4], qq * 4 + 4 < 16 ? head[(4 + qq * 4) & 15] : 0.f);
-                                else o = make_float4(sSig[qq * 4], sSig[qq * 4 + 1], sSig[qq * 4 + 2], sSig[qq * 4 + 3]);
-                                reinterpret_cast<float4*>(dst)[qq] = o;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 15; ++j)
-                            if (j < p.A) dst[j] = (h == 1) ? head[1 + j] : sSig[j];
-                    }
-                }
-            } else if (h < 2) {
-                // padded rows of a partial tile: zero d_head so the backward kernels see no contribution
-                *reinterpret_cast<uint4*>(gd + tile_off(row, h, 2048u, 128u)) = make_uint4(0, 0, 0, 0);
-            }
-#endif
         } else if (h == 0) {
             mbar_wait(&bars[4], phase);
             fence_after_sync();

@@ -151,26 +151,28 @@ def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D, UNIT
         assert float(full[:, C:].abs().max()) == 0.0 if C < NATIVE[i] else True          # padded units are exactly zero
         got = full[:, :C]
         report[f'a{i + 1}'] = rel_l2(got, r)
-        assert report[f'a{i + 1}'] < 3e-3, (i, report)
+        assert report[f'a{i + 1}'] < (6e-3 if actname == 'tanh' else 3e-3), (i, report)
     got_mu = rows(mu_t)
-    torch.testing.assert_close(got_mu, mu.detach(), rtol=0, atol=2e-3)
+    # tanh runs on MUFU.TANH (tanh.approx.f32: ~2^-11 relative per activation), which the reference's torch.tanh does not share
+    torch.testing.assert_close(got_mu, mu.detach(), rtol=0, atol=1e-2 if actname == 'tanh' else 2e-3)
     ref_stats = [float(a_m), float(c_m), float(e_m), float(b_m), float(kl)]
     for k in range(5):
         report[f'stat{k}'] = (float(stats_t[k]), ref_stats[k])
-        assert float(stats_t[k]) == pytest.approx(ref_stats[k], rel=5e-3, abs=2e-5), (k, report)
+        assert float(stats_t[k]) == pytest.approx(ref_stats[k], rel=2e-2 if actname == 'tanh' else 5e-3, abs=2e-5), (k, report)
     dh_t = decode_tiles(dhead, n_tiles, 16)[:M, :A + 1]
     report['d_head'] = rel_l2(dh_t, dh)
-    assert report['d_head'] < 1e-2 and cosine(dh_t, dh) > 0.9999, report
+    tol_g, tol_c = (3e-2, 0.999) if actname == 'tanh' else (1e-2, 0.9999)
+    assert report['d_head'] < tol_g and cosine(dh_t, dh) > tol_c, report
     report['d_logstd'] = rel_l2(dls_t, ls.grad)
     assert report['d_logstd'] < 2e-3, report
     for name, buf, C, CN, r in (('delta2', delta2, UNITS[1], NATIVE[1], d2), ('delta1', delta1, UNITS[0], NATIVE[0], d1)):
         got = decode_tiles(buf, n_tiles, CN)[:M, :C]
         report[name] = rel_l2(got, r)
-        assert report[name] < 1.5e-2 and cosine(got, r) > 0.9999, report
+        assert report[name] < 1.5 * tol_g and cosine(got, r) > tol_c, report
     for k, r in ref.items():
         got = grad[offs[k]:offs[k] + r.numel()].view_as(r)
         report['g' + k] = rel_l2(got, r)
-        assert report['g' + k] < 1e-2 and cosine(got, r) > 0.9999, (k, report)
+        assert report['g' + k] < tol_g and cosine(got, r) > tol_c, (k, report)
     print('faithful-reference errors', (H, N, epm, masked, D, UNITS, actname), {k: (round(v, 6) if isinstance(v, float) else v) for k, v in report.items()})
 
 

@@ -22,12 +22,8 @@ LABELS = {
 TAIL = {'fwd': ['kernel end'], 'bwd1': ['flush done'], 'bwd2': ['last MMAs done', 'flush done'], 'bwd2_old': ['last MMAs done', 'flush done']}
 
 
-VARIANTS = {          # name -> extra -D flags for the A/B builds of the forward kernel's pieces (tools/r02 scripts time each one)
+VARIANTS = {          # name -> extra -D flags for A/B builds (round 2 used this for the forward kernel's pieces: profiles/r02_fwd_ab.md)
     'new': [],
-    'epi1_old': ['-DB200RL_V_EPI1_OLD'],
-    'loss_old': ['-DB200RL_V_LOSS_OLD'],
-    'prologue_old': ['-DB200RL_V_PROLOGUE_OLD'],
-    'all_old': ['-DB200RL_V_EPI1_OLD', '-DB200RL_V_LOSS_OLD', '-DB200RL_V_PROLOGUE_OLD'],
 }
 
 
@@ -100,7 +96,7 @@ def main():
         n = buf[base]
         st = [buf[base + 1 + i] for i in range(n)]
         lab = LABELS[kind]
-        head = ['kernel start'] + (['prologue done'] if kind == 'fwd' else [])
+        head = ['kernel start'] + (['setup (tmem, bars)', 'loads issued', 'barrier 1', 'prologue done'] if kind == 'fwd' else [])
         names = head + lab * ((n - len(head) - len(TAIL[kind])) // len(lab)) + TAIL[kind]
         print('  [%s] CTA0: %d stamps, total %.1f us @1.965GHz' % (kind, n, (st[-1] - st[0]) / 1965.0))
         for i in range(1, n):
