@@ -1062,15 +1062,16 @@ __device__ __forceinline__ void bwd1_body(const Bwd1Args& p, uint8_t* smem, cons
                     if (j < nv) dst[j * p.u2] = v[j];
             }
         }
-        if (h == 0 && row < p.u3) {   // dWh^T[i][o]: rows i < u3 valid; grad_Wh[o * u3 + i], o < A + 1
+        if (h == 0) {   // dWh^T[i][o]: rows i < u3 valid; grad_Wh[o * u3 + i], o < A + 1
+            // tcgen05.ld is warp-collective (.sync.aligned): every lane of the h == 0 warps executes it, whatever u3 is (a logical width
+            // that is not a multiple of 32 must not split a warp around it), only the stores are predicated
             float v[16];
             tmem_ld16(TWH + lane_base, v);
+            if (row < p.u3) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (j < p.A + 1) part[p.off_Wh + j * p.u3 + row] = v[j];
-        } else if (h == 0) {
-            float v[16];
-            tmem_ld16(TWH + lane_base, v);   // keep the warp-collective load converged
+                for (int j = 0; j < 16; ++j)
+                    if (j < p.A + 1) part[p.off_Wh + j * p.u3 + row] = v[j];
+            }
         }
     } else {
         for (int i = tid; i < p.u3 * p.u2; i += 256) part[p.off_W3 + i] = 0.f;
