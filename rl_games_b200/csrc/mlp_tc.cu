@@ -459,6 +459,35 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[7]);
         bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[7]);
     }
+#ifdef B200RL_V_PROLOGUE_REGS
+    // A/B variant: every global load of the prologue lands in a register first (one memory round trip), then the shared-memory stores
+    {
+        static_assert(N::U1 <= FWD_THREADS && N::DPAD <= FWD_THREADS, "one element per thread");
+        const float r1 = (tid < N::U1 && tid < p.u1) ? __ldg(p.b1 + tid) : 0.f;
+        const float r2 = (tid < N::U2 && tid < p.u2) ? __ldg(p.b2 + tid) : 0.f;
+        const float r3 = (tid < N::U3 && tid < p.u3) ? __ldg(p.b3 + tid) : 0.f;
+        const float rh = (tid < N::AP && tid < p.A + 1) ? __ldg(p.bh + tid) : 0.f;
+        const float rl = tid < p.A ? __ldg(p.logstd + tid) : 0.f;
+        const float rm = (p.nm && tid < p.D) ? __ldg(p.nm + tid) : 0.f;
+        const float rs = (p.ns && tid < p.D) ? __ldg(p.ns + tid) : 1.f;
+        if (tid < N::U1) sB1[tid] = r1;
+        if (tid < N::U2) sB2[tid] = r2;
+        if (tid < N::U3) sB3[tid] = r3;
+        if (tid < N::AP) sBh[tid] = rh;
+        if (tid < N::DPAD) { sNorm[tid] = rm; sNorm[N::DPAD + tid] = (p.ns && tid < p.D) ? __frcp_rn(rs) : 1.f; }
+        if (tid < p.A) { const float sg = expf(rl); sSig[tid] = sg; sSig[p.A + tid] = rl; sSig[2 * p.A + tid] = 1.0f / sg; sSig[3 * p.A + tid] = logf(sg); }
+    }
+    TSTAMP();   // weight copies issued, parameter loads done
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    TSTAMP();   // the prologue barrier passed
+    if (tid == 0) {      // row-independent constants: sum(logstd) and the entropy of the diagonal Gaussian (first reader: the loss epilogue)
+        float sl = 0.f, en = 0.f;
+        for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
+        sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
+    }
+#else
     for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = i < p.u1 ? __ldg(p.b1 + i) : 0.f;
     for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = i < p.u2 ? __ldg(p.b2 + i) : 0.f;
     for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = i < p.u3 ? __ldg(p.b3 + i) : 0.f;
@@ -476,6 +505,7 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+#endif
     TSTAMP();   // prologue done
     const uint32_t tmem = *tmem_slot;
     const uint32_t T1 = tmem, T2 = tmem + 256, T3 = tmem + 384, T4 = tmem + 448;     // accumulator column bases

@@ -586,6 +586,9 @@ def test_rollout_precision_option_reproduces_the_fp32_rollout_exactly():
         a._minibatch_update(0, 0)
     torch.cuda.synchronize()
     kl_default, kl_split = float(t.stats[0, 4]), float(tf.stats[0, 4])
-    assert abs(kl_default) < 1e-6, kl_default              # same arithmetic in rollout and update: the policy has not moved yet
-    assert 0.0 <= kl_split < 5e-3, kl_split                # fp32 behaviour policy vs bf16 re-evaluation: bf16 noise shows up as a spurious KL
+    # policy_kl of two IDENTICAL Gaussians is not 0 but A * (log(1 + 1e-5) + 1 / (2 (1 + 1e-5)) - 1/2) (the 1e-5 terms of torch_ext.py:27-36), sigma = 1 here
+    import math
+    kl_same = A * (math.log1p(1e-5) + 0.5 / (1.0 + 1e-5) - 0.5)
+    assert abs(kl_default - kl_same) < 2e-6, (kl_default, kl_same)      # same arithmetic in rollout and update: the policy has not moved yet
+    assert kl_default < kl_split < 5e-3, (kl_default, kl_split)          # fp32 behaviour policy vs bf16 re-evaluation: bf16 noise shows up as a spurious KL
     print('rollout precision: first-minibatch KL default (bf16 rollout) %.3e, reference split (fp32 rollout) %.3e' % (kl_default, kl_split))
