@@ -33,7 +33,8 @@ WORKLOADS = {
     # BASELINE.json configs[4] per-GPU shard (131072 envs / 8), obs 256, horizon 32
     'c5': dict(num_actors=16384, horizon=32, obs_dim=256, act_dim=8, units=[256, 128, 64], minibatch=32768, mini_epochs=4),
     # BASELINE.json configs[3]: Humanoid-shaped LSTM policy (obs 348, 17 actions, LSTM 256 before the MLP [512,256,128] of
-    # configs/mujoco/humanoid_envpool.yaml, seq_length 4), 8192 envs -- BPTT minibatch path; fp32 kernels (rnn.cu + mlp_simt.cu)
+    # configs/mujoco/humanoid_envpool.yaml, seq_length 4), 8192 envs -- BPTT minibatch path; every GEMM on the tensor cores (gemm_tc.cu),
+    # cell / loss / optimiser kernels as on the fp32 path (--fp32: CUDA-core GEMMs)
     'c4': dict(num_actors=8192, horizon=32, obs_dim=348, act_dim=17, units=[512, 256, 128], minibatch=32768, mini_epochs=4,
                rnn_units=256, rnn_before_mlp=True, seq_length=4),
 }
@@ -47,7 +48,6 @@ def make_params(w, device, env_name, multi_gpu, graph=True, seed=5, mixed_precis
                'mlp': {'units': list(w['units']), 'activation': 'elu', 'initializer': {'name': 'default'}}}
     if w.get('rnn_units'):
         network['rnn'] = {'name': 'lstm', 'units': w['rnn_units'], 'layers': 1, 'before_mlp': w.get('rnn_before_mlp', True)}
-        mixed_precision = False          # the LSTM path runs on the fp32 kernels
     config = {'name': 'bench', 'env_name': env_name, 'reward_shaper': {'scale_value': 1.0}, 'device': device,
               'multi_gpu': multi_gpu, 'mixed_precision': mixed_precision, 'normalize_input': True, 'normalize_value': True,
               'value_bootstrap': True, 'normalize_advantage': True, 'gamma': 0.99, 'tau': 0.95, 'learning_rate': 3e-4,
@@ -359,7 +359,7 @@ def b200_arm(args, w):
     launches_per_step = sum(v['n'] for v in prof.values())
     line = {'metric': 'ppo_env_steps_per_sec', 'value': value, 'unit': 'env-steps/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': W, 'ms_per_step': 1e3 * total_s / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32' if (args.fp32 or w.get('rnn_units')) else 'bf16', 'data': 'synthetic',
+            'vs_baseline': None, 'dtype': 'f32' if args.fp32 else 'bf16', 'data': 'synthetic',
             'config': workload_config(args.workload, w, 'b200_synthetic (on-GPU Philox env, one kernel per step)'),
             'clocks': clocks, 'gpu_launches': launches_per_step * args.steps, 'gpu_launches_per_step': launches_per_step,
             'cuda_graph': ('whole-epoch' if agent._graph_epoch is not None else ('update-phase' if agent._graph_update is not None else 'none')), 'kernels': kernels[:12]}
@@ -368,14 +368,15 @@ def b200_arm(args, w):
     if rank == 0:
         # dominant kernel family of the step -> roofline
         line['roofline_gae'] = gae_roofline(w, peaks)
-        mlp_ms = sum(v['ms'] for k, v in prof.items() if 'linear' in k or 'tc_mlp' in k)
+        mlp_ms = sum(v['ms'] for k, v in prof.items() if 'linear' in k or 'tc_mlp' in k)       # linear_* covers the _f32 and the _tc GEMMs
         mlp_in = w.get('rnn_units') or w['obs_dim']
         flops = 2 * sum(a * b for a, b in zip([mlp_in] + w['units'], w['units'] + [w['act_dim'] + 1]))
         if w.get('rnn_units'):          # LSTM gate GEMMs: [obs + hidden] x 4 hidden per row
             flops += 2 * (w['obs_dim'] + w['rnn_units']) * 4 * w['rnn_units']
         step_flops = B * flops * (1 + 1.0 / w['horizon'] + 3 * w['mini_epochs'])   # rollout fwd (+ last-value fwd) + (fwd + dgrad + wgrad) per mini-epoch
         tf = step_flops / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else 0.0
-        fam = ('MLP / LSTM GEMM kernels: fp32 CUDA-core path (mixed_precision: False)' if (args.fp32 or w.get('rnn_units')) else
+        fam = ('MLP / LSTM GEMM kernels: fp32 CUDA-core path (mixed_precision: False)' if args.fp32 else
+               'layer-wise bf16 tcgen05 GEMMs (gemm_tc_kernel<fwd|dgrad|wgrad>: LSTM gates + MLP)' if w.get('rnn_units') else
                'tcgen05 bf16 MLP kernels (mlp_fwd_tc<train|rollout>, mlp_bwd_tc)')
         family = {'kernels': fam, 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                   'frac': tf / peaks['bf16_tflops_sustained'], 'share_of_step': round(mlp_ms / ktot, 4), 'alg_flops_per_step': step_flops}

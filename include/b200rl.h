@@ -144,6 +144,19 @@ int b200rl_linear_bwd_weight_f32(const float* dY, const float* X, int rows_per_c
                                  float* dW_part, float* db_part, int64_t split_stride, int M, int K, int Nout,
                                  int n_splits, void* stream);
 /* out[i] = sum_s part[s*split_stride + i]  (deterministic, fixed order) */
+/* The same three building blocks on the 5th-gen tensor cores (tcgen05, bf16 operands rounded while they are staged, fp32 accumulate in
+ * TMEM, fp32 bias / activation / outputs) for ANY layer width: the mixed_precision path of LSTM gate GEMMs and of MLPs the fused
+ * kernels (b200rl_tc_mlp_*) have no geometry for.  Same arguments, same row / split semantics as the _f32 functions. */
+int b200rl_linear_fwd_tc(const float* X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
+                         const float* norm_mean, const float* norm_std,
+                         const float* W, const float* b, float* Y, int M, int K, int Nout, int act,
+                         int accumulate, void* stream);
+int b200rl_linear_bwd_data_tc(const float* dY, const float* W, const float* A_prev, float* dX,
+                              int M, int K, int Nout, int act_prev, void* stream);
+int b200rl_linear_bwd_weight_tc(const float* dY, const float* X, int rows_per_chunk, int64_t chunk_stride,
+                                int64_t x_ld, const float* norm_mean, const float* norm_std,
+                                float* dW_part, float* db_part, int64_t split_stride, int M, int K, int Nout,
+                                int n_splits, void* stream);
 int b200rl_reduce_splits_f32(const float* part, float* out, int n, int n_splits, int64_t split_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -296,25 +296,27 @@ class A2CAgent(CompileTolerantModel):
         # zero-padded), elu / relu / tanh, obs <= 256, <= 15 actions; anything else runs on the fp32 kernels
         tc_ok = self.model.activation in ('elu', 'relu', 'tanh') and \
             ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
+        fused_ok = tc_ok and not self.is_rnn
         if self.mixed_precision is None:
-            self.mixed_precision = (not self.is_rnn) and tc_ok
+            self.mixed_precision = fused_ok
             if not self.mixed_precision and self.global_rank == 0:
                 print(f'b200: mixed_precision not set -> fp32 kernels for this geometry (obs={self.model.D}, units={self.model.units}, '
-                      f'actions={self.actions_num}, activation={self.model.activation}{", rnn" if self.is_rnn else ""}); the bf16 tcgen05 kernels cover '
-                      f'obs<=256, three-layer MLPs up to [256,128,64] with elu / relu / tanh, actions<=15')
+                      f'actions={self.actions_num}, activation={self.model.activation}{", rnn" if self.is_rnn else ""}); mixed_precision: True runs it '
+                      f'on the tensor cores layer by layer; the FUSED bf16 tcgen05 kernels cover obs<=256, three-layer MLPs up to [256,128,64] '
+                      f'with elu / relu / tanh, actions<=15')
         if self.is_rnn:
             if self.horizon_length % self.seq_length != 0:
                 raise ValueError(f"Horizon length ({self.horizon_length}) must be divisible by sequence length ({self.seq_length})")
             if not self.zero_rnn_on_done:
                 raise NotImplementedError('zero_rnn_on_done: False is not on the B200 hot path')
-            if self.mixed_precision:
-                raise NotImplementedError('rnn (LSTM) policies run on the fp32 path: set mixed_precision: False')
-        self.use_tc = bool(self.mixed_precision)
-        if self.use_tc and not tc_ok:
-            raise NotImplementedError(
-                f'mixed_precision: True (bf16 tcgen05 path) supports obs<=256, three-layer MLPs up to [256,128,64] with elu / relu / tanh, actions<=15 in this build; got '
-                f'obs={self.model.D}, units={self.model.units}, activation={self.model.activation}, actions={self.actions_num}.  '
-                f'Set mixed_precision: False for the fp32 path.')
+        # mixed_precision: True -> the fused tcgen05 MLP kernels where they have the geometry (use_tc), else the SAME host composition as the
+        # fp32 path with every GEMM on the tensor cores (gemm_tc: bf16 operands, fp32 accumulate -- gemm_tc.cu): LSTM policies (gate GEMMs,
+        # BPTT), MLPs wider / deeper than the fused tiles.  The reference's autocast covers nn.LSTM and nn.Linear alike (a2c_continuous.py:173).
+        self.use_tc = bool(self.mixed_precision) and fused_ok
+        self.gemm_tc = bool(self.mixed_precision) and not fused_ok
+        self._lin_fwd = ops.linear_fwd_tc if self.gemm_tc else ops.linear_fwd
+        self._lin_bwd = ops.linear_bwd_data_tc if self.gemm_tc else ops.linear_bwd_data
+        self._lin_bww = ops.linear_bwd_weight_tc if self.gemm_tc else ops.linear_bwd_weight
         self.tc_wide = self.use_tc and ops.tc_kind(self.model.D, self.model.units, self.actions_num) == 2
         # Rollout precision.  The reference evaluates the policy during the rollout OUTSIDE autocast (a2c_common.py:581-600: fp32 / TF32)
         # and only calc_gradients under bf16 autocast (a2c_continuous.py:173).  Default here: the rollout uses the same bf16 tcgen05
@@ -656,10 +658,10 @@ class A2CAgent(CompileTolerantModel):
         m = self.model
         # with an LSTM in front the MLP input is h (dense, not normalised)
         nm, ns = (None, None) if (self.is_rnn and m.rnn_before_mlp) else self._norm()
-        ops.linear_fwd(x, m.W[0], m.b[0], acts[0], m.act_id, rows_per_chunk=rows_per_chunk, chunk_stride=chunk_stride,
+        self._lin_fwd(x, m.W[0], m.b[0], acts[0], m.act_id, rows_per_chunk=rows_per_chunk, chunk_stride=chunk_stride,
                        x_ld=m.mlp_in, norm_mean=nm, norm_std=ns, M=M)
         for i in range(1, len(m.units)):
-            ops.linear_fwd(acts[i - 1], m.W[i], m.b[i], acts[i], m.act_id, M=M)
+            self._lin_fwd(acts[i - 1], m.W[i], m.b[i], acts[i], m.act_id, M=M)
 
     def _repack(self):
         """bf16 operand copy of the weights for the tcgen05 kernels (after every optimiser step / weight load)."""
@@ -675,8 +677,8 @@ class A2CAgent(CompileTolerantModel):
         """one LSTM step for all N envs (seq_length 1, models.py -> network_builder.py:452-492 -> recurrent.py): returns h_out"""
         m, N = self.model, self.num_actors
         nm, ns = self._norm() if m.rnn_before_mlp else (None, None)      # after the MLP the LSTM reads the trunk output
-        ops.linear_fwd(obs, m.W_ih, m.b_ih, self.r_gates, 0, x_ld=m.rnn_in, norm_mean=nm, norm_std=ns, M=N)
-        ops.linear_fwd(h_in, m.W_hh, m.b_hh, self.r_gates, 0, M=N, accumulate=True)
+        self._lin_fwd(obs, m.W_ih, m.b_ih, self.r_gates, 0, x_ld=m.rnn_in, norm_mean=nm, norm_std=ns, M=N)
+        self._lin_fwd(h_in, m.W_hh, m.b_hh, self.r_gates, 0, M=N, accumulate=True)
         ops.lstm_cell_fwd(self.r_gates, c_in, c_out, h_out, N, m.rnn_units)
         return h_out
 
@@ -881,7 +883,7 @@ class A2CAgent(CompileTolerantModel):
         P, S = m.num_params, self.n_splits
         off_wh, _ = m.layout['W_head']
         off_bh, _ = m.layout['b_head']
-        ops.linear_bwd_weight(self.d_head, a_last, self.part[0, off_wh:], self.part[0, off_bh:], m.Hl, A + 1, S, M=mb,
+        self._lin_bww(self.d_head, a_last, self.part[0, off_wh:], self.part[0, off_bh:], m.Hl, A + 1, S, M=mb,
                               split_stride=P)
         if rnn_last:
             self._lstm_window_bwd(e0)       # also fills dA[-1] = dL/d(pre-activation of the last MLP layer)
@@ -891,16 +893,16 @@ class A2CAgent(CompileTolerantModel):
             off_w, shp = m.layout[f'W{l}']
             off_b, _ = m.layout[f'b{l}']
             if l > 0:
-                ops.linear_bwd_weight(self.dA[l], self.ta[l - 1], self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
+                self._lin_bww(self.dA[l], self.ta[l - 1], self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
                                       M=mb, split_stride=P)
-                ops.linear_bwd_data(self.dA[l], m.W[l], self.ta[l - 1], self.dA[l - 1], m.act_id, M=mb)
+                self._lin_bwd(self.dA[l], m.W[l], self.ta[l - 1], self.dA[l - 1], m.act_id, M=mb)
             elif rnn_first:
-                ops.linear_bwd_weight(self.dA[0], self.t_hmlp, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S, M=mb,
+                self._lin_bww(self.dA[0], self.t_hmlp, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S, M=mb,
                                       split_stride=P)
-                ops.linear_bwd_data(self.dA[0], m.W[0], None, self.t_dHmlp, 0, M=mb)
+                self._lin_bwd(self.dA[0], m.W[0], None, self.t_dHmlp, 0, M=mb)
                 self._lstm_window_bwd(e0)
             else:
-                ops.linear_bwd_weight(self.dA[0], x, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
+                self._lin_bww(self.dA[0], x, self.part[0, off_w:], self.part[0, off_b:], shp[1], shp[0], S,
                                       rows_per_chunk=epm, chunk_stride=N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=mb,
                                       split_stride=P)
         ops.reduce_splits(self.part[0, A:], gv['grad'][A:], P - A, self.part_rows, split_stride=P)
@@ -920,9 +922,9 @@ class A2CAgent(CompileTolerantModel):
         for t in range(T):
             # step-t inputs of all S sequences: arena observations (LSTM first) or the trunk output rows (j*T + t)*epm + e (LSTM last)
             xin, xstride = (self.obses[t, e0:], T * N) if m.rnn_before_mlp else (self.ta[-1][t * epm:], T * epm)
-            ops.linear_fwd(xin, m.W_ih, m.b_ih, self.t_gates[t], 0, rows_per_chunk=epm, chunk_stride=xstride, x_ld=m.rnn_in,
+            self._lin_fwd(xin, m.W_ih, m.b_ih, self.t_gates[t], 0, rows_per_chunk=epm, chunk_stride=xstride, x_ld=m.rnn_in,
                            norm_mean=nm, norm_std=ns, M=S)
-            ops.linear_fwd(self.t_hin[t], m.W_hh, m.b_hh, self.t_gates[t], 0, M=S, accumulate=True)
+            self._lin_fwd(self.t_hin[t], m.W_hh, m.b_hh, self.t_gates[t], 0, M=S, accumulate=True)
             last = t == T - 1
             ops.lstm_cell_fwd(self.t_gates[t], self.t_cin[t], self.t_c[t], self.t_hdense, S, Hd,
                               h_scatter=self.t_hmlp[t * epm:], scatter_rpc=epm, scatter_stride=T * epm,
@@ -946,18 +948,18 @@ class A2CAgent(CompileTolerantModel):
                               done_next=None if last else dn[t + 1, e0:], done_rpc=epm, done_stride=T * N)
             row = t * Ssp
             xin, xstride = (self.obses[t, e0:], T * N) if m.rnn_before_mlp else (self.ta[-1][t * epm:], T * epm)
-            ops.linear_bwd_weight(self.t_dgates, xin, self.part[row, o_wih:], self.part[row, o_bih:], m.rnn_in, 4 * Hd, Ssp,
+            self._lin_bww(self.t_dgates, xin, self.part[row, o_wih:], self.part[row, o_bih:], m.rnn_in, 4 * Hd, Ssp,
                                   rows_per_chunk=epm, chunk_stride=xstride, x_ld=m.rnn_in, norm_mean=nm, norm_std=ns, M=S, split_stride=P)
-            ops.linear_bwd_weight(self.t_dgates, self.t_hin[t], self.part[row, o_whh:], self.part[row, o_bhh:], Hd, 4 * Hd, Ssp, M=S,
+            self._lin_bww(self.t_dgates, self.t_hin[t], self.part[row, o_whh:], self.part[row, o_bhh:], Hd, 4 * Hd, Ssp, M=S,
                                   split_stride=P)
             if t > 0:
-                ops.linear_bwd_data(self.t_dgates, m.W_hh, None, self.t_dhin, 0, M=S)
+                self._lin_bwd(self.t_dgates, m.W_hh, None, self.t_dhin, 0, M=S)
             if not m.rnn_before_mlp:
                 # dgrad through W_ih into the trunk: sequences j*epm..(j+1)*epm-1 at step t are trunk rows (j*T + t)*epm.., one dense
                 # epm-row block each; the last MLP layer's activation derivative is folded in (dA[-1] is d pre-activation)
                 for j in range(H // T):
                     r0 = (j * T + t) * epm
-                    ops.linear_bwd_data(self.t_dgates[j * epm:], m.W_ih, self.ta[-1][r0:], self.dA[-1][r0:], m.act_id, M=epm)
+                    self._lin_bwd(self.t_dgates[j * epm:], m.W_ih, self.ta[-1][r0:], self.dA[-1][r0:], m.act_id, M=epm)
 
     def _minibatch_update_tc(self, i, u, x, e0):
         """bf16 tcgen05 edition: fused fwd+loss kernel, two backward kernels, split reduce, Adam, repack."""

@@ -1,0 +1,294 @@
+// Layer-wise bf16 tensor-core GEMMs (tcgen05 / TMEM) for ARBITRARY layer widths: the `mixed_precision: True` path of everything the
+// fused MLP kernels (mlp_tc.cu) have no geometry for -- LSTM gate GEMMs (common/layers/recurrent.py:20-80, network_builder.py:452-492:
+// [S, in + hidden] x [4 hidden] per step), MLPs wider / deeper than [256,128,64] (configs/mujoco/humanoid_envpool.yaml:23
+// [512,256,128]).  Same three operations, same signatures and same fp32 row-major operands as the CUDA-core building blocks of
+// mlp_simt.cu, so the host code composes them identically; only the products run on the tensor cores:
+//   fwd   : Y[M,N]   = act( norm(X)[M,K] . W[N,K]^T + b [+ Y] )
+//   dgrad : dX[M,K]  = ( dY[M,N] . W[N,K] ) * act'(A_prev)
+//   wgrad : dW_s[N,K] = dY_s^T . norm(X_s),  db_s[N] = colsum(dY_s)          (rows split s = blockIdx.z, summed by reduce_splits)
+// Precision contract = the reference's bf16 autocast of nn.Linear / nn.LSTM (a2c_continuous.py:173): operands rounded to bf16 while
+// they are staged into shared memory, fp32 accumulation in TMEM, fp32 bias / activation / outputs.
+//
+// One CTA = one [128 x BN] output tile (BN <= 256 TMEM columns), reduction in 64-element slabs through a two-stage shared-memory ring:
+// all 256 threads load fp32 (16-byte vector loads, every load of a slab issued before the first use), convert and store the slab as
+// INTERLEAVE operand tiles while the single issuing thread's MMAs of the previous slab run; a stage is reused when the tcgen05.commit
+// of its MMAs has arrived.  Operand views (tc_common.cuh): K-major when the source's contiguous index is the reduction index (X and W
+// in fwd, dY in dgrad), MN-major when it is the output index (W in dgrad, dY and X in wgrad) -- no transposes anywhere.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+using namespace tc;
+
+constexpr int GT = 256;              // threads per CTA: lane quarter q = warp & 3, column half h = warp >> 2
+constexpr int SLAB = 64;             // reduction elements per ring stage
+constexpr int BM = 128;              // output rows per CTA (TMEM lanes)
+constexpr int BNMAX = 256;           // output columns per CTA (TMEM columns)
+constexpr uint32_t A_BYTES = BM * SLAB * 2, B_BYTES = BNMAX * SLAB * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+
+// fp32 source matrix [rows, cols]; rows may be chunked (arena addressing) and normalised on the fly (first layer reads observations)
+struct Src {
+    const float* p; int64_t ld; int rows_per_chunk; int64_t chunk_stride; const float* nm; const float* ns;
+    int rows, cols;          // logical extent (everything outside reads as 0)
+};
+__device__ __forceinline__ const float* src_row(const Src& s, int r) {
+    return s.p + (s.rows_per_chunk > 0 ? chunk_row(r, s.rows_per_chunk, s.chunk_stride) : (int64_t)r) * s.ld;
+}
+
+// Stage a [TR rows x ncg*8 cols] bf16 INTERLEAVE tile (16-byte chunks adjacent along the columns: CS = 128, RS = ncg * 128) from rows
+// [r0, r0 + TR) x cols [c0, c0 + ncg*8) of `s`.  ITEMS chunks per thread, all global loads first.
+template <int ITEMS>
+__device__ __forceinline__ void stage_part(uint8_t* sT, const Src& s, int r0, int c0, int ncg, int i_base, int n_items, int tid, int row_end) {
+    float4 va[ITEMS], vb[ITEMS];
+    const bool vec = ((s.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(s.p) & 15) == 0) && ((c0 & 3) == 0);
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = i_base + tid + it * GT;
+        va[it] = make_float4(0.f, 0.f, 0.f, 0.f); vb[it] = va[it];
+        if (i < n_items) {
+            const int r = i / ncg, cg = i - r * ncg;
+            const int gr = r0 + r, gc = c0 + cg * 8;
+            if (gr < row_end && gc < s.cols) {
+                const float* src = src_row(s, gr) + gc;
+                if (vec && gc + 8 <= s.cols) {
+                    va[it] = __ldg(reinterpret_cast<const float4*>(src));
+                    vb[it] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                } else {
+                    float t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = (gc + j < s.cols) ? __ldg(src + j) : 0.f;
+                    va[it] = make_float4(t[0], t[1], t[2], t[3]); vb[it] = make_float4(t[4], t[5], t[6], t[7]);
+                }
+            }
+        }
+    }
+    const uint32_t RS = (uint32_t)ncg * 128u;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = i_base + tid + it * GT;
+        if (i < n_items) {
+            const int r = i / ncg, cg = i - r * ncg;
+            float f[8] = {va[it].x, va[it].y, va[it].z, va[it].w, vb[it].x, vb[it].y, vb[it].z, vb[it].w};
+            if (s.nm) {
+                const int gr = r0 + r, gc = c0 + cg * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    f[j] = (gr < row_end && gc + j < s.cols)
+                               ? fminf(fmaxf(__fdiv_rn(__fsub_rn(f[j], __ldg(s.nm + gc + j)), __ldg(s.ns + gc + j)), -5.0f), 5.0f) : 0.f;
+            }
+            *reinterpret_cast<uint4*>(sT + tile_off(r, cg, 128u, RS)) = pack8_bf16(f);
+        }
+    }
+}
+// row_end: rows >= row_end read as zeros (the end of this CTA's reduction range when the rows ARE the reduction index, else s.rows)
+__device__ __forceinline__ void stage_tile(uint8_t* sT, const Src& s, int r0, int c0, int tr, int ncg, int tid, int row_end) {
+    const int n_items = tr * ncg;
+    for (int base = 0; base < n_items; base += 4 * GT) stage_part<4>(sT, s, r0, c0, ncg, base, n_items, tid, row_end);
+}
+
+enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
+
+struct GemmArgs {
+    Src a, b;                    // the two operand sources (see the mode table in the kernel)
+    int Mo, No, R;               // output rows, output cols, reduction length
+    int BN;                      // output columns per CTA: 64, 128 or 256
+    // epilogue
+    const float* bias; float* Y; int act; int accumulate;              // fwd: Y[Mo, No]
+    const float* A_prev; float* dX; int act_prev;                       // dgrad: dX[Mo, No]
+    float* dW; float* db; int64_t split_stride; int rows_per_split;     // wgrad: dW[s][Mo (= layer N), No (= layer K)], db[s][Mo]
+};
+
+// mode        output rows (TMEM lanes)   output cols        reduction   A operand (rows m)            B operand (rows n)
+// FWD         batch rows                 layer outputs N    K           X[m, k]   K-major            W[n, k]   K-major
+// DGRAD       batch rows                 layer inputs K     N           dY[m, n]  K-major            W[n, k]   MN-major (rows = reduction n)
+// WGRAD       layer outputs N            layer inputs K     batch rows  dY[r, n]  MN-major           X[r, k]   MN-major (rows = reduction r)
+template <int MODE>
+__global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int BN = p.BN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // reduction range: the whole K (fwd / dgrad) or this split's batch rows (wgrad)
+    int r_begin = 0, r_end = p.R;
+    if (MODE == MODE_WGRAD) { r_begin = min((int)blockIdx.z * p.rows_per_split, p.R); r_end = min(r_begin + p.rows_per_split, p.R); }
+    const int n_slabs = (r_end - r_begin + SLAB - 1) / SLAB;
+    if (warp == 0) tmem_alloc(&tmem_slot, 256);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    constexpr bool A_MN = MODE == MODE_WGRAD, B_MN = MODE != MODE_FWD;
+    const uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    float bsum = 0.f;        // wgrad: bias gradient of output feature m0 + tid (threads < 128 of the CTAs with blockIdx.y == 0)
+    for (int sl = 0; sl < n_slabs; ++sl) {
+        const int st = sl & 1, use = sl >> 1;
+        uint8_t* sA = smem + st * STAGE_BYTES; uint8_t* sB = sA + A_BYTES;
+        if (use > 0) mbar_wait(&bars[st], (uint32_t)(use - 1) & 1u);       // the MMAs that read this stage two slabs ago are done
+        const int rr = r_begin + sl * SLAB;
+        // ---- stage the slab (out-of-range elements are zeros: they add nothing) ----
+        // (K-major tiles: the reduction runs along the columns, whose range [rr, rr + 64) is clipped by s.cols = R; MN-major tiles: along
+        //  the rows, clipped by r_end)
+        if (!A_MN) stage_tile(sA, p.a, m0, rr, BM, SLAB / 8, tid, p.a.rows);          // [128 rows m x 64 reduction cols]
+        else stage_tile(sA, p.a, rr, m0, SLAB, BM / 8, tid, r_end);                  // [64 reduction rows x 128 cols m]
+        if (!B_MN) stage_tile(sB, p.b, n0, rr, BN, SLAB / 8, tid, p.b.rows);          // [BN rows n x 64 reduction cols]
+        else stage_tile(sB, p.b, rr, n0, SLAB, BN / 8, tid, min(r_end, p.b.rows));   // [64 reduction rows x BN cols n]
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_sync();
+            const uint32_t a_rs = A_MN ? (uint32_t)(BM / 8) * 128u : (uint32_t)(SLAB / 8) * 128u;
+            const uint32_t b_rs = B_MN ? (uint32_t)(BN / 8) * 128u : (uint32_t)(SLAB / 8) * 128u;
+#pragma unroll
+            for (int k = 0; k < SLAB / 16; ++k) {
+                const uint64_t ad = A_MN ? make_smem_desc(smem_u32(sA) + k * 2 * a_rs, a_rs, 128u) : make_smem_desc(smem_u32(sA) + k * 2 * 128u, 128u, a_rs);
+                const uint64_t bd = B_MN ? make_smem_desc(smem_u32(sB) + k * 2 * b_rs, b_rs, 128u) : make_smem_desc(smem_u32(sB) + k * 2 * 128u, 128u, b_rs);
+                umma_bf16(tmem, ad, bd, idesc, (sl > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&bars[st]);
+        }
+        if (MODE == MODE_WGRAD && p.db && blockIdx.y == 0 && tid < BM) {
+            // column sum of the (bf16) dY slab just staged: element (r, c = tid) of the [64 x 128] MN-major tile
+            const uint8_t* col = sA + (uint32_t)(tid >> 3) * 128u + (uint32_t)(tid & 7) * 2u;
+            float s = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < SLAB; ++r)
+                s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(col + (uint32_t)(r & 7) * 16u + (uint32_t)(r >> 3) * (uint32_t)(BM / 8) * 128u));
+            bsum += s;
+        }
+    }
+    if (n_slabs > 0) {
+        const int last = n_slabs - 1;
+        mbar_wait(&bars[last & 1], (uint32_t)(last >> 1) & 1u);          // commits are ordered: the last one covers every MMA
+        fence_after_sync();
+    }
+    // ---- epilogue: lane = output row, this thread's columns [h * BN/2, (h+1) * BN/2) in chunks of 32 ----
+    const int row = q * 32 + lane;
+    const int gm = m0 + row;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    for (int c0 = h * (BN / 2); c0 < (h + 1) * (BN / 2); c0 += 32) {
+        float v[32];
+        if (n_slabs > 0) {
+            uint32_t r[32];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+                "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(tmem + lane_base + (uint32_t)c0)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        const int gn = n0 + c0;
+        if (gm < p.Mo && gn < p.No) {            // (the TMEM load above is warp-collective; nothing in here is)
+            const int nv = min(32, p.No - gn);
+            float* out;
+            if (MODE == MODE_FWD) {
+                out = p.Y + (int64_t)gm * p.No + gn;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < nv) {
+                        float x = v[j] + (p.bias ? __ldg(p.bias + gn + j) : 0.f);
+                        if (p.accumulate) x += out[j];
+                        v[j] = act_fwd(x, p.act);
+                    }
+                }
+            } else if (MODE == MODE_DGRAD) {
+                out = p.dX + (int64_t)gm * p.No + gn;
+                if (p.A_prev) {
+                    const float* ap = p.A_prev + (int64_t)gm * p.No + gn;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < nv) v[j] *= act_bwd_from_out(__ldg(ap + j), p.act_prev);
+                }
+            } else {
+                out = p.dW + (int64_t)blockIdx.z * p.split_stride + (int64_t)gm * p.No + gn;
+            }
+            if (nv == 32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < nv) out[j] = v[j];
+            }
+        }
+    }
+    if (MODE == MODE_WGRAD && p.db && blockIdx.y == 0 && tid < BM && m0 + tid < p.Mo)
+        p.db[(int64_t)blockIdx.z * p.split_stride + m0 + tid] = bsum;
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static inline int pick_bn(int n_out) { return n_out > 128 ? 256 : (n_out > 64 ? 128 : 64); }
+
+template <int MODE>
+static int launch_gemm(const GemmArgs& a, int grid_z, void* stream) {
+    constexpr size_t smem = 2 * STAGE_BYTES;
+    static bool raised = false;
+    if (!raised) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        raised = true;
+    }
+    dim3 grid((a.Mo + BM - 1) / BM, (a.No + a.BN - 1) / a.BN, grid_z);
+    gemm_tc_kernel<MODE><<<grid, GT, smem, as_stream(stream)>>>(a);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
+}
+
+}  // namespace
+
+B200RL_EXPORT int b200rl_linear_fwd_tc(const float* X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
+                                       const float* norm_mean, const float* norm_std,
+                                       const float* W, const float* b, float* Y, int M, int K, int Nout, int act,
+                                       int accumulate, void* stream) {
+    if (!X || !W || !Y || M <= 0 || K <= 0 || Nout <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
+    if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200RL_EINVAL;
+    GemmArgs a{};
+    a.a = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K};
+    a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K};
+    a.Mo = M; a.No = Nout; a.R = K; a.BN = pick_bn(Nout);
+    a.bias = b; a.Y = Y; a.act = act; a.accumulate = accumulate;
+    return launch_gemm<MODE_FWD>(a, 1, stream);
+}
+
+B200RL_EXPORT int b200rl_linear_bwd_data_tc(const float* dY, const float* W, const float* A_prev, float* dX,
+                                            int M, int K, int Nout, int act_prev, void* stream) {
+    if (!dY || !W || !dX || M <= 0 || K <= 0 || Nout <= 0) return B200RL_EINVAL;
+    GemmArgs a{};
+    a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout};            // [m, n]: reduction index n contiguous -> K-major
+    a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K};                // [n, k]: rows = reduction n, cols = outputs k -> MN-major
+    a.Mo = M; a.No = K; a.R = Nout; a.BN = pick_bn(K);
+    a.A_prev = A_prev; a.dX = dX; a.act_prev = act_prev;
+    return launch_gemm<MODE_DGRAD>(a, 1, stream);
+}
+
+B200RL_EXPORT int b200rl_linear_bwd_weight_tc(const float* dY, const float* X, int rows_per_chunk, int64_t chunk_stride,
+                                              int64_t x_ld, const float* norm_mean, const float* norm_std,
+                                              float* dW_part, float* db_part, int64_t split_stride, int M, int K, int Nout,
+                                              int n_splits, void* stream) {
+    if (!dY || !X || !dW_part || M <= 0 || K <= 0 || Nout <= 0 || n_splits <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
+    if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200RL_EINVAL;
+    GemmArgs a{};
+    a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout};            // [r, n]: rows = reduction r, cols = outputs n -> MN-major
+    a.b = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K};   // [r, k]: rows = reduction r, cols = outputs k -> MN-major
+    a.Mo = Nout; a.No = K; a.R = M; a.BN = pick_bn(K);
+    a.dW = dW_part; a.db = db_part; a.split_stride = split_stride;
+    int rps = (M + n_splits - 1) / n_splits;
+    a.rows_per_split = ((rps + SLAB - 1) / SLAB) * SLAB;       // trailing splits may be empty: they write zeros, which the reducer expects
+    return launch_gemm<MODE_WGRAD>(a, n_splits, stream);
+}

@@ -164,6 +164,34 @@ def linear_bwd_weight(dY, X, dW_part, db_part, K, Nout, n_splits, rows_per_chunk
           'linear_bwd_weight')
 
 
+def linear_fwd_tc(X, W, b, Y, act, rows_per_chunk=None, chunk_stride=0, x_ld=None, norm_mean=None, norm_std=None, M=None,
+                  accumulate=False):
+    """linear_fwd on the tensor cores (bf16 operands, fp32 accumulate), any layer width"""
+    Nout, K = W.shape
+    M = Y.shape[0] if M is None else M
+    check(lib.b200rl_linear_fwd_tc(ptr(X), M if rows_per_chunk is None else rows_per_chunk, chunk_stride,
+                                   K if x_ld is None else x_ld, ptr(norm_mean), ptr(norm_std), ptr(W), ptr(b), ptr(Y),
+                                   M, K, Nout, act, int(accumulate), _stream()), 'linear_fwd_tc')
+
+
+def linear_bwd_data_tc(dY, W, A_prev, dX, act_prev, M=None):
+    Nout, K = W.shape
+    M = dY.shape[0] if M is None else M
+    check(lib.b200rl_linear_bwd_data_tc(ptr(dY), ptr(W), ptr(A_prev), ptr(dX), M, K, Nout, act_prev, _stream()),
+          'linear_bwd_data_tc')
+
+
+def linear_bwd_weight_tc(dY, X, dW_part, db_part, K, Nout, n_splits, rows_per_chunk=None, chunk_stride=0, x_ld=None,
+                         norm_mean=None, norm_std=None, M=None, split_stride=None):
+    M = dY.shape[0] if M is None else M
+    if split_stride is None:
+        split_stride = dW_part.stride(0)
+    check(lib.b200rl_linear_bwd_weight_tc(ptr(dY), ptr(X), M if rows_per_chunk is None else rows_per_chunk,
+                                          chunk_stride, K if x_ld is None else x_ld, ptr(norm_mean), ptr(norm_std),
+                                          ptr(dW_part), ptr(db_part), split_stride, M, K, Nout, n_splits, _stream()),
+          'linear_bwd_weight_tc')
+
+
 def reduce_splits(part, out, n, n_splits, split_stride=None):
     check(lib.b200rl_reduce_splits_f32(ptr(part), ptr(out), n, n_splits, n if split_stride is None else split_stride,
                                        _stream()), 'reduce_splits')

@@ -526,6 +526,9 @@ def install_continuous(monkeypatch):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, 'adam_step', adam_step_full)
     monkeypatch.setattr(ops, 'set_pdl', lambda enable: False)
+    # layer-wise tensor-core GEMMs (mixed_precision: True on LSTM policies / geometries without fused kernels): same contract, fp32 here
+    for name in ('linear_fwd', 'linear_bwd_data', 'linear_bwd_weight'):
+        monkeypatch.setattr(ops, name + '_tc', globals()[name])
 
 
 # ---------------------------------------------------------------------------------------------- tcgen05 path (host logic only: fp32 maths)

@@ -110,6 +110,9 @@ CASES = {
     'lstm before the mlp, next_step autoreset': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, autoreset='next_step',
                                                      over={'seq_length': 4},
                                                      rnn={'name': 'lstm', 'units': 8, 'layers': 1, 'before_mlp': True}),
+    'lstm after the mlp on the tensor cores (layer-wise GEMMs)': dict(N=8, H_=8, D=6, A=3, units=(16, 8), mb=32, over={'seq_length': 4, 'mixed_precision': True},
+                                                                  rnn={'name': 'lstm', 'units': 12, 'layers': 1, 'before_mlp': False}),
+    'mlp [512,256,128] on the tensor cores (layer-wise GEMMs)': dict(N=16, H_=8, D=20, A=17, units=(512, 256, 128), mb=64, over={'mixed_precision': True}),
     'tcgen05': dict(N=256, H_=4, D=60, A=8, units=(256, 128, 64), mb=512, over={'mixed_precision': True}),
     'tcgen05, pipelined wgrad + masked': dict(N=256, H_=4, D=60, A=8, units=(256, 128, 64), mb=512, autoreset='next_step',
                                               over={'mixed_precision': True, 'b200_pipelined_wgrad': True}),
@@ -127,6 +130,11 @@ def test_continuous_agent_calls_match_the_header(case, monkeypatch, tmp_path):
         a.train_epoch()                     # device RNG path (no noise tape): the Philox arguments are exercised too
     a.get_full_state_weights()
     assert rec.calls, 'no kernel call was made'
+    if 'layer-wise' in case:
+        assert a.gemm_tc and not a.use_tc
+        for n in ('b200rl_linear_fwd_tc', 'b200rl_linear_bwd_data_tc', 'b200rl_linear_bwd_weight_tc'):
+            assert n in rec.calls, (n, sorted(rec.calls))
+        assert 'b200rl_linear_fwd_f32' not in rec.calls
     want = {'tcgen05': ['b200rl_tc_mlp_fwd_train', 'b200rl_tc_mlp_bwd', 'b200rl_tc_mlp_fwd_rollout', 'b200rl_reduce_adam_f32'],
             'lstm': ['b200rl_lstm_cell_fwd_f32', 'b200rl_lstm_cell_bwd_f32'], 'fp32': ['b200rl_ppo_head_loss_f32', 'b200rl_gae_fused_f32']}
     for key, names in want.items():

@@ -592,3 +592,37 @@ def test_rollout_precision_option_reproduces_the_fp32_rollout_exactly():
     assert abs(kl_default - kl_same) < 2e-6, (kl_default, kl_same)      # same arithmetic in rollout and update: the policy has not moved yet
     assert kl_default < kl_split < 5e-3, (kl_default, kl_split)          # fp32 behaviour policy vs bf16 re-evaluation: bf16 noise shows up as a spurious KL
     print('rollout precision: first-minibatch KL default (bf16 rollout) %.3e, reference split (fp32 rollout) %.3e' % (kl_default, kl_split))
+
+
+@pytest.mark.parametrize('case', ['lstm_before_mlp', 'lstm_after_mlp', 'mlp_512_256_128'])
+def test_layerwise_tensor_core_path_tracks_fp32_agent(case):
+    """mixed_precision: True on an LSTM policy / an MLP wider than the fused tiles: every GEMM on the tensor cores (gemm_tc.cu, bf16
+    operands, fp32 accumulate), the same host composition as the fp32 path.  Against the fp32 kernels on the same tapes / weights /
+    noise: bf16 tolerance class (rollout outputs atol 6e-2, per-minibatch losses rtol 0.1, update direction cosine > 0.8)."""
+    N, H, D, A, mb = 256, 8, 44, 5, 1024
+    units, rnn, before = ([64, 32], 32, True) if case == 'lstm_before_mlp' else (([64, 32], 32, False) if case == 'lstm_after_mlp' else ([512, 256, 128], 0, True))
+    obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=51, p_done=0.08)
+    params = O.init_params(D, units, A, seed=6, rnn_units=rnn, rnn_before_mlp=before)
+    g = torch.Generator().manual_seed(16)
+    noise = torch.randn(H, N, A, generator=g).to(DEV)
+    agents = []
+    for mp in (False, True):
+        a = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False, 'seq_length': 4}, N, H, D, A, units, mb,
+                       TapeEnvGPU(obs_tape, done_tape, tout_tape, A), params, rnn_units=rnn, rnn_before_mlp=before)
+        assert a.gemm_tc == mp and not a.use_tc
+        a.epoch_num += 1
+        a.train_epoch(noise=noise)
+        agents.append(a)
+    f, t = agents
+    torch.testing.assert_close(t.values, f.values, rtol=0, atol=6e-2)
+    torch.testing.assert_close(t.mus, f.mus, rtol=0, atol=6e-2)
+    sf, st = f.last_stats, t.last_stats
+    torch.testing.assert_close(st[:, 0], sf[:, 0], rtol=0.1, atol=2e-2)
+    torch.testing.assert_close(st[:, 1], sf[:, 1], rtol=0.1, atol=2e-2)
+    torch.testing.assert_close(st[:, 4], sf[:, 4], rtol=0.35, atol=3e-4)
+    sdf, sdt = f.model.state_dict(), t.model.state_dict()
+    for k in O.param_names(len(units), lstm=bool(rnn)):
+        if k.endswith('weight') or 'weight_' in k:
+            du_f = (sdf[k].cpu() - params[k]).flatten(); du_t = (sdt[k].cpu() - params[k]).flatten()
+            cos = float(du_f @ du_t / (du_f.norm() * du_t.norm() + 1e-20))
+            assert cos > 0.8, (k, cos)

@@ -315,13 +315,16 @@ def test_manager_based_adapter_and_isaac_observer_in_the_training_loop(monkeypat
 
 def test_mixed_precision_auto_resolves_by_geometry_and_explicit_true_never_downgrades(monkeypatch, tmp_path, capsys):
     """key absent = the reference's 'auto' (a2c_common.py:427-429): tcgen05 path where this build has kernels for the geometry, fp32
-    otherwise (with a note); an explicit True on an unsupported geometry raises instead of silently changing precision"""
+    otherwise (with a note); an explicit True on a geometry without fused kernels runs layer by layer on the tensor cores"""
     g = dict(torch.load(os.path.join(GOLDEN, 'agent_base.pt'), weights_only=False))
     a = _build(monkeypatch, tmp_path, g, _Env(g), over={'mixed_precision': None})      # MLP (16, 8): no tcgen05 kernel
     assert a.use_tc is False and a.mixed_precision is False
     assert 'mixed_precision not set -> fp32 kernels' in capsys.readouterr().out
-    with pytest.raises(NotImplementedError, match='bf16 tcgen05 path'):
-        _build(monkeypatch, tmp_path, g, _Env(g), tc=False, over={'mixed_precision': True})
+    # an explicit True on a geometry without FUSED kernels is served layer by layer on the tensor cores (gemm_tc), never by fp32 kernels
+    c = _build(monkeypatch, tmp_path, g, _Env(g), tc=False, over={'mixed_precision': True})
+    assert c.mixed_precision is True and c.use_tc is False and c.gemm_tc is True
+    from rl_games_b200 import ops
+    assert c._lin_fwd is ops.linear_fwd_tc and c._lin_bww is ops.linear_bwd_weight_tc and c._lin_bwd is ops.linear_bwd_data_tc
     g2 = dict(torch.load(os.path.join(GOLDEN, 'agent_tcshape.pt'), weights_only=False))
     import _torch_ops
     _torch_ops.install_tc(monkeypatch)          # its tc_supported stand-in accepts the fixture's small three-layer geometry

@@ -23,16 +23,17 @@ def test_bench_b200_arm_reaches_its_json_line(extra):
     for k in KEYS:
         assert k in out, k
     assert out['metric'] == 'ppo_env_steps_per_sec' and out['n_gpus'] == 1 and out['steps'] == 2 and out['warmup'] >= 3
-    fp32 = '--fp32' in extra or 'c4' in extra          # the LSTM workload runs on the fp32 kernels
+    fp32 = '--fp32' in extra
     assert out['dtype'] == ('f32' if fp32 else 'bf16')
     assert set(out['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'}
     assert ('c5' in out['config']['workload']) == ('c5' in extra)
     if not extra:       # the default (c2) line also carries BASELINE configs[4]'s per-GPU shard
         assert out['c5']['n_gpus'] == 1 and out['c5']['value'] > 0 and 'obs 256' in out['c5']['config']['workload']
     rec = json.loads([ln for ln in r.stderr.splitlines() if ln.startswith('RECORDED ')][-1][len('RECORDED '):])
-    if 'c4' in extra:
+    if 'c4' in extra:       # LSTM policy: gate / MLP GEMMs on the tensor cores layer by layer, cell kernels as on the fp32 path
         assert rec['b200rl_lstm_cell_fwd_f32'] > 0 and rec['b200rl_lstm_cell_bwd_f32'] > 0 and 'LSTM 256' in out['config']['workload']
-    if fp32:
+        assert rec['b200rl_linear_fwd_tc'] > 0 and rec['b200rl_linear_bwd_weight_tc'] > 0 and 'b200rl_linear_fwd_f32' not in rec
+    elif fp32:
         assert 'b200rl_ppo_head_loss_f32' in rec and 'b200rl_tc_mlp_fwd_train' not in rec
     else:
         assert rec['b200rl_tc_mlp_fwd_train'] > 0 and rec['b200rl_tc_mlp_bwd'] > 0 and rec['b200rl_synth_env_step'] > 0
