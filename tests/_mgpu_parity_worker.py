@@ -27,11 +27,15 @@ def main():
     obs_tape, done_tape, tout_tape = O.make_tapes(8 * H + 1, N, D, seed=100 + rank)
     g = torch.Generator().manual_seed(50 + rank)
     noise = [torch.randn(H, N, A, generator=g).to(dev) for _ in range(8)]
+    # '--clip': grad_norm small enough that the global-norm clip is ACTIVE (the default 1.0 never clips at this size).  The clip scale is
+    # grad_norm / (||g|| + 1e-6) and the two optimiser kernels sum ||g||^2 in different orders (adam_step_kernel: every CTA over the whole
+    # vector; allreduce_adam_kernel: per-CTA slices, then the partials) -> a last-bit difference in the scale, which Adam amplifies
+    grad_norm = 0.05 if '--clip' in sys.argv else 1.0
     res, P = {}, None
     for mode, fused in (('nccl', False), ('fused', True)):
         env = T.TapeEnvGPU(obs_tape, done_tape, tout_tape, A)
         a = T.make_agent({'mixed_precision': mp, 'mini_epochs': 1, 'multi_gpu': True, 'device': dev, 'b200_cuda_graph': False,
-                          'b200_fused_allreduce': fused}, N, H, D, A, units, mb, env, params)
+                          'b200_fused_allreduce': fused, 'grad_norm': grad_norm}, N, H, D, A, units, mb, env, params)
         assert a.fused_allreduce == fused and a.world_size == world and a.use_tc == mp
         P = a.model.num_params
         # ---- one minibatch through the exchange ----
@@ -59,7 +63,7 @@ def main():
         dist.barrier()
     n, f = res['nccl'], res['fused']
     gscale = float(n['red'][:P].abs().max())
-    out = {'world': world, 'P': P, 'mixed_precision': mp,
+    out = {'world': world, 'P': P, 'mixed_precision': mp, 'grad_norm': grad_norm,
            'grad_max_abs': gscale,
            'grad_max_abs_diff': float((n['red'][:P] - f['red'][:P]).abs().max()),
            'grad_rel_l2': float((n['red'][:P] - f['red'][:P]).norm() / n['red'][:P].norm()),

@@ -28,7 +28,7 @@ def _run(world, extra=()):
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-3000:])
     out = json.loads(lines[-1][len('MGPU_PARITY '):])
     os.makedirs(os.path.join(os.path.dirname(HERE), 'gpurun_out'), exist_ok=True)
-    with open(os.path.join(os.path.dirname(HERE), 'gpurun_out', f'mgpu_parity_w{world}{"_fp32" if extra else ""}.json'), 'w') as f:
+    with open(os.path.join(os.path.dirname(HERE), 'gpurun_out', f'mgpu_parity_w{world}{"".join(e.replace("--", "_") for e in extra)}.json'), 'w') as f:
         json.dump(out, f, indent=1)
     return out
 
@@ -42,3 +42,19 @@ def test_fused_peer_allreduce_matches_nccl_allreduce_one_minibatch(extra):
     assert o['grad_rel_l2'] < 1e-6 and o['grad_max_abs_diff'] <= 1e-5 * o['grad_max_abs'], o
     assert o['kl_sum'][0] == pytest.approx(o['kl_sum'][1], rel=1e-6), o
     assert o['w1_frac_gt_1e-6'] < 1e-3 and o['w1_max_abs_diff'] <= 2 * 3e-4 * 1.0001, o
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs >= 2 GPUs on one box (gpurun --gpus 2)')
+def test_divergence_of_whole_runs_comes_from_the_clip_scale_not_from_the_exchange():
+    """round-1 finding: after 6 epochs the fused and the NCCL run differ by ~0.1 in some weights.  With the clip inactive (grad_norm 1.0 at this
+    size) the two runs stay BIT-identical through six epochs at world 2 (a + b is order-free); with the clip active the all-reduced gradient
+    is still identical, the first step differs by at most an ulp-sized change of the clip scale (two summation orders of ||g||^2), and that
+    seed grows under Adam -- the exchange is exact, the optimiser tail's norm order is the only difference."""
+    world = 2 if torch.cuda.device_count() < 8 else 8
+    o = _run(world, ('--clip',))
+    assert o['ranks_identical'] == [True, True]
+    assert o['grad_rel_l2'] < 1e-6, o                        # the exchange itself
+    assert o['w1_max_abs_diff'] <= 2e-6, o                   # one step: an ulp of the clip scale times lr
+    if world == 2:
+        plain = _run(world, ())
+        assert plain['epochs_max_abs_diff'] == [0.0] * 6 and plain['grad_max_abs_diff'] == 0.0, plain
