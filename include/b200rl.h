@@ -146,12 +146,15 @@ int b200rl_linear_bwd_weight_f32(const float* dY, const float* X, int rows_per_c
 /* out[i] = sum_s part[s*split_stride + i]  (deterministic, fixed order) */
 /* The same three building blocks on the 5th-gen tensor cores (tcgen05, bf16 operands rounded while they are staged, fp32 accumulate in
  * TMEM, fp32 bias / activation / outputs) for ANY layer width: the mixed_precision path of LSTM gate GEMMs and of MLPs the fused
- * kernels (b200rl_tc_mlp_*) have no geometry for.  Same arguments, same row / split semantics as the _f32 functions. */
+ * kernels (b200rl_tc_mlp_*) have no geometry for.  Same arguments, same row / split semantics as the _f32 functions, plus W_bf16
+ * (optional): a bf16 copy of W, same [Nout, K] row-major layout (b200rl_cast_bf16 of the flat parameter arena), staged without
+ * conversion instead of the fp32 weights. */
+int b200rl_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 int b200rl_linear_fwd_tc(const float* X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
                          const float* norm_mean, const float* norm_std,
-                         const float* W, const float* b, float* Y, int M, int K, int Nout, int act,
+                         const float* W, const void* W_bf16, const float* b, float* Y, int M, int K, int Nout, int act,
                          int accumulate, void* stream);
-int b200rl_linear_bwd_data_tc(const float* dY, const float* W, const float* A_prev, float* dX,
+int b200rl_linear_bwd_data_tc(const float* dY, const float* W, const void* W_bf16, const float* A_prev, float* dX,
                               int M, int K, int Nout, int act_prev, void* stream);
 int b200rl_linear_bwd_weight_tc(const float* dY, const float* X, int rows_per_chunk, int64_t chunk_stride,
                                 int64_t x_ld, const float* norm_mean, const float* norm_std,

@@ -407,6 +407,15 @@ class A2CAgent(CompileTolerantModel):
             self.ta = self.dA = []
             if not self.rollout_fp32:
                 self.ra = []
+        elif self.gemm_tc:
+            # layer-wise tensor-core GEMMs: a weight-gradient CTA owns a [128 x <=256] tile of dW and a row split; 16 splits keep the
+            # c4 gate GEMM (16 tiles) at 256 CTAs while the split partials stay small (64 splits: 91 MB of partials per gate GEMM)
+            self.n_splits = max(1, min(16, mb // 512))
+            self.wbf = torch.empty(m.num_params, dtype=torch.bfloat16, device=dev)     # bf16 twin of the parameter arena (weight operands)
+            import functools
+            arena = (m.flat, self.wbf)
+            self._lin_fwd = functools.partial(ops.linear_fwd_tc, bf16_arena=arena)
+            self._lin_bwd = functools.partial(ops.linear_bwd_data_tc, bf16_arena=arena)
         else:
             self.n_splits = max(1, min(64, mb // 256))
         self.part_rows = self.n_splits * (self.seq_length if self.is_rnn else 1)
@@ -527,11 +536,15 @@ class A2CAgent(CompileTolerantModel):
             ops.allreduce_adam(self.peer_table, u & 1, self.global_rank, self.my_flags_ptr, self.ar_seq, self.ar_red, self.ar_nrm,
                                self.ar_bar, m.flat, m.exp_avg, m.exp_avg_sq, P, self.opt_state, self.opt_cfg, self.stats[u],
                                self.counters[2:3], wpack=wpack, pack_table=pack_table, merge_next=mn)
+            if self.gemm_tc:
+                ops.cast_bf16(m.flat, self.wbf)
             return
         if self.multi_gpu:
             dist.all_reduce(gv['comm'], op=dist.ReduceOp.SUM)
         ops.adam_step(m.flat, gv['grad'], m.exp_avg, m.exp_avg_sq, self.opt_state, gv['kl'], self.opt_cfg, self.stats[u],
                       self.counters[2:3], n=P, wpack=wpack, pack_table=pack_table, merge_next=mn)
+        if self.gemm_tc:
+            ops.cast_bf16(m.flat, self.wbf)
 
     def _set_sched_mode(self, u):
         """schedule_type 'standard' (a2c_common.py:1565-1571): the optimiser kernel of every minibatch adds its KL to the mini-epoch's
@@ -668,6 +681,8 @@ class A2CAgent(CompileTolerantModel):
         if self.use_tc and self._tensors_ready:
             m = self.model
             ops.tc_pack_weights(m.W[0], m.W[1], m.W[2], m.W_head, m.D, m.units, self.actions_num, self.wpack)
+        if getattr(self, 'gemm_tc', False) and self._tensors_ready:
+            ops.cast_bf16(self.model.flat, self.wbf)
 
     def _norm(self):
         m = self.model

@@ -31,6 +31,8 @@ constexpr uint32_t A_BYTES = BM * SLAB * 2, B_BYTES = BNMAX * SLAB * 2, STAGE_BY
 struct Src {
     const float* p; int64_t ld; int rows_per_chunk; int64_t chunk_stride; const float* nm; const float* ns;
     int rows, cols;          // logical extent (everything outside reads as 0)
+    const __nv_bfloat16* pb; // optional bf16 copy of a DENSE source (weights: refreshed once per optimiser step by b200rl_cast_bf16):
+                             // staged with plain 16 / 8-byte copies, no conversion, half the bytes
 };
 __device__ __forceinline__ const float* src_row(const Src& s, int r) {
     return s.p + (s.rows_per_chunk > 0 ? chunk_row(r, s.rows_per_chunk, s.chunk_stride) : (int64_t)r) * s.ld;
@@ -82,7 +84,33 @@ __device__ __forceinline__ void stage_part(uint8_t* sT, const Src& s, int r0, in
     }
 }
 // row_end: rows >= row_end read as zeros (the end of this CTA's reduction range when the rows ARE the reduction index, else s.rows)
+__device__ __forceinline__ void stage_tile_bf16(uint8_t* sT, const Src& s, int r0, int c0, int tr, int ncg, int tid, int row_end) {
+    const int n_items = tr * ncg;
+    const uint32_t RS = (uint32_t)ncg * 128u;
+    const int al = (int)(((s.ld * 2) | (int64_t)(reinterpret_cast<uintptr_t>(s.pb) & 15)) & 15);     // 0: rows 16-byte aligned, 8: 8-byte aligned
+    for (int i = tid; i < n_items; i += GT) {
+        const int r = i / ncg, cg = i - r * ncg;
+        const int gr = r0 + r, gc = c0 + cg * 8;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (gr < row_end && gc < s.cols) {
+            const __nv_bfloat16* src = s.pb + (int64_t)gr * s.ld + gc;
+            if (gc + 8 <= s.cols && al == 0) {
+                u = __ldg(reinterpret_cast<const uint4*>(src));
+            } else if (gc + 8 <= s.cols && (al & 7) == 0) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(src)), b = __ldg(reinterpret_cast<const uint2*>(src) + 1);
+                u = make_uint4(a.x, a.y, b.x, b.y);
+            } else {
+                __nv_bfloat16 t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = (gc + j < s.cols) ? src[j] : __float2bfloat16_rn(0.f);
+                u = *reinterpret_cast<const uint4*>(t);
+            }
+        }
+        *reinterpret_cast<uint4*>(sT + tile_off(r, cg, 128u, RS)) = u;
+    }
+}
 __device__ __forceinline__ void stage_tile(uint8_t* sT, const Src& s, int r0, int c0, int tr, int ncg, int tid, int row_end) {
+    if (s.pb) { stage_tile_bf16(sT, s, r0, c0, tr, ncg, tid, row_end); return; }
     const int n_items = tr * ncg;
     for (int base = 0; base < n_items; base += 4 * GT) stage_part<4>(sT, s, r0, c0, ncg, base, n_items, tid, row_end);
 }
@@ -254,24 +282,24 @@ static int launch_gemm(const GemmArgs& a, int grid_z, void* stream) {
 
 B200RL_EXPORT int b200rl_linear_fwd_tc(const float* X, int rows_per_chunk, int64_t chunk_stride, int64_t x_ld,
                                        const float* norm_mean, const float* norm_std,
-                                       const float* W, const float* b, float* Y, int M, int K, int Nout, int act,
+                                       const float* W, const void* W_bf16, const float* b, float* Y, int M, int K, int Nout, int act,
                                        int accumulate, void* stream) {
     if (!X || !W || !Y || M <= 0 || K <= 0 || Nout <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
     if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200RL_EINVAL;
     GemmArgs a{};
-    a.a = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K};
-    a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K};
+    a.a = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K, nullptr};
+    a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K, (const __nv_bfloat16*)W_bf16};
     a.Mo = M; a.No = Nout; a.R = K; a.BN = pick_bn(Nout);
     a.bias = b; a.Y = Y; a.act = act; a.accumulate = accumulate;
     return launch_gemm<MODE_FWD>(a, 1, stream);
 }
 
-B200RL_EXPORT int b200rl_linear_bwd_data_tc(const float* dY, const float* W, const float* A_prev, float* dX,
+B200RL_EXPORT int b200rl_linear_bwd_data_tc(const float* dY, const float* W, const void* W_bf16, const float* A_prev, float* dX,
                                             int M, int K, int Nout, int act_prev, void* stream) {
     if (!dY || !W || !dX || M <= 0 || K <= 0 || Nout <= 0) return B200RL_EINVAL;
     GemmArgs a{};
-    a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout};            // [m, n]: reduction index n contiguous -> K-major
-    a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K};                // [n, k]: rows = reduction n, cols = outputs k -> MN-major
+    a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout, nullptr};            // [m, n]: reduction index n contiguous -> K-major
+    a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K, (const __nv_bfloat16*)W_bf16};   // [n, k]: rows = reduction n, cols = outputs k -> MN-major
     a.Mo = M; a.No = K; a.R = Nout; a.BN = pick_bn(K);
     a.A_prev = A_prev; a.dX = dX; a.act_prev = act_prev;
     return launch_gemm<MODE_DGRAD>(a, 1, stream);
@@ -284,11 +312,26 @@ B200RL_EXPORT int b200rl_linear_bwd_weight_tc(const float* dY, const float* X, i
     if (!dY || !X || !dW_part || M <= 0 || K <= 0 || Nout <= 0 || n_splits <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
     if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200RL_EINVAL;
     GemmArgs a{};
-    a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout};            // [r, n]: rows = reduction r, cols = outputs n -> MN-major
-    a.b = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K};   // [r, k]: rows = reduction r, cols = outputs k -> MN-major
+    a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout, nullptr};            // [r, n]: rows = reduction r, cols = outputs n -> MN-major
+    a.b = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K, nullptr};   // [r, k]: rows = reduction r, cols = outputs k -> MN-major
     a.Mo = Nout; a.No = K; a.R = M; a.BN = pick_bn(K);
     a.dW = dW_part; a.db = db_part; a.split_stride = split_stride;
     int rps = (M + n_splits - 1) / n_splits;
     a.rows_per_split = ((rps + SLAB - 1) / SLAB) * SLAB;       // trailing splits may be empty: they write zeros, which the reducer expects
     return launch_gemm<MODE_WGRAD>(a, n_splits, stream);
+}
+
+
+// fp32 -> bf16 copy of the flat parameter arena (same offsets): the weight operand of the layer-wise GEMMs, refreshed once per optimiser step
+namespace {
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = __float2bfloat16_rn(__ldg(src + i));
+}
+}  // namespace
+B200RL_EXPORT int b200rl_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
+    if (!src || !dst_bf16 || n <= 0) return B200RL_EINVAL;
+    const int blocks = (int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
+    cast_bf16_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, (__nv_bfloat16*)dst_bf16, n);
+    B200RL_LAUNCH_CHECK();
+    return B200RL_OK;
 }

@@ -164,20 +164,36 @@ def linear_bwd_weight(dY, X, dW_part, db_part, K, Nout, n_splits, rows_per_chunk
           'linear_bwd_weight')
 
 
+def cast_bf16(src, dst):
+    """bf16 copy of an fp32 arena (same offsets): the weight operand of the layer-wise tensor-core GEMMs, refreshed once per optimiser step"""
+    check(lib.b200rl_cast_bf16(ptr(src), ptr(dst), src.numel(), _stream()), 'cast_bf16')
+
+
+def _bf16_view_ptr(W, bf16_arena):
+    """address of W's twin inside the bf16 copy of the arena W is a view of (bf16_arena = (fp32 arena, bf16 arena)), or None"""
+    if bf16_arena is None:
+        return None
+    flat, fb = bf16_arena
+    off = W.data_ptr() - flat.data_ptr()
+    if 0 <= off < flat.numel() * 4 and W.is_contiguous():
+        return fb.data_ptr() + off // 2
+    return None
+
+
 def linear_fwd_tc(X, W, b, Y, act, rows_per_chunk=None, chunk_stride=0, x_ld=None, norm_mean=None, norm_std=None, M=None,
-                  accumulate=False):
+                  accumulate=False, bf16_arena=None):
     """linear_fwd on the tensor cores (bf16 operands, fp32 accumulate), any layer width"""
     Nout, K = W.shape
     M = Y.shape[0] if M is None else M
     check(lib.b200rl_linear_fwd_tc(ptr(X), M if rows_per_chunk is None else rows_per_chunk, chunk_stride,
-                                   K if x_ld is None else x_ld, ptr(norm_mean), ptr(norm_std), ptr(W), ptr(b), ptr(Y),
+                                   K if x_ld is None else x_ld, ptr(norm_mean), ptr(norm_std), ptr(W), _bf16_view_ptr(W, bf16_arena), ptr(b), ptr(Y),
                                    M, K, Nout, act, int(accumulate), _stream()), 'linear_fwd_tc')
 
 
-def linear_bwd_data_tc(dY, W, A_prev, dX, act_prev, M=None):
+def linear_bwd_data_tc(dY, W, A_prev, dX, act_prev, M=None, bf16_arena=None):
     Nout, K = W.shape
     M = dY.shape[0] if M is None else M
-    check(lib.b200rl_linear_bwd_data_tc(ptr(dY), ptr(W), ptr(A_prev), ptr(dX), M, K, Nout, act_prev, _stream()),
+    check(lib.b200rl_linear_bwd_data_tc(ptr(dY), ptr(W), _bf16_view_ptr(W, bf16_arena), ptr(A_prev), ptr(dX), M, K, Nout, act_prev, _stream()),
           'linear_bwd_data_tc')
 
 

@@ -528,7 +528,8 @@ def install_continuous(monkeypatch):
     monkeypatch.setattr(ops, 'set_pdl', lambda enable: False)
     # layer-wise tensor-core GEMMs (mixed_precision: True on LSTM policies / geometries without fused kernels): same contract, fp32 here
     for name in ('linear_fwd', 'linear_bwd_data', 'linear_bwd_weight'):
-        monkeypatch.setattr(ops, name + '_tc', globals()[name])
+        monkeypatch.setattr(ops, name + '_tc', (lambda f: (lambda *a, bf16_arena=None, **k: f(*a, **k)))(globals()[name]))
+    monkeypatch.setattr(ops, 'cast_bf16', lambda src, dst: dst.copy_(src))
 
 
 # ---------------------------------------------------------------------------------------------- tcgen05 path (host logic only: fp32 maths)

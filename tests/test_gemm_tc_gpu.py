@@ -35,6 +35,16 @@ def test_linear_fwd_tc(M, K, N, act, accumulate):
     torch.cuda.synchronize()
     ref = bf(X) @ bf(W).t() + b.double() + (Y0.double() if accumulate else 0.0)
     close(Y, ACT[act](ref))
+    # weights taken from a bf16 twin of the parameter arena (what the agent does): W is a view at a non-zero offset of a flat arena
+    off = 8      # keeps the bf16 rows 16-byte aligned when K % 8 == 0; other K exercise the 8-byte / scalar copies
+    flat = torch.zeros(off + N * K, device=DEV); flat[off:] = W.reshape(-1)
+    fb = torch.empty(flat.numel(), dtype=torch.bfloat16, device=DEV)
+    ops.cast_bf16(flat, fb)
+    Wv = flat[off:].view(N, K)
+    Y2 = Y0.clone()
+    ops.linear_fwd_tc(X, Wv, b, Y2, act, accumulate=accumulate, bf16_arena=(flat, fb))
+    torch.cuda.synchronize()
+    assert torch.equal(Y2, Y)          # same bf16 operand values either way -> bit-identical
 
 
 def test_linear_fwd_tc_chunked_rows_with_normalisation():
@@ -67,6 +77,13 @@ def test_linear_bwd_data_tc(M, K, N, act_prev):
     if act_prev:
         ref = ref * DACT[act_prev](A_prev).double()
     close(dX, ref)
+    flat = torch.zeros(4 + N * K, device=DEV); flat[4:] = W.reshape(-1)
+    fb = torch.empty(flat.numel(), dtype=torch.bfloat16, device=DEV)
+    ops.cast_bf16(flat, fb)
+    dX2 = torch.empty(M, K, device=DEV)
+    ops.linear_bwd_data_tc(dY, flat[4:].view(N, K), A_prev if act_prev else None, dX2, act_prev, bf16_arena=(flat, fb))
+    torch.cuda.synchronize()
+    assert torch.equal(dX2, dX)
 
 
 @pytest.mark.parametrize('M,K,N,splits', [(5000, 348, 1024, 7), (4096, 256, 512, 16), (1000, 60, 18, 3), (130, 17, 65, 1), (8192, 512, 256, 64)])
