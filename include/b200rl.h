@@ -338,7 +338,7 @@ int b200rl_lr_schedule_apply(double* state_d, const float* kl_dev, double kl_sca
  * the reduced gradient through memory; one grid barrier, grid <= 148 co-resident CTAs).
  *  part: split partial gradients, entry i of split k at part[k*split_stride + i], valid for i in [A, n);
  *  entries [0, A) of the flat gradient (d_logstd) come from the loss partials.  grads[n] receives the reduced gradient.
- *  nrm_part: double[>= 148] scratch; grid_bar: uint32[1] zero-initialised once (monotonic). */
+ *  nrm_part: double[>= 148] scratch; grid_bar: uint64[1] zero-initialised once (monotonic 64-bit arrival counter: never reset, cannot wrap). */
 int b200rl_reduce_adam_f32(const float* part, int n_splits, int64_t split_stride, const double* loss_partials,
                            int n_loss_partials, int A, const float* entropy_coef_dev, float* stats, float* kl_out,
                            float* grads, float* params, float* exp_avg, float* exp_avg_sq, int n, double* state_d,
@@ -368,7 +368,7 @@ int b200rl_reduce_allreduce_adam_f32(const float* part, int n_splits, int64_t sp
  * torch.distributed.all_gather_object).  peer_grads_host[r] / peer_flags_host[r]: device addresses (valid in THIS
  * process) of rank r's gradient buffer for this step's parity and of rank r's flag array (u64[world]);
  * my_flags == peer_flags_host[rank].  seq_ptr: u64[1] step counter, red: float[n+1] local reduced copy,
- * nrm_part: double[>= grid], grid_bar: u32[1] (zeroed once).  Gradient buffers must be double-buffered by step parity.
+ * nrm_part: double[>= grid], grid_bar: u64[1] (zeroed once).  Gradient buffers must be double-buffered by step parity.
  * ------------------------------------------------------------------------------------------- */
 int b200rl_ipc_alloc(int64_t bytes, void** dev_ptr_out_host, void* handle64_out_host);
 int b200rl_ipc_open(const void* handle64_host, void** dev_ptr_out_host);

@@ -473,7 +473,7 @@ class A2CAgent(CompileTolerantModel):
             self.adv_ema_state = torch.zeros(2, dtype=torch.float32, device=dev)     # GeneralizedMovingStats: mean, mean of squares
             self.adv_ema_step = torch.ones(1, dtype=torch.int32, device=dev)
         self.ra_nrm = torch.zeros(148, dtype=torch.float64, device=dev)      # reduce_adam: per-CTA sum-of-squares partials
-        self.ra_bar = torch.zeros(1, dtype=torch.int32, device=dev)          # reduce_adam: monotonic grid-barrier counter
+        self.ra_bar = torch.zeros(1, dtype=torch.int64, device=dev)          # reduce_adam: monotonic grid-barrier counter
         self.host_stats = torch.zeros(self.n_updates, 16, dtype=torch.float32).pin_memory()
         self.host_state = torch.zeros(10, dtype=torch.float64).pin_memory()
         self._events = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
@@ -515,7 +515,7 @@ class A2CAgent(CompileTolerantModel):
         self.ar_seq = torch.zeros(1, dtype=torch.int64, device=dev)
         self.ar_red = torch.zeros(P + 1, dtype=torch.float32, device=dev)
         self.ar_nrm = torch.zeros(128, dtype=torch.float64, device=dev)
-        self.ar_bar = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ar_bar = torch.zeros(1, dtype=torch.int64, device=dev)
         self._ar_parity = 0
         self.fused_allreduce = True
         dist.barrier()

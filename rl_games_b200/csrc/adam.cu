@@ -185,15 +185,21 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+// Grid barrier on a monotonic 64-bit arrival counter (never reset, never wraps: 2^64 arrivals).  All CTAs are co-resident (grid <= #SMs).
+__device__ __forceinline__ void grid_barrier_arrive_wait(unsigned long long* grid_bar) {
+    const unsigned long long arrived = atomicAdd(grid_bar, 1ull);
+    const unsigned long long target = (arrived / gridDim.x + 1ull) * gridDim.x;
+    while (ld_acquire_gpu_u64(grid_bar) < target) { }
 }
 
 __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, int world, int rank, unsigned long long* my_flags,
                                                              unsigned long long* seq_ptr, float* __restrict__ red, double* __restrict__ nrm_part,
-                                                             unsigned* grid_bar, float* __restrict__ params, float* __restrict__ exp_avg,
+                                                             unsigned long long* grid_bar, float* __restrict__ params, float* __restrict__ exp_avg,
                                                              float* __restrict__ exp_avg_sq, int n, double* state_d, OptCfgDev c,
                                                              float* __restrict__ stats_out, int* counter, unsigned char* __restrict__ wpack,
                                                              PackTabDev tab, ObsMergeDev om) {
@@ -230,9 +236,7 @@ __global__ void __launch_bounds__(1024) allreduce_adam_kernel(PeerPtrs peers, in
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned arrived = atomicAdd(grid_bar, 1u);
-        const unsigned target = (arrived / gridDim.x + 1u) * gridDim.x;
-        while (ld_acquire_gpu_u32(grid_bar) < target) { }
+        grid_barrier_arrive_wait(grid_bar);
     }
     __syncthreads();
     // ---- 3. clip + Adam on my slice ----
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
                                                           const float* __restrict__ entropy_coef_dev, float* __restrict__ stats,
                                                           float* __restrict__ kl_out, float* __restrict__ grads, float* __restrict__ params,
                                                           float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq, int n, double* state_d,
-                                                          OptCfgDev c, int* counter, double* __restrict__ nrm_part, unsigned* grid_bar,
+                                                          OptCfgDev c, int* counter, double* __restrict__ nrm_part, unsigned long long* grid_bar,
                                                           unsigned char* __restrict__ wpack, PackTabDev tab, ObsMergeDev om, int kg_log2, int per, int vec4, PeerStage ps) {
     __shared__ double sm[32];
     __shared__ double smf[256];
@@ -473,9 +477,7 @@ __global__ void __launch_bounds__(1024) reduce_adam_kernel(const float* __restri
     __threadfence();
     __syncthreads();
     if (tid == 0) {
-        const unsigned arrived = atomicAdd(grid_bar, 1u);
-        const unsigned target = (arrived / gridDim.x + 1u) * gridDim.x;
-        while (ld_acquire_gpu_u32(grid_bar) < target) { }
+        grid_barrier_arrive_wait(grid_bar);
     }
     __syncthreads();
     RA_STAMP(3);      // grid barrier passed
@@ -570,12 +572,12 @@ static int reduce_adam_launch(const float* part, int n_splits, int64_t split_str
     if (ps)
         le = launch_k(reduce_adam_kernel<true>, dim3(blocks), dim3(1024), 0, as_stream(stream), part, n_splits, split_stride, loss_partials,
                       n_loss_partials, b200rl_loss_partial_stride(), A, entropy_coef_dev, stats, kl_out, grads, params, exp_avg, exp_avg_sq, n,
-                      state_d, make_opt_cfg(cfg_host), counter, nrm_part, (unsigned*)grid_bar, (unsigned char*)wpack, tab,
+                      state_d, make_opt_cfg(cfg_host), counter, nrm_part, (unsigned long long*)grid_bar, (unsigned char*)wpack, tab,
                       make_obs_merge(merge_next_host), kg_log2, per, vec4, *ps);
     else
         le = launch_k(reduce_adam_kernel<false>, dim3(blocks), dim3(1024), 0, as_stream(stream), part, n_splits, split_stride, loss_partials,
                       n_loss_partials, b200rl_loss_partial_stride(), A, entropy_coef_dev, stats, kl_out, grads, params, exp_avg, exp_avg_sq, n,
-                      state_d, make_opt_cfg(cfg_host), counter, nrm_part, (unsigned*)grid_bar, (unsigned char*)wpack, tab,
+                      state_d, make_opt_cfg(cfg_host), counter, nrm_part, (unsigned long long*)grid_bar, (unsigned char*)wpack, tab,
                       make_obs_merge(merge_next_host), kg_log2, per, vec4, PeerStage{});
     if (le != cudaSuccess) return (int)le;
     return B200RL_OK;
@@ -724,7 +726,7 @@ B200RL_EXPORT int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, 
     if (blocks < 1) blocks = 1;
     if (blocks > nrm_part_len) return B200RL_EINVAL;
     cudaError_t le = launch_k(allreduce_adam_kernel, dim3(blocks), dim3(1024), 0, as_stream(stream), pp, world, rank, (unsigned long long*)my_flags, (unsigned long long*)seq_ptr,
-                                                                 red, nrm_part, (unsigned*)grid_bar, params, exp_avg, exp_avg_sq, n, state_d, c,
+                                                                 red, nrm_part, (unsigned long long*)grid_bar, params, exp_avg, exp_avg_sq, n, state_d, c,
                                                                  stats_out, counter, (unsigned char*)wpack, tab, make_obs_merge(merge_next_host));
     if (le != cudaSuccess) return (int)le;
     return B200RL_OK;

@@ -416,7 +416,7 @@ def test_per_mini_epoch_scheduler_modes(ops, kernel):
     state = torch.tensor([3e-4] + [0.0] * 7, dtype=torch.float64, device=DEV)
     counter = torch.zeros(1, dtype=torch.int32, device=DEV); stats = torch.zeros(16, device=DEV)
     grad = torch.zeros(n, device=DEV); klt = torch.zeros(1, device=DEV); ec = torch.tensor([0.0], device=DEV)
-    nrm = torch.zeros(148, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+    nrm = torch.zeros(148, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int64, device=DEV)
     lr = 3e-4
     kl_rows = [[0.001, 0.002, 0.0015], [0.05, 0.03, 0.001], [0.006, 0.007, 0.008], [0.0001, 0.03, 0.0001]]
     for me, row in enumerate(kl_rows):
@@ -459,7 +459,7 @@ def test_reduce_adam_vs_two_kernel_path(ops, n, n_splits, pad):
                         state=torch.tensor([3e-4, 0.0, 0.0, 0.0], dtype=torch.float64, device=DEV),
                         counter=torch.zeros(1, dtype=torch.int32, device=DEV), stats=torch.zeros(16, device=DEV),
                         grad=torch.zeros(n, device=DEV), kl=torch.zeros(1, device=DEV))
-    nrm = torch.zeros(148, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+    nrm = torch.zeros(148, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int64, device=DEV)
     for it in range(4):
         pstride = (n + 3) // 4 * 4 if pad else n         # padded rows take the float4 path; the pad / [0, A) entries are never read
         part = torch.full((n_splits, pstride), float('nan'), device=DEV)
@@ -636,7 +636,7 @@ def test_fused_allreduce_adam_world1_matches_adam_step(ops):
     ca, cb = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
     cfg = OptCfg(0.9, 0.999, 1e-8, 0.0, 1.0, 0.008, 1e-6, 1e-2, 1.5, 1.0, 1, 1)
     seq = torch.zeros(1, dtype=torch.int64, device=DEV); red = torch.zeros(n + 1, device=DEV)
-    nrm = torch.zeros(128, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+    nrm = torch.zeros(128, dtype=torch.float64, device=DEV); bar = torch.zeros(1, dtype=torch.int64, device=DEV)
     sta, stb = torch.zeros(16, device=DEV), torch.zeros(16, device=DEV)
     for it, klv in enumerate([0.001, 0.05, 0.01, 0.0001]):
         grad = torch.randn(n, generator=g) * (0.02 if it % 2 else 0.001)

@@ -131,7 +131,7 @@ def main():
     flat, m1, m2, grad = torch.randn(P, device=DEV) * 0.1, torch.zeros(P, device=DEV), torch.zeros(P, device=DEV), torch.zeros(P, device=DEV)
     state = torch.tensor([3e-4, 0.0, 0.0, 0.0], dtype=torch.float64, device=DEV)
     cfg_o = OptCfg(0.9, 0.999, 1e-8, 0.0, 1.0, 0.008, 1e-6, 1e-2, 1.5, 1.0, 1, 1)
-    counter, bar = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    counter, bar = torch.zeros(1, dtype=torch.int32, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
     nrm, stats, kl, ec = torch.zeros(148, dtype=torch.float64, device=DEV), torch.zeros(16, device=DEV), torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
     for it in range(4):
         part4.mul_(1.0)          # rewrite the partial rows so that they sit in L2 as after the backward kernel
