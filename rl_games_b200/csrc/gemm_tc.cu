@@ -38,20 +38,30 @@ __device__ __forceinline__ const float* src_row(const Src& s, int r) {
     return s.p + (s.rows_per_chunk > 0 ? chunk_row(r, s.rows_per_chunk, s.chunk_stride) : (int64_t)r) * s.ld;
 }
 
-// Stage a [TR rows x ncg*8 cols] bf16 INTERLEAVE tile (16-byte chunks adjacent along the columns: CS = 128, RS = ncg * 128) from rows
-// [r0, r0 + TR) x cols [c0, c0 + ncg*8) of `s`.  ITEMS chunks per thread, all global loads first.
+// ---- staging: global -> registers -> bf16 INTERLEAVE operand tile ------------------------------------------------------------------
+// A tile is [tr rows x ncg * 8 cols] of 16-byte bf16 chunks (CS = 128, RS = ncg * 128; tc_common.cuh); tr is a multiple of 8 and ncg a
+// power of two (8, 16 or 32).  Item i of a tile = chunk (r, cg) with  r = (i & 7) | ((i >> (3 + lg ncg)) << 3),  cg = (i >> 3) & (ncg - 1):
+// the 32 lanes of a warp cover 8 rows x 4 adjacent chunks, so a warp's global loads are 8 full 128-byte lines (fp32) and its 16-byte
+// shared-memory stores fall into 4 conflict-free wavefronts (8 consecutive lanes write one 128-byte core matrix).
+// Loading and storing are separate so that EVERY load of a slab (both operands) is in flight before the first use, and so that the
+// loads of slab s + 1 can be issued before the barrier / MMA issue of slab s (register prefetch).
+struct TileGeo { int r0, c0, lg, n_items, row_end; };     // tile origin in the source, log2(ncg), tr * ncg, rows >= row_end read as 0
+__device__ __forceinline__ void item_rc(int i, int lg, int& r, int& cg) {
+    cg = (i >> 3) & ((1 << lg) - 1);
+    r = (i & 7) | ((i >> (3 + lg)) << 3);
+}
+
 template <int ITEMS>
-__device__ __forceinline__ void stage_part(uint8_t* sT, const Src& s, int r0, int c0, int ncg, int i_base, int n_items, int tid, int row_end) {
-    float4 va[ITEMS], vb[ITEMS];
-    const bool vec = ((s.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(s.p) & 15) == 0) && ((c0 & 3) == 0);
+__device__ __forceinline__ void load_f32(float4 (&va)[ITEMS], float4 (&vb)[ITEMS], const Src& s, const TileGeo& g, int tid) {
+    const bool vec = ((s.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(s.p) & 15) == 0) && ((g.c0 & 3) == 0);
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        const int i = i_base + tid + it * GT;
+        const int i = tid + it * GT;
         va[it] = make_float4(0.f, 0.f, 0.f, 0.f); vb[it] = va[it];
-        if (i < n_items) {
-            const int r = i / ncg, cg = i - r * ncg;
-            const int gr = r0 + r, gc = c0 + cg * 8;
-            if (gr < row_end && gc < s.cols) {
+        if (i < g.n_items) {
+            int r, cg; item_rc(i, g.lg, r, cg);
+            const int gr = g.r0 + r, gc = g.c0 + cg * 8;
+            if (gr < g.row_end && gc < s.cols) {
                 const float* src = src_row(s, gr) + gc;
                 if (vec && gc + 8 <= s.cols) {
                     va[it] = __ldg(reinterpret_cast<const float4*>(src));
@@ -65,55 +75,68 @@ __device__ __forceinline__ void stage_part(uint8_t* sT, const Src& s, int r0, in
             }
         }
     }
-    const uint32_t RS = (uint32_t)ncg * 128u;
+}
+template <int ITEMS>
+__device__ __forceinline__ void store_f32(uint8_t* sT, const float4 (&va)[ITEMS], const float4 (&vb)[ITEMS], const Src& s, const TileGeo& g, int tid) {
+    const uint32_t RS = 128u << g.lg;
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
-        const int i = i_base + tid + it * GT;
-        if (i < n_items) {
-            const int r = i / ncg, cg = i - r * ncg;
+        const int i = tid + it * GT;
+        if (i < g.n_items) {
+            int r, cg; item_rc(i, g.lg, r, cg);
             float f[8] = {va[it].x, va[it].y, va[it].z, va[it].w, vb[it].x, vb[it].y, vb[it].z, vb[it].w};
             if (s.nm) {
-                const int gr = r0 + r, gc = c0 + cg * 8;
+                const int gr = g.r0 + r, gc = g.c0 + cg * 8;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    f[j] = (gr < row_end && gc + j < s.cols)
+                    f[j] = (gr < g.row_end && gc + j < s.cols)
                                ? fminf(fmaxf(__fdiv_rn(__fsub_rn(f[j], __ldg(s.nm + gc + j)), __ldg(s.ns + gc + j)), -5.0f), 5.0f) : 0.f;
             }
             *reinterpret_cast<uint4*>(sT + tile_off(r, cg, 128u, RS)) = pack8_bf16(f);
         }
     }
 }
-// row_end: rows >= row_end read as zeros (the end of this CTA's reduction range when the rows ARE the reduction index, else s.rows)
-__device__ __forceinline__ void stage_tile_bf16(uint8_t* sT, const Src& s, int r0, int c0, int tr, int ncg, int tid, int row_end) {
-    const int n_items = tr * ncg;
-    const uint32_t RS = (uint32_t)ncg * 128u;
+// bf16 twin of a dense source (weights): plain 16 / 8-byte copies, no conversion, half the bytes
+template <int ITEMS>
+__device__ __forceinline__ void load_b16(uint4 (&u)[ITEMS], const Src& s, const TileGeo& g, int tid) {
     const int al = (int)(((s.ld * 2) | (int64_t)(reinterpret_cast<uintptr_t>(s.pb) & 15)) & 15);     // 0: rows 16-byte aligned, 8: 8-byte aligned
-    for (int i = tid; i < n_items; i += GT) {
-        const int r = i / ncg, cg = i - r * ncg;
-        const int gr = r0 + r, gc = c0 + cg * 8;
-        uint4 u = make_uint4(0, 0, 0, 0);
-        if (gr < row_end && gc < s.cols) {
-            const __nv_bfloat16* src = s.pb + (int64_t)gr * s.ld + gc;
-            if (gc + 8 <= s.cols && al == 0) {
-                u = __ldg(reinterpret_cast<const uint4*>(src));
-            } else if (gc + 8 <= s.cols && (al & 7) == 0) {
-                const uint2 a = __ldg(reinterpret_cast<const uint2*>(src)), b = __ldg(reinterpret_cast<const uint2*>(src) + 1);
-                u = make_uint4(a.x, a.y, b.x, b.y);
-            } else {
-                __nv_bfloat16 t[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = (gc + j < s.cols) ? src[j] : __float2bfloat16_rn(0.f);
-                u = *reinterpret_cast<const uint4*>(t);
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = tid + it * GT;
+        u[it] = make_uint4(0, 0, 0, 0);
+        if (i < g.n_items) {
+            int r, cg; item_rc(i, g.lg, r, cg);
+            const int gr = g.r0 + r, gc = g.c0 + cg * 8;
+            if (gr < g.row_end && gc < s.cols) {
+                const __nv_bfloat16* src = s.pb + (int64_t)gr * s.ld + gc;
+                if (gc + 8 <= s.cols && al == 0) {
+                    u[it] = __ldg(reinterpret_cast<const uint4*>(src));
+                } else if (gc + 8 <= s.cols && (al & 7) == 0) {
+                    const uint2 a = __ldg(reinterpret_cast<const uint2*>(src)), b = __ldg(reinterpret_cast<const uint2*>(src) + 1);
+                    u[it] = make_uint4(a.x, a.y, b.x, b.y);
+                } else {
+                    __nv_bfloat16 t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = (gc + j < s.cols) ? src[j] : __float2bfloat16_rn(0.f);
+                    u[it] = *reinterpret_cast<const uint4*>(t);
+                }
             }
         }
-        *reinterpret_cast<uint4*>(sT + tile_off(r, cg, 128u, RS)) = u;
     }
 }
-__device__ __forceinline__ void stage_tile(uint8_t* sT, const Src& s, int r0, int c0, int tr, int ncg, int tid, int row_end) {
-    if (s.pb) { stage_tile_bf16(sT, s, r0, c0, tr, ncg, tid, row_end); return; }
-    const int n_items = tr * ncg;
-    for (int base = 0; base < n_items; base += 4 * GT) stage_part<4>(sT, s, r0, c0, ncg, base, n_items, tid, row_end);
+template <int ITEMS>
+__device__ __forceinline__ void store_b16(uint8_t* sT, const uint4 (&u)[ITEMS], const TileGeo& g, int tid) {
+    const uint32_t RS = 128u << g.lg;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = tid + it * GT;
+        if (i < g.n_items) {
+            int r, cg; item_rc(i, g.lg, r, cg);
+            *reinterpret_cast<uint4*>(sT + tile_off(r, cg, 128u, RS)) = u[it];
+        }
+    }
 }
+__device__ __forceinline__ int ilog2_pow2(int v) { return 31 - __clz(v); }
 
 enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
 
@@ -131,14 +154,14 @@ struct GemmArgs {
 // FWD         batch rows                 layer outputs N    K           X[m, k]   K-major            W[n, k]   K-major
 // DGRAD       batch rows                 layer inputs K     N           dY[m, n]  K-major            W[n, k]   MN-major (rows = reduction n)
 // WGRAD       layer outputs N            layer inputs K     batch rows  dY[r, n]  MN-major           X[r, k]   MN-major (rows = reduction r)
-template <int MODE>
+template <int MODE, bool BB16>
 __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
-    const int BN = p.BN;
+    const int BN = p.BN;                 // 64, 128 or (bf16 B operand only) 256
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     // reduction range: the whole K (fwd / dgrad) or this split's batch rows (wgrad)
     int r_begin = 0, r_end = p.R;
@@ -146,25 +169,49 @@ __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
     const int n_slabs = (r_end - r_begin + SLAB - 1) / SLAB;
     if (warp == 0) tmem_alloc(&tmem_slot, 256);
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    constexpr bool A_MN = MODE == MODE_WGRAD, B_MN = MODE != MODE_FWD;
+    const int lgb = B_MN ? ilog2_pow2(BN / 8) : 3;
+    // tile geometry of slab `sl` (out-of-range elements are zeros: they add nothing).  K-major tiles: the reduction runs along the
+    // columns, whose range [rr, rr + 64) is clipped by s.cols = R; MN-major tiles: along the rows, clipped by r_end.
+    auto geo_a = [&](int sl) {
+        const int rr = r_begin + sl * SLAB;
+        return A_MN ? TileGeo{rr, m0, 4, SLAB * (BM / 8), r_end}                      // [64 reduction rows x 128 cols m]
+                    : TileGeo{m0, rr, 3, BM * (SLAB / 8), p.a.rows};                  // [128 rows m x 64 reduction cols]
+    };
+    auto geo_b = [&](int sl) {
+        const int rr = r_begin + sl * SLAB;
+        return B_MN ? TileGeo{rr, n0, lgb, SLAB * (BN / 8), min(r_end, p.b.rows)}     // [64 reduction rows x BN cols n]
+                    : TileGeo{n0, rr, 3, BN * (SLAB / 8), p.b.rows};                  // [BN rows n x 64 reduction cols]
+    };
+    // one slab of both operands in registers: A 4 chunks of 8 fp32, B 8 chunks of 8 bf16 (BN <= 256) or 4 chunks of 8 fp32 (BN <= 128)
+    float4 a_lo[4], a_hi[4];
+    float4 b_lo[BB16 ? 1 : 4], b_hi[BB16 ? 1 : 4];
+    uint4 b_u[BB16 ? 8 : 1];
+    if (n_slabs > 0) {
+        const TileGeo ga = geo_a(0), gb = geo_b(0);
+        load_f32<4>(a_lo, a_hi, p.a, ga, tid);
+        if constexpr (BB16) load_b16<8>(b_u, p.b, gb, tid); else load_f32<4>(b_lo, b_hi, p.b, gb, tid);
+    }
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    constexpr bool A_MN = MODE == MODE_WGRAD, B_MN = MODE != MODE_FWD;
     const uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     float bsum = 0.f;        // wgrad: bias gradient of output feature m0 + tid (threads < 128 of the CTAs with blockIdx.y == 0)
     for (int sl = 0; sl < n_slabs; ++sl) {
         const int st = sl & 1, use = sl >> 1;
         uint8_t* sA = smem + st * STAGE_BYTES; uint8_t* sB = sA + A_BYTES;
         if (use > 0) mbar_wait(&bars[st], (uint32_t)(use - 1) & 1u);       // the MMAs that read this stage two slabs ago are done
-        const int rr = r_begin + sl * SLAB;
-        // ---- stage the slab (out-of-range elements are zeros: they add nothing) ----
-        // (K-major tiles: the reduction runs along the columns, whose range [rr, rr + 64) is clipped by s.cols = R; MN-major tiles: along
-        //  the rows, clipped by r_end)
-        if (!A_MN) stage_tile(sA, p.a, m0, rr, BM, SLAB / 8, tid, p.a.rows);          // [128 rows m x 64 reduction cols]
-        else stage_tile(sA, p.a, rr, m0, SLAB, BM / 8, tid, r_end);                  // [64 reduction rows x 128 cols m]
-        if (!B_MN) stage_tile(sB, p.b, n0, rr, BN, SLAB / 8, tid, p.b.rows);          // [BN rows n x 64 reduction cols]
-        else stage_tile(sB, p.b, rr, n0, SLAB, BN / 8, tid, min(r_end, p.b.rows));   // [64 reduction rows x BN cols n]
+        {
+            const TileGeo ga = geo_a(sl), gb = geo_b(sl);
+            store_f32<4>(sA, a_lo, a_hi, p.a, ga, tid);
+            if constexpr (BB16) store_b16<8>(sB, b_u, gb, tid); else store_f32<4>(sB, b_lo, b_hi, p.b, gb, tid);
+        }
+        if (sl + 1 < n_slabs) {             // prefetch: in flight across the barrier, the MMA issue and the next stage wait
+            const TileGeo ga = geo_a(sl + 1), gb = geo_b(sl + 1);
+            load_f32<4>(a_lo, a_hi, p.a, ga, tid);
+            if constexpr (BB16) load_b16<8>(b_u, p.b, gb, tid); else load_f32<4>(b_lo, b_hi, p.b, gb, tid);
+        }
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -195,12 +242,13 @@ __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
         mbar_wait(&bars[last & 1], (uint32_t)(last >> 1) & 1u);          // commits are ordered: the last one covers every MMA
         fence_after_sync();
     }
-    // ---- epilogue: lane = output row, this thread's columns [h * BN/2, (h+1) * BN/2) in chunks of 32 ----
-    const int row = q * 32 + lane;
-    const int gm = m0 + row;
+    __syncthreads();          // every MMA has read its operands and the bias sums are done: the stages become the epilogue's transpose scratch
+    // ---- epilogue: TMEM lane = output row; each warp owns rows [q * 32, +32) x columns [h * BN/2, +BN/2), in chunks of 32 columns that
+    //      it transposes through a private [32][33] shared-memory patch so that every global access is one 128-byte row segment ----
+    float* sT = reinterpret_cast<float*>(smem) + warp * (32 * 33);
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const int gm0 = m0 + q * 32;
     for (int c0 = h * (BN / 2); c0 < (h + 1) * (BN / 2); c0 += 32) {
-        float v[32];
         if (n_slabs > 0) {
             uint32_t r[32];
             asm volatile(
@@ -214,45 +262,40 @@ __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) sT[lane * 33 + j] = __uint_as_float(r[j]);
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int j = 0; j < 32; ++j) sT[lane * 33 + j] = 0.f;
         }
-        const int gn = n0 + c0;
-        if (gm < p.Mo && gn < p.No) {            // (the TMEM load above is warp-collective; nothing in here is)
-            const int nv = min(32, p.No - gn);
-            float* out;
+        __syncwarp();
+        const int gn = n0 + c0 + lane;              // this lane's output column for the whole chunk
+        if (gn < p.No) {
+            const int n_rows = min(32, p.Mo - gm0);
             if (MODE == MODE_FWD) {
-                out = p.Y + (int64_t)gm * p.No + gn;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < nv) {
-                        float x = v[j] + (p.bias ? __ldg(p.bias + gn + j) : 0.f);
-                        if (p.accumulate) x += out[j];
-                        v[j] = act_fwd(x, p.act);
-                    }
+                const float bias = p.bias ? __ldg(p.bias + gn) : 0.f;
+                float* out = p.Y + (int64_t)gm0 * p.No + gn;
+#pragma unroll 4
+                for (int k = 0; k < n_rows; ++k) {
+                    float x = sT[k * 33 + lane] + bias;
+                    if (p.accumulate) x += out[(int64_t)k * p.No];
+                    out[(int64_t)k * p.No] = act_fwd(x, p.act);
                 }
             } else if (MODE == MODE_DGRAD) {
-                out = p.dX + (int64_t)gm * p.No + gn;
-                if (p.A_prev) {
-                    const float* ap = p.A_prev + (int64_t)gm * p.No + gn;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < nv) v[j] *= act_bwd_from_out(__ldg(ap + j), p.act_prev);
+                float* out = p.dX + (int64_t)gm0 * p.No + gn;
+                const float* ap = p.A_prev ? p.A_prev + (int64_t)gm0 * p.No + gn : nullptr;
+#pragma unroll 4
+                for (int k = 0; k < n_rows; ++k) {
+                    float x = sT[k * 33 + lane];
+                    if (ap) x *= act_bwd_from_out(__ldg(ap + (int64_t)k * p.No), p.act_prev);
+                    out[(int64_t)k * p.No] = x;
                 }
             } else {
-                out = p.dW + (int64_t)blockIdx.z * p.split_stride + (int64_t)gm * p.No + gn;
-            }
-            if (nv == 32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j < nv) out[j] = v[j];
+                float* out = p.dW + (int64_t)blockIdx.z * p.split_stride + (int64_t)gm0 * p.No + gn;
+#pragma unroll 4
+                for (int k = 0; k < n_rows; ++k) out[(int64_t)k * p.No] = sT[k * 33 + lane];
             }
         }
+        __syncwarp();       // the patch is rewritten by the next chunk
     }
     if (MODE == MODE_WGRAD && p.db && blockIdx.y == 0 && tid < BM && m0 + tid < p.Mo)
         p.db[(int64_t)blockIdx.z * p.split_stride + m0 + tid] = bsum;
@@ -261,21 +304,34 @@ __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-static inline int pick_bn(int n_out) { return n_out > 128 ? 256 : (n_out > 64 ? 128 : 64); }
+// Output columns per CTA: the widest tile the B operand's register staging allows (256 with a bf16 twin, 128 for fp32 sources), halved
+// while the grid would leave SMs idle (fewer than one CTA per SM) -- narrower tiles re-read the A operand from L2, idle SMs cost more.
+static inline int pick_bn(int n_out, int m_tiles, int grid_z, int bn_cap) {
+    int bn = n_out > 128 ? 256 : (n_out > 64 ? 128 : 64);
+    if (bn > bn_cap) bn = bn_cap;
+    while (bn > 64 && (int64_t)m_tiles * ((n_out + bn - 1) / bn) * grid_z < 148) bn >>= 1;
+    return bn;
+}
 
-template <int MODE>
-static int launch_gemm(const GemmArgs& a, int grid_z, void* stream) {
+template <int MODE, bool BB16>
+static int launch_gemm_t(const GemmArgs& a, int grid_z, void* stream) {
     constexpr size_t smem = 2 * STAGE_BYTES;
     static bool raised = false;
     if (!raised) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<MODE, BB16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         raised = true;
     }
     dim3 grid((a.Mo + BM - 1) / BM, (a.No + a.BN - 1) / a.BN, grid_z);
-    gemm_tc_kernel<MODE><<<grid, GT, smem, as_stream(stream)>>>(a);
+    gemm_tc_kernel<MODE, BB16><<<grid, GT, smem, as_stream(stream)>>>(a);
     B200RL_LAUNCH_CHECK();
     return B200RL_OK;
+}
+template <int MODE>
+static int launch_gemm(GemmArgs& a, int grid_z, void* stream) {
+    const bool bb16 = a.b.pb != nullptr;
+    a.BN = pick_bn(a.No, (a.Mo + BM - 1) / BM, grid_z, bb16 ? 256 : 128);
+    return bb16 ? launch_gemm_t<MODE, true>(a, grid_z, stream) : launch_gemm_t<MODE, false>(a, grid_z, stream);
 }
 
 }  // namespace
@@ -289,7 +345,7 @@ B200RL_EXPORT int b200rl_linear_fwd_tc(const float* X, int rows_per_chunk, int64
     GemmArgs a{};
     a.a = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K, nullptr};
     a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K, (const __nv_bfloat16*)W_bf16};
-    a.Mo = M; a.No = Nout; a.R = K; a.BN = pick_bn(Nout);
+    a.Mo = M; a.No = Nout; a.R = K;
     a.bias = b; a.Y = Y; a.act = act; a.accumulate = accumulate;
     return launch_gemm<MODE_FWD>(a, 1, stream);
 }
@@ -300,7 +356,7 @@ B200RL_EXPORT int b200rl_linear_bwd_data_tc(const float* dY, const float* W, con
     GemmArgs a{};
     a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout, nullptr};            // [m, n]: reduction index n contiguous -> K-major
     a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K, (const __nv_bfloat16*)W_bf16};   // [n, k]: rows = reduction n, cols = outputs k -> MN-major
-    a.Mo = M; a.No = K; a.R = Nout; a.BN = pick_bn(K);
+    a.Mo = M; a.No = K; a.R = Nout;
     a.A_prev = A_prev; a.dX = dX; a.act_prev = act_prev;
     return launch_gemm<MODE_DGRAD>(a, 1, stream);
 }
@@ -314,7 +370,7 @@ B200RL_EXPORT int b200rl_linear_bwd_weight_tc(const float* dY, const float* X, i
     GemmArgs a{};
     a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout, nullptr};            // [r, n]: rows = reduction r, cols = outputs n -> MN-major
     a.b = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K, nullptr};   // [r, k]: rows = reduction r, cols = outputs k -> MN-major
-    a.Mo = Nout; a.No = K; a.R = M; a.BN = pick_bn(K);
+    a.Mo = Nout; a.No = K; a.R = M;
     a.dW = dW_part; a.db = db_part; a.split_stride = split_stride;
     int rps = (M + n_splits - 1) / n_splits;
     a.rows_per_split = ((rps + SLAB - 1) / SLAB) * SLAB;       // trailing splits may be empty: they write zeros, which the reducer expects
