@@ -895,7 +895,10 @@ class A2CAgent(CompileTolerantModel):
                                d_alast, act_last, self.loss_partials)
         gv = self._gv[u & 1]
         ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], gv['g_sigma'], gv['kl'])
-        P, S = m.num_params, self.n_splits
+        P = m.num_params
+        # row splits of the head / MLP weight gradients.  A recurrent policy's partial arena has seq_length x n_splits rows (one group per
+        # BPTT step, _lstm_window_bwd); the layers outside the window may spread over all of them: more CTAs per GEMM, same reduction
+        S = min(self.part_rows, max(self.n_splits, mb // 256)) if self.gemm_tc else self.n_splits
         off_wh, _ = m.layout['W_head']
         off_bh, _ = m.layout['b_head']
         self._lin_bww(self.d_head, a_last, self.part[0, off_wh:], self.part[0, off_bh:], m.Hl, A + 1, S, M=mb,

@@ -9,11 +9,16 @@
 // Precision contract = the reference's bf16 autocast of nn.Linear / nn.LSTM (a2c_continuous.py:173): operands rounded to bf16 while
 // they are staged into shared memory, fp32 accumulation in TMEM, fp32 bias / activation / outputs.
 //
-// One CTA = one [128 x BN] output tile (BN <= 256 TMEM columns), reduction in 64-element slabs through a two-stage shared-memory ring:
-// all 256 threads load fp32 (16-byte vector loads, every load of a slab issued before the first use), convert and store the slab as
-// INTERLEAVE operand tiles while the single issuing thread's MMAs of the previous slab run; a stage is reused when the tcgen05.commit
-// of its MMAs has arrived.  Operand views (tc_common.cuh): K-major when the source's contiguous index is the reduction index (X and W
-// in fwd, dY in dgrad), MN-major when it is the output index (W in dgrad, dY and X in wgrad) -- no transposes anywhere.
+// One CTA = one [128 x BN] output tile (BN <= 256 TMEM columns), reduction in 64-element slabs through a two-stage shared-memory ring.
+// Data movement: all 256 threads load one slab of BOTH operands into registers (16-byte vector loads, every load issued before the
+// first use: one global round trip per slab), convert to bf16 and store it as INTERLEAVE operand tiles, then issue the loads of the NEXT
+// slab before the barrier -- they are in flight while the single issuing thread's MMAs run and while the next stage is awaited; a stage
+// is reused when the tcgen05.commit of its MMAs has arrived.  Two CTAs per SM alternate, so the tensor pipe and the memory system stay
+// busy while either waits.  Operand views (tc_common.cuh): K-major when the source's contiguous index is the reduction index (X and W
+// in fwd, dY in dgrad), MN-major when it is the output index (W in dgrad, dY and X in wgrad) -- no transposes anywhere.  Epilogue: each
+// warp transposes its 32 x 32 accumulator patches through shared memory so that every global access (bias, accumulate, activation
+// derivative input, output) is a whole 128-byte row segment.  These GEMMs keep fp32 activations in HBM on both sides (the CUDA-core
+// path's contract), so at K <= 512 they are bound by HBM / L2 bandwidth, not by the tensor pipe: tools/gemm_tc_sweep.py prints both bounds.
 #include "common.cuh"
 #include "tc_common.cuh"
 
