@@ -143,6 +143,39 @@ __device__ __forceinline__ void store_b16(uint8_t* sT, const uint4 (&u)[ITEMS], 
 }
 __device__ __forceinline__ int ilog2_pow2(int v) { return 31 - __clz(v); }
 
+// forward epilogue rows of one 32 x 32 patch: lane = column, k = row; ACT is a compile-time constant so the loop body is straight-line.
+// ELU uses the fast exponential like the fused kernels of mlp_tc.cu (mixed-precision contract: |error| ~ 1e-7, far below the bf16
+// operand rounding); tanh stays tanhf.
+template <int ACT>
+__device__ __forceinline__ void fwd_rows(float* out, const float* sT, const float (&pre)[32], bool has_pre, float bias, int lane, int n_rows,
+                                         int ld) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k < n_rows) {
+            float x = sT[k * 33 + lane] + bias;
+            if (has_pre) x += pre[k];
+            if (ACT == B200RL_ACT_ELU) x = x > 0.f ? x : (__expf(x) - 1.0f);
+            else if (ACT == B200RL_ACT_RELU) x = x > 0.f ? x : 0.f;
+            else if (ACT == B200RL_ACT_TANH) x = tanhf(x);
+            out[(int64_t)k * ld] = x;
+        }
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ void dgrad_rows(float* out, const float* sT, const float (&pre)[32], int lane, int n_rows, int ld) {
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+        if (k < n_rows) {
+            float x = sT[k * 33 + lane];
+            if (ACT == B200RL_ACT_ELU) x *= pre[k] > 0.f ? 1.f : pre[k] + 1.f;          // derivative through the activation OUTPUT (common.cuh)
+            else if (ACT == B200RL_ACT_RELU) x = pre[k] > 0.f ? x : 0.f;
+            else if (ACT == B200RL_ACT_TANH) x *= 1.f - pre[k] * pre[k];
+            out[(int64_t)k * ld] = x;
+        }
+    }
+}
+
 enum { MODE_FWD = 0, MODE_DGRAD = 1, MODE_WGRAD = 2 };
 
 struct GemmArgs {
@@ -253,7 +286,19 @@ __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
     float* sT = reinterpret_cast<float*>(smem) + warp * (32 * 33);
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int gm0 = m0 + q * 32;
+    const int n_rows = min(32, p.Mo - gm0);
     for (int c0 = h * (BN / 2); c0 < (h + 1) * (BN / 2); c0 += 32) {
+        const int gn = n0 + c0 + lane;              // this lane's output column for the whole chunk
+        const bool col_ok = gn < p.No;
+        const int64_t o0 = (int64_t)gm0 * p.No + gn;
+        // per-element inputs of the chunk (the accumulate operand / the activation-derivative input): all 32 rows in flight before the
+        // TMEM load and the transpose, instead of one dependent global round trip per row
+        float pre[32];
+        const float* psrc = (MODE == MODE_FWD) ? (p.accumulate ? p.Y : nullptr) : (MODE == MODE_DGRAD ? p.A_prev : nullptr);
+        if (psrc) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) pre[k] = (col_ok && k < n_rows) ? __ldcg(psrc + o0 + (int64_t)k * p.No) : 0.f;
+        }
         if (n_slabs > 0) {
             uint32_t r[32];
             asm volatile(
@@ -273,31 +318,30 @@ __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
             for (int j = 0; j < 32; ++j) sT[lane * 33 + j] = 0.f;
         }
         __syncwarp();
-        const int gn = n0 + c0 + lane;              // this lane's output column for the whole chunk
-        if (gn < p.No) {
-            const int n_rows = min(32, p.Mo - gm0);
+        if (col_ok) {
             if (MODE == MODE_FWD) {
                 const float bias = p.bias ? __ldg(p.bias + gn) : 0.f;
-                float* out = p.Y + (int64_t)gm0 * p.No + gn;
-#pragma unroll 4
-                for (int k = 0; k < n_rows; ++k) {
-                    float x = sT[k * 33 + lane] + bias;
-                    if (p.accumulate) x += out[(int64_t)k * p.No];
-                    out[(int64_t)k * p.No] = act_fwd(x, p.act);
+                float* out = p.Y + o0;
+                // the activation switch is hoisted out of the row loop (one uniform branch per chunk, not per element)
+                switch (p.act) {
+                    case B200RL_ACT_ELU:  fwd_rows<B200RL_ACT_ELU>(out, sT, pre, psrc != nullptr, bias, lane, n_rows, p.No); break;
+                    case B200RL_ACT_RELU: fwd_rows<B200RL_ACT_RELU>(out, sT, pre, psrc != nullptr, bias, lane, n_rows, p.No); break;
+                    case B200RL_ACT_TANH: fwd_rows<B200RL_ACT_TANH>(out, sT, pre, psrc != nullptr, bias, lane, n_rows, p.No); break;
+                    default:              fwd_rows<B200RL_ACT_NONE>(out, sT, pre, psrc != nullptr, bias, lane, n_rows, p.No); break;
                 }
             } else if (MODE == MODE_DGRAD) {
-                float* out = p.dX + (int64_t)gm0 * p.No + gn;
-                const float* ap = p.A_prev ? p.A_prev + (int64_t)gm0 * p.No + gn : nullptr;
-#pragma unroll 4
-                for (int k = 0; k < n_rows; ++k) {
-                    float x = sT[k * 33 + lane];
-                    if (ap) x *= act_bwd_from_out(__ldg(ap + (int64_t)k * p.No), p.act_prev);
-                    out[(int64_t)k * p.No] = x;
+                float* out = p.dX + o0;
+                switch (psrc ? p.act_prev : B200RL_ACT_NONE) {
+                    case B200RL_ACT_ELU:  dgrad_rows<B200RL_ACT_ELU>(out, sT, pre, lane, n_rows, p.No); break;
+                    case B200RL_ACT_RELU: dgrad_rows<B200RL_ACT_RELU>(out, sT, pre, lane, n_rows, p.No); break;
+                    case B200RL_ACT_TANH: dgrad_rows<B200RL_ACT_TANH>(out, sT, pre, lane, n_rows, p.No); break;
+                    default:              dgrad_rows<B200RL_ACT_NONE>(out, sT, pre, lane, n_rows, p.No); break;
                 }
             } else {
-                float* out = p.dW + (int64_t)blockIdx.z * p.split_stride + (int64_t)gm0 * p.No + gn;
-#pragma unroll 4
-                for (int k = 0; k < n_rows; ++k) out[(int64_t)k * p.No] = sT[k * 33 + lane];
+                float* out = p.dW + (int64_t)blockIdx.z * p.split_stride + o0;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (k < n_rows) out[(int64_t)k * p.No] = sT[k * 33 + lane];
             }
         }
         __syncwarp();       // the patch is rewritten by the next chunk
@@ -311,6 +355,9 @@ __global__ void __launch_bounds__(GT, 2) gemm_tc_kernel(const GemmArgs p) {
 
 // Output columns per CTA: the widest tile the B operand's register staging allows (256 with a bf16 twin, 128 for fp32 sources), halved
 // while the grid would leave SMs idle (fewer than one CTA per SM) -- narrower tiles re-read the A operand from L2, idle SMs cost more.
+// a source whose chunk covers all its rows is dense: no per-row division on the device
+static inline int dense_or(int rows_per_chunk, int rows) { return rows_per_chunk >= rows ? 0 : rows_per_chunk; }
+
 static inline int pick_bn(int n_out, int m_tiles, int grid_z, int bn_cap) {
     int bn = n_out > 128 ? 256 : (n_out > 64 ? 128 : 64);
     if (bn > bn_cap) bn = bn_cap;
@@ -348,7 +395,7 @@ B200RL_EXPORT int b200rl_linear_fwd_tc(const float* X, int rows_per_chunk, int64
     if (!X || !W || !Y || M <= 0 || K <= 0 || Nout <= 0 || rows_per_chunk <= 0) return B200RL_EINVAL;
     if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200RL_EINVAL;
     GemmArgs a{};
-    a.a = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K, nullptr};
+    a.a = Src{X, x_ld, dense_or(rows_per_chunk, M), chunk_stride, norm_mean, norm_std, M, K, nullptr};
     a.b = Src{W, (int64_t)K, 0, 0, nullptr, nullptr, Nout, K, (const __nv_bfloat16*)W_bf16};
     a.Mo = M; a.No = Nout; a.R = K;
     a.bias = b; a.Y = Y; a.act = act; a.accumulate = accumulate;
@@ -374,7 +421,7 @@ B200RL_EXPORT int b200rl_linear_bwd_weight_tc(const float* dY, const float* X, i
     if ((norm_mean == nullptr) != (norm_std == nullptr)) return B200RL_EINVAL;
     GemmArgs a{};
     a.a = Src{dY, (int64_t)Nout, 0, 0, nullptr, nullptr, M, Nout, nullptr};            // [r, n]: rows = reduction r, cols = outputs n -> MN-major
-    a.b = Src{X, x_ld, rows_per_chunk, chunk_stride, norm_mean, norm_std, M, K, nullptr};   // [r, k]: rows = reduction r, cols = outputs k -> MN-major
+    a.b = Src{X, x_ld, dense_or(rows_per_chunk, M), chunk_stride, norm_mean, norm_std, M, K, nullptr};   // [r, k]: rows = reduction r, cols = outputs k -> MN-major
     a.Mo = Nout; a.No = K; a.R = M;
     a.dW = dW_part; a.db = db_part; a.split_stride = split_stride;
     int rps = (M + n_splits - 1) / n_splits;

@@ -198,6 +198,11 @@ class B200Model:
         off = 0
         for n, shp in sizes:
             numel = int(torch.Size(shp).numel())
+            # every tensor starts on an 8-element boundary (32 bytes in the fp32 arenas, 16 bytes in the bf16 twin the tensor-core GEMMs
+            # read): weight rows can then be staged with 16-byte loads whatever the action count did to the offsets.  The gaps hold
+            # zeros in every arena (weights, gradients, moments), so norms, Adam and the all-reduce are unaffected; layouts whose tensor
+            # sizes are all multiples of 8 (the BASELINE MLPs with 8 actions) have no gaps at all.
+            off = (off + 7) // 8 * 8
             self.layout[n] = (off, shp)
             off += numel
         self.num_params = off

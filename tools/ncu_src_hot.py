@@ -11,7 +11,7 @@ def main(rep, kernel_regex, skip=0, top=25):
     print(rows[0][1][:110])
     hdr = rows[1]
     si, src = hdr.index('Warp Stall Sampling (All Samples)'), hdr.index('Source')
-    data = [r for r in rows[2:] if len(r) > si]
+    data = [r for r in rows[2:] if len(r) > si and r[si].strip().isdigit()]
     tot = sum(int(r[si]) for r in data)
     print('total samples', tot, 'instructions', len(data))
     for s, i, t in sorted(((int(r[si]), i, r[src].strip()) for i, r in enumerate(data)), reverse=True)[:top]:
