@@ -732,8 +732,10 @@ B200RL_EXPORT int b200rl_allreduce_adam_f32(const void* const* peer_grads_host, 
     return B200RL_OK;
 }
 
+#ifdef B200RL_TEST_HOOKS   // test-only host entry points: compiled into tests/libb200rl_testhooks.so (csrc/build.py), not into the product library
 // host test entry point: the scheduler step of the optimiser kernels (lr_schedule_step, __host__ __device__) on HOST memory;
 // cfg->adaptive_lr selects the mode (1 per minibatch, 2 accumulate, 3 accumulate + step on the mean + reset).  Not in include/b200rl.h.
 B200RL_EXPORT double b200rl_hosttest_lr_schedule_step(double lr, double kl, const b200rl_opt_cfg* cfg_host, double* state_d) {
     return lr_schedule_step(lr, kl, make_opt_cfg(cfg_host), state_d);
 }
+#endif  // B200RL_TEST_HOOKS

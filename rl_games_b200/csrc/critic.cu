@@ -74,6 +74,7 @@ B200RL_EXPORT int b200rl_value_loss_f32(const float* values, int value_ld, const
     return B200RL_OK;
 }
 
+#ifdef B200RL_TEST_HOOKS   // test-only host entry points: compiled into tests/libb200rl_testhooks.so (csrc/build.py), not into the product library
 // host test entry point (CPU, host arrays): the same row function; not declared in include/b200rl.h, never called by the product
 B200RL_EXPORT int b200rl_hosttest_value_loss_rows(const float* values, const float* old_values_n, const float* returns_n, const float* w,
                                                  int M, float e_clip, int clip_value, float* d_value, double* loss_sum) {
@@ -103,3 +104,4 @@ B200RL_EXPORT int b200rl_hosttest_value_loss_arena(const float* values, int valu
     for (int i = 0; i < 8; ++i) partial8[i] = tot[i];
     return B200RL_OK;
 }
+#endif  // B200RL_TEST_HOOKS

@@ -304,6 +304,7 @@ B200RL_EXPORT int b200rl_categorical_loss_f32(const float* logits, int ld, int K
     return B200RL_OK;
 }
 
+#ifdef B200RL_TEST_HOOKS   // test-only host entry points: compiled into tests/libb200rl_testhooks.so (csrc/build.py), not into the product library
 // ---- host test entry points: the per-row functions above, run on the CPU over HOST arrays (no GPU involved).  Test infrastructure for
 //      tests/test_discrete_rows_cpu.py; not declared in include/b200rl.h and never called by the product. -----------------------------
 B200RL_EXPORT int b200rl_hosttest_categorical_sample_rows(const float* logits, int K, int n_heads, const int* head_sizes, const uint8_t* masks,
@@ -370,3 +371,4 @@ B200RL_EXPORT int b200rl_hosttest_categorical_loss_arena(const float* logits, in
     for (int i = 0; i < 8; ++i) partial8[i] = tot[i];
     return B200RL_OK;
 }
+#endif  // B200RL_TEST_HOOKS

@@ -2006,6 +2006,7 @@ B200RL_EXPORT int b200rl_tc_mlp_bwd(const float* obs, int rows_per_chunk, int64_
 }
 #undef B200RL_TC_DISPATCH
 
+#ifdef B200RL_TEST_HOOKS   // test-only host entry points: compiled into tests/libb200rl_testhooks.so (csrc/build.py), not into the product library
 // host test entry point (tests/test_tc_rows_cpu.py): the X-tile staging of the wide-observation kernels (stage_x_cols, __host__ __device__)
 // run thread by thread on the CPU -- out_tile receives the 128 x 256 bf16 INTERLEAVE tile (64 KB).  n_threads: 512 (l1_fwd) or 256 (l1_wgrad).
 B200RL_EXPORT int b200rl_hosttest_stage_x_cols(const float* obs, int64_t row0, int rows_valid, int D, const float* norm_mean, const float* norm_std,
@@ -2047,4 +2048,5 @@ B200RL_EXPORT int b200rl_hosttest_pack_weights_wide(const float* W1, const float
     }
     return B200RL_OK;
 }
+#endif  // B200RL_TEST_HOOKS
 #endif  // B200RL_TC_MAIN

@@ -132,8 +132,10 @@ B200RL_EXPORT int b200rl_rnn_train_dones_u8(const uint8_t* dones, const float* v
     return B200RL_OK;
 }
 
+#ifdef B200RL_TEST_HOOKS   // test-only host entry points: compiled into tests/libb200rl_testhooks.so (csrc/build.py), not into the product library
 // host test entry point (tests/test_rnn_rows_cpu.py): the element function above over HOST arrays; not in include/b200rl.h
 B200RL_EXPORT int b200rl_hosttest_rnn_train_dones(const uint8_t* dones, const float* valid, uint8_t* out, int H, int N) {
     for (int64_t i = 0; i < (int64_t)H * N; ++i) out[i] = rnn_train_done(dones, valid, i, N);
     return B200RL_OK;
 }
+#endif  // B200RL_TEST_HOOKS

@@ -1,18 +1,16 @@
 """Row arithmetic of the central-value loss kernel (csrc/critic.cu::value_loss_row, __host__ __device__) on the CPU vs autograd."""
 import ctypes
-import os
 
 import pytest
 import torch
 
 from oracle import ppo_oracle as O
-
-LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'rl_games_b200', 'libb200rl.so')
+from tests import _hooks
 
 
 @pytest.mark.parametrize('clip_value', [True, False])
 def test_value_loss_rows_match_autograd(clip_value):
-    lib = ctypes.CDLL(LIB)
+    lib = _hooks.load()
     fn = lib.b200rl_hosttest_value_loss_rows
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

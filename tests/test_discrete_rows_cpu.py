@@ -2,15 +2,13 @@
 THE CPU through the library's host test entry points and checked against the oracle (sampling rule, neglogp) and against autograd
 (loss pieces and gradients).  No GPU is involved: this validates the arithmetic the kernels execute, not their launch/indexing code."""
 import ctypes
-import os
 
 import pytest
 import torch
 
 from oracle import ppo_discrete_oracle as DO
 from oracle import ppo_oracle as O
-
-LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'rl_games_b200', 'libb200rl.so')
+from tests import _hooks
 
 
 class CatLossCfg(ctypes.Structure):
@@ -24,7 +22,7 @@ def _p(t):
 
 @pytest.fixture(scope='module')
 def lib():
-    cdll = ctypes.CDLL(LIB)
+    cdll = _hooks.load()
     cdll.b200rl_hosttest_categorical_sample_rows.restype = ctypes.c_int
     cdll.b200rl_hosttest_categorical_sample_rows.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

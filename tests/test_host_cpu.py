@@ -29,6 +29,29 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib.b200rl_loss_partial_stride() == 40
 
 
+def test_product_library_exports_exactly_the_header_and_no_test_hooks():
+    """include/b200rl.h IS the export list: nothing undeclared leaves the product library; the test-only host entry points
+    (b200rl_hosttest_*, `#ifdef B200RL_TEST_HOOKS`) live in tests/libb200rl_testhooks.so, which nothing under rl_games_b200/ loads"""
+    import subprocess
+    from rl_games_b200 import _lib
+    from tests import _hooks
+
+    def exported(path):
+        out = subprocess.run(['nm', '-D', '--defined-only', path], capture_output=True, text=True, check=True).stdout
+        return {ln.split()[-1] for ln in out.splitlines() if ' T ' in ln and ln.split()[-1].startswith('b200rl_')}
+    declared = set(_lib.parse_header())
+    assert exported(_lib.LIB_PATH) == declared
+    _hooks.load()
+    extra = exported(_hooks.HOOKS_LIB_PATH) - declared
+    assert extra and all(n.startswith('b200rl_hosttest_') for n in extra), extra
+    for root, _, files in os.walk(os.path.join(ROOT, 'rl_games_b200')):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(root, f)).read()
+                if f != 'build.py':      # only the build script names the test library
+                    assert 'testhooks' not in src and 'hosttest' not in src, f
+
+
 def test_header_prototypes_parse_types():
     from rl_games_b200 import _lib
     p = _lib.parse_header()

@@ -4,11 +4,11 @@ import ctypes
 
 import torch
 
-from rl_games_b200._lib import LIB_PATH
+from tests import _hooks
 
 
 def test_rnn_train_dones_rows_match_reference_expression():
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = _hooks.load()
     g = torch.Generator().manual_seed(0)
     for H, N in ((1, 7), (8, 5), (16, 33)):
         dones = (torch.rand(H, N, generator=g) < 0.3).to(torch.uint8)

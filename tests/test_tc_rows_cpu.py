@@ -6,7 +6,7 @@ import ctypes
 import pytest
 import torch
 
-from rl_games_b200._lib import LIB_PATH
+from tests import _hooks
 
 
 def _decode(tile_u8, C=256):
@@ -20,7 +20,7 @@ def _decode(tile_u8, C=256):
 @pytest.mark.parametrize('D,rows_valid,norm', [(256, 128, True), (105, 128, True), (65, 77, True), (200, 1, False), (256, 128, False),
                                                (72, 128, True)])
 def test_stage_x_cols_builds_the_operand_tile(D, rows_valid, norm, n_threads):
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = _hooks.load()
     g = torch.Generator().manual_seed(D * 1000 + rows_valid)
     row0 = 3
     obs = (torch.randn(row0 + 128, D, generator=g) * 3 + 0.5).contiguous()
@@ -43,7 +43,7 @@ def test_packed_weight_layout_of_the_wide_net():
     """one packed bf16 copy of all weights; W1 is [256 x 256] (observation columns >= D zero), W2 [128 x 256], W3 [64 x 128], heads [16 x 64]
     (rows > A zero); a weight tile [R x C] keeps chunk (r, cg) at cg * (R / 8) * 128 + (r // 8) * 128 + (r % 8) * 16"""
     from rl_games_b200 import ops
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = _hooks.load()
     D, A = 105, 8
     assert ops.tc_kind(D, [256, 128, 64], A) == 2 and ops.tc_kind(60, [256, 128, 64], A) == 1 and ops.tc_kind(300, [256, 128, 64], A) == 0
     g = torch.Generator().manual_seed(1)
