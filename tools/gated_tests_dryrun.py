@@ -58,7 +58,7 @@ class _Any:
     def __eq__(self, o): return True
     def __req__(self, o): return True
 pytest.approx = lambda *a, **k: _Any()
-mods = ['test_agent_gpu', 'test_kernels_gpu', 'test_mlp_tc_gpu', 'test_tc_faithful_gpu', 'test_gemm_tc_gpu', 'test_discrete_gpu', 'test_cv_gpu', 'test_tc_gpu']
+mods = ['test_agent_gpu', 'test_kernels_gpu', 'test_mlp_tc_gpu', 'test_tc_faithful_gpu', 'test_gemm_tc_gpu', 'test_discrete_gpu', 'test_cv_gpu', 'test_tc_gpu', 'test_zz_env_adapters_gpu']
 # tests that need a real device object even to get going (CUDA generator, IPC allocation): nothing to learn from them here
 NEEDS_DEVICE = {'test_fused_allreduce_adam_world1_matches_adam_step', 'test_gae_full_size_properties'}
 bad = 0
