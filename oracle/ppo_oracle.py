@@ -434,8 +434,9 @@ class OracleModel:
     """ModelA2CContinuousLogStd.Network (models.py:304-364) + BaseModelNetwork (:38-63)."""
 
     def __init__(self, params, obs_dim, units, act_dim, normalize_input=True, normalize_value=True,
-                 activation='elu', value_size=1, matmul_dtype=None, rnn_units=0, rnn_before_mlp=True):
+                 activation='elu', value_size=1, matmul_dtype=None, rnn_units=0, rnn_before_mlp=True, min_sigma=0.0):
         self.p = {k: v.clone().float().requires_grad_(True) for k, v in params.items()}
+        self.min_sigma = float(min_sigma)      # 'exp' sigma parametrisation with a floor (models.py:272-300, network_builder.py:312)
         self.rnn_units = rnn_units
         self.rnn_before_mlp = rnn_before_mlp
         self.names = param_names(len(units), lstm=rnn_units > 0)
@@ -481,6 +482,9 @@ class OracleModel:
         self.last_rnn_states = new_states
         mu, logstd, value = mu.float(), logstd.float(), value.float()
         sigma = torch.exp(logstd)
+        if self.min_sigma > 0:                 # models.py:296-300: the floor is ADDED, and the log-std is recomputed from the final sigma
+            sigma = sigma + self.min_sigma
+            logstd = torch.log(sigma)
         if is_train:
             entropy = (0.5 + 0.5 * math.log(2 * math.pi) + torch.log(sigma)).sum(dim=-1)
             prev_neglogp = neglogp_fn(prev_actions, mu, sigma, logstd)
@@ -573,7 +577,7 @@ DEFAULT_CFG = dict(
     mini_epochs=4, weight_decay=0.0, ppo=True, reward_scale=1.0, reward_shift=0.0, reward_min=-float('inf'), reward_max=float('inf'),
     reward_log=False, max_epochs=-1, max_frames=-1, schedule_entropy=False, actions_low=-1.0, actions_high=1.0, seq_length=4, rnn_units=0, zero_rnn_on_done=True,
     games_to_track=100, activation='elu', clip_actions=True, mask_autoreset_rows=False,
-    normalize_rms_advantage=False, adv_rms_momentum=0.5,
+    normalize_rms_advantage=False, adv_rms_momentum=0.5, min_sigma=0.0,
 )
 
 
@@ -700,7 +704,7 @@ class OracleAgent:
         self.num_minibatches = self.batch_size // minibatch_size
         self.model = OracleModel(params, obs_dim, units, act_dim, c['normalize_input'], c['normalize_value'],
                                  c['activation'], matmul_dtype=matmul_dtype, rnn_units=c['rnn_units'],
-                                 rnn_before_mlp=c.get('rnn_before_mlp', True))
+                                 rnn_before_mlp=c.get('rnn_before_mlp', True), min_sigma=c.get('min_sigma', 0.0))
         self.is_rnn = c['rnn_units'] > 0
         self.seq_length = c['seq_length']
         self.last_lr = float(c['learning_rate'])

@@ -162,7 +162,8 @@ class A2CAgent(CompileTolerantModel):
             raise NotImplementedError('action masks are a discrete-PPO feature')
         self.has_central_value = config.get('central_value_config') is not None
         if self.has_central_value:
-            raise NotImplementedError('central_value_config is not on the B200 hot path yet (SURVEY 8f)')
+            raise NotImplementedError('central_value_config is served by rl_games_b200.agent_cv.A2CAgentCV: build the agent through '
+                                      'rl_games_b200.register(runner) / rl_games_b200.runner.continuous_agent, which pick it')
         self.central_value_net = None
         self.truncate_grads = config.get('truncate_grads', False)
         self.save_freq = config.get('save_frequency', 0)
@@ -296,7 +297,9 @@ class A2CAgent(CompileTolerantModel):
         # zero-padded), elu / relu / tanh, obs <= 256, <= 15 actions; anything else runs on the fp32 kernels
         tc_ok = self.model.activation in ('elu', 'relu', 'tanh') and \
             ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
-        fused_ok = tc_ok and not self.is_rnn
+        # (a sigma floor -- min_sigma > 0 -- is applied outside the kernels on the log-std vector they read; the fused kernels take the raw
+        #  parameter from the packed arena, so such policies run layer by layer)
+        fused_ok = tc_ok and not self.is_rnn and getattr(self.model, 'min_sigma', 0.0) == 0
         if self.mixed_precision is None:
             self.mixed_precision = fused_ok
             if not self.mixed_precision and self.global_rank == 0:
@@ -714,7 +717,7 @@ class A2CAgent(CompileTolerantModel):
         a_last = self.ra[-1]
         if self.is_rnn and not m.rnn_before_mlp:
             a_last = self._lstm_step(a_last, self.rnn_h, self.rnn_c, self.rnn_h, self.rnn_c)
-        ops.policy_head_sample(a_last, m.W_head, m.b_head, m.sigma, m.value_mean_std.running_mean,
+        ops.policy_head_sample(a_last, m.W_head, m.b_head, m.logstd_in, m.value_mean_std.running_mean,
                                m.value_mean_std.running_var, self.normalize_value, noise, self.rng_seed, self.rng_epoch, t,
                                self.actions[t], self.mus[t], self.sigmas[t], self.neglogpacs[t], self.values[t],
                                self.env_actions, self.clip_actions, self.actions_low, self.actions_high,
@@ -759,6 +762,7 @@ class A2CAgent(CompileTolerantModel):
         wants_infos = getattr(self.algo_observer, 'wants_infos', False)
         if hasattr(self.vec_env, 'begin_rollout'):
             self.vec_env.begin_rollout()
+        self.model.refresh_sigma_floor()          # weights may have been loaded since the last update (no-op unless min_sigma > 0)
         for t in range(H):
             obs = self.obs['obs']
             self.obses[t].copy_(obs)
@@ -888,13 +892,15 @@ class A2CAgent(CompileTolerantModel):
             a_last, d_alast, act_last = self.t_hmlp, self.t_dHmlp, 0
         else:
             a_last, d_alast, act_last = self.ta[-1], self.dA[-1], m.act_id
-        nb = ops.ppo_head_loss(a_last, m.W_head, m.b_head, m.sigma, self.actions[0, e0:], self.mus[0, e0:],
+        nb = ops.ppo_head_loss(a_last, m.W_head, m.b_head, m.logstd_in, self.actions[0, e0:], self.mus[0, e0:],
                                self.sigmas[0, e0:], self.old_values_n[0, e0:], self.returns_n[0, e0:], self.neglogpacs[0, e0:],
                                self.advs_n[0, e0:], None if self.valid is None else self.valid[0, e0:], epm, N, mb, A,
                                self.loss_cfg, None if self.inv_counts is None else self.inv_counts[i:i + 1], self.d_head,
                                d_alast, act_last, self.loss_partials)
         gv = self._gv[u & 1]
         ops.ppo_loss_finalize(self.loss_partials, nb, A, self.entropy_coef_dev, self.stats[u], gv['g_sigma'], gv['kl'])
+        if m.min_sigma > 0:      # the kernels differentiated with respect to log(exp(raw) + min_sigma): chain to the raw parameter
+            gv['g_sigma'].mul_(m.sigma_chain)
         P = m.num_params
         # row splits of the head / MLP weight gradients.  A recurrent policy's partial arena has seq_length x n_splits rows (one group per
         # BPTT step, _lstm_window_bwd); the layers outside the window may spread over all of them: more CTAs per GEMM, same reduction
@@ -925,6 +931,7 @@ class A2CAgent(CompileTolerantModel):
                                       split_stride=P)
         ops.reduce_splits(self.part[0, A:], gv['grad'][A:], P - A, self.part_rows, split_stride=P)
         self._step_optimizer(u, gv, P)
+        m.refresh_sigma_floor()          # no-op unless min_sigma > 0
 
     def _lstm_window_fwd(self, e0):
         """Training forward of the LSTM over the seq_length window of every sequence of the minibatch (network_builder.py:452-492,
@@ -1418,7 +1425,8 @@ class A2CAgent(CompileTolerantModel):
         self.set_full_state_weights(checkpoint, set_epoch=set_epoch)
 
     def restore_central_value_function(self, fn):
-        raise NotImplementedError('central value is not on the B200 hot path yet')
+        # the reference's Runner refuses this before it gets here (torch_runner.py:45-46)
+        raise ValueError('Loading critic only works only for asymmetric actor critic')
 
     def get_param(self, param_name):
         if param_name in ['grad_norm', 'critic_coef', 'bounds_loss_coef', 'entropy_coef', 'kl_threshold', 'gamma', 'tau',

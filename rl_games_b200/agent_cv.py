@@ -30,6 +30,23 @@ from .model import _RunningStats, check_network_params
 class CentralValueNet:
     """CentralValueTrain on the fp32 kernels: flat arena [W0 b0 ... W_v b_v] in the reference's parameter order."""
 
+    # `CentralValueTrain.model` (central_value.py:44): the reference's Runner wraps it with torch.compile unless the YAML says
+    # `torch_compile: False` (torch_runner.py:308-313).  Here the net IS its model and there is no nn.Module to compile: reading `.model`
+    # gives the net, assigning anything else to it is ignored with a note (like CompileTolerantModel does for `agent.model`).
+    @property
+    def model(self):
+        return self
+
+    @model.setter
+    def model(self, m):
+        if m is not self and not self.__dict__.get('_b200_compile_noted'):
+            print('b200: torch.compile of central_value_net.model ignored (no nn.Module on this path; set torch_compile: False to silence)')
+            self.__dict__['_b200_compile_noted'] = True
+
+    def __call__(self, *args, **kwargs):
+        raise NotImplementedError('the central value net is a flat parameter arena driven by kernels (get_value / train_net); '
+                                  'it has no module-style forward')
+
     def __init__(self, cv_config, state_dim, num_actors, horizon, normalize_value, max_epochs, device, multi_gpu=False, world_size=1):
         net = cv_config['network']
         self.multi_gpu, self.world_size = bool(multi_gpu) and world_size > 1, int(world_size)
@@ -304,6 +321,16 @@ class A2CAgentCV(A2CAgent):
         state['assymetric_vf_optimizer'] = {'state': st, 'param_groups': [{'lr': cv.lr, 'betas': (0.9, 0.999), 'eps': 1e-08,
                                                                           'weight_decay': cv.weight_decay, 'params': list(range(len(st)))}]}
         return state
+
+    def restore_central_value_function(self, fn):
+        """a2c_continuous.py:90-92: the critic's weights and normalisers only (`load_critic_only` of the Runner, torch_runner.py:43-50)"""
+        checkpoint = torch.load(fn, map_location=self.device_t, weights_only=False)
+        self.set_central_value_function_weights(checkpoint)
+
+    def set_central_value_function_weights(self, weights):
+        """a2c_common.py:885-887"""
+        self.central_value_net.load_state_dict(weights['assymetric_vf_nets'])
+        self._seed_stats_sync_snapshots()
 
     def set_full_state_weights(self, weights, set_epoch=True):
         super().set_full_state_weights(weights, set_epoch=set_epoch)

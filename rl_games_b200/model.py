@@ -42,6 +42,18 @@ def _apply_init(t, spec, fan_in):
         torch.nn.init.uniform_(t, **kw)
     elif name == 'kaiming_normal':
         torch.nn.init.kaiming_normal_(t, **kw)
+    elif name == 'variance_scaling_initializer':
+        # torch_ext.py:114-144 (configs/mujoco/halfcheetah*.yaml): N(0, scale / fan) by inverse CDF of uniforms drawn from NUMPY's global
+        # generator (the one the runner seeds), restricted to [-2, 2] in ABSOLUTE units -- not in sigmas -- and clamped there
+        import numpy as np
+        sigma = math.sqrt(kw.get('scale', 2.0) / torch.nn.init._calculate_correct_fan(t, kw.get('mode', 'fan_in')))
+        u = torch.from_numpy(np.random.uniform(0, 1, tuple(t.shape)))
+        std_normal = torch.distributions.Normal(0.0, 1.0, validate_args=False)
+        lo = std_normal.cdf(torch.tensor(-2.0 / sigma, dtype=torch.float64))
+        hi = std_normal.cdf(torch.tensor(2.0 / sigma, dtype=torch.float64))
+        eps = torch.finfo(torch.float64).eps
+        z = (2.0 * (lo + (hi - lo) * u) - 1.0).clamp(-1.0 + eps, 1.0 - eps)
+        t.copy_((sigma * math.sqrt(2.0) * torch.erfinv(z)).clamp(-2.0, 2.0))
     else:
         raise ValueError(f'unsupported initializer {name}')
 
@@ -173,8 +185,10 @@ class B200Model:
         for k in ('mu_activation', 'sigma_activation'):
             if space.get(k, 'None') not in ('None', None):
                 raise NotImplementedError(f'{k}={space[k]}')
-        if space.get('sigma_parametrization', 'exp') != 'exp' or space.get('logstd_bounds') or float(space.get('min_sigma', 0)) > 0:
-            raise NotImplementedError("only the plain 'exp' sigma parametrisation is on the B200 hot path")
+        if space.get('sigma_parametrization', 'exp') != 'exp' or space.get('logstd_bounds'):
+            raise NotImplementedError("only the 'exp' sigma parametrisation (optionally floored by min_sigma) is on the B200 hot path")
+        # models.py:272-300, 'exp' branch with a floor (configs/mjlab/ppo_lift_cube_yam.yaml: min_sigma 0.15): sigma = exp(raw) + min_sigma
+        self.min_sigma = float(space.get('min_sigma', 0.0) or 0.0)
         if network_params.get('value_activation', 'None') not in ('None', None):
             raise NotImplementedError('value_activation')
         self.D, self.A = int(obs_dim), int(act_dim)
@@ -213,6 +227,10 @@ class B200Model:
         self.W = [self.view(f'W{i}') for i in range(len(self.units))]
         self.b = [self.view(f'b{i}') for i in range(len(self.units))]
         self.sigma = self.view('sigma')
+        if self.min_sigma > 0:
+            # what the kernels are handed instead of the raw parameter, and the chain factor of its gradient (refresh_sigma_floor)
+            self.logstd_eff = torch.zeros(self.A, dtype=torch.float32, device=self.device)
+            self.sigma_chain = torch.ones(self.A, dtype=torch.float32, device=self.device)
         if self.rnn_units:
             self.W_ih, self.W_hh, self.b_ih, self.b_hh = (self.view(n) for n in ('W_ih', 'W_hh', 'b_ih', 'b_hh'))
         self.mlp_in = self.rnn_units if (self.rnn_units and self.rnn_before_mlp) else self.D
@@ -228,6 +246,24 @@ class B200Model:
         self.training = False
 
     # -------------------------------------------------------------------------------------------
+    @property
+    def logstd_in(self):
+        """The log-std vector the policy kernels read.  They compute sigma = exp(logstd) -- with a floor (min_sigma > 0) that is the
+        EFFECTIVE log-std log(exp(raw) + min_sigma) (models.py:296-300: `sigma + min_sigma`, `logstd = log(sigma)`), kept in its own
+        buffer by refresh_sigma_floor(); without a floor it is the parameter itself."""
+        return self.logstd_eff if self.min_sigma > 0 else self.sigma
+
+    def refresh_sigma_floor(self):
+        """After anything that changes the raw sigma parameter (optimiser step, weight load): logstd_eff = log(e^raw + min_sigma) and
+        sigma_chain = d logstd_eff / d raw = e^raw / (e^raw + min_sigma), the factor that turns the kernels' gradient with respect to
+        the log-std they were handed into the gradient of the raw parameter.  Three in-place launches on [A] vectors, no allocation
+        (CUDA-graph capturable); a no-op without a floor."""
+        if self.min_sigma > 0:
+            torch.exp(self.sigma, out=self.sigma_chain)
+            torch.add(self.sigma_chain, self.min_sigma, out=self.logstd_eff)
+            self.sigma_chain.div_(self.logstd_eff)
+            self.logstd_eff.log_()
+
     def view(self, name, arena=None):
         off, shp = self.layout[name]
         arena = self.flat if arena is None else arena

@@ -6,8 +6,8 @@ injection), ``.run(args)`` / ``.run_train(args)`` (create -> restore -> override
 rl_games YAML (``params: {seed, algo, model, network, config}``) runs unchanged with the B200 agent
 registered under the reference's algo name ``a2c_continuous``.
 
-When rl_games itself is importable, register the agent into ITS runner instead:
-    runner.algo_factory.register_builder('a2c_continuous', lambda **kw: rl_games_b200.agent.A2CAgent(**kw))
+When rl_games itself is importable, register the agents into ITS runner instead:
+    rl_games_b200.register(runner)      # = runner.algo_factory.register_builder('a2c_continuous' / 'a2c_discrete', ...)
 """
 import os
 import random
@@ -26,6 +26,11 @@ from . import env_adapters  # noqa: F401  (registers vecenv type MJLAB)
 def _restore(agent, args):
     """torch_runner.py:43-50"""
     if args.get('checkpoint'):
+        if args.get('train', True) and args.get('load_critic_only', False):
+            if not getattr(agent, 'has_central_value', False):
+                raise ValueError('Loading critic only works only for asymmetric actor critic')
+            agent.restore_central_value_function(args['checkpoint'])
+            return
         agent.restore(args['checkpoint'])
 
 
@@ -41,24 +46,37 @@ def _override_sigma(agent, args):
                 print('Cannot set new sigma because fixed_sigma is False')
 
 
-def _continuous_agent(**kwargs):
-    """central_value_config selects the (not yet hardware-validated, opt-in) asymmetric-critic subclass; everything else is A2CAgent"""
+def continuous_agent(**kwargs):
+    """Builder for the algo name `a2c_continuous` (a2c_continuous.py:18): `central_value_config` in the YAML selects the
+    asymmetric-critic subclass (the reference's A2CAgent builds its CentralValueTrain itself, a2c_common.py:250-262); everything else
+    is A2CAgent"""
     if kwargs.get('params', {}).get('config', {}).get('central_value_config') is not None:
         from .agent_cv import A2CAgentCV
         return A2CAgentCV(**kwargs)
     return A2CAgent(**kwargs)
 
 
-def _discrete_agent(**kwargs):
+def discrete_agent(**kwargs):
+    """Builder for the algo name `a2c_discrete` (a2c_discrete.py:15)"""
     from .agent_discrete import DiscreteA2CAgent
     return DiscreteA2CAgent(**kwargs)
+
+
+_continuous_agent, _discrete_agent = continuous_agent, discrete_agent
+
+
+def register(runner):
+    """Put the B200 agents behind the reference's algo names in ANY runner with an `algo_factory` ObjectFactory -- the reference's own
+    `rl_games.torch_runner.Runner` (torch_runner.py:117-120) or this module's mirror -- so that stock YAMLs run unchanged."""
+    runner.algo_factory.register_builder('a2c_continuous', lambda **kwargs: continuous_agent(**kwargs))
+    runner.algo_factory.register_builder('a2c_discrete', lambda **kwargs: discrete_agent(**kwargs))
+    return runner
 
 
 class Runner:
     def __init__(self, algo_observer=None):
         self.algo_factory = ObjectFactory()
-        self.algo_factory.register_builder('a2c_continuous', lambda **kwargs: _continuous_agent(**kwargs))
-        self.algo_factory.register_builder('a2c_discrete', lambda **kwargs: _discrete_agent(**kwargs))
+        register(self)
         self.player_factory = ObjectFactory()
         self._observer_was_injected = algo_observer is not None
         self.algo_observer = algo_observer if algo_observer else DefaultAlgoObserver()

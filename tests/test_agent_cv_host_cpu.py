@@ -130,3 +130,28 @@ def test_central_value_agent_host_logic_matches_reference_golden(host_kernels, m
     assert [k for k in ck['assymetric_vf_nets'] if 'a2c_network' in k] == ['model.' + k for k in g['cv_param_order']]
     for i, mref in enumerate(g['epochs_out'][-1]['cv_adam_exp_avg']):
         torch.testing.assert_close(ck['assymetric_vf_optimizer']['state'][i]['exp_avg'].reshape(mref.shape), mref, rtol=1e-3, atol=1e-7)
+
+
+def test_load_critic_only_restores_the_critic_and_leaves_the_actor(monkeypatch, tmp_path):
+    """torch_runner.py:43-50 `load_critic_only` -> a2c_continuous.py:90-92 restore_central_value_function -> a2c_common.py:885-887: the
+    critic's weights / normalisers come from the checkpoint, the actor and both optimisers are untouched; an agent without a central value
+    refuses like the reference's Runner does"""
+    from rl_games_b200 import runner as R
+    g = torch.load(os.path.join(GOLDEN, 'agent_cv.pt'), weights_only=False)
+    a = _build_cv(monkeypatch, tmp_path, g)
+    flat_noise = g['noise'].reshape(-1, g['N'], g['A'])
+    a.epoch_num += 1
+    a.train_epoch(noise=flat_noise[:g['H']])
+    a.save(str(tmp_path / 'ck'))
+    b = _build_cv(monkeypatch, tmp_path, g)
+    actor0, exp0 = b.model.flat.clone(), b.central_value_net.exp_avg.clone()
+    assert not torch.equal(b.central_value_net.flat, a.central_value_net.flat)
+    R._restore(b, {'train': True, 'checkpoint': str(tmp_path / 'ck.pth'), 'load_critic_only': True})
+    for k, v in a.central_value_net.state_dict().items():
+        assert torch.equal(b.central_value_net.state_dict()[k], v), k
+    assert torch.equal(b.model.flat, actor0) and torch.equal(b.central_value_net.exp_avg, exp0) and b.epoch_num == 0
+    R._restore(b, {'train': True, 'checkpoint': str(tmp_path / 'ck.pth')})          # the full restore still works on the same file
+    assert torch.equal(b.model.flat, a.model.flat) and b.epoch_num == a.epoch_num
+    plain = type('A', (), {'has_central_value': False})()
+    with pytest.raises(ValueError, match='asymmetric actor critic'):
+        R._restore(plain, {'train': True, 'checkpoint': 'x.pth', 'load_critic_only': True})

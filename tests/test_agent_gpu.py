@@ -51,12 +51,13 @@ class TapeEnvGPU:
         pass
 
 
-def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0, rnn_before_mlp=True, activation='elu'):
+def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0, rnn_before_mlp=True, activation='elu', space_over=None):
     from rl_games_b200.runner import Runner
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': list(units), 'activation': activation, 'initializer': {'name': 'default'}}}
+    network['space']['continuous'].update(space_over or {})          # e.g. min_sigma (agent_minsigma.pt)
     if rnn_units:
         network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': rnn_before_mlp}
     config = {'name': 'gpu_parity', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0}, 'device': DEV,
@@ -128,12 +129,15 @@ def test_standard_schedule_agent_matches_reference_golden(graph):
     _golden_run('agent_sched_standard.pt', graph, {})
 
 
-@pytest.mark.parametrize('name', ['agent_misc.pt', 'agent_rescale.pt'])
+@pytest.mark.parametrize('name', ['agent_misc.pt', 'agent_rescale.pt', 'agent_minsigma.pt'])
 @pytest.mark.parametrize('graph', [False, True])
 def test_agent_matches_reference_golden_more_config_keys(name, graph):
     """agent_misc.pt: linear LR + entropy schedule (first minibatch of an epoch on the previous epoch's value), all normalisers off,
     full reward shaper, unclipped actions into a non-unit box; agent_rescale.pt: ppo: False, clip + rescale into that box, masked
-    rows, bound loss.  Validated kernels, flag combinations no other GPU test sets."""
+    rows, bound loss; agent_minsigma.pt: the sigma floor of the 'exp' parametrisation (models.py:296-300; configs/mjlab/ppo_lift_cube_yam.yaml):
+    the kernels read log(exp(raw) + min_sigma) and their log-std gradient is chained to the raw parameter, with an entropy bonus (whose
+    gradient reaches only sigma), hard clip, bound loss, unclipped actions, masked rows.  Validated kernels, flag combinations no other
+    GPU test sets."""
     _golden_run(name, graph)
 
 
@@ -162,7 +166,7 @@ def _golden_run(name, graph, extra=None):
     env = TapeEnvGPU(g['obs_tape'], g['done_tape'], g['timeout_tape'], g['A'], g['autoreset'], g.get('act_bounds', (-1.0, 1.0)))
     lstm = g.get('rnn_units', 0) > 0
     agent = make_agent(over, g['N'], g['H'], g['D'], g['A'], g['units'], g['mb'], env, g['init_state'], rnn_units=g.get('rnn_units', 0),
-                       rnn_before_mlp=bool(g.get('rnn_before_mlp', True)))
+                       rnn_before_mlp=bool(g.get('rnn_before_mlp', True)), space_over=g.get('space_over'))
     for ep, ref in enumerate(g['epochs_out']):
         agent.epoch_num += 1
         agent.train_epoch(noise=g['noise'][ep].to(DEV))

@@ -74,7 +74,8 @@ class _Env:
 @pytest.mark.parametrize('name,tc', [('agent_base.pt', False), ('agent_masked.pt', False), ('agent_hardclip.pt', False), ('agent_rmsadv.pt', False),
                                      ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_tcshape.pt', 2), ('agent_lstm.pt', False),
                                      ('agent_lstm_after.pt', False), ('agent_sched_standard.pt', False), ('agent_misc.pt', False),
-                                     ('agent_rescale.pt', False), ('agent_lstm_masked.pt', False), ('agent_lstm_after_masked.pt', False)])
+                                     ('agent_rescale.pt', False), ('agent_lstm_masked.pt', False), ('agent_lstm_after_masked.pt', False),
+                                     ('agent_minsigma.pt', False)])
 def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
     """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
     stride, fused reduce+Adam tail, per-minibatch obs moments merged by the optimiser tail) with fp32 stand-ins for its kernels"""
@@ -102,6 +103,7 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    network['space']['continuous'].update(g.get('space_over') or {})          # min_sigma (agent_minsigma.pt)
     lstm = g.get('rnn_units', 0) > 0
     if lstm:
         network['rnn'] = {'name': 'lstm', 'units': g['rnn_units'], 'layers': 1, 'before_mlp': bool(g.get('rnn_before_mlp', True))}
@@ -111,6 +113,7 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
     r.params['config']['vec_env'] = env
     agent = r.algo_factory.create(r.algo_name, base_name='parity', params=r.params)
     assert agent.use_tc == bool(tc) and getattr(agent, 'tc_wide', False) == (tc == 2)
+    assert agent.model.min_sigma == (g.get('space_over') or {}).get('min_sigma', 0.0)
     agent.model.load_state_dict(g['init_state'], strict=False)
     agent.init_tensors()
     agent._repack()
@@ -164,6 +167,7 @@ def _build(monkeypatch, tmp_path, g, env, tc=False, over=None):
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
+    network['space']['continuous'].update(g.get('space_over') or {})
     r = Runner()
     r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
                        'config': config}})
@@ -332,6 +336,13 @@ def test_mixed_precision_auto_resolves_by_geometry_and_explicit_true_never_downg
     _torch_ops.install_tc(monkeypatch)          # its tc_supported stand-in accepts the fixture's small three-layer geometry
     b = _build(monkeypatch, tmp_path, g2, _Env(g2), tc=True, over={'mixed_precision': None})
     assert b.use_tc is True and b.mixed_precision is True
+    # a sigma floor is applied on the log-std vector handed to the kernels; the fused kernels read the raw parameter from the packed arena,
+    # so a floored policy on a fused geometry is served layer by layer (mixed_precision: True) / by the fp32 kernels (absent key)
+    g3 = dict(g2, space_over={'min_sigma': 0.15})
+    d = _build(monkeypatch, tmp_path, g3, _Env(g3), tc=True, over={'mixed_precision': True})
+    assert d.model.min_sigma == 0.15 and d.use_tc is False and d.gemm_tc is True
+    e = _build(monkeypatch, tmp_path, g3, _Env(g3), tc=True, over={'mixed_precision': None})
+    assert e.use_tc is False and e.gemm_tc is False and e.mixed_precision is False
 
 
 @pytest.mark.parametrize('name', ['agent_trainloop.pt', 'agent_trainloop_adaptive.pt'])

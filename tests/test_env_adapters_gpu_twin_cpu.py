@@ -1,4 +1,4 @@
-"""The bodies of the `-m gpu` adapter tests (tests/test_zz_env_adapters_gpu.py) executed on the CPU with the torch stand-ins of every C-ABI
+"""The bodies of the newest `-m gpu` tests (tests/test_zz_env_adapters_gpu.py, the min_sigma golden run of tests/test_agent_gpu.py) executed on the CPU with the torch stand-ins of every C-ABI
 op (tests/_torch_ops.py), golden assertions ACTIVE: the test code, the adapter / observer host path and the expected values are checked
 against the reference's golden runs before a GPU box is spent on them.  Says nothing about the kernels (the GPU run does)."""
 import sys
@@ -34,3 +34,9 @@ def test_adapter_and_observer_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
 
 def test_critic_group_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
     cpu_twin.test_critic_group_feeds_the_central_value_net_like_the_reference_golden_run(False)
+
+
+def test_min_sigma_golden_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
+    import tests.test_agent_gpu as G
+    G.test_agent_matches_reference_golden_more_config_keys('agent_minsigma.pt', False)
+    G.test_agent_matches_reference_golden_more_config_keys('agent_misc.pt', False)        # the unchanged path through the same helper

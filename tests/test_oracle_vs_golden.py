@@ -113,6 +113,7 @@ def _oracle_from_golden(g):
     cfg['rnn_units'] = g.get('rnn_units', 0)
     cfg['rnn_before_mlp'] = g.get('rnn_before_mlp', True)
     cfg['seq_length'] = cfgk.get('seq_length', 4)
+    cfg['min_sigma'] = (g.get('space_over') or {}).get('min_sigma', 0.0)
     env = O.TapeEnv(g['obs_tape'], g['done_tape'], g['timeout_tape'])
     params = {k: v for k, v in g['init_state'].items() if k.startswith('a2c_network')}
     ag = O.OracleAgent(env, params, g['D'], g['A'], g['units'], g['N'], g['H'], g['mb'], cfg)
@@ -122,7 +123,7 @@ def _oracle_from_golden(g):
 
 @pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt',
                                   'agent_lstm_after.pt', 'agent_sched_standard.pt', 'agent_misc.pt', 'agent_rescale.pt', 'agent_lstm_masked.pt',
-                                  'agent_lstm_after_masked.pt', 'agent_trainloop.pt', 'agent_trainloop_adaptive.pt'])
+                                  'agent_lstm_after_masked.pt', 'agent_trainloop.pt', 'agent_trainloop_adaptive.pt', 'agent_minsigma.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
