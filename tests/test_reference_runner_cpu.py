@@ -112,21 +112,51 @@ def test_stock_yaml_trains_through_the_reference_runner(obs_dim, monkeypatch, tm
 
 
 # ---------------------------------------------------------------------------------------------------------------- every shipped PPO YAML
+# Families whose PPO configs are single-agent, flat-observation tasks (the path this repo builds); atari / minigrid (CNN), smac / ma
+# (multi-agent, self-play) are outside it by construction and are not listed.
+_FAMILIES = ('.', 'dm_control', 'maniskill', 'mujoco', 'mjlab', 'pufferlib', 'test')
 _DIMS = {'ant': (105, 8), 'halfcheetah': (17, 6), 'hopper': (11, 3), 'humanoid': (348, 17), 'walker2d': (17, 6)}       # Gymnasium v5 obs / act
-# ppo_wujihand_reorient.yaml: state-dependent sigma (fixed_sigma: false, softplus parametrisation) and a minibatch (16384) that is not a whole
-# number of envs' horizons (40) -- both outside the built path
-_REFUSED = {'ppo_wujihand_reorient.yaml': 'minibatch_size must be a multiple of horizon_length|state-dependent sigma'}
-_MJLAB_DIMS = (48, 63, 12)          # policy group, critic group, actions (any manager-based task: the YAMLs do not fix them)
+_GENERIC_DIMS = (24, 6)             # the other tasks' YAMLs do not fix the env's dimensions
+_CV_STATE_DIM = 30
+# What is NOT built raises NotImplementedError at construction -- never a silent reinterpretation.  file -> the reason it gives:
+_REFUSED = {
+    'carracing_ppo.yaml': "'cnn' networks", 'maniskill/ppo_pick_cube_rgbd_NOT_WORKING_YET.yaml': "'cnn' networks",
+    'ppo_cartpole_masked_velocity_rnn.yaml': "'rnn' networks are not supported by the discrete", 'test/test_rnn.yaml': "'rnn' networks are not supported by the discrete",
+    'test/test_rnn_multidiscrete_mhv.yaml': "'rnn' networks are not supported by the discrete",
+    'ppo_continuous.yaml': 'separate actor/critic trunks', 'ppo_lunar.yaml': 'separate actor/critic trunks',
+    'ppo_lunar_continiuos_torch.yaml': 'separate actor/critic trunks', 'ppo_pendulum.yaml': 'separate actor/critic trunks',
+    'ppo_pendulum_torch.yaml': 'separate actor/critic trunks', 'ppo_reacher.yaml': 'separate actor/critic trunks',
+    'test/test_asymmetric_continuous.yaml': 'separate actor/critic trunks|rnn: only a single-layer',
+    'ppo_continuous_lstm.yaml': "model 'continuous_a2c_lstm_logstd'", 'ppo_walker_rnn.yaml': "rnn: only a single-layer 'lstm'",
+    'ppo_walker_tcnn.yaml': "network 'tcnnnet'", 'test/test_discrite_testnet_aux_loss.yaml': "network 'testnet_aux_loss'",
+    'test/test_asymmetric_discrete.yaml': 'central_value_config|rnn', 'test/test_asymmetric_discrete_mhv.yaml': 'central_value_config',
+    'test/test_asymmetric_discrete_mhv_mops.yaml': 'central_value_config|testnet', 'test/test_rnn_multidiscrete.yaml': 'central_value_config',
+    # state-dependent sigma (fixed_sigma: false, softplus) and a minibatch (16384) that is not a whole number of envs' horizons (40)
+    'mjlab/ppo_wujihand_reorient.yaml': 'minibatch_size must be a multiple of horizon_length|state-dependent sigma',
+}
+_MULTI_AGENT = {'ppo_multiwalker.yaml', 'ppo_smac.yaml'}          # multi-agent envs: refused by construction (test_host_cpu), need an env to say so
 
 
 def _shipped_ppo_yamls():
     if REF is None:
         return []
+    import yaml
     out = []
-    for sub in ('mujoco', 'mjlab'):
-        d = os.path.join(REF, 'rl_games', 'configs', sub)
-        if os.path.isdir(d):
-            out += [os.path.join(sub, f) for f in sorted(os.listdir(d)) if f.endswith('.yaml') and not f.startswith('sac_')]
+    base = os.path.join(REF, 'rl_games', 'configs')
+    for fam in _FAMILIES:
+        d = os.path.join(base, fam)
+        if not os.path.isdir(d):
+            continue
+        for f in sorted(os.listdir(d)):
+            rel = f if fam == '.' else os.path.join(fam, f)
+            if not f.endswith('.yaml') or rel in _MULTI_AGENT:
+                continue
+            try:
+                algo = yaml.safe_load(open(os.path.join(d, f)))['params']['algo']['name']
+            except Exception:
+                continue
+            if algo in ('a2c_continuous', 'a2c_discrete'):
+                out.append(rel)
     return out
 
 
@@ -155,12 +185,29 @@ class _GymEnvCV(_GymEnv):
         return info
 
 
+class _GymEnvDiscrete(_GymEnv):
+    def __init__(self, N, D, K):
+        self.N, self.D, self.K = N, D, K
+
+    def step(self, actions):
+        z8 = torch.zeros(self.N, dtype=torch.uint8)
+        return torch.zeros(self.N, self.D), torch.zeros(self.N), z8, {'time_outs': z8}
+
+    def get_env_info(self):
+        import gymnasium as gym
+        import numpy as np
+        space = gym.spaces.Discrete(self.K) if isinstance(self.K, int) else gym.spaces.Tuple([gym.spaces.Discrete(k) for k in self.K])
+        return {'observation_space': gym.spaces.Box(-np.inf, np.inf, (self.D,), np.float32), 'action_space': space}
+
+
 @pytest.mark.parametrize('rel', _shipped_ppo_yamls())
-def test_every_shipped_mujoco_and_mjlab_ppo_yaml_runs_through_the_reference_runner(rel, monkeypatch, tmp_path):
-    """`rl_games_b200.register(runner)` into the reference's own Runner, then each PPO YAML the reference ships for MuJoCo (Gymnasium / envpool /
-    Ray back-ends) and mjlab (central value + `schedule_type: standard` + `algo_observer: isaac`) UNCHANGED: only what a launcher injects is
-    set (`env_info` / `vec_env`, `device`, `max_epochs`, `train_dir`).  One epoch of `runner.run`, every C-ABI call header-checked: the right
-    agent class, the kernel family the geometry selects, the reference's own observer objects driving our agent."""
+def test_every_shipped_ppo_yaml_of_the_in_scope_families_runs_through_the_reference_runner(rel, monkeypatch, tmp_path):
+    """`rl_games_b200.register(runner)` into the reference's own Runner, then EVERY PPO YAML the reference ships for single-agent
+    flat-observation tasks -- MuJoCo (Gymnasium / envpool / Ray back-ends), dm_control, ManiSkill, pufferlib, mjlab (central value +
+    `schedule_type: standard` + `algo_observer: isaac`), the top-level and test configs -- UNCHANGED: only what a launcher injects is set
+    (`env_info` / `vec_env`, `device`, `max_epochs`, `train_dir`, single process).  Each one either trains (one epoch of `runner.run`, every
+    C-ABI call header-checked, the right agent class, the kernel family its geometry selects, the reference's own observer objects driving our
+    agent) or is in `_REFUSED` and raises NotImplementedError with the listed reason."""
     import yaml
     for p in (os.path.join(HERE, 'golden', '_stubs'), REF):
         if p not in sys.path:
@@ -168,21 +215,28 @@ def test_every_shipped_mujoco_and_mjlab_ppo_yaml_runs_through_the_reference_runn
     from rl_games.torch_runner import Runner
     import rl_games.common.algo_observer as ref_obs
     import rl_games_b200
+    from rl_games_b200 import agent_discrete
     from rl_games_b200.agent import A2CAgent
     from rl_games_b200.agent_cv import A2CAgentCV
 
     rec = ABI._patch(monkeypatch)
+    monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_require_cuda', lambda self: None)
+    monkeypatch.setattr(agent_discrete.DiscreteA2CAgent, '_sync', staticmethod(lambda: None))
     cfg = yaml.safe_load(open(os.path.join(REF, 'rl_games', 'configs', rel)))
-    c = cfg['params']['config']
-    mjlab = rel.startswith('mjlab')
-    if mjlab:
-        D, S, A = _MJLAB_DIMS
-        env = _GymEnvCV(c['num_actors'], D, S, A)
+    c, net = cfg['params']['config'], cfg['params']['network']
+    discrete = cfg['params']['algo']['name'] == 'a2c_discrete'
+    cv = bool(c.get('central_value_config'))
+    N = c['num_actors']
+    D, A = _DIMS.get(os.path.basename(rel).split('_')[0].split('.')[0], _GENERIC_DIMS) if rel.startswith('mujoco') else _GENERIC_DIMS
+    if discrete:
+        env = _GymEnvDiscrete(N, 12, [3, 4] if 'multi_discrete' in net.get('space', {}) else 4)
+    elif cv:
+        env = _GymEnvCV(N, D, _CV_STATE_DIM, A)
     else:
-        D, A = _DIMS[os.path.basename(rel).split('_')[0].split('.')[0]]
-        env = _GymEnv(c['num_actors'], D, A)
-    c.update({'env_info': env.get_env_info(), 'vec_env': env, 'device': H._CudaLookingStr('cpu'), 'max_epochs': 1, 'train_dir': str(tmp_path),
-              'b200_cuda_graph': False})
+        env = _GymEnv(N, D, A)
+    c.update({'env_info': env.get_env_info(), 'vec_env': env, 'device': 'cpu' if discrete else H._CudaLookingStr('cpu'), 'max_epochs': 1,
+              'train_dir': str(tmp_path), 'b200_cuda_graph': False, 'multi_gpu': False})
+    c.pop('max_frames', None)
     runner = Runner()
     assert rl_games_b200.register(runner) is runner
     runner.load(cfg)
@@ -190,27 +244,31 @@ def test_every_shipped_mujoco_and_mjlab_ppo_yaml_runs_through_the_reference_runn
     made = []
     orig_create = runner.algo_factory.create
     monkeypatch.setattr(runner.algo_factory, 'create', lambda name, **kw: (made.append(orig_create(name, **kw)), made[-1])[1])
-    if os.path.basename(rel) in _REFUSED:
-        # the one shipped PPO YAML of these two families outside the built path: it raises at construction, it is never silently reinterpreted
-        with pytest.raises(NotImplementedError, match=_REFUSED[os.path.basename(rel)]):
+    if rel in _REFUSED:
+        with pytest.raises(NotImplementedError, match=_REFUSED[rel]):
             runner.run({'train': True, 'play': False, 'checkpoint': None, 'sigma': None})
         return
     runner.run({'train': True, 'play': False, 'checkpoint': None, 'sigma': None})
     agent, = made
-    assert type(agent) is (A2CAgentCV if mjlab else A2CAgent) and agent.has_central_value == mjlab
-    assert agent.model.min_sigma == cfg['params']['network']['space']['continuous'].get('min_sigma', 0.0)
-    assert agent.epoch_num == 1 and agent.frame == c['num_actors'] * c['horizon_length']
-    assert isinstance(agent.algo_observer, ref_obs.IsaacAlgoObserver if mjlab else ref_obs.DefaultAlgoObserver)
-    units = cfg['params']['network']['mlp']['units']
-    fused = units in ([256, 128, 64], [128, 64, 32])                     # geometries with fused tcgen05 kernels (obs <= 256, <= 15 actions)
+    assert agent.epoch_num == 1 and agent.frame == N * c['horizon_length']
+    assert isinstance(agent.algo_observer, ref_obs.IsaacAlgoObserver if c.get('algo_observer') == 'isaac' else ref_obs.DefaultAlgoObserver)
+    if discrete:
+        assert type(agent) is agent_discrete.DiscreteA2CAgent and rec.calls['b200rl_categorical_loss_f32'] > 0
+        return
+    assert type(agent) is (A2CAgentCV if cv else A2CAgent) and agent.has_central_value == cv
+    assert agent.model.min_sigma == net['space']['continuous'].get('min_sigma', 0.0)
+    units = net['mlp']['units']
+    fused = len(units) == 3 and all(u <= m for u, m in zip(units, (256, 128, 64))) and 'rnn' not in net and agent.model.min_sigma == 0 \
+        and net['mlp']['activation'] in ('elu', 'relu', 'tanh')
     mp = c.get('mixed_precision')
-    n_upd = c['mini_epochs'] * (c['num_actors'] * c['horizon_length'] // c['minibatch_size'])
-    if fused and mp is not False:                                        # absent key = auto -> fused kernels where the geometry has them
+    mb = c.get('minibatch_size') or N * c['minibatch_size_per_env']
+    n_upd = c['mini_epochs'] * (N * c['horizon_length'] // mb)
+    if fused and mp is not False:                                        # absent key = auto -> fused tcgen05 kernels where the geometry has them
         assert agent.use_tc and rec.calls['b200rl_tc_mlp_fwd_train'] == n_upd and rec.calls['b200rl_tc_mlp_bwd'] == n_upd
-    elif mp is True:                                                     # [512,256,128] with mixed_precision: True -> layer-wise tcgen05 GEMMs
-        assert agent.gemm_tc and rec.calls['b200rl_linear_fwd_tc'] > 0 and rec.calls['b200rl_linear_bwd_weight_tc'] == n_upd * 4
+    elif mp is True:                                                     # e.g. [512,256,128] with mixed_precision: True -> layer-wise tcgen05 GEMMs
+        assert agent.gemm_tc and rec.calls['b200rl_linear_fwd_tc'] > 0 and rec.calls['b200rl_linear_bwd_weight_tc'] >= n_upd * (len(units) + 1)
         assert rec.calls.get('b200rl_linear_fwd_f32', 0) == 0
-    else:                                                                # [512,256,128], key absent -> fp32 kernels (a printed note says so)
-        assert not agent.use_tc and not agent.gemm_tc and rec.calls['b200rl_linear_bwd_weight_f32'] >= n_upd * 4
-    if mjlab:
+    else:                                                                # key absent on such a geometry -> fp32 kernels (a printed note says so)
+        assert not agent.use_tc and not agent.gemm_tc and rec.calls['b200rl_linear_bwd_weight_f32'] >= n_upd * (len(units) + 1)
+    if cv:
         assert agent.schedule_type == c.get('schedule_type', 'per_minibatch') and rec.calls['b200rl_value_loss_f32'] > 0
