@@ -598,22 +598,27 @@ def test_rollout_precision_option_reproduces_the_fp32_rollout_exactly():
     print('rollout precision: first-minibatch KL default (bf16 rollout) %.3e, reference split (fp32 rollout) %.3e' % (kl_default, kl_split))
 
 
-@pytest.mark.parametrize('case', ['lstm_before_mlp', 'lstm_after_mlp', 'mlp_512_256_128'])
+@pytest.mark.parametrize('case', ['lstm_before_mlp', 'lstm_after_mlp', 'mlp_512_256_128', 'mlp_128_64_32_min_sigma'])
 def test_layerwise_tensor_core_path_tracks_fp32_agent(case):
     """mixed_precision: True on an LSTM policy / an MLP wider than the fused tiles: every GEMM on the tensor cores (gemm_tc.cu, bf16
     operands, fp32 accumulate), the same host composition as the fp32 path.  Against the fp32 kernels on the same tapes / weights /
-    noise: bf16 tolerance class (rollout outputs atol 6e-2, per-minibatch losses rtol 0.1, update direction cosine > 0.8)."""
+    noise: bf16 tolerance class (rollout outputs atol 6e-2, per-minibatch losses rtol 0.1, update direction cosine > 0.8).
+    mlp_128_64_32_min_sigma: a geometry the FUSED kernels have, with a sigma floor (min_sigma; the fused kernels read the raw parameter from
+    the packed arena, so the floored policy is routed layer by layer) -- the floor, its gradient chain and an entropy bonus on both paths."""
     N, H, D, A, mb = 256, 8, 44, 5, 1024
     units, rnn, before = ([64, 32], 32, True) if case == 'lstm_before_mlp' else (([64, 32], 32, False) if case == 'lstm_after_mlp' else ([512, 256, 128], 0, True))
+    space_over, extra = None, {}
+    if case == 'mlp_128_64_32_min_sigma':
+        units, space_over, extra = [128, 64, 32], {'min_sigma': 0.2}, {'entropy_coef': 0.01}
     obs_tape, done_tape, tout_tape = O.make_tapes(H + 1, N, D, seed=51, p_done=0.08)
     params = O.init_params(D, units, A, seed=6, rnn_units=rnn, rnn_before_mlp=before)
     g = torch.Generator().manual_seed(16)
     noise = torch.randn(H, N, A, generator=g).to(DEV)
     agents = []
     for mp in (False, True):
-        a = make_agent({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False, 'seq_length': 4}, N, H, D, A, units, mb,
-                       TapeEnvGPU(obs_tape, done_tape, tout_tape, A), params, rnn_units=rnn, rnn_before_mlp=before)
-        assert a.gemm_tc == mp and not a.use_tc
+        a = make_agent(dict({'mixed_precision': mp, 'mini_epochs': 2, 'b200_cuda_graph': False, 'seq_length': 4}, **extra), N, H, D, A, units, mb,
+                       TapeEnvGPU(obs_tape, done_tape, tout_tape, A), params, rnn_units=rnn, rnn_before_mlp=before, space_over=space_over)
+        assert a.gemm_tc == mp and not a.use_tc and a.model.min_sigma == (space_over or {}).get('min_sigma', 0.0)
         a.epoch_num += 1
         a.train_epoch(noise=noise)
         agents.append(a)
@@ -630,3 +635,8 @@ def test_layerwise_tensor_core_path_tracks_fp32_agent(case):
             du_f = (sdf[k].cpu() - params[k]).flatten(); du_t = (sdt[k].cpu() - params[k]).flatten()
             cos = float(du_f @ du_t / (du_f.norm() * du_t.norm() + 1e-20))
             assert cos > 0.8, (k, cos)
+    if space_over:          # the floored sigma: the stored sigmas are exp(raw) + min_sigma on both paths, and the raw parameter moved the same way
+        torch.testing.assert_close(t.sigmas, f.sigmas, rtol=0, atol=1e-6)
+        assert float(f.sigmas.min()) > space_over['min_sigma']
+        ds_f, ds_t = sdf['a2c_network.sigma'].cpu() - params['a2c_network.sigma'], sdt['a2c_network.sigma'].cpu() - params['a2c_network.sigma']
+        assert float(ds_f @ ds_t / (ds_f.norm() * ds_t.norm() + 1e-20)) > 0.8

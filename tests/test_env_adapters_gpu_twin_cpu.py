@@ -40,3 +40,8 @@ def test_min_sigma_golden_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
     import tests.test_agent_gpu as G
     G.test_agent_matches_reference_golden_more_config_keys('agent_minsigma.pt', False)
     G.test_agent_matches_reference_golden_more_config_keys('agent_misc.pt', False)        # the unchanged path through the same helper
+
+
+def test_layerwise_min_sigma_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
+    import tests.test_agent_gpu as G
+    G.test_layerwise_tensor_core_path_tracks_fp32_agent('mlp_128_64_32_min_sigma')
