@@ -29,7 +29,7 @@ from . import ops
 from .common import (AdaptiveScheduler, IdentityScheduler, LinearScheduler, DefaultAlgoObserver, DefaultRewardsShaper,
                      create_vec_env, make_summary_writer)
 from .dist_utils import PackedStatsSync
-from .model import B200Model, CompileTolerantModel
+from .model import B200Model, CompileTolerantModel, resolve_device
 
 STATS_SYNC_MODES = ('pooled', 'broadcast')
 
@@ -142,7 +142,7 @@ class A2CAgent(CompileTolerantModel):
         self.ppo_device = config.get('device', 'cuda:0')
         if not str(self.ppo_device).startswith('cuda'):
             raise RuntimeError("rl_games_b200.A2CAgent runs on CUDA only (device=%r): there is no CPU fallback" % self.ppo_device)
-        self.device_t = torch.device(self.ppo_device)
+        self.device_t = resolve_device(self.ppo_device)          # 'cuda' without an index = the current device
         torch.cuda.set_device(self.device_t)
 
         self.network_path = config.get('network_path', './nn/')

@@ -22,7 +22,7 @@ import torch.distributed as dist
 
 from . import ops
 from .agent import _MeterView
-from .model import check_network_params, CompileTolerantModel, _model_call
+from .model import check_network_params, CompileTolerantModel, _model_call, resolve_device
 from .dist_utils import PackedStatsSync
 from .common import (AdaptiveScheduler, DefaultAlgoObserver, DefaultRewardsShaper, IdentityScheduler, LinearScheduler, create_vec_env,
                      make_summary_writer)
@@ -185,7 +185,7 @@ class DiscreteA2CAgent(CompileTolerantModel):
             raise NotImplementedError("multi_gpu_sync_stats_mode: only 'pooled' for the discrete agent")
         self.ppo_device = config.get('device', 'cuda:0')
         self._require_cuda()
-        self.device_t = torch.device(self.ppo_device)
+        self.device_t = resolve_device(self.ppo_device)          # 'cuda' without an index (configs/ppo_cartpole.yaml) = the current device
         self.num_actors = config['num_actors']
         self.env_name = config['env_name']
         self.env_info = config.get('env_info')
@@ -305,7 +305,7 @@ class DiscreteA2CAgent(CompileTolerantModel):
         """no CPU fallback: the kernels are the product (the host-logic test replaces this hook together with every op)"""
         if not str(self.ppo_device).startswith('cuda'):
             raise RuntimeError('rl_games_b200 agents run on CUDA only (device=%r): there is no CPU fallback' % self.ppo_device)
-        torch.cuda.set_device(torch.device(self.ppo_device))
+        torch.cuda.set_device(resolve_device(self.ppo_device))
 
     @staticmethod
     def _sync():

@@ -121,6 +121,16 @@ class _NetworkView:
         return self._m.rnn_units > 0
 
 
+def resolve_device(name):
+    """torch.device for a config's `device` value.  An index-less 'cuda' (configs/ppo_cartpole.yaml, ppo_lunar_discrete.yaml) means the
+    CURRENT device, as every torch op resolves it; it is made explicit here because raw pointers cross the C ABI and
+    `torch.cuda.set_device` refuses a device without an index.  Anything else is returned as torch parses it."""
+    dev = torch.device(name)
+    if dev.type == 'cuda' and dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    return dev
+
+
 class CompileTolerantModel:
     """Mixin for agents: `Runner.run_train` of the reference wraps `agent.model` with torch.compile unless the YAML says
     `torch_compile: False` (torch_runner.py:282-312).  There is no nn.Module to compile here (the hand-written kernels subsume those

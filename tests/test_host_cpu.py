@@ -275,3 +275,20 @@ def test_network_options_without_a_kernel_fail_loudly(patch, what):
     net.update(patch)
     with pytest.raises(NotImplementedError, match=what):
         B200Model(net, 6, 3, 'cpu', True, True)
+
+
+def test_index_less_cuda_device_resolves_to_the_current_device(monkeypatch):
+    """`device: cuda` (configs/ppo_cartpole.yaml = BASELINE configs[0], ppo_lunar_discrete.yaml): the reference hands the string to torch, which
+    resolves it to the current device; here raw pointers cross the C ABI and torch.cuda.set_device refuses an index-less device, so the agents
+    make the index explicit.  'cuda:N' and non-CUDA names pass through untouched (the latter are refused by the agents: no CPU fallback)."""
+    from rl_games_b200.model import resolve_device
+    monkeypatch.setattr(torch.cuda, 'current_device', lambda: 3)
+    assert resolve_device('cuda') == torch.device('cuda', 3)
+    assert resolve_device('cuda:1') == torch.device('cuda', 1) and resolve_device(torch.device('cuda:0')) == torch.device('cuda', 0)
+    assert resolve_device('cpu') == torch.device('cpu')
+    seen = []
+    monkeypatch.setattr(torch.cuda, 'set_device', lambda d: seen.append(d))
+    from rl_games_b200 import agent_discrete
+    stub = type('A', (), {'ppo_device': 'cuda', '_require_cuda': agent_discrete.DiscreteA2CAgent._require_cuda})()
+    stub._require_cuda()
+    assert seen == [torch.device('cuda', 3)]
