@@ -110,6 +110,17 @@ def register_env(name, config):
 
 
 def create_vec_env(config_name, num_actors, **kwargs):
+    """common/vecenv.py:379-391.  A name that is not registered HERE is looked up in the reference's own registries when rl_games is
+    importable (the agent running under the reference's Runner): `env_name: envpool` / `gymnasium` / `ray` /
+    anything the user registered through `rl_games.common.vecenv.register` + `env_configurations.register` keeps working without an
+    injected `vec_env`."""
+    if config_name not in configurations:
+        try:
+            from rl_games.common import vecenv as reference_vecenv
+        except ImportError:
+            raise KeyError(f"env '{config_name}' is not registered (rl_games_b200.common.register_env; registered: {sorted(configurations)}) "
+                           f"and rl_games is not importable to look it up there") from None
+        return reference_vecenv.create_vec_env(config_name, num_actors, **kwargs)
     config = configurations[config_name]
     vec_env_name = config['vecenv_type']
     merged = {**config.get('default_env_config', {}), **kwargs}

@@ -272,3 +272,39 @@ def test_every_shipped_ppo_yaml_of_the_in_scope_families_runs_through_the_refere
         assert not agent.use_tc and not agent.gemm_tc and rec.calls['b200rl_linear_bwd_weight_f32'] >= n_upd * (len(units) + 1)
     if cv:
         assert agent.schedule_type == c.get('schedule_type', 'per_minibatch') and rec.calls['b200rl_value_loss_f32'] > 0
+
+
+def test_env_registered_in_the_reference_registries_is_built_without_injection(monkeypatch, tmp_path):
+    """No `vec_env` / `env_info` injection: the YAML names an env that is registered only in the REFERENCE's registries
+    (rl_games.common.vecenv.register + env_configurations.register, what envpool / gymnasium / user plugins do); the agent, running under the
+    reference's Runner, builds it through those registries (common/vecenv.py:379-391) and reads its spaces from `get_env_info()`."""
+    import yaml
+    for p in (os.path.join(HERE, 'golden', '_stubs'), REF):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from rl_games.torch_runner import Runner
+    from rl_games.common import vecenv, env_configurations
+    import rl_games_b200
+    from rl_games_b200 import common as C
+
+    built = []
+
+    def make(config_name, num_actors, **kw):
+        built.append((config_name, num_actors, kw))
+        return _GymEnv(num_actors, 17, 6)
+    monkeypatch.setitem(vecenv.vecenv_config, 'B200_TEST_PLUGIN', make)
+    monkeypatch.setitem(env_configurations.configurations, 'plugin_env_only_the_reference_knows', {'vecenv_type': 'B200_TEST_PLUGIN'})
+    assert 'plugin_env_only_the_reference_knows' not in C.configurations
+    ABI._patch(monkeypatch)
+    cfg = yaml.safe_load(open(os.path.join(REF, 'rl_games', 'configs', 'mujoco', 'halfcheetah_envpool.yaml')))
+    c = cfg['params']['config']
+    c.update({'env_name': 'plugin_env_only_the_reference_knows', 'device': H._CudaLookingStr('cpu'), 'max_epochs': 1, 'train_dir': str(tmp_path),
+              'b200_cuda_graph': False})
+    runner = rl_games_b200.register(Runner())
+    runner.load(cfg)
+    runner.run({'train': True, 'play': False, 'checkpoint': None, 'sigma': None})
+    (name, n, kw), = built
+    assert name == 'plugin_env_only_the_reference_knows' and n == c['num_actors'] and kw.get('env_name') == c['env_config']['env_name']
+    # a name nobody knows: the reference's own KeyError
+    with pytest.raises(KeyError):
+        C.create_vec_env('no_such_env_anywhere', 4)
