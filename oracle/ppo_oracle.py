@@ -346,12 +346,15 @@ RNN_NAMES = ['a2c_network.rnn.rnn.weight_ih_l0', 'a2c_network.rnn.rnn.weight_hh_
              'a2c_network.rnn.rnn.bias_hh_l0']
 
 
-def param_names(n_layers, lstm=False):
-    """reference model.parameters() order: sigma, actor_mlp.*, [rnn.rnn.*], value.*, mu.* (module registration order of
-    A2CBuilder.Network.__init__, network_builder.py:219-325: actor_mlp placeholder is registered before self.rnn)"""
+def param_names(n_layers, lstm=False, separate=False):
+    """reference model.parameters() order: sigma, actor_mlp.*, [critic_mlp.* when `separate`], [rnn.rnn.*], value.*, mu.* (module
+    registration order of A2CBuilder.Network.__init__, network_builder.py:219-325: actor_mlp placeholder is registered before self.rnn)"""
     names = ['a2c_network.sigma']
     for i in range(n_layers):
         names += [f'a2c_network.actor_mlp.{2 * i}.weight', f'a2c_network.actor_mlp.{2 * i}.bias']
+    if separate:
+        for i in range(n_layers):
+            names += [f'a2c_network.critic_mlp.{2 * i}.weight', f'a2c_network.critic_mlp.{2 * i}.bias']
     if lstm:
         names += RNN_NAMES
     names += ['a2c_network.value.weight', 'a2c_network.value.bias', 'a2c_network.mu.weight', 'a2c_network.mu.bias']
@@ -406,7 +409,12 @@ def network_forward(p, obs, n_layers, activation='elu', matmul_dtype=None, heads
         out = act(lin(out, p[f'a2c_network.actor_mlp.{2 * i}.weight'], p[f'a2c_network.actor_mlp.{2 * i}.bias']))
     if heads_after is not None:          # rnn after the MLP (before_mlp: False, network_builder.py:466-492): trunk -> rnn -> heads
         out = heads_after(out)
-    value = lin(out, p['a2c_network.value.weight'], p['a2c_network.value.bias'])
+    c_out = out
+    if 'a2c_network.critic_mlp.0.weight' in p:      # separate: True (network_builder.py:494-512): the value head reads a trunk of its own
+        c_out = obs
+        for i in range(n_layers):
+            c_out = act(lin(c_out, p[f'a2c_network.critic_mlp.{2 * i}.weight'], p[f'a2c_network.critic_mlp.{2 * i}.bias']))
+    value = lin(c_out, p['a2c_network.value.weight'], p['a2c_network.value.bias'])
     mu = lin(out, p['a2c_network.mu.weight'], p['a2c_network.mu.bias'])
     logstd = mu * 0 + p['a2c_network.sigma']
     return mu, logstd, value
@@ -439,7 +447,7 @@ class OracleModel:
         self.min_sigma = float(min_sigma)      # 'exp' sigma parametrisation with a floor (models.py:272-300, network_builder.py:312)
         self.rnn_units = rnn_units
         self.rnn_before_mlp = rnn_before_mlp
-        self.names = param_names(len(units), lstm=rnn_units > 0)
+        self.names = param_names(len(units), lstm=rnn_units > 0, separate='a2c_network.critic_mlp.0.weight' in params)
         self.n_layers = len(units)
         self.activation = activation
         self.normalize_input, self.normalize_value = normalize_input, normalize_value

@@ -298,8 +298,9 @@ class A2CAgent(CompileTolerantModel):
         tc_ok = self.model.activation in ('elu', 'relu', 'tanh') and \
             ops.tc_supported(self.model.D, self.model.units, self.actions_num, allow_wide)
         # (a sigma floor -- min_sigma > 0 -- is applied outside the kernels on the log-std vector they read; the fused kernels take the raw
-        #  parameter from the packed arena, so such policies run layer by layer)
-        fused_ok = tc_ok and not self.is_rnn and getattr(self.model, 'min_sigma', 0.0) == 0
+        #  parameter from the packed arena, so such policies run layer by layer.  Separate actor / critic trunks need their gradient mask
+        #  applied between the split reduction and the optimiser, which the fused tail does in one launch: layer by layer as well)
+        fused_ok = tc_ok and not self.is_rnn and getattr(self.model, 'min_sigma', 0.0) == 0 and not getattr(self.model, 'separate', False)
         if self.mixed_precision is None:
             self.mixed_precision = fused_ok
             if not self.mixed_precision and self.global_rank == 0:
@@ -930,6 +931,8 @@ class A2CAgent(CompileTolerantModel):
                                       rows_per_chunk=epm, chunk_stride=N, x_ld=m.D, norm_mean=nm, norm_std=ns, M=mb,
                                       split_stride=P)
         ops.reduce_splits(self.part[0, A:], gv['grad'][A:], P - A, self.part_rows, split_stride=P)
+        if m.grad_mask is not None:      # separate trunks: the structural zeros of the block layout get no gradient (model.py)
+            gv['grad'][:P].mul_(m.grad_mask)
         self._step_optimizer(u, gv, P)
         m.refresh_sigma_floor()          # no-op unless min_sigma > 0
 

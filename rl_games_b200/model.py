@@ -175,8 +175,19 @@ class B200Model:
         if self.activation not in ops.ACT:
             raise NotImplementedError(f'activation {self.activation}')
         self.act_id = ops.ACT[self.activation]
-        if network_params.get('separate', False):
-            raise NotImplementedError('separate actor/critic trunks are not on the B200 hot path yet')
+        # separate: True (network_builder.py:494-512; configs/ppo_continuous.yaml, ppo_lunar.yaml ...): actor_mlp feeds mu, critic_mlp feeds the
+        # value.  Here the two trunks are ONE MLP of twice the width whose weights are block-structured -- layer 0 stacks [W_actor; W_critic] (both
+        # read the observation), layers >= 1 are block-diagonal, the value row of the head reads the critic half and the mu rows the actor half --
+        # so every kernel, arena and code path of the shared-trunk policy is used as it is.  The structural zeros stay exactly zero: their
+        # gradient entries are masked before the optimiser (grad_mask), and a zero weight with a zero gradient is a fixed point of Adam and of
+        # weight decay; multiplied by zero they add exact zeros to the products.  `units` = the EFFECTIVE widths everything downstream sees,
+        # `trunk_units` = the reference's per-trunk widths (state-dict shapes).
+        self.separate = bool(network_params.get('separate', False))
+        self.trunk_units = list(self.units)
+        if self.separate:
+            if 'rnn' in network_params:
+                raise NotImplementedError('separate actor/critic trunks with an rnn (two recurrent cores) are not on the B200 hot path')
+            self.units = [2 * u for u in self.trunk_units]
         if 'cnn' in network_params:
             raise NotImplementedError("'cnn' networks are not on the B200 hot path yet")
         self.rnn_units = 0
@@ -245,6 +256,11 @@ class B200Model:
             self.W_ih, self.W_hh, self.b_ih, self.b_hh = (self.view(n) for n in ('W_ih', 'W_hh', 'b_ih', 'b_hh'))
         self.mlp_in = self.rnn_units if (self.rnn_units and self.rnn_before_mlp) else self.D
         self.W_head, self.b_head = self.view('W_head'), self.view('b_head')
+        self.grad_mask = None
+        if self.separate:       # 1 on the entries the reference has a parameter for, 0 on the structural zeros of the block layout
+            self.grad_mask = torch.zeros(off, dtype=torch.float32, device=self.device)
+            for v in self._param_views(self.grad_mask):
+                v.fill_(1.0)
         self.gW = [self.view(f'W{i}', self.grad) for i in range(len(self.units))]
         self.gb = [self.view(f'b{i}', self.grad) for i in range(len(self.units))]
         self.g_sigma = self.view('sigma', self.grad)
@@ -290,20 +306,29 @@ class B200Model:
             k = 1.0 / math.sqrt(Hd)
             for n, shp in (('W_ih', (4 * Hd, self.rnn_in)), ('W_hh', (4 * Hd, Hd)), ('b_ih', (4 * Hd,)), ('b_hh', (4 * Hd,))):
                 cpu[n] = torch.empty(*shp).uniform_(-k, k)
-        ins = self.mlp_in
-        for i, u in enumerate(self.units):
-            w = torch.empty(u, ins)
-            _apply_init(w, mlp_init, ins)
-            cpu[f'W{i}'] = w
-            ins = u
-        ins = self.Hl
-        wh = torch.empty(self.A + 1, ins)
-        _apply_init(wh[:1], mlp_init, ins)                                   # value head: mlp_init
-        _apply_init(wh[1:], mlp_init, ins)
         mu_init = space.get('mu_init', {'name': 'default'})
-        if mu_init.get('name', 'default') != 'default':
-            _apply_init(wh[1:], mu_init, ins)
-        cpu['W_head'] = wh
+        if self.separate:       # every Linear of both trunks and both heads is initialised on its own (true fan-in), written into its block
+            blocks = self._param_views(self.flat)[1:]               # actor W, b ... critic W, b ... value W, b, mu W, b
+            for k in range(0, len(blocks), 2):
+                w = torch.empty(*blocks[k].shape)
+                _apply_init(w, mlp_init, w.shape[1])
+                if k == len(blocks) - 2 and mu_init.get('name', 'default') != 'default':
+                    _apply_init(w, mu_init, w.shape[1])
+                blocks[k].copy_(w)
+        else:
+            ins = self.mlp_in
+            for i, u in enumerate(self.units):
+                w = torch.empty(u, ins)
+                _apply_init(w, mlp_init, ins)
+                cpu[f'W{i}'] = w
+                ins = u
+            ins = self.Hl
+            wh = torch.empty(self.A + 1, ins)
+            _apply_init(wh[:1], mlp_init, ins)                                   # value head: mlp_init
+            _apply_init(wh[1:], mlp_init, ins)
+            if mu_init.get('name', 'default') != 'default':
+                _apply_init(wh[1:], mu_init, ins)
+            cpu['W_head'] = wh
         sg = torch.empty(self.A)
         _apply_init(sg, space.get('sigma_init', {'name': 'const_initializer', 'val': 0}), 1)
         cpu['sigma'] = sg
@@ -339,6 +364,8 @@ class B200Model:
         return self._param_views(self.flat)
 
     def _param_views(self, arena):
+        if self.separate:
+            return self._param_views_separate(arena)
         out = [self.view('sigma', arena)]
         for i in range(len(self.units)):
             out += [self.view(f'W{i}', arena), self.view(f'b{i}', arena)]
@@ -348,12 +375,38 @@ class B200Model:
         out += [wh[:1], bh[:1], wh[1:], bh[1:]]
         return out
 
+    def _param_views_separate(self, arena):
+        """separate: True -- the reference's parameters (order: sigma, actor_mlp.*, critic_mlp.*, value.*, mu.*) as block views of the
+        double-width layout: trunk t of layer i owns rows [t u_i, (t + 1) u_i); layer 0 reads all observation columns, layers >= 1 the
+        columns [t u_(i-1), (t + 1) u_(i-1)) of their own trunk; value = head row 0 on the critic half, mu = head rows 1.. on the actor half"""
+        tu = self.trunk_units
+        out = [self.view('sigma', arena)]
+        for t in (0, 1):
+            for i, u in enumerate(tu):
+                w, b = self.view(f'W{i}', arena), self.view(f'b{i}', arena)
+                cols = slice(None) if i == 0 else slice(t * tu[i - 1], (t + 1) * tu[i - 1])
+                out += [w[t * u:(t + 1) * u, cols], b[t * u:(t + 1) * u]]
+        wh, bh = self.view('W_head', arena), self.view('b_head', arena)
+        out += [wh[:1, tu[-1]:], bh[:1], wh[1:, :tu[-1]], bh[1:]]
+        return out
+
+    def _separate_keys(self):
+        keys = ['a2c_network.sigma']
+        for trunk in ('actor_mlp', 'critic_mlp'):
+            for i in range(len(self.trunk_units)):
+                keys += [f'a2c_network.{trunk}.{2 * i}.weight', f'a2c_network.{trunk}.{2 * i}.bias']
+        return keys + ['a2c_network.value.weight', 'a2c_network.value.bias', 'a2c_network.mu.weight', 'a2c_network.mu.bias']
+
     def state_dict(self):
         sd = OrderedDict()
         if self.normalize_value:
             sd.update(self.value_mean_std.state_dict('value_mean_std.'))
         if self.normalize_input:
             sd.update(self.running_mean_std.state_dict('running_mean_std.'))
+        if self.separate:
+            for k, v in zip(self._separate_keys(), self._param_views(self.flat)):
+                sd[k] = v.clone()
+            return sd
         sd['a2c_network.sigma'] = self.sigma.clone()
         for i in range(len(self.units)):
             sd[f'a2c_network.actor_mlp.{2 * i}.weight'] = self.W[i].clone()
@@ -374,6 +427,12 @@ class B200Model:
         if missing and strict:
             raise KeyError(f'missing keys in state_dict: {missing}')
         with torch.no_grad():
+            if self.separate:
+                for k, v in zip(self._separate_keys(), self._param_views(self.flat)):
+                    if k in sd:
+                        v.copy_(sd[k].reshape(v.shape))
+                self._load_normalisers(sd)
+                return
             if 'a2c_network.sigma' in sd:
                 self.sigma.copy_(sd['a2c_network.sigma'])
             for i in range(len(self.units)):
@@ -386,10 +445,13 @@ class B200Model:
             self.b_head[:1].copy_(sd['a2c_network.value.bias'])
             self.W_head[1:].copy_(sd['a2c_network.mu.weight'])
             self.b_head[1:].copy_(sd['a2c_network.mu.bias'])
-            if self.normalize_value and 'value_mean_std.running_mean' in sd:
-                self.value_mean_std.load_state_dict(sd, 'value_mean_std.')
-            if self.normalize_input and 'running_mean_std.running_mean' in sd:
-                self.running_mean_std.load_state_dict(sd, 'running_mean_std.')
+            self._load_normalisers(sd)
+
+    def _load_normalisers(self, sd):
+        if self.normalize_value and 'value_mean_std.running_mean' in sd:
+            self.value_mean_std.load_state_dict(sd, 'value_mean_std.')
+        if self.normalize_input and 'running_mean_std.running_mean' in sd:
+            self.running_mean_std.load_state_dict(sd, 'running_mean_std.')
 
     # ------------------------------------------------------------------------------------------- optimizer state
     def optimizer_state_dict(self, lr, step, weight_decay):

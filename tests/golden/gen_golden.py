@@ -189,7 +189,7 @@ class TapeVecEnv:
         pass
 
 
-def make_params(N, H, mb, units, overrides=None, rnn_units=0, rnn_before_mlp=True, space_over=None):
+def make_params(N, H, mb, units, overrides=None, rnn_units=0, rnn_before_mlp=True, space_over=None, network_over=None):
     network = {
         'name': 'actor_critic', 'separate': False,
         'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None',
@@ -199,6 +199,7 @@ def make_params(N, H, mb, units, overrides=None, rnn_units=0, rnn_before_mlp=Tru
         'mlp': {'units': list(units), 'activation': 'elu', 'initializer': {'name': 'default'}},
     }
     network['space']['continuous'].update(space_over or {})          # e.g. min_sigma (configs/mjlab/ppo_lift_cube_yam.yaml)
+    network.update(network_over or {})                               # e.g. separate: True (configs/ppo_continuous.yaml)
     if rnn_units:
         network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': rnn_before_mlp}
     # hyper-parameters of configs/mujoco/ant_envpool.yaml:28-56
@@ -219,7 +220,7 @@ def make_params(N, H, mb, units, overrides=None, rnn_units=0, rnn_before_mlp=Tru
 
 
 def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, overrides=None, autoreset='same_step',
-              seed=3, rnn_units=0, rnn_before_mlp=True, act_bounds=(-1.0, 1.0), train_loop=False, space_over=None):
+              seed=3, rnn_units=0, rnn_before_mlp=True, act_bounds=(-1.0, 1.0), train_loop=False, space_over=None, network_over=None):
     from rl_games.torch_runner import Runner
     from oracle.ppo_oracle import make_tapes
     torch.manual_seed(seed)
@@ -229,7 +230,7 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
     env = TapeVecEnv(obs_tape, done_tape, tout_tape, autoreset)
     env.A = A
     env.act_bounds = act_bounds
-    params = make_params(N, H, mb, units, overrides, rnn_units, rnn_before_mlp, space_over)
+    params = make_params(N, H, mb, units, overrides, rnn_units, rnn_before_mlp, space_over, network_over)
     params['config']['env_info'] = env.get_env_info()
     shaper_cfg = dict(params['config']['reward_shaper'])        # Runner.load_config replaces the dict by a DefaultRewardsShaper object
     runner = Runner()
@@ -307,7 +308,7 @@ def gen_agent(name, N=8, H=8, D=6, A=3, units=(16, 8), mb=32, epochs=2, override
         torch.normal = orig_normal
     save(name, {'N': N, 'H': H, 'D': D, 'A': A, 'units': list(units), 'mb': mb, 'epochs': epochs,
                 'config': {k: v for k, v in params['config'].items() if isinstance(v, (int, float, str, bool, type(None)))},
-                'reward_shaper': shaper_cfg, 'space_over': dict(space_over or {}),
+                'reward_shaper': shaper_cfg, 'space_over': dict(space_over or {}), 'network_over': dict(network_over or {}),
                 'act_bounds': tuple(act_bounds), 'autoreset': autoreset, 'rnn_units': rnn_units, 'rnn_before_mlp': rnn_before_mlp, 'obs_tape': obs_tape, 'done_tape': done_tape, 'timeout_tape': tout_tape,
                 'noise': noise, 'init_state': init_state, 'epochs_out': epochs_out, 'train_loop': loop_out,
                 'param_order': [k for k, _ in agent.model.named_parameters()]})
@@ -663,7 +664,7 @@ def gen_agent_discrete(name, N=16, H=8, D=4, K=2, units=(32, 32), mb=64, epochs=
 
 
 if __name__ == '__main__':
-    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train', 'resume', 'lstm_masked', 'train_discrete', 'minsigma'}      # e.g. `gen_golden.py discrete` regenerates only that group
+    which = set(sys.argv[1:]) or {'gae', 'math', 'continuous', 'discrete', 'rmsadv', 'checkpoint', 'cv', 'tcshape', 'lstm_after', 'sched', 'misc', 'train', 'resume', 'lstm_masked', 'train_discrete', 'minsigma', 'separate'}      # e.g. `gen_golden.py discrete` regenerates only that group
     if 'gae' in which:
         gen_gae()
     if 'math' in which:
@@ -676,6 +677,11 @@ if __name__ == '__main__':
             'clip_value': False, 'truncate_grads': False, 'value_bootstrap': False, 'mini_epochs': 2,
             'weight_decay': 0.01, 'lr_schedule': None})
         gen_agent('agent_lstm.pt', seed=6, rnn_units=8, overrides={'seq_length': 4})
+    if 'separate' in which:
+        # separate actor / critic trunks of a continuous policy (network_builder.py:494-512; configs/ppo_continuous.yaml, ppo_lunar.yaml ...):
+        # masked rows, global-norm clip over both trunks, weight decay, an entropy bonus and a bound loss on top
+        gen_agent('agent_separate.pt', seed=25, autoreset='next_step', network_over={'separate': True}, overrides={
+            'weight_decay': 0.01, 'entropy_coef': 0.002, 'bounds_loss_coef': 0.001, 'bound_loss_type': 'bound', 'mini_epochs': 3})
     if 'minsigma' in which:
         # sigma floor of the 'exp' parametrisation (models.py:296-300; configs/mjlab/ppo_lift_cube_yam.yaml: min_sigma 0.15 with the hard
         # clip, a bound loss, an entropy bonus -- whose gradient reaches only sigma -- and unclipped actions), masked rows on top

@@ -51,13 +51,14 @@ class TapeEnvGPU:
         pass
 
 
-def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0, rnn_before_mlp=True, activation='elu', space_over=None):
+def make_agent(cfg_over, N, H, D, A, units, mb, env, init_state, rnn_units=0, rnn_before_mlp=True, activation='elu', space_over=None, network_over=None):
     from rl_games_b200.runner import Runner
     network = {'name': 'actor_critic', 'separate': False,
                'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': list(units), 'activation': activation, 'initializer': {'name': 'default'}}}
     network['space']['continuous'].update(space_over or {})          # e.g. min_sigma (agent_minsigma.pt)
+    network.update(network_over or {})                               # e.g. separate: True (agent_separate.pt)
     if rnn_units:
         network['rnn'] = {'name': 'lstm', 'units': rnn_units, 'layers': 1, 'before_mlp': rnn_before_mlp}
     config = {'name': 'gpu_parity', 'env_name': 'unused', 'reward_shaper': {'scale_value': 1.0}, 'device': DEV,
@@ -98,7 +99,7 @@ def _check_epoch(agent, ref_state, ref_ds, ref_losses, ref_lr, units, tight=True
             torch.testing.assert_close(st[:, col], ref_losses[key], rtol=2e-3, atol=2e-6, msg=lambda m: key + ': ' + m)
     assert agent.last_lr == pytest.approx(ref_lr, rel=1e-12)
     sd = agent.model.state_dict()
-    for k in O.param_names(len(units), lstm=lstm):
+    for k in O.param_names(len(units), lstm=lstm, separate=getattr(agent.model, 'separate', False)):
         torch.testing.assert_close(sd[k].cpu(), ref_state[k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
     for pre in ('running_mean_std.', 'value_mean_std.'):
         if pre + 'count' not in ref_state:          # that normaliser is switched off in this fixture: same key set as the reference
@@ -166,7 +167,7 @@ def _golden_run(name, graph, extra=None):
     env = TapeEnvGPU(g['obs_tape'], g['done_tape'], g['timeout_tape'], g['A'], g['autoreset'], g.get('act_bounds', (-1.0, 1.0)))
     lstm = g.get('rnn_units', 0) > 0
     agent = make_agent(over, g['N'], g['H'], g['D'], g['A'], g['units'], g['mb'], env, g['init_state'], rnn_units=g.get('rnn_units', 0),
-                       rnn_before_mlp=bool(g.get('rnn_before_mlp', True)), space_over=g.get('space_over'))
+                       rnn_before_mlp=bool(g.get('rnn_before_mlp', True)), space_over=g.get('space_over'), network_over=g.get('network_over'))
     for ep, ref in enumerate(g['epochs_out']):
         agent.epoch_num += 1
         agent.train_epoch(noise=g['noise'][ep].to(DEV))
@@ -183,6 +184,7 @@ def _golden_run(name, graph, extra=None):
         torch.testing.assert_close(agent.game_rewards.mean, ref['game_rewards_mean'].reshape(-1), rtol=1e-4, atol=1e-5)
         assert agent.game_rewards.current_size == ref['game_rewards_size']
         torch.testing.assert_close(agent.game_lengths.mean, ref['game_lengths_mean'].reshape(-1), rtol=1e-5, atol=1e-5)
+    return agent
 
 
 @pytest.mark.parametrize('masked', [False, True])

@@ -75,7 +75,7 @@ class _Env:
                                      ('agent_tcshape.pt', False), ('agent_tcshape.pt', True), ('agent_tcshape.pt', 2), ('agent_lstm.pt', False),
                                      ('agent_lstm_after.pt', False), ('agent_sched_standard.pt', False), ('agent_misc.pt', False),
                                      ('agent_rescale.pt', False), ('agent_lstm_masked.pt', False), ('agent_lstm_after_masked.pt', False),
-                                     ('agent_minsigma.pt', False)])
+                                     ('agent_minsigma.pt', False), ('agent_separate.pt', False)])
 def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypatch, tmp_path):
     """tc=True drives the HOST code of the tcgen05 path (mixed_precision: True: packed-weight bookkeeping, split-partial offsets and
     stride, fused reduce+Adam tail, per-minibatch obs moments merged by the optimiser tail) with fp32 stand-ins for its kernels"""
@@ -104,6 +104,7 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
     network['space']['continuous'].update(g.get('space_over') or {})          # min_sigma (agent_minsigma.pt)
+    network.update(g.get('network_over') or {})                               # separate: True (agent_separate.pt)
     lstm = g.get('rnn_units', 0) > 0
     if lstm:
         network['rnn'] = {'name': 'lstm', 'units': g['rnn_units'], 'layers': 1, 'before_mlp': bool(g.get('rnn_before_mlp', True))}
@@ -136,7 +137,7 @@ def test_continuous_agent_host_logic_matches_reference_golden(name, tc, monkeypa
         torch.testing.assert_close(st[:, 2], ref['entropies'], rtol=1e-4, atol=1e-6)
         assert agent.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
         sd = agent.model.state_dict()
-        for k in O.param_names(len(g['units']), lstm=lstm):
+        for k in O.param_names(len(g['units']), lstm=lstm, separate=bool((g.get('network_over') or {}).get('separate', False))):
             torch.testing.assert_close(sd[k], ref['state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: k + ': ' + m)
         for pre, key in (('running_mean_std.', 'normalize_input'), ('value_mean_std.', 'normalize_value')):
             if cfgk.get(key, True):
@@ -168,6 +169,7 @@ def _build(monkeypatch, tmp_path, g, env, tc=False, over=None):
                                         'sigma_init': {'name': 'const_initializer', 'val': 0}, 'fixed_sigma': True}},
                'mlp': {'units': g['units'], 'activation': 'elu', 'initializer': {'name': 'default'}}}
     network['space']['continuous'].update(g.get('space_over') or {})
+    network.update(g.get('network_over') or {})
     r = Runner()
     r.load({'params': {'seed': 7, 'algo': {'name': 'a2c_continuous'}, 'model': {'name': 'continuous_a2c_logstd'}, 'network': network,
                        'config': config}})
@@ -565,3 +567,38 @@ def test_set_param_reaches_the_device_copies_the_kernels_read(monkeypatch, tmp_p
     a.epoch_num += 1
     res = a.train_epoch(noise=g['noise'][0])
     assert len(res[4]) == a.num_minibatches and a.last_stats.shape[0] == a.num_minibatches
+
+
+def test_separate_trunks_are_one_block_structured_mlp_whose_zeros_never_move(monkeypatch, tmp_path):
+    """separate: True (network_builder.py:494-512) = one MLP of twice the width with block-structured weights (model.py).  After two epochs
+    with weight decay, a global-norm clip and an entropy bonus: every structural zero of weights, gradients and both Adam moments is
+    still EXACTLY zero (masked gradient -> fixed point of Adam and of weight decay), the state dict has the reference's keys / shapes /
+    order, a reference state dict loads into the blocks, and the policy is never routed to the fused kernels (their optimiser tail has no
+    place for the mask)."""
+    from oracle import ppo_oracle as O
+    g = dict(torch.load(os.path.join(GOLDEN, 'agent_separate.pt'), weights_only=False))
+    a = _build(monkeypatch, tmp_path, g, _Env(g))
+    m = a.model
+    assert m.separate and m.trunk_units == g['units'] and m.units == [2 * u for u in g['units']] and not a.use_tc and not a.gemm_tc
+    structural = m.grad_mask == 0
+    assert int((~structural).sum()) == sum(g['init_state'][k].numel() for k in g['param_order'])
+    for ep in range(2):
+        a.epoch_num += 1
+        a.train_epoch(noise=g['noise'][ep])
+    assert float(m.exp_avg.abs().sum()) > 0
+    for arena in (m.flat, m.grad, m.exp_avg, m.exp_avg_sq):
+        assert float(arena[structural].abs().max()) == 0.0
+    sd = m.state_dict()
+    assert [k for k in sd if k.startswith('a2c_network')] == O.param_names(len(g['units']), separate=True) == g['param_order']
+    ref = g['epochs_out'][-1]['state']
+    for k in g['param_order']:
+        assert sd[k].shape == ref[k].shape
+    m.load_state_dict(ref)                       # a reference checkpoint's model goes into the blocks ...
+    for k in g['param_order']:
+        assert torch.equal(m.state_dict()[k], ref[k])
+    assert float(m.flat[structural].abs().max()) == 0.0          # ... and nowhere else
+    # tensor cores: layer by layer (the fused kernels' optimiser tail reduces and steps in one launch: no place for the mask)
+    g2 = dict(torch.load(os.path.join(GOLDEN, 'agent_tcshape.pt'), weights_only=False), network_over={'separate': True})
+    import _torch_ops
+    b = _build(monkeypatch, tmp_path, dict(g2, init_state={}), _Env(g2), tc=True, over={'mixed_precision': True})
+    assert b.model.separate and b.use_tc is False and b.gemm_tc is True

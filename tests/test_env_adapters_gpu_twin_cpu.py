@@ -45,3 +45,7 @@ def test_min_sigma_golden_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
 def test_layerwise_min_sigma_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
     import tests.test_agent_gpu as G
     G.test_layerwise_tensor_core_path_tracks_fp32_agent('mlp_128_64_32_min_sigma')
+
+
+def test_separate_trunks_gpu_test_body_holds_on_the_stand_ins(cpu_twin):
+    cpu_twin.test_separate_actor_critic_trunks_match_the_reference_golden_run(False)

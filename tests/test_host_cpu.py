@@ -264,7 +264,8 @@ def test_bench_reference_arm_prints_one_contract_line():
 
 @pytest.mark.parametrize('patch,what', [({'normalization': 'layer_norm'}, 'normalization'), ({'name': 'resnet_actor_critic'}, 'resnet_actor_critic'),
                                         ({'mlp': {'units': [16, 8], 'activation': 'elu', 'initializer': {'name': 'default'}, 'd2rl': True}}, 'd2rl'),
-                                        ({'separate': True}, 'separate'), ({'joint_obs_actions': {}}, 'joint_obs_actions')])
+                                        ({'separate': True, 'rnn': {'name': 'lstm', 'units': 8, 'layers': 1}}, 'separate actor/critic trunks with an rnn'),
+                                        ({'joint_obs_actions': {}}, 'joint_obs_actions')])
 def test_network_options_without_a_kernel_fail_loudly(patch, what):
     """a config option that changes the network's maths (network_builder.py:545-589) is either implemented or refused -- never ignored"""
     from rl_games_b200.model import B200Model

@@ -123,12 +123,13 @@ def _oracle_from_golden(g):
 
 @pytest.mark.parametrize('name', ['agent_base.pt', 'agent_masked.pt', 'agent_hardclip.pt', 'agent_lstm.pt', 'agent_rmsadv.pt',
                                   'agent_lstm_after.pt', 'agent_sched_standard.pt', 'agent_misc.pt', 'agent_rescale.pt', 'agent_lstm_masked.pt',
-                                  'agent_lstm_after_masked.pt', 'agent_trainloop.pt', 'agent_trainloop_adaptive.pt', 'agent_minsigma.pt'])
+                                  'agent_lstm_after_masked.pt', 'agent_trainloop.pt', 'agent_trainloop_adaptive.pt', 'agent_minsigma.pt', 'agent_separate.pt'])
 def test_full_train_epochs_match_reference_agent(name):
     """Two full train_epoch()s of the reference A2CAgent vs the oracle restatement, same tapes/noise."""
     g = load(name)
     lstm = g.get('rnn_units', 0) > 0
-    assert g['param_order'] == O.param_names(len(g['units']), lstm=lstm)
+    separate = bool((g.get('network_over') or {}).get('separate', False))
+    assert g['param_order'] == O.param_names(len(g['units']), lstm=lstm, separate=separate)
     ag = _oracle_from_golden(g)
     for ep, ref in enumerate(g['epochs_out']):
         out = ag.train_epoch(g['noise'][ep])
@@ -148,7 +149,7 @@ def test_full_train_epochs_match_reference_agent(name):
         torch.testing.assert_close(torch.stack(out['c_loss']), ref['c_losses'], rtol=1e-3, atol=1e-6)
         torch.testing.assert_close(torch.stack(out['entropy']), ref['entropies'], rtol=1e-5, atol=1e-6)
         assert ag.last_lr == pytest.approx(ref['last_lr'], rel=1e-12)
-        for k in O.param_names(len(g['units']), lstm=lstm):
+        for k in O.param_names(len(g['units']), lstm=lstm, separate=separate):
             torch.testing.assert_close(ag.model.p[k].detach(), ref['state'][k], rtol=1e-4, atol=2e-6, msg=lambda m: k + m)
         st = ref['state']
         if g['config'].get('normalize_input', True):

@@ -123,10 +123,8 @@ _REFUSED = {
     'carracing_ppo.yaml': "'cnn' networks", 'maniskill/ppo_pick_cube_rgbd_NOT_WORKING_YET.yaml': "'cnn' networks",
     'ppo_cartpole_masked_velocity_rnn.yaml': "'rnn' networks are not supported by the discrete", 'test/test_rnn.yaml': "'rnn' networks are not supported by the discrete",
     'test/test_rnn_multidiscrete_mhv.yaml': "'rnn' networks are not supported by the discrete",
-    'ppo_continuous.yaml': 'separate actor/critic trunks', 'ppo_lunar.yaml': 'separate actor/critic trunks',
-    'ppo_lunar_continiuos_torch.yaml': 'separate actor/critic trunks', 'ppo_pendulum.yaml': 'separate actor/critic trunks',
-    'ppo_pendulum_torch.yaml': 'separate actor/critic trunks', 'ppo_reacher.yaml': 'separate actor/critic trunks',
-    'test/test_asymmetric_continuous.yaml': 'separate actor/critic trunks|rnn: only a single-layer',
+    'ppo_lunar_continiuos_torch.yaml': 'separate actor/critic trunks with an rnn', 'ppo_pendulum.yaml': 'state-dependent sigma',
+    'test/test_asymmetric_continuous.yaml': 'separate actor/critic trunks with an rnn|rnn: only a single-layer',
     'ppo_continuous_lstm.yaml': "model 'continuous_a2c_lstm_logstd'", 'ppo_walker_rnn.yaml': "rnn: only a single-layer 'lstm'",
     'ppo_walker_tcnn.yaml': "network 'tcnnnet'", 'test/test_discrite_testnet_aux_loss.yaml': "network 'testnet_aux_loss'",
     'test/test_asymmetric_discrete.yaml': 'central_value_config|rnn', 'test/test_asymmetric_discrete_mhv.yaml': 'central_value_config',
@@ -258,8 +256,10 @@ def test_every_shipped_ppo_yaml_of_the_in_scope_families_runs_through_the_refere
     assert type(agent) is (A2CAgentCV if cv else A2CAgent) and agent.has_central_value == cv
     assert agent.model.min_sigma == net['space']['continuous'].get('min_sigma', 0.0)
     units = net['mlp']['units']
+    separate = bool(net.get('separate', False))          # two trunks = one block-structured MLP of twice the width, never on the fused kernels
+    assert agent.model.separate == separate and agent.model.trunk_units == units and agent.model.units == [u * (2 if separate else 1) for u in units]
     fused = len(units) == 3 and all(u <= m for u, m in zip(units, (256, 128, 64))) and 'rnn' not in net and agent.model.min_sigma == 0 \
-        and net['mlp']['activation'] in ('elu', 'relu', 'tanh')
+        and net['mlp']['activation'] in ('elu', 'relu', 'tanh') and not separate
     mp = c.get('mixed_precision')
     mb = c.get('minibatch_size') or N * c['minibatch_size_per_env']
     n_upd = c['mini_epochs'] * (N * c['horizon_length'] // mb)

@@ -167,3 +167,18 @@ def test_critic_group_feeds_the_central_value_net_like_the_reference_golden_run(
         for k in g['cv_param_order']:
             torch.testing.assert_close(csd[k].cpu(), ref['cv_state'][k], rtol=1e-3, atol=2e-5, msg=lambda m: 'cv ' + k + ': ' + m)
         assert int(csd['value_mean_std.count']) == int(ref['cv_state']['value_mean_std.count'])
+
+
+@pytest.mark.parametrize('graph', [False, True])
+def test_separate_actor_critic_trunks_match_the_reference_golden_run(graph):
+    """separate: True for a CONTINUOUS policy (network_builder.py:494-512; configs/ppo_continuous.yaml, ppo_lunar.yaml, ppo_reacher.yaml ...):
+    the two trunks run as one block-structured MLP of twice the width through the same fp32 kernels (rl_games_b200/model.py); the gradient
+    entries of the structural zeros are masked before the optimiser.  Against the reference's own run (`agent_separate.pt`: masked rows,
+    global-norm clip over both trunks, weight decay, entropy bonus, bound loss); the structural zeros are still exactly zero afterwards."""
+    from tests.test_agent_gpu import _golden_run
+    agent = _golden_run('agent_separate.pt', graph)
+    m = agent.model
+    assert m.separate and m.units == [2 * u for u in m.trunk_units]
+    structural = m.grad_mask == 0
+    for arena in (m.flat, m.grad, m.exp_avg, m.exp_avg_sq):
+        assert float(arena[structural].abs().max()) == 0.0
